@@ -1,0 +1,209 @@
+/*
+ * tfgpu.h — C-ABI of the B200 columnar transform engine.
+ *
+ * This is the drop-in boundary for ONE hot path of transferia/transferia:
+ *
+ *   Sinker.Push([]abstract.ChangeItem) -> pkg/middlewares -> pkg/transformer chain
+ *     -> sink typesystem cast -> sink wire format
+ *
+ * The Go side (cgo shim) transposes a []ChangeItem batch of
+ * one table into the columnar `tf_batch` below (pinned host memory it owns),
+ * calls one of the tfgpu_* entry points, and rebuilds ChangeItems / writes the
+ * wire bytes from the result.  No torch / C++ types cross this boundary: plain
+ * pointers, sizes and NUL-terminated JSON strings only.
+ *
+ * Reference interfaces each entry point stands in for (paths relative to the
+ * reference repository root):
+ *
+ *   tfgpu_engine_create / _destroy
+ *       middleware construction: func(Sinker) Sinker
+ *       pkg/abstract/middleware.go:3, pkg/middlewares/pluggable_transformer.go:19-30,
+ *       pkg/abstract/sink.go:14-19 (Close)
+ *   tfgpu_plan
+ *       transformation.AddTablePlan (Suitable + ResultSchema per transformer,
+ *       cached by TableSchema.Hash())  pkg/transformer/transformation.go:46-85,93-121
+ *       pkg/abstract/transformer.go:32-48, pkg/abstract/changeitem/table_schema.go:54-67
+ *   tfgpu_push_columns
+ *       transformation.Push / do -> Transformer.Apply chain
+ *       pkg/transformer/transformation.go:122-158,236-282
+ *   tfgpu_push_encode
+ *       the same chain followed by the destination's per-row cast + wire encode:
+ *       pkg/providers/clickhouse/sink_table.go:605-684 (doOperation),
+ *       :698-704 (restoreVals) -> columntypes.Restore columntypes/types.go:74-115
+ *       -> clickhouse-go/v2 native block + LZ4 frames (conn/connection.go:46)
+ *   tfgpu_result_* accessors
+ *       abstract.TransformerResult{Transformed, Errors}  pkg/abstract/transformer.go:40-48
+ *
+ * Threading (pkg/abstract/sink.go:12): calls on ONE engine handle are never
+ * concurrent; distinct handles are independent (one per pipeline / per GPU).
+ *
+ * Error classes (pkg/abstract/sink.go:16-17, pkg/abstract/errors.go:14):
+ *   rc == 0  ok
+ *   rc  > 0  retriable (device OOM, launch failure) — Push may be retried
+ *   rc  < 0  fatal (unsupported schema/type, malformed config) — NewFatalError
+ * Per-row transformer failures are DATA, not errors: they come back as an
+ * error-row list (row index + message id), mirroring TransformerResult.Errors.
+ */
+#ifndef TFGPU_H_
+#define TFGPU_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- return codes ------------------------------------------------------- */
+#define TF_OK                 0
+#define TF_E_RETRY_OOM        1   /* retriable: device / pinned allocation failed  */
+#define TF_E_RETRY_LAUNCH     2   /* retriable: kernel launch / stream error       */
+#define TF_E_FATAL_CONFIG    -1   /* fatal: malformed cfg / schema / transformers   */
+#define TF_E_FATAL_UNSUPPORTED -2 /* fatal: type or transformer not supported       */
+#define TF_E_FATAL_ARG       -3   /* fatal: bad handle / NULL argument              */
+#define TF_E_FATAL_NODEVICE  -4   /* fatal: no CUDA device — there is no CPU fallback */
+
+/* ---- logical column types: the YT type strings of pkg/abstract/typesystem/schema.go:48-68.
+ * NOTE the naming trap: YT "string" is BYTES, YT "utf8" is text. */
+typedef enum tf_type {
+    TF_INT8 = 1, TF_INT16 = 2, TF_INT32 = 3, TF_INT64 = 4,
+    TF_UINT8 = 5, TF_UINT16 = 6, TF_UINT32 = 7, TF_UINT64 = 8,
+    TF_FLOAT = 9,        /* "float"    -> Go float32            */
+    TF_DOUBLE = 10,      /* "double"   -> Go float64            */
+    TF_BOOLEAN = 11,     /* "boolean"  -> Go bool, 1 byte       */
+    TF_BYTES = 12,       /* "string"   -> Go []byte             */
+    TF_UTF8 = 13,        /* "utf8"     -> Go string             */
+    TF_ANY = 14,         /* "any"      -> JSON text (or raw Go string, see aux tags) */
+    TF_DATE = 15,        /* "date"     -> Go time.Time          */
+    TF_DATETIME = 16,    /* "datetime" -> Go time.Time          */
+    TF_TIMESTAMP = 17,   /* "timestamp"-> Go time.Time          */
+    TF_INTERVAL = 18     /* "interval" -> Go time.Duration (int64 ns) */
+} tf_type;
+
+/* ---- physical layout of one column ---------------------------------------
+ * fixed-width (ints, float, double, boolean, interval):
+ *     values = nrows little-endian elements of the natural width (boolean: u8 0/1).
+ * time types (date / datetime / timestamp), i.e. Go time.Time:
+ *     values = nrows int64 Unix seconds (UTC instant),
+ *     aux    = optional nrows uint32 nanoseconds [0, 1e9); NULL = all zero.
+ * var-width (string / utf8 / any):
+ *     offsets = nrows+1 uint32, heap = offsets[nrows] bytes.
+ *     any: heap holds the value's JSON text (what json.Marshal gives); aux is an
+ *     optional nrows uint8 tag array, tag 1 = the Go value was a `string` and the
+ *     heap holds its raw bytes (columntypes.Restore passes such values through
+ *     unquoted, columntypes/types.go:77-79).
+ * validity: optional bitmap, bit r (LSB-first in byte r/8) = 1 means non-nil.
+ */
+typedef struct tf_col {
+    int32_t         type;       /* tf_type */
+    int32_t         flags;      /* reserved, 0 */
+    const void*     values;
+    const uint8_t*  validity;
+    const uint32_t* offsets;
+    const uint8_t*  heap;
+    const void*     aux;
+    uint64_t        heap_len;
+} tf_col;
+
+#define TF_MEM_HOST   0   /* pointers are host memory (pinned preferred): copies are inside the call */
+#define TF_MEM_DEVICE 1   /* pointers are device memory on the engine's GPU: batch is HBM-resident   */
+
+/* abstract.Kind of each row (pkg/abstract/changeitem/kind.go:5-43); only row kinds travel */
+#define TF_KIND_INSERT 0
+#define TF_KIND_UPDATE 1
+#define TF_KIND_DELETE 2
+
+typedef struct tf_batch {
+    uint64_t        nrows;
+    uint32_t        ncols;
+    uint32_t        mem;        /* TF_MEM_HOST | TF_MEM_DEVICE */
+    const tf_col*   cols;       /* ncols entries, host memory, schema order */
+    const uint8_t*  kinds;      /* optional nrows TF_KIND_*; NULL = all insert */
+} tf_batch;
+
+/* ---- per-row transformer errors (TransformerResult.Errors) ----------------- */
+#define TF_ROWERR_FILTER_KIND      1  /* filter_rows.go:103-107 "Found non-supported kind '%s'"  */
+#define TF_ROWERR_FILTER_OVERFLOW  2  /* filter_rows util.go:66-68 errIntOverflow                  */
+#define TF_ROWERR_FILTER_TYPEPAIR  3  /* filter_rows.go:364 "Unsupported type pair"                */
+
+typedef struct tf_rowerr {
+    uint32_t row;      /* index into the INPUT batch */
+    uint16_t code;     /* TF_ROWERR_* */
+    uint16_t term;     /* index of the transformer in the plan that raised it */
+} tf_rowerr;
+
+/* ---- wire formats for tfgpu_push_encode ----------------------------------- */
+#define TF_WIRE_CH_NATIVE      1  /* ClickHouse native block, uncompressed                       */
+#define TF_WIRE_CH_NATIVE_LZ4  2  /* same, cut into [CityHash128][0x82][sizes][LZ4 block] frames */
+#define TF_WIRE_CH_JSONEACHROW 3  /* httpuploader/marshal.go:88-253                              */
+
+typedef struct tfgpu_engine tfgpu_engine;
+typedef struct tfgpu_result tfgpu_result;
+
+/* cfg_json: {"frame_bytes":32768,"max_rows":N,...} or NULL for defaults.
+ * One engine drives one device (device_ids[0]); n_devices must be 1 — multi-GPU
+ * is one engine per GPU with batches dealt round-robin by the host. */
+int tfgpu_engine_create(const char* cfg_json, const int* device_ids, int n_devices,
+                        tfgpu_engine** out);
+int tfgpu_engine_destroy(tfgpu_engine* e);
+const char* tfgpu_last_error(const tfgpu_engine* e);
+
+/* Launch all work on this CUstream/cudaStream_t (NULL = the engine's own stream). */
+int tfgpu_engine_set_stream(tfgpu_engine* e, void* cuda_stream);
+
+/* Build (or fetch from the schema-hash cache) the plan for one table.
+ *   table_namespace/table_name : abstract.TableID
+ *   schema_json       : JSON array of ColSchema objects with the reference's tags
+ *                       (pkg/abstract/changeitem/col_schema.go:14-29)
+ *   transformers_json : the transfer YAML's `transformation.transformers` list as JSON
+ *                       (pkg/transformer/abstract.go:20-48)
+ *   sink_json         : {"type":"clickhouse", ...} or NULL when only push_columns is used
+ * Returns plan id >= 0 in *plan_id. */
+int tfgpu_plan(tfgpu_engine* e, const char* table_namespace, const char* table_name,
+               const char* schema_json, const char* transformers_json, const char* sink_json,
+               int* plan_id);
+/* JSON of the plan: result schema (ResultSchema chain), transformers kept by Suitable(),
+ * the compiled predicate terms — owned by the engine, valid until the engine is destroyed. */
+const char* tfgpu_plan_describe(tfgpu_engine* e, int plan_id);
+
+/* Transformer chain only: Transformed rows come back columnar (host memory owned by the
+ * result), Errors as a row-error list. */
+int tfgpu_push_columns(tfgpu_engine* e, int plan_id, const tf_batch* in, tfgpu_result** out);
+
+/* Transformer chain + sink cast + wire encode, fused on the device. */
+int tfgpu_push_encode(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch* in,
+                      tfgpu_result** out);
+
+/* Same as tfgpu_push_encode but asynchronous and HBM-resident: `in` must be
+ * TF_MEM_DEVICE, nothing is copied back and no host sync happens; the wire
+ * bytes stay in the engine's device arena (tfgpu_result_device_*) until the
+ * next call on this engine. Used to time kernels without PCIe in the way. */
+int tfgpu_push_encode_resident(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch* in);
+/* After a stream sync: counters of the last resident call. */
+int tfgpu_resident_stats(tfgpu_engine* e, uint64_t* rows_out, uint64_t* raw_bytes,
+                         uint64_t* wire_bytes, uint64_t* n_errors);
+/* Copy the last resident call's uncompressed block / wire bytes to host (tests). */
+int tfgpu_resident_fetch(tfgpu_engine* e, int what /*0=raw block,1=wire*/, uint8_t* dst, uint64_t cap);
+
+/* Result accessors (all memory is owned by the result until tfgpu_result_release). */
+uint64_t          tfgpu_result_rows_in(const tfgpu_result* r);
+uint64_t          tfgpu_result_rows_out(const tfgpu_result* r);
+uint64_t          tfgpu_result_n_errors(const tfgpu_result* r);
+const tf_rowerr*  tfgpu_result_errors(const tfgpu_result* r);
+const tf_batch*   tfgpu_result_batch(const tfgpu_result* r);      /* push_columns only   */
+const uint8_t*    tfgpu_result_bytes(const tfgpu_result* r);      /* push_encode: wire    */
+uint64_t          tfgpu_result_bytes_len(const tfgpu_result* r);
+uint64_t          tfgpu_result_raw_len(const tfgpu_result* r);    /* uncompressed block   */
+uint64_t          tfgpu_result_n_frames(const tfgpu_result* r);
+void              tfgpu_result_release(tfgpu_result* r);
+
+/* Number of kernel launches issued by this engine since creation (bench `gpu_launches`). */
+uint64_t tfgpu_engine_launch_count(const tfgpu_engine* e);
+
+/* Library identity: "tfgpu <version> sm_100a". */
+const char* tfgpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFGPU_H_ */

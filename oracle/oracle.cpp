@@ -1,0 +1,480 @@
+// ORACLE — test infrastructure only. Never linked into or called from the product path.
+// CPU restatement (row-at-a-time, boxed values) of transferia's per-batch hot path.
+// Every function names the reference file:line it follows (paths relative to the
+// reference repository root).  See oracle.h for the parity status.
+#include "oracle.h"
+#include "go_strconv.hpp"
+#include "hashes.hpp"
+#include "lz4_block.hpp"
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <limits>
+
+using namespace orc;
+
+namespace {
+
+// ------------------------------------------------------------------ boxed values
+struct Boxed {
+    orc_val v;
+    std::string own;     // storage when the value was produced by a transformer
+    void set_string(std::string s, int kind) { own = std::move(s); v.kind = kind; v.s = (const uint8_t*)own.data(); v.slen = own.size(); }
+};
+
+inline bool col_valid(const tf_col& c, uint64_t r) { return !c.validity || ((c.validity[r >> 3] >> (r & 7)) & 1); }
+
+// The Go dynamic type a column's value has under the typesystem contract
+// pkg/abstract/typesystem/values/type_checkers.go:39-84.
+void box(const tf_col& c, uint64_t r, orc_val& v) {
+    std::memset(&v, 0, sizeof v);
+    if (!col_valid(c, r)) { v.kind = OG_NIL; return; }
+    switch (c.type) {
+    case TF_INT8:  v.kind = OG_INT8;  v.i = ((const int8_t*)c.values)[r]; break;
+    case TF_INT16: v.kind = OG_INT16; v.i = ((const int16_t*)c.values)[r]; break;
+    case TF_INT32: v.kind = OG_INT32; v.i = ((const int32_t*)c.values)[r]; break;
+    case TF_INT64: v.kind = OG_INT64; v.i = ((const int64_t*)c.values)[r]; break;
+    case TF_UINT8:  v.kind = OG_UINT8;  v.u = ((const uint8_t*)c.values)[r]; break;
+    case TF_UINT16: v.kind = OG_UINT16; v.u = ((const uint16_t*)c.values)[r]; break;
+    case TF_UINT32: v.kind = OG_UINT32; v.u = ((const uint32_t*)c.values)[r]; break;
+    case TF_UINT64: v.kind = OG_UINT64; v.u = ((const uint64_t*)c.values)[r]; break;
+    case TF_FLOAT:  v.kind = OG_FLOAT32; v.f = ((const float*)c.values)[r]; break;
+    case TF_DOUBLE: v.kind = OG_FLOAT64; v.f = ((const double*)c.values)[r]; break;
+    case TF_BOOLEAN: v.kind = OG_BOOL; v.i = ((const uint8_t*)c.values)[r] != 0; break;
+    case TF_INTERVAL: v.kind = OG_DURATION; v.i = ((const int64_t*)c.values)[r]; break;
+    case TF_DATE: case TF_DATETIME: case TF_TIMESTAMP:
+        v.kind = OG_TIME; v.i = ((const int64_t*)c.values)[r]; v.nsec = c.aux ? ((const uint32_t*)c.aux)[r] : 0; break;
+    case TF_BYTES: v.kind = OG_BYTES; v.s = c.heap + c.offsets[r]; v.slen = c.offsets[r + 1] - c.offsets[r]; break;
+    case TF_UTF8:  v.kind = OG_STRING; v.s = c.heap + c.offsets[r]; v.slen = c.offsets[r + 1] - c.offsets[r]; break;
+    case TF_ANY:
+        v.kind = (c.aux && ((const uint8_t*)c.aux)[r] == 1) ? OG_STRING : OG_JSON;
+        v.s = c.heap + c.offsets[r]; v.slen = c.offsets[r + 1] - c.offsets[r]; break;
+    default: v.kind = OG_NIL;
+    }
+}
+
+// encoding/json string encoder with escapeHTML=true (json.Marshal default): Go 1.25 encode.go appendString
+std::string go_json_quote(const uint8_t* s, size_t n) {
+    static const char* hex = "0123456789abcdef";
+    std::string d; d += '"';
+    size_t i = 0;
+    while (i < n) {
+        uint8_t b = s[i];
+        if (b < 0x80) {
+            if (b >= 0x20 && b != '"' && b != '\\' && b != '<' && b != '>' && b != '&') { d += (char)b; i++; continue; }
+            d += '\\';
+            switch (b) {
+            case '\\': case '"': d += (char)b; break;
+            case '\b': d += 'b'; break; case '\f': d += 'f'; break; case '\n': d += 'n'; break; case '\r': d += 'r'; break; case '\t': d += 't'; break;
+            default: d += "u00"; d += hex[b >> 4]; d += hex[b & 15];
+            }
+            i++; continue;
+        }
+        // decode one UTF-8 rune (Go utf8.DecodeRune semantics: invalid -> RuneError width 1)
+        uint32_t r = 0xFFFD; size_t w = 1;
+        if (b >= 0xC2 && b <= 0xDF && i + 1 < n && (s[i + 1] & 0xC0) == 0x80) { r = ((b & 0x1F) << 6) | (s[i + 1] & 0x3F); w = 2; }
+        else if (b >= 0xE0 && b <= 0xEF && i + 2 < n && (s[i + 1] & 0xC0) == 0x80 && (s[i + 2] & 0xC0) == 0x80) {
+            uint32_t t = ((b & 0x0F) << 12) | ((s[i + 1] & 0x3F) << 6) | (s[i + 2] & 0x3F);
+            if (t >= 0x800 && !(t >= 0xD800 && t <= 0xDFFF)) { r = t; w = 3; }
+        } else if (b >= 0xF0 && b <= 0xF4 && i + 3 < n && (s[i + 1] & 0xC0) == 0x80 && (s[i + 2] & 0xC0) == 0x80 && (s[i + 3] & 0xC0) == 0x80) {
+            uint32_t t = ((b & 0x07) << 18) | ((s[i + 1] & 0x3F) << 12) | ((s[i + 2] & 0x3F) << 6) | (s[i + 3] & 0x3F);
+            if (t >= 0x10000 && t <= 0x10FFFF) { r = t; w = 4; }
+        }
+        if (r == 0xFFFD && w == 1) { d += "\\ufffd"; i++; continue; }
+        if (r == 0x2028 || r == 0x2029) { d += "\\u202"; d += hex[r & 0xF]; i += w; continue; }
+        d.append((const char*)s + i, w); i += w;
+    }
+    d += '"';
+    return d;
+}
+
+// fmt.Sprintf("%v", value) for the dynamic types the typesystem produces
+std::string go_sprint_v(const orc_val& v) {
+    switch (v.kind) {
+    case OG_NIL: return "<nil>";
+    case OG_INT8: case OG_INT16: case OG_INT32: case OG_INT64: case OG_INT: return fmt_i64(v.i);
+    case OG_UINT8: case OG_UINT16: case OG_UINT32: case OG_UINT64: case OG_UINT: return fmt_u64(v.u);
+    case OG_FLOAT32: return fmt_f32((float)v.f, FMT_G_V);
+    case OG_FLOAT64: return fmt_f64(v.f, FMT_G_V);
+    case OG_BOOL: return v.i ? "true" : "false";
+    case OG_STRING: case OG_JSON: return std::string((const char*)v.s, v.slen);
+    case OG_BYTES: {   // %v of []byte: [1 2 3]
+        std::string s = "[";
+        for (uint64_t i = 0; i < v.slen; i++) { if (i) s += ' '; s += fmt_u64(v.s[i]); }
+        return s + "]";
+    }
+    case OG_DURATION: return fmt_duration(v.i);
+    case OG_TIME: {    // time.Time.String(): "2006-01-02 15:04:05.999999999 -0700 MST" (UTC)
+        std::string r = fmt_rfc3339nano_utc(v.i, v.nsec);
+        r[10] = ' '; r.pop_back(); return r + " +0000 UTC";
+    }
+    }
+    return "";
+}
+
+// to_string.SerializeToString: pkg/transformer/registry/to_string/to_string.go:145-171 (skipUTCConversion=false)
+std::string serialize_to_string(const orc_val& v, int32_t yt) {
+    switch (yt) {
+    case TF_BYTES: if (v.kind == OG_BYTES) return std::string((const char*)v.s, v.slen); break;   // :151-155
+    case TF_ANY:                                                                                   // :156-160 json.Marshal(value)
+        if (v.kind == OG_NIL) return "null";
+        if (v.kind == OG_STRING) return go_json_quote(v.s, v.slen);
+        if (v.kind == OG_JSON) return std::string((const char*)v.s, v.slen);
+        if (v.kind == OG_BOOL) return v.i ? "true" : "false";
+        if (v.kind == OG_FLOAT64) return fmt_f64(v.f, FMT_JSON);
+        if (v.kind == OG_FLOAT32) return fmt_f32((float)v.f, FMT_JSON);
+        if (v.kind >= OG_INT8 && v.kind <= OG_UINT64) return go_sprint_v(v);
+        break;
+    case TF_DATE: if (v.kind == OG_TIME) return fmt_date_only(v.i); break;                         // :161-164
+    case TF_DATETIME: case TF_TIMESTAMP: if (v.kind == OG_TIME) return fmt_rfc3339nano_utc(v.i, v.nsec); break;  // :165-168
+    }
+    return go_sprint_v(v);                                                                         // :170
+}
+
+// ------------------------------------------------------------------ filter_rows
+// toInt64E: pkg/transformer/registry/filter_rows/util.go:47-79
+// returns 0 ok, 1 not-int, 2 overflow
+int to_int64e(const orc_val& v, int64_t& out) {
+    switch (v.kind) {
+    case OG_INT: case OG_INT8: case OG_INT16: case OG_INT32: case OG_INT64: out = v.i; return 0;
+    case OG_UINT: case OG_UINT8: case OG_UINT16: case OG_UINT32: out = (int64_t)v.u; return 0;
+    case OG_UINT64: if (v.u > (uint64_t)std::numeric_limits<int64_t>::max()) return 2; out = (int64_t)v.u; return 0;
+    default: return 1;
+    }
+}
+// spf13/cast v1.7.1 ToFloat64E (filter_rows.go:201)
+bool to_float64e(const orc_val& v, double& out) {
+    switch (v.kind) {
+    case OG_FLOAT64: case OG_FLOAT32: out = v.f; return true;
+    case OG_INT: case OG_INT8: case OG_INT16: case OG_INT32: case OG_INT64: out = (double)v.i; return true;
+    case OG_UINT: case OG_UINT8: case OG_UINT16: case OG_UINT32: case OG_UINT64: out = (double)v.u; return true;
+    case OG_BOOL: out = v.i ? 1 : 0; return true;
+    case OG_NIL: out = 0; return true;
+    case OG_STRING: {   // strconv.ParseFloat(s, 64)
+        if (v.slen == 0 || v.slen > 400) return false;
+        std::string s((const char*)v.s, v.slen);
+        for (char c : s) if (!(std::isdigit((unsigned char)c) || c == '.' || c == 'e' || c == 'E' || c == '+' || c == '-' || c == '_' )) {
+            // Go also accepts inf/nan/hex floats; not reachable from typed columns
+            return false;
+        }
+        char* end = nullptr; double d = std::strtod(s.c_str(), &end);
+        if (end != s.c_str() + s.size()) return false;
+        out = d; return true;
+    }
+    default: return false;   // time.Time, []byte, json text, Duration(int64 kind via fmt.Stringer? no: cast handles time.Duration? -> not numeric here)
+    }
+}
+
+template <typename T> bool ordered(T a, T b, int op, bool& res) {   // matchOrderedValue filter_rows.go:367-383
+    switch (op) {
+    case OP_EQ: res = a == b; return true; case OP_NE: res = a != b; return true;
+    case OP_LT: res = a < b; return true;  case OP_LE: res = a <= b; return true;
+    case OP_GT: res = a > b; return true;  case OP_GE: res = a >= b; return true;
+    }
+    return false;
+}
+int cmp_bytes(const uint8_t* a, size_t an, const uint8_t* b, size_t bn) {
+    size_t m = an < bn ? an : bn; int c = m ? std::memcmp(a, b, m) : 0;
+    if (c) return c < 0 ? -1 : 1;
+    return an < bn ? -1 : (an > bn ? 1 : 0);
+}
+bool contains_bytes(const uint8_t* h, size_t hn, const uint8_t* n, size_t nn) {
+    if (nn == 0) return true;
+    if (nn > hn) return false;
+    for (size_t i = 0; i + nn <= hn; i++) if (std::memcmp(h + i, n, nn) == 0) return true;
+    return false;
+}
+
+// matchValue: pkg/transformer/registry/filter_rows/filter_rows.go:180-365
+int match_value(const orc_val& v1, const orc_term& t, bool& matched) {
+    const int op = t.op; const bool is_set = (op == OP_IN || op == OP_NOTIN);
+    const int base = t.vtype & 15; const bool is_list = (t.vtype & LV_LIST) != 0;
+    int64_t int1 = 0; bool is_int1 = false, is_float1 = false;
+    int r = to_int64e(v1, int1);
+    if (r == 0) is_int1 = true; else if (r == 2) return TF_ROWERR_FILTER_OVERFLOW;          // :190-197
+    double float1 = 0; bool fok = to_float64e(v1, float1);
+    if (!is_int1 && fok) is_float1 = true;                                                     // :199-205
+    auto in_ilist = [&](int64_t x) { for (int k = 0; k < t.nlist; k++) if (t.ilist[k] == x) return true; return false; };
+    auto in_flist = [&](double x) { for (int k = 0; k < t.nlist; k++) if (t.flist[k] == x) return true; return false; };
+    auto set_res = [&](bool contained) { matched = (op == OP_IN) ? contained : !contained; return 0; };
+    switch (base) {
+    case LV_INT:                                                                                // :213-241
+        if (is_int1) {
+            if (is_set) return set_res(in_ilist(int1));
+            return ordered<int64_t>(int1, t.i, op, matched) ? 0 : TF_ROWERR_FILTER_TYPEPAIR;
+        }
+        if (is_float1) {
+            if (is_set) { if (std::trunc(float1) == float1) return set_res(in_ilist((int64_t)float1)); matched = false; return 0; }
+            return ordered<double>(float1, (double)t.i, op, matched) ? 0 : TF_ROWERR_FILTER_TYPEPAIR;
+        }
+        break;
+    case LV_FLOAT:                                                                              // :243-267
+        if (is_int1) {
+            if (is_set) return set_res(in_flist((double)int1));
+            return ordered<double>((double)int1, t.f, op, matched) ? 0 : TF_ROWERR_FILTER_TYPEPAIR;
+        }
+        if (is_float1) {
+            if (is_set) return set_res(in_flist(float1));
+            return ordered<double>(float1, t.f, op, matched) ? 0 : TF_ROWERR_FILTER_TYPEPAIR;
+        }
+        break;
+    case LV_BOOL:                                                                               // :269-285
+        if (is_list) break;   // val2.IsBool() is false for lists -> falls to default/unsupported
+        if (v1.kind == OG_BOOL) return ordered<int>(v1.i ? 1 : 0, t.i ? 1 : 0, op, matched) ? 0 : TF_ROWERR_FILTER_TYPEPAIR;
+        break;
+    case LV_STRING: {                                                                           // :287-328
+        const bool isb = v1.kind == OG_BYTES;
+        if (!is_list && isb) {
+            if (op == OP_MATCH) { matched = contains_bytes(v1.s, v1.slen, t.s, t.slen); return 0; }
+            if (op == OP_NOTMATCH) { matched = !contains_bytes(v1.s, v1.slen, t.s, t.slen); return 0; }
+            int c = cmp_bytes(v1.s, v1.slen, t.s, t.slen);                                      // matchBytesValue :385-401
+            switch (op) {
+            case OP_EQ: matched = c == 0; return 0; case OP_NE: matched = c != 0; return 0;
+            case OP_LT: matched = c < 0; return 0;  case OP_LE: matched = c < 1; return 0;
+            case OP_GT: matched = c > 0; return 0;  case OP_GE: matched = c > -1; return 0;
+            }
+            return TF_ROWERR_FILTER_TYPEPAIR;
+        }
+        if (isb || v1.kind == OG_STRING) {
+            if (op == OP_MATCH) { matched = contains_bytes(v1.s, v1.slen, t.s, t.slen); return 0; }
+            if (op == OP_NOTMATCH) { matched = !contains_bytes(v1.s, v1.slen, t.s, t.slen); return 0; }
+            if (is_set) {
+                bool c = false;
+                for (int k = 0; k < t.nlist && !c; k++) { uint32_t a = t.soffs[k], b = t.soffs[k + 1]; c = (b - a == v1.slen) && std::memcmp(t.sheap + a, v1.s, v1.slen) == 0; }
+                return set_res(c);
+            }
+            int c = cmp_bytes(v1.s, v1.slen, t.s, t.slen);
+            switch (op) {
+            case OP_EQ: matched = c == 0; return 0; case OP_NE: matched = c != 0; return 0;
+            case OP_LT: matched = c < 0; return 0;  case OP_LE: matched = c <= 0; return 0;
+            case OP_GT: matched = c > 0; return 0;  case OP_GE: matched = c >= 0; return 0;
+            }
+            return TF_ROWERR_FILTER_TYPEPAIR;
+        }
+        break;
+    }
+    case LV_TIME:                                                                               // :330-351
+        if (v1.kind == OG_TIME) {
+            int64_t um = v1.i * 1000000 + (int64_t)(v1.nsec / 1000);                           // time.UnixMicro()
+            if (is_set) return set_res(in_ilist(um));
+            return ordered<int64_t>(um, t.i, op, matched) ? 0 : TF_ROWERR_FILTER_TYPEPAIR;
+        }
+        break;   // string-typed dates (stringToTime, util.go:15-45) do not occur in typed columns
+    case LV_NULL:                                                                               // :353-358
+        if (op == OP_EQ) { matched = v1.kind == OG_NIL; return 0; }
+        if (op == OP_NE) { matched = v1.kind != OG_NIL; return 0; }
+        break;
+    }
+    return TF_ROWERR_FILTER_TYPEPAIR;                                                           // :364
+}
+
+// ------------------------------------------------------------------ ClickHouse sink
+// columntypes.ToChType + Nullable(!Required): pkg/providers/clickhouse/columntypes/types.go:210-248,
+// sink_table.go:196-208,229-235.  ch:-prefixed original types are not handled (fatal).
+std::string ch_base_type(int32_t yt) {
+    switch (yt) {
+    case TF_ANY: case TF_BYTES: case TF_UTF8: return "String";
+    case TF_DOUBLE: return "Float64"; case TF_FLOAT: return "Float32"; case TF_BOOLEAN: return "UInt8";
+    case TF_INT8: return "Int8"; case TF_INT16: return "Int16"; case TF_INT32: return "Int32"; case TF_INT64: return "Int64";
+    case TF_UINT8: return "UInt8"; case TF_UINT16: return "UInt16"; case TF_UINT32: return "UInt32"; case TF_UINT64: return "UInt64";
+    case TF_DATE: return "Date"; case TF_DATETIME: return "DateTime"; case TF_TIMESTAMP: return "DateTime64(6)";
+    case TF_INTERVAL: return "Int64";
+    }
+    return "String";
+}
+std::string ch_type(const orc_colschema& c, int32_t yt) {
+    std::string b = ch_base_type(yt);
+    return c.required ? b : "Nullable(" + b + ")";
+}
+
+const int64_t CH_MIN_DATE = 0;              // 1970-01-01  columntypes/types.go:15-18
+const int64_t CH_MAX_DATE = 4291747200LL;   // 2106-01-01
+
+struct ColBuilder {
+    int32_t yt; bool nullable;
+    std::vector<uint8_t> nulls, data;
+    void put(const void* p, size_t n) { const uint8_t* b = (const uint8_t*)p; data.insert(data.end(), b, b + n); }
+    void put_varint(uint64_t v) { while (v >= 0x80) { data.push_back((uint8_t)(v | 0x80)); v >>= 7; } data.push_back((uint8_t)v); }
+    void put_str(const uint8_t* s, size_t n) { put_varint(n); put(s, n); }
+};
+
+// One value: columntypes.Restore (columntypes/types.go:74-115) -> abstract.Restore
+// (pkg/abstract/restore.go:20-223) -> driver column append (clickhouse-go/v2 lib/column, third-party).
+// Returns false on a value the driver would reject.
+bool append_value(ColBuilder& cb, const orc_val& v) {
+    const bool is_null = v.kind == OG_NIL;
+    if (cb.nullable) cb.nulls.push_back(is_null ? 1 : 0);
+    else if (is_null && !(cb.yt == TF_ANY || cb.yt == TF_BYTES || cb.yt == TF_UTF8)) {
+        // nil into a non-Nullable column: the reference relies on insert_null_as_default / the driver's zero value
+    }
+    switch (cb.yt) {
+    case TF_INT8: { int8_t x = is_null ? 0 : (int8_t)v.i; cb.put(&x, 1); return true; }
+    case TF_INT16: { int16_t x = is_null ? 0 : (int16_t)v.i; cb.put(&x, 2); return true; }
+    case TF_INT32: { int32_t x = is_null ? 0 : (int32_t)v.i; cb.put(&x, 4); return true; }
+    case TF_INT64: { int64_t x = is_null ? 0 : v.i; cb.put(&x, 8); return true; }
+    case TF_INTERVAL: { int64_t x = is_null ? 0 : v.i; cb.put(&x, 8); return true; }
+    case TF_UINT8: { uint8_t x = is_null ? 0 : (uint8_t)v.u; cb.put(&x, 1); return true; }
+    case TF_UINT16: { uint16_t x = is_null ? 0 : (uint16_t)v.u; cb.put(&x, 2); return true; }
+    case TF_UINT32: { uint32_t x = is_null ? 0 : (uint32_t)v.u; cb.put(&x, 4); return true; }
+    case TF_UINT64: { uint64_t x = is_null ? 0 : v.u; cb.put(&x, 8); return true; }
+    case TF_BOOLEAN: { uint8_t x = is_null ? 0 : (v.i ? 1 : 0); cb.put(&x, 1); return true; }
+    case TF_FLOAT: { float x = is_null ? 0 : (float)v.f; cb.put(&x, 4); return true; }
+    case TF_DOUBLE: { double x = is_null ? 0 : v.f; cb.put(&x, 8); return true; }
+    case TF_DATE: {        // applyClickhouseDateBoundaries types.go:20-29, then Date = days since epoch (u16)
+        int64_t s = is_null ? 0 : v.i;
+        if (!is_null) { if (s > CH_MAX_DATE || (s == CH_MAX_DATE && v.nsec > 0)) s = CH_MAX_DATE; if (s < CH_MIN_DATE) s = CH_MIN_DATE; }
+        uint16_t d = (uint16_t)(s / 86400); cb.put(&d, 2); return true;
+    }
+    case TF_DATETIME: {    // same clamp, DateTime = u32 Unix seconds
+        int64_t s = is_null ? 0 : v.i;
+        if (!is_null) { if (s > CH_MAX_DATE || (s == CH_MAX_DATE && v.nsec > 0)) s = CH_MAX_DATE; if (s < CH_MIN_DATE) s = CH_MIN_DATE; }
+        uint32_t x = (uint32_t)s; cb.put(&x, 4); return true;
+    }
+    case TF_TIMESTAMP: {   // no clamp (types.go:94 covers only date/datetime); DateTime64(6) = UnixMicro
+        int64_t x = is_null ? 0 : v.i * 1000000 + (int64_t)(v.nsec / 1000); cb.put(&x, 8); return true;
+    }
+    case TF_BYTES: case TF_UTF8:
+        if (is_null) { cb.put_varint(0); return true; }
+        cb.put_str(v.s, v.slen); return true;
+    case TF_ANY:           // types.go:76-91: string passes through, anything else is JSON text (marshalAny)
+        if (is_null) { cb.put_varint(0); return true; }
+        cb.put_str(v.s, v.slen); return true;
+    }
+    return false;
+}
+
+void put_uvarint(std::vector<uint8_t>& o, uint64_t v) { while (v >= 0x80) { o.push_back((uint8_t)(v | 0x80)); v >>= 7; } o.push_back((uint8_t)v); }
+void put_string(std::vector<uint8_t>& o, const std::string& s) { put_uvarint(o, s.size()); o.insert(o.end(), s.begin(), s.end()); }
+
+// ClickHouse native-protocol Data block at client revision 54460 (clickhouse-go/v2 v2.46.0
+// lib/proto/block.go Encode: block info, #columns, #rows, then per column name, type,
+// has-custom-serialization byte (revision >= 54454), data).
+std::vector<uint8_t> native_block(const std::vector<std::string>& names, const std::vector<std::string>& types,
+                                  const std::vector<ColBuilder>& cols, uint64_t nrows) {
+    std::vector<uint8_t> o;
+    put_uvarint(o, 1); o.push_back(0);                       // field 1: is_overflows = false
+    put_uvarint(o, 2); int32_t bucket = -1; const uint8_t* b = (const uint8_t*)&bucket; o.insert(o.end(), b, b + 4);  // field 2: bucket_num = -1
+    put_uvarint(o, 0);
+    put_uvarint(o, names.size()); put_uvarint(o, nrows);
+    for (size_t c = 0; c < names.size(); c++) {
+        put_string(o, names[c]); put_string(o, types[c]); o.push_back(0);
+        if (nrows == 0) continue;
+        if (cols[c].nullable) o.insert(o.end(), cols[c].nulls.begin(), cols[c].nulls.end());
+        o.insert(o.end(), cols[c].data.begin(), cols[c].data.end());
+    }
+    return o;
+}
+
+void to_buf(const std::vector<uint8_t>& v, orc_buf* b) {
+    if (!b) return;
+    b->len = v.size(); b->data = (uint8_t*)std::malloc(v.size() ? v.size() : 1);
+    if (v.size()) std::memcpy(b->data, v.data(), v.size());
+}
+int copy_out(const std::string& s, char* dst, int cap) { if ((int)s.size() + 1 > cap) return -1; std::memcpy(dst, s.data(), s.size()); dst[s.size()] = 0; return (int)s.size(); }
+
+}  // namespace
+
+extern "C" {
+
+void orc_free(orc_buf* b) { if (b && b->data) { std::free(b->data); b->data = nullptr; b->len = 0; } }
+
+int orc_fmt_float64(double v, int f, char* dst, int cap) { return copy_out(fmt_f64(v, (FloatFmt)f), dst, cap); }
+int orc_fmt_float32(float v, int f, char* dst, int cap) { return copy_out(fmt_f32(v, (FloatFmt)f), dst, cap); }
+int orc_fmt_duration(int64_t ns, char* dst, int cap) { return copy_out(fmt_duration(ns), dst, cap); }
+int orc_fmt_rfc3339nano(int64_t sec, uint32_t nsec, char* dst, int cap) { return copy_out(fmt_rfc3339nano_utc(sec, nsec), dst, cap); }
+int orc_serialize_to_string(const orc_val* v, int32_t yt, char* dst, int cap) { return copy_out(serialize_to_string(*v, yt), dst, cap); }
+
+// HmacHasher.hash: pkg/transformer/registry/mask/hmac_hasher.go:29-33
+void orc_hmac_sha256_hex(const uint8_t* key, uint64_t klen, const uint8_t* msg, uint64_t mlen, char out[65]) {
+    uint8_t d[32]; hmac_sha256(key, klen, msg, mlen, d); std::string h = hex_lower(d, 32); std::memcpy(out, h.data(), 64); out[64] = 0;
+}
+void orc_sha256(const uint8_t* msg, uint64_t mlen, uint8_t out[32]) { Sha256 s; s.init(); s.update(msg, mlen); s.final(out); }
+void orc_cityhash128(const uint8_t* p, uint64_t n, uint64_t* lo, uint64_t* hi) { city::u128 h = city::hash128(p, n); *lo = h.first; *hi = h.second; }
+uint64_t orc_lz4_bound(uint64_t n) { return lz4_bound(n); }
+uint64_t orc_lz4_compress(const uint8_t* src, uint64_t n, uint8_t* dst) { return lz4_compress(src, n, dst); }
+int64_t orc_lz4_decompress(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t cap) { size_t r = lz4_decompress(src, n, dst, cap); return r == (size_t)-1 ? -1 : (int64_t)r; }
+
+int orc_match_value(const orc_val* v, const orc_term* t, int* matched) { bool m = false; int rc = match_value(*v, *t, m); *matched = m; return rc; }
+
+int orc_ch_type(const orc_colschema* c, char* dst, int cap) { return copy_out(ch_type(*c, c->type), dst, cap); }
+
+int orc_push_encode(const tf_batch* in, const orc_colschema* schema, const orc_step* steps, int nsteps,
+                    int wire_fmt, uint64_t frame_bytes, orc_buf* out_raw, orc_buf* out_wire,
+                    uint64_t* rows_out, tf_rowerr* errs, uint64_t* nerrs) {
+    const uint32_t nc = in->ncols;
+    // result schema after the ResultSchema chain (mask / to_string turn columns into utf8 / string)
+    std::vector<int32_t> out_type(nc);
+    for (uint32_t c = 0; c < nc; c++) out_type[c] = in->cols[c].type;
+    for (int s = 0; s < nsteps; s++) {
+        if (steps[s].kind == STEP_MASK) for (int k = 0; k < steps[s].ncols; k++) out_type[steps[s].cols[k]] = TF_UTF8;        // hmac_hasher.go:35-47
+        if (steps[s].kind == STEP_TO_STRING) for (int k = 0; k < steps[s].ncols; k++) out_type[steps[s].cols[k]] = steps[s].convert_to_bytes ? TF_BYTES : TF_UTF8;  // to_string.go:66-74
+    }
+    std::vector<ColBuilder> cbs(nc);
+    std::vector<std::string> names(nc), types(nc);
+    for (uint32_t c = 0; c < nc; c++) {
+        cbs[c].yt = out_type[c]; cbs[c].nullable = !schema[c].required;
+        names[c] = schema[c].name; types[c] = ch_type(schema[c], out_type[c]);
+    }
+    uint64_t kept = 0, ne = 0;
+    std::vector<Boxed> row(nc);
+    std::vector<int32_t> cur_type(nc);
+    for (uint64_t r = 0; r < in->nrows; r++) {
+        // []interface{} of this ChangeItem
+        for (uint32_t c = 0; c < nc; c++) { box(in->cols[c], r, row[c].v); cur_type[c] = in->cols[c].type; }
+        const int kind = in->kinds ? in->kinds[r] : TF_KIND_INSERT;
+        bool keep = true;
+        for (int s = 0; s < nsteps && keep; s++) {
+            const orc_step& st = steps[s];
+            if (st.kind == STEP_FILTER_ROWS) {                       // FilterRowsTransformer.Apply filter_rows.go:99-130
+                if (kind == TF_KIND_UPDATE || kind == TF_KIND_DELETE) { errs[ne++] = tf_rowerr{(uint32_t)r, TF_ROWERR_FILTER_KIND, (uint16_t)s}; keep = false; break; }
+                bool any = false; int err = 0;
+                for (int e = 0; e < st.nexpr && !any && !err; e++) {   // matchItem :137-148 (OR), matchExpression :150-177 (AND)
+                    bool all = true;
+                    for (uint32_t k = st.expr_off[e]; k < st.expr_off[e + 1]; k++) {
+                        bool m = false; int rc = match_value(row[st.terms[k].col].v, st.terms[k], m);
+                        if (rc) { err = rc; break; }
+                        if (!m) { all = false; break; }
+                    }
+                    if (!err && all) any = true;
+                }
+                if (err) { errs[ne++] = tf_rowerr{(uint32_t)r, (uint16_t)err, (uint16_t)s}; keep = false; break; }
+                if (!any) keep = false;
+            } else if (st.kind == STEP_MASK) {                        // HmacHasher.Apply hmac_hasher.go:52-74
+                for (int k = 0; k < st.ncols; k++) {
+                    int c = st.cols[k];
+                    std::string text = serialize_to_string(row[c].v, cur_type[c]);
+                    uint8_t d[32]; hmac_sha256(st.salt, st.salt_len, (const uint8_t*)text.data(), text.size(), d);
+                    row[c].set_string(hex_lower(d, 32), OG_STRING); cur_type[c] = TF_UTF8;
+                }
+            } else if (st.kind == STEP_TO_STRING) {                   // ToStringTransformer.Apply to_string.go:58-97
+                for (int k = 0; k < st.ncols; k++) {
+                    int c = st.cols[k];
+                    row[c].set_string(serialize_to_string(row[c].v, cur_type[c]), st.convert_to_bytes ? OG_BYTES : OG_STRING);
+                    cur_type[c] = st.convert_to_bytes ? TF_BYTES : TF_UTF8;
+                }
+            }
+        }
+        if (!keep) continue;
+        // sink: restoreVals sink_table.go:698-704 + driver append
+        for (uint32_t c = 0; c < nc; c++) if (!append_value(cbs[c], row[c].v)) return TF_E_FATAL_UNSUPPORTED;
+        kept++;
+    }
+    if (rows_out) *rows_out = kept;
+    if (nerrs) *nerrs = ne;
+    if (wire_fmt == 0) return 0;
+    std::vector<uint8_t> raw = native_block(names, types, cbs, kept);
+    to_buf(raw, out_raw);
+    if (wire_fmt == TF_WIRE_CH_NATIVE) { to_buf(raw, out_wire); return 0; }
+    if (wire_fmt == TF_WIRE_CH_NATIVE_LZ4) { to_buf(ch_compress_frames(raw.data(), raw.size(), frame_bytes), out_wire); return 0; }
+    return TF_E_FATAL_UNSUPPORTED;
+}
+
+int orc_ch_decode_frames(const uint8_t* wire, uint64_t n, orc_buf* raw, uint64_t* n_frames) {
+    std::vector<uint8_t> r; size_t nf = 0;
+    if (!ch_decompress_frames(wire, n, r, &nf)) return -1;
+    to_buf(r, raw); if (n_frames) *n_frames = nf; return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+/* ORACLE — test infrastructure only (tests/, __graft_entry__.smoke(), bench.py cpu_baseline /
+ * --impl reference).  Never linked into or called from the product path.
+ *
+ * C API of the CPU restatement of transferia's per-batch hot path.  Every function cites the
+ * reference file:line it follows in oracle.cpp.  The batch layout is the product's tf_batch
+ * (include/tfgpu.h) with HOST pointers; processing is row-at-a-time over boxed values, like
+ * the Go reference (`[]interface{}` per ChangeItem).
+ *
+ * Parity status (also in DESIGN.md):
+ *   pinned by reference goldens: mask_field digests, %v / RFC3339 text forms, filter_rows
+ *     matrices, filter grammar;  pinned by independent implementations here: shortest float
+ *     digits (CPython repr / numpy), SHA-256/HMAC (hashlib), LZ4 decode (liblz4, pyarrow);
+ *   PARITY UNPINNED: ClickHouse native block bytes, LZ4 compressed bytes, CityHash128 — third
+ *     party in the reference (clickhouse-go/v2 v2.46.0, ch-go v0.71.0, pierrec/lz4/v4 v4.1.25,
+ *     go-faster/city v1.0.1), not vendored, and no reference test pins them.
+ */
+#ifndef ORACLE_H_
+#define ORACLE_H_
+#include <stdint.h>
+#include "../include/tfgpu.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Go dynamic type of a boxed value */
+enum { OG_NIL = 0, OG_INT8, OG_INT16, OG_INT32, OG_INT64, OG_UINT8, OG_UINT16, OG_UINT32, OG_UINT64,
+       OG_FLOAT32, OG_FLOAT64, OG_BOOL, OG_STRING, OG_BYTES, OG_TIME, OG_DURATION, OG_JSON /* any: non-string value, JSON text */,
+       OG_INT /* Go int */, OG_UINT };
+
+typedef struct orc_val {
+    int32_t kind; uint32_t nsec;
+    int64_t i;          /* signed ints, bool, duration ns, time seconds */
+    uint64_t u;         /* unsigned ints */
+    double f;           /* float32 (exactly representable) / float64 */
+    const uint8_t* s; uint64_t slen;
+} orc_val;
+
+/* filter.OperatorType order: library/go/yandex/cloud/filter/filters.go:12-23 */
+enum { OP_EQ = 0, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE, OP_IN, OP_NOTIN, OP_MATCH, OP_NOTMATCH };
+/* literal kinds */
+enum { LV_INT = 1, LV_FLOAT = 2, LV_BOOL = 3, LV_STRING = 4, LV_TIME = 5, LV_NULL = 6, LV_LIST = 16 };
+
+typedef struct orc_term {
+    int32_t col;        /* column index in the batch */
+    int32_t op;
+    int32_t vtype;      /* LV_* (| LV_LIST) */
+    int32_t nlist;
+    int64_t i;          /* int / bool / time as UnixMicro */
+    double f;
+    const uint8_t* s; uint64_t slen;
+    const int64_t* ilist;       /* int list, time list (UnixMicro) */
+    const double* flist;
+    const uint32_t* soffs; const uint8_t* sheap;  /* string list: nlist+1 offsets */
+} orc_term;
+
+typedef struct orc_colschema {
+    const char* name;
+    int32_t type;       /* tf_type */
+    int32_t required;
+    const char* original_type;  /* may be NULL */
+} orc_colschema;
+
+enum { STEP_FILTER_ROWS = 1, STEP_MASK = 2, STEP_TO_STRING = 3 };
+typedef struct orc_step {
+    int32_t kind;
+    /* filter_rows */
+    const orc_term* terms; const uint32_t* expr_off; int32_t nexpr;
+    /* mask_field / convert_to_string: column indexes */
+    const int32_t* cols; int32_t ncols;
+    const uint8_t* salt; uint64_t salt_len;
+    int32_t convert_to_bytes;
+} orc_step;
+
+typedef struct orc_buf { uint8_t* data; uint64_t len; } orc_buf;
+void orc_free(orc_buf* b);
+
+/* ---- scalar entry points (golden-vector tests) ---- */
+int  orc_fmt_float64(double v, int fmt /*0 %v,1 'f',2 json*/, char* dst, int cap);
+int  orc_fmt_float32(float v, int fmt, char* dst, int cap);
+int  orc_fmt_duration(int64_t ns, char* dst, int cap);
+int  orc_fmt_rfc3339nano(int64_t sec, uint32_t nsec, char* dst, int cap);
+int  orc_serialize_to_string(const orc_val* v, int32_t yt_type, char* dst, int cap);  /* to_string.go:149-171 */
+void orc_hmac_sha256_hex(const uint8_t* key, uint64_t klen, const uint8_t* msg, uint64_t mlen, char out[65]);
+void orc_sha256(const uint8_t* msg, uint64_t mlen, uint8_t out[32]);
+void orc_cityhash128(const uint8_t* p, uint64_t n, uint64_t* lo, uint64_t* hi);
+uint64_t orc_lz4_bound(uint64_t n);
+uint64_t orc_lz4_compress(const uint8_t* src, uint64_t n, uint8_t* dst);
+int64_t  orc_lz4_decompress(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t cap);
+/* matchValue: returns 0 ok (*matched set), else TF_ROWERR_* */
+int  orc_match_value(const orc_val* v, const orc_term* t, int* matched);
+
+/* ---- batch entry points ---- */
+/* ClickHouse column type the sink DDL gives this column: sink_table.go:196-208 + columntypes/types.go:210-248 */
+int  orc_ch_type(const orc_colschema* c, char* dst, int cap);
+
+/* Whole hot path, row by row: transformer steps -> columntypes.Restore -> native block (-> LZ4 frames).
+ * out_raw: uncompressed native block; out_wire: what goes on the socket for wire_fmt.
+ * errs must hold nrows entries. Returns 0 or a negative fatal code. */
+int orc_push_encode(const tf_batch* in, const orc_colschema* schema,
+                    const orc_step* steps, int nsteps,
+                    int wire_fmt, uint64_t frame_bytes,
+                    orc_buf* out_raw, orc_buf* out_wire,
+                    uint64_t* rows_out, tf_rowerr* errs, uint64_t* nerrs);
+
+/* Verify + decode a frame stream with the oracle's own LZ4 decoder and CityHash. */
+int orc_ch_decode_frames(const uint8_t* wire, uint64_t n, orc_buf* raw, uint64_t* n_frames);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,586 @@
+"""ORACLE — test infrastructure only (tests/, __graft_entry__.smoke(), bench.py cpu_baseline /
+--impl reference).  Never imported by the product package.
+
+Python front of the CPU oracle:
+  * loads oracle/liboracle.so (C++ restatement of the per-row hot path, oracle.cpp);
+  * restates the filter-expression grammar used by `filter_rows`
+        library/go/yandex/cloud/filter/grammar/grammar.go:256-313 (lexer regexp + participle grammar)
+        library/go/yandex/cloud/filter/filters.go:237-313      (opFromG / validateTerm / Parse)
+    config-level logic runs once per plan, so pure Python is adequate here;
+  * restates plan building for the transformers on the path
+        pkg/transformer/transformation.go:46-85 (Suitable -> ResultSchema chain)
+        filter_rows.go:445-519, hmac_hasher.go:76-89, mask.go:20-67, to_string.go:99-113.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(_HERE))
+from transferia_b200 import abi  # noqa: E402  (memory layout only)
+
+# ----------------------------------------------------------------------------- library
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.cpp", "oracle.h", "go_strconv.hpp", "hashes.hpp", "lz4_block.hpp")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=subprocess.DEVNULL)
+    return so
+
+
+class OrcVal(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("nsec", C.c_uint32), ("i", C.c_int64), ("u", C.c_uint64),
+                ("f", C.c_double), ("s", C.c_char_p), ("slen", C.c_uint64)]
+
+
+class OrcTerm(C.Structure):
+    _fields_ = [("col", C.c_int32), ("op", C.c_int32), ("vtype", C.c_int32), ("nlist", C.c_int32),
+                ("i", C.c_int64), ("f", C.c_double), ("s", C.c_char_p), ("slen", C.c_uint64),
+                ("ilist", C.c_void_p), ("flist", C.c_void_p), ("soffs", C.c_void_p), ("sheap", C.c_void_p)]
+
+
+class OrcColSchema(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("type", C.c_int32), ("required", C.c_int32), ("original_type", C.c_char_p)]
+
+
+class OrcStep(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("terms", C.POINTER(OrcTerm)), ("expr_off", C.c_void_p), ("nexpr", C.c_int32),
+                ("cols", C.c_void_p), ("ncols", C.c_int32), ("salt", C.c_char_p), ("salt_len", C.c_uint64),
+                ("convert_to_bytes", C.c_int32)]
+
+
+class OrcBuf(C.Structure):
+    _fields_ = [("data", C.POINTER(C.c_uint8)), ("len", C.c_uint64)]
+
+
+(OG_NIL, OG_INT8, OG_INT16, OG_INT32, OG_INT64, OG_UINT8, OG_UINT16, OG_UINT32, OG_UINT64, OG_FLOAT32, OG_FLOAT64,
+ OG_BOOL, OG_STRING, OG_BYTES, OG_TIME, OG_DURATION, OG_JSON, OG_INT, OG_UINT) = range(19)
+OP_EQ, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE, OP_IN, OP_NOTIN, OP_MATCH, OP_NOTMATCH = range(10)
+LV_INT, LV_FLOAT, LV_BOOL, LV_STRING, LV_TIME, LV_NULL, LV_LIST = 1, 2, 3, 4, 5, 6, 16
+STEP_FILTER_ROWS, STEP_MASK, STEP_TO_STRING = 1, 2, 3
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        L.orc_fmt_float64.argtypes = [C.c_double, C.c_int, C.c_char_p, C.c_int]
+        L.orc_fmt_float32.argtypes = [C.c_float, C.c_int, C.c_char_p, C.c_int]
+        L.orc_fmt_duration.argtypes = [C.c_int64, C.c_char_p, C.c_int]
+        L.orc_fmt_rfc3339nano.argtypes = [C.c_int64, C.c_uint32, C.c_char_p, C.c_int]
+        L.orc_serialize_to_string.argtypes = [C.POINTER(OrcVal), C.c_int32, C.c_char_p, C.c_int]
+        L.orc_hmac_sha256_hex.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_char_p]
+        L.orc_hmac_sha256_hex.restype = None
+        L.orc_sha256.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p]
+        L.orc_sha256.restype = None
+        L.orc_cityhash128.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.orc_cityhash128.restype = None
+        L.orc_lz4_bound.argtypes = [C.c_uint64]; L.orc_lz4_bound.restype = C.c_uint64
+        L.orc_lz4_compress.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]; L.orc_lz4_compress.restype = C.c_uint64
+        L.orc_lz4_decompress.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]; L.orc_lz4_decompress.restype = C.c_int64
+        L.orc_match_value.argtypes = [C.POINTER(OrcVal), C.POINTER(OrcTerm), C.POINTER(C.c_int)]
+        L.orc_ch_type.argtypes = [C.POINTER(OrcColSchema), C.c_char_p, C.c_int]
+        L.orc_push_encode.argtypes = [C.POINTER(abi.TfBatch), C.POINTER(OrcColSchema), C.POINTER(OrcStep), C.c_int,
+                                      C.c_int, C.c_uint64, C.POINTER(OrcBuf), C.POINTER(OrcBuf),
+                                      C.POINTER(C.c_uint64), C.POINTER(abi.TfRowErr), C.POINTER(C.c_uint64)]
+        L.orc_ch_decode_frames.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(OrcBuf), C.POINTER(C.c_uint64)]
+        L.orc_free.argtypes = [C.POINTER(OrcBuf)]; L.orc_free.restype = None
+        _lib = L
+    return _lib
+
+
+# ----------------------------------------------------------------------------- scalar helpers
+
+def fmt_float64(v: float, fmt: int = 0) -> str:
+    b = C.create_string_buffer(400); n = lib().orc_fmt_float64(v, fmt, b, 400); return b.raw[:n].decode()
+
+
+def fmt_float32(v, fmt: int = 0) -> str:
+    b = C.create_string_buffer(400); n = lib().orc_fmt_float32(float(np.float32(v)), fmt, b, 400); return b.raw[:n].decode()
+
+
+def fmt_duration(ns: int) -> str:
+    b = C.create_string_buffer(64); n = lib().orc_fmt_duration(ns, b, 64); return b.raw[:n].decode()
+
+
+def fmt_rfc3339nano(sec: int, nsec: int = 0) -> str:
+    b = C.create_string_buffer(64); n = lib().orc_fmt_rfc3339nano(sec, nsec, b, 64); return b.raw[:n].decode()
+
+
+def make_val(kind: int, *, i: int = 0, u: int = 0, f: float = 0.0, s: bytes = b"", nsec: int = 0) -> OrcVal:
+    v = OrcVal(); v.kind = kind; v.i = i; v.u = u; v.f = f; v.nsec = nsec
+    v._s = s; v.s = s; v.slen = len(s)
+    return v
+
+
+def serialize_to_string(v: OrcVal, yt_type: int) -> bytes:
+    b = C.create_string_buffer(1 << 16); n = lib().orc_serialize_to_string(C.byref(v), yt_type, b, 1 << 16); return b.raw[:n]
+
+
+def hmac_hex(salt: bytes, msg: bytes) -> str:
+    out = C.create_string_buffer(65); lib().orc_hmac_sha256_hex(salt, len(salt), msg, len(msg), out); return out.value.decode()
+
+
+def cityhash128(data: bytes) -> Tuple[int, int]:
+    lo, hi = C.c_uint64(), C.c_uint64()
+    buf = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data or b"\0")
+    lib().orc_cityhash128(buf, len(data), C.byref(lo), C.byref(hi)); return lo.value, hi.value
+
+
+def lz4_compress(data: bytes) -> bytes:
+    n = len(data); cap = lib().orc_lz4_bound(n)
+    src = (C.c_uint8 * max(1, n)).from_buffer_copy(data or b"\0"); dst = (C.c_uint8 * cap)()
+    c = lib().orc_lz4_compress(src, n, dst); return bytes(dst[:c])
+
+
+def lz4_decompress(data: bytes, raw_len: int) -> Optional[bytes]:
+    src = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data or b"\0"); dst = (C.c_uint8 * max(1, raw_len))()
+    r = lib().orc_lz4_decompress(src, len(data), dst, raw_len)
+    return None if r < 0 else bytes(dst[:r])
+
+
+def ch_decode_frames(wire: bytes) -> Tuple[Optional[bytes], int]:
+    src = (C.c_uint8 * max(1, len(wire))).from_buffer_copy(wire or b"\0")
+    raw = OrcBuf(); nf = C.c_uint64()
+    rc = lib().orc_ch_decode_frames(src, len(wire), C.byref(raw), C.byref(nf))
+    if rc != 0:
+        return None, 0
+    out = C.string_at(raw.data, raw.len); lib().orc_free(C.byref(raw)); return out, nf.value
+
+
+# ----------------------------------------------------------------------------- filter grammar
+# grammar.go:256-266 — the lexer is literally this regexp, tried at every position, first alternative wins.
+_LEX = re.compile(
+    r"(?P<Operator>!=|<=|>=|!~|[=<>~])"
+    r"|(?P<String>'((\\'|[^']))*'|\"(\\\"|[^\"])*\")"
+    r"|(?P<DateTime>\d{4}-\d{2}-\d{2}(T\d{2}:\d{2}(:\d{2}(\.\d+)?)?(Z|[+-]\d+(:\d+)?)?)?)"
+    r"|(?P<Ident>[a-zA-Z][a-zA-Z0-9_.]*)"
+    r"|(?P<Float>[-+]?\d+\.\d+)"
+    r"|(?P<Int>[-+]?\d+)"
+    r"|(?P<Punctuation>[(),])"
+    r"|(?P<WS>\s+)")
+
+
+class FilterSyntaxError(ValueError):
+    pass
+
+
+def _unquote(tok: str) -> str:
+    """participle.Unquote("String"): strconv.UnquoteChar over the body with the token's own quote."""
+    q, body, out, i = tok[0], tok[1:-1], [], 0
+    raw = body.encode("utf-8", "surrogateescape")
+    res = bytearray()
+    while i < len(raw):
+        c = raw[i]
+        if c != 0x5C:
+            res.append(c); i += 1; continue
+        i += 1
+        if i >= len(raw):
+            raise FilterSyntaxError("invalid syntax")
+        e = chr(raw[i]); i += 1
+        simple = {"a": 7, "b": 8, "f": 12, "n": 10, "r": 13, "t": 9, "v": 11, "\\": 0x5C}
+        if e in simple:
+            res.append(simple[e])
+        elif e in ("'", '"'):
+            if e != q:
+                raise FilterSyntaxError("invalid syntax")
+            res.append(ord(e))
+        elif e == "x":
+            res.append(int(raw[i:i + 2], 16)); i += 2
+        elif e in "uU":
+            n = 4 if e == "u" else 8
+            res += chr(int(raw[i:i + n], 16)).encode(); i += n
+        elif e in "01234567":
+            res.append(int(raw[i - 1:i + 2], 8)); i += 2
+        else:
+            raise FilterSyntaxError("invalid syntax")
+    return bytes(res)
+
+
+_DAYS = [0, 31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31]
+
+
+def _days_from_civil(y, m, d):
+    y -= m <= 2
+    era = (y if y >= 0 else y - 399) // 400
+    yoe = y - era * 400
+    doy = (153 * (m - 3 if m > 2 else m + 9) + 2) // 5 + d - 1
+    doe = yoe * 365 + yoe // 4 - yoe // 100 + doy
+    return era * 146097 + doe - 719468
+
+
+def parse_filter_time(value: str) -> int:
+    """DateTime.delayedParse grammar.go:176-188 with findTimeLayout :120-149; returns UnixMicro."""
+    m = re.fullmatch(r"(\d{4})-(\d{2})-(\d{2})(?:T(\d{2}):(\d{2})(?::(\d{2})(?:\.(\d+))?)?(Z|[+-]\d+(?::\d+)?)?)?", value)
+    if not m:
+        raise FilterSyntaxError("bad time " + value)
+    y, mo, d = int(m[1]), int(m[2]), int(m[3])
+    leap = (y % 4 == 0 and y % 100 != 0) or y % 400 == 0
+    if not (1 <= mo <= 12) or not (1 <= d <= _DAYS[mo] + (1 if mo == 2 and leap else 0)):
+        raise FilterSyntaxError("day out of range")
+    hh = int(m[4] or 0); mi = int(m[5] or 0); ss = int(m[6] or 0)
+    if hh > 23 or mi > 59 or ss > 59:
+        raise FilterSyntaxError("time out of range")
+    frac = (m[7] or "")
+    nsec = int((frac + "000000000")[:9]) if frac else 0
+    off = 0
+    tz = m[8]
+    if tz and tz != "Z":
+        sign = -1 if tz[0] == "-" else 1
+        if ":" in tz:
+            h, mm = tz[1:].split(":")
+            if len(h) != 2 or len(mm) != 2:
+                raise FilterSyntaxError("bad zone")
+            off = sign * (int(h) * 3600 + int(mm) * 60)
+        else:
+            if len(tz) != 3:
+                raise FilterSyntaxError("bad zone")
+            off = sign * int(tz[1:]) * 3600
+    sec = _days_from_civil(y, mo, d) * 86400 + hh * 3600 + mi * 60 + ss - off
+    return sec * 1_000_000 + nsec // 1000
+
+
+@dataclass
+class Term:
+    attribute: str
+    op: int
+    vtype: int            # LV_* | LV_LIST
+    value: Any            # python value / list
+
+
+_OPS = {"=": OP_EQ, "!=": OP_NE, "<": OP_LT, "<=": OP_LE, ">": OP_GT, ">=": OP_GE, "~": OP_MATCH, "!~": OP_NOTMATCH}
+
+
+def parse_filter(src: str) -> List[Term]:
+    """filter.Parse (filters.go:293-313) over grammar.Parse (grammar.go:275-313)."""
+    if src == "":
+        return []
+    toks: List[Tuple[str, str]] = []
+    pos = 0
+    while pos < len(src):
+        m = _LEX.match(src, pos)
+        if not m or m.end() == pos:
+            raise FilterSyntaxError(f"invalid token at {pos}")
+        kind = next(k for k in ("Operator", "String", "DateTime", "Ident", "Float", "Int", "Punctuation", "WS") if m.group(k) is not None)
+        toks.append((kind, m.group(0))); pos = m.end()
+    p = 0
+
+    def peek(k=0):
+        return toks[p + k] if p + k < len(toks) else ("EOF", "")
+
+    def skip_ws():
+        nonlocal p
+        while peek()[0] == "WS":
+            p += 1
+
+    def is_kw(tok, *names):
+        return tok[0] == "Ident" and tok[1].upper() in names
+
+    def parse_value() -> Tuple[int, Any]:
+        nonlocal p
+        kind, text = peek()
+        if kind == "String":
+            p += 1; return LV_STRING, _unquote(text)
+        if kind == "DateTime":
+            p += 1; return LV_TIME, parse_filter_time(text)
+        if is_kw((kind, text), "TRUE", "FALSE"):
+            p += 1; return LV_BOOL, text.upper() == "TRUE"
+        if kind == "Float":
+            p += 1; return LV_FLOAT, float(text)
+        if kind == "Int":
+            p += 1
+            v = int(text)
+            if not (-(1 << 63) <= v < (1 << 63)):
+                raise FilterSyntaxError("value out of range")
+            return LV_INT, v
+        if is_kw((kind, text), "NULL", "NIL"):
+            p += 1; return LV_NULL, None
+        if kind == "Punctuation" and text == "(":
+            p += 1; skip_ws()
+            items = [parse_value()]; skip_ws()
+            while True:
+                skip_ws()
+                if peek() == ("Punctuation", ","):
+                    p += 1; skip_ws(); items.append(parse_value()); skip_ws(); continue
+                break
+            if peek() != ("Punctuation", ")"):
+                raise FilterSyntaxError(f"unexpected token {peek()[1]!r}")
+            p += 1
+            head = items[0][0]
+            for i, it in enumerate(items):                      # validateTerm filters.go:255-270
+                if it[0] != head:
+                    raise FilterSyntaxError("list items should have same type")
+                if it[0] & LV_LIST:
+                    raise FilterSyntaxError("nested list are not supported")
+            return head | LV_LIST, [it[1] for it in items]
+        raise FilterSyntaxError(f"unexpected token {text!r}")
+
+    def parse_term() -> Term:
+        nonlocal p
+        kind, text = peek()
+        if kind != "Ident":
+            raise FilterSyntaxError(f"unexpected token {text!r}")
+        attr = text; p += 1; skip_ws()
+        kind, text = peek()
+        if kind == "Operator":
+            op = _OPS[text]; p += 1
+        elif is_kw((kind, text), "IN"):
+            op = OP_IN; p += 1
+        elif is_kw((kind, text), "NOT"):
+            p += 1; skip_ws()
+            if not is_kw(peek(), "IN"):
+                raise FilterSyntaxError(f"unexpected token {peek()[1]!r}")
+            op = OP_NOTIN; p += 1
+        else:
+            raise FilterSyntaxError(f"unexpected token {text!r}")
+        skip_ws()
+        vt, val = parse_value(); skip_ws()
+        is_list = bool(vt & LV_LIST)
+        if is_list and op not in (OP_IN, OP_NOTIN):
+            raise FilterSyntaxError("list values require [ NOT ] IN operator")
+        if not is_list and op in (OP_IN, OP_NOTIN):
+            raise FilterSyntaxError("operator expect list value")
+        if vt == LV_NULL and op not in (OP_EQ, OP_NE):
+            raise FilterSyntaxError('NULL expects "=" or "!=" operator')
+        return Term(attr, op, vt, val)
+
+    terms: List[Term] = []
+    skip_ws()
+    if peek()[0] != "EOF":
+        terms.append(parse_term())
+        while True:
+            skip_ws()
+            if peek()[0] == "EOF":
+                break
+            if not is_kw(peek(), "AND"):
+                raise FilterSyntaxError(f"unexpected token {peek()[1]!r}")
+            p += 1; skip_ws()
+            terms.append(parse_term())
+    return terms
+
+
+# ----------------------------------------------------------------------------- plan (Suitable / ResultSchema)
+
+def _fqtn_variants(ns: str, name: str) -> List[str]:
+    """transformer_common.go:9-23 + table_id.go:14-30."""
+    full = name if ns == "" else f"{ns}.{name}"
+    q = lambda s: '"' + s.replace('"', '""') + '"'
+    parts = ([q(ns)] if ns else []) + ([name] if name == "*" else [q(name)])
+    return [full, ".".join(parts)]
+
+
+def _filter_match(include: List[str], exclude: List[str], value: str) -> bool:
+    """filter.Filter.Match filter.go:27-44 (Go regexp ~ Python re for the anchored/simple patterns used in configs)."""
+    for ex in exclude or []:
+        if re.search(ex, value):
+            return False
+    if not include:
+        return True
+    return any(re.search(inc, value) for inc in include)
+
+
+def _tables_match(tables_cfg: Optional[dict], ns: str, name: str) -> bool:
+    inc = (tables_cfg or {}).get("includeTables") or (tables_cfg or {}).get("include_tables") or []
+    exc = (tables_cfg or {}).get("excludeTables") or (tables_cfg or {}).get("exclude_tables") or []
+    if not inc and not exc:
+        return True
+    return any(_filter_match(inc, exc, v) for v in _fqtn_variants(ns, name))
+
+
+_NUMERIC = {"int8", "int16", "int32", "int64", "uint8", "uint16", "uint32", "uint64", "float", "double"}
+
+
+def _column_suitable(term: Term, yt: str) -> bool:
+    """checkColumnSuitable filter_rows.go:489-519."""
+    base, is_list = term.vtype & 15, bool(term.vtype & LV_LIST)
+    if is_list and base in (LV_INT, LV_FLOAT, LV_STRING, LV_TIME):
+        return True
+    if is_list:
+        return False
+    if base == LV_BOOL:
+        return yt == "boolean"
+    if base in (LV_FLOAT, LV_INT):
+        return yt in _NUMERIC
+    if base == LV_STRING:
+        return yt in ("utf8", "string", "any")
+    if base == LV_TIME:
+        return yt in ("timestamp", "date", "datetime")
+    if base == LV_NULL:
+        return True
+    return False
+
+
+@dataclass
+class Plan:
+    schema: List[dict]                 # input ColSchema dicts
+    result_schema: List[dict]
+    steps: List[dict]                  # {"kind":..., ...} kept by Suitable()
+
+
+def build_plan(ns: str, name: str, schema: List[dict], transformers: List[dict]) -> Plan:
+    """transformation.AddTablePlan transformation.go:46-85."""
+    cur = [dict(c) for c in schema]
+    steps: List[dict] = []
+    for tr in transformers:
+        (ttype, cfg), = [(k, v) for k, v in tr.items() if k != "transformerId"]
+        cfg = cfg or {}
+        names = [c["name"] for c in cur]
+        if ttype == "filter_rows":
+            if cfg.get("filter") and cfg.get("filters"):
+                raise ValueError("Settings 'filters' and 'filter' cannot be enabled at the same time")
+            filters = cfg.get("filters") or [cfg.get("filter", "")]
+            exprs = [parse_filter(f) for f in filters]
+            if not _tables_match(cfg.get("tables"), ns, name):
+                continue
+            ok = True
+            for terms in exprs:                                  # Suitable filter_rows.go:445-476
+                for t in terms:
+                    if t.attribute not in names:
+                        ok = False; break
+                    if not _column_suitable(t, cur[names.index(t.attribute)]["type"]):
+                        ok = False; break
+                if not ok:
+                    break
+            if not ok:
+                continue
+            steps.append({"kind": "filter_rows", "exprs": [[(names.index(t.attribute), t) for t in terms] for terms in exprs]})
+        elif ttype == "mask_field":
+            if not _tables_match(cfg.get("tables"), ns, name):
+                continue
+            cols = cfg.get("columns") or []
+            if cols and not any(c in names for c in cols):       # hmac_hasher.go:76-89
+                continue
+            salt = ((cfg.get("maskFunctionHash") or {}).get("userDefinedSalt", ""))
+            idx = [names.index(c) for c in names if c in cols]
+            steps.append({"kind": "mask_field", "cols": idx, "salt": salt.encode()})
+            for i in idx:                                        # hmac_hasher.go:35-47
+                cur[i] = dict(cur[i]); cur[i]["type"] = "utf8"; cur[i]["original_type"] = ""
+        elif ttype == "convert_to_string":
+            if not _tables_match(cfg.get("tables"), ns, name):
+                continue
+            ccfg = cfg.get("columns") or {}
+            inc = ccfg.get("includeColumns") or []; exc = ccfg.get("excludeColumns") or []
+            idx = [i for i, n in enumerate(names) if _filter_match(inc, exc, n)]
+            if (inc or exc) and not idx:
+                continue
+            to_bytes = bool(cfg.get("convert_to_bytes"))
+            steps.append({"kind": "convert_to_string", "cols": idx, "to_bytes": to_bytes})
+            for i in idx:
+                cur[i] = dict(cur[i]); cur[i]["type"] = "string" if to_bytes else "utf8"
+        else:
+            raise NotImplementedError(ttype)
+    return Plan(schema, cur, steps)
+
+
+# ----------------------------------------------------------------------------- marshaling to liboracle
+
+class _Keep:
+    def __init__(self):
+        self.refs = []
+
+    def add(self, x):
+        self.refs.append(x); return x
+
+
+def term_to_c(col: int, t: Term, keep: _Keep) -> OrcTerm:
+    ct = OrcTerm(); ct.col = col; ct.op = t.op; ct.vtype = t.vtype; ct.nlist = 0
+    base, is_list = t.vtype & 15, bool(t.vtype & LV_LIST)
+    if not is_list:
+        if base == LV_INT or base == LV_TIME:
+            ct.i = t.value
+        elif base == LV_BOOL:
+            ct.i = 1 if t.value else 0
+        elif base == LV_FLOAT:
+            ct.f = t.value
+        elif base == LV_STRING:
+            b = keep.add(bytes(t.value)); ct.s = b; ct.slen = len(b)
+    else:
+        ct.nlist = len(t.value)
+        if base in (LV_INT, LV_TIME):
+            a = keep.add(np.asarray(t.value, dtype=np.int64)); ct.ilist = a.ctypes.data
+        elif base == LV_FLOAT:
+            a = keep.add(np.asarray(t.value, dtype=np.float64)); ct.flist = a.ctypes.data
+        elif base == LV_STRING:
+            offs = keep.add(np.zeros(len(t.value) + 1, dtype=np.uint32)); np.cumsum([len(x) for x in t.value], out=offs[1:])
+            heap = keep.add(np.frombuffer(b"".join(t.value) or b"\0", dtype=np.uint8).copy())
+            ct.soffs = offs.ctypes.data; ct.sheap = heap.ctypes.data
+    return ct
+
+
+def match_value(v: OrcVal, t: Term) -> Tuple[int, bool]:
+    keep = _Keep(); ct = term_to_c(0, t, keep); m = C.c_int(0)
+    rc = lib().orc_match_value(C.byref(v), C.byref(ct), C.byref(m)); return rc, bool(m.value)
+
+
+def _schema_to_c(schema: List[dict], keep: _Keep):
+    arr = (OrcColSchema * len(schema))()
+    for i, c in enumerate(schema):
+        arr[i].name = keep.add(c["name"].encode())
+        arr[i].type = abi.YT_NAME_TO_TF[c["type"]]
+        arr[i].required = 1 if c.get("required") else 0
+        arr[i].original_type = keep.add((c.get("original_type") or "").encode())
+    return arr
+
+
+def ch_type(col: dict) -> str:
+    keep = _Keep(); arr = _schema_to_c([col], keep); b = C.create_string_buffer(128)
+    n = lib().orc_ch_type(arr, b, 128); return b.raw[:n].decode()
+
+
+@dataclass
+class PushResult:
+    rows_out: int
+    raw: bytes
+    wire: bytes
+    errors: List[Tuple[int, int, int]]
+    raw_len: int = 0
+    wire_len: int = 0
+
+
+def push_encode(batch: abi.Batch, plan: Plan, wire_fmt: int, frame_bytes: int = 32768, want_bytes: bool = True) -> PushResult:
+    """Row-at-a-time reference path over one batch: transformers -> Restore -> native block -> LZ4 frames."""
+    keep = _Keep()
+    cschema = _schema_to_c(plan.schema, keep)
+    csteps = (OrcStep * max(1, len(plan.steps)))()
+    for si, st in enumerate(plan.steps):
+        s = csteps[si]
+        if st["kind"] == "filter_rows":
+            flat = [(c, t) for terms in st["exprs"] for (c, t) in terms]
+            tarr = keep.add((OrcTerm * max(1, len(flat)))())
+            for k, (c, t) in enumerate(flat):
+                tarr[k] = term_to_c(c, t, keep)
+            off = keep.add(np.zeros(len(st["exprs"]) + 1, dtype=np.uint32)); np.cumsum([len(x) for x in st["exprs"]], out=off[1:])
+            s.kind = STEP_FILTER_ROWS; s.terms = C.cast(tarr, C.POINTER(OrcTerm)); s.expr_off = off.ctypes.data; s.nexpr = len(st["exprs"])
+        elif st["kind"] == "mask_field":
+            cols = keep.add(np.asarray(st["cols"], dtype=np.int32))
+            s.kind = STEP_MASK; s.cols = cols.ctypes.data; s.ncols = len(st["cols"]); s.salt = keep.add(st["salt"]); s.salt_len = len(st["salt"])
+        elif st["kind"] == "convert_to_string":
+            cols = keep.add(np.asarray(st["cols"], dtype=np.int32))
+            s.kind = STEP_TO_STRING; s.cols = cols.ctypes.data; s.ncols = len(st["cols"]); s.convert_to_bytes = 1 if st["to_bytes"] else 0
+    tb = batch.as_struct()
+    raw, wire = OrcBuf(), OrcBuf()
+    rows = C.c_uint64(); nerr = C.c_uint64()
+    errs = (abi.TfRowErr * max(1, batch.nrows))()
+    rc = lib().orc_push_encode(C.byref(tb), cschema, csteps, len(plan.steps), wire_fmt, frame_bytes,
+                               C.byref(raw), C.byref(wire), C.byref(rows), errs, C.byref(nerr))
+    if rc != 0:
+        raise RuntimeError(f"oracle push_encode rc={rc}")
+    res = PushResult(rows.value,
+                     C.string_at(raw.data, raw.len) if (want_bytes and raw.len) else b"",
+                     C.string_at(wire.data, wire.len) if (want_bytes and wire.len) else b"",
+                     [(errs[i].row, errs[i].code, errs[i].term) for i in range(nerr.value)])
+    res.raw_len = raw.len; res.wire_len = wire.len
+    lib().orc_free(C.byref(raw)); lib().orc_free(C.byref(wire))
+    return res

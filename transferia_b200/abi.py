@@ -1,0 +1,201 @@
+"""ctypes view of include/tfgpu.h: the columnar batch that crosses the C-ABI.
+
+This module only describes memory; it computes nothing.  It is shared by the engine
+binding (transferia_b200.engine) and by the test oracle binding (oracle/pyoracle.py) because
+both consume the same `tf_batch` struct.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Any, List, Optional, Sequence
+
+import numpy as np
+
+# tf_type — YT type strings of pkg/abstract/typesystem/schema.go:48-68
+TF_INT8, TF_INT16, TF_INT32, TF_INT64 = 1, 2, 3, 4
+TF_UINT8, TF_UINT16, TF_UINT32, TF_UINT64 = 5, 6, 7, 8
+TF_FLOAT, TF_DOUBLE, TF_BOOLEAN = 9, 10, 11
+TF_BYTES, TF_UTF8, TF_ANY = 12, 13, 14
+TF_DATE, TF_DATETIME, TF_TIMESTAMP, TF_INTERVAL = 15, 16, 17, 18
+
+YT_NAME_TO_TF = {
+    "int8": TF_INT8, "int16": TF_INT16, "int32": TF_INT32, "int64": TF_INT64,
+    "uint8": TF_UINT8, "uint16": TF_UINT16, "uint32": TF_UINT32, "uint64": TF_UINT64,
+    "float": TF_FLOAT, "double": TF_DOUBLE, "boolean": TF_BOOLEAN,
+    "string": TF_BYTES, "utf8": TF_UTF8, "any": TF_ANY,
+    "date": TF_DATE, "datetime": TF_DATETIME, "timestamp": TF_TIMESTAMP, "interval": TF_INTERVAL,
+}
+TF_TO_YT_NAME = {v: k for k, v in YT_NAME_TO_TF.items()}
+
+FIXED_DTYPE = {
+    TF_INT8: np.int8, TF_INT16: np.int16, TF_INT32: np.int32, TF_INT64: np.int64,
+    TF_UINT8: np.uint8, TF_UINT16: np.uint16, TF_UINT32: np.uint32, TF_UINT64: np.uint64,
+    TF_FLOAT: np.float32, TF_DOUBLE: np.float64, TF_BOOLEAN: np.uint8,
+    TF_DATE: np.int64, TF_DATETIME: np.int64, TF_TIMESTAMP: np.int64, TF_INTERVAL: np.int64,
+}
+VAR_TYPES = (TF_BYTES, TF_UTF8, TF_ANY)
+TIME_TYPES = (TF_DATE, TF_DATETIME, TF_TIMESTAMP)
+
+TF_MEM_HOST, TF_MEM_DEVICE = 0, 1
+TF_KIND_INSERT, TF_KIND_UPDATE, TF_KIND_DELETE = 0, 1, 2
+
+TF_WIRE_CH_NATIVE, TF_WIRE_CH_NATIVE_LZ4, TF_WIRE_CH_JSONEACHROW = 1, 2, 3
+
+TF_ROWERR_FILTER_KIND, TF_ROWERR_FILTER_OVERFLOW, TF_ROWERR_FILTER_TYPEPAIR = 1, 2, 3
+
+
+class TfCol(C.Structure):
+    _fields_ = [
+        ("type", C.c_int32), ("flags", C.c_int32),
+        ("values", C.c_void_p), ("validity", C.c_void_p), ("offsets", C.c_void_p),
+        ("heap", C.c_void_p), ("aux", C.c_void_p), ("heap_len", C.c_uint64),
+    ]
+
+
+class TfBatch(C.Structure):
+    _fields_ = [
+        ("nrows", C.c_uint64), ("ncols", C.c_uint32), ("mem", C.c_uint32),
+        ("cols", C.POINTER(TfCol)), ("kinds", C.c_void_p),
+    ]
+
+
+class TfRowErr(C.Structure):
+    _fields_ = [("row", C.c_uint32), ("code", C.c_uint16), ("term", C.c_uint16)]
+
+
+def _ptr(a) -> Optional[int]:
+    """Address of a numpy array or torch tensor (None stays NULL)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data if a.size else None
+    # torch tensor (host pinned or device)
+    return a.data_ptr() if a.numel() else None
+
+
+@dataclass
+class Column:
+    """One column in the physical layout documented in include/tfgpu.h."""
+    type: int
+    values: Any = None      # fixed-width / time seconds
+    validity: Any = None    # uint8 bitmap, bit=1 non-null
+    offsets: Any = None     # uint32[nrows+1]
+    heap: Any = None        # uint8[]
+    aux: Any = None         # time: uint32 nanos; any: uint8 tags
+
+    def heap_len(self) -> int:
+        if self.heap is None:
+            return 0
+        return int(self.heap.size if isinstance(self.heap, np.ndarray) else self.heap.numel())
+
+
+@dataclass
+class Batch:
+    """A single-table batch of ChangeItems, transposed (pkg/abstract/changeitem/change_item.go:27-78)."""
+    nrows: int
+    columns: List[Column]
+    kinds: Any = None
+    mem: int = TF_MEM_HOST
+    _keep: list = field(default_factory=list, repr=False)
+
+    def as_struct(self) -> TfBatch:
+        arr = (TfCol * len(self.columns))()
+        for i, c in enumerate(self.columns):
+            arr[i].type = c.type
+            arr[i].flags = 0
+            arr[i].values = _ptr(c.values)
+            arr[i].validity = _ptr(c.validity)
+            arr[i].offsets = _ptr(c.offsets)
+            arr[i].heap = _ptr(c.heap)
+            arr[i].aux = _ptr(c.aux)
+            arr[i].heap_len = c.heap_len()
+        b = TfBatch()
+        b.nrows = self.nrows
+        b.ncols = len(self.columns)
+        b.mem = self.mem
+        b.cols = C.cast(arr, C.POINTER(TfCol))
+        b.kinds = _ptr(self.kinds)
+        self._keep = [arr]
+        return b
+
+    def input_bytes(self) -> int:
+        """Columnar input bytes (SURVEY §8d `I`): values + offsets + heap (+validity/aux when present)."""
+        tot = 0
+        for c in self.columns:
+            for a in (c.values, c.validity, c.offsets, c.heap, c.aux):
+                if a is None:
+                    continue
+                tot += int(a.nbytes if isinstance(a, np.ndarray) else a.numel() * a.element_size())
+        if self.kinds is not None:
+            a = self.kinds
+            tot += int(a.nbytes if isinstance(a, np.ndarray) else a.numel() * a.element_size())
+        return tot
+
+    def slice(self, lo: int, hi: int) -> "Batch":
+        """Host-only row slice [lo, hi) — used to deal sub-batches to pipelines / ranks."""
+        assert self.mem == TF_MEM_HOST
+        cols = []
+        for c in self.columns:
+            if c.type in VAR_TYPES:
+                off = c.offsets[lo:hi + 1]
+                base = int(off[0]) if len(off) else 0
+                end = int(off[-1]) if len(off) else 0
+                cols.append(Column(c.type, offsets=(off - np.uint32(base)).astype(np.uint32),
+                                   heap=np.ascontiguousarray(c.heap[base:end]),
+                                   validity=_slice_bits(c.validity, lo, hi),
+                                   aux=None if c.aux is None else np.ascontiguousarray(c.aux[lo:hi])))
+            else:
+                cols.append(Column(c.type, values=np.ascontiguousarray(c.values[lo:hi]),
+                                   validity=_slice_bits(c.validity, lo, hi),
+                                   aux=None if c.aux is None else np.ascontiguousarray(c.aux[lo:hi])))
+        kinds = None if self.kinds is None else np.ascontiguousarray(self.kinds[lo:hi])
+        return Batch(hi - lo, cols, kinds)
+
+    def to_device(self, device="cuda:0", pinned_first: bool = False) -> "Batch":
+        """Copy every buffer to HBM with torch (plumbing only)."""
+        import torch
+        def mv(a):
+            if a is None:
+                return None
+            t = torch.from_numpy(np.ascontiguousarray(a).reshape(-1).view(np.uint8))
+            if pinned_first:
+                t = t.pin_memory()
+            return t.to(device, non_blocking=pinned_first)
+        cols = [Column(c.type, mv(c.values), mv(c.validity), mv(c.offsets), mv(c.heap), mv(c.aux)) for c in self.columns]
+        return Batch(self.nrows, cols, mv(self.kinds), TF_MEM_DEVICE)
+
+
+def _slice_bits(bm, lo, hi):
+    if bm is None:
+        return None
+    bits = np.unpackbits(bm, bitorder="little")[lo:hi]
+    return np.packbits(bits, bitorder="little")
+
+
+def pack_validity(mask: np.ndarray) -> np.ndarray:
+    """bool[nrows] (True = non-null) -> LSB-first bitmap."""
+    return np.packbits(mask.astype(np.uint8), bitorder="little")
+
+
+def strings_to_column(tf_type: int, values: Sequence[Optional[bytes]], tags=None) -> Column:
+    """Build a var-width column from python bytes (None = nil)."""
+    n = len(values)
+    lens = np.fromiter((0 if v is None else len(v) for v in values), dtype=np.int64, count=n)
+    offs = np.zeros(n + 1, dtype=np.uint32)
+    np.cumsum(lens, out=offs[1:])
+    heap = np.frombuffer(b"".join(v for v in values if v is not None), dtype=np.uint8).copy()
+    validity = None
+    if any(v is None for v in values):
+        validity = pack_validity(np.array([v is not None for v in values]))
+    aux = None if tags is None else np.asarray(tags, dtype=np.uint8)
+    return Column(tf_type, offsets=offs, heap=heap, validity=validity, aux=aux)
+
+
+def fixed_to_column(tf_type: int, values: Sequence, nulls: Optional[Sequence[bool]] = None, nanos=None) -> Column:
+    arr = np.asarray(values, dtype=FIXED_DTYPE[tf_type])
+    validity = None
+    if nulls is not None and any(nulls):
+        validity = pack_validity(~np.asarray(nulls, dtype=bool))
+    aux = None if nanos is None else np.asarray(nanos, dtype=np.uint32)
+    return Column(tf_type, values=arr, validity=validity, aux=aux)

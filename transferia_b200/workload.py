@@ -1,0 +1,185 @@
+"""Seeded synthetic ClickBench-`hits`-shaped batches in the C-ABI columnar layout.
+
+The schema is the first 99 columns of the reference's fixture
+(pkg/providers/postgres/testdata/hits_data.json: parse_schema), committed as
+tests/golden/hits_schema.json by tests/golden/make_hits_schema.py.  Value generators:
+
+  ints        column-specific range taken from the fixture cell magnitude: |v| <= 1 -> {0,1};
+              int64 and id-like int32 (|v| >= 1e6) -> uniform over the full magnitude (incompressible);
+              otherwise a 64-value palette drawn from [0, 2|v|] (sign kept), picked Zipf-like, which
+              is how low-cardinality ClickBench dimensions (os, resolution, region ...) behave
+  timestamps  in [2013-07-01, 2013-07-31) at second resolution, ascending within a batch (snapshot
+              order); eventdate = day of eventtime; the other two are eventtime +- 1 day
+  strings     per-column dictionary of 4096 base strings (length ~ geometric, mean = fixture cell
+              length, 64-symbol alphabet with ~10 % two-byte Cyrillic), rows draw Zipf-like from it
+              and half of the non-empty rows get a short random tail, so LZ4 sees realistic
+              repetition; columns whose fixture cell is empty are 85 % empty, others 5 % empty
+  sessions    rows arrive in visitor sessions (geometric, mean 8 rows): flag / palette ints and the
+              string dimensions other than title/url/referer/searchphrase/params/originalurl keep one
+              value per session, as consecutive hits of one visitor do
+  nulls       none: every fixture column is `required: true`
+
+Everything here is host-side numpy; the engine never sees this module.
+"""
+from __future__ import annotations
+
+import base64
+import json
+import os
+from typing import List, Tuple
+
+import numpy as np
+
+from . import abi
+
+SEED = 0x7F4A7C15
+_SCHEMA_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "hits_schema.json")
+
+T0 = 1372636800   # 2013-07-01T00:00:00Z
+T1 = 1375228800   # 2013-07-31T00:00:00Z
+
+_ALPHA = np.frombuffer(b"abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789/.", dtype=np.uint8)
+
+
+def hits_schema() -> List[dict]:
+    cols = json.load(open(_SCHEMA_PATH))["columns"]
+    out = []
+    for c in cols:
+        d = {k: v for k, v in c.items() if k != "fixture_cell_b64"}
+        d["_fixture"] = base64.b64decode(c["fixture_cell_b64"])
+        out.append(d)
+    return out
+
+
+def schema_json(schema: List[dict]) -> str:
+    """ColSchema JSON with the reference's tags (col_schema.go:14-29)."""
+    return json.dumps([{k: v for k, v in c.items() if not k.startswith("_")} for c in schema])
+
+
+def _make_dict(rng: np.random.Generator, mean_len: float, n_entries: int = 4096) -> Tuple[np.ndarray, np.ndarray]:
+    p = 1.0 / max(mean_len, 1.0)
+    lens = np.minimum(rng.geometric(p, n_entries), 120).astype(np.int64)
+    offs = np.zeros(n_entries + 1, dtype=np.int64)
+    np.cumsum(lens, out=offs[1:])
+    total = int(offs[-1])
+    heap = _ALPHA[rng.integers(0, 64, total)]
+    # ~10 % of positions become the lead of a 2-byte Cyrillic sequence (0xD0 0x90..0xBF)
+    lead = np.nonzero(rng.random(total) < 0.05)[0]
+    lead = lead[lead + 1 < total]
+    # keep pairs inside one entry
+    ent = np.searchsorted(offs, lead, side="right") - 1
+    lead = lead[lead + 1 < offs[ent + 1]]
+    heap = heap.copy()
+    heap[lead] = 0xD0
+    heap[lead + 1] = (0x90 + rng.integers(0, 48, lead.size)).astype(np.uint8)
+    return offs, heap
+
+
+def _gen_string_column(rng: np.random.Generator, n: int, mean_len: float, empty_frac: float, prefix: bytes = b"", sess=None):
+    d_off, d_heap = _make_dict(rng, max(mean_len - len(prefix), 1.0))
+    if prefix:   # e.g. URLs all start with http://
+        nent = d_off.size - 1
+        lens = np.diff(d_off) + len(prefix)
+        new_off = np.zeros(nent + 1, dtype=np.int64); np.cumsum(lens, out=new_off[1:])
+        new_heap = np.empty(int(new_off[-1]), dtype=np.uint8)
+        pidx = (new_off[:-1, None] + np.arange(len(prefix))[None, :]).ravel()
+        new_heap[pidx] = np.tile(np.frombuffer(prefix, dtype=np.uint8), nent)
+        mask = np.ones(new_heap.size, dtype=bool); mask[pidx] = False
+        new_heap[mask] = d_heap
+        d_off, d_heap = new_off, new_heap
+    nent = d_off.size - 1
+    # Zipf-like pick: squared uniform concentrates on low indexes
+    if sess is None:
+        idx = (rng.random(n) ** 2.5 * nent).astype(np.int64)
+        empty = rng.random(n) < empty_frac
+        tail_len = np.where(rng.random(n) < 0.5, rng.integers(1, 9, n), 0)
+    else:
+        ns = int(sess[-1]) + 1
+        idx = (rng.random(ns) ** 2.5 * nent).astype(np.int64)[sess]
+        empty = (rng.random(ns) < empty_frac)[sess]
+        tail_len = np.zeros(n, dtype=np.int64)
+    base_len = (d_off[idx + 1] - d_off[idx])
+    base_len = np.where(empty, 0, base_len); tail_len = np.where(empty, 0, tail_len)
+    lens = base_len + tail_len
+    offs = np.zeros(n + 1, dtype=np.int64); np.cumsum(lens, out=offs[1:])
+    total = int(offs[-1])
+    assert total < 2 ** 32
+    heap = np.empty(total, dtype=np.uint8)
+    # dictionary part
+    rep_rows = np.repeat(np.arange(n), base_len)
+    pos_in = np.arange(int(base_len.sum())) - np.repeat(np.cumsum(base_len) - base_len, base_len)
+    heap[offs[rep_rows] + pos_in] = d_heap[d_off[idx[rep_rows]] + pos_in]
+    # random tail
+    tr = np.repeat(np.arange(n), tail_len)
+    tpos = np.arange(int(tail_len.sum())) - np.repeat(np.cumsum(tail_len) - tail_len, tail_len)
+    heap[offs[tr] + base_len[tr] + tpos] = _ALPHA[rng.integers(0, 64, tr.size)]
+    return offs.astype(np.uint32), heap
+
+
+def make_hits_batch(nrows: int, seed: int = SEED, schema: List[dict] | None = None) -> Tuple[abi.Batch, List[dict]]:
+    schema = schema or hits_schema()
+    rng = np.random.default_rng(seed)
+    cols: List[abi.Column] = []
+    eventtime = np.sort(rng.integers(T0, T1, nrows, dtype=np.int64))
+    sess = np.cumsum(rng.random(nrows) < 0.125).astype(np.int64)
+    nsess = int(sess[-1]) + 1 if nrows else 0
+    for c in schema:
+        t = abi.YT_NAME_TO_TF[c["type"]]
+        fx = c["_fixture"]
+        if t in (abi.TF_INT16, abi.TF_INT32, abi.TF_INT64):
+            v = int(fx.decode() or "0")
+            dt = abi.FIXED_DTYPE[t]
+            info = np.iinfo(dt)
+            if t == abi.TF_INT64:
+                arr = rng.integers(info.min, info.max, nrows, dtype=np.int64, endpoint=True)
+            elif abs(v) <= 1:
+                arr = (rng.random(nsess) < 0.1)[sess].astype(dt)
+            elif abs(v) >= 1_000_000:
+                hi = min(2 * abs(v), info.max)
+                a = rng.integers(0, hi + 1, nrows, dtype=np.int64)
+                if v < 0:
+                    a = -a
+                arr = a.astype(dt)
+            else:
+                hi = min(2 * abs(v), info.max)
+                palette = rng.integers(0, hi + 1, 64, dtype=np.int64)
+                a = palette[(rng.random(nsess) ** 3 * 64).astype(np.int64)][sess]
+                if v < 0:
+                    a = -a
+                arr = a.astype(dt)
+            cols.append(abi.Column(t, values=arr))
+        elif t == abi.TF_TIMESTAMP:
+            if c["name"] == "eventtime":
+                arr = eventtime.copy()
+            else:
+                arr = eventtime + rng.integers(-86400, 86400, nrows)
+            cols.append(abi.Column(t, values=arr.astype(np.int64)))
+        elif t == abi.TF_DATE:
+            cols.append(abi.Column(t, values=(eventtime // 86400 * 86400).astype(np.int64)))
+        elif t in (abi.TF_UTF8, abi.TF_ANY):
+            mean_len = float(len(fx))
+            empty_frac = 0.85 if len(fx) == 0 else 0.05
+            if len(fx) == 0:
+                mean_len = 12.0
+            prefix = b"http://" if c["name"] in ("url", "referer", "originalurl") else b""
+            per_row = c["name"] in ("title", "url", "referer", "searchphrase", "params", "originalurl")
+            offs, heap = _gen_string_column(rng, nrows, mean_len, empty_frac, prefix, None if per_row else sess)
+            aux = None
+            if t == abi.TF_ANY:
+                # pg "char" arrives as a Go string inside an `any` column (fixture: hitcolor = "5")
+                aux = np.ones(nrows, dtype=np.uint8)
+            cols.append(abi.Column(t, offsets=offs, heap=heap, aux=aux))
+        else:
+            raise NotImplementedError(c["type"])
+    return abi.Batch(nrows, cols), schema
+
+
+def counterid_threshold(batch: abi.Batch, schema: List[dict], keep_frac: float = 0.5) -> int:
+    i = [c["name"] for c in schema].index("counterid")
+    return int(np.quantile(batch.columns[i].values, 1.0 - keep_frac))
+
+
+def headline_transformers(k: int) -> List[dict]:
+    """BASELINE.json configs[2]: cast + filter_rows (1 int term AND 1 string `~` term)."""
+    return [{"filter_rows": {"tables": {"includeTables": ["^public\\.hits$"]},
+                             "filter": f"counterid > {k} AND url ~ '://'"}}]
