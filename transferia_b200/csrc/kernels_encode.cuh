@@ -1,0 +1,438 @@
+// filter_rows predicate, row compaction, typesystem cast + ClickHouse native block encode.
+// All kernels are HBM-streaming: coalesced element loads along rows, one launch covers every
+// column (blockIdx.y = column slot), no tensor cores (there is no contraction on this path).
+#pragma once
+#include "device_types.cuh"
+
+namespace tfk {
+
+// ------------------------------------------------------------------ small block-scan helpers
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+    const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= (unsigned)d) v += t; }
+    return v;
+}
+// exclusive scan over blockDim.x (<= 1024) threads; returns exclusive prefix, *total = block sum
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total, uint32_t* smem33) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    uint32_t inc = warp_incl_scan(v);
+    if (lane == 31) smem33[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < nw ? smem33[lane] : 0;
+        uint32_t wi = warp_incl_scan(w);
+        smem33[lane] = wi - w;
+        if (lane == 31) smem33[32] = wi;
+    }
+    __syncthreads();
+    uint32_t res = inc - v + smem33[warp];
+    *total = smem33[32];
+    __syncthreads();
+    return res;
+}
+
+// ------------------------------------------------------------------ filter_rows
+// matchValue (pkg/transformer/registry/filter_rows/filter_rows.go:180-365) for typed columns.
+struct RowVal {
+    int cls;            // 0 nil, 1 int, 2 float, 3 bool, 4 string(Go string), 5 bytes, 6 time, 7 opaque (Duration / JSON tree), 8 uint64 overflow
+    int64_t i; double f; const uint8_t* s; uint32_t slen; uint32_t nsec;
+};
+
+__device__ __forceinline__ bool row_valid(const DCol& c, uint64_t r) { return !c.validity || ((c.validity[r >> 3] >> (r & 7)) & 1); }
+
+__device__ __forceinline__ RowVal load_val(const DCol& c, uint64_t r) {
+    RowVal v; v.cls = 0; v.i = 0; v.f = 0; v.s = nullptr; v.slen = 0; v.nsec = 0;
+    if (!row_valid(c, r)) return v;
+    switch (c.type) {
+    case TF_INT8:  v.cls = 1; v.i = ((const int8_t*)c.values)[r]; break;
+    case TF_INT16: v.cls = 1; v.i = ((const int16_t*)c.values)[r]; break;
+    case TF_INT32: v.cls = 1; v.i = ((const int32_t*)c.values)[r]; break;
+    case TF_INT64: v.cls = 1; v.i = ((const int64_t*)c.values)[r]; break;
+    case TF_UINT8:  v.cls = 1; v.i = ((const uint8_t*)c.values)[r]; break;
+    case TF_UINT16: v.cls = 1; v.i = ((const uint16_t*)c.values)[r]; break;
+    case TF_UINT32: v.cls = 1; v.i = ((const uint32_t*)c.values)[r]; break;
+    case TF_UINT64: { uint64_t u = ((const uint64_t*)c.values)[r]; if (u > 0x7fffffffffffffffULL) v.cls = 8; else { v.cls = 1; v.i = (int64_t)u; } break; }   // util.go:66-68
+    case TF_FLOAT:  v.cls = 2; v.f = ((const float*)c.values)[r]; break;
+    case TF_DOUBLE: v.cls = 2; v.f = ((const double*)c.values)[r]; break;
+    case TF_BOOLEAN: v.cls = 3; v.i = c.values[r] != 0; v.f = v.i ? 1.0 : 0.0; break;
+    case TF_INTERVAL: v.cls = 7; break;
+    case TF_DATE: case TF_DATETIME: case TF_TIMESTAMP:
+        v.cls = 6; v.i = ((const int64_t*)c.values)[r]; v.nsec = c.aux ? ((const uint32_t*)c.aux)[r] : 0; break;
+    case TF_BYTES: v.cls = 5; v.s = c.heap + c.offsets[r]; v.slen = c.offsets[r + 1] - c.offsets[r]; break;
+    case TF_UTF8:  v.cls = 4; v.s = c.heap + c.offsets[r]; v.slen = c.offsets[r + 1] - c.offsets[r]; break;
+    case TF_ANY:
+        if (c.aux && c.aux[r] == 1) { v.cls = 4; v.s = c.heap + c.offsets[r]; v.slen = c.offsets[r + 1] - c.offsets[r]; }
+        else v.cls = 7;
+        break;
+    }
+    return v;
+}
+
+template <typename T> __device__ __forceinline__ bool ordered(T a, T b, int op) {
+    switch (op) { case 0: return a == b; case 1: return a != b; case 2: return a < b; case 3: return a <= b; case 4: return a > b; default: return a >= b; }
+}
+__device__ __forceinline__ int cmp_bytes(const uint8_t* a, uint32_t an, const uint8_t* b, uint32_t bn) {
+    uint32_t m = an < bn ? an : bn;
+    for (uint32_t k = 0; k < m; k++) { int d = (int)a[k] - (int)b[k]; if (d) return d < 0 ? -1 : 1; }
+    return an < bn ? -1 : (an > bn ? 1 : 0);
+}
+__device__ __forceinline__ bool contains_bytes(const uint8_t* h, uint32_t hn, const uint8_t* n, uint32_t nn) {
+    if (nn == 0) return true;
+    if (nn > hn) return false;
+    const uint8_t n0 = n[0];
+    for (uint32_t i = 0; i + nn <= hn; i++) {
+        if (h[i] != n0) continue;
+        uint32_t k = 1; while (k < nn && h[i + k] == n[k]) k++;
+        if (k == nn) return true;
+    }
+    return false;
+}
+
+// returns 0 and sets matched, or a TF_ROWERR_* code
+__device__ int eval_term(const RowVal& v, const DTerm& t, const uint8_t* blob, bool& matched) {
+    const int op = t.op; const bool is_set = (op == 6 || op == 7);
+    const int base = t.vtype & 15; const bool is_list = (t.vtype & 16) != 0;
+    if (v.cls == 8) return TF_ROWERR_FILTER_OVERFLOW;                       // filter_rows.go:193-197
+    const bool is_int1 = v.cls == 1;
+    const bool is_float1 = v.cls == 2 || v.cls == 3 || v.cls == 0;          // cast.ToFloat64E: floats, bool, nil (-> 0)
+    const double float1 = v.cls == 2 ? v.f : (v.cls == 3 ? v.f : 0.0);
+    const int64_t* il = (const int64_t*)(blob + t.list_off);
+    const double* fl = (const double*)(blob + t.list_off);
+    switch (base) {
+    case 1:   // int literal(s)
+        if (is_int1) {
+            if (is_set) { bool c = false; for (int k = 0; k < t.nlist; k++) c |= (il[k] == v.i); matched = (op == 6) ? c : !c; return 0; }
+            matched = ordered<int64_t>(v.i, t.i, op); return 0;
+        }
+        if (is_float1) {
+            if (is_set) {
+                if (trunc(float1) == float1) { int64_t x = (int64_t)float1; bool c = false; for (int k = 0; k < t.nlist; k++) c |= (il[k] == x); matched = (op == 6) ? c : !c; }
+                else matched = false;
+                return 0;
+            }
+            matched = ordered<double>(float1, (double)t.i, op); return 0;
+        }
+        break;
+    case 2:   // float literal(s)
+        if (is_int1 || is_float1) {
+            const double x = is_int1 ? (double)v.i : float1;
+            if (is_set) { bool c = false; for (int k = 0; k < t.nlist; k++) c |= (fl[k] == x); matched = (op == 6) ? c : !c; return 0; }
+            matched = ordered<double>(x, t.f, op); return 0;
+        }
+        break;
+    case 3:   // bool
+        if (!is_list && v.cls == 3) { matched = ordered<int>(v.i ? 1 : 0, t.i ? 1 : 0, op); return 0; }
+        break;
+    case 4:   // string
+        if (v.cls == 4 || v.cls == 5) {
+            const uint8_t* lit = blob + t.s_off;
+            if (!is_list) {
+                if (op == 8) { matched = contains_bytes(v.s, v.slen, lit, t.s_len); return 0; }
+                if (op == 9) { matched = !contains_bytes(v.s, v.slen, lit, t.s_len); return 0; }
+                if (is_set) return TF_ROWERR_FILTER_TYPEPAIR;
+                const int c = cmp_bytes(v.s, v.slen, lit, t.s_len);
+                matched = ordered<int>(c, 0, op); return 0;
+            }
+            if (!is_set) return TF_ROWERR_FILTER_TYPEPAIR;
+            const uint32_t* so = (const uint32_t*)(blob + t.list_off);
+            const uint8_t* sh = (const uint8_t*)(so + t.nlist + 1);
+            bool c = false;
+            for (int k = 0; k < t.nlist && !c; k++) { uint32_t a = so[k], b = so[k + 1]; c = (b - a == v.slen) && cmp_bytes(sh + a, b - a, v.s, v.slen) == 0; }
+            matched = (op == 6) ? c : !c; return 0;
+        }
+        break;
+    case 5:   // time: compared as UnixMicro (filter_rows.go:330-339)
+        if (v.cls == 6) {
+            const int64_t um = v.i * 1000000LL + (int64_t)(v.nsec / 1000u);
+            if (is_set) { bool c = false; for (int k = 0; k < t.nlist; k++) c |= (il[k] == um); matched = (op == 6) ? c : !c; return 0; }
+            matched = ordered<int64_t>(um, t.i, op); return 0;
+        }
+        break;
+    case 6:   // NULL
+        if (op == 0) { matched = v.cls == 0; return 0; }
+        if (op == 1) { matched = v.cls != 0; return 0; }
+        break;
+    }
+    return TF_ROWERR_FILTER_TYPEPAIR;
+}
+
+struct FilterArgs {
+    const DCol* cols; const uint8_t* kinds; uint64_t nrows;
+    const DFilterStep* steps; int nsteps;
+    const uint32_t* expr_off;      // term ranges per expression (global expr index)
+    const DTerm* terms; const uint8_t* blob;
+    uint8_t* keep; uint8_t* errcode; uint8_t* errstep; uint32_t* blockcnt;
+};
+
+// FilterRowsTransformer.Apply (filter_rows.go:99-130): one thread per row.
+__global__ void __launch_bounds__(256) k_filter(FilterArgs a) {
+    __shared__ uint32_t s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false;
+    if (r < a.nrows) {
+        keep = true; int err = 0, estep = 0;
+        const int kind = a.kinds ? a.kinds[r] : TF_KIND_INSERT;
+        for (int s = 0; s < a.nsteps && keep; s++) {
+            const DFilterStep st = a.steps[s];
+            if (kind == TF_KIND_UPDATE || kind == TF_KIND_DELETE) { err = TF_ROWERR_FILTER_KIND; estep = st.step_index; keep = false; break; }
+            bool any = false;
+            for (int e = 0; e < st.nexpr && !any && !err; e++) {            // matchItem: OR over filters
+                bool all = true;
+                const uint32_t kb = a.expr_off[st.expr_begin + e], ke = a.expr_off[st.expr_begin + e + 1];
+                for (uint32_t k = kb; k < ke; k++) {                         // matchExpression: AND over terms
+                    const DTerm t = a.terms[k];
+                    const RowVal v = load_val(a.cols[t.col], r);
+                    bool m = false; const int rc = eval_term(v, t, a.blob, m);
+                    if (rc) { err = rc; break; }
+                    if (!m) { all = false; break; }
+                }
+                if (!err && all) any = true;
+            }
+            if (err) { estep = st.step_index; keep = false; break; }
+            if (!any) keep = false;
+        }
+        a.keep[r] = keep ? 1 : 0;
+        a.errcode[r] = (uint8_t)err; a.errstep[r] = (uint8_t)estep;
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, keep);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&s_cnt, __popc(b));
+    __syncthreads();
+    if (threadIdx.x == 0) a.blockcnt[blockIdx.x] = s_cnt;
+}
+
+// exclusive scan of per-block kept counts (single block), total -> state.n_kept
+__global__ void __launch_bounds__(1024) k_scan_blockcnt(const uint32_t* blockcnt, uint32_t* blockoff, uint32_t nblocks, DState* st,
+                                                       const uint8_t* errcode, uint64_t nrows) {
+    __shared__ uint32_t sm[33];
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < nblocks; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < nblocks ? blockcnt[i] : 0;
+        uint32_t tot; const uint32_t ex = block_excl_scan(v, &tot, sm);
+        if (i < nblocks) blockoff[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) st->n_kept = carry;
+    // count error rows (rare): strided sum
+    uint32_t ne = 0;
+    for (uint64_t r = threadIdx.x; r < nrows; r += blockDim.x) ne += errcode[r] != 0;
+    uint32_t tot; block_excl_scan(ne, &tot, sm);
+    if (threadIdx.x == 0) st->n_errors = tot;
+}
+
+// sel[j] = index of the j-th kept row (order preserved)
+__global__ void __launch_bounds__(256) k_compact_sel(const uint8_t* keep, const uint32_t* blockoff, uint64_t nrows, uint32_t* sel) {
+    __shared__ uint32_t sm[33];
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t k = (r < nrows && keep[r]) ? 1u : 0u;
+    uint32_t tot; const uint32_t ex = block_excl_scan(k, &tot, sm);
+    if (k) sel[blockoff[blockIdx.x] + ex] = (uint32_t)r;
+}
+
+// ------------------------------------------------------------------ layout of the native block
+struct LayoutArgs {
+    DCol* cols; int ncols;
+    const int32_t* str_cols; int nstr;         // column index of each OK_STR slot
+    const uint32_t* tile_sum;                  // [nstr][ntiles_cap] encoded bytes per tile of STR_TILE kept rows
+    uint64_t* tile_base;                       // [nstr][ntiles_cap] exclusive prefix within the column
+    uint32_t ntiles_cap;
+    const uint8_t* col_headers; const uint32_t* col_header_off;   // pre-serialized "name,type,0" per column
+    uint8_t* raw; DState* st;
+    uint64_t nrows_in; int has_sel; uint32_t frame_bytes;
+};
+
+#define TF_STR_TILE 1024
+
+// One block: per-string-column prefix over tiles, then column offsets, then the block / column headers.
+// Block layout (clickhouse-go/v2 v2.46.0 lib/proto/block.go, revision 54460):
+//   uvarint 1, u8 is_overflows=0, uvarint 2, i32 bucket_num=-1, uvarint 0, uvarint ncols, uvarint nrows,
+//   per column: string name, string type, u8 custom_serialization=0, [null map], data
+__global__ void __launch_bounds__(1024) k_layout(LayoutArgs a) {
+    __shared__ uint32_t sm[33];
+    __shared__ uint64_t s_colbytes[256];       // encoded bytes of each OK_STR column (nstr <= 256 checked on host)
+    if (!a.has_sel && threadIdx.x == 0) a.st->n_kept = a.nrows_in;
+    __syncthreads();
+    const uint64_t n = a.st->n_kept;
+    const uint32_t ntiles = (uint32_t)((n + TF_STR_TILE - 1) / TF_STR_TILE);
+    for (int s = 0; s < a.nstr; s++) {
+        uint64_t carry = 0;
+        for (uint32_t base = 0; base < ntiles; base += blockDim.x) {
+            const uint32_t i = base + threadIdx.x;
+            const uint32_t v = i < ntiles ? a.tile_sum[(size_t)s * a.ntiles_cap + i] : 0;
+            uint32_t tot; const uint32_t ex = block_excl_scan(v, &tot, sm);
+            if (i < ntiles) a.tile_base[(size_t)s * a.ntiles_cap + i] = carry + ex;
+            carry += tot;
+        }
+        if (threadIdx.x == 0) s_colbytes[s] = carry;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint8_t* o = a.raw; uint64_t p = 0;
+        o[p++] = 1; o[p++] = 0; o[p++] = 2; o[p++] = 0xff; o[p++] = 0xff; o[p++] = 0xff; o[p++] = 0xff; o[p++] = 0;
+        uint64_t v = (uint64_t)a.ncols; while (v >= 0x80) { o[p++] = (uint8_t)(v | 0x80); v >>= 7; } o[p++] = (uint8_t)v;
+        v = n; while (v >= 0x80) { o[p++] = (uint8_t)(v | 0x80); v >>= 7; } o[p++] = (uint8_t)v;
+        for (int c = 0; c < a.ncols; c++) {
+            DCol& d = a.cols[c];
+            d.hdr_off = p; p += a.col_header_off[c + 1] - a.col_header_off[c];
+            d.null_off = p; if (d.nullable && n) p += n;
+            d.out_off = p;
+            if (n) p += (d.out_kind == OK_STR) ? s_colbytes[d.str_slot] : (uint64_t)d.out_w * n;
+        }
+        a.st->raw_total = p;
+        a.st->n_frames = p ? (p + a.frame_bytes - 1) / a.frame_bytes : 1;
+        a.st->frame_ticket = 0;
+    }
+    __syncthreads();
+    // column headers, copied by all threads
+    for (int c = 0; c < a.ncols; c++) {
+        const uint32_t hb = a.col_header_off[c], he = a.col_header_off[c + 1];
+        for (uint32_t k = hb + threadIdx.x; k < he; k += blockDim.x) a.raw[a.cols[c].hdr_off + (k - hb)] = a.col_headers[k];
+    }
+}
+
+// ------------------------------------------------------------------ fixed-width columns
+struct EncodeArgs {
+    const DCol* cols;
+    const int32_t* slots;          // per blockIdx.y: column index, bit 30 set = this slot is the column's null map
+    const uint32_t* sel; const DState* st; uint8_t* raw;
+    uint32_t* tile_sum; const uint64_t* tile_base; uint32_t ntiles_cap;
+};
+
+#define TF_SLOT_NULLMAP (1 << 30)
+#define TF_FIX_TILE_WORDS 2048
+#define CH_MAX_DATE_SEC 4291747200LL   // 2106-01-01T00:00:00Z (columntypes/types.go:15-18)
+
+// One output element after the typesystem cast (columntypes.Restore -> abstract.Restore are the identity
+// for values whose Go type already matches the column type; what remains is the ClickHouse clamp/unit rule).
+__device__ __forceinline__ uint64_t elem_value(const DCol& c, const uint32_t* sel, uint64_t j, uint64_t n, bool nullmap) {
+    if (j >= n) return 0;
+    const uint64_t r = sel ? sel[j] : j;
+    const bool valid = row_valid(c, r);
+    if (nullmap) return valid ? 0 : 1;
+    if (!valid) return 0;
+    switch (c.out_kind) {
+    case OK_COPY:
+        switch (c.in_w) {
+        case 1: return c.values[r];
+        case 2: return ((const uint16_t*)c.values)[r];
+        case 4: return ((const uint32_t*)c.values)[r];
+        default: return ((const uint64_t*)c.values)[r];
+        }
+    case OK_BOOL: return c.values[r] != 0;
+    case OK_DATE: case OK_DATETIME: {
+        int64_t s = ((const int64_t*)c.values)[r];
+        const uint32_t ns = c.aux ? ((const uint32_t*)c.aux)[r] : 0;
+        if (s > CH_MAX_DATE_SEC || (s == CH_MAX_DATE_SEC && ns > 0)) s = CH_MAX_DATE_SEC;
+        if (s < 0) s = 0;
+        return c.out_kind == OK_DATE ? (uint64_t)(s / 86400) : (uint64_t)s;
+    }
+    case OK_TS64: {
+        const int64_t s = ((const int64_t*)c.values)[r];
+        const uint32_t ns = c.aux ? ((const uint32_t*)c.aux)[r] : 0;
+        return (uint64_t)(s * 1000000LL + (int64_t)(ns / 1000u));
+    }
+    }
+    return 0;
+}
+
+// 4 consecutive bytes [4q, 4q+4) of the column's little-endian element stream
+__device__ __forceinline__ uint32_t stream_word(const DCol& c, const uint32_t* sel, uint64_t q, uint64_t n, int w, bool nullmap) {
+    switch (w) {
+    case 1: return (uint32_t)elem_value(c, sel, 4 * q, n, nullmap) | ((uint32_t)elem_value(c, sel, 4 * q + 1, n, nullmap) << 8) |
+                   ((uint32_t)elem_value(c, sel, 4 * q + 2, n, nullmap) << 16) | ((uint32_t)elem_value(c, sel, 4 * q + 3, n, nullmap) << 24);
+    case 2: return (uint32_t)(elem_value(c, sel, 2 * q, n, nullmap) & 0xffff) | ((uint32_t)(elem_value(c, sel, 2 * q + 1, n, nullmap) & 0xffff) << 16);
+    case 4: return (uint32_t)elem_value(c, sel, q, n, nullmap);
+    default: { const uint64_t v = elem_value(c, sel, q >> 1, n, nullmap); return (uint32_t)(v >> ((q & 1) * 32)); }
+    }
+}
+
+// Fixed-width columns and null maps. The column's data starts at an arbitrary byte of the block
+// (ClickHouse's format has no padding), so each lane builds one 4-byte word of the element stream,
+// takes its left neighbour's word by shuffle and funnel-shifts the pair onto the 4-byte grid of the
+// OUTPUT address: every store is an aligned, fully coalesced 128 B per warp.
+__global__ void __launch_bounds__(256) k_encode_fixed(EncodeArgs a) {
+    const int32_t slot = a.slots[blockIdx.y];
+    const bool nullmap = (slot & TF_SLOT_NULLMAP) != 0;
+    const DCol c = a.cols[slot & ~TF_SLOT_NULLMAP];
+    const uint64_t n = a.st->n_kept;
+    const int w = nullmap ? 1 : c.out_w;
+    const uint64_t base = nullmap ? c.null_off : c.out_off;
+    const uint32_t m = (uint32_t)(base & 3);
+    const uint64_t total = n * (uint64_t)w;
+    const uint64_t T = (m + total + 3) >> 2;
+    const uint64_t t0 = (uint64_t)blockIdx.x * TF_FIX_TILE_WORDS;
+    if (t0 >= T || n == 0) return;
+    uint8_t* dst0 = a.raw + (base - m);
+    const unsigned lane = threadIdx.x & 31;
+#pragma unroll 2
+    for (uint32_t it = 0; it < TF_FIX_TILE_WORDS / 256; it++) {
+        const uint64_t t = t0 + it * 256 + threadIdx.x;      // uniform trip count: shuffles below need the whole warp
+        const uint32_t wcur = (t < T) ? stream_word(c, a.sel, t, n, w, nullmap) : 0;
+        uint32_t wprev = __shfl_up_sync(0xffffffffu, wcur, 1);
+        if (lane == 0) wprev = (m && t > 0 && t <= T) ? stream_word(c, a.sel, t - 1, n, w, nullmap) : 0;
+        if (t >= T) continue;
+        const uint32_t val = m ? __funnelshift_r(wprev, wcur, 8 * (4 - m)) : wcur;
+        const int64_t sb = (int64_t)(4 * t) - (int64_t)m;          // stream offset of this word's first byte
+        uint8_t* dst = dst0 + 4 * t;
+        if (sb >= 0 && (uint64_t)sb + 4 <= total) *(uint32_t*)dst = val;
+        else {
+#pragma unroll
+            for (int b = 0; b < 4; b++) { const int64_t x = sb + b; if (x >= 0 && (uint64_t)x < total) dst[b] = (uint8_t)(val >> (8 * b)); }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ String columns
+__device__ __forceinline__ uint32_t str_len(const DCol& c, const uint32_t* sel, uint64_t j, uint64_t n, uint64_t& r) {
+    if (j >= n) { r = 0; return 0xffffffffu; }
+    r = sel ? sel[j] : j;
+    if (!row_valid(c, r)) return 0;
+    return c.offsets[r + 1] - c.offsets[r];
+}
+
+// encoded size (LEB128 length + payload) of every tile of TF_STR_TILE kept rows, for every String column
+__global__ void __launch_bounds__(256) k_str_sizes(EncodeArgs a) {
+    __shared__ uint32_t sm[33];
+    const DCol c = a.cols[a.slots[blockIdx.y]];
+    const uint64_t n = a.st->n_kept;
+    const uint64_t j0 = (uint64_t)blockIdx.x * TF_STR_TILE;
+    if (j0 >= n) return;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint64_t r; const uint32_t L = str_len(c, a.sel, j0 + 4 * threadIdx.x + k, n, r);
+        if (L != 0xffffffffu) sum += L + varint_len(L);
+    }
+    uint32_t tot; block_excl_scan(sum, &tot, sm);
+    if (threadIdx.x == 0) a.tile_sum[(size_t)c.str_slot * a.ntiles_cap + blockIdx.x] = tot;
+}
+
+// LEB128 length + bytes for 4 consecutive kept rows per thread; neighbouring threads own neighbouring
+// rows, so a warp reads one contiguous span of the source heap and writes one contiguous span of the block.
+__global__ void __launch_bounds__(256) k_encode_str(EncodeArgs a) {
+    __shared__ uint32_t sm[33];
+    const DCol c = a.cols[a.slots[blockIdx.y]];
+    const uint64_t n = a.st->n_kept;
+    const uint64_t j0 = (uint64_t)blockIdx.x * TF_STR_TILE;
+    if (j0 >= n) return;
+    uint32_t L[4]; uint64_t R[4]; uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { L[k] = str_len(c, a.sel, j0 + 4 * threadIdx.x + k, n, R[k]); if (L[k] != 0xffffffffu) sum += L[k] + varint_len(L[k]); }
+    uint32_t tot; const uint32_t ex = block_excl_scan(sum, &tot, sm);
+    uint8_t* o = a.raw + c.out_off + a.tile_base[(size_t)c.str_slot * a.ntiles_cap + blockIdx.x] + ex;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (L[k] == 0xffffffffu) break;
+        uint32_t v = L[k];
+        while (v >= 0x80) { *o++ = (uint8_t)(v | 0x80); v >>= 7; }
+        *o++ = (uint8_t)v;
+        const uint8_t* s = c.heap + c.offsets[R[k]];
+        for (uint32_t b = 0; b < L[k]; b++) o[b] = s[b];
+        o += L[k];
+    }
+}
+
+}  // namespace tfk

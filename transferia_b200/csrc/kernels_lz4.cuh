@@ -1,0 +1,386 @@
+// LZ4 block compression of the native block, cut into ClickHouse compressed frames, plus the
+// CityHash128 (v1.0.2) frame checksum and the final gather into one contiguous wire buffer.
+//
+// GPU-native LZ4 (not a port of any CPU compressor): one CTA per frame, the frame lives in shared
+// memory, and every phase is data-parallel:
+//   P1  stage the frame in shared memory (16-byte coalesced loads)
+//   P2  match finding: 512 positions per round probe/update a 4096-entry u16 hash table in shared
+//       memory (round-synchronous, so a candidate is always an earlier position); a second probe
+//       after the round's inserts recovers most intra-round repeats; candidates are verified
+//       against the data immediately; result = 1 valid bit + u16 candidate per position
+//   P3  greedy parse, one thread per 64-byte segment (matches are cut at the segment end), sequence
+//       descriptors overwrite the segment's own candidate slots in place
+//   P4  segmented scan carries pending literals across segments; block scan gives every segment its
+//       output offset; a suffix-min tells each segment which later sequence owns its trailing literals
+//   P5  all threads emit tokens/lengths/offsets and copy their own segment's literals
+// The emitted stream is a standard LZ4 block (last 5 bytes literals, last match starts >= 12 bytes
+// before the end) and decodes with stock liblz4; the bytes are NOT those of pierrec/lz4 (parity for
+// compressed bytes is unpinned in the reference).
+#pragma once
+#include "device_types.cuh"
+#include "kernels_encode.cuh"
+
+namespace tfk {
+
+#define LZ_THREADS 512
+#define LZ_SEG 64
+#define LZ_HASH_BITS 12
+#define LZ_MAX_FRAME 32768
+#define LZ_HDR 25          // 16 checksum + 1 method + 4 compressed size + 4 raw size
+
+__host__ __device__ inline uint32_t lz4_bound(uint32_t n) { return n + n / 255 + 16; }
+__host__ __device__ inline uint32_t lz_slot_stride(uint32_t frame_bytes) { return (LZ_HDR + 7 + lz4_bound(frame_bytes) + 15) & ~15u; }
+// slot layout: [7 pad][16 checksum][0x82][u32][u32][lz4 block]; the checksum field starts at +7 so that
+// the hashed region (+23) ... keep it simple: the slot starts 16-byte aligned and the LZ4 block at +25.
+
+struct Lz4Args {
+    const uint8_t* raw; DState* st; uint8_t* slots; uint32_t slot_stride; uint32_t* comp_size; uint32_t frame_bytes;
+};
+
+__device__ __forceinline__ uint32_t ld32u(const uint32_t* w, uint32_t p) {   // 4 bytes at byte offset p of a word array in shared memory
+    const uint32_t i = p >> 2, s = (p & 3) * 8;
+    return __funnelshift_r(w[i], w[i + 1], s);
+}
+__device__ __forceinline__ uint32_t ext_bytes(uint32_t x) { return x < 15 ? 0u : 1u + (x - 15u) / 255u; }
+__device__ __forceinline__ uint8_t* put_ext(uint8_t* o, uint32_t x) {   // x >= 15
+    x -= 15; while (x >= 255) { *o++ = 255; x -= 255; } *o++ = (uint8_t)x; return o;
+}
+__device__ __forceinline__ void copy_s2g(uint8_t* dst, const uint8_t* src, uint32_t n) { for (uint32_t i = 0; i < n; i++) dst[i] = src[i]; }
+
+__global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t F = a.frame_bytes;
+    uint32_t* data_w = (uint32_t*)smem;                                  // F + 16 bytes
+    uint8_t* data = smem;
+    uint16_t* cand = (uint16_t*)(smem + F + 16);                         // 2F bytes; later: sequence descriptors
+    uint16_t* table = (uint16_t*)(smem + F + 16 + 2 * F);               // 8 KB; later: per-segment arrays
+    uint32_t* vmask = (uint32_t*)(smem + F + 16 + 2 * F + (2u << LZ_HASH_BITS));   // F/8 bytes
+    uint32_t* scratch = vmask + F / 32;                                  // 40 words
+    __shared__ uint32_t s_frame;
+    // per-segment arrays aliased onto the hash table after P2 (nseg <= 512)
+    uint32_t* seg_off = (uint32_t*)table;            // [513]
+    int32_t* delta0 = (int32_t*)(seg_off + 516);     // [512]
+    uint16_t* carry_incl = (uint16_t*)(delta0 + 512);   // [512]
+    uint16_t* next_has = carry_incl + 512;           // [512]
+    uint8_t* nseq_s = (uint8_t*)(next_has + 512);    // [512]
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t raw_total = a.st->raw_total, n_frames = a.st->n_frames;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_frame = atomicAdd(&a.st->frame_ticket, 1u);
+        __syncthreads();
+        const uint32_t f = s_frame;
+        if (f >= n_frames) break;
+        const uint64_t pos0 = (uint64_t)f * F;
+        const uint32_t len = (uint32_t)((raw_total - pos0 < F) ? raw_total - pos0 : F);
+        uint8_t* out = a.slots + (size_t)f * a.slot_stride + LZ_HDR;
+
+        // ---- P1: stage
+        {
+            const int4* g = (const int4*)(a.raw + pos0);
+            int4* s4 = (int4*)smem;
+            const uint32_t nv = (len + 15) >> 4;
+            for (uint32_t i = tid; i < (F + 16) / 16; i += LZ_THREADS) {
+                int4 v = make_int4(0, 0, 0, 0);
+                if (i < nv) v = __ldg(g + i);
+                s4[i] = v;
+            }
+            for (uint32_t i = tid; i < (1u << LZ_HASH_BITS) / 2; i += LZ_THREADS) ((uint32_t*)table)[i] = 0;
+        }
+        __syncthreads();
+        if (len & 15) {   // zero the bytes past len inside the last 16-byte chunk (they belong to the next frame)
+            if (tid < 16 && (len & ~15u) + tid >= len) data[(len & ~15u) + tid] = 0;
+        }
+        __syncthreads();
+
+        // ---- P2: match finding
+        const uint32_t nrounds = (len + LZ_THREADS - 1) / LZ_THREADS;
+        for (uint32_t rd = 0; rd < nrounds; rd++) {
+            const uint32_t p = rd * LZ_THREADS + tid;
+            const uint32_t seq = ld32u(data_w, p);
+            const uint32_t h = (seq * 2654435761u) >> (32 - LZ_HASH_BITS);
+            uint32_t c = table[h];
+            __syncthreads();
+            const bool inside = p < len;
+            if (inside) table[h] = (uint16_t)p;
+            const bool ok = p + 12 <= len;                     // a match may start here (MFLIMIT)
+            bool valid = ok && c < p && ld32u(data_w, c) == seq;
+            __syncthreads();
+            if (ok && !valid) { const uint32_t c2 = table[h]; if (c2 < p && ld32u(data_w, c2) == seq) { valid = true; c = c2; } }
+            if (valid) cand[p] = (uint16_t)c;
+            const uint32_t b = __ballot_sync(0xffffffffu, valid);
+            if (lane == 0) vmask[p >> 5] = b;
+        }
+        __syncthreads();
+
+        // ---- P3: greedy parse, one thread per 64-byte segment
+        const uint32_t nseg = (len + LZ_SEG - 1) / LZ_SEG;
+        uint32_t my_nseq = 0, my_trail = 0, seg_start = tid * LZ_SEG, seg_end = 0;
+        uint2* desc = (uint2*)(cand + seg_start);
+        if (tid < nseg) {
+            seg_end = seg_start + LZ_SEG < len ? seg_start + LZ_SEG : len;
+            const uint32_t lim5 = len >= 5 ? len - 5 : 0;
+            const uint32_t limit = seg_end < lim5 ? seg_end : lim5;       // matches end before the last 5 bytes and inside the segment
+            const uint64_t m64 = (uint64_t)vmask[2 * tid] | ((uint64_t)(((2 * tid + 1) * 32 < ((len + 31) & ~31u)) ? vmask[2 * tid + 1] : 0u) << 32);
+            uint32_t cur = 0, last_end = seg_start;
+            while (cur < LZ_SEG) {
+                const uint64_t mm = m64 >> cur;
+                if (!mm) break;
+                const uint32_t r = cur + (uint32_t)__ffsll((long long)mm) - 1;
+                const uint32_t p = seg_start + r;
+                if (p + 4 > limit) break;
+                const uint32_t c = cand[p];
+                const uint32_t maxl = limit - p;
+                uint32_t ml = 4;
+                while (ml < maxl) {
+                    const uint32_t x = ld32u(data_w, c + ml) ^ ld32u(data_w, p + ml);
+                    if (x) { ml += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+                    ml += 4;
+                }
+                if (ml > maxl) ml = maxl;
+                desc[my_nseq] = make_uint2(p | (ml << 16), p - c);
+                my_nseq++; cur = r + ml; last_end = p + ml;
+            }
+            my_trail = seg_end - last_end;
+        }
+        __syncthreads();   // everyone is done reading the hash table region? (P2 finished before P3) -> reuse it now
+
+        // ---- P4a: segmented scan of pending literals: combine(a, b) = b.has ? b : (a.has, a.tr + b.tr)
+        {
+            uint32_t has = my_nseq > 0, tr = my_trail;
+            if (tid >= nseg) { has = 0; tr = 0; }
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t h2 = __shfl_up_sync(0xffffffffu, has, d), t2 = __shfl_up_sync(0xffffffffu, tr, d);
+                if (lane >= (uint32_t)d && !has) { tr += t2; has = h2; }
+            }
+            if (lane == 31) { scratch[warp] = has; scratch[16 + warp] = tr; }
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t wh = lane < LZ_THREADS / 32 ? scratch[lane] : 0, wt = lane < LZ_THREADS / 32 ? scratch[16 + lane] : 0;
+#pragma unroll
+                for (int d = 1; d < 16; d <<= 1) {
+                    const uint32_t h2 = __shfl_up_sync(0xffffffffu, wh, d), t2 = __shfl_up_sync(0xffffffffu, wt, d);
+                    if (lane >= (uint32_t)d && !wh) { wt += t2; wh = h2; }
+                }
+                // exclusive prefix for warp w = inclusive of w-1
+                const uint32_t eh = __shfl_up_sync(0xffffffffu, wh, 1), et = __shfl_up_sync(0xffffffffu, wt, 1);
+                if (lane < LZ_THREADS / 32) { scratch[lane] = lane ? eh : 0; scratch[16 + lane] = lane ? et : 0; }
+            }
+            __syncthreads();
+            if (!has) { tr += scratch[16 + warp]; }
+            if (tid < nseg) { carry_incl[tid] = (uint16_t)tr; nseq_s[tid] = (uint8_t)my_nseq; next_has[tid] = my_nseq ? (uint16_t)tid : (uint16_t)0xffff; }
+            else if (tid < 512) { next_has[tid] = 0xffff; }
+        }
+        __syncthreads();
+        const uint32_t carry_in = (tid > 0 && tid < nseg) ? carry_incl[tid - 1] : 0;
+
+        // ---- P4b: encoded bytes per segment, block scan -> output offsets
+        uint32_t my_bytes = 0;
+        if (tid < nseg) {
+            uint32_t prev_end = seg_start;
+            for (uint32_t k = 0; k < my_nseq; k++) {
+                const uint2 d = desc[k];
+                const uint32_t p = d.x & 0xffff, ml = d.x >> 16;
+                const uint32_t ll = (k == 0 ? carry_in : 0) + (p - prev_end);
+                my_bytes += 1 + ext_bytes(ll) + ll + 2 + ext_bytes(ml - 4);
+                prev_end = p + ml;
+            }
+        }
+        uint32_t total_seq_bytes;
+        const uint32_t my_off = block_excl_scan(my_bytes, &total_seq_bytes, scratch);
+        if (tid < nseg && my_nseq) {
+            const uint32_t p0 = desc[0].x & 0xffff;
+            const uint32_t ll0 = carry_in + (p0 - seg_start);
+            delta0[tid] = (int32_t)(my_off + 1 + ext_bytes(ll0)) - (int32_t)(p0 - ll0);
+        }
+        // suffix-min over next_has: next_has[s] = first segment > s that has a sequence
+        __syncthreads();
+        {
+            uint16_t v = (tid + 1 < 512) ? next_has[tid + 1] : (uint16_t)0xffff;    // shift: strictly later segments
+            __syncthreads();
+            next_has[tid] = v;
+            __syncthreads();
+            for (uint32_t d = 1; d < 512; d <<= 1) {
+                const uint16_t o = (tid + d < 512) ? next_has[tid + d] : (uint16_t)0xffff;
+                __syncthreads();
+                if (o < v) v = o;
+                next_has[tid] = v;
+                __syncthreads();
+            }
+        }
+        const uint32_t ll_final = nseg ? carry_incl[nseg - 1] : 0;
+        const int32_t delta_final = (int32_t)(total_seq_bytes + 1 + ext_bytes(ll_final)) - (int32_t)(len - ll_final);
+
+        // ---- P5: emit
+        if (tid < nseg) {
+            uint8_t* o = out + my_off; uint32_t prev_end = seg_start;
+            for (uint32_t k = 0; k < my_nseq; k++) {
+                const uint2 d = desc[k];
+                const uint32_t p = d.x & 0xffff, ml = d.x >> 16, off = d.y;
+                const uint32_t cin = (k == 0 ? carry_in : 0);
+                const uint32_t ll = cin + (p - prev_end);
+                const uint32_t mt = ml - 4;
+                *o++ = (uint8_t)(((ll < 15 ? ll : 15) << 4) | (mt < 15 ? mt : 15));
+                if (ll >= 15) o = put_ext(o, ll);
+                copy_s2g(o + cin, data + prev_end, p - prev_end);
+                o += ll;
+                *o++ = (uint8_t)off; *o++ = (uint8_t)(off >> 8);
+                if (mt >= 15) o = put_ext(o, mt);
+                prev_end = p + ml;
+            }
+            if (seg_end > prev_end) {   // trailing literals belong to the next sequence downstream
+                const uint32_t nh = next_has[tid];
+                const int32_t dl = (nh != 0xffff && nh < nseg) ? delta0[nh] : delta_final;
+                copy_s2g(out + (int32_t)prev_end + dl, data + prev_end, seg_end - prev_end);
+            }
+        }
+        if (tid == 0) {
+            uint8_t* o = out + total_seq_bytes;
+            *o++ = (uint8_t)((ll_final < 15 ? ll_final : 15) << 4);
+            if (ll_final >= 15) o = put_ext(o, ll_final);
+            a.comp_size[f] = total_seq_bytes + 1 + ext_bytes(ll_final) + ll_final;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ CityHash128 v1.0.2 over [method byte .. end of block]
+namespace cityd {
+#define CK0 0xc3a5c85c97cb3127ULL
+#define CK1 0xb492b66fbe98f273ULL
+#define CK2 0x9ae16a3b2f90404fULL
+#define CK3 0xc949d7c7509e6557ULL
+__device__ __forceinline__ uint64_t f64(const uint8_t* p) {
+    const uintptr_t a = (uintptr_t)p; const uint64_t* q = (const uint64_t*)(a & ~(uintptr_t)7); const uint32_t s = (uint32_t)(a & 7) * 8;
+    if (s == 0) return q[0];
+    return (q[0] >> s) | (q[1] << (64 - s));
+}
+__device__ __forceinline__ uint32_t f32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+__device__ __forceinline__ uint64_t rot(uint64_t v, int s) { return s == 0 ? v : ((v >> s) | (v << (64 - s))); }
+__device__ __forceinline__ uint64_t smix(uint64_t v) { return v ^ (v >> 47); }
+__device__ __forceinline__ uint64_t hl16(uint64_t u, uint64_t v) {
+    const uint64_t kMul = 0x9ddfea08eb382d69ULL;
+    uint64_t a = (u ^ v) * kMul; a ^= (a >> 47);
+    uint64_t b = (v ^ a) * kMul; b ^= (b >> 47); b *= kMul; return b;
+}
+__device__ uint64_t hl0to16(const uint8_t* s, size_t len) {
+    if (len > 8) { uint64_t a = f64(s), b = f64(s + len - 8); return hl16(a, rot(b + len, (int)len)) ^ b; }
+    if (len >= 4) { uint64_t a = f32(s); return hl16(len + (a << 3), f32(s + len - 4)); }
+    if (len > 0) { uint8_t a = s[0], b = s[len >> 1], c = s[len - 1]; uint32_t y = (uint32_t)a + ((uint32_t)b << 8); uint32_t z = (uint32_t)len + ((uint32_t)c << 2); return smix(y * CK2 ^ z * CK3) * CK2; }
+    return CK2;
+}
+struct P { uint64_t first, second; };
+__device__ __forceinline__ P weak32(uint64_t w, uint64_t x, uint64_t y, uint64_t z, uint64_t a, uint64_t b) {
+    a += w; b = rot(b + a + z, 21); const uint64_t c = a; a += x; a += y; b += rot(a, 44); P r; r.first = a + z; r.second = b + c; return r;
+}
+__device__ __forceinline__ P weak32p(const uint8_t* s, uint64_t a, uint64_t b) { return weak32(f64(s), f64(s + 8), f64(s + 16), f64(s + 24), a, b); }
+__device__ P murmur(const uint8_t* s, size_t len, P seed) {
+    uint64_t a = seed.first, b = seed.second, c = 0, d = 0; long l = (long)len - 16;
+    if (l <= 0) { a = smix(a * CK1) * CK1; c = b * CK1 + hl0to16(s, len); d = smix(a + (len >= 8 ? f64(s) : c)); }
+    else {
+        c = hl16(f64(s + len - 8) + CK1, a); d = hl16(b + len, c + f64(s + len - 16)); a += d;
+        do { a ^= smix(f64(s) * CK1) * CK1; a *= CK1; b ^= a; c ^= smix(f64(s + 8) * CK1) * CK1; c *= CK1; d ^= c; s += 16; l -= 16; } while (l > 0);
+    }
+    a = hl16(a, c); b = hl16(d, b);
+    P r; r.first = a ^ b; r.second = hl16(b, a); return r;
+}
+__device__ P hash128_seed(const uint8_t* s, size_t len, P seed) {
+    if (len < 128) return murmur(s, len, seed);
+    P v, w; uint64_t x = seed.first, y = seed.second, z = len * CK1;
+    v.first = rot(y ^ CK1, 49) * CK1 + f64(s);
+    v.second = rot(v.first, 42) * CK1 + f64(s + 8);
+    w.first = rot(y + z, 35) * CK1 + x;
+    w.second = rot(x + f64(s + 88), 53) * CK1;
+    do {
+#pragma unroll
+        for (int rep = 0; rep < 2; rep++) {
+            x = rot(x + y + v.first + f64(s + 16), 37) * CK1;
+            y = rot(y + v.second + f64(s + 48), 42) * CK1;
+            x ^= w.second; y ^= v.first; z = rot(z ^ w.first, 33);
+            v = weak32p(s, v.second * CK1, x + w.first);
+            w = weak32p(s + 32, z + w.second, y);
+            const uint64_t t = z; z = x; x = t; s += 64;
+        }
+        len -= 128;
+    } while (len >= 128);
+    y += rot(w.first, 37) * CK0 + z;
+    x += rot(v.first + z, 49) * CK0;
+    for (size_t tail = 0; tail < len;) {
+        tail += 32;
+        y = rot(y - x, 42) * CK0 + v.second;
+        w.first += f64(s + len - tail + 16);
+        x = rot(x, 49) * CK0 + w.first;
+        w.first += v.first;
+        v = weak32p(s + len - tail, v.first, v.second);
+    }
+    x = hl16(x, v.first); y = hl16(y, w.first);
+    P r; r.first = hl16(x + v.second, w.second) + y; r.second = hl16(x + w.second, y + v.second); return r;
+}
+__device__ P hash128(const uint8_t* s, size_t len) {
+    P seed;
+    if (len >= 16) { seed.first = f64(s) ^ CK3; seed.second = f64(s + 8); return hash128_seed(s + 16, len - 16, seed); }
+    if (len >= 8) { seed.first = f64(s) ^ (len * CK0); seed.second = f64(s + len - 8) ^ CK1; return hash128_seed(nullptr, 0, seed); }
+    seed.first = CK0; seed.second = CK1; return hash128_seed(s, len, seed);
+}
+}  // namespace cityd
+
+struct FrameArgs { uint8_t* slots; uint32_t slot_stride; const uint32_t* comp_size; DState* st; uint32_t frame_bytes; uint64_t* wire_off; uint8_t* wire; };
+
+// one thread per frame: fill [0x82][compressed+9][raw] and the CityHash128 of everything after the checksum
+__global__ void __launch_bounds__(128) k_frame_seal(FrameArgs a) {
+    const uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= a.st->n_frames) return;
+    uint8_t* s = a.slots + f * a.slot_stride;
+    const uint32_t cs = a.comp_size[f] + 9;
+    const uint64_t pos0 = f * a.frame_bytes;
+    const uint32_t rs = (uint32_t)((a.st->raw_total - pos0 < a.frame_bytes) ? a.st->raw_total - pos0 : a.frame_bytes);
+    s[16] = 0x82;
+    s[17] = (uint8_t)cs; s[18] = (uint8_t)(cs >> 8); s[19] = (uint8_t)(cs >> 16); s[20] = (uint8_t)(cs >> 24);
+    s[21] = (uint8_t)rs; s[22] = (uint8_t)(rs >> 8); s[23] = (uint8_t)(rs >> 16); s[24] = (uint8_t)(rs >> 24);
+    const cityd::P h = cityd::hash128(s + 16, cs);
+    ((uint64_t*)s)[0] = h.first; ((uint64_t*)s)[1] = h.second;
+}
+
+// exclusive scan of frame sizes (single block) -> position of every frame in the wire buffer
+__global__ void __launch_bounds__(1024) k_frame_scan(FrameArgs a) {
+    __shared__ uint32_t sm[33];
+    const uint64_t nf = a.st->n_frames;
+    uint64_t carry = 0;
+    for (uint64_t base = 0; base < nf; base += blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        const uint32_t v = i < nf ? a.comp_size[i] + LZ_HDR : 0;
+        uint32_t tot; const uint32_t ex = block_excl_scan(v, &tot, sm);
+        if (i < nf) a.wire_off[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) a.st->wire_total = carry;
+}
+
+// gather the sealed frames into one contiguous stream; source slots are 16-byte aligned, the destination
+// is re-aligned with the same shuffle + funnel-shift trick as k_encode_fixed so stores are aligned words
+__global__ void __launch_bounds__(256) k_wire_gather(FrameArgs a) {
+    const uint64_t nf = a.st->n_frames;
+    for (uint64_t f = blockIdx.x; f < nf; f += gridDim.x) {
+        const uint32_t* src = (const uint32_t*)(a.slots + f * a.slot_stride);
+        const uint32_t total = a.comp_size[f] + LZ_HDR;
+        const uint64_t base = a.wire_off[f];
+        const uint32_t m = (uint32_t)(base & 3);
+        const uint32_t T = (m + total + 3) >> 2;
+        uint8_t* dst0 = a.wire + (base - m);
+        for (uint32_t t = threadIdx.x; t < T; t += blockDim.x) {
+            const uint32_t wcur = src[t];                       // slot has >= 8 bytes of slack past the block
+            const uint32_t wprev = t ? src[t - 1] : 0;
+            const uint32_t val = m ? __funnelshift_r(wprev, wcur, 8 * (4 - m)) : wcur;
+            const int32_t sb = (int32_t)(4 * t) - (int32_t)m;
+            uint8_t* dst = dst0 + 4 * (uint64_t)t;
+            if (sb >= 0 && (uint32_t)sb + 4 <= total) *(uint32_t*)dst = val;
+            else {
+#pragma unroll
+                for (int b = 0; b < 4; b++) { const int32_t x = sb + b; if (x >= 0 && (uint32_t)x < total) dst[b] = (uint8_t)(val >> (8 * b)); }
+            }
+        }
+    }
+}
+
+}  // namespace tfk

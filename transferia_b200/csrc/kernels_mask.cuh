@@ -1,0 +1,237 @@
+// mask_field: hex(HMAC-SHA256(salt, text(value))) fused with the ClickHouse String encode.
+//   reference: pkg/transformer/registry/mask/hmac_hasher.go:29-33,52-74 (hash / Apply),
+//              pkg/transformer/registry/to_string/to_string.go:145-171 (SerializeToString).
+// The reference builds hmac.New(...) per value (two key-pad compressions each time); here the
+// ipad/opad states are computed once per plan on the host and every value costs
+// ceil((len+9)/64) + 1 compressions.  Integer-ALU bound, not HBM bound.
+#pragma once
+#include "device_types.cuh"
+#include "kernels_encode.cuh"
+
+namespace tfk {
+
+struct MaskKey { uint32_t istate[8]; uint32_t ostate[8]; };
+
+__host__ __device__ inline uint32_t sha_rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+
+#define TF_SHA_K_VALUES \
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, \
+    0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, \
+    0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, \
+    0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2
+__constant__ uint32_t d_sha_k[64] = {TF_SHA_K_VALUES};
+static const uint32_t h_sha_k[64] = {TF_SHA_K_VALUES};
+#ifdef __CUDA_ARCH__
+#define SHA_K d_sha_k
+#else
+#define SHA_K h_sha_k
+#endif
+
+// one SHA-256 compression; w[16] is consumed (rolling schedule)
+__host__ __device__ inline void sha256_compress(uint32_t st[8], uint32_t w[16]) {
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll 8
+    for (int i = 0; i < 64; i++) {
+        uint32_t wi;
+        if (i < 16) wi = w[i];
+        else {
+            const uint32_t w15 = w[(i - 15) & 15], w2 = w[(i - 2) & 15];
+            const uint32_t s0 = sha_rotr(w15, 7) ^ sha_rotr(w15, 18) ^ (w15 >> 3);
+            const uint32_t s1 = sha_rotr(w2, 17) ^ sha_rotr(w2, 19) ^ (w2 >> 10);
+            wi = w[i & 15] + s0 + w[(i - 7) & 15] + s1; w[i & 15] = wi;
+        }
+        const uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
+        const uint32_t ch = (e & f) ^ (~e & g);
+        const uint32_t t1 = h + S1 + ch + SHA_K[i] + wi;
+        const uint32_t S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
+        const uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + S0 + mj;
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
+// host: precompute the inner/outer pad states (crypto/hmac: keys longer than the block are hashed first)
+inline MaskKey make_mask_key(const uint8_t* key, size_t klen) {
+    static const uint32_t iv[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    uint8_t k[64]; memset(k, 0, 64);
+    if (klen > 64) {
+        uint32_t st[8]; memcpy(st, iv, 32);
+        size_t full = klen / 64; uint32_t w[16];
+        for (size_t b = 0; b < full; b++) { for (int i = 0; i < 16; i++) w[i] = (uint32_t)key[64 * b + 4 * i] << 24 | (uint32_t)key[64 * b + 4 * i + 1] << 16 | (uint32_t)key[64 * b + 4 * i + 2] << 8 | key[64 * b + 4 * i + 3]; sha256_compress(st, w); }
+        uint8_t tail[128]; memset(tail, 0, 128); size_t rem = klen - full * 64; memcpy(tail, key + full * 64, rem); tail[rem] = 0x80;
+        size_t tl = rem + 9 <= 64 ? 64 : 128; uint64_t bits = (uint64_t)klen * 8;
+        for (int i = 0; i < 8; i++) tail[tl - 1 - i] = (uint8_t)(bits >> (8 * i));
+        for (size_t b = 0; b < tl / 64; b++) { for (int i = 0; i < 16; i++) w[i] = (uint32_t)tail[64 * b + 4 * i] << 24 | (uint32_t)tail[64 * b + 4 * i + 1] << 16 | (uint32_t)tail[64 * b + 4 * i + 2] << 8 | tail[64 * b + 4 * i + 3]; sha256_compress(st, w); }
+        for (int i = 0; i < 8; i++) { k[4 * i] = (uint8_t)(st[i] >> 24); k[4 * i + 1] = (uint8_t)(st[i] >> 16); k[4 * i + 2] = (uint8_t)(st[i] >> 8); k[4 * i + 3] = (uint8_t)st[i]; }
+    } else memcpy(k, key, klen);
+    MaskKey mk; uint32_t w[16];
+    memcpy(mk.istate, iv, 32); memcpy(mk.ostate, iv, 32);
+    for (int i = 0; i < 16; i++) w[i] = ((uint32_t)(k[4 * i] ^ 0x36) << 24) | ((uint32_t)(k[4 * i + 1] ^ 0x36) << 16) | ((uint32_t)(k[4 * i + 2] ^ 0x36) << 8) | (uint32_t)(k[4 * i + 3] ^ 0x36);
+    sha256_compress(mk.istate, w);
+    for (int i = 0; i < 16; i++) w[i] = ((uint32_t)(k[4 * i] ^ 0x5c) << 24) | ((uint32_t)(k[4 * i + 1] ^ 0x5c) << 16) | ((uint32_t)(k[4 * i + 2] ^ 0x5c) << 8) | (uint32_t)(k[4 * i + 3] ^ 0x5c);
+    sha256_compress(mk.ostate, w);
+    return mk;
+}
+
+// streaming message sink: bytes -> big-endian words -> compress
+struct ShaSink {
+    uint32_t st[8]; uint32_t w[16]; uint32_t n;   // n = message bytes so far (excluding the 64-byte pad block)
+    __device__ __forceinline__ void init(const uint32_t* s) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) st[i] = s[i];
+#pragma unroll
+        for (int i = 0; i < 16; i++) w[i] = 0;
+        n = 0;
+    }
+    __device__ __forceinline__ void put(uint8_t b) {
+        const uint32_t k = n & 63;
+        w[k >> 2] |= (uint32_t)b << (24 - 8 * (k & 3));
+        n++;
+        if ((n & 63) == 0) {
+            sha256_compress(st, w);
+#pragma unroll
+            for (int i = 0; i < 16; i++) w[i] = 0;
+        }
+    }
+    __device__ __forceinline__ void finish(uint32_t prefix_bytes) {   // total length = prefix (pad block) + n
+        const uint64_t bits = ((uint64_t)prefix_bytes + n) * 8;
+        const uint32_t k = n & 63;
+        w[k >> 2] |= 0x80u << (24 - 8 * (k & 3));
+        if (k >= 56) {
+            sha256_compress(st, w);
+#pragma unroll
+            for (int i = 0; i < 16; i++) w[i] = 0;
+        }
+        w[14] = (uint32_t)(bits >> 32); w[15] = (uint32_t)bits;
+        sha256_compress(st, w);
+    }
+};
+
+__device__ __forceinline__ void put_dec(ShaSink& s, uint64_t u) {
+    char buf[20]; int n = 0;
+    do { buf[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    while (n) s.put((uint8_t)buf[--n]);
+}
+__device__ __forceinline__ void put_pad(ShaSink& s, int64_t v, int wdt) {   // Go appendInt(b, v, width)
+    if (v < 0) { s.put('-'); v = -v; }
+    char buf[20]; int n = 0; uint64_t u = (uint64_t)v;
+    do { buf[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    for (int i = n; i < wdt; i++) s.put('0');
+    while (n) s.put((uint8_t)buf[--n]);
+}
+__device__ __forceinline__ void put_lit(ShaSink& s, const char* t) { while (*t) s.put((uint8_t)*t++); }
+
+__device__ inline void civil_from_days(int64_t z, int64_t& y, unsigned& m, unsigned& d) {
+    z += 719468;
+    const int64_t era = (z >= 0 ? z : z - 146096) / 146097;
+    const unsigned doe = (unsigned)(z - era * 146097);
+    const unsigned yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+    y = (int64_t)yoe + era * 400;
+    const unsigned doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+    const unsigned mp = (5 * doy + 2) / 153;
+    d = doy - (153 * mp + 2) / 5 + 1;
+    m = mp < 10 ? mp + 3 : mp - 9;
+    y += (m <= 2);
+}
+// time.Time.UTC().Format("2006-01-02") / RFC3339Nano
+__device__ inline void put_time(ShaSink& s, int64_t sec, uint32_t nsec, bool date_only) {
+    int64_t days = sec / 86400; int64_t sod = sec - days * 86400; if (sod < 0) { sod += 86400; days--; }
+    int64_t y; unsigned m, d; civil_from_days(days, y, m, d);
+    put_pad(s, y, 4); s.put('-'); put_pad(s, m, 2); s.put('-'); put_pad(s, d, 2);
+    if (date_only) return;
+    s.put('T'); put_pad(s, sod / 3600, 2); s.put(':'); put_pad(s, (sod / 60) % 60, 2); s.put(':'); put_pad(s, sod % 60, 2);
+    if (nsec) {
+        char b[9]; uint32_t v = nsec; for (int i = 8; i >= 0; i--) { b[i] = (char)('0' + v % 10); v /= 10; }
+        int n = 9; while (n > 0 && b[n - 1] == '0') n--;
+        s.put('.'); for (int i = 0; i < n; i++) s.put((uint8_t)b[i]);
+    }
+    s.put('Z');
+}
+// encoding/json string encoder, escapeHTML = true (json.Marshal of a Go string inside an `any` column)
+__device__ inline void put_json_string(ShaSink& s, const uint8_t* p, uint32_t n) {
+    const char* hex = "0123456789abcdef";
+    s.put('"');
+    uint32_t i = 0;
+    while (i < n) {
+        const uint8_t b = p[i];
+        if (b < 0x80) {
+            if (b >= 0x20 && b != '"' && b != '\\' && b != '<' && b != '>' && b != '&') { s.put(b); i++; continue; }
+            s.put('\\');
+            switch (b) {
+            case '\\': case '"': s.put(b); break;
+            case '\b': s.put('b'); break; case '\f': s.put('f'); break; case '\n': s.put('n'); break; case '\r': s.put('r'); break; case '\t': s.put('t'); break;
+            default: s.put('u'); s.put('0'); s.put('0'); s.put((uint8_t)hex[b >> 4]); s.put((uint8_t)hex[b & 15]);
+            }
+            i++; continue;
+        }
+        uint32_t r = 0xFFFD, w = 1;
+        if (b >= 0xC2 && b <= 0xDF && i + 1 < n && (p[i + 1] & 0xC0) == 0x80) { r = ((b & 0x1Fu) << 6) | (p[i + 1] & 0x3Fu); w = 2; }
+        else if (b >= 0xE0 && b <= 0xEF && i + 2 < n && (p[i + 1] & 0xC0) == 0x80 && (p[i + 2] & 0xC0) == 0x80) {
+            const uint32_t t = ((b & 0x0Fu) << 12) | ((p[i + 1] & 0x3Fu) << 6) | (p[i + 2] & 0x3Fu);
+            if (t >= 0x800 && !(t >= 0xD800 && t <= 0xDFFF)) { r = t; w = 3; }
+        } else if (b >= 0xF0 && b <= 0xF4 && i + 3 < n && (p[i + 1] & 0xC0) == 0x80 && (p[i + 2] & 0xC0) == 0x80 && (p[i + 3] & 0xC0) == 0x80) {
+            const uint32_t t = ((b & 0x07u) << 18) | ((p[i + 1] & 0x3Fu) << 12) | ((p[i + 2] & 0x3Fu) << 6) | (p[i + 3] & 0x3Fu);
+            if (t >= 0x10000 && t <= 0x10FFFF) { r = t; w = 4; }
+        }
+        if (r == 0xFFFD && w == 1) { put_lit(s, "\\ufffd"); i++; continue; }
+        if (r == 0x2028 || r == 0x2029) { put_lit(s, "\\u202"); s.put((uint8_t)hex[r & 0xF]); i += w; continue; }
+        for (uint32_t k = 0; k < w; k++) s.put(p[i + k]);
+        i += w;
+    }
+    s.put('"');
+}
+
+struct MaskArgs { const DCol* cols; const int32_t* slots; const MaskKey* keys; const uint32_t* sel; const DState* st; uint8_t* raw; };
+
+// one thread per (kept row, masked column): text form -> HMAC -> "\x40" + 64 hex chars into the block
+__global__ void __launch_bounds__(128) k_mask_encode(MaskArgs a) {
+    const DCol c = a.cols[a.slots[blockIdx.y]];
+    const uint64_t n = a.st->n_kept;
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t r = a.sel ? a.sel[j] : j;
+    const MaskKey& mk = a.keys[c.mask_slot];
+    ShaSink s; s.init(mk.istate);
+    const bool valid = row_valid(c, r);
+    if (!valid) { if (c.type == TF_ANY) put_lit(s, "null"); else put_lit(s, "<nil>"); }   // json.Marshal(nil) / fmt %v of nil
+    else switch (c.type) {
+        case TF_INT8: { int64_t v = ((const int8_t*)c.values)[r]; if (v < 0) { s.put('-'); put_dec(s, (uint64_t)(-v)); } else put_dec(s, (uint64_t)v); break; }
+        case TF_INT16: { int64_t v = ((const int16_t*)c.values)[r]; if (v < 0) { s.put('-'); put_dec(s, (uint64_t)(-v)); } else put_dec(s, (uint64_t)v); break; }
+        case TF_INT32: { int64_t v = ((const int32_t*)c.values)[r]; if (v < 0) { s.put('-'); put_dec(s, (uint64_t)(-v)); } else put_dec(s, (uint64_t)v); break; }
+        case TF_INT64: { int64_t v = ((const int64_t*)c.values)[r]; if (v < 0) { s.put('-'); put_dec(s, (uint64_t)0 - (uint64_t)v); } else put_dec(s, (uint64_t)v); break; }
+        case TF_UINT8: put_dec(s, c.values[r]); break;
+        case TF_UINT16: put_dec(s, ((const uint16_t*)c.values)[r]); break;
+        case TF_UINT32: put_dec(s, ((const uint32_t*)c.values)[r]); break;
+        case TF_UINT64: put_dec(s, ((const uint64_t*)c.values)[r]); break;
+        case TF_BOOLEAN: put_lit(s, c.values[r] ? "true" : "false"); break;
+        case TF_DATE: put_time(s, ((const int64_t*)c.values)[r], 0, true); break;
+        case TF_DATETIME: case TF_TIMESTAMP: put_time(s, ((const int64_t*)c.values)[r], c.aux ? ((const uint32_t*)c.aux)[r] : 0, false); break;
+        case TF_BYTES: case TF_UTF8: { const uint8_t* p = c.heap + c.offsets[r]; const uint32_t L = c.offsets[r + 1] - c.offsets[r]; for (uint32_t k = 0; k < L; k++) s.put(p[k]); break; }
+        case TF_ANY: {
+            const uint8_t* p = c.heap + c.offsets[r]; const uint32_t L = c.offsets[r + 1] - c.offsets[r];
+            if (c.aux && c.aux[r] == 1) put_json_string(s, p, L); else for (uint32_t k = 0; k < L; k++) s.put(p[k]);
+            break;
+        }
+    }
+    s.finish(64);
+    // outer hash over opad state + 32-byte inner digest
+    uint32_t o[8]; uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { o[i] = mk.ostate[i]; w[i] = s.st[i]; }
+    w[8] = 0x80000000u;
+#pragma unroll
+    for (int i = 9; i < 15; i++) w[i] = 0;
+    w[15] = (64 + 32) * 8;
+    sha256_compress(o, w);
+    uint8_t* out = a.raw + c.out_off + j * 65;
+    if (c.nullable) a.raw[c.null_off + j] = 0;          // the digest of "<nil>" is a value, never NULL (hmac_hasher.go:60)
+    out[0] = 64;
+    const char* hex = "0123456789abcdef";
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+#pragma unroll
+        for (int b = 0; b < 4; b++) { const uint32_t by = (o[i] >> (24 - 8 * b)) & 0xff; out[1 + 8 * i + 2 * b] = (uint8_t)hex[by >> 4]; out[2 + 8 * i + 2 * b] = (uint8_t)hex[by & 15]; }
+    }
+}
+
+}  // namespace tfk

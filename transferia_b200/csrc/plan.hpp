@@ -1,0 +1,499 @@
+// Host-side plan builder: the per-table, per-schema-hash "transformation plan" of the
+// reference (pkg/transformer/transformation.go:46-85 AddTablePlan: Suitable() -> ResultSchema()
+// chain), compiled into flat device programs.  Config-time only.
+//
+// Mirrors, for the transformers on the hot path:
+//   filter_rows        pkg/transformer/registry/filter_rows/filter_rows.go:41-97,445-519
+//     filter grammar   library/go/yandex/cloud/filter/grammar/grammar.go:256-313,
+//                      library/go/yandex/cloud/filter/filters.go:237-313
+//   mask_field         pkg/transformer/registry/mask/mask.go:20-67, hmac_hasher.go:35-47,76-89
+//   table matching     pkg/transformer/registry/filter/filter.go:27-74, transformer_common.go:9-33,
+//                      pkg/abstract/changeitem/table_id.go:14-30
+//   ClickHouse types   pkg/providers/clickhouse/columntypes/types.go:210-248, sink_table.go:196-235
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <regex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "json_min.hpp"
+#include "../../include/tfgpu.h"
+
+namespace tfplan {
+
+struct FatalError : std::runtime_error { int code; FatalError(int c, const std::string& m) : std::runtime_error(m), code(c) {} };
+
+// ------------------------------------------------------------------ schema
+struct ColSchema {
+    std::string table_schema, table_name, path, name, type, expression, original_type;
+    bool key = false, fake_key = false, required = false;
+    int tf = 0;
+};
+
+inline int yt_to_tf(const std::string& t) {
+    static const std::pair<const char*, int> m[] = {
+        {"int8", TF_INT8}, {"int16", TF_INT16}, {"int32", TF_INT32}, {"int64", TF_INT64},
+        {"uint8", TF_UINT8}, {"uint16", TF_UINT16}, {"uint32", TF_UINT32}, {"uint64", TF_UINT64},
+        {"float", TF_FLOAT}, {"double", TF_DOUBLE}, {"boolean", TF_BOOLEAN}, {"string", TF_BYTES},
+        {"utf8", TF_UTF8}, {"any", TF_ANY}, {"date", TF_DATE}, {"datetime", TF_DATETIME},
+        {"timestamp", TF_TIMESTAMP}, {"interval", TF_INTERVAL}};
+    for (auto& kv : m) if (t == kv.first) return kv.second;
+    return 0;
+}
+inline const char* tf_to_yt(int tf) {
+    static const char* n[] = {"", "int8", "int16", "int32", "int64", "uint8", "uint16", "uint32", "uint64", "float", "double",
+                              "boolean", "string", "utf8", "any", "date", "datetime", "timestamp", "interval"};
+    return (tf >= 1 && tf <= 18) ? n[tf] : "";
+}
+
+inline std::vector<ColSchema> parse_schema(const std::string& js) {
+    auto root = tfj::parse(js);
+    if (root->kind != tfj::Value::Arr) throw FatalError(TF_E_FATAL_CONFIG, "schema_json must be an array of ColSchema");
+    std::vector<ColSchema> out;
+    for (auto& e : root->arr) {
+        ColSchema c;
+        c.table_schema = e->get_str("table_schema"); c.table_name = e->get_str("table_name"); c.path = e->get_str("path");
+        c.name = e->get_str("name"); c.type = e->get_str("type"); c.expression = e->get_str("expression");
+        c.original_type = e->get_str("original_type");
+        c.key = e->get_bool("key"); c.fake_key = e->get_bool("fake_key"); c.required = e->get_bool("required");
+        c.tf = yt_to_tf(c.type);
+        if (!c.tf) throw FatalError(TF_E_FATAL_UNSUPPORTED, "unsupported column type '" + c.type + "' for column " + c.name);
+        out.push_back(c);
+    }
+    return out;
+}
+
+inline std::string schema_to_json(const std::vector<ColSchema>& s) {
+    std::string o = "[";
+    for (size_t i = 0; i < s.size(); i++) {
+        const ColSchema& c = s[i];
+        if (i) o += ",";
+        o += "{\"table_schema\":" + tfj::quote(c.table_schema) + ",\"table_name\":" + tfj::quote(c.table_name) + ",\"path\":" + tfj::quote(c.path) +
+             ",\"name\":" + tfj::quote(c.name) + ",\"type\":" + tfj::quote(c.type) + ",\"key\":" + (c.key ? "true" : "false") +
+             ",\"fake_key\":" + (c.fake_key ? "true" : "false") + ",\"required\":" + (c.required ? "true" : "false") +
+             ",\"expression\":" + tfj::quote(c.expression) + ",\"original_type\":" + tfj::quote(c.original_type) + "}";
+    }
+    return o + "]";
+}
+
+// ------------------------------------------------------------------ filter grammar
+enum { OP_EQ = 0, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE, OP_IN, OP_NOTIN, OP_MATCH, OP_NOTMATCH };
+enum { LV_INT = 1, LV_FLOAT = 2, LV_BOOL = 3, LV_STRING = 4, LV_TIME = 5, LV_NULL = 6, LV_LIST = 16 };
+
+struct Literal { int kind = 0; int64_t i = 0; double f = 0; std::string s; };
+struct Term { std::string attribute; int op = 0; int vtype = 0; Literal v; std::vector<Literal> list; };
+
+struct Tok { int kind; std::string text; };   // kinds: 0 Operator 1 String 2 DateTime 3 Ident 4 Float 5 Int 6 Punct 7 WS 8 EOF
+enum { T_OP, T_STR, T_DT, T_ID, T_FLOAT, T_INT, T_PUNCT, T_WS, T_EOF };
+
+inline bool is_d(char c) { return c >= '0' && c <= '9'; }
+inline bool is_a(char c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z'); }
+
+// grammar.go:256-266: one regexp, alternatives tried in order at each position
+inline std::vector<Tok> lex(const std::string& s) {
+    std::vector<Tok> out; size_t p = 0, n = s.size();
+    auto digits = [&](size_t q, int cnt) { for (int i = 0; i < cnt; i++) if (q + i >= n || !is_d(s[q + i])) return false; return true; };
+    while (p < n) {
+        char c = s[p];
+        // Operator
+        if (p + 1 < n && ((c == '!' && (s[p + 1] == '=' || s[p + 1] == '~')) || ((c == '<' || c == '>') && s[p + 1] == '='))) { out.push_back({T_OP, s.substr(p, 2)}); p += 2; continue; }
+        if (c == '=' || c == '<' || c == '>' || c == '~') { out.push_back({T_OP, std::string(1, c)}); p++; continue; }
+        // String
+        if (c == '\'' || c == '"') {
+            size_t i = p + 1, last_esc = std::string::npos; bool closed = false;
+            while (i < n) {
+                if (s[i] == '\\' && i + 1 < n && s[i + 1] == c) { last_esc = i; i += 2; continue; }
+                if (s[i] == c) { closed = true; break; }
+                i++;
+            }
+            if (!closed && last_esc != std::string::npos) { i = last_esc + 1; closed = true; }   // regexp backtracking: "\'" re-read as '\' + closing quote
+            if (closed) { out.push_back({T_STR, s.substr(p, i - p + 1)}); p = i + 1; continue; }
+            throw FatalError(TF_E_FATAL_CONFIG, "filter: invalid token at " + std::to_string(p));
+        }
+        // DateTime
+        if (digits(p, 4) && p + 4 < n && s[p + 4] == '-' && digits(p + 5, 2) && p + 7 < n && s[p + 7] == '-' && digits(p + 8, 2)) {
+            size_t q = p + 10;
+            if (q < n && s[q] == 'T' && digits(q + 1, 2) && q + 3 < n && s[q + 3] == ':' && digits(q + 4, 2)) {
+                q += 6;
+                if (q < n && s[q] == ':' && digits(q + 1, 2)) {
+                    q += 3;
+                    if (q + 1 < n && s[q] == '.' && is_d(s[q + 1])) { q++; while (q < n && is_d(s[q])) q++; }
+                }
+                if (q < n && s[q] == 'Z') q++;
+                else if (q + 1 < n && (s[q] == '+' || s[q] == '-') && is_d(s[q + 1])) {
+                    q++; while (q < n && is_d(s[q])) q++;
+                    if (q + 1 < n && s[q] == ':' && is_d(s[q + 1])) { q++; while (q < n && is_d(s[q])) q++; }
+                }
+            }
+            out.push_back({T_DT, s.substr(p, q - p)}); p = q; continue;
+        }
+        // Ident
+        if (is_a(c)) { size_t q = p + 1; while (q < n && (is_a(s[q]) || is_d(s[q]) || s[q] == '_' || s[q] == '.')) q++; out.push_back({T_ID, s.substr(p, q - p)}); p = q; continue; }
+        // Float / Int
+        {
+            size_t q = p; if (s[q] == '-' || s[q] == '+') q++;
+            if (q < n && is_d(s[q])) {
+                size_t r = q; while (r < n && is_d(s[r])) r++;
+                if (r + 1 < n && s[r] == '.' && is_d(s[r + 1])) { size_t t = r + 1; while (t < n && is_d(s[t])) t++; out.push_back({T_FLOAT, s.substr(p, t - p)}); p = t; continue; }
+                out.push_back({T_INT, s.substr(p, r - p)}); p = r; continue;
+            }
+        }
+        if (c == '(' || c == ')' || c == ',') { out.push_back({T_PUNCT, std::string(1, c)}); p++; continue; }
+        if (c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v') { size_t q = p; while (q < n && (s[q] == ' ' || s[q] == '\t' || s[q] == '\n' || s[q] == '\r' || s[q] == '\f' || s[q] == '\v')) q++; out.push_back({T_WS, s.substr(p, q - p)}); p = q; continue; }
+        throw FatalError(TF_E_FATAL_CONFIG, "filter: invalid token at " + std::to_string(p));
+    }
+    out.push_back({T_EOF, ""});
+    return out;
+}
+
+inline void put_utf8(std::string& o, uint32_t cp) {
+    if (cp < 0x80) o += (char)cp;
+    else if (cp < 0x800) { o += (char)(0xC0 | (cp >> 6)); o += (char)(0x80 | (cp & 0x3F)); }
+    else if (cp < 0x10000) { o += (char)(0xE0 | (cp >> 12)); o += (char)(0x80 | ((cp >> 6) & 0x3F)); o += (char)(0x80 | (cp & 0x3F)); }
+    else { o += (char)(0xF0 | (cp >> 18)); o += (char)(0x80 | ((cp >> 12) & 0x3F)); o += (char)(0x80 | ((cp >> 6) & 0x3F)); o += (char)(0x80 | (cp & 0x3F)); }
+}
+// participle.Unquote("String") == strconv.UnquoteChar over the body
+inline std::string unquote(const std::string& tok) {
+    char q = tok[0]; std::string b = tok.substr(1, tok.size() - 2), o; size_t i = 0;
+    auto bad = [&]() -> FatalError { return FatalError(TF_E_FATAL_CONFIG, "filter: invalid quoted string " + tok); };
+    while (i < b.size()) {
+        char c = b[i];
+        if (c != '\\') { o += c; i++; continue; }
+        if (++i >= b.size()) throw bad();
+        char e = b[i++];
+        switch (e) {
+        case 'a': o += '\a'; break; case 'b': o += '\b'; break; case 'f': o += '\f'; break; case 'n': o += '\n'; break;
+        case 'r': o += '\r'; break; case 't': o += '\t'; break; case 'v': o += '\v'; break; case '\\': o += '\\'; break;
+        case '\'': case '"': if (e != q) throw bad(); o += e; break;
+        case 'x': { if (i + 2 > b.size()) throw bad(); o += (char)strtoul(b.substr(i, 2).c_str(), nullptr, 16); i += 2; break; }
+        case 'u': case 'U': { size_t k = e == 'u' ? 4 : 8; if (i + k > b.size()) throw bad(); put_utf8(o, (uint32_t)strtoul(b.substr(i, k).c_str(), nullptr, 16)); i += k; break; }
+        default:
+            if (e >= '0' && e <= '7') { if (i + 2 > b.size()) throw bad(); o += (char)strtoul(b.substr(i - 1, 3).c_str(), nullptr, 8); i += 2; break; }
+            throw bad();
+        }
+    }
+    return o;
+}
+
+inline int64_t days_from_civil(int64_t y, unsigned m, unsigned d) {
+    y -= m <= 2;
+    const int64_t era = (y >= 0 ? y : y - 399) / 400;
+    const unsigned yoe = (unsigned)(y - era * 400);
+    const unsigned doy = (153 * (m > 2 ? m - 3 : m + 9) + 2) / 5 + d - 1;
+    const unsigned doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+    return era * 146097 + (int64_t)doe - 719468;
+}
+// DateTime.delayedParse grammar.go:176-188 (layout chosen by findTimeLayout :120-149); returns UnixMicro
+inline int64_t parse_time_micro(const std::string& v) {
+    auto bad = [&](const char* m) -> FatalError { return FatalError(TF_E_FATAL_CONFIG, std::string("filter: ") + m + " in '" + v + "'"); };
+    auto num = [&](size_t p, size_t k) { return (int)strtol(v.substr(p, k).c_str(), nullptr, 10); };
+    int y = num(0, 4), mo = num(5, 2), d = num(8, 2);
+    static const int dm[] = {0, 31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    bool leap = (y % 4 == 0 && y % 100 != 0) || y % 400 == 0;
+    if (mo < 1 || mo > 12) throw bad("month out of range");
+    if (d < 1 || d > dm[mo] + ((mo == 2 && leap) ? 1 : 0)) throw bad("day out of range");
+    int hh = 0, mi = 0, ss = 0; int64_t nsec = 0, off = 0; size_t p = 10;
+    if (p < v.size() && v[p] == 'T') {
+        hh = num(p + 1, 2); mi = num(p + 4, 2); p += 6;
+        if (p < v.size() && v[p] == ':') { ss = num(p + 1, 2); p += 3;
+            if (p < v.size() && v[p] == '.') { size_t q = p + 1; std::string fr; while (q < v.size() && is_d(v[q])) fr += v[q++]; fr += "000000000"; nsec = strtoll(fr.substr(0, 9).c_str(), nullptr, 10); p = q; } }
+        if (hh > 23) throw bad("hour out of range");
+        if (mi > 59) throw bad("minute out of range");
+        if (ss > 59) throw bad("second out of range");
+        if (p < v.size() && v[p] != 'Z') {
+            int sign = v[p] == '-' ? -1 : 1; std::string tz = v.substr(p + 1); size_t colon = tz.find(':');
+            if (colon != std::string::npos) { if (colon != 2 || tz.size() != 5) throw bad("bad zone"); off = sign * (strtol(tz.substr(0, 2).c_str(), nullptr, 10) * 3600 + strtol(tz.substr(3, 2).c_str(), nullptr, 10) * 60); }
+            else { if (tz.size() != 2) throw bad("bad zone"); off = sign * strtol(tz.c_str(), nullptr, 10) * 3600; }
+        }
+    }
+    int64_t sec = days_from_civil(y, (unsigned)mo, (unsigned)d) * 86400 + hh * 3600 + mi * 60 + ss - off;
+    return sec * 1000000 + nsec / 1000;
+}
+
+inline std::string upper(std::string s) { for (auto& c : s) if (c >= 'a' && c <= 'z') c -= 32; return s; }
+
+class FilterParser {
+public:
+    explicit FilterParser(const std::string& src) : t_(lex(src)) {}
+    std::vector<Term> parse() {
+        std::vector<Term> out; ws();
+        if (peek().kind == T_EOF) return out;
+        out.push_back(term());
+        for (;;) {
+            ws(); if (peek().kind == T_EOF) break;
+            if (!kw(peek(), "AND")) unexpected();
+            p_++; ws(); out.push_back(term());
+        }
+        return out;
+    }
+private:
+    std::vector<Tok> t_; size_t p_ = 0;
+    const Tok& peek() const { return t_[p_ < t_.size() ? p_ : t_.size() - 1]; }
+    void ws() { while (peek().kind == T_WS) p_++; }
+    static bool kw(const Tok& t, const char* n) { return t.kind == T_ID && upper(t.text) == n; }
+    [[noreturn]] void unexpected() { throw FatalError(TF_E_FATAL_CONFIG, "filter: unexpected token \"" + peek().text + "\""); }
+    Literal scalar(int& kind) {
+        Literal l; const Tok& t = peek();
+        if (t.kind == T_STR) { kind = LV_STRING; l.s = unquote(t.text); p_++; }
+        else if (t.kind == T_DT) { kind = LV_TIME; l.i = parse_time_micro(t.text); p_++; }
+        else if (kw(t, "TRUE") || kw(t, "FALSE")) { kind = LV_BOOL; l.i = upper(t.text) == "TRUE"; p_++; }
+        else if (t.kind == T_FLOAT) { kind = LV_FLOAT; l.f = strtod(t.text.c_str(), nullptr); p_++; }
+        else if (t.kind == T_INT) {
+            kind = LV_INT; errno = 0; l.i = strtoll(t.text.c_str(), nullptr, 10);
+            if (errno == ERANGE) throw FatalError(TF_E_FATAL_CONFIG, "filter: value out of range");
+            p_++;
+        }
+        else if (kw(t, "NULL") || kw(t, "NIL")) { kind = LV_NULL; p_++; }
+        else unexpected();
+        l.kind = kind; return l;
+    }
+    Term term() {
+        Term tm; if (peek().kind != T_ID) unexpected();
+        tm.attribute = peek().text; p_++; ws();
+        const Tok& o = peek();
+        if (o.kind == T_OP) {
+            const std::string& x = o.text;
+            tm.op = x == "=" ? OP_EQ : x == "!=" ? OP_NE : x == "<" ? OP_LT : x == "<=" ? OP_LE : x == ">" ? OP_GT : x == ">=" ? OP_GE : x == "~" ? OP_MATCH : OP_NOTMATCH;
+            p_++;
+        } else if (kw(o, "IN")) { tm.op = OP_IN; p_++; }
+        else if (kw(o, "NOT")) { p_++; ws(); if (!kw(peek(), "IN")) unexpected(); tm.op = OP_NOTIN; p_++; }
+        else unexpected();
+        ws();
+        bool is_list = false;
+        if (peek().kind == T_PUNCT && peek().text == "(") {
+            is_list = true; p_++; ws();
+            int k0 = 0; tm.list.push_back(scalar(k0)); ws();
+            while (peek().kind == T_PUNCT && peek().text == ",") {
+                p_++; ws(); int k = 0; Literal l = scalar(k);
+                if (k != k0) throw FatalError(TF_E_FATAL_CONFIG, "filter: list items should have same type");
+                tm.list.push_back(l); ws();
+            }
+            if (!(peek().kind == T_PUNCT && peek().text == ")")) unexpected();
+            p_++; tm.vtype = k0 | LV_LIST;
+        } else { int k = 0; tm.v = scalar(k); tm.vtype = k; }
+        ws();
+        // validateTerm filters.go:255-287
+        if (is_list && tm.op != OP_IN && tm.op != OP_NOTIN) throw FatalError(TF_E_FATAL_CONFIG, "filter: list values require [ NOT ] IN operator");
+        if (!is_list && (tm.op == OP_IN || tm.op == OP_NOTIN)) throw FatalError(TF_E_FATAL_CONFIG, "filter: IN operator expect list value");
+        if (tm.vtype == LV_NULL && tm.op != OP_EQ && tm.op != OP_NE) throw FatalError(TF_E_FATAL_CONFIG, "filter: NULL expects \"=\" or \"!=\" operator");
+        return tm;
+    }
+};
+
+// ------------------------------------------------------------------ table / column name filters
+struct NameFilter {
+    std::vector<std::string> inc_src, exc_src;
+    std::vector<std::regex> inc, exc;
+    bool empty() const { return inc_src.empty() && exc_src.empty(); }
+    bool match(const std::string& v) const {          // filter.go:27-44
+        for (auto& r : exc) if (std::regex_search(v, r)) return false;
+        if (inc_src.empty()) return true;
+        for (auto& r : inc) if (std::regex_search(v, r)) return true;
+        return false;
+    }
+};
+inline NameFilter make_filter(const std::vector<std::string>& inc, const std::vector<std::string>& exc) {
+    NameFilter f; f.inc_src = inc; f.exc_src = exc;
+    try {
+        for (auto& s : inc) f.inc.emplace_back(s, std::regex::ECMAScript);
+        for (auto& s : exc) f.exc.emplace_back(s, std::regex::ECMAScript);
+    } catch (const std::regex_error& e) { throw FatalError(TF_E_FATAL_CONFIG, std::string("unable to compile regexp: ") + e.what()); }
+    return f;
+}
+inline NameFilter tables_filter(const tfj::Value* cfg) {
+    if (!cfg) return NameFilter();
+    auto inc = cfg->get_str_list("includeTables"); if (inc.empty()) inc = cfg->get_str_list("include_tables");
+    auto exc = cfg->get_str_list("excludeTables"); if (exc.empty()) exc = cfg->get_str_list("exclude_tables");
+    return make_filter(inc, exc);
+}
+inline std::string dq(const std::string& s) { std::string o = "\""; for (char c : s) { if (c == '"') o += "\"\""; else o += c; } return o + "\""; }
+inline bool match_table(const NameFilter& f, const std::string& ns, const std::string& name) {   // transformer_common.go:9-33
+    if (f.empty()) return true;
+    std::string full = ns.empty() ? name : ns + "." + name;
+    std::string fq = (ns.empty() ? "" : dq(ns) + ".") + (name == "*" ? name : dq(name));
+    return f.match(full) || f.match(fq);
+}
+
+// ------------------------------------------------------------------ compiled plan
+struct DTerm {            // device-visible predicate term (POD)
+    int32_t col, op, vtype, nlist;
+    int64_t i; double f;
+    uint32_t s_off, s_len;      // string literal in the literal blob
+    uint32_t list_off, pad;     // int64[] / double[] / (uint32 offs[nlist+1], bytes) in the blob, 8-byte aligned
+};
+struct FilterStep { std::vector<std::vector<DTerm>> exprs; std::vector<std::vector<Term>> src; };
+struct MaskStep { std::vector<int> cols; std::string salt; };
+
+struct Plan {
+    std::string ns, name, schema_json;
+    std::vector<ColSchema> in_schema, out_schema;
+    std::vector<FilterStep> filters;   // in plan order
+    std::vector<int> filter_step_index;
+    std::vector<MaskStep> masks;
+    std::vector<int> mask_step_index;
+    std::vector<uint8_t> blob;         // literal pool referenced by DTerm
+    std::string describe;
+    // sink
+    bool has_sink = false;
+    std::vector<std::string> ch_types;
+    std::vector<uint8_t> col_headers;        // per column: varint name, name, varint type, type, 0x00
+    std::vector<uint32_t> col_header_off;    // ncols+1
+};
+
+inline uint32_t blob_put(std::vector<uint8_t>& b, const void* p, size_t n, size_t align = 8) {
+    while (b.size() % align) b.push_back(0);
+    uint32_t off = (uint32_t)b.size(); const uint8_t* q = (const uint8_t*)p; b.insert(b.end(), q, q + n); return off;
+}
+
+inline bool column_suitable(const Term& t, int tf) {   // checkColumnSuitable filter_rows.go:489-519
+    int base = t.vtype & 15; bool list = t.vtype & LV_LIST;
+    if (list) return base == LV_INT || base == LV_FLOAT || base == LV_STRING || base == LV_TIME;
+    switch (base) {
+    case LV_BOOL: return tf == TF_BOOLEAN;
+    case LV_INT: case LV_FLOAT: return (tf >= TF_INT8 && tf <= TF_DOUBLE);
+    case LV_STRING: return tf == TF_UTF8 || tf == TF_BYTES || tf == TF_ANY;
+    case LV_TIME: return tf == TF_TIMESTAMP || tf == TF_DATE || tf == TF_DATETIME;
+    case LV_NULL: return true;
+    }
+    return false;
+}
+
+inline std::string ch_type_of(const ColSchema& c) {    // columntypes.ToChType types.go:210-248 + sink_table.go:196-208
+    if (c.original_type.rfind("ch:", 0) == 0) throw FatalError(TF_E_FATAL_UNSUPPORTED, "ch: original types are not supported by the device encoder (column " + c.name + ")");
+    std::string b;
+    switch (c.tf) {
+    case TF_ANY: case TF_BYTES: case TF_UTF8: b = "String"; break;
+    case TF_DOUBLE: b = "Float64"; break; case TF_FLOAT: b = "Float32"; break; case TF_BOOLEAN: b = "UInt8"; break;
+    case TF_INT8: b = "Int8"; break; case TF_INT16: b = "Int16"; break; case TF_INT32: b = "Int32"; break; case TF_INT64: b = "Int64"; break;
+    case TF_UINT8: b = "UInt8"; break; case TF_UINT16: b = "UInt16"; break; case TF_UINT32: b = "UInt32"; break; case TF_UINT64: b = "UInt64"; break;
+    case TF_DATE: b = "Date"; break; case TF_DATETIME: b = "DateTime"; break; case TF_TIMESTAMP: b = "DateTime64(6)"; break;
+    case TF_INTERVAL: b = "Int64"; break;
+    default: b = "String";
+    }
+    return c.required ? b : "Nullable(" + b + ")";
+}
+
+inline void put_uvarint(std::vector<uint8_t>& o, uint64_t v) { while (v >= 0x80) { o.push_back((uint8_t)(v | 0x80)); v >>= 7; } o.push_back((uint8_t)v); }
+
+inline std::string lit_json(int kind, const Literal& l) {
+    switch (kind) {
+    case LV_INT: case LV_TIME: return std::to_string(l.i);
+    case LV_BOOL: return l.i ? "true" : "false";
+    case LV_FLOAT: { char b[64]; snprintf(b, sizeof b, "%.17g", l.f); return b; }
+    case LV_STRING: { std::string h; static const char* H = "0123456789abcdef"; for (unsigned char c : l.s) { h += H[c >> 4]; h += H[c & 15]; } return "\"" + h + "\""; }
+    case LV_NULL: return "null";
+    }
+    return "null";
+}
+
+inline Plan build_plan(const std::string& ns, const std::string& name, const std::string& schema_json,
+                       const std::string& transformers_json, const std::string& sink_json) {
+    Plan pl; pl.ns = ns; pl.name = name; pl.schema_json = schema_json;
+    pl.in_schema = parse_schema(schema_json);
+    if (pl.in_schema.empty()) throw FatalError(TF_E_FATAL_CONFIG, "empty schema");
+    std::vector<ColSchema> cur = pl.in_schema;
+    std::string steps_desc;
+    auto trs = transformers_json.empty() ? tfj::parse("[]") : tfj::parse(transformers_json);
+    if (trs->kind != tfj::Value::Arr) throw FatalError(TF_E_FATAL_CONFIG, "transformers_json must be a list");
+    int step_no = 0;
+    for (auto& tr : trs->arr) {
+        if (tr->kind != tfj::Value::Obj) throw FatalError(TF_E_FATAL_CONFIG, "transformer entry must be an object");
+        std::string ttype; const tfj::Value* cfg = nullptr;
+        for (auto& kv : tr->obj) if (kv.first != "transformerId") { ttype = kv.first; cfg = kv.second.get(); }
+        if (ttype.empty()) throw FatalError(TF_E_FATAL_CONFIG, "transformer entry without a type");
+        static const tfj::Value empty_obj = [] { tfj::Value v; v.kind = tfj::Value::Obj; return v; }();
+        if (!cfg || cfg->kind != tfj::Value::Obj) cfg = &empty_obj;
+        auto col_index = [&](const std::string& n) { for (size_t i = 0; i < cur.size(); i++) if (cur[i].name == n) return (int)i; return -1; };
+        if (ttype == "filter_rows") {
+            std::string one = cfg->get_str("filter"); auto many = cfg->get_str_list("filters");
+            if (!one.empty() && !many.empty()) throw FatalError(TF_E_FATAL_CONFIG, "Settings 'filters' and 'filter' cannot be enabled at the same time");
+            if (many.empty()) many.push_back(one);
+            FilterStep fs;
+            for (auto& f : many) fs.src.push_back(FilterParser(f).parse());
+            if (!match_table(tables_filter(cfg->get("tables")), ns, name)) continue;
+            bool ok = true;                                         // Suitable filter_rows.go:445-476
+            for (auto& terms : fs.src) for (auto& t : terms) { int ci = col_index(t.attribute); if (ci < 0 || !column_suitable(t, cur[ci].tf)) ok = false; }
+            if (!ok) continue;
+            std::string d = "{\"type\":\"filter_rows\",\"exprs\":[";
+            for (size_t e = 0; e < fs.src.size(); e++) {
+                std::vector<DTerm> dt; if (e) d += ",";
+                d += "[";
+                for (size_t k = 0; k < fs.src[e].size(); k++) {
+                    const Term& t = fs.src[e][k]; DTerm x; std::memset(&x, 0, sizeof x);
+                    x.col = col_index(t.attribute); x.op = t.op; x.vtype = t.vtype; x.nlist = (int)t.list.size();
+                    int base = t.vtype & 15; int ctf = cur[x.col].tf;
+                    bool col_is_str = ctf == TF_UTF8 || ctf == TF_ANY;
+                    if ((base == LV_INT || base == LV_FLOAT) && (col_is_str))
+                        throw FatalError(TF_E_FATAL_UNSUPPORTED, "filter_rows: numeric literal against text column '" + t.attribute + "' (strconv.ParseFloat path) is not implemented on the device");
+                    if (k) d += ",";
+                    d += "{\"col\":" + std::to_string(x.col) + ",\"op\":" + std::to_string(x.op) + ",\"vtype\":" + std::to_string(x.vtype) + ",\"value\":";
+                    if (!(t.vtype & LV_LIST)) {
+                        x.i = t.v.i; x.f = t.v.f;
+                        if (base == LV_STRING) { x.s_off = blob_put(pl.blob, t.v.s.data(), t.v.s.size(), 1); x.s_len = (uint32_t)t.v.s.size(); }
+                        d += lit_json(base, t.v);
+                    } else {
+                        d += "[";
+                        for (size_t q = 0; q < t.list.size(); q++) { if (q) d += ","; d += lit_json(base, t.list[q]); }
+                        d += "]";
+                        if (base == LV_INT || base == LV_TIME) { std::vector<int64_t> v; for (auto& l : t.list) v.push_back(l.i); x.list_off = blob_put(pl.blob, v.data(), v.size() * 8); }
+                        else if (base == LV_FLOAT) { std::vector<double> v; for (auto& l : t.list) v.push_back(l.f); x.list_off = blob_put(pl.blob, v.data(), v.size() * 8); }
+                        else if (base == LV_STRING) {
+                            std::vector<uint32_t> offs(1, 0); std::string bytes;
+                            for (auto& l : t.list) { bytes += l.s; offs.push_back((uint32_t)bytes.size()); }
+                            x.list_off = blob_put(pl.blob, offs.data(), offs.size() * 4); blob_put(pl.blob, bytes.data(), bytes.size(), 1);
+                        }
+                    }
+                    d += "}";
+                    dt.push_back(x);
+                }
+                d += "]";
+                fs.exprs.push_back(dt);
+            }
+            d += "]}";
+            if (!steps_desc.empty()) steps_desc += ","; steps_desc += d;
+            pl.filters.push_back(fs); pl.filter_step_index.push_back(step_no++);
+        } else if (ttype == "mask_field") {
+            if (!match_table(tables_filter(cfg->get("tables")), ns, name)) continue;
+            auto cols = cfg->get_str_list("columns");
+            MaskStep ms; const tfj::Value* mf = cfg->get("maskFunctionHash");
+            ms.salt = mf ? mf->get_str("userDefinedSalt") : "";
+            for (size_t i = 0; i < cur.size(); i++) for (auto& c : cols) if (cur[i].name == c) { ms.cols.push_back((int)i); break; }
+            if (!cols.empty() && ms.cols.empty()) continue;          // Suitable hmac_hasher.go:76-89
+            std::string d = "{\"type\":\"mask_field\",\"cols\":[";
+            for (size_t i = 0; i < ms.cols.size(); i++) { if (i) d += ","; d += std::to_string(ms.cols[i]); cur[ms.cols[i]].type = "utf8"; cur[ms.cols[i]].tf = TF_UTF8; cur[ms.cols[i]].original_type = ""; }
+            d += "]}";
+            if (!steps_desc.empty()) steps_desc += ","; steps_desc += d;
+            pl.masks.push_back(ms); pl.mask_step_index.push_back(step_no++);
+        } else {
+            throw FatalError(TF_E_FATAL_UNSUPPORTED, "transformer '" + ttype + "' is not implemented by the device engine");
+        }
+    }
+    // a filter placed after a mask of the same column would see the digest, which the fused kernel does not model
+    for (size_t m = 0; m < pl.masks.size(); m++) for (size_t f = 0; f < pl.filters.size(); f++)
+        if (pl.filter_step_index[f] > pl.mask_step_index[m])
+            for (auto& e : pl.filters[f].exprs) for (auto& t : e) for (int c : pl.masks[m].cols)
+                if (t.col == c) throw FatalError(TF_E_FATAL_UNSUPPORTED, "filter_rows on a column masked earlier in the chain is not supported");
+    pl.out_schema = cur;
+    std::string sink_desc = "null";
+    if (!sink_json.empty()) {
+        auto sk = tfj::parse(sink_json);
+        std::string st = sk->get_str("type", "clickhouse");
+        if (st != "clickhouse") throw FatalError(TF_E_FATAL_UNSUPPORTED, "sink type '" + st + "' is not implemented");
+        pl.has_sink = true; pl.col_header_off.push_back(0);
+        sink_desc = "{\"type\":\"clickhouse\",\"revision\":54460,\"columns\":[";
+        for (size_t i = 0; i < cur.size(); i++) {
+            std::string t = ch_type_of(cur[i]); pl.ch_types.push_back(t);
+            put_uvarint(pl.col_headers, cur[i].name.size()); pl.col_headers.insert(pl.col_headers.end(), cur[i].name.begin(), cur[i].name.end());
+            put_uvarint(pl.col_headers, t.size()); pl.col_headers.insert(pl.col_headers.end(), t.begin(), t.end());
+            pl.col_headers.push_back(0);   // has-custom-serialization = false (revision >= 54454)
+            pl.col_header_off.push_back((uint32_t)pl.col_headers.size());
+            if (i) sink_desc += ","; sink_desc += tfj::quote(t);
+        }
+        sink_desc += "]}";
+    }
+    pl.describe = "{\"table\":" + tfj::quote(ns.empty() ? name : ns + "." + name) + ",\"steps\":[" + steps_desc + "],\"result_schema\":" + schema_to_json(cur) + ",\"sink\":" + sink_desc + "}";
+    return pl;
+}
+
+}  // namespace tfplan

@@ -1,0 +1,484 @@
+// C-ABI of the B200 columnar transform engine (include/tfgpu.h). Host orchestration only: every
+// per-row operation runs in the sm_100a kernels of kernels_*.cuh.  There is no CPU fallback: without
+// a CUDA device tfgpu_engine_create fails with TF_E_FATAL_NODEVICE.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/tfgpu.h"
+#include "plan.hpp"
+#include "device_types.cuh"
+#include "kernels_encode.cuh"
+#include "kernels_lz4.cuh"
+#include "kernels_mask.cuh"
+
+using namespace tfk;
+
+namespace {
+
+struct CudaError { cudaError_t e; const char* what; };
+#define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) throw CudaError{_e, #x}; } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct DevBuf {
+    uint8_t* p = nullptr; size_t cap = 0;
+    void ensure(size_t n) {
+        if (n <= cap) return;
+        if (p) { CK(cudaDeviceSynchronize()); CK(cudaFree(p)); p = nullptr; cap = 0; }
+        size_t want = align_up(n + n / 8 + 4096, 1 << 20);
+        CK(cudaMalloc(&p, want)); cap = want;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PlanDev {
+    tfplan::Plan plan;
+    // device copies of plan constants
+    DevBuf consts;
+    DTerm* d_terms = nullptr; uint32_t* d_expr_off = nullptr; DFilterStep* d_fsteps = nullptr; uint8_t* d_blob = nullptr;
+    uint8_t* d_col_headers = nullptr; uint32_t* d_col_header_off = nullptr;
+    int32_t* d_fixed_slots = nullptr; int32_t* d_str_slots = nullptr; int32_t* d_mask_slots = nullptr;
+    MaskKey* d_mask_keys = nullptr;
+    int n_fsteps = 0, n_fixed_slots = 0, n_str = 0, n_mask_cols = 0;
+    std::vector<int32_t> fixed_slots, str_slots, mask_slot_cols, mask_slot_key;
+    std::vector<int> col_out_kind, col_out_w, col_str_slot, col_mask_slot;
+};
+
+}  // namespace
+
+struct tfgpu_engine {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string last_error;
+    uint64_t launches = 0;
+    uint32_t frame_bytes = 32768;
+    int sm_count = 148;
+    std::vector<std::unique_ptr<PlanDev>> plans;
+    // arenas
+    DevBuf in_arena, work, raw, slots, wire;
+    DState* d_state = nullptr; DCol* d_cols = nullptr; size_t d_cols_cap = 0;
+    // pointers into `work` for the last call
+    uint8_t *keep = nullptr, *errcode = nullptr, *errstep = nullptr; uint32_t *blockcnt = nullptr, *blockoff = nullptr, *sel = nullptr;
+    uint32_t* tile_sum = nullptr; uint64_t* tile_base = nullptr; uint32_t* comp_size = nullptr; uint64_t* wire_off = nullptr;
+    uint64_t last_nrows = 0; bool last_has_filter = false; int last_wire_fmt = 0;
+    uint8_t* pinned = nullptr; size_t pinned_cap = 0;
+};
+
+struct tfgpu_result {
+    uint64_t rows_in = 0, rows_out = 0, raw_len = 0, n_frames = 0;
+    std::vector<tf_rowerr> errs;
+    uint8_t* bytes = nullptr; uint64_t bytes_len = 0; bool bytes_pinned = false;
+    // push_columns output
+    tf_batch batch{}; std::vector<tf_col> cols; std::vector<uint8_t*> owned;
+};
+
+namespace {
+
+int fail(tfgpu_engine* e, int code, const std::string& msg) { if (e) e->last_error = msg; return code; }
+int cuda_fail(tfgpu_engine* e, const CudaError& c) {
+    std::string m = std::string("CUDA error: ") + cudaGetErrorString(c.e) + " in " + c.what;
+    cudaGetLastError();
+    return fail(e, c.e == cudaErrorMemoryAllocation ? TF_E_RETRY_OOM : TF_E_RETRY_LAUNCH, m);
+}
+
+int in_width(int tf) {
+    switch (tf) {
+    case TF_INT8: case TF_UINT8: case TF_BOOLEAN: return 1;
+    case TF_INT16: case TF_UINT16: return 2;
+    case TF_INT32: case TF_UINT32: case TF_FLOAT: return 4;
+    case TF_INT64: case TF_UINT64: case TF_DOUBLE: case TF_INTERVAL: case TF_DATE: case TF_DATETIME: case TF_TIMESTAMP: return 8;
+    }
+    return 0;
+}
+
+template <typename T> T* carve(uint8_t*& p, size_t count) { T* r = (T*)p; p += align_up(count * sizeof(T), 256); return r; }
+
+void upload_plan(tfgpu_engine* e, PlanDev& pd) {
+    const tfplan::Plan& pl = pd.plan;
+    const size_t nc = pl.in_schema.size();
+    // which mask step (if any) owns each column
+    pd.col_mask_slot.assign(nc, -1);
+    std::vector<MaskKey> keys;
+    for (size_t m = 0; m < pl.masks.size(); m++) {
+        keys.push_back(make_mask_key((const uint8_t*)pl.masks[m].salt.data(), pl.masks[m].salt.size()));
+        for (int c : pl.masks[m].cols) {
+            if (pd.col_mask_slot[c] >= 0) throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "column masked twice in one chain");
+            pd.col_mask_slot[c] = (int)m;
+        }
+    }
+    pd.col_out_kind.assign(nc, 0); pd.col_out_w.assign(nc, 0); pd.col_str_slot.assign(nc, -1);
+    for (size_t c = 0; c < nc; c++) {
+        const int tf = pl.in_schema[c].tf;
+        int kind, w;
+        if (pd.col_mask_slot[c] >= 0) {
+            if (tf == TF_FLOAT || tf == TF_DOUBLE || tf == TF_INTERVAL)
+                throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "mask_field on " + pl.in_schema[c].type + " column '" + pl.in_schema[c].name + "' needs the device float/duration formatter (not in this build)");
+            kind = OK_MASK; w = 65;
+        } else switch (tf) {
+            case TF_BOOLEAN: kind = OK_BOOL; w = 1; break;
+            case TF_DATE: kind = OK_DATE; w = 2; break;
+            case TF_DATETIME: kind = OK_DATETIME; w = 4; break;
+            case TF_TIMESTAMP: kind = OK_TS64; w = 8; break;
+            case TF_BYTES: case TF_UTF8: case TF_ANY: kind = OK_STR; w = 0; break;
+            default: kind = OK_COPY; w = in_width(tf);
+        }
+        pd.col_out_kind[c] = kind; pd.col_out_w[c] = w;
+        const bool nullable = !pl.out_schema[c].required;
+        if (kind == OK_STR) { pd.col_str_slot[c] = (int)pd.str_slots.size(); pd.str_slots.push_back((int32_t)c); }
+        else if (kind == OK_MASK) { pd.mask_slot_cols.push_back((int32_t)c); }
+        else pd.fixed_slots.push_back((int32_t)c);
+        if (nullable && kind != OK_MASK) pd.fixed_slots.push_back((int32_t)c | TF_SLOT_NULLMAP);
+    }
+    if (pd.str_slots.size() > 256) throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "more than 256 String columns");
+    // flatten filter steps
+    std::vector<DTerm> terms; std::vector<uint32_t> expr_off(1, 0); std::vector<DFilterStep> fsteps;
+    for (size_t f = 0; f < pl.filters.size(); f++) {
+        DFilterStep st; st.expr_begin = (int32_t)expr_off.size() - 1; st.nexpr = (int32_t)pl.filters[f].exprs.size(); st.step_index = pl.filter_step_index[f]; st.pad = 0;
+        for (auto& ex : pl.filters[f].exprs) {
+            for (auto& t : ex) { DTerm d; static_assert(sizeof(DTerm) == sizeof(tfplan::DTerm), "DTerm mismatch"); std::memcpy(&d, &t, sizeof d); terms.push_back(d); }
+            expr_off.push_back((uint32_t)terms.size());
+        }
+        fsteps.push_back(st);
+    }
+    pd.n_fsteps = (int)fsteps.size(); pd.n_fixed_slots = (int)pd.fixed_slots.size(); pd.n_str = (int)pd.str_slots.size(); pd.n_mask_cols = (int)pd.mask_slot_cols.size();
+    size_t total = 0;
+    auto need = [&](size_t n) { total += align_up(n ? n : 1, 256); };
+    need(terms.size() * sizeof(DTerm)); need(expr_off.size() * 4); need(fsteps.size() * sizeof(DFilterStep)); need(pl.blob.size());
+    need(pl.col_headers.size()); need(pl.col_header_off.size() * 4); need(pd.fixed_slots.size() * 4); need(pd.str_slots.size() * 4);
+    need(pd.mask_slot_cols.size() * 4); need(keys.size() * sizeof(MaskKey));
+    pd.consts.ensure(total);
+    uint8_t* p = pd.consts.p;
+    auto put = [&](const void* src, size_t n) { uint8_t* d = p; if (n) CK(cudaMemcpy(d, src, n, cudaMemcpyHostToDevice)); p += align_up(n ? n : 1, 256); return d; };
+    pd.d_terms = (DTerm*)put(terms.data(), terms.size() * sizeof(DTerm));
+    pd.d_expr_off = (uint32_t*)put(expr_off.data(), expr_off.size() * 4);
+    pd.d_fsteps = (DFilterStep*)put(fsteps.data(), fsteps.size() * sizeof(DFilterStep));
+    pd.d_blob = put(pl.blob.data(), pl.blob.size());
+    pd.d_col_headers = put(pl.col_headers.data(), pl.col_headers.size());
+    pd.d_col_header_off = (uint32_t*)put(pl.col_header_off.data(), pl.col_header_off.size() * 4);
+    pd.d_fixed_slots = (int32_t*)put(pd.fixed_slots.data(), pd.fixed_slots.size() * 4);
+    pd.d_str_slots = (int32_t*)put(pd.str_slots.data(), pd.str_slots.size() * 4);
+    pd.d_mask_slots = (int32_t*)put(pd.mask_slot_cols.data(), pd.mask_slot_cols.size() * 4);
+    pd.d_mask_keys = (MaskKey*)put(keys.data(), keys.size() * sizeof(MaskKey));
+    (void)e;
+}
+
+struct Sizes { uint64_t raw_bound, n_frames_max, wire_bound; uint32_t ntiles_cap, nblocks; };
+
+Sizes compute_sizes(const tfgpu_engine* e, const PlanDev& pd, const tf_batch* in) {
+    const tfplan::Plan& pl = pd.plan; const uint64_t n = in->nrows;
+    uint64_t raw = 64 + pl.col_headers.size();
+    for (size_t c = 0; c < pl.in_schema.size(); c++) {
+        if (!pl.out_schema[c].required) raw += n;
+        if (pd.col_out_kind[c] == OK_STR) raw += in->cols[c].heap_len + 5 * n;
+        else raw += (uint64_t)pd.col_out_w[c] * n;
+    }
+    Sizes s;
+    s.raw_bound = raw + 256;
+    s.n_frames_max = (raw + e->frame_bytes - 1) / e->frame_bytes + 1;
+    s.wire_bound = s.n_frames_max * (uint64_t)(LZ_HDR + lz4_bound(e->frame_bytes)) + 256;
+    s.ntiles_cap = (uint32_t)((n + TF_STR_TILE - 1) / TF_STR_TILE + 1);
+    s.nblocks = (uint32_t)((n + 255) / 256 + 1);
+    return s;
+}
+
+// Launch the whole fused chain on e->stream. `cols_host` holds DEVICE pointers.
+void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* dev_cols, const uint8_t* dev_kinds, int wire_fmt) {
+    const tfplan::Plan& pl = pd.plan;
+    const size_t nc = pl.in_schema.size(); const uint64_t n = in->nrows;
+    const Sizes sz = compute_sizes(e, pd, in);
+    cudaStream_t s = e->stream;
+    // work arena
+    size_t wbytes = 0;
+    auto need = [&](size_t b) { wbytes += align_up(b ? b : 1, 256); };
+    need(n); need(n); need(n); need(sz.nblocks * 4); need(sz.nblocks * 4); need(n * 4);
+    need((size_t)pd.n_str * sz.ntiles_cap * 4); need((size_t)pd.n_str * sz.ntiles_cap * 8);
+    need(sz.n_frames_max * 4); need(sz.n_frames_max * 8);
+    e->work.ensure(wbytes);
+    uint8_t* p = e->work.p;
+    e->keep = carve<uint8_t>(p, n); e->errcode = carve<uint8_t>(p, n); e->errstep = carve<uint8_t>(p, n);
+    e->blockcnt = carve<uint32_t>(p, sz.nblocks); e->blockoff = carve<uint32_t>(p, sz.nblocks); e->sel = carve<uint32_t>(p, n);
+    e->tile_sum = carve<uint32_t>(p, (size_t)pd.n_str * sz.ntiles_cap); e->tile_base = carve<uint64_t>(p, (size_t)pd.n_str * sz.ntiles_cap);
+    e->comp_size = carve<uint32_t>(p, sz.n_frames_max); e->wire_off = carve<uint64_t>(p, sz.n_frames_max);
+    e->raw.ensure(sz.raw_bound);
+    const bool lz = wire_fmt == TF_WIRE_CH_NATIVE_LZ4;
+    const uint32_t stride = lz_slot_stride(e->frame_bytes);
+    if (lz) { e->slots.ensure(sz.n_frames_max * (uint64_t)stride + 256); e->wire.ensure(sz.wire_bound); }
+    if (e->d_cols_cap < nc) { if (e->d_cols) CK(cudaFree(e->d_cols)); CK(cudaMalloc(&e->d_cols, sizeof(DCol) * nc)); e->d_cols_cap = nc; }
+    // column descriptors
+    std::vector<DCol> hc(nc);
+    for (size_t c = 0; c < nc; c++) {
+        const tf_col& ic = dev_cols[c]; DCol& d = hc[c]; std::memset(&d, 0, sizeof d);
+        if (ic.type != pl.in_schema[c].tf) throw tfplan::FatalError(TF_E_FATAL_ARG, "column " + std::to_string(c) + " type does not match the plan schema");
+        d.type = ic.type; d.out_kind = pd.col_out_kind[c]; d.in_w = in_width(ic.type); d.out_w = pd.col_out_w[c];
+        d.nullable = pl.out_schema[c].required ? 0 : 1; d.str_slot = pd.col_str_slot[c]; d.mask_slot = pd.col_mask_slot[c];
+        d.values = (const uint8_t*)ic.values; d.validity = ic.validity; d.offsets = ic.offsets; d.heap = ic.heap; d.aux = (const uint8_t*)ic.aux;
+        if (n) {
+            if (d.in_w && !d.values) throw tfplan::FatalError(TF_E_FATAL_ARG, "column " + std::to_string(c) + ": values pointer is NULL");
+            if (!d.in_w && !d.offsets) throw tfplan::FatalError(TF_E_FATAL_ARG, "column " + std::to_string(c) + ": offsets pointer is NULL");
+        }
+    }
+    CK(cudaMemcpyAsync(e->d_cols, hc.data(), sizeof(DCol) * nc, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(e->d_state, 0, sizeof(DState), s));
+    const bool has_filter = pd.n_fsteps > 0;
+    e->last_nrows = n; e->last_has_filter = has_filter; e->last_wire_fmt = wire_fmt;
+    const uint32_t nb = (uint32_t)((n + 255) / 256);
+    if (has_filter && n) {
+        FilterArgs fa{e->d_cols, dev_kinds, n, pd.d_fsteps, pd.n_fsteps, pd.d_expr_off, pd.d_terms, pd.d_blob, e->keep, e->errcode, e->errstep, e->blockcnt};
+        k_filter<<<nb, 256, 0, s>>>(fa); e->launches++;
+        k_scan_blockcnt<<<1, 1024, 0, s>>>(e->blockcnt, e->blockoff, nb, e->d_state, e->errcode, n); e->launches++;
+        k_compact_sel<<<nb, 256, 0, s>>>(e->keep, e->blockoff, n, e->sel); e->launches++;
+    }
+    const uint32_t* sel = (has_filter && n) ? e->sel : nullptr;
+    const uint32_t ntiles = (uint32_t)((n + TF_STR_TILE - 1) / TF_STR_TILE);
+    EncodeArgs ea{e->d_cols, pd.d_str_slots, sel, e->d_state, e->raw.p, e->tile_sum, e->tile_base, sz.ntiles_cap};
+    if (!has_filter || !n) {
+        // n_kept = nrows is set inside k_layout (has_sel = 0); k_str_sizes needs it earlier:
+        DState init; std::memset(&init, 0, sizeof init); init.n_kept = n;
+        CK(cudaMemcpyAsync(e->d_state, &init, sizeof init, cudaMemcpyHostToDevice, s));
+    }
+    if (pd.n_str && ntiles) { k_str_sizes<<<dim3(ntiles, pd.n_str), 256, 0, s>>>(ea); e->launches++; }
+    LayoutArgs la{e->d_cols, (int)nc, pd.d_str_slots, pd.n_str, e->tile_sum, e->tile_base, sz.ntiles_cap, pd.d_col_headers, pd.d_col_header_off,
+                  e->raw.p, e->d_state, n, 1, e->frame_bytes};
+    k_layout<<<1, 1024, 0, s>>>(la); e->launches++;
+    if (n) {
+        if (pd.n_fixed_slots) {
+            // widest stream is 8 bytes per row: words = 2n (+1 for misalignment)
+            const uint32_t gx = (uint32_t)((2 * n + 2 + TF_FIX_TILE_WORDS - 1) / TF_FIX_TILE_WORDS);
+            EncodeArgs fa = ea; fa.slots = pd.d_fixed_slots;
+            k_encode_fixed<<<dim3(gx, pd.n_fixed_slots), 256, 0, s>>>(fa); e->launches++;
+        }
+        if (pd.n_str) { k_encode_str<<<dim3(ntiles, pd.n_str), 256, 0, s>>>(ea); e->launches++; }
+        if (pd.n_mask_cols) {
+            MaskArgs ma{e->d_cols, pd.d_mask_slots, pd.d_mask_keys, sel, e->d_state, e->raw.p};
+            k_mask_encode<<<dim3((uint32_t)((n + 127) / 128), pd.n_mask_cols), 128, 0, s>>>(ma); e->launches++;
+        }
+    }
+    if (lz) {
+        Lz4Args za{e->raw.p, e->d_state, e->slots.p, stride, e->comp_size, e->frame_bytes};
+        const size_t smem = e->frame_bytes + 16 + 2 * (size_t)e->frame_bytes + (2u << LZ_HASH_BITS) + e->frame_bytes / 8 + 48 * 4;
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * 2);
+        k_lz4_frames<<<grid, LZ_THREADS, smem, s>>>(za); e->launches++;
+        FrameArgs fa{e->slots.p, stride, e->comp_size, e->d_state, e->frame_bytes, e->wire_off, e->wire.p};
+        k_frame_seal<<<(uint32_t)((sz.n_frames_max + 127) / 128), 128, 0, s>>>(fa); e->launches++;
+        k_frame_scan<<<1, 1024, 0, s>>>(fa); e->launches++;
+        k_wire_gather<<<(uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * 8), 256, 0, s>>>(fa); e->launches++;
+    }
+    CK(cudaGetLastError());
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* tfgpu_version(void) { return "tfgpu 0.1.0 sm_100a"; }
+
+int tfgpu_engine_create(const char* cfg_json, const int* device_ids, int n_devices, tfgpu_engine** out) {
+    if (!out) return TF_E_FATAL_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return TF_E_FATAL_NODEVICE; }
+    if (n_devices > 1) return TF_E_FATAL_ARG;
+    auto e = std::make_unique<tfgpu_engine>();
+    e->device = (n_devices == 1 && device_ids) ? device_ids[0] : 0;
+    if (e->device < 0 || e->device >= ndev) return TF_E_FATAL_ARG;
+    try {
+        if (cfg_json && *cfg_json) {
+            auto cfg = tfj::parse(cfg_json);
+            double fb = cfg->get_num("frame_bytes", 32768);
+            if (fb < 1024 || fb > LZ_MAX_FRAME || ((uint32_t)fb & 63)) return TF_E_FATAL_CONFIG;
+            e->frame_bytes = (uint32_t)fb;
+        }
+        CK(cudaSetDevice(e->device));
+        cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, e->device));
+        e->sm_count = prop.multiProcessorCount;
+        CK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+        e->stream = e->own_stream;
+        CK(cudaMalloc(&e->d_state, sizeof(DState)));
+        CK(cudaFuncSetAttribute(k_lz4_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024));
+    } catch (const CudaError& c) { return c.e == cudaErrorMemoryAllocation ? TF_E_RETRY_OOM : TF_E_RETRY_LAUNCH; }
+    catch (const std::exception&) { return TF_E_FATAL_CONFIG; }
+    *out = e.release();
+    return TF_OK;
+}
+
+int tfgpu_engine_destroy(tfgpu_engine* e) {
+    if (!e) return TF_E_FATAL_ARG;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    for (auto& p : e->plans) p->consts.release();
+    e->in_arena.release(); e->work.release(); e->raw.release(); e->slots.release(); e->wire.release();
+    if (e->d_state) cudaFree(e->d_state);
+    if (e->d_cols) cudaFree(e->d_cols);
+    if (e->pinned) cudaFreeHost(e->pinned);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+    return TF_OK;
+}
+
+const char* tfgpu_last_error(const tfgpu_engine* e) { return e ? e->last_error.c_str() : "null engine"; }
+uint64_t tfgpu_engine_launch_count(const tfgpu_engine* e) { return e ? e->launches : 0; }
+
+int tfgpu_engine_set_stream(tfgpu_engine* e, void* cuda_stream) {
+    if (!e) return TF_E_FATAL_ARG;
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return TF_OK;
+}
+
+int tfgpu_plan(tfgpu_engine* e, const char* ns, const char* name, const char* schema_json, const char* transformers_json,
+               const char* sink_json, int* plan_id) {
+    if (!e || !schema_json || !plan_id || !name) return TF_E_FATAL_ARG;
+    try {
+        CK(cudaSetDevice(e->device));
+        auto pd = std::make_unique<PlanDev>();
+        pd->plan = tfplan::build_plan(ns ? ns : "", name, schema_json, transformers_json ? transformers_json : "", sink_json ? sink_json : "");
+        upload_plan(e, *pd);
+        e->plans.push_back(std::move(pd));
+        *plan_id = (int)e->plans.size() - 1;
+        return TF_OK;
+    } catch (const tfplan::FatalError& f) { return fail(e, f.code, f.what()); }
+    catch (const CudaError& c) { return cuda_fail(e, c); }
+    catch (const std::exception& x) { return fail(e, TF_E_FATAL_CONFIG, x.what()); }
+}
+
+const char* tfgpu_plan_describe(tfgpu_engine* e, int plan_id) {
+    if (!e || plan_id < 0 || plan_id >= (int)e->plans.size()) return nullptr;
+    return e->plans[plan_id]->plan.describe.c_str();
+}
+
+int tfgpu_push_encode_resident(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch* in) {
+    if (!e || !in || plan_id < 0 || plan_id >= (int)e->plans.size()) return TF_E_FATAL_ARG;
+    PlanDev& pd = *e->plans[plan_id];
+    if (!pd.plan.has_sink) return fail(e, TF_E_FATAL_CONFIG, "plan was built without a sink");
+    if (in->mem != TF_MEM_DEVICE) return fail(e, TF_E_FATAL_ARG, "tfgpu_push_encode_resident needs a TF_MEM_DEVICE batch");
+    if (in->ncols != pd.plan.in_schema.size()) return fail(e, TF_E_FATAL_ARG, "batch column count does not match the plan schema");
+    if (wire_fmt != TF_WIRE_CH_NATIVE && wire_fmt != TF_WIRE_CH_NATIVE_LZ4) return fail(e, TF_E_FATAL_UNSUPPORTED, "wire format not implemented");
+    if (in->nrows >= (1ull << 31)) return fail(e, TF_E_FATAL_ARG, "batch too large (>= 2^31 rows)");
+    try {
+        CK(cudaSetDevice(e->device));
+        run_chain(e, pd, in, in->cols, in->kinds, wire_fmt);
+        return TF_OK;
+    } catch (const tfplan::FatalError& f) { return fail(e, f.code, f.what()); }
+    catch (const CudaError& c) { return cuda_fail(e, c); }
+}
+
+int tfgpu_resident_stats(tfgpu_engine* e, uint64_t* rows_out, uint64_t* raw_bytes, uint64_t* wire_bytes, uint64_t* n_errors) {
+    if (!e) return TF_E_FATAL_ARG;
+    try {
+        CK(cudaSetDevice(e->device));
+        DState st; CK(cudaMemcpyAsync(&st, e->d_state, sizeof st, cudaMemcpyDeviceToHost, e->stream)); CK(cudaStreamSynchronize(e->stream));
+        if (rows_out) *rows_out = st.n_kept; if (raw_bytes) *raw_bytes = st.raw_total;
+        if (wire_bytes) *wire_bytes = e->last_wire_fmt == TF_WIRE_CH_NATIVE_LZ4 ? st.wire_total : st.raw_total;
+        if (n_errors) *n_errors = st.n_errors;
+        return TF_OK;
+    } catch (const CudaError& c) { return cuda_fail(e, c); }
+}
+
+int tfgpu_resident_fetch(tfgpu_engine* e, int what, uint8_t* dst, uint64_t cap) {
+    if (!e || !dst) return TF_E_FATAL_ARG;
+    try {
+        CK(cudaSetDevice(e->device));
+        DState st; CK(cudaMemcpyAsync(&st, e->d_state, sizeof st, cudaMemcpyDeviceToHost, e->stream)); CK(cudaStreamSynchronize(e->stream));
+        const bool wire = what == 1 && e->last_wire_fmt == TF_WIRE_CH_NATIVE_LZ4;
+        const uint64_t n = wire ? st.wire_total : st.raw_total;
+        if (n > cap) return fail(e, TF_E_FATAL_ARG, "destination too small");
+        CK(cudaMemcpyAsync(dst, wire ? e->wire.p : e->raw.p, n, cudaMemcpyDeviceToHost, e->stream)); CK(cudaStreamSynchronize(e->stream));
+        return TF_OK;
+    } catch (const CudaError& c) { return cuda_fail(e, c); }
+}
+
+int tfgpu_push_encode(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch* in, tfgpu_result** out) {
+    if (!e || !in || !out || plan_id < 0 || plan_id >= (int)e->plans.size()) return TF_E_FATAL_ARG;
+    *out = nullptr;
+    PlanDev& pd = *e->plans[plan_id];
+    if (!pd.plan.has_sink) return fail(e, TF_E_FATAL_CONFIG, "plan was built without a sink");
+    if (in->ncols != pd.plan.in_schema.size()) return fail(e, TF_E_FATAL_ARG, "batch column count does not match the plan schema");
+    if (wire_fmt != TF_WIRE_CH_NATIVE && wire_fmt != TF_WIRE_CH_NATIVE_LZ4) return fail(e, TF_E_FATAL_UNSUPPORTED, "wire format not implemented");
+    if (in->nrows >= (1ull << 31)) return fail(e, TF_E_FATAL_ARG, "batch too large (>= 2^31 rows)");
+    try {
+        CK(cudaSetDevice(e->device));
+        const uint64_t n = in->nrows; const uint32_t nc = in->ncols;
+        std::vector<tf_col> dev(nc); const uint8_t* dev_kinds = in->kinds;
+        cudaStream_t s = e->stream;
+        if (in->mem == TF_MEM_HOST) {
+            // host -> HBM staging of every column buffer (inside the caller-visible call: counted in e2e timing)
+            size_t tot = 0;
+            auto sz_of = [&](const tf_col& c, int which) -> size_t {
+                const int w = in_width(c.type);
+                switch (which) {
+                case 0: return w ? (size_t)w * n : 0;
+                case 1: return c.validity ? (n + 7) / 8 : 0;
+                case 2: return (!w && c.offsets) ? (n + 1) * 4 : 0;
+                case 3: return (!w) ? c.heap_len : 0;
+                default: if (!c.aux) return 0; return (c.type == TF_ANY) ? n : (size_t)4 * n;
+                }
+            };
+            for (uint32_t c = 0; c < nc; c++) for (int k = 0; k < 5; k++) tot += align_up(sz_of(in->cols[c], k) + 16, 256);
+            tot += align_up(n + 16, 256);
+            e->in_arena.ensure(tot);
+            uint8_t* p = e->in_arena.p;
+            auto up = [&](const void* src, size_t bytes) -> uint8_t* {
+                if (!src || !bytes) { return nullptr; }
+                uint8_t* d = p; CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, s)); p += align_up(bytes + 16, 256); return d;
+            };
+            for (uint32_t c = 0; c < nc; c++) {
+                const tf_col& ic = in->cols[c]; tf_col& d = dev[c]; d = ic;
+                d.values = up(ic.values, sz_of(ic, 0)); d.validity = up(ic.validity, sz_of(ic, 1));
+                d.offsets = (const uint32_t*)up(ic.offsets, sz_of(ic, 2));
+                d.heap = up(ic.heap, sz_of(ic, 3));
+                if (!in_width(ic.type) && !d.heap) d.heap = e->in_arena.p;   // empty heap: any valid pointer
+                d.aux = up(ic.aux, sz_of(ic, 4));
+            }
+            dev_kinds = in->kinds ? up(in->kinds, n) : nullptr;
+        } else {
+            for (uint32_t c = 0; c < nc; c++) dev[c] = in->cols[c];
+        }
+        run_chain(e, pd, in, dev.data(), dev_kinds, wire_fmt);
+        DState st; CK(cudaMemcpyAsync(&st, e->d_state, sizeof st, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+        auto r = std::make_unique<tfgpu_result>();
+        r->rows_in = n; r->rows_out = st.n_kept; r->raw_len = st.raw_total;
+        const bool lz = wire_fmt == TF_WIRE_CH_NATIVE_LZ4;
+        r->n_frames = lz ? st.n_frames : 0;
+        r->bytes_len = lz ? st.wire_total : st.raw_total;
+        CK(cudaMallocHost(&r->bytes, r->bytes_len ? r->bytes_len : 1)); r->bytes_pinned = true;
+        CK(cudaMemcpyAsync(r->bytes, lz ? e->wire.p : e->raw.p, r->bytes_len, cudaMemcpyDeviceToHost, s));
+        if (st.n_errors) {
+            std::vector<uint8_t> ec(n), es(n);
+            CK(cudaMemcpyAsync(ec.data(), e->errcode, n, cudaMemcpyDeviceToHost, s)); CK(cudaMemcpyAsync(es.data(), e->errstep, n, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            for (uint64_t i = 0; i < n; i++) if (ec[i]) r->errs.push_back(tf_rowerr{(uint32_t)i, ec[i], es[i]});
+        }
+        CK(cudaStreamSynchronize(s));
+        *out = r.release();
+        return TF_OK;
+    } catch (const tfplan::FatalError& f) { return fail(e, f.code, f.what()); }
+    catch (const CudaError& c) { return cuda_fail(e, c); }
+    catch (const std::bad_alloc&) { return fail(e, TF_E_RETRY_OOM, "host allocation failed"); }
+}
+
+int tfgpu_push_columns(tfgpu_engine* e, int plan_id, const tf_batch* in, tfgpu_result** out) {
+    (void)plan_id; (void)in; if (out) *out = nullptr;
+    return fail(e, TF_E_FATAL_UNSUPPORTED, "tfgpu_push_columns: columnar Transformed output is not implemented in this build; use tfgpu_push_encode");
+}
+
+uint64_t tfgpu_result_rows_in(const tfgpu_result* r) { return r ? r->rows_in : 0; }
+uint64_t tfgpu_result_rows_out(const tfgpu_result* r) { return r ? r->rows_out : 0; }
+uint64_t tfgpu_result_n_errors(const tfgpu_result* r) { return r ? r->errs.size() : 0; }
+const tf_rowerr* tfgpu_result_errors(const tfgpu_result* r) { return (r && !r->errs.empty()) ? r->errs.data() : nullptr; }
+const tf_batch* tfgpu_result_batch(const tfgpu_result* r) { return (r && r->batch.ncols) ? &r->batch : nullptr; }
+const uint8_t* tfgpu_result_bytes(const tfgpu_result* r) { return r ? r->bytes : nullptr; }
+uint64_t tfgpu_result_bytes_len(const tfgpu_result* r) { return r ? r->bytes_len : 0; }
+uint64_t tfgpu_result_raw_len(const tfgpu_result* r) { return r ? r->raw_len : 0; }
+uint64_t tfgpu_result_n_frames(const tfgpu_result* r) { return r ? r->n_frames : 0; }
+void tfgpu_result_release(tfgpu_result* r) {
+    if (!r) return;
+    if (r->bytes) { if (r->bytes_pinned) cudaFreeHost(r->bytes); else free(r->bytes); }
+    for (auto p : r->owned) free(p);
+    delete r;
+}
+
+}  // extern "C"

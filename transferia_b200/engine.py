@@ -1,0 +1,170 @@
+"""Host-side mirror of the reference's plug-in surface for the hot path, bound to the C-ABI.
+
+    Engine                  ~ the Sinker middleware instance            pkg/abstract/middleware.go:3
+    Engine.plan()           ~ transformation.AddTablePlan               pkg/transformer/transformation.go:46-85
+    Engine.push_encode()    ~ transformation.Push + sink encode         transformation.go:122-158,
+                                                                        providers/clickhouse/sink_table.go:605-704
+    PushResult.errors       ~ TransformerResult.Errors                  pkg/abstract/transformer.go:40-48
+
+Everything computes in libtfgpu.so (hand-written sm_100a kernels).  There is NO CPU fallback: if the
+library is missing or no CUDA device is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtfgpu.so")
+
+TF_E_FATAL_NODEVICE = -4
+
+
+class EngineError(RuntimeError):
+    """rc > 0: retriable (Push may be retried); rc < 0: fatal (abstract.NewFatalError)."""
+
+    def __init__(self, rc: int, msg: str):
+        super().__init__(f"tfgpu rc={rc}: {msg}")
+        self.rc = rc
+        self.retriable = rc > 0
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen transferia_b200/libtfgpu.so and declare every symbol of include/tfgpu.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` — "
+                           "the engine has no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, cp, i, u64 = C.c_void_p, C.c_char_p, C.c_int, C.c_uint64
+    L.tfgpu_version.restype = cp
+    L.tfgpu_engine_create.argtypes = [cp, C.POINTER(C.c_int), i, C.POINTER(vp)]
+    L.tfgpu_engine_destroy.argtypes = [vp]
+    L.tfgpu_last_error.argtypes = [vp]; L.tfgpu_last_error.restype = cp
+    L.tfgpu_engine_set_stream.argtypes = [vp, vp]
+    L.tfgpu_plan.argtypes = [vp, cp, cp, cp, cp, cp, C.POINTER(C.c_int)]
+    L.tfgpu_plan_describe.argtypes = [vp, i]; L.tfgpu_plan_describe.restype = cp
+    L.tfgpu_push_columns.argtypes = [vp, i, C.POINTER(abi.TfBatch), C.POINTER(vp)]
+    L.tfgpu_push_encode.argtypes = [vp, i, i, C.POINTER(abi.TfBatch), C.POINTER(vp)]
+    L.tfgpu_push_encode_resident.argtypes = [vp, i, i, C.POINTER(abi.TfBatch)]
+    L.tfgpu_resident_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    L.tfgpu_resident_fetch.argtypes = [vp, i, vp, u64]
+    for name in ("rows_in", "rows_out", "n_errors", "bytes_len", "raw_len", "n_frames"):
+        f = getattr(L, "tfgpu_result_" + name); f.argtypes = [vp]; f.restype = u64
+    L.tfgpu_result_errors.argtypes = [vp]; L.tfgpu_result_errors.restype = C.POINTER(abi.TfRowErr)
+    L.tfgpu_result_batch.argtypes = [vp]; L.tfgpu_result_batch.restype = C.POINTER(abi.TfBatch)
+    L.tfgpu_result_bytes.argtypes = [vp]; L.tfgpu_result_bytes.restype = vp
+    L.tfgpu_result_release.argtypes = [vp]; L.tfgpu_result_release.restype = None
+    L.tfgpu_engine_launch_count.argtypes = [vp]; L.tfgpu_engine_launch_count.restype = u64
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "tfgpu_version", "tfgpu_engine_create", "tfgpu_engine_destroy", "tfgpu_last_error", "tfgpu_engine_set_stream",
+    "tfgpu_plan", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_push_encode_resident",
+    "tfgpu_resident_stats", "tfgpu_resident_fetch", "tfgpu_result_rows_in", "tfgpu_result_rows_out",
+    "tfgpu_result_n_errors", "tfgpu_result_errors", "tfgpu_result_batch", "tfgpu_result_bytes",
+    "tfgpu_result_bytes_len", "tfgpu_result_raw_len", "tfgpu_result_n_frames", "tfgpu_result_release",
+    "tfgpu_engine_launch_count",
+]
+
+
+@dataclass
+class PushResult:
+    rows_in: int
+    rows_out: int
+    raw_len: int
+    n_frames: int
+    wire: bytes
+    errors: List[Tuple[int, int, int]]     # (input row, TF_ROWERR_*, transformer index)
+
+
+class Engine:
+    def __init__(self, device: int = 0, frame_bytes: int = 32768):
+        self._L = load_library()
+        self._h = C.c_void_p()
+        dev = (C.c_int * 1)(device)
+        cfg = json.dumps({"frame_bytes": frame_bytes}).encode()
+        rc = self._L.tfgpu_engine_create(cfg, dev, 1, C.byref(self._h))
+        if rc != 0:
+            msg = "no CUDA device — this engine has no CPU fallback" if rc == TF_E_FATAL_NODEVICE else "engine_create failed"
+            raise EngineError(rc, msg)
+        self.device = device
+        self.frame_bytes = frame_bytes
+
+    def close(self):
+        if self._h:
+            self._L.tfgpu_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise EngineError(rc, (self._L.tfgpu_last_error(self._h) or b"").decode(errors="replace"))
+
+    def set_stream(self, cuda_stream_ptr: Optional[int]):
+        self._check(self._L.tfgpu_engine_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def plan(self, namespace: str, name: str, schema, transformers=None, sink=None) -> int:
+        sj = schema if isinstance(schema, str) else json.dumps([{k: v for k, v in c.items() if not k.startswith("_")} for c in schema])
+        tj = json.dumps(transformers or [])
+        kj = None if sink is None else json.dumps(sink).encode()
+        pid = C.c_int(-1)
+        self._check(self._L.tfgpu_plan(self._h, namespace.encode(), name.encode(), sj.encode(), tj.encode(), kj, C.byref(pid)))
+        return pid.value
+
+    def describe(self, plan_id: int) -> dict:
+        s = self._L.tfgpu_plan_describe(self._h, plan_id)
+        return json.loads(s.decode()) if s else {}
+
+    def push_encode(self, plan_id: int, batch: abi.Batch, wire_fmt: int = abi.TF_WIRE_CH_NATIVE_LZ4, copy_bytes: bool = True) -> PushResult:
+        tb = batch.as_struct()
+        res = C.c_void_p()
+        self._check(self._L.tfgpu_push_encode(self._h, plan_id, wire_fmt, C.byref(tb), C.byref(res)))
+        try:
+            L = self._L
+            n = L.tfgpu_result_bytes_len(res)
+            wire = C.string_at(L.tfgpu_result_bytes(res), n) if (copy_bytes and n) else b""
+            ne = L.tfgpu_result_n_errors(res)
+            ep = L.tfgpu_result_errors(res)
+            errs = [(ep[k].row, ep[k].code, ep[k].term) for k in range(ne)]
+            out = PushResult(L.tfgpu_result_rows_in(res), L.tfgpu_result_rows_out(res), L.tfgpu_result_raw_len(res),
+                             L.tfgpu_result_n_frames(res), wire, errs)
+            out.wire_len = n
+            return out
+        finally:
+            self._L.tfgpu_result_release(res)
+
+    def push_encode_resident(self, plan_id: int, batch: abi.Batch, wire_fmt: int = abi.TF_WIRE_CH_NATIVE_LZ4):
+        """Asynchronous, HBM-resident: no copies, no host sync (kernel-only timing)."""
+        tb = batch.as_struct()
+        self._check(self._L.tfgpu_push_encode_resident(self._h, plan_id, wire_fmt, C.byref(tb)))
+
+    def resident_stats(self) -> dict:
+        a, b, c, d = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self._L.tfgpu_resident_stats(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return {"rows_out": a.value, "raw_bytes": b.value, "wire_bytes": c.value, "n_errors": d.value}
+
+    def resident_fetch(self, what: int, nbytes: int) -> bytes:
+        buf = (C.c_uint8 * max(1, nbytes))()
+        self._check(self._L.tfgpu_resident_fetch(self._h, what, buf, nbytes))
+        return bytes(buf[:nbytes])
+
+    def launch_count(self) -> int:
+        return int(self._L.tfgpu_engine_launch_count(self._h))
