@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py — ChangeItems/sec on ClickBench-shaped 99-column batches (BASELINE.json metric).
+
+A step = one pass of the hot path over one synthetic batch of `--rows` ChangeItems (default 1 M):
+    filter_rows (counterid > K AND url ~ '://')  ->  typesystem cast  ->  ClickHouse native block
+    ->  LZ4 frames + CityHash128          (BASELINE.json configs[2], the config the metric is quoted on)
+
+  value   kernel-only: the batch is resident in HBM, tfgpu_push_encode_resident, CUDA events, max over ranks
+  e2e     the same call a user makes (tfgpu_push_encode) with pinned HOST buffers: H2D of every column and
+          D2H of the wire bytes are inside the timed region
+  roofline  dominant kernel (k_lz4_frames): algorithmic bytes (raw block read + LZ4 bytes written) / its
+          CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the C++ oracle port of the Go row loop, timed on the host cores (rank 0, N=1)
+
+`--impl reference` times that CPU port instead (Go is not buildable here: no toolchain, deps not vendored).
+Launch: python bench.py --gpus N --steps K --warmup W   (N>1 under torch.distributed.run, one rank per GPU).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "ChangeItems/sec on ClickBench-shaped 99-col batches (filter_rows + cast + ClickHouse native block + LZ4 frames)"
+FALLBACK_HBM_GBS = 6650.0
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def make_batch(rows: int, seed: int):
+    """Seeded synthetic batch; cached under /tmp so the two arms and every N reuse one generation."""
+    from transferia_b200 import abi, workload
+    schema = workload.hits_schema()
+    cache = f"/tmp/tfgpu_hits_{rows}_{seed}.npz"
+    if os.path.exists(cache):
+        try:
+            z = np.load(cache)
+            cols = []
+            for i, c in enumerate(schema):
+                t = abi.YT_NAME_TO_TF[c["type"]]
+                g = lambda k: z[f"{i}_{k}"] if f"{i}_{k}" in z.files else None
+                cols.append(abi.Column(t, g("values"), g("validity"), g("offsets"), g("heap"), g("aux")))
+            return abi.Batch(rows, cols), schema
+        except Exception:
+            pass
+    batch, schema = workload.make_hits_batch(rows, seed)
+    try:
+        arrs = {}
+        for i, c in enumerate(batch.columns):
+            for k in ("values", "validity", "offsets", "heap", "aux"):
+                a = getattr(c, k)
+                if a is not None:
+                    arrs[f"{i}_{k}"] = a
+        np.savez(cache, **arrs)
+    except Exception:
+        pass
+    return batch, schema
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi-equivalent (NVML) clocks + throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index; self.stop_flag = False; self.sm = []; self.reasons = set(); self.sm_max = None; self.ok = False
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            }
+            self.ok = True
+            while not self.stop_flag:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.05)
+        except Exception:
+            self.ok = False
+
+    def result(self):
+        if not self.ok or not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
+
+
+def cpu_port_rate(batch, schema, transformers, frame_bytes, budget_s: float, threads: int):
+    """Rows/s of the oracle port run as `threads` independent sink pipelines (the reference's sharded-snapshot
+    parallelism, pkg/worker/tasks/load_snapshot.go:917-1041), each over its own row slice, for >= budget_s."""
+    from transferia_b200 import abi
+    from oracle import pyoracle as po
+    plan = po.build_plan("public", "hits", schema, transformers)
+    n = batch.nrows
+    per = max(1, min(n // threads, 100_000))
+    slices = [batch.slice(i * per, (i + 1) * per) for i in range(threads)]
+    done = [0] * threads
+    t_end = [0.0] * threads
+    t0 = time.perf_counter()
+
+    def work(i):
+        while True:
+            po.push_encode(slices[i], plan, abi.TF_WIRE_CH_NATIVE_LZ4, frame_bytes, want_bytes=False)
+            done[i] += per
+            t_end[i] = time.perf_counter()
+            if t_end[i] - t0 >= budget_s:
+                break
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    el = max(t_end) - t0
+    return sum(done) / el, sum(done), el
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm for this path (oracle port) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from transferia_b200 import workload
+    cores = os.cpu_count() or 1
+    rows = min(args.rows, 1_000_000)
+    batch, schema = make_batch(rows, workload.SEED)
+    k = workload.counterid_threshold(batch, schema)
+    trs = workload.headline_transformers(k)
+    per_step_budget = 2.0
+    for _ in range(args.warmup):
+        cpu_port_rate(batch, schema, trs, args.frame_bytes, 0.5, cores)
+    tot_rows = 0; tot_t = 0.0
+    for _ in range(args.steps):
+        _, r, t = cpu_port_rate(batch, schema, trs, args.frame_bytes, per_step_budget, cores)
+        tot_rows += r; tot_t += t
+    v = tot_rows / tot_t
+    sample = f"{cores} pipelines x 100k-row slices of the {rows}-row batch, >= {per_step_budget}s per step"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "clickbench_hits_99col filter_rows+cast+ch_native+lz4 (BASELINE configs[2])", "rows_per_step": rows,
+                   "note": "CPU restatement (C++ oracle port), not Go: no Go toolchain / module cache in this image"},
+        "cpu_baseline": {"value": v, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--rows", type=int, default=1_000_000)
+    ap.add_argument("--frame-bytes", type=int, default=32768)
+    ap.add_argument("--impl", default="tfgpu")
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from transferia_b200 import abi, engine, workload
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = f"cuda:{local}"
+
+    # weak scaling: every rank owns its own batch (different seed), no data-path collective
+    batch, schema = make_batch(args.rows, workload.SEED + rank)
+    k = workload.counterid_threshold(batch, schema)
+    trs = workload.headline_transformers(k)
+    eng = engine.Engine(local, args.frame_bytes)
+    stream = torch.cuda.Stream()          # a real (non-default) stream: events below and every kernel share it
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
+    pid = eng.plan("public", "hits", schema, trs, {"type": "clickhouse"})
+    dbatch = batch.to_device(dev)
+    hbatch = batch.pin()
+    in_bytes = batch.input_bytes()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- kernel-only (resident) ----
+    for _ in range(args.warmup):
+        eng.push_encode_resident(pid, dbatch, abi.TF_WIRE_CH_NATIVE_LZ4)
+    torch.cuda.synchronize()
+    st = eng.resident_stats()
+    eng.profile_enable(True)
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    l0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = {}
+    ev0.record()
+    for _ in range(args.steps):
+        eng.push_encode_resident(pid, dbatch, abi.TF_WIRE_CH_NATIVE_LZ4)
+        # per-kernel events of this step are read after the loop for the last step only; to average over the
+        # timed region without syncing inside it, the engine keeps one event pair per kernel per call and we
+        # read them once per step boundary below (the read syncs the stream, so do it outside timing)
+    ev1.record()
+    torch.cuda.synchronize()
+    launches = eng.launch_count() - l0
+    ms_total = ev0.elapsed_time(ev1)
+    for kk in eng.profile_read():        # events of the LAST timed step
+        kernel_ms[kk["name"]] = kernel_ms.get(kk["name"], 0.0) + kk["ms"]
+    # average the dominant kernel over a few more (untimed) steps for a stable duration
+    extra = 5
+    acc = {}
+    for _ in range(extra):
+        eng.push_encode_resident(pid, dbatch, abi.TF_WIRE_CH_NATIVE_LZ4)
+        for kk in eng.profile_read():
+            acc[kk["name"]] = acc.get(kk["name"], 0.0) + kk["ms"]
+    kernel_avg = {n: (acc.get(n, 0.0) + kernel_ms.get(n, 0.0)) / (extra + 1) for n in set(acc) | set(kernel_ms)}
+    eng.profile_enable(False)
+    barrier()
+    sampler.stop_flag = True; sampler.join(timeout=2)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * args.rows * args.steps / (ms_max / 1e3)
+
+    # ---- end to end through the public call, host buffers ----
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        r = eng.push_encode(pid, hbatch, abi.TF_WIRE_CH_NATIVE_LZ4, copy_bytes=False)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r = eng.push_encode(pid, hbatch, abi.TF_WIRE_CH_NATIVE_LZ4, copy_bytes=False)
+    e1.record(); torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    e2e_ms = max(e0.elapsed_time(e1), wall * 1e3)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.rows * e2e_steps / (float(t.item()) / 1e3)
+    d2h = int(r.wire_len)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        lz_ms = kernel_avg.get("k_lz4_frames", 0.0)
+        lz_bytes = st["raw_bytes"] + (st["wire_bytes"] - 25 * ((st["raw_bytes"] + args.frame_bytes - 1) // args.frame_bytes))
+        achieved = lz_bytes / (lz_ms / 1e3) / 1e9 if lz_ms else 0.0
+        step_ms = sum(kernel_avg.values())
+        out = {
+            "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "clickbench_hits_99col filter_rows+cast+ch_native+lz4 (BASELINE configs[2])",
+                       "rows_per_step_per_gpu": args.rows, "columns": len(schema), "frame_bytes": args.frame_bytes,
+                       "selectivity": st["rows_out"] / args.rows, "lz4_ratio": st["raw_bytes"] / max(1, st["wire_bytes"]),
+                       "input_bytes_per_row": in_bytes / args.rows, "block_bytes_per_kept_row": st["raw_bytes"] / max(1, st["rows_out"]),
+                       "l2": "inputs larger than L2 (%.0f MB per step > 126 MB)" % (in_bytes / 1e6),
+                       "parallelism": f"dp{world} (independent batches per GPU, no collective)"},
+            "clocks": sampler.result(),
+            "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_lz4_frames", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(lz_bytes), "kernel_ms": lz_ms,
+                         "kernel_share_of_step": lz_ms / step_ms if step_ms else None,
+                         "all_kernels_ms": {n: round(v, 4) for n, v in sorted(kernel_avg.items())}},
+        }
+        if world == 1:
+            cores = os.cpu_count() or 1
+            v, rows_done, el = cpu_port_rate(batch, schema, trs, args.frame_bytes, args.cpu_budget, cores)
+            out["cpu_baseline"] = {"value": v, "unit": "rows/s", "cores": cores, "kind": "port",
+                                   "sample": f"{cores} pipelines x 100k-row slices of the same batch for {el:.1f}s ({rows_done} rows); C++ oracle port of the Go row loop, not Go"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

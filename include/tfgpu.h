@@ -162,6 +162,11 @@ int tfgpu_engine_set_stream(tfgpu_engine* e, void* cuda_stream);
 int tfgpu_plan(tfgpu_engine* e, const char* table_namespace, const char* table_name,
                const char* schema_json, const char* transformers_json, const char* sink_json,
                int* plan_id);
+/* Same plan construction, host-only (no device, no engine): validates a transfer's transformer list against a
+ * table schema and returns the describe JSON. rc < 0 with a message in err_out for configs the engine rejects. */
+int tfgpu_plan_validate(const char* table_namespace, const char* table_name, const char* schema_json,
+                        const char* transformers_json, const char* sink_json,
+                        char* describe_out, uint64_t describe_cap, char* err_out, uint64_t err_cap);
 /* JSON of the plan: result schema (ResultSchema chain), transformers kept by Suitable(),
  * the compiled predicate terms — owned by the engine, valid until the engine is destroyed. */
 const char* tfgpu_plan_describe(tfgpu_engine* e, int plan_id);
@@ -185,7 +190,9 @@ int tfgpu_resident_stats(tfgpu_engine* e, uint64_t* rows_out, uint64_t* raw_byte
 /* Copy the last resident call's uncompressed block / wire bytes to host (tests). */
 int tfgpu_resident_fetch(tfgpu_engine* e, int what /*0=raw block,1=wire*/, uint8_t* dst, uint64_t cap);
 
-/* Result accessors (all memory is owned by the result until tfgpu_result_release). */
+/* Result accessors. Row errors and the columnar batch are owned by the result until
+ * tfgpu_result_release; the wire bytes live in the engine's pinned landing buffer and stay valid
+ * until the NEXT push on the same engine (the Go shim writes them to the socket before that). */
 uint64_t          tfgpu_result_rows_in(const tfgpu_result* r);
 uint64_t          tfgpu_result_rows_out(const tfgpu_result* r);
 uint64_t          tfgpu_result_n_errors(const tfgpu_result* r);
@@ -199,6 +206,11 @@ void              tfgpu_result_release(tfgpu_result* r);
 
 /* Number of kernel launches issued by this engine since creation (bench `gpu_launches`). */
 uint64_t tfgpu_engine_launch_count(const tfgpu_engine* e);
+
+/* Optional per-kernel timing of the LAST call with CUDA events on the engine's stream (bench.py roofline).
+ * tfgpu_profile_read synchronises the stream and returns JSON [{"name":"k_lz4_frames","ms":..},..] owned by the engine. */
+int tfgpu_profile_enable(tfgpu_engine* e, int on);
+const char* tfgpu_profile_read(tfgpu_engine* e);
 
 /* Library identity: "tfgpu <version> sm_100a". */
 const char* tfgpu_version(void);

@@ -1,0 +1,266 @@
+"""GPU parity tests proper: the CUDA path through the C-ABI vs the CPU oracle on the same seeded inputs.
+Bar: bit-exact native block (integer / byte / index work); compressed frames must decode with stock liblz4
+AND the oracle's decoder to exactly that block and carry valid CityHash128 checksums (LZ4 bytes themselves are
+unpinned in the reference)."""
+import ctypes as C
+import struct
+
+import numpy as np
+import pytest
+
+from transferia_b200 import abi, engine, workload
+
+pytestmark = pytest.mark.gpu
+LZ = abi.TF_WIRE_CH_NATIVE_LZ4
+RAW = abi.TF_WIRE_CH_NATIVE
+
+
+def decode_with_liblz4(wire: bytes, po):
+    """Independent frame walk: header fields, CityHash128 (oracle), LZ4 block via stock liblz4."""
+    lz = C.CDLL("liblz4.so.1")
+    pos, out, nf = 0, bytearray(), 0
+    while pos < len(wire):
+        assert wire[pos + 16] == 0x82
+        cs, rs = struct.unpack_from("<II", wire, pos + 17)
+        lo, hi = po.cityhash128(wire[pos + 16: pos + 16 + cs])
+        assert struct.unpack_from("<QQ", wire, pos) == (lo, hi), f"bad checksum in frame {nf}"
+        dst = C.create_string_buffer(max(1, rs))
+        n = lz.LZ4_decompress_safe(wire[pos + 25: pos + 16 + cs], dst, cs - 9, rs)
+        assert n == rs, f"liblz4 rejected frame {nf}: {n}"
+        out += dst.raw[:rs]; pos += 16 + cs; nf += 1
+    return bytes(out), nf
+
+
+def check(eng, po, batch, schema, trs, ns="db", name="t", lz=True):
+    pid = eng.plan(ns, name, schema, trs, {"type": "clickhouse"})
+    plan = po.build_plan(ns, name, schema, trs)
+    ref = po.push_encode(batch, plan, RAW, eng.frame_bytes)
+    got = eng.push_encode(pid, batch, RAW)
+    assert got.rows_in == batch.nrows and got.rows_out == ref.rows_out
+    assert got.errors == ref.errors
+    assert got.raw_len == len(ref.raw)
+    if got.wire != ref.raw:
+        a = np.frombuffer(got.wire, dtype=np.uint8); b = np.frombuffer(ref.raw, dtype=np.uint8)
+        d = np.nonzero(a[:min(len(a), len(b))] != b[:min(len(a), len(b))])[0]
+        raise AssertionError(f"native block differs at byte {d[:5]} of {len(b)}")
+    if lz:
+        z = eng.push_encode(pid, batch, LZ)
+        raw, nf = decode_with_liblz4(z.wire, po)
+        assert raw == ref.raw and nf == z.n_frames == max(1, -(-len(ref.raw) // eng.frame_bytes))
+        raw2, nf2 = po.ch_decode_frames(z.wire)
+        assert raw2 == ref.raw and nf2 == nf
+    return got, ref
+
+
+def test_headline_parity_50k(eng, po):
+    batch, schema = workload.make_hits_batch(50_000)
+    k = workload.counterid_threshold(batch, schema)
+    got, ref = check(eng, po, batch, schema, workload.headline_transformers(k), "public", "hits")
+    assert 0 < got.rows_out < batch.nrows
+    check(eng, po, batch, schema, [], "public", "hits")
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 32, 33, 255, 256, 257, 1023, 1024, 1025, 2049, 4097])
+def test_ragged_row_counts(eng, po, n):
+    batch, schema = workload.make_hits_batch(max(n, 1))
+    batch = batch.slice(0, n)
+    trs = workload.headline_transformers(workload.counterid_threshold(batch, schema) if n else 0)
+    check(eng, po, batch, schema, trs, "public", "hits")
+    check(eng, po, batch, schema, [], "public", "hits", lz=(n in (0, 1, 33, 1025)))
+
+
+def all_types_batch(n=3000, seed=3):
+    rng = np.random.default_rng(seed)
+    nulls = lambda p: rng.random(n) < p
+    schema, cols = [], []
+    def add(name, typ, col, required):
+        schema.append({"name": name, "type": typ, "required": required, "key": False}); cols.append(col)
+    for typ in ("int8", "int16", "int32", "int64", "uint8", "uint16", "uint32", "uint64"):
+        dt = abi.FIXED_DTYPE[abi.YT_NAME_TO_TF[typ]]; info = np.iinfo(dt)
+        v = rng.integers(info.min, info.max, n, dtype=dt, endpoint=True)
+        v[:4] = [info.min, info.max, 0, 1]
+        add("c_" + typ, typ, abi.fixed_to_column(abi.YT_NAME_TO_TF[typ], v), True)
+        add("n_" + typ, typ, abi.fixed_to_column(abi.YT_NAME_TO_TF[typ], v, nulls(0.3)), False)
+    f32 = rng.standard_normal(n).astype(np.float32); f32[:3] = [np.inf, -0.0, np.nan]
+    add("c_float", "float", abi.fixed_to_column(abi.TF_FLOAT, f32), True)
+    add("n_double", "double", abi.fixed_to_column(abi.TF_DOUBLE, rng.standard_normal(n) * 1e100, nulls(0.2)), False)
+    add("n_bool", "boolean", abi.fixed_to_column(abi.TF_BOOLEAN, rng.integers(0, 2, n), nulls(0.2)), False)
+    add("c_interval", "interval", abi.fixed_to_column(abi.TF_INTERVAL, rng.integers(-10**15, 10**15, n)), True)
+    secs = rng.integers(-10**9, 5 * 10**9, n); secs[:6] = [-86400, 0, 86399, 4291747199, 4291747200, 4291747200 + 10**8]
+    nanos = rng.integers(0, 10**9, n)
+    add("c_date", "date", abi.fixed_to_column(abi.TF_DATE, secs, nanos=nanos), True)
+    add("n_datetime", "datetime", abi.fixed_to_column(abi.TF_DATETIME, secs, nulls(0.1), nanos=nanos), False)
+    add("n_timestamp", "timestamp", abi.fixed_to_column(abi.TF_TIMESTAMP, secs, nulls(0.1), nanos=nanos), False)
+    add("c_timestamp_nonanos", "timestamp", abi.fixed_to_column(abi.TF_TIMESTAMP, secs), True)
+    lens = [0, 1, 127, 128, 129, 300, 16383, 16384, 20000] + list(rng.integers(0, 60, n - 9))
+    strs = [bytes(rng.integers(0, 256, int(L), dtype=np.uint8)) for L in lens]
+    add("c_utf8", "utf8", abi.strings_to_column(abi.TF_UTF8, strs), True)
+    ns = [None if rng.random() < 0.25 else s for s in strs]
+    add("n_bytes", "string", abi.strings_to_column(abi.TF_BYTES, ns), False)
+    add("n_any", "any", abi.strings_to_column(abi.TF_ANY, [None if rng.random() < 0.1 else (b'{"k":%d}' % i) for i in range(n)],
+                                              tags=(rng.random(n) < 0.5).astype(np.uint8)), False)
+    return abi.Batch(n, cols), schema
+
+
+def test_all_types_nulls_clamps_long_strings(eng, po):
+    batch, schema = all_types_batch()
+    check(eng, po, batch, schema, [])
+    check(eng, po, batch, schema, [{"filter_rows": {"filter": "c_int32 > 0 AND n_int16 != NULL"}}])
+
+
+def typed_column(case):
+    tf = abi.YT_NAME_TO_TF[case["type"]]
+    vals = [v[1] if case["go"] == "mixed" else v for v in case["input"]]
+    if tf in abi.VAR_TYPES:
+        return abi.strings_to_column(tf, [v.encode() for v in vals])
+    if tf == abi.TF_TIMESTAMP:
+        import datetime as dt
+        us = [(dt.datetime.fromisoformat(v) - dt.datetime(1970, 1, 1, tzinfo=dt.timezone.utc)) // dt.timedelta(microseconds=1) for v in vals]
+        return abi.fixed_to_column(tf, [u // 10**6 for u in us], nanos=[(u % 10**6) * 1000 for u in us])
+    if tf == abi.TF_UINT64:
+        return abi.Column(tf, values=np.array(vals, dtype=np.uint64))
+    return abi.fixed_to_column(tf, vals)
+
+
+def test_filter_rows_reference_filters_on_device(eng, po, goldens):
+    """Every filter of filter_rows_test.go on a typed column: device result == oracle (rows, errors, bytes)."""
+    for case in goldens["filter_rows"]:
+        col = typed_column(case)
+        schema = [{"name": "column", "type": case["type"], "required": True, "key": True}]
+        batch = abi.Batch(len(case["input"]), [col])
+        got, ref = check(eng, po, batch, schema, [{"filter_rows": {"filter": case["filter"]}}], "db", "table", lz=False)
+        assert len(got.errors) == case["errors"], case["name"]
+        if case["type"] not in ("float",):      # the Go table feeds float64 values even to the float32 column
+            assert got.rows_out == len(case["expected"]), case["name"]
+
+
+def test_filter_rows_semantics_matrix(eng, po):
+    batch, schema = all_types_batch(2000, seed=9)
+    names = [c["name"] for c in schema]
+    kinds = np.zeros(batch.nrows, dtype=np.uint8); kinds[5] = abi.TF_KIND_UPDATE; kinds[17] = abi.TF_KIND_DELETE
+    filters = [
+        "c_int8 >= -5 AND c_int8 < 100", "c_uint64 > 5",                    # uint64 > MaxInt64 rows -> errIntOverflow
+        "n_int32 > -1",                                                     # nil -> cast.ToFloat64E(nil) = 0 -> matches
+        "n_int32 IN (0, 1, 2)", "n_double >= 0.5", "c_float < 0.0", "c_float IN (0.0, 1.5)", "n_bool = TRUE", "n_bool != false",
+        "n_bool > 0.5",                                                     # bool -> 1/0 through ToFloat64E
+        "c_utf8 ~ 'a'", "c_utf8 !~ 'ab'", "n_bytes >= 'M'", "c_utf8 IN ('', 'x')", "n_any ~ 'k'", "n_bytes = NULL", "n_any != NULL",
+        "n_timestamp >= 2001-09-09T01:46:40Z AND n_timestamp < 2033-05-18T03:33:20.5+00:00", "c_date NOT IN (1970-01-01, 2106-01-01)",
+        "n_datetime > 1999-12-31T23:59", "c_interval = NULL", "n_int16 > 2.5 AND n_int16 <= 100.0", "c_int64 NOT IN (1, 2, 3)",
+    ]
+    b2 = abi.Batch(batch.nrows, batch.columns, kinds)
+    for f in filters:
+        check(eng, po, b2, schema, [{"filter_rows": {"filter": f}}], lz=False)
+    # OR over `filters`, AND inside each (filter_rows.go:137-148)
+    check(eng, po, b2, schema, [{"filter_rows": {"filters": ["c_int8 > 100", "c_utf8 ~ 'zz' AND n_bool = true", "n_int32 = NULL"]}}], lz=False)
+    # two filter_rows steps in one chain
+    check(eng, po, b2, schema, [{"filter_rows": {"filter": "c_int16 > 0"}}, {"filter_rows": {"filter": "c_int32 < 0"}}], lz=False)
+    # type pair the reference rejects per row ("Unsupported type pair"): string literal list vs a numeric column
+    got, ref = check(eng, po, batch, schema, [{"filter_rows": {"filter": "c_int32 IN ('a', 'b')"}}], lz=False)
+    assert got.rows_out == 0 and len(got.errors) == batch.nrows and got.errors[0][1] == abi.TF_ROWERR_FILTER_TYPEPAIR
+
+
+def test_mask_field_on_device(eng, po):
+    batch, schema = all_types_batch(1500, seed=21)
+    cols = ["c_int8", "n_int32", "c_uint64", "n_bool", "c_date", "n_datetime", "n_timestamp", "c_utf8", "n_bytes", "n_any", "c_int64"]
+    trs = [{"mask_field": {"columns": cols, "maskFunctionHash": {"userDefinedSalt": "the-best-tasty-saint-petersburg-salt"}}}]
+    got, ref = check(eng, po, batch, schema, trs)
+    # a long key (> 64 bytes is hashed first by crypto/hmac), chained after a filter
+    trs2 = [{"filter_rows": {"filter": "c_int16 > 0"}}, {"mask_field": {"columns": ["c_utf8", "c_int32"], "maskFunctionHash": {"userDefinedSalt": "k" * 100}}}]
+    check(eng, po, batch, schema, trs2)
+
+
+def test_mask_golden_digests_on_device(eng, po, goldens):
+    """The reference's canondata digests reproduced by the device HMAC kernel (types the device formats)."""
+    salt = goldens["mask"]["salt"]
+    for c in goldens["mask"]["cases"]:
+        if c["go"] in ("float64", "float32", "duration"):
+            continue
+        tf = abi.YT_NAME_TO_TF[c["type"]]
+        if c["go"] == "string":
+            col = abi.strings_to_column(abi.TF_UTF8 if tf == abi.TF_BYTES else tf, [c["value"].encode()]); typ = "utf8" if tf == abi.TF_BYTES else c["type"]
+        elif c["go"] == "time":
+            col = abi.fixed_to_column(tf, [-8425641600]); typ = c["type"]       # 1703-01-02T00:00:00Z
+        elif c["go"] == "bool":
+            col = abi.fixed_to_column(tf, [1]); typ = c["type"]
+        else:
+            col = abi.fixed_to_column(tf, [c["value"]]); typ = c["type"]
+        schema = [{"name": "c", "type": typ, "required": True}]
+        pid = eng.plan("db", "t", schema, [{"mask_field": {"columns": ["c"], "maskFunctionHash": {"userDefinedSalt": salt}}}], {"type": "clickhouse"})
+        got = eng.push_encode(pid, abi.Batch(1, [col]), RAW)
+        assert got.wire.endswith(b"\x40" + c["digest"].encode()), c
+
+
+def test_resident_path_equals_host_path(eng, po):
+    batch, schema = workload.make_hits_batch(30_000, seed=77)
+    trs = workload.headline_transformers(workload.counterid_threshold(batch, schema))
+    pid = eng.plan("public", "hits", schema, trs, {"type": "clickhouse"})
+    host = eng.push_encode(pid, batch, LZ)
+    dbatch = batch.to_device("cuda:0")
+    eng.push_encode_resident(pid, dbatch, LZ)
+    st = eng.resident_stats()
+    assert st["rows_out"] == host.rows_out and st["raw_bytes"] == host.raw_len
+    plan = po.build_plan("public", "hits", schema, trs)
+    ref = po.push_encode(batch, plan, RAW).raw
+    assert eng.resident_fetch(0, st["raw_bytes"]) == ref
+    # compressed bytes may differ between runs (hash-table insert order inside a round is a race the kernel
+    # tolerates: any winner is a valid earlier position); what is invariant is what they decode to
+    raw, nf = decode_with_liblz4(eng.resident_fetch(1, st["wire_bytes"]), po)
+    assert raw == ref and nf == host.n_frames
+
+
+@pytest.mark.parametrize("frame_bytes", [1024, 4096, 16384])
+def test_other_frame_sizes(po, frame_bytes):
+    e = engine.Engine(0, frame_bytes)
+    try:
+        batch, schema = workload.make_hits_batch(5000, seed=5)
+        check(e, po, batch, schema, workload.headline_transformers(workload.counterid_threshold(batch, schema)), "public", "hits")
+    finally:
+        e.close()
+
+
+def test_compressible_and_incompressible_frames(eng, po):
+    """LZ4 edge cases: constant column (one long run per frame), pure noise, tiny blocks, tails shorter than 13 bytes."""
+    n = 70_000
+    rng = np.random.default_rng(1)
+    schema = [{"name": "z", "type": "int64", "required": True}, {"name": "r", "type": "int64", "required": True}, {"name": "s", "type": "utf8", "required": True}]
+    cols = [abi.fixed_to_column(abi.TF_INT64, np.zeros(n, dtype=np.int64)), abi.fixed_to_column(abi.TF_INT64, rng.integers(-2**63, 2**63 - 1, n)),
+            abi.strings_to_column(abi.TF_UTF8, [b"abcabcabc" * (i % 7) for i in range(n)])]
+    check(eng, po, abi.Batch(n, cols), schema, [])
+    for m in (1, 2, 3, 5):
+        check(eng, po, abi.Batch(m, [abi.fixed_to_column(abi.TF_INT8, list(range(m)))]), [{"name": "a", "type": "int8", "required": True}], [])
+
+
+def test_full_size_batch_properties(eng, po):
+    """BASELINE-size step (1 M rows x 99 columns): bit-exact block vs the oracle, frames decode with liblz4,
+    every frame checksum valid, the uncompressed path gives the same block (idempotence), kept rows = numpy's own count."""
+    batch, schema = workload.make_hits_batch(1_000_000)
+    k = workload.counterid_threshold(batch, schema)
+    trs = workload.headline_transformers(k)
+    pid = eng.plan("public", "hits", schema, trs, {"type": "clickhouse"})
+    a = eng.push_encode(pid, batch, LZ)
+    b = eng.push_encode(pid, batch, RAW)
+    assert a.rows_out == b.rows_out and a.raw_len == len(b.wire)
+    names = [c["name"] for c in schema]
+    cid = batch.columns[names.index("counterid")].values
+    url = batch.columns[names.index("url")]
+    heap = url.heap.tobytes(); offs = url.offsets
+    has = np.fromiter((heap.find(b"://", int(offs[i]), int(offs[i + 1])) >= 0 for i in range(batch.nrows)), dtype=bool, count=batch.nrows)
+    assert a.rows_out == int(((cid > k) & has).sum())
+    raw, nf = decode_with_liblz4(a.wire, po)
+    assert nf == a.n_frames and len(raw) == a.raw_len
+    ref = po.push_encode(batch, po.build_plan("public", "hits", schema, trs), RAW)
+    assert raw == ref.raw and b.wire == ref.raw
+
+
+def test_api_errors(eng):
+    schema = [{"name": "a", "type": "int32", "required": True}]
+    pid = eng.plan("db", "t", schema, [], {"type": "clickhouse"})
+    with pytest.raises(engine.EngineError) as ei:
+        eng.push_encode(pid, abi.Batch(1, [abi.fixed_to_column(abi.TF_INT32, [1]), abi.fixed_to_column(abi.TF_INT32, [1])]), RAW)
+    assert ei.value.rc < 0
+    with pytest.raises(engine.EngineError):
+        eng.push_encode(pid, abi.Batch(1, [abi.fixed_to_column(abi.TF_INT64, [1])]), RAW)
+    with pytest.raises(engine.EngineError):
+        eng.plan("db", "t", schema, [{"mask_field": {"columns": ["a"], "maskFunctionHash": {"userDefinedSalt": "s"}}}, {"filter_rows": {"filter": "a = 'x'"}}], {"type": "clickhouse"})
+    with pytest.raises(engine.EngineError):
+        eng.push_encode(pid, abi.Batch(1, [abi.fixed_to_column(abi.TF_INT32, [1])]), abi.TF_WIRE_CH_JSONEACHROW)

@@ -1,0 +1,198 @@
+"""CPU-side tests of the product's host logic: the C-ABI library loads and exports every declared symbol,
+the host plan builder (filter grammar, Suitable/ResultSchema, ClickHouse types) agrees with the oracle's
+restatement, batch dealing for N GPUs, and the engine refuses to run without a device (no CPU fallback)."""
+import json
+import os
+import re
+import subprocess
+import sys
+import ctypes as C
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+from transferia_b200 import abi, dispatch, engine, workload
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "tfgpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(tfgpu_\w+)\s*\(", hdr))
+    assert declared == set(engine.EXPORTED_SYMBOLS), declared ^ set(engine.EXPORTED_SYMBOLS)
+    L = engine.load_library()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.tfgpu_version().decode().startswith("tfgpu ") and b"sm_100a" in L.tfgpu_version()
+
+
+def test_library_is_sm100a_native():
+    out = subprocess.run(["cuobjdump", "-lelf", engine.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(engine.EngineError) as ei:
+        engine.Engine(0)
+    assert ei.value.rc == engine.TF_E_FATAL_NODEVICE and not ei.value.retriable
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "transferia_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|pyoracle|liboracle|#include\s+\"[^\"]*oracle", src, flags=re.M), f
+
+
+def _terms_from_describe(d):
+    out = []
+    for st in d["steps"]:
+        if st["type"] == "filter_rows":
+            out.append([[(t["col"], t["op"], t["vtype"], t["value"]) for t in e] for e in st["exprs"]])
+    return out
+
+
+def _oracle_terms(plan, po):
+    out = []
+    for st in plan.steps:
+        if st["kind"] != "filter_rows":
+            continue
+        exprs = []
+        for e in st["exprs"]:
+            row = []
+            for col, t in e:
+                base = t.vtype & 15
+                enc = lambda v: (v.hex() if base == po.LV_STRING else (None if base == po.LV_NULL else v))
+                val = [enc(x) for x in t.value] if t.vtype & po.LV_LIST else enc(t.value)
+                row.append((col, t.op, t.vtype, val))
+            exprs.append(row)
+        out.append(exprs)
+    return out
+
+
+def test_plan_matches_oracle_on_reference_filters(po, goldens):
+    """Every filter string of filter_rows_test.go through the product's C++ grammar vs the oracle's."""
+    for case in goldens["filter_rows"]:
+        schema = [{"name": "column", "type": case["type"], "key": True, "required": False}]
+        trs = [{"filter_rows": {"filter": case["filter"]}}]
+        d = engine.plan_validate("db", "table", schema, trs, {"type": "clickhouse"})
+        plan = po.build_plan("db", "table", schema, trs)
+        assert _terms_from_describe(d) == _oracle_terms(plan, po), case["name"]
+
+
+def test_plan_headline_and_result_schema(po):
+    schema = workload.hits_schema()
+    trs = workload.headline_transformers(1234) + [{"mask_field": {"columns": ["userid", "url"], "maskFunctionHash": {"userDefinedSalt": "s"}}}]
+    d = engine.plan_validate("public", "hits", schema, trs, {"type": "clickhouse"})
+    plan = po.build_plan("public", "hits", schema, trs)
+    assert [c["type"] for c in d["result_schema"]] == [c["type"] for c in plan.result_schema]
+    assert [c["name"] for c in d["result_schema"]] == [c["name"] for c in schema]
+    assert d["sink"]["columns"] == [po.ch_type(c) for c in plan.result_schema]
+    assert [s["type"] for s in d["steps"]] == ["filter_rows", "mask_field"]
+    assert d["steps"][1]["cols"] == plan.steps[1]["cols"]
+    masked = [c for c in d["result_schema"] if c["name"] in ("userid", "url")]
+    assert all(c["type"] == "utf8" and c["original_type"] == "" for c in masked)
+
+
+def test_plan_suitable_rules():
+    schema = [{"name": "colstr", "type": "utf8"}, {"name": "colint", "type": "int32"}]
+    # filter_rows_test.go "Compare different types": not Suitable -> transformer dropped from the plan
+    d = engine.plan_validate("db", "table", schema, [{"filter_rows": {"filter": 'colstr > 10 AND colint = "str"'}}])
+    assert d["steps"] == []
+    # missing column -> not Suitable
+    assert engine.plan_validate("db", "table", schema[:1], [{"filter_rows": {"filter": 'colstr = "s" AND colint > 4'}}])["steps"] == []
+    # table include / exclude (transformer_common.go:9-33: matches `db.table` or `"db"."table"`)
+    t = {"filter_rows": {"tables": {"includeTables": ["^db\\.table$"]}, "filter": "colint > 4"}}
+    assert len(engine.plan_validate("db", "table", schema, [t])["steps"]) == 1
+    assert engine.plan_validate("db", "other", schema, [t])["steps"] == []
+    # MatchAnyTableNameVariant: ANY variant passing the filter is enough, so an exclude that only hits the quoted
+    # form does not exclude the table, one that hits both forms does
+    t2 = {"filter_rows": {"tables": {"excludeTables": ['^"db"\\."table"$']}, "filter": "colint > 4"}}
+    assert len(engine.plan_validate("db", "table", schema, [t2])["steps"]) == 1
+    t3 = {"filter_rows": {"tables": {"excludeTables": ["table"]}, "filter": "colint > 4"}}
+    assert engine.plan_validate("db", "table", schema, [t3])["steps"] == []
+    # mask_field with no matching column is not Suitable (hmac_hasher.go:76-89)
+    assert engine.plan_validate("db", "table", schema, [{"mask_field": {"columns": ["nope"], "maskFunctionHash": {"userDefinedSalt": "x"}}}])["steps"] == []
+
+
+def test_plan_config_errors_are_fatal():
+    schema = [{"name": "c", "type": "int32"}]
+    for trs in ([{"filter_rows": {"filter": 'c = str"'}}], [{"filter_rows": {"filter": "c IN 5"}}],
+                [{"filter_rows": {"filter": "c > 1", "filters": ["c > 2"]}}], [{"no_such_transformer": {}}]):
+        with pytest.raises(engine.EngineError) as ei:
+            engine.plan_validate("db", "t", schema, trs)
+        assert ei.value.rc < 0
+    with pytest.raises(engine.EngineError):
+        engine.plan_validate("db", "t", [{"name": "c", "type": "decimal"}], [])
+
+
+def test_partition_rows():
+    for n in (0, 1, 7, 8, 1000003):
+        for w in (1, 2, 3, 8):
+            parts = dispatch.partition_rows(n, w)
+            assert parts[0][0] == 0 and parts[-1][1] == n and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_round_robin_dispatcher_keeps_order():
+    import time, random
+    seen = [[] for _ in range(3)]
+
+    def mk(i):
+        def w(b):
+            time.sleep(random.random() * 0.01); seen[i].append(b); return b * 10
+        return w
+    d = dispatch.RoundRobinDispatcher([mk(i) for i in range(3)])
+    assert list(d.run(range(50))) == [b * 10 for b in range(50)]
+    assert seen[0] == list(range(0, 50, 3)) and seen[1] == list(range(1, 50, 3))
+    d.close()
+
+
+def test_batch_slice_equals_oracle_on_parts(po):
+    """Row-sharding invariant used for N GPUs: the kept-row count over shards sums to the whole batch's."""
+    batch, schema = workload.make_hits_batch(3000)
+    trs = workload.headline_transformers(workload.counterid_threshold(batch, schema))
+    plan = po.build_plan("public", "hits", schema, trs)
+    whole = po.push_encode(batch, plan, abi.TF_WIRE_CH_NATIVE)
+    parts = [po.push_encode(batch.slice(lo, hi), plan, abi.TF_WIRE_CH_NATIVE) for lo, hi in dispatch.partition_rows(batch.nrows, 4)]
+    assert sum(p.rows_out for p in parts) == whole.rows_out
+
+
+_GLOO_WORKER = r'''
+import os, sys, json
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from transferia_b200 import abi, dispatch, workload
+from oracle import pyoracle as po
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+batch, schema = workload.make_hits_batch(4000)
+trs = workload.headline_transformers(workload.counterid_threshold(batch, schema))
+plan = po.build_plan("public", "hits", schema, trs)
+lo, hi = dispatch.partition_rows(batch.nrows, world)[rank]
+res = po.push_encode(batch.slice(lo, hi), plan, abi.TF_WIRE_CH_NATIVE)
+t = torch.tensor([res.rows_out, hi - lo], dtype=torch.int64)
+dist.all_reduce(t)
+if rank == 0:
+    whole = po.push_encode(batch, plan, abi.TF_WIRE_CH_NATIVE)
+    print(json.dumps({"sum_rows_out": int(t[0]), "sum_rows_in": int(t[1]), "whole_rows_out": whole.rows_out, "nrows": batch.nrows}))
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    """world_size-2 run of the N>1 path on CPU (gloo): shards by rank, no data-path collective, the only
+    exchange is the result count (what bench.py all-reduces)."""
+    script = tmp_path / "w.py"; script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29611", str(script), ROOT], capture_output=True, text=True, timeout=300, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["sum_rows_in"] == d["nrows"] and d["sum_rows_out"] == d["whole_rows_out"]

@@ -1,0 +1,235 @@
+"""Pins the CPU oracle against the reference's own golden vectors and against independent
+implementations available in this image (hashlib, CPython repr, numpy Dragon4, liblz4, pyarrow)."""
+import ctypes as C
+import datetime as dt
+import hashlib
+import hmac
+import math
+import random
+import struct
+
+import numpy as np
+import pytest
+
+from transferia_b200 import abi
+
+
+def _val(po, go, v):
+    if go == "string":
+        return po.make_val(po.OG_STRING, s=v.encode())
+    if go == "bytes":
+        return po.make_val(po.OG_BYTES, s=v.encode())
+    if go in ("int64", "int32", "int16", "int8", "int"):
+        return po.make_val({"int64": po.OG_INT64, "int32": po.OG_INT32, "int16": po.OG_INT16, "int8": po.OG_INT8, "int": po.OG_INT}[go], i=v)
+    if go in ("uint64", "uint32", "uint16", "uint8"):
+        return po.make_val({"uint64": po.OG_UINT64, "uint32": po.OG_UINT32, "uint16": po.OG_UINT16, "uint8": po.OG_UINT8}[go], u=v)
+    if go == "bool":
+        return po.make_val(po.OG_BOOL, i=1 if v else 0)
+    if go == "float64":
+        return po.make_val(po.OG_FLOAT64, f=v)
+    if go == "float32":
+        return po.make_val(po.OG_FLOAT32, f=float(np.float32(v)))
+    if go == "duration":
+        return po.make_val(po.OG_DURATION, i=v)
+    if go == "time":
+        t = dt.datetime.fromisoformat(v.replace("Z", "+00:00"))
+        us = (t - dt.datetime(1970, 1, 1, tzinfo=dt.timezone.utc)) // dt.timedelta(microseconds=1)
+        return po.make_val(po.OG_TIME, i=us // 1_000_000, nsec=(us % 1_000_000) * 1000)
+    if go == "nil":
+        return po.make_val(po.OG_NIL)
+    raise KeyError(go)
+
+
+def test_mask_golden_digests(po, goldens):
+    """pkg/transformer/registry/mask/gotest/canondata/result.json: all 11 digests."""
+    salt = goldens["mask"]["salt"].encode()
+    assert len(goldens["mask"]["cases"]) == 11
+    for c in goldens["mask"]["cases"]:
+        text = po.serialize_to_string(_val(po, c["go"], c["value"]), abi.YT_NAME_TO_TF[c["type"]])
+        assert po.hmac_hex(salt, text) == c["digest"], (c, text)
+        assert hmac.new(salt, text, hashlib.sha256).hexdigest() == c["digest"]
+
+
+def test_to_string_forms(po):
+    """to_string.go:145-171 text forms (mask golden inputs + to_string_test.go:16-194 style cases)."""
+    s = lambda go, v, t: po.serialize_to_string(_val(po, go, v), abi.YT_NAME_TO_TF[t]).decode()
+    assert s("float64", 123.123, "double") == "123.123"
+    assert s("float32", 312.321, "float") == "312.321"
+    assert s("duration", 60_000_000_000, "date") == "1m0s"
+    assert s("time", "1703-01-02T00:00:00Z", "date") == "1703-01-02"
+    assert s("time", "2022-02-03T04:05:06.123456Z", "timestamp") == "2022-02-03T04:05:06.123456Z"
+    assert s("time", "2022-02-03T04:05:06Z", "datetime") == "2022-02-03T04:05:06Z"
+    assert s("bool", True, "boolean") == "true"
+    assert s("int8", -3, "int8") == "-3"
+    assert s("uint32", 12345, "uint32") == "12345"
+    assert s("nil", None, "int32") == "<nil>"
+    assert s("nil", None, "any") == "null"
+    assert s("string", 'a"b<c', "any") == '"a\\"b\\u003cc"'
+    assert s("bytes", "raw", "string") == "raw"
+
+
+def test_float_shortest_matches_repr(po):
+    """strconv shortest digits == CPython repr digits (both: shortest round-trip, closest)."""
+    rnd = random.Random(7)
+    vals = [0.1, 0.3, 1 / 3, 1e21, 1e22, 1e23, 5e-324, 2.2250738585072014e-308, 1.7976931348623157e308, 9007199254740993.0, 123456.7, 1234567.0, 1e-5, 1e-4]
+    vals += [struct.unpack("<d", struct.pack("<Q", rnd.getrandbits(64) & 0x7FEFFFFFFFFFFFFF))[0] for _ in range(3000)]
+    vals += [rnd.random() * 10 ** rnd.randint(-20, 20) for _ in range(2000)]
+    for v in vals:
+        if v == 0 or math.isinf(v) or math.isnan(v):
+            continue
+        got = po.fmt_float64(v, 1)         # 'f', -1: plain decimal
+        assert float(got) == v, (v, got)
+        r = repr(v)
+        mant = r.split("e")[0].replace(".", "").lstrip("0").rstrip("0") or "0"
+        assert got.replace(".", "").strip("0") == mant.strip("0"), (v, got, r)
+
+
+def test_float32_shortest_matches_numpy(po):
+    rnd = np.random.default_rng(5)
+    bits = rnd.integers(1, 0x7F7FFFFF, 3000, dtype=np.uint32)
+    for f in bits.view(np.float32):
+        want = np.format_float_positional(f, unique=True, trim="-")
+        assert po.fmt_float32(f, 1) == want, (f, po.fmt_float32(f, 1), want)
+
+
+def test_float_layouts(po):
+    """%v ('g' shortest, exponent when exp < -4 || exp >= 21? no: >= 6... eprec = 6), 'f', encoding/json."""
+    f = po.fmt_float64
+    assert f(1000000.0) == "1e+06" and f(123456.0) == "123456" and f(1234567.0) == "1.234567e+06"
+    assert f(0.0001) == "0.0001" and f(0.00001) == "1e-05" and f(0.0) == "0" and f(-0.0) == "-0"
+    assert f(float("inf")) == "+Inf" and f(float("-inf")) == "-Inf" and f(float("nan")) == "NaN"
+    assert f(1e21, 2) == "1e+21" and f(1e20, 2) == "100000000000000000000" and f(1e-7, 2) == "1e-7" and f(0.000001, 2) == "0.000001"
+    assert f(123456789.0, 1) == "123456789" and f(1e-7, 1) == "0.0000001"
+
+
+def test_duration_and_time_text(po):
+    assert po.fmt_duration(0) == "0s" and po.fmt_duration(1) == "1ns" and po.fmt_duration(1500) == "1.5µs"
+    assert po.fmt_duration(1_000_000) == "1ms" and po.fmt_duration(3600 * 10**9 + 5 * 10**8) == "1h0m0.5s" and po.fmt_duration(-60 * 10**9) == "-1m0s"
+    for y, m, d, hh in ((1703, 1, 2, 0), (1970, 1, 1, 0), (2013, 7, 14, 21), (2106, 1, 1, 0), (1, 1, 1, 0), (1969, 12, 31, 23)):
+        t = dt.datetime(y, m, d, hh, 44, 35, tzinfo=dt.timezone.utc)
+        sec = (t - dt.datetime(1970, 1, 1, tzinfo=dt.timezone.utc)) // dt.timedelta(seconds=1)
+        assert po.fmt_rfc3339nano(sec, 0) == t.strftime("%Y-%m-%dT%H:%M:%SZ").replace(str(y) + "-", "%04d-" % y, 1)
+    assert po.fmt_rfc3339nano(0, 120_000_000) == "1970-01-01T00:00:00.12Z"
+
+
+def test_filter_rows_reference_tables(po, goldens):
+    """filter_rows_test.go:47-560 input/expected tables through parse_filter + matchValue."""
+    for case in goldens["filter_rows"]:
+        terms = po.parse_filter(case["filter"])
+        kept, nerr = [], 0
+        for item in case["input"]:
+            go, v = (item if case["go"] == "mixed" else (case["go"], item))
+            val = _val(po, go, v)
+            ok, err = True, False
+            for t in terms:
+                rc, m = po.match_value(val, t)
+                if rc:
+                    err = True
+                    assert rc == case.get("error_code", rc)
+                    break
+                if not m:
+                    ok = False
+                    break
+            if err:
+                nerr += 1
+            elif ok:
+                kept.append(v)
+        assert kept == case["expected"], (case["name"], kept)
+        assert nerr == case["errors"], case["name"]
+
+
+def test_filter_null_semantics(po):
+    """TestNullFiltering filter_rows_test.go:336-365."""
+    terms = po.parse_filter("column1 != NULL AND column2 = NULL")
+    rows = [("abc", 128), ("str", None), (None, 32), (None, None)]
+    keep = []
+    for s, i in rows:
+        v1 = _val(po, "nil", None) if s is None else _val(po, "string", s)
+        v2 = _val(po, "nil", None) if i is None else _val(po, "int", i)
+        r1 = po.match_value(v1, terms[0]); r2 = po.match_value(v2, terms[1])
+        keep.append(r1 == (0, True) and r2 == (0, True))
+    assert keep == [False, True, False, False]
+
+
+def test_filter_grammar_errors_and_forms(po):
+    assert [(t.attribute, t.op, t.vtype) for t in po.parse_filter("a>1 and b NOT  IN (1.5,2.5) AND c ~ 'x'")] == [("a", po.OP_GT, 1), ("b", po.OP_NOTIN, 18), ("c", po.OP_MATCH, 4)]
+    assert po.parse_filter("") == []
+    for bad in ('column = str"', "a IN 5", "a = (1,2)", "a > NULL", "a IN (1, 'x')", "a = ", "= 1"):
+        with pytest.raises(po.FilterSyntaxError):
+            po.parse_filter(bad)
+    (t,) = po.parse_filter("ts >= 1990-07-22T00:00:00.001+04:00")
+    want = dt.datetime(1990, 7, 21, 20, 0, 0, 1000, tzinfo=dt.timezone.utc)
+    assert t.value == (want - dt.datetime(1970, 1, 1, tzinfo=dt.timezone.utc)) // dt.timedelta(microseconds=1)
+    (t,) = po.parse_filter("d = 2020-02-29")
+    assert t.value == 1582934400 * 10**6
+
+
+def test_sha_hmac_vs_hashlib(po):
+    rnd = random.Random(3)
+    for n in (0, 1, 55, 56, 63, 64, 65, 119, 120, 1000):
+        msg = bytes(rnd.getrandbits(8) for _ in range(n))
+        for klen in (0, 5, 64, 65, 200):
+            key = bytes(rnd.getrandbits(8) for _ in range(klen))
+            assert po.hmac_hex(key, msg) == hmac.new(key, msg, hashlib.sha256).hexdigest()
+
+
+def test_lz4_oracle_vs_liblz4_and_pyarrow(po):
+    import pyarrow as pa
+    lz = C.CDLL("liblz4.so.1")
+    rnd = np.random.default_rng(11)
+    samples = [b"", b"a", b"abcabcabcabcabcabcabcabc" * 50, bytes(rnd.integers(0, 256, 5000, dtype=np.uint8)), bytes(rnd.integers(0, 4, 70000, dtype=np.uint8)), b"\0" * 100000]
+    codec = pa.Codec("lz4_raw")
+    for s in samples:
+        c = po.lz4_compress(s)
+        assert po.lz4_decompress(c, len(s)) == s
+        dst = C.create_string_buffer(max(1, len(s)))
+        assert lz.LZ4_decompress_safe(c, dst, len(c), len(s)) == len(s) and dst.raw[:len(s)] == s
+        if s:
+            assert codec.decompress(c, decompressed_size=len(s)).to_pybytes() == s
+        # and the other direction: liblz4's stream through the oracle decoder
+        cap = lz.LZ4_compressBound(len(s)); buf = C.create_string_buffer(max(1, cap))
+        n = lz.LZ4_compress_default(s, buf, len(s), cap)
+        assert po.lz4_decompress(buf.raw[:n], len(s)) == s
+
+
+def test_native_block_bytes_hand_computed(po):
+    """ClickHouse native block, revision 54460, two columns, two rows — bytes written out by hand from the
+    protocol description (block info, counts, name/type strings, custom-serialization byte, data)."""
+    schema = [{"name": "id", "type": "int32", "required": True}, {"name": "s", "type": "utf8", "required": False}]
+    b = abi.Batch(2, [abi.fixed_to_column(abi.TF_INT32, [7, -2]), abi.strings_to_column(abi.TF_UTF8, [b"ab", None])])
+    plan = po.build_plan("db", "t", schema, [])
+    r = po.push_encode(b, plan, abi.TF_WIRE_CH_NATIVE)
+    want = bytes([1, 0, 2, 0xFF, 0xFF, 0xFF, 0xFF, 0, 2, 2]) \
+        + b"\x02id\x05Int32\x00" + struct.pack("<ii", 7, -2) \
+        + b"\x01s\x10Nullable(String)\x00" + b"\x00\x01" + b"\x02ab" + b"\x00"
+    assert r.raw == want
+    fr = po.push_encode(b, plan, abi.TF_WIRE_CH_NATIVE_LZ4)
+    assert fr.wire[16] == 0x82 and struct.unpack_from("<II", fr.wire, 17) == (len(fr.wire) - 16, len(want))
+    raw, nf = po.ch_decode_frames(fr.wire)
+    assert raw == want and nf == 1
+    lo, hi = po.cityhash128(fr.wire[16:])
+    assert struct.unpack_from("<QQ", fr.wire, 0) == (lo, hi)
+
+
+def test_ch_types(po):
+    """columntypes.ToChType types.go:210-248 + Nullable(!required) sink_table.go:229-235."""
+    m = {"int8": "Int8", "uint64": "UInt64", "float": "Float32", "double": "Float64", "boolean": "UInt8", "string": "String", "utf8": "String",
+         "any": "String", "date": "Date", "datetime": "DateTime", "timestamp": "DateTime64(6)", "interval": "Int64"}
+    for yt, ch in m.items():
+        assert po.ch_type({"name": "c", "type": yt, "required": True}) == ch
+        assert po.ch_type({"name": "c", "type": yt, "required": False}) == f"Nullable({ch})"
+
+
+def test_date_clamp_and_units(po):
+    """columntypes/types.go:15-29: date/datetime clamped to [1970-01-01, 2106-01-01], timestamp not."""
+    secs = [-86400, 0, 86399, 4291747200 - 1, 4291747200, 4291747200 + 86400 * 400]
+    schema = [{"name": "d", "type": "date", "required": True}, {"name": "dt", "type": "datetime", "required": True}, {"name": "ts", "type": "timestamp", "required": True}]
+    b = abi.Batch(len(secs), [abi.fixed_to_column(abi.TF_DATE, secs), abi.fixed_to_column(abi.TF_DATETIME, secs), abi.fixed_to_column(abi.TF_TIMESTAMP, secs, nanos=[999] * len(secs))])
+    r = po.push_encode(b, po.build_plan("db", "t", schema, []), abi.TF_WIRE_CH_NATIVE)
+    tail = r.raw[r.raw.index(b"\x01d\x04Date\x00") + 8:]
+    days = struct.unpack_from("<6H", tail, 0)
+    assert days == (0, 0, 0, 49672, 49673, 49673)
+    off = tail.index(b"\x02dt\x08DateTime\x00") + 13
+    assert struct.unpack_from("<6I", tail, off) == (0, 0, 86399, 4291747199, 4291747200, 4291747200)
+    off = tail.index(b"DateTime64(6)\x00") + 14
+    assert struct.unpack_from("<6q", tail, off) == tuple(s * 10**6 for s in secs)

@@ -1,8 +1,8 @@
 """ctypes view of include/tfgpu.h: the columnar batch that crosses the C-ABI.
 
-This module only describes memory; it computes nothing.  It is shared by the engine
-binding (transferia_b200.engine) and by the test oracle binding (oracle/pyoracle.py) because
-both consume the same `tf_batch` struct.
+This module only describes memory; it computes nothing.  The engine binding
+(transferia_b200.engine) uses it, and so do the tests' CPU checker and the workload generator,
+because they all speak the same `tf_batch` struct.
 """
 from __future__ import annotations
 
@@ -151,6 +151,16 @@ class Batch:
                                    aux=None if c.aux is None else np.ascontiguousarray(c.aux[lo:hi])))
         kinds = None if self.kinds is None else np.ascontiguousarray(self.kinds[lo:hi])
         return Batch(hi - lo, cols, kinds)
+
+    def pin(self) -> "Batch":
+        """Same batch with every buffer in page-locked host memory (what the cgo shim hands over)."""
+        import torch
+        def pn(a):
+            if a is None:
+                return None
+            return torch.from_numpy(np.ascontiguousarray(a).reshape(-1).view(np.uint8)).pin_memory()
+        cols = [Column(c.type, pn(c.values), pn(c.validity), pn(c.offsets), pn(c.heap), pn(c.aux)) for c in self.columns]
+        return Batch(self.nrows, cols, pn(self.kinds), TF_MEM_HOST)
 
     def to_device(self, device="cuda:0", pinned_first: bool = False) -> "Batch":
         """Copy every buffer to HBM with torch (plumbing only)."""

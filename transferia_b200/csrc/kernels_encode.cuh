@@ -162,16 +162,16 @@ struct FilterArgs {
     const DFilterStep* steps; int nsteps;
     const uint32_t* expr_off;      // term ranges per expression (global expr index)
     const DTerm* terms; const uint8_t* blob;
-    uint8_t* keep; uint8_t* errcode; uint8_t* errstep; uint32_t* blockcnt;
+    uint8_t* keep; uint8_t* errcode; uint8_t* errstep; uint32_t* blockcnt; DState* st;
 };
 
 // FilterRowsTransformer.Apply (filter_rows.go:99-130): one thread per row.
 __global__ void __launch_bounds__(256) k_filter(FilterArgs a) {
-    __shared__ uint32_t s_cnt;
-    if (threadIdx.x == 0) s_cnt = 0;
+    __shared__ uint32_t s_cnt, s_err;
+    if (threadIdx.x == 0) { s_cnt = 0; s_err = 0; }
     __syncthreads();
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool keep = false;
+    bool keep = false, is_err = false;
     if (r < a.nrows) {
         keep = true; int err = 0, estep = 0;
         const int kind = a.kinds ? a.kinds[r] : TF_KIND_INSERT;
@@ -195,17 +195,17 @@ __global__ void __launch_bounds__(256) k_filter(FilterArgs a) {
             if (!any) keep = false;
         }
         a.keep[r] = keep ? 1 : 0;
-        a.errcode[r] = (uint8_t)err; a.errstep[r] = (uint8_t)estep;
+        a.errcode[r] = (uint8_t)err; a.errstep[r] = (uint8_t)estep; is_err = err != 0;
     }
     const unsigned b = __ballot_sync(0xffffffffu, keep);
-    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&s_cnt, __popc(b));
+    const unsigned be = __ballot_sync(0xffffffffu, is_err);
+    if ((threadIdx.x & 31) == 0) { if (b) atomicAdd(&s_cnt, __popc(b)); if (be) atomicAdd(&s_err, __popc(be)); }
     __syncthreads();
-    if (threadIdx.x == 0) a.blockcnt[blockIdx.x] = s_cnt;
+    if (threadIdx.x == 0) { a.blockcnt[blockIdx.x] = s_cnt; if (s_err) atomicAdd((unsigned long long*)&a.st->n_errors, (unsigned long long)s_err); }
 }
 
 // exclusive scan of per-block kept counts (single block), total -> state.n_kept
-__global__ void __launch_bounds__(1024) k_scan_blockcnt(const uint32_t* blockcnt, uint32_t* blockoff, uint32_t nblocks, DState* st,
-                                                       const uint8_t* errcode, uint64_t nrows) {
+__global__ void __launch_bounds__(1024) k_scan_blockcnt(const uint32_t* blockcnt, uint32_t* blockoff, uint32_t nblocks, DState* st) {
     __shared__ uint32_t sm[33];
     uint32_t carry = 0;
     for (uint32_t base = 0; base < nblocks; base += blockDim.x) {
@@ -216,11 +216,6 @@ __global__ void __launch_bounds__(1024) k_scan_blockcnt(const uint32_t* blockcnt
         carry += tot;
     }
     if (threadIdx.x == 0) st->n_kept = carry;
-    // count error rows (rare): strided sum
-    uint32_t ne = 0;
-    for (uint64_t r = threadIdx.x; r < nrows; r += blockDim.x) ne += errcode[r] != 0;
-    uint32_t tot; block_excl_scan(ne, &tot, sm);
-    if (threadIdx.x == 0) st->n_errors = tot;
 }
 
 // sel[j] = index of the j-th kept row (order preserved)

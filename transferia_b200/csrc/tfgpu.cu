@@ -67,6 +67,17 @@ struct tfgpu_engine {
     uint32_t* tile_sum = nullptr; uint64_t* tile_base = nullptr; uint32_t* comp_size = nullptr; uint64_t* wire_off = nullptr;
     uint64_t last_nrows = 0; bool last_has_filter = false; int last_wire_fmt = 0;
     uint8_t* pinned = nullptr; size_t pinned_cap = 0;
+    // optional per-kernel CUDA-event timing of the last call (bench roofline)
+    bool prof_on = false; std::vector<cudaEvent_t> prof_ev; std::vector<const char*> prof_names; int prof_n = 0;
+    std::string prof_json;
+    void prof_begin(const char* name, cudaStream_t s) {
+        launches++;
+        if (!prof_on) return;
+        while ((int)prof_ev.size() < 2 * (prof_n + 1)) { cudaEvent_t ev; cudaEventCreate(&ev); prof_ev.push_back(ev); }
+        if ((int)prof_names.size() <= prof_n) prof_names.resize(prof_n + 1);
+        prof_names[prof_n] = name; cudaEventRecord(prof_ev[2 * prof_n], s);
+    }
+    void prof_end(cudaStream_t s) { if (!prof_on) return; cudaEventRecord(prof_ev[2 * prof_n + 1], s); prof_n++; }
 };
 
 struct tfgpu_result {
@@ -224,14 +235,15 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
     }
     CK(cudaMemcpyAsync(e->d_cols, hc.data(), sizeof(DCol) * nc, cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(e->d_state, 0, sizeof(DState), s));
+    e->prof_n = 0;
     const bool has_filter = pd.n_fsteps > 0;
     e->last_nrows = n; e->last_has_filter = has_filter; e->last_wire_fmt = wire_fmt;
     const uint32_t nb = (uint32_t)((n + 255) / 256);
     if (has_filter && n) {
-        FilterArgs fa{e->d_cols, dev_kinds, n, pd.d_fsteps, pd.n_fsteps, pd.d_expr_off, pd.d_terms, pd.d_blob, e->keep, e->errcode, e->errstep, e->blockcnt};
-        k_filter<<<nb, 256, 0, s>>>(fa); e->launches++;
-        k_scan_blockcnt<<<1, 1024, 0, s>>>(e->blockcnt, e->blockoff, nb, e->d_state, e->errcode, n); e->launches++;
-        k_compact_sel<<<nb, 256, 0, s>>>(e->keep, e->blockoff, n, e->sel); e->launches++;
+        FilterArgs fa{e->d_cols, dev_kinds, n, pd.d_fsteps, pd.n_fsteps, pd.d_expr_off, pd.d_terms, pd.d_blob, e->keep, e->errcode, e->errstep, e->blockcnt, e->d_state};
+        e->prof_begin("k_filter", s); k_filter<<<nb, 256, 0, s>>>(fa); e->prof_end(s);
+        e->prof_begin("k_scan_blockcnt", s); k_scan_blockcnt<<<1, 1024, 0, s>>>(e->blockcnt, e->blockoff, nb, e->d_state); e->prof_end(s);
+        e->prof_begin("k_compact_sel", s); k_compact_sel<<<nb, 256, 0, s>>>(e->keep, e->blockoff, n, e->sel); e->prof_end(s);
     }
     const uint32_t* sel = (has_filter && n) ? e->sel : nullptr;
     const uint32_t ntiles = (uint32_t)((n + TF_STR_TILE - 1) / TF_STR_TILE);
@@ -241,32 +253,32 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         DState init; std::memset(&init, 0, sizeof init); init.n_kept = n;
         CK(cudaMemcpyAsync(e->d_state, &init, sizeof init, cudaMemcpyHostToDevice, s));
     }
-    if (pd.n_str && ntiles) { k_str_sizes<<<dim3(ntiles, pd.n_str), 256, 0, s>>>(ea); e->launches++; }
+    if (pd.n_str && ntiles) { e->prof_begin("k_str_sizes", s); k_str_sizes<<<dim3(ntiles, pd.n_str), 256, 0, s>>>(ea); e->prof_end(s); }
     LayoutArgs la{e->d_cols, (int)nc, pd.d_str_slots, pd.n_str, e->tile_sum, e->tile_base, sz.ntiles_cap, pd.d_col_headers, pd.d_col_header_off,
                   e->raw.p, e->d_state, n, 1, e->frame_bytes};
-    k_layout<<<1, 1024, 0, s>>>(la); e->launches++;
+    e->prof_begin("k_layout", s); k_layout<<<1, 1024, 0, s>>>(la); e->prof_end(s);
     if (n) {
         if (pd.n_fixed_slots) {
             // widest stream is 8 bytes per row: words = 2n (+1 for misalignment)
             const uint32_t gx = (uint32_t)((2 * n + 2 + TF_FIX_TILE_WORDS - 1) / TF_FIX_TILE_WORDS);
             EncodeArgs fa = ea; fa.slots = pd.d_fixed_slots;
-            k_encode_fixed<<<dim3(gx, pd.n_fixed_slots), 256, 0, s>>>(fa); e->launches++;
+            e->prof_begin("k_encode_fixed", s); k_encode_fixed<<<dim3(gx, pd.n_fixed_slots), 256, 0, s>>>(fa); e->prof_end(s);
         }
-        if (pd.n_str) { k_encode_str<<<dim3(ntiles, pd.n_str), 256, 0, s>>>(ea); e->launches++; }
+        if (pd.n_str) { e->prof_begin("k_encode_str", s); k_encode_str<<<dim3(ntiles, pd.n_str), 256, 0, s>>>(ea); e->prof_end(s); }
         if (pd.n_mask_cols) {
             MaskArgs ma{e->d_cols, pd.d_mask_slots, pd.d_mask_keys, sel, e->d_state, e->raw.p};
-            k_mask_encode<<<dim3((uint32_t)((n + 127) / 128), pd.n_mask_cols), 128, 0, s>>>(ma); e->launches++;
+            e->prof_begin("k_mask_encode", s); k_mask_encode<<<dim3((uint32_t)((n + 127) / 128), pd.n_mask_cols), 128, 0, s>>>(ma); e->prof_end(s);
         }
     }
     if (lz) {
         Lz4Args za{e->raw.p, e->d_state, e->slots.p, stride, e->comp_size, e->frame_bytes};
         const size_t smem = e->frame_bytes + 16 + 2 * (size_t)e->frame_bytes + (2u << LZ_HASH_BITS) + e->frame_bytes / 8 + 48 * 4;
         const uint32_t grid = (uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * 2);
-        k_lz4_frames<<<grid, LZ_THREADS, smem, s>>>(za); e->launches++;
+        e->prof_begin("k_lz4_frames", s); k_lz4_frames<<<grid, LZ_THREADS, smem, s>>>(za); e->prof_end(s);
         FrameArgs fa{e->slots.p, stride, e->comp_size, e->d_state, e->frame_bytes, e->wire_off, e->wire.p};
-        k_frame_seal<<<(uint32_t)((sz.n_frames_max + 127) / 128), 128, 0, s>>>(fa); e->launches++;
-        k_frame_scan<<<1, 1024, 0, s>>>(fa); e->launches++;
-        k_wire_gather<<<(uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * 8), 256, 0, s>>>(fa); e->launches++;
+        e->prof_begin("k_frame_seal", s); k_frame_seal<<<(uint32_t)((sz.n_frames_max + 127) / 128), 128, 0, s>>>(fa); e->prof_end(s);
+        e->prof_begin("k_frame_scan", s); k_frame_scan<<<1, 1024, 0, s>>>(fa); e->prof_end(s);
+        e->prof_begin("k_wire_gather", s); k_wire_gather<<<(uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * 8), 256, 0, s>>>(fa); e->prof_end(s);
     }
     CK(cudaGetLastError());
 }
@@ -315,6 +327,7 @@ int tfgpu_engine_destroy(tfgpu_engine* e) {
     if (e->d_state) cudaFree(e->d_state);
     if (e->d_cols) cudaFree(e->d_cols);
     if (e->pinned) cudaFreeHost(e->pinned);
+    for (auto ev : e->prof_ev) cudaEventDestroy(ev);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
     return TF_OK;
@@ -322,6 +335,21 @@ int tfgpu_engine_destroy(tfgpu_engine* e) {
 
 const char* tfgpu_last_error(const tfgpu_engine* e) { return e ? e->last_error.c_str() : "null engine"; }
 uint64_t tfgpu_engine_launch_count(const tfgpu_engine* e) { return e ? e->launches : 0; }
+
+int tfgpu_profile_enable(tfgpu_engine* e, int on) { if (!e) return TF_E_FATAL_ARG; e->prof_on = on != 0; e->prof_n = 0; return TF_OK; }
+
+const char* tfgpu_profile_read(tfgpu_engine* e) {
+    if (!e) return nullptr;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    std::string j = "[";
+    for (int i = 0; i < e->prof_n; i++) {
+        float ms = 0; cudaEventElapsedTime(&ms, e->prof_ev[2 * i], e->prof_ev[2 * i + 1]);
+        char b[160]; snprintf(b, sizeof b, "%s{\"name\":\"%s\",\"ms\":%.6f}", i ? "," : "", e->prof_names[i], ms); j += b;
+    }
+    e->prof_json = j + "]";
+    return e->prof_json.c_str();
+}
 
 int tfgpu_engine_set_stream(tfgpu_engine* e, void* cuda_stream) {
     if (!e) return TF_E_FATAL_ARG;
@@ -343,6 +371,22 @@ int tfgpu_plan(tfgpu_engine* e, const char* ns, const char* name, const char* sc
     } catch (const tfplan::FatalError& f) { return fail(e, f.code, f.what()); }
     catch (const CudaError& c) { return cuda_fail(e, c); }
     catch (const std::exception& x) { return fail(e, TF_E_FATAL_CONFIG, x.what()); }
+}
+
+// Host-only: build the plan (Suitable / ResultSchema chain, filter grammar, ClickHouse types) without touching a
+// device, so a transfer's YAML can be validated where no GPU is present (cmd/trcli validate does the same for the
+// reference's transformers: cmd/trcli/config/model.go:57-72).
+int tfgpu_plan_validate(const char* ns, const char* name, const char* schema_json, const char* transformers_json,
+                        const char* sink_json, char* describe_out, uint64_t cap, char* err_out, uint64_t err_cap) {
+    auto put = [](char* dst, uint64_t cap_, const std::string& s) { if (dst && cap_) { size_t n = s.size() < cap_ - 1 ? s.size() : cap_ - 1; std::memcpy(dst, s.data(), n); dst[n] = 0; } };
+    if (!schema_json || !name) return TF_E_FATAL_ARG;
+    try {
+        tfplan::Plan pl = tfplan::build_plan(ns ? ns : "", name, schema_json, transformers_json ? transformers_json : "", sink_json ? sink_json : "");
+        if (describe_out && pl.describe.size() + 1 > cap) { put(err_out, err_cap, "describe buffer too small"); return TF_E_FATAL_ARG; }
+        put(describe_out, cap, pl.describe);
+        return TF_OK;
+    } catch (const tfplan::FatalError& f) { put(err_out, err_cap, f.what()); return f.code; }
+    catch (const std::exception& x) { put(err_out, err_cap, x.what()); return TF_E_FATAL_CONFIG; }
 }
 
 const char* tfgpu_plan_describe(tfgpu_engine* e, int plan_id) {
@@ -444,7 +488,12 @@ int tfgpu_push_encode(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch
         const bool lz = wire_fmt == TF_WIRE_CH_NATIVE_LZ4;
         r->n_frames = lz ? st.n_frames : 0;
         r->bytes_len = lz ? st.wire_total : st.raw_total;
-        CK(cudaMallocHost(&r->bytes, r->bytes_len ? r->bytes_len : 1)); r->bytes_pinned = true;
+        if (e->pinned_cap < r->bytes_len + 64) {   // grow-only pinned landing buffer, owned by the engine
+            if (e->pinned) { CK(cudaFreeHost(e->pinned)); e->pinned = nullptr; e->pinned_cap = 0; }
+            const size_t want = align_up(r->bytes_len + r->bytes_len / 4 + 4096, 1 << 20);
+            CK(cudaMallocHost(&e->pinned, want)); e->pinned_cap = want;
+        }
+        r->bytes = e->pinned; r->bytes_pinned = false;
         CK(cudaMemcpyAsync(r->bytes, lz ? e->wire.p : e->raw.p, r->bytes_len, cudaMemcpyDeviceToHost, s));
         if (st.n_errors) {
             std::vector<uint8_t> ec(n), es(n);
@@ -476,7 +525,7 @@ uint64_t tfgpu_result_raw_len(const tfgpu_result* r) { return r ? r->raw_len : 0
 uint64_t tfgpu_result_n_frames(const tfgpu_result* r) { return r ? r->n_frames : 0; }
 void tfgpu_result_release(tfgpu_result* r) {
     if (!r) return;
-    if (r->bytes) { if (r->bytes_pinned) cudaFreeHost(r->bytes); else free(r->bytes); }
+    if (r->bytes && r->bytes_pinned) cudaFreeHost(r->bytes);   // otherwise the engine's landing buffer
     for (auto p : r->owned) free(p);
     delete r;
 }

@@ -54,6 +54,7 @@ def load_library():
     L.tfgpu_engine_set_stream.argtypes = [vp, vp]
     L.tfgpu_plan.argtypes = [vp, cp, cp, cp, cp, cp, C.POINTER(C.c_int)]
     L.tfgpu_plan_describe.argtypes = [vp, i]; L.tfgpu_plan_describe.restype = cp
+    L.tfgpu_plan_validate.argtypes = [cp, cp, cp, cp, cp, cp, u64, cp, u64]
     L.tfgpu_push_columns.argtypes = [vp, i, C.POINTER(abi.TfBatch), C.POINTER(vp)]
     L.tfgpu_push_encode.argtypes = [vp, i, i, C.POINTER(abi.TfBatch), C.POINTER(vp)]
     L.tfgpu_push_encode_resident.argtypes = [vp, i, i, C.POINTER(abi.TfBatch)]
@@ -66,18 +67,32 @@ def load_library():
     L.tfgpu_result_bytes.argtypes = [vp]; L.tfgpu_result_bytes.restype = vp
     L.tfgpu_result_release.argtypes = [vp]; L.tfgpu_result_release.restype = None
     L.tfgpu_engine_launch_count.argtypes = [vp]; L.tfgpu_engine_launch_count.restype = u64
+    L.tfgpu_profile_enable.argtypes = [vp, i]
+    L.tfgpu_profile_read.argtypes = [vp]; L.tfgpu_profile_read.restype = cp
     _lib = L
     return L
 
 
 EXPORTED_SYMBOLS = [
     "tfgpu_version", "tfgpu_engine_create", "tfgpu_engine_destroy", "tfgpu_last_error", "tfgpu_engine_set_stream",
-    "tfgpu_plan", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_push_encode_resident",
+    "tfgpu_plan", "tfgpu_plan_validate", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_push_encode_resident",
     "tfgpu_resident_stats", "tfgpu_resident_fetch", "tfgpu_result_rows_in", "tfgpu_result_rows_out",
     "tfgpu_result_n_errors", "tfgpu_result_errors", "tfgpu_result_batch", "tfgpu_result_bytes",
     "tfgpu_result_bytes_len", "tfgpu_result_raw_len", "tfgpu_result_n_frames", "tfgpu_result_release",
-    "tfgpu_engine_launch_count",
+    "tfgpu_engine_launch_count", "tfgpu_profile_enable", "tfgpu_profile_read",
 ]
+
+
+def plan_validate(namespace: str, name: str, schema, transformers=None, sink=None) -> dict:
+    """Host-only plan construction (no GPU needed): returns the describe JSON or raises EngineError."""
+    L = load_library()
+    sj = schema if isinstance(schema, str) else json.dumps([{k: v for k, v in c.items() if not k.startswith("_")} for c in schema])
+    out = C.create_string_buffer(1 << 20); err = C.create_string_buffer(4096)
+    rc = L.tfgpu_plan_validate(namespace.encode(), name.encode(), sj.encode(), json.dumps(transformers or []).encode(),
+                               None if sink is None else json.dumps(sink).encode(), out, len(out), err, len(err))
+    if rc != 0:
+        raise EngineError(rc, err.value.decode(errors="replace"))
+    return json.loads(out.value.decode())
 
 
 @dataclass
@@ -165,6 +180,14 @@ class Engine:
         buf = (C.c_uint8 * max(1, nbytes))()
         self._check(self._L.tfgpu_resident_fetch(self._h, what, buf, nbytes))
         return bytes(buf[:nbytes])
+
+    def profile_enable(self, on: bool = True):
+        self._check(self._L.tfgpu_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self) -> list:
+        """[{name, ms}] per kernel of the last call (synchronises the stream)."""
+        s = self._L.tfgpu_profile_read(self._h)
+        return json.loads(s.decode()) if s else []
 
     def launch_count(self) -> int:
         return int(self._L.tfgpu_engine_launch_count(self._h))
