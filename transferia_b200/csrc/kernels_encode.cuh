@@ -239,7 +239,9 @@ struct LayoutArgs {
     uint64_t nrows_in; int has_sel; uint32_t frame_bytes;
 };
 
-#define TF_STR_TILE 1024
+#define TF_STR_TILE 256
+#define TF_STR_THREADS 256
+#define TF_STR_STAGE 16384   // bytes of shared memory staging per tile in k_encode_str
 
 // One block: per-string-column prefix over tiles, then column offsets, then the block / column headers.
 // Block layout (clickhouse-go/v2 v2.46.0 lib/proto/block.go, revision 54460):
@@ -389,44 +391,63 @@ __device__ __forceinline__ uint32_t str_len(const DCol& c, const uint32_t* sel, 
 }
 
 // encoded size (LEB128 length + payload) of every tile of TF_STR_TILE kept rows, for every String column
-__global__ void __launch_bounds__(256) k_str_sizes(EncodeArgs a) {
+__global__ void __launch_bounds__(TF_STR_THREADS) k_str_sizes(EncodeArgs a) {
     __shared__ uint32_t sm[33];
     const DCol c = a.cols[a.slots[blockIdx.y]];
     const uint64_t n = a.st->n_kept;
     const uint64_t j0 = (uint64_t)blockIdx.x * TF_STR_TILE;
     if (j0 >= n) return;
-    uint32_t sum = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        uint64_t r; const uint32_t L = str_len(c, a.sel, j0 + 4 * threadIdx.x + k, n, r);
-        if (L != 0xffffffffu) sum += L + varint_len(L);
-    }
-    uint32_t tot; block_excl_scan(sum, &tot, sm);
+    uint64_t r; const uint32_t L = str_len(c, a.sel, j0 + threadIdx.x, n, r);
+    uint32_t tot; block_excl_scan(L != 0xffffffffu ? L + varint_len(L) : 0u, &tot, sm);
     if (threadIdx.x == 0) a.tile_sum[(size_t)c.str_slot * a.ntiles_cap + blockIdx.x] = tot;
 }
 
-// LEB128 length + bytes for 4 consecutive kept rows per thread; neighbouring threads own neighbouring
-// rows, so a warp reads one contiguous span of the source heap and writes one contiguous span of the block.
-__global__ void __launch_bounds__(256) k_encode_str(EncodeArgs a) {
+// LEB128 length + bytes, one kept row per thread; neighbouring threads own neighbouring rows, so a warp reads one
+// contiguous span of the source heap (L1 serves the loads). The tile's output (a contiguous span of the block at an
+// arbitrary byte address) is assembled in shared memory and written with aligned, coalesced 4-byte stores (same
+// funnel-shift re-alignment as k_encode_fixed); tiles larger than the staging buffer (long strings) go direct.
+__global__ void __launch_bounds__(TF_STR_THREADS) k_encode_str(EncodeArgs a) {
     __shared__ uint32_t sm[33];
+    __shared__ __align__(16) uint8_t stage[TF_STR_STAGE + 8];
     const DCol c = a.cols[a.slots[blockIdx.y]];
     const uint64_t n = a.st->n_kept;
     const uint64_t j0 = (uint64_t)blockIdx.x * TF_STR_TILE;
     if (j0 >= n) return;
-    uint32_t L[4]; uint64_t R[4]; uint32_t sum = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) { L[k] = str_len(c, a.sel, j0 + 4 * threadIdx.x + k, n, R[k]); if (L[k] != 0xffffffffu) sum += L[k] + varint_len(L[k]); }
-    uint32_t tot; const uint32_t ex = block_excl_scan(sum, &tot, sm);
-    uint8_t* o = a.raw + c.out_off + a.tile_base[(size_t)c.str_slot * a.ntiles_cap + blockIdx.x] + ex;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        if (L[k] == 0xffffffffu) break;
-        uint32_t v = L[k];
+    uint64_t R; const uint32_t L = str_len(c, a.sel, j0 + threadIdx.x, n, R);
+    const uint8_t* s = (L != 0xffffffffu && L) ? c.heap + c.offsets[R] : nullptr;
+    uint32_t tot; const uint32_t ex = block_excl_scan(L != 0xffffffffu ? L + varint_len(L) : 0u, &tot, sm);
+    uint8_t* gdst = a.raw + c.out_off + a.tile_base[(size_t)c.str_slot * a.ntiles_cap + blockIdx.x];
+    const bool staged = tot <= TF_STR_STAGE;
+    uint8_t* o = staged ? stage + ex : gdst + ex;
+    if (L != 0xffffffffu) {
+        uint32_t v = L;
         while (v >= 0x80) { *o++ = (uint8_t)(v | 0x80); v >>= 7; }
         *o++ = (uint8_t)v;
-        const uint8_t* s = c.heap + c.offsets[R[k]];
-        for (uint32_t b = 0; b < L[k]; b++) o[b] = s[b];
-        o += L[k];
+        uint32_t nb = L;
+        // head bytes up to a 4-byte boundary of the source, then whole words, then the tail
+        while (nb && ((uintptr_t)s & 3)) { *o++ = *s++; nb--; }
+        for (; nb >= 4; nb -= 4, s += 4, o += 4) {
+            const uint32_t w = *(const uint32_t*)s;
+            o[0] = (uint8_t)w; o[1] = (uint8_t)(w >> 8); o[2] = (uint8_t)(w >> 16); o[3] = (uint8_t)(w >> 24);
+        }
+        while (nb) { *o++ = *s++; nb--; }
+    }
+    if (!staged) return;
+    __syncthreads();
+    const uint32_t m = (uint32_t)((uintptr_t)gdst & 3);
+    const uint32_t T = (m + tot + 3) >> 2;
+    uint8_t* dst0 = gdst - m;
+    const uint32_t* sw = (const uint32_t*)stage;
+    for (uint32_t t = threadIdx.x; t < T; t += TF_STR_THREADS) {
+        const uint32_t wcur = sw[t], wprev = t ? sw[t - 1] : 0;
+        const uint32_t val = m ? __funnelshift_r(wprev, wcur, 8 * (4 - m)) : wcur;
+        const int32_t sb = (int32_t)(4 * t) - (int32_t)m;
+        uint8_t* dst = dst0 + 4 * (size_t)t;
+        if (sb >= 0 && (uint32_t)sb + 4 <= tot) *(uint32_t*)dst = val;
+        else {
+#pragma unroll
+            for (int b = 0; b < 4; b++) { const int32_t x = sb + b; if (x >= 0 && (uint32_t)x < tot) dst[b] = (uint8_t)(val >> (8 * b)); }
+        }
     }
 }
 

@@ -4,10 +4,11 @@
 // GPU-native LZ4 (not a port of any CPU compressor): one CTA per frame, the frame lives in shared
 // memory, and every phase is data-parallel:
 //   P1  stage the frame in shared memory (16-byte coalesced loads)
-//   P2  match finding: 512 positions per round probe/update a 4096-entry u16 hash table in shared
-//       memory (round-synchronous, so a candidate is always an earlier position); a second probe
-//       after the round's inserts recovers most intra-round repeats; candidates are verified
-//       against the data immediately; result = 1 valid bit + u16 candidate per position
+//   P2  match finding: 2048 positions per round (4 consecutive per thread: two shared-memory words give
+//       the four 4-byte sequences) probe a 4096-entry u16 hash table in shared memory, ONE barrier,
+//       then insert; a probe therefore only ever sees earlier rounds (or, harmlessly, racing inserts of
+//       this round, filtered by `cand < pos`); candidates are verified against the data immediately;
+//       result = 1 valid bit + u16 candidate per position
 //   P3  greedy parse, one thread per 64-byte segment (matches are cut at the segment end), sequence
 //       descriptors overwrite the segment's own candidate slots in place
 //   P4  segmented scan carries pending literals across segments; block scan gives every segment its
@@ -45,7 +46,14 @@ __device__ __forceinline__ uint32_t ext_bytes(uint32_t x) { return x < 15 ? 0u :
 __device__ __forceinline__ uint8_t* put_ext(uint8_t* o, uint32_t x) {   // x >= 15
     x -= 15; while (x >= 255) { *o++ = 255; x -= 255; } *o++ = (uint8_t)x; return o;
 }
-__device__ __forceinline__ void copy_s2g(uint8_t* dst, const uint8_t* src, uint32_t n) { for (uint32_t i = 0; i < n; i++) dst[i] = src[i]; }
+// literal copy shared -> global: bytes up to a 4-byte boundary of the destination, then aligned words
+// (source re-aligned with a funnel shift), then the tail
+__device__ __forceinline__ void copy_s2g(uint8_t* dst, const uint32_t* data_w, uint32_t src, uint32_t n) {
+    const uint8_t* data = (const uint8_t*)data_w;
+    while (n && ((uintptr_t)dst & 3)) { *dst++ = data[src++]; n--; }
+    for (; n >= 4; n -= 4, dst += 4, src += 4) *(uint32_t*)dst = ld32u(data_w, src);
+    while (n) { *dst++ = data[src++]; n--; }
+}
 
 __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -54,8 +62,8 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
     uint8_t* data = smem;
     uint16_t* cand = (uint16_t*)(smem + F + 16);                         // 2F bytes; later: sequence descriptors
     uint16_t* table = (uint16_t*)(smem + F + 16 + 2 * F);               // 8 KB; later: per-segment arrays
-    uint32_t* vmask = (uint32_t*)(smem + F + 16 + 2 * F + (2u << LZ_HASH_BITS));   // F/8 bytes
-    uint32_t* scratch = vmask + F / 32;                                  // 40 words
+    uint8_t* vnib = smem + F + 16 + 2 * F + (2u << LZ_HASH_BITS);       // F/4 bytes: 4 valid bits per aligned 4 positions
+    uint32_t* scratch = (uint32_t*)(vnib + F / 4);                       // 48 words
     __shared__ uint32_t s_frame;
     // per-segment arrays aliased onto the hash table after P2 (nseg <= 512)
     uint32_t* seg_off = (uint32_t*)table;            // [513]
@@ -95,22 +103,42 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
         __syncthreads();
 
         // ---- P2: match finding
-        const uint32_t nrounds = (len + LZ_THREADS - 1) / LZ_THREADS;
+        const uint32_t nrounds = (len + 2047) / 2048;
         for (uint32_t rd = 0; rd < nrounds; rd++) {
-            const uint32_t p = rd * LZ_THREADS + tid;
-            const uint32_t seq = ld32u(data_w, p);
-            const uint32_t h = (seq * 2654435761u) >> (32 - LZ_HASH_BITS);
-            uint32_t c = table[h];
+            const uint32_t p0 = rd * 2048 + tid * 4;
+            const bool active = p0 < F;                         // F is a multiple of 64, so p0 + 3 < F too
+            uint32_t seq[4], h[4], c[4];
+            if (active) {
+                const uint32_t w0 = data_w[p0 >> 2], w1 = data_w[(p0 >> 2) + 1];
+                seq[0] = w0; seq[1] = __funnelshift_r(w0, w1, 8); seq[2] = __funnelshift_r(w0, w1, 16); seq[3] = __funnelshift_r(w0, w1, 24);
+#pragma unroll
+                for (int k = 0; k < 4; k++) { h[k] = (seq[k] * 2654435761u) >> (32 - LZ_HASH_BITS); c[k] = table[h[k]]; }
+            }
             __syncthreads();
-            const bool inside = p < len;
-            if (inside) table[h] = (uint16_t)p;
-            const bool ok = p + 12 <= len;                     // a match may start here (MFLIMIT)
-            bool valid = ok && c < p && ld32u(data_w, c) == seq;
+            bool v[4];
+            if (active) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t p = p0 + k;
+                    if (p < len) table[h[k]] = (uint16_t)p;
+                    v[k] = (p + 12 <= len) && c[k] < p && ld32u(data_w, c[k]) == seq[k];   // MFLIMIT
+                }
+            }
             __syncthreads();
-            if (ok && !valid) { const uint32_t c2 = table[h]; if (c2 < p && ld32u(data_w, c2) == seq) { valid = true; c = c2; } }
-            if (valid) cand[p] = (uint16_t)c;
-            const uint32_t b = __ballot_sync(0xffffffffu, valid);
-            if (lane == 0) vmask[p >> 5] = b;
+            if (active) {   // second probe: sees this round's inserts, recovers repeats whose first occurrence is in this round
+                uint32_t nib = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t p = p0 + k;
+                    if (!v[k] && p + 12 <= len) {
+                        const uint32_t c2 = table[h[k]];
+                        if (c2 < p && ld32u(data_w, c2) == seq[k]) { v[k] = true; c[k] = c2; }
+                    }
+                    nib |= (v[k] ? 1u : 0u) << k;
+                }
+                *(uint2*)(cand + p0) = make_uint2(c[0] | (c[1] << 16), c[2] | (c[3] << 16));
+                vnib[p0 >> 2] = (uint8_t)nib;
+            }
         }
         __syncthreads();
 
@@ -122,7 +150,12 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
             seg_end = seg_start + LZ_SEG < len ? seg_start + LZ_SEG : len;
             const uint32_t lim5 = len >= 5 ? len - 5 : 0;
             const uint32_t limit = seg_end < lim5 ? seg_end : lim5;       // matches end before the last 5 bytes and inside the segment
-            const uint64_t m64 = (uint64_t)vmask[2 * tid] | ((uint64_t)(((2 * tid + 1) * 32 < ((len + 31) & ~31u)) ? vmask[2 * tid + 1] : 0u) << 32);
+            // 16 nibble bytes -> one 64-bit mask (bit i = position seg_start + i may start a match)
+            const uint4 nb = *(const uint4*)(vnib + 16 * tid);
+            uint64_t lo = (uint64_t)nb.x | ((uint64_t)nb.y << 32), hi = (uint64_t)nb.z | ((uint64_t)nb.w << 32);
+            lo = (lo | (lo >> 4)) & 0x00FF00FF00FF00FFULL; lo = (lo | (lo >> 8)) & 0x0000FFFF0000FFFFULL; lo = (lo | (lo >> 16)) & 0xFFFFFFFFULL;
+            hi = (hi | (hi >> 4)) & 0x00FF00FF00FF00FFULL; hi = (hi | (hi >> 8)) & 0x0000FFFF0000FFFFULL; hi = (hi | (hi >> 16)) & 0xFFFFFFFFULL;
+            const uint64_t m64 = lo | (hi << 32);
             uint32_t cur = 0, last_end = seg_start;
             while (cur < LZ_SEG) {
                 const uint64_t mm = m64 >> cur;
@@ -224,7 +257,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
                 const uint32_t mt = ml - 4;
                 *o++ = (uint8_t)(((ll < 15 ? ll : 15) << 4) | (mt < 15 ? mt : 15));
                 if (ll >= 15) o = put_ext(o, ll);
-                copy_s2g(o + cin, data + prev_end, p - prev_end);
+                copy_s2g(o + cin, data_w, prev_end, p - prev_end);
                 o += ll;
                 *o++ = (uint8_t)off; *o++ = (uint8_t)(off >> 8);
                 if (mt >= 15) o = put_ext(o, mt);
@@ -233,7 +266,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
             if (seg_end > prev_end) {   // trailing literals belong to the next sequence downstream
                 const uint32_t nh = next_has[tid];
                 const int32_t dl = (nh != 0xffff && nh < nseg) ? delta0[nh] : delta_final;
-                copy_s2g(out + (int32_t)prev_end + dl, data + prev_end, seg_end - prev_end);
+                copy_s2g(out + ((int32_t)prev_end + dl), data_w, prev_end, seg_end - prev_end);
             }
         }
         if (tid == 0) {
@@ -327,19 +360,119 @@ __device__ P hash128(const uint8_t* s, size_t len) {
 
 struct FrameArgs { uint8_t* slots; uint32_t slot_stride; const uint32_t* comp_size; DState* st; uint32_t frame_bytes; uint64_t* wire_off; uint8_t* wire; };
 
-// one thread per frame: fill [0x82][compressed+9][raw] and the CityHash128 of everything after the checksum
-__global__ void __launch_bounds__(128) k_frame_seal(FrameArgs a) {
-    const uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= a.st->n_frames) return;
-    uint8_t* s = a.slots + f * a.slot_stride;
-    const uint32_t cs = a.comp_size[f] + 9;
-    const uint64_t pos0 = f * a.frame_bytes;
-    const uint32_t rs = (uint32_t)((a.st->raw_total - pos0 < a.frame_bytes) ? a.st->raw_total - pos0 : a.frame_bytes);
-    s[16] = 0x82;
-    s[17] = (uint8_t)cs; s[18] = (uint8_t)(cs >> 8); s[19] = (uint8_t)(cs >> 16); s[20] = (uint8_t)(cs >> 24);
-    s[21] = (uint8_t)rs; s[22] = (uint8_t)(rs >> 8); s[23] = (uint8_t)(rs >> 16); s[24] = (uint8_t)(rs >> 24);
-    const cityd::P h = cityd::hash128(s + 16, cs);
-    ((uint64_t*)s)[0] = h.first; ((uint64_t*)s)[1] = h.second;
+// CityHash128 is a serial chain per frame, so the parallelism is ACROSS frames: one thread per frame. What a
+// thread-per-frame loop would ruin is the memory access (every lane striding through its own frame), so each
+// warp stages the next 512 bytes of all its 32 frames with coalesced 16-byte cp.async copies into shared
+// memory (double buffered) while the lanes hash the previous 512 bytes out of it.
+#define SEAL_STEP 512
+#define SEAL_STRIDE 528
+__device__ __forceinline__ uint64_t sm64(const uint8_t* base, uint32_t off) { return *(const uint64_t*)(base + off); }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(32) k_frame_seal(FrameArgs a) {
+    __shared__ __align__(16) uint8_t s_buf[2][32][SEAL_STRIDE];
+    __shared__ __align__(16) uint8_t s_tail[32][304];
+    const uint32_t lane = threadIdx.x;
+    const uint64_t nf = a.st->n_frames;
+    const uint64_t f = (uint64_t)blockIdx.x * 32 + lane;
+    const bool have = f < nf;
+    uint8_t* s = a.slots + (have ? f : 0) * a.slot_stride;
+    uint32_t cs = 0;
+    if (have) {
+        cs = a.comp_size[f] + 9;
+        const uint64_t pos0 = f * a.frame_bytes;
+        const uint32_t rs = (uint32_t)((a.st->raw_total - pos0 < a.frame_bytes) ? a.st->raw_total - pos0 : a.frame_bytes);
+        // bytes 16..31 of the slot as two aligned words: [0x82][cs][rs] + the first 7 bytes of the LZ4 block (kept)
+        uint64_t* q = (uint64_t*)(s + 16);
+        const uint64_t w0 = 0x82ull | ((uint64_t)cs << 8) | ((uint64_t)(rs & 0xffffff) << 40);
+        const uint64_t w1 = (q[1] & ~0xffull) | (uint64_t)(rs >> 24);
+        q[0] = w0; q[1] = w1;
+        __threadfence_block();
+    }
+    __syncwarp();
+    const uint8_t* H = s + 16;
+    const bool big = have && cs >= 16 + 128 + 16;
+    if (have && !big) { const cityd::P h = cityd::hash128(H, cs); ((uint64_t*)s)[0] = h.first; ((uint64_t*)s)[1] = h.second; }
+    const uint8_t* body = H + 16; const uint32_t len = big ? cs - 16 : 0;
+    const uint32_t nblk = len / 128, used = nblk * 128;
+    const uint32_t nsteps = (used + SEAL_STEP - 1) / SEAL_STEP;
+    uint32_t max_steps = nsteps;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) { const uint32_t o = __shfl_xor_sync(0xffffffffu, max_steps, d); max_steps = o > max_steps ? o : max_steps; }
+    if (max_steps == 0) return;
+    const uint32_t tail_base = (len > 272 ? (len - 272) : 0) & ~15u;
+    // cooperative staging helpers: lane l copies bytes [16 l, 16 l + 16) of every frame's current 512-byte step
+    auto stage_step = [&](uint32_t st, uint32_t bi) {
+#pragma unroll 4
+        for (int j = 0; j < 32; j++) {
+            const uint8_t* bj = (const uint8_t*)__shfl_sync(0xffffffffu, (unsigned long long)body, j);
+            const uint32_t uj = __shfl_sync(0xffffffffu, used, j);
+            const uint32_t off = st * SEAL_STEP + lane * 16;
+            if (off < uj) cp_async16(&s_buf[bi][j][lane * 16], bj + off);
+        }
+        cp_async_commit();
+    };
+    for (int j = 0; j < 32; j++) {      // tail windows (<= 288 bytes each)
+        const uint8_t* bj = (const uint8_t*)__shfl_sync(0xffffffffu, (unsigned long long)body, j);
+        const uint32_t lj = __shfl_sync(0xffffffffu, len, j), tj = __shfl_sync(0xffffffffu, tail_base, j);
+        if (lane < 18 && lj && tj + 16 * lane < lj + 16) cp_async16(&s_tail[j][16 * lane], bj + tj + 16 * lane);
+    }
+    stage_step(0, 0);
+    cityd::P v, w; uint64_t x = 0, y = 0, z = 0;
+    if (big) {
+        x = cityd::f64(H) ^ CK3; y = cityd::f64(H + 8); z = (uint64_t)len * CK1;
+        v.first = cityd::rot(y ^ CK1, 49) * CK1 + cityd::f64(body);
+        v.second = cityd::rot(v.first, 42) * CK1 + cityd::f64(body + 8);
+        w.first = cityd::rot(y + z, 35) * CK1 + x;
+        w.second = cityd::rot(x + cityd::f64(body + 88), 53) * CK1;
+    }
+    for (uint32_t st = 0; st < max_steps; st++) {
+        if (st + 1 < max_steps) { stage_step(st + 1, (st + 1) & 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+        __syncwarp();
+        if (st < nsteps) {
+            const uint8_t* b = s_buf[st & 1][lane];
+            const uint32_t nb = (nblk - st * 4 < 4) ? nblk - st * 4 : 4;
+            for (uint32_t i = 0; i < 2 * nb; i++) {
+                const uint32_t o = i * 64;
+                x = cityd::rot(x + y + v.first + sm64(b, o + 16), 37) * CK1;
+                y = cityd::rot(y + v.second + sm64(b, o + 48), 42) * CK1;
+                x ^= w.second; y ^= v.first; z = cityd::rot(z ^ w.first, 33);
+                v = cityd::weak32(sm64(b, o), sm64(b, o + 8), sm64(b, o + 16), sm64(b, o + 24), v.second * CK1, x + w.first);
+                w = cityd::weak32(sm64(b, o + 32), sm64(b, o + 40), sm64(b, o + 48), sm64(b, o + 56), z + w.second, y);
+                const uint64_t t = z; z = x; x = t;
+            }
+        }
+        __syncwarp();
+    }
+    if (big) {
+        const uint32_t rem = len - used;                 // 0..127 bytes; the tail reads reach back into hashed data
+        const uint8_t* tb = s_tail[lane];
+        auto t64 = [&](uint32_t off) -> uint64_t {      // unaligned 8 bytes at body + off (off >= tail_base)
+            const uint32_t o = off - tail_base; const uint32_t al = o & ~7u, sh = (o & 7) * 8;
+            const uint64_t lo = *(const uint64_t*)(tb + al);
+            if (!sh) return lo;
+            return (lo >> sh) | (*(const uint64_t*)(tb + al + 8) << (64 - sh));
+        };
+        y += cityd::rot(w.first, 37) * CK0 + z;
+        x += cityd::rot(v.first + z, 49) * CK0;
+        for (uint32_t td = 0; td < rem;) {
+            td += 32;
+            const uint32_t base = len - td;
+            y = cityd::rot(y - x, 42) * CK0 + v.second;
+            w.first += t64(base + 16);
+            x = cityd::rot(x, 49) * CK0 + w.first;
+            w.first += v.first;
+            v = cityd::weak32(t64(base), t64(base + 8), t64(base + 16), t64(base + 24), v.first, v.second);
+        }
+        x = cityd::hl16(x, v.first); y = cityd::hl16(y, w.first);
+        ((uint64_t*)s)[0] = cityd::hl16(x + v.second, w.second) + y;
+        ((uint64_t*)s)[1] = cityd::hl16(x + w.second, y + v.second);
+    }
 }
 
 // exclusive scan of frame sizes (single block) -> position of every frame in the wire buffer

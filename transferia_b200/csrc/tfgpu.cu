@@ -218,7 +218,7 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
     e->raw.ensure(sz.raw_bound);
     const bool lz = wire_fmt == TF_WIRE_CH_NATIVE_LZ4;
     const uint32_t stride = lz_slot_stride(e->frame_bytes);
-    if (lz) { e->slots.ensure(sz.n_frames_max * (uint64_t)stride + 256); e->wire.ensure(sz.wire_bound); }
+    if (lz) { e->slots.ensure(sz.n_frames_max * (uint64_t)stride + 4096); e->wire.ensure(sz.wire_bound); }
     if (e->d_cols_cap < nc) { if (e->d_cols) CK(cudaFree(e->d_cols)); CK(cudaMalloc(&e->d_cols, sizeof(DCol) * nc)); e->d_cols_cap = nc; }
     // column descriptors
     std::vector<DCol> hc(nc);
@@ -253,7 +253,7 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         DState init; std::memset(&init, 0, sizeof init); init.n_kept = n;
         CK(cudaMemcpyAsync(e->d_state, &init, sizeof init, cudaMemcpyHostToDevice, s));
     }
-    if (pd.n_str && ntiles) { e->prof_begin("k_str_sizes", s); k_str_sizes<<<dim3(ntiles, pd.n_str), 256, 0, s>>>(ea); e->prof_end(s); }
+    if (pd.n_str && ntiles) { e->prof_begin("k_str_sizes", s); k_str_sizes<<<dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
     LayoutArgs la{e->d_cols, (int)nc, pd.d_str_slots, pd.n_str, e->tile_sum, e->tile_base, sz.ntiles_cap, pd.d_col_headers, pd.d_col_header_off,
                   e->raw.p, e->d_state, n, 1, e->frame_bytes};
     e->prof_begin("k_layout", s); k_layout<<<1, 1024, 0, s>>>(la); e->prof_end(s);
@@ -264,7 +264,7 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
             EncodeArgs fa = ea; fa.slots = pd.d_fixed_slots;
             e->prof_begin("k_encode_fixed", s); k_encode_fixed<<<dim3(gx, pd.n_fixed_slots), 256, 0, s>>>(fa); e->prof_end(s);
         }
-        if (pd.n_str) { e->prof_begin("k_encode_str", s); k_encode_str<<<dim3(ntiles, pd.n_str), 256, 0, s>>>(ea); e->prof_end(s); }
+        if (pd.n_str) { e->prof_begin("k_encode_str", s); k_encode_str<<<dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
         if (pd.n_mask_cols) {
             MaskArgs ma{e->d_cols, pd.d_mask_slots, pd.d_mask_keys, sel, e->d_state, e->raw.p};
             e->prof_begin("k_mask_encode", s); k_mask_encode<<<dim3((uint32_t)((n + 127) / 128), pd.n_mask_cols), 128, 0, s>>>(ma); e->prof_end(s);
@@ -272,11 +272,11 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
     }
     if (lz) {
         Lz4Args za{e->raw.p, e->d_state, e->slots.p, stride, e->comp_size, e->frame_bytes};
-        const size_t smem = e->frame_bytes + 16 + 2 * (size_t)e->frame_bytes + (2u << LZ_HASH_BITS) + e->frame_bytes / 8 + 48 * 4;
+        const size_t smem = e->frame_bytes + 16 + 2 * (size_t)e->frame_bytes + (2u << LZ_HASH_BITS) + e->frame_bytes / 4 + 48 * 4;
         const uint32_t grid = (uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * 2);
         e->prof_begin("k_lz4_frames", s); k_lz4_frames<<<grid, LZ_THREADS, smem, s>>>(za); e->prof_end(s);
         FrameArgs fa{e->slots.p, stride, e->comp_size, e->d_state, e->frame_bytes, e->wire_off, e->wire.p};
-        e->prof_begin("k_frame_seal", s); k_frame_seal<<<(uint32_t)((sz.n_frames_max + 127) / 128), 128, 0, s>>>(fa); e->prof_end(s);
+        e->prof_begin("k_frame_seal", s); k_frame_seal<<<(uint32_t)((sz.n_frames_max + 31) / 32), 32, 0, s>>>(fa); e->prof_end(s);
         e->prof_begin("k_frame_scan", s); k_frame_scan<<<1, 1024, 0, s>>>(fa); e->prof_end(s);
         e->prof_begin("k_wire_gather", s); k_wire_gather<<<(uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * 8), 256, 0, s>>>(fa); e->prof_end(s);
     }
