@@ -74,42 +74,61 @@ def make_batch(rows: int, seed: int):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi-equivalent (NVML) clocks + throttle reasons sampled DURING the timed region."""
+    """SM clock + throttle reasons sampled while the benchmark runs (NVML; nvidia-smi query as a fallback).
+    Samples carry timestamps; the reported figures use the samples inside [mark_start, mark_end]."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index = index; self.stop_flag = False; self.sm = []; self.reasons = set(); self.sm_max = None; self.ok = False
-
-    def run(self):
+        self.index = index; self.stop_flag = False; self.samples = []; self.sm_max = None
+        self.t0 = self.t1 = None; self.nv = None; self.h = None
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {
-                getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
-                getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
-                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
-                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
-            }
-            self.ok = True
-            while not self.stop_flag:
-                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, nm in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
-                time.sleep(0.05)
+            self.nv = nv; self.h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
         except Exception:
-            self.ok = False
+            self.nv = None
+
+    def _sample(self):
+        if self.nv is not None:
+            nv = self.nv
+            clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            return float(clk), {nm for bit, nm in self.REASONS.items() if r & bit}
+        import subprocess
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        o = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+        self.sm_max = float(o[1])
+        return float(o[0]), {nm for nm, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), o[2:]) if val.strip().lower().startswith("active")}
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                clk, rs = self._sample()
+                self.samples.append((time.perf_counter(), clk, rs))
+            except Exception:
+                pass
+            time.sleep(0.002 if self.nv is not None else 0.1)
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def result(self):
-        if not self.ok or not self.sm:
-            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable"]}
-        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
+        inside = [x for x in self.samples if self.t0 is not None and self.t0 <= x[0] <= (self.t1 or 1e30)]
+        use = inside or self.samples[-3:]
+        if not use:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable"], "samples": 0}
+        reasons = set().union(*[x[2] for x in use])
+        return {"sm_mhz": float(np.median([x[1] for x in use])), "sm_max_mhz": self.sm_max, "reasons": sorted(reasons),
+                "samples": len(inside)}
 
 
 def cpu_port_rate(batch, schema, transformers, frame_bytes, budget_s: float, threads: int):
@@ -160,7 +179,7 @@ def run_reference(args):
         _, r, t = cpu_port_rate(batch, schema, trs, args.frame_bytes, per_step_budget, cores)
         tot_rows += r; tot_t += t
     v = tot_rows / tot_t
-    sample = f"{cores} pipelines x 100k-row slices of the {rows}-row batch, >= {per_step_budget}s per step"
+    sample = f"{cores} pipelines, each over its own {min(rows // cores, 100000)}-row slice of the {rows}-row batch, >= {per_step_budget}s per step"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
@@ -223,13 +242,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- kernel-only (resident) ----
+    sampler = ClockSampler(local); sampler.start()
     for _ in range(args.warmup):
         eng.push_encode_resident(pid, dbatch, abi.TF_WIRE_CH_NATIVE_LZ4)
     torch.cuda.synchronize()
     st = eng.resident_stats()
     eng.profile_enable(True)
-    sampler = ClockSampler(local); sampler.start()
     barrier()
+    sampler.mark_start()
     l0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = {}
@@ -241,6 +261,7 @@ def main():
         # read them once per step boundary below (the read syncs the stream, so do it outside timing)
     ev1.record()
     torch.cuda.synchronize()
+    sampler.mark_end()
     launches = eng.launch_count() - l0
     ms_total = ev0.elapsed_time(ev1)
     for kk in eng.profile_read():        # events of the LAST timed step
@@ -311,7 +332,7 @@ def main():
             cores = os.cpu_count() or 1
             v, rows_done, el = cpu_port_rate(batch, schema, trs, args.frame_bytes, args.cpu_budget, cores)
             out["cpu_baseline"] = {"value": v, "unit": "rows/s", "cores": cores, "kind": "port",
-                                   "sample": f"{cores} pipelines x 100k-row slices of the same batch for {el:.1f}s ({rows_done} rows); C++ oracle port of the Go row loop, not Go"}
+                                   "sample": f"{cores} pipelines, each over its own {min(args.rows // cores, 100000)}-row slice of the same batch, for {el:.1f}s ({rows_done} rows); C++ oracle port of the Go row loop, not Go"}
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

@@ -237,53 +237,76 @@ struct LayoutArgs {
     const uint8_t* col_headers; const uint32_t* col_header_off;   // pre-serialized "name,type,0" per column
     uint8_t* raw; DState* st;
     uint64_t nrows_in; int has_sel; uint32_t frame_bytes;
+    uint64_t* col_bytes;                       // [nstr] encoded bytes of each String column
 };
 
 #define TF_STR_TILE 256
 #define TF_STR_THREADS 256
 #define TF_STR_STAGE 16384   // bytes of shared memory staging per tile in k_encode_str
 
-// One block: per-string-column prefix over tiles, then column offsets, then the block / column headers.
+// k_layout_scan: one CTA per String column: exclusive prefix of the column's tile sizes, column total.
+// k_layout_finish: column offsets, then the block / column headers.
 // Block layout (clickhouse-go/v2 v2.46.0 lib/proto/block.go, revision 54460):
 //   uvarint 1, u8 is_overflows=0, uvarint 2, i32 bucket_num=-1, uvarint 0, uvarint ncols, uvarint nrows,
 //   per column: string name, string type, u8 custom_serialization=0, [null map], data
-__global__ void __launch_bounds__(1024) k_layout(LayoutArgs a) {
+__global__ void __launch_bounds__(1024) k_layout_scan(LayoutArgs a) {
     __shared__ uint32_t sm[33];
-    __shared__ uint64_t s_colbytes[256];       // encoded bytes of each OK_STR column (nstr <= 256 checked on host)
-    if (!a.has_sel && threadIdx.x == 0) a.st->n_kept = a.nrows_in;
-    __syncthreads();
+    const int s = blockIdx.x;
     const uint64_t n = a.st->n_kept;
     const uint32_t ntiles = (uint32_t)((n + TF_STR_TILE - 1) / TF_STR_TILE);
-    for (int s = 0; s < a.nstr; s++) {
-        uint64_t carry = 0;
-        for (uint32_t base = 0; base < ntiles; base += blockDim.x) {
-            const uint32_t i = base + threadIdx.x;
-            const uint32_t v = i < ntiles ? a.tile_sum[(size_t)s * a.ntiles_cap + i] : 0;
-            uint32_t tot; const uint32_t ex = block_excl_scan(v, &tot, sm);
-            if (i < ntiles) a.tile_base[(size_t)s * a.ntiles_cap + i] = carry + ex;
-            carry += tot;
-        }
-        if (threadIdx.x == 0) s_colbytes[s] = carry;
+    uint64_t carry = 0;
+    for (uint32_t base = 0; base < ntiles; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < ntiles ? a.tile_sum[(size_t)s * a.ntiles_cap + i] : 0;
+        uint32_t tot; const uint32_t ex = block_excl_scan(v, &tot, sm);
+        if (i < ntiles) a.tile_base[(size_t)s * a.ntiles_cap + i] = carry + ex;
+        carry += tot;
     }
-    __syncthreads();
+    if (threadIdx.x == 0) a.col_bytes[s] = carry;
+}
+
+__global__ void __launch_bounds__(256) k_layout_finish(LayoutArgs a) {
+    __shared__ uint64_t s_size[3][256];     // header, null map, data bytes per column (ncols <= 256 per pass)
+    __shared__ uint64_t s_pos[256];
+    __shared__ uint64_t s_run;
+    const uint64_t n = a.st->n_kept;
     if (threadIdx.x == 0) {
         uint8_t* o = a.raw; uint64_t p = 0;
         o[p++] = 1; o[p++] = 0; o[p++] = 2; o[p++] = 0xff; o[p++] = 0xff; o[p++] = 0xff; o[p++] = 0xff; o[p++] = 0;
         uint64_t v = (uint64_t)a.ncols; while (v >= 0x80) { o[p++] = (uint8_t)(v | 0x80); v >>= 7; } o[p++] = (uint8_t)v;
         v = n; while (v >= 0x80) { o[p++] = (uint8_t)(v | 0x80); v >>= 7; } o[p++] = (uint8_t)v;
-        for (int c = 0; c < a.ncols; c++) {
-            DCol& d = a.cols[c];
-            d.hdr_off = p; p += a.col_header_off[c + 1] - a.col_header_off[c];
-            d.null_off = p; if (d.nullable && n) p += n;
-            d.out_off = p;
-            if (n) p += (d.out_kind == OK_STR) ? s_colbytes[d.str_slot] : (uint64_t)d.out_w * n;
+        s_run = p;
+    }
+    for (int base = 0; base < a.ncols; base += 256) {
+        const int c = base + threadIdx.x;
+        __syncthreads();
+        if (c < a.ncols) {       // every thread fetches its own column's sizes (global latency paid once, in parallel)
+            const DCol& d = a.cols[c];
+            s_size[0][threadIdx.x] = a.col_header_off[c + 1] - a.col_header_off[c];
+            s_size[1][threadIdx.x] = (d.nullable && n) ? n : 0;
+            s_size[2][threadIdx.x] = n ? ((d.out_kind == OK_STR) ? a.col_bytes[d.str_slot] : (uint64_t)d.out_w * n) : 0;
         }
+        __syncthreads();
+        if (threadIdx.x == 0) {  // serial prefix over shared memory only
+            uint64_t p = s_run; const int m = a.ncols - base < 256 ? a.ncols - base : 256;
+            for (int k = 0; k < m; k++) { s_pos[k] = p; p += s_size[0][k] + s_size[1][k] + s_size[2][k]; }
+            s_run = p;
+        }
+        __syncthreads();
+        if (c < a.ncols) {
+            DCol& d = a.cols[c];
+            const uint64_t p = s_pos[threadIdx.x];
+            d.hdr_off = p; d.null_off = p + s_size[0][threadIdx.x]; d.out_off = d.null_off + s_size[1][threadIdx.x];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint64_t p = s_run;
         a.st->raw_total = p;
         a.st->n_frames = p ? (p + a.frame_bytes - 1) / a.frame_bytes : 1;
         a.st->frame_ticket = 0;
     }
     __syncthreads();
-    // column headers, copied by all threads
     for (int c = 0; c < a.ncols; c++) {
         const uint32_t hb = a.col_header_off[c], he = a.col_header_off[c + 1];
         for (uint32_t k = hb + threadIdx.x; k < he; k += blockDim.x) a.raw[a.cols[c].hdr_off + (k - hb)] = a.col_headers[k];

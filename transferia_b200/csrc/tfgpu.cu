@@ -64,7 +64,7 @@ struct tfgpu_engine {
     DState* d_state = nullptr; DCol* d_cols = nullptr; size_t d_cols_cap = 0;
     // pointers into `work` for the last call
     uint8_t *keep = nullptr, *errcode = nullptr, *errstep = nullptr; uint32_t *blockcnt = nullptr, *blockoff = nullptr, *sel = nullptr;
-    uint32_t* tile_sum = nullptr; uint64_t* tile_base = nullptr; uint32_t* comp_size = nullptr; uint64_t* wire_off = nullptr;
+    uint32_t* tile_sum = nullptr; uint64_t* tile_base = nullptr; uint64_t* col_bytes = nullptr; uint32_t* comp_size = nullptr; uint64_t* wire_off = nullptr;
     uint64_t last_nrows = 0; bool last_has_filter = false; int last_wire_fmt = 0;
     uint8_t* pinned = nullptr; size_t pinned_cap = 0;
     // optional per-kernel CUDA-event timing of the last call (bench roofline)
@@ -208,13 +208,13 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
     auto need = [&](size_t b) { wbytes += align_up(b ? b : 1, 256); };
     need(n); need(n); need(n); need(sz.nblocks * 4); need(sz.nblocks * 4); need(n * 4);
     need((size_t)pd.n_str * sz.ntiles_cap * 4); need((size_t)pd.n_str * sz.ntiles_cap * 8);
-    need(sz.n_frames_max * 4); need(sz.n_frames_max * 8);
+    need(sz.n_frames_max * 4); need(sz.n_frames_max * 8); need(256 * 8);
     e->work.ensure(wbytes);
     uint8_t* p = e->work.p;
     e->keep = carve<uint8_t>(p, n); e->errcode = carve<uint8_t>(p, n); e->errstep = carve<uint8_t>(p, n);
     e->blockcnt = carve<uint32_t>(p, sz.nblocks); e->blockoff = carve<uint32_t>(p, sz.nblocks); e->sel = carve<uint32_t>(p, n);
     e->tile_sum = carve<uint32_t>(p, (size_t)pd.n_str * sz.ntiles_cap); e->tile_base = carve<uint64_t>(p, (size_t)pd.n_str * sz.ntiles_cap);
-    e->comp_size = carve<uint32_t>(p, sz.n_frames_max); e->wire_off = carve<uint64_t>(p, sz.n_frames_max);
+    e->comp_size = carve<uint32_t>(p, sz.n_frames_max); e->wire_off = carve<uint64_t>(p, sz.n_frames_max); e->col_bytes = carve<uint64_t>(p, 256);
     e->raw.ensure(sz.raw_bound);
     const bool lz = wire_fmt == TF_WIRE_CH_NATIVE_LZ4;
     const uint32_t stride = lz_slot_stride(e->frame_bytes);
@@ -255,8 +255,9 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
     }
     if (pd.n_str && ntiles) { e->prof_begin("k_str_sizes", s); k_str_sizes<<<dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
     LayoutArgs la{e->d_cols, (int)nc, pd.d_str_slots, pd.n_str, e->tile_sum, e->tile_base, sz.ntiles_cap, pd.d_col_headers, pd.d_col_header_off,
-                  e->raw.p, e->d_state, n, 1, e->frame_bytes};
-    e->prof_begin("k_layout", s); k_layout<<<1, 1024, 0, s>>>(la); e->prof_end(s);
+                  e->raw.p, e->d_state, n, 1, e->frame_bytes, e->col_bytes};
+    if (pd.n_str) { e->prof_begin("k_layout_scan", s); k_layout_scan<<<pd.n_str, 1024, 0, s>>>(la); e->prof_end(s); }
+    e->prof_begin("k_layout_finish", s); k_layout_finish<<<1, 256, 0, s>>>(la); e->prof_end(s);
     if (n) {
         if (pd.n_fixed_slots) {
             // widest stream is 8 bytes per row: words = 2n (+1 for misalignment)
@@ -273,7 +274,8 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
     if (lz) {
         Lz4Args za{e->raw.p, e->d_state, e->slots.p, stride, e->comp_size, e->frame_bytes};
         const size_t smem = e->frame_bytes + 16 + 2 * (size_t)e->frame_bytes + (2u << LZ_HASH_BITS) + e->frame_bytes / 4 + 48 * 4;
-        const uint32_t grid = (uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * 2);
+        const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (smem + 1024)));
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * per_sm);
         e->prof_begin("k_lz4_frames", s); k_lz4_frames<<<grid, LZ_THREADS, smem, s>>>(za); e->prof_end(s);
         FrameArgs fa{e->slots.p, stride, e->comp_size, e->d_state, e->frame_bytes, e->wire_off, e->wire.p};
         e->prof_begin("k_frame_seal", s); k_frame_seal<<<(uint32_t)((sz.n_frames_max + 31) / 32), 32, 0, s>>>(fa); e->prof_end(s);
