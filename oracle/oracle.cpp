@@ -400,65 +400,96 @@ int orc_match_value(const orc_val* v, const orc_term* t, int* matched) { bool m 
 
 int orc_ch_type(const orc_colschema* c, char* dst, int cap) { return copy_out(ch_type(*c, c->type), dst, cap); }
 
-int orc_push_encode(const tf_batch* in, const orc_colschema* schema, const orc_step* steps, int nsteps,
-                    int wire_fmt, uint64_t frame_bytes, orc_buf* out_raw, orc_buf* out_wire,
-                    uint64_t* rows_out, tf_rowerr* errs, uint64_t* nerrs) {
+}  // extern "C" (reopened below)
+
+namespace {
+// Applies the transformer steps to row r (boxed in `row`); returns false when the row is dropped or errored.
+bool apply_steps(const tf_batch* in, uint64_t r, const orc_step* steps, int nsteps, std::vector<Boxed>& row, std::vector<int32_t>& cur_type,
+                 tf_rowerr* errs, uint64_t& ne) {
     const uint32_t nc = in->ncols;
-    // result schema after the ResultSchema chain (mask / to_string turn columns into utf8 / string)
-    std::vector<int32_t> out_type(nc);
+    for (uint32_t c = 0; c < nc; c++) { row[c].own.clear(); box(in->cols[c], r, row[c].v); cur_type[c] = in->cols[c].type; }   // []interface{} of this ChangeItem
+    const int kind = in->kinds ? in->kinds[r] : TF_KIND_INSERT;
+    for (int s = 0; s < nsteps; s++) {
+        const orc_step& st = steps[s];
+        if (st.kind == STEP_SKIP_EVENTS) {                        // SkipEvents.Apply skip_events.go:52-62
+            if ((st.kind_mask >> kind) & 1) return false;
+        } else if (st.kind == STEP_FILTER_ROWS) {                // FilterRowsTransformer.Apply filter_rows.go:99-130
+            if (kind == TF_KIND_UPDATE || kind == TF_KIND_DELETE) { errs[ne++] = tf_rowerr{(uint32_t)r, TF_ROWERR_FILTER_KIND, (uint16_t)st.convert_to_bytes}; return false; }
+            if (st.pass_all) continue;                            // :109-113 isNameMatching == false
+            bool any = false; int err = 0;
+            for (int e = 0; e < st.nexpr && !any && !err; e++) {   // matchItem :137-148 (OR), matchExpression :150-177 (AND)
+                bool all = true;
+                for (uint32_t k = st.expr_off[e]; k < st.expr_off[e + 1]; k++) {
+                    bool m = false; int rc = match_value(row[st.terms[k].col].v, st.terms[k], m);
+                    if (rc) { err = rc; break; }
+                    if (!m) { all = false; break; }
+                }
+                if (!err && all) any = true;
+            }
+            if (err) { errs[ne++] = tf_rowerr{(uint32_t)r, (uint16_t)err, (uint16_t)st.convert_to_bytes}; return false; }
+            if (!any) return false;
+        } else if (st.kind == STEP_MASK) {                        // HmacHasher.Apply hmac_hasher.go:52-74
+            for (int k = 0; k < st.ncols; k++) {
+                int c = st.cols[k];
+                std::string text = serialize_to_string(row[c].v, cur_type[c]);
+                uint8_t d[32]; hmac_sha256(st.salt, st.salt_len, (const uint8_t*)text.data(), text.size(), d);
+                row[c].set_string(hex_lower(d, 32), OG_STRING); cur_type[c] = TF_UTF8;
+            }
+        } else if (st.kind == STEP_TO_STRING) {                   // ToStringTransformer.Apply to_string.go:58-97
+            for (int k = 0; k < st.ncols; k++) {
+                int c = st.cols[k];
+                row[c].set_string(serialize_to_string(row[c].v, cur_type[c]), st.convert_to_bytes ? OG_BYTES : OG_STRING);
+                cur_type[c] = st.convert_to_bytes ? TF_BYTES : TF_UTF8;
+            }
+        }
+    }
+    return true;
+}
+void result_types(const tf_batch* in, const orc_step* steps, int nsteps, std::vector<int32_t>& out_type, std::vector<uint32_t>& out_cols) {
+    const uint32_t nc = in->ncols;
+    out_type.resize(nc);
     for (uint32_t c = 0; c < nc; c++) out_type[c] = in->cols[c].type;
     for (int s = 0; s < nsteps; s++) {
         if (steps[s].kind == STEP_MASK) for (int k = 0; k < steps[s].ncols; k++) out_type[steps[s].cols[k]] = TF_UTF8;        // hmac_hasher.go:35-47
         if (steps[s].kind == STEP_TO_STRING) for (int k = 0; k < steps[s].ncols; k++) out_type[steps[s].cols[k]] = steps[s].convert_to_bytes ? TF_BYTES : TF_UTF8;  // to_string.go:66-74
     }
-    std::vector<ColBuilder> cbs(nc);
-    std::vector<std::string> names(nc), types(nc);
-    for (uint32_t c = 0; c < nc; c++) {
-        cbs[c].yt = out_type[c]; cbs[c].nullable = !schema[c].required;
-        names[c] = schema[c].name; types[c] = ch_type(schema[c], out_type[c]);
+    // filter_columns (filter_columns_transformer.go:228-236): the surviving columns, schema order kept
+    bool sel = false;
+    for (int s = 0; s < nsteps; s++) if (steps[s].kind == STEP_SELECT_COLS) { sel = true; out_cols.clear(); for (int k = 0; k < steps[s].ncols; k++) out_cols.push_back((uint32_t)steps[s].cols[k]); }
+    if (!sel) for (uint32_t c = 0; c < nc; c++) out_cols.push_back(c);
+}
+int width_of(int32_t tf) {
+    switch (tf) {
+    case TF_INT8: case TF_UINT8: case TF_BOOLEAN: return 1;
+    case TF_INT16: case TF_UINT16: return 2;
+    case TF_INT32: case TF_UINT32: case TF_FLOAT: return 4;
+    case TF_BYTES: case TF_UTF8: case TF_ANY: return 0;
+    default: return 8;
+    }
+}
+}  // namespace
+
+extern "C" int orc_push_encode(const tf_batch* in, const orc_colschema* schema, const orc_step* steps, int nsteps,
+                    int wire_fmt, uint64_t frame_bytes, orc_buf* out_raw, orc_buf* out_wire,
+                    uint64_t* rows_out, tf_rowerr* errs, uint64_t* nerrs) {
+    const uint32_t nc = in->ncols;
+    std::vector<int32_t> out_type; std::vector<uint32_t> out_cols;
+    result_types(in, steps, nsteps, out_type, out_cols);
+    const uint32_t no = (uint32_t)out_cols.size();
+    std::vector<ColBuilder> cbs(no);
+    std::vector<std::string> names(no), types(no);
+    for (uint32_t k = 0; k < no; k++) {
+        const uint32_t c = out_cols[k];
+        cbs[k].yt = out_type[c]; cbs[k].nullable = !schema[c].required;
+        names[k] = schema[c].name; types[k] = ch_type(schema[c], out_type[c]);
     }
     uint64_t kept = 0, ne = 0;
     std::vector<Boxed> row(nc);
     std::vector<int32_t> cur_type(nc);
     for (uint64_t r = 0; r < in->nrows; r++) {
-        // []interface{} of this ChangeItem
-        for (uint32_t c = 0; c < nc; c++) { box(in->cols[c], r, row[c].v); cur_type[c] = in->cols[c].type; }
-        const int kind = in->kinds ? in->kinds[r] : TF_KIND_INSERT;
-        bool keep = true;
-        for (int s = 0; s < nsteps && keep; s++) {
-            const orc_step& st = steps[s];
-            if (st.kind == STEP_FILTER_ROWS) {                       // FilterRowsTransformer.Apply filter_rows.go:99-130
-                if (kind == TF_KIND_UPDATE || kind == TF_KIND_DELETE) { errs[ne++] = tf_rowerr{(uint32_t)r, TF_ROWERR_FILTER_KIND, (uint16_t)s}; keep = false; break; }
-                bool any = false; int err = 0;
-                for (int e = 0; e < st.nexpr && !any && !err; e++) {   // matchItem :137-148 (OR), matchExpression :150-177 (AND)
-                    bool all = true;
-                    for (uint32_t k = st.expr_off[e]; k < st.expr_off[e + 1]; k++) {
-                        bool m = false; int rc = match_value(row[st.terms[k].col].v, st.terms[k], m);
-                        if (rc) { err = rc; break; }
-                        if (!m) { all = false; break; }
-                    }
-                    if (!err && all) any = true;
-                }
-                if (err) { errs[ne++] = tf_rowerr{(uint32_t)r, (uint16_t)err, (uint16_t)s}; keep = false; break; }
-                if (!any) keep = false;
-            } else if (st.kind == STEP_MASK) {                        // HmacHasher.Apply hmac_hasher.go:52-74
-                for (int k = 0; k < st.ncols; k++) {
-                    int c = st.cols[k];
-                    std::string text = serialize_to_string(row[c].v, cur_type[c]);
-                    uint8_t d[32]; hmac_sha256(st.salt, st.salt_len, (const uint8_t*)text.data(), text.size(), d);
-                    row[c].set_string(hex_lower(d, 32), OG_STRING); cur_type[c] = TF_UTF8;
-                }
-            } else if (st.kind == STEP_TO_STRING) {                   // ToStringTransformer.Apply to_string.go:58-97
-                for (int k = 0; k < st.ncols; k++) {
-                    int c = st.cols[k];
-                    row[c].set_string(serialize_to_string(row[c].v, cur_type[c]), st.convert_to_bytes ? OG_BYTES : OG_STRING);
-                    cur_type[c] = st.convert_to_bytes ? TF_BYTES : TF_UTF8;
-                }
-            }
-        }
-        if (!keep) continue;
+        if (!apply_steps(in, r, steps, nsteps, row, cur_type, errs, ne)) continue;
         // sink: restoreVals sink_table.go:698-704 + driver append
-        for (uint32_t c = 0; c < nc; c++) if (!append_value(cbs[c], row[c].v)) return TF_E_FATAL_UNSUPPORTED;
+        for (uint32_t k = 0; k < no; k++) if (!append_value(cbs[k], row[out_cols[k]].v)) return TF_E_FATAL_UNSUPPORTED;
         kept++;
     }
     if (rows_out) *rows_out = kept;
@@ -470,6 +501,63 @@ int orc_push_encode(const tf_batch* in, const orc_colschema* schema, const orc_s
     if (wire_fmt == TF_WIRE_CH_NATIVE_LZ4) { to_buf(ch_compress_frames(raw.data(), raw.size(), frame_bytes), out_wire); return 0; }
     return TF_E_FATAL_UNSUPPORTED;
 }
+
+extern "C" int orc_push_columns(const tf_batch* in, const orc_colschema* schema, const orc_step* steps, int nsteps,
+                     orc_buf* out, orc_regions* regions, int32_t* out_types, uint64_t* rows_out, tf_rowerr* errs, uint64_t* nerrs) {
+    (void)schema;
+    const uint32_t nc = in->ncols;
+    std::vector<int32_t> out_type; std::vector<uint32_t> out_cols;
+    result_types(in, steps, nsteps, out_type, out_cols);
+    const uint32_t no = (uint32_t)out_cols.size();
+    struct CB { std::vector<uint8_t> values, valid_bits, aux, heap; std::vector<uint32_t> offs; bool has_valid, has_aux; };
+    std::vector<CB> cb(no);
+    for (uint32_t k = 0; k < no; k++) {
+        const tf_col& ic = in->cols[out_cols[k]];
+        const bool masked = out_type[out_cols[k]] != ic.type;
+        cb[k].has_valid = ic.validity && !masked; cb[k].has_aux = ic.aux && !masked; cb[k].offs.push_back(0);
+    }
+    uint64_t kept = 0, ne = 0;
+    std::vector<Boxed> row(nc); std::vector<int32_t> cur_type(nc);
+    for (uint64_t r = 0; r < in->nrows; r++) {
+        if (!apply_steps(in, r, steps, nsteps, row, cur_type, errs, ne)) continue;
+        for (uint32_t k = 0; k < no; k++) {
+            const uint32_t c = out_cols[k]; const orc_val& v = row[c].v; const tf_col& ic = in->cols[c]; CB& b = cb[k];
+            const int w = width_of(out_type[c]);
+            if (b.has_valid) { if ((kept & 7) == 0) b.valid_bits.push_back(0); if (v.kind != OG_NIL) b.valid_bits.back() |= (uint8_t)(1u << (kept & 7)); }
+            if (w) {   // the value keeps its input representation (zero for nil)
+                uint8_t tmp[8] = {0};
+                if (v.kind != OG_NIL) std::memcpy(tmp, (const uint8_t*)ic.values + (size_t)w * r, w);
+                b.values.insert(b.values.end(), tmp, tmp + w);
+            } else {
+                if (v.kind != OG_NIL) b.heap.insert(b.heap.end(), v.s, v.s + v.slen);
+                b.offs.push_back((uint32_t)b.heap.size());
+            }
+            if (b.has_aux) {
+                if (ic.type == TF_ANY) b.aux.push_back(((const uint8_t*)ic.aux)[r]);
+                else { uint32_t x = ((const uint32_t*)ic.aux)[r]; const uint8_t* q = (const uint8_t*)&x; b.aux.insert(b.aux.end(), q, q + 4); }
+            }
+        }
+        kept++;
+    }
+    std::vector<uint8_t> buf;
+    auto put = [&](const void* p, size_t n) -> uint64_t { while (buf.size() % 16) buf.push_back(0); uint64_t at = buf.size(); const uint8_t* q = (const uint8_t*)p; buf.insert(buf.end(), q, q + n); return at; };
+    for (uint32_t k = 0; k < no; k++) {
+        CB& b = cb[k]; orc_regions& g = regions[k]; const int w = width_of(out_type[out_cols[k]]);
+        out_types[k] = out_type[out_cols[k]];
+        g.values = w ? put(b.values.data(), b.values.size()) : ~0ull;
+        g.validity = b.has_valid ? put(b.valid_bits.data(), b.valid_bits.size()) : ~0ull;
+        g.aux = b.has_aux ? put(b.aux.data(), b.aux.size()) : ~0ull;
+        g.offsets = w ? ~0ull : put(b.offs.data(), b.offs.size() * 4);
+        g.heap = w ? ~0ull : put(b.heap.data(), b.heap.size());
+        g.heap_len = w ? 0 : b.heap.size();
+    }
+    to_buf(buf, out);
+    if (rows_out) *rows_out = kept;
+    if (nerrs) *nerrs = ne;
+    return 0;
+}
+
+extern "C" {
 
 int orc_ch_decode_frames(const uint8_t* wire, uint64_t n, orc_buf* raw, uint64_t* n_frames) {
     std::vector<uint8_t> r; size_t nf = 0;

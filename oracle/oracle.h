@@ -60,7 +60,7 @@ typedef struct orc_colschema {
     const char* original_type;  /* may be NULL */
 } orc_colschema;
 
-enum { STEP_FILTER_ROWS = 1, STEP_MASK = 2, STEP_TO_STRING = 3 };
+enum { STEP_FILTER_ROWS = 1, STEP_MASK = 2, STEP_TO_STRING = 3, STEP_SKIP_EVENTS = 4, STEP_SELECT_COLS = 5 };
 typedef struct orc_step {
     int32_t kind;
     /* filter_rows */
@@ -69,6 +69,8 @@ typedef struct orc_step {
     const int32_t* cols; int32_t ncols;
     const uint8_t* salt; uint64_t salt_len;
     int32_t convert_to_bytes;
+    int32_t pass_all;      /* filter_rows: table filter misses the renamed table -> rows pass, kinds still checked */
+    int32_t kind_mask;     /* skip_events: bit TF_KIND_* set = drop */
 } orc_step;
 
 typedef struct orc_buf { uint8_t* data; uint64_t len; } orc_buf;
@@ -101,6 +103,13 @@ int orc_push_encode(const tf_batch* in, const orc_colschema* schema,
                     int wire_fmt, uint64_t frame_bytes,
                     orc_buf* out_raw, orc_buf* out_wire,
                     uint64_t* rows_out, tf_rowerr* errs, uint64_t* nerrs);
+
+/* Transformer chain only (TransformerResult.Transformed, pkg/abstract/transformer.go:40-48): the kept rows, columnar,
+ * in one buffer; regions[k] = {values, validity, aux, offsets, heap, heap_len} offsets into it (~0 = absent). */
+typedef struct orc_regions { uint64_t values, validity, aux, offsets, heap, heap_len; } orc_regions;
+int orc_push_columns(const tf_batch* in, const orc_colschema* schema, const orc_step* steps, int nsteps,
+                     orc_buf* out, orc_regions* regions /* one per output column */, int32_t* out_types,
+                     uint64_t* rows_out, tf_rowerr* errs, uint64_t* nerrs);
 
 /* Verify + decode a frame stream with the oracle's own LZ4 decoder and CityHash. */
 int orc_ch_decode_frames(const uint8_t* wire, uint64_t n, orc_buf* raw, uint64_t* n_frames);

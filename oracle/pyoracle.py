@@ -56,7 +56,11 @@ class OrcColSchema(C.Structure):
 class OrcStep(C.Structure):
     _fields_ = [("kind", C.c_int32), ("terms", C.POINTER(OrcTerm)), ("expr_off", C.c_void_p), ("nexpr", C.c_int32),
                 ("cols", C.c_void_p), ("ncols", C.c_int32), ("salt", C.c_char_p), ("salt_len", C.c_uint64),
-                ("convert_to_bytes", C.c_int32)]
+                ("convert_to_bytes", C.c_int32), ("pass_all", C.c_int32), ("kind_mask", C.c_int32)]
+
+
+class OrcRegions(C.Structure):
+    _fields_ = [("values", C.c_uint64), ("validity", C.c_uint64), ("aux", C.c_uint64), ("offsets", C.c_uint64), ("heap", C.c_uint64), ("heap_len", C.c_uint64)]
 
 
 class OrcBuf(C.Structure):
@@ -67,7 +71,7 @@ class OrcBuf(C.Structure):
  OG_BOOL, OG_STRING, OG_BYTES, OG_TIME, OG_DURATION, OG_JSON, OG_INT, OG_UINT) = range(19)
 OP_EQ, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE, OP_IN, OP_NOTIN, OP_MATCH, OP_NOTMATCH = range(10)
 LV_INT, LV_FLOAT, LV_BOOL, LV_STRING, LV_TIME, LV_NULL, LV_LIST = 1, 2, 3, 4, 5, 6, 16
-STEP_FILTER_ROWS, STEP_MASK, STEP_TO_STRING = 1, 2, 3
+STEP_FILTER_ROWS, STEP_MASK, STEP_TO_STRING, STEP_SKIP_EVENTS, STEP_SELECT_COLS = 1, 2, 3, 4, 5
 
 _lib = None
 
@@ -95,6 +99,8 @@ def lib():
         L.orc_push_encode.argtypes = [C.POINTER(abi.TfBatch), C.POINTER(OrcColSchema), C.POINTER(OrcStep), C.c_int,
                                       C.c_int, C.c_uint64, C.POINTER(OrcBuf), C.POINTER(OrcBuf),
                                       C.POINTER(C.c_uint64), C.POINTER(abi.TfRowErr), C.POINTER(C.c_uint64)]
+        L.orc_push_columns.argtypes = [C.POINTER(abi.TfBatch), C.POINTER(OrcColSchema), C.POINTER(OrcStep), C.c_int, C.POINTER(OrcBuf),
+                                       C.POINTER(OrcRegions), C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(abi.TfRowErr), C.POINTER(C.c_uint64)]
         L.orc_ch_decode_frames.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(OrcBuf), C.POINTER(C.c_uint64)]
         L.orc_free.argtypes = [C.POINTER(OrcBuf)]; L.orc_free.restype = None
         _lib = L
@@ -426,13 +432,18 @@ def _column_suitable(term: Term, yt: str) -> bool:
 class Plan:
     schema: List[dict]                 # input ColSchema dicts
     result_schema: List[dict]
-    steps: List[dict]                  # {"kind":..., ...} kept by Suitable()
+    steps: List[dict]                  # {"kind":..., "index": position among the kept transformers, ...}
+    out_cols: List[int] = None         # input index of every surviving column
+    result_table: Tuple[str, str] = None
 
 
 def build_plan(ns: str, name: str, schema: List[dict], transformers: List[dict]) -> Plan:
-    """transformation.AddTablePlan transformation.go:46-85."""
-    cur = [dict(c) for c in schema]
+    """transformation.AddTablePlan transformation.go:46-85. Suitable() is asked with the ORIGINAL table id for every
+    transformer (:54); transformers that re-check item.TableID() inside Apply (filter_rows.go:109) see renames."""
+    cur = [dict(c, _in=i) for i, c in enumerate(schema)]
+    cur_ns, cur_name = ns, name
     steps: List[dict] = []
+    idx = 0
     for tr in transformers:
         (ttype, cfg), = [(k, v) for k, v in tr.items() if k != "transformerId"]
         cfg = cfg or {}
@@ -447,15 +458,40 @@ def build_plan(ns: str, name: str, schema: List[dict], transformers: List[dict])
             ok = True
             for terms in exprs:                                  # Suitable filter_rows.go:445-476
                 for t in terms:
-                    if t.attribute not in names:
-                        ok = False; break
-                    if not _column_suitable(t, cur[names.index(t.attribute)]["type"]):
-                        ok = False; break
-                if not ok:
-                    break
+                    if t.attribute not in names or not _column_suitable(t, cur[names.index(t.attribute)]["type"]):
+                        ok = False
             if not ok:
                 continue
-            steps.append({"kind": "filter_rows", "exprs": [[(names.index(t.attribute), t) for t in terms] for terms in exprs]})
+            steps.append({"kind": "filter_rows", "index": idx, "pass_all": not _tables_match(cfg.get("tables"), cur_ns, cur_name),
+                          "exprs": [[(cur[names.index(t.attribute)]["_in"], t) for t in terms] for terms in exprs]}); idx += 1
+        elif ttype == "skip_events":
+            if not _tables_match(cfg.get("tables"), ns, name):
+                continue
+            mask = 0
+            for ev in cfg.get("events") or []:
+                mask |= {"insert": 1, "update": 2, "delete": 4}.get(ev, 0)
+            steps.append({"kind": "skip_events", "index": idx, "kind_mask": mask}); idx += 1
+        elif ttype == "filter_columns":
+            if not _tables_match(cfg.get("tables"), ns, name):
+                continue
+            ccfg = cfg.get("columns") or {}
+            inc = ccfg.get("includeColumns") or ccfg.get("include_columns") or []
+            exc = ccfg.get("excludeColumns") or ccfg.get("exclude_columns") or []
+            if any((not _filter_match(inc, exc, c["name"])) and c.get("key") for c in cur):   # validSchema :219-226
+                continue
+            cur = [c for c in cur if _filter_match(inc, exc, c["name"])]
+            steps.append({"kind": "filter_columns", "index": idx, "keep": [c["_in"] for c in cur]}); idx += 1
+        elif ttype == "rename_tables":
+            hit = None
+            for r in cfg.get("renameTables") or []:
+                o, nw = r.get("originalName") or {}, r.get("newName") or {}
+                if o.get("nameSpace", "") == ns and o.get("name", "") == name:
+                    hit = (nw.get("nameSpace", ""), nw.get("name", ""))
+            if hit is None:
+                continue
+            if (cur_ns, cur_name) == (ns, name):
+                cur_ns, cur_name = hit
+            steps.append({"kind": "rename_tables", "index": idx}); idx += 1
         elif ttype == "mask_field":
             if not _tables_match(cfg.get("tables"), ns, name):
                 continue
@@ -463,25 +499,25 @@ def build_plan(ns: str, name: str, schema: List[dict], transformers: List[dict])
             if cols and not any(c in names for c in cols):       # hmac_hasher.go:76-89
                 continue
             salt = ((cfg.get("maskFunctionHash") or {}).get("userDefinedSalt", ""))
-            idx = [names.index(c) for c in names if c in cols]
-            steps.append({"kind": "mask_field", "cols": idx, "salt": salt.encode()})
-            for i in idx:                                        # hmac_hasher.go:35-47
+            pos = [i for i, n_ in enumerate(names) if n_ in cols]
+            steps.append({"kind": "mask_field", "index": idx, "cols": [cur[i]["_in"] for i in pos], "salt": salt.encode()}); idx += 1
+            for i in pos:                                        # hmac_hasher.go:35-47
                 cur[i] = dict(cur[i]); cur[i]["type"] = "utf8"; cur[i]["original_type"] = ""
         elif ttype == "convert_to_string":
             if not _tables_match(cfg.get("tables"), ns, name):
                 continue
             ccfg = cfg.get("columns") or {}
             inc = ccfg.get("includeColumns") or []; exc = ccfg.get("excludeColumns") or []
-            idx = [i for i, n in enumerate(names) if _filter_match(inc, exc, n)]
-            if (inc or exc) and not idx:
+            pos = [i for i, n_ in enumerate(names) if _filter_match(inc, exc, n_)]
+            if (inc or exc) and not pos:
                 continue
             to_bytes = bool(cfg.get("convert_to_bytes"))
-            steps.append({"kind": "convert_to_string", "cols": idx, "to_bytes": to_bytes})
-            for i in idx:
+            steps.append({"kind": "convert_to_string", "index": idx, "cols": [cur[i]["_in"] for i in pos], "to_bytes": to_bytes}); idx += 1
+            for i in pos:
                 cur[i] = dict(cur[i]); cur[i]["type"] = "string" if to_bytes else "utf8"
         else:
             raise NotImplementedError(ttype)
-    return Plan(schema, cur, steps)
+    return Plan(schema, [{k: v for k, v in c.items() if k != "_in"} for c in cur], steps, [c["_in"] for c in cur], (cur_ns, cur_name))
 
 
 # ----------------------------------------------------------------------------- marshaling to liboracle
@@ -549,8 +585,7 @@ class PushResult:
     wire_len: int = 0
 
 
-def push_encode(batch: abi.Batch, plan: Plan, wire_fmt: int, frame_bytes: int = 32768, want_bytes: bool = True) -> PushResult:
-    """Row-at-a-time reference path over one batch: transformers -> Restore -> native block -> LZ4 frames."""
+def _marshal(plan: Plan):
     keep = _Keep()
     cschema = _schema_to_c(plan.schema, keep)
     csteps = (OrcStep * max(1, len(plan.steps)))()
@@ -563,12 +598,26 @@ def push_encode(batch: abi.Batch, plan: Plan, wire_fmt: int, frame_bytes: int = 
                 tarr[k] = term_to_c(c, t, keep)
             off = keep.add(np.zeros(len(st["exprs"]) + 1, dtype=np.uint32)); np.cumsum([len(x) for x in st["exprs"]], out=off[1:])
             s.kind = STEP_FILTER_ROWS; s.terms = C.cast(tarr, C.POINTER(OrcTerm)); s.expr_off = off.ctypes.data; s.nexpr = len(st["exprs"])
+            s.pass_all = 1 if st.get("pass_all") else 0; s.convert_to_bytes = st["index"]     # (reused as the step's transformer index in error rows)
+        elif st["kind"] == "skip_events":
+            s.kind = STEP_SKIP_EVENTS; s.kind_mask = st["kind_mask"]
+        elif st["kind"] == "filter_columns":
+            cols = keep.add(np.asarray(st["keep"], dtype=np.int32))
+            s.kind = STEP_SELECT_COLS; s.cols = cols.ctypes.data; s.ncols = len(st["keep"])
+        elif st["kind"] == "rename_tables":
+            s.kind = 0
         elif st["kind"] == "mask_field":
             cols = keep.add(np.asarray(st["cols"], dtype=np.int32))
             s.kind = STEP_MASK; s.cols = cols.ctypes.data; s.ncols = len(st["cols"]); s.salt = keep.add(st["salt"]); s.salt_len = len(st["salt"])
         elif st["kind"] == "convert_to_string":
             cols = keep.add(np.asarray(st["cols"], dtype=np.int32))
             s.kind = STEP_TO_STRING; s.cols = cols.ctypes.data; s.ncols = len(st["cols"]); s.convert_to_bytes = 1 if st["to_bytes"] else 0
+    return keep, cschema, csteps
+
+
+def push_encode(batch: abi.Batch, plan: Plan, wire_fmt: int, frame_bytes: int = 32768, want_bytes: bool = True) -> PushResult:
+    """Row-at-a-time reference path over one batch: transformers -> Restore -> native block -> LZ4 frames."""
+    keep, cschema, csteps = _marshal(plan)
     tb = batch.as_struct()
     raw, wire = OrcBuf(), OrcBuf()
     rows = C.c_uint64(); nerr = C.c_uint64()
@@ -584,3 +633,35 @@ def push_encode(batch: abi.Batch, plan: Plan, wire_fmt: int, frame_bytes: int = 
     res.raw_len = raw.len; res.wire_len = wire.len
     lib().orc_free(C.byref(raw)); lib().orc_free(C.byref(wire))
     return res
+
+
+def push_columns(batch: abi.Batch, plan: Plan):
+    """TransformerResult of the chain: (Batch of Transformed rows, errors)."""
+    keep, cschema, csteps = _marshal(plan)
+    tb = batch.as_struct()
+    no = len(plan.out_cols)
+    out = OrcBuf(); regs = (OrcRegions * max(1, no))(); types = (C.c_int32 * max(1, no))()
+    rows = C.c_uint64(); nerr = C.c_uint64()
+    errs = (abi.TfRowErr * max(1, batch.nrows))()
+    rc = lib().orc_push_columns(C.byref(tb), cschema, csteps, len(plan.steps), C.byref(out), regs, types, C.byref(rows), errs, C.byref(nerr))
+    if rc != 0:
+        raise RuntimeError(f"oracle push_columns rc={rc}")
+    buf = C.string_at(out.data, out.len) if out.len else b""
+    lib().orc_free(C.byref(out))
+    n = rows.value
+    NONE = 2 ** 64 - 1
+    cols = []
+    for k in range(no):
+        g, t = regs[k], types[k]
+        def arr(off, nbytes, dtype):
+            if off == NONE:
+                return None
+            return np.frombuffer(buf[off:off + nbytes], dtype=dtype).copy()
+        if t in abi.VAR_TYPES:
+            cols.append(abi.Column(t, offsets=arr(g.offsets, 4 * (n + 1), np.uint32), heap=arr(g.heap, g.heap_len, np.uint8),
+                                   validity=arr(g.validity, (n + 7) // 8, np.uint8), aux=arr(g.aux, n, np.uint8)))
+        else:
+            dt = abi.FIXED_DTYPE[t]
+            cols.append(abi.Column(t, values=arr(g.values, n * np.dtype(dt).itemsize, dt), validity=arr(g.validity, (n + 7) // 8, np.uint8),
+                                   aux=arr(g.aux, 4 * n, np.uint32)))
+    return abi.Batch(n, cols), [(errs[i].row, errs[i].code, errs[i].term) for i in range(nerr.value)]

@@ -159,6 +159,26 @@ def test_filter_rows_semantics_matrix(eng, po):
     assert got.rows_out == 0 and len(got.errors) == batch.nrows and got.errors[0][1] == abi.TF_ROWERR_FILTER_TYPEPAIR
 
 
+def test_skip_events_filter_columns_rename_chain(eng, po):
+    """skip_events.go:52-62, filter_columns_transformer.go:228-236, rename.go:46-67 chained with filter_rows / mask_field."""
+    batch, schema = all_types_batch(2500, seed=13)
+    schema = [dict(c, key=(c["name"] == "c_int8")) for c in schema]
+    kinds = np.zeros(batch.nrows, dtype=np.uint8); kinds[::7] = abi.TF_KIND_DELETE; kinds[3::11] = abi.TF_KIND_UPDATE
+    b2 = abi.Batch(batch.nrows, batch.columns, kinds)
+    chains = [
+        [{"skip_events": {"events": ["delete", "update"]}}, {"filter_rows": {"filter": "c_int32 > 0"}}],        # kinds dropped before filter_rows can reject them
+        [{"skip_events": {"events": ["delete"]}}, {"filter_rows": {"filter": "c_int32 > 0"}}],                  # updates still become error rows
+        [{"filter_columns": {"columns": {"excludeColumns": ["^n_", "interval"]}}}],
+        [{"filter_rows": {"filter": "n_int16 != NULL"}}, {"skip_events": {"events": ["insert"]}}],
+        [{"rename_tables": {"renameTables": [{"originalName": {"nameSpace": "db", "name": "t"}, "newName": {"nameSpace": "x", "name": "y"}}]}},
+         {"filter_rows": {"tables": {"includeTables": ["^db\\.t$"]}, "filter": "c_int32 > 0"}},            # pass_all after the rename, kinds still rejected
+         {"filter_columns": {"columns": {"includeColumns": ["^c_"]}}},
+         {"mask_field": {"columns": ["c_utf8", "c_int64", "n_bool"], "maskFunctionHash": {"userDefinedSalt": "salt"}}}],
+    ]
+    for trs in chains:
+        check(eng, po, b2, schema, trs)
+
+
 def test_mask_field_on_device(eng, po):
     batch, schema = all_types_batch(1500, seed=21)
     cols = ["c_int8", "n_int32", "c_uint64", "n_bool", "c_date", "n_datetime", "n_timestamp", "c_utf8", "n_bytes", "n_any", "c_int64"]
@@ -264,3 +284,49 @@ def test_api_errors(eng):
         eng.plan("db", "t", schema, [{"mask_field": {"columns": ["a"], "maskFunctionHash": {"userDefinedSalt": "s"}}}, {"filter_rows": {"filter": "a = 'x'"}}], {"type": "clickhouse"})
     with pytest.raises(engine.EngineError):
         eng.push_encode(pid, abi.Batch(1, [abi.fixed_to_column(abi.TF_INT32, [1])]), abi.TF_WIRE_CH_JSONEACHROW)
+
+
+def assert_batches_equal(a: abi.Batch, b: abi.Batch):
+    assert a.nrows == b.nrows and len(a.columns) == len(b.columns)
+    n = a.nrows
+    for k, (x, y) in enumerate(zip(a.columns, b.columns)):
+        assert x.type == y.type, k
+        for f in ("values", "offsets", "heap", "aux"):
+            u, v = getattr(x, f), getattr(y, f)
+            assert (u is None) == (v is None), (k, f)
+            if u is not None:
+                assert np.array_equal(np.asarray(u).view(np.uint8), np.asarray(v).view(np.uint8)), (k, f)
+        assert (x.validity is None) == (y.validity is None), k
+        if x.validity is not None:
+            assert np.array_equal(np.unpackbits(x.validity, bitorder="little")[:n], np.unpackbits(y.validity, bitorder="little")[:n]), k
+
+
+def test_push_columns_transformed_batch(eng, po):
+    """tfgpu_push_columns: TransformerResult.Transformed comes back columnar and equals the oracle's, row errors too."""
+    batch, schema = all_types_batch(3000, seed=31)
+    schema = [dict(c, key=(c["name"] == "c_int8")) for c in schema]
+    kinds = np.zeros(batch.nrows, dtype=np.uint8); kinds[::9] = abi.TF_KIND_UPDATE
+    b2 = abi.Batch(batch.nrows, batch.columns, kinds)
+    chains = [
+        [],
+        [{"filter_rows": {"filter": "c_int32 > 0 AND n_int16 != NULL"}}],
+        [{"skip_events": {"events": ["update"]}}, {"filter_columns": {"columns": {"excludeColumns": ["double", "bytes"]}}},
+         {"mask_field": {"columns": ["c_utf8", "n_int32", "n_timestamp"], "maskFunctionHash": {"userDefinedSalt": "pepper"}}}],
+    ]
+    for trs in chains:
+        pid = eng.plan("db", "t", schema, trs)
+        plan = po.build_plan("db", "t", schema, trs)
+        got, gerr = eng.push_columns(pid, b2)
+        ref, rerr = po.push_columns(b2, plan)
+        assert gerr == rerr
+        assert_batches_equal(got, ref)
+    # and the Transformed batch can be pushed again (it is a valid tf_batch): encode(transform(x)) == encode_with_transform(x)
+    trs = [{"filter_rows": {"filter": "c_int64 > 0"}}]
+    pid = eng.plan("db", "t", schema, trs, {"type": "clickhouse"}); pid0 = eng.plan("db", "t", schema, [], {"type": "clickhouse"})
+    mid, _ = eng.push_columns(pid, batch)
+    assert eng.push_encode(pid0, mid, RAW).wire == eng.push_encode(pid, batch, RAW).wire
+    hb, hs = workload.make_hits_batch(20_000, seed=4)
+    pid = eng.plan("public", "hits", hs, workload.headline_transformers(workload.counterid_threshold(hb, hs)))
+    got, _ = eng.push_columns(pid, hb)
+    ref, _ = po.push_columns(hb, po.build_plan("public", "hits", hs, workload.headline_transformers(workload.counterid_threshold(hb, hs))))
+    assert_batches_equal(got, ref)

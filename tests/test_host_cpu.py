@@ -196,3 +196,28 @@ def test_two_rank_gloo_sharding(tmp_path):
     line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
     d = json.loads(line)
     assert d["sum_rows_in"] == d["nrows"] and d["sum_rows_out"] == d["whole_rows_out"]
+
+
+def test_plan_filter_columns_skip_events_rename(po):
+    """filter_columns_transformer.go:215-236, skip_events.go:52-66, rename.go:46-67 — plan-level agreement with the oracle."""
+    schema = [{"name": "id", "type": "int32", "key": True, "required": True}, {"name": "a", "type": "utf8"}, {"name": "b", "type": "int64"}, {"name": "secret", "type": "utf8"}]
+    trs = [
+        {"skip_events": {"events": ["delete", "truncate"]}},
+        {"rename_tables": {"renameTables": [{"originalName": {"nameSpace": "db", "name": "t"}, "newName": {"nameSpace": "dst", "name": "t2"}}]}},
+        {"filter_rows": {"tables": {"includeTables": ["^db\\.t$"]}, "filter": "b > 5"}},     # Suitable by the original id, but Apply sees dst.t2
+        {"filter_columns": {"columns": {"excludeColumns": ["^secret$"]}}},
+        {"filter_rows": {"filter": "secret = 'x'"}},                                          # column gone -> not Suitable
+        {"mask_field": {"columns": ["a"], "maskFunctionHash": {"userDefinedSalt": "s"}}},
+    ]
+    d = engine.plan_validate("db", "t", schema, trs, {"type": "clickhouse"})
+    plan = po.build_plan("db", "t", schema, trs)
+    assert d["result_table"] == "dst.t2" and plan.result_table == ("dst", "t2")
+    assert d["out_cols"] == plan.out_cols == [0, 1, 2]
+    assert [s["type"] for s in d["steps"]] == [s["kind"] for s in plan.steps] == ["skip_events", "rename_tables", "filter_rows", "filter_columns", "mask_field"]
+    assert d["steps"][2]["pass_all"] is True and plan.steps[2]["pass_all"] is True
+    assert d["steps"][0]["kind_mask"] == plan.steps[0]["kind_mask"] == 4
+    assert [c["name"] for c in d["result_schema"]] == ["id", "a", "b"] and d["result_schema"][1]["type"] == "utf8"
+    # a primary key cannot be dropped: the transformer is simply not Suitable
+    d2 = engine.plan_validate("db", "t", schema, [{"filter_columns": {"columns": {"includeColumns": ["^a$"]}}}])
+    assert d2["steps"] == [] and d2["out_cols"] == [0, 1, 2, 3]
+    assert po.build_plan("db", "t", schema, [{"filter_columns": {"columns": {"includeColumns": ["^a$"]}}}]).out_cols == [0, 1, 2, 3]

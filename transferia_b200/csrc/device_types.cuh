@@ -33,6 +33,8 @@ struct DCol {
     uint64_t hdr_off;   // where this column's name/type header starts in the block  (k_layout)
     uint64_t null_off;  // null map start                                               (k_layout)
     uint64_t out_off;   // data start                                                   (k_layout)
+    uint64_t aux_off;   // columnar output only: nanos / any-tags region
+    uint64_t offs_off;  // columnar output only: uint32 offsets region (nrows+1)
 };
 
 struct DTerm {          // must match tfplan::DTerm
@@ -42,7 +44,9 @@ struct DTerm {          // must match tfplan::DTerm
     uint32_t list_off, pad;
 };
 
-struct DFilterStep { int32_t expr_begin, nexpr, step_index, pad; };
+// flags: bit0 = skip_events step (expr_begin holds the kind mask), bit1 = filter_rows that lets every row pass
+// (its table filter does not match the renamed table) but still rejects update/delete kinds
+struct DFilterStep { int32_t expr_begin, nexpr, step_index, flags; };
 
 // counters / layout results living in device memory, read back only by the host API that needs them
 struct DState {

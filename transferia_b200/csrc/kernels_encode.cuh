@@ -177,7 +177,9 @@ __global__ void __launch_bounds__(256) k_filter(FilterArgs a) {
         const int kind = a.kinds ? a.kinds[r] : TF_KIND_INSERT;
         for (int s = 0; s < a.nsteps && keep; s++) {
             const DFilterStep st = a.steps[s];
+            if (st.flags & 1) { if ((st.expr_begin >> kind) & 1) keep = false; continue; }            // skip_events.go:52-62
             if (kind == TF_KIND_UPDATE || kind == TF_KIND_DELETE) { err = TF_ROWERR_FILTER_KIND; estep = st.step_index; keep = false; break; }
+            if (st.flags & 2) continue;
             bool any = false;
             for (int e = 0; e < st.nexpr && !any && !err; e++) {            // matchItem: OR over filters
                 bool all = true;
@@ -229,7 +231,8 @@ __global__ void __launch_bounds__(256) k_compact_sel(const uint8_t* keep, const 
 
 // ------------------------------------------------------------------ layout of the native block
 struct LayoutArgs {
-    DCol* cols; int ncols;
+    DCol* cols; int ncols;                     // ncols = OUTPUT columns; out_cols[k] = index into cols
+    const int32_t* out_cols;
     const int32_t* str_cols; int nstr;         // column index of each OK_STR slot
     const uint32_t* tile_sum;                  // [nstr][ntiles_cap] encoded bytes per tile of STR_TILE kept rows
     uint64_t* tile_base;                       // [nstr][ntiles_cap] exclusive prefix within the column
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(256) k_layout_finish(LayoutArgs a) {
         const int c = base + threadIdx.x;
         __syncthreads();
         if (c < a.ncols) {       // every thread fetches its own column's sizes (global latency paid once, in parallel)
-            const DCol& d = a.cols[c];
+            const DCol& d = a.cols[a.out_cols[c]];
             s_size[0][threadIdx.x] = a.col_header_off[c + 1] - a.col_header_off[c];
             s_size[1][threadIdx.x] = (d.nullable && n) ? n : 0;
             s_size[2][threadIdx.x] = n ? ((d.out_kind == OK_STR) ? a.col_bytes[d.str_slot] : (uint64_t)d.out_w * n) : 0;
@@ -294,9 +297,11 @@ __global__ void __launch_bounds__(256) k_layout_finish(LayoutArgs a) {
         }
         __syncthreads();
         if (c < a.ncols) {
-            DCol& d = a.cols[c];
+            DCol& d = a.cols[a.out_cols[c]];
             const uint64_t p = s_pos[threadIdx.x];
             d.hdr_off = p; d.null_off = p + s_size[0][threadIdx.x]; d.out_off = d.null_off + s_size[1][threadIdx.x];
+            const uint32_t hb = a.col_header_off[c], hn = (uint32_t)s_size[0][threadIdx.x];
+            for (uint32_t k = 0; k < hn; k++) a.raw[p + k] = a.col_headers[hb + k];       // this column's "name,type,0"
         }
     }
     __syncthreads();
@@ -306,11 +311,53 @@ __global__ void __launch_bounds__(256) k_layout_finish(LayoutArgs a) {
         a.st->n_frames = p ? (p + a.frame_bytes - 1) / a.frame_bytes : 1;
         a.st->frame_ticket = 0;
     }
-    __syncthreads();
-    for (int c = 0; c < a.ncols; c++) {
-        const uint32_t hb = a.col_header_off[c], he = a.col_header_off[c + 1];
-        for (uint32_t k = hb + threadIdx.x; k < he; k += blockDim.x) a.raw[a.cols[c].hdr_off + (k - hb)] = a.col_headers[k];
+}
+
+// Columnar (tf_batch-shaped) output for tfgpu_push_columns: per output column 16-byte aligned regions
+// [values | validity bitmap | aux | offsets | heap]; the region table goes back to the host with the data.
+struct ColRegions { uint64_t values, validity, aux, offsets, heap, heap_len; };   // offsets into the buffer; ~0 = absent
+
+__global__ void __launch_bounds__(256) k_layout_columnar(LayoutArgs a, ColRegions* regions) {
+    __shared__ uint64_t s_sz[5][256];
+    __shared__ uint64_t s_pos[256];
+    __shared__ uint64_t s_run;
+    const uint64_t n = a.st->n_kept;
+    if (threadIdx.x == 0) s_run = 0;
+    for (int base = 0; base < a.ncols; base += 256) {
+        const int k = base + threadIdx.x;
+        __syncthreads();
+        if (k < a.ncols) {
+            const DCol& d = a.cols[a.out_cols[k]];
+            const bool var = d.out_kind == OK_STR || d.out_kind == OK_MASK;
+            const uint64_t heap = d.out_kind == OK_STR ? a.col_bytes[d.str_slot] : (d.out_kind == OK_MASK ? 64 * n : 0);
+            s_sz[0][threadIdx.x] = var ? 0 : (uint64_t)d.out_w * n;                                   // values
+            s_sz[1][threadIdx.x] = (d.validity && d.out_kind != OK_MASK) ? (n + 7) / 8 : 0;          // validity bitmap
+            s_sz[2][threadIdx.x] = (d.aux && d.out_kind != OK_MASK) ? (d.type == TF_ANY ? n : 4 * n) : 0;   // aux
+            s_sz[3][threadIdx.x] = var ? 4 * (n + 1) : 0;                                             // offsets
+            s_sz[4][threadIdx.x] = heap;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint64_t p = s_run; const int m = a.ncols - base < 256 ? a.ncols - base : 256;
+            for (int q = 0; q < m; q++) { s_pos[q] = p; for (int z = 0; z < 5; z++) p += (s_sz[z][q] + 15) & ~15ull; }
+            s_run = p;
+        }
+        __syncthreads();
+        if (k < a.ncols) {
+            DCol& d = a.cols[a.out_cols[k]];
+            uint64_t p = s_pos[threadIdx.x]; ColRegions r;
+            auto take = [&](int z) { const uint64_t at = p; p += (s_sz[z][threadIdx.x] + 15) & ~15ull; return at; };
+            const uint64_t v = take(0), val = take(1), ax = take(2), of = take(3), hp = take(4);
+            const bool var = d.out_kind == OK_STR || d.out_kind == OK_MASK;
+            d.out_off = var ? hp : v; d.null_off = val; d.aux_off = ax; d.offs_off = of;
+            r.values = var ? ~0ull : v; r.validity = s_sz[1][threadIdx.x] ? val : ~0ull; r.aux = s_sz[2][threadIdx.x] ? ax : ~0ull;
+            r.offsets = var ? of : ~0ull; r.heap = var ? hp : ~0ull; r.heap_len = s_sz[4][threadIdx.x];
+            regions[k] = r;
+            if (var) ((uint32_t*)(a.raw + of))[n] = (uint32_t)s_sz[4][threadIdx.x];      // offsets[nrows] = heap length
+        }
     }
+    __syncthreads();
+    if (threadIdx.x == 0) { a.st->raw_total = s_run; a.st->n_frames = 0; a.st->frame_ticket = 0; }
 }
 
 // ------------------------------------------------------------------ fixed-width columns
@@ -319,17 +366,20 @@ struct EncodeArgs {
     const int32_t* slots;          // per blockIdx.y: column index, bit 30 set = this slot is the column's null map
     const uint32_t* sel; const DState* st; uint8_t* raw;
     uint32_t* tile_sum; const uint64_t* tile_base; uint32_t ntiles_cap;
+    int columnar;                  // 1: Transformed batch back in tf_batch layout (no LEB128, offsets arrays, no cast)
 };
 
 #define TF_SLOT_NULLMAP (1 << 30)
+#define TF_SLOT_AUX (1 << 29)       // columnar output: the column's aux array (time nanos u32 / any tags u8)
 #define TF_FIX_TILE_WORDS 2048
 #define CH_MAX_DATE_SEC 4291747200LL   // 2106-01-01T00:00:00Z (columntypes/types.go:15-18)
 
 // One output element after the typesystem cast (columntypes.Restore -> abstract.Restore are the identity
 // for values whose Go type already matches the column type; what remains is the ClickHouse clamp/unit rule).
-__device__ __forceinline__ uint64_t elem_value(const DCol& c, const uint32_t* sel, uint64_t j, uint64_t n, bool nullmap) {
+__device__ __forceinline__ uint64_t elem_value(const DCol& c, const uint32_t* sel, uint64_t j, uint64_t n, bool nullmap, bool aux = false) {
     if (j >= n) return 0;
     const uint64_t r = sel ? sel[j] : j;
+    if (aux) return c.type == TF_ANY ? (uint64_t)c.aux[r] : (uint64_t)((const uint32_t*)c.aux)[r];
     const bool valid = row_valid(c, r);
     if (nullmap) return valid ? 0 : 1;
     if (!valid) return 0;
@@ -359,13 +409,13 @@ __device__ __forceinline__ uint64_t elem_value(const DCol& c, const uint32_t* se
 }
 
 // 4 consecutive bytes [4q, 4q+4) of the column's little-endian element stream
-__device__ __forceinline__ uint32_t stream_word(const DCol& c, const uint32_t* sel, uint64_t q, uint64_t n, int w, bool nullmap) {
+__device__ __forceinline__ uint32_t stream_word(const DCol& c, const uint32_t* sel, uint64_t q, uint64_t n, int w, bool nullmap, bool aux = false) {
     switch (w) {
-    case 1: return (uint32_t)elem_value(c, sel, 4 * q, n, nullmap) | ((uint32_t)elem_value(c, sel, 4 * q + 1, n, nullmap) << 8) |
-                   ((uint32_t)elem_value(c, sel, 4 * q + 2, n, nullmap) << 16) | ((uint32_t)elem_value(c, sel, 4 * q + 3, n, nullmap) << 24);
-    case 2: return (uint32_t)(elem_value(c, sel, 2 * q, n, nullmap) & 0xffff) | ((uint32_t)(elem_value(c, sel, 2 * q + 1, n, nullmap) & 0xffff) << 16);
-    case 4: return (uint32_t)elem_value(c, sel, q, n, nullmap);
-    default: { const uint64_t v = elem_value(c, sel, q >> 1, n, nullmap); return (uint32_t)(v >> ((q & 1) * 32)); }
+    case 1: return (uint32_t)elem_value(c, sel, 4 * q, n, nullmap, aux) | ((uint32_t)elem_value(c, sel, 4 * q + 1, n, nullmap, aux) << 8) |
+                   ((uint32_t)elem_value(c, sel, 4 * q + 2, n, nullmap, aux) << 16) | ((uint32_t)elem_value(c, sel, 4 * q + 3, n, nullmap, aux) << 24);
+    case 2: return (uint32_t)(elem_value(c, sel, 2 * q, n, nullmap, aux) & 0xffff) | ((uint32_t)(elem_value(c, sel, 2 * q + 1, n, nullmap, aux) & 0xffff) << 16);
+    case 4: return (uint32_t)elem_value(c, sel, q, n, nullmap, aux);
+    default: { const uint64_t v = elem_value(c, sel, q >> 1, n, nullmap, aux); return (uint32_t)(v >> ((q & 1) * 32)); }
     }
 }
 
@@ -375,11 +425,11 @@ __device__ __forceinline__ uint32_t stream_word(const DCol& c, const uint32_t* s
 // OUTPUT address: every store is an aligned, fully coalesced 128 B per warp.
 __global__ void __launch_bounds__(256) k_encode_fixed(EncodeArgs a) {
     const int32_t slot = a.slots[blockIdx.y];
-    const bool nullmap = (slot & TF_SLOT_NULLMAP) != 0;
-    const DCol c = a.cols[slot & ~TF_SLOT_NULLMAP];
+    const bool nullmap = (slot & TF_SLOT_NULLMAP) != 0, aux = (slot & TF_SLOT_AUX) != 0;
+    const DCol c = a.cols[slot & ~(TF_SLOT_NULLMAP | TF_SLOT_AUX)];
     const uint64_t n = a.st->n_kept;
-    const int w = nullmap ? 1 : c.out_w;
-    const uint64_t base = nullmap ? c.null_off : c.out_off;
+    const int w = nullmap ? 1 : (aux ? (c.type == TF_ANY ? 1 : 4) : c.out_w);
+    const uint64_t base = nullmap ? c.null_off : (aux ? c.aux_off : c.out_off);
     const uint32_t m = (uint32_t)(base & 3);
     const uint64_t total = n * (uint64_t)w;
     const uint64_t T = (m + total + 3) >> 2;
@@ -390,9 +440,9 @@ __global__ void __launch_bounds__(256) k_encode_fixed(EncodeArgs a) {
 #pragma unroll 2
     for (uint32_t it = 0; it < TF_FIX_TILE_WORDS / 256; it++) {
         const uint64_t t = t0 + it * 256 + threadIdx.x;      // uniform trip count: shuffles below need the whole warp
-        const uint32_t wcur = (t < T) ? stream_word(c, a.sel, t, n, w, nullmap) : 0;
+        const uint32_t wcur = (t < T) ? stream_word(c, a.sel, t, n, w, nullmap, aux) : 0;
         uint32_t wprev = __shfl_up_sync(0xffffffffu, wcur, 1);
-        if (lane == 0) wprev = (m && t > 0 && t <= T) ? stream_word(c, a.sel, t - 1, n, w, nullmap) : 0;
+        if (lane == 0) wprev = (m && t > 0 && t <= T) ? stream_word(c, a.sel, t - 1, n, w, nullmap, aux) : 0;
         if (t >= T) continue;
         const uint32_t val = m ? __funnelshift_r(wprev, wcur, 8 * (4 - m)) : wcur;
         const int64_t sb = (int64_t)(4 * t) - (int64_t)m;          // stream offset of this word's first byte
@@ -421,7 +471,7 @@ __global__ void __launch_bounds__(TF_STR_THREADS) k_str_sizes(EncodeArgs a) {
     const uint64_t j0 = (uint64_t)blockIdx.x * TF_STR_TILE;
     if (j0 >= n) return;
     uint64_t r; const uint32_t L = str_len(c, a.sel, j0 + threadIdx.x, n, r);
-    uint32_t tot; block_excl_scan(L != 0xffffffffu ? L + varint_len(L) : 0u, &tot, sm);
+    uint32_t tot; block_excl_scan(L != 0xffffffffu ? L + (a.columnar ? 0 : varint_len(L)) : 0u, &tot, sm);
     if (threadIdx.x == 0) a.tile_sum[(size_t)c.str_slot * a.ntiles_cap + blockIdx.x] = tot;
 }
 
@@ -438,14 +488,18 @@ __global__ void __launch_bounds__(TF_STR_THREADS) k_encode_str(EncodeArgs a) {
     if (j0 >= n) return;
     uint64_t R; const uint32_t L = str_len(c, a.sel, j0 + threadIdx.x, n, R);
     const uint8_t* s = (L != 0xffffffffu && L) ? c.heap + c.offsets[R] : nullptr;
-    uint32_t tot; const uint32_t ex = block_excl_scan(L != 0xffffffffu ? L + varint_len(L) : 0u, &tot, sm);
-    uint8_t* gdst = a.raw + c.out_off + a.tile_base[(size_t)c.str_slot * a.ntiles_cap + blockIdx.x];
+    uint32_t tot; const uint32_t ex = block_excl_scan(L != 0xffffffffu ? L + (a.columnar ? 0 : varint_len(L)) : 0u, &tot, sm);
+    const uint64_t tb = a.tile_base[(size_t)c.str_slot * a.ntiles_cap + blockIdx.x];
+    uint8_t* gdst = a.raw + c.out_off + tb;
+    if (a.columnar && L != 0xffffffffu) ((uint32_t*)(a.raw + c.offs_off))[j0 + threadIdx.x] = (uint32_t)(tb + ex);
     const bool staged = tot <= TF_STR_STAGE;
     uint8_t* o = staged ? stage + ex : gdst + ex;
     if (L != 0xffffffffu) {
-        uint32_t v = L;
-        while (v >= 0x80) { *o++ = (uint8_t)(v | 0x80); v >>= 7; }
-        *o++ = (uint8_t)v;
+        if (!a.columnar) {
+            uint32_t v = L;
+            while (v >= 0x80) { *o++ = (uint8_t)(v | 0x80); v >>= 7; }
+            *o++ = (uint8_t)v;
+        }
         uint32_t nb = L;
         // head bytes up to a 4-byte boundary of the source, then whole words, then the tail
         while (nb && ((uintptr_t)s & 3)) { *o++ = *s++; nb--; }
@@ -473,5 +527,21 @@ __global__ void __launch_bounds__(TF_STR_THREADS) k_encode_str(EncodeArgs a) {
         }
     }
 }
+
+// validity bitmap of the kept rows: one thread per output byte (8 rows)
+__global__ void __launch_bounds__(256) k_pack_validity(EncodeArgs a) {
+    const DCol c = a.cols[a.slots[blockIdx.y]];
+    const uint64_t n = a.st->n_kept;
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b * 8 >= n) return;
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint64_t j = b * 8 + k;
+        if (j < n) { const uint64_t r = a.sel ? a.sel[j] : j; v |= (row_valid(c, r) ? 1u : 0u) << k; }
+    }
+    a.raw[c.null_off + b] = (uint8_t)v;
+}
+
 
 }  // namespace tfk

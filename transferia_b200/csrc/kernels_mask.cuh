@@ -181,7 +181,7 @@ __device__ inline void put_json_string(ShaSink& s, const uint8_t* p, uint32_t n)
     s.put('"');
 }
 
-struct MaskArgs { const DCol* cols; const int32_t* slots; const MaskKey* keys; const uint32_t* sel; const DState* st; uint8_t* raw; };
+struct MaskArgs { const DCol* cols; const int32_t* slots; const MaskKey* keys; const uint32_t* sel; const DState* st; uint8_t* raw; int columnar; };
 
 // one thread per (kept row, masked column): text form -> HMAC -> "\x40" + 64 hex chars into the block
 __global__ void __launch_bounds__(128) k_mask_encode(MaskArgs a) {
@@ -223,9 +223,15 @@ __global__ void __launch_bounds__(128) k_mask_encode(MaskArgs a) {
     for (int i = 9; i < 15; i++) w[i] = 0;
     w[15] = (64 + 32) * 8;
     sha256_compress(o, w);
-    uint8_t* out = a.raw + c.out_off + j * 65;
-    if (c.nullable) a.raw[c.null_off + j] = 0;          // the digest of "<nil>" is a value, never NULL (hmac_hasher.go:60)
-    out[0] = 64;
+    uint8_t* out;
+    if (a.columnar) {                                    // utf8 column: offsets 64 j, heap = hex digits
+        out = a.raw + c.out_off + j * 64 - 1;
+        ((uint32_t*)(a.raw + c.offs_off))[j] = (uint32_t)(64 * j);
+    } else {
+        out = a.raw + c.out_off + j * 65;
+        if (c.nullable) a.raw[c.null_off + j] = 0;      // the digest of "<nil>" is a value, never NULL (hmac_hasher.go:60)
+        out[0] = 64;
+    }
     const char* hex = "0123456789abcdef";
 #pragma unroll
     for (int i = 0; i < 8; i++) {

@@ -29,6 +29,7 @@ struct ColSchema {
     std::string table_schema, table_name, path, name, type, expression, original_type;
     bool key = false, fake_key = false, required = false;
     int tf = 0;
+    int in_index = -1;      // position in the INPUT batch (filter_columns drops columns, it never reorders them)
 };
 
 inline int yt_to_tf(const std::string& t) {
@@ -322,12 +323,18 @@ struct DTerm {            // device-visible predicate term (POD)
     uint32_t s_off, s_len;      // string literal in the literal blob
     uint32_t list_off, pad;     // int64[] / double[] / (uint32 offs[nlist+1], bytes) in the blob, 8-byte aligned
 };
-struct FilterStep { std::vector<std::vector<DTerm>> exprs; std::vector<std::vector<Term>> src; };
+struct FilterStep {
+    std::vector<std::vector<DTerm>> exprs; std::vector<std::vector<Term>> src;
+    bool is_skip = false; int kind_mask = 0;     // skip_events: bit TF_KIND_* set = drop rows of that kind
+    bool pass_all = false;                       // filter_rows whose table filter does not match the (renamed) table
+};
 struct MaskStep { std::vector<int> cols; std::string salt; };
 
 struct Plan {
     std::string ns, name, schema_json;
     std::vector<ColSchema> in_schema, out_schema;
+    std::string out_ns, out_name;      // table identity after rename_tables
+    std::vector<int> out_cols;         // input index of every output column, schema order
     std::vector<FilterStep> filters;   // in plan order
     std::vector<int> filter_step_index;
     std::vector<MaskStep> masks;
@@ -392,8 +399,11 @@ inline Plan build_plan(const std::string& ns, const std::string& name, const std
     Plan pl; pl.ns = ns; pl.name = name; pl.schema_json = schema_json;
     pl.in_schema = parse_schema(schema_json);
     if (pl.in_schema.empty()) throw FatalError(TF_E_FATAL_CONFIG, "empty schema");
+    for (size_t i = 0; i < pl.in_schema.size(); i++) pl.in_schema[i].in_index = (int)i;
     std::vector<ColSchema> cur = pl.in_schema;
+    std::string cur_ns = ns, cur_name = name;
     std::string steps_desc;
+    auto add_desc = [&](const std::string& d) { if (!steps_desc.empty()) steps_desc += ","; steps_desc += d; };
     auto trs = transformers_json.empty() ? tfj::parse("[]") : tfj::parse(transformers_json);
     if (trs->kind != tfj::Value::Arr) throw FatalError(TF_E_FATAL_CONFIG, "transformers_json must be a list");
     int step_no = 0;
@@ -404,25 +414,30 @@ inline Plan build_plan(const std::string& ns, const std::string& name, const std
         if (ttype.empty()) throw FatalError(TF_E_FATAL_CONFIG, "transformer entry without a type");
         static const tfj::Value empty_obj = [] { tfj::Value v; v.kind = tfj::Value::Obj; return v; }();
         if (!cfg || cfg->kind != tfj::Value::Obj) cfg = &empty_obj;
-        auto col_index = [&](const std::string& n) { for (size_t i = 0; i < cur.size(); i++) if (cur[i].name == n) return (int)i; return -1; };
+        auto col_pos = [&](const std::string& n) { for (size_t i = 0; i < cur.size(); i++) if (cur[i].name == n) return (int)i; return -1; };
+        // NOTE transformation.AddTablePlan asks Suitable() with the ORIGINAL table id for every transformer
+        // (transformation.go:54); only transformers that re-check the item's own id inside Apply see a rename.
         if (ttype == "filter_rows") {
             std::string one = cfg->get_str("filter"); auto many = cfg->get_str_list("filters");
             if (!one.empty() && !many.empty()) throw FatalError(TF_E_FATAL_CONFIG, "Settings 'filters' and 'filter' cannot be enabled at the same time");
             if (many.empty()) many.push_back(one);
             FilterStep fs;
             for (auto& f : many) fs.src.push_back(FilterParser(f).parse());
-            if (!match_table(tables_filter(cfg->get("tables")), ns, name)) continue;
+            NameFilter tf = tables_filter(cfg->get("tables"));
+            if (!match_table(tf, ns, name)) continue;
             bool ok = true;                                         // Suitable filter_rows.go:445-476
-            for (auto& terms : fs.src) for (auto& t : terms) { int ci = col_index(t.attribute); if (ci < 0 || !column_suitable(t, cur[ci].tf)) ok = false; }
+            for (auto& terms : fs.src) for (auto& t : terms) { int ci = col_pos(t.attribute); if (ci < 0 || !column_suitable(t, cur[ci].tf)) ok = false; }
             if (!ok) continue;
-            std::string d = "{\"type\":\"filter_rows\",\"exprs\":[";
+            fs.pass_all = !match_table(tf, cur_ns, cur_name);       // Apply re-checks item.TableID() (filter_rows.go:109-113)
+            std::string d = std::string("{\"type\":\"filter_rows\",\"pass_all\":") + (fs.pass_all ? "true" : "false") + ",\"exprs\":[";
             for (size_t e = 0; e < fs.src.size(); e++) {
                 std::vector<DTerm> dt; if (e) d += ",";
                 d += "[";
                 for (size_t k = 0; k < fs.src[e].size(); k++) {
                     const Term& t = fs.src[e][k]; DTerm x; std::memset(&x, 0, sizeof x);
-                    x.col = col_index(t.attribute); x.op = t.op; x.vtype = t.vtype; x.nlist = (int)t.list.size();
-                    int base = t.vtype & 15; int ctf = cur[x.col].tf;
+                    const int cp = col_pos(t.attribute);
+                    x.col = cur[cp].in_index; x.op = t.op; x.vtype = t.vtype; x.nlist = (int)t.list.size();
+                    int base = t.vtype & 15; int ctf = cur[cp].tf;
                     bool col_is_str = ctf == TF_UTF8 || ctf == TF_ANY;
                     if ((base == LV_INT || base == LV_FLOAT) && (col_is_str))
                         throw FatalError(TF_E_FATAL_UNSUPPORTED, "filter_rows: numeric literal against text column '" + t.attribute + "' (strconv.ParseFloat path) is not implemented on the device");
@@ -451,19 +466,59 @@ inline Plan build_plan(const std::string& ns, const std::string& name, const std
                 fs.exprs.push_back(dt);
             }
             d += "]}";
-            if (!steps_desc.empty()) steps_desc += ","; steps_desc += d;
+            add_desc(d);
             pl.filters.push_back(fs); pl.filter_step_index.push_back(step_no++);
+        } else if (ttype == "skip_events") {                         // registry/filter/skip_events.go:52-66
+            if (!match_table(tables_filter(cfg->get("tables")), ns, name)) continue;
+            FilterStep fs; fs.is_skip = true;
+            for (auto& ev : cfg->get_str_list("events")) {
+                if (ev == "insert") fs.kind_mask |= 1 << TF_KIND_INSERT;
+                else if (ev == "update") fs.kind_mask |= 1 << TF_KIND_UPDATE;
+                else if (ev == "delete") fs.kind_mask |= 1 << TF_KIND_DELETE;
+            }
+            add_desc("{\"type\":\"skip_events\",\"kind_mask\":" + std::to_string(fs.kind_mask) + "}");
+            pl.filters.push_back(fs); pl.filter_step_index.push_back(step_no++);
+        } else if (ttype == "filter_columns") {                      // registry/filter/filter_columns_transformer.go:215-236
+            if (!match_table(tables_filter(cfg->get("tables")), ns, name)) continue;
+            const tfj::Value* cc = cfg->get("columns");
+            std::vector<std::string> inc, exc;
+            if (cc) { inc = cc->get_str_list("includeColumns"); if (inc.empty()) inc = cc->get_str_list("include_columns");
+                      exc = cc->get_str_list("excludeColumns"); if (exc.empty()) exc = cc->get_str_list("exclude_columns"); }
+            NameFilter cf = make_filter(inc, exc);
+            bool valid = true;
+            for (auto& c : cur) if (!cf.match(c.name) && c.key) valid = false;   // a primary key may not be dropped -> not Suitable
+            if (!valid) continue;
+            std::vector<ColSchema> nxt; std::string d = "{\"type\":\"filter_columns\",\"keep\":[";
+            for (auto& c : cur) if (cf.match(c.name)) { if (!nxt.empty()) d += ","; d += std::to_string(c.in_index); nxt.push_back(c); }
+            if (nxt.empty()) throw FatalError(TF_E_FATAL_UNSUPPORTED, "filter_columns leaves no columns");
+            cur = nxt; add_desc(d + "]}"); step_no++;
+        } else if (ttype == "rename_tables") {                       // registry/rename/rename.go:46-67
+            const tfj::Value* lst = cfg->get("renameTables");
+            bool hit = false; std::string nns, nname;
+            if (lst && lst->kind == tfj::Value::Arr) for (auto& r : lst->arr) {
+                const tfj::Value* o = r->get("originalName"); const tfj::Value* nw = r->get("newName");
+                if (!o || !nw) continue;
+                if (o->get_str("nameSpace") == ns && o->get_str("name") == name) { hit = true; nns = nw->get_str("nameSpace"); nname = nw->get_str("name"); }
+            }
+            if (!hit) continue;                                      // Suitable: exact TableID in AltNames (ORIGINAL id)
+            // Apply looks the item's CURRENT id up again (rename.go:50-54); a chain of renames composes only if it matches
+            if (cur_ns == ns && cur_name == name) { cur_ns = nns; cur_name = nname; }
+            add_desc("{\"type\":\"rename_tables\",\"to\":" + tfj::quote(cur_ns.empty() ? cur_name : cur_ns + "." + cur_name) + "}"); step_no++;
         } else if (ttype == "mask_field") {
             if (!match_table(tables_filter(cfg->get("tables")), ns, name)) continue;
             auto cols = cfg->get_str_list("columns");
             MaskStep ms; const tfj::Value* mf = cfg->get("maskFunctionHash");
             ms.salt = mf ? mf->get_str("userDefinedSalt") : "";
-            for (size_t i = 0; i < cur.size(); i++) for (auto& c : cols) if (cur[i].name == c) { ms.cols.push_back((int)i); break; }
-            if (!cols.empty() && ms.cols.empty()) continue;          // Suitable hmac_hasher.go:76-89
+            std::vector<int> pos;
+            for (size_t i = 0; i < cur.size(); i++) for (auto& c : cols) if (cur[i].name == c) { pos.push_back((int)i); break; }
+            if (!cols.empty() && pos.empty()) continue;          // Suitable hmac_hasher.go:76-89
             std::string d = "{\"type\":\"mask_field\",\"cols\":[";
-            for (size_t i = 0; i < ms.cols.size(); i++) { if (i) d += ","; d += std::to_string(ms.cols[i]); cur[ms.cols[i]].type = "utf8"; cur[ms.cols[i]].tf = TF_UTF8; cur[ms.cols[i]].original_type = ""; }
-            d += "]}";
-            if (!steps_desc.empty()) steps_desc += ","; steps_desc += d;
+            for (size_t i = 0; i < pos.size(); i++) {
+                ColSchema& c = cur[pos[i]];
+                if (i) d += ","; d += std::to_string(c.in_index); ms.cols.push_back(c.in_index);
+                c.type = "utf8"; c.tf = TF_UTF8; c.original_type = "";
+            }
+            add_desc(d + "]}");
             pl.masks.push_back(ms); pl.mask_step_index.push_back(step_no++);
         } else {
             throw FatalError(TF_E_FATAL_UNSUPPORTED, "transformer '" + ttype + "' is not implemented by the device engine");
@@ -474,7 +529,8 @@ inline Plan build_plan(const std::string& ns, const std::string& name, const std
         if (pl.filter_step_index[f] > pl.mask_step_index[m])
             for (auto& e : pl.filters[f].exprs) for (auto& t : e) for (int c : pl.masks[m].cols)
                 if (t.col == c) throw FatalError(TF_E_FATAL_UNSUPPORTED, "filter_rows on a column masked earlier in the chain is not supported");
-    pl.out_schema = cur;
+    pl.out_schema = cur; pl.out_ns = cur_ns; pl.out_name = cur_name;
+    for (auto& c : cur) pl.out_cols.push_back(c.in_index);
     std::string sink_desc = "null";
     if (!sink_json.empty()) {
         auto sk = tfj::parse(sink_json);
@@ -492,7 +548,10 @@ inline Plan build_plan(const std::string& ns, const std::string& name, const std
         }
         sink_desc += "]}";
     }
-    pl.describe = "{\"table\":" + tfj::quote(ns.empty() ? name : ns + "." + name) + ",\"steps\":[" + steps_desc + "],\"result_schema\":" + schema_to_json(cur) + ",\"sink\":" + sink_desc + "}";
+    std::string oc = "[";
+    for (size_t i = 0; i < pl.out_cols.size(); i++) { if (i) oc += ","; oc += std::to_string(pl.out_cols[i]); }
+    pl.describe = "{\"table\":" + tfj::quote(ns.empty() ? name : ns + "." + name) + ",\"result_table\":" + tfj::quote(cur_ns.empty() ? cur_name : cur_ns + "." + cur_name) +
+                  ",\"steps\":[" + steps_desc + "],\"out_cols\":" + oc + "],\"result_schema\":" + schema_to_json(cur) + ",\"sink\":" + sink_desc + "}";
     return pl;
 }
 

@@ -42,11 +42,11 @@ struct PlanDev {
     DevBuf consts;
     DTerm* d_terms = nullptr; uint32_t* d_expr_off = nullptr; DFilterStep* d_fsteps = nullptr; uint8_t* d_blob = nullptr;
     uint8_t* d_col_headers = nullptr; uint32_t* d_col_header_off = nullptr;
-    int32_t* d_fixed_slots = nullptr; int32_t* d_str_slots = nullptr; int32_t* d_mask_slots = nullptr;
+    int32_t* d_fixed_slots = nullptr; int32_t* d_str_slots = nullptr; int32_t* d_mask_slots = nullptr; int32_t* d_out_cols = nullptr;
     MaskKey* d_mask_keys = nullptr;
     int n_fsteps = 0, n_fixed_slots = 0, n_str = 0, n_mask_cols = 0;
     std::vector<int32_t> fixed_slots, str_slots, mask_slot_cols, mask_slot_key;
-    std::vector<int> col_out_kind, col_out_w, col_str_slot, col_mask_slot;
+    std::vector<int> col_out_kind, col_out_w, col_str_slot, col_mask_slot, col_nullable;
 };
 
 }  // namespace
@@ -62,6 +62,7 @@ struct tfgpu_engine {
     // arenas
     DevBuf in_arena, work, raw, slots, wire;
     DState* d_state = nullptr; DCol* d_cols = nullptr; size_t d_cols_cap = 0;
+    int32_t* d_call_slots = nullptr; ColRegions* d_regions = nullptr; size_t d_call_cap = 0;   // columnar mode, per call
     // pointers into `work` for the last call
     uint8_t *keep = nullptr, *errcode = nullptr, *errstep = nullptr; uint32_t *blockcnt = nullptr, *blockoff = nullptr, *sel = nullptr;
     uint32_t* tile_sum = nullptr; uint64_t* tile_base = nullptr; uint64_t* col_bytes = nullptr; uint32_t* comp_size = nullptr; uint64_t* wire_off = nullptr;
@@ -123,7 +124,9 @@ void upload_plan(tfgpu_engine* e, PlanDev& pd) {
         }
     }
     pd.col_out_kind.assign(nc, 0); pd.col_out_w.assign(nc, 0); pd.col_str_slot.assign(nc, -1);
-    for (size_t c = 0; c < nc; c++) {
+    pd.col_nullable.assign(nc, 0);
+    for (size_t k = 0; k < pl.out_cols.size(); k++) {
+        const size_t c = (size_t)pl.out_cols[k];
         const int tf = pl.in_schema[c].tf;
         int kind, w;
         if (pd.col_mask_slot[c] >= 0) {
@@ -139,7 +142,7 @@ void upload_plan(tfgpu_engine* e, PlanDev& pd) {
             default: kind = OK_COPY; w = in_width(tf);
         }
         pd.col_out_kind[c] = kind; pd.col_out_w[c] = w;
-        const bool nullable = !pl.out_schema[c].required;
+        const bool nullable = !pl.out_schema[k].required; pd.col_nullable[c] = nullable ? 1 : 0;
         if (kind == OK_STR) { pd.col_str_slot[c] = (int)pd.str_slots.size(); pd.str_slots.push_back((int32_t)c); }
         else if (kind == OK_MASK) { pd.mask_slot_cols.push_back((int32_t)c); }
         else pd.fixed_slots.push_back((int32_t)c);
@@ -149,7 +152,9 @@ void upload_plan(tfgpu_engine* e, PlanDev& pd) {
     // flatten filter steps
     std::vector<DTerm> terms; std::vector<uint32_t> expr_off(1, 0); std::vector<DFilterStep> fsteps;
     for (size_t f = 0; f < pl.filters.size(); f++) {
-        DFilterStep st; st.expr_begin = (int32_t)expr_off.size() - 1; st.nexpr = (int32_t)pl.filters[f].exprs.size(); st.step_index = pl.filter_step_index[f]; st.pad = 0;
+        DFilterStep st; st.expr_begin = (int32_t)expr_off.size() - 1; st.nexpr = (int32_t)pl.filters[f].exprs.size(); st.step_index = pl.filter_step_index[f];
+        st.flags = (pl.filters[f].is_skip ? 1 : 0) | (pl.filters[f].pass_all ? 2 : 0);
+        if (pl.filters[f].is_skip) { st.expr_begin = pl.filters[f].kind_mask; st.nexpr = 0; }
         for (auto& ex : pl.filters[f].exprs) {
             for (auto& t : ex) { DTerm d; static_assert(sizeof(DTerm) == sizeof(tfplan::DTerm), "DTerm mismatch"); std::memcpy(&d, &t, sizeof d); terms.push_back(d); }
             expr_off.push_back((uint32_t)terms.size());
@@ -161,7 +166,7 @@ void upload_plan(tfgpu_engine* e, PlanDev& pd) {
     auto need = [&](size_t n) { total += align_up(n ? n : 1, 256); };
     need(terms.size() * sizeof(DTerm)); need(expr_off.size() * 4); need(fsteps.size() * sizeof(DFilterStep)); need(pl.blob.size());
     need(pl.col_headers.size()); need(pl.col_header_off.size() * 4); need(pd.fixed_slots.size() * 4); need(pd.str_slots.size() * 4);
-    need(pd.mask_slot_cols.size() * 4); need(keys.size() * sizeof(MaskKey));
+    need(pd.mask_slot_cols.size() * 4); need(keys.size() * sizeof(MaskKey)); need(pl.out_cols.size() * 4);
     pd.consts.ensure(total);
     uint8_t* p = pd.consts.p;
     auto put = [&](const void* src, size_t n) { uint8_t* d = p; if (n) CK(cudaMemcpy(d, src, n, cudaMemcpyHostToDevice)); p += align_up(n ? n : 1, 256); return d; };
@@ -175,18 +180,21 @@ void upload_plan(tfgpu_engine* e, PlanDev& pd) {
     pd.d_str_slots = (int32_t*)put(pd.str_slots.data(), pd.str_slots.size() * 4);
     pd.d_mask_slots = (int32_t*)put(pd.mask_slot_cols.data(), pd.mask_slot_cols.size() * 4);
     pd.d_mask_keys = (MaskKey*)put(keys.data(), keys.size() * sizeof(MaskKey));
+    { std::vector<int32_t> oc(pl.out_cols.begin(), pl.out_cols.end()); pd.d_out_cols = (int32_t*)put(oc.data(), oc.size() * 4); }
     (void)e;
 }
 
 struct Sizes { uint64_t raw_bound, n_frames_max, wire_bound; uint32_t ntiles_cap, nblocks; };
 
-Sizes compute_sizes(const tfgpu_engine* e, const PlanDev& pd, const tf_batch* in) {
+Sizes compute_sizes(const tfgpu_engine* e, const PlanDev& pd, const tf_batch* in, bool columnar = false) {
     const tfplan::Plan& pl = pd.plan; const uint64_t n = in->nrows;
     uint64_t raw = 64 + pl.col_headers.size();
-    for (size_t c = 0; c < pl.in_schema.size(); c++) {
-        if (!pl.out_schema[c].required) raw += n;
+    for (int oc : pl.out_cols) {
+        const size_t c = (size_t)oc;
+        if (pd.col_nullable[c]) raw += n;
         if (pd.col_out_kind[c] == OK_STR) raw += in->cols[c].heap_len + 5 * n;
         else raw += (uint64_t)pd.col_out_w[c] * n;
+        if (columnar) raw += 8 * n + 4 * (n + 1) + n / 8 + 6 * 16 + (pd.col_out_kind[c] == OK_MASK ? 64 * n : 0);   // widest value, aux, offsets, bitmap, padding
     }
     Sizes s;
     s.raw_bound = raw + 256;
@@ -198,10 +206,12 @@ Sizes compute_sizes(const tfgpu_engine* e, const PlanDev& pd, const tf_batch* in
 }
 
 // Launch the whole fused chain on e->stream. `cols_host` holds DEVICE pointers.
+#define TF_WIRE_COLUMNAR_INTERNAL 100
 void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* dev_cols, const uint8_t* dev_kinds, int wire_fmt) {
+    const bool columnar = wire_fmt == TF_WIRE_COLUMNAR_INTERNAL;
     const tfplan::Plan& pl = pd.plan;
     const size_t nc = pl.in_schema.size(); const uint64_t n = in->nrows;
-    const Sizes sz = compute_sizes(e, pd, in);
+    const Sizes sz = compute_sizes(e, pd, in, columnar);
     cudaStream_t s = e->stream;
     // work arena
     size_t wbytes = 0;
@@ -226,7 +236,8 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         const tf_col& ic = dev_cols[c]; DCol& d = hc[c]; std::memset(&d, 0, sizeof d);
         if (ic.type != pl.in_schema[c].tf) throw tfplan::FatalError(TF_E_FATAL_ARG, "column " + std::to_string(c) + " type does not match the plan schema");
         d.type = ic.type; d.out_kind = pd.col_out_kind[c]; d.in_w = in_width(ic.type); d.out_w = pd.col_out_w[c];
-        d.nullable = pl.out_schema[c].required ? 0 : 1; d.str_slot = pd.col_str_slot[c]; d.mask_slot = pd.col_mask_slot[c];
+        if (columnar && d.out_kind != OK_STR && d.out_kind != OK_MASK) { d.out_kind = OK_COPY; d.out_w = d.in_w; }   // Transformed values keep their type
+        d.nullable = pd.col_nullable[c]; d.str_slot = pd.col_str_slot[c]; d.mask_slot = pd.col_mask_slot[c];
         d.values = (const uint8_t*)ic.values; d.validity = ic.validity; d.offsets = ic.offsets; d.heap = ic.heap; d.aux = (const uint8_t*)ic.aux;
         if (n) {
             if (d.in_w && !d.values) throw tfplan::FatalError(TF_E_FATAL_ARG, "column " + std::to_string(c) + ": values pointer is NULL");
@@ -247,28 +258,63 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
     }
     const uint32_t* sel = (has_filter && n) ? e->sel : nullptr;
     const uint32_t ntiles = (uint32_t)((n + TF_STR_TILE - 1) / TF_STR_TILE);
-    EncodeArgs ea{e->d_cols, pd.d_str_slots, sel, e->d_state, e->raw.p, e->tile_sum, e->tile_base, sz.ntiles_cap};
+    EncodeArgs ea{e->d_cols, pd.d_str_slots, sel, e->d_state, e->raw.p, e->tile_sum, e->tile_base, sz.ntiles_cap, columnar ? 1 : 0};
     if (!has_filter || !n) {
         // n_kept = nrows is set inside k_layout (has_sel = 0); k_str_sizes needs it earlier:
         DState init; std::memset(&init, 0, sizeof init); init.n_kept = n;
         CK(cudaMemcpyAsync(e->d_state, &init, sizeof init, cudaMemcpyHostToDevice, s));
     }
     if (pd.n_str && ntiles) { e->prof_begin("k_str_sizes", s); k_str_sizes<<<dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
-    LayoutArgs la{e->d_cols, (int)nc, pd.d_str_slots, pd.n_str, e->tile_sum, e->tile_base, sz.ntiles_cap, pd.d_col_headers, pd.d_col_header_off,
+    LayoutArgs la{e->d_cols, (int)pl.out_cols.size(), pd.d_out_cols, pd.d_str_slots, pd.n_str, e->tile_sum, e->tile_base, sz.ntiles_cap, pd.d_col_headers, pd.d_col_header_off,
                   e->raw.p, e->d_state, n, 1, e->frame_bytes, e->col_bytes};
     if (pd.n_str) { e->prof_begin("k_layout_scan", s); k_layout_scan<<<pd.n_str, 1024, 0, s>>>(la); e->prof_end(s); }
-    e->prof_begin("k_layout_finish", s); k_layout_finish<<<1, 256, 0, s>>>(la); e->prof_end(s);
-    if (n) {
-        if (pd.n_fixed_slots) {
-            // widest stream is 8 bytes per row: words = 2n (+1 for misalignment)
-            const uint32_t gx = (uint32_t)((2 * n + 2 + TF_FIX_TILE_WORDS - 1) / TF_FIX_TILE_WORDS);
-            EncodeArgs fa = ea; fa.slots = pd.d_fixed_slots;
-            e->prof_begin("k_encode_fixed", s); k_encode_fixed<<<dim3(gx, pd.n_fixed_slots), 256, 0, s>>>(fa); e->prof_end(s);
+    if (!columnar) {
+        e->prof_begin("k_layout_finish", s); k_layout_finish<<<1, 256, 0, s>>>(la); e->prof_end(s);
+        if (n) {
+            if (pd.n_fixed_slots) {
+                // widest stream is 8 bytes per row: words = 2n (+1 for misalignment)
+                const uint32_t gx = (uint32_t)((2 * n + 2 + TF_FIX_TILE_WORDS - 1) / TF_FIX_TILE_WORDS);
+                EncodeArgs fa = ea; fa.slots = pd.d_fixed_slots;
+                e->prof_begin("k_encode_fixed", s); k_encode_fixed<<<dim3(gx, pd.n_fixed_slots), 256, 0, s>>>(fa); e->prof_end(s);
+            }
+            if (pd.n_str) { e->prof_begin("k_encode_str", s); k_encode_str<<<dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
+            if (pd.n_mask_cols) {
+                MaskArgs ma{e->d_cols, pd.d_mask_slots, pd.d_mask_keys, sel, e->d_state, e->raw.p, 0};
+                e->prof_begin("k_mask_encode", s); k_mask_encode<<<dim3((uint32_t)((n + 127) / 128), pd.n_mask_cols), 128, 0, s>>>(ma); e->prof_end(s);
+            }
         }
-        if (pd.n_str) { e->prof_begin("k_encode_str", s); k_encode_str<<<dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
-        if (pd.n_mask_cols) {
-            MaskArgs ma{e->d_cols, pd.d_mask_slots, pd.d_mask_keys, sel, e->d_state, e->raw.p};
-            e->prof_begin("k_mask_encode", s); k_mask_encode<<<dim3((uint32_t)((n + 127) / 128), pd.n_mask_cols), 128, 0, s>>>(ma); e->prof_end(s);
+    } else {
+        // Transformed rows back in tf_batch layout (tfgpu_push_columns)
+        const size_t no = pl.out_cols.size();
+        if (e->d_call_cap < no) {
+            if (e->d_call_slots) { CK(cudaFree(e->d_call_slots)); CK(cudaFree(e->d_regions)); }
+            CK(cudaMalloc(&e->d_call_slots, sizeof(int32_t) * 3 * no)); CK(cudaMalloc(&e->d_regions, sizeof(ColRegions) * no)); e->d_call_cap = no;
+        }
+        std::vector<int32_t> fixed, valid;
+        for (int oc : pl.out_cols) {
+            const DCol& d = hc[oc];
+            if (d.out_kind == OK_COPY) fixed.push_back(oc);
+            if (d.out_kind != OK_MASK && d.aux) fixed.push_back(oc | TF_SLOT_AUX);
+            if (d.out_kind != OK_MASK && d.validity) valid.push_back(oc);
+        }
+        std::vector<int32_t> both(fixed); both.insert(both.end(), valid.begin(), valid.end());
+        if (!both.empty()) CK(cudaMemcpyAsync(e->d_call_slots, both.data(), both.size() * 4, cudaMemcpyHostToDevice, s));
+        e->prof_begin("k_layout_columnar", s); k_layout_columnar<<<1, 256, 0, s>>>(la, e->d_regions); e->prof_end(s);
+        if (n) {
+            if (!fixed.empty()) {
+                const uint32_t gx = (uint32_t)((2 * n + 2 + TF_FIX_TILE_WORDS - 1) / TF_FIX_TILE_WORDS);
+                EncodeArgs fa = ea; fa.slots = e->d_call_slots;
+                e->prof_begin("k_encode_fixed", s); k_encode_fixed<<<dim3(gx, (uint32_t)fixed.size()), 256, 0, s>>>(fa); e->prof_end(s);
+            }
+            if (!valid.empty()) {
+                EncodeArgs va = ea; va.slots = e->d_call_slots + fixed.size();
+                e->prof_begin("k_pack_validity", s); k_pack_validity<<<dim3((uint32_t)((n / 8 + 256) / 256), (uint32_t)valid.size()), 256, 0, s>>>(va); e->prof_end(s);
+            }
+            if (pd.n_str) { e->prof_begin("k_encode_str", s); k_encode_str<<<dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
+            if (pd.n_mask_cols) {
+                MaskArgs ma{e->d_cols, pd.d_mask_slots, pd.d_mask_keys, sel, e->d_state, e->raw.p, 1};
+                e->prof_begin("k_mask_encode", s); k_mask_encode<<<dim3((uint32_t)((n + 127) / 128), pd.n_mask_cols), 128, 0, s>>>(ma); e->prof_end(s);
+            }
         }
     }
     if (lz) {
@@ -328,6 +374,7 @@ int tfgpu_engine_destroy(tfgpu_engine* e) {
     e->in_arena.release(); e->work.release(); e->raw.release(); e->slots.release(); e->wire.release();
     if (e->d_state) cudaFree(e->d_state);
     if (e->d_cols) cudaFree(e->d_cols);
+    if (e->d_call_slots) { cudaFree(e->d_call_slots); cudaFree(e->d_regions); }
     if (e->pinned) cudaFreeHost(e->pinned);
     for (auto ev : e->prof_ev) cudaEventDestroy(ev);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -437,6 +484,9 @@ int tfgpu_resident_fetch(tfgpu_engine* e, int what, uint8_t* dst, uint64_t cap) 
     } catch (const CudaError& c) { return cuda_fail(e, c); }
 }
 
+static const uint8_t* stage_input(tfgpu_engine* e, const tf_batch* in, std::vector<tf_col>& dev);
+static void fetch_errors(tfgpu_engine* e, uint64_t n, tfgpu_result* r);
+
 int tfgpu_push_encode(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch* in, tfgpu_result** out) {
     if (!e || !in || !out || plan_id < 0 || plan_id >= (int)e->plans.size()) return TF_E_FATAL_ARG;
     *out = nullptr;
@@ -447,42 +497,9 @@ int tfgpu_push_encode(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch
     if (in->nrows >= (1ull << 31)) return fail(e, TF_E_FATAL_ARG, "batch too large (>= 2^31 rows)");
     try {
         CK(cudaSetDevice(e->device));
-        const uint64_t n = in->nrows; const uint32_t nc = in->ncols;
-        std::vector<tf_col> dev(nc); const uint8_t* dev_kinds = in->kinds;
+        const uint64_t n = in->nrows;
+        std::vector<tf_col> dev; const uint8_t* dev_kinds = stage_input(e, in, dev);
         cudaStream_t s = e->stream;
-        if (in->mem == TF_MEM_HOST) {
-            // host -> HBM staging of every column buffer (inside the caller-visible call: counted in e2e timing)
-            size_t tot = 0;
-            auto sz_of = [&](const tf_col& c, int which) -> size_t {
-                const int w = in_width(c.type);
-                switch (which) {
-                case 0: return w ? (size_t)w * n : 0;
-                case 1: return c.validity ? (n + 7) / 8 : 0;
-                case 2: return (!w && c.offsets) ? (n + 1) * 4 : 0;
-                case 3: return (!w) ? c.heap_len : 0;
-                default: if (!c.aux) return 0; return (c.type == TF_ANY) ? n : (size_t)4 * n;
-                }
-            };
-            for (uint32_t c = 0; c < nc; c++) for (int k = 0; k < 5; k++) tot += align_up(sz_of(in->cols[c], k) + 16, 256);
-            tot += align_up(n + 16, 256);
-            e->in_arena.ensure(tot);
-            uint8_t* p = e->in_arena.p;
-            auto up = [&](const void* src, size_t bytes) -> uint8_t* {
-                if (!src || !bytes) { return nullptr; }
-                uint8_t* d = p; CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, s)); p += align_up(bytes + 16, 256); return d;
-            };
-            for (uint32_t c = 0; c < nc; c++) {
-                const tf_col& ic = in->cols[c]; tf_col& d = dev[c]; d = ic;
-                d.values = up(ic.values, sz_of(ic, 0)); d.validity = up(ic.validity, sz_of(ic, 1));
-                d.offsets = (const uint32_t*)up(ic.offsets, sz_of(ic, 2));
-                d.heap = up(ic.heap, sz_of(ic, 3));
-                if (!in_width(ic.type) && !d.heap) d.heap = e->in_arena.p;   // empty heap: any valid pointer
-                d.aux = up(ic.aux, sz_of(ic, 4));
-            }
-            dev_kinds = in->kinds ? up(in->kinds, n) : nullptr;
-        } else {
-            for (uint32_t c = 0; c < nc; c++) dev[c] = in->cols[c];
-        }
         run_chain(e, pd, in, dev.data(), dev_kinds, wire_fmt);
         DState st; CK(cudaMemcpyAsync(&st, e->d_state, sizeof st, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
         auto r = std::make_unique<tfgpu_result>();
@@ -497,12 +514,7 @@ int tfgpu_push_encode(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch
         }
         r->bytes = e->pinned; r->bytes_pinned = false;
         CK(cudaMemcpyAsync(r->bytes, lz ? e->wire.p : e->raw.p, r->bytes_len, cudaMemcpyDeviceToHost, s));
-        if (st.n_errors) {
-            std::vector<uint8_t> ec(n), es(n);
-            CK(cudaMemcpyAsync(ec.data(), e->errcode, n, cudaMemcpyDeviceToHost, s)); CK(cudaMemcpyAsync(es.data(), e->errstep, n, cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
-            for (uint64_t i = 0; i < n; i++) if (ec[i]) r->errs.push_back(tf_rowerr{(uint32_t)i, ec[i], es[i]});
-        }
+        if (st.n_errors) fetch_errors(e, n, r.get());
         CK(cudaStreamSynchronize(s));
         *out = r.release();
         return TF_OK;
@@ -511,9 +523,89 @@ int tfgpu_push_encode(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch
     catch (const std::bad_alloc&) { return fail(e, TF_E_RETRY_OOM, "host allocation failed"); }
 }
 
+// shared by push_encode / push_columns: stage host columns into HBM (or pass device pointers through)
+static const uint8_t* stage_input(tfgpu_engine* e, const tf_batch* in, std::vector<tf_col>& dev) {
+    const uint64_t n = in->nrows; const uint32_t nc = in->ncols;
+    cudaStream_t s = e->stream;
+    dev.resize(nc);
+    if (in->mem != TF_MEM_HOST) { for (uint32_t c = 0; c < nc; c++) dev[c] = in->cols[c]; return in->kinds; }
+    size_t tot = 0;
+    auto sz_of = [&](const tf_col& c, int which) -> size_t {
+        const int w = in_width(c.type);
+        switch (which) {
+        case 0: return w ? (size_t)w * n : 0;
+        case 1: return c.validity ? (n + 7) / 8 : 0;
+        case 2: return (!w && c.offsets) ? (n + 1) * 4 : 0;
+        case 3: return (!w) ? c.heap_len : 0;
+        default: if (!c.aux) return 0; return (c.type == TF_ANY) ? n : (size_t)4 * n;
+        }
+    };
+    for (uint32_t c = 0; c < nc; c++) for (int k = 0; k < 5; k++) tot += align_up(sz_of(in->cols[c], k) + 16, 256);
+    tot += align_up(n + 16, 256);
+    e->in_arena.ensure(tot);
+    uint8_t* p = e->in_arena.p;
+    auto up = [&](const void* src, size_t bytes) -> uint8_t* {
+        if (!src || !bytes) { return nullptr; }
+        uint8_t* d = p; CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, s)); p += align_up(bytes + 16, 256); return d;
+    };
+    for (uint32_t c = 0; c < nc; c++) {
+        const tf_col& ic = in->cols[c]; tf_col& d = dev[c]; d = ic;
+        d.values = up(ic.values, sz_of(ic, 0)); d.validity = up(ic.validity, sz_of(ic, 1));
+        d.offsets = (const uint32_t*)up(ic.offsets, sz_of(ic, 2));
+        d.heap = up(ic.heap, sz_of(ic, 3));
+        if (!in_width(ic.type) && !d.heap) d.heap = e->in_arena.p;   // empty heap: any valid pointer
+        d.aux = up(ic.aux, sz_of(ic, 4));
+    }
+    return in->kinds ? up(in->kinds, n) : nullptr;
+}
+
+static void fetch_errors(tfgpu_engine* e, uint64_t n, tfgpu_result* r) {
+    cudaStream_t s = e->stream;
+    std::vector<uint8_t> ec(n), es(n);
+    CK(cudaMemcpyAsync(ec.data(), e->errcode, n, cudaMemcpyDeviceToHost, s)); CK(cudaMemcpyAsync(es.data(), e->errstep, n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (uint64_t i = 0; i < n; i++) if (ec[i]) r->errs.push_back(tf_rowerr{(uint32_t)i, ec[i], es[i]});
+}
+
+// TransformerResult{Transformed, Errors}: the kept rows come back columnar in host memory owned by the result.
 int tfgpu_push_columns(tfgpu_engine* e, int plan_id, const tf_batch* in, tfgpu_result** out) {
-    (void)plan_id; (void)in; if (out) *out = nullptr;
-    return fail(e, TF_E_FATAL_UNSUPPORTED, "tfgpu_push_columns: columnar Transformed output is not implemented in this build; use tfgpu_push_encode");
+    if (!e || !in || !out || plan_id < 0 || plan_id >= (int)e->plans.size()) return TF_E_FATAL_ARG;
+    *out = nullptr;
+    PlanDev& pd = *e->plans[plan_id];
+    if (in->ncols != pd.plan.in_schema.size()) return fail(e, TF_E_FATAL_ARG, "batch column count does not match the plan schema");
+    if (in->nrows >= (1ull << 31)) return fail(e, TF_E_FATAL_ARG, "batch too large (>= 2^31 rows)");
+    try {
+        CK(cudaSetDevice(e->device));
+        const uint64_t n = in->nrows;
+        std::vector<tf_col> dev; const uint8_t* dev_kinds = stage_input(e, in, dev);
+        cudaStream_t s = e->stream;
+        run_chain(e, pd, in, dev.data(), dev_kinds, TF_WIRE_COLUMNAR_INTERNAL);
+        DState st; CK(cudaMemcpyAsync(&st, e->d_state, sizeof st, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+        auto r = std::make_unique<tfgpu_result>();
+        r->rows_in = n; r->rows_out = st.n_kept; r->raw_len = st.raw_total;
+        const size_t no = pd.plan.out_cols.size();
+        std::vector<ColRegions> reg(no);
+        CK(cudaMemcpyAsync(reg.data(), e->d_regions, sizeof(ColRegions) * no, cudaMemcpyDeviceToHost, s));
+        uint8_t* buf = (uint8_t*)malloc(st.raw_total ? st.raw_total : 1);
+        if (!buf) throw std::bad_alloc();
+        r->owned.push_back(buf);
+        if (st.raw_total) CK(cudaMemcpyAsync(buf, e->raw.p, st.raw_total, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (st.n_errors) fetch_errors(e, n, r.get());
+        r->cols.resize(no);
+        for (size_t k = 0; k < no; k++) {
+            tf_col& c = r->cols[k]; std::memset(&c, 0, sizeof c);
+            c.type = pd.plan.out_schema[k].tf;
+            auto at = [&](uint64_t off) -> const uint8_t* { return off == ~0ull ? nullptr : buf + off; };
+            c.values = at(reg[k].values); c.validity = at(reg[k].validity); c.aux = at(reg[k].aux);
+            c.offsets = (const uint32_t*)at(reg[k].offsets); c.heap = at(reg[k].heap); c.heap_len = reg[k].heap_len;
+        }
+        r->batch.nrows = st.n_kept; r->batch.ncols = (uint32_t)no; r->batch.mem = TF_MEM_HOST; r->batch.cols = r->cols.data(); r->batch.kinds = nullptr;
+        *out = r.release();
+        return TF_OK;
+    } catch (const tfplan::FatalError& f) { return fail(e, f.code, f.what()); }
+    catch (const CudaError& c) { return cuda_fail(e, c); }
+    catch (const std::bad_alloc&) { return fail(e, TF_E_RETRY_OOM, "host allocation failed"); }
 }
 
 uint64_t tfgpu_result_rows_in(const tfgpu_result* r) { return r ? r->rows_in : 0; }

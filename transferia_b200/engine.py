@@ -166,6 +166,39 @@ class Engine:
         finally:
             self._L.tfgpu_result_release(res)
 
+    def push_columns(self, plan_id: int, batch: abi.Batch) -> Tuple[abi.Batch, List[Tuple[int, int, int]]]:
+        """Transformer chain only: (Transformed rows as a host Batch, row errors) — abstract.TransformerResult."""
+        import numpy as np
+        tb = batch.as_struct()
+        res = C.c_void_p()
+        self._check(self._L.tfgpu_push_columns(self._h, plan_id, C.byref(tb), C.byref(res)))
+        try:
+            L = self._L
+            ob = L.tfgpu_result_batch(res)
+            n = int(L.tfgpu_result_rows_out(res))
+            cols = []
+            if ob:
+                b = ob.contents
+                for k in range(b.ncols):
+                    c = b.cols[k]
+                    def arr(ptr, nbytes, dtype):
+                        if not ptr or nbytes == 0:
+                            return None if not ptr else np.zeros(0, dtype=dtype)
+                        return np.frombuffer(C.string_at(ptr, nbytes), dtype=dtype).copy()
+                    t = c.type
+                    if t in abi.VAR_TYPES:
+                        cols.append(abi.Column(t, offsets=arr(c.offsets, 4 * (n + 1), np.uint32), heap=arr(c.heap, c.heap_len, np.uint8) if c.heap else np.zeros(0, np.uint8),
+                                               validity=arr(c.validity, (n + 7) // 8, np.uint8), aux=arr(c.aux, n, np.uint8)))
+                    else:
+                        dt = abi.FIXED_DTYPE[t]
+                        cols.append(abi.Column(t, values=arr(c.values, n * np.dtype(dt).itemsize, dt), validity=arr(c.validity, (n + 7) // 8, np.uint8),
+                                               aux=arr(c.aux, 4 * n, np.uint32)))
+            ne = L.tfgpu_result_n_errors(res); ep = L.tfgpu_result_errors(res)
+            errs = [(ep[k].row, ep[k].code, ep[k].term) for k in range(ne)]
+            return abi.Batch(n, cols), errs
+        finally:
+            self._L.tfgpu_result_release(res)
+
     def push_encode_resident(self, plan_id: int, batch: abi.Batch, wire_fmt: int = abi.TF_WIRE_CH_NATIVE_LZ4):
         """Asynchronous, HBM-resident: no copies, no host sync (kernel-only timing)."""
         tb = batch.as_struct()
