@@ -125,6 +125,15 @@ typedef struct tf_batch {
 #define TF_ROWERR_FILTER_KIND      1  /* filter_rows.go:103-107 "Found non-supported kind '%s'"  */
 #define TF_ROWERR_FILTER_OVERFLOW  2  /* filter_rows util.go:66-68 errIntOverflow                  */
 #define TF_ROWERR_FILTER_TYPEPAIR  3  /* filter_rows.go:364 "Unsupported type pair"                */
+#define TF_ROWERR_CSV_MISSING_CELL 16 /* reader_csv.go:299-312 missing row element                        */
+#define TF_ROWERR_CSV_SINGLE_QUOTE 17 /* reader.go:293-295 element is a lone quote (file-level in the reference) */
+#define TF_ROWERR_CSV_BAD_INT      18 /* strictify: cannot cast to int / negative into unsigned              */
+#define TF_ROWERR_CSV_RANGE        19 /* strictify.go:159-181 StrictifyRangeError                            */
+#define TF_ROWERR_CSV_BAD_BOOL     20
+#define TF_ROWERR_CSV_BAD_TIME     21
+#define TF_ROWERR_CSV_BAD_FLOAT    22
+#define TF_ROWERR_CSV_UNSUPPORTED  23 /* valid for Go's parsers, but a syntax the device does not implement   */
+#define TF_ROWERR_CSV_DQ_DISABLED  24 /* reader.go:305-311 errDoubleQuotesDisabled                           */
 
 typedef struct tf_rowerr {
     uint32_t row;      /* index into the INPUT batch */
@@ -178,6 +187,19 @@ int tfgpu_push_columns(tfgpu_engine* e, int plan_id, const tf_batch* in, tfgpu_r
 /* Transformer chain + sink cast + wire encode, fused on the device. */
 int tfgpu_push_encode(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch* in,
                       tfgpu_result** out);
+
+/* parsers.Parser for CSV (pkg/parsers/abstract.go:35-38 shape; algorithm of the S3 CSV reader:
+ * pkg/csv/reader.go:89-324 + pkg/providers/s3/reader/registry/csv/reader_csv.go:186-452 + strictify.go:18-181).
+ * One chunk of raw bytes (host or device, < 4 GiB) is split into lines and typed columns ON THE DEVICE and fed straight
+ * into the plan's transformer chain; wire_fmt 0 returns the Transformed rows columnar (tfgpu_result_batch), otherwise the
+ * sink wire bytes. The schema's `path` of each column is the field index (reader_csv.go:286); opts_json:
+ * {"delimiter":",","quote":"\"","escape":"\\","double_quote":true,"null_values":[..],"strings_can_be_null":false,
+ *  "quoted_strings_can_be_null":false,"true_values":[..],"false_values":[..],"include_missing_columns":false,"skip_lines":0}.
+ * Row-level failures come back as row errors with TF_ROWERR_CSV_* codes (row = data line index); an unterminated last
+ * line is left unconsumed (tfgpu_result_consumed) exactly as the reference drops it (reader.go:162-165). */
+int tfgpu_parse_csv(tfgpu_engine* e, int plan_id, const char* opts_json, const uint8_t* bytes, uint64_t len, int mem,
+                    int wire_fmt, tfgpu_result** out);
+uint64_t tfgpu_result_consumed(const tfgpu_result* r);
 
 /* Same as tfgpu_push_encode but asynchronous and HBM-resident: `in` must be
  * TF_MEM_DEVICE, nothing is copied back and no host sync happens; the wire

@@ -6,6 +6,7 @@
 #include "go_strconv.hpp"
 #include "hashes.hpp"
 #include "lz4_block.hpp"
+#include "csv_oracle.hpp"
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
@@ -558,6 +559,34 @@ extern "C" int orc_push_columns(const tf_batch* in, const orc_colschema* schema,
 }
 
 extern "C" {
+
+int orc_csv_parse(const uint8_t* buf, uint64_t len, const int32_t* types, const int32_t* paths, int ncols, const orc_csv_opts* o,
+                  orc_buf* out, orc_regions* regions, uint64_t* rows, uint64_t* lines, uint64_t* consumed,
+                  tf_rowerr* errs, uint64_t errs_cap, uint64_t* nerrs) {
+    CsvOpts co; co.delimiter = o->delimiter; co.quote = o->quote; co.escape = o->escape; co.double_quote = o->double_quote;
+    co.strings_can_be_null = o->strings_can_be_null; co.quoted_strings_can_be_null = o->quoted_strings_can_be_null; co.include_missing = o->include_missing;
+    auto split = [](const char* s, std::vector<std::string>& v) { if (!s) return; std::string cur; for (const char* p = s;; p++) { if (*p == '\n' || *p == 0) { v.push_back(cur); cur.clear(); if (!*p) break; } else cur += *p; } };
+    split(o->null_values, co.null_values); split(o->true_values, co.true_values); split(o->false_values, co.false_values);
+    std::vector<CsvCol> sc(ncols);
+    for (int c = 0; c < ncols; c++) { sc[c].tf = types[c]; sc[c].path = paths[c]; }
+    CsvResult R = csv_parse(buf, len, sc, co, o->skip_lines);
+    std::vector<uint8_t> b;
+    auto put = [&](const void* p, size_t n) -> uint64_t { while (b.size() % 16) b.push_back(0); uint64_t at = b.size(); const uint8_t* q = (const uint8_t*)p; b.insert(b.end(), q, q + n); return at; };
+    for (int c = 0; c < ncols; c++) {
+        CsvColOut& oc = R.cols[c]; orc_regions& g = regions[c]; const int w = width_tf(types[c]);
+        g.values = w ? put(oc.values.data(), oc.values.size()) : ~0ull;
+        g.validity = ~0ull;
+        g.aux = oc.aux.empty() && !(types[c] == TF_ANY || types[c] == TF_DATE || types[c] == TF_DATETIME || types[c] == TF_TIMESTAMP) ? ~0ull : put(oc.aux.data(), oc.aux.size());
+        g.offsets = w ? ~0ull : put(oc.offs.data(), oc.offs.size() * 4);
+        g.heap = w ? ~0ull : put(oc.heap.data(), oc.heap.size());
+        g.heap_len = w ? 0 : oc.heap.size();
+    }
+    to_buf(b, out);
+    *rows = R.rows; *lines = R.lines; *consumed = R.consumed;
+    uint64_t ne = 0; for (auto& e : R.errs) if (ne < errs_cap) errs[ne++] = e;
+    *nerrs = R.errs.size();
+    return 0;
+}
 
 int orc_ch_decode_frames(const uint8_t* wire, uint64_t n, orc_buf* raw, uint64_t* n_frames) {
     std::vector<uint8_t> r; size_t nf = 0;

@@ -111,6 +111,17 @@ int orc_push_columns(const tf_batch* in, const orc_colschema* schema, const orc_
                      orc_buf* out, orc_regions* regions /* one per output column */, int32_t* out_types,
                      uint64_t* rows_out, tf_rowerr* errs, uint64_t* nerrs);
 
+/* CSV: raw bytes -> typed columns (pkg/csv/reader.go + s3 reader_csv.go + strictify), see csv_oracle.hpp.
+ * list arguments are '\n'-separated. Output layout as orc_push_columns. errs[].row = data line index (after skip_lines). */
+typedef struct orc_csv_opts {
+    uint8_t delimiter, quote, escape, double_quote, strings_can_be_null, quoted_strings_can_be_null, include_missing, pad;
+    const char* null_values; const char* true_values; const char* false_values;
+    uint64_t skip_lines;
+} orc_csv_opts;
+int orc_csv_parse(const uint8_t* buf, uint64_t len, const int32_t* types, const int32_t* paths, int ncols, const orc_csv_opts* opts,
+                  orc_buf* out, orc_regions* regions, uint64_t* rows, uint64_t* lines, uint64_t* consumed,
+                  tf_rowerr* errs, uint64_t errs_cap, uint64_t* nerrs);
+
 /* Verify + decode a frame stream with the oracle's own LZ4 decoder and CityHash. */
 int orc_ch_decode_frames(const uint8_t* wire, uint64_t n, orc_buf* raw, uint64_t* n_frames);
 

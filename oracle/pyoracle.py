@@ -32,7 +32,7 @@ from transferia_b200 import abi  # noqa: E402  (memory layout only)
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle.cpp", "oracle.h", "go_strconv.hpp", "hashes.hpp", "lz4_block.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.cpp", "oracle.h", "go_strconv.hpp", "hashes.hpp", "lz4_block.hpp", "csv_oracle.hpp")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=subprocess.DEVNULL)
     return so
@@ -61,6 +61,12 @@ class OrcStep(C.Structure):
 
 class OrcRegions(C.Structure):
     _fields_ = [("values", C.c_uint64), ("validity", C.c_uint64), ("aux", C.c_uint64), ("offsets", C.c_uint64), ("heap", C.c_uint64), ("heap_len", C.c_uint64)]
+
+
+class OrcCsvOpts(C.Structure):
+    _fields_ = [("delimiter", C.c_uint8), ("quote", C.c_uint8), ("escape", C.c_uint8), ("double_quote", C.c_uint8), ("strings_can_be_null", C.c_uint8),
+                ("quoted_strings_can_be_null", C.c_uint8), ("include_missing", C.c_uint8), ("pad", C.c_uint8),
+                ("null_values", C.c_char_p), ("true_values", C.c_char_p), ("false_values", C.c_char_p), ("skip_lines", C.c_uint64)]
 
 
 class OrcBuf(C.Structure):
@@ -101,6 +107,8 @@ def lib():
                                       C.POINTER(C.c_uint64), C.POINTER(abi.TfRowErr), C.POINTER(C.c_uint64)]
         L.orc_push_columns.argtypes = [C.POINTER(abi.TfBatch), C.POINTER(OrcColSchema), C.POINTER(OrcStep), C.c_int, C.POINTER(OrcBuf),
                                        C.POINTER(OrcRegions), C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(abi.TfRowErr), C.POINTER(C.c_uint64)]
+        L.orc_csv_parse.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(OrcCsvOpts), C.POINTER(OrcBuf), C.POINTER(OrcRegions),
+                                    C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(abi.TfRowErr), C.c_uint64, C.POINTER(C.c_uint64)]
         L.orc_ch_decode_frames.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(OrcBuf), C.POINTER(C.c_uint64)]
         L.orc_free.argtypes = [C.POINTER(OrcBuf)]; L.orc_free.restype = None
         _lib = L
@@ -665,3 +673,59 @@ def push_columns(batch: abi.Batch, plan: Plan):
             cols.append(abi.Column(t, values=arr(g.values, n * np.dtype(dt).itemsize, dt), validity=arr(g.validity, (n + 7) // 8, np.uint8),
                                    aux=arr(g.aux, 4 * n, np.uint32)))
     return abi.Batch(n, cols), [(errs[i].row, errs[i].code, errs[i].term) for i in range(nerr.value)]
+
+
+def _regions_to_batch(buf: bytes, regs, types, n: int) -> abi.Batch:
+    NONE = 2 ** 64 - 1
+    cols = []
+    for k, t in enumerate(types):
+        g = regs[k]
+        def arr(off, nbytes, dtype):
+            if off == NONE:
+                return None
+            return np.frombuffer(buf[off:off + nbytes], dtype=dtype).copy()
+        if t in abi.VAR_TYPES:
+            cols.append(abi.Column(t, offsets=arr(g.offsets, 4 * (n + 1), np.uint32), heap=arr(g.heap, g.heap_len, np.uint8),
+                                   validity=arr(g.validity, (n + 7) // 8, np.uint8), aux=arr(g.aux, n, np.uint8)))
+        else:
+            dt = abi.FIXED_DTYPE[t]
+            cols.append(abi.Column(t, values=arr(g.values, n * np.dtype(dt).itemsize, dt), validity=arr(g.validity, (n + 7) // 8, np.uint8),
+                                   aux=arr(g.aux, 4 * n, np.uint32)))
+    return abi.Batch(n, cols)
+
+
+def csv_options(opts: Optional[dict], keep: "_Keep") -> OrcCsvOpts:
+    opts = opts or {}
+    o = OrcCsvOpts()
+    q = opts.get("quote", '"'); e = opts.get("escape", "\\")
+    o.delimiter = ord(opts.get("delimiter", ",")); o.quote = ord(q) if q else 0
+    o.escape = ord(e) if e else 0
+    o.double_quote = 1 if opts.get("double_quote", True) else 0
+    o.strings_can_be_null = 1 if opts.get("strings_can_be_null") else 0
+    o.quoted_strings_can_be_null = 1 if opts.get("quoted_strings_can_be_null") else 0
+    o.include_missing = 1 if opts.get("include_missing_columns") else 0
+    for k in ("null_values", "true_values", "false_values"):
+        v = opts.get(k)
+        setattr(o, k, keep.add("\n".join(v).encode()) if v else None)
+    o.skip_lines = int(opts.get("skip_lines", 0))
+    return o
+
+
+def csv_parse(data: bytes, schema: List[dict], opts: Optional[dict] = None):
+    """Reference CSV path over one chunk of bytes -> (Batch, errors[(data line, code, 0)], lines, consumed)."""
+    keep = _Keep()
+    o = csv_options(opts, keep)
+    types = keep.add(np.asarray([abi.YT_NAME_TO_TF[c["type"]] for c in schema], dtype=np.int32))
+    paths = keep.add(np.asarray([int(c.get("path", i)) if str(c.get("path", "")) != "" else i for i, c in enumerate(schema)], dtype=np.int32))
+    src = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data or b"\0")
+    out = OrcBuf(); regs = (OrcRegions * max(1, len(schema)))()
+    rows, lines, consumed, nerr = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+    cap = data.count(b"\n") + 1
+    errs = (abi.TfRowErr * cap)()
+    rc = lib().orc_csv_parse(src, len(data), types.ctypes.data, paths.ctypes.data, len(schema), C.byref(o), C.byref(out), regs,
+                             C.byref(rows), C.byref(lines), C.byref(consumed), errs, cap, C.byref(nerr))
+    assert rc == 0
+    buf = C.string_at(out.data, out.len) if out.len else b""
+    lib().orc_free(C.byref(out))
+    return (_regions_to_batch(buf, regs, list(types), rows.value), [(errs[i].row, errs[i].code, errs[i].term) for i in range(nerr.value)],
+            lines.value, consumed.value)

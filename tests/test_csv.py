@@ -1,0 +1,152 @@
+"""CSV path: the oracle against the reference's reader tests (pkg/csv/reader_test.go) on CPU, and the device parser
+against the oracle on GPU (tokenise -> typed columns -> transformer chain -> ClickHouse block, no host round trip)."""
+import numpy as np
+import pytest
+
+from transferia_b200 import abi, workload
+
+S = lambda n: [{"name": f"c{i}", "type": "utf8", "path": str(i)} for i in range(n)]
+
+
+def cells(batch):
+    return [[bytes(c.heap[c.offsets[r]:c.offsets[r + 1]]) for c in batch.columns] for r in range(batch.nrows)]
+
+
+def test_reader_reference_cases(po):
+    """pkg/csv/reader_test.go:13-240 expectations for the single-line reader."""
+    b, e, lines, cons = po.csv_parse(b"1, 2, 3\n\t\ta,b,c\n\t\t7,8,9\n", S(3))
+    assert cells(b) == [[b"1", b"2", b"3"], [b"a", b"b", b"c"], [b"7", b"8", b"9"]] and lines == 3 and not e
+    # "escape char outside of quotes treated as normal char" :85-96
+    b, e, _, _ = po.csv_parse(b'a, \\, "c \\" e , f"\n', S(3))
+    assert cells(b) == [[b"a", b"\\", b'c \\" e , f']]
+    # "no escape char configured" :98-113
+    b, e, _, _ = po.csv_parse(b'a, \\, "c \\" e , f"\n', S(4), {"escape": ""})
+    assert cells(b) == [[b"a", b"\\", b'"c \\" e', b'f"']]
+    # double quotes collapse / disallowed :115-140
+    b, e, _, _ = po.csv_parse(b'a, b, "the main ""test"" is this", d\n', S(4))
+    assert cells(b)[0][2] == b'the main "test" is this'
+    b, e, _, _ = po.csv_parse(b'a, b, "the main ""test"" is this", d\n', S(4), {"double_quote": False})
+    assert b.nrows == 0 and e[0][1] == 24
+    # an unterminated last line is dropped (reader.go:162-165)
+    b, e, lines, cons = po.csv_parse(b"a,b\nc,d", S(2))
+    assert cells(b) == [[b"a", b"b"]] and cons == 4
+    # a lone quote element is an error (reader.go:293-295)
+    b, e, _, _ = po.csv_parse(b'a,"\n', S(2))
+    assert b.nrows == 0 and e == [(0, 17, 0)]
+    # the reference takes line[lastDelimPosition+1:] for the last element, i.e. line[1:] when there is no delimiter
+    b, e, _, _ = po.csv_parse(b"abc\n", S(1))
+    assert cells(b) == [[b"bc"]]
+
+
+def test_typed_cells_and_errors(po):
+    sch = [{"name": "i", "type": "int32", "path": "0"}, {"name": "t", "type": "timestamp", "path": "1"}, {"name": "d", "type": "date", "path": "2"},
+           {"name": "f", "type": "double", "path": "3"}, {"name": "b", "type": "boolean", "path": "4"}, {"name": "u", "type": "uint8", "path": "5"},
+           {"name": "s", "type": "utf8", "path": "6"}, {"name": "a", "type": "any", "path": "6"}, {"name": "z", "type": "int64", "path": "-1"}]
+    data = (b"12,1373838275,2013-07-15,1.5,true,7,x\n"            # plain
+            b"010,2013-07-14 21:44:35,2013-07-15,2,0,255,\" q \"\"q\"\" \"\n"   # leading 0 = octal (ParseInt base 0); quoted text with "" inside
+            b"-5.000,2013-07-14T21:44:35.5+03:00,2013-07-15,3e2,T,1,\n"        # trimZeroDecimal; RFC3339 with zone
+            b"1,1,2013-07-15,1,1,300,x\n"                      # uint8 range error
+            b"1,1,2013-02-30,1,1,3,x\n"                        # bad date
+            b"1,1,2013-07-15,1,maybe,3,x\n"                    # bad bool
+            b"1,1\n"                                           # missing cells
+            b"\n")                                             # empty line -> no cells
+    b, errs, lines, cons = po.csv_parse(data, sch)
+    assert lines == 8 and b.nrows == 3
+    assert list(b.columns[0].values) == [12, 8, -5]
+    assert list(b.columns[1].values) == [1373838275, 1373838275, 1373827475] and list(b.columns[1].aux) == [0, 0, 500_000_000]
+    assert list(b.columns[3].values) == [1.5, 2.0, 300.0] and list(b.columns[4].values) == [1, 0, 1] and list(b.columns[5].values) == [7, 255, 1]
+    assert cells(abi.Batch(3, [b.columns[6]])) == [[b"x"], [b' q "q" '], [b""]]
+    assert list(b.columns[7].aux) == [1, 1, 1] and list(b.columns[8].values) == [0, 0, 0]
+    assert errs == [(3, 19, 0), (4, 21, 0), (5, 20, 0), (6, 16, 0), (7, 16, 0)]
+    # null lists and defaults (reader_csv.go:384-405, change_item_builders.go:87-109)
+    b, errs, _, _ = po.csv_parse(b"NULL,NULL,NULL\n5,t,z\n", [{"name": "i", "type": "int32", "path": "0"}, {"name": "b", "type": "boolean", "path": "1"}, {"name": "a", "type": "any", "path": "2"}],
+                                 {"null_values": ["NULL"], "strings_can_be_null": True})
+    assert list(b.columns[0].values) == [0, 5] and list(b.columns[1].values) == [0, 1] and cells(abi.Batch(2, [b.columns[2]])) == [[b"{}"], [b"z"]] and list(b.columns[2].aux) == [0, 1]
+
+
+def render_hits_csv(batch, schema, rng):
+    """hits-shaped batch -> CSV text the way a producer would write it (quotes around text with delimiters / quotes)."""
+    import datetime as dt
+    rows = []
+    cols = []
+    for c, sc in zip(batch.columns, schema):
+        if c.type in abi.VAR_TYPES:
+            vals = []
+            for r in range(batch.nrows):
+                s = bytes(c.heap[c.offsets[r]:c.offsets[r + 1]])
+                if b"," in s or b'"' in s or rng.random() < 0.1:
+                    s = b'"' + s.replace(b'"', b'""') + b'"'
+                vals.append(s)
+            cols.append(vals)
+        elif c.type == abi.TF_TIMESTAMP:
+            cols.append([dt.datetime.fromtimestamp(int(v), dt.timezone.utc).strftime("%Y-%m-%d %H:%M:%S").encode() for v in c.values])
+        elif c.type == abi.TF_DATE:
+            cols.append([dt.datetime.fromtimestamp(int(v), dt.timezone.utc).strftime("%Y-%m-%d").encode() for v in c.values])
+        else:
+            cols.append([str(int(v)).encode() for v in c.values])
+    for r in range(batch.nrows):
+        rows.append(b",".join(col[r] for col in cols))
+    return b"\n".join(rows) + b"\n"
+
+
+def _assert_equal(a, b):
+    from test_gpu_parity import assert_batches_equal
+    assert_batches_equal(a, b)
+
+
+@pytest.mark.gpu
+def test_device_csv_equals_oracle_on_hits(eng, po):
+    """BASELINE configs[4] shape: hits-shaped CSV -> parse -> cast -> ClickHouse native block, all on the device."""
+    rng = np.random.default_rng(3)
+    batch, schema = workload.make_hits_batch(20_000, seed=11)
+    schema = [dict(c, path=str(i)) for i, c in enumerate(schema)]
+    text = render_hits_csv(batch, schema, rng)
+    pid = eng.plan("public", "hits", schema, [], {"type": "clickhouse"})
+    got, gerr, consumed = eng.parse_csv(pid, text)
+    ref, rerr, lines, rcons = po.csv_parse(text, schema)
+    assert consumed == rcons == len(text) and gerr == rerr == [] and got.nrows == ref.nrows == batch.nrows
+    _assert_equal(got, ref)
+    # the parsed cells are the values the batch was rendered from (round trip): quoting is undone
+    names = [c["name"] for c in schema]
+    assert np.array_equal(got.columns[names.index("watchid")].values, batch.columns[names.index("watchid")].values)
+    assert np.array_equal(got.columns[names.index("eventtime")].values, batch.columns[names.index("eventtime")].values)
+    # fused: CSV -> filter_rows -> ClickHouse block + LZ4, vs oracle(parse) -> oracle(push_encode)
+    k = workload.counterid_threshold(batch, schema)
+    trs = workload.headline_transformers(k)
+    pid2 = eng.plan("public", "hits", schema, trs, {"type": "clickhouse"})
+    res, _ = eng.parse_csv(pid2, text, wire_fmt=abi.TF_WIRE_CH_NATIVE)
+    want = po.push_encode(ref, po.build_plan("public", "hits", schema, trs), abi.TF_WIRE_CH_NATIVE)
+    assert res.rows_out == want.rows_out and res.wire == want.raw
+    res_lz, _ = eng.parse_csv(pid2, text, wire_fmt=abi.TF_WIRE_CH_NATIVE_LZ4)
+    raw, _ = po.ch_decode_frames(res_lz.wire)
+    assert raw == want.raw
+
+
+@pytest.mark.gpu
+def test_device_csv_cases_and_errors(eng, po):
+    cases = [
+        (b"1, 2, 3\n\t\ta,b,c\n\t\t7,8,9\n", S(3), None),
+        (b'a, \\, "c \\" e , f"\n', S(3), None), (b'a, \\, "c \\" e , f"\n', S(4), {"escape": ""}),
+        (b'a, b, "the main ""test"" is this", d\n', S(4), None), (b'a, b, "the main ""test"" is this", d\n', S(4), {"double_quote": False}),
+        (b"a,b\nc,d", S(2), None), (b'a,"\nx,y\n', S(2), None), (b"abc\n\n\r\nq\n", S(1), {"include_missing_columns": True}),
+        (b"h1;h2\n1;\xc2\xa0 spaced \xe3\x80\x80\n", S(2), {"delimiter": ";", "skip_lines": 1}), (b"", S(2), None), (b"no newline", S(1), None),
+    ]
+    sch = [{"name": "i", "type": "int32", "path": "0"}, {"name": "t", "type": "timestamp", "path": "1"}, {"name": "d", "type": "date", "path": "2"},
+           {"name": "f", "type": "double", "path": "3"}, {"name": "b", "type": "boolean", "path": "4"}, {"name": "u", "type": "uint8", "path": "5"},
+           {"name": "s", "type": "utf8", "path": "6"}, {"name": "a", "type": "any", "path": "6"}, {"name": "z", "type": "int64", "path": "-1"},
+           {"name": "g", "type": "float", "path": "3"}, {"name": "dt", "type": "datetime", "path": "1"}, {"name": "n", "type": "uint64", "path": "0"}]
+    data = (b"12,2013-07-14 21:44:35,2013-07-15,1.5,true,7,x\n010,2013-07-14 21:44:35,2013-07-15,2,0,255,\" q \"\"q\"\" \"\n"
+            b"5.000,2013-07-14T21:44:35.5+03:00,2013-07-15,3e2,T,1,\n1,1,2013-07-15,1,1,300,x\n1,2013-07-14 21:44:35,2013-02-30,1,1,3,x\n"
+            b"1,2013-07-14 21:44:35,2013-07-15,1,maybe,3,x\n1,1\n\n-3,2013-07-14 21:44:35,2013-07-15,1,1,3,x\n0x1f,2013-07-14 21:44:35,2013-07-15,1e400,1,3,x\n"
+            b"99999999999,2013-07-14 21:44:35,2013-07-15,0.1234567890123456789,1,3,x\n1_0,2013-07-14 21:44:35,2013-07-15,nan,1,3,x\n")
+    cases.append((data, sch, None))
+    cases.append((b"NULL,NULL,NULL\n5,t,z\n'NULL',f,\"NULL\"\n", [{"name": "i", "type": "int32", "path": "0"}, {"name": "b", "type": "boolean", "path": "1"}, {"name": "a", "type": "any", "path": "2"}],
+                  {"null_values": ["NULL"], "strings_can_be_null": True}))
+    cases.append((b"NULL,x\n'NULL',y\n", [{"name": "s", "type": "utf8", "path": "0"}, {"name": "t", "type": "string", "path": "1"}], {"null_values": ["NULL"], "quoted_strings_can_be_null": True}))
+    for text, schema, opts in cases:
+        pid = eng.plan("db", "t", schema, [])
+        got, gerr, consumed = eng.parse_csv(pid, text, opts)
+        ref, rerr, lines, rcons = po.csv_parse(text, schema, opts)
+        assert consumed == rcons, text
+        assert [(r, c) for r, c, _ in gerr] == [(r, c) for r, c, _ in rerr], (text, gerr, rerr)
+        _assert_equal(got, ref)

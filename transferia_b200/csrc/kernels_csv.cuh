@@ -1,0 +1,368 @@
+// CSV -> typed columns on the device.
+//   reference: pkg/csv/reader.go:89-324 (ReadLine / splitString / sanitizeElement, single-line mode),
+//              pkg/providers/s3/reader/registry/csv/reader_csv.go:266-452 (constructCI, per-type value rules),
+//              pkg/abstract/changeitem/strictify/strictify.go:46-181 (text -> canonical type via spf13/cast),
+//              pkg/abstract/change_item_builders.go:87-109 (DefaultValue).
+// In single-line mode the quote state resets at every '\n' (reader.go:137-155), so lines are independent:
+//   k_csv_count_nl / k_csv_line_index   newline index (count per 8 KiB block, scan, positions)
+//   k_csv_pass1   one thread per line: the reference's split state machine (escape-inside-quotes, quote toggle,
+//                 delimiter outside quotes, the `line[lastDelim+1:]` last-element rule), TrimSpace, unquote, `""`
+//                 collapse; fixed-width cells are converted and stored column-major (coalesced across lines),
+//                 text cells leave (start, length) spans
+//   k_csv_offsets per text column: exclusive scan of lengths -> uint32 offsets
+//   k_csv_pass2   copy text cells into the column heaps
+// The result is an ordinary HBM-resident tf_batch that the transformer / encode chain consumes directly.
+#pragma once
+#include "device_types.cuh"
+#include "kernels_encode.cuh"
+
+namespace tfk {
+
+enum CsvErr : int { CSV_MISSING_CELL = 16, CSV_SINGLE_QUOTE = 17, CSV_BAD_INT = 18, CSV_RANGE = 19, CSV_BAD_BOOL = 20,
+                    CSV_BAD_TIME = 21, CSV_BAD_FLOAT = 22, CSV_UNSUPPORTED = 23, CSV_DOUBLE_QUOTE_DISABLED = 24 };
+
+#define CSV_NL_BLOCK 8192
+
+struct CsvCfg {
+    uint8_t delimiter, quote, escape, double_quote, strings_can_be_null, quoted_strings_can_be_null, include_missing, pad;
+    // value lists live in one blob: [n:u32][off:u32 x (n+1)][bytes]
+    uint32_t null_list, true_list, false_list;     // offsets into the blob, 0xffffffff = empty
+};
+
+struct CsvColDev {
+    int32_t tf; int32_t path;        // path < 0: default value
+    int32_t w;                       // fixed width, 0 = text
+    int32_t slot;                    // index among text columns (w == 0), else -1
+    uint8_t* values;                 // [nrows * w] staging, column-major
+    uint32_t* aux32;                 // time columns: nanoseconds
+    uint8_t* aux8;                   // any columns: tag (1 = Go string)
+};
+
+struct CsvArgs {
+    const uint8_t* text; uint64_t len;
+    const uint32_t* line_end;        // position after each '\n'
+    uint64_t nlines, skip;           // data rows = nlines - skip
+    CsvCfg cfg; const uint8_t* blob;
+    const CsvColDev* cols; int ncols;
+    const int16_t* field_col; int nfields;       // first schema column that reads field f, -1 none
+    const int16_t* next_same;                    // next schema column with the same path, -1 none
+    uint32_t* span_start; uint32_t* span_len;    // [nslots][nrows]; len bit31 = contains `""` (collapse on copy)
+    uint8_t* err;                                // [nrows] CSV_* code
+};
+
+__global__ void __launch_bounds__(256) k_csv_count_nl(const uint8_t* text, uint64_t len, uint32_t* blk_cnt) {
+    __shared__ uint32_t sm[33];
+    const uint64_t b0 = (uint64_t)blockIdx.x * CSV_NL_BLOCK;
+    uint32_t c = 0;
+    for (uint32_t k = 0; k < CSV_NL_BLOCK / 256; k++) { const uint64_t p = b0 + (uint64_t)threadIdx.x * (CSV_NL_BLOCK / 256) + k; if (p < len && text[p] == '\n') c++; }
+    uint32_t tot; block_excl_scan(c, &tot, sm);
+    if (threadIdx.x == 0) blk_cnt[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(256) k_csv_line_index(const uint8_t* text, uint64_t len, const uint32_t* blk_off, uint32_t* line_end) {
+    __shared__ uint32_t sm[33];
+    const uint64_t b0 = (uint64_t)blockIdx.x * CSV_NL_BLOCK;
+    const uint64_t t0 = b0 + (uint64_t)threadIdx.x * (CSV_NL_BLOCK / 256);
+    uint32_t c = 0;
+    for (uint32_t k = 0; k < CSV_NL_BLOCK / 256; k++) { const uint64_t p = t0 + k; if (p < len && text[p] == '\n') c++; }
+    uint32_t tot; uint32_t ex = block_excl_scan(c, &tot, sm);
+    uint32_t w = blk_off[blockIdx.x] + ex;
+    for (uint32_t k = 0; k < CSV_NL_BLOCK / 256; k++) { const uint64_t p = t0 + k; if (p < len && text[p] == '\n') line_end[w++] = (uint32_t)(p + 1); }
+}
+
+// ---- text -> value helpers (must agree with oracle/csv_oracle.hpp, which restates the Go functions)
+__device__ __forceinline__ bool d_space(const uint8_t* p, uint32_t n, uint32_t& w) {   // unicode.IsSpace
+    if (!n) return false;
+    const uint8_t b = p[0];
+    if (b == ' ' || (b >= 9 && b <= 13)) { w = 1; return true; }
+    if (b == 0xC2 && n >= 2 && (p[1] == 0x85 || p[1] == 0xA0)) { w = 2; return true; }
+    if (n >= 3) {
+        if (b == 0xE1 && p[1] == 0x9A && p[2] == 0x80) { w = 3; return true; }
+        if (b == 0xE2 && p[1] == 0x80 && ((p[2] >= 0x80 && p[2] <= 0x8A) || p[2] == 0xA8 || p[2] == 0xA9 || p[2] == 0xAF)) { w = 3; return true; }
+        if (b == 0xE2 && p[1] == 0x81 && p[2] == 0x9F) { w = 3; return true; }
+        if (b == 0xE3 && p[1] == 0x80 && p[2] == 0x80) { w = 3; return true; }
+    }
+    return false;
+}
+__device__ __forceinline__ void d_trim(const uint8_t*& p, uint32_t& n) {
+    uint32_t w;
+    while (n && d_space(p, n, w)) { p += w; n -= w; }
+    for (;;) {
+        if (!n) return;
+        if (d_space(p + n - 1, 1, w)) { n -= 1; continue; }
+        if (n >= 2 && d_space(p + n - 2, 2, w) && w == 2) { n -= 2; continue; }
+        if (n >= 3 && d_space(p + n - 3, 3, w) && w == 3) { n -= 3; continue; }
+        return;
+    }
+}
+__device__ __forceinline__ bool d_in_list(const uint8_t* blob, uint32_t list, const uint8_t* p, uint32_t n) {
+    if (list == 0xffffffffu) return false;
+    const uint32_t cnt = *(const uint32_t*)(blob + list); const uint32_t* off = (const uint32_t*)(blob + list + 4); const uint8_t* bytes = (const uint8_t*)(off + cnt + 1);
+    for (uint32_t k = 0; k < cnt; k++) {
+        const uint32_t a = off[k], b = off[k + 1];
+        if (b - a != n) continue;
+        uint32_t i = 0; while (i < n && bytes[a + i] == p[i]) i++;
+        if (i == n) return true;
+    }
+    return false;
+}
+// strconv.ParseInt(trimZeroDecimal(s), 0, 0): rc 0 ok, 1 error, 2 unsupported (underscores)
+__device__ int d_parse_int(const uint8_t* s, uint32_t n, int64_t& out) {
+    { bool zero = false; uint32_t i = n; for (; i > 0; i--) { const uint8_t c = s[i - 1]; if (c == '.') { if (zero) n = i - 1; break; } else if (c == '0') zero = true; else break; } }
+    if (!n) return 1;
+    uint32_t i = 0; bool neg = false;
+    if (s[0] == '+' || s[0] == '-') { neg = s[0] == '-'; i = 1; if (n == 1) return 1; }
+    uint32_t base = 10;
+    if (s[i] == '0' && i + 1 < n) {
+        const uint8_t c = s[i + 1] | 0x20;
+        if (c == 'x') { base = 16; i += 2; } else if (c == 'b') { base = 2; i += 2; } else if (c == 'o') { base = 8; i += 2; } else { base = 8; i += 1; }
+        if (i >= n) return 1;
+    }
+    uint64_t v = 0; const uint64_t lim = neg ? (1ull << 63) : ((1ull << 63) - 1);
+    for (; i < n; i++) {
+        const uint8_t c = s[i]; uint32_t d;
+        if (c == '_') return 2;
+        if (c >= '0' && c <= '9') d = c - '0'; else if ((c | 0x20) >= 'a' && (c | 0x20) <= 'z') d = (c | 0x20) - 'a' + 10; else return 1;
+        if (d >= base) return 1;
+        if (v > (lim - d) / base) return 1;      // v * base + d > lim
+        v = v * base + d;
+    }
+    out = neg ? (int64_t)(0 - v) : (int64_t)v; return 0;
+}
+__device__ __forceinline__ bool d_eq(const uint8_t* s, uint32_t n, const char* lit) { uint32_t i = 0; for (; lit[i]; i++) if (i >= n || s[i] != (uint8_t)lit[i]) return false; return i == n; }
+__device__ int d_parse_bool(const uint8_t* s, uint32_t n, bool& out) {   // strconv.ParseBool
+    if (d_eq(s, n, "1") || d_eq(s, n, "t") || d_eq(s, n, "T") || d_eq(s, n, "TRUE") || d_eq(s, n, "true") || d_eq(s, n, "True")) { out = true; return 0; }
+    if (d_eq(s, n, "0") || d_eq(s, n, "f") || d_eq(s, n, "F") || d_eq(s, n, "FALSE") || d_eq(s, n, "false") || d_eq(s, n, "False")) { out = false; return 0; }
+    return 1;
+}
+__constant__ double d_p10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+// decimal text -> double, exact when <= 15 significant digits and |exp10| <= 22 (one correctly rounded IEEE op); rc 2 otherwise
+__device__ int d_parse_float(const uint8_t* s, uint32_t n, double& out) {
+    uint32_t i = 0; bool neg = false;
+    if (!n) return 1;
+    if (s[0] == '+' || s[0] == '-') { neg = s[0] == '-'; i = 1; }
+    uint64_t m = 0; int nd = 0, dp = 0; bool any = false, dot = false;
+    for (; i < n; i++) {
+        const uint8_t c = s[i];
+        if (c >= '0' && c <= '9') { any = true; if (m || c != '0') { if (nd >= 19) return 2; m = m * 10 + (c - '0'); nd++; } if (dot) dp--; }
+        else if (c == '.' && !dot) dot = true;
+        else break;
+    }
+    if (!any) return (n - i >= 3) ? 2 : 1;
+    int e = 0;
+    if (i < n && (s[i] | 0x20) == 'e') {
+        i++; bool eneg = false; if (i < n && (s[i] == '+' || s[i] == '-')) { eneg = s[i] == '-'; i++; }
+        if (i >= n) return 1; int ev = 0;
+        for (; i < n; i++) { if (s[i] < '0' || s[i] > '9') return 1; if (ev < 10000) ev = ev * 10 + (s[i] - '0'); }
+        e = eneg ? -ev : ev;
+    }
+    if (i != n) return (s[i] == '_' || (s[i] | 0x20) == 'x' || (s[i] | 0x20) == 'p') ? 2 : 1;
+    e += dp;
+    if (m == 0) { out = neg ? -0.0 : 0.0; return 0; }
+    if (nd > 15 || e < -22 || e > 22) return 2;
+    double d = (double)m; d = e < 0 ? __ddiv_rn(d, d_p10[-e]) : __dmul_rn(d, d_p10[e]);
+    out = neg ? -d : d; return 0;
+}
+__device__ __forceinline__ int64_t d_days_from_civil(int64_t y, unsigned m, unsigned d) {
+    y -= m <= 2;
+    const int64_t era = (y >= 0 ? y : y - 399) / 400;
+    const unsigned yoe = (unsigned)(y - era * 400);
+    const unsigned doy = (153 * (m > 2 ? m - 3 : m + 9) + 2) / 5 + d - 1;
+    const unsigned doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+    return era * 146097 + (int64_t)doe - 719468;
+}
+__device__ int d_parse_time(const uint8_t* s, uint32_t n, int64_t& sec, uint32_t& nsec) {
+    auto dig = [&](uint32_t p, int k, int& v) { v = 0; for (int i = 0; i < k; i++) { if (p + i >= n || s[p + i] < '0' || s[p + i] > '9') return false; v = v * 10 + (s[p + i] - '0'); } return true; };
+    int y, mo, d, hh = 0, mi = 0, ss = 0; nsec = 0; int64_t off = 0;
+    if (!(dig(0, 4, y) && n >= 10 && s[4] == '-' && dig(5, 2, mo) && s[7] == '-' && dig(8, 2, d))) return 2;
+    const int dm[13] = {0, 31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    const bool leap = (y % 4 == 0 && y % 100 != 0) || y % 400 == 0;
+    if (mo < 1 || mo > 12 || d < 1 || d > dm[mo] + ((mo == 2 && leap) ? 1 : 0)) return 1;
+    uint32_t p = 10;
+    if (p < n) {
+        if (s[p] != 'T' && s[p] != ' ') return 2;
+        if (!(dig(p + 1, 2, hh) && p + 3 < n && s[p + 3] == ':' && dig(p + 4, 2, mi) && p + 6 < n && s[p + 6] == ':' && dig(p + 7, 2, ss))) return 2;
+        if (hh > 23 || mi > 59 || ss > 59) return 1;
+        p += 9;
+        if (p < n && s[p] == '.') { uint32_t q = p + 1; uint32_t f = 0; int k = 0; while (q < n && s[q] >= '0' && s[q] <= '9') { if (k < 9) { f = f * 10 + (s[q] - '0'); k++; } q++; } if (q == p + 1) return 2; while (k < 9) { f *= 10; k++; } nsec = f; p = q; }
+        if (p < n) {
+            if (s[p] == 'Z' && p + 1 == n) p++;
+            else if (s[p] == '+' || s[p] == '-') {
+                const int sign = s[p] == '-' ? -1 : 1; int oh, om;
+                if (dig(p + 1, 2, oh) && p + 3 < n && s[p + 3] == ':' && dig(p + 4, 2, om) && p + 6 == n) off = sign * (oh * 3600 + om * 60);
+                else if (dig(p + 1, 2, oh) && dig(p + 3, 2, om) && p + 5 == n) off = sign * (oh * 3600 + om * 60);
+                else return 2;
+                p = n;
+            } else return 2;
+        }
+    }
+    if (p != n) return 2;
+    sec = d_days_from_civil(y, (unsigned)mo, (unsigned)d) * 86400 + hh * 3600 + mi * 60 + ss - off;
+    return 0;
+}
+
+__device__ __forceinline__ void csv_store_fixed(const CsvColDev& c, uint64_t row, const uint64_t v, uint32_t nsec) {
+    switch (c.w) {
+    case 1: c.values[row] = (uint8_t)v; break;
+    case 2: ((uint16_t*)c.values)[row] = (uint16_t)v; break;
+    case 4: ((uint32_t*)c.values)[row] = (uint32_t)v; break;
+    default: ((uint64_t*)c.values)[row] = v; break;
+    }
+    if (c.aux32) c.aux32[row] = nsec;
+}
+
+// getCorrespondingValue + strictifyValue for one cell [p, p+n) (already sanitised); text cells return their span
+__device__ int csv_cell(const CsvArgs& a, const CsvColDev& c, uint64_t row, uint64_t nrows, const uint8_t* p, uint32_t n, bool has_dq) {
+    const CsvCfg& o = a.cfg;
+    if (has_dq && c.w) return CSV_UNSUPPORTED;       // a `""` inside a numeric cell: the collapsed text would have to be materialised first
+    switch (c.tf) {
+    case TF_BOOLEAN: {
+        bool b;
+        if (o.strings_can_be_null && d_in_list(a.blob, o.null_list, p, n)) b = false;
+        else if (d_in_list(a.blob, o.true_list, p, n)) b = true;
+        else if (d_in_list(a.blob, o.false_list, p, n)) b = false;
+        else if (d_parse_bool(p, n, b)) return CSV_BAD_BOOL;
+        csv_store_fixed(c, row, b ? 1 : 0, 0); return 0;
+    }
+    case TF_TIMESTAMP: {
+        bool num = n > 0; uint32_t i = (n && (p[0] == '+' || p[0] == '-')) ? 1 : 0; if (i == n) num = false;
+        for (uint32_t k = i; k < n && num; k++) if (p[k] < '0' || p[k] > '9') num = false;
+        int64_t sec = 0; uint32_t nsec = 0;
+        if (num) {
+            const bool neg = p[0] == '-'; const uint64_t lim = neg ? (1ull << 63) : ((1ull << 63) - 1); uint64_t v = 0;
+            for (uint32_t k = i; k < n; k++) { const uint32_t d = p[k] - '0'; if (v > (lim - d) / 10) { num = false; break; } v = v * 10 + d; }
+            if (num) sec = neg ? (int64_t)(0 - v) : (int64_t)v;
+        }
+        if (!num) { const int rc = d_parse_time(p, n, sec, nsec); if (rc) return rc == 2 ? CSV_UNSUPPORTED : CSV_BAD_TIME; }
+        csv_store_fixed(c, row, (uint64_t)sec, nsec); return 0;
+    }
+    case TF_DATE: case TF_DATETIME: {
+        int64_t sec; uint32_t nsec; const int rc = d_parse_time(p, n, sec, nsec); if (rc) return rc == 2 ? CSV_UNSUPPORTED : CSV_BAD_TIME;
+        csv_store_fixed(c, row, (uint64_t)sec, nsec); return 0;
+    }
+    case TF_FLOAT: case TF_DOUBLE: {
+        double d; const int rc = d_parse_float(p, n, d); if (rc) return rc == 2 ? CSV_UNSUPPORTED : CSV_BAD_FLOAT;
+        if (c.tf == TF_FLOAT) { const float f = (float)d; csv_store_fixed(c, row, __float_as_uint(f), 0); } else csv_store_fixed(c, row, (uint64_t)__double_as_longlong(d), 0);
+        return 0;
+    }
+    }
+    bool null;
+    if (o.quoted_strings_can_be_null) {
+        const uint8_t* q = p; uint32_t m = n;
+        if (m >= 2 && ((q[0] == '"' && q[m - 1] == '"') || (q[0] == '\'' && q[m - 1] == '\''))) { q++; m -= 2; }
+        else if (m == 1 && (q[0] == '"' || q[0] == '\'')) { q++; m = 0; }
+        null = d_in_list(a.blob, o.null_list, q, m);
+    } else null = o.strings_can_be_null && d_in_list(a.blob, o.null_list, p, n);
+    if (!c.w) {      // utf8 / string / any
+        uint32_t* ss = a.span_start + (size_t)c.slot * nrows; uint32_t* sl = a.span_len + (size_t)c.slot * nrows;
+        if (null) { if (c.tf == TF_ANY) { ss[row] = 0xffffffffu; sl[row] = 2; c.aux8[row] = 0; } else { ss[row] = 0; sl[row] = 0; } return 0; }
+        uint32_t fl = n;
+        if (has_dq) { uint32_t k = 0; fl = 0; while (k < n) { if (p[k] == '"' && k + 1 < n && p[k + 1] == '"') k += 2; else k++; fl++; } }
+        ss[row] = (uint32_t)(p - a.text); sl[row] = fl | (has_dq ? 0x80000000u : 0u);
+        if (c.tf == TF_ANY) c.aux8[row] = 1;
+        return 0;
+    }
+    if (c.tf == TF_INTERVAL) { if (null) { csv_store_fixed(c, row, 0, 0); return 0; } return CSV_UNSUPPORTED; }
+    if (null) { csv_store_fixed(c, row, 0, 0); return 0; }
+    int64_t v; const int rc = d_parse_int(p, n, v); if (rc) return rc == 2 ? CSV_UNSUPPORTED : CSV_BAD_INT;
+    int64_t lo, hi; bool uns = false;
+    switch (c.tf) {
+    case TF_INT8: lo = -128; hi = 127; break; case TF_INT16: lo = -32768; hi = 32767; break;
+    case TF_INT32: lo = -2147483648LL; hi = 2147483647LL; break; case TF_INT64: lo = (int64_t)(1ull << 63); hi = 0x7fffffffffffffffLL; break;
+    case TF_UINT8: uns = true; lo = 0; hi = 255; break; case TF_UINT16: uns = true; lo = 0; hi = 65535; break;
+    case TF_UINT32: uns = true; lo = 0; hi = 4294967295LL; break; default: uns = true; lo = 0; hi = 0x7fffffffffffffffLL; break;
+    }
+    if (uns && v < 0) return CSV_BAD_INT;
+    if (v < lo || v > hi) return CSV_RANGE;
+    csv_store_fixed(c, row, (uint64_t)v, 0); return 0;
+}
+
+__device__ __forceinline__ void csv_default(const CsvArgs& a, const CsvColDev& c, uint64_t row, uint64_t nrows) {   // abstract.DefaultValue
+    if (c.w) { csv_store_fixed(c, row, 0, 0); return; }
+    uint32_t* ss = a.span_start + (size_t)c.slot * nrows; uint32_t* sl = a.span_len + (size_t)c.slot * nrows;
+    if (c.tf == TF_ANY) { ss[row] = 0xffffffffu; sl[row] = 2; c.aux8[row] = 0; } else { ss[row] = 0; sl[row] = 0; }
+}
+
+__global__ void __launch_bounds__(128) k_csv_pass1(CsvArgs a) {
+    const uint64_t nrows = a.nlines - a.skip;
+    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    const uint64_t ln = row + a.skip;
+    const uint32_t ls = ln ? a.line_end[ln - 1] : 0, le = a.line_end[ln];
+    const uint8_t* line = a.text + ls; const uint32_t n = le - ls;
+    const CsvCfg& o = a.cfg;
+    int err = 0; int nf = 0;                      // split-level error (aborts the line); fields seen
+    int conv_err = 0, conv_col = 0x7fffffff;      // conversion error of the FIRST schema column that fails (strictify walks columns in order)
+    // one sanitised element -> every schema column that reads field f
+    auto element = [&](uint32_t ea, uint32_t eb, int f) {
+        const uint8_t* p = line + ea; uint32_t m = eb - ea;
+        d_trim(p, m);
+        bool has_dq = false;
+        if (o.quote) {
+            if (m == 1 && p[0] == o.quote) { err = CSV_SINGLE_QUOTE; return; }
+            if (m >= 2 && p[0] == o.quote && p[m - 1] == o.quote) { p++; m -= 2; }
+            for (uint32_t k = 0; k + 1 < m; k++) if (p[k] == '"' && p[k + 1] == '"') { has_dq = true; break; }
+            if (has_dq && !o.double_quote) { err = CSV_DOUBLE_QUOTE_DISABLED; return; }
+        }
+        if (f < a.nfields) for (int c = a.field_col[f]; c >= 0; c = a.next_same[c]) {
+            const int rc = csv_cell(a, a.cols[c], row, nrows, p, m, has_dq);
+            if (rc && c < conv_col) { conv_col = c; conv_err = rc; }
+        }
+    };
+    if (n > 1) {
+        uint8_t prev = 0; bool inq = false; uint32_t prev_delim = 0, last_delim = 0;
+        for (uint32_t i = 0; i < n && !err; i++) {
+            const uint8_t c = line[i];
+            if (o.escape && o.escape == prev && inq) { prev = c; continue; }
+            if (o.quote && c == o.quote) { inq = !inq; prev = c; continue; }
+            if (c == o.delimiter && !inq) { last_delim = i; element(prev_delim, last_delim, nf); nf++; prev_delim = last_delim + 1; }
+            prev = c;
+        }
+        if (!err) { element(last_delim + 1 <= n ? last_delim + 1 : n, n, nf); nf++; }    // line[lastDelimPosition+1:], lastDelimPosition == 0 without delimiters
+    }
+    // columns whose field is missing, or that take the default value (reader_csv.go:291-313). constructCI runs over
+    // every column before Strictify does, so a missing cell outranks any conversion error.
+    for (int c = 0; c < a.ncols && !err; c++) {
+        const CsvColDev& cd = a.cols[c];
+        if (cd.path < 0) csv_default(a, cd, row, nrows);
+        else if (cd.path >= nf) { if (o.include_missing) csv_default(a, cd, row, nrows); else err = CSV_MISSING_CELL; }
+    }
+    if (!err) err = conv_err;
+    if (err) {   // an error row is dropped later; give its cells harmless contents
+        for (int c = 0; c < a.ncols; c++) { const CsvColDev& cd = a.cols[c]; if (!cd.w) { a.span_start[(size_t)cd.slot * nrows + row] = 0; a.span_len[(size_t)cd.slot * nrows + row] = 0; if (cd.aux8) cd.aux8[row] = 0; } else csv_store_fixed(cd, row, 0, 0); }
+    }
+    a.err[row] = (uint8_t)err;
+}
+
+// per text column: offsets[r] = sum of lengths of rows < r. One CTA per column walks its rows in chunks.
+__global__ void __launch_bounds__(1024) k_csv_offsets(const uint32_t* span_len, uint64_t nrows, uint32_t* offsets /* [nslots][nrows+1] */, uint64_t* col_total) {
+    __shared__ uint32_t sm[33];
+    const uint32_t* len = span_len + (size_t)blockIdx.x * nrows; uint32_t* off = offsets + (size_t)blockIdx.x * (nrows + 1);
+    uint64_t carry = 0;
+    for (uint64_t base = 0; base < nrows; base += blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        const uint32_t v = i < nrows ? (len[i] & 0x7fffffffu) : 0;
+        uint32_t tot; const uint32_t ex = block_excl_scan(v, &tot, sm);
+        if (i < nrows) off[i] = (uint32_t)(carry + ex);
+        carry += tot;
+    }
+    if (threadIdx.x == 0) { off[nrows] = (uint32_t)carry; col_total[blockIdx.x] = carry; }
+}
+
+struct CsvCopyArgs { const uint8_t* text; const uint32_t* span_start; const uint32_t* span_len; const uint32_t* offsets; uint8_t* heap; const uint64_t* col_base; uint64_t nrows; };
+
+__global__ void __launch_bounds__(256) k_csv_pass2(CsvCopyArgs a) {
+    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= a.nrows) return;
+    const uint32_t slot = blockIdx.y;
+    const uint32_t st = a.span_start[(size_t)slot * a.nrows + row], lf = a.span_len[(size_t)slot * a.nrows + row];
+    const uint32_t L = lf & 0x7fffffffu;
+    if (!L) return;
+    uint8_t* o = a.heap + a.col_base[slot] + a.offsets[(size_t)slot * (a.nrows + 1) + row];
+    if (st == 0xffffffffu) { o[0] = '{'; o[1] = '}'; return; }
+    const uint8_t* s = a.text + st;
+    if (lf & 0x80000000u) { uint32_t k = 0; for (uint32_t w = 0; w < L; w++) { o[w] = s[k]; k += (s[k] == '"' && s[k + 1] == '"') ? 2 : 1; } }
+    else for (uint32_t k = 0; k < L; k++) o[k] = s[k];
+}
+
+}  // namespace tfk

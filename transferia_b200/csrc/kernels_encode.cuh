@@ -163,6 +163,7 @@ struct FilterArgs {
     const uint32_t* expr_off;      // term ranges per expression (global expr index)
     const DTerm* terms; const uint8_t* blob;
     uint8_t* keep; uint8_t* errcode; uint8_t* errstep; uint32_t* blockcnt; DState* st;
+    const uint8_t* pre_err;        // optional per-row error already raised upstream (parser): the row is dropped and reported
 };
 
 // FilterRowsTransformer.Apply (filter_rows.go:99-130): one thread per row.
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(256) k_filter(FilterArgs a) {
     if (r < a.nrows) {
         keep = true; int err = 0, estep = 0;
         const int kind = a.kinds ? a.kinds[r] : TF_KIND_INSERT;
+        if (a.pre_err && a.pre_err[r]) { err = a.pre_err[r]; estep = 0xff; keep = false; }
         for (int s = 0; s < a.nsteps && keep; s++) {
             const DFilterStep st = a.steps[s];
             if (st.flags & 1) { if ((st.expr_begin >> kind) & 1) keep = false; continue; }            // skip_events.go:52-62

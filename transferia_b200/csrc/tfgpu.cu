@@ -15,6 +15,7 @@
 #include "kernels_encode.cuh"
 #include "kernels_lz4.cuh"
 #include "kernels_mask.cuh"
+#include "kernels_csv.cuh"
 
 using namespace tfk;
 
@@ -60,7 +61,7 @@ struct tfgpu_engine {
     int sm_count = 148;
     std::vector<std::unique_ptr<PlanDev>> plans;
     // arenas
-    DevBuf in_arena, work, raw, slots, wire;
+    DevBuf in_arena, work, raw, slots, wire, csv_text, csv_stage;
     DState* d_state = nullptr; DCol* d_cols = nullptr; size_t d_cols_cap = 0;
     int32_t* d_call_slots = nullptr; ColRegions* d_regions = nullptr; size_t d_call_cap = 0;   // columnar mode, per call
     // pointers into `work` for the last call
@@ -82,7 +83,7 @@ struct tfgpu_engine {
 };
 
 struct tfgpu_result {
-    uint64_t rows_in = 0, rows_out = 0, raw_len = 0, n_frames = 0;
+    uint64_t rows_in = 0, rows_out = 0, raw_len = 0, n_frames = 0, consumed = 0;
     std::vector<tf_rowerr> errs;
     uint8_t* bytes = nullptr; uint64_t bytes_len = 0; bool bytes_pinned = false;
     // push_columns output
@@ -207,7 +208,7 @@ Sizes compute_sizes(const tfgpu_engine* e, const PlanDev& pd, const tf_batch* in
 
 // Launch the whole fused chain on e->stream. `cols_host` holds DEVICE pointers.
 #define TF_WIRE_COLUMNAR_INTERNAL 100
-void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* dev_cols, const uint8_t* dev_kinds, int wire_fmt) {
+void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* dev_cols, const uint8_t* dev_kinds, int wire_fmt, const uint8_t* pre_err = nullptr) {
     const bool columnar = wire_fmt == TF_WIRE_COLUMNAR_INTERNAL;
     const tfplan::Plan& pl = pd.plan;
     const size_t nc = pl.in_schema.size(); const uint64_t n = in->nrows;
@@ -246,12 +247,12 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
     }
     CK(cudaMemcpyAsync(e->d_cols, hc.data(), sizeof(DCol) * nc, cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(e->d_state, 0, sizeof(DState), s));
-    e->prof_n = 0;
-    const bool has_filter = pd.n_fsteps > 0;
+    if (!pre_err) e->prof_n = 0;
+    const bool has_filter = pd.n_fsteps > 0 || pre_err;
     e->last_nrows = n; e->last_has_filter = has_filter; e->last_wire_fmt = wire_fmt;
     const uint32_t nb = (uint32_t)((n + 255) / 256);
     if (has_filter && n) {
-        FilterArgs fa{e->d_cols, dev_kinds, n, pd.d_fsteps, pd.n_fsteps, pd.d_expr_off, pd.d_terms, pd.d_blob, e->keep, e->errcode, e->errstep, e->blockcnt, e->d_state};
+        FilterArgs fa{e->d_cols, dev_kinds, n, pd.d_fsteps, pd.n_fsteps, pd.d_expr_off, pd.d_terms, pd.d_blob, e->keep, e->errcode, e->errstep, e->blockcnt, e->d_state, pre_err};
         e->prof_begin("k_filter", s); k_filter<<<nb, 256, 0, s>>>(fa); e->prof_end(s);
         e->prof_begin("k_scan_blockcnt", s); k_scan_blockcnt<<<1, 1024, 0, s>>>(e->blockcnt, e->blockoff, nb, e->d_state); e->prof_end(s);
         e->prof_begin("k_compact_sel", s); k_compact_sel<<<nb, 256, 0, s>>>(e->keep, e->blockoff, n, e->sel); e->prof_end(s);
@@ -371,7 +372,7 @@ int tfgpu_engine_destroy(tfgpu_engine* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (auto& p : e->plans) p->consts.release();
-    e->in_arena.release(); e->work.release(); e->raw.release(); e->slots.release(); e->wire.release();
+    e->in_arena.release(); e->work.release(); e->raw.release(); e->slots.release(); e->wire.release(); e->csv_text.release(); e->csv_stage.release();
     if (e->d_state) cudaFree(e->d_state);
     if (e->d_cols) cudaFree(e->d_cols);
     if (e->d_call_slots) { cudaFree(e->d_call_slots); cudaFree(e->d_regions); }
@@ -486,6 +487,7 @@ int tfgpu_resident_fetch(tfgpu_engine* e, int what, uint8_t* dst, uint64_t cap) 
 
 static const uint8_t* stage_input(tfgpu_engine* e, const tf_batch* in, std::vector<tf_col>& dev);
 static void fetch_errors(tfgpu_engine* e, uint64_t n, tfgpu_result* r);
+static void finish_wire(tfgpu_engine* e, uint64_t n, int wire_fmt, tfgpu_result* r);
 
 int tfgpu_push_encode(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch* in, tfgpu_result** out) {
     if (!e || !in || !out || plan_id < 0 || plan_id >= (int)e->plans.size()) return TF_E_FATAL_ARG;
@@ -501,21 +503,8 @@ int tfgpu_push_encode(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch
         std::vector<tf_col> dev; const uint8_t* dev_kinds = stage_input(e, in, dev);
         cudaStream_t s = e->stream;
         run_chain(e, pd, in, dev.data(), dev_kinds, wire_fmt);
-        DState st; CK(cudaMemcpyAsync(&st, e->d_state, sizeof st, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
         auto r = std::make_unique<tfgpu_result>();
-        r->rows_in = n; r->rows_out = st.n_kept; r->raw_len = st.raw_total;
-        const bool lz = wire_fmt == TF_WIRE_CH_NATIVE_LZ4;
-        r->n_frames = lz ? st.n_frames : 0;
-        r->bytes_len = lz ? st.wire_total : st.raw_total;
-        if (e->pinned_cap < r->bytes_len + 64) {   // grow-only pinned landing buffer, owned by the engine
-            if (e->pinned) { CK(cudaFreeHost(e->pinned)); e->pinned = nullptr; e->pinned_cap = 0; }
-            const size_t want = align_up(r->bytes_len + r->bytes_len / 4 + 4096, 1 << 20);
-            CK(cudaMallocHost(&e->pinned, want)); e->pinned_cap = want;
-        }
-        r->bytes = e->pinned; r->bytes_pinned = false;
-        CK(cudaMemcpyAsync(r->bytes, lz ? e->wire.p : e->raw.p, r->bytes_len, cudaMemcpyDeviceToHost, s));
-        if (st.n_errors) fetch_errors(e, n, r.get());
-        CK(cudaStreamSynchronize(s));
+        finish_wire(e, n, wire_fmt, r.get());
         *out = r.release();
         return TF_OK;
     } catch (const tfplan::FatalError& f) { return fail(e, f.code, f.what()); }
@@ -567,6 +556,48 @@ static void fetch_errors(tfgpu_engine* e, uint64_t n, tfgpu_result* r) {
     for (uint64_t i = 0; i < n; i++) if (ec[i]) r->errs.push_back(tf_rowerr{(uint32_t)i, ec[i], es[i]});
 }
 
+static void finish_columnar(tfgpu_engine* e, PlanDev& pd, uint64_t n, tfgpu_result* r) {
+    cudaStream_t s = e->stream;
+    DState st; CK(cudaMemcpyAsync(&st, e->d_state, sizeof st, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+    r->rows_in = n; r->rows_out = st.n_kept; r->raw_len = st.raw_total;
+    const size_t no = pd.plan.out_cols.size();
+    std::vector<ColRegions> reg(no);
+    CK(cudaMemcpyAsync(reg.data(), e->d_regions, sizeof(ColRegions) * no, cudaMemcpyDeviceToHost, s));
+    uint8_t* buf = (uint8_t*)malloc(st.raw_total ? st.raw_total : 1);
+    if (!buf) throw std::bad_alloc();
+    r->owned.push_back(buf);
+    if (st.raw_total) CK(cudaMemcpyAsync(buf, e->raw.p, st.raw_total, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (st.n_errors) fetch_errors(e, n, r);
+    r->cols.resize(no);
+    for (size_t k = 0; k < no; k++) {
+        tf_col& c = r->cols[k]; std::memset(&c, 0, sizeof c);
+        c.type = pd.plan.out_schema[k].tf;
+        auto at = [&](uint64_t off) -> const uint8_t* { return off == ~0ull ? nullptr : buf + off; };
+        c.values = at(reg[k].values); c.validity = at(reg[k].validity); c.aux = at(reg[k].aux);
+        c.offsets = (const uint32_t*)at(reg[k].offsets); c.heap = at(reg[k].heap); c.heap_len = reg[k].heap_len;
+    }
+    r->batch.nrows = st.n_kept; r->batch.ncols = (uint32_t)no; r->batch.mem = TF_MEM_HOST; r->batch.cols = r->cols.data(); r->batch.kinds = nullptr;
+}
+
+static void finish_wire(tfgpu_engine* e, uint64_t n, int wire_fmt, tfgpu_result* r) {
+    cudaStream_t s = e->stream;
+    DState st; CK(cudaMemcpyAsync(&st, e->d_state, sizeof st, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+    r->rows_in = n; r->rows_out = st.n_kept; r->raw_len = st.raw_total;
+    const bool lz = wire_fmt == TF_WIRE_CH_NATIVE_LZ4;
+    r->n_frames = lz ? st.n_frames : 0;
+    r->bytes_len = lz ? st.wire_total : st.raw_total;
+    if (e->pinned_cap < r->bytes_len + 64) {   // grow-only pinned landing buffer, owned by the engine
+        if (e->pinned) { CK(cudaFreeHost(e->pinned)); e->pinned = nullptr; e->pinned_cap = 0; }
+        const size_t want = align_up(r->bytes_len + r->bytes_len / 4 + 4096, 1 << 20);
+        CK(cudaMallocHost(&e->pinned, want)); e->pinned_cap = want;
+    }
+    r->bytes = e->pinned; r->bytes_pinned = false;
+    CK(cudaMemcpyAsync(r->bytes, lz ? e->wire.p : e->raw.p, r->bytes_len, cudaMemcpyDeviceToHost, s));
+    if (st.n_errors) fetch_errors(e, n, r);
+    CK(cudaStreamSynchronize(s));
+}
+
 // TransformerResult{Transformed, Errors}: the kept rows come back columnar in host memory owned by the result.
 int tfgpu_push_columns(tfgpu_engine* e, int plan_id, const tf_batch* in, tfgpu_result** out) {
     if (!e || !in || !out || plan_id < 0 || plan_id >= (int)e->plans.size()) return TF_E_FATAL_ARG;
@@ -576,37 +607,162 @@ int tfgpu_push_columns(tfgpu_engine* e, int plan_id, const tf_batch* in, tfgpu_r
     if (in->nrows >= (1ull << 31)) return fail(e, TF_E_FATAL_ARG, "batch too large (>= 2^31 rows)");
     try {
         CK(cudaSetDevice(e->device));
-        const uint64_t n = in->nrows;
         std::vector<tf_col> dev; const uint8_t* dev_kinds = stage_input(e, in, dev);
-        cudaStream_t s = e->stream;
         run_chain(e, pd, in, dev.data(), dev_kinds, TF_WIRE_COLUMNAR_INTERNAL);
-        DState st; CK(cudaMemcpyAsync(&st, e->d_state, sizeof st, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
         auto r = std::make_unique<tfgpu_result>();
-        r->rows_in = n; r->rows_out = st.n_kept; r->raw_len = st.raw_total;
-        const size_t no = pd.plan.out_cols.size();
-        std::vector<ColRegions> reg(no);
-        CK(cudaMemcpyAsync(reg.data(), e->d_regions, sizeof(ColRegions) * no, cudaMemcpyDeviceToHost, s));
-        uint8_t* buf = (uint8_t*)malloc(st.raw_total ? st.raw_total : 1);
-        if (!buf) throw std::bad_alloc();
-        r->owned.push_back(buf);
-        if (st.raw_total) CK(cudaMemcpyAsync(buf, e->raw.p, st.raw_total, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        if (st.n_errors) fetch_errors(e, n, r.get());
-        r->cols.resize(no);
-        for (size_t k = 0; k < no; k++) {
-            tf_col& c = r->cols[k]; std::memset(&c, 0, sizeof c);
-            c.type = pd.plan.out_schema[k].tf;
-            auto at = [&](uint64_t off) -> const uint8_t* { return off == ~0ull ? nullptr : buf + off; };
-            c.values = at(reg[k].values); c.validity = at(reg[k].validity); c.aux = at(reg[k].aux);
-            c.offsets = (const uint32_t*)at(reg[k].offsets); c.heap = at(reg[k].heap); c.heap_len = reg[k].heap_len;
-        }
-        r->batch.nrows = st.n_kept; r->batch.ncols = (uint32_t)no; r->batch.mem = TF_MEM_HOST; r->batch.cols = r->cols.data(); r->batch.kinds = nullptr;
+        finish_columnar(e, pd, in->nrows, r.get());
         *out = r.release();
         return TF_OK;
     } catch (const tfplan::FatalError& f) { return fail(e, f.code, f.what()); }
     catch (const CudaError& c) { return cuda_fail(e, c); }
     catch (const std::bad_alloc&) { return fail(e, TF_E_RETRY_OOM, "host allocation failed"); }
 }
+
+// ---------------------------------------------------------------------------------------------- CSV
+// parsers.Parser for the S3 CSV source (pkg/providers/s3/reader/registry/csv/reader_csv.go:85-452) fused with the
+// transformer chain and, when wire_fmt != 0, the ClickHouse encode: raw bytes in, Transformed rows or wire bytes out.
+namespace {
+struct CsvHostOpts { CsvCfg cfg; std::vector<uint8_t> blob; uint64_t skip = 0; };
+
+uint32_t put_list(std::vector<uint8_t>& blob, const std::vector<std::string>& v) {
+    if (v.empty()) return 0xffffffffu;
+    while (blob.size() % 4) blob.push_back(0);
+    const uint32_t at = (uint32_t)blob.size();
+    std::vector<uint32_t> hdr; hdr.push_back((uint32_t)v.size()); uint32_t o = 0; hdr.push_back(0);
+    for (auto& x : v) { o += (uint32_t)x.size(); hdr.push_back(o); }
+    const uint8_t* h = (const uint8_t*)hdr.data(); blob.insert(blob.end(), h, h + hdr.size() * 4);
+    for (auto& x : v) blob.insert(blob.end(), x.begin(), x.end());
+    return at;
+}
+
+CsvHostOpts parse_csv_opts(const char* js) {
+    CsvHostOpts h; std::memset(&h.cfg, 0, sizeof h.cfg);
+    h.cfg.delimiter = ','; h.cfg.quote = '"'; h.cfg.escape = '\\'; h.cfg.double_quote = 1;
+    std::vector<std::string> nulls, trues, falses;
+    if (js && *js) {
+        auto v = tfj::parse(js);
+        auto ch = [&](const char* k, uint8_t def) -> uint8_t { const tfj::Value* x = v->get(k); if (!x) return def; if (x->kind == tfj::Value::Str) return x->str.empty() ? 0 : (uint8_t)x->str[0]; return def; };
+        h.cfg.delimiter = ch("delimiter", ','); h.cfg.quote = ch("quote", '"'); h.cfg.escape = ch("escape", '\\');
+        h.cfg.double_quote = v->get_bool("double_quote", true); h.cfg.strings_can_be_null = v->get_bool("strings_can_be_null");
+        h.cfg.quoted_strings_can_be_null = v->get_bool("quoted_strings_can_be_null"); h.cfg.include_missing = v->get_bool("include_missing_columns");
+        nulls = v->get_str_list("null_values"); trues = v->get_str_list("true_values"); falses = v->get_str_list("false_values");
+        h.skip = (uint64_t)v->get_num("skip_lines", 0);
+    }
+    if (!h.cfg.delimiter || h.cfg.delimiter == '\r' || h.cfg.delimiter == '\n' || h.cfg.delimiter >= 0x80)
+        throw tfplan::FatalError(TF_E_FATAL_CONFIG, "csv: invalid delimiter (reader.go:320-322; the device handles ASCII delimiters)");
+    if (h.cfg.quote >= 0x80 || h.cfg.escape >= 0x80) throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "csv: non-ASCII quote / escape characters");
+    h.blob.resize(4, 0);
+    h.cfg.null_list = put_list(h.blob, nulls); h.cfg.true_list = put_list(h.blob, trues); h.cfg.false_list = put_list(h.blob, falses);
+    return h;
+}
+}  // namespace
+
+int tfgpu_parse_csv(tfgpu_engine* e, int plan_id, const char* opts_json, const uint8_t* bytes, uint64_t len, int mem, int wire_fmt, tfgpu_result** out) {
+    if (!e || !out || (!bytes && len) || plan_id < 0 || plan_id >= (int)e->plans.size()) return TF_E_FATAL_ARG;
+    *out = nullptr;
+    PlanDev& pd = *e->plans[plan_id];
+    if (len >= (1ull << 32) - 16) return fail(e, TF_E_FATAL_ARG, "csv chunk must be < 4 GiB (line positions are uint32)");
+    if (wire_fmt != 0 && wire_fmt != TF_WIRE_CH_NATIVE && wire_fmt != TF_WIRE_CH_NATIVE_LZ4) return fail(e, TF_E_FATAL_UNSUPPORTED, "wire format not implemented");
+    if (wire_fmt != 0 && !pd.plan.has_sink) return fail(e, TF_E_FATAL_CONFIG, "plan was built without a sink");
+    try {
+        CK(cudaSetDevice(e->device));
+        cudaStream_t s = e->stream;
+        CsvHostOpts ho = parse_csv_opts(opts_json);
+        const tfplan::Plan& pl = pd.plan; const size_t nc = pl.in_schema.size();
+        // text into HBM
+        const uint8_t* d_text = bytes;
+        if (mem == TF_MEM_HOST) { e->csv_text.ensure(len + 64); if (len) CK(cudaMemcpyAsync(e->csv_text.p, bytes, len, cudaMemcpyHostToDevice, s)); d_text = e->csv_text.p; }
+        // newline index
+        const uint32_t nblk = (uint32_t)((len + CSV_NL_BLOCK - 1) / CSV_NL_BLOCK);
+        uint64_t nlines = 0;
+        e->work.ensure(((size_t)nblk * 8 + 1024) * 2 + 4096);
+        uint32_t* blk_cnt = (uint32_t*)e->work.p; uint32_t* blk_off = blk_cnt + align_up(nblk + 1, 64);
+        if (nblk) {
+            CK(cudaMemsetAsync(e->d_state, 0, sizeof(DState), s));
+            e->prof_n = 0;
+            e->prof_begin("k_csv_count_nl", s); k_csv_count_nl<<<nblk, 256, 0, s>>>(d_text, len, blk_cnt); e->prof_end(s);
+            e->prof_begin("k_scan_blockcnt", s); k_scan_blockcnt<<<1, 1024, 0, s>>>(blk_cnt, blk_off, nblk, e->d_state); e->prof_end(s);
+            DState st; CK(cudaMemcpyAsync(&st, e->d_state, sizeof st, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+            nlines = st.n_kept;
+        }
+        const uint64_t skip = ho.skip < nlines ? ho.skip : nlines;
+        const uint64_t nrows = nlines - skip;
+        // staging layout
+        std::vector<CsvColDev> hc(nc); std::vector<int16_t> next_same(nc, -1); int nfields = 0, nslots = 0, nany = 0;
+        for (size_t c = 0; c < nc; c++) {
+            const tfplan::ColSchema& cs = pl.in_schema[c]; CsvColDev& d = hc[c]; std::memset(&d, 0, sizeof d);
+            d.tf = cs.tf; d.w = in_width(cs.tf); d.slot = -1;
+            d.path = cs.path.empty() ? (int)c : atoi(cs.path.c_str());        // reader_csv.go:286 strconv.Atoi(col.Path)
+            if (!cs.path.empty() && cs.path.find_first_not_of("-0123456789") != std::string::npos) throw tfplan::FatalError(TF_E_FATAL_CONFIG, "csv: column path '" + cs.path + "' is not an index");
+            if (d.path >= 0 && d.path + 1 > nfields) nfields = d.path + 1;
+            if (!d.w) { d.slot = nslots++; if (cs.tf == TF_ANY) nany++; }
+        }
+        if (nfields > 32000) throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "csv: too many fields");
+        std::vector<int16_t> field_col(nfields ? nfields : 1, -1);
+        for (int c = (int)nc - 1; c >= 0; c--) if (hc[c].path >= 0) { next_same[c] = field_col[hc[c].path]; field_col[hc[c].path] = (int16_t)c; }
+        size_t sb = 0; auto need = [&](size_t b) { size_t at = sb; sb += align_up(b ? b : 1, 256); return at; };
+        const size_t o_line = need((nlines + 1) * 4), o_err = need(nrows), o_cols = need(nc * sizeof(CsvColDev)), o_fc = need(field_col.size() * 2), o_ns = need(nc * 2),
+                     o_blob = need(ho.blob.size()), o_ss = need((size_t)nslots * nrows * 4), o_sl = need((size_t)nslots * nrows * 4),
+                     o_off = need((size_t)nslots * (nrows + 1) * 4), o_tot = need((size_t)nslots * 8 + 8), o_base = need((size_t)nslots * 8 + 8);
+        std::vector<size_t> o_val(nc), o_aux(nc);
+        for (size_t c = 0; c < nc; c++) {
+            o_val[c] = hc[c].w ? need((size_t)hc[c].w * nrows) : 0;
+            const int tf = hc[c].tf;
+            o_aux[c] = (tf == TF_DATE || tf == TF_DATETIME || tf == TF_TIMESTAMP) ? need(4 * nrows) : (tf == TF_ANY ? need(nrows) : 0);
+        }
+        const size_t o_heap = need(len + 2 * nrows * (size_t)(nany ? nany : 0) + 64);
+        e->csv_stage.ensure(sb + 256);
+        uint8_t* B = e->csv_stage.p;
+        for (size_t c = 0; c < nc; c++) {
+            if (hc[c].w) hc[c].values = B + o_val[c];
+            const int tf = hc[c].tf;
+            if (tf == TF_DATE || tf == TF_DATETIME || tf == TF_TIMESTAMP) hc[c].aux32 = (uint32_t*)(B + o_aux[c]);
+            if (tf == TF_ANY) hc[c].aux8 = B + o_aux[c];
+        }
+        CK(cudaMemcpyAsync(B + o_cols, hc.data(), nc * sizeof(CsvColDev), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(B + o_fc, field_col.data(), field_col.size() * 2, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(B + o_ns, next_same.data(), nc * 2, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(B + o_blob, ho.blob.data(), ho.blob.size(), cudaMemcpyHostToDevice, s));
+        std::vector<uint64_t> col_total(nslots ? nslots : 1, 0), col_base(nslots ? nslots : 1, 0);
+        if (nlines) { e->prof_begin("k_csv_line_index", s); k_csv_line_index<<<nblk, 256, 0, s>>>(d_text, len, blk_off, (uint32_t*)(B + o_line)); e->prof_end(s); }
+        if (nrows) {
+            CsvArgs ca{d_text, len, (const uint32_t*)(B + o_line), nlines, skip, ho.cfg, B + o_blob, (const CsvColDev*)(B + o_cols), (int)nc,
+                       (const int16_t*)(B + o_fc), nfields, (const int16_t*)(B + o_ns), (uint32_t*)(B + o_ss), (uint32_t*)(B + o_sl), B + o_err};
+            e->prof_begin("k_csv_pass1", s); k_csv_pass1<<<(uint32_t)((nrows + 127) / 128), 128, 0, s>>>(ca); e->prof_end(s);
+            if (nslots) {
+                e->prof_begin("k_csv_offsets", s); k_csv_offsets<<<nslots, 1024, 0, s>>>((const uint32_t*)(B + o_sl), nrows, (uint32_t*)(B + o_off), (uint64_t*)(B + o_tot)); e->prof_end(s);
+                CK(cudaMemcpyAsync(col_total.data(), B + o_tot, (size_t)nslots * 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+                uint64_t run = 0; for (int k = 0; k < nslots; k++) { col_base[k] = run; run += col_total[k]; }
+                CK(cudaMemcpyAsync(B + o_base, col_base.data(), (size_t)nslots * 8, cudaMemcpyHostToDevice, s));
+                CsvCopyArgs cp{d_text, (const uint32_t*)(B + o_ss), (const uint32_t*)(B + o_sl), (const uint32_t*)(B + o_off), B + o_heap, (const uint64_t*)(B + o_base), nrows};
+                e->prof_begin("k_csv_pass2", s); k_csv_pass2<<<dim3((uint32_t)((nrows + 255) / 256), nslots), 256, 0, s>>>(cp); e->prof_end(s);
+            }
+        }
+        // the staged batch, device resident
+        std::vector<tf_col> dev(nc);
+        for (size_t c = 0; c < nc; c++) {
+            tf_col& d = dev[c]; std::memset(&d, 0, sizeof d); d.type = hc[c].tf;
+            if (hc[c].w) { d.values = hc[c].values; d.aux = hc[c].aux32; }
+            else { d.offsets = (const uint32_t*)(B + o_off) + (size_t)hc[c].slot * (nrows + 1); d.heap = B + o_heap + col_base[hc[c].slot]; d.heap_len = col_total[hc[c].slot]; d.aux = hc[c].aux8; }
+        }
+        tf_batch staged; staged.nrows = nrows; staged.ncols = (uint32_t)nc; staged.mem = TF_MEM_DEVICE; staged.cols = dev.data(); staged.kinds = nullptr;
+        const int saved_prof = e->prof_n;
+        run_chain(e, pd, &staged, dev.data(), nullptr, wire_fmt == 0 ? TF_WIRE_COLUMNAR_INTERNAL : wire_fmt, nrows ? B + o_err : nullptr);
+        (void)saved_prof;
+        auto r = std::make_unique<tfgpu_result>();
+        if (wire_fmt == 0) finish_columnar(e, pd, nrows, r.get()); else finish_wire(e, nrows, wire_fmt, r.get());
+        uint32_t last_end = 0;
+        if (nlines) { CK(cudaMemcpyAsync(&last_end, (uint32_t*)(B + o_line) + (nlines - 1), 4, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s)); }
+        r->consumed = last_end;
+        *out = r.release();
+        return TF_OK;
+    } catch (const tfplan::FatalError& f) { return fail(e, f.code, f.what()); }
+    catch (const CudaError& c) { return cuda_fail(e, c); }
+    catch (const std::bad_alloc&) { return fail(e, TF_E_RETRY_OOM, "host allocation failed"); }
+    catch (const std::exception& x) { return fail(e, TF_E_FATAL_CONFIG, x.what()); }
+}
+
+uint64_t tfgpu_result_consumed(const tfgpu_result* r) { return r ? r->consumed : 0; }
 
 uint64_t tfgpu_result_rows_in(const tfgpu_result* r) { return r ? r->rows_in : 0; }
 uint64_t tfgpu_result_rows_out(const tfgpu_result* r) { return r ? r->rows_out : 0; }

@@ -57,6 +57,8 @@ def load_library():
     L.tfgpu_plan_validate.argtypes = [cp, cp, cp, cp, cp, cp, u64, cp, u64]
     L.tfgpu_push_columns.argtypes = [vp, i, C.POINTER(abi.TfBatch), C.POINTER(vp)]
     L.tfgpu_push_encode.argtypes = [vp, i, i, C.POINTER(abi.TfBatch), C.POINTER(vp)]
+    L.tfgpu_parse_csv.argtypes = [vp, i, cp, vp, u64, i, i, C.POINTER(vp)]
+    L.tfgpu_result_consumed.argtypes = [vp]; L.tfgpu_result_consumed.restype = u64
     L.tfgpu_push_encode_resident.argtypes = [vp, i, i, C.POINTER(abi.TfBatch)]
     L.tfgpu_resident_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     L.tfgpu_resident_fetch.argtypes = [vp, i, vp, u64]
@@ -75,7 +77,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "tfgpu_version", "tfgpu_engine_create", "tfgpu_engine_destroy", "tfgpu_last_error", "tfgpu_engine_set_stream",
-    "tfgpu_plan", "tfgpu_plan_validate", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_push_encode_resident",
+    "tfgpu_plan", "tfgpu_plan_validate", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_parse_csv", "tfgpu_result_consumed", "tfgpu_push_encode_resident",
     "tfgpu_resident_stats", "tfgpu_resident_fetch", "tfgpu_result_rows_in", "tfgpu_result_rows_out",
     "tfgpu_result_n_errors", "tfgpu_result_errors", "tfgpu_result_batch", "tfgpu_result_bytes",
     "tfgpu_result_bytes_len", "tfgpu_result_raw_len", "tfgpu_result_n_frames", "tfgpu_result_release",
@@ -166,14 +168,10 @@ class Engine:
         finally:
             self._L.tfgpu_result_release(res)
 
-    def push_columns(self, plan_id: int, batch: abi.Batch) -> Tuple[abi.Batch, List[Tuple[int, int, int]]]:
-        """Transformer chain only: (Transformed rows as a host Batch, row errors) — abstract.TransformerResult."""
+    def _result_batch(self, res):
         import numpy as np
-        tb = batch.as_struct()
-        res = C.c_void_p()
-        self._check(self._L.tfgpu_push_columns(self._h, plan_id, C.byref(tb), C.byref(res)))
-        try:
-            L = self._L
+        L = self._L
+        if True:
             ob = L.tfgpu_result_batch(res)
             n = int(L.tfgpu_result_rows_out(res))
             cols = []
@@ -196,6 +194,34 @@ class Engine:
             ne = L.tfgpu_result_n_errors(res); ep = L.tfgpu_result_errors(res)
             errs = [(ep[k].row, ep[k].code, ep[k].term) for k in range(ne)]
             return abi.Batch(n, cols), errs
+
+    def push_columns(self, plan_id: int, batch: abi.Batch) -> Tuple[abi.Batch, List[Tuple[int, int, int]]]:
+        """Transformer chain only: (Transformed rows as a host Batch, row errors) — abstract.TransformerResult."""
+        tb = batch.as_struct()
+        res = C.c_void_p()
+        self._check(self._L.tfgpu_push_columns(self._h, plan_id, C.byref(tb), C.byref(res)))
+        try:
+            return self._result_batch(res)
+        finally:
+            self._L.tfgpu_result_release(res)
+
+    def parse_csv(self, plan_id: int, data: bytes, opts: Optional[dict] = None, wire_fmt: int = 0):
+        """CSV bytes -> typed columns -> the plan's transformer chain, all on the device.
+        wire_fmt 0: (Batch, row errors, consumed bytes); otherwise (PushResult, consumed bytes)."""
+        buf = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data or b"\0")
+        res = C.c_void_p()
+        self._check(self._L.tfgpu_parse_csv(self._h, plan_id, json.dumps(opts or {}).encode(), buf, len(data), abi.TF_MEM_HOST, wire_fmt, C.byref(res)))
+        try:
+            L = self._L
+            consumed = int(L.tfgpu_result_consumed(res))
+            if wire_fmt == 0:
+                b, errs = self._result_batch(res)
+                return b, errs, consumed
+            n = L.tfgpu_result_bytes_len(res)
+            ne = L.tfgpu_result_n_errors(res); ep = L.tfgpu_result_errors(res)
+            out = PushResult(L.tfgpu_result_rows_in(res), L.tfgpu_result_rows_out(res), L.tfgpu_result_raw_len(res), L.tfgpu_result_n_frames(res),
+                             C.string_at(L.tfgpu_result_bytes(res), n) if n else b"", [(ep[k].row, ep[k].code, ep[k].term) for k in range(ne)])
+            return out, consumed
         finally:
             self._L.tfgpu_result_release(res)
 
