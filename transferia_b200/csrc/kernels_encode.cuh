@@ -376,75 +376,66 @@ struct EncodeArgs {
 #define TF_FIX_TILE_WORDS 2048
 #define CH_MAX_DATE_SEC 4291747200LL   // 2106-01-01T00:00:00Z (columntypes/types.go:15-18)
 
-// One output element after the typesystem cast (columntypes.Restore -> abstract.Restore are the identity
-// for values whose Go type already matches the column type; what remains is the ClickHouse clamp/unit rule).
-__device__ __forceinline__ uint64_t elem_value(const DCol& c, const uint32_t* sel, uint64_t j, uint64_t n, bool nullmap, bool aux = false) {
+// Stream kinds of k_encode_fixed, resolved ONCE per CTA (every thread of a CTA works on the same column), so the
+// per-element code below is straight-line for its kind.
+enum StreamKind { SK_COPY = 0, SK_BOOL, SK_DATE, SK_DATETIME, SK_TS64, SK_NULLMAP, SK_AUX32, SK_AUX8 };
+
+// One output element after the typesystem cast (columntypes.Restore -> abstract.Restore are the identity for values
+// whose Go type already matches the column type; what remains is the ClickHouse clamp / unit rule).
+template <int K, int INW> __device__ __forceinline__ uint64_t elem_t(const DCol& c, const uint32_t* sel, uint64_t j, uint64_t n) {
     if (j >= n) return 0;
     const uint64_t r = sel ? sel[j] : j;
-    if (aux) return c.type == TF_ANY ? (uint64_t)c.aux[r] : (uint64_t)((const uint32_t*)c.aux)[r];
+    if (K == SK_AUX8) return (uint64_t)c.aux[r];
+    if (K == SK_AUX32) return (uint64_t)((const uint32_t*)c.aux)[r];
     const bool valid = row_valid(c, r);
-    if (nullmap) return valid ? 0 : 1;
+    if (K == SK_NULLMAP) return valid ? 0 : 1;
     if (!valid) return 0;
-    switch (c.out_kind) {
-    case OK_COPY:
-        switch (c.in_w) {
-        case 1: return c.values[r];
-        case 2: return ((const uint16_t*)c.values)[r];
-        case 4: return ((const uint32_t*)c.values)[r];
-        default: return ((const uint64_t*)c.values)[r];
-        }
-    case OK_BOOL: return c.values[r] != 0;
-    case OK_DATE: case OK_DATETIME: {
+    if (K == SK_COPY) {
+        if (INW == 1) return c.values[r];
+        if (INW == 2) return ((const uint16_t*)c.values)[r];
+        if (INW == 4) return ((const uint32_t*)c.values)[r];
+        return ((const uint64_t*)c.values)[r];
+    }
+    if (K == SK_BOOL) return c.values[r] != 0;
+    if (K == SK_DATE || K == SK_DATETIME) {
         int64_t s = ((const int64_t*)c.values)[r];
         const uint32_t ns = c.aux ? ((const uint32_t*)c.aux)[r] : 0;
         if (s > CH_MAX_DATE_SEC || (s == CH_MAX_DATE_SEC && ns > 0)) s = CH_MAX_DATE_SEC;
         if (s < 0) s = 0;
-        return c.out_kind == OK_DATE ? (uint64_t)(s / 86400) : (uint64_t)s;
+        return K == SK_DATE ? (uint64_t)(s / 86400) : (uint64_t)s;
     }
-    case OK_TS64: {
-        const int64_t s = ((const int64_t*)c.values)[r];
-        const uint32_t ns = c.aux ? ((const uint32_t*)c.aux)[r] : 0;
-        return (uint64_t)(s * 1000000LL + (int64_t)(ns / 1000u));
-    }
-    }
-    return 0;
+    // SK_TS64
+    const int64_t s = ((const int64_t*)c.values)[r];
+    const uint32_t ns = c.aux ? ((const uint32_t*)c.aux)[r] : 0;
+    return (uint64_t)(s * 1000000LL + (int64_t)(ns / 1000u));
 }
 
-// 4 consecutive bytes [4q, 4q+4) of the column's little-endian element stream
-__device__ __forceinline__ uint32_t stream_word(const DCol& c, const uint32_t* sel, uint64_t q, uint64_t n, int w, bool nullmap, bool aux = false) {
-    switch (w) {
-    case 1: return (uint32_t)elem_value(c, sel, 4 * q, n, nullmap, aux) | ((uint32_t)elem_value(c, sel, 4 * q + 1, n, nullmap, aux) << 8) |
-                   ((uint32_t)elem_value(c, sel, 4 * q + 2, n, nullmap, aux) << 16) | ((uint32_t)elem_value(c, sel, 4 * q + 3, n, nullmap, aux) << 24);
-    case 2: return (uint32_t)(elem_value(c, sel, 2 * q, n, nullmap, aux) & 0xffff) | ((uint32_t)(elem_value(c, sel, 2 * q + 1, n, nullmap, aux) & 0xffff) << 16);
-    case 4: return (uint32_t)elem_value(c, sel, q, n, nullmap, aux);
-    default: { const uint64_t v = elem_value(c, sel, q >> 1, n, nullmap, aux); return (uint32_t)(v >> ((q & 1) * 32)); }
-    }
+// 4 consecutive bytes [4q, 4q+4) of the column's little-endian element stream (W = output element width)
+template <int K, int INW, int W> __device__ __forceinline__ uint32_t stream_word_t(const DCol& c, const uint32_t* sel, uint64_t q, uint64_t n) {
+    if (W == 1) return (uint32_t)elem_t<K, INW>(c, sel, 4 * q, n) | ((uint32_t)elem_t<K, INW>(c, sel, 4 * q + 1, n) << 8) |
+                       ((uint32_t)elem_t<K, INW>(c, sel, 4 * q + 2, n) << 16) | ((uint32_t)elem_t<K, INW>(c, sel, 4 * q + 3, n) << 24);
+    if (W == 2) return (uint32_t)(elem_t<K, INW>(c, sel, 2 * q, n) & 0xffff) | ((uint32_t)(elem_t<K, INW>(c, sel, 2 * q + 1, n) & 0xffff) << 16);
+    if (W == 4) return (uint32_t)elem_t<K, INW>(c, sel, q, n);
+    const uint64_t v = elem_t<K, INW>(c, sel, q >> 1, n); return (uint32_t)(v >> ((q & 1) * 32));
 }
 
-// Fixed-width columns and null maps. The column's data starts at an arbitrary byte of the block
-// (ClickHouse's format has no padding), so each lane builds one 4-byte word of the element stream,
-// takes its left neighbour's word by shuffle and funnel-shifts the pair onto the 4-byte grid of the
-// OUTPUT address: every store is an aligned, fully coalesced 128 B per warp.
-__global__ void __launch_bounds__(256) k_encode_fixed(EncodeArgs a) {
-    const int32_t slot = a.slots[blockIdx.y];
-    const bool nullmap = (slot & TF_SLOT_NULLMAP) != 0, aux = (slot & TF_SLOT_AUX) != 0;
-    const DCol c = a.cols[slot & ~(TF_SLOT_NULLMAP | TF_SLOT_AUX)];
-    const uint64_t n = a.st->n_kept;
-    const int w = nullmap ? 1 : (aux ? (c.type == TF_ANY ? 1 : 4) : c.out_w);
-    const uint64_t base = nullmap ? c.null_off : (aux ? c.aux_off : c.out_off);
+// The column's data starts at an arbitrary byte of the block (ClickHouse's format has no padding), so each lane builds
+// one 4-byte word of the element stream, takes its left neighbour's word by shuffle and funnel-shifts the pair onto
+// the 4-byte grid of the OUTPUT address: every store is an aligned, fully coalesced 128 B per warp.
+template <int K, int INW, int W> __device__ __forceinline__ void encode_stream(const DCol& c, const EncodeArgs& a, uint64_t base, uint64_t n) {
     const uint32_t m = (uint32_t)(base & 3);
-    const uint64_t total = n * (uint64_t)w;
+    const uint64_t total = n * (uint64_t)W;
     const uint64_t T = (m + total + 3) >> 2;
     const uint64_t t0 = (uint64_t)blockIdx.x * TF_FIX_TILE_WORDS;
-    if (t0 >= T || n == 0) return;
+    if (t0 >= T) return;
     uint8_t* dst0 = a.raw + (base - m);
     const unsigned lane = threadIdx.x & 31;
 #pragma unroll 2
     for (uint32_t it = 0; it < TF_FIX_TILE_WORDS / 256; it++) {
-        const uint64_t t = t0 + it * 256 + threadIdx.x;      // uniform trip count: shuffles below need the whole warp
-        const uint32_t wcur = (t < T) ? stream_word(c, a.sel, t, n, w, nullmap, aux) : 0;
+        const uint64_t t = t0 + it * 256 + threadIdx.x;      // uniform trip count: the shuffle below needs the whole warp
+        const uint32_t wcur = (t < T) ? stream_word_t<K, INW, W>(c, a.sel, t, n) : 0;
         uint32_t wprev = __shfl_up_sync(0xffffffffu, wcur, 1);
-        if (lane == 0) wprev = (m && t > 0 && t <= T) ? stream_word(c, a.sel, t - 1, n, w, nullmap, aux) : 0;
+        if (lane == 0) wprev = (m && t > 0 && t <= T) ? stream_word_t<K, INW, W>(c, a.sel, t - 1, n) : 0;
         if (t >= T) continue;
         const uint32_t val = m ? __funnelshift_r(wprev, wcur, 8 * (4 - m)) : wcur;
         const int64_t sb = (int64_t)(4 * t) - (int64_t)m;          // stream offset of this word's first byte
@@ -454,6 +445,30 @@ __global__ void __launch_bounds__(256) k_encode_fixed(EncodeArgs a) {
 #pragma unroll
             for (int b = 0; b < 4; b++) { const int64_t x = sb + b; if (x >= 0 && (uint64_t)x < total) dst[b] = (uint8_t)(val >> (8 * b)); }
         }
+    }
+}
+
+// Fixed-width columns, null maps and (columnar output) aux arrays: blockIdx.y = stream slot.
+__global__ void __launch_bounds__(256) k_encode_fixed(EncodeArgs a) {
+    const int32_t slot = a.slots[blockIdx.y];
+    const DCol c = a.cols[slot & ~(TF_SLOT_NULLMAP | TF_SLOT_AUX)];
+    const uint64_t n = a.st->n_kept;
+    if (n == 0) return;
+    if (slot & TF_SLOT_NULLMAP) { encode_stream<SK_NULLMAP, 1, 1>(c, a, c.null_off, n); return; }
+    if (slot & TF_SLOT_AUX) { if (c.type == TF_ANY) encode_stream<SK_AUX8, 1, 1>(c, a, c.aux_off, n); else encode_stream<SK_AUX32, 4, 4>(c, a, c.aux_off, n); return; }
+    switch (c.out_kind) {
+    case OK_COPY:
+        switch (c.in_w) {
+        case 1: encode_stream<SK_COPY, 1, 1>(c, a, c.out_off, n); break;
+        case 2: encode_stream<SK_COPY, 2, 2>(c, a, c.out_off, n); break;
+        case 4: encode_stream<SK_COPY, 4, 4>(c, a, c.out_off, n); break;
+        default: encode_stream<SK_COPY, 8, 8>(c, a, c.out_off, n); break;
+        }
+        break;
+    case OK_BOOL: encode_stream<SK_BOOL, 1, 1>(c, a, c.out_off, n); break;
+    case OK_DATE: encode_stream<SK_DATE, 8, 2>(c, a, c.out_off, n); break;
+    case OK_DATETIME: encode_stream<SK_DATETIME, 8, 4>(c, a, c.out_off, n); break;
+    case OK_TS64: encode_stream<SK_TS64, 8, 8>(c, a, c.out_off, n); break;
     }
 }
 
@@ -502,14 +517,24 @@ __global__ void __launch_bounds__(TF_STR_THREADS) k_encode_str(EncodeArgs a) {
             while (v >= 0x80) { *o++ = (uint8_t)(v | 0x80); v >>= 7; }
             *o++ = (uint8_t)v;
         }
+        // The copy is latency bound if every byte waits for its own load, so each round issues four independent
+        // aligned word loads (16 source bytes, re-aligned with funnel shifts) before any byte is stored.
         uint32_t nb = L;
-        // head bytes up to a 4-byte boundary of the source, then whole words, then the tail
-        while (nb && ((uintptr_t)s & 3)) { *o++ = *s++; nb--; }
-        for (; nb >= 4; nb -= 4, s += 4, o += 4) {
-            const uint32_t w = *(const uint32_t*)s;
-            o[0] = (uint8_t)w; o[1] = (uint8_t)(w >> 8); o[2] = (uint8_t)(w >> 16); o[3] = (uint8_t)(w >> 24);
+        const uint32_t sh = ((uint32_t)(uintptr_t)s & 3) * 8;
+        const uint32_t* sw = (const uint32_t*)((uintptr_t)s & ~(uintptr_t)3);
+        while (nb) {
+            const uint32_t take = nb < 16 ? nb : 16;
+            const uint32_t need = (take + (sh >> 3) + 3) >> 2;            // aligned words that hold these bytes (1..5)
+            uint32_t w0 = __ldg(sw), w1 = need > 1 ? __ldg(sw + 1) : 0, w2 = need > 2 ? __ldg(sw + 2) : 0, w3 = need > 3 ? __ldg(sw + 3) : 0, w4 = need > 4 ? __ldg(sw + 4) : 0;
+            if (sh) { w0 = __funnelshift_r(w0, w1, sh); w1 = __funnelshift_r(w1, w2, sh); w2 = __funnelshift_r(w2, w3, sh); w3 = __funnelshift_r(w3, w4, sh); }
+            const uint32_t ww[4] = {w0, w1, w2, w3};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+#pragma unroll
+                for (int b = 0; b < 4; b++) if ((uint32_t)(4 * q + b) < take) o[4 * q + b] = (uint8_t)(ww[q] >> (8 * b));
+            }
+            o += take; sw += 4; nb -= take;
         }
-        while (nb) { *o++ = *s++; nb--; }
     }
     if (!staged) return;
     __syncthreads();

@@ -54,7 +54,8 @@ struct PlanDev {
 
 struct tfgpu_engine {
     int device = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, side_stream = nullptr;   // side_stream: string encode runs beside the fixed-width encode
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string last_error;
     uint64_t launches = 0;
     uint32_t frame_bytes = 32768;
@@ -359,6 +360,8 @@ int tfgpu_engine_create(const char* cfg_json, const int* device_ids, int n_devic
         e->sm_count = prop.multiProcessorCount;
         CK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
         e->stream = e->own_stream;
+        CK(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
         CK(cudaMalloc(&e->d_state, sizeof(DState)));
         CK(cudaFuncSetAttribute(k_lz4_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024));
     } catch (const CudaError& c) { return c.e == cudaErrorMemoryAllocation ? TF_E_RETRY_OOM : TF_E_RETRY_LAUNCH; }
@@ -378,6 +381,9 @@ int tfgpu_engine_destroy(tfgpu_engine* e) {
     if (e->d_call_slots) { cudaFree(e->d_call_slots); cudaFree(e->d_regions); }
     if (e->pinned) cudaFreeHost(e->pinned);
     for (auto ev : e->prof_ev) cudaEventDestroy(ev);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->side_stream) cudaStreamDestroy(e->side_stream);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
     return TF_OK;
