@@ -512,9 +512,11 @@ extern "C" int orc_push_columns(const tf_batch* in, const orc_colschema* schema,
     const uint32_t no = (uint32_t)out_cols.size();
     struct CB { std::vector<uint8_t> values, valid_bits, aux, heap; std::vector<uint32_t> offs; bool has_valid, has_aux; };
     std::vector<CB> cb(no);
+    std::vector<char> rewritten(nc, 0);     // mask_field / convert_to_string give the column a fresh, never-nil text value
+    for (int s = 0; s < nsteps; s++) if (steps[s].kind == STEP_MASK || steps[s].kind == STEP_TO_STRING) for (int k = 0; k < steps[s].ncols; k++) rewritten[steps[s].cols[k]] = 1;
     for (uint32_t k = 0; k < no; k++) {
         const tf_col& ic = in->cols[out_cols[k]];
-        const bool masked = out_type[out_cols[k]] != ic.type;
+        const bool masked = rewritten[out_cols[k]] != 0;
         cb[k].has_valid = ic.validity && !masked; cb[k].has_aux = ic.aux && !masked; cb[k].offs.push_back(0);
     }
     uint64_t kept = 0, ne = 0;

@@ -181,7 +181,8 @@ def test_skip_events_filter_columns_rename_chain(eng, po):
 
 def test_mask_field_on_device(eng, po):
     batch, schema = all_types_batch(1500, seed=21)
-    cols = ["c_int8", "n_int32", "c_uint64", "n_bool", "c_date", "n_datetime", "n_timestamp", "c_utf8", "n_bytes", "n_any", "c_int64"]
+    cols = ["c_int8", "n_int32", "c_uint64", "n_bool", "c_date", "n_datetime", "n_timestamp", "c_utf8", "n_bytes", "n_any", "c_int64",
+            "c_float", "n_double", "c_interval"]
     trs = [{"mask_field": {"columns": cols, "maskFunctionHash": {"userDefinedSalt": "the-best-tasty-saint-petersburg-salt"}}}]
     got, ref = check(eng, po, batch, schema, trs)
     # a long key (> 64 bytes is hashed first by crypto/hmac), chained after a filter
@@ -193,15 +194,15 @@ def test_mask_golden_digests_on_device(eng, po, goldens):
     """The reference's canondata digests reproduced by the device HMAC kernel (types the device formats)."""
     salt = goldens["mask"]["salt"]
     for c in goldens["mask"]["cases"]:
-        if c["go"] in ("float64", "float32", "duration"):
-            continue
-        tf = abi.YT_NAME_TO_TF[c["type"]]
+        tf = abi.YT_NAME_TO_TF["interval" if c["go"] == "duration" else c["type"]]
         if c["go"] == "string":
             col = abi.strings_to_column(abi.TF_UTF8 if tf == abi.TF_BYTES else tf, [c["value"].encode()]); typ = "utf8" if tf == abi.TF_BYTES else c["type"]
         elif c["go"] == "time":
             col = abi.fixed_to_column(tf, [-8425641600]); typ = c["type"]       # 1703-01-02T00:00:00Z
         elif c["go"] == "bool":
             col = abi.fixed_to_column(tf, [1]); typ = c["type"]
+        elif c["go"] == "duration":
+            col = abi.fixed_to_column(abi.TF_INTERVAL, [c["value"]]); typ = "interval"     # %v of time.Duration -> "1m0s"
         else:
             col = abi.fixed_to_column(tf, [c["value"]]); typ = c["type"]
         schema = [{"name": "c", "type": typ, "required": True}]
@@ -330,3 +331,49 @@ def test_push_columns_transformed_batch(eng, po):
     got, _ = eng.push_columns(pid, hb)
     ref, _ = po.push_columns(hb, po.build_plan("public", "hits", hs, workload.headline_transformers(workload.counterid_threshold(hb, hs))))
     assert_batches_equal(got, ref)
+
+
+def float_batch(n=200_000, seed=8):
+    rng = np.random.default_rng(seed)
+    bits = rng.integers(0, 2**63 - 1, n, dtype=np.int64).view(np.uint64) | (rng.integers(0, 2, n).astype(np.uint64) << np.uint64(63))
+    d = bits.view(np.float64).copy()
+    special = [0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324, 2.2250738585072014e-308, 1.7976931348623157e308, 1e21, 1e22, 1e23, 9007199254740993.0, 123456.7, 1234567.0,
+               1e-5, 1e-4, 1e-7, 1e-6, 9.999999999999999e-7, 1e20, 99999.95, 0.3, 1 / 3, 100.0, 1e6, 999999.0, 123.123]
+    d[:len(special)] = special
+    d[len(special):n // 2] = rng.random(n // 2 - len(special)) * 10.0 ** rng.integers(-25, 25, n // 2 - len(special))
+    f = rng.integers(0, 2**32 - 1, n, dtype=np.int64).astype(np.uint32).view(np.float32).copy()
+    f[:len(special)] = np.array(special, dtype=np.float64).astype(np.float32)
+    f[len(special):n // 2] = (rng.random(n // 2 - len(special)) * 10.0 ** rng.integers(-20, 20, n // 2 - len(special))).astype(np.float32)
+    dur = rng.integers(-2**62, 2**62, n); dur[:8] = [0, 1, 999, 1000, 1_500_000, 60 * 10**9, 3600 * 10**9 + 5 * 10**8, -(2**63)]
+    schema = [{"name": "d", "type": "double", "required": True}, {"name": "f", "type": "float", "required": True}, {"name": "iv", "type": "interval", "required": True}]
+    return abi.Batch(n, [abi.fixed_to_column(abi.TF_DOUBLE, d), abi.fixed_to_column(abi.TF_FLOAT, f), abi.fixed_to_column(abi.TF_INTERVAL, dur)]), schema
+
+
+def test_device_float_and_duration_text_forms(eng, po):
+    """Go %v of float64 / float32 / time.Duration on the device (Ryu shortest digits) vs the oracle's exact big-integer
+    printer, 200 k random bit patterns + the layout thresholds, through convert_to_string (to_string.go:145-171)."""
+    batch, schema = float_batch()
+    trs = [{"convert_to_string": {"columns": {"includeColumns": ["^d$", "^f$", "^iv$"]}}}]
+    pid = eng.plan("db", "t", schema, trs)
+    got, _ = eng.push_columns(pid, batch)
+    ref, _ = po.push_columns(batch, po.build_plan("db", "t", schema, trs))
+    for k in range(3):
+        g, r = got.columns[k], ref.columns[k]
+        if not (np.array_equal(g.offsets, r.offsets) and np.array_equal(g.heap, r.heap)):
+            bad = np.nonzero(np.diff(g.offsets.astype(np.int64)) != np.diff(r.offsets.astype(np.int64)))[0][:5]
+            show = [(int(i), bytes(g.heap[g.offsets[i]:g.offsets[i + 1]]), bytes(r.heap[r.offsets[i]:r.offsets[i + 1]])) for i in bad]
+            raise AssertionError(f"column {k}: text forms differ, e.g. {show}")
+    assert_batches_equal(got, ref)
+
+
+def test_convert_to_string_all_types(eng, po):
+    batch, schema = all_types_batch(2000, seed=17)
+    for trs in ([{"convert_to_string": {}}],                                                       # every column
+                [{"convert_to_string": {"columns": {"includeColumns": ["^n_", "date"]}, "convert_to_bytes": True}}],
+                [{"filter_rows": {"filter": "c_int32 > 0"}}, {"convert_to_string": {"columns": {"excludeColumns": ["utf8", "bytes"]}}}]):
+        check(eng, po, batch, schema, trs)
+        pid = eng.plan("db", "t", schema, trs)
+        got, gerr = eng.push_columns(pid, batch)
+        ref, rerr = po.push_columns(batch, po.build_plan("db", "t", schema, trs))
+        assert gerr == rerr
+        assert_batches_equal(got, ref)

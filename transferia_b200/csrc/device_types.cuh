@@ -13,7 +13,8 @@ enum OutKind : int32_t {
     OK_DATETIME = 3,  // time seconds -> same clamp -> u32 seconds
     OK_TS64 = 4,      // time (sec, nsec) -> DateTime64(6) = UnixMicro, no clamp          (columntypes/types.go:242)
     OK_STR = 5,       // LEB128 length + bytes
-    OK_MASK = 6       // mask_field digest: 0x40 + 64 lowercase hex chars                  (hmac_hasher.go:29-33)
+    OK_MASK = 6,      // mask_field digest: 0x40 + 64 lowercase hex chars                  (hmac_hasher.go:29-33)
+    OK_TOSTR = 7      // convert_to_string: LEB128 length + text form of the value         (to_string.go:145-171)
 };
 
 struct DCol {

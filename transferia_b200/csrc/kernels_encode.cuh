@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(256) k_layout_finish(LayoutArgs a) {
             const DCol& d = a.cols[a.out_cols[c]];
             s_size[0][threadIdx.x] = a.col_header_off[c + 1] - a.col_header_off[c];
             s_size[1][threadIdx.x] = (d.nullable && n) ? n : 0;
-            s_size[2][threadIdx.x] = n ? ((d.out_kind == OK_STR) ? a.col_bytes[d.str_slot] : (uint64_t)d.out_w * n) : 0;
+            s_size[2][threadIdx.x] = n ? ((d.out_kind == OK_STR || d.out_kind == OK_TOSTR) ? a.col_bytes[d.str_slot] : (uint64_t)d.out_w * n) : 0;
         }
         __syncthreads();
         if (threadIdx.x == 0) {  // serial prefix over shared memory only
@@ -330,11 +330,12 @@ __global__ void __launch_bounds__(256) k_layout_columnar(LayoutArgs a, ColRegion
         __syncthreads();
         if (k < a.ncols) {
             const DCol& d = a.cols[a.out_cols[k]];
-            const bool var = d.out_kind == OK_STR || d.out_kind == OK_MASK;
-            const uint64_t heap = d.out_kind == OK_STR ? a.col_bytes[d.str_slot] : (d.out_kind == OK_MASK ? 64 * n : 0);
+            const bool var = d.out_kind == OK_STR || d.out_kind == OK_MASK || d.out_kind == OK_TOSTR;
+            const bool fresh = d.out_kind == OK_MASK || d.out_kind == OK_TOSTR;      // a new text value: never nil, no aux
+            const uint64_t heap = (d.out_kind == OK_STR || d.out_kind == OK_TOSTR) ? a.col_bytes[d.str_slot] : (d.out_kind == OK_MASK ? 64 * n : 0);
             s_sz[0][threadIdx.x] = var ? 0 : (uint64_t)d.out_w * n;                                   // values
-            s_sz[1][threadIdx.x] = (d.validity && d.out_kind != OK_MASK) ? (n + 7) / 8 : 0;          // validity bitmap
-            s_sz[2][threadIdx.x] = (d.aux && d.out_kind != OK_MASK) ? (d.type == TF_ANY ? n : 4 * n) : 0;   // aux
+            s_sz[1][threadIdx.x] = (d.validity && !fresh) ? (n + 7) / 8 : 0;          // validity bitmap
+            s_sz[2][threadIdx.x] = (d.aux && !fresh) ? (d.type == TF_ANY ? n : 4 * n) : 0;   // aux
             s_sz[3][threadIdx.x] = var ? 4 * (n + 1) : 0;                                             // offsets
             s_sz[4][threadIdx.x] = heap;
         }
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__(256) k_layout_columnar(LayoutArgs a, ColRegion
             uint64_t p = s_pos[threadIdx.x]; ColRegions r;
             auto take = [&](int z) { const uint64_t at = p; p += (s_sz[z][threadIdx.x] + 15) & ~15ull; return at; };
             const uint64_t v = take(0), val = take(1), ax = take(2), of = take(3), hp = take(4);
-            const bool var = d.out_kind == OK_STR || d.out_kind == OK_MASK;
+            const bool var = d.out_kind == OK_STR || d.out_kind == OK_MASK || d.out_kind == OK_TOSTR;
             d.out_off = var ? hp : v; d.null_off = val; d.aux_off = ax; d.offs_off = of;
             r.values = var ? ~0ull : v; r.validity = s_sz[1][threadIdx.x] ? val : ~0ull; r.aux = s_sz[2][threadIdx.x] ? ax : ~0ull;
             r.offsets = var ? of : ~0ull; r.heap = var ? hp : ~0ull; r.heap_len = s_sz[4][threadIdx.x];
@@ -469,89 +470,6 @@ __global__ void __launch_bounds__(256) k_encode_fixed(EncodeArgs a) {
     case OK_DATE: encode_stream<SK_DATE, 8, 2>(c, a, c.out_off, n); break;
     case OK_DATETIME: encode_stream<SK_DATETIME, 8, 4>(c, a, c.out_off, n); break;
     case OK_TS64: encode_stream<SK_TS64, 8, 8>(c, a, c.out_off, n); break;
-    }
-}
-
-// ------------------------------------------------------------------ String columns
-__device__ __forceinline__ uint32_t str_len(const DCol& c, const uint32_t* sel, uint64_t j, uint64_t n, uint64_t& r) {
-    if (j >= n) { r = 0; return 0xffffffffu; }
-    r = sel ? sel[j] : j;
-    if (!row_valid(c, r)) return 0;
-    return c.offsets[r + 1] - c.offsets[r];
-}
-
-// encoded size (LEB128 length + payload) of every tile of TF_STR_TILE kept rows, for every String column
-__global__ void __launch_bounds__(TF_STR_THREADS) k_str_sizes(EncodeArgs a) {
-    __shared__ uint32_t sm[33];
-    const DCol c = a.cols[a.slots[blockIdx.y]];
-    const uint64_t n = a.st->n_kept;
-    const uint64_t j0 = (uint64_t)blockIdx.x * TF_STR_TILE;
-    if (j0 >= n) return;
-    uint64_t r; const uint32_t L = str_len(c, a.sel, j0 + threadIdx.x, n, r);
-    uint32_t tot; block_excl_scan(L != 0xffffffffu ? L + (a.columnar ? 0 : varint_len(L)) : 0u, &tot, sm);
-    if (threadIdx.x == 0) a.tile_sum[(size_t)c.str_slot * a.ntiles_cap + blockIdx.x] = tot;
-}
-
-// LEB128 length + bytes, one kept row per thread; neighbouring threads own neighbouring rows, so a warp reads one
-// contiguous span of the source heap (L1 serves the loads). The tile's output (a contiguous span of the block at an
-// arbitrary byte address) is assembled in shared memory and written with aligned, coalesced 4-byte stores (same
-// funnel-shift re-alignment as k_encode_fixed); tiles larger than the staging buffer (long strings) go direct.
-__global__ void __launch_bounds__(TF_STR_THREADS) k_encode_str(EncodeArgs a) {
-    __shared__ uint32_t sm[33];
-    __shared__ __align__(16) uint8_t stage[TF_STR_STAGE + 8];
-    const DCol c = a.cols[a.slots[blockIdx.y]];
-    const uint64_t n = a.st->n_kept;
-    const uint64_t j0 = (uint64_t)blockIdx.x * TF_STR_TILE;
-    if (j0 >= n) return;
-    uint64_t R; const uint32_t L = str_len(c, a.sel, j0 + threadIdx.x, n, R);
-    const uint8_t* s = (L != 0xffffffffu && L) ? c.heap + c.offsets[R] : nullptr;
-    uint32_t tot; const uint32_t ex = block_excl_scan(L != 0xffffffffu ? L + (a.columnar ? 0 : varint_len(L)) : 0u, &tot, sm);
-    const uint64_t tb = a.tile_base[(size_t)c.str_slot * a.ntiles_cap + blockIdx.x];
-    uint8_t* gdst = a.raw + c.out_off + tb;
-    if (a.columnar && L != 0xffffffffu) ((uint32_t*)(a.raw + c.offs_off))[j0 + threadIdx.x] = (uint32_t)(tb + ex);
-    const bool staged = tot <= TF_STR_STAGE;
-    uint8_t* o = staged ? stage + ex : gdst + ex;
-    if (L != 0xffffffffu) {
-        if (!a.columnar) {
-            uint32_t v = L;
-            while (v >= 0x80) { *o++ = (uint8_t)(v | 0x80); v >>= 7; }
-            *o++ = (uint8_t)v;
-        }
-        // The copy is latency bound if every byte waits for its own load, so each round issues four independent
-        // aligned word loads (16 source bytes, re-aligned with funnel shifts) before any byte is stored.
-        uint32_t nb = L;
-        const uint32_t sh = ((uint32_t)(uintptr_t)s & 3) * 8;
-        const uint32_t* sw = (const uint32_t*)((uintptr_t)s & ~(uintptr_t)3);
-        while (nb) {
-            const uint32_t take = nb < 16 ? nb : 16;
-            const uint32_t need = (take + (sh >> 3) + 3) >> 2;            // aligned words that hold these bytes (1..5)
-            uint32_t w0 = __ldg(sw), w1 = need > 1 ? __ldg(sw + 1) : 0, w2 = need > 2 ? __ldg(sw + 2) : 0, w3 = need > 3 ? __ldg(sw + 3) : 0, w4 = need > 4 ? __ldg(sw + 4) : 0;
-            if (sh) { w0 = __funnelshift_r(w0, w1, sh); w1 = __funnelshift_r(w1, w2, sh); w2 = __funnelshift_r(w2, w3, sh); w3 = __funnelshift_r(w3, w4, sh); }
-            const uint32_t ww[4] = {w0, w1, w2, w3};
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-#pragma unroll
-                for (int b = 0; b < 4; b++) if ((uint32_t)(4 * q + b) < take) o[4 * q + b] = (uint8_t)(ww[q] >> (8 * b));
-            }
-            o += take; sw += 4; nb -= take;
-        }
-    }
-    if (!staged) return;
-    __syncthreads();
-    const uint32_t m = (uint32_t)((uintptr_t)gdst & 3);
-    const uint32_t T = (m + tot + 3) >> 2;
-    uint8_t* dst0 = gdst - m;
-    const uint32_t* sw = (const uint32_t*)stage;
-    for (uint32_t t = threadIdx.x; t < T; t += TF_STR_THREADS) {
-        const uint32_t wcur = sw[t], wprev = t ? sw[t - 1] : 0;
-        const uint32_t val = m ? __funnelshift_r(wprev, wcur, 8 * (4 - m)) : wcur;
-        const int32_t sb = (int32_t)(4 * t) - (int32_t)m;
-        uint8_t* dst = dst0 + 4 * (size_t)t;
-        if (sb >= 0 && (uint32_t)sb + 4 <= tot) *(uint32_t*)dst = val;
-        else {
-#pragma unroll
-            for (int b = 0; b < 4; b++) { const int32_t x = sb + b; if (x >= 0 && (uint32_t)x < tot) dst[b] = (uint8_t)(val >> (8 * b)); }
-        }
     }
 }
 

@@ -7,6 +7,7 @@
 #pragma once
 #include "device_types.cuh"
 #include "kernels_encode.cuh"
+#include "kernels_fmt.cuh"
 
 namespace tfk {
 
@@ -107,80 +108,6 @@ struct ShaSink {
     }
 };
 
-__device__ __forceinline__ void put_dec(ShaSink& s, uint64_t u) {
-    char buf[20]; int n = 0;
-    do { buf[n++] = (char)('0' + u % 10); u /= 10; } while (u);
-    while (n) s.put((uint8_t)buf[--n]);
-}
-__device__ __forceinline__ void put_pad(ShaSink& s, int64_t v, int wdt) {   // Go appendInt(b, v, width)
-    if (v < 0) { s.put('-'); v = -v; }
-    char buf[20]; int n = 0; uint64_t u = (uint64_t)v;
-    do { buf[n++] = (char)('0' + u % 10); u /= 10; } while (u);
-    for (int i = n; i < wdt; i++) s.put('0');
-    while (n) s.put((uint8_t)buf[--n]);
-}
-__device__ __forceinline__ void put_lit(ShaSink& s, const char* t) { while (*t) s.put((uint8_t)*t++); }
-
-__device__ inline void civil_from_days(int64_t z, int64_t& y, unsigned& m, unsigned& d) {
-    z += 719468;
-    const int64_t era = (z >= 0 ? z : z - 146096) / 146097;
-    const unsigned doe = (unsigned)(z - era * 146097);
-    const unsigned yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
-    y = (int64_t)yoe + era * 400;
-    const unsigned doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
-    const unsigned mp = (5 * doy + 2) / 153;
-    d = doy - (153 * mp + 2) / 5 + 1;
-    m = mp < 10 ? mp + 3 : mp - 9;
-    y += (m <= 2);
-}
-// time.Time.UTC().Format("2006-01-02") / RFC3339Nano
-__device__ inline void put_time(ShaSink& s, int64_t sec, uint32_t nsec, bool date_only) {
-    int64_t days = sec / 86400; int64_t sod = sec - days * 86400; if (sod < 0) { sod += 86400; days--; }
-    int64_t y; unsigned m, d; civil_from_days(days, y, m, d);
-    put_pad(s, y, 4); s.put('-'); put_pad(s, m, 2); s.put('-'); put_pad(s, d, 2);
-    if (date_only) return;
-    s.put('T'); put_pad(s, sod / 3600, 2); s.put(':'); put_pad(s, (sod / 60) % 60, 2); s.put(':'); put_pad(s, sod % 60, 2);
-    if (nsec) {
-        char b[9]; uint32_t v = nsec; for (int i = 8; i >= 0; i--) { b[i] = (char)('0' + v % 10); v /= 10; }
-        int n = 9; while (n > 0 && b[n - 1] == '0') n--;
-        s.put('.'); for (int i = 0; i < n; i++) s.put((uint8_t)b[i]);
-    }
-    s.put('Z');
-}
-// encoding/json string encoder, escapeHTML = true (json.Marshal of a Go string inside an `any` column)
-__device__ inline void put_json_string(ShaSink& s, const uint8_t* p, uint32_t n) {
-    const char* hex = "0123456789abcdef";
-    s.put('"');
-    uint32_t i = 0;
-    while (i < n) {
-        const uint8_t b = p[i];
-        if (b < 0x80) {
-            if (b >= 0x20 && b != '"' && b != '\\' && b != '<' && b != '>' && b != '&') { s.put(b); i++; continue; }
-            s.put('\\');
-            switch (b) {
-            case '\\': case '"': s.put(b); break;
-            case '\b': s.put('b'); break; case '\f': s.put('f'); break; case '\n': s.put('n'); break; case '\r': s.put('r'); break; case '\t': s.put('t'); break;
-            default: s.put('u'); s.put('0'); s.put('0'); s.put((uint8_t)hex[b >> 4]); s.put((uint8_t)hex[b & 15]);
-            }
-            i++; continue;
-        }
-        uint32_t r = 0xFFFD, w = 1;
-        if (b >= 0xC2 && b <= 0xDF && i + 1 < n && (p[i + 1] & 0xC0) == 0x80) { r = ((b & 0x1Fu) << 6) | (p[i + 1] & 0x3Fu); w = 2; }
-        else if (b >= 0xE0 && b <= 0xEF && i + 2 < n && (p[i + 1] & 0xC0) == 0x80 && (p[i + 2] & 0xC0) == 0x80) {
-            const uint32_t t = ((b & 0x0Fu) << 12) | ((p[i + 1] & 0x3Fu) << 6) | (p[i + 2] & 0x3Fu);
-            if (t >= 0x800 && !(t >= 0xD800 && t <= 0xDFFF)) { r = t; w = 3; }
-        } else if (b >= 0xF0 && b <= 0xF4 && i + 3 < n && (p[i + 1] & 0xC0) == 0x80 && (p[i + 2] & 0xC0) == 0x80 && (p[i + 3] & 0xC0) == 0x80) {
-            const uint32_t t = ((b & 0x07u) << 18) | ((p[i + 1] & 0x3Fu) << 12) | ((p[i + 2] & 0x3Fu) << 6) | (p[i + 3] & 0x3Fu);
-            if (t >= 0x10000 && t <= 0x10FFFF) { r = t; w = 4; }
-        }
-        if (r == 0xFFFD && w == 1) { put_lit(s, "\\ufffd"); i++; continue; }
-        if (r == 0x2028 || r == 0x2029) { put_lit(s, "\\u202"); s.put((uint8_t)hex[r & 0xF]); i += w; continue; }
-        for (uint32_t k = 0; k < w; k++) s.put(p[i + k]);
-        i += w;
-    }
-    s.put('"');
-}
-
 struct MaskArgs { const DCol* cols; const int32_t* slots; const MaskKey* keys; const uint32_t* sel; const DState* st; uint8_t* raw; int columnar; };
 
 // one thread per (kept row, masked column): text form -> HMAC -> "\x40" + 64 hex chars into the block
@@ -192,27 +119,7 @@ __global__ void __launch_bounds__(128) k_mask_encode(MaskArgs a) {
     const uint64_t r = a.sel ? a.sel[j] : j;
     const MaskKey& mk = a.keys[c.mask_slot];
     ShaSink s; s.init(mk.istate);
-    const bool valid = row_valid(c, r);
-    if (!valid) { if (c.type == TF_ANY) put_lit(s, "null"); else put_lit(s, "<nil>"); }   // json.Marshal(nil) / fmt %v of nil
-    else switch (c.type) {
-        case TF_INT8: { int64_t v = ((const int8_t*)c.values)[r]; if (v < 0) { s.put('-'); put_dec(s, (uint64_t)(-v)); } else put_dec(s, (uint64_t)v); break; }
-        case TF_INT16: { int64_t v = ((const int16_t*)c.values)[r]; if (v < 0) { s.put('-'); put_dec(s, (uint64_t)(-v)); } else put_dec(s, (uint64_t)v); break; }
-        case TF_INT32: { int64_t v = ((const int32_t*)c.values)[r]; if (v < 0) { s.put('-'); put_dec(s, (uint64_t)(-v)); } else put_dec(s, (uint64_t)v); break; }
-        case TF_INT64: { int64_t v = ((const int64_t*)c.values)[r]; if (v < 0) { s.put('-'); put_dec(s, (uint64_t)0 - (uint64_t)v); } else put_dec(s, (uint64_t)v); break; }
-        case TF_UINT8: put_dec(s, c.values[r]); break;
-        case TF_UINT16: put_dec(s, ((const uint16_t*)c.values)[r]); break;
-        case TF_UINT32: put_dec(s, ((const uint32_t*)c.values)[r]); break;
-        case TF_UINT64: put_dec(s, ((const uint64_t*)c.values)[r]); break;
-        case TF_BOOLEAN: put_lit(s, c.values[r] ? "true" : "false"); break;
-        case TF_DATE: put_time(s, ((const int64_t*)c.values)[r], 0, true); break;
-        case TF_DATETIME: case TF_TIMESTAMP: put_time(s, ((const int64_t*)c.values)[r], c.aux ? ((const uint32_t*)c.aux)[r] : 0, false); break;
-        case TF_BYTES: case TF_UTF8: { const uint8_t* p = c.heap + c.offsets[r]; const uint32_t L = c.offsets[r + 1] - c.offsets[r]; for (uint32_t k = 0; k < L; k++) s.put(p[k]); break; }
-        case TF_ANY: {
-            const uint8_t* p = c.heap + c.offsets[r]; const uint32_t L = c.offsets[r + 1] - c.offsets[r];
-            if (c.aux && c.aux[r] == 1) put_json_string(s, p, L); else for (uint32_t k = 0; k < L; k++) s.put(p[k]);
-            break;
-        }
-    }
+    fmt_value(s, c, r);       // to_string.SerializeToString(value, column type)
     s.finish(64);
     // outer hash over opad state + 32-byte inner digest
     uint32_t o[8]; uint32_t w[16];

@@ -337,6 +337,8 @@ struct Plan {
     std::vector<int> out_cols;         // input index of every output column, schema order
     std::vector<FilterStep> filters;   // in plan order
     std::vector<int> filter_step_index;
+    std::vector<uint8_t> tostr_col;    // [input column] 1 = convert_to_string applies (to_string.go:58-97)
+    std::vector<int> tostr_step_index; std::vector<std::vector<int>> tostr_cols;
     std::vector<MaskStep> masks;
     std::vector<int> mask_step_index;
     std::vector<uint8_t> blob;         // literal pool referenced by DTerm
@@ -520,6 +522,28 @@ inline Plan build_plan(const std::string& ns, const std::string& name, const std
             }
             add_desc(d + "]}");
             pl.masks.push_back(ms); pl.mask_step_index.push_back(step_no++);
+        } else if (ttype == "convert_to_string") {                   // registry/to_string/to_string.go:24-113
+            if (!match_table(tables_filter(cfg->get("tables")), ns, name)) continue;
+            if (cfg->get_bool("skip_utc_conversion")) throw FatalError(TF_E_FATAL_UNSUPPORTED, "convert_to_string: skip_utc_conversion needs time zones, which the columnar layout does not carry");
+            const tfj::Value* cc = cfg->get("columns");
+            std::vector<std::string> inc, exc;
+            if (cc) { inc = cc->get_str_list("includeColumns"); exc = cc->get_str_list("excludeColumns"); }
+            NameFilter cf = make_filter(inc, exc);
+            std::vector<int> pos;
+            for (size_t i = 0; i < cur.size(); i++) if (cf.match(cur[i].name)) pos.push_back((int)i);
+            if (!cf.empty() && pos.empty()) continue;                // Suitable :99-113
+            const bool to_bytes = cfg->get_bool("convert_to_bytes");
+            if (pl.tostr_col.empty()) pl.tostr_col.assign(pl.in_schema.size(), 0);
+            std::vector<int> cols; std::string d = std::string("{\"type\":\"convert_to_string\",\"to_bytes\":") + (to_bytes ? "true" : "false") + ",\"cols\":[";
+            for (size_t i = 0; i < pos.size(); i++) {
+                ColSchema& c = cur[pos[i]];
+                if (pl.tostr_col[c.in_index] || c.tf != pl.in_schema[c.in_index].tf)
+                    throw FatalError(TF_E_FATAL_UNSUPPORTED, "convert_to_string on column '" + c.name + "' that an earlier transformer already rewrote");
+                if (i) d += ","; d += std::to_string(c.in_index); cols.push_back(c.in_index); pl.tostr_col[c.in_index] = 1;
+                c.type = to_bytes ? "string" : "utf8"; c.tf = to_bytes ? TF_BYTES : TF_UTF8;
+            }
+            add_desc(d + "]}");
+            pl.tostr_cols.push_back(cols); pl.tostr_step_index.push_back(step_no++);
         } else {
             throw FatalError(TF_E_FATAL_UNSUPPORTED, "transformer '" + ttype + "' is not implemented by the device engine");
         }
@@ -529,6 +553,13 @@ inline Plan build_plan(const std::string& ns, const std::string& name, const std
         if (pl.filter_step_index[f] > pl.mask_step_index[m])
             for (auto& e : pl.filters[f].exprs) for (auto& t : e) for (int c : pl.masks[m].cols)
                 if (t.col == c) throw FatalError(TF_E_FATAL_UNSUPPORTED, "filter_rows on a column masked earlier in the chain is not supported");
+    for (size_t m = 0; m < pl.tostr_cols.size(); m++) {
+        for (size_t f = 0; f < pl.filters.size(); f++) if (pl.filter_step_index[f] > pl.tostr_step_index[m])
+            for (auto& e : pl.filters[f].exprs) for (auto& t : e) for (int c : pl.tostr_cols[m])
+                if (t.col == c) throw FatalError(TF_E_FATAL_UNSUPPORTED, "filter_rows on a column converted to string earlier in the chain is not supported");
+        for (size_t k = 0; k < pl.masks.size(); k++) for (int c : pl.masks[k].cols) for (int c2 : pl.tostr_cols[m])
+            if (c == c2) throw FatalError(TF_E_FATAL_UNSUPPORTED, "mask_field and convert_to_string on the same column are not supported together");
+    }
     pl.out_schema = cur; pl.out_ns = cur_ns; pl.out_name = cur_name;
     for (auto& c : cur) pl.out_cols.push_back(c.in_index);
     std::string sink_desc = "null";

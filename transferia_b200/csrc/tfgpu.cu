@@ -14,6 +14,7 @@
 #include "device_types.cuh"
 #include "kernels_encode.cuh"
 #include "kernels_lz4.cuh"
+#include "kernels_str.cuh"
 #include "kernels_mask.cuh"
 #include "kernels_csv.cuh"
 
@@ -132,10 +133,9 @@ void upload_plan(tfgpu_engine* e, PlanDev& pd) {
         const int tf = pl.in_schema[c].tf;
         int kind, w;
         if (pd.col_mask_slot[c] >= 0) {
-            if (tf == TF_FLOAT || tf == TF_DOUBLE || tf == TF_INTERVAL)
-                throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "mask_field on " + pl.in_schema[c].type + " column '" + pl.in_schema[c].name + "' needs the device float/duration formatter (not in this build)");
             kind = OK_MASK; w = 65;
-        } else switch (tf) {
+        } else if (pl.tostr_col.size() > c && pl.tostr_col[c]) { kind = OK_TOSTR; w = 0; }
+        else switch (tf) {
             case TF_BOOLEAN: kind = OK_BOOL; w = 1; break;
             case TF_DATE: kind = OK_DATE; w = 2; break;
             case TF_DATETIME: kind = OK_DATETIME; w = 4; break;
@@ -145,10 +145,10 @@ void upload_plan(tfgpu_engine* e, PlanDev& pd) {
         }
         pd.col_out_kind[c] = kind; pd.col_out_w[c] = w;
         const bool nullable = !pl.out_schema[k].required; pd.col_nullable[c] = nullable ? 1 : 0;
-        if (kind == OK_STR) { pd.col_str_slot[c] = (int)pd.str_slots.size(); pd.str_slots.push_back((int32_t)c); }
+        if (kind == OK_STR || kind == OK_TOSTR) { pd.col_str_slot[c] = (int)pd.str_slots.size(); pd.str_slots.push_back((int32_t)c); }
         else if (kind == OK_MASK) { pd.mask_slot_cols.push_back((int32_t)c); }
         else pd.fixed_slots.push_back((int32_t)c);
-        if (nullable && kind != OK_MASK) pd.fixed_slots.push_back((int32_t)c | TF_SLOT_NULLMAP);
+        if (nullable && kind != OK_MASK && kind != OK_TOSTR) pd.fixed_slots.push_back((int32_t)c | TF_SLOT_NULLMAP);
     }
     if (pd.str_slots.size() > 256) throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "more than 256 String columns");
     // flatten filter steps
@@ -195,6 +195,7 @@ Sizes compute_sizes(const tfgpu_engine* e, const PlanDev& pd, const tf_batch* in
         const size_t c = (size_t)oc;
         if (pd.col_nullable[c]) raw += n;
         if (pd.col_out_kind[c] == OK_STR) raw += in->cols[c].heap_len + 5 * n;
+        else if (pd.col_out_kind[c] == OK_TOSTR) raw += (in_width(in->cols[c].type) ? 40 * n : 6 * in->cols[c].heap_len + 8 * n) + 5 * n;   // longest text form (RFC3339Nano / %v float / \\u00XX-escaped JSON string)
         else raw += (uint64_t)pd.col_out_w[c] * n;
         if (columnar) raw += 8 * n + 4 * (n + 1) + n / 8 + 6 * 16 + (pd.col_out_kind[c] == OK_MASK ? 64 * n : 0);   // widest value, aux, offsets, bitmap, padding
     }
@@ -238,7 +239,7 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         const tf_col& ic = dev_cols[c]; DCol& d = hc[c]; std::memset(&d, 0, sizeof d);
         if (ic.type != pl.in_schema[c].tf) throw tfplan::FatalError(TF_E_FATAL_ARG, "column " + std::to_string(c) + " type does not match the plan schema");
         d.type = ic.type; d.out_kind = pd.col_out_kind[c]; d.in_w = in_width(ic.type); d.out_w = pd.col_out_w[c];
-        if (columnar && d.out_kind != OK_STR && d.out_kind != OK_MASK) { d.out_kind = OK_COPY; d.out_w = d.in_w; }   // Transformed values keep their type
+        if (columnar && d.out_kind != OK_STR && d.out_kind != OK_MASK && d.out_kind != OK_TOSTR) { d.out_kind = OK_COPY; d.out_w = d.in_w; }   // Transformed values keep their type
         d.nullable = pd.col_nullable[c]; d.str_slot = pd.col_str_slot[c]; d.mask_slot = pd.col_mask_slot[c];
         d.values = (const uint8_t*)ic.values; d.validity = ic.validity; d.offsets = ic.offsets; d.heap = ic.heap; d.aux = (const uint8_t*)ic.aux;
         if (n) {
@@ -296,8 +297,8 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         for (int oc : pl.out_cols) {
             const DCol& d = hc[oc];
             if (d.out_kind == OK_COPY) fixed.push_back(oc);
-            if (d.out_kind != OK_MASK && d.aux) fixed.push_back(oc | TF_SLOT_AUX);
-            if (d.out_kind != OK_MASK && d.validity) valid.push_back(oc);
+            if (d.out_kind != OK_MASK && d.out_kind != OK_TOSTR && d.aux) fixed.push_back(oc | TF_SLOT_AUX);
+            if (d.out_kind != OK_MASK && d.out_kind != OK_TOSTR && d.validity) valid.push_back(oc);
         }
         std::vector<int32_t> both(fixed); both.insert(both.end(), valid.begin(), valid.end());
         if (!both.empty()) CK(cudaMemcpyAsync(e->d_call_slots, both.data(), both.size() * 4, cudaMemcpyHostToDevice, s));
