@@ -368,6 +368,52 @@ std::vector<uint8_t> native_block(const std::vector<std::string>& names, const s
     return o;
 }
 
+// MarshalCItoJSON: pkg/providers/clickhouse/httpuploader/marshal.go:88-253 for the value types of typed columns.
+// ch_base = the target column's ClickHouse base type (columntypes.ToChType of the RESULT type), nullability aside.
+void json_each_row_value(std::string& o, const orc_val& v, int32_t yt_result, const std::string& ch_base) {
+    const bool is_string = ch_base == "String";
+    auto quoted_raw = [&](const uint8_t* p, size_t n) {            // :127-137 / :215-223 + questionableQuoter :264-266
+        o += '"';
+        bool need = false; for (size_t i = 0; i < n; i++) if (p[i] == '"' || p[i] == '\\') { need = true; break; }
+        if (!need) o.append((const char*)p, n);
+        else for (size_t i = 0; i < n; i++) { if (p[i] == '\\' || p[i] == '"') o += '\\'; o += (char)p[i]; }
+        o += '"';
+    };
+    switch (v.kind) {
+    case OG_TIME: {                                                  // marshalTime :63-78
+        if (is_string) { std::string r = fmt_rfc3339nano_utc(v.i, v.nsec); r[10] = ' '; r.pop_back(); o += '"' + r + " +0000 UTC\""; }
+        else if (ch_base.rfind("DateTime64", 0) == 0) {
+            const int prec = std::atoi(ch_base.c_str() + 11);
+            int64_t full = v.i * 1000000000LL + (int64_t)v.nsec;     // UnixNano
+            if (prec > 0 && prec < 9) { int64_t div = 1; for (int i = 0; i < 9 - prec; i++) div *= 10; full = full / div; }
+            o += fmt_i64(full);
+        }
+        else if (ch_base == "Date") o += '"' + fmt_date_only(v.i) + '"';
+        else o += fmt_i64(v.i);
+        return;
+    }
+    case OG_STRING: quoted_raw(v.s, v.slen); return;
+    case OG_BYTES: quoted_raw(v.s, v.slen); return;
+    case OG_INT8: case OG_INT16: case OG_INT32: case OG_INT64: case OG_INT:
+        if (is_string) o += '"'; o += fmt_i64(v.i); if (is_string) o += '"'; return;
+    case OG_UINT8: case OG_UINT16: case OG_UINT32: case OG_UINT64: case OG_UINT:
+        if (is_string) o += '"'; o += fmt_u64(v.u); if (is_string) o += '"'; return;
+    case OG_FLOAT32: if (is_string) o += '"'; o += fmt_f32((float)v.f, FMT_F); if (is_string) o += '"'; return;
+    case OG_FLOAT64: if (is_string) o += '"'; o += fmt_f64(v.f, FMT_F); if (is_string) o += '"'; return;
+    case OG_BOOL:                                                    // :186-205
+        if (yt_result == TF_BOOLEAN) o += v.i ? "true" : "false";
+        else if (is_string) o += v.i ? "\"true\"" : "\"false\"";
+        else o += v.i ? "1" : "0";
+        return;
+    case OG_DURATION: {                                              // default branch: json.Marshal(Duration) = integer, type != any -> quoted
+        o += go_json_quote((const uint8_t*)fmt_i64(v.i).data(), fmt_i64(v.i).size()); return;
+    }
+    case OG_JSON:                                                    // default branch :224-243 with r = the JSON text
+        if (yt_result != TF_ANY || is_string) o += go_json_quote(v.s, v.slen); else o.append((const char*)v.s, v.slen);
+        return;
+    }
+}
+
 void to_buf(const std::vector<uint8_t>& v, orc_buf* b) {
     if (!b) return;
     b->len = v.size(); b->data = (uint8_t*)std::malloc(v.size() ? v.size() : 1);
@@ -436,6 +482,12 @@ bool apply_steps(const tf_batch* in, uint64_t r, const orc_step* steps, int nste
                 uint8_t d[32]; hmac_sha256(st.salt, st.salt_len, (const uint8_t*)text.data(), text.size(), d);
                 row[c].set_string(hex_lower(d, 32), OG_STRING); cur_type[c] = TF_UTF8;
             }
+        } else if (st.kind == STEP_TO_DATETIME) {                 // ToDateTimeTransformer.Apply / SerializeToDateTime to_datetime.go:89-151
+            for (int k = 0; k < st.ncols; k++) {
+                int c = st.cols[k]; orc_val& v = row[c].v; int64_t sec = 0;
+                if (v.kind == OG_INT32) sec = v.i; else if (v.kind == OG_UINT32) sec = (int64_t)v.u;
+                std::memset(&v, 0, sizeof v); v.kind = OG_TIME; v.i = sec; cur_type[c] = TF_DATETIME;
+            }
         } else if (st.kind == STEP_TO_STRING) {                   // ToStringTransformer.Apply to_string.go:58-97
             for (int k = 0; k < st.ncols; k++) {
                 int c = st.cols[k];
@@ -453,6 +505,7 @@ void result_types(const tf_batch* in, const orc_step* steps, int nsteps, std::ve
     for (int s = 0; s < nsteps; s++) {
         if (steps[s].kind == STEP_MASK) for (int k = 0; k < steps[s].ncols; k++) out_type[steps[s].cols[k]] = TF_UTF8;        // hmac_hasher.go:35-47
         if (steps[s].kind == STEP_TO_STRING) for (int k = 0; k < steps[s].ncols; k++) out_type[steps[s].cols[k]] = steps[s].convert_to_bytes ? TF_BYTES : TF_UTF8;  // to_string.go:66-74
+        if (steps[s].kind == STEP_TO_DATETIME) for (int k = 0; k < steps[s].ncols; k++) out_type[steps[s].cols[k]] = TF_DATETIME;                                  // to_datetime.go:126-135
     }
     // filter_columns (filter_columns_transformer.go:228-236): the surviving columns, schema order kept
     bool sel = false;
@@ -487,6 +540,30 @@ extern "C" int orc_push_encode(const tf_batch* in, const orc_colschema* schema, 
     uint64_t kept = 0, ne = 0;
     std::vector<Boxed> row(nc);
     std::vector<int32_t> cur_type(nc);
+    if (wire_fmt == TF_WIRE_CH_JSONEACHROW) {                     // uploadAsJSON: rows as text, no Restore (sink_table.go:289-344, httpuploader/uploader.go:62-96)
+        std::string text;
+        std::vector<std::string> base(no);
+        for (uint32_t k = 0; k < no; k++) base[k] = ch_base_type(out_type[out_cols[k]]);
+        for (uint64_t r = 0; r < in->nrows; r++) {
+            if (!apply_steps(in, r, steps, nsteps, row, cur_type, errs, ne)) continue;
+            text += '{'; bool has = false;
+            for (uint32_t k = 0; k < no; k++) {
+                const orc_val& v = row[out_cols[k]].v;
+                if (v.kind == OG_NIL) continue;                   // isNilValue -> the column is omitted (marshal.go:103-105)
+                if (v.kind == OG_JSON && v.slen == 4 && std::memcmp(v.s, "null", 4) == 0) continue;   // json.Marshal gives "null": name rolled back (:229-233)
+                text += '"'; text += names[k]; text += "\":";
+                json_each_row_value(text, v, out_type[out_cols[k]], base[k]);
+                text += ','; has = true;
+            }
+            if (has) text.pop_back();
+            text += "}\n"; kept++;
+        }
+        if (rows_out) *rows_out = kept;
+        if (nerrs) *nerrs = ne;
+        std::vector<uint8_t> bytes(text.begin(), text.end());
+        to_buf(bytes, out_raw); to_buf(bytes, out_wire);
+        return 0;
+    }
     for (uint64_t r = 0; r < in->nrows; r++) {
         if (!apply_steps(in, r, steps, nsteps, row, cur_type, errs, ne)) continue;
         // sink: restoreVals sink_table.go:698-704 + driver append
@@ -513,7 +590,7 @@ extern "C" int orc_push_columns(const tf_batch* in, const orc_colschema* schema,
     struct CB { std::vector<uint8_t> values, valid_bits, aux, heap; std::vector<uint32_t> offs; bool has_valid, has_aux; };
     std::vector<CB> cb(no);
     std::vector<char> rewritten(nc, 0);     // mask_field / convert_to_string give the column a fresh, never-nil text value
-    for (int s = 0; s < nsteps; s++) if (steps[s].kind == STEP_MASK || steps[s].kind == STEP_TO_STRING) for (int k = 0; k < steps[s].ncols; k++) rewritten[steps[s].cols[k]] = 1;
+    for (int s = 0; s < nsteps; s++) if (steps[s].kind == STEP_MASK || steps[s].kind == STEP_TO_STRING || steps[s].kind == STEP_TO_DATETIME) for (int k = 0; k < steps[s].ncols; k++) rewritten[steps[s].cols[k]] = 1;
     for (uint32_t k = 0; k < no; k++) {
         const tf_col& ic = in->cols[out_cols[k]];
         const bool masked = rewritten[out_cols[k]] != 0;
@@ -529,7 +606,8 @@ extern "C" int orc_push_columns(const tf_batch* in, const orc_colschema* schema,
             if (b.has_valid) { if ((kept & 7) == 0) b.valid_bits.push_back(0); if (v.kind != OG_NIL) b.valid_bits.back() |= (uint8_t)(1u << (kept & 7)); }
             if (w) {   // the value keeps its input representation (zero for nil)
                 uint8_t tmp[8] = {0};
-                if (v.kind != OG_NIL) std::memcpy(tmp, (const uint8_t*)ic.values + (size_t)w * r, w);
+                if (rewritten[c]) std::memcpy(tmp, &v.i, 8);          // convert_to_datetime: time.Time seconds
+                else if (v.kind != OG_NIL) std::memcpy(tmp, (const uint8_t*)ic.values + (size_t)w * r, w);
                 b.values.insert(b.values.end(), tmp, tmp + w);
             } else {
                 if (v.kind != OG_NIL) b.heap.insert(b.heap.end(), v.s, v.s + v.slen);

@@ -77,7 +77,7 @@ class OrcBuf(C.Structure):
  OG_BOOL, OG_STRING, OG_BYTES, OG_TIME, OG_DURATION, OG_JSON, OG_INT, OG_UINT) = range(19)
 OP_EQ, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE, OP_IN, OP_NOTIN, OP_MATCH, OP_NOTMATCH = range(10)
 LV_INT, LV_FLOAT, LV_BOOL, LV_STRING, LV_TIME, LV_NULL, LV_LIST = 1, 2, 3, 4, 5, 6, 16
-STEP_FILTER_ROWS, STEP_MASK, STEP_TO_STRING, STEP_SKIP_EVENTS, STEP_SELECT_COLS = 1, 2, 3, 4, 5
+STEP_FILTER_ROWS, STEP_MASK, STEP_TO_STRING, STEP_SKIP_EVENTS, STEP_SELECT_COLS, STEP_TO_DATETIME = 1, 2, 3, 4, 5, 6
 
 _lib = None
 
@@ -511,6 +511,19 @@ def build_plan(ns: str, name: str, schema: List[dict], transformers: List[dict])
             steps.append({"kind": "mask_field", "index": idx, "cols": [cur[i]["_in"] for i in pos], "salt": salt.encode()}); idx += 1
             for i in pos:                                        # hmac_hasher.go:35-47
                 cur[i] = dict(cur[i]); cur[i]["type"] = "utf8"; cur[i]["original_type"] = ""
+        elif ttype == "convert_to_datetime":                     # to_datetime.go:56-135
+            if not _tables_match(cfg.get("tables"), ns, name):
+                continue
+            ccfg = cfg.get("columns") or {}
+            inc = ccfg.get("includeColumns") or []; exc = ccfg.get("excludeColumns") or []
+            if not inc and not exc:
+                continue
+            pos = [i for i, c in enumerate(cur) if _filter_match(inc, exc, c["name"]) and c["type"] in ("int32", "uint32")]
+            if not pos:
+                continue
+            steps.append({"kind": "convert_to_datetime", "index": idx, "cols": [cur[i]["_in"] for i in pos]}); idx += 1
+            for i in pos:
+                cur[i] = dict(cur[i]); cur[i]["type"] = "datetime"
         elif ttype == "convert_to_string":
             if not _tables_match(cfg.get("tables"), ns, name):
                 continue
@@ -607,6 +620,9 @@ def _marshal(plan: Plan):
             off = keep.add(np.zeros(len(st["exprs"]) + 1, dtype=np.uint32)); np.cumsum([len(x) for x in st["exprs"]], out=off[1:])
             s.kind = STEP_FILTER_ROWS; s.terms = C.cast(tarr, C.POINTER(OrcTerm)); s.expr_off = off.ctypes.data; s.nexpr = len(st["exprs"])
             s.pass_all = 1 if st.get("pass_all") else 0; s.convert_to_bytes = st["index"]     # (reused as the step's transformer index in error rows)
+        elif st["kind"] == "convert_to_datetime":
+            cols = keep.add(np.asarray(st["cols"], dtype=np.int32))
+            s.kind = STEP_TO_DATETIME; s.cols = cols.ctypes.data; s.ncols = len(st["cols"])
         elif st["kind"] == "skip_events":
             s.kind = STEP_SKIP_EVENTS; s.kind_mask = st["kind_mask"]
         elif st["kind"] == "filter_columns":

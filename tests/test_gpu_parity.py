@@ -284,7 +284,7 @@ def test_api_errors(eng):
     with pytest.raises(engine.EngineError):
         eng.plan("db", "t", schema, [{"mask_field": {"columns": ["a"], "maskFunctionHash": {"userDefinedSalt": "s"}}}, {"filter_rows": {"filter": "a = 'x'"}}], {"type": "clickhouse"})
     with pytest.raises(engine.EngineError):
-        eng.push_encode(pid, abi.Batch(1, [abi.fixed_to_column(abi.TF_INT32, [1])]), abi.TF_WIRE_CH_JSONEACHROW)
+        eng.push_encode(pid, abi.Batch(1, [abi.fixed_to_column(abi.TF_INT32, [1])]), 99)          # unknown wire format
 
 
 def assert_batches_equal(a: abi.Batch, b: abi.Batch):
@@ -377,3 +377,46 @@ def test_convert_to_string_all_types(eng, po):
         ref, rerr = po.push_columns(batch, po.build_plan("db", "t", schema, trs))
         assert gerr == rerr
         assert_batches_equal(got, ref)
+
+
+def test_convert_to_datetime(eng, po):
+    """to_datetime.go:89-151: int32 / uint32 seconds -> time.Unix(s, 0), nil -> time.Unix(0, 0); then the ClickHouse DateTime clamp."""
+    batch, schema = all_types_batch(2000, seed=23)
+    trs = [{"convert_to_datetime": {"columns": {"includeColumns": ["int32", "int64"]}}}]      # int64 is not a supported type: left alone
+    check(eng, po, batch, schema, trs)
+    pid = eng.plan("db", "t", schema, trs)
+    d = eng.describe(pid)
+    assert [c["type"] for c in d["result_schema"] if "int32" in c["name"]] == ["datetime"] * 4
+    got, _ = eng.push_columns(pid, batch)
+    ref, _ = po.push_columns(batch, po.build_plan("db", "t", schema, trs))
+    assert_batches_equal(got, ref)
+    assert eng.describe(eng.plan("db", "t", schema, [{"convert_to_datetime": {}}]))["steps"] == []          # empty column filter: not Suitable
+
+
+def test_jsoneachrow_on_device(eng, po):
+    """ClickHouse JSONEachRow (httpuploader/marshal.go:88-253): device rows == oracle rows, byte for byte."""
+    JS = abi.TF_WIRE_CH_JSONEACHROW
+    batch, schema = all_types_batch(2500, seed=41)
+    chains = [[], [{"filter_rows": {"filter": "c_int32 > 0"}}],
+              [{"mask_field": {"columns": ["c_utf8", "n_double"], "maskFunctionHash": {"userDefinedSalt": "s"}}}, {"convert_to_string": {"columns": {"includeColumns": ["c_float", "n_timestamp", "n_any"]}}},
+               {"convert_to_datetime": {"columns": {"includeColumns": ["c_uint32"]}}}, {"filter_columns": {"columns": {"excludeColumns": ["c_interval"]}}}]]
+    for trs in chains:
+        pid = eng.plan("db", "t", schema, trs, {"type": "clickhouse"})
+        got = eng.push_encode(pid, batch, JS)
+        ref = po.push_encode(batch, po.build_plan("db", "t", schema, trs), JS)
+        assert got.rows_out == ref.rows_out
+        if got.wire != ref.wire:
+            gl, rl = got.wire.split(b"\n"), ref.wire.split(b"\n")
+            for i, (x, y) in enumerate(zip(gl, rl)):
+                if x != y:
+                    raise AssertionError(f"row {i}:\n got {x[:400]}\n exp {y[:400]}")
+            raise AssertionError("row count differs")
+    # the reference's own etalons (marshal_test.go:16-37 DateTime64 scaling; :84-110 non-UTF-8 bytes kept; null -> {})
+    sch = [{"name": "t", "type": "timestamp", "required": True}, {"name": "b", "type": "string"}, {"name": "n", "type": "utf8"}]
+    b = abi.Batch(1, [abi.fixed_to_column(abi.TF_TIMESTAMP, [1580637742], nanos=[123456789]), abi.strings_to_column(abi.TF_BYTES, [b'"Hello\xfe\xe4\xb8\x96']), abi.strings_to_column(abi.TF_UTF8, [None])])
+    got = eng.push_encode(eng.plan("db", "t", sch, [], {"type": "clickhouse"}), b, JS)
+    assert got.wire == b'{"t":1580637742123456,"b":"\\"Hello\xfe\xe4\xb8\x96"}\n'
+    hb, hs = workload.make_hits_batch(30_000, seed=6)
+    trs = workload.headline_transformers(workload.counterid_threshold(hb, hs))
+    got = eng.push_encode(eng.plan("public", "hits", hs, trs, {"type": "clickhouse"}), hb, JS)
+    assert got.wire == po.push_encode(hb, po.build_plan("public", "hits", hs, trs), JS).wire

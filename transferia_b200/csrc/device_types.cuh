@@ -14,6 +14,7 @@ enum OutKind : int32_t {
     OK_TS64 = 4,      // time (sec, nsec) -> DateTime64(6) = UnixMicro, no clamp          (columntypes/types.go:242)
     OK_STR = 5,       // LEB128 length + bytes
     OK_MASK = 6,      // mask_field digest: 0x40 + 64 lowercase hex chars                  (hmac_hasher.go:29-33)
+    OK_TODT = 8,      // convert_to_datetime: int32/uint32 seconds -> time.Unix(s, 0), never nil     (to_datetime.go:137-151)
     OK_TOSTR = 7      // convert_to_string: LEB128 length + text form of the value         (to_string.go:145-171)
 };
 

@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256) k_layout_columnar(LayoutArgs a, ColRegion
         if (k < a.ncols) {
             const DCol& d = a.cols[a.out_cols[k]];
             const bool var = d.out_kind == OK_STR || d.out_kind == OK_MASK || d.out_kind == OK_TOSTR;
-            const bool fresh = d.out_kind == OK_MASK || d.out_kind == OK_TOSTR;      // a new text value: never nil, no aux
+            const bool fresh = d.out_kind == OK_MASK || d.out_kind == OK_TOSTR || d.out_kind == OK_TODT;      // a new value: never nil, no aux
             const uint64_t heap = (d.out_kind == OK_STR || d.out_kind == OK_TOSTR) ? a.col_bytes[d.str_slot] : (d.out_kind == OK_MASK ? 64 * n : 0);
             s_sz[0][threadIdx.x] = var ? 0 : (uint64_t)d.out_w * n;                                   // values
             s_sz[1][threadIdx.x] = (d.validity && !fresh) ? (n + 7) / 8 : 0;          // validity bitmap
@@ -373,19 +373,29 @@ struct EncodeArgs {
 };
 
 #define TF_SLOT_NULLMAP (1 << 30)
-#define TF_SLOT_AUX (1 << 29)       // columnar output: the column's aux array (time nanos u32 / any tags u8)
+#define TF_SLOT_AUX (1 << 29)
+#define TF_SLOT_ZEROMAP (1 << 28)   // null map of a column whose transformer made every value non-nil: all zeros       // columnar output: the column's aux array (time nanos u32 / any tags u8)
 #define TF_FIX_TILE_WORDS 2048
 #define CH_MAX_DATE_SEC 4291747200LL   // 2106-01-01T00:00:00Z (columntypes/types.go:15-18)
 
 // Stream kinds of k_encode_fixed, resolved ONCE per CTA (every thread of a CTA works on the same column), so the
 // per-element code below is straight-line for its kind.
-enum StreamKind { SK_COPY = 0, SK_BOOL, SK_DATE, SK_DATETIME, SK_TS64, SK_NULLMAP, SK_AUX32, SK_AUX8 };
+enum StreamKind { SK_COPY = 0, SK_BOOL, SK_DATE, SK_DATETIME, SK_TS64, SK_NULLMAP, SK_AUX32, SK_AUX8, SK_ZERO, SK_TODT_CH, SK_TODT_SEC };
 
 // One output element after the typesystem cast (columntypes.Restore -> abstract.Restore are the identity for values
 // whose Go type already matches the column type; what remains is the ClickHouse clamp / unit rule).
 template <int K, int INW> __device__ __forceinline__ uint64_t elem_t(const DCol& c, const uint32_t* sel, uint64_t j, uint64_t n) {
     if (j >= n) return 0;
     const uint64_t r = sel ? sel[j] : j;
+    if (K == SK_ZERO) return 0;
+    if (K == SK_TODT_CH || K == SK_TODT_SEC) {     // SerializeToDateTime to_datetime.go:137-151: nil -> time.Unix(0, 0)
+        int64_t s = 0;
+        if (row_valid(c, r)) s = c.type == TF_INT32 ? (int64_t)((const int32_t*)c.values)[r] : (int64_t)((const uint32_t*)c.values)[r];
+        if (K == SK_TODT_SEC) return (uint64_t)s;
+        if (s > CH_MAX_DATE_SEC) s = CH_MAX_DATE_SEC;          // applyClickhouseDateBoundaries columntypes/types.go:20-29
+        if (s < 0) s = 0;
+        return (uint64_t)s;
+    }
     if (K == SK_AUX8) return (uint64_t)c.aux[r];
     if (K == SK_AUX32) return (uint64_t)((const uint32_t*)c.aux)[r];
     const bool valid = row_valid(c, r);
@@ -452,9 +462,11 @@ template <int K, int INW, int W> __device__ __forceinline__ void encode_stream(c
 // Fixed-width columns, null maps and (columnar output) aux arrays: blockIdx.y = stream slot.
 __global__ void __launch_bounds__(256) k_encode_fixed(EncodeArgs a) {
     const int32_t slot = a.slots[blockIdx.y];
-    const DCol c = a.cols[slot & ~(TF_SLOT_NULLMAP | TF_SLOT_AUX)];
+    const DCol c = a.cols[slot & ~(TF_SLOT_NULLMAP | TF_SLOT_AUX | TF_SLOT_ZEROMAP)];
     const uint64_t n = a.st->n_kept;
     if (n == 0) return;
+    const DCol& cc = c;
+    if (slot & TF_SLOT_ZEROMAP) { encode_stream<SK_ZERO, 1, 1>(cc, a, c.null_off, n); return; }
     if (slot & TF_SLOT_NULLMAP) { encode_stream<SK_NULLMAP, 1, 1>(c, a, c.null_off, n); return; }
     if (slot & TF_SLOT_AUX) { if (c.type == TF_ANY) encode_stream<SK_AUX8, 1, 1>(c, a, c.aux_off, n); else encode_stream<SK_AUX32, 4, 4>(c, a, c.aux_off, n); return; }
     switch (c.out_kind) {
@@ -470,6 +482,7 @@ __global__ void __launch_bounds__(256) k_encode_fixed(EncodeArgs a) {
     case OK_DATE: encode_stream<SK_DATE, 8, 2>(c, a, c.out_off, n); break;
     case OK_DATETIME: encode_stream<SK_DATETIME, 8, 4>(c, a, c.out_off, n); break;
     case OK_TS64: encode_stream<SK_TS64, 8, 8>(c, a, c.out_off, n); break;
+    case OK_TODT: if (a.columnar) encode_stream<SK_TODT_SEC, 4, 8>(c, a, c.out_off, n); else encode_stream<SK_TODT_CH, 4, 4>(c, a, c.out_off, n); break;
     }
 }
 

@@ -110,18 +110,11 @@ struct ShaSink {
 
 struct MaskArgs { const DCol* cols; const int32_t* slots; const MaskKey* keys; const uint32_t* sel; const DState* st; uint8_t* raw; int columnar; };
 
-// one thread per (kept row, masked column): text form -> HMAC -> "\x40" + 64 hex chars into the block
-__global__ void __launch_bounds__(128) k_mask_encode(MaskArgs a) {
-    const DCol c = a.cols[a.slots[blockIdx.y]];
-    const uint64_t n = a.st->n_kept;
-    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const uint64_t r = a.sel ? a.sel[j] : j;
-    const MaskKey& mk = a.keys[c.mask_slot];
+// hex(HMAC-SHA256(salt, text(value))) of one value: 64 lowercase hex characters into out64
+__device__ inline void mask_digest_hex(const DCol& c, uint64_t r, const MaskKey& mk, uint8_t* out64) {
     ShaSink s; s.init(mk.istate);
     fmt_value(s, c, r);       // to_string.SerializeToString(value, column type)
     s.finish(64);
-    // outer hash over opad state + 32-byte inner digest
     uint32_t o[8]; uint32_t w[16];
 #pragma unroll
     for (int i = 0; i < 8; i++) { o[i] = mk.ostate[i]; w[i] = s.st[i]; }
@@ -130,21 +123,31 @@ __global__ void __launch_bounds__(128) k_mask_encode(MaskArgs a) {
     for (int i = 9; i < 15; i++) w[i] = 0;
     w[15] = (64 + 32) * 8;
     sha256_compress(o, w);
-    uint8_t* out;
-    if (a.columnar) {                                    // utf8 column: offsets 64 j, heap = hex digits
-        out = a.raw + c.out_off + j * 64 - 1;
-        ((uint32_t*)(a.raw + c.offs_off))[j] = (uint32_t)(64 * j);
-    } else {
-        out = a.raw + c.out_off + j * 65;
-        if (c.nullable) a.raw[c.null_off + j] = 0;      // the digest of "<nil>" is a value, never NULL (hmac_hasher.go:60)
-        out[0] = 64;
-    }
     const char* hex = "0123456789abcdef";
 #pragma unroll
     for (int i = 0; i < 8; i++) {
 #pragma unroll
-        for (int b = 0; b < 4; b++) { const uint32_t by = (o[i] >> (24 - 8 * b)) & 0xff; out[1 + 8 * i + 2 * b] = (uint8_t)hex[by >> 4]; out[2 + 8 * i + 2 * b] = (uint8_t)hex[by & 15]; }
+        for (int b = 0; b < 4; b++) { const uint32_t by = (o[i] >> (24 - 8 * b)) & 0xff; out64[8 * i + 2 * b] = (uint8_t)hex[by >> 4]; out64[8 * i + 2 * b + 1] = (uint8_t)hex[by & 15]; }
     }
+}
+
+// one thread per (kept row, masked column): "\x40" + 64 hex chars into the block (or the bare digest, columnar output)
+__global__ void __launch_bounds__(128) k_mask_encode(MaskArgs a) {
+    const DCol c = a.cols[a.slots[blockIdx.y]];
+    const uint64_t n = a.st->n_kept;
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t r = a.sel ? a.sel[j] : j;
+    uint8_t* out;
+    if (a.columnar) {                                    // utf8 column: offsets 64 j, heap = hex digits
+        out = a.raw + c.out_off + j * 64;
+        ((uint32_t*)(a.raw + c.offs_off))[j] = (uint32_t)(64 * j);
+    } else {
+        out = a.raw + c.out_off + j * 65;
+        if (c.nullable) a.raw[c.null_off + j] = 0;      // the digest of "<nil>" is a value, never NULL (hmac_hasher.go:60)
+        *out++ = 64;
+    }
+    mask_digest_hex(c, r, a.keys[c.mask_slot], out);
 }
 
 }  // namespace tfk

@@ -337,6 +337,8 @@ struct Plan {
     std::vector<int> out_cols;         // input index of every output column, schema order
     std::vector<FilterStep> filters;   // in plan order
     std::vector<int> filter_step_index;
+    std::vector<uint8_t> todt_col;     // [input column] 1 = convert_to_datetime applies (to_datetime.go:89-135)
+    std::vector<int> todt_step_index; std::vector<std::vector<int>> todt_cols;
     std::vector<uint8_t> tostr_col;    // [input column] 1 = convert_to_string applies (to_string.go:58-97)
     std::vector<int> tostr_step_index; std::vector<std::vector<int>> tostr_cols;
     std::vector<MaskStep> masks;
@@ -522,6 +524,26 @@ inline Plan build_plan(const std::string& ns, const std::string& name, const std
             }
             add_desc(d + "]}");
             pl.masks.push_back(ms); pl.mask_step_index.push_back(step_no++);
+        } else if (ttype == "convert_to_datetime") {                 // registry/to_datetime/to_datetime.go:56-151
+            if (!match_table(tables_filter(cfg->get("tables")), ns, name)) continue;
+            const tfj::Value* cc = cfg->get("columns");
+            std::vector<std::string> inc, exc;
+            if (cc) { inc = cc->get_str_list("includeColumns"); exc = cc->get_str_list("excludeColumns"); }
+            NameFilter cf = make_filter(inc, exc);
+            if (cf.empty()) continue;                                // Suitable :64-66
+            std::vector<int> pos;
+            for (size_t i = 0; i < cur.size(); i++) if (cf.match(cur[i].name) && (cur[i].tf == TF_INT32 || cur[i].tf == TF_UINT32)) pos.push_back((int)i);
+            if (pos.empty()) continue;
+            if (pl.todt_col.empty()) pl.todt_col.assign(pl.in_schema.size(), 0);
+            std::vector<int> cols; std::string d = "{\"type\":\"convert_to_datetime\",\"cols\":[";
+            for (size_t i = 0; i < pos.size(); i++) {
+                ColSchema& c = cur[pos[i]];
+                if (c.tf != pl.in_schema[c.in_index].tf || (pl.tostr_col.size() && pl.tostr_col[c.in_index])) throw FatalError(TF_E_FATAL_UNSUPPORTED, "convert_to_datetime on a column an earlier transformer already rewrote");
+                if (i) d += ","; d += std::to_string(c.in_index); cols.push_back(c.in_index); pl.todt_col[c.in_index] = 1;
+                c.type = "datetime"; c.tf = TF_DATETIME;
+            }
+            add_desc(d + "]}");
+            pl.todt_cols.push_back(cols); pl.todt_step_index.push_back(step_no++);
         } else if (ttype == "convert_to_string") {                   // registry/to_string/to_string.go:24-113
             if (!match_table(tables_filter(cfg->get("tables")), ns, name)) continue;
             if (cfg->get_bool("skip_utc_conversion")) throw FatalError(TF_E_FATAL_UNSUPPORTED, "convert_to_string: skip_utc_conversion needs time zones, which the columnar layout does not carry");
@@ -537,7 +559,7 @@ inline Plan build_plan(const std::string& ns, const std::string& name, const std
             std::vector<int> cols; std::string d = std::string("{\"type\":\"convert_to_string\",\"to_bytes\":") + (to_bytes ? "true" : "false") + ",\"cols\":[";
             for (size_t i = 0; i < pos.size(); i++) {
                 ColSchema& c = cur[pos[i]];
-                if (pl.tostr_col[c.in_index] || c.tf != pl.in_schema[c.in_index].tf)
+                if (pl.tostr_col[c.in_index] || c.tf != pl.in_schema[c.in_index].tf || (pl.todt_col.size() && pl.todt_col[c.in_index]))
                     throw FatalError(TF_E_FATAL_UNSUPPORTED, "convert_to_string on column '" + c.name + "' that an earlier transformer already rewrote");
                 if (i) d += ","; d += std::to_string(c.in_index); cols.push_back(c.in_index); pl.tostr_col[c.in_index] = 1;
                 c.type = to_bytes ? "string" : "utf8"; c.tf = to_bytes ? TF_BYTES : TF_UTF8;
@@ -553,6 +575,13 @@ inline Plan build_plan(const std::string& ns, const std::string& name, const std
         if (pl.filter_step_index[f] > pl.mask_step_index[m])
             for (auto& e : pl.filters[f].exprs) for (auto& t : e) for (int c : pl.masks[m].cols)
                 if (t.col == c) throw FatalError(TF_E_FATAL_UNSUPPORTED, "filter_rows on a column masked earlier in the chain is not supported");
+    for (size_t m = 0; m < pl.todt_cols.size(); m++) {
+        for (size_t f = 0; f < pl.filters.size(); f++) if (pl.filter_step_index[f] > pl.todt_step_index[m])
+            for (auto& e : pl.filters[f].exprs) for (auto& t : e) for (int c : pl.todt_cols[m])
+                if (t.col == c) throw FatalError(TF_E_FATAL_UNSUPPORTED, "filter_rows on a column converted to datetime earlier in the chain is not supported");
+        for (size_t k = 0; k < pl.masks.size(); k++) for (int c : pl.masks[k].cols) for (int c2 : pl.todt_cols[m])
+            if (c == c2) throw FatalError(TF_E_FATAL_UNSUPPORTED, "mask_field and convert_to_datetime on the same column are not supported together");
+    }
     for (size_t m = 0; m < pl.tostr_cols.size(); m++) {
         for (size_t f = 0; f < pl.filters.size(); f++) if (pl.filter_step_index[f] > pl.tostr_step_index[m])
             for (auto& e : pl.filters[f].exprs) for (auto& t : e) for (int c : pl.tostr_cols[m])

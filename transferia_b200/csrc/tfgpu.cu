@@ -17,6 +17,7 @@
 #include "kernels_str.cuh"
 #include "kernels_mask.cuh"
 #include "kernels_csv.cuh"
+#include "kernels_json_out.cuh"
 
 using namespace tfk;
 
@@ -44,6 +45,7 @@ struct PlanDev {
     DevBuf consts;
     DTerm* d_terms = nullptr; uint32_t* d_expr_off = nullptr; DFilterStep* d_fsteps = nullptr; uint8_t* d_blob = nullptr;
     uint8_t* d_col_headers = nullptr; uint32_t* d_col_header_off = nullptr;
+    JsonCol* d_jcols = nullptr; uint8_t* d_jnames = nullptr; size_t jnames_len = 0;
     int32_t* d_fixed_slots = nullptr; int32_t* d_str_slots = nullptr; int32_t* d_mask_slots = nullptr; int32_t* d_out_cols = nullptr;
     MaskKey* d_mask_keys = nullptr;
     int n_fsteps = 0, n_fixed_slots = 0, n_str = 0, n_mask_cols = 0;
@@ -71,6 +73,8 @@ struct tfgpu_engine {
     uint32_t* tile_sum = nullptr; uint64_t* tile_base = nullptr; uint64_t* col_bytes = nullptr; uint32_t* comp_size = nullptr; uint64_t* wire_off = nullptr;
     uint64_t last_nrows = 0; bool last_has_filter = false; int last_wire_fmt = 0;
     uint8_t* pinned = nullptr; size_t pinned_cap = 0;
+    DevBuf json_sizes;
+    void* work_json_sizes(uint64_t n) { json_sizes.ensure(n * 4 + 256); return json_sizes.p; }
     // optional per-kernel CUDA-event timing of the last call (bench roofline)
     bool prof_on = false; std::vector<cudaEvent_t> prof_ev; std::vector<const char*> prof_names; int prof_n = 0;
     std::string prof_json;
@@ -135,6 +139,7 @@ void upload_plan(tfgpu_engine* e, PlanDev& pd) {
         if (pd.col_mask_slot[c] >= 0) {
             kind = OK_MASK; w = 65;
         } else if (pl.tostr_col.size() > c && pl.tostr_col[c]) { kind = OK_TOSTR; w = 0; }
+        else if (pl.todt_col.size() > c && pl.todt_col[c]) { kind = OK_TODT; w = 4; }
         else switch (tf) {
             case TF_BOOLEAN: kind = OK_BOOL; w = 1; break;
             case TF_DATE: kind = OK_DATE; w = 2; break;
@@ -148,9 +153,21 @@ void upload_plan(tfgpu_engine* e, PlanDev& pd) {
         if (kind == OK_STR || kind == OK_TOSTR) { pd.col_str_slot[c] = (int)pd.str_slots.size(); pd.str_slots.push_back((int32_t)c); }
         else if (kind == OK_MASK) { pd.mask_slot_cols.push_back((int32_t)c); }
         else pd.fixed_slots.push_back((int32_t)c);
-        if (nullable && kind != OK_MASK && kind != OK_TOSTR) pd.fixed_slots.push_back((int32_t)c | TF_SLOT_NULLMAP);
+        if (nullable && kind == OK_TODT) pd.fixed_slots.push_back((int32_t)c | TF_SLOT_ZEROMAP);
+        else if (nullable && kind != OK_MASK && kind != OK_TOSTR) pd.fixed_slots.push_back((int32_t)c | TF_SLOT_NULLMAP);
     }
     if (pd.str_slots.size() > 256) throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "more than 256 String columns");
+    // JSONEachRow descriptors: column name + the ClickHouse class of the RESULT type (columntypes.ToChType)
+    std::vector<JsonCol> jcols; std::vector<uint8_t> jnames;
+    for (size_t k = 0; k < pl.out_cols.size(); k++) {
+        JsonCol jc; std::memset(&jc, 0, sizeof jc); jc.col = pl.out_cols[k]; jc.name_off = (int32_t)jnames.size(); jc.name_len = (int32_t)pl.out_schema[k].name.size();
+        jnames.insert(jnames.end(), pl.out_schema[k].name.begin(), pl.out_schema[k].name.end());
+        const int rt = pl.out_schema[k].tf; jc.result_tf = rt;
+        jc.ch_class = (rt == TF_ANY || rt == TF_BYTES || rt == TF_UTF8) ? JC_STRING : rt == TF_DATE ? JC_DATE : rt == TF_DATETIME ? JC_DATETIME : rt == TF_TIMESTAMP ? JC_DT64 : JC_OTHER;
+        jc.prec = 6;
+        jcols.push_back(jc);
+    }
+    pd.jnames_len = jnames.size();
     // flatten filter steps
     std::vector<DTerm> terms; std::vector<uint32_t> expr_off(1, 0); std::vector<DFilterStep> fsteps;
     for (size_t f = 0; f < pl.filters.size(); f++) {
@@ -168,7 +185,7 @@ void upload_plan(tfgpu_engine* e, PlanDev& pd) {
     auto need = [&](size_t n) { total += align_up(n ? n : 1, 256); };
     need(terms.size() * sizeof(DTerm)); need(expr_off.size() * 4); need(fsteps.size() * sizeof(DFilterStep)); need(pl.blob.size());
     need(pl.col_headers.size()); need(pl.col_header_off.size() * 4); need(pd.fixed_slots.size() * 4); need(pd.str_slots.size() * 4);
-    need(pd.mask_slot_cols.size() * 4); need(keys.size() * sizeof(MaskKey)); need(pl.out_cols.size() * 4);
+    need(pd.mask_slot_cols.size() * 4); need(keys.size() * sizeof(MaskKey)); need(pl.out_cols.size() * 4); need(jcols.size() * sizeof(JsonCol)); need(jnames.size());
     pd.consts.ensure(total);
     uint8_t* p = pd.consts.p;
     auto put = [&](const void* src, size_t n) { uint8_t* d = p; if (n) CK(cudaMemcpy(d, src, n, cudaMemcpyHostToDevice)); p += align_up(n ? n : 1, 256); return d; };
@@ -183,12 +200,13 @@ void upload_plan(tfgpu_engine* e, PlanDev& pd) {
     pd.d_mask_slots = (int32_t*)put(pd.mask_slot_cols.data(), pd.mask_slot_cols.size() * 4);
     pd.d_mask_keys = (MaskKey*)put(keys.data(), keys.size() * sizeof(MaskKey));
     { std::vector<int32_t> oc(pl.out_cols.begin(), pl.out_cols.end()); pd.d_out_cols = (int32_t*)put(oc.data(), oc.size() * 4); }
+    pd.d_jcols = (JsonCol*)put(jcols.data(), jcols.size() * sizeof(JsonCol)); pd.d_jnames = put(jnames.data(), jnames.size());
     (void)e;
 }
 
 struct Sizes { uint64_t raw_bound, n_frames_max, wire_bound; uint32_t ntiles_cap, nblocks; };
 
-Sizes compute_sizes(const tfgpu_engine* e, const PlanDev& pd, const tf_batch* in, bool columnar = false) {
+Sizes compute_sizes(const tfgpu_engine* e, const PlanDev& pd, const tf_batch* in, bool columnar = false, bool json = false) {
     const tfplan::Plan& pl = pd.plan; const uint64_t n = in->nrows;
     uint64_t raw = 64 + pl.col_headers.size();
     for (int oc : pl.out_cols) {
@@ -198,6 +216,7 @@ Sizes compute_sizes(const tfgpu_engine* e, const PlanDev& pd, const tf_batch* in
         else if (pd.col_out_kind[c] == OK_TOSTR) raw += (in_width(in->cols[c].type) ? 40 * n : 6 * in->cols[c].heap_len + 8 * n) + 5 * n;   // longest text form (RFC3339Nano / %v float / \\u00XX-escaped JSON string)
         else raw += (uint64_t)pd.col_out_w[c] * n;
         if (columnar) raw += 8 * n + 4 * (n + 1) + n / 8 + 6 * 16 + (pd.col_out_kind[c] == OK_MASK ? 64 * n : 0);   // widest value, aux, offsets, bitmap, padding
+        if (json) raw += (uint64_t)(pl.in_schema[c].name.size() + 4 + 48) * n + (in_width(in->cols[c].type) ? 0 : 6 * in->cols[c].heap_len);   // name, quotes, longest scalar text, escaped payload
     }
     Sizes s;
     s.raw_bound = raw + 256;
@@ -214,19 +233,21 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
     const bool columnar = wire_fmt == TF_WIRE_COLUMNAR_INTERNAL;
     const tfplan::Plan& pl = pd.plan;
     const size_t nc = pl.in_schema.size(); const uint64_t n = in->nrows;
-    const Sizes sz = compute_sizes(e, pd, in, columnar);
+    const bool json_rows = wire_fmt == TF_WIRE_CH_JSONEACHROW;
+    const Sizes sz = compute_sizes(e, pd, in, columnar, json_rows);
     cudaStream_t s = e->stream;
     // work arena
     size_t wbytes = 0;
     auto need = [&](size_t b) { wbytes += align_up(b ? b : 1, 256); };
     need(n); need(n); need(n); need(sz.nblocks * 4); need(sz.nblocks * 4); need(n * 4);
-    need((size_t)pd.n_str * sz.ntiles_cap * 4); need((size_t)pd.n_str * sz.ntiles_cap * 8);
+    const size_t nslot_alloc = (size_t)(pd.n_str > 0 ? pd.n_str : 1);
+    need(nslot_alloc * sz.ntiles_cap * 4); need(nslot_alloc * sz.ntiles_cap * 8);
     need(sz.n_frames_max * 4); need(sz.n_frames_max * 8); need(256 * 8);
     e->work.ensure(wbytes);
     uint8_t* p = e->work.p;
     e->keep = carve<uint8_t>(p, n); e->errcode = carve<uint8_t>(p, n); e->errstep = carve<uint8_t>(p, n);
     e->blockcnt = carve<uint32_t>(p, sz.nblocks); e->blockoff = carve<uint32_t>(p, sz.nblocks); e->sel = carve<uint32_t>(p, n);
-    e->tile_sum = carve<uint32_t>(p, (size_t)pd.n_str * sz.ntiles_cap); e->tile_base = carve<uint64_t>(p, (size_t)pd.n_str * sz.ntiles_cap);
+    e->tile_sum = carve<uint32_t>(p, nslot_alloc * sz.ntiles_cap); e->tile_base = carve<uint64_t>(p, nslot_alloc * sz.ntiles_cap);
     e->comp_size = carve<uint32_t>(p, sz.n_frames_max); e->wire_off = carve<uint64_t>(p, sz.n_frames_max); e->col_bytes = carve<uint64_t>(p, 256);
     e->raw.ensure(sz.raw_bound);
     const bool lz = wire_fmt == TF_WIRE_CH_NATIVE_LZ4;
@@ -239,7 +260,8 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         const tf_col& ic = dev_cols[c]; DCol& d = hc[c]; std::memset(&d, 0, sizeof d);
         if (ic.type != pl.in_schema[c].tf) throw tfplan::FatalError(TF_E_FATAL_ARG, "column " + std::to_string(c) + " type does not match the plan schema");
         d.type = ic.type; d.out_kind = pd.col_out_kind[c]; d.in_w = in_width(ic.type); d.out_w = pd.col_out_w[c];
-        if (columnar && d.out_kind != OK_STR && d.out_kind != OK_MASK && d.out_kind != OK_TOSTR) { d.out_kind = OK_COPY; d.out_w = d.in_w; }   // Transformed values keep their type
+        if (columnar && d.out_kind == OK_TODT) d.out_w = 8;          // Transformed value is a time.Time: int64 seconds
+        else if (columnar && d.out_kind != OK_STR && d.out_kind != OK_MASK && d.out_kind != OK_TOSTR) { d.out_kind = OK_COPY; d.out_w = d.in_w; }   // Transformed values keep their type
         d.nullable = pd.col_nullable[c]; d.str_slot = pd.col_str_slot[c]; d.mask_slot = pd.col_mask_slot[c];
         d.values = (const uint8_t*)ic.values; d.validity = ic.validity; d.offsets = ic.offsets; d.heap = ic.heap; d.aux = (const uint8_t*)ic.aux;
         if (n) {
@@ -266,6 +288,19 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         // n_kept = nrows is set inside k_layout (has_sel = 0); k_str_sizes needs it earlier:
         DState init; std::memset(&init, 0, sizeof init); init.n_kept = n;
         CK(cudaMemcpyAsync(e->d_state, &init, sizeof init, cudaMemcpyHostToDevice, s));
+    }
+    if (json_rows) {
+        // JSONEachRow: rows sized, placed by a tile scan, then written (kernels_json_out.cuh)
+        const uint32_t jt = (uint32_t)((n + TF_JSON_TILE - 1) / TF_JSON_TILE);
+            JsonArgs ja{e->d_cols, pd.d_jcols, (int)pl.out_cols.size(), pd.d_jnames, pd.d_mask_keys, sel, e->d_state, e->raw.p,
+                    (uint32_t*)e->work_json_sizes(n), e->tile_sum, e->tile_base, e->col_bytes};
+        if (jt) { e->prof_begin("k_json_sizes", s); k_json_sizes<<<jt, TF_JSON_TILE, 0, s>>>(ja); e->prof_end(s); }
+        LayoutArgs lj{e->d_cols, 0, pd.d_out_cols, pd.d_str_slots, 1, e->tile_sum, e->tile_base, sz.ntiles_cap, pd.d_col_headers, pd.d_col_header_off,
+                      e->raw.p, e->d_state, n, 1, e->frame_bytes, e->col_bytes};
+        e->prof_begin("k_layout_scan", s); k_layout_scan<<<1, 1024, 0, s>>>(lj); e->prof_end(s);
+        e->prof_begin("k_json_write", s); k_json_write<<<jt ? jt : 1, TF_JSON_TILE, 0, s>>>(ja); e->prof_end(s);
+        CK(cudaGetLastError());
+        return;
     }
     if (pd.n_str && ntiles) { e->prof_begin("k_str_sizes", s); k_str_sizes<<<dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
     LayoutArgs la{e->d_cols, (int)pl.out_cols.size(), pd.d_out_cols, pd.d_str_slots, pd.n_str, e->tile_sum, e->tile_base, sz.ntiles_cap, pd.d_col_headers, pd.d_col_header_off,
@@ -296,9 +331,10 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         std::vector<int32_t> fixed, valid;
         for (int oc : pl.out_cols) {
             const DCol& d = hc[oc];
-            if (d.out_kind == OK_COPY) fixed.push_back(oc);
-            if (d.out_kind != OK_MASK && d.out_kind != OK_TOSTR && d.aux) fixed.push_back(oc | TF_SLOT_AUX);
-            if (d.out_kind != OK_MASK && d.out_kind != OK_TOSTR && d.validity) valid.push_back(oc);
+            if (d.out_kind == OK_COPY || d.out_kind == OK_TODT) fixed.push_back(oc);
+            const bool fresh = d.out_kind == OK_MASK || d.out_kind == OK_TOSTR || d.out_kind == OK_TODT;
+            if (!fresh && d.aux) fixed.push_back(oc | TF_SLOT_AUX);
+            if (!fresh && d.validity) valid.push_back(oc);
         }
         std::vector<int32_t> both(fixed); both.insert(both.end(), valid.begin(), valid.end());
         if (!both.empty()) CK(cudaMemcpyAsync(e->d_call_slots, both.data(), both.size() * 4, cudaMemcpyHostToDevice, s));
@@ -376,7 +412,7 @@ int tfgpu_engine_destroy(tfgpu_engine* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (auto& p : e->plans) p->consts.release();
-    e->in_arena.release(); e->work.release(); e->raw.release(); e->slots.release(); e->wire.release(); e->csv_text.release(); e->csv_stage.release();
+    e->in_arena.release(); e->work.release(); e->raw.release(); e->slots.release(); e->wire.release(); e->csv_text.release(); e->csv_stage.release(); e->json_sizes.release();
     if (e->d_state) cudaFree(e->d_state);
     if (e->d_cols) cudaFree(e->d_cols);
     if (e->d_call_slots) { cudaFree(e->d_call_slots); cudaFree(e->d_regions); }
@@ -502,7 +538,7 @@ int tfgpu_push_encode(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch
     PlanDev& pd = *e->plans[plan_id];
     if (!pd.plan.has_sink) return fail(e, TF_E_FATAL_CONFIG, "plan was built without a sink");
     if (in->ncols != pd.plan.in_schema.size()) return fail(e, TF_E_FATAL_ARG, "batch column count does not match the plan schema");
-    if (wire_fmt != TF_WIRE_CH_NATIVE && wire_fmt != TF_WIRE_CH_NATIVE_LZ4) return fail(e, TF_E_FATAL_UNSUPPORTED, "wire format not implemented");
+    if (wire_fmt != TF_WIRE_CH_NATIVE && wire_fmt != TF_WIRE_CH_NATIVE_LZ4 && wire_fmt != TF_WIRE_CH_JSONEACHROW) return fail(e, TF_E_FATAL_UNSUPPORTED, "wire format not implemented");
     if (in->nrows >= (1ull << 31)) return fail(e, TF_E_FATAL_ARG, "batch too large (>= 2^31 rows)");
     try {
         CK(cudaSetDevice(e->device));
@@ -669,7 +705,7 @@ int tfgpu_parse_csv(tfgpu_engine* e, int plan_id, const char* opts_json, const u
     *out = nullptr;
     PlanDev& pd = *e->plans[plan_id];
     if (len >= (1ull << 32) - 16) return fail(e, TF_E_FATAL_ARG, "csv chunk must be < 4 GiB (line positions are uint32)");
-    if (wire_fmt != 0 && wire_fmt != TF_WIRE_CH_NATIVE && wire_fmt != TF_WIRE_CH_NATIVE_LZ4) return fail(e, TF_E_FATAL_UNSUPPORTED, "wire format not implemented");
+    if (wire_fmt != 0 && wire_fmt != TF_WIRE_CH_NATIVE && wire_fmt != TF_WIRE_CH_NATIVE_LZ4 && wire_fmt != TF_WIRE_CH_JSONEACHROW) return fail(e, TF_E_FATAL_UNSUPPORTED, "wire format not implemented");
     if (wire_fmt != 0 && !pd.plan.has_sink) return fail(e, TF_E_FATAL_CONFIG, "plan was built without a sink");
     try {
         CK(cudaSetDevice(e->device));
