@@ -7,6 +7,7 @@
 #include "hashes.hpp"
 #include "lz4_block.hpp"
 #include "csv_oracle.hpp"
+#include "json_oracle.hpp"
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
@@ -422,6 +423,7 @@ void to_buf(const std::vector<uint8_t>& v, orc_buf* b) {
 int copy_out(const std::string& s, char* dst, int cap) { if ((int)s.size() + 1 > cap) return -1; std::memcpy(dst, s.data(), s.size()); dst[s.size()] = 0; return (int)s.size(); }
 
 }  // namespace
+std::string jsn::go_quote(const uint8_t* s, size_t n) { return go_json_quote(s, n); }
 
 extern "C" {
 
@@ -663,6 +665,37 @@ int orc_csv_parse(const uint8_t* buf, uint64_t len, const int32_t* types, const 
     }
     to_buf(b, out);
     *rows = R.rows; *lines = R.lines; *consumed = R.consumed;
+    uint64_t ne = 0; for (auto& e : R.errs) if (ne < errs_cap) errs[ne++] = e;
+    *nerrs = R.errs.size();
+    return 0;
+}
+
+int orc_json_parse(const uint8_t* buf, uint64_t len, const orc_json_msg* msgs, uint64_t nmsgs,
+                   const char* const* names, const int32_t* types, const uint8_t* keys, const uint8_t* required, int ncols,
+                   const orc_json_opts* o, orc_buf* out, orc_regions* regions, uint64_t* rows, uint64_t* lines,
+                   tf_rowerr* errs, uint64_t errs_cap, uint64_t* nerrs) {
+    jsn::Opts jo; jo.add_rest = o->add_rest; jo.add_dedupe_keys = o->add_dedupe_keys; jo.null_keys_allowed = o->null_keys_allowed;
+    jo.use_numbers_in_any = o->use_numbers_in_any; jo.unpack_bytes_base64 = o->unpack_bytes_base64; jo.partition = o->partition ? o->partition : "";
+    std::vector<jsn::Field> fs(ncols);
+    for (int c = 0; c < ncols; c++) { fs[c].name = names[c]; fs[c].tf = types[c]; fs[c].key = keys[c]; fs[c].required = required[c]; }
+    std::vector<jsn::Msg> ms(nmsgs);
+    for (uint64_t k = 0; k < nmsgs; k++) ms[k] = jsn::Msg{msgs[k].end, msgs[k].offset, msgs[k].write_sec, msgs[k].write_nsec};
+    jsn::Result R = jsn::parse(buf, len, ms, fs, jo);
+    std::vector<uint8_t> b;
+    auto put = [&](const void* p, size_t n) -> uint64_t { while (b.size() % 16) b.push_back(0); uint64_t at = b.size(); const uint8_t* q = (const uint8_t*)p; b.insert(b.end(), q, q + n); return at; };
+    for (int c = 0; c < ncols; c++) {
+        jsn::ColOut& oc = R.cols[c]; orc_regions& g = regions[c]; const int w = jsn::width_tf(types[c]);
+        g.values = w ? put(oc.values.data(), oc.values.size()) : ~0ull;
+        oc.valid.resize((R.rows + 7) / 8, 0);
+        g.validity = R.rows ? put(oc.valid.data(), oc.valid.size()) : ~0ull;
+        const bool has_aux = types[c] == TF_ANY || types[c] == TF_DATE || types[c] == TF_DATETIME || types[c] == TF_TIMESTAMP;
+        g.aux = has_aux ? put(oc.aux.data(), oc.aux.size()) : ~0ull;
+        g.offsets = w ? ~0ull : put(oc.offs.data(), oc.offs.size() * 4);
+        g.heap = w ? ~0ull : put(oc.heap.data(), oc.heap.size());
+        g.heap_len = w ? 0 : oc.heap.size();
+    }
+    to_buf(b, out);
+    *rows = R.rows; *lines = R.lines;
     uint64_t ne = 0; for (auto& e : R.errs) if (ne < errs_cap) errs[ne++] = e;
     *nerrs = R.errs.size();
     return 0;

@@ -122,6 +122,16 @@ int orc_csv_parse(const uint8_t* buf, uint64_t len, const int32_t* types, const 
                   orc_buf* out, orc_regions* regions, uint64_t* rows, uint64_t* lines, uint64_t* consumed,
                   tf_rowerr* errs, uint64_t errs_cap, uint64_t* nerrs);
 
+/* Generic JSON parser (pkg/parsers/generic/generic_parser.go, format "json"), see json_oracle.hpp. `cols` is the parser's
+ * RESULT schema: the declared fields, then `_rest` (add_rest), then _timestamp,_partition,_offset,_idx (add_dedupe_keys).
+ * names/keys/required are parallel arrays; msgs[k].end = one past message k in buf. errs[].row = non-empty line index. */
+typedef struct orc_json_opts { uint8_t add_rest, add_dedupe_keys, null_keys_allowed, use_numbers_in_any, unpack_bytes_base64, pad[3]; const char* partition; } orc_json_opts;
+typedef struct orc_json_msg { uint64_t end, offset; int64_t write_sec; uint32_t write_nsec, pad; } orc_json_msg;
+int orc_json_parse(const uint8_t* buf, uint64_t len, const orc_json_msg* msgs, uint64_t nmsgs,
+                   const char* const* names, const int32_t* types, const uint8_t* keys, const uint8_t* required, int ncols,
+                   const orc_json_opts* opts, orc_buf* out, orc_regions* regions, uint64_t* rows, uint64_t* lines,
+                   tf_rowerr* errs, uint64_t errs_cap, uint64_t* nerrs);
+
 /* Verify + decode a frame stream with the oracle's own LZ4 decoder and CityHash. */
 int orc_ch_decode_frames(const uint8_t* wire, uint64_t n, orc_buf* raw, uint64_t* n_frames);
 

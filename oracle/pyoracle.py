@@ -69,6 +69,15 @@ class OrcCsvOpts(C.Structure):
                 ("null_values", C.c_char_p), ("true_values", C.c_char_p), ("false_values", C.c_char_p), ("skip_lines", C.c_uint64)]
 
 
+class OrcJsonOpts(C.Structure):
+    _fields_ = [("add_rest", C.c_uint8), ("add_dedupe_keys", C.c_uint8), ("null_keys_allowed", C.c_uint8), ("use_numbers_in_any", C.c_uint8),
+                ("unpack_bytes_base64", C.c_uint8), ("pad", C.c_uint8 * 3), ("partition", C.c_char_p)]
+
+
+class OrcJsonMsg(C.Structure):
+    _fields_ = [("end", C.c_uint64), ("offset", C.c_uint64), ("write_sec", C.c_int64), ("write_nsec", C.c_uint32), ("pad", C.c_uint32)]
+
+
 class OrcBuf(C.Structure):
     _fields_ = [("data", C.POINTER(C.c_uint8)), ("len", C.c_uint64)]
 
@@ -109,6 +118,9 @@ def lib():
                                        C.POINTER(OrcRegions), C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(abi.TfRowErr), C.POINTER(C.c_uint64)]
         L.orc_csv_parse.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(OrcCsvOpts), C.POINTER(OrcBuf), C.POINTER(OrcRegions),
                                     C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(abi.TfRowErr), C.c_uint64, C.POINTER(C.c_uint64)]
+        L.orc_json_parse.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(OrcJsonMsg), C.c_uint64, C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                     C.POINTER(OrcJsonOpts), C.POINTER(OrcBuf), C.POINTER(OrcRegions), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                     C.POINTER(abi.TfRowErr), C.c_uint64, C.POINTER(C.c_uint64)]
         L.orc_ch_decode_frames.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(OrcBuf), C.POINTER(C.c_uint64)]
         L.orc_free.argtypes = [C.POINTER(OrcBuf)]; L.orc_free.restype = None
         _lib = L
@@ -745,3 +757,64 @@ def csv_parse(data: bytes, schema: List[dict], opts: Optional[dict] = None):
     lib().orc_free(C.byref(out))
     return (_regions_to_batch(buf, regs, list(types), rows.value), [(errs[i].row, errs[i].code, errs[i].term) for i in range(nerr.value)],
             lines.value, consumed.value)
+
+
+# ----------------------------------------------------------------------------- generic JSON parser
+JSON_FIELD_TYPES = ("int8", "int16", "int32", "int64", "uint8", "uint16", "uint32", "uint64", "double", "boolean", "utf8", "string", "any", "datetime")
+
+
+def json_result_schema(fields: List[dict], opts: Optional[dict] = None) -> List[dict]:
+    """addAuxFields (generic_parser.go:115-164): the parser's result schema for declared `fields`."""
+    opts = opts or {}
+    out = [dict(f) for f in fields]
+    for f in out:
+        if f["type"] not in JSON_FIELD_TYPES:
+            raise ValueError(f"json parser: field type {f['type']} is not handled")
+        if f.get("path"):
+            raise ValueError("json parser: nested paths are not handled")
+        if f.get("key"):
+            f["required"] = True
+    def dedup(name):
+        while any(c["name"] == name for c in out):
+            name = "_delivery_" + name
+        return name
+    if opts.get("add_rest"):
+        out.append({"name": dedup("_rest"), "type": "any"})
+    if opts.get("add_dedupe_keys"):
+        sys_key = not (opts.get("mark_dedupe_keys_as_system") and any(f.get("key") for f in fields))
+        for n, t in (("_timestamp", "timestamp"), ("_partition", "string"), ("_offset", "uint64"), ("_idx", "uint32")):
+            out.append({"name": dedup(n), "type": t, "key": sys_key, "required": sys_key})
+    return out
+
+
+def json_parse(data: bytes, fields: List[dict], opts: Optional[dict] = None, msgs: Optional[list] = None):
+    """Reference generic JSON parser over concatenated messages -> (Batch of the result schema, errors[(line, code, col)], lines).
+    msgs: [(end, offset, write_sec, write_nsec)], default = one message covering `data` with offset 0 / time 0."""
+    opts = opts or {}
+    schema = json_result_schema(fields, opts)
+    msgs = msgs if msgs is not None else [(len(data), 0, 0, 0)]
+    keep = _Keep()
+    o = OrcJsonOpts()
+    o.add_rest = 1 if opts.get("add_rest") else 0; o.add_dedupe_keys = 1 if opts.get("add_dedupe_keys") else 0
+    o.null_keys_allowed = 1 if opts.get("null_keys_allowed") else 0; o.use_numbers_in_any = 1 if opts.get("use_numbers_in_any") else 0
+    o.unpack_bytes_base64 = 1 if opts.get("unpack_bytes_base64") else 0
+    o.partition = keep.add(opts.get("partition", "").encode())
+    nc = len(schema)
+    names = (C.c_char_p * nc)(*[c["name"].encode() for c in schema])
+    types = keep.add(np.asarray([abi.YT_NAME_TO_TF[c["type"]] for c in schema], dtype=np.int32))
+    keys = keep.add(np.asarray([1 if c.get("key") else 0 for c in schema], dtype=np.uint8))
+    req = keep.add(np.asarray([1 if c.get("required") else 0 for c in schema], dtype=np.uint8))
+    ms = (OrcJsonMsg * max(1, len(msgs)))()
+    for k, (end, off, ws, wn) in enumerate(msgs):
+        ms[k].end, ms[k].offset, ms[k].write_sec, ms[k].write_nsec = end, off, ws, wn
+    src = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data or b"\0")
+    out = OrcBuf(); regs = (OrcRegions * nc)()
+    rows, lines, nerr = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    cap = data.count(b"\n") + len(msgs) + 1
+    errs = (abi.TfRowErr * cap)()
+    rc = lib().orc_json_parse(src, len(data), ms, len(msgs), names, types.ctypes.data, keys.ctypes.data, req.ctypes.data, nc, C.byref(o),
+                              C.byref(out), regs, C.byref(rows), C.byref(lines), errs, cap, C.byref(nerr))
+    assert rc == 0
+    buf = C.string_at(out.data, out.len) if out.len else b""
+    lib().orc_free(C.byref(out))
+    return (_regions_to_batch(buf, regs, list(types), rows.value), [(errs[i].row, errs[i].code, errs[i].term) for i in range(nerr.value)], lines.value)
