@@ -135,6 +135,17 @@ typedef struct tf_batch {
 #define TF_ROWERR_CSV_UNSUPPORTED  23 /* valid for Go's parsers, but a syntax the device does not implement   */
 #define TF_ROWERR_CSV_DQ_DISABLED  24 /* reader.go:305-311 errDoubleQuotesDisabled                           */
 
+/* generic JSON parser (tfgpu_parse_json) */
+#define TF_ROWERR_JSON_PARSE        32 /* fastjson rejects the line -> unparsed row (generic_parser.go:548-553)            */
+#define TF_ROWERR_JSON_SKIP         33 /* valid JSON but not an object with keys: the line yields nothing (:536)           */
+#define TF_ROWERR_JSON_NIL_REQUIRED 34 /* "ParseVal nil": key / required column without a value (:369-371); term = column  */
+#define TF_ROWERR_JSON_PARSEVAL     35 /* "ParseVal error" on a key / required column (:361-366); term = column             */
+#define TF_ROWERR_JSON_HOST         36 /* the line needs the Go parser (see tfgpu_parse_json); term = column                */
+
+/* serializers: a value encoding/json refuses (NaN / Inf float, time.Time with a year outside [0,9999]); the reference
+ * fails the whole Serialize call on it, so a result carrying this code must not be written; term = output column */
+#define TF_ROWERR_SER_VALUE 40
+
 typedef struct tf_rowerr {
     uint32_t row;      /* index into the INPUT batch */
     uint16_t code;     /* TF_ROWERR_* */
@@ -145,6 +156,12 @@ typedef struct tf_rowerr {
 #define TF_WIRE_CH_NATIVE      1  /* ClickHouse native block, uncompressed                       */
 #define TF_WIRE_CH_NATIVE_LZ4  2  /* same, cut into [CityHash128][0x82][sizes][LZ4 block] frames */
 #define TF_WIRE_CH_JSONEACHROW 3  /* httpuploader/marshal.go:88-253                              */
+/* batch serializers (pkg/serializer/batch.go:73-231 over json.go:29-114 + json_format.go:32-82 / csv.go:22-74 +
+ * csv_format.go:32-144): the object-storage / queue sinks' row text. OR the flags into the format id. */
+#define TF_WIRE_SER_JSON       4  /* one JSON object per row, keys sorted, rows joined by '\n'    */
+#define TF_WIRE_SER_CSV        5  /* encoding/csv records, each ending in '\n'                    */
+#define TF_WIRE_F_CLOSING_NEWLINE 0x100  /* JSONSerializerConfig.AddClosingNewLine (json.go:15)   */
+#define TF_WIRE_F_ANY_AS_STRING   0x200  /* JSONSerializerConfig.AnyAsString (json_format.go:69-76) */
 
 typedef struct tfgpu_engine tfgpu_engine;
 typedef struct tfgpu_result tfgpu_result;
@@ -216,6 +233,27 @@ int tfgpu_resident_fetch(tfgpu_engine* e, int what /*0=raw block,1=wire*/, uint8
  * tfgpu_result_release; the wire bytes live in the engine's pinned landing buffer and stay valid
  * until the NEXT push on the same engine (the Go shim writes them to the socket before that). */
 uint64_t          tfgpu_result_rows_in(const tfgpu_result* r);
+/* parsers.Parser.DoBatch for the generic JSON parser (pkg/parsers/abstract.go:35-38; algorithm
+ * pkg/parsers/generic/generic_parser.go:406-430 DoBatch, :519-555 doGenericParser, :672-730 Unmarshal, :888-1123 ParseVal,
+ * :297-404 makeChangeItem; config pkg/parsers/registry/json/parser_json.go:51-87).
+ * `bytes` holds n_msgs message payloads back to back (host or device, < 4 GiB); msgs[k] gives message k's end offset and
+ * the queue metadata the aux columns need. The plan's schema is the parser's RESULT schema (addAuxFields :115-164): the
+ * declared fields (int8..uint64, double, boolean, utf8, string, any, datetime; flat keys), then `_rest` when add_rest,
+ * then _timestamp,_partition,_offset,_idx when add_dedupe_keys. Lines are split, parsed and typed ON THE DEVICE and fed
+ * straight into the plan's transformer chain; wire_fmt 0 returns the rows columnar, otherwise the sink wire bytes.
+ * opts_json: {"add_rest":false,"add_dedupe_keys":false,"null_keys_allowed":false,"use_numbers_in_any":false,
+ *             "unpack_bytes_base64":false,"partition":"<abstract.Partition.String()>"}; any other AuxParserOpts switch
+ * (time_field, table_splitter, unescape_string_values, add_system_columns, ...) is refused with TF_E_FATAL_UNSUPPORTED.
+ * Row errors: row = index of the line among the non-empty lines of the call, code TF_ROWERR_JSON_*, term = column.
+ * PARSE / NIL_REQUIRED / PARSEVAL lines are the reference's `_unparsed` rows (the shim builds them, reason text from Go);
+ * SKIP lines produce nothing; HOST lines carry a value whose reference result needs a Go library the device does not
+ * restate (dateparse, goccy re-parse of JSON inside a string, > 19 digit floats with undecided rounding, NaN/Inf or an
+ * invalid number inside `any`, nesting deeper than 24, a key named like an aux column) and must be re-parsed by the
+ * host parser. */
+typedef struct tf_msg { uint64_t end; uint64_t offset; int64_t write_sec; uint32_t write_nsec; uint32_t pad; } tf_msg;
+int tfgpu_parse_json(tfgpu_engine* e, int plan_id, const char* opts_json, const uint8_t* bytes, uint64_t len, int mem,
+                     const tf_msg* msgs, uint32_t n_msgs, int wire_fmt, tfgpu_result** out);
+
 uint64_t          tfgpu_result_rows_out(const tfgpu_result* r);
 uint64_t          tfgpu_result_n_errors(const tfgpu_result* r);
 const tf_rowerr*  tfgpu_result_errors(const tfgpu_result* r);

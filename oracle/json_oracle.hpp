@@ -21,7 +21,10 @@
 // Values the tf_batch layout cannot carry, or that need a Go library this file does not restate, mark the row
 // JSN_HOST in BOTH oracle and device (the shim re-parses that line with the Go parser):
 //   NaN / Inf or an invalid json.Number inside `any`;  a string value in a `datetime` column (araddon/dateparse);
-//   a string value in an `any` column that starts with '{' or 'n' (goccy/go-json re-parse of JSON-in-a-string).
+//   a string value in an `any` column that starts with '{' or 'n' (goccy/go-json re-parse of JSON-in-a-string);
+//   a line with a key named like one of the aux columns.
+// The device additionally hands over lines it cannot decide (nesting > 24 inside `any`, floats whose correct rounding
+// Eisel-Lemire leaves open, numeric strings > 96 bytes); tests/test_json_parser.py covers those by code only.
 #pragma once
 #include <cstdint>
 #include <cstring>
@@ -173,6 +176,7 @@ inline void fj_marshal(const FV& v, std::string& d) {
 }
 
 // ------------------------------------------------------------------ strconv (Go 1.2x)
+inline double go_nan() { const uint64_t b = 0x7FF8000000000001ull; double d; std::memcpy(&d, &b, 8); return d; }   // math.NaN()
 inline bool underscore_ok(sv s) {                                // strconv/atoi.go underscoreOK
     char i = '^'; size_t p = 0;
     if (!s.empty() && (s[0] == '-' || s[0] == '+')) p = 1;
@@ -233,7 +237,7 @@ inline int go_parse_float(sv s, double& out) {
         sv t = s; double sign = 1; bool had_sign = false;
         if (t[0] == '+' || t[0] == '-') { sign = t[0] == '-' ? -1 : 1; t = t.substr(1); had_sign = true; }
         if (fold_eq(t, "inf") || fold_eq(t, "infinity")) { out = sign * INFINITY; return 0; }
-        if (!had_sign && fold_eq(t, "nan")) { out = NAN; return 0; }
+        if (!had_sign && fold_eq(t, "nan")) { out = go_nan(); return 0; }
     }
     // readFloat syntax
     size_t i = 0; if (s[i] == '+' || s[i] == '-') i++;
@@ -306,7 +310,7 @@ inline double ff_best_effort(sv s) {
     if (i <= j && s[i] != '.') {
         sv t = s.substr(i); if (!t.empty() && t[0] == '+') t = t.substr(1);
         if (fold_eq(t, "inf") || fold_eq(t, "infinity")) return minus ? -INFINITY : INFINITY;
-        if (fold_eq(t, "nan")) return NAN;
+        if (fold_eq(t, "nan")) return go_nan();
         return 0;
     }
     double f = (double)d;
@@ -514,6 +518,9 @@ inline int parse_line(sv line, const std::vector<Field>& all_cols, size_t nfield
         map_set(item, k, std::move(g));
     }
     if (item.empty()) return JSN_SKIP;                              // :536 len(item) > 0
+    // a key named like an aux column is extracted with THAT column's type (colTypeMap covers the whole result schema, :1226-1233)
+    // and lands in `_rest` as such; rare enough that oracle and device both hand the line to the host parser
+    for (auto& kv : item) for (size_t c = nfields; c < all_cols.size(); c++) if (all_cols[c].name == kv.first) { err_col = (int)nfields; return JSN_HOST; }
     row.cells.assign(nfields, GV());
     for (size_t f = 0; f < nfields; f++) {                          // :325-376 (non-nested keys)
         const Field& fd = all_cols[f];

@@ -8,6 +8,7 @@
 #include "lz4_block.hpp"
 #include "csv_oracle.hpp"
 #include "json_oracle.hpp"
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
@@ -415,6 +416,101 @@ void json_each_row_value(std::string& o, const orc_val& v, int32_t yt_result, co
     }
 }
 
+
+// ------------------------------------------------------------------ batch serializers (pkg/serializer)
+// encoding/json appendString with escapeHTML = false (json.go:56-58 SetEscapeHTML(false)): only `"`, `\`, control
+// characters, invalid UTF-8 and U+2028/2029 are escaped
+std::string go_json_quote_nohtml(const uint8_t* s, size_t n) {
+    std::string q = go_json_quote(s, n), d; d.reserve(q.size());
+    for (size_t i = 0; i < q.size();) {
+        if (q[i] == '\\' && i + 1 < q.size()) {
+            if (q[i + 1] == 'u' && i + 5 < q.size() && (q.compare(i + 2, 4, "003c") == 0 || q.compare(i + 2, 4, "003e") == 0 || q.compare(i + 2, 4, "0026") == 0)) {
+                d += q.compare(i + 2, 4, "003c") == 0 ? '<' : q.compare(i + 2, 4, "003e") == 0 ? '>' : '&'; i += 6; continue;
+            }
+            d += q[i]; d += q[i + 1]; i += 2; continue;
+        }
+        d += q[i++];
+    }
+    return d;
+}
+// JSON text produced by json.Marshal (HTML escaping on) as a second encoder with SetEscapeHTML(false) would write the same value
+std::string json_unescape_html(const uint8_t* s, size_t n) {
+    std::string d; bool ins = false;
+    for (size_t i = 0; i < n;) {
+        const char c = (char)s[i];
+        if (!ins) { if (c == '"') ins = true; d += c; i++; continue; }
+        if (c == '\\' && i + 1 < n) {
+            if (s[i + 1] == 'u' && i + 5 < n && (!std::memcmp(s + i + 2, "003c", 4) || !std::memcmp(s + i + 2, "003e", 4) || !std::memcmp(s + i + 2, "0026", 4))) {
+                d += !std::memcmp(s + i + 2, "003c", 4) ? '<' : !std::memcmp(s + i + 2, "003e", 4) ? '>' : '&'; i += 6; continue;
+            }
+            d += c; d += (char)s[i + 1]; i += 2; continue;
+        }
+        if (c == '"') ins = false;
+        d += c; i++;
+    }
+    return d;
+}
+std::string base64_std(const uint8_t* s, size_t n) {
+    static const char* A = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+    std::string d;
+    for (size_t i = 0; i < n; i += 3) {
+        const uint32_t v = (uint32_t)s[i] << 16 | (i + 1 < n ? (uint32_t)s[i + 1] << 8 : 0) | (i + 2 < n ? s[i + 2] : 0);
+        d += A[v >> 18]; d += A[(v >> 12) & 63]; d += i + 1 < n ? A[(v >> 6) & 63] : '='; d += i + 2 < n ? A[v & 63] : '=';
+    }
+    return d;
+}
+bool year_in_json_range(int64_t sec) { return sec >= -62167219200LL && sec < 253402300800LL; }   // [0000-01-01, 10000-01-01)
+// toJsonValue + json.Encoder for one cell (json_format.go:32-82). false: the encoder would fail
+bool ser_json_value(std::string& o, const orc_val& v, int32_t yt, bool any_as_string) {
+    switch (v.kind) {
+    case OG_NIL: o += "null"; return true;
+    case OG_INT8: case OG_INT16: case OG_INT32: case OG_INT64: case OG_INT: o += fmt_i64(v.i); return true;
+    case OG_UINT8: case OG_UINT16: case OG_UINT32: case OG_UINT64: case OG_UINT: o += fmt_u64(v.u); return true;
+    case OG_FLOAT32: if (std::isnan(v.f) || std::isinf(v.f)) return false; o += fmt_f32((float)v.f, FMT_JSON); return true;
+    case OG_FLOAT64: if (std::isnan(v.f) || std::isinf(v.f)) return false; o += fmt_f64(v.f, FMT_F); return true;   // strictify: json.Number(FormatFloat(f,'f',-1,64)) castx/caste.go:36-60
+    case OG_BOOL: o += v.i ? "true" : "false"; return true;
+    case OG_STRING:
+        if (yt == TF_ANY && any_as_string) { std::string j = go_json_quote(v.s, v.slen); o += go_json_quote_nohtml((const uint8_t*)j.data(), j.size()); }
+        else o += go_json_quote_nohtml(v.s, v.slen);
+        return true;
+    case OG_BYTES: o += '"'; o += base64_std(v.s, v.slen); o += '"'; return true;
+    case OG_TIME: if (!year_in_json_range(v.i)) return false; o += '"'; o += fmt_rfc3339nano_utc(v.i, v.nsec); o += '"'; return true;
+    case OG_DURATION: o += fmt_i64(v.i); return true;
+    case OG_JSON:
+        if (any_as_string) o += go_json_quote_nohtml(v.s, v.slen); else o += json_unescape_html(v.s, v.slen);
+        return true;
+    }
+    return false;
+}
+// toCsvValue (csv_format.go:32-120) -> one encoding/csv field
+std::string ser_csv_cell(const orc_val& v, int32_t yt) {
+    switch (v.kind) {
+    case OG_NIL: return "";
+    case OG_INT8: case OG_INT16: case OG_INT32: case OG_INT64: case OG_INT: return fmt_i64(v.i);
+    case OG_UINT8: case OG_UINT16: case OG_UINT32: case OG_UINT64: case OG_UINT: return fmt_u64(v.u);
+    case OG_FLOAT32: return fmt_f32((float)v.f, FMT_F);
+    case OG_FLOAT64: return fmt_f64(v.f, FMT_F);
+    case OG_BOOL: return v.i ? "true" : "false";
+    case OG_STRING: if (yt == TF_ANY) return go_json_quote(v.s, v.slen);        // csv_format.go:109-116 json.Marshal(value)
+                    return std::string((const char*)v.s, v.slen);
+    case OG_BYTES: return base64_std(v.s, v.slen);
+    case OG_TIME: { std::string r = fmt_rfc3339nano_utc(v.i, v.nsec); r[10] = ' '; r.pop_back(); return r + " +0000 UTC"; }    // castx.ToStringE -> fmt.Stringer -> Time.String()
+    case OG_DURATION: return fmt_duration(v.i);
+    case OG_JSON: return std::string((const char*)v.s, v.slen);
+    }
+    return "";
+}
+void csv_write_field(std::string& o, const std::string& f) {     // encoding/csv Writer.Write, Comma ',' UseCRLF false
+    bool q = false;
+    if (!f.empty()) {
+        if (f == "\\.") q = true;
+        for (char c : f) if (c == '\n' || c == '\r' || c == '"' || c == ',') q = true;
+        if (!q) { size_t w; q = go_space_fwd((const uint8_t*)f.data(), f.size(), w); }
+    }
+    if (!q) { o += f; return; }
+    o += '"'; for (char c : f) { if (c == '"') o += "\"\""; else o += c; } o += '"';
+}
+
 void to_buf(const std::vector<uint8_t>& v, orc_buf* b) {
     if (!b) return;
     b->len = v.size(); b->data = (uint8_t*)std::malloc(v.size() ? v.size() : 1);
@@ -559,6 +655,36 @@ extern "C" int orc_push_encode(const tf_batch* in, const orc_colschema* schema, 
             }
             if (has) text.pop_back();
             text += "}\n"; kept++;
+        }
+        if (rows_out) *rows_out = kept;
+        if (nerrs) *nerrs = ne;
+        std::vector<uint8_t> bytes(text.begin(), text.end());
+        to_buf(bytes, out_raw); to_buf(bytes, out_wire);
+        return 0;
+    }
+    if ((wire_fmt & 0xff) == TF_WIRE_SER_JSON || (wire_fmt & 0xff) == TF_WIRE_SER_CSV) {   // pkg/serializer batch serializers
+        const bool csv = (wire_fmt & 0xff) == TF_WIRE_SER_CSV, nl = wire_fmt & TF_WIRE_F_CLOSING_NEWLINE, aas = wire_fmt & TF_WIRE_F_ANY_AS_STRING;
+        std::vector<uint32_t> order(no); for (uint32_t k = 0; k < no; k++) order[k] = k;
+        if (!csv) std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return names[a] < names[b]; });   // encoding/json sorts map keys
+        std::string text;
+        for (uint64_t r = 0; r < in->nrows; r++) {
+            if (!apply_steps(in, r, steps, nsteps, row, cur_type, errs, ne)) continue;
+            if (csv) {
+                for (uint32_t k = 0; k < no; k++) { if (k) text += ','; csv_write_field(text, ser_csv_cell(row[out_cols[k]].v, out_type[out_cols[k]])); }
+                text += '\n';
+            } else {
+                if (kept && !nl) text += '\n';                        // separator "\n" between items, none after the last (batch.go:205-219, batch_factory.go:36-39)
+                text += '{'; bool row_err = false;
+                for (uint32_t j = 0; j < no; j++) {
+                    const uint32_t k = order[j];
+                    if (j) text += ',';
+                    text += go_json_quote_nohtml((const uint8_t*)names[k].data(), names[k].size()); text += ':';
+                    if (!ser_json_value(text, row[out_cols[k]].v, out_type[out_cols[k]], aas)) { text += "null"; if (!row_err) errs[ne++] = tf_rowerr{(uint32_t)r, TF_ROWERR_SER_VALUE, (uint16_t)k}; row_err = true; }
+                }
+                text += '}';
+                if (nl) text += '\n';
+            }
+            kept++;
         }
         if (rows_out) *rows_out = kept;
         if (nerrs) *nerrs = ne;

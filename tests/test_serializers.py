@@ -1,0 +1,92 @@
+"""Batch serializers: JSON / CSV row text. The oracle is pinned on CPU by the reference's own canonised
+ChangeItems and the bytes its batch serializers wrote for them; the device encoders are compared with the oracle on GPU."""
+import base64
+import json
+import os
+
+import numpy as np
+import pytest
+
+from transferia_b200 import abi
+
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "serializer_goldens.json"), encoding="utf-8"))
+SER_JSON, SER_CSV, F_NL, F_AAS = 4, 5, 0x100, 0x200
+
+
+def case_batch(case):
+    cols = []
+    for k, c in enumerate(case["schema"]):
+        tf = abi.YT_NAME_TO_TF[c["type"]]
+        cells = [r[k] for r in case["rows"]]
+        if tf in abi.VAR_TYPES:
+            if tf == abi.TF_ANY:
+                cols.append(abi.strings_to_column(tf, [None if v is None else v["any"].encode() for v in cells], tags=[0 if v is None else v["tag"] for v in cells]))
+            elif tf == abi.TF_BYTES:
+                cols.append(abi.strings_to_column(tf, [None if v is None else base64.b64decode(v["b64"]) for v in cells]))
+            else:
+                cols.append(abi.strings_to_column(tf, [None if v is None else v.encode() for v in cells]))
+            continue
+        nulls = [v is None for v in cells]
+        nanos = None
+        if tf in (abi.TF_DATE, abi.TF_DATETIME, abi.TF_TIMESTAMP):
+            vals = [0 if v is None else v["t"][0] for v in cells]; nanos = [0 if v is None else v["t"][1] for v in cells]
+        elif tf == abi.TF_DOUBLE:
+            vals = [0.0 if v is None else float(v["f64"]) for v in cells]
+        elif tf == abi.TF_FLOAT:
+            vals = [0.0 if v is None else v["f32"] for v in cells]
+        elif tf == abi.TF_INTERVAL:
+            vals = [0 if v is None else v["dur"] for v in cells]
+        else:
+            vals = [0 if v is None else int(v) for v in cells]
+        cols.append(abi.fixed_to_column(tf, vals, nulls, nanos))
+    return abi.Batch(len(case["rows"]), cols)
+
+
+def csv_records(text):
+    """Split the golden CSV into records (a quoted field may hold a newline)."""
+    out, cur, inq = [], [], False
+    for ch in text:
+        cur.append(ch)
+        if ch == '"': inq = not inq
+        elif ch == "\n" and not inq:
+            out.append("".join(cur)); cur = []
+    return out
+
+
+def test_oracle_matches_reference_serializer_goldens(po):
+    """Every canon ChangeItem the columnar layout carries losslessly serialises to a line the reference wrote
+    (pkg/serializer/reference/canondata TestBatchSerializer json:default / csv:default)."""
+    jgold = set(G["json_lines"]); cgold = set(csv_records(G["csv_text"]))
+    hit_j = hit_c = tot = 0
+    for case in G["cases"]:
+        b = case_batch(case)
+        plan = po.build_plan("s", "t", case["schema"], [])
+        jl = po.push_encode(b, plan, SER_JSON).wire.decode("utf-8").split("\n")
+        cl = csv_records(po.push_encode(b, plan, SER_CSV).wire.decode("utf-8"))
+        assert len(jl) == len(cl) == b.nrows
+        tot += b.nrows
+        hit_j += sum(1 for x in jl if x in jgold); hit_c += sum(1 for x in cl if x in cgold)
+    # the reference serialised only the first 10 items of each canon case: not every fixture row is in its output, but
+    # every golden line whose item we could extract must be reproduced byte for byte
+    assert hit_j >= 61 and hit_c >= 61, (hit_j, hit_c, tot)
+
+
+def test_oracle_serializer_forms(po):
+    """Separators, closing newline, AnyAsString, HTML characters, csv quoting (json.go:56-70, batch_factory.go:36-39, encoding/csv)."""
+    schema = [{"name": "b", "type": "utf8"}, {"name": "a", "type": "any"}, {"name": "d", "type": "double"}, {"name": "y", "type": "string"}, {"name": "t", "type": "timestamp"}]
+    batch = abi.Batch(2, [abi.strings_to_column(abi.TF_UTF8, [b"<x> & \"q\"\n", b" lead,comma"]),
+                          abi.strings_to_column(abi.TF_ANY, [b'{"k":"a\\u003cb"}', b"plain <s>"], tags=[0, 1]),
+                          abi.fixed_to_column(abi.TF_DOUBLE, [1e21, -0.5]), abi.strings_to_column(abi.TF_BYTES, [b"\xff\x00", None]),
+                          abi.fixed_to_column(abi.TF_TIMESTAMP, [1_700_000_000, 0], None, [123_000_000, 0])])
+    plan = po.build_plan("s", "t", schema, [])
+    assert po.push_encode(batch, plan, SER_JSON).wire == (
+        b'{"a":{"k":"a<b"},"b":"<x> & \\"q\\"\\n","d":1000000000000000000000,"t":"2023-11-14T22:13:20.123Z","y":"/wA="}\n'
+        b'{"a":"plain <s>","b":" lead,comma","d":-0.5,"t":"1970-01-01T00:00:00Z","y":null}')
+    assert po.push_encode(batch, plan, SER_JSON | F_NL).wire.endswith(b'"y":null}\n')
+    assert po.push_encode(batch, plan, SER_JSON | F_AAS).wire.startswith(b'{"a":"{\\"k\\":\\"a\\\\u003cb\\"}","b"')
+    assert po.push_encode(batch, plan, SER_CSV).wire == (
+        b'"<x> & ""q""\n","{""k"":""a\\u003cb""}",1000000000000000000000,/wA=,2023-11-14 22:13:20.123 +0000 UTC\n'
+        b'" lead,comma","""plain \\u003cs\\u003e""",-0.5,,1970-01-01 00:00:00 +0000 UTC\n')
+    nan = abi.Batch(1, [abi.fixed_to_column(abi.TF_DOUBLE, [float("nan")])])
+    r = po.push_encode(nan, po.build_plan("s", "t", [{"name": "d", "type": "double"}], []), SER_JSON)
+    assert r.errors == [(0, 40, 0)]

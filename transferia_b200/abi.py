@@ -64,6 +64,14 @@ class TfRowErr(C.Structure):
     _fields_ = [("row", C.c_uint32), ("code", C.c_uint16), ("term", C.c_uint16)]
 
 
+class TfMsg(C.Structure):
+    """tf_msg: one queue message of a tfgpu_parse_json call (parsers.Message, pkg/parsers/abstract.go:13-27)."""
+    _fields_ = [("end", C.c_uint64), ("offset", C.c_uint64), ("write_sec", C.c_int64), ("write_nsec", C.c_uint32), ("pad", C.c_uint32)]
+
+
+TF_ROWERR_JSON_PARSE, TF_ROWERR_JSON_SKIP, TF_ROWERR_JSON_NIL_REQUIRED, TF_ROWERR_JSON_PARSEVAL, TF_ROWERR_JSON_HOST = 32, 33, 34, 35, 36
+
+
 def _ptr(a) -> Optional[int]:
     """Address of a numpy array or torch tensor (None stays NULL)."""
     if a is None:

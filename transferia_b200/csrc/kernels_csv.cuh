@@ -50,24 +50,27 @@ struct CsvArgs {
     uint8_t* err;                                // [nrows] CSV_* code
 };
 
-__global__ void __launch_bounds__(256) k_csv_count_nl(const uint8_t* text, uint64_t len, uint32_t* blk_cnt) {
+// `endbits` (JSON parser): bit p set = byte p is the last byte of a message, which ends a line like '\n' does
+__device__ __forceinline__ bool csv_line_end(const uint8_t* text, const uint32_t* endbits, uint64_t p) { return text[p] == '\n' || (endbits && ((endbits[p >> 5] >> (p & 31)) & 1)); }
+
+__global__ void __launch_bounds__(256) k_csv_count_nl(const uint8_t* text, uint64_t len, uint32_t* blk_cnt, const uint32_t* endbits) {
     __shared__ uint32_t sm[33];
     const uint64_t b0 = (uint64_t)blockIdx.x * CSV_NL_BLOCK;
     uint32_t c = 0;
-    for (uint32_t k = 0; k < CSV_NL_BLOCK / 256; k++) { const uint64_t p = b0 + (uint64_t)threadIdx.x * (CSV_NL_BLOCK / 256) + k; if (p < len && text[p] == '\n') c++; }
+    for (uint32_t k = 0; k < CSV_NL_BLOCK / 256; k++) { const uint64_t p = b0 + (uint64_t)threadIdx.x * (CSV_NL_BLOCK / 256) + k; if (p < len && csv_line_end(text, endbits, p)) c++; }
     uint32_t tot; block_excl_scan(c, &tot, sm);
     if (threadIdx.x == 0) blk_cnt[blockIdx.x] = tot;
 }
 
-__global__ void __launch_bounds__(256) k_csv_line_index(const uint8_t* text, uint64_t len, const uint32_t* blk_off, uint32_t* line_end) {
+__global__ void __launch_bounds__(256) k_csv_line_index(const uint8_t* text, uint64_t len, const uint32_t* blk_off, uint32_t* line_end, const uint32_t* endbits) {
     __shared__ uint32_t sm[33];
     const uint64_t b0 = (uint64_t)blockIdx.x * CSV_NL_BLOCK;
     const uint64_t t0 = b0 + (uint64_t)threadIdx.x * (CSV_NL_BLOCK / 256);
     uint32_t c = 0;
-    for (uint32_t k = 0; k < CSV_NL_BLOCK / 256; k++) { const uint64_t p = t0 + k; if (p < len && text[p] == '\n') c++; }
+    for (uint32_t k = 0; k < CSV_NL_BLOCK / 256; k++) { const uint64_t p = t0 + k; if (p < len && csv_line_end(text, endbits, p)) c++; }
     uint32_t tot; uint32_t ex = block_excl_scan(c, &tot, sm);
     uint32_t w = blk_off[blockIdx.x] + ex;
-    for (uint32_t k = 0; k < CSV_NL_BLOCK / 256; k++) { const uint64_t p = t0 + k; if (p < len && text[p] == '\n') line_end[w++] = (uint32_t)(p + 1); }
+    for (uint32_t k = 0; k < CSV_NL_BLOCK / 256; k++) { const uint64_t p = t0 + k; if (p < len && csv_line_end(text, endbits, p)) line_end[w++] = (uint32_t)(p + 1); }
 }
 
 // ---- text -> value helpers (must agree with oracle/csv_oracle.hpp, which restates the Go functions)

@@ -17,6 +17,7 @@
 #include "kernels_str.cuh"
 #include "kernels_mask.cuh"
 #include "kernels_csv.cuh"
+#include "kernels_json_in.cuh"
 #include "kernels_json_out.cuh"
 
 using namespace tfk;
@@ -65,7 +66,7 @@ struct tfgpu_engine {
     int sm_count = 148;
     std::vector<std::unique_ptr<PlanDev>> plans;
     // arenas
-    DevBuf in_arena, work, raw, slots, wire, csv_text, csv_stage;
+    DevBuf in_arena, work, raw, slots, wire, csv_text, csv_stage, json_msgs;
     DState* d_state = nullptr; DCol* d_cols = nullptr; size_t d_cols_cap = 0;
     int32_t* d_call_slots = nullptr; ColRegions* d_regions = nullptr; size_t d_call_cap = 0;   // columnar mode, per call
     // pointers into `work` for the last call
@@ -412,7 +413,7 @@ int tfgpu_engine_destroy(tfgpu_engine* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (auto& p : e->plans) p->consts.release();
-    e->in_arena.release(); e->work.release(); e->raw.release(); e->slots.release(); e->wire.release(); e->csv_text.release(); e->csv_stage.release(); e->json_sizes.release();
+    e->in_arena.release(); e->work.release(); e->raw.release(); e->slots.release(); e->wire.release(); e->csv_text.release(); e->csv_stage.release(); e->json_msgs.release(); e->json_sizes.release();
     if (e->d_state) cudaFree(e->d_state);
     if (e->d_cols) cudaFree(e->d_cols);
     if (e->d_call_slots) { cudaFree(e->d_call_slots); cudaFree(e->d_regions); }
@@ -723,7 +724,7 @@ int tfgpu_parse_csv(tfgpu_engine* e, int plan_id, const char* opts_json, const u
         if (nblk) {
             CK(cudaMemsetAsync(e->d_state, 0, sizeof(DState), s));
             e->prof_n = 0;
-            e->prof_begin("k_csv_count_nl", s); k_csv_count_nl<<<nblk, 256, 0, s>>>(d_text, len, blk_cnt); e->prof_end(s);
+            e->prof_begin("k_csv_count_nl", s); k_csv_count_nl<<<nblk, 256, 0, s>>>(d_text, len, blk_cnt, nullptr); e->prof_end(s);
             e->prof_begin("k_scan_blockcnt", s); k_scan_blockcnt<<<1, 1024, 0, s>>>(blk_cnt, blk_off, nblk, e->d_state); e->prof_end(s);
             DState st; CK(cudaMemcpyAsync(&st, e->d_state, sizeof st, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
             nlines = st.n_kept;
@@ -767,7 +768,7 @@ int tfgpu_parse_csv(tfgpu_engine* e, int plan_id, const char* opts_json, const u
         CK(cudaMemcpyAsync(B + o_ns, next_same.data(), nc * 2, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(B + o_blob, ho.blob.data(), ho.blob.size(), cudaMemcpyHostToDevice, s));
         std::vector<uint64_t> col_total(nslots ? nslots : 1, 0), col_base(nslots ? nslots : 1, 0);
-        if (nlines) { e->prof_begin("k_csv_line_index", s); k_csv_line_index<<<nblk, 256, 0, s>>>(d_text, len, blk_off, (uint32_t*)(B + o_line)); e->prof_end(s); }
+        if (nlines) { e->prof_begin("k_csv_line_index", s); k_csv_line_index<<<nblk, 256, 0, s>>>(d_text, len, blk_off, (uint32_t*)(B + o_line), nullptr); e->prof_end(s); }
         if (nrows) {
             CsvArgs ca{d_text, len, (const uint32_t*)(B + o_line), nlines, skip, ho.cfg, B + o_blob, (const CsvColDev*)(B + o_cols), (int)nc,
                        (const int16_t*)(B + o_fc), nfields, (const int16_t*)(B + o_ns), (uint32_t*)(B + o_ss), (uint32_t*)(B + o_sl), B + o_err};
@@ -798,6 +799,172 @@ int tfgpu_parse_csv(tfgpu_engine* e, int plan_id, const char* opts_json, const u
         if (nlines) { CK(cudaMemcpyAsync(&last_end, (uint32_t*)(B + o_line) + (nlines - 1), 4, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s)); }
         r->consumed = last_end;
         *out = r.release();
+        return TF_OK;
+    } catch (const tfplan::FatalError& f) { return fail(e, f.code, f.what()); }
+    catch (const CudaError& c) { return cuda_fail(e, c); }
+    catch (const std::bad_alloc&) { return fail(e, TF_E_RETRY_OOM, "host allocation failed"); }
+    catch (const std::exception& x) { return fail(e, TF_E_FATAL_CONFIG, x.what()); }
+}
+
+// ---------------------------------------------------------------------------------------------- JSON lines
+// parsers.Parser.DoBatch of the generic JSON parser (pkg/parsers/generic/generic_parser.go:406-430,519-555) fused with the
+// transformer chain and the sink encode: message bytes in, Transformed rows or wire bytes out.
+int tfgpu_parse_json(tfgpu_engine* e, int plan_id, const char* opts_json, const uint8_t* bytes, uint64_t len, int mem,
+                     const tf_msg* msgs, uint32_t n_msgs, int wire_fmt, tfgpu_result** out) {
+    if (!e || !out || (!bytes && len) || (!msgs && n_msgs) || plan_id < 0 || plan_id >= (int)e->plans.size()) return TF_E_FATAL_ARG;
+    *out = nullptr;
+    PlanDev& pd = *e->plans[plan_id];
+    if (len >= (1ull << 32) - 16) return fail(e, TF_E_FATAL_ARG, "json batch must be < 4 GiB (line positions are uint32)");
+    if (wire_fmt != 0 && wire_fmt != TF_WIRE_CH_NATIVE && wire_fmt != TF_WIRE_CH_NATIVE_LZ4 && wire_fmt != TF_WIRE_CH_JSONEACHROW) return fail(e, TF_E_FATAL_UNSUPPORTED, "wire format not implemented");
+    if (wire_fmt != 0 && !pd.plan.has_sink) return fail(e, TF_E_FATAL_CONFIG, "plan was built without a sink");
+    { uint64_t prev = 0; for (uint32_t m = 0; m < n_msgs; m++) { if (msgs[m].end < prev || msgs[m].end > len) return fail(e, TF_E_FATAL_ARG, "message ends must be non-decreasing and inside the buffer"); prev = msgs[m].end; }
+      if ((n_msgs ? msgs[n_msgs - 1].end : 0) != len) return fail(e, TF_E_FATAL_ARG, "the messages must cover the whole buffer"); }
+    try {
+        CK(cudaSetDevice(e->device));
+        cudaStream_t s = e->stream;
+        const tfplan::Plan& pl = pd.plan; const size_t nc = pl.in_schema.size();
+        // ---- options (AuxParserOpts, generic_parser.go:41-84)
+        bool add_rest = false, add_dedupe = false, nka = false, use_numbers = false, b64 = false; std::string partition;
+        if (opts_json && *opts_json) {
+            auto v = tfj::parse(opts_json);
+            add_rest = v->get_bool("add_rest"); add_dedupe = v->get_bool("add_dedupe_keys"); nka = v->get_bool("null_keys_allowed");
+            use_numbers = v->get_bool("use_numbers_in_any"); b64 = v->get_bool("unpack_bytes_base64"); partition = v->get_str("partition");
+            for (const char* k : {"unescape_string_values", "add_system_columns", "add_topic_column", "infer_time_zone", "ignore_column_paths", "mask_secrets"})
+                if (v->get_bool(k)) throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, std::string("json parser option not handled on the device: ") + k);
+            for (const char* k : {"time_field", "table_splitter"}) if (v->get(k) && v->get(k)->kind != tfj::Value::Null) throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, std::string("json parser option not handled on the device: ") + k);
+        }
+        const size_t naux = (add_rest ? 1 : 0) + (add_dedupe ? 4 : 0);
+        if (nc < naux || nc > JSN_MAX_COLS) throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "json parser: the result schema must hold the aux columns and at most 128 columns");
+        const size_t nf = nc - naux;
+        // ---- columns
+        std::vector<JsnColDev> hc(nc); std::vector<uint8_t> names; int nslots = 0;
+        for (size_t c = 0; c < nc; c++) {
+            const tfplan::ColSchema& cs = pl.in_schema[c]; JsnColDev& d = hc[c]; std::memset(&d, 0, sizeof d);
+            d.tf = cs.tf; d.w = in_width(cs.tf); d.slot = d.w ? -1 : nslots++; d.key = cs.key; d.required = cs.required || cs.key;      // newColSchema: a key is required (:102-113)
+            d.name_off = (uint32_t)names.size(); d.name_len = (uint32_t)cs.name.size(); names.insert(names.end(), cs.name.begin(), cs.name.end());
+            if (c < nf) {
+                switch (cs.tf) { case TF_INT8: case TF_INT16: case TF_INT32: case TF_INT64: case TF_UINT8: case TF_UINT16: case TF_UINT32: case TF_UINT64:
+                                 case TF_DOUBLE: case TF_BOOLEAN: case TF_UTF8: case TF_BYTES: case TF_ANY: case TF_DATETIME: break;
+                                 default: throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "json parser: field '" + cs.name + "' has a type the device parser does not handle (" + cs.type + ")"); }
+                if (!cs.path.empty()) throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "json parser: nested column paths are not handled on the device");
+                for (size_t k = 0; k < c; k++) if (pl.in_schema[k].name == cs.name) throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "json parser: duplicate column name " + cs.name);
+            }
+        }
+        {   // addAuxFields order and types (:115-164)
+            size_t c = nf; bool ok = true;
+            if (add_rest) ok = ok && pl.in_schema[c++].tf == TF_ANY;
+            if (add_dedupe) ok = ok && pl.in_schema[c].tf == TF_TIMESTAMP && pl.in_schema[c + 1].tf == TF_BYTES && pl.in_schema[c + 2].tf == TF_UINT64 && pl.in_schema[c + 3].tf == TF_UINT32;
+            if (!ok) throw tfplan::FatalError(TF_E_FATAL_CONFIG, "json parser: the plan schema does not end with the aux columns the options add (_rest any; _timestamp timestamp, _partition string, _offset uint64, _idx uint32)");
+        }
+        const uint32_t part_off = (uint32_t)names.size(); names.insert(names.end(), partition.begin(), partition.end());
+        // ---- text and message table into HBM
+        const uint8_t* d_text = bytes;
+        if (mem == TF_MEM_HOST) { e->csv_text.ensure(len + 64); if (len) CK(cudaMemcpyAsync(e->csv_text.p, bytes, len, cudaMemcpyHostToDevice, s)); d_text = e->csv_text.p; }
+        const uint32_t nblk = (uint32_t)((len + CSV_NL_BLOCK - 1) / CSV_NL_BLOCK);
+        const size_t bits_words = (size_t)(len / 32 + 2);
+        std::vector<uint64_t> h_end(n_msgs ? n_msgs : 1), h_off(n_msgs ? n_msgs : 1); std::vector<int64_t> h_ws(n_msgs ? n_msgs : 1); std::vector<uint32_t> h_wn(n_msgs ? n_msgs : 1);
+        for (uint32_t m = 0; m < n_msgs; m++) { h_end[m] = msgs[m].end; h_off[m] = msgs[m].offset; h_ws[m] = msgs[m].write_sec; h_wn[m] = msgs[m].write_nsec; }
+        {
+            size_t wb = 0; auto need = [&](size_t b) { size_t at = wb; wb += align_up(b ? b : 1, 256); return at; };
+            const size_t w_cnt = need(((size_t)nblk + 64) * 4), w_off = need(((size_t)nblk + 64) * 4), w_bits = need(bits_words * 4),
+                         w_end = need((size_t)n_msgs * 8), w_moff = need((size_t)n_msgs * 8), w_ws = need((size_t)n_msgs * 8), w_wn = need((size_t)n_msgs * 4), w_r0 = need((size_t)n_msgs * 4);
+            e->json_msgs.ensure(wb + 256);                       // message table + line-count scratch live here until the text heap is sized
+            uint8_t* W = e->json_msgs.p;
+            uint32_t* blk_cnt = (uint32_t*)(W + w_cnt); uint32_t* blk_off = (uint32_t*)(W + w_off); uint32_t* endbits = (uint32_t*)(W + w_bits);
+            uint64_t nlines = 0;
+            e->prof_n = 0;
+            if (nblk) {
+                CK(cudaMemsetAsync(e->d_state, 0, sizeof(DState), s));
+                CK(cudaMemsetAsync(endbits, 0, bits_words * 4, s));
+                CK(cudaMemcpyAsync(W + w_end, h_end.data(), (size_t)n_msgs * 8, cudaMemcpyHostToDevice, s)); CK(cudaMemcpyAsync(W + w_moff, h_off.data(), (size_t)n_msgs * 8, cudaMemcpyHostToDevice, s));
+                CK(cudaMemcpyAsync(W + w_ws, h_ws.data(), (size_t)n_msgs * 8, cudaMemcpyHostToDevice, s)); CK(cudaMemcpyAsync(W + w_wn, h_wn.data(), (size_t)n_msgs * 4, cudaMemcpyHostToDevice, s));
+                e->prof_begin("k_json_mark_msgs", s); k_json_mark_msgs<<<(n_msgs + 255) / 256, 256, 0, s>>>((const uint64_t*)(W + w_end), n_msgs, endbits); e->prof_end(s);
+                e->prof_begin("k_csv_count_nl", s); k_csv_count_nl<<<nblk, 256, 0, s>>>(d_text, len, blk_cnt, endbits); e->prof_end(s);
+                e->prof_begin("k_scan_blockcnt", s); k_scan_blockcnt<<<1, 1024, 0, s>>>(blk_cnt, blk_off, nblk, e->d_state); e->prof_end(s);
+                DState st; CK(cudaMemcpyAsync(&st, e->d_state, sizeof st, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+                nlines = st.n_kept;
+            }
+            const uint64_t nrows = nlines;
+            // ---- staging layout (csv_stage arena)
+            size_t sb = 0; auto sneed = [&](size_t b) { size_t at = sb; sb += align_up(b ? b : 1, 256); return at; };
+            const uint32_t nlb = (uint32_t)((nlines + 127) / 128);
+            const size_t o_line = sneed((nlines + 1) * 4), o_rank = sneed((nlines + 2) * 4), o_lcnt = sneed(((size_t)nlb + 64) * 4), o_loff = sneed(((size_t)nlb + 64) * 4),
+                         o_err = sneed(nrows), o_ecol = sneed(nrows), o_cols = sneed(nc * sizeof(JsnColDev)), o_names = sneed(names.size()),
+                         o_ss = sneed((size_t)nf * nrows * 4), o_sl = sneed((size_t)nf * nrows * 4), o_len = sneed((size_t)nslots * nrows * 4),
+                         o_off = sneed((size_t)nslots * (nrows + 1) * 4), o_tot = sneed((size_t)nslots * 8 + 8), o_base = sneed((size_t)nslots * 8 + 8);
+            std::vector<size_t> o_val(nc), o_aux(nc), o_vld(nc);
+            for (size_t c = 0; c < nc; c++) {
+                o_val[c] = hc[c].w ? sneed((size_t)hc[c].w * nrows) : 0;
+                const int tf = hc[c].tf;
+                o_aux[c] = (tf == TF_DATE || tf == TF_DATETIME || tf == TF_TIMESTAMP) ? sneed(4 * nrows) : (tf == TF_ANY ? sneed(nrows) : 0);
+                o_vld[c] = sneed((nrows / 32 + 2) * 4);
+            }
+            e->csv_stage.ensure(sb + 256);
+            uint8_t* B = e->csv_stage.p;
+            for (size_t c = 0; c < nc; c++) {
+                if (hc[c].w) hc[c].values = B + o_val[c];
+                const int tf = hc[c].tf;
+                if (tf == TF_DATE || tf == TF_DATETIME || tf == TF_TIMESTAMP) hc[c].aux32 = (uint32_t*)(B + o_aux[c]);
+                if (tf == TF_ANY) hc[c].aux8 = B + o_aux[c];
+                hc[c].validity = (uint32_t*)(B + o_vld[c]);
+            }
+            std::vector<uint64_t> col_total(nslots ? nslots : 1, 0), col_base(nslots ? nslots : 1, 0);
+            uint32_t n_nonempty = 0;
+            const uint8_t* heap = nullptr;
+            if (nrows) {
+                CK(cudaMemcpyAsync(B + o_cols, hc.data(), nc * sizeof(JsnColDev), cudaMemcpyHostToDevice, s));
+                CK(cudaMemcpyAsync(B + o_names, names.data(), names.size(), cudaMemcpyHostToDevice, s));
+                CK(cudaMemsetAsync(B + o_sl, 0, (size_t)nf * nrows * 4, s));
+                e->prof_begin("k_csv_line_index", s); k_csv_line_index<<<nblk, 256, 0, s>>>(d_text, len, blk_off, (uint32_t*)(B + o_line), endbits); e->prof_end(s);
+                e->prof_begin("k_json_count_nonempty", s); k_json_count_nonempty<<<nlb, 128, 0, s>>>(d_text, (const uint32_t*)(B + o_line), nlines, (uint32_t*)(B + o_lcnt)); e->prof_end(s);
+                e->prof_begin("k_scan_blockcnt", s); k_scan_blockcnt<<<1, 1024, 0, s>>>((const uint32_t*)(B + o_lcnt), (uint32_t*)(B + o_loff), nlb, e->d_state); e->prof_end(s);
+                e->prof_begin("k_json_rank", s); k_json_rank<<<nlb, 128, 0, s>>>(d_text, (const uint32_t*)(B + o_line), nlines, (const uint32_t*)(B + o_loff), (uint32_t*)(B + o_rank)); e->prof_end(s);
+                e->prof_begin("k_json_msg_first", s); k_json_msg_first<<<(n_msgs + 255) / 256, 256, 0, s>>>((const uint64_t*)(W + w_end), n_msgs, (const uint32_t*)(B + o_line), nlines, (const uint32_t*)(B + o_rank), (uint32_t*)(W + w_r0)); e->prof_end(s);
+                JsnArgs ja; std::memset(&ja, 0, sizeof ja);
+                ja.text = d_text; ja.len = len; ja.line_end = (const uint32_t*)(B + o_line); ja.nlines = nlines;
+                ja.msg_end = (const uint64_t*)(W + w_end); ja.msg_offset = (const uint64_t*)(W + w_moff); ja.msg_wsec = (const int64_t*)(W + w_ws); ja.msg_wnsec = (const uint32_t*)(W + w_wn); ja.nmsgs = n_msgs;
+                ja.rank = (const uint32_t*)(B + o_rank); ja.msg_rank0 = (const uint32_t*)(W + w_r0);
+                ja.cols = (const JsnColDev*)(B + o_cols); ja.ncols = (int)nc; ja.nfields = (int)nf; ja.names = B + o_names;
+                ja.add_rest = add_rest; ja.add_dedupe = add_dedupe; ja.null_keys_allowed = nka; ja.use_numbers = use_numbers; ja.unpack_b64 = b64;
+                ja.part_off = part_off; ja.part_len = (uint32_t)partition.size();
+                ja.span_start = (uint32_t*)(B + o_ss); ja.span_len = (uint32_t*)(B + o_sl); ja.out_len = (uint32_t*)(B + o_len);
+                ja.err = B + o_err; ja.errcol = B + o_ecol;
+                e->prof_begin("k_json_pass1", s); k_json_pass1<<<nlb, 128, 0, s>>>(ja); e->prof_end(s);
+                CK(cudaMemcpyAsync(&n_nonempty, (uint32_t*)(B + o_rank) + nlines, 4, cudaMemcpyDeviceToHost, s));
+                if (nslots) {
+                    e->prof_begin("k_csv_offsets", s); k_csv_offsets<<<nslots, 1024, 0, s>>>((const uint32_t*)(B + o_len), nrows, (uint32_t*)(B + o_off), (uint64_t*)(B + o_tot)); e->prof_end(s);
+                    CK(cudaMemcpyAsync(col_total.data(), B + o_tot, (size_t)nslots * 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+                    uint64_t run = 0; for (int k = 0; k < nslots; k++) { col_base[k] = run; run += align_up(col_total[k], 16); }
+                    if (run >= (1ull << 32)) throw tfplan::FatalError(TF_E_FATAL_ARG, "json batch: a text column exceeds 4 GiB");
+                    e->in_arena.ensure(run + 256);               // text heaps (the staged batch is device resident, in_arena is free)
+                    heap = e->in_arena.p;
+                    CK(cudaMemcpyAsync(B + o_base, col_base.data(), (size_t)nslots * 8, cudaMemcpyHostToDevice, s));
+                    JsnWriteArgs wa{ja, (const uint32_t*)(B + o_off), e->in_arena.p, (const uint64_t*)(B + o_base)};
+                    e->prof_begin("k_json_pass2", s); k_json_pass2<<<nlb, 128, 0, s>>>(wa); e->prof_end(s);
+                } else CK(cudaStreamSynchronize(s));
+            }
+            // ---- the staged batch, device resident
+            std::vector<tf_col> dev(nc);
+            for (size_t c = 0; c < nc; c++) {
+                tf_col& d = dev[c]; std::memset(&d, 0, sizeof d); d.type = hc[c].tf; d.validity = (const uint8_t*)hc[c].validity;
+                if (hc[c].w) { d.values = hc[c].values; d.aux = hc[c].aux32; }
+                else { d.offsets = (const uint32_t*)(B + o_off) + (size_t)hc[c].slot * (nrows + 1); d.heap = heap ? heap + col_base[hc[c].slot] : nullptr; d.heap_len = col_total[hc[c].slot]; d.aux = hc[c].aux8; }
+            }
+            tf_batch staged; staged.nrows = nrows; staged.ncols = (uint32_t)nc; staged.mem = TF_MEM_DEVICE; staged.cols = dev.data(); staged.kinds = nullptr;
+            run_chain(e, pd, &staged, dev.data(), nullptr, wire_fmt == 0 ? TF_WIRE_COLUMNAR_INTERNAL : wire_fmt, nrows ? B + o_err : nullptr);
+            auto r = std::make_unique<tfgpu_result>();
+            if (wire_fmt == 0) finish_columnar(e, pd, nrows, r.get()); else finish_wire(e, nrows, wire_fmt, r.get());
+            // row errors: row = index among the NON-EMPTY lines (empty lines are not lines to the reference, :528-530), term = column
+            if (!r->errs.empty()) {
+                std::vector<uint8_t> ecol(nrows); CK(cudaMemcpyAsync(ecol.data(), B + o_ecol, nrows, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+                std::vector<tf_rowerr> keep; uint32_t empties = 0;
+                for (auto& x : r->errs) { if (x.code == JSN_EMPTY) { empties++; continue; } tf_rowerr y = x; if (y.term == 0xff) y.term = ecol[x.row]; y.row = x.row - empties; keep.push_back(y); }
+                r->errs.swap(keep);
+            }
+            r->rows_in = n_nonempty;
+            r->consumed = len;
+            *out = r.release();
+        }
         return TF_OK;
     } catch (const tfplan::FatalError& f) { return fail(e, f.code, f.what()); }
     catch (const CudaError& c) { return cuda_fail(e, c); }

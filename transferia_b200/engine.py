@@ -58,6 +58,7 @@ def load_library():
     L.tfgpu_push_columns.argtypes = [vp, i, C.POINTER(abi.TfBatch), C.POINTER(vp)]
     L.tfgpu_push_encode.argtypes = [vp, i, i, C.POINTER(abi.TfBatch), C.POINTER(vp)]
     L.tfgpu_parse_csv.argtypes = [vp, i, cp, vp, u64, i, i, C.POINTER(vp)]
+    L.tfgpu_parse_json.argtypes = [vp, i, cp, vp, u64, i, C.POINTER(abi.TfMsg), C.c_uint32, i, C.POINTER(vp)]
     L.tfgpu_result_consumed.argtypes = [vp]; L.tfgpu_result_consumed.restype = u64
     L.tfgpu_push_encode_resident.argtypes = [vp, i, i, C.POINTER(abi.TfBatch)]
     L.tfgpu_resident_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
@@ -77,12 +78,32 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "tfgpu_version", "tfgpu_engine_create", "tfgpu_engine_destroy", "tfgpu_last_error", "tfgpu_engine_set_stream",
-    "tfgpu_plan", "tfgpu_plan_validate", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_parse_csv", "tfgpu_result_consumed", "tfgpu_push_encode_resident",
+    "tfgpu_plan", "tfgpu_plan_validate", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_parse_csv", "tfgpu_parse_json", "tfgpu_result_consumed", "tfgpu_push_encode_resident",
     "tfgpu_resident_stats", "tfgpu_resident_fetch", "tfgpu_result_rows_in", "tfgpu_result_rows_out",
     "tfgpu_result_n_errors", "tfgpu_result_errors", "tfgpu_result_batch", "tfgpu_result_bytes",
     "tfgpu_result_bytes_len", "tfgpu_result_raw_len", "tfgpu_result_n_frames", "tfgpu_result_release",
     "tfgpu_engine_launch_count", "tfgpu_profile_enable", "tfgpu_profile_read",
 ]
+
+
+def json_result_schema(fields, opts: Optional[dict] = None):
+    """The generic parser's result schema for declared `fields` (addAuxFields, pkg/parsers/generic/generic_parser.go:115-164):
+    `_rest` when add_rest, then _timestamp/_partition/_offset/_idx when add_dedupe_keys (system keys unless
+    mark_dedupe_keys_as_system and a declared field is a key); a name already taken gets the `_delivery_` prefix (:93-100)."""
+    opts = opts or {}
+    out = [dict(f, required=bool(f.get("required") or f.get("key"))) for f in fields]
+
+    def dedup(name):
+        while any(c["name"] == name for c in out):
+            name = "_delivery_" + name
+        return name
+    if opts.get("add_rest"):
+        out.append({"name": dedup("_rest"), "type": "any"})
+    if opts.get("add_dedupe_keys"):
+        sys_key = not (opts.get("mark_dedupe_keys_as_system") and any(f.get("key") for f in fields))
+        for n, t in (("_timestamp", "timestamp"), ("_partition", "string"), ("_offset", "uint64"), ("_idx", "uint32")):
+            out.append({"name": dedup(n), "type": t, "key": sys_key, "required": sys_key})
+    return out
 
 
 def plan_validate(namespace: str, name: str, schema, transformers=None, sink=None) -> dict:
@@ -222,6 +243,29 @@ class Engine:
             out = PushResult(L.tfgpu_result_rows_in(res), L.tfgpu_result_rows_out(res), L.tfgpu_result_raw_len(res), L.tfgpu_result_n_frames(res),
                              C.string_at(L.tfgpu_result_bytes(res), n) if n else b"", [(ep[k].row, ep[k].code, ep[k].term) for k in range(ne)])
             return out, consumed
+        finally:
+            self._L.tfgpu_result_release(res)
+
+    def parse_json(self, plan_id: int, data: bytes, opts: Optional[dict] = None, msgs: Optional[list] = None, wire_fmt: int = 0):
+        """JSON-lines messages -> typed columns of the parser's result schema -> the plan's transformer chain, on the device.
+        msgs: [(end, offset, write_sec, write_nsec)] (default: one message = all of `data`).
+        wire_fmt 0: (Batch, row errors, non-empty lines); otherwise PushResult."""
+        msgs = msgs if msgs is not None else [(len(data), 0, 0, 0)]
+        ms = (abi.TfMsg * max(1, len(msgs)))()
+        for k, (end, off, ws, wn) in enumerate(msgs):
+            ms[k].end, ms[k].offset, ms[k].write_sec, ms[k].write_nsec = end, off, ws, wn
+        buf = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data or b"\0")
+        res = C.c_void_p()
+        self._check(self._L.tfgpu_parse_json(self._h, plan_id, json.dumps(opts or {}).encode(), buf, len(data), abi.TF_MEM_HOST, ms, len(msgs), wire_fmt, C.byref(res)))
+        try:
+            L = self._L
+            if wire_fmt == 0:
+                b, errs = self._result_batch(res)
+                return b, errs, int(L.tfgpu_result_rows_in(res))
+            n = L.tfgpu_result_bytes_len(res)
+            ne = L.tfgpu_result_n_errors(res); ep = L.tfgpu_result_errors(res)
+            return PushResult(L.tfgpu_result_rows_in(res), L.tfgpu_result_rows_out(res), L.tfgpu_result_raw_len(res), L.tfgpu_result_n_frames(res),
+                              C.string_at(L.tfgpu_result_bytes(res), n) if n else b"", [(ep[k].row, ep[k].code, ep[k].term) for k in range(ne)])
         finally:
             self._L.tfgpu_result_release(res)
 

@@ -183,3 +183,31 @@ def headline_transformers(k: int) -> List[dict]:
     """BASELINE.json configs[2]: cast + filter_rows (1 int term AND 1 string `~` term)."""
     return [{"filter_rows": {"tables": {"includeTables": ["^public\\.hits$"]},
                              "filter": f"counterid > {k} AND url ~ '://'"}}]
+
+
+# ----------------------------------------------------------------------------------------------- JSON lines (BASELINE configs[1])
+JSON_FIELDS = [
+    {"name": "id", "type": "int64", "key": True}, {"name": "ts", "type": "datetime"}, {"name": "user", "type": "utf8"}, {"name": "url", "type": "utf8"},
+    {"name": "score", "type": "double"}, {"name": "ok", "type": "boolean"}, {"name": "cnt", "type": "uint32"}, {"name": "tags", "type": "any"},
+]
+
+
+def make_json_lines(nlines: int, seed: int = SEED + 1) -> Tuple[bytes, List[dict]]:
+    """~160-byte JSON lines with 8 declared fields (plus one undeclared key every 16th line, a
+    null every 11th, an escaped string every 13th), newline-terminated, as a queue producer would write them."""
+    rng = np.random.default_rng(seed)
+    ids = rng.integers(1, 1 << 53, nlines); ts = rng.integers(1_372_636_800, 1_375_315_200, nlines)
+    users = [f"user_{int(x):06d}" for x in rng.integers(0, 200_000, nlines)]
+    hosts = ["example.com", "yandex.ru", "news.site.org", "shop.example.net", "пример.рф"]
+    hsel = rng.integers(0, len(hosts), nlines); paths = rng.integers(0, 1 << 30, nlines)
+    score = np.round(rng.random(nlines) * 1000, 6); okv = rng.random(nlines) < 0.5; cnt = rng.integers(0, 100_000, nlines)
+    tagsel = rng.integers(0, 4, nlines)
+    tags = ['["a","b"]', '{"k":1,"j":[1,2]}', '[]', '{"z":"q","a":null}']
+    out = []
+    for i in range(nlines):
+        u = users[i] if i % 13 else "us\\\"er\\n\\u00e9_" + users[i]
+        t = "null" if i % 11 == 0 else tags[tagsel[i]]
+        extra = ',"trace":"%08x"' % paths[i] if i % 16 == 0 else ""
+        out.append('{"id":%d,"ts":%d,"user":"%s","url":"https://%s/p/%d?ref=%d","score":%r,"ok":%s,"cnt":%d,"tags":%s%s}'
+                   % (ids[i], ts[i], u, hosts[hsel[i]], paths[i], cnt[i], float(score[i]), "true" if okv[i] else "false", cnt[i], t, extra))
+    return ("\n".join(out) + "\n").encode("utf-8"), [dict(f) for f in JSON_FIELDS]
