@@ -160,6 +160,44 @@ def cpu_port_rate(batch, schema, transformers, frame_bytes, budget_s: float, thr
     return sum(done) / el, sum(done), el
 
 
+def extra_paths(eng, args):
+    """Secondary §8 paths, measured end to end through the public call with HOST bytes (not the headline metric):
+    BASELINE configs[1] JSON lines -> parse -> mask_field -> ClickHouse JSONEachRow / native+LZ4, and the batch serializers."""
+    import torch
+    from transferia_b200 import abi, engine, workload
+    sys.path.insert(0, ROOT)
+    res = {}
+    cache = f"/tmp/tf_json_lines_{args.json_lines}.bin"
+    if os.path.exists(cache):
+        text = open(cache, "rb").read(); fields = [dict(f) for f in workload.JSON_FIELDS]
+    else:
+        text, fields = workload.make_json_lines(args.json_lines)
+        open(cache, "wb").write(text)
+    opts = {"add_rest": True, "add_dedupe_keys": True, "partition": '{"partition":0,"topic":"events"}'}
+    schema = engine.json_result_schema(fields, opts)
+    trs = [{"mask_field": {"columns": ["user"], "maskFunctionHash": {"userDefinedSalt": "pepper"}}}]
+    pid = eng.plan("", "events", schema, trs, {"type": "clickhouse"})
+    n = text.count(b"\n")
+    for name, fmt in (("json_parse_mask_ch_jsoneachrow", abi.TF_WIRE_CH_JSONEACHROW), ("json_parse_mask_ch_native_lz4", abi.TF_WIRE_CH_NATIVE_LZ4)):
+        for _ in range(2):
+            r = eng.parse_json(pid, text, opts, None, wire_fmt=fmt)
+        torch.cuda.synchronize(); t0 = time.perf_counter(); k = 5
+        for _ in range(k):
+            r = eng.parse_json(pid, text, opts, None, wire_fmt=fmt)
+        torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / k
+        eng.profile_enable(True); eng.parse_json(pid, text, opts, None, wire_fmt=fmt); prof = {kk["name"]: round(kk["ms"], 4) for kk in eng.profile_read()}; eng.profile_enable(False)
+        res[name] = {"rows_per_s": n / dt, "lines": n, "input_MB": len(text) / 1e6, "ms": dt * 1e3, "rows_out": r.rows_out, "out_bytes": len(r.wire), "kernels_ms": prof,
+                     "note": "wall clock around the public call incl. H2D of the message bytes and D2H of the wire bytes (ctypes copy of the input included)"}
+    try:
+        from oracle import pyoracle as po
+        sample = text[: text.rfind(b"\n", 0, len(text) // 20) + 1]
+        t0 = time.perf_counter(); b, _, _ = po.json_parse(sample, fields, opts); po.push_encode(b, po.build_plan("", "events", schema, trs), abi.TF_WIRE_CH_JSONEACHROW); dt = time.perf_counter() - t0
+        res["json_parse_mask_ch_jsoneachrow"]["cpu_port_rows_per_s_1core"] = sample.count(b"\n") / dt
+    except Exception as ex:  # the oracle is optional here
+        res["cpu_port_error"] = str(ex)
+    return res
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm for this path (oracle port) on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -201,6 +239,8 @@ def main():
     ap.add_argument("--frame-bytes", type=int, default=32768)
     ap.add_argument("--impl", default="tfgpu")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary paths (JSON-lines parse, serializers)")
+    ap.add_argument("--json-lines", type=int, default=400_000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -328,6 +368,8 @@ def main():
                          "kernel_share_of_step": lz_ms / step_ms if step_ms else None,
                          "all_kernels_ms": {n: round(v, 4) for n, v in sorted(kernel_avg.items())}},
         }
+        if world == 1 and not args.no_extra:
+            out["other_paths"] = extra_paths(eng, args)
         if world == 1:
             cores = os.cpu_count() or 1
             v, rows_done, el = cpu_port_rate(batch, schema, trs, args.frame_bytes, args.cpu_budget, cores)

@@ -111,7 +111,7 @@ std::string go_sprint_v(const orc_val& v) {
     case OG_DURATION: return fmt_duration(v.i);
     case OG_TIME: {    // time.Time.String(): "2006-01-02 15:04:05.999999999 -0700 MST" (UTC)
         std::string r = fmt_rfc3339nano_utc(v.i, v.nsec);
-        r[10] = ' '; r.pop_back(); return r + " +0000 UTC";
+        r[r.find('T')] = ' '; r.pop_back(); return r + " +0000 UTC";
     }
     }
     return "";
@@ -383,7 +383,7 @@ void json_each_row_value(std::string& o, const orc_val& v, int32_t yt_result, co
     };
     switch (v.kind) {
     case OG_TIME: {                                                  // marshalTime :63-78
-        if (is_string) { std::string r = fmt_rfc3339nano_utc(v.i, v.nsec); r[10] = ' '; r.pop_back(); o += '"' + r + " +0000 UTC\""; }
+        if (is_string) { std::string r = fmt_rfc3339nano_utc(v.i, v.nsec); r[r.find('T')] = ' '; r.pop_back(); o += '"' + r + " +0000 UTC\""; }
         else if (ch_base.rfind("DateTime64", 0) == 0) {
             const int prec = std::atoi(ch_base.c_str() + 11);
             int64_t full = v.i * 1000000000LL + (int64_t)v.nsec;     // UnixNano
@@ -494,7 +494,7 @@ std::string ser_csv_cell(const orc_val& v, int32_t yt) {
     case OG_STRING: if (yt == TF_ANY) return go_json_quote(v.s, v.slen);        // csv_format.go:109-116 json.Marshal(value)
                     return std::string((const char*)v.s, v.slen);
     case OG_BYTES: return base64_std(v.s, v.slen);
-    case OG_TIME: { std::string r = fmt_rfc3339nano_utc(v.i, v.nsec); r[10] = ' '; r.pop_back(); return r + " +0000 UTC"; }    // castx.ToStringE -> fmt.Stringer -> Time.String()
+    case OG_TIME: { std::string r = fmt_rfc3339nano_utc(v.i, v.nsec); r[r.find('T')] = ' '; r.pop_back(); return r + " +0000 UTC"; }    // castx.ToStringE -> fmt.Stringer -> Time.String()
     case OG_DURATION: return fmt_duration(v.i);
     case OG_JSON: return std::string((const char*)v.s, v.slen);
     }
@@ -815,7 +815,7 @@ int orc_json_parse(const uint8_t* buf, uint64_t len, const orc_json_msg* msgs, u
         oc.valid.resize((R.rows + 7) / 8, 0);
         g.validity = R.rows ? put(oc.valid.data(), oc.valid.size()) : ~0ull;
         const bool has_aux = types[c] == TF_ANY || types[c] == TF_DATE || types[c] == TF_DATETIME || types[c] == TF_TIMESTAMP;
-        g.aux = has_aux ? put(oc.aux.data(), oc.aux.size()) : ~0ull;
+        g.aux = has_aux && R.rows ? put(oc.aux.data(), oc.aux.size()) : ~0ull;
         g.offsets = w ? ~0ull : put(oc.offs.data(), oc.offs.size() * 4);
         g.heap = w ? ~0ull : put(oc.heap.data(), oc.heap.size());
         g.heap_len = w ? 0 : oc.heap.size();

@@ -90,3 +90,40 @@ def test_oracle_serializer_forms(po):
     nan = abi.Batch(1, [abi.fixed_to_column(abi.TF_DOUBLE, [float("nan")])])
     r = po.push_encode(nan, po.build_plan("s", "t", [{"name": "d", "type": "double"}], []), SER_JSON)
     assert r.errors == [(0, 40, 0)]
+
+
+# ----------------------------------------------------------------------------------------------------------- GPU parity
+def _ser_cases():
+    from test_gpu_parity import all_types_batch
+    return all_types_batch
+
+
+@pytest.mark.gpu
+def test_device_serializers_equal_oracle(eng, po):
+    """JSON / CSV batch serializers on the device == oracle: the canon fixtures, the all-types batch with nulls, after transformers."""
+    fmts = (SER_JSON, SER_JSON | F_NL, SER_JSON | F_AAS, SER_JSON | F_NL | F_AAS, SER_CSV)
+    for case in G["cases"]:
+        b = case_batch(case)
+        pid = eng.plan("s", "t", case["schema"], []); plan = po.build_plan("s", "t", case["schema"], [])
+        for fmt in fmts:
+            got = eng.push_encode(pid, b, fmt); want = po.push_encode(b, plan, fmt)
+            assert got.wire == want.wire and got.errors == want.errors, (case["source"], fmt)
+    batch, schema = _ser_cases()(4000, seed=9)
+    chains = [[], [{"filter_rows": {"filter": "c_int32 > 0"}}, {"mask_field": {"columns": ["c_utf8", "n_int64"], "maskFunctionHash": {"userDefinedSalt": "s"}}}],
+              [{"convert_to_string": {"columns": {"includeColumns": ["c_int16", "c_double", "c_timestamp", "c_utf8", "n_utf8"]}}}],
+              [{"convert_to_string": {"columns": {"includeColumns": ["c_int32", "c_utf8"]}, "convertToBytes": True}}]]
+    for trs in chains:
+        pid = eng.plan("db", "t", schema, trs); plan = po.build_plan("db", "t", schema, trs)
+        for fmt in fmts:
+            got = eng.push_encode(pid, batch, fmt); want = po.push_encode(batch, plan, fmt)
+            assert got.rows_out == want.rows_out and got.errors == want.errors, (trs, fmt)
+            assert got.wire == want.wire, (trs, fmt)
+    # special values: NaN / Inf are row errors for JSON, text for CSV; quoting corner cases
+    sch = [{"name": "d", "type": "double"}, {"name": "f", "type": "float"}, {"name": "s", "type": "utf8"}, {"name": "t", "type": "timestamp"}]
+    sb = abi.Batch(6, [abi.fixed_to_column(abi.TF_DOUBLE, [float("nan"), float("inf"), 1e300, -0.0, 5e-324, 1.0]), abi.fixed_to_column(abi.TF_FLOAT, [1.5, float("-inf"), 3.4e38, 1e-7, 1e21, 0.0]),
+                       abi.strings_to_column(abi.TF_UTF8, [b"\\.", b"\xc2\xa0nbsp", b"", b"cr\rlf", b'q"q', b"\xff\xfe<&>\xe2\x80\xa8"]),
+                       abi.fixed_to_column(abi.TF_TIMESTAMP, [0, 253402300800, -62167219201, 1, 2, 3], None, [0, 0, 0, 999999999, 1000, 0])])
+    pid = eng.plan("db", "t", sch, []); plan = po.build_plan("db", "t", sch, [])
+    for fmt in fmts:
+        got = eng.push_encode(pid, sb, fmt); want = po.push_encode(sb, plan, fmt)
+        assert got.errors == want.errors and got.wire == want.wire, fmt

@@ -193,14 +193,14 @@ template <typename Sink> __device__ void fmt_duration(Sink& s, int64_t d) {
 }
 
 // encoding/json string encoder, escapeHTML = true (json.Marshal of a Go string inside an `any` column)
-template <typename Sink> __device__ void fmt_json_string(Sink& s, const uint8_t* p, uint32_t n) {
+template <typename Sink> __device__ void fmt_json_string(Sink& s, const uint8_t* p, uint32_t n, bool html = true) {
     const char* hex = "0123456789abcdef";
     s.put('"');
     uint32_t i = 0;
     while (i < n) {
         const uint8_t b = p[i];
         if (b < 0x80) {
-            if (b >= 0x20 && b != '"' && b != '\\' && b != '<' && b != '>' && b != '&') { s.put(b); i++; continue; }
+            if (b >= 0x20 && b != '"' && b != '\\' && (!html || (b != '<' && b != '>' && b != '&'))) { s.put(b); i++; continue; }
             s.put('\\');
             switch (b) {
             case '\\': case '"': s.put(b); break;

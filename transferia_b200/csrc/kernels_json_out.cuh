@@ -9,6 +9,7 @@
 #include "kernels_encode.cuh"
 #include "kernels_fmt.cuh"
 #include "kernels_mask.cuh"
+#include "kernels_csv.cuh"
 
 namespace tfk {
 
@@ -108,10 +109,177 @@ template <typename Sink> __device__ void json_row(Sink& s, const DCol* cols, con
     s.put('}'); s.put('\n');
 }
 
+
+// ------------------------------------------------------------------ batch serializers (pkg/serializer)
+//   JSON: json.go:29-114 buildJsonKV + json.Encoder(SetEscapeHTML(false)) over a map (keys sorted: the host orders jcols and
+//         pre-quotes `"name":`), values per json_format.go:32-82 on the canonical (strictified) Go type of the result schema
+//   CSV:  csv.go:22-74 + csv_format.go:32-144 cells through encoding/csv (Comma ',', UseCRLF false)
+// sink flags
+#define TF_SER_NL 1u        /* AddClosingNewLine */
+#define TF_SER_AAS 2u       /* AnyAsString */
+
+template <typename Inner> struct B64Sink {       // base64.StdEncoding over a byte stream
+    Inner* in; uint32_t acc; int n;
+    __device__ __forceinline__ static uint8_t a(uint32_t v) { return (uint8_t)(v < 26 ? 'A' + v : v < 52 ? 'a' + v - 26 : v < 62 ? '0' + v - 52 : v == 62 ? '+' : '/'); }
+    __device__ __forceinline__ void put(uint8_t b) { acc = (acc << 8) | b; if (++n == 3) { in->put(a(acc >> 18)); in->put(a((acc >> 12) & 63)); in->put(a((acc >> 6) & 63)); in->put(a(acc & 63)); acc = 0; n = 0; } }
+    __device__ __forceinline__ void finish() {
+        if (n == 1) { acc <<= 16; in->put(a(acc >> 18)); in->put(a((acc >> 12) & 63)); in->put('='); in->put('='); }
+        else if (n == 2) { acc <<= 8; in->put(a(acc >> 18)); in->put(a((acc >> 12) & 63)); in->put(a((acc >> 6) & 63)); in->put('='); }
+    }
+};
+template <typename Inner> struct CsvQuoteSink { Inner* in; __device__ __forceinline__ void put(uint8_t b) { if (b == '"') in->put('"'); in->put(b); } };
+
+template <typename Sink> __device__ void ser_time_string(Sink& s, int64_t sec, uint32_t nsec) {     // Time.String() in UTC
+    int64_t days = sec / 86400; int64_t sod = sec - days * 86400; if (sod < 0) { sod += 86400; days--; }
+    int64_t y; unsigned m, d; civil_from_days_d(days, y, m, d);
+    fmt_pad(s, y, 4); s.put('-'); fmt_pad(s, m, 2); s.put('-'); fmt_pad(s, d, 2); s.put(' ');
+    fmt_pad(s, sod / 3600, 2); s.put(':'); fmt_pad(s, (sod / 60) % 60, 2); s.put(':'); fmt_pad(s, sod % 60, 2);
+    if (nsec) { char b[9]; uint32_t v = nsec; for (int i = 8; i >= 0; i--) { b[i] = (char)('0' + v % 10); v /= 10; } int n = 9; while (n > 0 && b[n - 1] == '0') n--; s.put('.'); for (int i = 0; i < n; i++) s.put((uint8_t)b[i]); }
+    fmt_lit(s, " +0000 UTC");
+}
+// JSON text written by json.Marshal (HTML escaping on) as a SetEscapeHTML(false) encoder writes the same value
+template <typename Sink> __device__ void ser_unescape_html(Sink& s, const uint8_t* p, uint32_t n) {
+    bool ins = false;
+    for (uint32_t i = 0; i < n;) {
+        const uint8_t c = p[i];
+        if (!ins) { if (c == '"') ins = true; s.put(c); i++; continue; }
+        if (c == '\\' && i + 1 < n) {
+            if (p[i + 1] == 'u' && i + 5 < n && p[i + 2] == '0' && p[i + 3] == '0' && ((p[i + 4] == '3' && (p[i + 5] == 'c' || p[i + 5] == 'e')) || (p[i + 4] == '2' && p[i + 5] == '6'))) {
+                s.put(p[i + 4] == '2' ? '&' : p[i + 5] == 'c' ? '<' : '>'); i += 6; continue;
+            }
+            s.put(c); s.put(p[i + 1]); i += 2; continue;
+        }
+        if (c == '"') ins = false;
+        s.put(c); i++;
+    }
+}
+
+// one JSON value; false = encoding/json would fail (NaN / Inf, year outside [0, 9999]) and `null` stands in
+template <typename Sink> __device__ bool ser_json_value(Sink& s, const DCol& c, uint64_t r, const JsonCol& jc, const MaskKey* keys, bool sizing, uint32_t flags) {
+    if (c.out_kind == OK_MASK) {
+        s.put('"');
+        if (sizing) { for (int i = 0; i < 64; i++) s.put('0'); }
+        else { uint8_t hx[64]; mask_digest_hex(c, r, keys[c.mask_slot], hx); for (int i = 0; i < 64; i++) s.put(hx[i]); }
+        s.put('"'); return true;
+    }
+    if (c.out_kind == OK_TOSTR) {                 // text of the value: a Go string (utf8) or []byte (string) cell
+        s.put('"');
+        if (jc.result_tf == TF_BYTES) { B64Sink<Sink> b{&s, 0, 0}; fmt_value(b, c, r); b.finish(); }
+        else fmt_value(s, c, r);                  // numbers, times, "<nil>": ASCII (text cells are written by ser_json_row)
+        s.put('"'); return true;
+    }
+    if (c.out_kind == OK_TODT) {
+        int64_t sec = 0; if (row_valid(c, r)) sec = c.type == TF_INT32 ? (int64_t)((const int32_t*)c.values)[r] : (int64_t)((const uint32_t*)c.values)[r];
+        s.put('"'); fmt_time(s, sec, 0, false); s.put('"'); return true;
+    }
+    if (!row_valid(c, r)) { fmt_lit(s, "null"); return true; }
+    switch (c.type) {
+    case TF_INT8: fmt_i64(s, ((const int8_t*)c.values)[r]); break;
+    case TF_INT16: fmt_i64(s, ((const int16_t*)c.values)[r]); break;
+    case TF_INT32: fmt_i64(s, ((const int32_t*)c.values)[r]); break;
+    case TF_INT64: case TF_INTERVAL: fmt_i64(s, ((const int64_t*)c.values)[r]); break;
+    case TF_UINT8: fmt_u64(s, c.values[r]); break;
+    case TF_UINT16: fmt_u64(s, ((const uint16_t*)c.values)[r]); break;
+    case TF_UINT32: fmt_u64(s, ((const uint32_t*)c.values)[r]); break;
+    case TF_UINT64: fmt_u64(s, ((const uint64_t*)c.values)[r]); break;
+    case TF_FLOAT: { const uint32_t b = ((const uint32_t*)c.values)[r]; if ((b & 0x7F800000u) == 0x7F800000u) { fmt_lit(s, "null"); return false; } fmt_float_bits(s, b, true, FM_JSON); break; }
+    case TF_DOUBLE: { const uint64_t b = ((const uint64_t*)c.values)[r]; if ((b & 0x7FF0000000000000ull) == 0x7FF0000000000000ull) { fmt_lit(s, "null"); return false; } fmt_float_bits(s, b, false, FM_F); break; }
+    case TF_BOOLEAN: fmt_lit(s, c.values[r] ? "true" : "false"); break;
+    case TF_DATE: case TF_DATETIME: case TF_TIMESTAMP: {
+        const int64_t sec = ((const int64_t*)c.values)[r];
+        if (sec < -62167219200LL || sec >= 253402300800LL) { fmt_lit(s, "null"); return false; }
+        s.put('"'); fmt_time(s, sec, c.aux ? ((const uint32_t*)c.aux)[r] : 0, false); s.put('"'); break;
+    }
+    case TF_UTF8: fmt_json_string(s, c.heap + c.offsets[r], c.offsets[r + 1] - c.offsets[r], false); break;
+    case TF_BYTES: { s.put('"'); B64Sink<Sink> b{&s, 0, 0}; const uint8_t* p = c.heap + c.offsets[r]; const uint32_t L = c.offsets[r + 1] - c.offsets[r]; for (uint32_t k = 0; k < L; k++) b.put(p[k]); b.finish(); s.put('"'); break; }
+    case TF_ANY: {
+        const uint8_t* p = c.heap + c.offsets[r]; const uint32_t L = c.offsets[r + 1] - c.offsets[r];
+        const bool gostr = c.aux && c.aux[r] == 1, aas = flags & TF_SER_AAS;
+        if (gostr && aas) { s.put('"'); EscSink<Sink> es{&s}; fmt_json_string(es, p, L, true); s.put('"'); }     // string(json.Marshal(v)) re-encoded
+        else if (gostr || aas) fmt_json_string(s, p, L, false);
+        else ser_unescape_html(s, p, L);
+        break;
+    }
+    }
+    return true;
+}
+
+template <typename Sink> __device__ int ser_json_row(Sink& s, const DCol* cols, const JsonCol* jcols, int njc, const uint8_t* names, const MaskKey* keys, uint64_t r, uint64_t j, bool sizing, uint32_t flags) {
+    int bad = -1;
+    if (!(flags & TF_SER_NL) && j) s.put('\n');               // items joined by "\n" (batch_factory.go:36-39)
+    s.put('{');
+    for (int k = 0; k < njc; k++) {
+        const JsonCol jc = jcols[k]; const DCol& c = cols[jc.col];
+        if (k) s.put(',');
+        for (int i = 0; i < jc.name_len; i++) s.put(names[jc.name_off + i]);       // `"name":` quoted on the host
+        if (c.out_kind == OK_TOSTR && jc.result_tf != TF_BYTES && (c.type == TF_UTF8 || c.type == TF_BYTES) && row_valid(c, r))
+            fmt_json_string(s, c.heap + c.offsets[r], c.offsets[r + 1] - c.offsets[r], false);      // convert_to_string of a text cell: the same bytes
+        else if (!ser_json_value(s, c, r, jc, keys, sizing, flags) && bad < 0) bad = jc.pad0;
+    }
+    s.put('}');
+    if (flags & TF_SER_NL) s.put('\n');
+    return bad;
+}
+
+// does the encoding/csv field need quotes? (fieldNeedsQuotes: empty no; `\.` yes; , " \r \n yes; leading unicode space yes)
+__device__ bool ser_csv_needs_quotes(const uint8_t* p, uint32_t n) {
+    if (!n) return false;
+    if (n == 2 && p[0] == '\\' && p[1] == '.') return true;
+    for (uint32_t i = 0; i < n; i++) { const uint8_t c = p[i]; if (c == '\n' || c == '\r' || c == '"' || c == ',') return true; }
+    uint32_t w; return d_space(p, n, w);
+}
+
+template <typename Sink> __device__ void ser_csv_row(Sink& s, const DCol* cols, const JsonCol* jcols, int njc, const MaskKey* keys, uint64_t r, bool sizing) {
+    for (int k = 0; k < njc; k++) {
+        const JsonCol jc = jcols[k]; const DCol& c = cols[jc.col];
+        if (k) s.put(',');
+        if (c.out_kind == OK_MASK) {
+            if (sizing) { for (int i = 0; i < 64; i++) s.put('0'); }
+            else { uint8_t hx[64]; mask_digest_hex(c, r, keys[c.mask_slot], hx); for (int i = 0; i < 64; i++) s.put(hx[i]); }
+            continue;
+        }
+        if (c.out_kind == OK_TODT) { int64_t sec = 0; if (row_valid(c, r)) sec = c.type == TF_INT32 ? (int64_t)((const int32_t*)c.values)[r] : (int64_t)((const uint32_t*)c.values)[r]; ser_time_string(s, sec, 0); continue; }
+        const bool tostr = c.out_kind == OK_TOSTR;
+        if (tostr && jc.result_tf == TF_BYTES) { B64Sink<Sink> b{&s, 0, 0}; fmt_value(b, c, r); b.finish(); continue; }
+        if (!row_valid(c, r)) { if (tostr) fmt_value(s, c, r); continue; }      // nil -> "" ; convert_to_string of nil is "<nil>" / "null"
+        switch (c.type) {
+        case TF_FLOAT: fmt_float_bits(s, ((const uint32_t*)c.values)[r], true, FM_F); break;
+        case TF_DOUBLE: fmt_float_bits(s, ((const uint64_t*)c.values)[r], false, FM_F); break;
+        case TF_DATE: case TF_DATETIME: case TF_TIMESTAMP:
+            if (tostr) fmt_value(s, c, r); else ser_time_string(s, ((const int64_t*)c.values)[r], c.aux ? ((const uint32_t*)c.aux)[r] : 0);
+            break;
+        case TF_BYTES: if (!tostr) { B64Sink<Sink> b{&s, 0, 0}; const uint8_t* p = c.heap + c.offsets[r]; const uint32_t L = c.offsets[r + 1] - c.offsets[r]; for (uint32_t i = 0; i < L; i++) b.put(p[i]); b.finish(); break; }
+        // fall through: convert_to_string of bytes is the raw text
+        case TF_UTF8: {
+            const uint8_t* p = c.heap + c.offsets[r]; const uint32_t L = c.offsets[r + 1] - c.offsets[r];
+            if (ser_csv_needs_quotes(p, L)) { s.put('"'); for (uint32_t i = 0; i < L; i++) { if (p[i] == '"') s.put('"'); s.put(p[i]); } s.put('"'); }
+            else for (uint32_t i = 0; i < L; i++) s.put(p[i]);
+            break;
+        }
+        case TF_ANY: {
+            const uint8_t* p = c.heap + c.offsets[r]; const uint32_t L = c.offsets[r + 1] - c.offsets[r];
+            if (c.aux && c.aux[r] == 1) { s.put('"'); CsvQuoteSink<Sink> q{&s}; fmt_json_string(q, p, L, true); s.put('"'); }     // json.Marshal(string) always holds a quote
+            else if (ser_csv_needs_quotes(p, L)) { s.put('"'); for (uint32_t i = 0; i < L; i++) { if (p[i] == '"') s.put('"'); s.put(p[i]); } s.put('"'); }
+            else for (uint32_t i = 0; i < L; i++) s.put(p[i]);
+            break;
+        }
+        default: fmt_value(s, c, r);       // ints, bool, interval (Duration.String()): never quoted
+        }
+    }
+    s.put('\n');
+}
+
 struct JsonArgs {
     const DCol* cols; const JsonCol* jcols; int njc; const uint8_t* names; const MaskKey* keys;
     const uint32_t* sel; DState* st; uint8_t* raw; uint32_t* row_size; uint32_t* tile_sum; const uint64_t* tile_base; const uint64_t* col_bytes;
+    int mode; uint32_t flags; uint8_t* errcode; uint8_t* errstep;      // mode 0 ClickHouse JSONEachRow, 1 serializer JSON, 2 serializer CSV
 };
+
+template <typename Sink> __device__ __forceinline__ int json_any_row(Sink& s, const JsonArgs& a, uint64_t r, uint64_t j, bool sizing) {
+    if (a.mode == 1) return ser_json_row(s, a.cols, a.jcols, a.njc, a.names, a.keys, r, j, sizing, a.flags);
+    if (a.mode == 2) { ser_csv_row(s, a.cols, a.jcols, a.njc, a.keys, r, sizing); return -1; }
+    json_row(s, a.cols, a.jcols, a.njc, a.names, a.keys, r, sizing); return -1;
+}
 
 #define TF_JSON_TILE 256
 
@@ -121,7 +289,11 @@ __global__ void __launch_bounds__(TF_JSON_TILE) k_json_sizes(JsonArgs a) {
     const uint64_t j = (uint64_t)blockIdx.x * TF_JSON_TILE + threadIdx.x;
     if ((uint64_t)blockIdx.x * TF_JSON_TILE >= n) return;
     uint32_t sz = 0;
-    if (j < n) { const uint64_t r = a.sel ? a.sel[j] : j; CountSink cs; cs.n = 0; json_row(cs, a.cols, a.jcols, a.njc, a.names, a.keys, r, true); sz = cs.n; a.row_size[j] = sz; }
+    if (j < n) {
+        const uint64_t r = a.sel ? a.sel[j] : j; CountSink cs; cs.n = 0;
+        const int bad = json_any_row(cs, a, r, j, true); sz = cs.n; a.row_size[j] = sz;
+        if (bad >= 0) { a.errcode[r] = TF_ROWERR_SER_VALUE; a.errstep[r] = (uint8_t)bad; atomicAdd((unsigned long long*)&a.st->n_errors, 1ull); }
+    }
     uint32_t tot; block_excl_scan(sz, &tot, sm);
     if (threadIdx.x == 0) a.tile_sum[blockIdx.x] = tot;
 }
@@ -137,7 +309,7 @@ __global__ void __launch_bounds__(TF_JSON_TILE) k_json_write(JsonArgs a) {
     if (j >= n) return;
     const uint64_t r = a.sel ? a.sel[j] : j;
     MemSink ms; ms.p = a.raw + a.tile_base[blockIdx.x] + ex;
-    json_row(ms, a.cols, a.jcols, a.njc, a.names, a.keys, r, false);
+    json_any_row(ms, a, r, j, false);
 }
 
 }  // namespace tfk

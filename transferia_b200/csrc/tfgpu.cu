@@ -2,6 +2,7 @@
 // per-row operation runs in the sm_100a kernels of kernels_*.cuh.  There is no CPU fallback: without
 // a CUDA device tfgpu_engine_create fails with TF_E_FATAL_NODEVICE.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -47,6 +48,7 @@ struct PlanDev {
     DTerm* d_terms = nullptr; uint32_t* d_expr_off = nullptr; DFilterStep* d_fsteps = nullptr; uint8_t* d_blob = nullptr;
     uint8_t* d_col_headers = nullptr; uint32_t* d_col_header_off = nullptr;
     JsonCol* d_jcols = nullptr; uint8_t* d_jnames = nullptr; size_t jnames_len = 0;
+    JsonCol* d_sjcols = nullptr; JsonCol* d_scsvcols = nullptr; uint8_t* d_snames = nullptr;      // batch serializers: sorted JSON keys (pre-quoted), CSV order
     int32_t* d_fixed_slots = nullptr; int32_t* d_str_slots = nullptr; int32_t* d_mask_slots = nullptr; int32_t* d_out_cols = nullptr;
     MaskKey* d_mask_keys = nullptr;
     int n_fsteps = 0, n_fixed_slots = 0, n_str = 0, n_mask_cols = 0;
@@ -104,6 +106,30 @@ int cuda_fail(tfgpu_engine* e, const CudaError& c) {
     std::string m = std::string("CUDA error: ") + cudaGetErrorString(c.e) + " in " + c.what;
     cudaGetLastError();
     return fail(e, c.e == cudaErrorMemoryAllocation ? TF_E_RETRY_OOM : TF_E_RETRY_LAUNCH, m);
+}
+
+// encoding/json appendString with escapeHTML off, for column names (json.go:56-58)
+std::string host_json_quote_nohtml(const std::string& in) {
+    static const char* hex = "0123456789abcdef";
+    std::string d = "\""; const uint8_t* s = (const uint8_t*)in.data(); const size_t n = in.size();
+    for (size_t i = 0; i < n;) {
+        const uint8_t b = s[i];
+        if (b < 0x80) {
+            if (b >= 0x20 && b != '"' && b != '\\') d += (char)b;
+            else { d += '\\'; switch (b) { case '"': case '\\': d += (char)b; break; case '\b': d += 'b'; break; case '\f': d += 'f'; break; case '\n': d += 'n'; break; case '\r': d += 'r'; break; case '\t': d += 't'; break;
+                                            default: d += "u00"; d += hex[b >> 4]; d += hex[b & 15]; } }
+            i++; continue;
+        }
+        uint32_t r = 0xFFFD; size_t w = 1;
+        if (b >= 0xC2 && b <= 0xDF && i + 1 < n && (s[i + 1] & 0xC0) == 0x80) { r = ((b & 0x1Fu) << 6) | (s[i + 1] & 0x3Fu); w = 2; }
+        else if (b >= 0xE0 && b <= 0xEF && i + 2 < n && (s[i + 1] & 0xC0) == 0x80 && (s[i + 2] & 0xC0) == 0x80) { const uint32_t t = ((b & 0x0Fu) << 12) | ((s[i + 1] & 0x3Fu) << 6) | (s[i + 2] & 0x3Fu); if (t >= 0x800 && !(t >= 0xD800 && t <= 0xDFFF)) { r = t; w = 3; } }
+        else if (b >= 0xF0 && b <= 0xF4 && i + 3 < n && (s[i + 1] & 0xC0) == 0x80 && (s[i + 2] & 0xC0) == 0x80 && (s[i + 3] & 0xC0) == 0x80) { const uint32_t t = ((b & 0x07u) << 18) | ((s[i + 1] & 0x3Fu) << 12) | ((s[i + 2] & 0x3Fu) << 6) | (s[i + 3] & 0x3Fu); if (t >= 0x10000 && t <= 0x10FFFF) { r = t; w = 4; } }
+        if (r == 0xFFFD && w == 1) d += "\\ufffd";
+        else if (r == 0x2028 || r == 0x2029) { d += "\\u202"; d += hex[r & 0xF]; }
+        else d.append((const char*)s + i, w);
+        i += w;
+    }
+    return d + "\"";
 }
 
 int in_width(int tf) {
@@ -169,6 +195,19 @@ void upload_plan(tfgpu_engine* e, PlanDev& pd) {
         jcols.push_back(jc);
     }
     pd.jnames_len = jnames.size();
+    // batch serializers (pkg/serializer): encoding/json writes map keys sorted; the key text `"name":` is quoted here once
+    std::vector<JsonCol> sjcols, scsvcols; std::vector<uint8_t> snames;
+    {
+        std::vector<size_t> order(pl.out_cols.size()); for (size_t k = 0; k < order.size(); k++) order[k] = k;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return pl.out_schema[a].name < pl.out_schema[b].name; });
+        for (size_t j = 0; j < order.size(); j++) {
+            const size_t k = order[j]; JsonCol jc = jcols[k]; jc.pad0 = (int32_t)k;
+            const std::string q = host_json_quote_nohtml(pl.out_schema[k].name) + ":";
+            jc.name_off = (int32_t)snames.size(); jc.name_len = (int32_t)q.size(); snames.insert(snames.end(), q.begin(), q.end());
+            sjcols.push_back(jc);
+        }
+        for (size_t k = 0; k < jcols.size(); k++) { JsonCol jc = jcols[k]; jc.pad0 = (int32_t)k; scsvcols.push_back(jc); }
+    }
     // flatten filter steps
     std::vector<DTerm> terms; std::vector<uint32_t> expr_off(1, 0); std::vector<DFilterStep> fsteps;
     for (size_t f = 0; f < pl.filters.size(); f++) {
@@ -187,6 +226,7 @@ void upload_plan(tfgpu_engine* e, PlanDev& pd) {
     need(terms.size() * sizeof(DTerm)); need(expr_off.size() * 4); need(fsteps.size() * sizeof(DFilterStep)); need(pl.blob.size());
     need(pl.col_headers.size()); need(pl.col_header_off.size() * 4); need(pd.fixed_slots.size() * 4); need(pd.str_slots.size() * 4);
     need(pd.mask_slot_cols.size() * 4); need(keys.size() * sizeof(MaskKey)); need(pl.out_cols.size() * 4); need(jcols.size() * sizeof(JsonCol)); need(jnames.size());
+    need(sjcols.size() * sizeof(JsonCol)); need(scsvcols.size() * sizeof(JsonCol)); need(snames.size());
     pd.consts.ensure(total);
     uint8_t* p = pd.consts.p;
     auto put = [&](const void* src, size_t n) { uint8_t* d = p; if (n) CK(cudaMemcpy(d, src, n, cudaMemcpyHostToDevice)); p += align_up(n ? n : 1, 256); return d; };
@@ -202,6 +242,7 @@ void upload_plan(tfgpu_engine* e, PlanDev& pd) {
     pd.d_mask_keys = (MaskKey*)put(keys.data(), keys.size() * sizeof(MaskKey));
     { std::vector<int32_t> oc(pl.out_cols.begin(), pl.out_cols.end()); pd.d_out_cols = (int32_t*)put(oc.data(), oc.size() * 4); }
     pd.d_jcols = (JsonCol*)put(jcols.data(), jcols.size() * sizeof(JsonCol)); pd.d_jnames = put(jnames.data(), jnames.size());
+    pd.d_sjcols = (JsonCol*)put(sjcols.data(), sjcols.size() * sizeof(JsonCol)); pd.d_scsvcols = (JsonCol*)put(scsvcols.data(), scsvcols.size() * sizeof(JsonCol)); pd.d_snames = put(snames.data(), snames.size());
     (void)e;
 }
 
@@ -234,7 +275,11 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
     const bool columnar = wire_fmt == TF_WIRE_COLUMNAR_INTERNAL;
     const tfplan::Plan& pl = pd.plan;
     const size_t nc = pl.in_schema.size(); const uint64_t n = in->nrows;
-    const bool json_rows = wire_fmt == TF_WIRE_CH_JSONEACHROW;
+    const int wire_base = wire_fmt == TF_WIRE_COLUMNAR_INTERNAL ? wire_fmt : (wire_fmt & 0xff);
+    const bool ser = wire_base == TF_WIRE_SER_JSON || wire_base == TF_WIRE_SER_CSV;
+    const bool json_rows = wire_base == TF_WIRE_CH_JSONEACHROW || ser;
+    if (ser) for (size_t c = 0; c < nc; c++) if (pd.col_out_kind[c] == OK_TOSTR && pl.in_schema[c].tf == TF_ANY)
+        throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "serializer sinks after convert_to_string on an `any` column are not handled on the device");
     const Sizes sz = compute_sizes(e, pd, in, columnar, json_rows);
     cudaStream_t s = e->stream;
     // work arena
@@ -293,12 +338,18 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
     if (json_rows) {
         // JSONEachRow: rows sized, placed by a tile scan, then written (kernels_json_out.cuh)
         const uint32_t jt = (uint32_t)((n + TF_JSON_TILE - 1) / TF_JSON_TILE);
-            JsonArgs ja{e->d_cols, pd.d_jcols, (int)pl.out_cols.size(), pd.d_jnames, pd.d_mask_keys, sel, e->d_state, e->raw.p,
-                    (uint32_t*)e->work_json_sizes(n), e->tile_sum, e->tile_base, e->col_bytes};
+        JsonArgs ja{e->d_cols, ser ? (wire_base == TF_WIRE_SER_JSON ? pd.d_sjcols : pd.d_scsvcols) : pd.d_jcols, (int)pl.out_cols.size(), ser ? pd.d_snames : pd.d_jnames, pd.d_mask_keys, sel, e->d_state, e->raw.p,
+                    (uint32_t*)e->work_json_sizes(n), e->tile_sum, e->tile_base, e->col_bytes,
+                    ser ? (wire_base == TF_WIRE_SER_JSON ? 1 : 2) : 0, (uint32_t)(((wire_fmt & TF_WIRE_F_CLOSING_NEWLINE) ? TF_SER_NL : 0) | ((wire_fmt & TF_WIRE_F_ANY_AS_STRING) ? TF_SER_AAS : 0)), e->errcode, e->errstep};
+        if (ser && !has_filter && n) { CK(cudaMemsetAsync(e->errcode, 0, n, s)); CK(cudaMemsetAsync(e->errstep, 0, n, s)); }
         if (jt) { e->prof_begin("k_json_sizes", s); k_json_sizes<<<jt, TF_JSON_TILE, 0, s>>>(ja); e->prof_end(s); }
         LayoutArgs lj{e->d_cols, 0, pd.d_out_cols, pd.d_str_slots, 1, e->tile_sum, e->tile_base, sz.ntiles_cap, pd.d_col_headers, pd.d_col_header_off,
                       e->raw.p, e->d_state, n, 1, e->frame_bytes, e->col_bytes};
         e->prof_begin("k_layout_scan", s); k_layout_scan<<<1, 1024, 0, s>>>(lj); e->prof_end(s);
+        {   // row text has no useful upper bound ('f' floats reach 300+ characters): size the output from the measured total
+            uint64_t total = 0; CK(cudaMemcpyAsync(&total, e->col_bytes, 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+            e->raw.ensure(total + 256); ja.raw = e->raw.p;
+        }
         e->prof_begin("k_json_write", s); k_json_write<<<jt ? jt : 1, TF_JSON_TILE, 0, s>>>(ja); e->prof_end(s);
         CK(cudaGetLastError());
         return;
@@ -372,6 +423,11 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
 }
 
 }  // namespace
+
+
+// wire format ids accepted by the encode entry points; serializer formats need no sink in the plan
+static bool wire_is_ser(int wire_fmt) { const int b = wire_fmt & 0xff; return (b == TF_WIRE_SER_JSON || b == TF_WIRE_SER_CSV) && (wire_fmt & ~(0xff | TF_WIRE_F_CLOSING_NEWLINE | TF_WIRE_F_ANY_AS_STRING)) == 0; }
+static bool wire_known(int wire_fmt) { return wire_fmt == TF_WIRE_CH_NATIVE || wire_fmt == TF_WIRE_CH_NATIVE_LZ4 || wire_fmt == TF_WIRE_CH_JSONEACHROW || wire_is_ser(wire_fmt); }
 
 extern "C" {
 
@@ -537,9 +593,9 @@ int tfgpu_push_encode(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch
     if (!e || !in || !out || plan_id < 0 || plan_id >= (int)e->plans.size()) return TF_E_FATAL_ARG;
     *out = nullptr;
     PlanDev& pd = *e->plans[plan_id];
-    if (!pd.plan.has_sink) return fail(e, TF_E_FATAL_CONFIG, "plan was built without a sink");
+    if (!wire_known(wire_fmt)) return fail(e, TF_E_FATAL_UNSUPPORTED, "wire format not implemented");
+    if (!wire_is_ser(wire_fmt) && !pd.plan.has_sink) return fail(e, TF_E_FATAL_CONFIG, "plan was built without a sink");
     if (in->ncols != pd.plan.in_schema.size()) return fail(e, TF_E_FATAL_ARG, "batch column count does not match the plan schema");
-    if (wire_fmt != TF_WIRE_CH_NATIVE && wire_fmt != TF_WIRE_CH_NATIVE_LZ4 && wire_fmt != TF_WIRE_CH_JSONEACHROW) return fail(e, TF_E_FATAL_UNSUPPORTED, "wire format not implemented");
     if (in->nrows >= (1ull << 31)) return fail(e, TF_E_FATAL_ARG, "batch too large (>= 2^31 rows)");
     try {
         CK(cudaSetDevice(e->device));
@@ -706,8 +762,8 @@ int tfgpu_parse_csv(tfgpu_engine* e, int plan_id, const char* opts_json, const u
     *out = nullptr;
     PlanDev& pd = *e->plans[plan_id];
     if (len >= (1ull << 32) - 16) return fail(e, TF_E_FATAL_ARG, "csv chunk must be < 4 GiB (line positions are uint32)");
-    if (wire_fmt != 0 && wire_fmt != TF_WIRE_CH_NATIVE && wire_fmt != TF_WIRE_CH_NATIVE_LZ4 && wire_fmt != TF_WIRE_CH_JSONEACHROW) return fail(e, TF_E_FATAL_UNSUPPORTED, "wire format not implemented");
-    if (wire_fmt != 0 && !pd.plan.has_sink) return fail(e, TF_E_FATAL_CONFIG, "plan was built without a sink");
+    if (wire_fmt != 0 && !wire_known(wire_fmt)) return fail(e, TF_E_FATAL_UNSUPPORTED, "wire format not implemented");
+    if (wire_fmt != 0 && !wire_is_ser(wire_fmt) && !pd.plan.has_sink) return fail(e, TF_E_FATAL_CONFIG, "plan was built without a sink");
     try {
         CK(cudaSetDevice(e->device));
         cudaStream_t s = e->stream;
@@ -815,8 +871,8 @@ int tfgpu_parse_json(tfgpu_engine* e, int plan_id, const char* opts_json, const 
     *out = nullptr;
     PlanDev& pd = *e->plans[plan_id];
     if (len >= (1ull << 32) - 16) return fail(e, TF_E_FATAL_ARG, "json batch must be < 4 GiB (line positions are uint32)");
-    if (wire_fmt != 0 && wire_fmt != TF_WIRE_CH_NATIVE && wire_fmt != TF_WIRE_CH_NATIVE_LZ4 && wire_fmt != TF_WIRE_CH_JSONEACHROW) return fail(e, TF_E_FATAL_UNSUPPORTED, "wire format not implemented");
-    if (wire_fmt != 0 && !pd.plan.has_sink) return fail(e, TF_E_FATAL_CONFIG, "plan was built without a sink");
+    if (wire_fmt != 0 && !wire_known(wire_fmt)) return fail(e, TF_E_FATAL_UNSUPPORTED, "wire format not implemented");
+    if (wire_fmt != 0 && !wire_is_ser(wire_fmt) && !pd.plan.has_sink) return fail(e, TF_E_FATAL_CONFIG, "plan was built without a sink");
     { uint64_t prev = 0; for (uint32_t m = 0; m < n_msgs; m++) { if (msgs[m].end < prev || msgs[m].end > len) return fail(e, TF_E_FATAL_ARG, "message ends must be non-decreasing and inside the buffer"); prev = msgs[m].end; }
       if ((n_msgs ? msgs[n_msgs - 1].end : 0) != len) return fail(e, TF_E_FATAL_ARG, "the messages must cover the whole buffer"); }
     try {
