@@ -205,6 +205,12 @@ int tfgpu_push_columns(tfgpu_engine* e, int plan_id, const tf_batch* in, tfgpu_r
 int tfgpu_push_encode(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch* in,
                       tfgpu_result** out);
 
+/* Measurer middleware (pkg/middlewares/synchronizer/measurer.go:38-42): ChangeItem.Size.Values = util.DeepSizeof(ColumnValues)
+ * (pkg/util/sizeof.go:7-110) for every row of `in`, computed in closed form from the column types and lengths instead of a
+ * reflection walk. per_row (host, nrows entries) may be NULL; *total receives the sum. `any` cells that are not Go strings
+ * are counted as their JSON text (the reference walks the map / slice). */
+int tfgpu_measure(tfgpu_engine* e, const tf_batch* in, uint64_t* per_row, uint64_t* total);
+
 /* parsers.Parser for CSV (pkg/parsers/abstract.go:35-38 shape; algorithm of the S3 CSV reader:
  * pkg/csv/reader.go:89-324 + pkg/providers/s3/reader/registry/csv/reader_csv.go:186-452 + strictify.go:18-181).
  * One chunk of raw bytes (host or device, < 4 GiB) is split into lines and typed columns ON THE DEVICE and fed straight
@@ -262,6 +268,17 @@ const uint8_t*    tfgpu_result_bytes(const tfgpu_result* r);      /* push_encode
 uint64_t          tfgpu_result_bytes_len(const tfgpu_result* r);
 uint64_t          tfgpu_result_raw_len(const tfgpu_result* r);    /* uncompressed block   */
 uint64_t          tfgpu_result_n_frames(const tfgpu_result* r);
+/* Row-text formats (TF_WIRE_SER_JSON/CSV, TF_WIRE_CH_JSONEACHROW): bytes of every output row in the order written,
+ * separator included (SER_JSON without CLOSING_NEWLINE: rows after the first start with '\n'). rows_out entries or NULL. */
+const uint32_t*   tfgpu_result_row_sizes(const tfgpu_result* r);
+
+/* Queue JSON serializer (pkg/serializer/queue/json_serializer.go:22-83 + json_batcher.go:13-66): the message VALUES are the
+ * TF_WIRE_SER_JSON rows (key = ChangeItem.Fqtn(), built by the shim); with batching enabled BatchJSON packs consecutive rows
+ * joined by '\n' greedily under MaxMessageSize / MaxChangeItems. Given the JSON length of every row (row_sizes minus the
+ * separator byte) this returns the first row of every message: message k = rows [starts[k], starts[k+1]); starts needs
+ * n + 1 entries. Host only. Update / delete items are refused by the reference (json_serializer.go:17-20): check kinds first. */
+int tfgpu_queue_json_batches(const uint32_t* json_row_sizes, uint64_t n, uint64_t max_message_size, uint64_t max_change_items,
+                             uint64_t* starts, uint64_t cap, uint64_t* n_msgs);
 void              tfgpu_result_release(tfgpu_result* r);
 
 /* Number of kernel launches issued by this engine since creation (bench `gpu_launches`). */

@@ -827,6 +827,49 @@ int orc_json_parse(const uint8_t* buf, uint64_t len, const orc_json_msg* msgs, u
     return 0;
 }
 
+// BatchJSON (pkg/serializer/queue/json_batcher.go:29-66) over the lengths of the serialized items: start row of each message
+int orc_queue_json_batches(const uint64_t* len_elements, uint64_t n, uint64_t max_message_size, uint64_t max_change_items, uint64_t* starts, uint64_t* n_msgs) {
+    uint64_t k = 0; int64_t startIndex = 0; uint64_t sumBodies = 0;
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        // isJSONExtraElementViolatesConstraint :13-28
+        const int64_t numNew = i - startIndex + 1; bool viol = false;
+        if (max_message_size != 0) { const int64_t newLines = numNew - 1; if (sumBodies + (uint64_t)newLines + len_elements[i] > max_message_size) viol = true; }
+        if (max_change_items != 0 && (uint64_t)numNew > max_change_items) viol = true;
+        if (viol) {
+            const int64_t numPrev = i - startIndex;
+            if (numPrev == 0) { starts[k++] = (uint64_t)startIndex; startIndex = i + 1; sumBodies = 0; }
+            else { starts[k++] = (uint64_t)startIndex; startIndex = i; sumBodies = len_elements[i]; }
+        } else sumBodies += len_elements[i];
+    }
+    if ((uint64_t)startIndex != n) starts[k++] = (uint64_t)startIndex;
+    starts[k] = n; *n_msgs = k; return 0;
+}
+
+// util.DeepSizeof(item.ColumnValues) (pkg/util/sizeof.go:7-110) over the canonical Go values of one row
+int orc_measure(const tf_batch* in, uint64_t* per_row, uint64_t* total) {
+    uint64_t sum = 0;
+    for (uint64_t r = 0; r < in->nrows; r++) {
+        uint64_t sz = 24;                                                // sizeofSlice: reflect.Type.Size() of []interface{}
+        for (uint32_t c = 0; c < in->ncols; c++) {
+            orc_val v; box(in->cols[c], r, v);
+            sz += 16;                                                    // element kind Interface: + Type().Size()
+            switch (v.kind) {
+            case OG_NIL: break;                                          // DeepSizeof(nil): reflect.Invalid -> 0
+            case OG_INT8: case OG_UINT8: case OG_BOOL: sz += 1; break;
+            case OG_INT16: case OG_UINT16: sz += 2; break;
+            case OG_INT32: case OG_UINT32: case OG_FLOAT32: sz += 4; break;
+            case OG_INT64: case OG_UINT64: case OG_FLOAT64: case OG_DURATION: case OG_INT: case OG_UINT: sz += 8; break;
+            case OG_STRING: case OG_JSON: sz += 16 + v.slen; break;      // reflect.String: Size() + Len()
+            case OG_BYTES: sz += 24 + v.slen; break;                     // sizeofSlice of uint8
+            case OG_TIME: sz += 24; break;                               // SizeOfStruct(time.Time): wall, ext, loc are unexported -> Type().Size() each
+            }
+        }
+        if (per_row) per_row[r] = sz;
+        sum += sz;
+    }
+    *total = sum; return 0;
+}
+
 int orc_ch_decode_frames(const uint8_t* wire, uint64_t n, orc_buf* raw, uint64_t* n_frames) {
     std::vector<uint8_t> r; size_t nf = 0;
     if (!ch_decompress_frames(wire, n, r, &nf)) return -1;

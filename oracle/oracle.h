@@ -132,6 +132,12 @@ int orc_json_parse(const uint8_t* buf, uint64_t len, const orc_json_msg* msgs, u
                    const orc_json_opts* opts, orc_buf* out, orc_regions* regions, uint64_t* rows, uint64_t* lines,
                    tf_rowerr* errs, uint64_t errs_cap, uint64_t* nerrs);
 
+/* BatchJSON (pkg/serializer/queue/json_batcher.go:29-66): starts needs n + 1 entries. */
+int orc_queue_json_batches(const uint64_t* len_elements, uint64_t n, uint64_t max_message_size, uint64_t max_change_items, uint64_t* starts, uint64_t* n_msgs);
+
+/* Measurer middleware: Size.Values = util.DeepSizeof(ColumnValues) per row (pkg/util/sizeof.go:7-110). */
+int orc_measure(const tf_batch* in, uint64_t* per_row, uint64_t* total);
+
 /* Verify + decode a frame stream with the oracle's own LZ4 decoder and CityHash. */
 int orc_ch_decode_frames(const uint8_t* wire, uint64_t n, orc_buf* raw, uint64_t* n_frames);
 

@@ -121,6 +121,8 @@ def lib():
         L.orc_json_parse.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(OrcJsonMsg), C.c_uint64, C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                      C.POINTER(OrcJsonOpts), C.POINTER(OrcBuf), C.POINTER(OrcRegions), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                      C.POINTER(abi.TfRowErr), C.c_uint64, C.POINTER(C.c_uint64)]
+        L.orc_queue_json_batches.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.orc_measure.argtypes = [C.POINTER(abi.TfBatch), C.c_void_p, C.POINTER(C.c_uint64)]
         L.orc_ch_decode_frames.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(OrcBuf), C.POINTER(C.c_uint64)]
         L.orc_free.argtypes = [C.POINTER(OrcBuf)]; L.orc_free.restype = None
         _lib = L
@@ -818,3 +820,17 @@ def json_parse(data: bytes, fields: List[dict], opts: Optional[dict] = None, msg
     buf = C.string_at(out.data, out.len) if out.len else b""
     lib().orc_free(C.byref(out))
     return (_regions_to_batch(buf, regs, list(types), rows.value), [(errs[i].row, errs[i].code, errs[i].term) for i in range(nerr.value)], lines.value)
+
+
+def measure(batch: abi.Batch):
+    """Measurer middleware: (per-row Size.Values, total)."""
+    tb = batch.as_struct(); per = np.zeros(batch.nrows, dtype=np.uint64); tot = C.c_uint64()
+    assert lib().orc_measure(C.byref(tb), per.ctypes.data, C.byref(tot)) == 0
+    return per, tot.value
+
+
+def queue_json_batches(lens, max_message_size=0, max_change_items=0):
+    """BatchJSON: start row of every message (+ n at the end)."""
+    a = np.asarray(lens, dtype=np.uint64); st = np.zeros(len(a) + 1, dtype=np.uint64); k = C.c_uint64()
+    assert lib().orc_queue_json_batches(a.ctypes.data, len(a), max_message_size, max_change_items, st.ctypes.data, C.byref(k)) == 0
+    return [int(x) for x in st[:k.value + 1]]

@@ -420,3 +420,16 @@ def test_jsoneachrow_on_device(eng, po):
     trs = workload.headline_transformers(workload.counterid_threshold(hb, hs))
     got = eng.push_encode(eng.plan("public", "hits", hs, trs, {"type": "clickhouse"}), hb, JS)
     assert got.wire == po.push_encode(hb, po.build_plan("public", "hits", hs, trs), JS).wire
+
+
+def test_measurer_sizes(eng, po):
+    """Measurer middleware (synchronizer/measurer.go:38-42): DeepSizeof(ColumnValues) per row in closed form == the oracle's walk."""
+    batch, schema = all_types_batch(5000, seed=21)
+    per, tot = eng.measure(batch); rper, rtot = po.measure(batch)
+    assert tot == rtot and np.array_equal(per, rper) and tot == int(per.sum())
+    hb, hs = workload.make_hits_batch(50_000, seed=6)
+    per, tot = eng.measure(hb); rper, rtot = po.measure(hb)
+    assert tot == rtot and np.array_equal(per, rper)
+    # closed form by hand: one int32 + one nil utf8 + one 3-byte utf8 row
+    b = abi.Batch(2, [abi.fixed_to_column(abi.TF_INT32, [1, 2]), abi.strings_to_column(abi.TF_UTF8, [None, b"abc"])])
+    assert list(po.measure(b)[0]) == [24 + 16 + 4 + 16, 24 + 16 + 4 + 16 + 16 + 3]

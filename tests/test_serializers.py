@@ -118,6 +118,9 @@ def test_device_serializers_equal_oracle(eng, po):
             got = eng.push_encode(pid, batch, fmt); want = po.push_encode(batch, plan, fmt)
             assert got.rows_out == want.rows_out and got.errors == want.errors, (trs, fmt)
             assert got.wire == want.wire, (trs, fmt)
+            if fmt == SER_JSON:       # row sizes: the queue serializer cuts messages on them
+                rows = want.wire.split(b"\n")
+                assert got.row_sizes == [len(r) + (1 if k else 0) for k, r in enumerate(rows)]
     # special values: NaN / Inf are row errors for JSON, text for CSV; quoting corner cases
     sch = [{"name": "d", "type": "double"}, {"name": "f", "type": "float"}, {"name": "s", "type": "utf8"}, {"name": "t", "type": "timestamp"}]
     sb = abi.Batch(6, [abi.fixed_to_column(abi.TF_DOUBLE, [float("nan"), float("inf"), 1e300, -0.0, 5e-324, 1.0]), abi.fixed_to_column(abi.TF_FLOAT, [1.5, float("-inf"), 3.4e38, 1e-7, 1e21, 0.0]),
@@ -127,3 +130,28 @@ def test_device_serializers_equal_oracle(eng, po):
     for fmt in fmts:
         got = eng.push_encode(pid, sb, fmt); want = po.push_encode(sb, plan, fmt)
         assert got.errors == want.errors and got.wire == want.wire, fmt
+
+
+def test_queue_json_batching_reference_cases(po):
+    """pkg/serializer/queue/test.go:63-120 commonTest through json_batcher_test.go: five identical items
+    {"id":4,"val1":5,"val2":6}; expected message counts per (MaxChangeItems, MaxMessageSize). Oracle and the product's
+    host-only tfgpu_queue_json_batches (no GPU needed) must both give them."""
+    from transferia_b200 import engine
+    item = b'{"id":4,"val1":5,"val2":6}'; L = len(item)
+    schema = [{"name": "id", "type": "int32", "key": True}, {"name": "val1", "type": "int32"}, {"name": "val2", "type": "int32"}]
+    batch = abi.Batch(5, [abi.fixed_to_column(abi.TF_INT32, [4] * 5), abi.fixed_to_column(abi.TF_INT32, [5] * 5), abi.fixed_to_column(abi.TF_INT32, [6] * 5)])
+    text = po.push_encode(batch, po.build_plan("public", "t", schema, []), SER_JSON).wire
+    assert text == b"\n".join([item] * 5)
+    bs = lambda size, num: (num - 1) + size * num
+    cases = [(1, 0, 5), (2, 0, 3), (0, 1, 5), (0, bs(L, 1), 5), (0, bs(L, 2) - 1, 5), (0, bs(L, 2), 3), (0, bs(L, 2) + 1, 3), (0, bs(L, 3) - 1, 3), (0, bs(L, 3), 2),
+             (0, bs(L, 3) + 1, 2), (1, bs(L, 2), 5), (2, bs(L, 2), 3), (2, bs(L, 1), 5)]
+    for max_items, max_size, want in cases:
+        a = po.queue_json_batches([L] * 5, max_size, max_items)
+        b = engine.queue_json_batches([L] * 5, max_size, max_items)
+        assert len(a) - 1 == want and a == b, (max_items, max_size, a, b)
+    # ragged lengths: both restatements agree, every row lands in exactly one message, limits hold unless a single row is too big
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        lens = rng.integers(1, 60, rng.integers(0, 40)).tolist(); ms = int(rng.integers(0, 120)); mi = int(rng.integers(0, 6))
+        a = po.queue_json_batches(lens, ms, mi); b = engine.queue_json_batches(lens, ms, mi)
+        assert a == b and a[-1] == len(lens) and all(x < y for x, y in zip(a, a[1:]))

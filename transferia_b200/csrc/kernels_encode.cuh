@@ -502,4 +502,39 @@ __global__ void __launch_bounds__(256) k_pack_validity(EncodeArgs a) {
 }
 
 
+// ------------------------------------------------------------------ Measurer
+// middlewares/synchronizer/measurer.go:38-42: item.Size.Values = util.DeepSizeof(item.ColumnValues) (pkg/util/sizeof.go:7-110),
+// a reflection walk over every value in the reference. For the canonical Go types the walk is a closed form:
+//   []interface{} header 24, then per value 16 (interface) + its payload: nil 0; bool/int8/uint8 1; int16/uint16 2;
+//   int32/uint32/float32 4; int64/uint64/float64/Duration 8; string 16 + len; []byte 24 + len; time.Time 24 (three words).
+// `any` holding a Go string counts as a string; other `any` values (maps / slices in the reference) are counted as their
+// JSON text in a string -- an estimate, flagged in DESIGN.md.
+struct MeasureArgs { const DCol* cols; int ncols; uint64_t nrows; uint64_t* per_row; unsigned long long* total; };
+
+__global__ void __launch_bounds__(256) k_measure(MeasureArgs a) {
+    __shared__ uint32_t sm[33];
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t sz = 0;
+    if (r < a.nrows) {
+        sz = 24;
+        for (int c = 0; c < a.ncols; c++) {
+            const DCol& d = a.cols[c];
+            sz += 16;
+            if (!row_valid(d, r)) continue;
+            switch (d.type) {
+            case TF_UTF8: sz += 16 + (d.offsets[r + 1] - d.offsets[r]); break;
+            case TF_ANY: sz += 16 + (d.offsets[r + 1] - d.offsets[r]); break;
+            case TF_BYTES: sz += 24 + (d.offsets[r + 1] - d.offsets[r]); break;
+            case TF_DATE: case TF_DATETIME: case TF_TIMESTAMP: sz += 24; break;
+            default: sz += (uint64_t)d.in_w;
+            }
+        }
+        if (a.per_row) a.per_row[r] = sz;
+    }
+    // block sum (sizes of one block fit 32 bits: 256 rows x < 16 MiB would not, so reduce in two halves)
+    const uint32_t lo = (uint32_t)(sz & 0xffffffu), hi = (uint32_t)(sz >> 24);
+    uint32_t tl, th; block_excl_scan(lo, &tl, sm); __syncthreads(); block_excl_scan(hi, &th, sm);
+    if (threadIdx.x == 0) atomicAdd(a.total, (unsigned long long)tl + ((unsigned long long)th << 24));
+}
+
 }  // namespace tfk

@@ -95,6 +95,7 @@ struct tfgpu_result {
     uint64_t rows_in = 0, rows_out = 0, raw_len = 0, n_frames = 0, consumed = 0;
     std::vector<tf_rowerr> errs;
     uint8_t* bytes = nullptr; uint64_t bytes_len = 0; bool bytes_pinned = false;
+    std::vector<uint32_t> row_sizes;       // row-text formats: bytes of every output row (incl. its separator / newline)
     // push_columns output
     tf_batch batch{}; std::vector<tf_col> cols; std::vector<uint8_t*> owned;
 };
@@ -694,6 +695,8 @@ static void finish_wire(tfgpu_engine* e, uint64_t n, int wire_fmt, tfgpu_result*
     }
     r->bytes = e->pinned; r->bytes_pinned = false;
     CK(cudaMemcpyAsync(r->bytes, lz ? e->wire.p : e->raw.p, r->bytes_len, cudaMemcpyDeviceToHost, s));
+    { const int b = wire_fmt & 0xff;
+      if ((b == TF_WIRE_SER_JSON || b == TF_WIRE_SER_CSV || b == TF_WIRE_CH_JSONEACHROW) && st.n_kept) { r->row_sizes.resize(st.n_kept); CK(cudaMemcpyAsync(r->row_sizes.data(), e->json_sizes.p, st.n_kept * 4, cudaMemcpyDeviceToHost, s)); } }
     if (st.n_errors) fetch_errors(e, n, r);
     CK(cudaStreamSynchronize(s));
 }
@@ -712,6 +715,32 @@ int tfgpu_push_columns(tfgpu_engine* e, int plan_id, const tf_batch* in, tfgpu_r
         auto r = std::make_unique<tfgpu_result>();
         finish_columnar(e, pd, in->nrows, r.get());
         *out = r.release();
+        return TF_OK;
+    } catch (const tfplan::FatalError& f) { return fail(e, f.code, f.what()); }
+    catch (const CudaError& c) { return cuda_fail(e, c); }
+    catch (const std::bad_alloc&) { return fail(e, TF_E_RETRY_OOM, "host allocation failed"); }
+}
+
+// Measurer middleware (synchronizer/measurer.go:38-42): Size.Values of every row and their sum, in one pass over the columns.
+int tfgpu_measure(tfgpu_engine* e, const tf_batch* in, uint64_t* per_row, uint64_t* total) {
+    if (!e || !in || !total) return TF_E_FATAL_ARG;
+    try {
+        CK(cudaSetDevice(e->device));
+        cudaStream_t s = e->stream;
+        std::vector<tf_col> dev; stage_input(e, in, dev);
+        const size_t nc = in->ncols; const uint64_t n = in->nrows;
+        if (e->d_cols_cap < nc) { if (e->d_cols) CK(cudaFree(e->d_cols)); CK(cudaMalloc(&e->d_cols, sizeof(DCol) * (nc ? nc : 1))); e->d_cols_cap = nc; }
+        std::vector<DCol> hc(nc);
+        for (size_t c = 0; c < nc; c++) { const tf_col& ic = dev[c]; DCol& d = hc[c]; std::memset(&d, 0, sizeof d); d.type = ic.type; d.in_w = in_width(ic.type); d.values = (const uint8_t*)ic.values; d.validity = ic.validity; d.offsets = ic.offsets; d.heap = ic.heap; d.aux = (const uint8_t*)ic.aux; }
+        e->work.ensure(n * 8 + 256);
+        unsigned long long* d_total = (unsigned long long*)e->work.p; uint64_t* d_rows = per_row ? (uint64_t*)(e->work.p + 64) : nullptr;
+        CK(cudaMemcpyAsync(e->d_cols, hc.data(), sizeof(DCol) * nc, cudaMemcpyHostToDevice, s));
+        CK(cudaMemsetAsync(d_total, 0, 8, s));
+        e->prof_n = 0;
+        if (n) { MeasureArgs ma{e->d_cols, (int)nc, n, d_rows, d_total}; e->prof_begin("k_measure", s); k_measure<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(ma); e->prof_end(s); CK(cudaGetLastError()); }
+        CK(cudaMemcpyAsync(total, d_total, 8, cudaMemcpyDeviceToHost, s));
+        if (per_row && n) CK(cudaMemcpyAsync(per_row, d_rows, n * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
         return TF_OK;
     } catch (const tfplan::FatalError& f) { return fail(e, f.code, f.what()); }
     catch (const CudaError& c) { return cuda_fail(e, c); }
@@ -1039,6 +1068,26 @@ const uint8_t* tfgpu_result_bytes(const tfgpu_result* r) { return r ? r->bytes :
 uint64_t tfgpu_result_bytes_len(const tfgpu_result* r) { return r ? r->bytes_len : 0; }
 uint64_t tfgpu_result_raw_len(const tfgpu_result* r) { return r ? r->raw_len : 0; }
 uint64_t tfgpu_result_n_frames(const tfgpu_result* r) { return r ? r->n_frames : 0; }
+const uint32_t* tfgpu_result_row_sizes(const tfgpu_result* r) { return (r && !r->row_sizes.empty()) ? r->row_sizes.data() : nullptr; }
+
+// queue JSON serializer batching (pkg/serializer/queue/json_batcher.go:13-66): host only, no device needed
+int tfgpu_queue_json_batches(const uint32_t* row_sizes, uint64_t n, uint64_t max_message_size, uint64_t max_change_items, uint64_t* starts, uint64_t cap, uint64_t* n_msgs) {
+    if ((!row_sizes && n) || !starts || !n_msgs) return TF_E_FATAL_ARG;
+    uint64_t k = 0, start = 0, sum = 0;
+    auto emit = [&](uint64_t s) -> bool { if (k >= cap) return false; starts[k++] = s; return true; };
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t count = i - start + 1;
+        const bool viol = (max_message_size && sum + (count - 1) + row_sizes[i] > max_message_size) || (max_change_items && count > max_change_items);
+        if (!viol) { sum += row_sizes[i]; continue; }
+        if (!emit(start)) return TF_E_FATAL_ARG;
+        if (i == start) { start = i + 1; sum = 0; }        // a single item over the size limit goes out alone
+        else { start = i; sum = row_sizes[i]; }
+    }
+    if (start != n && !emit(start)) return TF_E_FATAL_ARG;
+    if (k >= cap) return TF_E_FATAL_ARG;
+    starts[k] = n; *n_msgs = k;
+    return TF_OK;
+}
 void tfgpu_result_release(tfgpu_result* r) {
     if (!r) return;
     if (r->bytes && r->bytes_pinned) cudaFreeHost(r->bytes);   // otherwise the engine's landing buffer

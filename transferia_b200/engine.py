@@ -58,6 +58,9 @@ def load_library():
     L.tfgpu_push_columns.argtypes = [vp, i, C.POINTER(abi.TfBatch), C.POINTER(vp)]
     L.tfgpu_push_encode.argtypes = [vp, i, i, C.POINTER(abi.TfBatch), C.POINTER(vp)]
     L.tfgpu_parse_csv.argtypes = [vp, i, cp, vp, u64, i, i, C.POINTER(vp)]
+    L.tfgpu_result_row_sizes.argtypes = [vp]; L.tfgpu_result_row_sizes.restype = C.POINTER(C.c_uint32)
+    L.tfgpu_queue_json_batches.argtypes = [vp, u64, u64, u64, vp, u64, C.POINTER(u64)]
+    L.tfgpu_measure.argtypes = [vp, C.POINTER(abi.TfBatch), vp, C.POINTER(u64)]
     L.tfgpu_parse_json.argtypes = [vp, i, cp, vp, u64, i, C.POINTER(abi.TfMsg), C.c_uint32, i, C.POINTER(vp)]
     L.tfgpu_result_consumed.argtypes = [vp]; L.tfgpu_result_consumed.restype = u64
     L.tfgpu_push_encode_resident.argtypes = [vp, i, i, C.POINTER(abi.TfBatch)]
@@ -78,12 +81,23 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "tfgpu_version", "tfgpu_engine_create", "tfgpu_engine_destroy", "tfgpu_last_error", "tfgpu_engine_set_stream",
-    "tfgpu_plan", "tfgpu_plan_validate", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_parse_csv", "tfgpu_parse_json", "tfgpu_result_consumed", "tfgpu_push_encode_resident",
+    "tfgpu_plan", "tfgpu_plan_validate", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_parse_csv", "tfgpu_parse_json", "tfgpu_measure", "tfgpu_result_row_sizes", "tfgpu_queue_json_batches", "tfgpu_result_consumed", "tfgpu_push_encode_resident",
     "tfgpu_resident_stats", "tfgpu_resident_fetch", "tfgpu_result_rows_in", "tfgpu_result_rows_out",
     "tfgpu_result_n_errors", "tfgpu_result_errors", "tfgpu_result_batch", "tfgpu_result_bytes",
     "tfgpu_result_bytes_len", "tfgpu_result_raw_len", "tfgpu_result_n_frames", "tfgpu_result_release",
     "tfgpu_engine_launch_count", "tfgpu_profile_enable", "tfgpu_profile_read",
 ]
+
+
+def queue_json_batches(json_row_sizes, max_message_size: int = 0, max_change_items: int = 0):
+    """BatchJSON of the queue JSON serializer (host only): first row of every message, then n."""
+    import numpy as np
+    L = load_library()
+    a = np.asarray(json_row_sizes, dtype=np.uint32); st = np.zeros(len(a) + 1, dtype=np.uint64); k = C.c_uint64()
+    rc = L.tfgpu_queue_json_batches(a.ctypes.data, len(a), max_message_size, max_change_items, st.ctypes.data, len(st), C.byref(k))
+    if rc != 0:
+        raise EngineError(rc, "tfgpu_queue_json_batches")
+    return [int(x) for x in st[:k.value + 1]]
 
 
 def json_result_schema(fields, opts: Optional[dict] = None):
@@ -185,6 +199,8 @@ class Engine:
             out = PushResult(L.tfgpu_result_rows_in(res), L.tfgpu_result_rows_out(res), L.tfgpu_result_raw_len(res),
                              L.tfgpu_result_n_frames(res), wire, errs)
             out.wire_len = n
+            rs = L.tfgpu_result_row_sizes(res)
+            out.row_sizes = [int(rs[k]) for k in range(out.rows_out)] if rs else None
             return out
         finally:
             self._L.tfgpu_result_release(res)
@@ -245,6 +261,13 @@ class Engine:
             return out, consumed
         finally:
             self._L.tfgpu_result_release(res)
+
+    def measure(self, batch: abi.Batch):
+        """Measurer middleware: ChangeItem.Size.Values of every row (numpy uint64) and their sum."""
+        import numpy as np
+        tb = batch.as_struct(); per = np.zeros(batch.nrows, dtype=np.uint64); tot = C.c_uint64()
+        self._check(self._L.tfgpu_measure(self._h, C.byref(tb), per.ctypes.data, C.byref(tot)))
+        return per, tot.value
 
     def parse_json(self, plan_id: int, data: bytes, opts: Optional[dict] = None, msgs: Optional[list] = None, wire_fmt: int = 0):
         """JSON-lines messages -> typed columns of the parser's result schema -> the plan's transformer chain, on the device.
