@@ -8,6 +8,7 @@
 #include "lz4_block.hpp"
 #include "csv_oracle.hpp"
 #include "json_oracle.hpp"
+#include "debezium_oracle.hpp"
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -824,6 +825,51 @@ int orc_json_parse(const uint8_t* buf, uint64_t len, const orc_json_msg* msgs, u
     *rows = R.rows; *lines = R.lines;
     uint64_t ne = 0; for (auto& e : R.errs) if (ne < errs_cap) errs[ne++] = e;
     *nerrs = R.errs.size();
+    return 0;
+}
+
+int orc_base64_to_numeric(const char* b64, int scale, char* dst, int cap) { std::string o; const int rc = dbz::base64_to_numeric(b64, scale, o); if (rc) return -rc; return copy_out(o, dst, cap); }
+
+int orc_debezium_parse(const uint8_t* buf, uint64_t len, const uint64_t* msg_ends, uint64_t nmsgs, const orc_dbz_field* fields, int nfields, const orc_dbz_opts* o,
+                       orc_buf* out, orc_regions* regions, int32_t* out_types, uint8_t* kinds, uint32_t* tx_ids, uint64_t* lsns, uint64_t* commit_times, uint32_t* row_msg,
+                       uint64_t* rows, tf_rowerr* errs, uint64_t* nerrs) {
+    dbz::Plan pl; pl.use_sr = o->use_sr; pl.schema_id = o->schema_id; pl.check_table = o->check_table;
+    pl.schema_text.assign((const char*)o->schema_text, o->schema_len); pl.table_schema = o->table_schema ? o->table_schema : ""; pl.table_name = o->table_name ? o->table_name : "";
+    for (int i = 0; i < nfields; i++) { dbz::Field f; f.name = fields[i].name; f.recv = fields[i].recv; f.scale = fields[i].scale; f.key = fields[i].key; pl.after.push_back(f); }
+    pl.before = pl.after;
+    auto tf_of = [](int recv) { switch (recv) { case dbz::R_INT8: return (int)TF_INT8; case dbz::R_INT16: return (int)TF_INT16; case dbz::R_INT32: return (int)TF_INT32; case dbz::R_INT64: return (int)TF_INT64; case dbz::R_BOOL: return (int)TF_BOOLEAN;
+                                             case dbz::R_F64: case dbz::R_VSD: return (int)TF_DOUBLE; case dbz::R_BYTES: return (int)TF_BYTES; default: return (int)TF_UTF8; } };
+    std::vector<jsn::ColOut> cols(nfields); uint64_t nrow = 0, ne = 0, start = 0;
+    for (uint64_t m = 0; m < nmsgs; m++) {
+        const uint64_t end = msg_ends[m] <= len ? msg_ends[m] : len;
+        std::string_view msg((const char*)buf + start, end - start); start = end;
+        int events = 0; int rc0 = 0; dbz::Row row0;
+        dbz::do_message(pl, msg, [&](int rc, const dbz::Row& r) { if (events == 0) { rc0 = rc; row0 = r; } events++; });
+        if (events > 1) rc0 = dbz::DBZ_HOST;                          // several events in one registry-framed message: left to the host parser
+        if (rc0) { errs[ne++] = tf_rowerr{(uint32_t)m, (uint16_t)rc0, 0}; continue; }
+        const uint64_t r = nrow++;
+        kinds[r] = (uint8_t)row0.kind; tx_ids[r] = row0.tx_id; lsns[r] = row0.lsn; commit_times[r] = row0.commit_time; row_msg[r] = (uint32_t)m;
+        for (int c = 0; c < nfields; c++) {
+            jsn::ColOut& oc = cols[c]; const dbz::Cell& ce = row0.cells[c]; const int tf = tf_of(fields[c].recv); const int w = jsn::width_tf(tf);
+            if (oc.valid.size() < r / 8 + 1) oc.valid.resize(r / 8 + 1, 0);
+            if (!ce.is_null) oc.valid[r / 8] |= (uint8_t)(1u << (r % 8));
+            if (w) { uint64_t v = 0; if (tf == TF_DOUBLE) std::memcpy(&v, &ce.f, 8); else v = (uint64_t)ce.i; if (ce.is_null) v = 0; for (int k = 0; k < w; k++) oc.values.push_back((uint8_t)(v >> (8 * k))); }
+            else { if (!ce.is_null) oc.heap.insert(oc.heap.end(), ce.s.begin(), ce.s.end()); oc.offs.push_back((uint32_t)oc.heap.size()); }
+        }
+    }
+    std::vector<uint8_t> b;
+    auto put = [&](const void* p, size_t n) -> uint64_t { while (b.size() % 16) b.push_back(0); uint64_t at = b.size(); const uint8_t* q = (const uint8_t*)p; b.insert(b.end(), q, q + n); return at; };
+    for (int c = 0; c < nfields; c++) {
+        jsn::ColOut& oc = cols[c]; orc_regions& g = regions[c]; const int tf = tf_of(fields[c].recv); const int w = jsn::width_tf(tf); out_types[c] = tf;
+        g.values = w ? put(oc.values.data(), oc.values.size()) : ~0ull;
+        oc.valid.resize((nrow + 7) / 8, 0);
+        g.validity = nrow ? put(oc.valid.data(), oc.valid.size()) : ~0ull;
+        g.aux = ~0ull;
+        g.offsets = w ? ~0ull : put(oc.offs.data(), oc.offs.size() * 4);
+        g.heap = w ? ~0ull : put(oc.heap.data(), oc.heap.size());
+        g.heap_len = w ? 0 : oc.heap.size();
+    }
+    to_buf(b, out); *rows = nrow; *nerrs = ne;
     return 0;
 }
 

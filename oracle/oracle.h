@@ -132,6 +132,16 @@ int orc_json_parse(const uint8_t* buf, uint64_t len, const orc_json_msg* msgs, u
                    const orc_json_opts* opts, orc_buf* out, orc_regions* regions, uint64_t* rows, uint64_t* lines,
                    tf_rowerr* errs, uint64_t errs_cap, uint64_t* nerrs);
 
+/* Debezium parser (pkg/parsers/registry/debezium/engine/parser.go + pkg/debezium/receiver*.go), see debezium_oracle.hpp.
+ * One row per message (a schema-registry message holding several events is reported DBZ_HOST). errs[].row = message index.
+ * Outputs: columns of `fields` (validity always present) + per-row kind / txId / lsn / commit time / message index. */
+typedef struct orc_dbz_field { const char* name; int32_t recv; int32_t scale; int32_t key; } orc_dbz_field;
+typedef struct orc_dbz_opts { const uint8_t* schema_text; uint64_t schema_len; uint8_t use_sr, check_table, pad[2]; uint32_t schema_id; const char* table_schema; const char* table_name; } orc_dbz_opts;
+int orc_debezium_parse(const uint8_t* buf, uint64_t len, const uint64_t* msg_ends, uint64_t nmsgs, const orc_dbz_field* fields, int nfields, const orc_dbz_opts* o,
+                       orc_buf* out, orc_regions* regions, int32_t* out_types, uint8_t* kinds, uint32_t* tx_ids, uint64_t* lsns, uint64_t* commit_times, uint32_t* row_msg,
+                       uint64_t* rows, tf_rowerr* errs, uint64_t* nerrs);
+int orc_base64_to_numeric(const char* b64, int scale, char* dst, int cap);
+
 /* BatchJSON (pkg/serializer/queue/json_batcher.go:29-66): starts needs n + 1 entries. */
 int orc_queue_json_batches(const uint64_t* len_elements, uint64_t n, uint64_t max_message_size, uint64_t max_change_items, uint64_t* starts, uint64_t* n_msgs);
 

@@ -32,7 +32,7 @@ from transferia_b200 import abi  # noqa: E402  (memory layout only)
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle.cpp", "oracle.h", "go_strconv.hpp", "hashes.hpp", "lz4_block.hpp", "csv_oracle.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h", ".hpp"))] + [os.path.join(_HERE, "..", "include", "tfgpu.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=subprocess.DEVNULL)
     return so
@@ -834,3 +834,86 @@ def queue_json_batches(lens, max_message_size=0, max_change_items=0):
     a = np.asarray(lens, dtype=np.uint64); st = np.zeros(len(a) + 1, dtype=np.uint64); k = C.c_uint64()
     assert lib().orc_queue_json_batches(a.ctypes.data, len(a), max_message_size, max_change_items, st.ctypes.data, C.byref(k)) == 0
     return [int(x) for x in st[:k.value + 1]]
+
+
+# ----------------------------------------------------------------------------- debezium
+class OrcDbzField(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("recv", C.c_int32), ("scale", C.c_int32), ("key", C.c_int32)]
+
+
+class OrcDbzOpts(C.Structure):
+    _fields_ = [("schema_text", C.c_char_p), ("schema_len", C.c_uint64), ("use_sr", C.c_uint8), ("check_table", C.c_uint8), ("pad", C.c_uint8 * 2),
+                ("schema_id", C.c_uint32), ("table_schema", C.c_char_p), ("table_name", C.c_char_p)]
+
+
+(R_INT8, R_INT16, R_INT32, R_INT64, R_BOOL, R_STRING, R_F64, R_BYTES, R_DECIMAL, R_POINT, R_VSD) = range(1, 12)
+_RECV_YT = {R_INT8: "int8", R_INT16: "int16", R_INT32: "int32", R_INT64: "int64", R_BOOL: "boolean", R_STRING: "utf8", R_F64: "double", R_BYTES: "string",
+            R_DECIMAL: "utf8", R_POINT: "utf8", R_VSD: "double"}
+
+
+def debezium_fields(schema_text: str, which: str = "after"):
+    """receiveTableSchema / receiveFieldColSchema (pkg/debezium/receiver.go:46-62, receiver_engine.go:104-141) with the DEFAULT
+    receivers (common/field_receiver_default.go:15-30): [(name, receiver, scale, key)], and the yt schema of the result."""
+    import json as _json
+    sch = _json.loads(schema_text)
+    node = next((f for f in sch.get("fields", []) if f.get("field") == which), None)
+    if node is None:
+        raise ValueError(f"schema has no '{which}' struct")
+    out = []
+    for f in node.get("fields", []):
+        if (f.get("__dt_original_type_info") or {}).get("original_type"):
+            raise ValueError("database specific receivers are not handled")
+        kt, nm = f.get("type"), f.get("name", "")
+        scale = 0
+        if kt in ("int8", "int16", "int32", "int64"): recv = {"int8": R_INT8, "int16": R_INT16, "int32": R_INT32, "int64": R_INT64}[kt]
+        elif kt == "boolean": recv = R_BOOL
+        elif kt == "string": recv = R_STRING
+        elif kt in ("float", "double"): recv = R_F64
+        elif kt == "bytes":
+            if nm == "org.apache.kafka.connect.data.Decimal":
+                recv = R_DECIMAL; sc = (f.get("parameters") or {}).get("scale", "")
+                scale = int(sc) if sc != "" else 0
+            else: recv = R_BYTES
+        elif kt == "struct" and nm == "io.debezium.data.geometry.Point": recv = R_POINT
+        elif kt == "struct" and nm == "io.debezium.data.VariableScaleDecimal": recv = R_VSD
+        else: raise ValueError(f"kafka type {kt} / {nm} has no default receiver handled here")
+        out.append((f["field"], recv, scale, not f.get("optional", False)))
+    schema = [{"name": n, "type": _RECV_YT[r], "key": k} for n, r, _, k in out]
+    return out, schema
+
+
+def debezium_parse(data: bytes, msg_ends, schema_text: str, use_sr: bool = False, schema_id: int = 0, table=None):
+    """Reference debezium parser over concatenated messages -> (Batch, kinds, tx_ids, lsns, commit_times, row_msg, errors)."""
+    fields, schema = debezium_fields(schema_text)
+    if debezium_fields(schema_text, "before")[0] != fields:
+        raise ValueError("before / after structs differ")
+    nf = len(fields); nm = len(msg_ends)
+    fa = (OrcDbzField * max(1, nf))()
+    keep = _Keep()
+    for k, (n, r, sc, key) in enumerate(fields):
+        fa[k].name = keep.add(n.encode()); fa[k].recv = r; fa[k].scale = sc; fa[k].key = 1 if key else 0
+    o = OrcDbzOpts(); st = keep.add(schema_text.encode()); o.schema_text = st; o.schema_len = len(st); o.use_sr = 1 if use_sr else 0; o.schema_id = schema_id
+    if table: o.check_table = 1; o.table_schema = keep.add(table[0].encode()); o.table_name = keep.add(table[1].encode())
+    ends = keep.add(np.asarray(msg_ends, dtype=np.uint64))
+    src = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data or b"\0")
+    out = OrcBuf(); regs = (OrcRegions * max(1, nf))(); types = np.zeros(max(1, nf), dtype=np.int32)
+    kinds = np.zeros(nm, dtype=np.uint8); tx = np.zeros(nm, dtype=np.uint32); lsn = np.zeros(nm, dtype=np.uint64); ct = np.zeros(nm, dtype=np.uint64); rm = np.zeros(nm, dtype=np.uint32)
+    rows, nerr = C.c_uint64(), C.c_uint64(); errs = (abi.TfRowErr * max(1, nm))()
+    L = lib()
+    L.orc_debezium_parse.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(OrcDbzField), C.c_int, C.POINTER(OrcDbzOpts), C.POINTER(OrcBuf), C.POINTER(OrcRegions),
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(abi.TfRowErr), C.POINTER(C.c_uint64)]
+    rc = L.orc_debezium_parse(src, len(data), ends.ctypes.data, nm, fa, nf, C.byref(o), C.byref(out), regs, types.ctypes.data, kinds.ctypes.data, tx.ctypes.data, lsn.ctypes.data,
+                              ct.ctypes.data, rm.ctypes.data, C.byref(rows), errs, C.byref(nerr))
+    assert rc == 0
+    buf = C.string_at(out.data, out.len) if out.len else b""
+    L.orc_free(C.byref(out))
+    n = rows.value
+    return (_regions_to_batch(buf, regs, [int(t) for t in types[:nf]], n), kinds[:n].copy(), tx[:n].copy(), lsn[:n].copy(), ct[:n].copy(), rm[:n].copy(),
+            [(errs[i].row, errs[i].code, errs[i].term) for i in range(nerr.value)], schema)
+
+
+def base64_to_numeric(b64: str, scale: int) -> str:
+    L = lib(); L.orc_base64_to_numeric.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    b = C.create_string_buffer(4096); n = L.orc_base64_to_numeric(b64.encode(), scale, b, 4096)
+    if n < 0: raise ValueError(f"base64_to_numeric rc {n}")
+    return b.raw[:n].decode()

@@ -1,0 +1,69 @@
+"""Debezium parser: the oracle against the reference's canon ChangeItem on CPU; the device parser against the
+oracle on GPU."""
+import base64
+import json
+import os
+
+import numpy as np
+import pytest
+
+from transferia_b200 import abi
+
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "debezium_goldens.json")))
+
+
+def cell(batch, c, r):
+    col = batch.columns[c]
+    if col.validity is not None and not (col.validity[r >> 3] >> (r & 7)) & 1:
+        return None
+    if col.type in abi.VAR_TYPES:
+        return bytes(col.heap[col.offsets[r]:col.offsets[r + 1]])
+    return col.values[r].item()
+
+
+def test_parser_canon(po):
+    """TestParser (parser_test.go:42-57): the pg basic_types message -> the canonised ChangeItem, column by column."""
+    msg = G["messages"][0].encode(); it = G["items"][0]
+    schema_text = json.dumps(json.loads(msg)["schema"], separators=(",", ":"))
+    # the exact bytes of the embedded schema are what the plan is keyed on
+    raw = msg.decode(); a = raw.index('"schema":') + len('"schema":'); b = raw.index(',"payload":'); schema_text = raw[a:b]
+    batch, kinds, tx, lsn, ct, rm, errs, schema = po.debezium_parse(msg, [len(msg)], schema_text)
+    assert errs == [] and batch.nrows == 1
+    assert [(c["name"], c["type"], c["key"]) for c in schema] == [tuple(t) for t in it["types"]]
+    assert kinds[0] == abi.TF_KIND_INSERT and tx[0] == it["id"] and lsn[0] == it["nextlsn"] and ct[0] == it["commitTime"]
+    for c, (name, want) in enumerate(zip(it["columnnames"], it["columnvalues"])):
+        got = cell(batch, c, 0); ty = schema[c]["type"]
+        if want is None: assert got is None, name
+        elif ty == "string": assert got == base64.b64decode(want), name          # []byte cells are printed as base64 in the canon file
+        elif ty == "utf8": assert got.decode() == want, name
+        elif ty == "boolean": assert bool(got) is want, name
+        else: assert got == want, (name, got, want)
+
+
+def test_base64_to_numeric(po):
+    """typeutil.Base64ToNumeric (helpers.go:972-998) incl. its quirks: scale == len gives ".12", negative two's complement."""
+    f = po.base64_to_numeric
+    assert f("MDk=", 0) == "12345" and f("ME8=", 2) == "123.67" and f("AeJA", 0) == "123456" and f("EAAAAAAAAAAAAAAAAA==", 0) == "1267650600228229401496703205376"
+    assert f(base64.b64encode(b"\xff").decode(), 0) == "-1" and f(base64.b64encode(b"\x80\x00").decode(), 1) == "-3276.8"
+    assert f(base64.b64encode(b"\x0c").decode(), 2) == ".12" and f(base64.b64encode(b"\x01").decode(), 2) == "0.01" and f(base64.b64encode(b"\x00").decode(), 3) == "0"
+
+
+def test_oracle_message_shapes(po):
+    """Envelope handling: unparsed / other-schema / host classes (parser.go:34-66, include_schema.go, debezium_schema.go)."""
+    schema_text = '{"type":"struct","fields":[{"type":"struct","fields":[{"type":"int32","optional":false,"field":"id"},{"type":"string","optional":true,"field":"s"}],"optional":true,"field":"before"},{"type":"struct","fields":[{"type":"int32","optional":false,"field":"id"},{"type":"string","optional":true,"field":"s"}],"optional":true,"field":"after"}]}'
+    src = '"source":{"lsn":7,"ts_ms":5,"txId":3,"schema":"public","table":"t","snapshot":"false"}'
+    def m(payload, schema=schema_text): return ('{"schema":%s,"payload":%s}' % (schema, payload)).encode()
+    msgs = [m('{"before":null,"after":{"id":1,"s":"a"},%s,"op":"c"}' % src), m('{"after":{"id":2,"s":null},%s,"op":"r"}' % src), m('{"after":{"id":3,"s":"x"},%s,"op":"u"}' % src),
+            m('{"before":{"id":4,"s":"d"},"after":null,%s,"op":"d"}' % src), b"", b"{}", b'{"schema":1}', m("null"), m('{"op":"c"}'), m('{"after":{"id":1},%s,"op":"c"}' % src),
+            m('{"after":{"id":"1","s":"a"},%s,"op":"c"}' % src), m('{"after":{"id":1.5,"s":"a"},%s,"op":"c"}' % src), m('{"after":{"id":1,"s":5},%s,"op":"c"}' % src), m('{"after":{"id":1,"s":true},%s,"op":"c"}' % src),
+            m('{"after":{"id":1,"s":"a"},%s,"op":"x"}' % src), m('{"after":{"id":1,"s":"a"},%s,"op":7}' % src), m('{"after":{"id":1,"s":"a"},"source":{"lsn":-1},"op":"c"}'), m('{"after":{"id":1,"s":"a"},"source":{"txId":4294967296},"op":"c"}'),
+            m('{"after":{"id":1,"s":"a"},%s,"op":"c"} trailing' % src)[:-10] + b'} x', m('{"after":{"id":1,"s":"a"},%s,"op":"c"}' % src, '{"type":"struct","fields":[]}'), m('{"after":{"id":1,"s":"__debezium_unavailable_value"},%s,"op":"c"}' % src),
+            m('{"AFTER":{"id":1,"s":"a"},%s,"op":"c"}' % src), m('{"after":{"id":1,"s":"a\\u00e9\\ud83d\\ude00 \xff"},%s,"op":"c","extra":[1,{"a":null}]}' % src), m('{"after":{"id":9,"s":"dup"},"after":null,%s,"op":"c"}' % src),
+            m('{"after":{"id":2147483648,"s":"wrap"},%s,"op":"c"}' % src), b'{"schema":%s,"payload":{"after":{"id":1,"s":"ctl\x01"},"op":"c"}}' % schema_text.encode()]
+    data = b"".join(msgs); ends = np.cumsum([len(x) for x in msgs]).tolist()
+    batch, kinds, tx, lsn, ct, rm, errs, schema = po.debezium_parse(data, ends, schema_text)
+    assert list(rm) == [0, 1, 2, 3, 12, 22, 24] and list(kinds) == [0, 0, 1, 2, 0, 0, 0] and list(tx) == [3] * 7 and list(lsn) == [7] * 7 and list(ct) == [5_000_000] * 7
+    assert [cell(batch, 0, r) for r in range(7)] == [1, 2, 3, 4, 1, 1, -2147483648]
+    assert [cell(batch, 1, r) for r in range(7)] == [b"a", None, b"x", b"d", b"5", "aé\U0001F600 ÿ".encode(), b"wrap"]
+    U, H, S = 48, 49, 50
+    assert [(r, c) for r, c, _ in errs] == [(4, U), (5, U), (6, U), (7, U), (8, U), (9, U), (10, U), (11, U), (13, U), (14, U), (15, U), (16, U), (17, U), (18, U), (19, S), (20, H), (21, H), (23, U), (25, U)]
