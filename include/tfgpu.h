@@ -260,6 +260,33 @@ typedef struct tf_msg { uint64_t end; uint64_t offset; int64_t write_sec; uint32
 int tfgpu_parse_json(tfgpu_engine* e, int plan_id, const char* opts_json, const uint8_t* bytes, uint64_t len, int mem,
                      const tf_msg* msgs, uint32_t n_msgs, int wire_fmt, tfgpu_result** out);
 
+/* parsers.Parser.DoBatch for the Debezium parser (pkg/parsers/registry/debezium/engine/parser.go:34-137; receive path
+ * pkg/debezium/receiver.go:142-220, receiver_engine.go:143-330, common/field_receiver_default.go:15-330).
+ * `bytes` holds n_msgs queue messages back to back (msg_ends[k] = end offset of message k), each either
+ * {"schema":<Kafka Connect schema>,"payload":{before,after,source,op,ts_ms}} or, with "schema_registry":true, a confluent
+ * frame 0x00 | u32be schema id | payload JSON. opts_json: {"schema_text":"<the exact schema JSON text the plan was built
+ * for>","schema_registry":false,"schema_id":0,"check_table":false}. The plan's schema must be the table schema the
+ * reference derives from the schema's `after` struct with the DEFAULT receivers: int8/16/32/64, boolean, string -> utf8,
+ * float/double -> double, bytes -> string (base64) or utf8 for org.apache.kafka.connect.data.Decimal, struct -> utf8 for
+ * io.debezium.data.geometry.Point / double for io.debezium.data.VariableScaleDecimal; key = !optional. Messages are validated
+ * with encoding/json's grammar, typed and fed into the plan's chain ON THE DEVICE; one row per message.
+ * Row errors (row = message index): TF_ROWERR_DBZ_UNPARSED = the reference's `_unparsed` row; TF_ROWERR_DBZ_HOST = the
+ * message needs the Go parser (several events in one frame, keys matching only case-insensitively or with escapes,
+ * __debezium_unavailable_value, magnitudes over 256 bits, nesting over 256); TF_ROWERR_DBZ_OTHER_SCHEMA / _OTHER_TABLE = the
+ * message belongs to another plan. Per message metadata (ChangeItem.Kind / ID / LSN / CommitTime, receiver.go:182-190) comes
+ * back through tfgpu_result_meta_*; tfgpu_result_selection maps output rows to messages. */
+#define TF_ROWERR_DBZ_UNPARSED     48
+#define TF_ROWERR_DBZ_HOST         49
+#define TF_ROWERR_DBZ_OTHER_SCHEMA 50
+#define TF_ROWERR_DBZ_OTHER_TABLE  51
+int tfgpu_parse_debezium(tfgpu_engine* e, int plan_id, const char* opts_json, const uint8_t* bytes, uint64_t len, int mem,
+                         const uint64_t* msg_ends, uint32_t n_msgs, int wire_fmt, tfgpu_result** out);
+const uint32_t*   tfgpu_result_selection(const tfgpu_result* r);          /* rows_out entries: input row of each output row */
+const uint8_t*    tfgpu_result_meta_kinds(const tfgpu_result* r);         /* per message (rows_in entries) */
+const uint32_t*   tfgpu_result_meta_tx_id(const tfgpu_result* r);
+const uint64_t*   tfgpu_result_meta_lsn(const tfgpu_result* r);
+const uint64_t*   tfgpu_result_meta_commit_time(const tfgpu_result* r);
+
 uint64_t          tfgpu_result_rows_out(const tfgpu_result* r);
 uint64_t          tfgpu_result_n_errors(const tfgpu_result* r);
 const tf_rowerr*  tfgpu_result_errors(const tfgpu_result* r);

@@ -188,7 +188,7 @@ inline int receive(const Field& fd, const JV& v, Cell& c) {
 
 struct Plan { std::vector<Field> after, before; std::string schema_text; bool use_sr = false; uint32_t schema_id = 0; std::string table_schema, table_name; bool check_table = false; };
 struct Msg { uint64_t end; };
-struct Row { int kind = 0; uint32_t tx_id = 0; uint64_t lsn = 0, commit_time = 0; std::vector<Cell> cells; };
+struct Row { int err_col = 0; int kind = 0; uint32_t tx_id = 0; uint64_t lsn = 0, commit_time = 0; std::vector<Cell> cells; };
 
 // strconv.ParseUint of a JSON number literal the way encoding/json fills an unsigned struct field
 inline bool lit_uint(const JV& v, int bits, uint64_t& out) { out = 0; if (v.t == JV::NUL) return true; if (v.t != JV::NUM) return false; uint64_t n; if (jsn::go_parse_uint(v.s, 10, 64, n)) return false; if (bits < 64 && (n >> bits)) return false; out = n; return true; }
@@ -196,7 +196,7 @@ inline bool lit_uint(const JV& v, int bits, uint64_t& out) { out = 0; if (v.t ==
 // Receive() of one event text (schema + payload already separated). rc as above; `row` filled on 0
 inline int receive_event(const Plan& pl, sv schema, bool have_payload, const JV& payload, Row& row) {
     if (!have_payload) return DBZ_UNPARSED;                          // UnmarshalPayload(nil): EOF
-    bool bad = false; std::string op; JV source; const JV* after = nullptr; const JV* before = nullptr; uint64_t dummy;
+    bool bad = false; std::string op; JV source; source.t = JV::OBJ; const JV* after = nullptr; const JV* before = nullptr; uint64_t dummy;
     if (payload.t == JV::OBJ) {
         if (has_folded_only(payload, {"after", "before", "op", "source", "transaction", "ts_ms"})) return DBZ_HOST;
         for (auto& kv : payload.kv) {                                 // decode in key order: later duplicates overwrite / merge
@@ -232,9 +232,11 @@ inline int receive_event(const Plan& pl, sv schema, bool have_payload, const JV&
     row.cells.assign(fs.size(), Cell());
     for (size_t i = 0; i < fs.size(); i++) {
         const JV* v = vals ? get(*vals, fs[i].name.c_str()) : nullptr;
+        row.err_col = (int)i;
         if (!v) return DBZ_UNPARSED;                                 // "unable to get field %s from 'after'" :214-216
         const int rc = receive(fs[i], *v, row.cells[i]); if (rc) return rc;
     }
+    row.err_col = 0;
     return 0;
 }
 

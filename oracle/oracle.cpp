@@ -844,9 +844,11 @@ int orc_debezium_parse(const uint8_t* buf, uint64_t len, const uint64_t* msg_end
         const uint64_t end = msg_ends[m] <= len ? msg_ends[m] : len;
         std::string_view msg((const char*)buf + start, end - start); start = end;
         int events = 0; int rc0 = 0; dbz::Row row0;
-        dbz::do_message(pl, msg, [&](int rc, const dbz::Row& r) { if (events == 0) { rc0 = rc; row0 = r; } events++; });
-        if (events > 1) rc0 = dbz::DBZ_HOST;                          // several events in one registry-framed message: left to the host parser
-        if (rc0) { errs[ne++] = tf_rowerr{(uint32_t)m, (uint16_t)rc0, 0}; continue; }
+        // several events in one registry-framed message (parser.go:42-50 splits at the next 0x00): left to the host parser
+        const bool multi = pl.use_sr && msg.size() >= 5 && msg[0] == 0 && msg.find('\0', 5) != std::string_view::npos;
+        if (multi) { rc0 = dbz::DBZ_HOST; events = 1; }
+        else dbz::do_message(pl, msg, [&](int rc, const dbz::Row& r) { if (events == 0) { rc0 = rc; row0 = r; } events++; });
+        if (rc0) { errs[ne++] = tf_rowerr{(uint32_t)m, (uint16_t)rc0, (uint16_t)row0.err_col}; continue; }
         const uint64_t r = nrow++;
         kinds[r] = (uint8_t)row0.kind; tx_ids[r] = row0.tx_id; lsns[r] = row0.lsn; commit_times[r] = row0.commit_time; row_msg[r] = (uint32_t)m;
         for (int c = 0; c < nfields; c++) {

@@ -67,3 +67,87 @@ def test_oracle_message_shapes(po):
     assert [cell(batch, 1, r) for r in range(7)] == [b"a", None, b"x", b"d", b"5", "aé\U0001F600 ÿ".encode(), b"wrap"]
     U, H, S = 48, 49, 50
     assert [(r, c) for r, c, _ in errs] == [(4, U), (5, U), (6, U), (7, U), (8, U), (9, U), (10, U), (11, U), (13, U), (14, U), (15, U), (16, U), (17, U), (18, U), (19, S), (20, H), (21, H), (23, U), (25, U)]
+
+
+# ----------------------------------------------------------------------------------------------------------- GPU parity
+def _shape_msgs():
+    schema_text = '{"type":"struct","fields":[{"type":"struct","fields":[{"type":"int32","optional":false,"field":"id"},{"type":"string","optional":true,"field":"s"}],"optional":true,"field":"before"},{"type":"struct","fields":[{"type":"int32","optional":false,"field":"id"},{"type":"string","optional":true,"field":"s"}],"optional":true,"field":"after"}]}'
+    src = '"source":{"lsn":7,"ts_ms":5,"txId":3,"schema":"public","table":"t","snapshot":"false"}'
+    def m(payload, schema=schema_text): return ('{"schema":%s,"payload":%s}' % (schema, payload)).encode()
+    msgs = [m('{"before":null,"after":{"id":1,"s":"a"},%s,"op":"c"}' % src), m('{"after":{"id":2,"s":null},%s,"op":"r"}' % src), m('{"after":{"id":3,"s":"x"},%s,"op":"u"}' % src),
+            m('{"before":{"id":4,"s":"d"},"after":null,%s,"op":"d"}' % src), b"", b"{}", b'{"schema":1}', m("null"), m('{"op":"c"}'), m('{"after":{"id":1},%s,"op":"c"}' % src),
+            m('{"after":{"id":"1","s":"a"},%s,"op":"c"}' % src), m('{"after":{"id":1.5,"s":"a"},%s,"op":"c"}' % src), m('{"after":{"id":1,"s":5},%s,"op":"c"}' % src), m('{"after":{"id":1,"s":true},%s,"op":"c"}' % src),
+            m('{"after":{"id":1,"s":"a"},%s,"op":"x"}' % src), m('{"after":{"id":1,"s":"a"},%s,"op":7}' % src), m('{"after":{"id":1,"s":"a"},"source":{"lsn":-1},"op":"c"}'), m('{"after":{"id":1,"s":"a"},"source":{"txId":4294967296},"op":"c"}'),
+            m('{"after":{"id":1,"s":"a"},%s,"op":"c"}' % src) + b" x", m('{"after":{"id":1,"s":"a"},%s,"op":"c"}' % src, '{"type":"struct","fields":[]}'), m('{"after":{"id":1,"s":"__debezium_unavailable_value"},%s,"op":"c"}' % src),
+            m('{"AFTER":{"id":1,"s":"a"},%s,"op":"c"}' % src), m('{"after":{"id":1,"s":"a\\u00e9\\ud83d\\ude00 \\ud800 \\udc00x"},%s,"op":"c","extra":[1,{"a":null}]}' % src), m('{"after":{"id":9,"s":"dup"},"after":null,%s,"op":"c"}' % src),
+            m('{"after":{"id":2147483648,"s":"wrap"},%s,"op":"c"}' % src), b'{"schema":%s,"payload":{"after":{"id":1,"s":"ctl\x01"},"op":"c"}}' % schema_text.encode(),
+            b'{"schema":%s,"payload":{"after":{"id":5,"s":"bad utf8 \xff\xc3 \xe2\x82"},"op":"c"}}' % schema_text.encode(), m('{"after":{"id":1,"s":"a"},"after":{"id":2,"s":"b"},%s,"op":"c"}' % src),
+            m('{"after":{"id":1,"s":"a"},%s,"op":"c","Op":"u"}' % src), m('{"after":{"id":1,"s":"a"},"source":{"LSN":1},"op":"c"}'), m('{"after":{"id":1,"s":"a","id":77},"source":null,"op":"c","ts_ms":1.5}'),
+            m('{"after":{"id":1,"s":"a","id":78},"source":null,"op":null,"op":"c","ts_ms":null}'), b' \n{"schema":%s , "payload" : {"after":{"s":"ws","id": 6 },"op":"c"} }\t' % schema_text.encode(),
+            m('{"after":{"id":1e2,"s":"a"},%s,"op":"c"}' % src), m('{"after":{"id":-0,"s":"\\"q\\\\\\/\\b\\f\\n\\r\\t"},%s,"op":"c"}' % src), m('[1]'), b'[{"schema":1}]', m('{"after":[],%s,"op":"c"}' % src)]
+    return schema_text, msgs
+
+
+def _dbz_cmp(eng, po, schema_text, msgs, **kw):
+    from transferia_b200 import engine
+    from test_gpu_parity import assert_batches_equal
+    data = b"".join(msgs); ends = np.cumsum([len(x) for x in msgs]).tolist() if msgs else []
+    schema = engine.debezium_table_schema(schema_text)
+    table = kw.pop("table", ("public", "t"))
+    pid = eng.plan(table[0], table[1], schema, [])
+    got, gerr, meta = eng.parse_debezium(pid, data, ends, schema_text, **kw)
+    ref, kinds, tx, lsn, ct, rm, rerr, rschema = po.debezium_parse(data, ends, schema_text, use_sr=kw.get("schema_registry", False), schema_id=kw.get("schema_id", 0),
+                                                                   table=table if kw.get("check_table") else None)
+    assert [{k: c[k] for k in ("name", "type", "key")} for c in rschema] == schema
+    allow = kw.pop("_allow_host", 0)
+    extra = [e for e in gerr if e not in rerr]
+    if extra and allow:
+        # messages the device hands to the host parser although the oracle decides them (magnitudes over 256 bits, float text
+        # whose rounding Eisel-Lemire leaves open): bounded in number, then replaced by `{}` so that everything else is compared
+        assert all(c == abi.TF_ROWERR_DBZ_HOST for _, c, _ in extra) and len(extra) <= allow, extra
+        msgs = list(msgs)
+        for r, _, _ in extra: msgs[r] = b"{}"
+        return _dbz_cmp(eng, po, schema_text, msgs, table=table, **kw)
+    assert gerr == rerr, (gerr, rerr)
+    assert list(meta["selection"]) == list(rm)
+    assert_batches_equal(got, ref)
+    sel = meta["selection"]
+    assert list(meta["kinds"][sel]) == list(kinds) and list(meta["tx_id"][sel]) == list(tx) and list(meta["lsn"][sel]) == list(lsn) and list(meta["commit_time"][sel]) == list(ct)
+    return got, gerr
+
+
+@pytest.mark.gpu
+def test_device_debezium_canon_and_shapes(eng, po):
+    msg = G["messages"][0].encode(); raw = msg.decode(); a = raw.index('"schema":') + len('"schema":'); b = raw.index(',"payload":')
+    _dbz_cmp(eng, po, raw[a:b], [msg, msg, b"{}", msg], table=("public", "basic_types"))
+    _dbz_cmp(eng, po, raw[a:b], [msg], table=("public", "basic_types"), check_table=True)
+    _dbz_cmp(eng, po, raw[a:b], [msg], table=("public", "other"), check_table=True)
+    schema_text, msgs = _shape_msgs()
+    _dbz_cmp(eng, po, schema_text, msgs)
+    _dbz_cmp(eng, po, schema_text, [])
+    # schema-registry frames: 0x00 | u32be id | payload
+    pay = b'{"after":{"id":1,"s":"sr"},"source":{"lsn":9,"ts_ms":1,"txId":2},"op":"c"}'
+    fr = lambda i, p: b"\x00" + int(i).to_bytes(4, "big") + p
+    _dbz_cmp(eng, po, schema_text, [fr(7, pay), fr(8, pay), b"\x01" + pay, fr(7, pay)[:4], fr(7, pay) + fr(7, pay), fr(7, pay + b" trailing"), fr(7, b"  " + pay), fr(7, b"{"), b""], schema_registry=True, schema_id=7)
+
+
+@pytest.mark.gpu
+def test_device_debezium_numeric_receivers(eng, po):
+    """Decimal / VariableScaleDecimal / Bits / Point over many magnitudes and scales."""
+    st = ('{"type":"struct","fields":[{"type":"struct","fields":[%s],"optional":true,"field":"before"},{"type":"struct","fields":[%s],"optional":true,"field":"after"}]}')
+    fl = ('{"type":"int64","optional":false,"field":"k"},{"type":"bytes","optional":true,"name":"org.apache.kafka.connect.data.Decimal","version":1,"parameters":{"scale":"3"},"field":"d3"},'
+          '{"type":"bytes","optional":true,"name":"org.apache.kafka.connect.data.Decimal","version":1,"field":"d0"},'
+          '{"type":"struct","fields":[],"optional":true,"name":"io.debezium.data.VariableScaleDecimal","version":1,"field":"v"},{"type":"bytes","optional":true,"field":"raw"},'
+          '{"type":"struct","fields":[],"optional":true,"name":"io.debezium.data.geometry.Point","version":1,"field":"pt"},{"type":"float","optional":true,"field":"f"},{"type":"boolean","optional":true,"field":"b"},{"type":"int8","optional":true,"field":"i8"}')
+    schema_text = st % (fl, fl)
+    rng = np.random.default_rng(8); msgs = []
+    for k in range(400):
+        nb = int(rng.integers(0, 40)); mag = bytes(rng.integers(0, 256, nb, dtype=np.uint8)) if k % 7 else b"\x00" * nb
+        b64 = base64.b64encode(mag).decode()
+        if k % 11 == 0: b64 = b64[:-1] + "!"
+        scale = int(rng.integers(-2, 12))
+        pt = rng.choice(['{"x":1.5,"y":-2}', '{"x":"s","y":null,"srid":4}', '{"y":1}', '{"x":true,"y":false,"x":7}', '{"x":[1],"y":2}', 'null', '"str"'])
+        f = rng.choice(["1.5", "1e400", "0.1", "123456789012345678901234567890", "-0.0", "null", '"1.5"', "2.2250738585072014e-308"])
+        msgs.append(('{"schema":%s,"payload":{"after":{"k":%d,"d3":"%s","d0":"%s","v":{"scale":%d,"value":"%s"},"raw":"%s","pt":%s,"f":%s,"b":%s,"i8":%d},"op":"c"}}'
+                     % (schema_text, k, b64, b64, scale, b64, b64, pt, f, rng.choice(["true", "false", "null"]), int(rng.integers(-300, 300)))).encode())
+    _dbz_cmp(eng, po, schema_text, msgs, _allow_host=80)

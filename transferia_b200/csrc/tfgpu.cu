@@ -19,6 +19,7 @@
 #include "kernels_mask.cuh"
 #include "kernels_csv.cuh"
 #include "kernels_json_in.cuh"
+#include "kernels_dbz.cuh"
 #include "kernels_json_out.cuh"
 
 using namespace tfk;
@@ -95,6 +96,8 @@ struct tfgpu_result {
     uint64_t rows_in = 0, rows_out = 0, raw_len = 0, n_frames = 0, consumed = 0;
     std::vector<tf_rowerr> errs;
     uint8_t* bytes = nullptr; uint64_t bytes_len = 0; bool bytes_pinned = false;
+    std::vector<uint32_t> selection;       // parsers: input row (line / message) of every output row
+    std::vector<uint8_t> meta_kinds; std::vector<uint32_t> meta_tx; std::vector<uint64_t> meta_lsn, meta_ct;   // debezium: per message
     std::vector<uint32_t> row_sizes;       // row-text formats: bytes of every output row (incl. its separator / newline)
     // push_columns output
     tf_batch batch{}; std::vector<tf_col> cols; std::vector<uint8_t*> owned;
@@ -1056,6 +1059,146 @@ int tfgpu_parse_json(tfgpu_engine* e, int plan_id, const char* opts_json, const 
     catch (const std::bad_alloc&) { return fail(e, TF_E_RETRY_OOM, "host allocation failed"); }
     catch (const std::exception& x) { return fail(e, TF_E_FATAL_CONFIG, x.what()); }
 }
+
+// ---------------------------------------------------------------------------------------------- Debezium
+// parsers.Parser.DoBatch of the Debezium parser (pkg/parsers/registry/debezium/engine/parser.go:34-137 over
+// pkg/debezium/receiver.go:142-220) fused with the transformer chain and the sink encode.
+namespace {
+struct DbzHostField { std::string name; int recv, scale, tf; bool key; };
+// receiveTableSchema / receiveFieldColSchema (receiver.go:46-62, receiver_engine.go:104-141) with the default receivers
+std::vector<DbzHostField> dbz_fields(const tfj::Value& schema, const char* which) {
+    const tfj::Value* fields = schema.get("fields"); const tfj::Value* node = nullptr;
+    if (fields && fields->kind == tfj::Value::Arr) for (auto& f : fields->arr) if (f->get_str("field") == which) node = f.get();
+    if (!node) throw tfplan::FatalError(TF_E_FATAL_CONFIG, std::string("debezium schema has no '") + which + "' struct");
+    std::vector<DbzHostField> out; const tfj::Value* fs = node->get("fields");
+    if (fs && fs->kind == tfj::Value::Arr) for (auto& f : fs->arr) {
+        DbzHostField h; h.name = f->get_str("field"); h.scale = 0; h.key = !f->get_bool("optional");
+        const std::string kt = f->get_str("type"), nm = f->get_str("name");
+        if (const tfj::Value* oti = f->get("__dt_original_type_info")) if (oti->kind == tfj::Value::Obj && !oti->get_str("original_type").empty())
+            throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "debezium: database specific receivers (original types) are not handled on the device");
+        if (kt == "int8") { h.recv = DR_INT8; h.tf = TF_INT8; } else if (kt == "int16") { h.recv = DR_INT16; h.tf = TF_INT16; } else if (kt == "int32") { h.recv = DR_INT32; h.tf = TF_INT32; }
+        else if (kt == "int64") { h.recv = DR_INT64; h.tf = TF_INT64; } else if (kt == "boolean") { h.recv = DR_BOOL; h.tf = TF_BOOLEAN; } else if (kt == "string") { h.recv = DR_STRING; h.tf = TF_UTF8; }
+        else if (kt == "float" || kt == "double") { h.recv = DR_F64; h.tf = TF_DOUBLE; }
+        else if (kt == "bytes") {
+            if (nm == "org.apache.kafka.connect.data.Decimal") { h.recv = DR_DECIMAL; h.tf = TF_UTF8; const tfj::Value* pa = f->get("parameters"); const std::string sc = pa ? pa->get_str("scale") : ""; if (!sc.empty()) h.scale = atoi(sc.c_str()); }
+            else { h.recv = DR_BYTES; h.tf = TF_BYTES; }
+        } else if (kt == "struct" && nm == "io.debezium.data.geometry.Point") { h.recv = DR_POINT; h.tf = TF_UTF8; }
+        else if (kt == "struct" && nm == "io.debezium.data.VariableScaleDecimal") { h.recv = DR_VSD; h.tf = TF_DOUBLE; }
+        else throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "debezium: field '" + h.name + "' of kafka type " + kt + " / " + nm + " has no default receiver on the device");
+        out.push_back(h);
+    }
+    return out;
+}
+}  // namespace
+
+int tfgpu_parse_debezium(tfgpu_engine* e, int plan_id, const char* opts_json, const uint8_t* bytes, uint64_t len, int mem,
+                         const uint64_t* msg_ends, uint32_t n_msgs, int wire_fmt, tfgpu_result** out) {
+    if (!e || !out || !opts_json || (!bytes && len) || (!msg_ends && n_msgs) || plan_id < 0 || plan_id >= (int)e->plans.size()) return TF_E_FATAL_ARG;
+    *out = nullptr;
+    PlanDev& pd = *e->plans[plan_id];
+    if (len >= (1ull << 32) - 16) return fail(e, TF_E_FATAL_ARG, "debezium batch must be < 4 GiB");
+    if (wire_fmt != 0 && !wire_known(wire_fmt)) return fail(e, TF_E_FATAL_UNSUPPORTED, "wire format not implemented");
+    if (wire_fmt != 0 && !wire_is_ser(wire_fmt) && !pd.plan.has_sink) return fail(e, TF_E_FATAL_CONFIG, "plan was built without a sink");
+    { uint64_t prev = 0; for (uint32_t m = 0; m < n_msgs; m++) { if (msg_ends[m] < prev || msg_ends[m] > len) return fail(e, TF_E_FATAL_ARG, "message ends must be non-decreasing and inside the buffer"); prev = msg_ends[m]; }
+      if ((n_msgs ? msg_ends[n_msgs - 1] : 0) != len) return fail(e, TF_E_FATAL_ARG, "the messages must cover the whole buffer"); }
+    try {
+        CK(cudaSetDevice(e->device));
+        cudaStream_t s = e->stream;
+        const tfplan::Plan& pl = pd.plan; const size_t nc = pl.in_schema.size();
+        auto ov = tfj::parse(opts_json);
+        const std::string schema_text = ov->get_str("schema_text");
+        const bool use_sr = ov->get_bool("schema_registry"), check_table = ov->get_bool("check_table");
+        const uint32_t schema_id = (uint32_t)ov->get_num("schema_id", 0);
+        if (schema_text.empty()) throw tfplan::FatalError(TF_E_FATAL_CONFIG, "debezium: opts.schema_text (the Kafka Connect schema this plan was built for) is required");
+        auto sv = tfj::parse(schema_text.c_str());
+        const std::vector<DbzHostField> fs = dbz_fields(*sv, "after"), fb = dbz_fields(*sv, "before");
+        if (fs.size() != fb.size()) throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "debezium: 'before' and 'after' structs differ");
+        for (size_t i = 0; i < fs.size(); i++) if (fs[i].name != fb[i].name || fs[i].recv != fb[i].recv || fs[i].scale != fb[i].scale) throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "debezium: 'before' and 'after' structs differ");
+        if (fs.size() != nc || nc > JSN_MAX_COLS) throw tfplan::FatalError(TF_E_FATAL_CONFIG, "debezium: the plan schema must be the table schema of the 'after' struct (at most 128 columns)");
+        std::vector<DbzColDev> hc(nc); std::vector<uint8_t> names; int nslots = 0;
+        for (size_t c = 0; c < nc; c++) {
+            const tfplan::ColSchema& cs = pl.in_schema[c]; DbzColDev& d = hc[c]; std::memset(&d, 0, sizeof d);
+            if (cs.name != fs[c].name || cs.tf != fs[c].tf) throw tfplan::FatalError(TF_E_FATAL_CONFIG, "debezium: plan column '" + cs.name + "' does not match the schema field '" + fs[c].name + "' (receiveFieldColSchema type)");
+            for (size_t k = 0; k < c; k++) if (fs[k].name == fs[c].name) throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "debezium: duplicate field " + fs[c].name);
+            for (unsigned char ch : fs[c].name) if (ch >= 0x80 || ch == '\\' || ch == '"' || ch < 0x20) throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "debezium: field names must be plain ASCII on the device");
+            d.recv = fs[c].recv; d.scale = fs[c].scale; d.tf = cs.tf; d.w = in_width(cs.tf); d.slot = d.w ? -1 : nslots++; d.key = fs[c].key;
+            d.name_off = (uint32_t)names.size(); d.name_len = (uint32_t)cs.name.size(); names.insert(names.end(), cs.name.begin(), cs.name.end());
+        }
+        const uint32_t ts_off = (uint32_t)names.size(); names.insert(names.end(), pl.ns.begin(), pl.ns.end());
+        const uint32_t tn_off = (uint32_t)names.size(); names.insert(names.end(), pl.name.begin(), pl.name.end());
+        const uint32_t st_off = (uint32_t)names.size(); names.insert(names.end(), schema_text.begin(), schema_text.end());
+        const uint8_t* d_text = bytes;
+        if (mem == TF_MEM_HOST) { e->csv_text.ensure(len + 64); if (len) CK(cudaMemcpyAsync(e->csv_text.p, bytes, len, cudaMemcpyHostToDevice, s)); d_text = e->csv_text.p; }
+        const uint64_t n = n_msgs;
+        size_t sb = 0; auto need = [&](size_t b) { size_t at = sb; sb += align_up(b ? b : 1, 256); return at; };
+        const size_t o_end = need(n * 8), o_err = need(n), o_ecol = need(n), o_cols = need(nc * sizeof(DbzColDev)), o_names = need(names.size()),
+                     o_ss = need(nc * n * 4), o_sl = need(nc * n * 4), o_len = need((size_t)nslots * n * 4), o_off = need((size_t)nslots * (n + 1) * 4),
+                     o_tot = need((size_t)nslots * 8 + 8), o_base = need((size_t)nslots * 8 + 8), o_kind = need(n), o_tx = need(n * 4), o_lsn = need(n * 8), o_ct = need(n * 8);
+        std::vector<size_t> o_val(nc), o_vld(nc);
+        for (size_t c = 0; c < nc; c++) { o_val[c] = hc[c].w ? need((size_t)hc[c].w * n) : 0; o_vld[c] = need((n / 32 + 2) * 4); }
+        e->csv_stage.ensure(sb + 256);
+        uint8_t* B = e->csv_stage.p;
+        for (size_t c = 0; c < nc; c++) { if (hc[c].w) hc[c].values = B + o_val[c]; hc[c].validity = (uint32_t*)(B + o_vld[c]); }
+        std::vector<uint64_t> col_total(nslots ? nslots : 1, 0), col_base(nslots ? nslots : 1, 0);
+        const uint8_t* heap = nullptr;
+        e->prof_n = 0;
+        if (n) {
+            CK(cudaMemcpyAsync(B + o_end, msg_ends, n * 8, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(B + o_cols, hc.data(), nc * sizeof(DbzColDev), cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(B + o_names, names.data(), names.size(), cudaMemcpyHostToDevice, s));
+            CK(cudaMemsetAsync(B + o_sl, 0, nc * n * 4, s));
+            DbzArgs da; std::memset(&da, 0, sizeof da);
+            da.text = d_text; da.msg_end = (const uint64_t*)(B + o_end); da.nmsgs = n; da.cols = (const DbzColDev*)(B + o_cols); da.ncols = (int)nc; da.names = B + o_names;
+            da.schema_text = B + o_names + st_off; da.schema_len = (uint32_t)schema_text.size(); da.schema_id = schema_id; da.use_sr = use_sr; da.check_table = check_table;
+            da.tbl_schema_off = ts_off; da.tbl_schema_len = (uint32_t)pl.ns.size(); da.tbl_name_off = tn_off; da.tbl_name_len = (uint32_t)pl.name.size();
+            da.span_start = (uint32_t*)(B + o_ss); da.span_len = (uint32_t*)(B + o_sl); da.out_len = (uint32_t*)(B + o_len);
+            da.kinds = B + o_kind; da.tx_id = (uint32_t*)(B + o_tx); da.lsn = (uint64_t*)(B + o_lsn); da.commit_time = (uint64_t*)(B + o_ct); da.err = B + o_err; da.errcol = B + o_ecol;
+            const uint32_t nb = (uint32_t)((n + 127) / 128);
+            e->prof_begin("k_dbz_pass1", s); k_dbz_pass1<<<nb, 128, 0, s>>>(da); e->prof_end(s);
+            if (nslots) {
+                e->prof_begin("k_csv_offsets", s); k_csv_offsets<<<nslots, 1024, 0, s>>>((const uint32_t*)(B + o_len), n, (uint32_t*)(B + o_off), (uint64_t*)(B + o_tot)); e->prof_end(s);
+                CK(cudaMemcpyAsync(col_total.data(), B + o_tot, (size_t)nslots * 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+                uint64_t run = 0; for (int k = 0; k < nslots; k++) { col_base[k] = run; run += align_up(col_total[k], 16); }
+                if (run >= (1ull << 32)) throw tfplan::FatalError(TF_E_FATAL_ARG, "debezium batch: a text column exceeds 4 GiB");
+                e->in_arena.ensure(run + 256); heap = e->in_arena.p;
+                CK(cudaMemcpyAsync(B + o_base, col_base.data(), (size_t)nslots * 8, cudaMemcpyHostToDevice, s));
+                DbzWriteArgs wa{da, (const uint32_t*)(B + o_off), e->in_arena.p, (const uint64_t*)(B + o_base)};
+                e->prof_begin("k_dbz_pass2", s); k_dbz_pass2<<<nb, 128, 0, s>>>(wa); e->prof_end(s);
+            }
+            CK(cudaGetLastError());
+        }
+        std::vector<tf_col> dev(nc);
+        for (size_t c = 0; c < nc; c++) {
+            tf_col& d = dev[c]; std::memset(&d, 0, sizeof d); d.type = hc[c].tf; d.validity = (const uint8_t*)hc[c].validity;
+            if (hc[c].w) d.values = hc[c].values;
+            else { d.offsets = (const uint32_t*)(B + o_off) + (size_t)hc[c].slot * (n + 1); d.heap = heap ? heap + col_base[hc[c].slot] : nullptr; d.heap_len = col_total[hc[c].slot]; }
+        }
+        tf_batch staged; staged.nrows = n; staged.ncols = (uint32_t)nc; staged.mem = TF_MEM_DEVICE; staged.cols = dev.data(); staged.kinds = nullptr;
+        run_chain(e, pd, &staged, dev.data(), n ? B + o_kind : nullptr, wire_fmt == 0 ? TF_WIRE_COLUMNAR_INTERNAL : wire_fmt, n ? B + o_err : nullptr);
+        auto r = std::make_unique<tfgpu_result>();
+        if (wire_fmt == 0) finish_columnar(e, pd, n, r.get()); else finish_wire(e, n, wire_fmt, r.get());
+        if (n) {
+            if (!r->errs.empty()) { std::vector<uint8_t> ecol(n); CK(cudaMemcpyAsync(ecol.data(), B + o_ecol, n, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s)); for (auto& x : r->errs) if (x.term == 0xff) x.term = ecol[x.row]; }
+            r->meta_kinds.resize(n); r->meta_tx.resize(n); r->meta_lsn.resize(n); r->meta_ct.resize(n); r->selection.resize(r->rows_out);
+            CK(cudaMemcpyAsync(r->meta_kinds.data(), B + o_kind, n, cudaMemcpyDeviceToHost, s)); CK(cudaMemcpyAsync(r->meta_tx.data(), B + o_tx, n * 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(r->meta_lsn.data(), B + o_lsn, n * 8, cudaMemcpyDeviceToHost, s)); CK(cudaMemcpyAsync(r->meta_ct.data(), B + o_ct, n * 8, cudaMemcpyDeviceToHost, s));
+            if (r->rows_out) CK(cudaMemcpyAsync(r->selection.data(), e->sel, r->rows_out * 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+        }
+        r->consumed = len;
+        *out = r.release();
+        return TF_OK;
+    } catch (const tfplan::FatalError& f) { return fail(e, f.code, f.what()); }
+    catch (const CudaError& c) { return cuda_fail(e, c); }
+    catch (const std::bad_alloc&) { return fail(e, TF_E_RETRY_OOM, "host allocation failed"); }
+    catch (const std::exception& x) { return fail(e, TF_E_FATAL_CONFIG, x.what()); }
+}
+
+const uint32_t* tfgpu_result_selection(const tfgpu_result* r) { return (r && !r->selection.empty()) ? r->selection.data() : nullptr; }
+const uint8_t* tfgpu_result_meta_kinds(const tfgpu_result* r) { return (r && !r->meta_kinds.empty()) ? r->meta_kinds.data() : nullptr; }
+const uint32_t* tfgpu_result_meta_tx_id(const tfgpu_result* r) { return (r && !r->meta_tx.empty()) ? r->meta_tx.data() : nullptr; }
+const uint64_t* tfgpu_result_meta_lsn(const tfgpu_result* r) { return (r && !r->meta_lsn.empty()) ? r->meta_lsn.data() : nullptr; }
+const uint64_t* tfgpu_result_meta_commit_time(const tfgpu_result* r) { return (r && !r->meta_ct.empty()) ? r->meta_ct.data() : nullptr; }
 
 uint64_t tfgpu_result_consumed(const tfgpu_result* r) { return r ? r->consumed : 0; }
 

@@ -60,6 +60,9 @@ def load_library():
     L.tfgpu_parse_csv.argtypes = [vp, i, cp, vp, u64, i, i, C.POINTER(vp)]
     L.tfgpu_result_row_sizes.argtypes = [vp]; L.tfgpu_result_row_sizes.restype = C.POINTER(C.c_uint32)
     L.tfgpu_queue_json_batches.argtypes = [vp, u64, u64, u64, vp, u64, C.POINTER(u64)]
+    L.tfgpu_parse_debezium.argtypes = [vp, i, cp, vp, u64, i, vp, C.c_uint32, i, C.POINTER(vp)]
+    for fn, ty in (("tfgpu_result_selection", C.c_uint32), ("tfgpu_result_meta_kinds", C.c_uint8), ("tfgpu_result_meta_tx_id", C.c_uint32), ("tfgpu_result_meta_lsn", u64), ("tfgpu_result_meta_commit_time", u64)):
+        getattr(L, fn).argtypes = [vp]; getattr(L, fn).restype = C.POINTER(ty)
     L.tfgpu_measure.argtypes = [vp, C.POINTER(abi.TfBatch), vp, C.POINTER(u64)]
     L.tfgpu_parse_json.argtypes = [vp, i, cp, vp, u64, i, C.POINTER(abi.TfMsg), C.c_uint32, i, C.POINTER(vp)]
     L.tfgpu_result_consumed.argtypes = [vp]; L.tfgpu_result_consumed.restype = u64
@@ -81,12 +84,33 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "tfgpu_version", "tfgpu_engine_create", "tfgpu_engine_destroy", "tfgpu_last_error", "tfgpu_engine_set_stream",
-    "tfgpu_plan", "tfgpu_plan_validate", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_parse_csv", "tfgpu_parse_json", "tfgpu_measure", "tfgpu_result_row_sizes", "tfgpu_queue_json_batches", "tfgpu_result_consumed", "tfgpu_push_encode_resident",
+    "tfgpu_plan", "tfgpu_plan_validate", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_parse_csv", "tfgpu_parse_json", "tfgpu_measure", "tfgpu_result_row_sizes", "tfgpu_queue_json_batches", "tfgpu_parse_debezium", "tfgpu_result_selection", "tfgpu_result_meta_kinds", "tfgpu_result_meta_tx_id", "tfgpu_result_meta_lsn", "tfgpu_result_meta_commit_time", "tfgpu_result_consumed", "tfgpu_push_encode_resident",
     "tfgpu_resident_stats", "tfgpu_resident_fetch", "tfgpu_result_rows_in", "tfgpu_result_rows_out",
     "tfgpu_result_n_errors", "tfgpu_result_errors", "tfgpu_result_batch", "tfgpu_result_bytes",
     "tfgpu_result_bytes_len", "tfgpu_result_raw_len", "tfgpu_result_n_frames", "tfgpu_result_release",
     "tfgpu_engine_launch_count", "tfgpu_profile_enable", "tfgpu_profile_read",
 ]
+
+
+def debezium_table_schema(schema_text: str):
+    """The table schema the reference derives from a Kafka Connect envelope schema's `after` struct with the default receivers
+    (pkg/debezium/receiver.go:46-62, receiver_engine.go:104-141, common/field_receiver_default.go:15-30): key = !optional."""
+    sch = json.loads(schema_text)
+    node = next((f for f in sch.get("fields", []) if f.get("field") == "after"), None)
+    if node is None:
+        raise EngineError(-1, "debezium schema has no 'after' struct")
+    out = []
+    for f in node.get("fields", []):
+        kt, nm = f.get("type"), f.get("name", "")
+        if kt in ("int8", "int16", "int32", "int64", "boolean"): yt = kt
+        elif kt == "string": yt = "utf8"
+        elif kt in ("float", "double"): yt = "double"
+        elif kt == "bytes": yt = "utf8" if nm == "org.apache.kafka.connect.data.Decimal" else "string"
+        elif kt == "struct" and nm == "io.debezium.data.geometry.Point": yt = "utf8"
+        elif kt == "struct" and nm == "io.debezium.data.VariableScaleDecimal": yt = "double"
+        else: raise EngineError(-1, f"debezium: kafka type {kt} / {nm} has no default receiver on the device")
+        out.append({"name": f["field"], "type": yt, "key": not f.get("optional", False)})
+    return out
 
 
 def queue_json_batches(json_row_sizes, max_message_size: int = 0, max_change_items: int = 0):
@@ -259,6 +283,34 @@ class Engine:
             out = PushResult(L.tfgpu_result_rows_in(res), L.tfgpu_result_rows_out(res), L.tfgpu_result_raw_len(res), L.tfgpu_result_n_frames(res),
                              C.string_at(L.tfgpu_result_bytes(res), n) if n else b"", [(ep[k].row, ep[k].code, ep[k].term) for k in range(ne)])
             return out, consumed
+        finally:
+            self._L.tfgpu_result_release(res)
+
+    def parse_debezium(self, plan_id: int, data: bytes, msg_ends, schema_text: str, schema_registry: bool = False, schema_id: int = 0,
+                       check_table: bool = False, wire_fmt: int = 0):
+        """Debezium messages -> typed columns (default receivers) -> the plan's chain, on the device; one row per message.
+        wire_fmt 0: (Batch, row errors, meta) with meta = {"selection", "kinds", "tx_id", "lsn", "commit_time"} (numpy; the last four
+        per MESSAGE, selection per output row); otherwise (PushResult, meta)."""
+        import numpy as np
+        ends = np.asarray(msg_ends, dtype=np.uint64)
+        opts = {"schema_text": schema_text, "schema_registry": schema_registry, "schema_id": schema_id, "check_table": check_table}
+        buf = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data or b"\0")
+        res = C.c_void_p()
+        self._check(self._L.tfgpu_parse_debezium(self._h, plan_id, json.dumps(opts).encode(), buf, len(data), abi.TF_MEM_HOST, ends.ctypes.data, len(ends), wire_fmt, C.byref(res)))
+        try:
+            L = self._L
+            nin, nout = int(L.tfgpu_result_rows_in(res)), int(L.tfgpu_result_rows_out(res))
+            def arr(fn, n, dt):
+                p = getattr(L, fn)(res)
+                return np.ctypeslib.as_array(p, shape=(n,)).astype(dt).copy() if (p and n) else np.zeros(0, dtype=dt)
+            meta = {"selection": arr("tfgpu_result_selection", nout, np.uint32), "kinds": arr("tfgpu_result_meta_kinds", nin, np.uint8), "tx_id": arr("tfgpu_result_meta_tx_id", nin, np.uint32),
+                    "lsn": arr("tfgpu_result_meta_lsn", nin, np.uint64), "commit_time": arr("tfgpu_result_meta_commit_time", nin, np.uint64)}
+            if wire_fmt == 0:
+                b, errs = self._result_batch(res)
+                return b, errs, meta
+            nb = L.tfgpu_result_bytes_len(res); ne = L.tfgpu_result_n_errors(res); ep = L.tfgpu_result_errors(res)
+            return PushResult(nin, nout, L.tfgpu_result_raw_len(res), L.tfgpu_result_n_frames(res), C.string_at(L.tfgpu_result_bytes(res), nb) if nb else b"",
+                              [(ep[k].row, ep[k].code, ep[k].term) for k in range(ne)]), meta
         finally:
             self._L.tfgpu_result_release(res)
 
