@@ -281,6 +281,8 @@ int tfgpu_parse_json(tfgpu_engine* e, int plan_id, const char* opts_json, const 
 #define TF_ROWERR_DBZ_OTHER_TABLE  51
 int tfgpu_parse_debezium(tfgpu_engine* e, int plan_id, const char* opts_json, const uint8_t* bytes, uint64_t len, int mem,
                          const uint64_t* msg_ends, uint32_t n_msgs, int wire_fmt, tfgpu_result** out);
+/* Profiling aid: cycles thread 0 of every k_lz4_frames CTA spent in {stage, match finding, parse, scan, emit} since the last read. */
+int tfgpu_debug_lz4_phases(tfgpu_engine* e, int enable, uint64_t out[8]);
 const uint32_t*   tfgpu_result_selection(const tfgpu_result* r);          /* rows_out entries: input row of each output row */
 const uint8_t*    tfgpu_result_meta_kinds(const tfgpu_result* r);         /* per message (rows_in entries) */
 const uint32_t*   tfgpu_result_meta_tx_id(const tfgpu_result* r);

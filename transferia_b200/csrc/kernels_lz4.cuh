@@ -36,7 +36,9 @@ __host__ __device__ inline uint32_t lz_slot_stride(uint32_t frame_bytes) { retur
 
 struct Lz4Args {
     const uint8_t* raw; DState* st; uint8_t* slots; uint32_t slot_stride; uint32_t* comp_size; uint32_t frame_bytes;
+    unsigned long long* phases;     // optional [8]: cycles thread 0 of every CTA spent in P1..P5 (tfgpu_debug_lz4_phases), NULL = off
 };
+#define LZ_PHASE(k) do { if (a.phases && tid == 0) { const long long t_ = clock64(); atomicAdd(&a.phases[k], (unsigned long long)(t_ - t_ph)); t_ph = t_; } } while (0)
 
 __device__ __forceinline__ uint32_t ld32u(const uint32_t* w, uint32_t p) {   // 4 bytes at byte offset p of a word array in shared memory
     const uint32_t i = p >> 2, s = (p & 3) * 8;
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
     uint16_t* cand = (uint16_t*)(smem + F + 16);                         // 2F bytes; later: sequence descriptors
     uint16_t* table = (uint16_t*)(smem + F + 16 + 2 * F);               // 8 KB; later: per-segment arrays
     uint8_t* vnib = smem + F + 16 + 2 * F + (2u << LZ_HASH_BITS);       // F/4 bytes: 4 valid bits per aligned 4 positions
-    uint32_t* scratch = (uint32_t*)(vnib + F / 4);                       // 48 words
+    uint32_t* scratch = (uint32_t*)(vnib + F / 4);                       // 64 words
     __shared__ uint32_t s_frame;
     // per-segment arrays aliased onto the hash table after P2 (nseg <= 512)
     uint32_t* seg_off = (uint32_t*)table;            // [513]
@@ -80,6 +82,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
         __syncthreads();
         const uint32_t f = s_frame;
         if (f >= n_frames) break;
+        long long t_ph = a.phases ? clock64() : 0;
         const uint64_t pos0 = (uint64_t)f * F;
         const uint32_t len = (uint32_t)((raw_total - pos0 < F) ? raw_total - pos0 : F);
         uint8_t* out = a.slots + (size_t)f * a.slot_stride + LZ_HDR;
@@ -102,6 +105,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
         }
         __syncthreads();
 
+        LZ_PHASE(0);
         // ---- P2: match finding
         const uint32_t nrounds = (len + 2047) / 2048;
         for (uint32_t rd = 0; rd < nrounds; rd++) {
@@ -142,6 +146,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
         }
         __syncthreads();
 
+        LZ_PHASE(1);
         // ---- P3: greedy parse, one thread per 64-byte segment
         const uint32_t nseg = (len + LZ_SEG - 1) / LZ_SEG;
         uint32_t my_nseq = 0, my_trail = 0, seg_start = tid * LZ_SEG, seg_end = 0;
@@ -179,6 +184,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
         }
         __syncthreads();   // everyone is done reading the hash table region? (P2 finished before P3) -> reuse it now
 
+        LZ_PHASE(2);
         // ---- P4a: segmented scan of pending literals: combine(a, b) = b.has ? b : (a.has, a.tr + b.tr)
         {
             uint32_t has = my_nseq > 0, tr = my_trail;
@@ -203,8 +209,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
             }
             __syncthreads();
             if (!has) { tr += scratch[16 + warp]; }
-            if (tid < nseg) { carry_incl[tid] = (uint16_t)tr; nseq_s[tid] = (uint8_t)my_nseq; next_has[tid] = my_nseq ? (uint16_t)tid : (uint16_t)0xffff; }
-            else if (tid < 512) { next_has[tid] = 0xffff; }
+            if (tid < nseg) { carry_incl[tid] = (uint16_t)tr; nseq_s[tid] = (uint8_t)my_nseq; }
         }
         __syncthreads();
         const uint32_t carry_in = (tid > 0 && tid < nseg) ? carry_incl[tid - 1] : 0;
@@ -228,24 +233,20 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
             const uint32_t ll0 = carry_in + (p0 - seg_start);
             delta0[tid] = (int32_t)(my_off + 1 + ext_bytes(ll0)) - (int32_t)(p0 - ll0);
         }
-        // suffix-min over next_has: next_has[s] = first segment > s that has a sequence
-        __syncthreads();
+        // first later segment that has a sequence (it owns this segment's trailing literals): warp ballots + one barrier
+        uint32_t my_next_has = 0xffff;
         {
-            uint16_t v = (tid + 1 < 512) ? next_has[tid + 1] : (uint16_t)0xffff;    // shift: strictly later segments
+            const uint32_t hm = __ballot_sync(0xffffffffu, tid < nseg && my_nseq > 0);
+            if (lane == 0) scratch[40 + warp] = hm;
             __syncthreads();
-            next_has[tid] = v;
-            __syncthreads();
-            for (uint32_t d = 1; d < 512; d <<= 1) {
-                const uint16_t o = (tid + d < 512) ? next_has[tid + d] : (uint16_t)0xffff;
-                __syncthreads();
-                if (o < v) v = o;
-                next_has[tid] = v;
-                __syncthreads();
-            }
+            const uint32_t above = lane == 31 ? 0u : (hm >> (lane + 1));
+            if (above) my_next_has = tid + (uint32_t)__ffs((int)above);
+            else for (uint32_t w = warp + 1; w < LZ_THREADS / 32; w++) { const uint32_t m = scratch[40 + w]; if (m) { my_next_has = w * 32 + (uint32_t)__ffs((int)m) - 1; break; } }
         }
         const uint32_t ll_final = nseg ? carry_incl[nseg - 1] : 0;
         const int32_t delta_final = (int32_t)(total_seq_bytes + 1 + ext_bytes(ll_final)) - (int32_t)(len - ll_final);
 
+        LZ_PHASE(3);
         // ---- P5: emit
         if (tid < nseg) {
             uint8_t* o = out + my_off; uint32_t prev_end = seg_start;
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
                 prev_end = p + ml;
             }
             if (seg_end > prev_end) {   // trailing literals belong to the next sequence downstream
-                const uint32_t nh = next_has[tid];
+                const uint32_t nh = my_next_has;
                 const int32_t dl = (nh != 0xffff && nh < nseg) ? delta0[nh] : delta_final;
                 copy_s2g(out + ((int32_t)prev_end + dl), data_w, prev_end, seg_end - prev_end);
             }
@@ -275,6 +276,8 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
             if (ll_final >= 15) o = put_ext(o, ll_final);
             a.comp_size[f] = total_seq_bytes + 1 + ext_bytes(ll_final) + ll_final;
         }
+        __syncthreads();
+        LZ_PHASE(4);
     }
 }
 

@@ -78,6 +78,7 @@ struct tfgpu_engine {
     uint64_t last_nrows = 0; bool last_has_filter = false; int last_wire_fmt = 0;
     uint8_t* pinned = nullptr; size_t pinned_cap = 0;
     DevBuf json_sizes;
+    unsigned long long* lz_phases = nullptr;      // debug: per-phase cycle counters of k_lz4_frames
     void* work_json_sizes(uint64_t n) { json_sizes.ensure(n * 4 + 256); return json_sizes.p; }
     // optional per-kernel CUDA-event timing of the last call (bench roofline)
     bool prof_on = false; std::vector<cudaEvent_t> prof_ev; std::vector<const char*> prof_names; int prof_n = 0;
@@ -413,8 +414,8 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         }
     }
     if (lz) {
-        Lz4Args za{e->raw.p, e->d_state, e->slots.p, stride, e->comp_size, e->frame_bytes};
-        const size_t smem = e->frame_bytes + 16 + 2 * (size_t)e->frame_bytes + (2u << LZ_HASH_BITS) + e->frame_bytes / 4 + 48 * 4;
+        Lz4Args za{e->raw.p, e->d_state, e->slots.p, stride, e->comp_size, e->frame_bytes, e->lz_phases};
+        const size_t smem = e->frame_bytes + 16 + 2 * (size_t)e->frame_bytes + (2u << LZ_HASH_BITS) + e->frame_bytes / 4 + 64 * 4;
         const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (smem + 1024)));
         const uint32_t grid = (uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * per_sm);
         e->prof_begin("k_lz4_frames", s); k_lz4_frames<<<grid, LZ_THREADS, smem, s>>>(za); e->prof_end(s);
@@ -1192,6 +1193,18 @@ int tfgpu_parse_debezium(tfgpu_engine* e, int plan_id, const char* opts_json, co
     catch (const CudaError& c) { return cuda_fail(e, c); }
     catch (const std::bad_alloc&) { return fail(e, TF_E_RETRY_OOM, "host allocation failed"); }
     catch (const std::exception& x) { return fail(e, TF_E_FATAL_CONFIG, x.what()); }
+}
+
+// debug / profiling aid: cycles thread 0 of every k_lz4_frames CTA spent per phase since enabling (stage, match, parse, scan, emit)
+int tfgpu_debug_lz4_phases(tfgpu_engine* e, int enable, uint64_t out[8]) {
+    if (!e) return TF_E_FATAL_ARG;
+    try {
+        CK(cudaSetDevice(e->device));
+        if (enable && !e->lz_phases) { CK(cudaMalloc(&e->lz_phases, 64)); CK(cudaMemset(e->lz_phases, 0, 64)); }
+        if (out && e->lz_phases) { CK(cudaStreamSynchronize(e->stream)); CK(cudaMemcpy(out, e->lz_phases, 64, cudaMemcpyDeviceToHost)); CK(cudaMemset(e->lz_phases, 0, 64)); }
+        if (!enable && e->lz_phases) { CK(cudaFree(e->lz_phases)); e->lz_phases = nullptr; }
+        return TF_OK;
+    } catch (const CudaError& c) { return cuda_fail(e, c); }
 }
 
 const uint32_t* tfgpu_result_selection(const tfgpu_result* r) { return (r && !r->selection.empty()) ? r->selection.data() : nullptr; }

@@ -63,6 +63,7 @@ def load_library():
     L.tfgpu_parse_debezium.argtypes = [vp, i, cp, vp, u64, i, vp, C.c_uint32, i, C.POINTER(vp)]
     for fn, ty in (("tfgpu_result_selection", C.c_uint32), ("tfgpu_result_meta_kinds", C.c_uint8), ("tfgpu_result_meta_tx_id", C.c_uint32), ("tfgpu_result_meta_lsn", u64), ("tfgpu_result_meta_commit_time", u64)):
         getattr(L, fn).argtypes = [vp]; getattr(L, fn).restype = C.POINTER(ty)
+    L.tfgpu_debug_lz4_phases.argtypes = [vp, i, C.POINTER(u64)]
     L.tfgpu_measure.argtypes = [vp, C.POINTER(abi.TfBatch), vp, C.POINTER(u64)]
     L.tfgpu_parse_json.argtypes = [vp, i, cp, vp, u64, i, C.POINTER(abi.TfMsg), C.c_uint32, i, C.POINTER(vp)]
     L.tfgpu_result_consumed.argtypes = [vp]; L.tfgpu_result_consumed.restype = u64
@@ -84,7 +85,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "tfgpu_version", "tfgpu_engine_create", "tfgpu_engine_destroy", "tfgpu_last_error", "tfgpu_engine_set_stream",
-    "tfgpu_plan", "tfgpu_plan_validate", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_parse_csv", "tfgpu_parse_json", "tfgpu_measure", "tfgpu_result_row_sizes", "tfgpu_queue_json_batches", "tfgpu_parse_debezium", "tfgpu_result_selection", "tfgpu_result_meta_kinds", "tfgpu_result_meta_tx_id", "tfgpu_result_meta_lsn", "tfgpu_result_meta_commit_time", "tfgpu_result_consumed", "tfgpu_push_encode_resident",
+    "tfgpu_plan", "tfgpu_plan_validate", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_parse_csv", "tfgpu_parse_json", "tfgpu_measure", "tfgpu_result_row_sizes", "tfgpu_queue_json_batches", "tfgpu_parse_debezium", "tfgpu_debug_lz4_phases", "tfgpu_result_selection", "tfgpu_result_meta_kinds", "tfgpu_result_meta_tx_id", "tfgpu_result_meta_lsn", "tfgpu_result_meta_commit_time", "tfgpu_result_consumed", "tfgpu_push_encode_resident",
     "tfgpu_resident_stats", "tfgpu_resident_fetch", "tfgpu_result_rows_in", "tfgpu_result_rows_out",
     "tfgpu_result_n_errors", "tfgpu_result_errors", "tfgpu_result_batch", "tfgpu_result_bytes",
     "tfgpu_result_bytes_len", "tfgpu_result_raw_len", "tfgpu_result_n_frames", "tfgpu_result_release",
@@ -313,6 +314,12 @@ class Engine:
                               [(ep[k].row, ep[k].code, ep[k].term) for k in range(ne)]), meta
         finally:
             self._L.tfgpu_result_release(res)
+
+    def lz4_phases(self, enable: bool = True):
+        """Cycles spent per k_lz4_frames phase (stage, match, parse, scan, emit) since the last read (profiling aid)."""
+        out = (C.c_uint64 * 8)()
+        self._check(self._L.tfgpu_debug_lz4_phases(self._h, 1 if enable else 0, out))
+        return [int(x) for x in out[:5]]
 
     def measure(self, batch: abi.Batch):
         """Measurer middleware: ChangeItem.Size.Values of every row (numpy uint64) and their sum."""
