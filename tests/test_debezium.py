@@ -93,13 +93,12 @@ def _dbz_cmp(eng, po, schema_text, msgs, **kw):
     from test_gpu_parity import assert_batches_equal
     data = b"".join(msgs); ends = np.cumsum([len(x) for x in msgs]).tolist() if msgs else []
     schema = engine.debezium_table_schema(schema_text)
-    table = kw.pop("table", ("public", "t"))
+    table = kw.pop("table", ("public", "t")); allow = kw.pop("_allow_host", 0)
     pid = eng.plan(table[0], table[1], schema, [])
     got, gerr, meta = eng.parse_debezium(pid, data, ends, schema_text, **kw)
     ref, kinds, tx, lsn, ct, rm, rerr, rschema = po.debezium_parse(data, ends, schema_text, use_sr=kw.get("schema_registry", False), schema_id=kw.get("schema_id", 0),
                                                                    table=table if kw.get("check_table") else None)
     assert [{k: c[k] for k in ("name", "type", "key")} for c in rschema] == schema
-    allow = kw.pop("_allow_host", 0)
     extra = [e for e in gerr if e not in rerr]
     if extra and allow:
         # messages the device hands to the host parser although the oracle decides them (magnitudes over 256 bits, float text

@@ -25,7 +25,7 @@ namespace tfk {
 
 #define LZ_THREADS 512
 #define LZ_SEG 64
-#define LZ_HASH_BITS 12
+#define LZ_HASH_BITS 11      /* 2048 entries of u32: tag16 << 16 | position */
 #define LZ_MAX_FRAME 32768
 #define LZ_HDR 25          // 16 checksum + 1 method + 4 compressed size + 4 raw size
 
@@ -63,9 +63,9 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
     uint32_t* data_w = (uint32_t*)smem;                                  // F + 16 bytes
     uint8_t* data = smem;
     uint16_t* cand = (uint16_t*)(smem + F + 16);                         // 2F bytes; later: sequence descriptors
-    uint16_t* table = (uint16_t*)(smem + F + 16 + 2 * F);               // 8 KB; later: per-segment arrays
-    uint8_t* vnib = smem + F + 16 + 2 * F + (2u << LZ_HASH_BITS);       // F/4 bytes: 4 valid bits per aligned 4 positions
-    uint32_t* scratch = (uint32_t*)(vnib + F / 4);                       // 64 words
+    uint32_t* table = (uint32_t*)(smem + F + 16 + 2 * F);               // 8 KB; later: per-segment arrays
+    uint8_t* vbits = smem + F + 16 + 2 * F + (4u << LZ_HASH_BITS);      // F/8 bytes: 1 candidate bit per position
+    uint32_t* scratch = (uint32_t*)(vbits + F / 8);                      // 64 words
     __shared__ uint32_t s_frame;
     // per-segment arrays aliased onto the hash table after P2 (nseg <= 512)
     uint32_t* seg_off = (uint32_t*)table;            // [513]
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
                 if (i < nv) v = __ldg(g + i);
                 s4[i] = v;
             }
-            for (uint32_t i = tid; i < (1u << LZ_HASH_BITS) / 2; i += LZ_THREADS) ((uint32_t*)table)[i] = 0;
+            for (uint32_t i = tid; i < (1u << LZ_HASH_BITS); i += LZ_THREADS) table[i] = 0;
         }
         __syncthreads();
         if (len & 15) {   // zero the bytes past len inside the last 16-byte chunk (they belong to the next frame)
@@ -111,38 +111,39 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
         for (uint32_t rd = 0; rd < nrounds; rd++) {
             const uint32_t p0 = rd * 2048 + tid * 4;
             const bool active = p0 < F;                         // F is a multiple of 64, so p0 + 3 < F too
-            uint32_t seq[4], h[4], c[4];
+            uint32_t idx[4], tag[4], c[4];
             if (active) {
                 const uint32_t w0 = data_w[p0 >> 2], w1 = data_w[(p0 >> 2) + 1];
+                uint32_t seq[4];
                 seq[0] = w0; seq[1] = __funnelshift_r(w0, w1, 8); seq[2] = __funnelshift_r(w0, w1, 16); seq[3] = __funnelshift_r(w0, w1, 24);
 #pragma unroll
-                for (int k = 0; k < 4; k++) { h[k] = (seq[k] * 2654435761u) >> (32 - LZ_HASH_BITS); c[k] = table[h[k]]; }
+                for (int k = 0; k < 4; k++) { const uint32_t h = seq[k] * 2654435761u; idx[k] = h >> (32 - LZ_HASH_BITS); tag[k] = (h << LZ_HASH_BITS) & 0xffff0000u; c[k] = table[idx[k]]; }
             }
             __syncthreads();
-            bool v[4];
+            uint32_t vm = 0;      // candidate bits: the 27 known hash bits agree; the bytes are compared by the parser (P3)
             if (active) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const uint32_t p = p0 + k;
-                    if (p < len) table[h[k]] = (uint16_t)p;
-                    v[k] = (p + 12 <= len) && c[k] < p && ld32u(data_w, c[k]) == seq[k];   // MFLIMIT
+                    if (p < len) table[idx[k]] = tag[k] | p;
+                    if ((p + 12 <= len) && (c[k] & 0xffff0000u) == tag[k] && (c[k] & 0xffffu) < p) vm |= 1u << k;   // MFLIMIT
                 }
             }
             __syncthreads();
             if (active) {   // second probe: sees this round's inserts, recovers repeats whose first occurrence is in this round
-                uint32_t nib = 0;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const uint32_t p = p0 + k;
-                    if (!v[k] && p + 12 <= len) {
-                        const uint32_t c2 = table[h[k]];
-                        if (c2 < p && ld32u(data_w, c2) == seq[k]) { v[k] = true; c[k] = c2; }
+                    if (!((vm >> k) & 1) && p + 12 <= len) {
+                        const uint32_t c2 = table[idx[k]];
+                        if ((c2 & 0xffff0000u) == tag[k] && (c2 & 0xffffu) < p) { vm |= 1u << k; c[k] = c2; }
                     }
-                    nib |= (v[k] ? 1u : 0u) << k;
                 }
-                *(uint2*)(cand + p0) = make_uint2(c[0] | (c[1] << 16), c[2] | (c[3] << 16));
-                vnib[p0 >> 2] = (uint8_t)nib;
+                *(uint2*)(cand + p0) = make_uint2((c[0] & 0xffffu) | (c[1] << 16), (c[2] & 0xffffu) | (c[3] << 16));
             }
+            // two lanes share one byte of the bit map
+            const uint32_t other = __shfl_down_sync(0xffffffffu, vm, 1);
+            if (active && !(lane & 1)) vbits[p0 >> 3] = (uint8_t)(vm | (other << 4));
         }
         __syncthreads();
 
@@ -155,12 +156,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
             seg_end = seg_start + LZ_SEG < len ? seg_start + LZ_SEG : len;
             const uint32_t lim5 = len >= 5 ? len - 5 : 0;
             const uint32_t limit = seg_end < lim5 ? seg_end : lim5;       // matches end before the last 5 bytes and inside the segment
-            // 16 nibble bytes -> one 64-bit mask (bit i = position seg_start + i may start a match)
-            const uint4 nb = *(const uint4*)(vnib + 16 * tid);
-            uint64_t lo = (uint64_t)nb.x | ((uint64_t)nb.y << 32), hi = (uint64_t)nb.z | ((uint64_t)nb.w << 32);
-            lo = (lo | (lo >> 4)) & 0x00FF00FF00FF00FFULL; lo = (lo | (lo >> 8)) & 0x0000FFFF0000FFFFULL; lo = (lo | (lo >> 16)) & 0xFFFFFFFFULL;
-            hi = (hi | (hi >> 4)) & 0x00FF00FF00FF00FFULL; hi = (hi | (hi >> 8)) & 0x0000FFFF0000FFFFULL; hi = (hi | (hi >> 16)) & 0xFFFFFFFFULL;
-            const uint64_t m64 = lo | (hi << 32);
+            const uint64_t m64 = *(const uint64_t*)(vbits + 8 * tid);      // bit i = position seg_start + i has a candidate
             uint32_t cur = 0, last_end = seg_start;
             while (cur < LZ_SEG) {
                 const uint64_t mm = m64 >> cur;
@@ -170,13 +166,14 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
                 if (p + 4 > limit) break;
                 const uint32_t c = cand[p];
                 const uint32_t maxl = limit - p;
-                uint32_t ml = 4;
+                uint32_t ml = 0;
                 while (ml < maxl) {
                     const uint32_t x = ld32u(data_w, c + ml) ^ ld32u(data_w, p + ml);
                     if (x) { ml += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
                     ml += 4;
                 }
                 if (ml > maxl) ml = maxl;
+                if (ml < 4) { cur = r + 1; continue; }            // the tag agreed but the bytes do not: not a match
                 desc[my_nseq] = make_uint2(p | (ml << 16), p - c);
                 my_nseq++; cur = r + ml; last_end = p + ml;
             }

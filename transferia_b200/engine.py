@@ -328,17 +328,18 @@ class Engine:
         self._check(self._L.tfgpu_measure(self._h, C.byref(tb), per.ctypes.data, C.byref(tot)))
         return per, tot.value
 
-    def parse_json(self, plan_id: int, data: bytes, opts: Optional[dict] = None, msgs: Optional[list] = None, wire_fmt: int = 0):
+    def parse_json(self, plan_id: int, data: bytes, opts: Optional[dict] = None, msgs: Optional[list] = None, wire_fmt: int = 0, copy_bytes: bool = True):
         """JSON-lines messages -> typed columns of the parser's result schema -> the plan's transformer chain, on the device.
         msgs: [(end, offset, write_sec, write_nsec)] (default: one message = all of `data`).
-        wire_fmt 0: (Batch, row errors, non-empty lines); otherwise PushResult."""
+        wire_fmt 0: (Batch, row errors, non-empty lines); otherwise PushResult (copy_bytes=False leaves the wire bytes in the
+        engine's pinned landing buffer and only reports their length)."""
         msgs = msgs if msgs is not None else [(len(data), 0, 0, 0)]
         ms = (abi.TfMsg * max(1, len(msgs)))()
         for k, (end, off, ws, wn) in enumerate(msgs):
             ms[k].end, ms[k].offset, ms[k].write_sec, ms[k].write_nsec = end, off, ws, wn
-        buf = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data or b"\0")
+        buf = C.c_char_p(data if data else b"\0")          # the bytes object's own storage: no copy
         res = C.c_void_p()
-        self._check(self._L.tfgpu_parse_json(self._h, plan_id, json.dumps(opts or {}).encode(), buf, len(data), abi.TF_MEM_HOST, ms, len(msgs), wire_fmt, C.byref(res)))
+        self._check(self._L.tfgpu_parse_json(self._h, plan_id, json.dumps(opts or {}).encode(), C.cast(buf, C.c_void_p), len(data), abi.TF_MEM_HOST, ms, len(msgs), wire_fmt, C.byref(res)))
         try:
             L = self._L
             if wire_fmt == 0:
@@ -346,8 +347,10 @@ class Engine:
                 return b, errs, int(L.tfgpu_result_rows_in(res))
             n = L.tfgpu_result_bytes_len(res)
             ne = L.tfgpu_result_n_errors(res); ep = L.tfgpu_result_errors(res)
-            return PushResult(L.tfgpu_result_rows_in(res), L.tfgpu_result_rows_out(res), L.tfgpu_result_raw_len(res), L.tfgpu_result_n_frames(res),
-                              C.string_at(L.tfgpu_result_bytes(res), n) if n else b"", [(ep[k].row, ep[k].code, ep[k].term) for k in range(ne)])
+            out = PushResult(L.tfgpu_result_rows_in(res), L.tfgpu_result_rows_out(res), L.tfgpu_result_raw_len(res), L.tfgpu_result_n_frames(res),
+                             C.string_at(L.tfgpu_result_bytes(res), n) if (n and copy_bytes) else b"", [(ep[k].row, ep[k].code, ep[k].term) for k in range(ne)])
+            out.wire_len = n
+            return out
         finally:
             self._L.tfgpu_result_release(res)
 
