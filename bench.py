@@ -33,6 +33,9 @@ METRIC = "ChangeItems/sec on ClickBench-shaped 99-col batches (filter_rows + cas
 FALLBACK_HBM_GBS = 6650.0
 
 
+TRAFFIC_PROFILE = "profiles/r1c_traffic.json"   # written by scripts/ncu_summary.py from the capture under profiles/
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -348,6 +351,12 @@ def main():
         lz_bytes = st["raw_bytes"] + (st["wire_bytes"] - 25 * ((st["raw_bytes"] + args.frame_bytes - 1) // args.frame_bytes))
         achieved = lz_bytes / (lz_ms / 1e3) / 1e9 if lz_ms else 0.0
         step_ms = sum(kernel_avg.values())
+        traffic, traffic_src = None, None      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, TRAFFIC_PROFILE)))["k_lz4_frames"]
+            traffic = int(tj["dram_bytes_read"] + tj["dram_bytes_write"]); traffic_src = TRAFFIC_PROFILE
+        except Exception:
+            pass
         out = {
             "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -363,7 +372,7 @@ def main():
                     "steps": e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_lz4_frames", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(lz_bytes), "kernel_ms": lz_ms,
                          "kernel_share_of_step": lz_ms / step_ms if step_ms else None,
                          "all_kernels_ms": {n: round(v, 4) for n, v in sorted(kernel_avg.items())}},

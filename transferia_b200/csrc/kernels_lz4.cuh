@@ -57,6 +57,27 @@ __device__ __forceinline__ void copy_s2g(uint8_t* dst, const uint32_t* data_w, u
     while (n) { *dst++ = data[src++]; n--; }
 }
 
+// Byte stream writer into global memory that stores whole aligned words: bytes are collected in a register and written as
+// one 4-byte store; only the first / last word of a thread's span (shared with its neighbours) falls back to byte stores.
+struct LzWriter {
+    uint8_t* wp; uint32_t acc, lo, fill;       // bytes [lo, fill) of the word at wp are ours and sit in acc
+    __device__ __forceinline__ void start(uint8_t* p) { const uint32_t al = (uint32_t)((uintptr_t)p & 3); wp = p - al; acc = 0; lo = al; fill = al; }
+    __device__ __forceinline__ void flush() {
+        if (fill == lo) return;
+        if (lo == 0 && fill == 4) *(uint32_t*)wp = acc;
+        else for (uint32_t b = lo; b < fill; b++) wp[b] = (uint8_t)(acc >> (8 * b));
+    }
+    __device__ __forceinline__ void put(uint32_t b) { acc |= b << (8 * fill); if (++fill == 4) { flush(); wp += 4; acc = 0; lo = 0; fill = 0; } }
+    __device__ __forceinline__ void skip(uint32_t n) { if (!n) return; flush(); start(wp + fill + n); }
+    __device__ __forceinline__ void ext(uint32_t x) { x -= 15; while (x >= 255) { put(255); x -= 255; } put(x); }      // x >= 15
+    __device__ __forceinline__ void copy(const uint32_t* data_w, uint32_t src, uint32_t n) {                             // literals from shared memory
+        const uint8_t* d = (const uint8_t*)data_w;
+        while (n && fill) { put(d[src++]); n--; }
+        for (; n >= 4; n -= 4, src += 4, wp += 4) *(uint32_t*)wp = ld32u(data_w, src);
+        while (n) { put(d[src++]); n--; }
+    }
+};
+
 __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t F = a.frame_bytes;
@@ -246,21 +267,22 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
         LZ_PHASE(3);
         // ---- P5: emit
         if (tid < nseg) {
-            uint8_t* o = out + my_off; uint32_t prev_end = seg_start;
+            LzWriter w; w.start(out + my_off); uint32_t prev_end = seg_start;
             for (uint32_t k = 0; k < my_nseq; k++) {
                 const uint2 d = desc[k];
                 const uint32_t p = d.x & 0xffff, ml = d.x >> 16, off = d.y;
                 const uint32_t cin = (k == 0 ? carry_in : 0);
                 const uint32_t ll = cin + (p - prev_end);
                 const uint32_t mt = ml - 4;
-                *o++ = (uint8_t)(((ll < 15 ? ll : 15) << 4) | (mt < 15 ? mt : 15));
-                if (ll >= 15) o = put_ext(o, ll);
-                copy_s2g(o + cin, data_w, prev_end, p - prev_end);
-                o += ll;
-                *o++ = (uint8_t)off; *o++ = (uint8_t)(off >> 8);
-                if (mt >= 15) o = put_ext(o, mt);
+                w.put(((ll < 15 ? ll : 15) << 4) | (mt < 15 ? mt : 15));
+                if (ll >= 15) w.ext(ll);
+                w.skip(cin);                                  // literals carried in from earlier segments: their owners write them
+                w.copy(data_w, prev_end, p - prev_end);
+                w.put(off & 0xff); w.put(off >> 8);
+                if (mt >= 15) w.ext(mt);
                 prev_end = p + ml;
             }
+            w.flush();
             if (seg_end > prev_end) {   // trailing literals belong to the next sequence downstream
                 const uint32_t nh = my_next_has;
                 const int32_t dl = (nh != 0xffff && nh < nseg) ? delta0[nh] : delta_final;
@@ -366,6 +388,8 @@ struct FrameArgs { uint8_t* slots; uint32_t slot_stride; const uint32_t* comp_si
 // memory (double buffered) while the lanes hash the previous 512 bytes out of it.
 #define SEAL_STEP 512
 #define SEAL_STRIDE 528
+#define SEAL_STAGES 4
+#define SEAL_SMEM ((size_t)SEAL_STAGES * 32 * SEAL_STRIDE + 32 * 304)
 __device__ __forceinline__ uint64_t sm64(const uint8_t* base, uint32_t off) { return *(const uint64_t*)(base + off); }
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -375,8 +399,10 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(32) k_frame_seal(FrameArgs a) {
-    __shared__ __align__(16) uint8_t s_buf[2][32][SEAL_STRIDE];
-    __shared__ __align__(16) uint8_t s_tail[32][304];
+    // SEAL_STAGES steps of 512 bytes per frame in flight: with one warp per SM nothing else hides the load latency
+    extern __shared__ __align__(16) uint8_t seal_smem[];
+    uint8_t (*s_buf)[32][SEAL_STRIDE] = (uint8_t (*)[32][SEAL_STRIDE])seal_smem;                                  // [SEAL_STAGES][32][SEAL_STRIDE]
+    uint8_t (*s_tail)[304] = (uint8_t (*)[304])(seal_smem + (size_t)SEAL_STAGES * 32 * SEAL_STRIDE);              // [32][304]
     const uint32_t lane = threadIdx.x;
     const uint64_t nf = a.st->n_frames;
     const uint64_t f = (uint64_t)blockIdx.x * 32 + lane;
@@ -422,7 +448,8 @@ __global__ void __launch_bounds__(32) k_frame_seal(FrameArgs a) {
         const uint32_t lj = __shfl_sync(0xffffffffu, len, j), tj = __shfl_sync(0xffffffffu, tail_base, j);
         if (lane < 18 && lj && tj + 16 * lane < lj + 16) cp_async16(&s_tail[j][16 * lane], bj + tj + 16 * lane);
     }
-    stage_step(0, 0);
+#pragma unroll
+    for (int k = 0; k < SEAL_STAGES - 1; k++) { if ((uint32_t)k < max_steps) stage_step(k, k); else cp_async_commit(); }      // the tail windows ride in the first group
     cityd::P v, w; uint64_t x = 0, y = 0, z = 0;
     if (big) {
         x = cityd::f64(H) ^ CK3; y = cityd::f64(H + 8); z = (uint64_t)len * CK1;
@@ -432,10 +459,11 @@ __global__ void __launch_bounds__(32) k_frame_seal(FrameArgs a) {
         w.second = cityd::rot(x + cityd::f64(body + 88), 53) * CK1;
     }
     for (uint32_t st = 0; st < max_steps; st++) {
-        if (st + 1 < max_steps) { stage_step(st + 1, (st + 1) & 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+        if (st + SEAL_STAGES - 1 < max_steps) stage_step(st + SEAL_STAGES - 1, (st + SEAL_STAGES - 1) % SEAL_STAGES); else cp_async_commit();
+        cp_async_wait<SEAL_STAGES - 1>();      // every group but the newest SEAL_STAGES - 1 has landed: step st is in shared memory
         __syncwarp();
         if (st < nsteps) {
-            const uint8_t* b = s_buf[st & 1][lane];
+            const uint8_t* b = s_buf[st % SEAL_STAGES][lane];
             const uint32_t nb = (nblk - st * 4 < 4) ? nblk - st * 4 : 4;
             for (uint32_t i = 0; i < 2 * nb; i++) {
                 const uint32_t o = i * 64;

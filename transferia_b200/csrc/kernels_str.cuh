@@ -27,14 +27,83 @@ __global__ void __launch_bounds__(TF_STR_THREADS) k_str_sizes(EncodeArgs a) {
     if (threadIdx.x == 0) a.tile_sum[(size_t)c.str_slot * a.ntiles_cap + blockIdx.x] = tot;
 }
 
-// LEB128 length + bytes, one kept row per thread; neighbouring threads own neighbouring rows, so a warp reads one
-// contiguous span of the source heap (L1 serves the loads). The tile's output (a contiguous span of the block at an
-// arbitrary byte address) is assembled in shared memory and written with aligned, coalesced 4-byte stores (same
-// funnel-shift re-alignment as k_encode_fixed); tiles larger than the staging buffer (long strings) go direct.
+// LEB128 length + bytes. Plain String columns (the hot case): every thread first publishes its row's piece (offset in the
+// tile, heap offset, length) in shared memory; then the tile's OUTPUT is cut into aligned 4-byte words and every thread
+// produces whole words: a binary search over the piece offsets finds the row that owns the word, payload bytes come from
+// two aligned source words re-aligned with a funnel shift. Work is proportional to output bytes (no skew between short
+// and long strings, no staging limit) and every store is an aligned, coalesced word.
+// convert_to_string columns produce their text with fmt_value: those tiles keep the row-per-thread path below.
+__device__ __forceinline__ uint32_t str_find_row(const uint32_t* ex, uint32_t x) {      // largest r with ex[r] <= x, ex[0] = 0
+    uint32_t lo = 0, hi = TF_STR_TILE;
+#pragma unroll
+    for (int it = 0; it < 8; it++) { const uint32_t mid = (lo + hi) >> 1; if (ex[mid] <= x) lo = mid; else hi = mid; }
+    return lo;
+}
+__global__ void __launch_bounds__(TF_STR_THREADS) k_encode_str_plain(EncodeArgs a) {
+    __shared__ uint32_t sm[33];
+    __shared__ uint32_t s_ex[TF_STR_TILE + 1];
+    __shared__ uint32_t s_src[TF_STR_TILE];
+    const DCol c = a.cols[a.slots[blockIdx.y]];
+    if (c.out_kind == OK_TOSTR) return;                       // handled by k_encode_str
+    const uint64_t n = a.st->n_kept;
+    const uint64_t j0 = (uint64_t)blockIdx.x * TF_STR_TILE;
+    if (j0 >= n) return;
+    uint64_t R; const uint32_t L = str_len(c, a.sel, j0 + threadIdx.x, n, R);
+    const bool have = L != 0xffffffffu;
+    const uint32_t vlb = a.columnar ? 0u : 1u;                // a length prefix exists
+    uint32_t tot; const uint32_t ex = block_excl_scan(have ? L + (vlb ? varint_len(L) : 0) : 0u, &tot, sm);
+    const uint64_t tb = a.tile_base[(size_t)c.str_slot * a.ntiles_cap + blockIdx.x];
+    uint8_t* gdst = a.raw + c.out_off + tb;
+    if (a.columnar && have) ((uint32_t*)(a.raw + c.offs_off))[j0 + threadIdx.x] = (uint32_t)(tb + ex);
+    s_ex[threadIdx.x] = ex; s_src[threadIdx.x] = (have && L) ? c.offsets[R] : 0u;
+    if (threadIdx.x == 0) s_ex[TF_STR_TILE] = tot;
+    __syncthreads();
+    const uint32_t m = (uint32_t)((uintptr_t)gdst & 3);
+    const uint32_t T = (m + tot + 3) >> 2;
+    uint8_t* dst0 = gdst - m;
+    const uint32_t hsh = ((uint32_t)(uintptr_t)c.heap & 3);   // alignment of the heap base
+    const uint32_t* hw = (const uint32_t*)(c.heap - hsh);
+    for (uint32_t t = threadIdx.x; t < T; t += TF_STR_THREADS) {
+        const int32_t sb = (int32_t)(4 * t) - (int32_t)m;      // stream offset of this word's first byte
+        const uint32_t x0 = sb < 0 ? 0u : (uint32_t)sb;
+        uint32_t r = str_find_row(s_ex, x0);
+        // piece r = [s_ex[r], s_ex[r+1]): LEB128 of its payload length, then the payload
+        uint32_t pe = s_ex[r + 1], pl = pe - s_ex[r];
+        uint32_t plen = pl, vl = 0;
+        if (vlb) { vl = pl < 128 + 1 ? 1 : (pl < 16384 + 2 ? 2 : (pl < 2097152 + 3 ? 3 : (pl < 268435456 + 4 ? 4 : 5))); plen = pl - vl; }
+        const uint32_t k0 = x0 - s_ex[r];
+        if (sb >= 0 && (uint32_t)sb + 4 <= pe && k0 >= vl) {   // the whole word is payload of one row
+            const uint32_t so = s_src[r] + (k0 - vl) + hsh; const uint32_t sh = (so & 3) * 8;
+            const uint32_t w0 = __ldg(hw + (so >> 2)); uint32_t val = w0;
+            if (sh) val = __funnelshift_r(w0, __ldg(hw + (so >> 2) + 1), sh);
+            *(uint32_t*)(dst0 + 4 * (size_t)t) = val;
+            continue;
+        }
+        uint32_t val = 0, mask = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int32_t xs = sb + b;
+            if (xs < 0 || (uint32_t)xs >= tot) continue;
+            const uint32_t x = (uint32_t)xs;
+            while (x >= pe) { r++; pe = s_ex[r + 1]; pl = pe - s_ex[r]; if (vlb) { vl = pl < 129 ? 1 : (pl < 16386 ? 2 : (pl < 2097155 ? 3 : (pl < 268435460 ? 4 : 5))); plen = pl - vl; } else plen = pl; }
+            const uint32_t k = x - s_ex[r];
+            uint32_t byte;
+            if (k < vl) { const uint32_t v = plen >> (7 * k); byte = (v & 0x7f) | ((v >> 7) ? 0x80u : 0u); }
+            else byte = c.heap[s_src[r] + (k - vl)];
+            val |= byte << (8 * b); mask |= 1u << b;
+        }
+        uint8_t* dst = dst0 + 4 * (size_t)t;
+        if (mask == 15) *(uint32_t*)dst = val;
+        else { for (int b = 0; b < 4; b++) if ((mask >> b) & 1) dst[b] = (uint8_t)(val >> (8 * b)); }
+    }
+}
+
+// LEB128 length + text of convert_to_string columns, one kept row per thread, staged in shared memory.
 __global__ void __launch_bounds__(TF_STR_THREADS) k_encode_str(EncodeArgs a) {
     __shared__ uint32_t sm[33];
     __shared__ __align__(16) uint8_t stage[TF_STR_STAGE + 8];
     const DCol c = a.cols[a.slots[blockIdx.y]];
+    if (c.out_kind != OK_TOSTR) return;                       // plain String columns: k_encode_str_plain
     const uint64_t n = a.st->n_kept;
     const uint64_t j0 = (uint64_t)blockIdx.x * TF_STR_TILE;
     if (j0 >= n) return;

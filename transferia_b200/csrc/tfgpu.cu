@@ -52,7 +52,7 @@ struct PlanDev {
     JsonCol* d_sjcols = nullptr; JsonCol* d_scsvcols = nullptr; uint8_t* d_snames = nullptr;      // batch serializers: sorted JSON keys (pre-quoted), CSV order
     int32_t* d_fixed_slots = nullptr; int32_t* d_str_slots = nullptr; int32_t* d_mask_slots = nullptr; int32_t* d_out_cols = nullptr;
     MaskKey* d_mask_keys = nullptr;
-    int n_fsteps = 0, n_fixed_slots = 0, n_str = 0, n_mask_cols = 0;
+    int n_fsteps = 0, n_fixed_slots = 0, n_str = 0, n_mask_cols = 0, n_tostr = 0;
     std::vector<int32_t> fixed_slots, str_slots, mask_slot_cols, mask_slot_key;
     std::vector<int> col_out_kind, col_out_w, col_str_slot, col_mask_slot, col_nullable;
 };
@@ -226,6 +226,7 @@ void upload_plan(tfgpu_engine* e, PlanDev& pd) {
         fsteps.push_back(st);
     }
     pd.n_fsteps = (int)fsteps.size(); pd.n_fixed_slots = (int)pd.fixed_slots.size(); pd.n_str = (int)pd.str_slots.size(); pd.n_mask_cols = (int)pd.mask_slot_cols.size();
+    pd.n_tostr = 0; for (size_t c = 0; c < pd.col_out_kind.size(); c++) if (pd.col_out_kind[c] == OK_TOSTR) pd.n_tostr++;
     size_t total = 0;
     auto need = [&](size_t n) { total += align_up(n ? n : 1, 256); };
     need(terms.size() * sizeof(DTerm)); need(expr_off.size() * 4); need(fsteps.size() * sizeof(DFilterStep)); need(pl.blob.size());
@@ -372,7 +373,8 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
                 EncodeArgs fa = ea; fa.slots = pd.d_fixed_slots;
                 e->prof_begin("k_encode_fixed", s); k_encode_fixed<<<dim3(gx, pd.n_fixed_slots), 256, 0, s>>>(fa); e->prof_end(s);
             }
-            if (pd.n_str) { e->prof_begin("k_encode_str", s); k_encode_str<<<dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
+            if (pd.n_str) { e->prof_begin("k_encode_str_plain", s); k_encode_str_plain<<<dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
+            if (pd.n_str && pd.n_tostr) { e->prof_begin("k_encode_str", s); k_encode_str<<<dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
             if (pd.n_mask_cols) {
                 MaskArgs ma{e->d_cols, pd.d_mask_slots, pd.d_mask_keys, sel, e->d_state, e->raw.p, 0};
                 e->prof_begin("k_mask_encode", s); k_mask_encode<<<dim3((uint32_t)((n + 127) / 128), pd.n_mask_cols), 128, 0, s>>>(ma); e->prof_end(s);
@@ -406,7 +408,8 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
                 EncodeArgs va = ea; va.slots = e->d_call_slots + fixed.size();
                 e->prof_begin("k_pack_validity", s); k_pack_validity<<<dim3((uint32_t)((n / 8 + 256) / 256), (uint32_t)valid.size()), 256, 0, s>>>(va); e->prof_end(s);
             }
-            if (pd.n_str) { e->prof_begin("k_encode_str", s); k_encode_str<<<dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
+            if (pd.n_str) { e->prof_begin("k_encode_str_plain", s); k_encode_str_plain<<<dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
+            if (pd.n_str && pd.n_tostr) { e->prof_begin("k_encode_str", s); k_encode_str<<<dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
             if (pd.n_mask_cols) {
                 MaskArgs ma{e->d_cols, pd.d_mask_slots, pd.d_mask_keys, sel, e->d_state, e->raw.p, 1};
                 e->prof_begin("k_mask_encode", s); k_mask_encode<<<dim3((uint32_t)((n + 127) / 128), pd.n_mask_cols), 128, 0, s>>>(ma); e->prof_end(s);
@@ -420,7 +423,7 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         const uint32_t grid = (uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * per_sm);
         e->prof_begin("k_lz4_frames", s); k_lz4_frames<<<grid, LZ_THREADS, smem, s>>>(za); e->prof_end(s);
         FrameArgs fa{e->slots.p, stride, e->comp_size, e->d_state, e->frame_bytes, e->wire_off, e->wire.p};
-        e->prof_begin("k_frame_seal", s); k_frame_seal<<<(uint32_t)((sz.n_frames_max + 31) / 32), 32, 0, s>>>(fa); e->prof_end(s);
+        e->prof_begin("k_frame_seal", s); k_frame_seal<<<(uint32_t)((sz.n_frames_max + 31) / 32), 32, SEAL_SMEM, s>>>(fa); e->prof_end(s);
         e->prof_begin("k_frame_scan", s); k_frame_scan<<<1, 1024, 0, s>>>(fa); e->prof_end(s);
         e->prof_begin("k_wire_gather", s); k_wire_gather<<<(uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * 8), 256, 0, s>>>(fa); e->prof_end(s);
     }
@@ -463,6 +466,7 @@ int tfgpu_engine_create(const char* cfg_json, const int* device_ids, int n_devic
         CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
         CK(cudaMalloc(&e->d_state, sizeof(DState)));
         CK(cudaFuncSetAttribute(k_lz4_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024));
+        CK(cudaFuncSetAttribute(k_frame_seal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEAL_SMEM));
     } catch (const CudaError& c) { return c.e == cudaErrorMemoryAllocation ? TF_E_RETRY_OOM : TF_E_RETRY_LAUNCH; }
     catch (const std::exception&) { return TF_E_FATAL_CONFIG; }
     *out = e.release();
