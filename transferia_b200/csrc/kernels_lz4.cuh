@@ -57,27 +57,6 @@ __device__ __forceinline__ void copy_s2g(uint8_t* dst, const uint32_t* data_w, u
     while (n) { *dst++ = data[src++]; n--; }
 }
 
-// Byte stream writer into global memory that stores whole aligned words: bytes are collected in a register and written as
-// one 4-byte store; only the first / last word of a thread's span (shared with its neighbours) falls back to byte stores.
-struct LzWriter {
-    uint8_t* wp; uint32_t acc, lo, fill;       // bytes [lo, fill) of the word at wp are ours and sit in acc
-    __device__ __forceinline__ void start(uint8_t* p) { const uint32_t al = (uint32_t)((uintptr_t)p & 3); wp = p - al; acc = 0; lo = al; fill = al; }
-    __device__ __forceinline__ void flush() {
-        if (fill == lo) return;
-        if (lo == 0 && fill == 4) *(uint32_t*)wp = acc;
-        else for (uint32_t b = lo; b < fill; b++) wp[b] = (uint8_t)(acc >> (8 * b));
-    }
-    __device__ __forceinline__ void put(uint32_t b) { acc |= b << (8 * fill); if (++fill == 4) { flush(); wp += 4; acc = 0; lo = 0; fill = 0; } }
-    __device__ __forceinline__ void skip(uint32_t n) { if (!n) return; flush(); start(wp + fill + n); }
-    __device__ __forceinline__ void ext(uint32_t x) { x -= 15; while (x >= 255) { put(255); x -= 255; } put(x); }      // x >= 15
-    __device__ __forceinline__ void copy(const uint32_t* data_w, uint32_t src, uint32_t n) {                             // literals from shared memory
-        const uint8_t* d = (const uint8_t*)data_w;
-        while (n && fill) { put(d[src++]); n--; }
-        for (; n >= 4; n -= 4, src += 4, wp += 4) *(uint32_t*)wp = ld32u(data_w, src);
-        while (n) { put(d[src++]); n--; }
-    }
-};
-
 __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t F = a.frame_bytes;
@@ -267,22 +246,21 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
         LZ_PHASE(3);
         // ---- P5: emit
         if (tid < nseg) {
-            LzWriter w; w.start(out + my_off); uint32_t prev_end = seg_start;
+            uint8_t* o = out + my_off; uint32_t prev_end = seg_start;
             for (uint32_t k = 0; k < my_nseq; k++) {
                 const uint2 d = desc[k];
                 const uint32_t p = d.x & 0xffff, ml = d.x >> 16, off = d.y;
                 const uint32_t cin = (k == 0 ? carry_in : 0);
                 const uint32_t ll = cin + (p - prev_end);
                 const uint32_t mt = ml - 4;
-                w.put(((ll < 15 ? ll : 15) << 4) | (mt < 15 ? mt : 15));
-                if (ll >= 15) w.ext(ll);
-                w.skip(cin);                                  // literals carried in from earlier segments: their owners write them
-                w.copy(data_w, prev_end, p - prev_end);
-                w.put(off & 0xff); w.put(off >> 8);
-                if (mt >= 15) w.ext(mt);
+                *o++ = (uint8_t)(((ll < 15 ? ll : 15) << 4) | (mt < 15 ? mt : 15));
+                if (ll >= 15) o = put_ext(o, ll);
+                copy_s2g(o + cin, data_w, prev_end, p - prev_end);
+                o += ll;
+                *o++ = (uint8_t)off; *o++ = (uint8_t)(off >> 8);
+                if (mt >= 15) o = put_ext(o, mt);
                 prev_end = p + ml;
             }
-            w.flush();
             if (seg_end > prev_end) {   // trailing literals belong to the next sequence downstream
                 const uint32_t nh = my_next_has;
                 const int32_t dl = (nh != 0xffff && nh < nseg) ? delta0[nh] : delta_final;
@@ -388,7 +366,7 @@ struct FrameArgs { uint8_t* slots; uint32_t slot_stride; const uint32_t* comp_si
 // memory (double buffered) while the lanes hash the previous 512 bytes out of it.
 #define SEAL_STEP 512
 #define SEAL_STRIDE 528
-#define SEAL_STAGES 4
+#define SEAL_STAGES 2      /* deeper pipelines do not help: the per-frame hash is a serial dependency chain (~43 k instructions) */
 #define SEAL_SMEM ((size_t)SEAL_STAGES * 32 * SEAL_STRIDE + 32 * 304)
 __device__ __forceinline__ uint64_t sm64(const uint8_t* base, uint32_t off) { return *(const uint64_t*)(base + off); }
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
