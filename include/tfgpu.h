@@ -142,6 +142,10 @@ typedef struct tf_batch {
 #define TF_ROWERR_JSON_PARSEVAL     35 /* "ParseVal error" on a key / required column (:361-366); term = column             */
 #define TF_ROWERR_JSON_HOST         36 /* the line needs the Go parser (see tfgpu_parse_json); term = column                */
 
+/* number_to_float: a number literal inside an `any` value whose float64 rounding the device cannot decide (hex / underscored /
+ * > 19 digit literals with an open Eisel-Lemire result); the shim applies the Go transformer to that row */
+#define TF_ROWERR_N2F_HOST 52
+
 /* serializers: a value encoding/json refuses (NaN / Inf float, time.Time with a year outside [0,9999]); the reference
  * fails the whole Serialize call on it, so a result carrying this code must not be written; term = output column */
 #define TF_ROWERR_SER_VALUE 40

@@ -418,6 +418,25 @@ void json_each_row_value(std::string& o, const orc_val& v, int32_t yt_result, co
 }
 
 
+// number_to_float on the JSON text of an `any` value: every json.Number becomes float64 (json.Number.Float64 = strconv.ParseFloat),
+// which json.Marshal then prints in its float format; a literal that does not fit float64 stays a json.Number (its text).
+std::string number_to_float_text(const uint8_t* s, size_t n) {
+    std::string d; bool ins = false;
+    for (size_t i = 0; i < n;) {
+        const char c = (char)s[i];
+        if (ins) { d += c; if (c == '\\' && i + 1 < n) { d += (char)s[i + 1]; i += 2; continue; } if (c == '"') ins = false; i++; continue; }
+        if (c == '"') { ins = true; d += c; i++; continue; }
+        if (c == '-' || (c >= '0' && c <= '9')) {
+            size_t q = i; while (q < n && ((s[q] >= '0' && s[q] <= '9') || s[q] == '-' || s[q] == '+' || s[q] == '.' || s[q] == 'e' || s[q] == 'E')) q++;
+            std::string_view lit((const char*)s + i, q - i); double f;
+            if (jsn::go_parse_float(lit, f) == 0 && !std::isnan(f) && !std::isinf(f)) d += fmt_f64(f, FMT_JSON); else d += lit;
+            i = q; continue;
+        }
+        d += c; i++;
+    }
+    return d;
+}
+
 // ------------------------------------------------------------------ batch serializers (pkg/serializer)
 // encoding/json appendString with escapeHTML = false (json.go:56-58 SetEscapeHTML(false)): only `"`, `\`, control
 // characters, invalid UTF-8 and U+2028/2029 are escaped
@@ -587,6 +606,13 @@ bool apply_steps(const tf_batch* in, uint64_t r, const orc_step* steps, int nste
                 if (v.kind == OG_INT32) sec = v.i; else if (v.kind == OG_UINT32) sec = (int64_t)v.u;
                 std::memset(&v, 0, sizeof v); v.kind = OG_TIME; v.i = sec; cur_type[c] = TF_DATETIME;
             }
+        } else if (st.kind == STEP_NUMBER_TO_FLOAT) {             // NumberToFloatTransformer.processItem number_to_float.go:75-123
+            if (kind != TF_KIND_INSERT && kind != TF_KIND_UPDATE) continue;                     // supportedKinds :21, :64
+            for (int k = 0; k < st.ncols; k++) {
+                int c = st.cols[k]; orc_val& v = row[c].v;
+                if (cur_type[c] != TF_ANY || v.kind != OG_JSON) continue;                      // a Go string / nil inside `any` is left alone
+                row[c].set_string(number_to_float_text(v.s, v.slen), OG_JSON);
+            }
         } else if (st.kind == STEP_TO_STRING) {                   // ToStringTransformer.Apply to_string.go:58-97
             for (int k = 0; k < st.ncols; k++) {
                 int c = st.cols[k];
@@ -719,7 +745,7 @@ extern "C" int orc_push_columns(const tf_batch* in, const orc_colschema* schema,
     struct CB { std::vector<uint8_t> values, valid_bits, aux, heap; std::vector<uint32_t> offs; bool has_valid, has_aux; };
     std::vector<CB> cb(no);
     std::vector<char> rewritten(nc, 0);     // mask_field / convert_to_string give the column a fresh, never-nil text value
-    for (int s = 0; s < nsteps; s++) if (steps[s].kind == STEP_MASK || steps[s].kind == STEP_TO_STRING || steps[s].kind == STEP_TO_DATETIME) for (int k = 0; k < steps[s].ncols; k++) rewritten[steps[s].cols[k]] = 1;
+    for (int s = 0; s < nsteps; s++) if (steps[s].kind == STEP_MASK || steps[s].kind == STEP_TO_STRING || steps[s].kind == STEP_TO_DATETIME || steps[s].kind == STEP_NUMBER_TO_FLOAT) for (int k = 0; k < steps[s].ncols; k++) rewritten[steps[s].cols[k]] = 1;
     for (uint32_t k = 0; k < no; k++) {
         const tf_col& ic = in->cols[out_cols[k]];
         const bool masked = rewritten[out_cols[k]] != 0;

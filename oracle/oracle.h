@@ -60,7 +60,7 @@ typedef struct orc_colschema {
     const char* original_type;  /* may be NULL */
 } orc_colschema;
 
-enum { STEP_FILTER_ROWS = 1, STEP_MASK = 2, STEP_TO_STRING = 3, STEP_SKIP_EVENTS = 4, STEP_SELECT_COLS = 5, STEP_TO_DATETIME = 6 };
+enum { STEP_FILTER_ROWS = 1, STEP_MASK = 2, STEP_TO_STRING = 3, STEP_SKIP_EVENTS = 4, STEP_SELECT_COLS = 5, STEP_TO_DATETIME = 6, STEP_NUMBER_TO_FLOAT = 7 };
 typedef struct orc_step {
     int32_t kind;
     /* filter_rows */

@@ -86,7 +86,7 @@ class OrcBuf(C.Structure):
  OG_BOOL, OG_STRING, OG_BYTES, OG_TIME, OG_DURATION, OG_JSON, OG_INT, OG_UINT) = range(19)
 OP_EQ, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE, OP_IN, OP_NOTIN, OP_MATCH, OP_NOTMATCH = range(10)
 LV_INT, LV_FLOAT, LV_BOOL, LV_STRING, LV_TIME, LV_NULL, LV_LIST = 1, 2, 3, 4, 5, 6, 16
-STEP_FILTER_ROWS, STEP_MASK, STEP_TO_STRING, STEP_SKIP_EVENTS, STEP_SELECT_COLS, STEP_TO_DATETIME = 1, 2, 3, 4, 5, 6
+STEP_FILTER_ROWS, STEP_MASK, STEP_TO_STRING, STEP_SKIP_EVENTS, STEP_SELECT_COLS, STEP_TO_DATETIME, STEP_NUMBER_TO_FLOAT = 1, 2, 3, 4, 5, 6, 7
 
 _lib = None
 
@@ -538,6 +538,13 @@ def build_plan(ns: str, name: str, schema: List[dict], transformers: List[dict])
             steps.append({"kind": "convert_to_datetime", "index": idx, "cols": [cur[i]["_in"] for i in pos]}); idx += 1
             for i in pos:
                 cur[i] = dict(cur[i]); cur[i]["type"] = "datetime"
+        elif ttype == "number_to_float_transformer":             # number_to_float.go:54-125
+            if not _tables_match(cfg.get("tables"), ns, name):
+                continue                                             # Suitable :123-125 (original id)
+            if not _tables_match(cfg.get("tables"), cur_ns, cur_name):
+                idx += 1; continue                                   # Apply re-checks item.TableID() :62-66: a renamed table no longer matches
+            pos = [i for i, c in enumerate(cur) if c["type"] == "any"]
+            steps.append({"kind": "number_to_float", "index": idx, "cols": [cur[i]["_in"] for i in pos]}); idx += 1
         elif ttype == "convert_to_string":
             if not _tables_match(cfg.get("tables"), ns, name):
                 continue
@@ -637,6 +644,9 @@ def _marshal(plan: Plan):
         elif st["kind"] == "convert_to_datetime":
             cols = keep.add(np.asarray(st["cols"], dtype=np.int32))
             s.kind = STEP_TO_DATETIME; s.cols = cols.ctypes.data; s.ncols = len(st["cols"])
+        elif st["kind"] == "number_to_float":
+            cols = keep.add(np.asarray(st["cols"], dtype=np.int32))
+            s.kind = STEP_NUMBER_TO_FLOAT; s.cols = cols.ctypes.data; s.ncols = len(st["cols"])
         elif st["kind"] == "skip_events":
             s.kind = STEP_SKIP_EVENTS; s.kind_mask = st["kind_mask"]
         elif st["kind"] == "filter_columns":

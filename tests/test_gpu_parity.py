@@ -433,3 +433,33 @@ def test_measurer_sizes(eng, po):
     # closed form by hand: one int32 + one nil utf8 + one 3-byte utf8 row
     b = abi.Batch(2, [abi.fixed_to_column(abi.TF_INT32, [1, 2]), abi.strings_to_column(abi.TF_UTF8, [None, b"abc"])])
     assert list(po.measure(b)[0]) == [24 + 16 + 4 + 16, 24 + 16 + 4 + 16 + 16 + 3]
+
+
+def test_number_to_float(eng, po):
+    """number_to_float_transformer (number_to_float.go:75-123) as a rewrite of the `any` JSON text, alone and before mask / to_string / sinks."""
+    vals = [b'{"a":1,"b":[1.50,2e3,-0,1e21,1e-7,0.000001,123456789012345678901234567890],"s":"12 \\" 3e4","n":null}', b"17", b"1e400", b"-1.0E+2", b'"just a string 5"', b"true",
+            b"[]", b'{"deep":{"x":[{"y":0.1000}]},"big":18446744073709551616,"i":9007199254740993}', None, b"3.14159265358979323846264338327950288", b'{"k":"\\\\","v":1.0}', b"0.30000000000000004"]
+    tags = [0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0]
+    n = len(vals)
+    kinds = np.zeros(n, dtype=np.uint8); kinds[1] = abi.TF_KIND_DELETE; kinds[3] = abi.TF_KIND_UPDATE
+    schema = [{"name": "id", "type": "int32", "key": True}, {"name": "a", "type": "any"}, {"name": "b", "type": "any"}]
+    b = abi.Batch(n, [abi.fixed_to_column(abi.TF_INT32, list(range(n))), abi.strings_to_column(abi.TF_ANY, vals, tags=tags), abi.strings_to_column(abi.TF_ANY, vals[::-1], tags=tags[::-1])], kinds)
+    chains = [[{"number_to_float_transformer": {}}],
+              [{"number_to_float_transformer": {"tables": {"includeTables": ["^db.t$"]}}}, {"mask_field": {"columns": ["a"], "maskFunctionHash": {"userDefinedSalt": "s"}}}],
+              [{"mask_field": {"columns": ["a"], "maskFunctionHash": {"userDefinedSalt": "s"}}}, {"number_to_float_transformer": {}}, {"convert_to_string": {"columns": {"includeColumns": ["b"]}}}],
+              [{"rename_tables": {"renameTables": [{"originalName": {"nameSpace": "db", "name": "t"}, "newName": {"nameSpace": "db", "name": "u"}}]}}, {"number_to_float_transformer": {"tables": {"includeTables": ["^db.t$"]}}}],
+              [{"number_to_float_transformer": {"tables": {"includeTables": ["^other$"]}}}]]
+    for trs in chains:
+        pid = eng.plan("db", "t", schema, trs, {"type": "clickhouse"}); plan = po.build_plan("db", "t", schema, trs)
+        got, gerr = eng.push_columns(pid, b); ref, rerr = po.push_columns(b, plan)
+        assert gerr == rerr, (trs, gerr, rerr)
+        assert_batches_equal(got, ref)
+        for fmt in (RAW, JS):
+            if any("skip" in t for t in trs): continue
+            bi = abi.Batch(n, b.columns, np.zeros(n, dtype=np.uint8))       # sinks take insert rows
+            assert eng.push_encode(pid, bi, fmt).wire == po.push_encode(bi, plan, fmt).raw, (trs, fmt)
+    # spot values
+    ref, _ = po.push_columns(b, po.build_plan("db", "t", schema, chains[0]))
+    a = ref.columns[1]; cell = lambda r: bytes(a.heap[a.offsets[r]:a.offsets[r + 1]])
+    assert cell(0) == b'{"a":1,"b":[1.5,2000,-0,1e+21,1e-7,0.000001,1.2345678901234568e+29],"s":"12 \\" 3e4","n":null}'
+    assert cell(1) == b"17" and cell(2) == b"1e400" and cell(3) == b"-100" and cell(4) == b"just a string 5" and cell(9) == b"3.141592653589793"

@@ -339,6 +339,7 @@ struct Plan {
     std::vector<int> filter_step_index;
     std::vector<uint8_t> todt_col;     // [input column] 1 = convert_to_datetime applies (to_datetime.go:89-135)
     std::vector<int> todt_step_index; std::vector<std::vector<int>> todt_cols;
+    std::vector<int> n2f_cols;         // input columns (still `any` at that step) number_to_float rewrites (number_to_float.go:75-85)
     std::vector<uint8_t> tostr_col;    // [input column] 1 = convert_to_string applies (to_string.go:58-97)
     std::vector<int> tostr_step_index; std::vector<std::vector<int>> tostr_cols;
     std::vector<MaskStep> masks;
@@ -544,6 +545,16 @@ inline Plan build_plan(const std::string& ns, const std::string& name, const std
             }
             add_desc(d + "]}");
             pl.todt_cols.push_back(cols); pl.todt_step_index.push_back(step_no++);
+        } else if (ttype == "number_to_float_transformer") {         // registry/number_to_float/number_to_float.go:54-125
+            if (!match_table(tables_filter(cfg->get("tables")), ns, name)) continue;              // Suitable :123-125, original id
+            if (!match_table(tables_filter(cfg->get("tables")), cur_ns, cur_name)) { add_desc("{\"type\":\"number_to_float_transformer\",\"cols\":[]}"); step_no++; continue; }   // Apply re-checks item.TableID() :62-66
+            std::string d = "{\"type\":\"number_to_float_transformer\",\"cols\":["; bool first = true;
+            for (size_t i = 0; i < cur.size(); i++) if (cur[i].tf == TF_ANY && cur[i].tf == pl.in_schema[cur[i].in_index].tf && !(pl.tostr_col.size() && pl.tostr_col[cur[i].in_index])) {
+                bool dup = false; for (int c : pl.n2f_cols) if (c == cur[i].in_index) dup = true;
+                if (!dup) pl.n2f_cols.push_back(cur[i].in_index);
+                if (!first) d += ","; first = false; d += std::to_string(cur[i].in_index);
+            }
+            add_desc(d + "]}"); step_no++;
         } else if (ttype == "convert_to_string") {                   // registry/to_string/to_string.go:24-113
             if (!match_table(tables_filter(cfg->get("tables")), ns, name)) continue;
             if (cfg->get_bool("skip_utc_conversion")) throw FatalError(TF_E_FATAL_UNSUPPORTED, "convert_to_string: skip_utc_conversion needs time zones, which the columnar layout does not carry");

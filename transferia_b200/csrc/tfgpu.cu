@@ -20,6 +20,7 @@
 #include "kernels_csv.cuh"
 #include "kernels_json_in.cuh"
 #include "kernels_dbz.cuh"
+#include "kernels_n2f.cuh"
 #include "kernels_json_out.cuh"
 
 using namespace tfk;
@@ -69,7 +70,7 @@ struct tfgpu_engine {
     int sm_count = 148;
     std::vector<std::unique_ptr<PlanDev>> plans;
     // arenas
-    DevBuf in_arena, work, raw, slots, wire, csv_text, csv_stage, json_msgs;
+    DevBuf in_arena, work, raw, slots, wire, csv_text, csv_stage, json_msgs, n2f_stage, n2f_heap;
     DState* d_state = nullptr; DCol* d_cols = nullptr; size_t d_cols_cap = 0;
     int32_t* d_call_slots = nullptr; ColRegions* d_regions = nullptr; size_t d_call_cap = 0;   // columnar mode, per call
     // pointers into `work` for the last call
@@ -260,11 +261,12 @@ Sizes compute_sizes(const tfgpu_engine* e, const PlanDev& pd, const tf_batch* in
     for (int oc : pl.out_cols) {
         const size_t c = (size_t)oc;
         if (pd.col_nullable[c]) raw += n;
-        if (pd.col_out_kind[c] == OK_STR) raw += in->cols[c].heap_len + 5 * n;
-        else if (pd.col_out_kind[c] == OK_TOSTR) raw += (in_width(in->cols[c].type) ? 40 * n : 6 * in->cols[c].heap_len + 8 * n) + 5 * n;   // longest text form (RFC3339Nano / %v float / \\u00XX-escaped JSON string)
+        bool n2f = false; for (int q : pl.n2f_cols) if ((size_t)q == c) n2f = true;       // number_to_float may lengthen literals (1e20 -> 100000000000000000000)
+        if (pd.col_out_kind[c] == OK_STR) raw += (n2f ? 6 : 1) * in->cols[c].heap_len + 5 * n;
+        else if (pd.col_out_kind[c] == OK_TOSTR) raw += (in_width(in->cols[c].type) ? 40 * n : (n2f ? 36 : 6) * in->cols[c].heap_len + 8 * n) + 5 * n;   // longest text form (RFC3339Nano / %v float / \\u00XX-escaped JSON string)
         else raw += (uint64_t)pd.col_out_w[c] * n;
         if (columnar) raw += 8 * n + 4 * (n + 1) + n / 8 + 6 * 16 + (pd.col_out_kind[c] == OK_MASK ? 64 * n : 0);   // widest value, aux, offsets, bitmap, padding
-        if (json) raw += (uint64_t)(pl.in_schema[c].name.size() + 4 + 48) * n + (in_width(in->cols[c].type) ? 0 : 6 * in->cols[c].heap_len);   // name, quotes, longest scalar text, escaped payload
+        if (json) raw += (uint64_t)(pl.in_schema[c].name.size() + 4 + 48) * n + (in_width(in->cols[c].type) ? 0 : (n2f ? 36 : 6) * in->cols[c].heap_len);   // name, quotes, longest scalar text, escaped payload
     }
     Sizes s;
     s.raw_bound = raw + 256;
@@ -324,6 +326,30 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
     CK(cudaMemcpyAsync(e->d_cols, hc.data(), sizeof(DCol) * nc, cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(e->d_state, 0, sizeof(DState), s));
     if (!pre_err) e->prof_n = 0;
+    if (!pl.n2f_cols.empty() && n) {        // number_to_float: rewrite the JSON text of the `any` columns before anything reads them
+        const size_t k2 = pl.n2f_cols.size();
+        size_t sb = 0; auto need2 = [&](size_t b) { size_t at = sb; sb += align_up(b ? b : 1, 256); return at; };
+        const size_t o_which = need2(k2 * 4), o_len = need2(k2 * n * 4), o_off = need2(k2 * (n + 1) * 4), o_tot = need2(k2 * 8 + 8), o_base = need2(k2 * 8 + 8), o_err = need2(n);
+        e->n2f_stage.ensure(sb + 256);
+        uint8_t* B = e->n2f_stage.p;
+        std::vector<int32_t> which(pl.n2f_cols.begin(), pl.n2f_cols.end());
+        CK(cudaMemcpyAsync(B + o_which, which.data(), k2 * 4, cudaMemcpyHostToDevice, s));
+        if (pre_err) CK(cudaMemcpyAsync(B + o_err, pre_err, n, cudaMemcpyDeviceToDevice, s)); else CK(cudaMemsetAsync(B + o_err, 0, n, s));
+        N2fArgs na{e->d_cols, (const int32_t*)(B + o_which), dev_kinds, n, (uint32_t*)(B + o_len), (const uint32_t*)(B + o_off), nullptr, (const uint64_t*)(B + o_base), B + o_err};
+        e->prof_begin("k_n2f_sizes", s); k_n2f_sizes<<<dim3((uint32_t)((n + 127) / 128), (uint32_t)k2), 128, 0, s>>>(na); e->prof_end(s);
+        e->prof_begin("k_csv_offsets", s); k_csv_offsets<<<(uint32_t)k2, 1024, 0, s>>>((const uint32_t*)(B + o_len), n, (uint32_t*)(B + o_off), (uint64_t*)(B + o_tot)); e->prof_end(s);
+        std::vector<uint64_t> tot(k2), base(k2);
+        CK(cudaMemcpyAsync(tot.data(), B + o_tot, k2 * 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+        uint64_t run = 0; for (size_t k = 0; k < k2; k++) { base[k] = run; run += align_up(tot[k], 16); }
+        if (run >= (1ull << 32)) throw tfplan::FatalError(TF_E_FATAL_ARG, "number_to_float: a rewritten column exceeds 4 GiB");
+        e->n2f_heap.ensure(run + 256);
+        CK(cudaMemcpyAsync(B + o_base, base.data(), k2 * 8, cudaMemcpyHostToDevice, s));
+        na.heap = e->n2f_heap.p;
+        e->prof_begin("k_n2f_write", s); k_n2f_write<<<dim3((uint32_t)((n + 127) / 128), (uint32_t)k2), 128, 0, s>>>(na); e->prof_end(s);
+        for (size_t k = 0; k < k2; k++) { DCol& d = hc[pl.n2f_cols[k]]; d.offsets = (const uint32_t*)(B + o_off) + k * (n + 1); d.heap = e->n2f_heap.p + base[k]; }
+        CK(cudaMemcpyAsync(e->d_cols, hc.data(), sizeof(DCol) * nc, cudaMemcpyHostToDevice, s));
+        pre_err = B + o_err;                 // parser errors carried over + N2F_HOST rows
+    }
     const bool has_filter = pd.n_fsteps > 0 || pre_err;
     e->last_nrows = n; e->last_has_filter = has_filter; e->last_wire_fmt = wire_fmt;
     const uint32_t nb = (uint32_t)((n + 255) / 256);
@@ -360,7 +386,7 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         CK(cudaGetLastError());
         return;
     }
-    if (pd.n_str && ntiles) { e->prof_begin("k_str_sizes", s); k_str_sizes<<<dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
+    if (pd.n_str && ntiles) { e->prof_begin("k_str_sizes", s); k_str_sizes<<<dim3((ntiles + TF_STR_GROUP - 1) / TF_STR_GROUP, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
     LayoutArgs la{e->d_cols, (int)pl.out_cols.size(), pd.d_out_cols, pd.d_str_slots, pd.n_str, e->tile_sum, e->tile_base, sz.ntiles_cap, pd.d_col_headers, pd.d_col_header_off,
                   e->raw.p, e->d_state, n, 1, e->frame_bytes, e->col_bytes};
     if (pd.n_str) { e->prof_begin("k_layout_scan", s); k_layout_scan<<<pd.n_str, 1024, 0, s>>>(la); e->prof_end(s); }
@@ -373,7 +399,7 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
                 EncodeArgs fa = ea; fa.slots = pd.d_fixed_slots;
                 e->prof_begin("k_encode_fixed", s); k_encode_fixed<<<dim3(gx, pd.n_fixed_slots), 256, 0, s>>>(fa); e->prof_end(s);
             }
-            if (pd.n_str) { e->prof_begin("k_encode_str_plain", s); k_encode_str_plain<<<dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
+            if (pd.n_str) { e->prof_begin("k_encode_str_plain", s); k_encode_str_plain<<<dim3((ntiles + TF_STR_GROUP - 1) / TF_STR_GROUP, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
             if (pd.n_str && pd.n_tostr) { e->prof_begin("k_encode_str", s); k_encode_str<<<dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
             if (pd.n_mask_cols) {
                 MaskArgs ma{e->d_cols, pd.d_mask_slots, pd.d_mask_keys, sel, e->d_state, e->raw.p, 0};
@@ -408,7 +434,7 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
                 EncodeArgs va = ea; va.slots = e->d_call_slots + fixed.size();
                 e->prof_begin("k_pack_validity", s); k_pack_validity<<<dim3((uint32_t)((n / 8 + 256) / 256), (uint32_t)valid.size()), 256, 0, s>>>(va); e->prof_end(s);
             }
-            if (pd.n_str) { e->prof_begin("k_encode_str_plain", s); k_encode_str_plain<<<dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
+            if (pd.n_str) { e->prof_begin("k_encode_str_plain", s); k_encode_str_plain<<<dim3((ntiles + TF_STR_GROUP - 1) / TF_STR_GROUP, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
             if (pd.n_str && pd.n_tostr) { e->prof_begin("k_encode_str", s); k_encode_str<<<dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
             if (pd.n_mask_cols) {
                 MaskArgs ma{e->d_cols, pd.d_mask_slots, pd.d_mask_keys, sel, e->d_state, e->raw.p, 1};
@@ -478,7 +504,7 @@ int tfgpu_engine_destroy(tfgpu_engine* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (auto& p : e->plans) p->consts.release();
-    e->in_arena.release(); e->work.release(); e->raw.release(); e->slots.release(); e->wire.release(); e->csv_text.release(); e->csv_stage.release(); e->json_msgs.release(); e->json_sizes.release();
+    e->in_arena.release(); e->work.release(); e->raw.release(); e->slots.release(); e->wire.release(); e->csv_text.release(); e->csv_stage.release(); e->json_msgs.release(); e->n2f_stage.release(); e->n2f_heap.release(); e->json_sizes.release();
     if (e->d_state) cudaFree(e->d_state);
     if (e->d_cols) cudaFree(e->d_cols);
     if (e->d_call_slots) { cudaFree(e->d_call_slots); cudaFree(e->d_regions); }
