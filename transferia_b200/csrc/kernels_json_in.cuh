@@ -285,6 +285,11 @@ __device__ int d_go_parse_float(const uint8_t* s, uint32_t n, double& out) {
             if (ok) { f = __dmul_rn(f, d_p10[e2]); out = neg ? -f : f; return 0; }
         } else if (exp < 0 && exp >= -22) { f = __ddiv_rn(f, d_p10[-exp]); out = neg ? -f : f; return 0; }
     }
+    if (!trunc && exp >= 0 && exp <= 19) {                     // an integer below 2^64: the u64 -> f64 conversion rounds to nearest even exactly
+        uint64_t m = man; bool fits = true;                     // (Eisel-Lemire gives up on exact half-way integers such as 2^53 + 1)
+        for (int k = 0; k < exp; k++) { if (__umul64hi(m, 10ull)) { fits = false; break; } m *= 10ull; }
+        if (fits) { const double f = __ull2double_rn(m); out = neg ? -f : f; return 0; }
+    }
     uint64_t b0, b1;
     if (d_eisel_lemire(man, exp, neg, b0)) {
         if (!trunc) { out = __longlong_as_double((long long)b0); return 0; }

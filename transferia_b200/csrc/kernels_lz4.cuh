@@ -40,9 +40,14 @@ struct Lz4Args {
 };
 #define LZ_PHASE(k) do { if (a.phases && tid == 0) { const long long t_ = clock64(); atomicAdd(&a.phases[k], (unsigned long long)(t_ - t_ph)); t_ph = t_; } } while (0)
 
-__device__ __forceinline__ uint32_t ld32u(const uint32_t* w, uint32_t p) {   // 4 bytes at byte offset p of a word array in shared memory
+// The frame is kept in shared memory with one padding word after every 16 words (64 bytes): the parser and the emitter give
+// every thread its own 64-byte segment, so without the padding the 32 lanes of a warp would hit only two banks.
+#define LZ_PW(i) ((i) + ((i) >> 4))                 /* padded word index of data word i */
+#define LZ_PB(p) ((p) + (((p) >> 6) << 2))          /* padded byte address of data byte p */
+__host__ __device__ inline uint32_t lz_data_bytes(uint32_t frame_bytes) { return (frame_bytes + frame_bytes / 16 + 32 + 15) & ~15u; }
+__device__ __forceinline__ uint32_t ld32u(const uint32_t* w, uint32_t p) {   // 4 bytes at byte offset p of the (padded) frame in shared memory
     const uint32_t i = p >> 2, s = (p & 3) * 8;
-    return __funnelshift_r(w[i], w[i + 1], s);
+    return __funnelshift_r(w[LZ_PW(i)], w[LZ_PW(i + 1)], s);
 }
 __device__ __forceinline__ uint32_t ext_bytes(uint32_t x) { return x < 15 ? 0u : 1u + (x - 15u) / 255u; }
 __device__ __forceinline__ uint8_t* put_ext(uint8_t* o, uint32_t x) {   // x >= 15
@@ -52,19 +57,20 @@ __device__ __forceinline__ uint8_t* put_ext(uint8_t* o, uint32_t x) {   // x >= 
 // (source re-aligned with a funnel shift), then the tail
 __device__ __forceinline__ void copy_s2g(uint8_t* dst, const uint32_t* data_w, uint32_t src, uint32_t n) {
     const uint8_t* data = (const uint8_t*)data_w;
-    while (n && ((uintptr_t)dst & 3)) { *dst++ = data[src++]; n--; }
+    while (n && ((uintptr_t)dst & 3)) { *dst++ = data[LZ_PB(src)]; src++; n--; }
     for (; n >= 4; n -= 4, dst += 4, src += 4) *(uint32_t*)dst = ld32u(data_w, src);
-    while (n) { *dst++ = data[src++]; n--; }
+    while (n) { *dst++ = data[LZ_PB(src)]; src++; n--; }
 }
 
 __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t F = a.frame_bytes;
-    uint32_t* data_w = (uint32_t*)smem;                                  // F + 16 bytes
+    const uint32_t DB = lz_data_bytes(F);
+    uint32_t* data_w = (uint32_t*)smem;                                  // the frame, padded (LZ_PW / LZ_PB)
     uint8_t* data = smem;
-    uint16_t* cand = (uint16_t*)(smem + F + 16);                         // 2F bytes; later: sequence descriptors
-    uint32_t* table = (uint32_t*)(smem + F + 16 + 2 * F);               // 8 KB; later: per-segment arrays
-    uint8_t* vbits = smem + F + 16 + 2 * F + (4u << LZ_HASH_BITS);      // F/8 bytes: 1 candidate bit per position
+    uint16_t* cand = (uint16_t*)(smem + DB);                             // 2F bytes; later: sequence descriptors
+    uint32_t* table = (uint32_t*)(smem + DB + 2 * F);                   // 8 KB; later: per-segment arrays
+    uint8_t* vbits = smem + DB + 2 * F + (4u << LZ_HASH_BITS);          // F/8 bytes: 1 candidate bit per position
     uint32_t* scratch = (uint32_t*)(vbits + F / 8);                      // 64 words
     __shared__ uint32_t s_frame;
     // per-segment arrays aliased onto the hash table after P2 (nseg <= 512)
@@ -90,18 +96,18 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
         // ---- P1: stage
         {
             const int4* g = (const int4*)(a.raw + pos0);
-            int4* s4 = (int4*)smem;
             const uint32_t nv = (len + 15) >> 4;
             for (uint32_t i = tid; i < (F + 16) / 16; i += LZ_THREADS) {
                 int4 v = make_int4(0, 0, 0, 0);
                 if (i < nv) v = __ldg(g + i);
-                s4[i] = v;
+                uint32_t* d = data_w + LZ_PW(4 * i);                      // the 4 words of a chunk share one 16-word group
+                d[0] = (uint32_t)v.x; d[1] = (uint32_t)v.y; d[2] = (uint32_t)v.z; d[3] = (uint32_t)v.w;
             }
             for (uint32_t i = tid; i < (1u << LZ_HASH_BITS); i += LZ_THREADS) table[i] = 0;
         }
         __syncthreads();
         if (len & 15) {   // zero the bytes past len inside the last 16-byte chunk (they belong to the next frame)
-            if (tid < 16 && (len & ~15u) + tid >= len) data[(len & ~15u) + tid] = 0;
+            if (tid < 16 && (len & ~15u) + tid >= len) data[LZ_PB((len & ~15u) + tid)] = 0;
         }
         __syncthreads();
 
@@ -113,7 +119,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
             const bool active = p0 < F;                         // F is a multiple of 64, so p0 + 3 < F too
             uint32_t idx[4], tag[4], c[4];
             if (active) {
-                const uint32_t w0 = data_w[p0 >> 2], w1 = data_w[(p0 >> 2) + 1];
+                const uint32_t w0 = data_w[LZ_PW(p0 >> 2)], w1 = data_w[LZ_PW((p0 >> 2) + 1)];
                 uint32_t seq[4];
                 seq[0] = w0; seq[1] = __funnelshift_r(w0, w1, 8); seq[2] = __funnelshift_r(w0, w1, 16); seq[3] = __funnelshift_r(w0, w1, 24);
 #pragma unroll

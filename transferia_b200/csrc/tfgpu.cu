@@ -444,7 +444,7 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
     }
     if (lz) {
         Lz4Args za{e->raw.p, e->d_state, e->slots.p, stride, e->comp_size, e->frame_bytes, e->lz_phases};
-        const size_t smem = e->frame_bytes + 16 + 2 * (size_t)e->frame_bytes + (4u << LZ_HASH_BITS) + e->frame_bytes / 8 + 64 * 4;
+        const size_t smem = lz_data_bytes(e->frame_bytes) + 2 * (size_t)e->frame_bytes + (4u << LZ_HASH_BITS) + e->frame_bytes / 8 + 64 * 4;
         const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (smem + 1024)));
         const uint32_t grid = (uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * per_sm);
         e->prof_begin("k_lz4_frames", s); k_lz4_frames<<<grid, LZ_THREADS, smem, s>>>(za); e->prof_end(s);
