@@ -745,7 +745,7 @@ extern "C" int orc_push_columns(const tf_batch* in, const orc_colschema* schema,
     struct CB { std::vector<uint8_t> values, valid_bits, aux, heap; std::vector<uint32_t> offs; bool has_valid, has_aux; };
     std::vector<CB> cb(no);
     std::vector<char> rewritten(nc, 0);     // mask_field / convert_to_string give the column a fresh, never-nil text value
-    for (int s = 0; s < nsteps; s++) if (steps[s].kind == STEP_MASK || steps[s].kind == STEP_TO_STRING || steps[s].kind == STEP_TO_DATETIME || steps[s].kind == STEP_NUMBER_TO_FLOAT) for (int k = 0; k < steps[s].ncols; k++) rewritten[steps[s].cols[k]] = 1;
+    for (int s = 0; s < nsteps; s++) if (steps[s].kind == STEP_MASK || steps[s].kind == STEP_TO_STRING || steps[s].kind == STEP_TO_DATETIME) for (int k = 0; k < steps[s].ncols; k++) rewritten[steps[s].cols[k]] = 1;   // number_to_float keeps nil / tags: only the text changes
     for (uint32_t k = 0; k < no; k++) {
         const tf_col& ic = in->cols[out_cols[k]];
         const bool masked = rewritten[out_cols[k]] != 0;
