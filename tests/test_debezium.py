@@ -150,3 +150,43 @@ def test_device_debezium_numeric_receivers(eng, po):
         msgs.append(('{"schema":%s,"payload":{"after":{"k":%d,"d3":"%s","d0":"%s","v":{"scale":%d,"value":"%s"},"raw":"%s","pt":%s,"f":%s,"b":%s,"i8":%d},"op":"c"}}'
                      % (schema_text, k, b64, b64, scale, b64, b64, pt, f, rng.choice(["true", "false", "null"]), int(rng.integers(-300, 300)))).encode())
     _dbz_cmp(eng, po, schema_text, msgs, _allow_host=80)
+
+
+def _dbz_fuzz_msgs(n, seed):
+    rng = np.random.default_rng(seed)
+    schema_text, base = _shape_msgs()
+    good = [m for m in base if m.startswith(b'{"schema":') and b'"op":"' in m][:6]
+    vals = [b"1", b"-5", b"2147483647", b"2147483648", b"1.0", b"1e3", b'"7"', b"null", b"true", b'"x"', b'"a\\u00e9"', b'"\\ud83d"', b"[1]", b"{}", b'"__debezium_unavailable_value"']
+    ops = [b'"c"', b'"r"', b'"u"', b'"d"', b'"x"', b"1", b"null"]
+    out = []
+    for _ in range(n):
+        if rng.random() < 0.5:
+            m = bytearray(good[rng.integers(0, len(good))])
+            for _ in range(rng.integers(0, 3)):
+                p = int(rng.integers(0, len(m))); k = rng.integers(0, 3)
+                if k == 0: del m[p]
+                elif k == 1: m[p:p] = m[p:p + 1]
+                else: m[p] = int(rng.integers(32, 127))
+            out.append(bytes(m))
+        else:
+            after = b'{"id":%s,"s":%s}' % (vals[rng.integers(0, len(vals))], vals[rng.integers(0, len(vals))])
+            src = b'{"lsn":%s,"ts_ms":%s,"txId":%s,"schema":"public","table":"t"}' % (vals[rng.integers(0, 4)], vals[rng.integers(0, 8)], vals[rng.integers(0, 6)])
+            parts = [b'"after":' + after, b'"before":' + (after if rng.random() < 0.5 else b"null"), b'"source":' + src, b'"op":' + ops[rng.integers(0, len(ops))], b'"ts_ms":' + vals[rng.integers(0, 8)]]
+            order = rng.permutation(len(parts))[: rng.integers(2, len(parts) + 1)]
+            out.append(b'{"schema":' + schema_text.encode() + b',"payload":{' + b",".join(parts[i] for i in order) + b"}}")
+    return schema_text, out
+
+
+def test_oracle_debezium_fuzz_smoke(po):
+    schema_text, msgs = _dbz_fuzz_msgs(2000, 3)
+    data = b"".join(msgs); ends = np.cumsum([len(x) for x in msgs]).tolist()
+    batch, kinds, tx, lsn, ct, rm, errs, _ = po.debezium_parse(data, ends, schema_text)
+    assert batch.nrows + len(errs) == len(msgs) and batch.nrows > 100
+
+
+@pytest.mark.gpu
+def test_device_debezium_fuzz(eng, po):
+    """Differential fuzz: mutated envelopes and random payload shapes; the device agrees with the oracle on every message."""
+    for seed in (1, 2):
+        schema_text, msgs = _dbz_fuzz_msgs(8000, seed)
+        _dbz_cmp(eng, po, schema_text, msgs, _allow_host=40)

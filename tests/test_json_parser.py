@@ -202,3 +202,60 @@ def test_device_json_config2_workload(eng, po):
     res = eng.parse_json(pid, text, opts, msgs, wire_fmt=abi.TF_WIRE_CH_NATIVE_LZ4)
     raw, _ = po.ch_decode_frames(res.wire)
     assert raw == po.push_encode(ref, plan, abi.TF_WIRE_CH_NATIVE).raw
+
+
+def _fuzz_lines(n, seed):
+    """Random JSON-ish lines: values of every shape under the declared keys, then byte-level mutations of a share of them."""
+    rng = np.random.default_rng(seed)
+    scal = [b"null", b"true", b"false", b"0", b"-1", b"7", b"255", b"256", b"-129", b"65536", b"4294967296", b"1.5", b"-2.25e3", b"1e-7", b"0.1", b"123456789.125", b"12e", b"1e+2",
+            b'""', b'"x"', b'"42"', b'"-7"', b'"1.5"', b'"true"', b'"a\\tb\\u00e9\\\\"', b'"\xd1\x8f\xd0\xb7\xd1\x8b\xd0\xba"', b'"dGVzdA=="', b'"2013-07-15"', b'"q\\"uote"']
+    def value(depth=0):
+        k = rng.integers(0, 10)
+        if k < 6 or depth > 3: return scal[rng.integers(0, len(scal))]
+        if k < 8: return b"[" + b",".join(value(depth + 1) for _ in range(rng.integers(0, 4))) + b"]"
+        keys = [b"k%d" % rng.integers(0, 5) for _ in range(rng.integers(0, 4))]
+        return b"{" + b",".join(b'"' + kk + b'":' + value(depth + 1) for kk in keys) + b"}"
+    names = [f["name"].encode() for f in ALL_FIELDS] + [b"extra", b"zz", b"_rest_not"]
+    out = []
+    for _ in range(n):
+        ks = [names[i] for i in rng.permutation(len(names))[: rng.integers(0, len(names))]]
+        sp = b" " if rng.random() < 0.2 else b""
+        ln = b"{" + (b"," + sp).join(b'"' + kk + b'"' + sp + b":" + sp + value() for kk in ks) + b"}"
+        if rng.random() < 0.15 and len(ln) > 2:       # mutate: delete / duplicate / replace one byte
+            p = int(rng.integers(0, len(ln))); m = rng.integers(0, 3)
+            ln = ln[:p] + ln[p + 1:] if m == 0 else (ln[:p] + ln[p:p + 1] + ln[p:] if m == 1 else ln[:p] + bytes([rng.integers(32, 127)]) + ln[p + 1:])
+        if b"\n" in ln: ln = ln.replace(b"\n", b" ")
+        out.append(ln)
+    return out
+
+
+def test_oracle_json_fuzz_smoke(po):
+    """The oracle itself survives the fuzz corpus (the GPU test compares the device against it line by line)."""
+    lines = _fuzz_lines(3000, 5)
+    b, errs, n = po.json_parse(b"\n".join(lines), [dict(f) for f in ALL_FIELDS], {"add_rest": True})
+    assert n == len([x for x in lines if x.rstrip(b"\r")]) and b.nrows + len(errs) == n and b.nrows > 500
+
+
+@pytest.mark.gpu
+def test_device_json_fuzz(eng, po):
+    """Differential fuzz: 40 k random / mutated lines, every option set; the device must agree with the oracle on every line
+    (rows, nulls, text bytes, error codes), except lines it hands to the host parser."""
+    for seed, opts in ((1, {}), (2, {"add_rest": True, "use_numbers_in_any": True}), (3, {"add_rest": True, "add_dedupe_keys": True, "unpack_bytes_base64": True, "null_keys_allowed": True}),
+                       (4, {"add_dedupe_keys": True})):
+        lines = _fuzz_lines(10_000, seed)
+        fields = [dict(f, required=(f["name"] == "i64" and seed == 4)) for f in ALL_FIELDS]
+        text = b"\n".join(lines)
+        schema = _engine.json_result_schema(fields, opts)
+        pid = eng.plan("db", "fz", schema, [])
+        got, gerr, gl = eng.parse_json(pid, text, opts)
+        ref, rerr, rl = po.json_parse(text, fields, opts)
+        extra = [e for e in gerr if e not in rerr]
+        assert gl == rl and all(c == abi.TF_ROWERR_JSON_HOST for _, c, _ in extra) and len(extra) < 200, (extra[:5], [e for e in rerr if e not in gerr][:5])
+        if extra:
+            nonempty = [k for k, ln in enumerate(lines) if ln.rstrip(b"\r")]
+            for r, _, _ in extra: lines[nonempty[r]] = b"[]"
+            text = b"\n".join(lines)
+            got, gerr, gl = eng.parse_json(pid, text, opts); ref, rerr, rl = po.json_parse(text, fields, opts)
+        assert gerr == rerr, ([e for e in gerr if e not in rerr][:5], [e for e in rerr if e not in gerr][:5])
+        from test_gpu_parity import assert_batches_equal
+        assert_batches_equal(got, ref)
