@@ -454,7 +454,7 @@ def test_number_to_float(eng, po):
         got, gerr = eng.push_columns(pid, b); ref, rerr = po.push_columns(b, plan)
         assert gerr == rerr, (trs, gerr, rerr)
         assert_batches_equal(got, ref)
-        for fmt in (RAW, JS):
+        for fmt in (RAW, abi.TF_WIRE_CH_JSONEACHROW):
             if any("skip" in t for t in trs): continue
             bi = abi.Batch(n, b.columns, np.zeros(n, dtype=np.uint8))       # sinks take insert rows
             assert eng.push_encode(pid, bi, fmt).wire == po.push_encode(bi, plan, fmt).raw, (trs, fmt)
