@@ -462,4 +462,4 @@ def test_number_to_float(eng, po):
     ref, _ = po.push_columns(b, po.build_plan("db", "t", schema, chains[0]))
     a = ref.columns[1]; cell = lambda r: bytes(a.heap[a.offsets[r]:a.offsets[r + 1]])
     assert cell(0) == b'{"a":1,"b":[1.5,2000,-0,1e+21,1e-7,0.000001,1.2345678901234568e+29],"s":"12 \\" 3e4","n":null}'
-    assert cell(1) == b"17" and cell(2) == b"1e400" and cell(3) == b"-100" and cell(4) == b"just a string 5" and cell(9) == b"3.141592653589793"
+    assert cell(1) == b"17" and cell(2) == b"1e400" and cell(3) == b"-100" and cell(4) == b'"just a string 5"' and cell(9) == b"3.141592653589793"
