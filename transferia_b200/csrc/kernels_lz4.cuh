@@ -25,7 +25,6 @@ namespace tfk {
 
 #define LZ_THREADS 512
 #define LZ_SEG 64
-#define LZ_ROUND (LZ_THREADS * 8)      /* positions per match-finding round: 8 consecutive ones per thread */
 #define LZ_HASH_BITS 11      /* 2048 entries of u32: tag16 << 16 | position */
 #define LZ_MAX_FRAME 32768
 #define LZ_HDR 25          // 16 checksum + 1 method + 4 compressed size + 4 raw size
@@ -114,41 +113,43 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
 
         LZ_PHASE(0);
         // ---- P2: match finding
-        const uint32_t nrounds = (len + LZ_ROUND - 1) / LZ_ROUND;
+        const uint32_t nrounds = (len + 2047) / 2048;
         for (uint32_t rd = 0; rd < nrounds; rd++) {
-            const uint32_t p0 = rd * LZ_ROUND + tid * 8;
-            const bool active = p0 < F;                         // F is a multiple of 64, so p0 + 7 < F too
-            uint32_t h[8], c[8];                                 // hash (index = top LZ_HASH_BITS bits, tag = the next 16) and candidate entry
+            const uint32_t p0 = rd * 2048 + tid * 4;
+            const bool active = p0 < F;                         // F is a multiple of 64, so p0 + 3 < F too
+            uint32_t idx[4], tag[4], c[4];
             if (active) {
-                const uint32_t w0 = data_w[LZ_PW(p0 >> 2)], w1 = data_w[LZ_PW((p0 >> 2) + 1)], w2 = data_w[LZ_PW((p0 >> 2) + 2)];
-                h[0] = w0; h[1] = __funnelshift_r(w0, w1, 8); h[2] = __funnelshift_r(w0, w1, 16); h[3] = __funnelshift_r(w0, w1, 24);
-                h[4] = w1; h[5] = __funnelshift_r(w1, w2, 8); h[6] = __funnelshift_r(w1, w2, 16); h[7] = __funnelshift_r(w1, w2, 24);
+                const uint32_t w0 = data_w[LZ_PW(p0 >> 2)], w1 = data_w[LZ_PW((p0 >> 2) + 1)];
+                uint32_t seq[4];
+                seq[0] = w0; seq[1] = __funnelshift_r(w0, w1, 8); seq[2] = __funnelshift_r(w0, w1, 16); seq[3] = __funnelshift_r(w0, w1, 24);
 #pragma unroll
-                for (int k = 0; k < 8; k++) { h[k] *= 2654435761u; c[k] = table[h[k] >> (32 - LZ_HASH_BITS)]; }
+                for (int k = 0; k < 4; k++) { const uint32_t h = seq[k] * 2654435761u; idx[k] = h >> (32 - LZ_HASH_BITS); tag[k] = (h << LZ_HASH_BITS) & 0xffff0000u; c[k] = table[idx[k]]; }
             }
             __syncthreads();
             uint32_t vm = 0;      // candidate bits: the 27 known hash bits agree; the bytes are compared by the parser (P3)
             if (active) {
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const uint32_t p = p0 + k, tag = (h[k] << LZ_HASH_BITS) & 0xffff0000u;
-                    if (p < len) table[h[k] >> (32 - LZ_HASH_BITS)] = tag | p;
-                    if ((p + 12 <= len) && (c[k] & 0xffff0000u) == tag && (c[k] & 0xffffu) < p) vm |= 1u << k;   // MFLIMIT
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t p = p0 + k;
+                    if (p < len) table[idx[k]] = tag[k] | p;
+                    if ((p + 12 <= len) && (c[k] & 0xffff0000u) == tag[k] && (c[k] & 0xffffu) < p) vm |= 1u << k;   // MFLIMIT
                 }
             }
             __syncthreads();
             if (active) {   // second probe: sees this round's inserts, recovers repeats whose first occurrence is in this round
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
+                for (int k = 0; k < 4; k++) {
                     const uint32_t p = p0 + k;
                     if (!((vm >> k) & 1) && p + 12 <= len) {
-                        const uint32_t c2 = table[h[k] >> (32 - LZ_HASH_BITS)];
-                        if ((c2 & 0xffff0000u) == ((h[k] << LZ_HASH_BITS) & 0xffff0000u) && (c2 & 0xffffu) < p) { vm |= 1u << k; c[k] = c2; }
+                        const uint32_t c2 = table[idx[k]];
+                        if ((c2 & 0xffff0000u) == tag[k] && (c2 & 0xffffu) < p) { vm |= 1u << k; c[k] = c2; }
                     }
                 }
-                *(uint4*)(cand + p0) = make_uint4((c[0] & 0xffffu) | (c[1] << 16), (c[2] & 0xffffu) | (c[3] << 16), (c[4] & 0xffffu) | (c[5] << 16), (c[6] & 0xffffu) | (c[7] << 16));
-                vbits[p0 >> 3] = (uint8_t)vm;
+                *(uint2*)(cand + p0) = make_uint2((c[0] & 0xffffu) | (c[1] << 16), (c[2] & 0xffffu) | (c[3] << 16));
             }
+            // two lanes share one byte of the bit map
+            const uint32_t other = __shfl_down_sync(0xffffffffu, vm, 1);
+            if (active && !(lane & 1)) vbits[p0 >> 3] = (uint8_t)(vm | (other << 4));
         }
         __syncthreads();
 
