@@ -181,16 +181,17 @@ def extra_paths(eng, args):
     trs = [{"mask_field": {"columns": ["user"], "maskFunctionHash": {"userDefinedSalt": "pepper"}}}]
     pid = eng.plan("", "events", schema, trs, {"type": "clickhouse"})
     n = text.count(b"\n")
+    pinned = torch.frombuffer(bytearray(text), dtype=torch.uint8).pin_memory()      # the message bytes as a consumer would hold them: pinned
     for name, fmt in (("json_parse_mask_ch_jsoneachrow", abi.TF_WIRE_CH_JSONEACHROW), ("json_parse_mask_ch_native_lz4", abi.TF_WIRE_CH_NATIVE_LZ4)):
         for _ in range(2):
-            r = eng.parse_json(pid, text, opts, None, wire_fmt=fmt, copy_bytes=False)
+            r = eng.parse_json(pid, pinned, opts, None, wire_fmt=fmt, copy_bytes=False)
         torch.cuda.synchronize(); t0 = time.perf_counter(); k = 5
         for _ in range(k):
-            r = eng.parse_json(pid, text, opts, None, wire_fmt=fmt, copy_bytes=False)
+            r = eng.parse_json(pid, pinned, opts, None, wire_fmt=fmt, copy_bytes=False)
         torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / k
         eng.profile_enable(True); eng.parse_json(pid, text, opts, None, wire_fmt=fmt); prof = {kk["name"]: round(kk["ms"], 4) for kk in eng.profile_read()}; eng.profile_enable(False)
         res[name] = {"rows_per_s": n / dt, "lines": n, "input_MB": len(text) / 1e6, "ms": dt * 1e3, "rows_out": r.rows_out, "out_bytes": int(r.wire_len), "kernels_ms": prof,
-                     "note": "wall clock around the public call with a pageable host buffer: H2D of the message bytes and D2H of the wire bytes into the pinned landing buffer included"}
+                     "note": "wall clock around the public call with the message bytes in a pinned host buffer: H2D of the bytes and D2H of the wire bytes into the pinned landing buffer included"}
     try:
         from oracle import pyoracle as po
         sample = text[: text.rfind(b"\n", 0, len(text) // 20) + 1]

@@ -333,13 +333,19 @@ class Engine:
         msgs: [(end, offset, write_sec, write_nsec)] (default: one message = all of `data`).
         wire_fmt 0: (Batch, row errors, non-empty lines); otherwise PushResult (copy_bytes=False leaves the wire bytes in the
         engine's pinned landing buffer and only reports their length)."""
-        msgs = msgs if msgs is not None else [(len(data), 0, 0, 0)]
+        tensor = hasattr(data, "data_ptr")                  # a (pinned) torch uint8 tensor: its storage is used in place
+        total = int(data.numel()) if tensor else len(data)
+        msgs = msgs if msgs is not None else [(total, 0, 0, 0)]
         ms = (abi.TfMsg * max(1, len(msgs)))()
         for k, (end, off, ws, wn) in enumerate(msgs):
             ms[k].end, ms[k].offset, ms[k].write_sec, ms[k].write_nsec = end, off, ws, wn
-        buf = C.c_char_p(data if data else b"\0")          # the bytes object's own storage: no copy
+        if tensor:
+            ptr = C.c_void_p(data.data_ptr())
+        else:
+            buf = C.c_char_p(data if data else b"\0")      # the bytes object's own storage: no copy
+            ptr = C.cast(buf, C.c_void_p)
         res = C.c_void_p()
-        self._check(self._L.tfgpu_parse_json(self._h, plan_id, json.dumps(opts or {}).encode(), C.cast(buf, C.c_void_p), len(data), abi.TF_MEM_HOST, ms, len(msgs), wire_fmt, C.byref(res)))
+        self._check(self._L.tfgpu_parse_json(self._h, plan_id, json.dumps(opts or {}).encode(), ptr, total, abi.TF_MEM_HOST, ms, len(msgs), wire_fmt, C.byref(res)))
         try:
             L = self._L
             if wire_fmt == 0:
