@@ -145,6 +145,7 @@ typedef struct tf_batch {
 /* number_to_float: a number literal inside an `any` value whose float64 rounding the device cannot decide (hex / underscored /
  * > 19 digit literals with an open Eisel-Lemire result); the shim applies the Go transformer to that row */
 #define TF_ROWERR_N2F_HOST 52
+#define TF_ROWERR_DBZ_EMIT_HOST 53 /* tfgpu_emit_debezium: update / delete rows need ChangeItem.OldKeys — the shim emits them with the Go emitter */
 
 /* serializers: a value encoding/json refuses (NaN / Inf float, time.Time with a year outside [0,9999]); the reference
  * fails the whole Serialize call on it, so a result carrying this code must not be written; term = output column */
@@ -164,6 +165,7 @@ typedef struct tf_rowerr {
  * csv_format.go:32-144): the object-storage / queue sinks' row text. OR the flags into the format id. */
 #define TF_WIRE_SER_JSON       4  /* one JSON object per row, keys sorted, rows joined by '\n'    */
 #define TF_WIRE_SER_CSV        5  /* encoding/csv records, each ending in '\n'                    */
+#define TF_WIRE_DEBEZIUM       6  /* tfgpu_emit_debezium only: key message + value message per row  */
 #define TF_WIRE_F_CLOSING_NEWLINE 0x100  /* JSONSerializerConfig.AddClosingNewLine (json.go:15)   */
 #define TF_WIRE_F_ANY_AS_STRING   0x200  /* JSONSerializerConfig.AnyAsString (json_format.go:69-76) */
 
@@ -208,6 +210,38 @@ int tfgpu_push_columns(tfgpu_engine* e, int plan_id, const tf_batch* in, tfgpu_r
 /* Transformer chain + sink cast + wire encode, fused on the device. */
 int tfgpu_push_encode(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch* in,
                       tfgpu_result** out);
+
+/* Queue Debezium serializer (pkg/serializer/queue/debezium_serializer.go:25-92 -> debezium.Emitter.EmitKV
+ * pkg/debezium/emitter_value_converter.go:566-690; values by addCommon emitter_common.go:67-180, i.e. columns WITHOUT a
+ * pg: / mysql: / ydb: original_type). Runs the plan's chain on the device and writes, for every surviving INSERT row, the
+ * Kafka key message immediately followed by the value message:
+ *   key   = pack({"<pk col>":v,...})                                   (keys sorted: encoding/json map order)
+ *   value = pack({"after":{...},"before":null,"op":"c"|"r","source":{...},"transaction":null,"ts_ms":CommitTime/1e6})
+ *   pack(p) = p                                        schemas disabled (packer_skip_schema.go)
+ *           | {"payload":p,"schema":<schema text>}      packer_include_schema.go:24-44
+ *           | 0x00 | u32be schema id | p                packer_schema_registry.go:66-76
+ * tfgpu_result_bytes holds the messages back to back; tfgpu_result_row_sizes[j] = key + value bytes of output row j,
+ * tfgpu_result_key_sizes[j] = the key part (0 with drop_keys). Values: ints / uints bare, float / double as encoding/json
+ * writes float32 / float64, boolean, `string` (bytes) base64, `utf8` JSON string (SetEscapeHTML(false)), datetime /
+ * timestamp RFC3339Nano, `any`: Go string as is, object -> its JSON text as a string, JSON null -> null; anything else
+ * (date, interval, any arrays / scalars, NaN, years outside [0,9999]) makes EmitKV fail in the reference: the row is
+ * reported as TF_ROWERR_SER_VALUE (term = output column) and the shim fails the batch like Serialize does.
+ * UPDATE / DELETE rows need OldKeys, which tf_batch does not carry: TF_ROWERR_DBZ_EMIT_HOST, emitted by the shim in Go.
+ * opts_json: {"ignore_unknown_sources":true (required: without it the reference answers errUnknownSource for such columns,
+ *   emitter_value_converter.go:183-191), "snapshot":bool, "drop_keys":bool, "source_type":""|"pg"|"mysql", "version":"..",
+ *   "topic_prefix":"..", "database":"..", "key_schema":"<json>"|null, "val_schema":"<json>"|null (what
+ *   Emitter.ToKafkaSchemaKey/Val return for the plan's result schema; the lightning cache computes them once per table,
+ *   packer/lightning_cache), "key_schema_id":N, "val_schema_id":N (confluent framing instead)}.
+ * meta: the ChangeItem fields the envelope's `source` block carries (buildSource :329-372). */
+typedef struct tf_row_meta {
+    const uint32_t* id;            /* ChangeItem.ID  -> source.txId (pg); NULL = 0              */
+    const uint64_t* lsn;           /* ChangeItem.LSN -> source.lsn (pg) / file + pos (mysql)    */
+    const uint64_t* commit_time;   /* ChangeItem.CommitTime ns -> source.ts_ms and payload ts_ms */
+    const uint32_t* txid_offsets;  /* ChangeItem.TxID -> source.gtid (mysql): nrows+1 offsets    */
+    const uint8_t*  txid_heap;     /*   into this heap; NULL = "" (gtid null)                    */
+} tf_row_meta;
+int tfgpu_emit_debezium(tfgpu_engine* e, int plan_id, const char* opts_json, const tf_batch* in, const tf_row_meta* meta,
+                        tfgpu_result** out);
 
 /* Measurer middleware (pkg/middlewares/synchronizer/measurer.go:38-42): ChangeItem.Size.Values = util.DeepSizeof(ColumnValues)
  * (pkg/util/sizeof.go:7-110) for every row of `in`, computed in closed form from the column types and lengths instead of a
@@ -304,6 +338,7 @@ uint64_t          tfgpu_result_n_frames(const tfgpu_result* r);
 /* Row-text formats (TF_WIRE_SER_JSON/CSV, TF_WIRE_CH_JSONEACHROW): bytes of every output row in the order written,
  * separator included (SER_JSON without CLOSING_NEWLINE: rows after the first start with '\n'). rows_out entries or NULL. */
 const uint32_t*   tfgpu_result_row_sizes(const tfgpu_result* r);
+const uint32_t*   tfgpu_result_key_sizes(const tfgpu_result* r);  /* tfgpu_emit_debezium: key bytes of every output row */
 
 /* Queue JSON serializer (pkg/serializer/queue/json_serializer.go:22-83 + json_batcher.go:13-66): the message VALUES are the
  * TF_WIRE_SER_JSON rows (key = ChangeItem.Fqtn(), built by the shim); with batching enabled BatchJSON packs consecutive rows

@@ -735,6 +735,131 @@ extern "C" int orc_push_encode(const tf_batch* in, const orc_colschema* schema, 
     return TF_E_FATAL_UNSUPPORTED;
 }
 
+// ------------------------------------------------------------------ Debezium emitter, common (no original_type) path
+// One column value as addCommon stores it (pkg/debezium/emitter_common.go:67-180) and util.JSONMarshalUnescape then writes it.
+// false: addCommon or the encoder returns an error (EmitKV fails).
+namespace {
+bool dbz_emit_value(std::string& o, const orc_val& v, int32_t yt) {
+    if (v.kind == OG_NIL) { o += "null"; return true; }                                         // :68-71
+    const bool sint = v.kind == OG_INT8 || v.kind == OG_INT16 || v.kind == OG_INT32 || v.kind == OG_INT64 || v.kind == OG_INT;
+    const bool uint = v.kind == OG_UINT8 || v.kind == OG_UINT16 || v.kind == OG_UINT32 || v.kind == OG_UINT64 || v.kind == OG_UINT;
+    switch (yt) {
+    case TF_INT8: case TF_INT16: case TF_INT32: case TF_INT64:                                   // :74-79 the value itself is stored
+        if (!sint) return false; o += fmt_i64(v.i); return true;
+    case TF_UINT8: case TF_UINT16: case TF_UINT32: case TF_UINT64:                               // :81-86 uint64(t)
+        if (uint) { o += fmt_u64(v.u); return true; }
+        if (sint) { o += fmt_u64((uint64_t)v.i); return true; }
+        return false;
+    case TF_FLOAT: case TF_DOUBLE:                                                               // :88-98
+        if (v.kind == OG_FLOAT32) { if (std::isnan(v.f) || std::isinf(v.f)) return false; o += fmt_f32((float)v.f, FMT_JSON); return true; }
+        if (v.kind == OG_FLOAT64) { if (std::isnan(v.f) || std::isinf(v.f)) return false; o += fmt_f64(v.f, FMT_JSON); return true; }
+        return false;
+    case TF_BYTES:                                                                               // :100-108
+        if (v.kind != OG_STRING && v.kind != OG_BYTES) return false;
+        o += '"'; o += base64_std(v.s, v.slen); o += '"'; return true;
+    case TF_UTF8:                                                                                // :110-120
+        if (v.kind == OG_STRING) { o += go_json_quote_nohtml(v.s, v.slen); return true; }
+        if (v.kind == OG_BYTES) { o += '"'; o += base64_std(v.s, v.slen); o += '"'; return true; }   // a []byte value is marshalled as base64
+        if (v.kind == OG_TIME) { o += fmt_i64(v.i / 86400); return true; }                       // mysql:date
+        return false;
+    case TF_BOOLEAN:                                                                             // :122-130
+        if (v.kind == OG_BOOL) { o += v.i ? "true" : "false"; return true; }
+        if (v.kind == OG_INT8) { o += v.i == 1 ? "true" : "false"; return true; }
+        return false;
+    case TF_DATETIME: case TF_TIMESTAMP:                                                         // :132-146 time.Time.MarshalJSON
+        if (v.kind != OG_TIME || !year_in_json_range(v.i)) return false;
+        o += '"'; o += fmt_rfc3339nano_utc(v.i, v.nsec); o += '"'; return true;
+    case TF_ANY:                                                                                 // :148-160
+        if (v.kind == OG_STRING) { o += go_json_quote_nohtml(v.s, v.slen); return true; }
+        if (v.kind == OG_JSON) {
+            if (v.slen == 4 && !std::memcmp(v.s, "null", 4)) { o += "null"; return true; }     // a nil interface: colVal == nil
+            if (v.slen && v.s[0] == '"') { o += json_unescape_html(v.s, v.slen); return true; }  // a Go string
+            if (v.slen && v.s[0] == '{') {                                                       // map -> string(JSONMarshalUnescape(t)) stored as a string
+                const std::string t = json_unescape_html(v.s, v.slen);
+                o += go_json_quote_nohtml((const uint8_t*)t.data(), t.size()); return true;
+            }
+        }
+        return false;
+    default: return false;                                                                       // :161-163 unknown input data type
+    }
+}
+std::string dbz_pack(const std::string& payload, const char* schema, int64_t schema_id) {
+    if (schema_id >= 0) {                                                                        // packer_schema_registry.go:66-76
+        std::string m; m += '\0'; for (int sh = 24; sh >= 0; sh -= 8) m += (char)(((uint32_t)schema_id >> sh) & 0xff);
+        return m + payload;
+    }
+    if (schema) return "{\"payload\":" + payload + ",\"schema\":" + schema + "}";                // packer_include_schema.go:34-38 (map keys sorted)
+    return payload;                                                                              // packer_skip_schema.go:12-19
+}
+}  // namespace
+
+// Emitter.EmitKV for the rows of one batch (pkg/debezium/emitter_value_converter.go:626-690; valPayload :453-512,
+// buildSource :329-372, makeKey / buildKV :259-327). INSERT rows only: update / delete events read ChangeItem.OldKeys.
+extern "C" int orc_debezium_emit(const tf_batch* in, const orc_colschema* schema, const uint8_t* is_key, const orc_step* steps, int nsteps,
+                                 const tf_row_meta* meta, const orc_dbz_emit_opts* o, orc_buf* out, uint32_t* key_sizes, uint32_t* row_sizes,
+                                 uint64_t* rows_out, tf_rowerr* errs, uint64_t* nerrs) {
+    const uint32_t nc = in->ncols;
+    std::vector<int32_t> out_type; std::vector<uint32_t> out_cols;
+    result_types(in, steps, nsteps, out_type, out_cols);
+    const uint32_t no = (uint32_t)out_cols.size();
+    std::vector<std::string> names(no);
+    for (uint32_t k = 0; k < no; k++) names[k] = schema[out_cols[k]].name;
+    std::vector<uint32_t> order(no); for (uint32_t k = 0; k < no; k++) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return names[a] < names[b]; });
+    auto q = [](const char* t) { const std::string s = t ? t : ""; return go_json_quote_nohtml((const uint8_t*)s.data(), s.size()); };
+    uint64_t kept = 0, ne = 0;
+    std::vector<Boxed> row(nc); std::vector<int32_t> cur_type(nc);
+    std::string text;
+    for (uint64_t r = 0; r < in->nrows; r++) {
+        const int kind = in->kinds ? in->kinds[r] : TF_KIND_INSERT;
+        if (kind != TF_KIND_INSERT) { errs[ne++] = tf_rowerr{(uint32_t)r, TF_ROWERR_DBZ_EMIT_HOST, 0}; continue; }
+        if (!apply_steps(in, r, steps, nsteps, row, cur_type, errs, ne)) continue;
+        bool row_err = false;
+        auto obj = [&](bool keys_only) {
+            std::string t = "{"; bool first = true;
+            for (uint32_t j = 0; j < no; j++) {
+                const uint32_t k = order[j];
+                if (keys_only && !is_key[out_cols[k]]) continue;
+                if (!first) t += ','; first = false;
+                t += go_json_quote_nohtml((const uint8_t*)names[k].data(), names[k].size()); t += ':';
+                if (!dbz_emit_value(t, row[out_cols[k]].v, out_type[out_cols[k]])) { t += "null"; if (!row_err) errs[ne++] = tf_rowerr{(uint32_t)r, TF_ROWERR_SER_VALUE, (uint16_t)k}; row_err = true; }
+            }
+            return t + "}";
+        };
+        const uint64_t lsn = meta && meta->lsn ? meta->lsn[r] : 0, ct = meta && meta->commit_time ? meta->commit_time[r] : 0;
+        const uint32_t id = meta && meta->id ? meta->id[r] : 0;
+        std::string key_msg;
+        if (!o->drop_keys) key_msg = dbz_pack(obj(true), o->key_schema, o->key_schema_id);
+        const std::string snap = o->snapshot ? "\"true\"" : "\"false\"";
+        std::string src = "{";
+        if (o->source_type == 1) {            // pg: connector db lsn name schema snapshot table ts_ms txId version xmin
+            src += "\"connector\":\"postgresql\",\"db\":" + q(o->database) + ",\"lsn\":" + fmt_u64(lsn) + ",\"name\":" + q(o->name) + ",\"schema\":" + q(o->schema) +
+                   ",\"snapshot\":" + snap + ",\"table\":" + q(o->table) + ",\"ts_ms\":" + fmt_u64(ct / 1000000) + ",\"txId\":" + fmt_u64(id) + ",\"version\":" + q(o->version) + ",\"xmin\":null";
+        } else if (o->source_type == 2) {     // mysql: connector db file gtid name pos query row server_id snapshot table thread ts_ms version
+            char file[64]; std::snprintf(file, sizeof file, "mysql-log.%06llu", (unsigned long long)(lsn / 1000000000000ull));      // typeutil/helpers.go:1101-1105
+            std::string gtid = "null";
+            if (meta && meta->txid_offsets && meta->txid_heap && meta->txid_offsets[r + 1] > meta->txid_offsets[r])
+                gtid = go_json_quote_nohtml(meta->txid_heap + meta->txid_offsets[r], meta->txid_offsets[r + 1] - meta->txid_offsets[r]);
+            src += "\"connector\":\"mysql\",\"db\":" + q(o->schema) + ",\"file\":" + q(file) + ",\"gtid\":" + gtid + ",\"name\":" + q(o->name) + ",\"pos\":" + fmt_u64(lsn % 1000000000000ull) +
+                   ",\"query\":null,\"row\":0,\"server_id\":0,\"snapshot\":" + snap + ",\"table\":" + q(o->table) + ",\"thread\":null,\"ts_ms\":" + fmt_u64(ct / 1000000) + ",\"version\":" + q(o->version);
+        } else {
+            src += "\"db\":" + q(o->database) + ",\"name\":" + q(o->name) + ",\"snapshot\":" + snap + ",\"table\":" + q(o->table) + ",\"ts_ms\":" + fmt_u64(ct / 1000000) + ",\"version\":" + q(o->version);
+        }
+        src += "}";
+        // payloadTSMS = time.Unix(CommitTime/1e9, CommitTime%1e9) (GetPayloadTSMS :697-699); UnixNano()/1e6 in int64
+        const std::string payload = "{\"after\":" + obj(false) + ",\"before\":null,\"op\":" + (o->snapshot ? "\"r\"" : "\"c\"") + ",\"source\":" + src +
+                                    ",\"transaction\":null,\"ts_ms\":" + fmt_i64((int64_t)ct / 1000000) + "}";
+        const std::string val_msg = dbz_pack(payload, o->val_schema, o->val_schema_id);
+        key_sizes[kept] = (uint32_t)key_msg.size(); row_sizes[kept] = (uint32_t)(key_msg.size() + val_msg.size());
+        text += key_msg; text += val_msg; kept++;
+    }
+    if (rows_out) *rows_out = kept;
+    if (nerrs) *nerrs = ne;
+    std::vector<uint8_t> bytes(text.begin(), text.end());
+    to_buf(bytes, out);
+    return 0;
+}
+
 extern "C" int orc_push_columns(const tf_batch* in, const orc_colschema* schema, const orc_step* steps, int nsteps,
                      orc_buf* out, orc_regions* regions, int32_t* out_types, uint64_t* rows_out, tf_rowerr* errs, uint64_t* nerrs) {
     (void)schema;

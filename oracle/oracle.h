@@ -106,6 +106,19 @@ int orc_push_encode(const tf_batch* in, const orc_colschema* schema,
 
 /* Transformer chain only (TransformerResult.Transformed, pkg/abstract/transformer.go:40-48): the kept rows, columnar,
  * in one buffer; regions[k] = {values, validity, aux, offsets, heap, heap_len} offsets into it (~0 = absent). */
+/* Debezium emitter (pkg/debezium/emitter_value_converter.go:626-690 + emitter_common.go:67-180), INSERT rows, columns without
+ * a database-specific original_type. Messages back to back: key then value per output row. */
+typedef struct orc_dbz_emit_opts {
+    const char* version; const char* name; const char* database; const char* schema; const char* table;
+    int32_t source_type;                   /* 0 none, 1 pg, 2 mysql */
+    uint8_t snapshot, drop_keys, pad[2];
+    const char* key_schema; const char* val_schema;      /* NULL: schemas disabled */
+    int64_t key_schema_id, val_schema_id;                /* >= 0: confluent schema registry framing */
+} orc_dbz_emit_opts;
+int orc_debezium_emit(const tf_batch* in, const orc_colschema* schema, const uint8_t* is_key, const orc_step* steps, int nsteps,
+                      const tf_row_meta* meta, const orc_dbz_emit_opts* opts, orc_buf* out, uint32_t* key_sizes, uint32_t* row_sizes,
+                      uint64_t* rows_out, tf_rowerr* errs, uint64_t* nerrs);
+
 typedef struct orc_regions { uint64_t values, validity, aux, offsets, heap, heap_len; } orc_regions;
 int orc_push_columns(const tf_batch* in, const orc_colschema* schema, const orc_step* steps, int nsteps,
                      orc_buf* out, orc_regions* regions /* one per output column */, int32_t* out_types,

@@ -927,3 +927,58 @@ def base64_to_numeric(b64: str, scale: int) -> str:
     b = C.create_string_buffer(4096); n = L.orc_base64_to_numeric(b64.encode(), scale, b, 4096)
     if n < 0: raise ValueError(f"base64_to_numeric rc {n}")
     return b.raw[:n].decode()
+
+
+# ----------------------------------------------------------------------------- Debezium emitter
+
+class OrcDbzEmitOpts(C.Structure):
+    _fields_ = [("version", C.c_char_p), ("name", C.c_char_p), ("database", C.c_char_p), ("schema", C.c_char_p), ("table", C.c_char_p),
+                ("source_type", C.c_int32), ("snapshot", C.c_uint8), ("drop_keys", C.c_uint8), ("pad", C.c_uint8 * 2),
+                ("key_schema", C.c_char_p), ("val_schema", C.c_char_p), ("key_schema_id", C.c_int64), ("val_schema_id", C.c_int64)]
+
+
+_DBZ_SOURCE = {"": 0, None: 0, "pg": 1, "mysql": 2}
+
+
+def debezium_emit(batch: abi.Batch, plan: Plan, opts: dict, meta: Optional[dict] = None):
+    """Emitter.EmitKV over the INSERT rows of `batch` after the plan's chain (emitter_value_converter.go:626-690).
+    Returns (messages bytes, key_sizes, row_sizes, errors); key then value per row."""
+    L = lib()
+    keep, cschema, csteps = _marshal(plan)
+    tb = batch.as_struct()
+    key_by_name = {c["name"]: bool(c.get("key")) for c in plan.result_schema}
+    is_key = np.zeros(len(plan.schema), dtype=np.uint8)
+    for k, ci in enumerate(plan.out_cols):
+        is_key[ci] = 1 if key_by_name.get(plan.result_schema[k]["name"]) else 0
+    meta = meta or {}
+    m, mkeep = abi.make_row_meta(meta.get("id"), meta.get("lsn"), meta.get("commit_time"), meta.get("txid_offsets"), meta.get("txid_heap"))
+    o = OrcDbzEmitOpts()
+    enc = lambda v: None if v is None else keep.add(str(v).encode())
+    o.version = enc(opts.get("version", "")); o.name = enc(opts.get("topic_prefix", "")); o.database = enc(opts.get("database", ""))
+    o.schema = enc(plan.result_table[0]); o.table = enc(plan.result_table[1])
+    o.source_type = _DBZ_SOURCE[opts.get("source_type", "")]; o.snapshot = 1 if opts.get("snapshot") else 0; o.drop_keys = 1 if opts.get("drop_keys") else 0
+    o.key_schema = enc(opts.get("key_schema")); o.val_schema = enc(opts.get("val_schema"))
+    o.key_schema_id = opts["key_schema_id"] if opts.get("key_schema_id") is not None else -1
+    o.val_schema_id = opts["val_schema_id"] if opts.get("val_schema_id") is not None else -1
+    n = batch.nrows
+    ks = np.zeros(max(1, n), dtype=np.uint32); rs = np.zeros(max(1, n), dtype=np.uint32)
+    out = OrcBuf(); rows = C.c_uint64(); nerr = C.c_uint64()
+    errs = (abi.TfRowErr * max(1, 2 * n))()
+    L.orc_debezium_emit.argtypes = [C.POINTER(abi.TfBatch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(abi.TfRowMeta), C.POINTER(OrcDbzEmitOpts),
+                                    C.POINTER(OrcBuf), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_uint64)]
+    rc = L.orc_debezium_emit(C.byref(tb), C.cast(cschema, C.c_void_p), is_key.ctypes.data, C.cast(csteps, C.c_void_p), len(plan.steps), C.byref(m), C.byref(o),
+                             C.byref(out), ks.ctypes.data, rs.ctypes.data, C.byref(rows), C.cast(errs, C.c_void_p), C.byref(nerr))
+    if rc != 0:
+        raise RuntimeError(f"oracle debezium_emit rc={rc}")
+    data = C.string_at(out.data, out.len) if out.len else b""
+    L.orc_free(C.byref(out))
+    k = rows.value
+    return data, ks[:k].copy(), rs[:k].copy(), [(errs[i].row, errs[i].code, errs[i].term) for i in range(nerr.value)]
+
+
+def debezium_split(data: bytes, key_sizes, row_sizes):
+    """[(key bytes, value bytes)] of a debezium_emit / tfgpu_emit_debezium result."""
+    out = []; at = 0
+    for k, r in zip(key_sizes, row_sizes):
+        out.append((data[at:at + int(k)], data[at + int(k):at + int(r)])); at += int(r)
+    return out

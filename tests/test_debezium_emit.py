@@ -1,0 +1,222 @@
+"""Queue Debezium serializer: Emitter.EmitKV on columns without a database-specific original_type
+(pkg/debezium/emitter_value_converter.go:626-690, emitter_common.go:67-180).
+
+The reference holds no byte-level golden for this path (its pg / mysql canon files go through the database converters), so
+the oracle is pinned by (1) the assertions of the reference's own unit tests on it, (2) the message a real Debezium wrote
+for the reference's CRUD fixture, restricted to the columns whose pg converter is the identity. The device emitter is then
+compared with the oracle byte for byte."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from transferia_b200 import abi
+
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "debezium_emit_goldens.json"), encoding="utf-8"))
+OPTS = {"ignore_unknown_sources": True, "version": "1.1.2.Final", "topic_prefix": "fullfillment", "database": "pguser", "source_type": "pg"}
+
+
+def _golden_batch():
+    schema, cols = [], []
+    for c in G["columns"]:
+        tf = abi.YT_NAME_TO_TF[c["type"]]
+        schema.append({"name": c["name"], "type": c["type"], "key": c["key"], "required": c["required"]})
+        if tf == abi.TF_UTF8:
+            cols.append(abi.strings_to_column(tf, [c["value"].encode()]))
+        else:
+            cols.append(abi.fixed_to_column(tf, [c["value"]]))
+    meta = {"id": np.array([G["id"]], np.uint32), "lsn": np.array([G["lsn"]], np.uint64), "commit_time": np.array([G["commit_time"]], np.uint64)}
+    return abi.Batch(1, cols), schema, meta
+
+
+def test_oracle_against_real_debezium_message(po):
+    """pg/tests/emitter_crud_test.go: the insert fixture, identity-converter columns. Values as the real message holds them
+    (doubles compared as numbers: Java prints 3.14E-100), envelope and `source` key sets, constants of the source block."""
+    batch, schema, meta = _golden_batch()
+    plan = po.build_plan(G["table"][0], G["table"][1], schema, [])
+    data, ks, rs, errs = po.debezium_emit(batch, plan, OPTS, meta)
+    assert errs == [] and len(ks) == 1
+    (key, val), = po.debezium_split(data, ks, rs)
+    assert key == b'{"i":1}'
+    v = json.loads(val)
+    assert sorted(v.keys()) == G["payload_keys"] and v["op"] == G["op"] and v["before"] is None and v["transaction"] is None
+    assert list(v.keys()) == sorted(v.keys()) and list(v["after"].keys()) == sorted(v["after"].keys()) and list(v["source"].keys()) == sorted(v["source"].keys())
+    for c in G["columns"]:
+        m = ('"%s":' % c["name"]).encode()
+        at = val.index(m, val.index(b'"after"')) + len(m)
+        if c["type"] == "double":
+            assert v["after"][c["name"]] == float(c["after_text"])
+        else:
+            assert val[at:at + len(c["after_text"].encode())] == c["after_text"].encode(), c["name"]
+    want = G["source_block"]; got = v["source"]
+    assert sorted(got.keys()) == sorted(want.keys())
+    for k in ("version", "connector", "name", "snapshot", "db", "schema", "table", "xmin"):
+        assert got[k] == want[k], k
+    assert got["txId"] == G["id"] and got["lsn"] == G["lsn"] and got["ts_ms"] == G["commit_time"] // 10**6 and v["ts_ms"] == G["commit_time"] // 10**6
+
+
+def test_oracle_against_reference_unit_test_assertions(po):
+    """emitter_value_converter_test.go:41-79 (schema wrapper on/off, no HTML escaping), mysql/tests/emitter_meta_test.go (file / pos / gtid)."""
+    schema = [{"name": "id", "type": "int32", "key": True}, {"name": "value", "type": "utf8"}]
+    b = abi.Batch(1, [abi.fixed_to_column(abi.TF_INT32, [1]), abi.strings_to_column(abi.TF_UTF8, [b"<>!@#$%^&*()_"])])
+    plan = po.build_plan("", "", schema, [])
+    base = {"ignore_unknown_sources": True, "version": "1.1.2.Final", "topic_prefix": "my_topic", "database": "pguser", "source_type": "pg", "snapshot": True}
+    d, ks, rs, _ = po.debezium_emit(b, plan, base)
+    (k1, v1), = po.debezium_split(d, ks, rs)
+    assert G["substrings"]["html"].encode() in v1 and b'"payload"' not in v1 and b'"payload"' not in k1 and b'"op":"r"' in v1
+    d, ks, rs, _ = po.debezium_emit(b, plan, dict(base, key_schema='{"type":"struct"}', val_schema='{"type":"struct","x":1}'))
+    (k0, v0), = po.debezium_split(d, ks, rs)
+    assert json.loads(k0) == {"payload": {"id": 1}, "schema": {"type": "struct"}} and json.loads(v0)["schema"] == {"type": "struct", "x": 1}
+    assert k0.startswith(b'{"payload":') and v0.startswith(b'{"payload":{"after":')
+    d, ks, rs, _ = po.debezium_emit(b, plan, dict(base, key_schema_id=7, val_schema_id=0x01020304, drop_keys=False))
+    (k2, v2), = po.debezium_split(d, ks, rs)
+    assert k2 == b"\x00\x00\x00\x00\x07" + k1 and v2 == b"\x00\x01\x02\x03\x04" + v1          # packer_schema_registry.go:66-76
+    d, ks, rs, _ = po.debezium_emit(b, plan, dict(base, drop_keys=True))
+    assert list(ks) == [0] and d == v1
+    # mysql meta
+    schema = [{"name": "pk", "type": "uint32", "key": True}, {"name": "bigint_u", "type": "uint64"}]
+    b = abi.Batch(1, [abi.fixed_to_column(abi.TF_UINT32, [2]), abi.fixed_to_column(abi.TF_UINT64, [18446744073709551615])])
+    tx = b"58c4f6fc-27b5-11ed-b434-0242ac1e0002:2"
+    meta = {"lsn": np.array([2000000013747], np.uint64), "txid_offsets": np.array([0, len(tx)], np.uint32), "txid_heap": np.frombuffer(tx, np.uint8)}
+    d, ks, rs, _ = po.debezium_emit(b, po.build_plan("", "customers3", schema, []), dict(base, source_type="mysql"), meta)
+    (_, v), = po.debezium_split(d, ks, rs)
+    for name in ("mysql_file", "mysql_pos", "mysql_gtid"):
+        assert G["substrings"][name].encode() in v
+    assert b'"bigint_u":18446744073709551615' in v and json.loads(v)["source"]["gtid"] == tx.decode()
+
+
+def _matrix():
+    """Every value form addCommon distinguishes, with the rows that make EmitKV fail."""
+    schema = [{"name": "k", "type": "int64", "key": True}, {"name": "f", "type": "float"}, {"name": "d", "type": "double"}, {"name": "y", "type": "string"},
+              {"name": "s", "type": "utf8"}, {"name": "b", "type": "boolean"}, {"name": "ts", "type": "timestamp"}, {"name": "dt", "type": "datetime"},
+              {"name": "a", "type": "any"}, {"name": "dd", "type": "date"}, {"name": "iv", "type": "interval"}, {"name": "u", "type": "uint64", "key": True}]
+    n = 8
+    nul = lambda *idx: [i in idx for i in range(n)]
+    cols = [abi.fixed_to_column(abi.TF_INT64, [-2**63, 2**63 - 1, 0, 1, 2, 3, 4, 5]),
+            abi.fixed_to_column(abi.TF_FLOAT, np.array([1.5, 1e21, 1e-7, 3.4e38, -0.0, 16777216.0, float("inf"), 0.1], np.float32)),
+            abi.fixed_to_column(abi.TF_DOUBLE, [1e21, 1e20, 1e-7, 5e-324, -0.0, 0.1, 1.0, float("nan")]),
+            abi.strings_to_column(abi.TF_BYTES, [b"", b"\xff", b"ab", b"abc", None, b"\x00\x01\x02\x03", b"x", b"y"]),
+            abi.strings_to_column(abi.TF_UTF8, [b"<&>", b'q"\\\n\t\x01', b"\xff\xfe", b"\xe2\x80\xa8", None, "ключ".encode(), b"", b"z"]),
+            abi.fixed_to_column(abi.TF_BOOLEAN, [1, 0, 1, 0, 1, 0, 1, 0], nul(3)),
+            abi.fixed_to_column(abi.TF_TIMESTAMP, [0, 1_700_000_000, -62167219200, 253402300799, 253402300800, -62167219201, 1, 2], nul(6), [0, 123456789, 0, 999999999, 0, 0, 1000, 0]),
+            abi.fixed_to_column(abi.TF_DATETIME, [0, 1, 2, 3, 4, 5, 6, 7], nul(7)),
+            abi.strings_to_column(abi.TF_ANY, [b'{"k":"a\\u003cb","n":[1,2]}', b"plain <s>", b'"js\\u0026on"', b"null", None, b"[1,2]", b"12", b"true"], tags=[0, 1, 0, 0, 0, 0, 0, 0]),
+            abi.fixed_to_column(abi.TF_DATE, [0] * n, [True] * 7 + [False]),
+            abi.fixed_to_column(abi.TF_INTERVAL, [5] * n, [True] * 6 + [False, True]),
+            abi.fixed_to_column(abi.TF_UINT64, [2**64 - 1, 0, 1, 2, 3, 4, 5, 6])]
+    meta = {"id": np.arange(n, dtype=np.uint32) + 4294967290, "lsn": np.array([0, 1, 10**12 - 1, 10**12, 2**64 - 1, 5, 6, 7], np.uint64),
+            "commit_time": np.array([0, 999999, 10**6, 1649273150231781000, 2**63, 2**64 - 1, 7, 8], np.uint64)}
+    return abi.Batch(n, cols), schema, meta
+
+
+def test_oracle_value_forms(po):
+    batch, schema, meta = _matrix()
+    plan = po.build_plan("public", "t", schema, [])
+    data, ks, rs, errs = po.debezium_emit(batch, plan, dict(OPTS, source_type=""), meta)
+    kv = po.debezium_split(data, ks, rs)
+    assert len(kv) == 8
+    assert kv[0][0] == b'{"k":-9223372036854775808,"u":18446744073709551615}'
+    assert kv[0][1] == (b'{"after":{"a":"{\\"k\\":\\"a<b\\",\\"n\\":[1,2]}","b":true,"d":1e+21,"dd":null,"dt":"1970-01-01T00:00:00Z","f":1.5,"iv":null,'
+                        b'"k":-9223372036854775808,"s":"<&>","ts":"1970-01-01T00:00:00Z","u":18446744073709551615,"y":""},"before":null,"op":"c",'
+                        b'"source":{"db":"pguser","name":"fullfillment","snapshot":"false","table":"t","ts_ms":0,"version":"1.1.2.Final"},"transaction":null,"ts_ms":0}')
+    v1 = kv[1][1]
+    assert b'"a":"plain <s>"' in v1 and b'"d":100000000000000000000,' in v1 and b'"f":1e+21' in v1 and b'"y":"/w=="' in v1 and b'"s":"q\\"\\\\\\n\\t\\u0001"' in v1
+    assert b'"ts":"2023-11-14T22:13:20.123456789Z"' in v1
+    assert b'"a":"js&on"' in kv[2][1] and b'"s":"\\ufffd\\ufffd"' in kv[2][1] and b'"ts":"0000-01-01T00:00:00Z"' in kv[2][1] and b'"d":1e-7,' in kv[2][1] and b'"f":1e-7,' in kv[2][1]
+    assert b'"a":null' in kv[3][1] and b'"s":"\\u2028"' in kv[3][1] and b'"d":5e-324' in kv[3][1] and b'"b":null' in kv[3][1]
+    assert b'"ts_ms":1649273150231}' in kv[3][1] and b'"ts_ms":1649273150231,' in kv[3][1]
+    # CommitTime >= 2^63: source.ts_ms is unsigned, the payload's goes through time.Unix(...).UnixNano() (int64)
+    assert b'"ts_ms":9223372036854,"version"' in kv[4][1] and kv[4][1].endswith(b'"ts_ms":-9223372036854}')
+    assert b'"ts_ms":18446744073709,"version"' in kv[5][1] and kv[5][1].endswith(b'"ts_ms":0}')
+    # rows EmitKV fails on: year 10000 / year -1, any array / number / bool, +Inf float, NaN double, non-nil date and interval
+    # (only the first failing column of a row is reported, in the sorted-key order the encoder walks: a, b, d, dd, dt, f, iv, ...)
+    assert errs == [(4, 40, 6), (5, 40, 8), (6, 40, 8), (7, 40, 8)]
+    one = [abi.fixed_to_column(abi.TF_FLOAT, np.array([np.inf], np.float32)), abi.fixed_to_column(abi.TF_DOUBLE, [float("nan")]), abi.fixed_to_column(abi.TF_DATE, [0]), abi.fixed_to_column(abi.TF_INTERVAL, [1])]
+    for k, typ in enumerate(("float", "double", "date", "interval")):
+        sub = abi.Batch(1, [one[k]])
+        assert po.debezium_emit(sub, po.build_plan("s", "t", [{"name": "c", "type": typ}], []), OPTS)[3] == [(0, 40, 0)], typ
+
+
+def test_oracle_kinds_and_chain(po):
+    """UPDATE / DELETE rows are handed back (OldKeys), the chain runs first, key columns follow the result schema."""
+    schema = [{"name": "id", "type": "int32", "key": True}, {"name": "name", "type": "utf8"}, {"name": "x", "type": "int64"}]
+    b = abi.Batch(5, [abi.fixed_to_column(abi.TF_INT32, [1, 2, 3, 4, 5]), abi.strings_to_column(abi.TF_UTF8, [b"a", b"b", b"c", b"d", b"e"]),
+                      abi.fixed_to_column(abi.TF_INT64, [10, 20, 30, 40, 50])], kinds=np.array([0, 1, 0, 2, 0], np.uint8))
+    trs = [{"filter_rows": {"filter": "x > 10"}}, {"mask_field": {"columns": ["name"], "maskFunctionHash": {"userDefinedSalt": "s"}}}]
+    plan = po.build_plan("db", "t", schema, trs)
+    data, ks, rs, errs = po.debezium_emit(b, plan, OPTS)
+    assert errs == [(1, abi.TF_ROWERR_DBZ_EMIT_HOST, 0), (3, abi.TF_ROWERR_DBZ_EMIT_HOST, 0)]
+    kv = po.debezium_split(data, ks, rs)
+    assert [k for k, _ in kv] == [b'{"id":3}', b'{"id":5}']
+    after = json.loads(kv[0][1])["after"]
+    assert after["x"] == 30 and len(after["name"]) == 64 and after["name"] == po.hmac_hex(b"s", b"c")
+
+
+# ----------------------------------------------------------------------------------------------------------- GPU parity
+def _same(eng, po, batch, schema, trs, opts, meta, ns="public", name="t"):
+    pid = eng.plan(ns, name, schema, trs); plan = po.build_plan(ns, name, schema, trs)
+    want = po.debezium_emit(batch, plan, opts, meta)
+    got = eng.emit_debezium(pid, batch, opts, meta)
+    assert got.errors == want[3], (opts, trs)
+    assert list(got.key_sizes) == list(want[1]) and list(got.row_sizes) == list(want[2]), (opts, trs)
+    assert got.wire == want[0], (opts, trs)
+    return got
+
+
+@pytest.mark.gpu
+def test_device_emitter_equals_oracle(eng, po):
+    batch, schema, meta = _golden_batch()
+    _same(eng, po, batch, schema, [], OPTS, meta, *G["table"])
+    batch, schema, meta = _matrix()
+    tx = [b"", b"58c4f6fc-27b5-11ed-b434-0242ac1e0002:2", b"<gt&id>", b"\xff", b"", b"x", b"y", b"z"]
+    off = np.zeros(9, np.uint32); np.cumsum([len(t) for t in tx], out=off[1:])
+    meta = dict(meta, txid_offsets=off, txid_heap=np.frombuffer(b"".join(tx), np.uint8))
+    for st in ("", "pg", "mysql"):
+        for extra in ({}, {"snapshot": True}, {"drop_keys": True}, {"key_schema": '{"type":"struct","fields":[]}', "val_schema": '{"type":"struct","name":"<e>"}'},
+                      {"key_schema_id": 1, "val_schema_id": 4000000000}):
+            _same(eng, po, batch, schema, [], dict(OPTS, source_type=st, **extra), meta)
+    _same(eng, po, batch, schema, [], OPTS, None)
+    # kinds + chain
+    schema = [{"name": "id", "type": "int32", "key": True}, {"name": "name", "type": "utf8"}, {"name": "x", "type": "int64"}]
+    b = abi.Batch(5, [abi.fixed_to_column(abi.TF_INT32, [1, 2, 3, 4, 5]), abi.strings_to_column(abi.TF_UTF8, [b"a", b"b", b"c", b"d", b"e"]),
+                      abi.fixed_to_column(abi.TF_INT64, [10, 20, 30, 40, 50])], kinds=np.array([0, 1, 0, 2, 0], np.uint8))
+    for trs in ([], [{"filter_rows": {"filter": "x > 10"}}, {"mask_field": {"columns": ["name"], "maskFunctionHash": {"userDefinedSalt": "s"}}}],
+                [{"convert_to_string": {"columns": {"includeColumns": ["x", "name"]}}}], [{"rename_tables": {"renameTables": [{"originalName": {"namespace": "public", "name": "t"}, "newName": {"namespace": "ns2", "name": "t<2>"}}]}}]):
+        _same(eng, po, b, schema, trs, OPTS, None)
+
+
+@pytest.mark.gpu
+def test_device_emitter_all_types_and_resident(eng, po):
+    """The all-types batch (nulls, long strings, NaN, out-of-range years, non-UTF-8 text) with keys, from host and from HBM."""
+    from test_gpu_parity import all_types_batch
+    batch, schema = all_types_batch(3000, seed=11)
+    for c in schema:
+        if c["name"] in ("c_int64", "c_utf8"):
+            c["key"] = True
+    rng = np.random.default_rng(5)
+    meta = {"id": rng.integers(0, 2**32, batch.nrows, dtype=np.uint32), "lsn": rng.integers(0, 2**63, batch.nrows, dtype=np.uint64),
+            "commit_time": rng.integers(0, 2**62, batch.nrows, dtype=np.uint64)}
+    drop_bad = [{"filter_columns": {"columns": {"excludeColumns": ["c_date", "c_interval"]}}}]
+    for trs in ([], drop_bad, drop_bad + [{"filter_rows": {"filter": "c_int32 > 0"}}]):
+        got = _same(eng, po, batch, schema, trs, OPTS, meta)
+    assert got.rows_out > 0
+    import torch
+    dbatch = batch.to_device("cuda:0")
+    dmeta = {k: torch.from_numpy(v.view(np.int32 if v.dtype == np.uint32 else np.int64)).cuda() for k, v in meta.items()}
+    pid = eng.plan("public", "t", schema, drop_bad); plan = po.build_plan("public", "t", schema, drop_bad)
+    want = po.debezium_emit(batch, plan, OPTS, meta)
+    res = eng.emit_debezium(pid, dbatch, OPTS, dmeta)
+    assert res.wire == want[0] and list(res.key_sizes) == list(want[1]) and res.errors == want[3]
+
+
+@pytest.mark.gpu
+def test_device_emitter_refusals(eng):
+    from transferia_b200.engine import EngineError
+    b = abi.Batch(1, [abi.fixed_to_column(abi.TF_INT32, [1])])
+    pid = eng.plan("s", "t", [{"name": "i", "type": "int32", "key": True}], [])
+    with pytest.raises(EngineError):        # errUnknownSource (emitter_value_converter.go:183-191)
+        eng.emit_debezium(pid, b, {"version": "1"})
+    pid = eng.plan("s", "t", [{"name": "i", "type": "int32", "key": True, "original_type": "pg:integer"}], [])
+    with pytest.raises(EngineError):
+        eng.emit_debezium(pid, b, OPTS)

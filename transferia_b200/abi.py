@@ -69,6 +69,19 @@ class TfMsg(C.Structure):
     _fields_ = [("end", C.c_uint64), ("offset", C.c_uint64), ("write_sec", C.c_int64), ("write_nsec", C.c_uint32), ("pad", C.c_uint32)]
 
 
+class TfRowMeta(C.Structure):
+    """tf_row_meta: the ChangeItem fields Debezium's `source` block carries (change_item.go:27-40)."""
+    _fields_ = [("id", C.c_void_p), ("lsn", C.c_void_p), ("commit_time", C.c_void_p), ("txid_offsets", C.c_void_p), ("txid_heap", C.c_void_p)]
+
+
+def make_row_meta(id=None, lsn=None, commit_time=None, txid_offsets=None, txid_heap=None):
+    """(struct, keepalive) from numpy arrays / torch tensors; None stays NULL."""
+    m = TfRowMeta(_ptr(id), _ptr(lsn), _ptr(commit_time), _ptr(txid_offsets), _ptr(txid_heap))
+    return m, (id, lsn, commit_time, txid_offsets, txid_heap)
+
+
+TF_WIRE_DEBEZIUM = 6
+TF_ROWERR_DBZ_EMIT_HOST = 53
 TF_ROWERR_DBZ_UNPARSED, TF_ROWERR_DBZ_HOST, TF_ROWERR_DBZ_OTHER_SCHEMA, TF_ROWERR_DBZ_OTHER_TABLE = 48, 49, 50, 51
 TF_ROWERR_JSON_PARSE, TF_ROWERR_JSON_SKIP, TF_ROWERR_JSON_NIL_REQUIRED, TF_ROWERR_JSON_PARSEVAL, TF_ROWERR_JSON_HOST = 32, 33, 34, 35, 36
 

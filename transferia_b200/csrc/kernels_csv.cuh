@@ -352,6 +352,48 @@ __global__ void __launch_bounds__(1024) k_csv_offsets(const uint32_t* span_len, 
     if (threadIdx.x == 0) { off[nrows] = (uint32_t)carry; col_total[blockIdx.x] = carry; }
 }
 
+// The same scan over many CTAs: chunk sums, a scan of the chunk sums per column, then the offsets (3 short launches instead
+// of one CTA per column walking every row).
+#define CSV_OFF_CHUNK 4096
+__global__ void __launch_bounds__(1024) k_offsets_sum(const uint32_t* span_len, uint64_t nrows, uint32_t nchunks, uint64_t* chunk_sum /* [nslots][nchunks] */) {
+    __shared__ uint32_t sm[33];
+    const uint32_t* len = span_len + (size_t)blockIdx.y * nrows;
+    const uint64_t base = (uint64_t)blockIdx.x * CSV_OFF_CHUNK;
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < CSV_OFF_CHUNK / 1024; k++) { const uint64_t i = base + (uint64_t)k * 1024 + threadIdx.x; if (i < nrows) v += len[i] & 0x7fffffffu; }
+    uint32_t tot; block_excl_scan(v, &tot, sm);
+    if (threadIdx.x == 0) chunk_sum[(size_t)blockIdx.y * nchunks + blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(32) k_offsets_chunks(uint64_t* chunk_sum, uint32_t nchunks, uint64_t* col_total) {     // in place: exclusive scan per column, one warp
+    uint64_t* cs = chunk_sum + (size_t)blockIdx.x * nchunks;
+    const uint32_t lane = threadIdx.x;
+    uint64_t carry = 0;
+    for (uint32_t base = 0; base < nchunks; base += 32) {
+        const uint32_t i = base + lane;
+        const uint64_t v = i < nchunks ? cs[i] : 0;
+        uint64_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint64_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (uint32_t)d) inc += o; }
+        if (i < nchunks) cs[i] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) col_total[blockIdx.x] = carry;
+}
+__global__ void __launch_bounds__(1024) k_offsets_write(const uint32_t* span_len, uint64_t nrows, uint32_t nchunks, const uint64_t* chunk_base, const uint64_t* col_total, uint32_t* offsets /* [nslots][nrows+1] */) {
+    __shared__ uint32_t sm[33];
+    const uint32_t* len = span_len + (size_t)blockIdx.y * nrows; uint32_t* off = offsets + (size_t)blockIdx.y * (nrows + 1);
+    const uint64_t base = (uint64_t)blockIdx.x * CSV_OFF_CHUNK + (uint64_t)threadIdx.x * (CSV_OFF_CHUNK / 1024);      // 4 consecutive rows per thread
+    uint32_t v[CSV_OFF_CHUNK / 1024]; uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < CSV_OFF_CHUNK / 1024; k++) { const uint64_t i = base + k; v[k] = i < nrows ? (len[i] & 0x7fffffffu) : 0; sum += v[k]; }
+    uint32_t tot; uint32_t ex = block_excl_scan(sum, &tot, sm);
+    uint64_t run = chunk_base[(size_t)blockIdx.y * nchunks + blockIdx.x] + ex;
+#pragma unroll
+    for (int k = 0; k < CSV_OFF_CHUNK / 1024; k++) { const uint64_t i = base + k; if (i < nrows) off[i] = (uint32_t)run; run += v[k]; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) off[nrows] = (uint32_t)col_total[blockIdx.y];
+}
+
 struct CsvCopyArgs { const uint8_t* text; const uint32_t* span_start; const uint32_t* span_len; const uint32_t* offsets; uint8_t* heap; const uint64_t* col_base; uint64_t nrows; };
 
 __global__ void __launch_bounds__(256) k_csv_pass2(CsvCopyArgs a) {

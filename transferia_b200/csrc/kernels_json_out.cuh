@@ -269,15 +269,102 @@ template <typename Sink> __device__ void ser_csv_row(Sink& s, const DCol* cols, 
     s.put('\n');
 }
 
+// ------------------------------------------------------------------ Debezium emitter (pkg/debezium), common path
+//   Emitter.EmitKV emitter_value_converter.go:626-690 for INSERT rows: key message then value message. Everything that does not
+//   change per row (envelope keys, `source` constants, schema wrapper / confluent prefix) is a host-built template of text
+//   segments; a segment's code names the per-row piece that follows its text. Values: addCommon emitter_common.go:67-180.
+__device__ __forceinline__ uint32_t sink_count(const CountSink& s) { return s.n; }
+__device__ __forceinline__ uint32_t sink_count(const MemSink&) { return 0; }
+enum DbzCode : int32_t { DZ_NONE = 0, DZ_AFTER = 1, DZ_KEY = 2, DZ_LSN = 3, DZ_SRC_TS = 4, DZ_ID = 5, DZ_FILE = 6, DZ_POS = 7, DZ_GTID = 8, DZ_TS = 9, DZ_KEY_END = 10 };
+struct DbzSeg { int32_t text_off, text_len, code, pad; };
+struct DbzEmitArgs {
+    const DbzSeg* segs; int nseg; const uint8_t* text; const JsonCol* kcols; int nkc;
+    const uint32_t* id; const uint64_t* lsn; const uint64_t* ct; const uint32_t* gt_off; const uint8_t* gt_heap; uint32_t* key_size;
+};
+template <typename Inner> struct JStrSink {      // the inside of a JSON string over text that is already valid JSON (ASCII escapes, UTF-8 intact)
+    Inner* in;
+    __device__ __forceinline__ void put(uint8_t b) {
+        if (b >= 0x20 && b != '"' && b != '\\') { in->put(b); return; }
+        in->put('\\');
+        switch (b) {
+        case '\\': case '"': in->put(b); break;
+        case '\b': in->put('b'); break; case '\f': in->put('f'); break; case '\n': in->put('n'); break; case '\r': in->put('r'); break; case '\t': in->put('t'); break;
+        default: { const char* hex = "0123456789abcdef"; in->put('u'); in->put('0'); in->put('0'); in->put((uint8_t)hex[b >> 4]); in->put((uint8_t)hex[b & 15]); }
+        }
+    }
+};
+template <typename Sink> __device__ bool dbz_json_value(Sink& s, const DCol& c, uint64_t r, const JsonCol& jc, const MaskKey* keys, bool sizing) {
+    if (c.out_kind == OK_COPY || c.out_kind == OK_STR) {
+        if (!row_valid(c, r)) { fmt_lit(s, "null"); return true; }
+        switch (c.type) {
+        case TF_DATE: case TF_INTERVAL: fmt_lit(s, "null"); return false;            // emitter_common.go:161-163 unknown input data type
+        case TF_DOUBLE: { const uint64_t b = ((const uint64_t*)c.values)[r]; if ((b & 0x7FF0000000000000ull) == 0x7FF0000000000000ull) { fmt_lit(s, "null"); return false; } fmt_float_bits(s, b, false, FM_JSON); return true; }
+        case TF_ANY: {
+            const uint8_t* p = c.heap + c.offsets[r]; const uint32_t L = c.offsets[r + 1] - c.offsets[r];
+            if (c.aux && c.aux[r] == 1) { fmt_json_string(s, p, L, false); return true; }
+            if (L == 4 && p[0] == 'n' && p[1] == 'u' && p[2] == 'l' && p[3] == 'l') { fmt_lit(s, "null"); return true; }
+            if (L && p[0] == '"') { ser_unescape_html(s, p, L); return true; }
+            if (L && p[0] == '{') { s.put('"'); JStrSink<Sink> js{&s}; ser_unescape_html(js, p, L); s.put('"'); return true; }
+            fmt_lit(s, "null"); return false;                                        // :157-159 arrays / numbers / booleans
+        }
+        default: break;
+        }
+    }
+    return ser_json_value(s, c, r, jc, keys, sizing, 0);
+}
+template <typename Sink> __device__ int dbz_object(Sink& s, const DCol* cols, const JsonCol* jcols, int njc, const uint8_t* names, const MaskKey* keys, uint64_t r, bool sizing) {
+    int bad = -1;
+    s.put('{');
+    for (int k = 0; k < njc; k++) {
+        const JsonCol jc = jcols[k]; const DCol& c = cols[jc.col];
+        if (k) s.put(',');
+        for (int i = 0; i < jc.name_len; i++) s.put(names[jc.name_off + i]);
+        if (c.out_kind == OK_TOSTR && jc.result_tf != TF_BYTES && (c.type == TF_UTF8 || c.type == TF_BYTES) && row_valid(c, r))
+            fmt_json_string(s, c.heap + c.offsets[r], c.offsets[r + 1] - c.offsets[r], false);
+        else if (!dbz_json_value(s, c, r, jc, keys, sizing) && bad < 0) bad = jc.pad0;
+    }
+    s.put('}');
+    return bad;
+}
+template <typename Sink> __device__ int dbz_row(Sink& s, const DCol* cols, const JsonCol* jcols, int njc, const uint8_t* names, const MaskKey* keys,
+                                               const DbzEmitArgs& z, uint64_t r, uint64_t j, bool sizing) {
+    int bad = -1;
+    const uint64_t lsn = z.lsn ? z.lsn[r] : 0, ct = z.ct ? z.ct[r] : 0;
+    for (int g = 0; g < z.nseg; g++) {
+        const DbzSeg sg = z.segs[g];
+        for (int i = 0; i < sg.text_len; i++) s.put(z.text[sg.text_off + i]);
+        switch (sg.code) {
+        case DZ_AFTER: { const int b = dbz_object(s, cols, jcols, njc, names, keys, r, sizing); if (bad < 0) bad = b; break; }
+        case DZ_KEY: { const int b = dbz_object(s, cols, z.kcols, z.nkc, names, keys, r, sizing); if (bad < 0) bad = b; break; }
+        case DZ_LSN: fmt_u64(s, lsn); break;
+        case DZ_SRC_TS: fmt_u64(s, ct / 1000000ull); break;
+        case DZ_ID: fmt_u64(s, z.id ? z.id[r] : 0); break;
+        case DZ_FILE: { const uint64_t f = lsn / 1000000000000ull; fmt_pad(s, (int64_t)f, 6); break; }      // "mysql-log.%06d"
+        case DZ_POS: fmt_u64(s, lsn % 1000000000000ull); break;
+        case DZ_GTID: {
+            const uint32_t a = z.gt_off ? z.gt_off[r] : 0, b = z.gt_off ? z.gt_off[r + 1] : 0;
+            if (z.gt_heap && b > a) fmt_json_string(s, z.gt_heap + a, b - a, false); else fmt_lit(s, "null");
+            break;
+        }
+        case DZ_TS: fmt_i64(s, (int64_t)ct / 1000000); break;
+        case DZ_KEY_END: if (sizing) z.key_size[j] = sink_count(s); break;
+        default: break;
+        }
+    }
+    return bad;
+}
+
 struct JsonArgs {
     const DCol* cols; const JsonCol* jcols; int njc; const uint8_t* names; const MaskKey* keys;
     const uint32_t* sel; DState* st; uint8_t* raw; uint32_t* row_size; uint32_t* tile_sum; const uint64_t* tile_base; const uint64_t* col_bytes;
-    int mode; uint32_t flags; uint8_t* errcode; uint8_t* errstep;      // mode 0 ClickHouse JSONEachRow, 1 serializer JSON, 2 serializer CSV
+    int mode; uint32_t flags; uint8_t* errcode; uint8_t* errstep;      // mode 0 ClickHouse JSONEachRow, 1 serializer JSON, 2 serializer CSV, 3 Debezium messages
+    DbzEmitArgs dz;
 };
 
 template <typename Sink> __device__ __forceinline__ int json_any_row(Sink& s, const JsonArgs& a, uint64_t r, uint64_t j, bool sizing) {
     if (a.mode == 1) return ser_json_row(s, a.cols, a.jcols, a.njc, a.names, a.keys, r, j, sizing, a.flags);
     if (a.mode == 2) { ser_csv_row(s, a.cols, a.jcols, a.njc, a.keys, r, sizing); return -1; }
+    if (a.mode == 3) return dbz_row(s, a.cols, a.jcols, a.njc, a.names, a.keys, a.dz, r, j, sizing);
     json_row(s, a.cols, a.jcols, a.njc, a.names, a.keys, r, sizing); return -1;
 }
 

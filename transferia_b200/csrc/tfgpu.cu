@@ -56,6 +56,8 @@ struct PlanDev {
     int n_fsteps = 0, n_fixed_slots = 0, n_str = 0, n_mask_cols = 0, n_tostr = 0;
     std::vector<int32_t> fixed_slots, str_slots, mask_slot_cols, mask_slot_key;
     std::vector<int> col_out_kind, col_out_w, col_str_slot, col_mask_slot, col_nullable;
+    std::vector<JsonCol> h_sjcols;                 // host copy of d_sjcols (the Debezium emitter picks the key columns out of it)
+    DevBuf dbz_consts; std::string dbz_opts_key; DbzEmitArgs dbz{};      // Debezium emitter: message template of the last opts_json
 };
 
 }  // namespace
@@ -70,7 +72,7 @@ struct tfgpu_engine {
     int sm_count = 148;
     std::vector<std::unique_ptr<PlanDev>> plans;
     // arenas
-    DevBuf in_arena, work, raw, slots, wire, csv_text, csv_stage, json_msgs, n2f_stage, n2f_heap;
+    DevBuf in_arena, work, raw, slots, wire, csv_text, csv_stage, json_msgs, n2f_stage, n2f_heap, off_scratch;
     DState* d_state = nullptr; DCol* d_cols = nullptr; size_t d_cols_cap = 0;
     int32_t* d_call_slots = nullptr; ColRegions* d_regions = nullptr; size_t d_call_cap = 0;   // columnar mode, per call
     // pointers into `work` for the last call
@@ -78,7 +80,8 @@ struct tfgpu_engine {
     uint32_t* tile_sum = nullptr; uint64_t* tile_base = nullptr; uint64_t* col_bytes = nullptr; uint32_t* comp_size = nullptr; uint64_t* wire_off = nullptr;
     uint64_t last_nrows = 0; bool last_has_filter = false; int last_wire_fmt = 0;
     uint8_t* pinned = nullptr; size_t pinned_cap = 0;
-    DevBuf json_sizes;
+    DevBuf json_sizes, dbz_keysz, dbz_meta;
+    DbzEmitArgs dbz{};                                 // set by tfgpu_emit_debezium for the TF_WIRE_DEBEZIUM branch of run_chain
     unsigned long long* lz_phases = nullptr;      // debug: per-phase cycle counters of k_lz4_frames
     void* work_json_sizes(uint64_t n) { json_sizes.ensure(n * 4 + 256); return json_sizes.p; }
     // optional per-kernel CUDA-event timing of the last call (bench roofline)
@@ -101,6 +104,7 @@ struct tfgpu_result {
     std::vector<uint32_t> selection;       // parsers: input row (line / message) of every output row
     std::vector<uint8_t> meta_kinds; std::vector<uint32_t> meta_tx; std::vector<uint64_t> meta_lsn, meta_ct;   // debezium: per message
     std::vector<uint32_t> row_sizes;       // row-text formats: bytes of every output row (incl. its separator / newline)
+    std::vector<uint32_t> key_sizes;       // Debezium emitter: key message bytes of every output row
     // push_columns output
     tf_batch batch{}; std::vector<tf_col> cols; std::vector<uint8_t*> owned;
 };
@@ -213,6 +217,7 @@ void upload_plan(tfgpu_engine* e, PlanDev& pd) {
             sjcols.push_back(jc);
         }
         for (size_t k = 0; k < jcols.size(); k++) { JsonCol jc = jcols[k]; jc.pad0 = (int32_t)k; scsvcols.push_back(jc); }
+        pd.h_sjcols = sjcols;
     }
     // flatten filter steps
     std::vector<DTerm> terms; std::vector<uint32_t> expr_off(1, 0); std::vector<DFilterStep> fsteps;
@@ -277,6 +282,18 @@ Sizes compute_sizes(const tfgpu_engine* e, const PlanDev& pd, const tf_batch* in
     return s;
 }
 
+
+// exclusive scan of the text-cell lengths of every var-width column: offsets[slot][row], col_total[slot]
+static void launch_offsets(tfgpu_engine* e, const uint32_t* d_len, uint64_t nrows, uint32_t nslots, uint32_t* d_off, uint64_t* d_tot, cudaStream_t s) {
+    const uint32_t nchunks = (uint32_t)((nrows + CSV_OFF_CHUNK - 1) / CSV_OFF_CHUNK);
+    if (!nchunks || !nslots) { k_csv_offsets<<<nslots ? nslots : 1, 1024, 0, s>>>(d_len, nrows, d_off, d_tot); return; }
+    e->off_scratch.ensure((size_t)nslots * nchunks * 8 + 256);
+    uint64_t* cs = (uint64_t*)e->off_scratch.p;
+    e->prof_begin("k_offsets_sum", s); k_offsets_sum<<<dim3(nchunks, nslots), 1024, 0, s>>>(d_len, nrows, nchunks, cs); e->prof_end(s);
+    e->prof_begin("k_offsets_chunks", s); k_offsets_chunks<<<nslots, 32, 0, s>>>(cs, nchunks, d_tot); e->prof_end(s);
+    e->prof_begin("k_offsets_write", s); k_offsets_write<<<dim3(nchunks, nslots), 1024, 0, s>>>(d_len, nrows, nchunks, cs, d_tot, d_off); e->prof_end(s);
+}
+
 // Launch the whole fused chain on e->stream. `cols_host` holds DEVICE pointers.
 #define TF_WIRE_COLUMNAR_INTERNAL 100
 void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* dev_cols, const uint8_t* dev_kinds, int wire_fmt, const uint8_t* pre_err = nullptr) {
@@ -284,7 +301,8 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
     const tfplan::Plan& pl = pd.plan;
     const size_t nc = pl.in_schema.size(); const uint64_t n = in->nrows;
     const int wire_base = wire_fmt == TF_WIRE_COLUMNAR_INTERNAL ? wire_fmt : (wire_fmt & 0xff);
-    const bool ser = wire_base == TF_WIRE_SER_JSON || wire_base == TF_WIRE_SER_CSV;
+    const bool dbz = wire_base == TF_WIRE_DEBEZIUM;
+    const bool ser = wire_base == TF_WIRE_SER_JSON || wire_base == TF_WIRE_SER_CSV || dbz;
     const bool json_rows = wire_base == TF_WIRE_CH_JSONEACHROW || ser;
     if (ser) for (size_t c = 0; c < nc; c++) if (pd.col_out_kind[c] == OK_TOSTR && pl.in_schema[c].tf == TF_ANY)
         throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "serializer sinks after convert_to_string on an `any` column are not handled on the device");
@@ -337,7 +355,7 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         if (pre_err) CK(cudaMemcpyAsync(B + o_err, pre_err, n, cudaMemcpyDeviceToDevice, s)); else CK(cudaMemsetAsync(B + o_err, 0, n, s));
         N2fArgs na{e->d_cols, (const int32_t*)(B + o_which), dev_kinds, n, (uint32_t*)(B + o_len), (const uint32_t*)(B + o_off), nullptr, (const uint64_t*)(B + o_base), B + o_err};
         e->prof_begin("k_n2f_sizes", s); k_n2f_sizes<<<dim3((uint32_t)((n + 127) / 128), (uint32_t)k2), 128, 0, s>>>(na); e->prof_end(s);
-        e->prof_begin("k_csv_offsets", s); k_csv_offsets<<<(uint32_t)k2, 1024, 0, s>>>((const uint32_t*)(B + o_len), n, (uint32_t*)(B + o_off), (uint64_t*)(B + o_tot)); e->prof_end(s);
+        launch_offsets(e, (const uint32_t*)(B + o_len), n, (uint32_t)k2, (uint32_t*)(B + o_off), (uint64_t*)(B + o_tot), s);
         std::vector<uint64_t> tot(k2), base(k2);
         CK(cudaMemcpyAsync(tot.data(), B + o_tot, k2 * 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
         uint64_t run = 0; for (size_t k = 0; k < k2; k++) { base[k] = run; run += align_up(tot[k], 16); }
@@ -370,9 +388,10 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
     if (json_rows) {
         // JSONEachRow: rows sized, placed by a tile scan, then written (kernels_json_out.cuh)
         const uint32_t jt = (uint32_t)((n + TF_JSON_TILE - 1) / TF_JSON_TILE);
-        JsonArgs ja{e->d_cols, ser ? (wire_base == TF_WIRE_SER_JSON ? pd.d_sjcols : pd.d_scsvcols) : pd.d_jcols, (int)pl.out_cols.size(), ser ? pd.d_snames : pd.d_jnames, pd.d_mask_keys, sel, e->d_state, e->raw.p,
+        JsonArgs ja{e->d_cols, ser ? (wire_base == TF_WIRE_SER_CSV ? pd.d_scsvcols : pd.d_sjcols) : pd.d_jcols, (int)pl.out_cols.size(), ser ? pd.d_snames : pd.d_jnames, pd.d_mask_keys, sel, e->d_state, e->raw.p,
                     (uint32_t*)e->work_json_sizes(n), e->tile_sum, e->tile_base, e->col_bytes,
-                    ser ? (wire_base == TF_WIRE_SER_JSON ? 1 : 2) : 0, (uint32_t)(((wire_fmt & TF_WIRE_F_CLOSING_NEWLINE) ? TF_SER_NL : 0) | ((wire_fmt & TF_WIRE_F_ANY_AS_STRING) ? TF_SER_AAS : 0)), e->errcode, e->errstep};
+                    dbz ? 3 : ser ? (wire_base == TF_WIRE_SER_JSON ? 1 : 2) : 0, (uint32_t)(((wire_fmt & TF_WIRE_F_CLOSING_NEWLINE) ? TF_SER_NL : 0) | ((wire_fmt & TF_WIRE_F_ANY_AS_STRING) ? TF_SER_AAS : 0)), e->errcode, e->errstep, DbzEmitArgs{}};
+        if (dbz) { ja.jcols = pd.d_sjcols; e->dbz_keysz.ensure(n * 4 + 256); ja.dz = e->dbz; ja.dz.key_size = (uint32_t*)e->dbz_keysz.p; }
         if (ser && !has_filter && n) { CK(cudaMemsetAsync(e->errcode, 0, n, s)); CK(cudaMemsetAsync(e->errstep, 0, n, s)); }
         if (jt) { e->prof_begin("k_json_sizes", s); k_json_sizes<<<jt, TF_JSON_TILE, 0, s>>>(ja); e->prof_end(s); }
         LayoutArgs lj{e->d_cols, 0, pd.d_out_cols, pd.d_str_slots, 1, e->tile_sum, e->tile_base, sz.ntiles_cap, pd.d_col_headers, pd.d_col_header_off,
@@ -504,7 +523,7 @@ int tfgpu_engine_destroy(tfgpu_engine* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (auto& p : e->plans) p->consts.release();
-    e->in_arena.release(); e->work.release(); e->raw.release(); e->slots.release(); e->wire.release(); e->csv_text.release(); e->csv_stage.release(); e->json_msgs.release(); e->n2f_stage.release(); e->n2f_heap.release(); e->json_sizes.release();
+    e->in_arena.release(); e->work.release(); e->raw.release(); e->slots.release(); e->wire.release(); e->csv_text.release(); e->csv_stage.release(); e->json_msgs.release(); e->n2f_stage.release(); e->n2f_heap.release(); e->off_scratch.release(); e->json_sizes.release();
     if (e->d_state) cudaFree(e->d_state);
     if (e->d_cols) cudaFree(e->d_cols);
     if (e->d_call_slots) { cudaFree(e->d_call_slots); cudaFree(e->d_regions); }
@@ -730,7 +749,8 @@ static void finish_wire(tfgpu_engine* e, uint64_t n, int wire_fmt, tfgpu_result*
     r->bytes = e->pinned; r->bytes_pinned = false;
     CK(cudaMemcpyAsync(r->bytes, lz ? e->wire.p : e->raw.p, r->bytes_len, cudaMemcpyDeviceToHost, s));
     { const int b = wire_fmt & 0xff;
-      if ((b == TF_WIRE_SER_JSON || b == TF_WIRE_SER_CSV || b == TF_WIRE_CH_JSONEACHROW) && st.n_kept) { r->row_sizes.resize(st.n_kept); CK(cudaMemcpyAsync(r->row_sizes.data(), e->json_sizes.p, st.n_kept * 4, cudaMemcpyDeviceToHost, s)); } }
+      if ((b == TF_WIRE_SER_JSON || b == TF_WIRE_SER_CSV || b == TF_WIRE_CH_JSONEACHROW || b == TF_WIRE_DEBEZIUM) && st.n_kept) { r->row_sizes.resize(st.n_kept); CK(cudaMemcpyAsync(r->row_sizes.data(), e->json_sizes.p, st.n_kept * 4, cudaMemcpyDeviceToHost, s)); }
+      if (b == TF_WIRE_DEBEZIUM && st.n_kept) { r->key_sizes.resize(st.n_kept); CK(cudaMemcpyAsync(r->key_sizes.data(), e->dbz_keysz.p, st.n_kept * 4, cudaMemcpyDeviceToHost, s)); } }
     if (st.n_errors) fetch_errors(e, n, r);
     CK(cudaStreamSynchronize(s));
 }
@@ -748,6 +768,111 @@ int tfgpu_push_columns(tfgpu_engine* e, int plan_id, const tf_batch* in, tfgpu_r
         run_chain(e, pd, in, dev.data(), dev_kinds, TF_WIRE_COLUMNAR_INTERNAL);
         auto r = std::make_unique<tfgpu_result>();
         finish_columnar(e, pd, in->nrows, r.get());
+        *out = r.release();
+        return TF_OK;
+    } catch (const tfplan::FatalError& f) { return fail(e, f.code, f.what()); }
+    catch (const CudaError& c) { return cuda_fail(e, c); }
+    catch (const std::bad_alloc&) { return fail(e, TF_E_RETRY_OOM, "host allocation failed"); }
+}
+
+// Queue Debezium serializer for columns without a database-specific original_type (Emitter.EmitKV
+// pkg/debezium/emitter_value_converter.go:626-690). The per-table constants become a text template once per (plan, opts).
+namespace {
+__global__ void k_dbz_kinds(const uint8_t* kinds, uint64_t n, uint8_t* pre_err) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) pre_err[r] = kinds[r] == TF_KIND_INSERT ? 0 : TF_ROWERR_DBZ_EMIT_HOST;
+}
+void dbz_build_template(PlanDev& pd, const std::string& opts_json) {
+    if (pd.dbz_opts_key == opts_json && pd.dbz.segs) return;
+    const tfplan::Plan& pl = pd.plan;
+    auto ov = tfj::parse(opts_json);
+    if (!ov->get_bool("ignore_unknown_sources")) throw tfplan::FatalError(TF_E_FATAL_CONFIG, "unknown source type (emitter_value_converter.go:183-191): set ignore_unknown_sources");
+    for (auto& c : pl.out_schema)
+        if (c.original_type.rfind("pg:", 0) == 0 || c.original_type.rfind("mysql:", 0) == 0 || c.original_type.rfind("ydb:", 0) == 0)
+            throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "column " + c.name + ": original_type " + c.original_type + " is emitted by the database-specific converters (not on the device)");
+    const bool snapshot = ov->get_bool("snapshot"), drop_keys = ov->get_bool("drop_keys");
+    const std::string st = ov->get_str("source_type");
+    if (!(st.empty() || st == "pg" || st == "mysql")) throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "source_type " + st);
+    auto q = [](const std::string& t) { return host_json_quote_nohtml(t); };
+    auto wrap = [&](const char* schema_key, const char* id_key, std::string& prefix, std::string& suffix) {
+        const tfj::Value* idv = ov->get(id_key); const tfj::Value* sv = ov->get(schema_key);
+        if (idv && idv->kind == tfj::Value::Num) {                                   // packer_schema_registry.go:66-76
+            const uint32_t id = (uint32_t)idv->num; prefix.push_back('\0'); for (int sh = 24; sh >= 0; sh -= 8) prefix.push_back((char)((id >> sh) & 0xff));
+        } else if (sv && sv->kind == tfj::Value::Str) { prefix = "{\"payload\":"; suffix = ",\"schema\":" + sv->str + "}"; }     // packer_include_schema.go:34-38
+    };
+    std::string text; std::vector<DbzSeg> segs;
+    auto seg = [&](const std::string& t, int code) { segs.push_back(DbzSeg{(int32_t)text.size(), (int32_t)t.size(), code, 0}); text += t; };
+    if (drop_keys) seg("", DZ_KEY_END);
+    else { std::string pre, suf; wrap("key_schema", "key_schema_id", pre, suf); seg(pre, DZ_KEY); seg(suf, DZ_KEY_END); }
+    std::string pre, suf; wrap("val_schema", "val_schema_id", pre, suf);
+    seg(pre + "{\"after\":", DZ_AFTER);
+    const std::string name = q(ov->get_str("topic_prefix")), db = q(ov->get_str("database")), ver = q(ov->get_str("version"));
+    const std::string snap = snapshot ? "\"true\"" : "\"false\"", tbl = q(pl.out_name), sch = q(pl.out_ns);
+    const std::string head = std::string(",\"before\":null,\"op\":") + (snapshot ? "\"r\"" : "\"c\"") + ",\"source\":{";        // kindToOp kind.go:8-14
+    if (st == "pg") {                 // buildSource :329-372, keys in encoding/json's sorted order
+        seg(head + "\"connector\":\"postgresql\",\"db\":" + db + ",\"lsn\":", DZ_LSN);
+        seg(",\"name\":" + name + ",\"schema\":" + sch + ",\"snapshot\":" + snap + ",\"table\":" + tbl + ",\"ts_ms\":", DZ_SRC_TS);
+        seg(",\"txId\":", DZ_ID);
+        seg(",\"version\":" + ver + ",\"xmin\":null},\"transaction\":null,\"ts_ms\":", DZ_TS);
+    } else if (st == "mysql") {
+        seg(head + "\"connector\":\"mysql\",\"db\":" + sch + ",\"file\":\"mysql-log.", DZ_FILE);
+        seg("\",\"gtid\":", DZ_GTID);
+        seg(",\"name\":" + name + ",\"pos\":", DZ_POS);
+        seg(",\"query\":null,\"row\":0,\"server_id\":0,\"snapshot\":" + snap + ",\"table\":" + tbl + ",\"thread\":null,\"ts_ms\":", DZ_SRC_TS);
+        seg(",\"version\":" + ver + "},\"transaction\":null,\"ts_ms\":", DZ_TS);
+    } else {
+        seg(head + "\"db\":" + db + ",\"name\":" + name + ",\"snapshot\":" + snap + ",\"table\":" + tbl + ",\"ts_ms\":", DZ_SRC_TS);
+        seg(",\"version\":" + ver + "},\"transaction\":null,\"ts_ms\":", DZ_TS);
+    }
+    seg("}" + suf, DZ_NONE);
+    std::vector<JsonCol> kcols;
+    for (const JsonCol& jc : pd.h_sjcols) if (pl.out_schema[(size_t)jc.pad0].key) kcols.push_back(jc);
+    const size_t o_seg = 0, o_text = align_up(segs.size() * sizeof(DbzSeg), 256), o_k = o_text + align_up(text.size() + 1, 256);
+    pd.dbz_consts.ensure(o_k + kcols.size() * sizeof(JsonCol) + 256);
+    CK(cudaMemcpy(pd.dbz_consts.p + o_seg, segs.data(), segs.size() * sizeof(DbzSeg), cudaMemcpyHostToDevice));
+    if (!text.empty()) CK(cudaMemcpy(pd.dbz_consts.p + o_text, text.data(), text.size(), cudaMemcpyHostToDevice));
+    if (!kcols.empty()) CK(cudaMemcpy(pd.dbz_consts.p + o_k, kcols.data(), kcols.size() * sizeof(JsonCol), cudaMemcpyHostToDevice));
+    pd.dbz = DbzEmitArgs{}; pd.dbz.segs = (const DbzSeg*)(pd.dbz_consts.p + o_seg); pd.dbz.nseg = (int)segs.size(); pd.dbz.text = pd.dbz_consts.p + o_text;
+    pd.dbz.kcols = (const JsonCol*)(pd.dbz_consts.p + o_k); pd.dbz.nkc = (int)kcols.size();
+    pd.dbz_opts_key = opts_json;
+}
+}  // namespace
+
+int tfgpu_emit_debezium(tfgpu_engine* e, int plan_id, const char* opts_json, const tf_batch* in, const tf_row_meta* meta, tfgpu_result** out) {
+    if (!e || !in || !out || !opts_json || plan_id < 0 || plan_id >= (int)e->plans.size()) return TF_E_FATAL_ARG;
+    *out = nullptr;
+    PlanDev& pd = *e->plans[plan_id];
+    if (in->ncols != pd.plan.in_schema.size()) return fail(e, TF_E_FATAL_ARG, "batch column count does not match the plan schema");
+    if (in->nrows >= (1ull << 31)) return fail(e, TF_E_FATAL_ARG, "batch too large (>= 2^31 rows)");
+    try {
+        CK(cudaSetDevice(e->device));
+        const uint64_t n = in->nrows;
+        cudaStream_t s = e->stream;
+        try { dbz_build_template(pd, opts_json); } catch (const std::runtime_error& x) { return fail(e, TF_E_FATAL_CONFIG, std::string("opts_json: ") + x.what()); }
+        std::vector<tf_col> dev; const uint8_t* dev_kinds = stage_input(e, in, dev);
+        e->dbz = pd.dbz;
+        const size_t o_id = 0, o_lsn = align_up(n * 4 + 16, 256), o_ct = o_lsn + align_up(n * 8 + 16, 256), o_off = o_ct + align_up(n * 8 + 16, 256), o_pre = o_off + align_up((n + 1) * 4 + 16, 256), o_heap = o_pre + align_up(n + 16, 256);
+        uint64_t gt_len = 0;
+        if (meta && in->mem == TF_MEM_HOST && meta->txid_offsets && meta->txid_heap) gt_len = meta->txid_offsets[n];
+        e->dbz_meta.ensure(o_heap + gt_len + 256);
+        uint8_t* M = e->dbz_meta.p;
+        if (meta) {
+            if (in->mem == TF_MEM_HOST) {
+                if (meta->id && n) { CK(cudaMemcpyAsync(M + o_id, meta->id, n * 4, cudaMemcpyHostToDevice, s)); e->dbz.id = (const uint32_t*)(M + o_id); }
+                if (meta->lsn && n) { CK(cudaMemcpyAsync(M + o_lsn, meta->lsn, n * 8, cudaMemcpyHostToDevice, s)); e->dbz.lsn = (const uint64_t*)(M + o_lsn); }
+                if (meta->commit_time && n) { CK(cudaMemcpyAsync(M + o_ct, meta->commit_time, n * 8, cudaMemcpyHostToDevice, s)); e->dbz.ct = (const uint64_t*)(M + o_ct); }
+                if (meta->txid_offsets && meta->txid_heap && n) {
+                    CK(cudaMemcpyAsync(M + o_off, meta->txid_offsets, (n + 1) * 4, cudaMemcpyHostToDevice, s)); e->dbz.gt_off = (const uint32_t*)(M + o_off);
+                    if (gt_len) CK(cudaMemcpyAsync(M + o_heap, meta->txid_heap, gt_len, cudaMemcpyHostToDevice, s));
+                    e->dbz.gt_heap = M + o_heap;
+                }
+            } else { e->dbz.id = meta->id; e->dbz.lsn = meta->lsn; e->dbz.ct = meta->commit_time; e->dbz.gt_off = meta->txid_offsets; e->dbz.gt_heap = meta->txid_heap; }
+        }
+        const uint8_t* pre = nullptr;
+        if (dev_kinds && n) { e->launches++; k_dbz_kinds<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(dev_kinds, n, M + o_pre); pre = M + o_pre; }
+        run_chain(e, pd, in, dev.data(), dev_kinds, TF_WIRE_DEBEZIUM, pre);
+        auto r = std::make_unique<tfgpu_result>();
+        finish_wire(e, n, TF_WIRE_DEBEZIUM, r.get());
         *out = r.release();
         return TF_OK;
     } catch (const tfplan::FatalError& f) { return fail(e, f.code, f.what()); }
@@ -893,7 +1018,7 @@ int tfgpu_parse_csv(tfgpu_engine* e, int plan_id, const char* opts_json, const u
                        (const int16_t*)(B + o_fc), nfields, (const int16_t*)(B + o_ns), (uint32_t*)(B + o_ss), (uint32_t*)(B + o_sl), B + o_err};
             e->prof_begin("k_csv_pass1", s); k_csv_pass1<<<(uint32_t)((nrows + 127) / 128), 128, 0, s>>>(ca); e->prof_end(s);
             if (nslots) {
-                e->prof_begin("k_csv_offsets", s); k_csv_offsets<<<nslots, 1024, 0, s>>>((const uint32_t*)(B + o_sl), nrows, (uint32_t*)(B + o_off), (uint64_t*)(B + o_tot)); e->prof_end(s);
+                launch_offsets(e, (const uint32_t*)(B + o_sl), nrows, (uint32_t)nslots, (uint32_t*)(B + o_off), (uint64_t*)(B + o_tot), s);
                 CK(cudaMemcpyAsync(col_total.data(), B + o_tot, (size_t)nslots * 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
                 uint64_t run = 0; for (int k = 0; k < nslots; k++) { col_base[k] = run; run += col_total[k]; }
                 CK(cudaMemcpyAsync(B + o_base, col_base.data(), (size_t)nslots * 8, cudaMemcpyHostToDevice, s));
@@ -1051,7 +1176,7 @@ int tfgpu_parse_json(tfgpu_engine* e, int plan_id, const char* opts_json, const 
                 e->prof_begin("k_json_pass1", s); k_json_pass1<<<nlb, 128, 0, s>>>(ja); e->prof_end(s);
                 CK(cudaMemcpyAsync(&n_nonempty, (uint32_t*)(B + o_rank) + nlines, 4, cudaMemcpyDeviceToHost, s));
                 if (nslots) {
-                    e->prof_begin("k_csv_offsets", s); k_csv_offsets<<<nslots, 1024, 0, s>>>((const uint32_t*)(B + o_len), nrows, (uint32_t*)(B + o_off), (uint64_t*)(B + o_tot)); e->prof_end(s);
+                    launch_offsets(e, (const uint32_t*)(B + o_len), nrows, (uint32_t)nslots, (uint32_t*)(B + o_off), (uint64_t*)(B + o_tot), s);
                     CK(cudaMemcpyAsync(col_total.data(), B + o_tot, (size_t)nslots * 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
                     uint64_t run = 0; for (int k = 0; k < nslots; k++) { col_base[k] = run; run += align_up(col_total[k], 16); }
                     if (run >= (1ull << 32)) throw tfplan::FatalError(TF_E_FATAL_ARG, "json batch: a text column exceeds 4 GiB");
@@ -1187,7 +1312,7 @@ int tfgpu_parse_debezium(tfgpu_engine* e, int plan_id, const char* opts_json, co
             const uint32_t nb = (uint32_t)((n + 127) / 128);
             e->prof_begin("k_dbz_pass1", s); k_dbz_pass1<<<nb, 128, 0, s>>>(da); e->prof_end(s);
             if (nslots) {
-                e->prof_begin("k_csv_offsets", s); k_csv_offsets<<<nslots, 1024, 0, s>>>((const uint32_t*)(B + o_len), n, (uint32_t*)(B + o_off), (uint64_t*)(B + o_tot)); e->prof_end(s);
+                launch_offsets(e, (const uint32_t*)(B + o_len), n, (uint32_t)nslots, (uint32_t*)(B + o_off), (uint64_t*)(B + o_tot), s);
                 CK(cudaMemcpyAsync(col_total.data(), B + o_tot, (size_t)nslots * 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
                 uint64_t run = 0; for (int k = 0; k < nslots; k++) { col_base[k] = run; run += align_up(col_total[k], 16); }
                 if (run >= (1ull << 32)) throw tfplan::FatalError(TF_E_FATAL_ARG, "debezium batch: a text column exceeds 4 GiB");
@@ -1254,6 +1379,7 @@ const uint8_t* tfgpu_result_bytes(const tfgpu_result* r) { return r ? r->bytes :
 uint64_t tfgpu_result_bytes_len(const tfgpu_result* r) { return r ? r->bytes_len : 0; }
 uint64_t tfgpu_result_raw_len(const tfgpu_result* r) { return r ? r->raw_len : 0; }
 uint64_t tfgpu_result_n_frames(const tfgpu_result* r) { return r ? r->n_frames : 0; }
+const uint32_t* tfgpu_result_key_sizes(const tfgpu_result* r) { return (r && !r->key_sizes.empty()) ? r->key_sizes.data() : nullptr; }
 const uint32_t* tfgpu_result_row_sizes(const tfgpu_result* r) { return (r && !r->row_sizes.empty()) ? r->row_sizes.data() : nullptr; }
 
 // queue JSON serializer batching (pkg/serializer/queue/json_batcher.go:13-66): host only, no device needed

@@ -59,6 +59,8 @@ def load_library():
     L.tfgpu_push_encode.argtypes = [vp, i, i, C.POINTER(abi.TfBatch), C.POINTER(vp)]
     L.tfgpu_parse_csv.argtypes = [vp, i, cp, vp, u64, i, i, C.POINTER(vp)]
     L.tfgpu_result_row_sizes.argtypes = [vp]; L.tfgpu_result_row_sizes.restype = C.POINTER(C.c_uint32)
+    L.tfgpu_result_key_sizes.argtypes = [vp]; L.tfgpu_result_key_sizes.restype = C.POINTER(C.c_uint32)
+    L.tfgpu_emit_debezium.argtypes = [vp, i, cp, C.POINTER(abi.TfBatch), C.POINTER(abi.TfRowMeta), C.POINTER(vp)]
     L.tfgpu_queue_json_batches.argtypes = [vp, u64, u64, u64, vp, u64, C.POINTER(u64)]
     L.tfgpu_parse_debezium.argtypes = [vp, i, cp, vp, u64, i, vp, C.c_uint32, i, C.POINTER(vp)]
     for fn, ty in (("tfgpu_result_selection", C.c_uint32), ("tfgpu_result_meta_kinds", C.c_uint8), ("tfgpu_result_meta_tx_id", C.c_uint32), ("tfgpu_result_meta_lsn", u64), ("tfgpu_result_meta_commit_time", u64)):
@@ -85,7 +87,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "tfgpu_version", "tfgpu_engine_create", "tfgpu_engine_destroy", "tfgpu_last_error", "tfgpu_engine_set_stream",
-    "tfgpu_plan", "tfgpu_plan_validate", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_parse_csv", "tfgpu_parse_json", "tfgpu_measure", "tfgpu_result_row_sizes", "tfgpu_queue_json_batches", "tfgpu_parse_debezium", "tfgpu_debug_lz4_phases", "tfgpu_result_selection", "tfgpu_result_meta_kinds", "tfgpu_result_meta_tx_id", "tfgpu_result_meta_lsn", "tfgpu_result_meta_commit_time", "tfgpu_result_consumed", "tfgpu_push_encode_resident",
+    "tfgpu_plan", "tfgpu_plan_validate", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_parse_csv", "tfgpu_parse_json", "tfgpu_measure", "tfgpu_emit_debezium", "tfgpu_result_key_sizes", "tfgpu_result_row_sizes", "tfgpu_queue_json_batches", "tfgpu_parse_debezium", "tfgpu_debug_lz4_phases", "tfgpu_result_selection", "tfgpu_result_meta_kinds", "tfgpu_result_meta_tx_id", "tfgpu_result_meta_lsn", "tfgpu_result_meta_commit_time", "tfgpu_result_consumed", "tfgpu_push_encode_resident",
     "tfgpu_resident_stats", "tfgpu_resident_fetch", "tfgpu_result_rows_in", "tfgpu_result_rows_out",
     "tfgpu_result_n_errors", "tfgpu_result_errors", "tfgpu_result_batch", "tfgpu_result_bytes",
     "tfgpu_result_bytes_len", "tfgpu_result_raw_len", "tfgpu_result_n_frames", "tfgpu_result_release",
@@ -320,6 +322,32 @@ class Engine:
         out = (C.c_uint64 * 8)()
         self._check(self._L.tfgpu_debug_lz4_phases(self._h, 1 if enable else 0, out))
         return [int(x) for x in out[:5]]
+
+    def emit_debezium(self, plan_id: int, batch: abi.Batch, opts: dict, meta: Optional[dict] = None, copy_bytes: bool = True) -> PushResult:
+        """Queue Debezium serializer (Emitter.EmitKV) over the INSERT rows that survive the plan's chain: PushResult whose
+        `wire` holds key message + value message per row, `key_sizes` / `row_sizes` split them. meta: {"id", "lsn",
+        "commit_time", "txid_offsets", "txid_heap"} arrays in the same memory space as the batch."""
+        import numpy as np
+        tb = batch.as_struct()
+        meta = meta or {}
+        m, keep = abi.make_row_meta(meta.get("id"), meta.get("lsn"), meta.get("commit_time"), meta.get("txid_offsets"), meta.get("txid_heap"))
+        res = C.c_void_p()
+        self._check(self._L.tfgpu_emit_debezium(self._h, plan_id, json.dumps(opts).encode(), C.byref(tb), C.byref(m), C.byref(res)))
+        try:
+            L = self._L
+            n = L.tfgpu_result_bytes_len(res)
+            wire = C.string_at(L.tfgpu_result_bytes(res), n) if (copy_bytes and n) else b""
+            ne = L.tfgpu_result_n_errors(res); ep = L.tfgpu_result_errors(res)
+            out = PushResult(L.tfgpu_result_rows_in(res), L.tfgpu_result_rows_out(res), L.tfgpu_result_raw_len(res), 0, wire,
+                             [(ep[k].row, ep[k].code, ep[k].term) for k in range(ne)])
+            out.wire_len = n
+            k = int(out.rows_out)
+            rs = L.tfgpu_result_row_sizes(res); ks = L.tfgpu_result_key_sizes(res)
+            out.row_sizes = np.ctypeslib.as_array(rs, shape=(k,)).copy() if (rs and k) else np.zeros(0, np.uint32)
+            out.key_sizes = np.ctypeslib.as_array(ks, shape=(k,)).copy() if (ks and k) else np.zeros(0, np.uint32)
+            return out
+        finally:
+            self._L.tfgpu_result_release(res)
 
     def measure(self, batch: abi.Batch):
         """Measurer middleware: ChangeItem.Size.Values of every row (numpy uint64) and their sum."""
