@@ -154,7 +154,7 @@ typedef struct tf_batch {
 typedef struct tf_rowerr {
     uint32_t row;      /* index into the INPUT batch */
     uint16_t code;     /* TF_ROWERR_* */
-    uint16_t term;     /* index of the transformer in the plan that raised it */
+    uint16_t term;     /* index of the transformer in the plan that raised it; 0xff = raised before the chain (parser, host hand-off) */
 } tf_rowerr;
 
 /* ---- wire formats for tfgpu_push_encode ----------------------------------- */

@@ -812,7 +812,7 @@ extern "C" int orc_debezium_emit(const tf_batch* in, const orc_colschema* schema
     std::string text;
     for (uint64_t r = 0; r < in->nrows; r++) {
         const int kind = in->kinds ? in->kinds[r] : TF_KIND_INSERT;
-        if (kind != TF_KIND_INSERT) { errs[ne++] = tf_rowerr{(uint32_t)r, TF_ROWERR_DBZ_EMIT_HOST, 0}; continue; }
+        if (kind != TF_KIND_INSERT) { errs[ne++] = tf_rowerr{(uint32_t)r, TF_ROWERR_DBZ_EMIT_HOST, 0xff}; continue; }      // term 0xff: not raised by a transformer
         if (!apply_steps(in, r, steps, nsteps, row, cur_type, errs, ne)) continue;
         bool row_err = false;
         auto obj = [&](bool keys_only) {

@@ -146,7 +146,7 @@ def test_oracle_kinds_and_chain(po):
     trs = [{"filter_rows": {"filter": "x > 10"}}, {"mask_field": {"columns": ["name"], "maskFunctionHash": {"userDefinedSalt": "s"}}}]
     plan = po.build_plan("db", "t", schema, trs)
     data, ks, rs, errs = po.debezium_emit(b, plan, OPTS)
-    assert errs == [(1, abi.TF_ROWERR_DBZ_EMIT_HOST, 0), (3, abi.TF_ROWERR_DBZ_EMIT_HOST, 0)]
+    assert errs == [(1, abi.TF_ROWERR_DBZ_EMIT_HOST, 255), (3, abi.TF_ROWERR_DBZ_EMIT_HOST, 255)]
     kv = po.debezium_split(data, ks, rs)
     assert [k for k, _ in kv] == [b'{"id":3}', b'{"id":5}']
     after = json.loads(kv[0][1])["after"]

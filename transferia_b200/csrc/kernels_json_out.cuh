@@ -294,7 +294,7 @@ template <typename Inner> struct JStrSink {      // the inside of a JSON string 
     }
 };
 template <typename Sink> __device__ bool dbz_json_value(Sink& s, const DCol& c, uint64_t r, const JsonCol& jc, const MaskKey* keys, bool sizing) {
-    if (c.out_kind == OK_COPY || c.out_kind == OK_STR) {
+    if (c.out_kind != OK_MASK && c.out_kind != OK_TOSTR && c.out_kind != OK_TODT) {      // the value keeps its input type (the sink cast kinds do not apply)
         if (!row_valid(c, r)) { fmt_lit(s, "null"); return true; }
         switch (c.type) {
         case TF_DATE: case TF_INTERVAL: fmt_lit(s, "null"); return false;            // emitter_common.go:161-163 unknown input data type
