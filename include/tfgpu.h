@@ -338,6 +338,10 @@ uint64_t          tfgpu_result_n_frames(const tfgpu_result* r);
 /* Row-text formats (TF_WIRE_SER_JSON/CSV, TF_WIRE_CH_JSONEACHROW): bytes of every output row in the order written,
  * separator included (SER_JSON without CLOSING_NEWLINE: rows after the first start with '\n'). rows_out entries or NULL. */
 const uint32_t*   tfgpu_result_row_sizes(const tfgpu_result* r);
+/* sharder_transformer in the plan (pkg/transformer/registry/sharder/sharder.go:130-145): ChangeItem.PartID of every output row
+ * as the integer the reference prints with %d (CRC32-IEEE of the joined text forms of the matched columns, modulo ShardsNum);
+ * rows_out entries, NULL when the plan has no sharder. is_random sharders are refused by tfgpu_plan (uuid + rand.Intn: host). */
+const uint32_t*   tfgpu_result_part_ids(const tfgpu_result* r);
 const uint32_t*   tfgpu_result_key_sizes(const tfgpu_result* r);  /* tfgpu_emit_debezium: key bytes of every output row */
 
 /* Queue JSON serializer (pkg/serializer/queue/json_serializer.go:22-83 + json_batcher.go:13-66): the message VALUES are the

@@ -568,15 +568,26 @@ int orc_ch_type(const orc_colschema* c, char* dst, int cap) { return copy_out(ch
 }  // extern "C" (reopened below)
 
 namespace {
+uint32_t crc32_ieee(const uint8_t* p, size_t n) {            // hash/crc32 IEEE: reflected 0xEDB88320, init and final xor 0xFFFFFFFF
+    uint32_t c = 0xFFFFFFFFu;
+    for (size_t i = 0; i < n; i++) { c ^= p[i]; for (int k = 0; k < 8; k++) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u))); }
+    return ~c;
+}
+thread_local uint32_t g_part_id = 0; thread_local bool g_has_part = false;     // PartID the last sharder step gave the current row
 // Applies the transformer steps to row r (boxed in `row`); returns false when the row is dropped or errored.
 bool apply_steps(const tf_batch* in, uint64_t r, const orc_step* steps, int nsteps, std::vector<Boxed>& row, std::vector<int32_t>& cur_type,
                  tf_rowerr* errs, uint64_t& ne) {
     const uint32_t nc = in->ncols;
     for (uint32_t c = 0; c < nc; c++) { row[c].own.clear(); box(in->cols[c], r, row[c].v); cur_type[c] = in->cols[c].type; }   // []interface{} of this ChangeItem
     const int kind = in->kinds ? in->kinds[r] : TF_KIND_INSERT;
+    g_has_part = false;
     for (int s = 0; s < nsteps; s++) {
         const orc_step& st = steps[s];
-        if (st.kind == STEP_SKIP_EVENTS) {                        // SkipEvents.Apply skip_events.go:52-62
+        if (st.kind == STEP_SHARDER) {                            // SharderTransformer.generatePartID sharder.go:130-145
+            std::string joined;
+            for (int k = 0; k < st.ncols; k++) { if (k) joined += '.'; joined += serialize_to_string(row[st.cols[k]].v, cur_type[st.cols[k]]); }
+            g_part_id = crc32_ieee((const uint8_t*)joined.data(), joined.size()) % (uint32_t)st.kind_mask; g_has_part = true;
+        } else if (st.kind == STEP_SKIP_EVENTS) {                        // SkipEvents.Apply skip_events.go:52-62
             if ((st.kind_mask >> kind) & 1) return false;
         } else if (st.kind == STEP_FILTER_ROWS) {                // FilterRowsTransformer.Apply filter_rows.go:99-130
             if (kind == TF_KIND_UPDATE || kind == TF_KIND_DELETE) { errs[ne++] = tf_rowerr{(uint32_t)r, TF_ROWERR_FILTER_KIND, (uint16_t)st.convert_to_bytes}; return false; }
@@ -857,6 +868,19 @@ extern "C" int orc_debezium_emit(const tf_batch* in, const orc_colschema* schema
     if (nerrs) *nerrs = ne;
     std::vector<uint8_t> bytes(text.begin(), text.end());
     to_buf(bytes, out);
+    return 0;
+}
+
+extern "C" uint32_t orc_crc32_ieee(const uint8_t* p, uint64_t n) { return crc32_ieee(p, n); }
+extern "C" int orc_shard_ids(const tf_batch* in, const orc_colschema* schema, const orc_step* steps, int nsteps, uint32_t* part_ids, uint64_t* rows_out) {
+    (void)schema;
+    std::vector<Boxed> row(in->ncols); std::vector<int32_t> cur_type(in->ncols);
+    std::vector<tf_rowerr> errs(in->nrows + 1); uint64_t ne = 0, kept = 0;
+    for (uint64_t r = 0; r < in->nrows; r++) {
+        if (!apply_steps(in, r, steps, nsteps, row, cur_type, errs.data(), ne)) continue;
+        part_ids[kept++] = g_has_part ? g_part_id : 0xFFFFFFFFu;
+    }
+    if (rows_out) *rows_out = kept;
     return 0;
 }
 

@@ -60,7 +60,7 @@ typedef struct orc_colschema {
     const char* original_type;  /* may be NULL */
 } orc_colschema;
 
-enum { STEP_FILTER_ROWS = 1, STEP_MASK = 2, STEP_TO_STRING = 3, STEP_SKIP_EVENTS = 4, STEP_SELECT_COLS = 5, STEP_TO_DATETIME = 6, STEP_NUMBER_TO_FLOAT = 7 };
+enum { STEP_FILTER_ROWS = 1, STEP_MASK = 2, STEP_TO_STRING = 3, STEP_SKIP_EVENTS = 4, STEP_SELECT_COLS = 5, STEP_TO_DATETIME = 6, STEP_NUMBER_TO_FLOAT = 7, STEP_SHARDER = 8 };
 typedef struct orc_step {
     int32_t kind;
     /* filter_rows */
@@ -70,7 +70,7 @@ typedef struct orc_step {
     const uint8_t* salt; uint64_t salt_len;
     int32_t convert_to_bytes;
     int32_t pass_all;      /* filter_rows: table filter misses the renamed table -> rows pass, kinds still checked */
-    int32_t kind_mask;     /* skip_events: bit TF_KIND_* set = drop */
+    int32_t kind_mask;     /* skip_events: bit TF_KIND_* set = drop; sharder: ShardsNum */
 } orc_step;
 
 typedef struct orc_buf { uint8_t* data; uint64_t len; } orc_buf;
@@ -118,6 +118,11 @@ typedef struct orc_dbz_emit_opts {
 int orc_debezium_emit(const tf_batch* in, const orc_colschema* schema, const uint8_t* is_key, const orc_step* steps, int nsteps,
                       const tf_row_meta* meta, const orc_dbz_emit_opts* opts, orc_buf* out, uint32_t* key_sizes, uint32_t* row_sizes,
                       uint64_t* rows_out, tf_rowerr* errs, uint64_t* nerrs);
+
+/* sharder transformer (pkg/transformer/registry/sharder/sharder.go:130-145): ChangeItem.PartID of every row the chain keeps =
+ * decimal(CRC32-IEEE(join(".", SerializeToString(value) of the matched columns)) % uint32(ShardsNum)). part_ids: nrows entries. */
+int orc_shard_ids(const tf_batch* in, const orc_colschema* schema, const orc_step* steps, int nsteps, uint32_t* part_ids, uint64_t* rows_out);
+uint32_t orc_crc32_ieee(const uint8_t* p, uint64_t n);
 
 typedef struct orc_regions { uint64_t values, validity, aux, offsets, heap, heap_len; } orc_regions;
 int orc_push_columns(const tf_batch* in, const orc_colschema* schema, const orc_step* steps, int nsteps,

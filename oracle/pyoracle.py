@@ -87,6 +87,7 @@ class OrcBuf(C.Structure):
 OP_EQ, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE, OP_IN, OP_NOTIN, OP_MATCH, OP_NOTMATCH = range(10)
 LV_INT, LV_FLOAT, LV_BOOL, LV_STRING, LV_TIME, LV_NULL, LV_LIST = 1, 2, 3, 4, 5, 6, 16
 STEP_FILTER_ROWS, STEP_MASK, STEP_TO_STRING, STEP_SKIP_EVENTS, STEP_SELECT_COLS, STEP_TO_DATETIME, STEP_NUMBER_TO_FLOAT = 1, 2, 3, 4, 5, 6, 7
+STEP_SHARDER = 8
 
 _lib = None
 
@@ -545,6 +546,20 @@ def build_plan(ns: str, name: str, schema: List[dict], transformers: List[dict])
                 idx += 1; continue                                   # Apply re-checks item.TableID() :62-66: a renamed table no longer matches
             pos = [i for i, c in enumerate(cur) if c["type"] == "any"]
             steps.append({"kind": "number_to_float", "index": idx, "cols": [cur[i]["_in"] for i in pos]}); idx += 1
+        elif ttype == "sharder_transformer":                      # sharder.go:83-145
+            if cfg.get("is_random"):
+                raise NotImplementedError("sharder is_random: PartID is uuid + rand.Intn, host only")
+            ccfg = cfg.get("columns") or {}
+            inc = ccfg.get("includeColumns") or []; exc = ccfg.get("excludeColumns") or []
+            if not _tables_match(cfg.get("tables"), ns, name):
+                continue
+            pos = [i for i, n_ in enumerate(names) if _filter_match(inc, exc, n_)]
+            if (inc or exc) and not pos:
+                continue                                             # Suitable :93-105
+            shards = int(cfg.get("shardsCount"))
+            if shards & 0xffffffff == 0:
+                raise ValueError("sharder: shardsCount is zero modulo 2^32 (the reference divides by zero)")
+            steps.append({"kind": "sharder", "index": idx, "cols": [cur[i]["_in"] for i in pos], "shards": shards & 0xffffffff}); idx += 1
         elif ttype == "convert_to_string":
             if not _tables_match(cfg.get("tables"), ns, name):
                 continue
@@ -647,6 +662,9 @@ def _marshal(plan: Plan):
         elif st["kind"] == "number_to_float":
             cols = keep.add(np.asarray(st["cols"], dtype=np.int32))
             s.kind = STEP_NUMBER_TO_FLOAT; s.cols = cols.ctypes.data; s.ncols = len(st["cols"])
+        elif st["kind"] == "sharder":
+            cols = keep.add(np.asarray(st["cols"], dtype=np.int32))
+            s.kind = STEP_SHARDER; s.cols = cols.ctypes.data; s.ncols = len(st["cols"]); s.kind_mask = C.c_int32(st["shards"] & 0xffffffff).value
         elif st["kind"] == "skip_events":
             s.kind = STEP_SKIP_EVENTS; s.kind_mask = st["kind_mask"]
         elif st["kind"] == "filter_columns":
@@ -681,6 +699,24 @@ def push_encode(batch: abi.Batch, plan: Plan, wire_fmt: int, frame_bytes: int = 
     res.raw_len = raw.len; res.wire_len = wire.len
     lib().orc_free(C.byref(raw)); lib().orc_free(C.byref(wire))
     return res
+
+
+def shard_ids(batch: abi.Batch, plan: Plan):
+    """ChangeItem.PartID (as the integer the sharder prints) of every row the chain keeps; 0xFFFFFFFF without a sharder."""
+    keep, cschema, csteps = _marshal(plan)
+    tb = batch.as_struct()
+    out = np.zeros(max(1, batch.nrows), dtype=np.uint32); rows = C.c_uint64()
+    L = lib()
+    L.orc_shard_ids.argtypes = [C.POINTER(abi.TfBatch), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_uint64)]
+    rc = L.orc_shard_ids(C.byref(tb), C.cast(cschema, C.c_void_p), C.cast(csteps, C.c_void_p), len(plan.steps), out.ctypes.data, C.byref(rows))
+    if rc != 0:
+        raise RuntimeError(f"oracle shard_ids rc={rc}")
+    return out[:rows.value].copy()
+
+
+def crc32_ieee(data: bytes) -> int:
+    L = lib(); L.orc_crc32_ieee.argtypes = [C.c_char_p, C.c_uint64]; L.orc_crc32_ieee.restype = C.c_uint32
+    return int(L.orc_crc32_ieee(data, len(data)))
 
 
 def push_columns(batch: abi.Batch, plan: Plan):

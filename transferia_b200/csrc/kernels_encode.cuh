@@ -437,10 +437,11 @@ template <int K, int INW, int W> __device__ __forceinline__ void encode_stream(c
     const uint32_t m = (uint32_t)(base & 3);
     const uint64_t total = n * (uint64_t)W;
     const uint64_t T = (m + total + 3) >> 2;
-    const uint64_t t0 = (uint64_t)blockIdx.x * TF_FIX_TILE_WORDS;
-    if (t0 >= T) return;
     uint8_t* dst0 = a.raw + (base - m);
     const unsigned lane = threadIdx.x & 31;
+    // the grid is sized on the host for at most n INPUT rows of the widest type; the CTAs stride over the tiles the kept
+    // rows actually fill, so a selective filter does not leave tens of thousands of CTAs that only start and exit
+    for (uint64_t t0 = (uint64_t)blockIdx.x * TF_FIX_TILE_WORDS; t0 < T; t0 += (uint64_t)gridDim.x * TF_FIX_TILE_WORDS)
 #pragma unroll 2
     for (uint32_t it = 0; it < TF_FIX_TILE_WORDS / 256; it++) {
         const uint64_t t = t0 + it * 256 + threadIdx.x;      // uniform trip count: the shuffle below needs the whole warp

@@ -17,6 +17,18 @@ namespace tfk {
 
 struct CountSink { uint32_t n; __device__ __forceinline__ void put(uint8_t) { n++; } };
 struct MemSink { uint8_t* p; __device__ __forceinline__ void put(uint8_t b) { *p++ = b; } };
+// MemSink that gathers 8 bytes in a register and stores aligned 64-bit words: row text is written by one thread per row, and a
+// byte store per character makes the LSU the bottleneck. flush() must follow the last put().
+struct WordSink {
+    uint8_t* p; uint64_t acc; uint32_t nb;
+    __device__ __forceinline__ explicit WordSink(uint8_t* dst) : p(dst), acc(0), nb(0) {}
+    __device__ __forceinline__ void put(uint8_t b) {
+        if (nb == 0 && ((uintptr_t)p & 7)) { *p++ = b; return; }          // head: up to the first 8-byte boundary
+        acc |= (uint64_t)b << (8 * nb);
+        if (++nb == 8) { *(uint64_t*)p = acc; p += 8; acc = 0; nb = 0; }
+    }
+    __device__ __forceinline__ void flush() { for (uint32_t i = 0; i < nb; i++) p[i] = (uint8_t)(acc >> (8 * i)); p += nb; nb = 0; acc = 0; }
+};
 
 // ------------------------------------------------------------------ Ryu core
 struct DecF { uint64_t digits; int32_t exp10; };   // value = digits * 10^exp10

@@ -765,7 +765,7 @@ __global__ void __launch_bounds__(128) k_json_pass2(JsnWriteArgs w) {
         if (cd.w) continue;
         const uint32_t sl = a.span_len[(size_t)f * a.nlines + L]; const uint32_t t = sl >> 28, len = sl & 0x0FFFFFFFu;
         if (t == JT_ABSENT || t == JT_NULL) continue;
-        MemSink ms{w.heap + w.col_base[cd.slot] + w.offsets[(size_t)cd.slot * (a.nlines + 1) + L]}; uint8_t tag;
+        MemSink ms{w.heap + w.col_base[cd.slot] + w.offsets[(size_t)cd.slot * (a.nlines + 1) + L]}; uint8_t tag;      // (short cells: a word-gathering sink measured slower here)
         jsn_emit_text(ms, a, cd, a.text, a.span_start[(size_t)f * a.nlines + L], len, t, tag);
     }
     int c = nf;

@@ -275,6 +275,7 @@ template <typename Sink> __device__ void ser_csv_row(Sink& s, const DCol* cols, 
 //   segments; a segment's code names the per-row piece that follows its text. Values: addCommon emitter_common.go:67-180.
 __device__ __forceinline__ uint32_t sink_count(const CountSink& s) { return s.n; }
 __device__ __forceinline__ uint32_t sink_count(const MemSink&) { return 0; }
+__device__ __forceinline__ uint32_t sink_count(const WordSink&) { return 0; }
 enum DbzCode : int32_t { DZ_NONE = 0, DZ_AFTER = 1, DZ_KEY = 2, DZ_LSN = 3, DZ_SRC_TS = 4, DZ_ID = 5, DZ_FILE = 6, DZ_POS = 7, DZ_GTID = 8, DZ_TS = 9, DZ_KEY_END = 10 };
 struct DbzSeg { int32_t text_off, text_len, code, pad; };
 struct DbzEmitArgs {
@@ -395,8 +396,9 @@ __global__ void __launch_bounds__(TF_JSON_TILE) k_json_write(JsonArgs a) {
     uint32_t tot; const uint32_t ex = block_excl_scan(sz, &tot, sm);
     if (j >= n) return;
     const uint64_t r = a.sel ? a.sel[j] : j;
-    MemSink ms; ms.p = a.raw + a.tile_base[blockIdx.x] + ex;
+    WordSink ms(a.raw + a.tile_base[blockIdx.x] + ex);
     json_any_row(ms, a, r, j, false);
+    ms.flush();
 }
 
 }  // namespace tfk

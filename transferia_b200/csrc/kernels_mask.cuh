@@ -150,4 +150,32 @@ __global__ void __launch_bounds__(128) k_mask_encode(MaskArgs a) {
     mask_digest_hex(c, r, a.keys[c.mask_slot], out);
 }
 
+// ------------------------------------------------------------------ sharder transformer
+//   SharderTransformer.generatePartID pkg/transformer/registry/sharder/sharder.go:130-145:
+//   PartID = decimal(crc32.ChecksumIEEE(join(".", SerializeToString(value, type) of the matched columns)) % uint32(ShardsNum)).
+//   One thread per kept row streams the text forms through a table-driven CRC (table built per CTA in shared memory).
+struct ShardCol { int32_t col, form, pad0, pad1; };       // form: 0 text of the input value, 1 mask digest, 3 converted datetime
+struct ShardArgs { const DCol* cols; const ShardCol* sc; int nsc; const MaskKey* keys; const uint32_t* sel; DState* st; uint32_t shards; uint32_t* part; };
+struct CrcSink { uint32_t c; const uint32_t* tab; __device__ __forceinline__ void put(uint8_t b) { c = tab[(c ^ b) & 0xffu] ^ (c >> 8); } };
+
+__global__ void __launch_bounds__(256) k_shard_ids(ShardArgs a) {
+    __shared__ uint32_t tab[256];
+    { uint32_t c = threadIdx.x; for (int k = 0; k < 8; k++) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u))); tab[threadIdx.x] = c; }
+    __syncthreads();
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.st->n_kept) return;
+    const uint64_t r = a.sel ? a.sel[j] : j;
+    CrcSink s{0xFFFFFFFFu, tab};
+    for (int k = 0; k < a.nsc; k++) {
+        const ShardCol sc = a.sc[k]; const DCol& c = a.cols[sc.col];
+        if (k) s.put('.');
+        if (sc.form == 1) { uint8_t hx[64]; mask_digest_hex(c, r, a.keys[c.mask_slot], hx); for (int i = 0; i < 64; i++) s.put(hx[i]); }
+        else if (sc.form == 3) {           // SerializeToDateTime: nil -> time.Unix(0, 0) (to_datetime.go:137-151), then RFC3339Nano
+            int64_t sec = 0; if (row_valid(c, r)) sec = c.type == TF_INT32 ? (int64_t)((const int32_t*)c.values)[r] : (int64_t)((const uint32_t*)c.values)[r];
+            fmt_time(s, sec, 0, false);
+        } else fmt_value(s, c, r);
+    }
+    a.part[j] = (~s.c) % a.shards;
+}
+
 }  // namespace tfk

@@ -11,7 +11,9 @@
 //                      pkg/abstract/changeitem/table_id.go:14-30
 //   ClickHouse types   pkg/providers/clickhouse/columntypes/types.go:210-248, sink_table.go:196-235
 #pragma once
+#include <cerrno>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <regex>
 #include <stdexcept>
@@ -343,6 +345,9 @@ struct Plan {
     std::vector<uint8_t> tostr_col;    // [input column] 1 = convert_to_string applies (to_string.go:58-97)
     std::vector<int> tostr_step_index; std::vector<std::vector<int>> tostr_cols;
     std::vector<MaskStep> masks;
+    // sharder (registry/sharder/sharder.go:63-145): the LAST sharder of the chain sets ChangeItem.PartID. form: 0 = the text of the
+    // input value (also after convert_to_string: the text of a text is itself), 1 = the mask digest, 3 = the converted datetime
+    bool has_sharder = false; uint32_t shards = 0; std::vector<int> shard_cols, shard_form; int shard_step_index = -1;
     std::vector<int> mask_step_index;
     std::vector<uint8_t> blob;         // literal pool referenced by DTerm
     std::string describe;
@@ -555,6 +560,31 @@ inline Plan build_plan(const std::string& ns, const std::string& name, const std
                 if (!first) d += ","; first = false; d += std::to_string(cur[i].in_index);
             }
             add_desc(d + "]}"); step_no++;
+        } else if (ttype == "sharder_transformer") {                 // registry/sharder/sharder.go:20-145
+            if (cfg->get_bool("is_random")) throw FatalError(TF_E_FATAL_UNSUPPORTED, "sharder_transformer is_random: PartID = uuid + rand.Intn, host only");
+            const tfj::Value* cc = cfg->get("columns");
+            std::vector<std::string> inc, exc;
+            if (cc) { inc = cc->get_str_list("includeColumns"); exc = cc->get_str_list("excludeColumns"); }
+            NameFilter cf = make_filter(inc, exc);
+            const std::string sc = cfg->get_str("shardsCount");
+            char* endp = nullptr; errno = 0; const long long sn = std::strtoll(sc.c_str(), &endp, 10);
+            if (sc.empty() || *endp || errno) throw FatalError(TF_E_FATAL_CONFIG, "sharder_transformer: cannot parse shardsCount as int");        // :38-41
+            if (!match_table(tables_filter(cfg->get("tables")), ns, name)) continue;
+            std::vector<int> pos;
+            for (size_t i = 0; i < cur.size(); i++) if (cf.match(cur[i].name)) pos.push_back((int)i);
+            if (!cf.empty() && pos.empty()) continue;                // Suitable :93-105
+            if ((uint32_t)sn == 0) throw FatalError(TF_E_FATAL_CONFIG, "sharder_transformer: shardsCount is zero modulo 2^32 (the reference divides by zero)");
+            pl.has_sharder = true; pl.shards = (uint32_t)sn; pl.shard_cols.clear(); pl.shard_form.clear(); pl.shard_step_index = step_no;
+            std::string d = "{\"type\":\"sharder_transformer\",\"shards\":" + std::to_string(pl.shards) + ",\"cols\":[";
+            for (size_t i = 0; i < pos.size(); i++) {
+                const ColSchema& c = cur[pos[i]];
+                int form = 0;
+                for (auto& ms : pl.masks) for (int mc : ms.cols) if (mc == c.in_index) form = 1;
+                if (pl.todt_col.size() && pl.todt_col[c.in_index]) form = 3;
+                if (i) d += ","; d += std::to_string(c.in_index);
+                pl.shard_cols.push_back(c.in_index); pl.shard_form.push_back(form);
+            }
+            add_desc(d + "]}"); step_no++;
         } else if (ttype == "convert_to_string") {                   // registry/to_string/to_string.go:24-113
             if (!match_table(tables_filter(cfg->get("tables")), ns, name)) continue;
             if (cfg->get_bool("skip_utc_conversion")) throw FatalError(TF_E_FATAL_UNSUPPORTED, "convert_to_string: skip_utc_conversion needs time zones, which the columnar layout does not carry");
@@ -599,6 +629,16 @@ inline Plan build_plan(const std::string& ns, const std::string& name, const std
                 if (t.col == c) throw FatalError(TF_E_FATAL_UNSUPPORTED, "filter_rows on a column converted to string earlier in the chain is not supported");
         for (size_t k = 0; k < pl.masks.size(); k++) for (int c : pl.masks[k].cols) for (int c2 : pl.tostr_cols[m])
             if (c == c2) throw FatalError(TF_E_FATAL_UNSUPPORTED, "mask_field and convert_to_string on the same column are not supported together");
+    }
+    if (pl.has_sharder) {     // transformers placed AFTER the sharder must not change what it read (the device evaluates it on the final column forms)
+        for (size_t k = 0; k < pl.shard_cols.size(); k++) {
+            const int c = pl.shard_cols[k];
+            for (size_t m = 0; m < pl.masks.size(); m++) if (pl.mask_step_index[m] > pl.shard_step_index) for (int mc : pl.masks[m].cols) if (mc == c)
+                pl.shard_form[k] = 0;                                 // masked later: the sharder saw the value itself
+            for (size_t m = 0; m < pl.todt_cols.size(); m++) if (pl.todt_step_index[m] > pl.shard_step_index) for (int tc : pl.todt_cols[m]) if (tc == c) pl.shard_form[k] = 0;
+            if (pl.in_schema[c].tf == TF_ANY) for (int nc : pl.n2f_cols) if (nc == c)
+                throw FatalError(TF_E_FATAL_UNSUPPORTED, "sharder_transformer over an `any` column that number_to_float rewrites is not supported");
+        }
     }
     pl.out_schema = cur; pl.out_ns = cur_ns; pl.out_name = cur_name;
     for (auto& c : cur) pl.out_cols.push_back(c.in_index);

@@ -56,6 +56,7 @@ struct PlanDev {
     int n_fsteps = 0, n_fixed_slots = 0, n_str = 0, n_mask_cols = 0, n_tostr = 0;
     std::vector<int32_t> fixed_slots, str_slots, mask_slot_cols, mask_slot_key;
     std::vector<int> col_out_kind, col_out_w, col_str_slot, col_mask_slot, col_nullable;
+    ShardCol* d_shard_cols = nullptr;              // sharder_transformer: columns it reads (plan.has_sharder)
     std::vector<JsonCol> h_sjcols;                 // host copy of d_sjcols (the Debezium emitter picks the key columns out of it)
     DevBuf dbz_consts; std::string dbz_opts_key; DbzEmitArgs dbz{};      // Debezium emitter: message template of the last opts_json
 };
@@ -78,9 +79,9 @@ struct tfgpu_engine {
     // pointers into `work` for the last call
     uint8_t *keep = nullptr, *errcode = nullptr, *errstep = nullptr; uint32_t *blockcnt = nullptr, *blockoff = nullptr, *sel = nullptr;
     uint32_t* tile_sum = nullptr; uint64_t* tile_base = nullptr; uint64_t* col_bytes = nullptr; uint32_t* comp_size = nullptr; uint64_t* wire_off = nullptr;
-    uint64_t last_nrows = 0; bool last_has_filter = false; int last_wire_fmt = 0;
+    uint64_t last_nrows = 0; bool last_has_filter = false, last_has_sharder = false; int last_wire_fmt = 0;
     uint8_t* pinned = nullptr; size_t pinned_cap = 0;
-    DevBuf json_sizes, dbz_keysz, dbz_meta;
+    DevBuf json_sizes, dbz_keysz, dbz_meta, part_ids;
     DbzEmitArgs dbz{};                                 // set by tfgpu_emit_debezium for the TF_WIRE_DEBEZIUM branch of run_chain
     unsigned long long* lz_phases = nullptr;      // debug: per-phase cycle counters of k_lz4_frames
     void* work_json_sizes(uint64_t n) { json_sizes.ensure(n * 4 + 256); return json_sizes.p; }
@@ -105,6 +106,7 @@ struct tfgpu_result {
     std::vector<uint8_t> meta_kinds; std::vector<uint32_t> meta_tx; std::vector<uint64_t> meta_lsn, meta_ct;   // debezium: per message
     std::vector<uint32_t> row_sizes;       // row-text formats: bytes of every output row (incl. its separator / newline)
     std::vector<uint32_t> key_sizes;       // Debezium emitter: key message bytes of every output row
+    std::vector<uint32_t> part_ids;        // sharder_transformer: ChangeItem.PartID (as an integer) of every output row
     // push_columns output
     tf_batch batch{}; std::vector<tf_col> cols; std::vector<uint8_t*> owned;
 };
@@ -239,6 +241,9 @@ void upload_plan(tfgpu_engine* e, PlanDev& pd) {
     need(pl.col_headers.size()); need(pl.col_header_off.size() * 4); need(pd.fixed_slots.size() * 4); need(pd.str_slots.size() * 4);
     need(pd.mask_slot_cols.size() * 4); need(keys.size() * sizeof(MaskKey)); need(pl.out_cols.size() * 4); need(jcols.size() * sizeof(JsonCol)); need(jnames.size());
     need(sjcols.size() * sizeof(JsonCol)); need(scsvcols.size() * sizeof(JsonCol)); need(snames.size());
+    std::vector<ShardCol> shcols;
+    for (size_t k = 0; k < pl.shard_cols.size(); k++) shcols.push_back(ShardCol{pl.shard_cols[k], pl.shard_form[k], 0, 0});
+    need(shcols.size() * sizeof(ShardCol));
     pd.consts.ensure(total);
     uint8_t* p = pd.consts.p;
     auto put = [&](const void* src, size_t n) { uint8_t* d = p; if (n) CK(cudaMemcpy(d, src, n, cudaMemcpyHostToDevice)); p += align_up(n ? n : 1, 256); return d; };
@@ -255,6 +260,7 @@ void upload_plan(tfgpu_engine* e, PlanDev& pd) {
     { std::vector<int32_t> oc(pl.out_cols.begin(), pl.out_cols.end()); pd.d_out_cols = (int32_t*)put(oc.data(), oc.size() * 4); }
     pd.d_jcols = (JsonCol*)put(jcols.data(), jcols.size() * sizeof(JsonCol)); pd.d_jnames = put(jnames.data(), jnames.size());
     pd.d_sjcols = (JsonCol*)put(sjcols.data(), sjcols.size() * sizeof(JsonCol)); pd.d_scsvcols = (JsonCol*)put(scsvcols.data(), scsvcols.size() * sizeof(JsonCol)); pd.d_snames = put(snames.data(), snames.size());
+    pd.d_shard_cols = (ShardCol*)put(shcols.data(), shcols.size() * sizeof(ShardCol));
     (void)e;
 }
 
@@ -296,6 +302,13 @@ static void launch_offsets(tfgpu_engine* e, const uint32_t* d_len, uint64_t nrow
 
 // Launch the whole fused chain on e->stream. `cols_host` holds DEVICE pointers.
 #define TF_WIRE_COLUMNAR_INTERNAL 100
+// x-extent of a (tiles, slots) grid whose kernel strides over its tiles: enough CTAs for `waves` full waves of the device
+// (resident CTAs per SM taken as 6 for the 256-thread encode kernels), never more than the tiles there can be
+uint32_t grid_cap(const tfgpu_engine* e, uint32_t tiles_upper, uint32_t nslots, uint32_t waves) {
+    const uint32_t want = ((uint32_t)e->sm_count * 6u * waves + nslots - 1) / (nslots ? nslots : 1);
+    return std::max(1u, std::min(tiles_upper, std::max(want, 8u)));
+}
+
 void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* dev_cols, const uint8_t* dev_kinds, int wire_fmt, const uint8_t* pre_err = nullptr) {
     const bool columnar = wire_fmt == TF_WIRE_COLUMNAR_INTERNAL;
     const tfplan::Plan& pl = pd.plan;
@@ -379,12 +392,21 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
     }
     const uint32_t* sel = (has_filter && n) ? e->sel : nullptr;
     const uint32_t ntiles = (uint32_t)((n + TF_STR_TILE - 1) / TF_STR_TILE);
+    // (the string kernels keep one CTA per tile group and exit early past the kept rows: a capped grid with a stride loop
+    // makes the CTAs of the heavy columns run several groups back to back; measured 0.18 -> 0.25 ms on the headline batch)
+    const uint32_t str_gx = std::max(1u, (ntiles + TF_STR_GROUP - 1) / TF_STR_GROUP);
     EncodeArgs ea{e->d_cols, pd.d_str_slots, sel, e->d_state, e->raw.p, e->tile_sum, e->tile_base, sz.ntiles_cap, columnar ? 1 : 0};
     if (!has_filter || !n) {
         // n_kept = nrows is set inside k_layout (has_sel = 0); k_str_sizes needs it earlier:
         DState init; std::memset(&init, 0, sizeof init); init.n_kept = n;
         CK(cudaMemcpyAsync(e->d_state, &init, sizeof init, cudaMemcpyHostToDevice, s));
     }
+    if (pl.has_sharder && n) {
+        e->part_ids.ensure(n * 4 + 256);
+        ShardArgs sa{e->d_cols, pd.d_shard_cols, (int)pl.shard_cols.size(), pd.d_mask_keys, sel, e->d_state, pl.shards, (uint32_t*)e->part_ids.p};
+        e->prof_begin("k_shard_ids", s); k_shard_ids<<<nb, 256, 0, s>>>(sa); e->prof_end(s);
+    }
+    e->last_has_sharder = pl.has_sharder;
     if (json_rows) {
         // JSONEachRow: rows sized, placed by a tile scan, then written (kernels_json_out.cuh)
         const uint32_t jt = (uint32_t)((n + TF_JSON_TILE - 1) / TF_JSON_TILE);
@@ -405,7 +427,7 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         CK(cudaGetLastError());
         return;
     }
-    if (pd.n_str && ntiles) { e->prof_begin("k_str_sizes", s); k_str_sizes<<<dim3((ntiles + TF_STR_GROUP - 1) / TF_STR_GROUP, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
+    if (pd.n_str && ntiles) { e->prof_begin("k_str_sizes", s); k_str_sizes<<<dim3(str_gx, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
     LayoutArgs la{e->d_cols, (int)pl.out_cols.size(), pd.d_out_cols, pd.d_str_slots, pd.n_str, e->tile_sum, e->tile_base, sz.ntiles_cap, pd.d_col_headers, pd.d_col_header_off,
                   e->raw.p, e->d_state, n, 1, e->frame_bytes, e->col_bytes};
     if (pd.n_str) { e->prof_begin("k_layout_scan", s); k_layout_scan<<<pd.n_str, 1024, 0, s>>>(la); e->prof_end(s); }
@@ -414,11 +436,11 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         if (n) {
             if (pd.n_fixed_slots) {
                 // widest stream is 8 bytes per row: words = 2n (+1 for misalignment)
-                const uint32_t gx = (uint32_t)((2 * n + 2 + TF_FIX_TILE_WORDS - 1) / TF_FIX_TILE_WORDS);
+                const uint32_t gx = grid_cap(e, (uint32_t)((2 * n + 2 + TF_FIX_TILE_WORDS - 1) / TF_FIX_TILE_WORDS), (uint32_t)pd.n_fixed_slots, 6);
                 EncodeArgs fa = ea; fa.slots = pd.d_fixed_slots;
                 e->prof_begin("k_encode_fixed", s); k_encode_fixed<<<dim3(gx, pd.n_fixed_slots), 256, 0, s>>>(fa); e->prof_end(s);
             }
-            if (pd.n_str) { e->prof_begin("k_encode_str_plain", s); k_encode_str_plain<<<dim3((ntiles + TF_STR_GROUP - 1) / TF_STR_GROUP, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
+            if (pd.n_str) { e->prof_begin("k_encode_str_plain", s); k_encode_str_plain<<<dim3(str_gx, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
             if (pd.n_str && pd.n_tostr) { e->prof_begin("k_encode_str", s); k_encode_str<<<dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
             if (pd.n_mask_cols) {
                 MaskArgs ma{e->d_cols, pd.d_mask_slots, pd.d_mask_keys, sel, e->d_state, e->raw.p, 0};
@@ -445,7 +467,7 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         e->prof_begin("k_layout_columnar", s); k_layout_columnar<<<1, 256, 0, s>>>(la, e->d_regions); e->prof_end(s);
         if (n) {
             if (!fixed.empty()) {
-                const uint32_t gx = (uint32_t)((2 * n + 2 + TF_FIX_TILE_WORDS - 1) / TF_FIX_TILE_WORDS);
+                const uint32_t gx = grid_cap(e, (uint32_t)((2 * n + 2 + TF_FIX_TILE_WORDS - 1) / TF_FIX_TILE_WORDS), (uint32_t)fixed.size(), 6);
                 EncodeArgs fa = ea; fa.slots = e->d_call_slots;
                 e->prof_begin("k_encode_fixed", s); k_encode_fixed<<<dim3(gx, (uint32_t)fixed.size()), 256, 0, s>>>(fa); e->prof_end(s);
             }
@@ -453,7 +475,7 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
                 EncodeArgs va = ea; va.slots = e->d_call_slots + fixed.size();
                 e->prof_begin("k_pack_validity", s); k_pack_validity<<<dim3((uint32_t)((n / 8 + 256) / 256), (uint32_t)valid.size()), 256, 0, s>>>(va); e->prof_end(s);
             }
-            if (pd.n_str) { e->prof_begin("k_encode_str_plain", s); k_encode_str_plain<<<dim3((ntiles + TF_STR_GROUP - 1) / TF_STR_GROUP, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
+            if (pd.n_str) { e->prof_begin("k_encode_str_plain", s); k_encode_str_plain<<<dim3(str_gx, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
             if (pd.n_str && pd.n_tostr) { e->prof_begin("k_encode_str", s); k_encode_str<<<dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
             if (pd.n_mask_cols) {
                 MaskArgs ma{e->d_cols, pd.d_mask_slots, pd.d_mask_keys, sel, e->d_state, e->raw.p, 1};
@@ -721,6 +743,7 @@ static void finish_columnar(tfgpu_engine* e, PlanDev& pd, uint64_t n, tfgpu_resu
     if (!buf) throw std::bad_alloc();
     r->owned.push_back(buf);
     if (st.raw_total) CK(cudaMemcpyAsync(buf, e->raw.p, st.raw_total, cudaMemcpyDeviceToHost, s));
+    if (e->last_has_sharder && st.n_kept) { r->part_ids.resize(st.n_kept); CK(cudaMemcpyAsync(r->part_ids.data(), e->part_ids.p, st.n_kept * 4, cudaMemcpyDeviceToHost, s)); }
     CK(cudaStreamSynchronize(s));
     if (st.n_errors) fetch_errors(e, n, r);
     r->cols.resize(no);
@@ -751,6 +774,7 @@ static void finish_wire(tfgpu_engine* e, uint64_t n, int wire_fmt, tfgpu_result*
     { const int b = wire_fmt & 0xff;
       if ((b == TF_WIRE_SER_JSON || b == TF_WIRE_SER_CSV || b == TF_WIRE_CH_JSONEACHROW || b == TF_WIRE_DEBEZIUM) && st.n_kept) { r->row_sizes.resize(st.n_kept); CK(cudaMemcpyAsync(r->row_sizes.data(), e->json_sizes.p, st.n_kept * 4, cudaMemcpyDeviceToHost, s)); }
       if (b == TF_WIRE_DEBEZIUM && st.n_kept) { r->key_sizes.resize(st.n_kept); CK(cudaMemcpyAsync(r->key_sizes.data(), e->dbz_keysz.p, st.n_kept * 4, cudaMemcpyDeviceToHost, s)); } }
+    if (e->last_has_sharder && st.n_kept) { r->part_ids.resize(st.n_kept); CK(cudaMemcpyAsync(r->part_ids.data(), e->part_ids.p, st.n_kept * 4, cudaMemcpyDeviceToHost, s)); }
     if (st.n_errors) fetch_errors(e, n, r);
     CK(cudaStreamSynchronize(s));
 }
@@ -1379,6 +1403,7 @@ const uint8_t* tfgpu_result_bytes(const tfgpu_result* r) { return r ? r->bytes :
 uint64_t tfgpu_result_bytes_len(const tfgpu_result* r) { return r ? r->bytes_len : 0; }
 uint64_t tfgpu_result_raw_len(const tfgpu_result* r) { return r ? r->raw_len : 0; }
 uint64_t tfgpu_result_n_frames(const tfgpu_result* r) { return r ? r->n_frames : 0; }
+const uint32_t* tfgpu_result_part_ids(const tfgpu_result* r) { return (r && !r->part_ids.empty()) ? r->part_ids.data() : nullptr; }
 const uint32_t* tfgpu_result_key_sizes(const tfgpu_result* r) { return (r && !r->key_sizes.empty()) ? r->key_sizes.data() : nullptr; }
 const uint32_t* tfgpu_result_row_sizes(const tfgpu_result* r) { return (r && !r->row_sizes.empty()) ? r->row_sizes.data() : nullptr; }
 

@@ -60,6 +60,7 @@ def load_library():
     L.tfgpu_parse_csv.argtypes = [vp, i, cp, vp, u64, i, i, C.POINTER(vp)]
     L.tfgpu_result_row_sizes.argtypes = [vp]; L.tfgpu_result_row_sizes.restype = C.POINTER(C.c_uint32)
     L.tfgpu_result_key_sizes.argtypes = [vp]; L.tfgpu_result_key_sizes.restype = C.POINTER(C.c_uint32)
+    L.tfgpu_result_part_ids.argtypes = [vp]; L.tfgpu_result_part_ids.restype = C.POINTER(C.c_uint32)
     L.tfgpu_emit_debezium.argtypes = [vp, i, cp, C.POINTER(abi.TfBatch), C.POINTER(abi.TfRowMeta), C.POINTER(vp)]
     L.tfgpu_queue_json_batches.argtypes = [vp, u64, u64, u64, vp, u64, C.POINTER(u64)]
     L.tfgpu_parse_debezium.argtypes = [vp, i, cp, vp, u64, i, vp, C.c_uint32, i, C.POINTER(vp)]
@@ -87,7 +88,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "tfgpu_version", "tfgpu_engine_create", "tfgpu_engine_destroy", "tfgpu_last_error", "tfgpu_engine_set_stream",
-    "tfgpu_plan", "tfgpu_plan_validate", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_parse_csv", "tfgpu_parse_json", "tfgpu_measure", "tfgpu_emit_debezium", "tfgpu_result_key_sizes", "tfgpu_result_row_sizes", "tfgpu_queue_json_batches", "tfgpu_parse_debezium", "tfgpu_debug_lz4_phases", "tfgpu_result_selection", "tfgpu_result_meta_kinds", "tfgpu_result_meta_tx_id", "tfgpu_result_meta_lsn", "tfgpu_result_meta_commit_time", "tfgpu_result_consumed", "tfgpu_push_encode_resident",
+    "tfgpu_plan", "tfgpu_plan_validate", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_parse_csv", "tfgpu_parse_json", "tfgpu_measure", "tfgpu_emit_debezium", "tfgpu_result_key_sizes", "tfgpu_result_part_ids", "tfgpu_result_row_sizes", "tfgpu_queue_json_batches", "tfgpu_parse_debezium", "tfgpu_debug_lz4_phases", "tfgpu_result_selection", "tfgpu_result_meta_kinds", "tfgpu_result_meta_tx_id", "tfgpu_result_meta_lsn", "tfgpu_result_meta_commit_time", "tfgpu_result_consumed", "tfgpu_push_encode_resident",
     "tfgpu_resident_stats", "tfgpu_resident_fetch", "tfgpu_result_rows_in", "tfgpu_result_rows_out",
     "tfgpu_result_n_errors", "tfgpu_result_errors", "tfgpu_result_batch", "tfgpu_result_bytes",
     "tfgpu_result_bytes_len", "tfgpu_result_raw_len", "tfgpu_result_n_frames", "tfgpu_result_release",
@@ -228,9 +229,16 @@ class Engine:
             out.wire_len = n
             rs = L.tfgpu_result_row_sizes(res)
             out.row_sizes = [int(rs[k]) for k in range(out.rows_out)] if rs else None
+            out.part_ids = self._part_ids(res, out.rows_out)
             return out
         finally:
             self._L.tfgpu_result_release(res)
+
+    def _part_ids(self, res, rows_out):
+        """sharder_transformer: ChangeItem.PartID of every output row as an integer (numpy uint32), None without a sharder."""
+        import numpy as np
+        pp = self._L.tfgpu_result_part_ids(res)
+        return np.ctypeslib.as_array(pp, shape=(int(rows_out),)).copy() if (pp and rows_out) else None
 
     def _result_batch(self, res):
         import numpy as np
@@ -257,7 +265,9 @@ class Engine:
                                                aux=arr(c.aux, 4 * n, np.uint32)))
             ne = L.tfgpu_result_n_errors(res); ep = L.tfgpu_result_errors(res)
             errs = [(ep[k].row, ep[k].code, ep[k].term) for k in range(ne)]
-            return abi.Batch(n, cols), errs
+            out = abi.Batch(n, cols)
+            self.last_part_ids = self._part_ids(res, n)       # of the batch just returned (push_columns / parsers)
+            return out, errs
 
     def push_columns(self, plan_id: int, batch: abi.Batch) -> Tuple[abi.Batch, List[Tuple[int, int, int]]]:
         """Transformer chain only: (Transformed rows as a host Batch, row errors) — abstract.TransformerResult."""
