@@ -674,15 +674,35 @@ __device__ int jsn_fixed_cell(const JsnArgs& a, const JsnColDev& cd, const uint8
     v = num ? d_ff_uint64(s + off, len) : 0; return 0;                             // jsn_store truncates to the column width
 }
 
+// The lines of one CTA are a contiguous span of the input. One thread per line walks its own line byte by byte, so straight from
+// global memory every load instruction of a warp touches 32 different cache lines; the CTA therefore first copies its span into
+// shared memory with coalesced 16-byte loads (when it fits) and the per-line code reads that copy through the same offsets.
+#define JSN_STAGE 40960
+__device__ __forceinline__ const uint8_t* jsn_stage_span(const JsnArgs& a, uint8_t* stage) {
+    const uint64_t L0 = (uint64_t)blockIdx.x * blockDim.x;
+    if (L0 >= a.nlines) return a.text;
+    const uint64_t Le = (L0 + blockDim.x < a.nlines) ? L0 + blockDim.x : a.nlines;
+    const uint32_t lo = L0 ? a.line_end[L0 - 1] : 0, hi = a.line_end[Le - 1];
+    const uint32_t lo16 = lo & ~15u;
+    if (hi - lo16 > JSN_STAGE || ((uintptr_t)a.text & 15)) return a.text;           // uniform over the CTA
+    const uint32_t full = (uint32_t)(((a.len < hi ? a.len : hi) - lo16) & ~15ull);    // whole 16-byte chunks inside the buffer
+    for (uint32_t i = threadIdx.x * 16; i < full; i += blockDim.x * 16) *(int4*)(stage + i) = __ldg((const int4*)(a.text + lo16 + i));
+    for (uint32_t i = full + threadIdx.x; lo16 + i < hi; i += blockDim.x) stage[i] = a.text[lo16 + i];
+    __syncthreads();
+    return stage - lo16;
+}
+
 // ------------------------------------------------------------------ pass 1
 __global__ void __launch_bounds__(128) k_json_pass1(JsnArgs a) {
+    extern __shared__ __align__(16) uint8_t jsn_stage[];
+    const uint8_t* const text = jsn_stage_span(a, jsn_stage);
     const uint64_t L = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = L < a.nlines;
     uint32_t vb[JSN_MAX_COLS / 32]; for (int i = 0; i < JSN_MAX_COLS / 32; i++) vb[i] = 0;
     int err = 0, ecol = 0;
     if (active) {
-        uint32_t ls, n; jsn_line(a.text, a.line_end, L, ls, n);
-        const uint8_t* s = a.text + ls;
+        uint32_t ls, n; jsn_line(text, a.line_end, L, ls, n);
+        const uint8_t* s = text + ls;
         const int nf = a.nfields;
         if (!n) err = JSN_EMPTY;
         uint32_t nmembers = 0; bool host = false;
@@ -704,11 +724,11 @@ __global__ void __launch_bounds__(128) k_json_pass1(JsnArgs a) {
             const uint32_t t = sl >> 28, len = sl & 0x0FFFFFFFu;
             bool null = false; int rc = 0;
             if (cd.w) {
-                uint64_t v; rc = jsn_fixed_cell(a, cd, a.text, off, len, t, v, null);
+                uint64_t v; rc = jsn_fixed_cell(a, cd, text, off, len, t, v, null);
                 if (!rc) jsn_store(cd, L, null ? 0 : v, 0);
             } else {
                 if (t == JT_ABSENT || t == JT_NULL) null = true;
-                else { CountSink cs{0}; uint8_t tag; rc = jsn_emit_text(cs, a, cd, a.text, off, len, t, tag); if (!rc) { a.out_len[(size_t)cd.slot * a.nlines + L] = cs.n; if (cd.aux8) cd.aux8[L] = tag; } }
+                else { CountSink cs{0}; uint8_t tag; rc = jsn_emit_text(cs, a, cd, text, off, len, t, tag); if (!rc) { a.out_len[(size_t)cd.slot * a.nlines + L] = cs.n; if (cd.aux8) cd.aux8[L] = tag; } }
                 if (null) { a.out_len[(size_t)cd.slot * a.nlines + L] = 0; if (cd.aux8) cd.aux8[L] = 0; }
             }
             if (rc == JSN_HOST) { err = JSN_HOST; ecol = f; break; }
@@ -756,7 +776,9 @@ __global__ void __launch_bounds__(128) k_json_pass1(JsnArgs a) {
 struct JsnWriteArgs { JsnArgs a; const uint32_t* offsets; uint8_t* heap; const uint64_t* col_base; };
 
 __global__ void __launch_bounds__(128) k_json_pass2(JsnWriteArgs w) {
+    extern __shared__ __align__(16) uint8_t jsn_stage[];
     const JsnArgs& a = w.a;
+    const uint8_t* const text = jsn_stage_span(a, jsn_stage);
     const uint64_t L = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (L >= a.nlines || a.err[L]) return;
     const int nf = a.nfields;
@@ -766,12 +788,12 @@ __global__ void __launch_bounds__(128) k_json_pass2(JsnWriteArgs w) {
         const uint32_t sl = a.span_len[(size_t)f * a.nlines + L]; const uint32_t t = sl >> 28, len = sl & 0x0FFFFFFFu;
         if (t == JT_ABSENT || t == JT_NULL) continue;
         MemSink ms{w.heap + w.col_base[cd.slot] + w.offsets[(size_t)cd.slot * (a.nlines + 1) + L]}; uint8_t tag;      // (short cells: a word-gathering sink measured slower here)
-        jsn_emit_text(ms, a, cd, a.text, a.span_start[(size_t)f * a.nlines + L], len, t, tag);
+        jsn_emit_text(ms, a, cd, text, a.span_start[(size_t)f * a.nlines + L], len, t, tag);
     }
     int c = nf;
     if (a.add_rest) {
         const JsnColDev& cd = a.cols[c];
-        uint32_t ls, n; jsn_line(a.text, a.line_end, L, ls, n); const uint8_t* s = a.text + ls;
+        uint32_t ls, n; jsn_line(text, a.line_end, L, ls, n); const uint8_t* s = text + ls;
         uint32_t b = 0; while (b < n && jsn_ws(s[b])) b++;
         uint32_t e = n; while (e > b && jsn_ws(s[e - 1])) e--;
         MemSink ms{w.heap + w.col_base[cd.slot] + w.offsets[(size_t)cd.slot * (a.nlines + 1) + L]};

@@ -392,22 +392,17 @@ __global__ void __launch_bounds__(32) k_frame_seal(FrameArgs a) {
     const uint64_t f = (uint64_t)blockIdx.x * 32 + lane;
     const bool have = f < nf;
     uint8_t* s = a.slots + (have ? f : 0) * a.slot_stride;
-    uint32_t cs = 0;
-    if (have) {
-        cs = a.comp_size[f] + 9;
-        const uint64_t pos0 = f * a.frame_bytes;
-        const uint32_t rs = (uint32_t)((a.st->raw_total - pos0 < a.frame_bytes) ? a.st->raw_total - pos0 : a.frame_bytes);
-        // bytes 16..31 of the slot as two aligned words: [0x82][cs][rs] + the first 7 bytes of the LZ4 block (kept)
-        uint64_t* q = (uint64_t*)(s + 16);
-        const uint64_t w0 = 0x82ull | ((uint64_t)cs << 8) | ((uint64_t)(rs & 0xffffff) << 40);
-        const uint64_t w1 = (q[1] & ~0xffull) | (uint64_t)(rs >> 24);
-        q[0] = w0; q[1] = w1;
-        __threadfence_block();
-    }
-    __syncwarp();
+    // the 9 header bytes [0x82][cs][rs] at slot + 16 were written by k_frame_scan; the checksum goes straight into the wire
+    // buffer (k_wire_gather copies everything after it, concurrently, on the side stream)
+    const uint32_t cs = have ? a.comp_size[f] + 9 : 0;
+    uint8_t* wck = a.wire + (have ? a.wire_off[f] : 0);
+    auto put_checksum = [&](uint64_t lo, uint64_t hi) {
+#pragma unroll
+        for (int b = 0; b < 8; b++) { wck[b] = (uint8_t)(lo >> (8 * b)); wck[8 + b] = (uint8_t)(hi >> (8 * b)); }
+    };
     const uint8_t* H = s + 16;
     const bool big = have && cs >= 16 + 128 + 16;
-    if (have && !big) { const cityd::P h = cityd::hash128(H, cs); ((uint64_t*)s)[0] = h.first; ((uint64_t*)s)[1] = h.second; }
+    if (have && !big) { const cityd::P h = cityd::hash128(H, cs); put_checksum(h.first, h.second); }
     const uint8_t* body = H + 16; const uint32_t len = big ? cs - 16 : 0;
     const uint32_t nblk = len / 128, used = nblk * 128;
     const uint32_t nsteps = (used + SEAL_STEP - 1) / SEAL_STEP;
@@ -482,12 +477,12 @@ __global__ void __launch_bounds__(32) k_frame_seal(FrameArgs a) {
             v = cityd::weak32(t64(base), t64(base + 8), t64(base + 16), t64(base + 24), v.first, v.second);
         }
         x = cityd::hl16(x, v.first); y = cityd::hl16(y, w.first);
-        ((uint64_t*)s)[0] = cityd::hl16(x + v.second, w.second) + y;
-        ((uint64_t*)s)[1] = cityd::hl16(x + w.second, y + v.second);
+        put_checksum(cityd::hl16(x + v.second, w.second) + y, cityd::hl16(x + w.second, y + v.second));
     }
 }
 
-// exclusive scan of frame sizes (single block) -> position of every frame in the wire buffer
+// exclusive scan of frame sizes (single block) -> position of every frame in the wire buffer; also stamps the 9-byte
+// [method][sizes] header of every frame, which both the checksum (k_frame_seal) and the gather read
 __global__ void __launch_bounds__(1024) k_frame_scan(FrameArgs a) {
     __shared__ uint32_t sm[33];
     const uint64_t nf = a.st->n_frames;
@@ -496,7 +491,16 @@ __global__ void __launch_bounds__(1024) k_frame_scan(FrameArgs a) {
         const uint64_t i = base + threadIdx.x;
         const uint32_t v = i < nf ? a.comp_size[i] + LZ_HDR : 0;
         uint32_t tot; const uint32_t ex = block_excl_scan(v, &tot, sm);
-        if (i < nf) a.wire_off[i] = carry + ex;
+        if (i < nf) {
+            a.wire_off[i] = carry + ex;
+            // bytes 16..31 of the slot as two aligned words: [0x82][compressed size + 9][raw size] + the first 7 bytes of the LZ4 block (kept)
+            const uint32_t cs = v - LZ_HDR + 9;
+            const uint64_t pos0 = i * a.frame_bytes;
+            const uint32_t rs = (uint32_t)((a.st->raw_total - pos0 < a.frame_bytes) ? a.st->raw_total - pos0 : a.frame_bytes);
+            uint64_t* q = (uint64_t*)(a.slots + i * a.slot_stride + 16);
+            q[0] = 0x82ull | ((uint64_t)cs << 8) | ((uint64_t)(rs & 0xffffff) << 40);
+            q[1] = (q[1] & ~0xffull) | (uint64_t)(rs >> 24);
+        }
         carry += tot;
     }
     if (threadIdx.x == 0) a.st->wire_total = carry;
@@ -513,16 +517,16 @@ __global__ void __launch_bounds__(256) k_wire_gather(FrameArgs a) {
         const uint32_t m = (uint32_t)(base & 3);
         const uint32_t T = (m + total + 3) >> 2;
         uint8_t* dst0 = a.wire + (base - m);
-        for (uint32_t t = threadIdx.x; t < T; t += blockDim.x) {
+        for (uint32_t t = 4 + threadIdx.x; t < T; t += blockDim.x) {       // words 0..3 hold only checksum bytes (m <= 3: word 3 ends at stream byte <= 15)
             const uint32_t wcur = src[t];                       // slot has >= 8 bytes of slack past the block
             const uint32_t wprev = t ? src[t - 1] : 0;
             const uint32_t val = m ? __funnelshift_r(wprev, wcur, 8 * (4 - m)) : wcur;
             const int32_t sb = (int32_t)(4 * t) - (int32_t)m;
             uint8_t* dst = dst0 + 4 * (uint64_t)t;
-            if (sb >= 0 && (uint32_t)sb + 4 <= total) *(uint32_t*)dst = val;
+            if (sb >= 16 && (uint32_t)sb + 4 <= total) *(uint32_t*)dst = val;          // bytes [0, 16) are the checksum: k_frame_seal writes them
             else {
 #pragma unroll
-                for (int b = 0; b < 4; b++) { const int32_t x = sb + b; if (x >= 0 && (uint32_t)x < total) dst[b] = (uint8_t)(val >> (8 * b)); }
+                for (int b = 0; b < 4; b++) { const int32_t x = sb + b; if (x >= 16 && (uint32_t)x < total) dst[b] = (uint8_t)(val >> (8 * b)); }
             }
         }
     }

@@ -434,6 +434,8 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
     if (!columnar) {
         e->prof_begin("k_layout_finish", s); k_layout_finish<<<1, 256, 0, s>>>(la); e->prof_end(s);
         if (n) {
+            // (the fixed-width streams and the String columns write disjoint parts of the block, but running them on two streams
+            // was measured slower: both are latency-bound gathers that already fill the SMs: 0.087 + 0.182 ms in sequence, 0.30 ms side by side)
             if (pd.n_fixed_slots) {
                 // widest stream is 8 bytes per row: words = 2n (+1 for misalignment)
                 const uint32_t gx = grid_cap(e, (uint32_t)((2 * n + 2 + TF_FIX_TILE_WORDS - 1) / TF_FIX_TILE_WORDS), (uint32_t)pd.n_fixed_slots, 6);
@@ -490,9 +492,15 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         const uint32_t grid = (uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * per_sm);
         e->prof_begin("k_lz4_frames", s); k_lz4_frames<<<grid, LZ_THREADS, smem, s>>>(za); e->prof_end(s);
         FrameArgs fa{e->slots.p, stride, e->comp_size, e->d_state, e->frame_bytes, e->wire_off, e->wire.p};
-        e->prof_begin("k_frame_seal", s); k_frame_seal<<<(uint32_t)((sz.n_frames_max + 31) / 32), 32, SEAL_SMEM, s>>>(fa); e->prof_end(s);
+        // frame offsets + [method][sizes] headers first; then the checksum chain (one thread per frame: latency-bound, a few warps
+        // per SM) and the gather of everything behind the checksum run side by side on two streams
         e->prof_begin("k_frame_scan", s); k_frame_scan<<<1, 1024, 0, s>>>(fa); e->prof_end(s);
-        e->prof_begin("k_wire_gather", s); k_wire_gather<<<(uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * 8), 256, 0, s>>>(fa); e->prof_end(s);
+        cudaStream_t s2 = e->side_stream ? e->side_stream : s;
+        if (s2 != s) { CK(cudaEventRecord(e->ev_fork, s)); CK(cudaStreamWaitEvent(s2, e->ev_fork, 0)); }
+        e->prof_begin("k_wire_gather", s2); k_wire_gather<<<(uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * 8), 256, 0, s2>>>(fa); e->prof_end(s2);
+        if (s2 != s) CK(cudaEventRecord(e->ev_join, s2));
+        e->prof_begin("k_frame_seal", s); k_frame_seal<<<(uint32_t)((sz.n_frames_max + 31) / 32), 32, SEAL_SMEM, s>>>(fa); e->prof_end(s);
+        if (s2 != s) CK(cudaStreamWaitEvent(s, e->ev_join, 0));
     }
     CK(cudaGetLastError());
 }
@@ -1197,7 +1205,7 @@ int tfgpu_parse_json(tfgpu_engine* e, int plan_id, const char* opts_json, const 
                 ja.part_off = part_off; ja.part_len = (uint32_t)partition.size();
                 ja.span_start = (uint32_t*)(B + o_ss); ja.span_len = (uint32_t*)(B + o_sl); ja.out_len = (uint32_t*)(B + o_len);
                 ja.err = B + o_err; ja.errcol = B + o_ecol;
-                e->prof_begin("k_json_pass1", s); k_json_pass1<<<nlb, 128, 0, s>>>(ja); e->prof_end(s);
+                e->prof_begin("k_json_pass1", s); k_json_pass1<<<nlb, 128, JSN_STAGE, s>>>(ja); e->prof_end(s);
                 CK(cudaMemcpyAsync(&n_nonempty, (uint32_t*)(B + o_rank) + nlines, 4, cudaMemcpyDeviceToHost, s));
                 if (nslots) {
                     launch_offsets(e, (const uint32_t*)(B + o_len), nrows, (uint32_t)nslots, (uint32_t*)(B + o_off), (uint64_t*)(B + o_tot), s);
@@ -1208,7 +1216,7 @@ int tfgpu_parse_json(tfgpu_engine* e, int plan_id, const char* opts_json, const 
                     heap = e->in_arena.p;
                     CK(cudaMemcpyAsync(B + o_base, col_base.data(), (size_t)nslots * 8, cudaMemcpyHostToDevice, s));
                     JsnWriteArgs wa{ja, (const uint32_t*)(B + o_off), e->in_arena.p, (const uint64_t*)(B + o_base)};
-                    e->prof_begin("k_json_pass2", s); k_json_pass2<<<nlb, 128, 0, s>>>(wa); e->prof_end(s);
+                    e->prof_begin("k_json_pass2", s); k_json_pass2<<<nlb, 128, JSN_STAGE, s>>>(wa); e->prof_end(s);
                 } else CK(cudaStreamSynchronize(s));
             }
             // ---- the staged batch, device resident
