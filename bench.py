@@ -306,6 +306,7 @@ def main():
         # per-kernel events of this step are read after the loop for the last step only; to average over the
         # timed region without syncing inside it, the engine keeps one event pair per kernel per call and we
         # read them once per step boundary below (the read syncs the stream, so do it outside timing)
+    eng.resident_stats()      # orders the stream after the last batch's checksum / gather tail (side streams): the K steps are complete
     ev1.record()
     torch.cuda.synchronize()
     sampler.mark_end()

@@ -229,6 +229,32 @@ def test_resident_path_equals_host_path(eng, po):
     assert raw == ref and nf == host.n_frames
 
 
+def test_resident_batches_back_to_back(eng, po):
+    """The checksum / gather tail of a resident LZ4 batch stays in flight while the next batch's kernels start: two different
+    batches of the same shape pushed without a sync in between, then a third call in another format; every fetch must see the
+    complete frames of the batch pushed last (checksums verified by the frame walk)."""
+    b1, schema = workload.make_hits_batch(40_000, seed=5)
+    b2, _ = workload.make_hits_batch(40_000, seed=6)
+    trs = workload.headline_transformers(workload.counterid_threshold(b1, schema))
+    pid = eng.plan("public", "hits", schema, trs, {"type": "clickhouse"})
+    plan = po.build_plan("public", "hits", schema, trs)
+    d1, d2 = b1.to_device("cuda:0"), b2.to_device("cuda:0")
+    for _ in range(3):
+        eng.push_encode_resident(pid, d1, LZ); eng.push_encode_resident(pid, d2, LZ); eng.push_encode_resident(pid, d1, LZ); eng.push_encode_resident(pid, d2, LZ)
+    st = eng.resident_stats()
+    ref2 = po.push_encode(b2, plan, RAW).raw
+    raw, nf = decode_with_liblz4(eng.resident_fetch(1, st["wire_bytes"]), po)
+    assert raw == ref2
+    eng.push_encode_resident(pid, d1, LZ)
+    got = eng.push_encode(pid, b2, RAW)                 # a synchronous call in another format right behind a pending tail
+    assert got.wire == ref2
+    eng.push_encode_resident(pid, d1, LZ)
+    small = b1.slice(0, 1000)                           # another layout of the work arena: the tail is joined first
+    host = eng.push_encode(pid, small, LZ)
+    raw, _ = decode_with_liblz4(host.wire, po)
+    assert raw == po.push_encode(small, plan, RAW).raw
+
+
 @pytest.mark.parametrize("frame_bytes", [1024, 4096, 16384])
 def test_other_frame_sizes(po, frame_bytes):
     e = engine.Engine(0, frame_bytes)

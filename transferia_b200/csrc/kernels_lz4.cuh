@@ -364,7 +364,8 @@ __device__ P hash128(const uint8_t* s, size_t len) {
 }
 }  // namespace cityd
 
-struct FrameArgs { uint8_t* slots; uint32_t slot_stride; const uint32_t* comp_size; DState* st; uint32_t frame_bytes; uint64_t* wire_off; uint8_t* wire; };
+struct FrameArgs { uint8_t* slots; uint32_t slot_stride; const uint32_t* comp_size; DState* st; uint32_t frame_bytes; uint64_t* wire_off; uint8_t* wire;
+                   uint64_t* tail; };   // tail[0] = frame count, written by k_frame_scan: the checksum / gather kernels of this batch may still run when the next batch resets DState
 
 // CityHash128 is a serial chain per frame, so the parallelism is ACROSS frames: one thread per frame. What a
 // thread-per-frame loop would ruin is the memory access (every lane striding through its own frame), so each
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(32) k_frame_seal(FrameArgs a) {
     uint8_t (*s_buf)[32][SEAL_STRIDE] = (uint8_t (*)[32][SEAL_STRIDE])seal_smem;                                  // [SEAL_STAGES][32][SEAL_STRIDE]
     uint8_t (*s_tail)[304] = (uint8_t (*)[304])(seal_smem + (size_t)SEAL_STAGES * 32 * SEAL_STRIDE);              // [32][304]
     const uint32_t lane = threadIdx.x;
-    const uint64_t nf = a.st->n_frames;
+    const uint64_t nf = a.tail[0];
     const uint64_t f = (uint64_t)blockIdx.x * 32 + lane;
     const bool have = f < nf;
     uint8_t* s = a.slots + (have ? f : 0) * a.slot_stride;
@@ -503,13 +504,13 @@ __global__ void __launch_bounds__(1024) k_frame_scan(FrameArgs a) {
         }
         carry += tot;
     }
-    if (threadIdx.x == 0) a.st->wire_total = carry;
+    if (threadIdx.x == 0) { a.st->wire_total = carry; a.tail[0] = nf; }
 }
 
 // gather the sealed frames into one contiguous stream; source slots are 16-byte aligned, the destination
 // is re-aligned with the same shuffle + funnel-shift trick as k_encode_fixed so stores are aligned words
 __global__ void __launch_bounds__(256) k_wire_gather(FrameArgs a) {
-    const uint64_t nf = a.st->n_frames;
+    const uint64_t nf = a.tail[0];
     for (uint64_t f = blockIdx.x; f < nf; f += gridDim.x) {
         const uint32_t* src = (const uint32_t*)(a.slots + f * a.slot_stride);
         const uint32_t total = a.comp_size[f] + LZ_HDR;

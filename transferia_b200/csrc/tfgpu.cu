@@ -67,6 +67,11 @@ struct tfgpu_engine {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr, side_stream = nullptr;   // side_stream: string encode runs beside the fixed-width encode
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // The checksum chain and the wire gather of an LZ4 batch run on two side streams and are NOT joined at the end of the call: the
+    // next batch's filter / encode kernels overlap them (they only wait before they reuse the frame slots). join_tail() orders the
+    // main stream after them; every path that reads results, changes layout or leaves the LZ4 format calls it.
+    cudaStream_t side2_stream = nullptr; cudaEvent_t ev_tail2 = nullptr; bool tail_pending = false; uint64_t tail_nrows = 0; const void* tail_plan = nullptr;
+    uint64_t* d_tail = nullptr;
     std::string last_error;
     uint64_t launches = 0;
     uint32_t frame_bytes = 32768;
@@ -113,6 +118,11 @@ struct tfgpu_result {
 
 namespace {
 
+void join_tail(tfgpu_engine* e) {
+    if (!e->tail_pending) return;
+    CK(cudaStreamWaitEvent(e->stream, e->ev_join, 0)); CK(cudaStreamWaitEvent(e->stream, e->ev_tail2, 0));
+    e->tail_pending = false;
+}
 int fail(tfgpu_engine* e, int code, const std::string& msg) { if (e) e->last_error = msg; return code; }
 int cuda_fail(tfgpu_engine* e, const CudaError& c) {
     std::string m = std::string("CUDA error: ") + cudaGetErrorString(c.e) + " in " + c.what;
@@ -321,6 +331,8 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "serializer sinks after convert_to_string on an `any` column are not handled on the device");
     const Sizes sz = compute_sizes(e, pd, in, columnar, json_rows);
     cudaStream_t s = e->stream;
+    // a pending checksum / gather tail may only stay in flight across a call that lays the work arena out identically
+    if (e->tail_pending && !(wire_fmt == TF_WIRE_CH_NATIVE_LZ4 && n == e->tail_nrows && (const void*)&pd == e->tail_plan)) join_tail(e);
     // work arena
     size_t wbytes = 0;
     auto need = [&](size_t b) { wbytes += align_up(b ? b : 1, 256); };
@@ -490,17 +502,19 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         const size_t smem = lz_data_bytes(e->frame_bytes) + 2 * (size_t)e->frame_bytes + (4u << LZ_HASH_BITS) + e->frame_bytes / 8 + 64 * 4;
         const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (smem + 1024)));
         const uint32_t grid = (uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * per_sm);
+        join_tail(e);            // the previous batch's checksum / gather still read the slots and sizes this kernel overwrites
         e->prof_begin("k_lz4_frames", s); k_lz4_frames<<<grid, LZ_THREADS, smem, s>>>(za); e->prof_end(s);
-        FrameArgs fa{e->slots.p, stride, e->comp_size, e->d_state, e->frame_bytes, e->wire_off, e->wire.p};
+        FrameArgs fa{e->slots.p, stride, e->comp_size, e->d_state, e->frame_bytes, e->wire_off, e->wire.p, e->d_tail};
         // frame offsets + [method][sizes] headers first; then the checksum chain (one thread per frame: latency-bound, a few warps
         // per SM) and the gather of everything behind the checksum run side by side on two streams
         e->prof_begin("k_frame_scan", s); k_frame_scan<<<1, 1024, 0, s>>>(fa); e->prof_end(s);
-        cudaStream_t s2 = e->side_stream ? e->side_stream : s;
-        if (s2 != s) { CK(cudaEventRecord(e->ev_fork, s)); CK(cudaStreamWaitEvent(s2, e->ev_fork, 0)); }
+        cudaStream_t s2 = e->side_stream, s3 = e->side2_stream;
+        CK(cudaEventRecord(e->ev_fork, s)); CK(cudaStreamWaitEvent(s2, e->ev_fork, 0)); CK(cudaStreamWaitEvent(s3, e->ev_fork, 0));
+        e->prof_begin("k_frame_seal", s3); k_frame_seal<<<(uint32_t)((sz.n_frames_max + 31) / 32), 32, SEAL_SMEM, s3>>>(fa); e->prof_end(s3);
+        CK(cudaEventRecord(e->ev_tail2, s3));
         e->prof_begin("k_wire_gather", s2); k_wire_gather<<<(uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * 8), 256, 0, s2>>>(fa); e->prof_end(s2);
-        if (s2 != s) CK(cudaEventRecord(e->ev_join, s2));
-        e->prof_begin("k_frame_seal", s); k_frame_seal<<<(uint32_t)((sz.n_frames_max + 31) / 32), 32, SEAL_SMEM, s>>>(fa); e->prof_end(s);
-        if (s2 != s) CK(cudaStreamWaitEvent(s, e->ev_join, 0));
+        CK(cudaEventRecord(e->ev_join, s2));
+        e->tail_pending = true; e->tail_nrows = n; e->tail_plan = (const void*)&pd;      // joined by whoever needs the wire bytes, or by the next batch before its LZ4
     }
     CK(cudaGetLastError());
 }
@@ -538,6 +552,9 @@ int tfgpu_engine_create(const char* cfg_json, const int* device_ids, int n_devic
         CK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
         e->stream = e->own_stream;
         CK(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&e->side2_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&e->ev_tail2, cudaEventDisableTiming));
+        CK(cudaMalloc(&e->d_tail, 64)); CK(cudaMemset(e->d_tail, 0, 64));
         CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
         CK(cudaMalloc(&e->d_state, sizeof(DState)));
         CK(cudaFuncSetAttribute(k_lz4_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024));
@@ -561,6 +578,10 @@ int tfgpu_engine_destroy(tfgpu_engine* e) {
     for (auto ev : e->prof_ev) cudaEventDestroy(ev);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->ev_tail2) cudaEventDestroy(e->ev_tail2);
+    if (e->side2_stream) cudaStreamDestroy(e->side2_stream);
+    if (e->d_tail) cudaFree(e->d_tail);
+    e->dbz_keysz.release(); e->dbz_meta.release(); e->part_ids.release();
     if (e->side_stream) cudaStreamDestroy(e->side_stream);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
@@ -575,6 +596,7 @@ int tfgpu_profile_enable(tfgpu_engine* e, int on) { if (!e) return TF_E_FATAL_AR
 const char* tfgpu_profile_read(tfgpu_engine* e) {
     if (!e) return nullptr;
     cudaSetDevice(e->device);
+    try { join_tail(e); } catch (const CudaError&) {}
     cudaStreamSynchronize(e->stream);
     std::string j = "[";
     for (int i = 0; i < e->prof_n; i++) {
@@ -587,6 +609,7 @@ const char* tfgpu_profile_read(tfgpu_engine* e) {
 
 int tfgpu_engine_set_stream(tfgpu_engine* e, void* cuda_stream) {
     if (!e) return TF_E_FATAL_ARG;
+    if (e->tail_pending) { cudaSetDevice(e->device); cudaStreamSynchronize(e->side_stream); cudaStreamSynchronize(e->side2_stream); e->tail_pending = false; }
     e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
     return TF_OK;
 }
@@ -648,6 +671,7 @@ int tfgpu_resident_stats(tfgpu_engine* e, uint64_t* rows_out, uint64_t* raw_byte
     if (!e) return TF_E_FATAL_ARG;
     try {
         CK(cudaSetDevice(e->device));
+        join_tail(e);
         DState st; CK(cudaMemcpyAsync(&st, e->d_state, sizeof st, cudaMemcpyDeviceToHost, e->stream)); CK(cudaStreamSynchronize(e->stream));
         if (rows_out) *rows_out = st.n_kept; if (raw_bytes) *raw_bytes = st.raw_total;
         if (wire_bytes) *wire_bytes = e->last_wire_fmt == TF_WIRE_CH_NATIVE_LZ4 ? st.wire_total : st.raw_total;
@@ -660,6 +684,7 @@ int tfgpu_resident_fetch(tfgpu_engine* e, int what, uint8_t* dst, uint64_t cap) 
     if (!e || !dst) return TF_E_FATAL_ARG;
     try {
         CK(cudaSetDevice(e->device));
+        join_tail(e);
         DState st; CK(cudaMemcpyAsync(&st, e->d_state, sizeof st, cudaMemcpyDeviceToHost, e->stream)); CK(cudaStreamSynchronize(e->stream));
         const bool wire = what == 1 && e->last_wire_fmt == TF_WIRE_CH_NATIVE_LZ4;
         const uint64_t n = wire ? st.wire_total : st.raw_total;
@@ -767,6 +792,7 @@ static void finish_columnar(tfgpu_engine* e, PlanDev& pd, uint64_t n, tfgpu_resu
 
 static void finish_wire(tfgpu_engine* e, uint64_t n, int wire_fmt, tfgpu_result* r) {
     cudaStream_t s = e->stream;
+    join_tail(e);
     DState st; CK(cudaMemcpyAsync(&st, e->d_state, sizeof st, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
     r->rows_in = n; r->rows_out = st.n_kept; r->raw_len = st.raw_total;
     const bool lz = wire_fmt == TF_WIRE_CH_NATIVE_LZ4;
