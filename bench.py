@@ -33,7 +33,7 @@ METRIC = "ChangeItems/sec on ClickBench-shaped 99-col batches (filter_rows + cas
 FALLBACK_HBM_GBS = 6650.0
 
 
-TRAFFIC_PROFILE = "profiles/r1d_traffic.json"   # written by scripts/ncu_summary.py from the capture under profiles/
+TRAFFIC_PROFILE = "profiles/r1e_traffic.json"   # written by scripts/ncu_summary.py from the capture under profiles/
 
 
 def load_peaks():
@@ -400,6 +400,7 @@ def main():
                          "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(lz_bytes), "kernel_ms": lz_ms,
                          "kernel_share_of_step": lz_ms / step_ms if step_ms else None,
+                         "kernel_share_basis": "sum of the per-kernel CUDA-event times (as in the serialised ncu launch list); k_frame_seal and k_wire_gather overlap the next step on side streams, so that sum exceeds ms_per_step",
                          "all_kernels_ms": {n: round(v, 4) for n, v in sorted(kernel_avg.items())}},
         }
         if world == 1 and not args.no_extra:

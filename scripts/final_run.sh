@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-end style run on one GPU: full GPU suite, smoke, bench (+ reference arm), ncu captures. Every step is hard-killed on timeout.
-TAG=${1:-r1d}
+TAG=${1:-r1e}
 mkdir -p gpurun_out
 timeout -s KILL 500 python -m pytest tests -q -m gpu 2>&1 < /dev/null | tail -8 | cut -c1-400
 timeout -s KILL 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 < /dev/null | tail -2
