@@ -212,27 +212,34 @@ int tfgpu_push_encode(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch
                       tfgpu_result** out);
 
 /* Queue Debezium serializer (pkg/serializer/queue/debezium_serializer.go:25-92 -> debezium.Emitter.EmitKV
- * pkg/debezium/emitter_value_converter.go:566-690; values by addCommon emitter_common.go:67-180, i.e. columns WITHOUT a
- * pg: / mysql: / ydb: original_type). Runs the plan's chain on the device and writes, for every surviving INSERT row, the
- * Kafka key message immediately followed by the value message:
+ * pkg/debezium/emitter_value_converter.go:566-690). Runs the plan's chain on the device and writes, for every surviving INSERT row,
+ * the Kafka key message immediately followed by the value message:
  *   key   = pack({"<pk col>":v,...})                                   (keys sorted: encoding/json map order)
  *   value = pack({"after":{...},"before":null,"op":"c"|"r","source":{...},"transaction":null,"ts_ms":CommitTime/1e6})
  *   pack(p) = p                                        schemas disabled (packer_skip_schema.go)
  *           | {"payload":p,"schema":<schema text>}      packer_include_schema.go:24-44
  *           | 0x00 | u32be schema id | p                packer_schema_registry.go:66-76
  * tfgpu_result_bytes holds the messages back to back; tfgpu_result_row_sizes[j] = key + value bytes of output row j,
- * tfgpu_result_key_sizes[j] = the key part (0 with drop_keys). Values: ints / uints bare, float / double as encoding/json
- * writes float32 / float64, boolean, `string` (bytes) base64, `utf8` JSON string (SetEscapeHTML(false)), datetime /
- * timestamp RFC3339Nano, `any`: Go string as is, object -> its JSON text as a string, JSON null -> null; anything else
- * (date, interval, any arrays / scalars, NaN, years outside [0,9999]) makes EmitKV fail in the reference: the row is
- * reported as TF_ROWERR_SER_VALUE (term = output column) and the shim fails the batch like Serialize does.
+ * tfgpu_result_key_sizes[j] = the key part (0 with drop_keys).
+ * Values, by the column's original_type (emitter_value_converter.go:139-193):
+ *   none              addCommon emitter_common.go:67-180: ints / uints bare, float / double as encoding/json writes float32 / float64,
+ *                     boolean, `string` (bytes) base64, `utf8` JSON string (SetEscapeHTML(false)), datetime / timestamp RFC3339Nano,
+ *                     `any`: Go string as is, object -> its JSON text as a string, JSON null -> null. Needs "ignore_unknown_sources"
+ *                     (without it the reference answers errUnknownSource for such columns, :183-191).
+ *   pg:...            AddPg pkg/debezium/pg/emitter.go:265-629 for boolean, smallint, integer, bigint, real (float32), double
+ *                     precision ("NaN" / "Infinity" strings), text, character[ varying][(n)], uuid, cidr, macaddr, citext, int4range,
+ *                     int8range, bytea (base64), json / jsonb (JSON text as a string), date (days), timestamp[(p)] without time zone
+ *                     (micro- or milliseconds by p), timestamp[(p)] with time zone (ZonedTimestamp string), on the column type the
+ *                     pg source gives them. Other pg types, mysql: / ydb: types, and pg-typed columns a transformer rewrote are
+ *                     refused by the call (TF_E_FATAL_UNSUPPORTED): the table stays on the Go emitter.
+ * A value EmitKV fails on (date / interval without a pg type, `any` arrays / scalars, NaN, years outside [0,9999], a non-string in a
+ * pg string type) is reported as TF_ROWERR_SER_VALUE (term = output column) and the shim fails the batch like Serialize does.
  * UPDATE / DELETE rows need OldKeys, which tf_batch does not carry: TF_ROWERR_DBZ_EMIT_HOST, emitted by the shim in Go.
- * opts_json: {"ignore_unknown_sources":true (required: without it the reference answers errUnknownSource for such columns,
- *   emitter_value_converter.go:183-191), "snapshot":bool, "drop_keys":bool, "source_type":""|"pg"|"mysql", "version":"..",
+ * opts_json: {"ignore_unknown_sources":bool, "snapshot":bool, "drop_keys":bool, "source_type":""|"pg"|"mysql", "version":"..",
  *   "topic_prefix":"..", "database":"..", "key_schema":"<json>"|null, "val_schema":"<json>"|null (what
  *   Emitter.ToKafkaSchemaKey/Val return for the plan's result schema; the lightning cache computes them once per table,
  *   packer/lightning_cache), "key_schema_id":N, "val_schema_id":N (confluent framing instead)}.
- * meta: the ChangeItem fields the envelope's `source` block carries (buildSource :329-372). */
+ * meta: the ChangeItem fields the envelope's `source` block carries (buildSource :329-372), in the memory space of `in`. */
 typedef struct tf_row_meta {
     const uint32_t* id;            /* ChangeItem.ID  -> source.txId (pg); NULL = 0              */
     const uint64_t* lsn;           /* ChangeItem.LSN -> source.lsn (pg) / file + pos (mysql)    */

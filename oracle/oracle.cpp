@@ -750,7 +750,47 @@ extern "C" int orc_push_encode(const tf_batch* in, const orc_colschema* schema, 
 // One column value as addCommon stores it (pkg/debezium/emitter_common.go:67-180) and util.JSONMarshalUnescape then writes it.
 // false: addCommon or the encoder returns an error (EmitKV fails).
 namespace {
-bool dbz_emit_value(std::string& o, const orc_val& v, int32_t yt) {
+// Columns with a pg: original type go through AddPg (pkg/debezium/pg/emitter.go:265-629). `form` names the branch the plan picked
+// for the (original type, column type) pair; the strict columnar layout fixes the Go type of the value (int16 / int32 / int64,
+// bool, float64, string, []byte, time.Time in UTC, `any` JSON).
+enum { DF_COMMON = 0, DF_PG_REAL = 2, DF_PG_DOUBLE = 3, DF_PG_STRING = 4, DF_PG_JSON = 6, DF_PG_DATE = 7, DF_PG_TS_MICROS = 8, DF_PG_TS_MILLIS = 9, DF_PG_TSTZ = 10 };
+bool dbz_emit_value_pg(std::string& o, const orc_val& v, int form) {
+    if (v.kind == OG_NIL) { o += "null"; return true; }                                         // :266-269
+    if (v.kind == OG_JSON && v.slen == 4 && !std::memcmp(v.s, "null", 4)) { o += "null"; return true; }   // a nil interface inside `any`
+    switch (form) {
+    case DF_PG_REAL:                                                                             // :342-356 float32(t)
+        if (v.kind != OG_FLOAT64 && v.kind != OG_FLOAT32) return false;
+        { const float f = (float)v.f; if (std::isnan(f) || std::isinf(f)) return false; o += fmt_f32(f, FMT_JSON); }
+        return true;
+    case DF_PG_DOUBLE:                                                                           // :357-370 convertFloatNanInf :180-191
+        if (v.kind != OG_FLOAT64) return false;
+        if (std::isnan(v.f)) o += "\"NaN\""; else if (std::isinf(v.f)) o += v.f < 0 ? "\"-Infinity\"" : "\"Infinity\""; else o += fmt_f64(v.f, FMT_JSON);
+        return true;
+    case DF_PG_STRING:                                                                           // colVal.(string): text, uuid, cidr, macaddr, citext, character*, int4range / int8range
+        if (v.kind == OG_STRING) { o += go_json_quote_nohtml(v.s, v.slen); return true; }
+        if (v.kind == OG_JSON && v.slen && v.s[0] == '"') { o += json_unescape_html(v.s, v.slen); return true; }
+        return false;                                                                            // the type assertion panics in the reference
+    case DF_PG_JSON: {                                                                           // :377-382 string(JSONMarshalUnescape(colVal))
+        std::string t;
+        if (v.kind == OG_STRING) t = go_json_quote_nohtml(v.s, v.slen);
+        else if (v.kind == OG_JSON) t = json_unescape_html(v.s, v.slen);
+        else return false;
+        o += go_json_quote_nohtml((const uint8_t*)t.data(), t.size()); return true;
+    }
+    case DF_PG_DATE: if (v.kind != OG_TIME) return false; o += fmt_i64(v.i / 86400); return true;            // :476-478 int(t.Unix()/(3600*24))
+    case DF_PG_TS_MICROS: case DF_PG_TS_MILLIS: {                                               // :558-580 ts.Time.UnixMicro() / divider (typeutil/helpers.go:104-120)
+        if (v.kind != OG_TIME) return false;
+        const int64_t micro = v.i * 1000000 + (int64_t)(v.nsec / 1000);
+        o += fmt_i64(form == DF_PG_TS_MILLIS ? micro / 1000 : micro); return true;
+    }
+    case DF_PG_TSTZ:                                                                             // :581-594 SprintfDebeziumTime typeutil/helpers.go:1107-1116
+        if (v.kind != OG_TIME) return false;
+        o += '"'; o += fmt_rfc3339nano_utc(v.i, v.nsec); o += '"'; return true;
+    }
+    return false;
+}
+bool dbz_emit_value(std::string& o, const orc_val& v, int32_t yt, int form = DF_COMMON) {
+    if (form != DF_COMMON) return dbz_emit_value_pg(o, v, form);
     if (v.kind == OG_NIL) { o += "null"; return true; }                                         // :68-71
     const bool sint = v.kind == OG_INT8 || v.kind == OG_INT16 || v.kind == OG_INT32 || v.kind == OG_INT64 || v.kind == OG_INT;
     const bool uint = v.kind == OG_UINT8 || v.kind == OG_UINT16 || v.kind == OG_UINT32 || v.kind == OG_UINT64 || v.kind == OG_UINT;
@@ -806,7 +846,7 @@ std::string dbz_pack(const std::string& payload, const char* schema, int64_t sch
 
 // Emitter.EmitKV for the rows of one batch (pkg/debezium/emitter_value_converter.go:626-690; valPayload :453-512,
 // buildSource :329-372, makeKey / buildKV :259-327). INSERT rows only: update / delete events read ChangeItem.OldKeys.
-extern "C" int orc_debezium_emit(const tf_batch* in, const orc_colschema* schema, const uint8_t* is_key, const orc_step* steps, int nsteps,
+extern "C" int orc_debezium_emit(const tf_batch* in, const orc_colschema* schema, const uint8_t* is_key, const uint8_t* forms, const orc_step* steps, int nsteps,
                                  const tf_row_meta* meta, const orc_dbz_emit_opts* o, orc_buf* out, uint32_t* key_sizes, uint32_t* row_sizes,
                                  uint64_t* rows_out, tf_rowerr* errs, uint64_t* nerrs) {
     const uint32_t nc = in->ncols;
@@ -833,7 +873,7 @@ extern "C" int orc_debezium_emit(const tf_batch* in, const orc_colschema* schema
                 if (keys_only && !is_key[out_cols[k]]) continue;
                 if (!first) t += ','; first = false;
                 t += go_json_quote_nohtml((const uint8_t*)names[k].data(), names[k].size()); t += ':';
-                if (!dbz_emit_value(t, row[out_cols[k]].v, out_type[out_cols[k]])) { t += "null"; if (!row_err) errs[ne++] = tf_rowerr{(uint32_t)r, TF_ROWERR_SER_VALUE, (uint16_t)k}; row_err = true; }
+                if (!dbz_emit_value(t, row[out_cols[k]].v, out_type[out_cols[k]], forms ? forms[out_cols[k]] : 0)) { t += "null"; if (!row_err) errs[ne++] = tf_rowerr{(uint32_t)r, TF_ROWERR_SER_VALUE, (uint16_t)k}; row_err = true; }
             }
             return t + "}";
         };

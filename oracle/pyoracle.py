@@ -976,6 +976,39 @@ class OrcDbzEmitOpts(C.Structure):
 _DBZ_SOURCE = {"": 0, None: 0, "pg": 1, "mysql": 2}
 
 
+_PG_STRING_TYPES = {"pg:text", "pg:uuid", "pg:cidr", "pg:macaddr", "pg:citext", "pg:int4range", "pg:int8range", "pg:character", "pg:character varying"}
+
+
+def debezium_pg_form(col: dict) -> int:
+    """The AddPg branch (pkg/debezium/pg/emitter.go:265-629) the emitter takes for a result column: 0 = addCommon (no original type, or
+    a pg type whose branch stores the typed value unchanged); -1 = a type or (type, column type) pair left to the Go emitter."""
+    import re
+    ot, yt = col.get("original_type") or "", col["type"]
+    if not ot.startswith(("pg:", "mysql:", "ydb:")):
+        return 0
+    same = {"pg:boolean": "boolean", "pg:smallint": "int16", "pg:integer": "int32", "pg:bigint": "int64", "pg:bytea": "string"}
+    if ot in same:
+        return 0 if yt == same[ot] else -1
+    if ot == "pg:real":
+        return 2 if yt in ("double", "float") else -1
+    if ot == "pg:double precision":
+        return 3 if yt == "double" else -1
+    if ot in _PG_STRING_TYPES or re.fullmatch(r"pg:character( varying)?\(\d+\)", ot):
+        return 4 if yt in ("utf8", "any") else -1
+    if ot in ("pg:json", "pg:jsonb"):
+        return 6 if yt == "any" else -1
+    if ot == "pg:date":
+        return 7 if yt == "date" else -1
+    m = re.fullmatch(r"pg:timestamp(?:\((\d)\))? without time zone", ot)
+    if m:
+        if yt != "timestamp":
+            return -1
+        return 9 if (m.group(1) and 1 <= int(m.group(1)) <= 3) else 8          # GetTimeDivider typeutil/helpers.go:104-120
+    if re.fullmatch(r"pg:timestamp(?:\([0-6]\))? with time zone", ot):
+        return 10 if yt == "timestamp" else -1
+    return -1
+
+
 def debezium_emit(batch: abi.Batch, plan: Plan, opts: dict, meta: Optional[dict] = None):
     """Emitter.EmitKV over the INSERT rows of `batch` after the plan's chain (emitter_value_converter.go:626-690).
     Returns (messages bytes, key_sizes, row_sizes, errors); key then value per row."""
@@ -984,8 +1017,13 @@ def debezium_emit(batch: abi.Batch, plan: Plan, opts: dict, meta: Optional[dict]
     tb = batch.as_struct()
     key_by_name = {c["name"]: bool(c.get("key")) for c in plan.result_schema}
     is_key = np.zeros(len(plan.schema), dtype=np.uint8)
+    forms = np.zeros(len(plan.schema), dtype=np.uint8)
     for k, ci in enumerate(plan.out_cols):
         is_key[ci] = 1 if key_by_name.get(plan.result_schema[k]["name"]) else 0
+        f = debezium_pg_form(plan.result_schema[k])
+        if f < 0:
+            raise NotImplementedError(f"column {plan.result_schema[k]['name']}: original type {plan.result_schema[k].get('original_type')} is emitted by the Go emitter")
+        forms[ci] = f
     meta = meta or {}
     m, mkeep = abi.make_row_meta(meta.get("id"), meta.get("lsn"), meta.get("commit_time"), meta.get("txid_offsets"), meta.get("txid_heap"))
     o = OrcDbzEmitOpts()
@@ -1000,9 +1038,9 @@ def debezium_emit(batch: abi.Batch, plan: Plan, opts: dict, meta: Optional[dict]
     ks = np.zeros(max(1, n), dtype=np.uint32); rs = np.zeros(max(1, n), dtype=np.uint32)
     out = OrcBuf(); rows = C.c_uint64(); nerr = C.c_uint64()
     errs = (abi.TfRowErr * max(1, 2 * n))()
-    L.orc_debezium_emit.argtypes = [C.POINTER(abi.TfBatch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(abi.TfRowMeta), C.POINTER(OrcDbzEmitOpts),
+    L.orc_debezium_emit.argtypes = [C.POINTER(abi.TfBatch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(abi.TfRowMeta), C.POINTER(OrcDbzEmitOpts),
                                     C.POINTER(OrcBuf), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_uint64)]
-    rc = L.orc_debezium_emit(C.byref(tb), C.cast(cschema, C.c_void_p), is_key.ctypes.data, C.cast(csteps, C.c_void_p), len(plan.steps), C.byref(m), C.byref(o),
+    rc = L.orc_debezium_emit(C.byref(tb), C.cast(cschema, C.c_void_p), is_key.ctypes.data, forms.ctypes.data, C.cast(csteps, C.c_void_p), len(plan.steps), C.byref(m), C.byref(o),
                              C.byref(out), ks.ctypes.data, rs.ctypes.data, C.byref(rows), C.cast(errs, C.c_void_p), C.byref(nerr))
     if rc != 0:
         raise RuntimeError(f"oracle debezium_emit rc={rc}")

@@ -56,6 +56,78 @@ def test_oracle_against_real_debezium_message(po):
     assert got["txId"] == G["id"] and got["lsn"] == G["lsn"] and got["ts_ms"] == G["commit_time"] // 10**6 and v["ts_ms"] == G["commit_time"] // 10**6
 
 
+def _pg_batch():
+    """The canon ChangeItem's columns whose pg: original type the device emitter takes, as strict typed cells."""
+    import base64
+    schema, cols = [], []
+    for c in G["pg_columns"]:
+        tf = abi.YT_NAME_TO_TF[c["type"]]
+        schema.append({"name": c["name"], "type": c["type"], "key": c["key"], "required": c["required"], "original_type": c["original_type"]})
+        k, v = c["kind"], c["cell"]
+        if k == "time":
+            cols.append(abi.fixed_to_column(tf, [v[0]], None, [v[1]]))
+        elif k == "str":
+            cols.append(abi.strings_to_column(tf, [v.encode()], tags=[1]) if tf == abi.TF_ANY else abi.strings_to_column(tf, [v.encode()]))
+        elif k == "json":
+            cols.append(abi.strings_to_column(tf, [v.encode()], tags=[0]))
+        elif k == "b64":
+            cols.append(abi.strings_to_column(tf, [base64.b64decode(v)]))
+        else:
+            cols.append(abi.fixed_to_column(tf, [v]))
+    meta = {"id": np.array([G["id"]], np.uint32), "lsn": np.array([G["lsn"]], np.uint64), "commit_time": np.array([G["commit_time"]], np.uint64)}
+    return abi.Batch(1, cols), schema, meta
+
+
+def test_oracle_pg_types_against_real_debezium_message(po):
+    """pkg/debezium/pg/emitter.go AddPg for 31 columns of the CRUD fixture: the emitted values equal what a real Debezium wrote
+    (pg/tests/testdata/emitter_crud_test__debezium_insert.txt); json / jsonb compare as JSON (pg keeps its own spacing), floats as numbers."""
+    batch, schema, meta = _pg_batch()
+    assert all(po.debezium_pg_form(c) >= 0 for c in schema)
+    plan = po.build_plan(G["table"][0], G["table"][1], schema, [])
+    opts = {k: v for k, v in OPTS.items() if k != "ignore_unknown_sources"}      # every column carries an original type: the production path
+    data, ks, rs, errs = po.debezium_emit(batch, plan, opts, meta)
+    assert errs == []
+    (key, val), = po.debezium_split(data, ks, rs)
+    assert key == b'{"i":1}'
+    after = json.loads(val)["after"]
+    assert sorted(after) == sorted(c["name"] for c in G["pg_columns"])
+    for c in G["pg_columns"]:
+        got, want = after[c["name"]], c["after"]
+        if c["kind"] == "json":
+            assert json.loads(got) == json.loads(want), c["name"]
+        elif c["kind"] == "f64":
+            assert got == pytest.approx(want, rel=1e-7) and isinstance(got, float), c["name"]
+        else:
+            assert got == want and type(got) is type(want), (c["name"], got, want)
+    assert b'"real_":1.45e-10,' in val and b'"timestamp1":1098181434900,' in val and b'"date_":10599,' in val and b'"j":"{\\"k1\\":\\"v1\\"}"' in val
+
+
+def test_oracle_pg_forms(po):
+    """Branch selection and the special values of AddPg (emitter.go:180-191 NaN / Infinity strings, :104-120 time divider)."""
+    F = po.debezium_pg_form
+    assert F({"type": "timestamp", "original_type": "pg:timestamp(3) without time zone"}) == 9 and F({"type": "timestamp", "original_type": "pg:timestamp(0) without time zone"}) == 8
+    assert F({"type": "timestamp", "original_type": "pg:timestamp(6) with time zone"}) == 10 and F({"type": "utf8", "original_type": "pg:character varying(5)"}) == 4
+    assert F({"type": "utf8", "original_type": "pg:integer"}) == -1 and F({"type": "utf8", "original_type": "pg:interval"}) == -1 and F({"type": "any", "original_type": "mysql:json"}) == -1
+    schema = [{"name": "d", "type": "double", "original_type": "pg:double precision"}, {"name": "r", "type": "double", "original_type": "pg:real"},
+              {"name": "t", "type": "timestamp", "original_type": "pg:timestamp(2) without time zone"}, {"name": "z", "type": "timestamp", "original_type": "pg:timestamp with time zone"},
+              {"name": "dd", "type": "date", "original_type": "pg:date"}, {"name": "s", "type": "any", "original_type": "pg:citext"}, {"name": "j", "type": "any", "original_type": "pg:jsonb"}]
+    b = abi.Batch(4, [abi.fixed_to_column(abi.TF_DOUBLE, [float("nan"), float("-inf"), float("inf"), 0.1]), abi.fixed_to_column(abi.TF_DOUBLE, [0.1, 1e39, 3.0, 16777217.0]),
+                      abi.fixed_to_column(abi.TF_TIMESTAMP, [-1, 0, 1, 253402300800], None, [999999999, 1999, 5000000, 0]), abi.fixed_to_column(abi.TF_TIMESTAMP, [-1, 0, 1, 253402300800], None, [999999999, 0, 5000000, 0]),
+                      abi.fixed_to_column(abi.TF_DATE, [-1, 86399, 86400, -86401]), abi.strings_to_column(abi.TF_ANY, [b"<Tom>", b'"q\\u003c"', b"12", None], tags=[1, 0, 0, 0]),
+                      abi.strings_to_column(abi.TF_ANY, [b'{"a":[1,"\\u003c"]}', b"plain", b"null", b"[1]"], tags=[0, 1, 0, 0])])
+    data, ks, rs, errs = po.debezium_emit(b, po.build_plan("s", "t", schema, []), {"version": "1", "source_type": "pg"})
+    kv = po.debezium_split(data, ks, rs)
+    a = [json.loads(v)["after"] for _, v in kv]
+    assert [x["d"] for x in a] == ["NaN", "-Infinity", "Infinity", 0.1]
+    assert a[0]["r"] == 0.1 and b'"r":0.1,' in kv[0][1] and a[2]["r"] == 3 and b'"r":16777216,' in kv[3][1]          # float32(t)
+    assert [x["t"] for x in a] == [0, 0, 1005, 253402300800000]            # UnixMicro() / 1000 truncates toward zero (-1 us -> 0)
+    assert [x["z"] for x in a] == ["1969-12-31T23:59:59.999999999Z", "1970-01-01T00:00:00Z", "1970-01-01T00:00:01.005Z", "10000-01-01T00:00:00Z"]
+    assert [x["dd"] for x in a] == [0, 0, 1, -1]
+    assert a[0]["s"] == "<Tom>" and a[1]["s"] == "q<" and a[3]["s"] is None
+    assert a[0]["j"] == '{"a":[1,"<"]}' and a[1]["j"] == '"plain"' and a[2]["j"] is None and a[3]["j"] == "[1]"
+    assert errs == [(1, 40, 1), (2, 40, 5)]              # float32(1e39) is +Inf; the citext cell of row 2 is not a string
+
+
 def test_oracle_against_reference_unit_test_assertions(po):
     """emitter_value_converter_test.go:41-79 (schema wrapper on/off, no HTML escaping), mysql/tests/emitter_meta_test.go (file / pos / gtid)."""
     schema = [{"name": "id", "type": "int32", "key": True}, {"name": "value", "type": "utf8"}]
@@ -177,6 +249,20 @@ def test_device_emitter_equals_oracle(eng, po):
                       {"key_schema_id": 1, "val_schema_id": 4000000000}):
             _same(eng, po, batch, schema, [], dict(OPTS, source_type=st, **extra), meta)
     _same(eng, po, batch, schema, [], OPTS, None)
+    # pg: original types (AddPg branches): the canon fixture and the special values
+    batch, schema, meta = _pg_batch()
+    _same(eng, po, batch, schema, [], {k: v for k, v in OPTS.items() if k != "ignore_unknown_sources"}, meta, *G["table"])
+    schema = [{"name": "d", "type": "double", "original_type": "pg:double precision"}, {"name": "r", "type": "double", "original_type": "pg:real"},
+              {"name": "t", "type": "timestamp", "original_type": "pg:timestamp(2) without time zone"}, {"name": "z", "type": "timestamp", "original_type": "pg:timestamp with time zone"},
+              {"name": "dd", "type": "date", "original_type": "pg:date"}, {"name": "s", "type": "any", "original_type": "pg:citext"}, {"name": "j", "type": "any", "original_type": "pg:jsonb"},
+              {"name": "k", "type": "int64", "original_type": "pg:bigint", "key": True}, {"name": "u", "type": "utf8"}]
+    b = abi.Batch(4, [abi.fixed_to_column(abi.TF_DOUBLE, [float("nan"), float("-inf"), float("inf"), 0.1]), abi.fixed_to_column(abi.TF_DOUBLE, [0.1, 1e39, 3.0, 16777217.0]),
+                      abi.fixed_to_column(abi.TF_TIMESTAMP, [-1, 0, 1, 253402300800], None, [999999999, 1999, 5000000, 0]), abi.fixed_to_column(abi.TF_TIMESTAMP, [-1, 0, 1, 253402300800], None, [999999999, 0, 5000000, 0]),
+                      abi.fixed_to_column(abi.TF_DATE, [-1, 86399, 86400, -86401]), abi.strings_to_column(abi.TF_ANY, [b"<Tom>", b'"q\\u003c"', b"12", None], tags=[1, 0, 0, 0]),
+                      abi.strings_to_column(abi.TF_ANY, [b'{"a":[1,"\\u003c"]}', b"plain", b"null", b"[1]"], tags=[0, 1, 0, 0]), abi.fixed_to_column(abi.TF_INT64, [1, 2, 3, 4]),
+                      abi.strings_to_column(abi.TF_UTF8, [b"a", None, b"<c>", b""])])
+    _same(eng, po, b, schema, [], dict(OPTS, source_type="pg"), None)
+    _same(eng, po, b, schema, [{"filter_rows": {"filter": "k > 1"}}], dict(OPTS, source_type="pg", key_schema='{"t":1}', val_schema='{"t":2}'), None)
     # kinds + chain
     schema = [{"name": "id", "type": "int32", "key": True}, {"name": "name", "type": "utf8"}, {"name": "x", "type": "int64"}]
     b = abi.Batch(5, [abi.fixed_to_column(abi.TF_INT32, [1, 2, 3, 4, 5]), abi.strings_to_column(abi.TF_UTF8, [b"a", b"b", b"c", b"d", b"e"]),
@@ -217,6 +303,11 @@ def test_device_emitter_refusals(eng):
     pid = eng.plan("s", "t", [{"name": "i", "type": "int32", "key": True}], [])
     with pytest.raises(EngineError):        # errUnknownSource (emitter_value_converter.go:183-191)
         eng.emit_debezium(pid, b, {"version": "1"})
-    pid = eng.plan("s", "t", [{"name": "i", "type": "int32", "key": True, "original_type": "pg:integer"}], [])
-    with pytest.raises(EngineError):
+    for col in ({"name": "i", "type": "int32", "key": True, "original_type": "pg:interval"}, {"name": "i", "type": "int32", "key": True, "original_type": "pg:bigint"},
+                {"name": "i", "type": "int32", "key": True, "original_type": "mysql:int(11)"}):
+        pid = eng.plan("s", "t", [col], [])
+        with pytest.raises(EngineError):
+            eng.emit_debezium(pid, b, OPTS)
+    pid = eng.plan("s", "t", [{"name": "i", "type": "int32", "key": True, "original_type": "pg:integer"}], [{"convert_to_string": {}}])
+    with pytest.raises(EngineError):        # a transformer rewrote a pg-typed column: AddPg would reject the value
         eng.emit_debezium(pid, b, OPTS)

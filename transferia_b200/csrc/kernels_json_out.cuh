@@ -279,7 +279,7 @@ __device__ __forceinline__ uint32_t sink_count(const WordSink&) { return 0; }
 enum DbzCode : int32_t { DZ_NONE = 0, DZ_AFTER = 1, DZ_KEY = 2, DZ_LSN = 3, DZ_SRC_TS = 4, DZ_ID = 5, DZ_FILE = 6, DZ_POS = 7, DZ_GTID = 8, DZ_TS = 9, DZ_KEY_END = 10 };
 struct DbzSeg { int32_t text_off, text_len, code, pad; };
 struct DbzEmitArgs {
-    const DbzSeg* segs; int nseg; const uint8_t* text; const JsonCol* kcols; int nkc;
+    const DbzSeg* segs; int nseg; const uint8_t* text; const JsonCol* kcols; int nkc; const JsonCol* acols;     // acols: the sorted columns with their AddPg branch in pad1
     const uint32_t* id; const uint64_t* lsn; const uint64_t* ct; const uint32_t* gt_off; const uint8_t* gt_heap; uint32_t* key_size;
 };
 template <typename Inner> struct JStrSink {      // the inside of a JSON string over text that is already valid JSON (ASCII escapes, UTF-8 intact)
@@ -294,7 +294,47 @@ template <typename Inner> struct JStrSink {      // the inside of a JSON string 
         }
     }
 };
+// AddPg branches (pkg/debezium/pg/emitter.go:265-629) for columns that carry a pg: original type; jc.pad1 = branch, 0 = addCommon
+enum DbzForm : int32_t { DF_COMMON = 0, DF_PG_REAL = 2, DF_PG_DOUBLE = 3, DF_PG_STRING = 4, DF_PG_JSON = 6, DF_PG_DATE = 7, DF_PG_TS_MICROS = 8, DF_PG_TS_MILLIS = 9, DF_PG_TSTZ = 10 };
+template <typename Sink> __device__ bool dbz_pg_value(Sink& s, const DCol& c, uint64_t r, int form) {
+    if (!row_valid(c, r)) { fmt_lit(s, "null"); return true; }                       // :266-269
+    const uint8_t* p = nullptr; uint32_t L = 0; bool gostr = false;
+    if (c.type == TF_UTF8 || c.type == TF_ANY || c.type == TF_BYTES) {
+        p = c.heap + c.offsets[r]; L = c.offsets[r + 1] - c.offsets[r]; gostr = c.type != TF_ANY || (c.aux && c.aux[r] == 1);
+        if (!gostr && L == 4 && p[0] == 'n' && p[1] == 'u' && p[2] == 'l' && p[3] == 'l') { fmt_lit(s, "null"); return true; }   // a nil interface inside `any`
+    }
+    switch (form) {
+    case DF_PG_REAL: {                                                               // :342-356 float32(t)
+        const float f = c.type == TF_FLOAT ? ((const float*)c.values)[r] : (float)((const double*)c.values)[r];
+        const uint32_t b = __float_as_uint(f);
+        if ((b & 0x7F800000u) == 0x7F800000u) { fmt_lit(s, "null"); return false; }
+        fmt_float_bits(s, b, true, FM_JSON); return true;
+    }
+    case DF_PG_DOUBLE: {                                                             // :357-370 convertFloatNanInf
+        const uint64_t b = ((const uint64_t*)c.values)[r];
+        if ((b & 0x7FF0000000000000ull) == 0x7FF0000000000000ull) { fmt_lit(s, (b & 0x000FFFFFFFFFFFFFull) ? "\"NaN\"" : (b >> 63) ? "\"-Infinity\"" : "\"Infinity\""); return true; }
+        fmt_float_bits(s, b, false, FM_JSON); return true;
+    }
+    case DF_PG_STRING:                                                               // colVal.(string)
+        if (gostr) { fmt_json_string(s, p, L, false); return true; }
+        if (L && p[0] == '"') { ser_unescape_html(s, p, L); return true; }
+        fmt_lit(s, "null"); return false;
+    case DF_PG_JSON:                                                                 // :377-382 string(JSONMarshalUnescape(colVal))
+        s.put('"');
+        { JStrSink<Sink> js{&s}; if (gostr) fmt_json_string(js, p, L, false); else ser_unescape_html(js, p, L); }
+        s.put('"'); return true;
+    case DF_PG_DATE: fmt_i64(s, ((const int64_t*)c.values)[r] / 86400); return true;                       // :476-478
+    case DF_PG_TS_MICROS: case DF_PG_TS_MILLIS: {                                    // :558-580 UnixMicro() / divider
+        const int64_t micro = ((const int64_t*)c.values)[r] * 1000000LL + (int64_t)((c.aux ? ((const uint32_t*)c.aux)[r] : 0u) / 1000u);
+        fmt_i64(s, form == DF_PG_TS_MILLIS ? micro / 1000 : micro); return true;
+    }
+    case DF_PG_TSTZ:                                                                 // :581-594 SprintfDebeziumTime
+        s.put('"'); fmt_time(s, ((const int64_t*)c.values)[r], c.aux ? ((const uint32_t*)c.aux)[r] : 0, false); s.put('"'); return true;
+    }
+    fmt_lit(s, "null"); return false;
+}
 template <typename Sink> __device__ bool dbz_json_value(Sink& s, const DCol& c, uint64_t r, const JsonCol& jc, const MaskKey* keys, bool sizing) {
+    if (jc.pad1 != DF_COMMON) return dbz_pg_value(s, c, r, jc.pad1);              // (the plan refuses pg-typed columns a transformer rewrote)
     if (c.out_kind != OK_MASK && c.out_kind != OK_TOSTR && c.out_kind != OK_TODT) {      // the value keeps its input type (the sink cast kinds do not apply)
         if (!row_valid(c, r)) { fmt_lit(s, "null"); return true; }
         switch (c.type) {
@@ -335,7 +375,7 @@ template <typename Sink> __device__ int dbz_row(Sink& s, const DCol* cols, const
         const DbzSeg sg = z.segs[g];
         for (int i = 0; i < sg.text_len; i++) s.put(z.text[sg.text_off + i]);
         switch (sg.code) {
-        case DZ_AFTER: { const int b = dbz_object(s, cols, jcols, njc, names, keys, r, sizing); if (bad < 0) bad = b; break; }
+        case DZ_AFTER: { const int b = dbz_object(s, cols, z.acols, njc, names, keys, r, sizing); if (bad < 0) bad = b; break; }
         case DZ_KEY: { const int b = dbz_object(s, cols, z.kcols, z.nkc, names, keys, r, sizing); if (bad < 0) bad = b; break; }
         case DZ_LSN: fmt_u64(s, lsn); break;
         case DZ_SRC_TS: fmt_u64(s, ct / 1000000ull); break;

@@ -844,10 +844,37 @@ void dbz_build_template(PlanDev& pd, const std::string& opts_json) {
     if (pd.dbz_opts_key == opts_json && pd.dbz.segs) return;
     const tfplan::Plan& pl = pd.plan;
     auto ov = tfj::parse(opts_json);
-    if (!ov->get_bool("ignore_unknown_sources")) throw tfplan::FatalError(TF_E_FATAL_CONFIG, "unknown source type (emitter_value_converter.go:183-191): set ignore_unknown_sources");
-    for (auto& c : pl.out_schema)
-        if (c.original_type.rfind("pg:", 0) == 0 || c.original_type.rfind("mysql:", 0) == 0 || c.original_type.rfind("ydb:", 0) == 0)
-            throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "column " + c.name + ": original_type " + c.original_type + " is emitted by the database-specific converters (not on the device)");
+
+    // per result column: addCommon, or the AddPg branch (pkg/debezium/pg/emitter.go:265-629) its (original type, column type) pair takes
+    std::vector<int> forms(pl.out_schema.size(), DF_COMMON); bool any_common = false;
+    for (size_t k = 0; k < pl.out_schema.size(); k++) {
+        const tfplan::ColSchema& c = pl.out_schema[k]; const std::string& ot = c.original_type;
+        const bool typed = ot.rfind("pg:", 0) == 0 || ot.rfind("mysql:", 0) == 0 || ot.rfind("ydb:", 0) == 0;
+        if (!typed) { any_common = true; continue; }
+        int f = -1;
+        const bool untouched = pd.col_out_kind[(size_t)c.in_index] != OK_MASK && pd.col_out_kind[(size_t)c.in_index] != OK_TOSTR && pd.col_out_kind[(size_t)c.in_index] != OK_TODT;
+        auto is = [&](const char* t) { return ot == t; };
+        static const std::regex re_char("pg:character( varying)?(\\([0-9]+\\))?"), re_ts("pg:timestamp(\\(([0-9])\\))? without time zone"), re_tstz("pg:timestamp(\\([0-6]\\))? with time zone");
+        std::smatch m;
+        if (is("pg:boolean")) f = c.tf == TF_BOOLEAN ? DF_COMMON : -1;
+        else if (is("pg:smallint")) f = c.tf == TF_INT16 ? DF_COMMON : -1;
+        else if (is("pg:integer")) f = c.tf == TF_INT32 ? DF_COMMON : -1;
+        else if (is("pg:bigint")) f = c.tf == TF_INT64 ? DF_COMMON : -1;
+        else if (is("pg:bytea")) f = c.tf == TF_BYTES ? DF_COMMON : -1;
+        else if (is("pg:real")) f = (c.tf == TF_DOUBLE || c.tf == TF_FLOAT) ? DF_PG_REAL : -1;
+        else if (is("pg:double precision")) f = c.tf == TF_DOUBLE ? DF_PG_DOUBLE : -1;
+        else if (is("pg:text") || is("pg:uuid") || is("pg:cidr") || is("pg:macaddr") || is("pg:citext") || is("pg:int4range") || is("pg:int8range") || std::regex_match(ot, re_char))
+            f = (c.tf == TF_UTF8 || c.tf == TF_ANY) ? DF_PG_STRING : -1;
+        else if (is("pg:json") || is("pg:jsonb")) f = c.tf == TF_ANY ? DF_PG_JSON : -1;
+        else if (is("pg:date")) f = c.tf == TF_DATE ? DF_PG_DATE : -1;
+        else if (std::regex_match(ot, m, re_ts)) f = c.tf != TF_TIMESTAMP ? -1 : (m[2].matched && m[2].str()[0] >= '1' && m[2].str()[0] <= '3') ? DF_PG_TS_MILLIS : DF_PG_TS_MICROS;   // GetTimeDivider typeutil/helpers.go:104-120
+        else if (std::regex_match(ot, re_tstz)) f = c.tf == TF_TIMESTAMP ? DF_PG_TSTZ : -1;
+        if (f < 0 || !untouched)
+            throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "column " + c.name + ": original_type " + ot + " (column type " + c.type + ") is emitted by the database-specific converters of the Go emitter");
+        forms[k] = f;
+    }
+    if (any_common && !ov->get_bool("ignore_unknown_sources"))
+        throw tfplan::FatalError(TF_E_FATAL_CONFIG, "unknown source type (emitter_value_converter.go:183-191): a column has no original_type; set ignore_unknown_sources");
     const bool snapshot = ov->get_bool("snapshot"), drop_keys = ov->get_bool("drop_keys");
     const std::string st = ov->get_str("source_type");
     if (!(st.empty() || st == "pg" || st == "mysql")) throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "source_type " + st);
@@ -883,15 +910,17 @@ void dbz_build_template(PlanDev& pd, const std::string& opts_json) {
         seg(",\"version\":" + ver + "},\"transaction\":null,\"ts_ms\":", DZ_TS);
     }
     seg("}" + suf, DZ_NONE);
-    std::vector<JsonCol> kcols;
-    for (const JsonCol& jc : pd.h_sjcols) if (pl.out_schema[(size_t)jc.pad0].key) kcols.push_back(jc);
-    const size_t o_seg = 0, o_text = align_up(segs.size() * sizeof(DbzSeg), 256), o_k = o_text + align_up(text.size() + 1, 256);
-    pd.dbz_consts.ensure(o_k + kcols.size() * sizeof(JsonCol) + 256);
+    std::vector<JsonCol> acols = pd.h_sjcols, kcols;
+    for (JsonCol& jc : acols) jc.pad1 = forms[(size_t)jc.pad0];
+    for (const JsonCol& jc : acols) if (pl.out_schema[(size_t)jc.pad0].key) kcols.push_back(jc);
+    const size_t o_seg = 0, o_text = align_up(segs.size() * sizeof(DbzSeg), 256), o_k = o_text + align_up(text.size() + 1, 256), o_a = o_k + align_up(kcols.size() * sizeof(JsonCol) + 1, 256);
+    pd.dbz_consts.ensure(o_a + acols.size() * sizeof(JsonCol) + 256);
+    if (!acols.empty()) CK(cudaMemcpy(pd.dbz_consts.p + o_a, acols.data(), acols.size() * sizeof(JsonCol), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(pd.dbz_consts.p + o_seg, segs.data(), segs.size() * sizeof(DbzSeg), cudaMemcpyHostToDevice));
     if (!text.empty()) CK(cudaMemcpy(pd.dbz_consts.p + o_text, text.data(), text.size(), cudaMemcpyHostToDevice));
     if (!kcols.empty()) CK(cudaMemcpy(pd.dbz_consts.p + o_k, kcols.data(), kcols.size() * sizeof(JsonCol), cudaMemcpyHostToDevice));
     pd.dbz = DbzEmitArgs{}; pd.dbz.segs = (const DbzSeg*)(pd.dbz_consts.p + o_seg); pd.dbz.nseg = (int)segs.size(); pd.dbz.text = pd.dbz_consts.p + o_text;
-    pd.dbz.kcols = (const JsonCol*)(pd.dbz_consts.p + o_k); pd.dbz.nkc = (int)kcols.size();
+    pd.dbz.kcols = (const JsonCol*)(pd.dbz_consts.p + o_k); pd.dbz.nkc = (int)kcols.size(); pd.dbz.acols = (const JsonCol*)(pd.dbz_consts.p + o_a);
     pd.dbz_opts_key = opts_json;
 }
 }  // namespace
