@@ -193,6 +193,33 @@ def extra_paths(eng, args):
         eng.profile_enable(True); eng.parse_json(pid, text, opts, None, wire_fmt=fmt); prof = {kk["name"]: round(kk["ms"], 4) for kk in eng.profile_read()}; eng.profile_enable(False)
         res[name] = {"rows_per_s": n / dt, "lines": n, "input_MB": len(text) / 1e6, "ms": dt * 1e3, "rows_out": r.rows_out, "out_bytes": int(r.wire_len), "kernels_ms": prof,
                      "note": "wall clock around the public call with the message bytes in a pinned host buffer: H2D of the bytes and D2H of the wire bytes into the pinned landing buffer included"}
+    # queue Debezium serializer on the ClickBench-shaped table (every column carries a pg original type: the production AddPg path)
+    try:
+        hb, hschema = make_batch(100_000, workload.SEED)
+        hpid = eng.plan("public", "hits", hschema, [])
+        dopts = {"source_type": "pg", "version": "2.1.4", "topic_prefix": "clickbench", "database": "db", "snapshot": True}
+        rngm = np.random.default_rng(1)
+        meta = {"id": rngm.integers(0, 2**31, hb.nrows).astype(np.uint32), "lsn": rngm.integers(0, 2**60, hb.nrows).astype(np.uint64),
+                "commit_time": rngm.integers(16 * 10**17, 17 * 10**17, hb.nrows).astype(np.uint64)}
+        hp = hb.pin()
+        for _ in range(2):
+            r = eng.emit_debezium(hpid, hp, dopts, meta, copy_bytes=False)
+        torch.cuda.synchronize(); t0 = time.perf_counter(); k = 3
+        for _ in range(k):
+            r = eng.emit_debezium(hpid, hp, dopts, meta, copy_bytes=False)
+        torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / k
+        eng.profile_enable(True); eng.emit_debezium(hpid, hp, dopts, meta, copy_bytes=False); prof = {kk["name"]: round(kk["ms"], 4) for kk in eng.profile_read()}; eng.profile_enable(False)
+        res["debezium_emit_pg_hits"] = {"rows_per_s": hb.nrows / dt, "rows": hb.nrows, "ms": dt * 1e3, "out_bytes": int(r.wire_len), "errors": len(r.errors), "kernels_ms": prof,
+                                        "note": "tfgpu_emit_debezium over pinned host columns (99 pg-typed columns per row): key + value message per row, D2H of the messages included"}
+        try:
+            from oracle import pyoracle as po
+            sl = hb.slice(0, 2000); sm = {kk: vv[:2000] for kk, vv in meta.items()}
+            t0 = time.perf_counter(); po.debezium_emit(sl, po.build_plan("public", "hits", hschema, []), dopts, sm); dtc = time.perf_counter() - t0
+            res["debezium_emit_pg_hits"]["cpu_port_rows_per_s_1core"] = 2000 / dtc
+        except Exception as ex:
+            res["debezium_emit_pg_hits"]["cpu_port_error"] = str(ex)
+    except Exception as ex:
+        res["debezium_emit_error"] = str(ex)
     try:
         from oracle import pyoracle as po
         sample = text[: text.rfind(b"\n", 0, len(text) // 20) + 1]

@@ -973,6 +973,7 @@ int tfgpu_measure(tfgpu_engine* e, const tf_batch* in, uint64_t* per_row, uint64
     try {
         CK(cudaSetDevice(e->device));
         cudaStream_t s = e->stream;
+        join_tail(e);                     // the work arena is reused below
         std::vector<tf_col> dev; stage_input(e, in, dev);
         const size_t nc = in->ncols; const uint64_t n = in->nrows;
         if (e->d_cols_cap < nc) { if (e->d_cols) CK(cudaFree(e->d_cols)); CK(cudaMalloc(&e->d_cols, sizeof(DCol) * (nc ? nc : 1))); e->d_cols_cap = nc; }
