@@ -227,7 +227,7 @@ int tfgpu_push_encode(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch
  *                     `any`: Go string as is, object -> its JSON text as a string, JSON null -> null. Needs "ignore_unknown_sources"
  *                     (without it the reference answers errUnknownSource for such columns, :183-191).
  *   pg:...            AddPg pkg/debezium/pg/emitter.go:265-629 for boolean, smallint, integer, bigint, real (float32), double
- *                     precision ("NaN" / "Infinity" strings), text, character[ varying][(n)], uuid, cidr, macaddr, citext, int4range,
+ *                     precision ("NaN" / "Infinity" strings), text, character[ varying][(n)], uuid, cidr, macaddr, citext, inet, int4range,
  *                     int8range, bytea (base64), json / jsonb (JSON text as a string), date (days), timestamp[(p)] without time zone
  *                     (micro- or milliseconds by p), timestamp[(p)] with time zone (ZonedTimestamp string), on the column type the
  *                     pg source gives them. Other pg types, mysql: / ydb: types, and pg-typed columns a transformer rewrote are

@@ -753,7 +753,7 @@ namespace {
 // Columns with a pg: original type go through AddPg (pkg/debezium/pg/emitter.go:265-629). `form` names the branch the plan picked
 // for the (original type, column type) pair; the strict columnar layout fixes the Go type of the value (int16 / int32 / int64,
 // bool, float64, string, []byte, time.Time in UTC, `any` JSON).
-enum { DF_COMMON = 0, DF_PG_REAL = 2, DF_PG_DOUBLE = 3, DF_PG_STRING = 4, DF_PG_JSON = 6, DF_PG_DATE = 7, DF_PG_TS_MICROS = 8, DF_PG_TS_MILLIS = 9, DF_PG_TSTZ = 10 };
+enum { DF_COMMON = 0, DF_PG_REAL = 2, DF_PG_DOUBLE = 3, DF_PG_STRING = 4, DF_PG_JSON = 6, DF_PG_DATE = 7, DF_PG_TS_MICROS = 8, DF_PG_TS_MILLIS = 9, DF_PG_TSTZ = 10, DF_PG_INET = 11 };
 bool dbz_emit_value_pg(std::string& o, const orc_val& v, int form) {
     if (v.kind == OG_NIL) { o += "null"; return true; }                                         // :266-269
     if (v.kind == OG_JSON && v.slen == 4 && !std::memcmp(v.s, "null", 4)) { o += "null"; return true; }   // a nil interface inside `any`
@@ -770,6 +770,13 @@ bool dbz_emit_value_pg(std::string& o, const orc_val& v, int form) {
         if (v.kind == OG_STRING) { o += go_json_quote_nohtml(v.s, v.slen); return true; }
         if (v.kind == OG_JSON && v.slen && v.s[0] == '"') { o += json_unescape_html(v.s, v.slen); return true; }
         return false;                                                                            // the type assertion panics in the reference
+    case DF_PG_INET: {                                                                           // :401-410 strings.TrimSuffix(t, "/32")
+        std::string t;
+        if (v.kind == OG_STRING) t.assign((const char*)v.s, v.slen);
+        else return false;                                                                       // (a JSON-quoted string inside `any` would need decoding: not produced by the pg source)
+        if (t.size() >= 3 && t.compare(t.size() - 3, 3, "/32") == 0) t.resize(t.size() - 3);
+        o += go_json_quote_nohtml((const uint8_t*)t.data(), t.size()); return true;
+    }
     case DF_PG_JSON: {                                                                           // :377-382 string(JSONMarshalUnescape(colVal))
         std::string t;
         if (v.kind == OG_STRING) t = go_json_quote_nohtml(v.s, v.slen);

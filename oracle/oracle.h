@@ -116,7 +116,7 @@ typedef struct orc_dbz_emit_opts {
     int64_t key_schema_id, val_schema_id;                /* >= 0: confluent schema registry framing */
 } orc_dbz_emit_opts;
 /* forms[input column]: 0 = addCommon, else the AddPg branch (pkg/debezium/pg/emitter.go:265-629): 2 real, 3 double precision, 4 string
- * types, 6 json / jsonb, 7 date, 8 / 9 timestamp without time zone (micros / millis), 10 timestamp with time zone */
+ * types, 6 json / jsonb, 7 date, 8 / 9 timestamp without time zone (micros / millis), 10 timestamp with time zone, 11 inet */
 int orc_debezium_emit(const tf_batch* in, const orc_colschema* schema, const uint8_t* is_key, const uint8_t* forms, const orc_step* steps, int nsteps,
                       const tf_row_meta* meta, const orc_dbz_emit_opts* opts, orc_buf* out, uint32_t* key_sizes, uint32_t* row_sizes,
                       uint64_t* rows_out, tf_rowerr* errs, uint64_t* nerrs);

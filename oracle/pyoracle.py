@@ -997,6 +997,8 @@ def debezium_pg_form(col: dict) -> int:
         return 4 if yt in ("utf8", "any") else -1
     if ot in ("pg:json", "pg:jsonb"):
         return 6 if yt == "any" else -1
+    if ot == "pg:inet":
+        return 11 if yt in ("utf8", "any") else -1
     if ot == "pg:date":
         return 7 if yt == "date" else -1
     m = re.fullmatch(r"pg:timestamp(?:\((\d)\))? without time zone", ot)

@@ -18,7 +18,7 @@ IDENTITY = re.compile(r"^pg:(integer|smallint|bigint|boolean|text|character vary
 # original types the device emitter handles (pkg/debezium/pg/emitter.go:265-629), with the cell the strict columnar layout holds
 PG_FORMS = {
     "pg:boolean": "bool", "pg:smallint": "int", "pg:integer": "int", "pg:bigint": "int", "pg:real": "f64", "pg:double precision": "f64",
-    "pg:text": "str", "pg:uuid": "str", "pg:cidr": "str", "pg:macaddr": "str", "pg:citext": "str", "pg:int4range": "str", "pg:int8range": "str",
+    "pg:text": "str", "pg:uuid": "str", "pg:cidr": "str", "pg:macaddr": "str", "pg:citext": "str", "pg:int4range": "str", "pg:int8range": "str", "pg:inet": "str",
     "pg:bytea": "b64", "pg:json": "json", "pg:jsonb": "json", "pg:date": "time", "pg:timestamp with time zone": "time",
 }
 

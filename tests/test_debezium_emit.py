@@ -79,7 +79,7 @@ def _pg_batch():
 
 
 def test_oracle_pg_types_against_real_debezium_message(po):
-    """pkg/debezium/pg/emitter.go AddPg for 31 columns of the CRUD fixture: the emitted values equal what a real Debezium wrote
+    """pkg/debezium/pg/emitter.go AddPg for 33 columns of the CRUD fixture: the emitted values equal what a real Debezium wrote
     (pg/tests/testdata/emitter_crud_test__debezium_insert.txt); json / jsonb compare as JSON (pg keeps its own spacing), floats as numbers."""
     batch, schema, meta = _pg_batch()
     assert all(po.debezium_pg_form(c) >= 0 for c in schema)

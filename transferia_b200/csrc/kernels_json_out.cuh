@@ -295,7 +295,7 @@ template <typename Inner> struct JStrSink {      // the inside of a JSON string 
     }
 };
 // AddPg branches (pkg/debezium/pg/emitter.go:265-629) for columns that carry a pg: original type; jc.pad1 = branch, 0 = addCommon
-enum DbzForm : int32_t { DF_COMMON = 0, DF_PG_REAL = 2, DF_PG_DOUBLE = 3, DF_PG_STRING = 4, DF_PG_JSON = 6, DF_PG_DATE = 7, DF_PG_TS_MICROS = 8, DF_PG_TS_MILLIS = 9, DF_PG_TSTZ = 10 };
+enum DbzForm : int32_t { DF_COMMON = 0, DF_PG_REAL = 2, DF_PG_DOUBLE = 3, DF_PG_STRING = 4, DF_PG_JSON = 6, DF_PG_DATE = 7, DF_PG_TS_MICROS = 8, DF_PG_TS_MILLIS = 9, DF_PG_TSTZ = 10, DF_PG_INET = 11 };
 template <typename Sink> __device__ bool dbz_pg_value(Sink& s, const DCol& c, uint64_t r, int form) {
     if (!row_valid(c, r)) { fmt_lit(s, "null"); return true; }                       // :266-269
     const uint8_t* p = nullptr; uint32_t L = 0; bool gostr = false;
@@ -319,6 +319,10 @@ template <typename Sink> __device__ bool dbz_pg_value(Sink& s, const DCol& c, ui
         if (gostr) { fmt_json_string(s, p, L, false); return true; }
         if (L && p[0] == '"') { ser_unescape_html(s, p, L); return true; }
         fmt_lit(s, "null"); return false;
+    case DF_PG_INET:                                                                 // :401-410 strings.TrimSuffix(t, "/32")
+        if (!gostr) { fmt_lit(s, "null"); return false; }
+        if (L >= 3 && p[L - 3] == '/' && p[L - 2] == '3' && p[L - 1] == '2') L -= 3;
+        fmt_json_string(s, p, L, false); return true;
     case DF_PG_JSON:                                                                 // :377-382 string(JSONMarshalUnescape(colVal))
         s.put('"');
         { JStrSink<Sink> js{&s}; if (gostr) fmt_json_string(js, p, L, false); else ser_unescape_html(js, p, L); }

@@ -866,6 +866,7 @@ void dbz_build_template(PlanDev& pd, const std::string& opts_json) {
         else if (is("pg:text") || is("pg:uuid") || is("pg:cidr") || is("pg:macaddr") || is("pg:citext") || is("pg:int4range") || is("pg:int8range") || std::regex_match(ot, re_char))
             f = (c.tf == TF_UTF8 || c.tf == TF_ANY) ? DF_PG_STRING : -1;
         else if (is("pg:json") || is("pg:jsonb")) f = c.tf == TF_ANY ? DF_PG_JSON : -1;
+        else if (is("pg:inet")) f = (c.tf == TF_UTF8 || c.tf == TF_ANY) ? DF_PG_INET : -1;
         else if (is("pg:date")) f = c.tf == TF_DATE ? DF_PG_DATE : -1;
         else if (std::regex_match(ot, m, re_ts)) f = c.tf != TF_TIMESTAMP ? -1 : (m[2].matched && m[2].str()[0] >= '1' && m[2].str()[0] <= '3') ? DF_PG_TS_MILLIS : DF_PG_TS_MICROS;   // GetTimeDivider typeutil/helpers.go:104-120
         else if (std::regex_match(ot, re_tstz)) f = c.tf == TF_TIMESTAMP ? DF_PG_TSTZ : -1;
