@@ -249,6 +249,11 @@ typedef struct tf_row_meta {
 } tf_row_meta;
 int tfgpu_emit_debezium(tfgpu_engine* e, int plan_id, const char* opts_json, const tf_batch* in, const tf_row_meta* meta,
                         tfgpu_result** out);
+/* Host-only (no GPU): the set-up tfgpu_emit_debezium derives from a table and opts_json — the value branch of every result column
+ * (0 addCommon, else the AddPg branch), the key columns in message order and the message template (text pieces + the per-row field
+ * that follows each) — or the error the call would return. Same arguments as tfgpu_plan_validate plus opts_json. */
+int tfgpu_emit_debezium_validate(const char* ns, const char* name, const char* schema_json, const char* transformers_json, const char* opts_json,
+                                 char* describe_out, uint64_t cap, char* err_out, uint64_t err_cap);
 
 /* Measurer middleware (pkg/middlewares/synchronizer/measurer.go:38-42): ChangeItem.Size.Values = util.DeepSizeof(ColumnValues)
  * (pkg/util/sizeof.go:7-110) for every row of `in`, computed in closed form from the column types and lengths instead of a

@@ -225,6 +225,59 @@ def test_oracle_kinds_and_chain(po):
     assert after["x"] == 30 and len(after["name"]) == 64 and after["name"] == po.hmac_hex(b"s", b"c")
 
 
+def test_product_host_template_matches_oracle(po):
+    """The product's host side of the emitter (libtfgpu.so, no GPU): the branch chosen per column equals the oracle's, and the message
+    template — constant text with the per-row fields between — matches every message the oracle writes, field by field."""
+    import re
+    from transferia_b200 import engine
+    batch, schema, meta = _pg_batch()
+    schema = schema + [{"name": "zz", "type": "utf8"}]
+    batch = abi.Batch(1, batch.columns + [abi.strings_to_column(abi.TF_UTF8, [b"plain"])])
+    plan = po.build_plan("public", "basic_types", schema, [])
+    tx = b"gt:1"
+    meta = dict(meta, txid_offsets=np.array([0, len(tx)], np.uint32), txid_heap=np.frombuffer(tx, np.uint8))
+    lsn, ct, rid = int(meta["lsn"][0]), int(meta["commit_time"][0]), int(meta["id"][0])
+    field = {3: str(lsn), 4: str(ct // 10**6), 5: str(rid), 6: "%06d" % (lsn // 10**12), 7: str(lsn % 10**12), 8: '"gt:1"', 9: str(ct // 10**6)}
+    variants = [{}, {"snapshot": True}, {"drop_keys": True}, {"key_schema": '{"k":"<s>"}', "val_schema": '{"v":1}'}, {"key_schema_id": 3, "val_schema_id": 0x01020304}]      # (ids whose bytes are ASCII: the describe JSON is text)
+    for st in ("", "pg", "mysql"):
+        for extra in variants:
+            opts = dict(OPTS, source_type=st, **extra)
+            d = engine.emit_debezium_validate("public", "basic_types", schema, [], opts)
+            assert d["forms"] == [po.debezium_pg_form(c) for c in plan.result_schema]
+            assert [schema[k]["name"] for k in d["keys"]] == sorted(c["name"] for c in schema if c.get("key"))
+            data, ks, rs, errs = po.debezium_emit(batch, plan, opts, meta)
+            msg = data[:int(rs[0])].decode("latin-1")
+            pat = "".join(re.escape(t.encode("utf-8").decode("latin-1")) + ("(.*)" if code else "") for t, code in d["template"])
+            m = re.fullmatch(pat, msg, re.S)
+            assert m, (st, extra)
+            groups = iter(m.groups())
+            for t, code in d["template"]:
+                if not code:
+                    continue
+                g = next(groups)
+                if code in field:
+                    assert g == field[code], (st, extra, code)
+                elif code == 10:          # end of the key message
+                    assert g == ""
+                else:                     # the key / after object
+                    obj = json.loads(g)
+                    assert list(obj) == sorted(obj) and (code == 1) == ("zz" in obj)
+            # the key message ends where the template says
+            key_end = sum(len(t.encode("utf-8")) for t, code in d["template"][:[c for _, c in d["template"]].index(10) + 1]) + (0 if extra.get("drop_keys") else len(b'{"i":1}'))
+            assert key_end == int(ks[0]), (st, extra)
+    # refusals decided on the host: errUnknownSource, types and (type, column type) pairs left to Go, rewritten pg columns, bad options
+    ok = {"name": "i", "type": "int32", "key": True, "original_type": "pg:integer"}
+    for sch, trs, opts in (([{"name": "i", "type": "int32"}], [], {"version": "1"}),
+                           ([dict(ok, original_type="pg:interval")], [], OPTS), ([dict(ok, original_type="pg:bigint")], [], OPTS), ([dict(ok, original_type="mysql:int(11)")], [], OPTS),
+                           ([ok], [{"convert_to_string": {}}], OPTS), ([ok], [{"mask_field": {"columns": ["i"], "maskFunctionHash": {"userDefinedSalt": "s"}}}], {"version": "1"}),
+                           ([ok], [], dict(OPTS, source_type="oracle"))):
+        with pytest.raises(engine.EngineError):
+            engine.emit_debezium_validate("s", "t", sch, trs, opts)
+    # a masked pg column loses its original type (hmac_hasher.go:41): common path, needs ignore_unknown_sources
+    d = engine.emit_debezium_validate("s", "t", [ok], [{"mask_field": {"columns": ["i"], "maskFunctionHash": {"userDefinedSalt": "s"}}}], OPTS)
+    assert d["forms"] == [0]
+
+
 # ----------------------------------------------------------------------------------------------------------- GPU parity
 def _same(eng, po, batch, schema, trs, opts, meta, ns="public", name="t"):
     pid = eng.plan(ns, name, schema, trs); plan = po.build_plan(ns, name, schema, trs)

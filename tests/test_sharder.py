@@ -66,6 +66,31 @@ def test_oracle_sharder_in_the_chain(po):
     assert list(po.shard_ids(b, po.build_plan("db", "table1", schema, two))) == [zlib.crc32(b"1234") % 1000]
 
 
+def test_product_plan_sharder_suitable_and_refusals(po):
+    """The product's host-side plan builder (libtfgpu.so, no GPU needed) against sharder_test.go:61-83 (Suitable per table / column
+    filter) and against the oracle's plan; configurations the device does not take are refused at plan time."""
+    from transferia_b200 import engine
+    t1 = [{"name": "column1", "type": "string", "key": True}, {"name": "column2", "type": "int64"}, {"name": "column3", "type": "int32"}, {"name": "column4", "type": "boolean"}]
+    t3 = [{"name": "column2", "type": "int8"}, {"name": "column3", "type": "uint32"}, {"name": "column4", "type": "date"}]
+    all_cols = {"sharder_transformer": {"shardsCount": "2"}}
+    excl = {"sharder_transformer": {"shardsCount": "4", "tables": {"includeTables": ["db.table"]}, "columns": {"excludeColumns": ["column2"]}}}
+    incl = {"sharder_transformer": {"shardsCount": "8", "tables": {"includeTables": ["db.a_table3"]}, "columns": {"includeColumns": ["column1", "column3"]}}}
+    cases = [(all_cols, "table1", t1, True), (all_cols, "a_table3", t3, True), (excl, "table1", t1, True), (excl, "a_table3", t3, False),
+             (incl, "table1", t1, False), (incl, "a_table3", t3, True)]
+    for tr, table, schema, suitable in cases:
+        d = engine.plan_validate("db", table, schema, [tr])
+        plan = po.build_plan("db", table, schema, [tr])
+        assert (len(d["steps"]) == 1) == suitable == (len(plan.steps) == 1), (tr, table)
+        if suitable:
+            assert d["steps"][0]["type"] == "sharder_transformer" and d["steps"][0]["cols"] == plan.steps[0]["cols"] and d["steps"][0]["shards"] == plan.steps[0]["shards"]
+    assert engine.plan_validate("db", "a_table3", t3, [incl])["steps"][0]["cols"] == [1]          # only column3 exists there
+    for bad in ({"shardsCount": "2", "is_random": True}, {"shardsCount": "x"}, {"shardsCount": ""}, {"shardsCount": "0"}, {"shardsCount": "4294967296"}):
+        with pytest.raises(engine.EngineError):
+            engine.plan_validate("db", "table1", t1, [{"sharder_transformer": bad}])
+    with pytest.raises(engine.EngineError):      # number_to_float rewrites the `any` text the sharder would read
+        engine.plan_validate("db", "t", [{"name": "a", "type": "any"}], [{"sharder_transformer": {"shardsCount": "2"}}, {"number_to_float_transformer": {}}])
+
+
 @pytest.mark.gpu
 def test_device_sharder_equals_oracle(eng, po):
     from test_gpu_parity import all_types_batch

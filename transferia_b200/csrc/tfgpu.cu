@@ -840,9 +840,10 @@ __global__ void k_dbz_kinds(const uint8_t* kinds, uint64_t n, uint8_t* pre_err) 
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r < n) pre_err[r] = kinds[r] == TF_KIND_INSERT ? 0 : TF_ROWERR_DBZ_EMIT_HOST;
 }
-void dbz_build_template(PlanDev& pd, const std::string& opts_json) {
-    if (pd.dbz_opts_key == opts_json && pd.dbz.segs) return;
-    const tfplan::Plan& pl = pd.plan;
+// Host part of the emitter set-up, independent of any device state (tfgpu_emit_debezium_validate exports it for tests without a GPU):
+// the AddPg / addCommon branch of every result column and the message template.
+struct DbzHostTpl { std::vector<int> forms; std::string text; std::vector<DbzSeg> segs; };
+DbzHostTpl dbz_host_template(const tfplan::Plan& pl, const std::string& opts_json) {
     auto ov = tfj::parse(opts_json);
 
     // per result column: addCommon, or the AddPg branch (pkg/debezium/pg/emitter.go:265-629) its (original type, column type) pair takes
@@ -852,7 +853,8 @@ void dbz_build_template(PlanDev& pd, const std::string& opts_json) {
         const bool typed = ot.rfind("pg:", 0) == 0 || ot.rfind("mysql:", 0) == 0 || ot.rfind("ydb:", 0) == 0;
         if (!typed) { any_common = true; continue; }
         int f = -1;
-        const bool untouched = pd.col_out_kind[(size_t)c.in_index] != OK_MASK && pd.col_out_kind[(size_t)c.in_index] != OK_TOSTR && pd.col_out_kind[(size_t)c.in_index] != OK_TODT;
+        bool untouched = !(pl.tostr_col.size() > (size_t)c.in_index && pl.tostr_col[(size_t)c.in_index]) && !(pl.todt_col.size() > (size_t)c.in_index && pl.todt_col[(size_t)c.in_index]);
+        for (auto& ms : pl.masks) for (int mc : ms.cols) if (mc == c.in_index) untouched = false;
         auto is = [&](const char* t) { return ot == t; };
         static const std::regex re_char("pg:character( varying)?(\\([0-9]+\\))?"), re_ts("pg:timestamp(\\(([0-9])\\))? without time zone"), re_tstz("pg:timestamp(\\([0-6]\\))? with time zone");
         std::smatch m;
@@ -911,6 +913,15 @@ void dbz_build_template(PlanDev& pd, const std::string& opts_json) {
         seg(",\"version\":" + ver + "},\"transaction\":null,\"ts_ms\":", DZ_TS);
     }
     seg("}" + suf, DZ_NONE);
+    DbzHostTpl t; t.forms = std::move(forms); t.text = std::move(text); t.segs = std::move(segs);
+    return t;
+}
+
+void dbz_build_template(PlanDev& pd, const std::string& opts_json) {
+    if (pd.dbz_opts_key == opts_json && pd.dbz.segs) return;
+    const tfplan::Plan& pl = pd.plan;
+    const DbzHostTpl ht = dbz_host_template(pl, opts_json);
+    const std::vector<int>& forms = ht.forms; const std::string& text = ht.text; const std::vector<DbzSeg>& segs = ht.segs;
     std::vector<JsonCol> acols = pd.h_sjcols, kcols;
     for (JsonCol& jc : acols) jc.pad1 = forms[(size_t)jc.pad0];
     for (const JsonCol& jc : acols) if (pl.out_schema[(size_t)jc.pad0].key) kcols.push_back(jc);
@@ -925,6 +936,34 @@ void dbz_build_template(PlanDev& pd, const std::string& opts_json) {
     pd.dbz_opts_key = opts_json;
 }
 }  // namespace
+
+// Host-only: what tfgpu_emit_debezium would set up for this table and opts_json (no GPU needed). describe_out receives
+// {"forms":[per result column],"keys":[result column indexes in key-message order],"template":[[text, code], ...]}.
+int tfgpu_emit_debezium_validate(const char* ns, const char* name, const char* schema_json, const char* transformers_json, const char* opts_json,
+                                 char* describe_out, uint64_t cap, char* err_out, uint64_t err_cap) {
+    auto put = [](char* dst, uint64_t cap_, const std::string& s) { if (dst && cap_) { size_t n = s.size() < cap_ - 1 ? s.size() : cap_ - 1; std::memcpy(dst, s.data(), n); dst[n] = 0; } };
+    if (!schema_json || !name || !opts_json) return TF_E_FATAL_ARG;
+    try {
+        const tfplan::Plan pl = tfplan::build_plan(ns ? ns : "", name, schema_json, transformers_json ? transformers_json : "", "");
+        const DbzHostTpl t = dbz_host_template(pl, opts_json);
+        std::vector<size_t> order(pl.out_schema.size()); for (size_t k = 0; k < order.size(); k++) order[k] = k;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return pl.out_schema[a].name < pl.out_schema[b].name; });
+        std::string d = "{\"forms\":[";
+        for (size_t k = 0; k < t.forms.size(); k++) { if (k) d += ","; d += std::to_string(t.forms[k]); }
+        d += "],\"keys\":["; bool first = true;
+        for (size_t k : order) if (pl.out_schema[k].key) { if (!first) d += ","; first = false; d += std::to_string(k); }
+        d += "],\"template\":[";
+        for (size_t g = 0; g < t.segs.size(); g++) {
+            if (g) d += ",";
+            d += "[" + host_json_quote_nohtml(t.text.substr((size_t)t.segs[g].text_off, (size_t)t.segs[g].text_len)) + "," + std::to_string(t.segs[g].code) + "]";
+        }
+        d += "]}";
+        if (describe_out && d.size() + 1 > cap) { put(err_out, err_cap, "describe buffer too small"); return TF_E_FATAL_ARG; }
+        put(describe_out, cap, d);
+        return TF_OK;
+    } catch (const tfplan::FatalError& f) { put(err_out, err_cap, f.what()); return f.code; }
+    catch (const std::exception& x) { put(err_out, err_cap, x.what()); return TF_E_FATAL_CONFIG; }
+}
 
 int tfgpu_emit_debezium(tfgpu_engine* e, int plan_id, const char* opts_json, const tf_batch* in, const tf_row_meta* meta, tfgpu_result** out) {
     if (!e || !in || !out || !opts_json || plan_id < 0 || plan_id >= (int)e->plans.size()) return TF_E_FATAL_ARG;
