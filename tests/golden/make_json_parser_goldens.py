@@ -12,4 +12,11 @@ for k, v in canon.items():
         return [{"columnnames": it["columnnames"], "columnvalues": it["columnvalues"], "table": it["table"], "nextlsn": it["nextlsn"],
                  "types": [c["type"] for c in it["table_schema"]]} for it in items]
     out["canon"][name] = {m: slim(x) for m, x in v.items()} if isinstance(v, dict) else slim(v)
+# pkg/parsers/tests/generic_parser_test.go:274-296 TestParser_DoJson: the sample, its field list, and what the test asserts (36 rows,
+# column `version` = 89488198116272410 + row: uint64 values beyond 2^53 must arrive exactly)
+S = "/root/reference/pkg/parsers/tests/samples"
+cfg = json.load(open(f"{S}/json_sample.json"))["ParserConfig"]["json.lb"]
+out["do_json"] = {"input": open(f"{S}/json_sample").read(), "add_rest": cfg["AddRest"], "null_keys_allowed": cfg["NullKeysAllowed"],
+                  "fields": [{"name": f["name"], "type": f["type"], "key": f["key"], "required": f["required"]} for f in cfg["Fields"]],
+                  "rows": 36, "version_base": 89488198116272410}
 json.dump(out, open(os.path.join(os.path.dirname(__file__), "json_parser_goldens.json"), "w"), indent=1, sort_keys=True)

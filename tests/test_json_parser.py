@@ -47,6 +47,17 @@ def test_number_types_canon(po):
     assert bytes(b.columns[4].heap) == b"[0,1,2,4,12313.12241632513,-123123.13117532,12345678987654321,-12345678987654321,1e5,0.0000001]"
 
 
+def test_do_json_sample(po):
+    """TestParser_DoJson (pkg/parsers/tests/generic_parser_test.go:274-296): 36 lines of the json.lb sample give 36 rows and the uint64
+    column `version` holds 89488198116272410 + row exactly (values beyond 2^53: the number text, not a float64, is converted)."""
+    d = G["do_json"]
+    b, errs, lines = po.json_parse(d["input"].encode(), d["fields"], {"add_rest": d["add_rest"], "null_keys_allowed": d["null_keys_allowed"]})
+    assert errs == [] and lines == b.nrows == d["rows"]
+    vi = [f["name"] for f in d["fields"]].index("version")
+    assert [cell(b, vi, r) for r in range(b.nrows)] == [d["version_base"] + r for r in range(b.nrows)]
+    assert cell(b, 0, 0) == b"mdbkbeut80vtiba04gid" and cell(b, len(d["fields"]), 0) == {}          # every key is declared: _rest is empty
+
+
 def test_base64_canon(po):
     """TestBase64Unpack (parser_test.go:233-276): `string` (bytes) cells are base64-decoded, utf8 cells are unescaped."""
     text = G["inputs"]["parse_base64_packed.jsonl"].encode()
