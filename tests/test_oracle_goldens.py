@@ -233,3 +233,66 @@ def test_date_clamp_and_units(po):
     assert struct.unpack_from("<6I", tail, off) == (0, 0, 86399, 4291747199, 4291747200, 4291747200)
     off = tail.index(b"DateTime64(6)\x00") + 14
     assert struct.unpack_from("<6q", tail, off) == tuple(s * 10**6 for s in secs)
+
+
+def test_to_datetime_canon(po):
+    """to_datetime/gotest/canondata/result.json (TestToDateTimeTransformer, to_datetime_test.go:16-118): include column2 + column3 —
+    int32 1759143061 -> 2025-09-29T10:51:01Z (int16 column3 untouched), uint32 1759143081 -> 2025-09-29T10:51:21Z (datetime column4
+    untouched); the Suitable table of :67-73, through the oracle plan and the product's host plan builder."""
+    from transferia_b200 import engine
+    t1 = [{"name": "column1", "type": "utf8", "key": True}, {"name": "column2", "type": "int32"}, {"name": "column3", "type": "int16"}]
+    t2 = [{"name": "column1", "type": "uint32"}, {"name": "column2", "type": "datetime"}, {"name": "column3", "type": "float"}]
+    t3 = [{"name": "column2", "type": "int8"}, {"name": "column3", "type": "uint32"}, {"name": "column4", "type": "datetime"}]
+    none = {"convert_to_datetime": {}}
+    two = {"convert_to_datetime": {"columns": {"includeColumns": ["column2", "column3"]}}}
+    for tr, table, schema, suitable in ((none, "table1", t1, False), (none, "table2", t2, False), (none, "a_table3", t3, False),
+                                        (two, "table1", t1, True), (two, "table2", t2, False), (two, "a_table3", t3, True)):
+        assert (len(po.build_plan("db", table, schema, [tr]).steps) == 1) == suitable == (len(engine.plan_validate("db", table, schema, [tr])["steps"]) == 1), (tr, table)
+    b1 = abi.Batch(1, [abi.strings_to_column(abi.TF_UTF8, [b"value1"]), abi.fixed_to_column(abi.TF_INT32, [1759143061]), abi.fixed_to_column(abi.TF_INT16, [1234])])
+    out, errs = po.push_columns(b1, po.build_plan("db", "table1", t1, [two]))
+    assert errs == [] and [c.type for c in out.columns] == [abi.TF_UTF8, abi.TF_DATETIME, abi.TF_INT16]
+    assert po.fmt_rfc3339nano(int(out.columns[1].values[0])) == "2025-09-29T10:51:01Z" and int(out.columns[2].values[0]) == 1234
+    b3 = abi.Batch(1, [abi.fixed_to_column(abi.TF_INT8, [-3]), abi.fixed_to_column(abi.TF_UINT32, [1759143081]), abi.fixed_to_column(abi.TF_DATETIME, [1759140000])])
+    plan3 = po.build_plan("db", "a_table3", t3, [two])
+    out, errs = po.push_columns(b3, plan3)
+    assert [c["type"] for c in plan3.result_schema] == ["int8", "datetime", "datetime"]
+    assert po.fmt_rfc3339nano(int(out.columns[1].values[0])) == "2025-09-29T10:51:21Z" and po.fmt_rfc3339nano(int(out.columns[2].values[0])) == "2025-09-29T10:00:00Z"
+    assert int(out.columns[0].values[0]) == -3
+
+
+def test_to_string_canon(po):
+    """to_string/gotest/canondata/result.json (TestToStringTransformer, to_string_test.go:16-120): the three transformers (all columns /
+    exclude column2 on db.table* / include column1+column3 on db.a_table3) over the three items; result types and text values as the
+    canon file holds them. (item3's column4 is a `date` column holding a time.Duration in the reference; an interval column gives the
+    same SerializeToString branch here.) The product's host plan builder must agree on Suitable and on the result schema."""
+    from transferia_b200 import engine
+    t1 = [{"name": "column1", "type": "utf8", "key": True}, {"name": "column2", "type": "int64"}, {"name": "column3", "type": "int32"}, {"name": "column4", "type": "boolean"}]
+    t2 = [{"name": "column1", "type": "string"}, {"name": "column2", "type": "date"}, {"name": "column3", "type": "double"}, {"name": "column4", "type": "float"}]
+    t3 = [{"name": "column2", "type": "int8"}, {"name": "column3", "type": "uint32"}, {"name": "column4", "type": "interval"}]
+    b1 = abi.Batch(1, [abi.strings_to_column(abi.TF_UTF8, [b"value1"]), abi.fixed_to_column(abi.TF_INT64, [123]), abi.fixed_to_column(abi.TF_INT32, [1234]), abi.fixed_to_column(abi.TF_BOOLEAN, [1])])
+    b2 = abi.Batch(1, [abi.strings_to_column(abi.TF_BYTES, [b"value1"]), abi.fixed_to_column(abi.TF_DATE, [-8425641600]), abi.fixed_to_column(abi.TF_DOUBLE, [123.123]),
+                       abi.fixed_to_column(abi.TF_FLOAT, np.array([312.321], np.float32))])
+    b3 = abi.Batch(1, [abi.fixed_to_column(abi.TF_INT8, [-3]), abi.fixed_to_column(abi.TF_UINT32, [12345]), abi.fixed_to_column(abi.TF_INTERVAL, [60 * 10**9])])
+    allc = {"convert_to_string": {}}
+    excl = {"convert_to_string": {"tables": {"includeTables": ["db.table"]}, "columns": {"excludeColumns": ["column2"]}}}
+    incl = {"convert_to_string": {"tables": {"includeTables": ["db.a_table3"]}, "columns": {"includeColumns": ["column1", "column3"]}}}
+
+    def text(col, r=0):
+        return bytes(col.heap[col.offsets[r]:col.offsets[r + 1]]).decode()
+
+    canon = [(allc, "table1", t1, b1, ["utf8"] * 4, ["value1", "123", "1234", "true"]),
+             (allc, "table2", t2, b2, ["utf8"] * 4, ["value1", "1703-01-02", "123.123", "312.321"]),
+             (allc, "a_table3", t3, b3, ["utf8"] * 3, ["-3", "12345", "1m0s"]),
+             (excl, "table1", t1, b1, ["utf8", "int64", "utf8", "utf8"], ["value1", 123, "1234", "true"]),
+             (excl, "table2", t2, b2, ["utf8", "date", "utf8", "utf8"], ["value1", -8425641600, "123.123", "312.321"]),
+             (incl, "a_table3", t3, b3, ["int8", "utf8", "interval"], [-3, "12345", 60 * 10**9])]
+    for tr, table, schema, batch, types, values in canon:
+        plan = po.build_plan("db", table, schema, [tr])
+        assert [c["type"] for c in plan.result_schema] == types, (tr, table)
+        d = engine.plan_validate("db", table, schema, [tr])
+        assert len(d["steps"]) == 1 and [c["type"] for c in d["result_schema"]] == types if "result_schema" in d else len(d["steps"]) == 1
+        out, errs = po.push_columns(batch, plan)
+        got = [text(c) if c.type in abi.VAR_TYPES else c.values[0].item() for c in out.columns]
+        assert errs == [] and got == values, (tr, table, got)
+    for tr, table, schema in ((excl, "a_table3", t3), (incl, "table1", t1), (incl, "table2", t2)):      # :77-87 not Suitable
+        assert po.build_plan("db", table, schema, [tr]).steps == [] and engine.plan_validate("db", table, schema, [tr])["steps"] == []
