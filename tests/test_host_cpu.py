@@ -221,3 +221,23 @@ def test_plan_filter_columns_skip_events_rename(po):
     d2 = engine.plan_validate("db", "t", schema, [{"filter_columns": {"columns": {"includeColumns": ["^a$"]}}}])
     assert d2["steps"] == [] and d2["out_cols"] == [0, 1, 2, 3]
     assert po.build_plan("db", "t", schema, [{"filter_columns": {"columns": {"includeColumns": ["^a$"]}}}]).out_cols == [0, 1, 2, 3]
+
+
+def test_bench_reference_arm_line(tmp_path):
+    """`bench.py --impl reference` (the CPU port of the path, no GPU): one JSON line with the contract's keys, the same metric / unit as the
+    GPU arm, an e2e block without copies and a cpu_baseline describing the run."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--rows", "20000", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300, cwd=root)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "rows/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
