@@ -370,8 +370,13 @@ def main():
     e2e_steps = ((e2e_steps + P - 1) // P) * P
     engs = [eng]
     for _ in range(P - 1):
-        e2 = engine.Engine(local, args.frame_bytes)
-        engs.append(e2)
+        try:
+            engs.append(engine.Engine(local, args.frame_bytes))
+        except Exception as ex:      # not enough memory for another set of arenas: fewer pipelines, reported as such
+            print(f"bench: extra pipeline not created ({ex}); continuing with {len(engs)}", file=sys.stderr)
+            break
+    P = len(engs)
+    e2e_steps = ((max(3, min(args.steps, 10)) + P - 1) // P) * P
     pids = [pid] + [e2.plan("public", "hits", schema, trs, {"type": "clickhouse"}) for e2 in engs[1:]]
     last = [None] * P
 
