@@ -366,8 +366,6 @@ def main():
     # snapshot, load_snapshot.go:986): `--e2e-pipelines P` host threads, each with its own engine handle on this GPU, push
     # alternate batches, so one pipeline's copies overlap another's kernels. P = 1 is the strictly serial call sequence.
     P = max(1, args.e2e_pipelines)
-    e2e_steps = max(3, min(args.steps, 10))
-    e2e_steps = ((e2e_steps + P - 1) // P) * P
     engs = [eng]
     for _ in range(P - 1):
         try:

@@ -256,31 +256,30 @@ class Engine:
     def _result_batch(self, res):
         import numpy as np
         L = self._L
-        if True:
-            ob = L.tfgpu_result_batch(res)
-            n = int(L.tfgpu_result_rows_out(res))
-            cols = []
-            if ob:
-                b = ob.contents
-                for k in range(b.ncols):
-                    c = b.cols[k]
-                    def arr(ptr, nbytes, dtype):
-                        if not ptr or nbytes == 0:
-                            return None if not ptr else np.zeros(0, dtype=dtype)
-                        return np.frombuffer(C.string_at(ptr, nbytes), dtype=dtype).copy()
-                    t = c.type
-                    if t in abi.VAR_TYPES:
-                        cols.append(abi.Column(t, offsets=arr(c.offsets, 4 * (n + 1), np.uint32), heap=arr(c.heap, c.heap_len, np.uint8) if c.heap else np.zeros(0, np.uint8),
-                                               validity=arr(c.validity, (n + 7) // 8, np.uint8), aux=arr(c.aux, n, np.uint8)))
-                    else:
-                        dt = abi.FIXED_DTYPE[t]
-                        cols.append(abi.Column(t, values=arr(c.values, n * np.dtype(dt).itemsize, dt), validity=arr(c.validity, (n + 7) // 8, np.uint8),
-                                               aux=arr(c.aux, 4 * n, np.uint32)))
-            ne = L.tfgpu_result_n_errors(res); ep = L.tfgpu_result_errors(res)
-            errs = [(ep[k].row, ep[k].code, ep[k].term) for k in range(ne)]
-            out = abi.Batch(n, cols)
-            self.last_part_ids = self._part_ids(res, n)       # of the batch just returned (push_columns / parsers)
-            return out, errs
+        ob = L.tfgpu_result_batch(res)
+        n = int(L.tfgpu_result_rows_out(res))
+        cols = []
+        if ob:
+            b = ob.contents
+            for k in range(b.ncols):
+                c = b.cols[k]
+                def arr(ptr, nbytes, dtype):
+                    if not ptr or nbytes == 0:
+                        return None if not ptr else np.zeros(0, dtype=dtype)
+                    return np.frombuffer(C.string_at(ptr, nbytes), dtype=dtype).copy()
+                t = c.type
+                if t in abi.VAR_TYPES:
+                    cols.append(abi.Column(t, offsets=arr(c.offsets, 4 * (n + 1), np.uint32), heap=arr(c.heap, c.heap_len, np.uint8) if c.heap else np.zeros(0, np.uint8),
+                                           validity=arr(c.validity, (n + 7) // 8, np.uint8), aux=arr(c.aux, n, np.uint8)))
+                else:
+                    dt = abi.FIXED_DTYPE[t]
+                    cols.append(abi.Column(t, values=arr(c.values, n * np.dtype(dt).itemsize, dt), validity=arr(c.validity, (n + 7) // 8, np.uint8),
+                                           aux=arr(c.aux, 4 * n, np.uint32)))
+        ne = L.tfgpu_result_n_errors(res); ep = L.tfgpu_result_errors(res)
+        errs = [(ep[k].row, ep[k].code, ep[k].term) for k in range(ne)]
+        out = abi.Batch(n, cols)
+        self.last_part_ids = self._part_ids(res, n)       # of the batch just returned (push_columns / parsers)
+        return out, errs
 
     def push_columns(self, plan_id: int, batch: abi.Batch) -> Tuple[abi.Batch, List[Tuple[int, int, int]]]:
         """Transformer chain only: (Transformed rows as a host Batch, row errors) — abstract.TransformerResult."""
