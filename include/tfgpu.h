@@ -363,6 +363,12 @@ const uint32_t*   tfgpu_result_key_sizes(const tfgpu_result* r);  /* tfgpu_emit_
  * n + 1 entries. Host only. Update / delete items are refused by the reference (json_serializer.go:17-20): check kinds first. */
 int tfgpu_queue_json_batches(const uint32_t* json_row_sizes, uint64_t n, uint64_t max_message_size, uint64_t max_change_items,
                              uint64_t* starts, uint64_t cap, uint64_t* n_msgs);
+/* Queue Debezium serializer with batching.max.size (pkg/serializer/queue/debezium_multithreading.go:67-106 MergeWithMaxMessageSize):
+ * the VALUES of consecutive messages are appended to one another (no separator, Key nil) while
+ * len(current) + 1 + len(next) <= max_message_size; the first value always opens a message. Given the value length of every row
+ * (tfgpu_result_row_sizes - tfgpu_result_key_sizes; emit with "drop_keys" so that the values lie back to back) this returns the first
+ * row of every merged message as tfgpu_queue_json_batches does. max_message_size == 0: the reference does not merge (MergeBack). Host only. */
+int tfgpu_queue_debezium_batches(const uint32_t* value_sizes, uint64_t n, uint64_t max_message_size, uint64_t* starts, uint64_t cap, uint64_t* n_msgs);
 void              tfgpu_result_release(tfgpu_result* r);
 
 /* Number of kernel launches issued by this engine since creation (bench `gpu_launches`). */

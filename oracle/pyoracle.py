@@ -882,6 +882,17 @@ def queue_json_batches(lens, max_message_size=0, max_change_items=0):
     return [int(x) for x in st[:k.value + 1]]
 
 
+def queue_debezium_merge(values, max_message_size):
+    """MergeWithMaxMessageSize (pkg/serializer/queue/debezium_multithreading.go:67-106) over the values of one TablePartID, restated
+    literally: the merged message values."""
+    out = []
+    for v in values:
+        if not out or len(out[-1]) + 1 + len(v) > max_message_size:      # expandArrIfNeeded :76-86
+            out.append(b"")
+        out[-1] += v
+    return out
+
+
 # ----------------------------------------------------------------------------- debezium
 class OrcDbzField(C.Structure):
     _fields_ = [("name", C.c_char_p), ("recv", C.c_int32), ("scale", C.c_int32), ("key", C.c_int32)]

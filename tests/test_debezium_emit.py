@@ -225,6 +225,23 @@ def test_oracle_kinds_and_chain(po):
     assert after["x"] == 30 and len(after["name"]) == 64 and after["name"] == po.hmac_hex(b"s", b"c")
 
 
+def test_queue_debezium_batching(po):
+    """debezium_multithreading_test.go:10-70 TestMergeWithMaxMessageSize (values {0,0} and {1,1}: one message under a big limit, two
+    under limit 1) and random sizes against the literal restatement; the product's host-only function gives the same cuts."""
+    from transferia_b200 import engine
+    vals = [bytes([0, 0]), bytes([1, 1])]
+    assert po.queue_debezium_merge(vals, 999999) == [bytes([0, 0, 1, 1])] and po.queue_debezium_merge(vals, 1) == vals
+    assert engine.queue_debezium_batches([2, 2], 999999) == [0, 2] and engine.queue_debezium_batches([2, 2], 1) == [0, 1, 2]
+    assert engine.queue_debezium_batches([2, 2], 0) == [0, 1, 2] and engine.queue_debezium_batches([], 10) == [0]
+    rng = np.random.default_rng(3)
+    for limit in (1, 7, 64, 1000):
+        sizes = [int(x) for x in rng.integers(0, 40, 300)]
+        values = [bytes([k % 251]) * s for k, s in enumerate(sizes)]
+        cuts = engine.queue_debezium_batches(sizes, limit)
+        got = [b"".join(values[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+        assert got == po.queue_debezium_merge(values, limit), limit
+
+
 def test_product_host_template_matches_oracle(po):
     """The product's host side of the emitter (libtfgpu.so, no GPU): the branch chosen per column equals the oracle's, and the message
     template — constant text with the per-row fields between — matches every message the oracle writes, field by field."""

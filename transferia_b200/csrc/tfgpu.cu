@@ -1512,6 +1512,19 @@ const uint32_t* tfgpu_result_key_sizes(const tfgpu_result* r) { return (r && !r-
 const uint32_t* tfgpu_result_row_sizes(const tfgpu_result* r) { return (r && !r->row_sizes.empty()) ? r->row_sizes.data() : nullptr; }
 
 // queue JSON serializer batching (pkg/serializer/queue/json_batcher.go:13-66): host only, no device needed
+int tfgpu_queue_debezium_batches(const uint32_t* value_sizes, uint64_t n, uint64_t max_message_size, uint64_t* starts, uint64_t cap, uint64_t* n_msgs) {
+    if ((!value_sizes && n) || !starts || !n_msgs) return TF_E_FATAL_ARG;
+    uint64_t k = 0, cur = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        // expandArrIfNeeded :76-86: a new message for the first value and whenever len(last) + 1 + len(new) > maxMessageSize;
+        // without a limit every value stays its own message (MergeBack :53-65)
+        if (i == 0 || !max_message_size || cur + 1 + value_sizes[i] > max_message_size) { if (k >= cap) return TF_E_FATAL_ARG; starts[k++] = i; cur = 0; }
+        cur += value_sizes[i];
+    }
+    if (k >= cap) return TF_E_FATAL_ARG;
+    starts[k] = n; *n_msgs = k;
+    return TF_OK;
+}
 int tfgpu_queue_json_batches(const uint32_t* row_sizes, uint64_t n, uint64_t max_message_size, uint64_t max_change_items, uint64_t* starts, uint64_t cap, uint64_t* n_msgs) {
     if ((!row_sizes && n) || !starts || !n_msgs) return TF_E_FATAL_ARG;
     uint64_t k = 0, start = 0, sum = 0;

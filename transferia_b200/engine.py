@@ -88,7 +88,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "tfgpu_version", "tfgpu_engine_create", "tfgpu_engine_destroy", "tfgpu_last_error", "tfgpu_engine_set_stream",
-    "tfgpu_plan", "tfgpu_plan_validate", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_parse_csv", "tfgpu_parse_json", "tfgpu_measure", "tfgpu_emit_debezium", "tfgpu_emit_debezium_validate", "tfgpu_result_key_sizes", "tfgpu_result_part_ids", "tfgpu_result_row_sizes", "tfgpu_queue_json_batches", "tfgpu_parse_debezium", "tfgpu_debug_lz4_phases", "tfgpu_result_selection", "tfgpu_result_meta_kinds", "tfgpu_result_meta_tx_id", "tfgpu_result_meta_lsn", "tfgpu_result_meta_commit_time", "tfgpu_result_consumed", "tfgpu_push_encode_resident",
+    "tfgpu_plan", "tfgpu_plan_validate", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_parse_csv", "tfgpu_parse_json", "tfgpu_measure", "tfgpu_emit_debezium", "tfgpu_emit_debezium_validate", "tfgpu_result_key_sizes", "tfgpu_result_part_ids", "tfgpu_result_row_sizes", "tfgpu_queue_json_batches", "tfgpu_queue_debezium_batches", "tfgpu_parse_debezium", "tfgpu_debug_lz4_phases", "tfgpu_result_selection", "tfgpu_result_meta_kinds", "tfgpu_result_meta_tx_id", "tfgpu_result_meta_lsn", "tfgpu_result_meta_commit_time", "tfgpu_result_consumed", "tfgpu_push_encode_resident",
     "tfgpu_resident_stats", "tfgpu_resident_fetch", "tfgpu_result_rows_in", "tfgpu_result_rows_out",
     "tfgpu_result_n_errors", "tfgpu_result_errors", "tfgpu_result_batch", "tfgpu_result_bytes",
     "tfgpu_result_bytes_len", "tfgpu_result_raw_len", "tfgpu_result_n_frames", "tfgpu_result_release",
@@ -115,6 +115,18 @@ def debezium_table_schema(schema_text: str):
         else: raise EngineError(-1, f"debezium: kafka type {kt} / {nm} has no default receiver on the device")
         out.append({"name": f["field"], "type": yt, "key": not f.get("optional", False)})
     return out
+
+
+def queue_debezium_batches(value_sizes, max_message_size: int = 0):
+    """MergeWithMaxMessageSize of the queue Debezium serializer (host only): first row of every merged message, then n."""
+    import numpy as np
+    L = load_library()
+    a = np.asarray(value_sizes, dtype=np.uint32); st = np.zeros(len(a) + 1, dtype=np.uint64); k = C.c_uint64()
+    L.tfgpu_queue_debezium_batches.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    rc = L.tfgpu_queue_debezium_batches(a.ctypes.data, len(a), max_message_size, st.ctypes.data, len(st), C.byref(k))
+    if rc != 0:
+        raise EngineError(rc, "tfgpu_queue_debezium_batches")
+    return [int(x) for x in st[:k.value + 1]]
 
 
 def queue_json_batches(json_row_sizes, max_message_size: int = 0, max_change_items: int = 0):
