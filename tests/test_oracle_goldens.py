@@ -296,3 +296,16 @@ def test_to_string_canon(po):
         assert errs == [] and got == values, (tr, table, got)
     for tr, table, schema in ((excl, "a_table3", t3), (incl, "table1", t1), (incl, "table2", t2)):      # :77-87 not Suitable
         assert po.build_plan("db", table, schema, [tr]).steps == [] and engine.plan_validate("db", table, schema, [tr])["steps"] == []
+
+
+def test_measure_reference_cases(po):
+    """pkg/util/sizeof_test.go:11-150 TestDeepSizeof, the cases a row of ColumnValues can hold: []interface{} = 24-byte slice header +
+    16 bytes per element (interface) + payload; bool 1, int64 / uint64 8, string 16 + len ("interface slice", "string", "bool", ...)."""
+    b = abi.Batch(1, [abi.strings_to_column(abi.TF_UTF8, [b"a"]), abi.strings_to_column(abi.TF_UTF8, [b"b"])])
+    assert list(po.measure(b)[0]) == [24 + 2 * 16 + 2 * 16 + 2]                     # the first two elements of the test's interface slice
+    b = abi.Batch(1, [abi.fixed_to_column(abi.TF_BOOLEAN, [1]), abi.fixed_to_column(abi.TF_INT64, [64]), abi.fixed_to_column(abi.TF_UINT64, [64]),
+                      abi.strings_to_column(abi.TF_UTF8, [b"0123456789"])])
+    per, tot = po.measure(b)
+    assert list(per) == [24 + 4 * 16 + 1 + 8 + 8 + (16 + 10)] and tot == int(per[0])
+    b = abi.Batch(2, [abi.strings_to_column(abi.TF_BYTES, [b"xyz", None]), abi.fixed_to_column(abi.TF_TIMESTAMP, [0, 1]), abi.fixed_to_column(abi.TF_INT16, [1, 2], [False, True])])
+    assert list(po.measure(b)[0]) == [24 + 3 * 16 + (24 + 3) + 24 + 2, 24 + 3 * 16 + 0 + 24 + 0]    # []byte = slice header + len; time.Time = 3 words; nil = the interface only
