@@ -241,3 +241,85 @@ def test_bench_reference_arm_line(tmp_path):
     assert d["impl"] == "reference" and d["unit"] == "rows/s" and d["higher_is_better"] is True and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
+
+
+def test_plan_fuzz_product_vs_oracle(po):
+    """Random transformer chains over a mixed schema: the product's C++ plan builder (libtfgpu.so, host only) and the oracle's Python
+    restatement of transformation.AddTablePlan must agree on which transformers are Suitable, on the columns each one touches, on the
+    result schema and on the surviving columns — or both must refuse the chain."""
+    import random
+    rnd = random.Random(20240923)
+    types = ["int8", "int16", "int32", "int64", "uint8", "uint32", "uint64", "float", "double", "boolean", "string", "utf8", "any", "date", "datetime", "timestamp", "interval"]
+    names = ["id", "a", "b", "c_x", "c_y", "ts", "payload", "n1", "n2", "flag"]
+    agreed = refused = 0
+    for it in range(1500):
+        ncol = rnd.randint(2, len(names))
+        schema = [{"name": names[k], "type": rnd.choice(types), "key": k == 0, "required": rnd.random() < 0.3} for k in range(ncol)]
+        ints = [c["name"] for c in schema if c["type"] in ("int8", "int16", "int32", "int64", "uint8", "uint32", "uint64")]
+
+        def cols_cfg():
+            k = rnd.random()
+            pool = [c["name"] for c in schema] + ["^c_", "nope", "^n"]
+            if k < 0.25:
+                return {}
+            if k < 0.65:
+                return {"includeColumns": rnd.sample(pool, rnd.randint(1, 3))}
+            return {"excludeColumns": rnd.sample(pool, rnd.randint(1, 2))}
+
+        def tables_cfg():
+            k = rnd.random()
+            return {} if k < 0.6 else ({"includeTables": ["^db\\.t$"]} if k < 0.8 else {"excludeTables": ["^db\\.t$"]} if k < 0.9 else {"includeTables": ["other"]})
+
+        chain = []
+        for _ in range(rnd.randint(1, 4)):
+            k = rnd.choice(["filter_rows", "skip_events", "filter_columns", "rename_tables", "mask_field", "convert_to_string", "convert_to_datetime", "number_to_float_transformer", "sharder_transformer"])
+            if k == "filter_rows":
+                if not ints:
+                    continue
+                chain.append({k: {"tables": tables_cfg(), "filter": f"{rnd.choice(ints)} > {rnd.randint(-5, 5)}"}})
+            elif k == "skip_events":
+                chain.append({k: {"tables": tables_cfg(), "events": rnd.sample(["insert", "update", "delete"], rnd.randint(1, 2))}})
+            elif k == "filter_columns":
+                chain.append({k: {"tables": tables_cfg(), "columns": cols_cfg()}})
+            elif k == "rename_tables":
+                chain.append({k: {"renameTables": [{"originalName": {"nameSpace": "db", "name": "t"}, "newName": {"nameSpace": "db2", "name": "u"}}]}})
+            elif k == "mask_field":
+                chain.append({k: {"tables": tables_cfg(), "columns": rnd.sample([c["name"] for c in schema] + ["nope"], rnd.randint(1, 2)), "maskFunctionHash": {"userDefinedSalt": "s"}}})
+            elif k == "convert_to_string":
+                chain.append({k: {"tables": tables_cfg(), "columns": cols_cfg(), "convert_to_bytes": rnd.random() < 0.3}})
+            elif k == "convert_to_datetime":
+                chain.append({k: {"tables": tables_cfg(), "columns": cols_cfg()}})
+            elif k == "number_to_float_transformer":
+                chain.append({k: {"tables": tables_cfg()}})
+            else:
+                chain.append({k: {"tables": tables_cfg(), "columns": cols_cfg(), "shardsCount": str(rnd.randint(1, 9))}})
+        if not chain:
+            continue
+        try:
+            d = engine.plan_validate("db", "t", schema, chain)
+        except engine.EngineError:
+            d = None
+        try:
+            plan = po.build_plan("db", "t", schema, chain)
+        except (NotImplementedError, ValueError):
+            plan = None
+        if d is None:
+            # combinations the device does not model (a column rewritten twice, a filter behind a mask of its column, ...) may be refused
+            # by the product only; the oracle applies steps one after another and has no such limits
+            refused += 1
+            continue
+        assert plan is not None, chain
+        agreed += 1
+        # (a number_to_float that is Suitable but touches nothing — no `any` column left, or the table was renamed away from its filter —
+        # keeps its place in the chain on both sides; only the product lists it)
+        dsteps = [s for s in d["steps"] if not (s["type"] == "number_to_float_transformer" and not s["cols"])]
+        psteps = [s for s in plan.steps if not (s["kind"] == "number_to_float" and not s["cols"])]
+        assert [s["type"] for s in dsteps] == [{"number_to_float": "number_to_float_transformer", "sharder": "sharder_transformer"}.get(s["kind"], s["kind"]) for s in psteps], (schema, chain)
+        assert [c["name"] for c in d["result_schema"]] == [c["name"] for c in plan.result_schema], (schema, chain)
+        assert [c["type"] for c in d["result_schema"]] == [c["type"] for c in plan.result_schema], (schema, chain)
+        assert d["out_cols"] == plan.out_cols, (schema, chain)
+        assert d["result_table"] == ".".join(x for x in plan.result_table if x), (schema, chain)
+        for ds, ps in zip(dsteps, psteps):
+            if "cols" in ds and "cols" in ps:
+                assert ds["cols"] == ps["cols"], (ds, ps, chain)
+    assert agreed > 900 and refused < 600, (agreed, refused)
