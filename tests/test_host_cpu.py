@@ -323,3 +323,65 @@ def test_plan_fuzz_product_vs_oracle(po):
             if "cols" in ds and "cols" in ps:
                 assert ds["cols"] == ps["cols"], (ds, ps, chain)
     assert agreed > 900 and refused < 600, (agreed, refused)
+
+
+def test_filter_grammar_fuzz_product_vs_oracle(po):
+    """Random filter_rows expressions (every operator, literal kind, list, quoting style, AND chains, several `filters`) through the
+    product's C++ grammar and the oracle's Python restatement of the yandex-cloud filter grammar: same terms or both a syntax error."""
+    import random
+    rnd = random.Random(7)
+    cols = {"i": "int64", "u": "uint32", "d": "double", "s": "utf8", "y": "string", "b": "boolean", "t": "timestamp", "dt": "date"}
+    schema = [{"name": n, "type": t, "key": n == "i"} for n, t in cols.items()]
+
+    def lit(kind):
+        if kind == "int":
+            return str(rnd.choice([0, 1, -1, 42, 2**31, -2**63, 2**63 - 1, 2**64 - 1, 10**20, -10**20]))
+        if kind == "float":
+            return rnd.choice(["1.5", "-0.25", "10.0", "1e3", "2.5E-3", ".5", "5.", "1e400", "-1e-400", "00.1"])
+        if kind == "str":
+            body = rnd.choice(["str", "", "a b", "☺", "it''s", 'say \\"hi\\"', "x\\\\y", "tab\\tq", "%like%", "O'Neil", 'dq"in'])
+            q = rnd.choice(['"', "'"])
+            return q + body + q
+        if kind == "bool":
+            return rnd.choice(["true", "false", "TRUE", "False"])
+        if kind == "null":
+            return rnd.choice(["NULL", "null", "Null"])
+        return rnd.choice(["1990-07-22T00:00:00+04:00", "2003-04-17T10:19:00.001+03:00", "2020-01-01T00:00:00Z", "2020-01-01", "2020-13-01T00:00:00Z", "1970-01-01T00:00:00.123456789Z"])
+
+    kinds = ["int", "float", "str", "bool", "null", "time"]
+    ops = ["=", "!=", "<", "<=", ">", ">=", "~", "!~", "IN", "NOT IN", "in", "not in"]
+    same = errs = 0
+    for it in range(6000):
+        terms = []
+        for _ in range(rnd.randint(1, 3)):
+            col, op = rnd.choice(list(cols)), rnd.choice(ops)
+            if op.upper().endswith("IN"):
+                k = rnd.choice(kinds)
+                val = "(" + rnd.choice([", ", ",", " , "]).join(lit(k if rnd.random() < 0.85 else rnd.choice(kinds)) for _ in range(rnd.randint(1, 4))) + ")"
+                if rnd.random() < 0.05:
+                    val = lit(k)                                   # IN without a list: a syntax error
+            else:
+                val = lit(rnd.choice(kinds))
+            terms.append(f"{col}{rnd.choice([' ', '  '])}{op}{rnd.choice([' ', ''])}{val}" if op in ("=", "!=", "<", "<=", ">", ">=", "~", "!~") else f"{col} {op} {val}")
+        flt = rnd.choice([" AND ", " and ", " And "]).join(terms)
+        if rnd.random() < 0.03:
+            flt += rnd.choice([" AND", " OR i = 1", ")", " i"])       # broken tails
+        cfg = {"filter": flt} if rnd.random() < 0.8 else {"filters": [flt, "i > 0"]}
+        trs = [{"filter_rows": cfg}]
+        try:
+            d = engine.plan_validate("db", "t", schema, trs)
+        except engine.EngineError as ex:
+            d = ex
+        try:
+            plan = po.build_plan("db", "t", schema, trs)
+        except Exception as ex:          # FilterSyntaxError / ValueError from the grammar
+            plan = ex
+        if isinstance(d, engine.EngineError) and d.rc == -2 and not isinstance(plan, Exception):
+            continue                     # valid for the grammar, but a comparison the device does not implement (TF_E_FATAL_UNSUPPORTED)
+        if isinstance(d, Exception) or isinstance(plan, Exception):
+            assert isinstance(d, Exception) and isinstance(plan, Exception), (flt, d, plan)
+            errs += 1
+            continue
+        assert _terms_from_describe(d) == _oracle_terms(plan, po), flt
+        same += 1
+    assert same > 1800 and errs > 50, (same, errs)
