@@ -119,6 +119,15 @@ def test_s3_reader_value_rule_cases(po):
     bools = {"strings_can_be_null": True, "null_values": ["NULL", "NA"], "true_values": ["true", "yes", "1"], "false_values": ["false", "no", "0"]}
     b, e, _, _ = po.csv_parse(b"1,NULL\n2,true\n3,false\n4,TRUE\n5,random\n6,yes\n7,no\n", S2("boolean"), bools)
     assert _col(b, 1) == [0, 1, 0, 1, 1, 0] and e == [(4, 20, 0)]        # NULL -> false, lists, strconv.ParseBool("TRUE"); "random" stays a string and fails the cast
+    # TestConstructCI (:168-233): a one-element row against a two-column schema (the line "ttrue" reads as the single element "true",
+    # see the reader quirk above): included as DefaultValue with IncludeMissingColumns, "missing row element" otherwise
+    ci = [{"name": "test-first-column", "type": "boolean", "path": "0"}, {"name": "test-missing-row-column", "type": "utf8", "path": "1"}]
+    b, e, _, _ = po.csv_parse(b"ttrue\n", ci, {"include_missing_columns": True})
+    assert [_col(b, 0), _col(b, 1)] == [[1], [b""]] and not e
+    b, e, _, _ = po.csv_parse(b"ttrue\n", ci)
+    assert b.nrows == 0 and e == [(0, 16, 0)]
+    b, e, _, _ = po.csv_parse(b"true,this is a test string\n", ci)
+    assert [_col(b, 0), _col(b, 1)] == [[1], [b"this is a test string"]] and not e
     b, e, _, _ = po.csv_parse(b"1,2024-03-22\n2,2024/03/22\n", S2("date"))
     assert _col(b, 1) == [1711065600] and [x[0] for x in e] == [1]      # yyyy-mm-dd parses; a text no parser takes stays a string
 
