@@ -40,6 +40,20 @@ def test_parser_canon(po):
         else: assert got == want, (name, got, want)
 
 
+def test_delete_envelope(po):
+    """pkg/debezium/receiver_test.go:15-26 TestDelete: op "d" -> kind delete, ID / LSN from `source`, the table schema from the
+    envelope (a_id int32 key, a_name utf8), and the `before` values — what the reference stores as OldKeys {a_id: 1}; the columnar
+    row carries them as the row's values with kind = delete, the shim moves the key columns into OldKeys (receiver.go:196-216)."""
+    d = G["delete_case"]; exp = d["expected"]
+    data = d["message"].encode()
+    b, kinds, tx, lsn, ct, rm, errs, schema = po.debezium_parse(data, [len(data)], d["schema_text"])
+    assert errs == [] and b.nrows == 1 and list(kinds) == [abi.TF_KIND_DELETE] and exp["kind"] == "delete"
+    assert int(tx[0]) == exp["id"] and int(lsn[0]) == exp["nextlsn"] and int(ct[0]) == 1672943646565 * 10**6
+    assert [[c["name"], c["type"], bool(c.get("key"))] for c in schema] == exp["types"]
+    row = {c["name"]: cell(b, k, 0) for k, c in enumerate(schema)}
+    assert {k: row[k] for k in exp["oldkeys"]["keynames"]} == dict(zip(exp["oldkeys"]["keynames"], exp["oldkeys"]["keyvalues"])) and row["a_name"] is None
+
+
 def test_base64_to_numeric(po):
     """typeutil.Base64ToNumeric (helpers.go:972-998) incl. its quirks: scale == len gives ".12", negative two's complement."""
     f = po.base64_to_numeric
