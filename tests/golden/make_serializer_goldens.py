@@ -136,5 +136,8 @@ for f in sorted(glob.glob(ROOT + "/**/extracted", recursive=True)):
         else:
             cases.append({"schema": schema, "rows": [row], "source": os.path.relpath(f, ROOT)})
 out = {"cases": cases, "json_lines": open(GOLD % "json", encoding="utf-8").read().split("\n"), "csv_text": open(GOLD % "csv", encoding="utf-8").read()}
+# pkg/serializer/queue/json_serializer_test.go:33-126 TestJSONSerializerTopicNameAllTypes: the value the queue JSON serializer wrote for an
+# item with every YT type (the item is not strict: its `string` column holds a Go string, its `timestamp` column a Duration)
+out["queue_json_all_types"] = open("/root/reference/pkg/serializer/queue/gotest/canondata/gotest.gotest.TestJSONSerializerTopicNameAllTypes/extracted", encoding="utf-8").read()
 json.dump(out, open(os.path.join(os.path.dirname(__file__), "serializer_goldens.json"), "w"), ensure_ascii=False, indent=0)
 print(len(cases), "schemas", sum(len(c["rows"]) for c in cases), "rows; skipped:", sorted(skipped.items(), key=lambda kv: -kv[1])[:12])
