@@ -225,6 +225,25 @@ def test_oracle_kinds_and_chain(po):
     assert after["x"] == 30 and len(after["name"]) == 64 and after["name"] == po.hmac_hex(b"s", b"c")
 
 
+def test_oracle_against_typeutil_unit_tests(po):
+    """pkg/debezium/typeutil/helpers_test.go: TestGetTimeDivider (:329-375, the timestamp rows), TestSprintfDebeziumTime (:488-496),
+    TestLSNToFileAndPos (:482-486) — through the emitter: one row, the pg branches that use those helpers."""
+    import calendar, datetime
+    F = po.debezium_pg_form
+    for p_, want in ((1, 9), (3, 9), (4, 8), (6, 8)):          # divider 1000 -> milliseconds (branch 9), 1 -> microseconds (branch 8)
+        assert F({"type": "timestamp", "original_type": f"pg:timestamp({p_}) without time zone"}) == want
+    assert F({"type": "timestamp", "original_type": "pg:timestamp without time zone"}) == 8
+    sec = calendar.timegm(datetime.datetime(2022, 8, 28, 19, 49, 47).timetuple())
+    schema = [{"name": "a", "type": "timestamp", "original_type": "pg:timestamp with time zone", "key": True}, {"name": "b", "type": "timestamp", "original_type": "pg:timestamp with time zone"}]
+    b = abi.Batch(1, [abi.fixed_to_column(abi.TF_TIMESTAMP, [sec], None, [749906000]), abi.fixed_to_column(abi.TF_TIMESTAMP, [sec], None, [90000000])])
+    meta = {"lsn": np.array([2000000013747], np.uint64)}
+    data, ks, rs, errs = po.debezium_emit(b, po.build_plan("db", "t", schema, []), {"source_type": "mysql", "version": "1"}, meta)
+    (_, val), = po.debezium_split(data, ks, rs)
+    v = json.loads(val)
+    assert v["after"] == {"a": "2022-08-28T19:49:47.749906Z", "b": "2022-08-28T19:49:47.09Z"}
+    assert v["source"]["file"] == "mysql-log.000002" and v["source"]["pos"] == 13747
+
+
 def test_queue_debezium_batching(po):
     """debezium_multithreading_test.go:10-70 TestMergeWithMaxMessageSize (values {0,0} and {1,1}: one message under a big limit, two
     under limit 1) and random sizes against the literal restatement; the product's host-only function gives the same cuts."""
