@@ -331,6 +331,10 @@ int tfgpu_parse_json(tfgpu_engine* e, int plan_id, const char* opts_json, const 
 #define TF_ROWERR_DBZ_OTHER_TABLE  51
 int tfgpu_parse_debezium(tfgpu_engine* e, int plan_id, const char* opts_json, const uint8_t* bytes, uint64_t len, int mem,
                          const uint64_t* msg_ends, uint32_t n_msgs, int wire_fmt, tfgpu_result** out);
+/* Host-only (no GPU): the table schema tfgpu_parse_debezium expects the plan to be built for — name, YT type, key = !optional — and the
+ * receiver of every field, derived from the envelope schema as the reference does (receiver.go:46-62, receiver_engine.go:104-141), or
+ * the error the call would return (database specific original types, struct kinds without a default receiver, before != after). */
+int tfgpu_debezium_schema_validate(const char* schema_text, char* describe_out, uint64_t cap, char* err_out, uint64_t err_cap);
 /* Profiling aid: cycles thread 0 of every k_lz4_frames CTA spent in {stage, match finding, parse, scan, emit} since the last read. */
 int tfgpu_debug_lz4_phases(tfgpu_engine* e, int enable, uint64_t out[8]);
 const uint32_t*   tfgpu_result_selection(const tfgpu_result* r);          /* rows_out entries: input row of each output row */

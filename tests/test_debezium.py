@@ -54,6 +54,30 @@ def test_delete_envelope(po):
     assert {k: row[k] for k in exp["oldkeys"]["keynames"]} == dict(zip(exp["oldkeys"]["keynames"], exp["oldkeys"]["keyvalues"])) and row["a_name"] is None
 
 
+def test_product_schema_derivation_matches_oracle(po):
+    """The product's host side of tfgpu_parse_debezium (libtfgpu.so, no GPU): table schema and receivers derived from the envelope schema
+    (receiver.go:46-62, receiver_engine.go:104-141) equal the oracle's for the reference's 59-column canon schema and for the Decimal /
+    VariableScaleDecimal / Point / Bits shapes; schemas the device does not take are refused on the host."""
+    from transferia_b200 import engine
+    canon = json.dumps(json.loads(G["messages"][0])["schema"], separators=(",", ":"))
+    fld = lambda typ, fname, opt=True, **kw: dict({"type": typ, "optional": opt, "field": fname}, **kw)
+    env = lambda fields: json.dumps({"type": "struct", "fields": [{"type": "struct", "fields": fields, "optional": True, "field": "before"}, {"type": "struct", "fields": fields, "optional": True, "field": "after"}]})
+    shapes = env([fld("int32", "id", False), fld("bytes", "dec", name="org.apache.kafka.connect.data.Decimal", parameters={"scale": "3"}), fld("bytes", "raw"),
+                  fld("struct", "vsd", name="io.debezium.data.VariableScaleDecimal", fields=[]), fld("struct", "pt", name="io.debezium.data.geometry.Point", fields=[]),
+                  fld("bytes", "bits", name="io.debezium.data.Bits", parameters={"length": "8"}), fld("float", "f"), fld("double", "d"), fld("int8", "i8"), fld("string", "s")])
+    for text in (canon, shapes):
+        got = engine.debezium_schema_validate(text)
+        fields, schema = po.debezium_fields(text)
+        assert [(x["name"], x["recv"], x["scale"], x["key"]) for x in got] == [tuple(f) for f in fields]
+        assert [(x["name"], x["type"], x["key"]) for x in got] == [(c["name"], c["type"], bool(c.get("key"))) for c in schema]
+        assert [(c["name"], c["type"], bool(c.get("key"))) for c in engine.debezium_table_schema(text)] == [(x["name"], x["type"], x["key"]) for x in got]
+    for bad in (env([fld("int32", "id", __dt_original_type_info={"original_type": "pg:integer"})]), env([fld("array", "a")]), env([fld("struct", "x", name="some.other.Struct", fields=[])]),
+                json.dumps({"type": "struct", "fields": [{"type": "struct", "fields": [fld("int32", "id")], "field": "after"}]}),
+                json.dumps({"type": "struct", "fields": [{"type": "struct", "fields": [fld("int32", "id")], "field": "after"}, {"type": "struct", "fields": [fld("int64", "id")], "field": "before"}]}), "{not json"):
+        with pytest.raises(engine.EngineError):
+            engine.debezium_schema_validate(bad)
+
+
 def test_base64_to_numeric(po):
     """typeutil.Base64ToNumeric (helpers.go:972-998) incl. its quirks: scale == len gives ".12", negative two's complement."""
     f = po.base64_to_numeric

@@ -1375,6 +1375,31 @@ std::vector<DbzHostField> dbz_fields(const tfj::Value& schema, const char* which
 }
 }  // namespace
 
+// Host-only: the table schema and receivers tfgpu_parse_debezium derives from a Kafka Connect envelope schema (no GPU needed):
+// [{"name","type","key","recv","scale"}, ...] in the order of the `after` struct, or the error the call would return.
+int tfgpu_debezium_schema_validate(const char* schema_text, char* describe_out, uint64_t cap, char* err_out, uint64_t err_cap) {
+    auto put = [](char* dst, uint64_t cap_, const std::string& s) { if (dst && cap_) { size_t n = s.size() < cap_ - 1 ? s.size() : cap_ - 1; std::memcpy(dst, s.data(), n); dst[n] = 0; } };
+    if (!schema_text) return TF_E_FATAL_ARG;
+    try {
+        auto sv = tfj::parse(schema_text);
+        const std::vector<DbzHostField> fs = dbz_fields(*sv, "after"), fb = dbz_fields(*sv, "before");
+        if (fs.size() != fb.size()) throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "debezium: 'before' and 'after' structs differ");
+        for (size_t i = 0; i < fs.size(); i++) if (fs[i].name != fb[i].name || fs[i].recv != fb[i].recv || fs[i].scale != fb[i].scale) throw tfplan::FatalError(TF_E_FATAL_UNSUPPORTED, "debezium: 'before' and 'after' structs differ");
+        static const char* yt[] = {"", "int8", "int16", "int32", "int64", "uint8", "uint16", "uint32", "uint64", "float", "double", "boolean", "string", "utf8", "any", "date", "datetime", "timestamp", "interval"};
+        std::string d = "[";
+        for (size_t i = 0; i < fs.size(); i++) {
+            if (i) d += ",";
+            d += "{\"name\":" + host_json_quote_nohtml(fs[i].name) + ",\"type\":\"" + yt[fs[i].tf] + "\",\"key\":" + (fs[i].key ? "true" : "false") +
+                 ",\"recv\":" + std::to_string(fs[i].recv) + ",\"scale\":" + std::to_string(fs[i].scale) + "}";
+        }
+        d += "]";
+        if (describe_out && d.size() + 1 > cap) { put(err_out, err_cap, "describe buffer too small"); return TF_E_FATAL_ARG; }
+        put(describe_out, cap, d);
+        return TF_OK;
+    } catch (const tfplan::FatalError& f) { put(err_out, err_cap, f.what()); return f.code; }
+    catch (const std::exception& x) { put(err_out, err_cap, x.what()); return TF_E_FATAL_CONFIG; }
+}
+
 int tfgpu_parse_debezium(tfgpu_engine* e, int plan_id, const char* opts_json, const uint8_t* bytes, uint64_t len, int mem,
                          const uint64_t* msg_ends, uint32_t n_msgs, int wire_fmt, tfgpu_result** out) {
     if (!e || !out || !opts_json || (!bytes && len) || (!msg_ends && n_msgs) || plan_id < 0 || plan_id >= (int)e->plans.size()) return TF_E_FATAL_ARG;

@@ -88,7 +88,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "tfgpu_version", "tfgpu_engine_create", "tfgpu_engine_destroy", "tfgpu_last_error", "tfgpu_engine_set_stream",
-    "tfgpu_plan", "tfgpu_plan_validate", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_parse_csv", "tfgpu_parse_json", "tfgpu_measure", "tfgpu_emit_debezium", "tfgpu_emit_debezium_validate", "tfgpu_result_key_sizes", "tfgpu_result_part_ids", "tfgpu_result_row_sizes", "tfgpu_queue_json_batches", "tfgpu_queue_debezium_batches", "tfgpu_parse_debezium", "tfgpu_debug_lz4_phases", "tfgpu_result_selection", "tfgpu_result_meta_kinds", "tfgpu_result_meta_tx_id", "tfgpu_result_meta_lsn", "tfgpu_result_meta_commit_time", "tfgpu_result_consumed", "tfgpu_push_encode_resident",
+    "tfgpu_plan", "tfgpu_plan_validate", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_parse_csv", "tfgpu_parse_json", "tfgpu_measure", "tfgpu_emit_debezium", "tfgpu_emit_debezium_validate", "tfgpu_result_key_sizes", "tfgpu_result_part_ids", "tfgpu_result_row_sizes", "tfgpu_queue_json_batches", "tfgpu_queue_debezium_batches", "tfgpu_parse_debezium", "tfgpu_debezium_schema_validate", "tfgpu_debug_lz4_phases", "tfgpu_result_selection", "tfgpu_result_meta_kinds", "tfgpu_result_meta_tx_id", "tfgpu_result_meta_lsn", "tfgpu_result_meta_commit_time", "tfgpu_result_consumed", "tfgpu_push_encode_resident",
     "tfgpu_resident_stats", "tfgpu_resident_fetch", "tfgpu_result_rows_in", "tfgpu_result_rows_out",
     "tfgpu_result_n_errors", "tfgpu_result_errors", "tfgpu_result_batch", "tfgpu_result_bytes",
     "tfgpu_result_bytes_len", "tfgpu_result_raw_len", "tfgpu_result_n_frames", "tfgpu_result_release",
@@ -158,6 +158,17 @@ def json_result_schema(fields, opts: Optional[dict] = None):
         for n, t in (("_timestamp", "timestamp"), ("_partition", "string"), ("_offset", "uint64"), ("_idx", "uint32")):
             out.append({"name": dedup(n), "type": t, "key": sys_key, "required": sys_key})
     return out
+
+
+def debezium_schema_validate(schema_text: str) -> list:
+    """Host-only: [{"name","type","key","recv","scale"}] the C++ side derives from an envelope schema (no GPU needed), or raises EngineError."""
+    L = load_library()
+    out = C.create_string_buffer(1 << 20); err = C.create_string_buffer(4096)
+    L.tfgpu_debezium_schema_validate.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
+    rc = L.tfgpu_debezium_schema_validate(schema_text.encode(), out, len(out), err, len(err))
+    if rc != 0:
+        raise EngineError(rc, err.value.decode(errors="replace"))
+    return json.loads(out.value.decode())
 
 
 def emit_debezium_validate(namespace: str, name: str, schema, transformers, opts: dict) -> dict:
