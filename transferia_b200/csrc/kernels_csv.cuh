@@ -53,6 +53,7 @@ struct CsvArgs {
 // `endbits` (JSON parser): bit p set = byte p is the last byte of a message, which ends a line like '\n' does
 __device__ __forceinline__ bool csv_line_end(const uint8_t* text, const uint32_t* endbits, uint64_t p) { return text[p] == '\n' || (endbits && ((endbits[p >> 5] >> (p & 31)) & 1)); }
 
+#ifdef TF_KERNELS_CSV
 __global__ void __launch_bounds__(256) k_csv_count_nl(const uint8_t* text, uint64_t len, uint32_t* blk_cnt, const uint32_t* endbits) {
     __shared__ uint32_t sm[33];
     const uint64_t b0 = (uint64_t)blockIdx.x * CSV_NL_BLOCK;
@@ -61,7 +62,9 @@ __global__ void __launch_bounds__(256) k_csv_count_nl(const uint8_t* text, uint6
     uint32_t tot; block_excl_scan(c, &tot, sm);
     if (threadIdx.x == 0) blk_cnt[blockIdx.x] = tot;
 }
+#endif  // TF_KERNELS_CSV
 
+#ifdef TF_KERNELS_CSV
 __global__ void __launch_bounds__(256) k_csv_line_index(const uint8_t* text, uint64_t len, const uint32_t* blk_off, uint32_t* line_end, const uint32_t* endbits) {
     __shared__ uint32_t sm[33];
     const uint64_t b0 = (uint64_t)blockIdx.x * CSV_NL_BLOCK;
@@ -72,6 +75,7 @@ __global__ void __launch_bounds__(256) k_csv_line_index(const uint8_t* text, uin
     uint32_t w = blk_off[blockIdx.x] + ex;
     for (uint32_t k = 0; k < CSV_NL_BLOCK / 256; k++) { const uint64_t p = t0 + k; if (p < len && csv_line_end(text, endbits, p)) line_end[w++] = (uint32_t)(p + 1); }
 }
+#endif  // TF_KERNELS_CSV
 
 // ---- text -> value helpers (must agree with oracle/csv_oracle.hpp, which restates the Go functions)
 __device__ __forceinline__ bool d_space(const uint8_t* p, uint32_t n, uint32_t& w) {   // unicode.IsSpace
@@ -110,7 +114,7 @@ __device__ __forceinline__ bool d_in_list(const uint8_t* blob, uint32_t list, co
     return false;
 }
 // strconv.ParseInt(trimZeroDecimal(s), 0, 0): rc 0 ok, 1 error, 2 unsupported (underscores)
-__device__ int d_parse_int(const uint8_t* s, uint32_t n, int64_t& out) {
+__device__ inline int d_parse_int(const uint8_t* s, uint32_t n, int64_t& out) {
     { bool zero = false; uint32_t i = n; for (; i > 0; i--) { const uint8_t c = s[i - 1]; if (c == '.') { if (zero) n = i - 1; break; } else if (c == '0') zero = true; else break; } }
     if (!n) return 1;
     uint32_t i = 0; bool neg = false;
@@ -133,14 +137,14 @@ __device__ int d_parse_int(const uint8_t* s, uint32_t n, int64_t& out) {
     out = neg ? (int64_t)(0 - v) : (int64_t)v; return 0;
 }
 __device__ __forceinline__ bool d_eq(const uint8_t* s, uint32_t n, const char* lit) { uint32_t i = 0; for (; lit[i]; i++) if (i >= n || s[i] != (uint8_t)lit[i]) return false; return i == n; }
-__device__ int d_parse_bool(const uint8_t* s, uint32_t n, bool& out) {   // strconv.ParseBool
+__device__ inline int d_parse_bool(const uint8_t* s, uint32_t n, bool& out) {   // strconv.ParseBool
     if (d_eq(s, n, "1") || d_eq(s, n, "t") || d_eq(s, n, "T") || d_eq(s, n, "TRUE") || d_eq(s, n, "true") || d_eq(s, n, "True")) { out = true; return 0; }
     if (d_eq(s, n, "0") || d_eq(s, n, "f") || d_eq(s, n, "F") || d_eq(s, n, "FALSE") || d_eq(s, n, "false") || d_eq(s, n, "False")) { out = false; return 0; }
     return 1;
 }
 __constant__ double d_p10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
 // decimal text -> double, exact when <= 15 significant digits and |exp10| <= 22 (one correctly rounded IEEE op); rc 2 otherwise
-__device__ int d_parse_float(const uint8_t* s, uint32_t n, double& out) {
+__device__ inline int d_parse_float(const uint8_t* s, uint32_t n, double& out) {
     uint32_t i = 0; bool neg = false;
     if (!n) return 1;
     if (s[0] == '+' || s[0] == '-') { neg = s[0] == '-'; i = 1; }
@@ -174,7 +178,7 @@ __device__ __forceinline__ int64_t d_days_from_civil(int64_t y, unsigned m, unsi
     const unsigned doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
     return era * 146097 + (int64_t)doe - 719468;
 }
-__device__ int d_parse_time(const uint8_t* s, uint32_t n, int64_t& sec, uint32_t& nsec) {
+__device__ inline int d_parse_time(const uint8_t* s, uint32_t n, int64_t& sec, uint32_t& nsec) {
     auto dig = [&](uint32_t p, int k, int& v) { v = 0; for (int i = 0; i < k; i++) { if (p + i >= n || s[p + i] < '0' || s[p + i] > '9') return false; v = v * 10 + (s[p + i] - '0'); } return true; };
     int y, mo, d, hh = 0, mi = 0, ss = 0; nsec = 0; int64_t off = 0;
     if (!(dig(0, 4, y) && n >= 10 && s[4] == '-' && dig(5, 2, mo) && s[7] == '-' && dig(8, 2, d))) return 2;
@@ -215,7 +219,7 @@ __device__ __forceinline__ void csv_store_fixed(const CsvColDev& c, uint64_t row
 }
 
 // getCorrespondingValue + strictifyValue for one cell [p, p+n) (already sanitised); text cells return their span
-__device__ int csv_cell(const CsvArgs& a, const CsvColDev& c, uint64_t row, uint64_t nrows, const uint8_t* p, uint32_t n, bool has_dq) {
+__device__ inline int csv_cell(const CsvArgs& a, const CsvColDev& c, uint64_t row, uint64_t nrows, const uint8_t* p, uint32_t n, bool has_dq) {
     const CsvCfg& o = a.cfg;
     if (has_dq && c.w) return CSV_UNSUPPORTED;       // a `""` inside a numeric cell: the collapsed text would have to be materialised first
     switch (c.tf) {
@@ -286,6 +290,7 @@ __device__ __forceinline__ void csv_default(const CsvArgs& a, const CsvColDev& c
     if (c.tf == TF_ANY) { ss[row] = 0xffffffffu; sl[row] = 2; c.aux8[row] = 0; } else { ss[row] = 0; sl[row] = 0; }
 }
 
+#ifdef TF_KERNELS_CSV
 __global__ void __launch_bounds__(128) k_csv_pass1(CsvArgs a) {
     const uint64_t nrows = a.nlines - a.skip;
     const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -336,8 +341,10 @@ __global__ void __launch_bounds__(128) k_csv_pass1(CsvArgs a) {
     }
     a.err[row] = (uint8_t)err;
 }
+#endif  // TF_KERNELS_CSV
 
 // per text column: offsets[r] = sum of lengths of rows < r. One CTA per column walks its rows in chunks.
+#ifdef TF_KERNELS_CSV
 __global__ void __launch_bounds__(1024) k_csv_offsets(const uint32_t* span_len, uint64_t nrows, uint32_t* offsets /* [nslots][nrows+1] */, uint64_t* col_total) {
     __shared__ uint32_t sm[33];
     const uint32_t* len = span_len + (size_t)blockIdx.x * nrows; uint32_t* off = offsets + (size_t)blockIdx.x * (nrows + 1);
@@ -351,10 +358,12 @@ __global__ void __launch_bounds__(1024) k_csv_offsets(const uint32_t* span_len, 
     }
     if (threadIdx.x == 0) { off[nrows] = (uint32_t)carry; col_total[blockIdx.x] = carry; }
 }
+#endif  // TF_KERNELS_CSV
 
 // The same scan over many CTAs: chunk sums, a scan of the chunk sums per column, then the offsets (3 short launches instead
 // of one CTA per column walking every row).
 #define CSV_OFF_CHUNK 4096
+#ifdef TF_KERNELS_CSV
 __global__ void __launch_bounds__(1024) k_offsets_sum(const uint32_t* span_len, uint64_t nrows, uint32_t nchunks, uint64_t* chunk_sum /* [nslots][nchunks] */) {
     __shared__ uint32_t sm[33];
     const uint32_t* len = span_len + (size_t)blockIdx.y * nrows;
@@ -365,6 +374,8 @@ __global__ void __launch_bounds__(1024) k_offsets_sum(const uint32_t* span_len, 
     uint32_t tot; block_excl_scan(v, &tot, sm);
     if (threadIdx.x == 0) chunk_sum[(size_t)blockIdx.y * nchunks + blockIdx.x] = tot;
 }
+#endif  // TF_KERNELS_CSV
+#ifdef TF_KERNELS_CSV
 __global__ void __launch_bounds__(32) k_offsets_chunks(uint64_t* chunk_sum, uint32_t nchunks, uint64_t* col_total) {     // in place: exclusive scan per column, one warp
     uint64_t* cs = chunk_sum + (size_t)blockIdx.x * nchunks;
     const uint32_t lane = threadIdx.x;
@@ -380,6 +391,8 @@ __global__ void __launch_bounds__(32) k_offsets_chunks(uint64_t* chunk_sum, uint
     }
     if (lane == 0) col_total[blockIdx.x] = carry;
 }
+#endif  // TF_KERNELS_CSV
+#ifdef TF_KERNELS_CSV
 __global__ void __launch_bounds__(1024) k_offsets_write(const uint32_t* span_len, uint64_t nrows, uint32_t nchunks, const uint64_t* chunk_base, const uint64_t* col_total, uint32_t* offsets /* [nslots][nrows+1] */) {
     __shared__ uint32_t sm[33];
     const uint32_t* len = span_len + (size_t)blockIdx.y * nrows; uint32_t* off = offsets + (size_t)blockIdx.y * (nrows + 1);
@@ -393,9 +406,11 @@ __global__ void __launch_bounds__(1024) k_offsets_write(const uint32_t* span_len
     for (int k = 0; k < CSV_OFF_CHUNK / 1024; k++) { const uint64_t i = base + k; if (i < nrows) off[i] = (uint32_t)run; run += v[k]; }
     if (blockIdx.x == 0 && threadIdx.x == 0) off[nrows] = (uint32_t)col_total[blockIdx.y];
 }
+#endif  // TF_KERNELS_CSV
 
 struct CsvCopyArgs { const uint8_t* text; const uint32_t* span_start; const uint32_t* span_len; const uint32_t* offsets; uint8_t* heap; const uint64_t* col_base; uint64_t nrows; };
 
+#ifdef TF_KERNELS_CSV
 __global__ void __launch_bounds__(256) k_csv_pass2(CsvCopyArgs a) {
     const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= a.nrows) return;
@@ -409,5 +424,6 @@ __global__ void __launch_bounds__(256) k_csv_pass2(CsvCopyArgs a) {
     if (lf & 0x80000000u) { uint32_t k = 0; for (uint32_t w = 0; w < L; w++) { o[w] = s[k]; k += (s[k] == '"' && s[k + 1] == '"') ? 2 : 1; } }
     else for (uint32_t k = 0; k < L; k++) o[k] = s[k];
 }
+#endif  // TF_KERNELS_CSV
 
 }  // namespace tfk

@@ -38,7 +38,7 @@ struct DbzArgs {
 // ------------------------------------------------------------------ encoding/json grammar (checkValid)
 // validates ONE value starting at s[p] (after optional whitespace); returns 0 ok / 1 syntax error / 2 too deep; p ends after the
 // value. odd_key is set when an object key holds a backslash or a non-ASCII byte (case folding / unescaping left to the host).
-__device__ int dbz_validate(const uint8_t* s, uint32_t n, uint32_t& p, bool& odd_key) {
+__device__ inline int dbz_validate(const uint8_t* s, uint32_t n, uint32_t& p, bool& odd_key) {
     while (p < n && jsn_ws(s[p])) p++;
     uint32_t stk[DBZ_MAX_DEPTH / 32]; int depth = 0; int st = 0;      // st 0 value, 1 key, 2 after value
     for (;;) {
@@ -253,6 +253,7 @@ __device__ __forceinline__ bool dbz_lit_uint(const uint8_t* s, uint32_t off, uin
     out = v; set = true; return true;
 }
 
+#ifdef TF_KERNELS_DBZ
 __global__ void __launch_bounds__(128) k_dbz_pass1(DbzArgs a) {
     const uint64_t M = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = M < a.nmsgs;
@@ -412,9 +413,11 @@ __global__ void __launch_bounds__(128) k_dbz_pass1(DbzArgs a) {
         if ((threadIdx.x & 31) == 0 && active) a.cols[c].validity[M >> 5] = word;
     }
 }
+#endif  // TF_KERNELS_DBZ
 
 struct DbzWriteArgs { DbzArgs a; const uint32_t* offsets; uint8_t* heap; const uint64_t* col_base; };
 
+#ifdef TF_KERNELS_DBZ
 __global__ void __launch_bounds__(128) k_dbz_pass2(DbzWriteArgs w) {
     const DbzArgs& a = w.a;
     const uint64_t M = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -428,5 +431,6 @@ __global__ void __launch_bounds__(128) k_dbz_pass2(DbzWriteArgs w) {
         dbz_emit_text(ms, cd, a.text, a.span_start[(size_t)c * a.nmsgs + M], len, t);
     }
 }
+#endif  // TF_KERNELS_DBZ
 
 }  // namespace tfk

@@ -90,7 +90,7 @@ __device__ __forceinline__ bool contains_bytes(const uint8_t* h, uint32_t hn, co
 }
 
 // returns 0 and sets matched, or a TF_ROWERR_* code
-__device__ int eval_term(const RowVal& v, const DTerm& t, const uint8_t* blob, bool& matched) {
+__device__ inline int eval_term(const RowVal& v, const DTerm& t, const uint8_t* blob, bool& matched) {
     const int op = t.op; const bool is_set = (op == 6 || op == 7);
     const int base = t.vtype & 15; const bool is_list = (t.vtype & 16) != 0;
     if (v.cls == 8) return TF_ROWERR_FILTER_OVERFLOW;                       // filter_rows.go:193-197
@@ -167,6 +167,7 @@ struct FilterArgs {
 };
 
 // FilterRowsTransformer.Apply (filter_rows.go:99-130): one thread per row.
+#ifdef TF_KERNELS_ENCODE
 __global__ void __launch_bounds__(256) k_filter(FilterArgs a) {
     __shared__ uint32_t s_cnt, s_err;
     if (threadIdx.x == 0) { s_cnt = 0; s_err = 0; }
@@ -207,8 +208,10 @@ __global__ void __launch_bounds__(256) k_filter(FilterArgs a) {
     __syncthreads();
     if (threadIdx.x == 0) { a.blockcnt[blockIdx.x] = s_cnt; if (s_err) atomicAdd((unsigned long long*)&a.st->n_errors, (unsigned long long)s_err); }
 }
+#endif  // TF_KERNELS_ENCODE
 
 // exclusive scan of per-block kept counts (single block), total -> state.n_kept
+#ifdef TF_KERNELS_ENCODE
 __global__ void __launch_bounds__(1024) k_scan_blockcnt(const uint32_t* blockcnt, uint32_t* blockoff, uint32_t nblocks, DState* st) {
     __shared__ uint32_t sm[33];
     uint32_t carry = 0;
@@ -221,8 +224,10 @@ __global__ void __launch_bounds__(1024) k_scan_blockcnt(const uint32_t* blockcnt
     }
     if (threadIdx.x == 0) st->n_kept = carry;
 }
+#endif  // TF_KERNELS_ENCODE
 
 // sel[j] = index of the j-th kept row (order preserved)
+#ifdef TF_KERNELS_ENCODE
 __global__ void __launch_bounds__(256) k_compact_sel(const uint8_t* keep, const uint32_t* blockoff, uint64_t nrows, uint32_t* sel) {
     __shared__ uint32_t sm[33];
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -230,6 +235,7 @@ __global__ void __launch_bounds__(256) k_compact_sel(const uint8_t* keep, const 
     uint32_t tot; const uint32_t ex = block_excl_scan(k, &tot, sm);
     if (k) sel[blockoff[blockIdx.x] + ex] = (uint32_t)r;
 }
+#endif  // TF_KERNELS_ENCODE
 
 // ------------------------------------------------------------------ layout of the native block
 struct LayoutArgs {
@@ -254,6 +260,7 @@ struct LayoutArgs {
 // Block layout (clickhouse-go/v2 v2.46.0 lib/proto/block.go, revision 54460):
 //   uvarint 1, u8 is_overflows=0, uvarint 2, i32 bucket_num=-1, uvarint 0, uvarint ncols, uvarint nrows,
 //   per column: string name, string type, u8 custom_serialization=0, [null map], data
+#ifdef TF_KERNELS_ENCODE
 __global__ void __launch_bounds__(1024) k_layout_scan(LayoutArgs a) {
     __shared__ uint32_t sm[33];
     const int s = blockIdx.x;
@@ -269,7 +276,9 @@ __global__ void __launch_bounds__(1024) k_layout_scan(LayoutArgs a) {
     }
     if (threadIdx.x == 0) a.col_bytes[s] = carry;
 }
+#endif  // TF_KERNELS_ENCODE
 
+#ifdef TF_KERNELS_ENCODE
 __global__ void __launch_bounds__(256) k_layout_finish(LayoutArgs a) {
     __shared__ uint64_t s_size[3][256];     // header, null map, data bytes per column (ncols <= 256 per pass)
     __shared__ uint64_t s_pos[256];
@@ -314,11 +323,13 @@ __global__ void __launch_bounds__(256) k_layout_finish(LayoutArgs a) {
         a.st->frame_ticket = 0;
     }
 }
+#endif  // TF_KERNELS_ENCODE
 
 // Columnar (tf_batch-shaped) output for tfgpu_push_columns: per output column 16-byte aligned regions
 // [values | validity bitmap | aux | offsets | heap]; the region table goes back to the host with the data.
 struct ColRegions { uint64_t values, validity, aux, offsets, heap, heap_len; };   // offsets into the buffer; ~0 = absent
 
+#ifdef TF_KERNELS_ENCODE
 __global__ void __launch_bounds__(256) k_layout_columnar(LayoutArgs a, ColRegions* regions) {
     __shared__ uint64_t s_sz[5][256];
     __shared__ uint64_t s_pos[256];
@@ -362,6 +373,7 @@ __global__ void __launch_bounds__(256) k_layout_columnar(LayoutArgs a, ColRegion
     __syncthreads();
     if (threadIdx.x == 0) { a.st->raw_total = s_run; a.st->n_frames = 0; a.st->frame_ticket = 0; }
 }
+#endif  // TF_KERNELS_ENCODE
 
 // ------------------------------------------------------------------ fixed-width columns
 struct EncodeArgs {
@@ -461,6 +473,7 @@ template <int K, int INW, int W> __device__ __forceinline__ void encode_stream(c
 }
 
 // Fixed-width columns, null maps and (columnar output) aux arrays: blockIdx.y = stream slot.
+#ifdef TF_KERNELS_ENCODE
 __global__ void __launch_bounds__(256) k_encode_fixed(EncodeArgs a) {
     const int32_t slot = a.slots[blockIdx.y];
     const DCol c = a.cols[slot & ~(TF_SLOT_NULLMAP | TF_SLOT_AUX | TF_SLOT_ZEROMAP)];
@@ -486,8 +499,10 @@ __global__ void __launch_bounds__(256) k_encode_fixed(EncodeArgs a) {
     case OK_TODT: if (a.columnar) encode_stream<SK_TODT_SEC, 4, 8>(c, a, c.out_off, n); else encode_stream<SK_TODT_CH, 4, 4>(c, a, c.out_off, n); break;
     }
 }
+#endif  // TF_KERNELS_ENCODE
 
 // validity bitmap of the kept rows: one thread per output byte (8 rows)
+#ifdef TF_KERNELS_ENCODE
 __global__ void __launch_bounds__(256) k_pack_validity(EncodeArgs a) {
     const DCol c = a.cols[a.slots[blockIdx.y]];
     const uint64_t n = a.st->n_kept;
@@ -501,6 +516,7 @@ __global__ void __launch_bounds__(256) k_pack_validity(EncodeArgs a) {
     }
     a.raw[c.null_off + b] = (uint8_t)v;
 }
+#endif  // TF_KERNELS_ENCODE
 
 
 // ------------------------------------------------------------------ Measurer
@@ -512,6 +528,7 @@ __global__ void __launch_bounds__(256) k_pack_validity(EncodeArgs a) {
 // JSON text in a string -- an estimate, flagged in DESIGN.md.
 struct MeasureArgs { const DCol* cols; int ncols; uint64_t nrows; uint64_t* per_row; unsigned long long* total; };
 
+#ifdef TF_KERNELS_ENCODE
 __global__ void __launch_bounds__(256) k_measure(MeasureArgs a) {
     __shared__ uint32_t sm[33];
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -537,5 +554,6 @@ __global__ void __launch_bounds__(256) k_measure(MeasureArgs a) {
     uint32_t tl, th; block_excl_scan(lo, &tl, sm); __syncthreads(); block_excl_scan(hi, &th, sm);
     if (threadIdx.x == 0) atomicAdd(a.total, (unsigned long long)tl + ((unsigned long long)th << 24));
 }
+#endif  // TF_KERNELS_ENCODE
 
 }  // namespace tfk

@@ -45,7 +45,7 @@ __device__ __forceinline__ uint64_t ryu_mulshift(uint64_t m, const uint64_t* mul
 }
 __device__ __forceinline__ uint32_t ryu_pow5factor(uint64_t v) { uint32_t c = 0; while (v && v % 5 == 0) { v /= 5; c++; } return c; }
 
-__device__ DecF ryu_d2d(uint64_t mant, uint32_t expo, int mbits, int bias) {
+__device__ inline DecF ryu_d2d(uint64_t mant, uint32_t expo, int mbits, int bias) {
     int32_t e2; uint64_t m2;
     if (expo == 0) { e2 = 1 - bias - mbits - 2; m2 = mant; } else { e2 = (int32_t)expo - bias - mbits - 2; m2 = (1ull << mbits) | mant; }
     const bool accept = (m2 & 1) == 0;

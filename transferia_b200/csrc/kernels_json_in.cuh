@@ -49,18 +49,21 @@ struct JsnArgs {
 };
 
 // ------------------------------------------------------------------ line helpers
+#ifdef TF_KERNELS_JSON_IN
 __global__ void __launch_bounds__(256) k_json_mark_msgs(const uint64_t* msg_end, uint32_t nmsgs, uint32_t* bits) {
     const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nmsgs) return;
     const uint64_t e = msg_end[m], b = m ? msg_end[m - 1] : 0;
     if (e > b) atomicOr(&bits[(e - 1) >> 5], 1u << ((e - 1) & 31));
 }
+#endif  // TF_KERNELS_JSON_IN
 __device__ __forceinline__ void jsn_line(const uint8_t* text, const uint32_t* line_end, uint64_t L, uint32_t& ls, uint32_t& n) {
     ls = L ? line_end[L - 1] : 0; uint32_t le = line_end[L];
     if (le > ls && text[le - 1] == '\n') le--;
     if (le > ls && text[le - 1] == '\r') le--;            // bufio.ScanLines dropCR
     n = le - ls;
 }
+#ifdef TF_KERNELS_JSON_IN
 __global__ void __launch_bounds__(128) k_json_count_nonempty(const uint8_t* text, const uint32_t* line_end, uint64_t nlines, uint32_t* blk_cnt) {
     __shared__ uint32_t sm[33];
     const uint64_t L = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -68,6 +71,8 @@ __global__ void __launch_bounds__(128) k_json_count_nonempty(const uint8_t* text
     uint32_t tot; block_excl_scan(f, &tot, sm);
     if (threadIdx.x == 0) blk_cnt[blockIdx.x] = tot;
 }
+#endif  // TF_KERNELS_JSON_IN
+#ifdef TF_KERNELS_JSON_IN
 __global__ void __launch_bounds__(128) k_json_rank(const uint8_t* text, const uint32_t* line_end, uint64_t nlines, const uint32_t* blk_off, uint32_t* rank) {
     __shared__ uint32_t sm[33];
     const uint64_t L = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -75,7 +80,9 @@ __global__ void __launch_bounds__(128) k_json_rank(const uint8_t* text, const ui
     uint32_t tot; const uint32_t ex = block_excl_scan(f, &tot, sm);
     if (L < nlines) { rank[L] = blk_off[blockIdx.x] + ex; if (L == nlines - 1) rank[nlines] = blk_off[blockIdx.x] + ex + f; }
 }
+#endif  // TF_KERNELS_JSON_IN
 // rank of the first line of every message: _idx counts the non-empty lines of its own message from 1 (:526-531)
+#ifdef TF_KERNELS_JSON_IN
 __global__ void __launch_bounds__(256) k_json_msg_first(const uint64_t* msg_end, uint32_t nmsgs, const uint32_t* line_end, uint64_t nlines, const uint32_t* rank, uint32_t* msg_rank0) {
     const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nmsgs) return;
@@ -84,6 +91,7 @@ __global__ void __launch_bounds__(256) k_json_msg_first(const uint64_t* msg_end,
     while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if ((uint64_t)line_end[mid] <= start) lo = mid + 1; else hi = mid; }
     msg_rank0[m] = rank[lo];
 }
+#endif  // TF_KERNELS_JSON_IN
 
 // ------------------------------------------------------------------ byte sources
 __device__ __forceinline__ bool jsn_ws(uint8_t c) { return c == 0x20 || c == 0x0A || c == 0x09 || c == 0x0D; }
@@ -150,7 +158,7 @@ struct Src {
 
 // ------------------------------------------------------------------ strconv on the device (mirrors oracle/json_oracle.hpp)
 #define D_GO_NAN __longlong_as_double(0x7FF8000000000001ll)      /* math.NaN() */
-__device__ bool d_underscore_ok(const uint8_t* s, uint32_t n) {
+__device__ inline bool d_underscore_ok(const uint8_t* s, uint32_t n) {
     char i = '^'; uint32_t p = 0;
     if (n && (s[0] == '-' || s[0] == '+')) p = 1;
     bool hex = false;
@@ -165,7 +173,7 @@ __device__ bool d_underscore_ok(const uint8_t* s, uint32_t n) {
     return i != '_';
 }
 // strconv.ParseUint(s, base, bits); base 0 = by prefix with underscores. rc 0 ok, 1 syntax, 2 range
-__device__ int d_go_parse_uint(const uint8_t* s0, uint32_t n0, int base, int bits, uint64_t& out) {
+__device__ inline int d_go_parse_uint(const uint8_t* s0, uint32_t n0, int base, int bits, uint64_t& out) {
     if (!n0) return 1;
     const uint8_t* s = s0; uint32_t n = n0; const bool base0 = base == 0;
     if (base == 0) {
@@ -190,7 +198,7 @@ __device__ int d_go_parse_uint(const uint8_t* s0, uint32_t n0, int base, int bit
     if (range) { out = maxv; return 2; }
     out = v; return 0;
 }
-__device__ int d_go_parse_int(const uint8_t* s, uint32_t n, int base, int bits, int64_t& out) {
+__device__ inline int d_go_parse_int(const uint8_t* s, uint32_t n, int base, int bits, int64_t& out) {
     if (!n) return 1;
     const uint8_t* s0 = s; const uint32_t n0 = n; bool neg = false;
     if (s[0] == '+') { s++; n--; } else if (s[0] == '-') { neg = true; s++; n--; }
@@ -206,7 +214,7 @@ __device__ int d_go_parse_int(const uint8_t* s, uint32_t n, int base, int bits, 
 
 // Eisel-Lemire (the algorithm strconv.ParseFloat uses after its exact path; scripts/el_proto.py checks this port against
 // CPython's correctly rounded float()). false = not decided here.
-__device__ bool d_eisel_lemire(uint64_t man, int exp10, bool neg, uint64_t& bits) {
+__device__ inline bool d_eisel_lemire(uint64_t man, int exp10, bool neg, uint64_t& bits) {
     if (man == 0) { bits = neg ? 0x8000000000000000ull : 0; return true; }
     if (exp10 < EL_QMIN || exp10 > EL_QMAX) return false;
     const int clz = __clzll((long long)man);
@@ -233,7 +241,7 @@ __device__ bool d_eisel_lemire(uint64_t man, int exp10, bool neg, uint64_t& bits
     return true;
 }
 // strconv.ParseFloat(s, 64). rc 0 ok, 1 syntax, 2 range (out = +-Inf), 3 needs the host (hex, underscores, undecided rounding)
-__device__ int d_go_parse_float(const uint8_t* s, uint32_t n, double& out) {
+__device__ inline int d_go_parse_float(const uint8_t* s, uint32_t n, double& out) {
     if (!n) return 1;
     {   // special()
         const uint8_t* t = s; uint32_t m = n; bool neg = false, sign = false;
@@ -301,14 +309,14 @@ __device__ int d_go_parse_float(const uint8_t* s, uint32_t n, double& out) {
 }
 
 // ------------------------------------------------------------------ fastjson/fastfloat number getters
-__device__ uint64_t d_ff_uint64(const uint8_t* s, uint32_t n) {
+__device__ inline uint64_t d_ff_uint64(const uint8_t* s, uint32_t n) {
     if (!n) return 0;
     uint32_t i = 0; uint64_t d = 0;
     while (i < n && s[i] >= '0' && s[i] <= '9') { d = d * 10 + (uint64_t)(s[i] - '0'); i++; if (i > 18) { uint64_t dd; return d_go_parse_uint(s, n, 10, 64, dd) == 0 ? dd : 0; } }
     if (i == 0 || i < n) return 0;
     return d;
 }
-__device__ int64_t d_ff_int64(const uint8_t* s, uint32_t n) {
+__device__ inline int64_t d_ff_int64(const uint8_t* s, uint32_t n) {
     if (!n) return 0;
     uint32_t i = 0; const bool minus = s[0] == '-';
     if (minus) { i++; if (i >= n) return 0; }
@@ -326,7 +334,7 @@ __device__ __forceinline__ double d_go_pow10(int n) {     // math.Pow10
     return n > 0 ? CUDART_INF : 0.0;
 }
 // fastfloat.ParseBestEffort. rc 0 ok, JSN_HOST when the strconv fall-back cannot be decided on the device
-__device__ int d_ff_best(const uint8_t* s, uint32_t n, double& out) {
+__device__ inline int d_ff_best(const uint8_t* s, uint32_t n, double& out) {
     out = 0;
     auto slow = [&]() -> int { double f; const int rc = d_go_parse_float(s, n, f); if (rc == 3) return JSN_HOST; out = rc == 1 ? 0.0 : f; return 0; };
     if (!n) return 0;
@@ -365,7 +373,7 @@ __device__ int d_ff_best(const uint8_t* s, uint32_t n, double& out) {
     return 0;
 }
 __device__ __forceinline__ int64_t d_f64_to_i64(double f) { if (!(f >= -9223372036854775808.0 && f < 9223372036854775808.0)) return (int64_t)0x8000000000000000ull; return __double2ll_rz(f); }   // amd64 CVTTSD2SQ
-__device__ bool d_valid_json_number(const uint8_t* s, uint32_t n) {      // encoding/json isValidNumber
+__device__ inline bool d_valid_json_number(const uint8_t* s, uint32_t n) {      // encoding/json isValidNumber
     uint32_t i = 0; if (!n) return false;
     if (s[i] == '-') { i++; if (i == n) return false; }
     if (s[i] == '0') i++; else if (s[i] >= '1' && s[i] <= '9') { while (i < n && s[i] >= '0' && s[i] <= '9') i++; } else return false;
@@ -376,7 +384,7 @@ __device__ bool d_valid_json_number(const uint8_t* s, uint32_t n) {      // enco
 
 // ------------------------------------------------------------------ fastjson grammar scan
 // skips one already validated value starting at p, returns the position after it
-__device__ uint32_t jsn_skip_value(const uint8_t* s, uint32_t p, uint32_t n, uint32_t& t) {
+__device__ inline uint32_t jsn_skip_value(const uint8_t* s, uint32_t p, uint32_t n, uint32_t& t) {
     const uint8_t c = s[p];
     if (c == '"') { p++; while (p < n) { if (s[p] == '\\') { p += 2; continue; } if (s[p] == '"') break; p++; } t = JT_STRING; return p + 1; }
     if (c == '{' || c == '[') {
@@ -462,17 +470,17 @@ template <typename F> __device__ int jsn_scan(const uint8_t* s, uint32_t n, bool
 }
 
 // ------------------------------------------------------------------ keys
-__device__ bool jsn_key_is(const uint8_t* k, uint32_t klen, const uint8_t* name, uint32_t nlen) {
+__device__ inline bool jsn_key_is(const uint8_t* k, uint32_t klen, const uint8_t* name, uint32_t nlen) {
     bool esc = false; for (uint32_t i = 0; i < klen; i++) if (k[i] == '\\') { esc = true; break; }
     if (!esc) { if (klen != nlen) return false; for (uint32_t i = 0; i < klen; i++) if (k[i] != name[i]) return false; return true; }
     Dec d(k, klen); uint32_t i = 0;
     for (;;) { const int c = d.next(); if (c < 0) return i == nlen; if (i >= nlen || name[i] != (uint8_t)c) return false; i++; }
 }
-__device__ int jsn_key_cmp(const uint8_t* a, uint32_t an, const uint8_t* b, uint32_t bn) {      // strings.Compare of the unescaped keys
+__device__ inline int jsn_key_cmp(const uint8_t* a, uint32_t an, const uint8_t* b, uint32_t bn) {      // strings.Compare of the unescaped keys
     Dec da(a, an), db(b, bn);
     for (;;) { const int x = da.next(), y = db.next(); if (x < 0 && y < 0) return 0; if (x != y) return x < y ? -1 : 1; }
 }
-__device__ int jsn_find_col(const JsnArgs& a, const uint8_t* k, uint32_t klen) {
+__device__ inline int jsn_find_col(const JsnArgs& a, const uint8_t* k, uint32_t klen) {
     int hit = -1;
     for (int c = 0; c < a.ncols; c++) if (jsn_key_is(k, klen, a.names + a.cols[c].name_off, a.cols[c].name_len)) hit = c;
     return hit;
@@ -648,7 +656,7 @@ __device__ __forceinline__ bool jsn_is_int(int tf) { return tf == TF_INT8 || tf 
 __device__ __forceinline__ bool jsn_is_uint(int tf) { return tf == TF_UINT8 || tf == TF_UINT16 || tf == TF_UINT32 || tf == TF_UINT64; }
 
 // Unmarshal's typed extraction + ParseVal for a fixed-width field. rc 0 (null set when the cell is nil) / JSN_PARSEVAL / JSN_HOST
-__device__ int jsn_fixed_cell(const JsnArgs& a, const JsnColDev& cd, const uint8_t* s, uint32_t off, uint32_t len, uint32_t t, uint64_t& v, bool& null) {
+__device__ inline int jsn_fixed_cell(const JsnArgs& a, const JsnColDev& cd, const uint8_t* s, uint32_t off, uint32_t len, uint32_t t, uint64_t& v, bool& null) {
     v = 0; null = false;
     const int tf = cd.tf;
     if (t == JT_ABSENT || t == JT_NULL) { null = true; return 0; }
@@ -693,6 +701,7 @@ __device__ __forceinline__ const uint8_t* jsn_stage_span(const JsnArgs& a, uint8
 }
 
 // ------------------------------------------------------------------ pass 1
+#ifdef TF_KERNELS_JSON_IN
 __global__ void __launch_bounds__(128) k_json_pass1(JsnArgs a) {
     extern __shared__ __align__(16) uint8_t jsn_stage[];
     const uint8_t* const text = jsn_stage_span(a, jsn_stage);
@@ -771,10 +780,12 @@ __global__ void __launch_bounds__(128) k_json_pass1(JsnArgs a) {
         if ((threadIdx.x & 31) == 0 && active) a.cols[c].validity[L >> 5] = word;
     }
 }
+#endif  // TF_KERNELS_JSON_IN
 
 // ------------------------------------------------------------------ pass 2: text cells
 struct JsnWriteArgs { JsnArgs a; const uint32_t* offsets; uint8_t* heap; const uint64_t* col_base; };
 
+#ifdef TF_KERNELS_JSON_IN
 __global__ void __launch_bounds__(128) k_json_pass2(JsnWriteArgs w) {
     extern __shared__ __align__(16) uint8_t jsn_stage[];
     const JsnArgs& a = w.a;
@@ -806,5 +817,6 @@ __global__ void __launch_bounds__(128) k_json_pass2(JsnWriteArgs w) {
         for (uint32_t k = 0; k < a.part_len; k++) o[k] = a.names[a.part_off + k];
     }
 }
+#endif  // TF_KERNELS_JSON_IN
 
 }  // namespace tfk

@@ -222,7 +222,7 @@ template <typename Sink> __device__ int ser_json_row(Sink& s, const DCol* cols, 
 }
 
 // does the encoding/csv field need quotes? (fieldNeedsQuotes: empty no; `\.` yes; , " \r \n yes; leading unicode space yes)
-__device__ bool ser_csv_needs_quotes(const uint8_t* p, uint32_t n) {
+__device__ inline bool ser_csv_needs_quotes(const uint8_t* p, uint32_t n) {
     if (!n) return false;
     if (n == 2 && p[0] == '\\' && p[1] == '.') return true;
     for (uint32_t i = 0; i < n; i++) { const uint8_t c = p[i]; if (c == '\n' || c == '\r' || c == '"' || c == ',') return true; }
@@ -415,6 +415,7 @@ template <typename Sink> __device__ __forceinline__ int json_any_row(Sink& s, co
 
 #define TF_JSON_TILE 256
 
+#ifdef TF_KERNELS_JSON_OUT
 __global__ void __launch_bounds__(TF_JSON_TILE) k_json_sizes(JsonArgs a) {
     __shared__ uint32_t sm[33];
     const uint64_t n = a.st->n_kept;
@@ -429,7 +430,9 @@ __global__ void __launch_bounds__(TF_JSON_TILE) k_json_sizes(JsonArgs a) {
     uint32_t tot; block_excl_scan(sz, &tot, sm);
     if (threadIdx.x == 0) a.tile_sum[blockIdx.x] = tot;
 }
+#endif  // TF_KERNELS_JSON_OUT
 
+#ifdef TF_KERNELS_JSON_OUT
 __global__ void __launch_bounds__(TF_JSON_TILE) k_json_write(JsonArgs a) {
     __shared__ uint32_t sm[33];
     const uint64_t n = a.st->n_kept;
@@ -444,5 +447,6 @@ __global__ void __launch_bounds__(TF_JSON_TILE) k_json_write(JsonArgs a) {
     json_any_row(ms, a, r, j, false);
     ms.flush();
 }
+#endif  // TF_KERNELS_JSON_OUT
 
 }  // namespace tfk

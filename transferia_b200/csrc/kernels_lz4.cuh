@@ -62,6 +62,7 @@ __device__ __forceinline__ void copy_s2g(uint8_t* dst, const uint32_t* data_w, u
     while (n) { *dst++ = data[LZ_PB(src)]; src++; n--; }
 }
 
+#ifdef TF_KERNELS_LZ4
 __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t F = a.frame_bytes;
@@ -283,6 +284,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
         LZ_PHASE(4);
     }
 }
+#endif  // TF_KERNELS_LZ4
 
 // ------------------------------------------------------------------ CityHash128 v1.0.2 over [method byte .. end of block]
 namespace cityd {
@@ -303,7 +305,7 @@ __device__ __forceinline__ uint64_t hl16(uint64_t u, uint64_t v) {
     uint64_t a = (u ^ v) * kMul; a ^= (a >> 47);
     uint64_t b = (v ^ a) * kMul; b ^= (b >> 47); b *= kMul; return b;
 }
-__device__ uint64_t hl0to16(const uint8_t* s, size_t len) {
+__device__ inline uint64_t hl0to16(const uint8_t* s, size_t len) {
     if (len > 8) { uint64_t a = f64(s), b = f64(s + len - 8); return hl16(a, rot(b + len, (int)len)) ^ b; }
     if (len >= 4) { uint64_t a = f32(s); return hl16(len + (a << 3), f32(s + len - 4)); }
     if (len > 0) { uint8_t a = s[0], b = s[len >> 1], c = s[len - 1]; uint32_t y = (uint32_t)a + ((uint32_t)b << 8); uint32_t z = (uint32_t)len + ((uint32_t)c << 2); return smix(y * CK2 ^ z * CK3) * CK2; }
@@ -314,7 +316,7 @@ __device__ __forceinline__ P weak32(uint64_t w, uint64_t x, uint64_t y, uint64_t
     a += w; b = rot(b + a + z, 21); const uint64_t c = a; a += x; a += y; b += rot(a, 44); P r; r.first = a + z; r.second = b + c; return r;
 }
 __device__ __forceinline__ P weak32p(const uint8_t* s, uint64_t a, uint64_t b) { return weak32(f64(s), f64(s + 8), f64(s + 16), f64(s + 24), a, b); }
-__device__ P murmur(const uint8_t* s, size_t len, P seed) {
+__device__ inline P murmur(const uint8_t* s, size_t len, P seed) {
     uint64_t a = seed.first, b = seed.second, c = 0, d = 0; long l = (long)len - 16;
     if (l <= 0) { a = smix(a * CK1) * CK1; c = b * CK1 + hl0to16(s, len); d = smix(a + (len >= 8 ? f64(s) : c)); }
     else {
@@ -324,7 +326,7 @@ __device__ P murmur(const uint8_t* s, size_t len, P seed) {
     a = hl16(a, c); b = hl16(d, b);
     P r; r.first = a ^ b; r.second = hl16(b, a); return r;
 }
-__device__ P hash128_seed(const uint8_t* s, size_t len, P seed) {
+__device__ inline P hash128_seed(const uint8_t* s, size_t len, P seed) {
     if (len < 128) return murmur(s, len, seed);
     P v, w; uint64_t x = seed.first, y = seed.second, z = len * CK1;
     v.first = rot(y ^ CK1, 49) * CK1 + f64(s);
@@ -356,7 +358,7 @@ __device__ P hash128_seed(const uint8_t* s, size_t len, P seed) {
     x = hl16(x, v.first); y = hl16(y, w.first);
     P r; r.first = hl16(x + v.second, w.second) + y; r.second = hl16(x + w.second, y + v.second); return r;
 }
-__device__ P hash128(const uint8_t* s, size_t len) {
+__device__ inline P hash128(const uint8_t* s, size_t len) {
     P seed;
     if (len >= 16) { seed.first = f64(s) ^ CK3; seed.second = f64(s + 8); return hash128_seed(s + 16, len - 16, seed); }
     if (len >= 8) { seed.first = f64(s) ^ (len * CK0); seed.second = f64(s + len - 8) ^ CK1; return hash128_seed(nullptr, 0, seed); }
@@ -383,6 +385,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+#ifdef TF_KERNELS_LZ4
 __global__ void __launch_bounds__(32) k_frame_seal(FrameArgs a) {
     // SEAL_STAGES steps of 512 bytes per frame in flight: with one warp per SM nothing else hides the load latency
     extern __shared__ __align__(16) uint8_t seal_smem[];
@@ -481,9 +484,11 @@ __global__ void __launch_bounds__(32) k_frame_seal(FrameArgs a) {
         put_checksum(cityd::hl16(x + v.second, w.second) + y, cityd::hl16(x + w.second, y + v.second));
     }
 }
+#endif  // TF_KERNELS_LZ4
 
 // exclusive scan of frame sizes (single block) -> position of every frame in the wire buffer; also stamps the 9-byte
 // [method][sizes] header of every frame, which both the checksum (k_frame_seal) and the gather read
+#ifdef TF_KERNELS_LZ4
 __global__ void __launch_bounds__(1024) k_frame_scan(FrameArgs a) {
     __shared__ uint32_t sm[33];
     const uint64_t nf = a.st->n_frames;
@@ -506,9 +511,11 @@ __global__ void __launch_bounds__(1024) k_frame_scan(FrameArgs a) {
     }
     if (threadIdx.x == 0) { a.st->wire_total = carry; a.tail[0] = nf; }
 }
+#endif  // TF_KERNELS_LZ4
 
 // gather the sealed frames into one contiguous stream; source slots are 16-byte aligned, the destination
 // is re-aligned with the same shuffle + funnel-shift trick as k_encode_fixed so stores are aligned words
+#ifdef TF_KERNELS_LZ4
 __global__ void __launch_bounds__(256) k_wire_gather(FrameArgs a) {
     const uint64_t nf = a.tail[0];
     for (uint64_t f = blockIdx.x; f < nf; f += gridDim.x) {
@@ -532,5 +539,6 @@ __global__ void __launch_bounds__(256) k_wire_gather(FrameArgs a) {
         }
     }
 }
+#endif  // TF_KERNELS_LZ4
 
 }  // namespace tfk

@@ -132,6 +132,7 @@ __device__ inline void mask_digest_hex(const DCol& c, uint64_t r, const MaskKey&
 }
 
 // one thread per (kept row, masked column): "\x40" + 64 hex chars into the block (or the bare digest, columnar output)
+#ifdef TF_KERNELS_MASK
 __global__ void __launch_bounds__(128) k_mask_encode(MaskArgs a) {
     const DCol c = a.cols[a.slots[blockIdx.y]];
     const uint64_t n = a.st->n_kept;
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(128) k_mask_encode(MaskArgs a) {
     }
     mask_digest_hex(c, r, a.keys[c.mask_slot], out);
 }
+#endif  // TF_KERNELS_MASK
 
 // ------------------------------------------------------------------ sharder transformer
 //   SharderTransformer.generatePartID pkg/transformer/registry/sharder/sharder.go:130-145:
@@ -158,6 +160,7 @@ struct ShardCol { int32_t col, form, pad0, pad1; };       // form: 0 text of the
 struct ShardArgs { const DCol* cols; const ShardCol* sc; int nsc; const MaskKey* keys; const uint32_t* sel; DState* st; uint32_t shards; uint32_t* part; };
 struct CrcSink { uint32_t c; const uint32_t* tab; __device__ __forceinline__ void put(uint8_t b) { c = tab[(c ^ b) & 0xffu] ^ (c >> 8); } };
 
+#ifdef TF_KERNELS_MASK
 __global__ void __launch_bounds__(256) k_shard_ids(ShardArgs a) {
     __shared__ uint32_t tab[256];
     { uint32_t c = threadIdx.x; for (int k = 0; k < 8; k++) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u))); tab[threadIdx.x] = c; }
@@ -177,5 +180,6 @@ __global__ void __launch_bounds__(256) k_shard_ids(ShardArgs a) {
     }
     a.part[j] = (~s.c) % a.shards;
 }
+#endif  // TF_KERNELS_MASK
 
 }  // namespace tfk

@@ -45,6 +45,7 @@ __device__ __forceinline__ bool n2f_applies(const N2fArgs& a, const DCol& c, uin
     return !(c.aux && c.aux[r] == 1);
 }
 
+#ifdef TF_KERNELS_N2F
 __global__ void __launch_bounds__(128) k_n2f_sizes(N2fArgs a) {
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.nrows) return;
@@ -54,6 +55,8 @@ __global__ void __launch_bounds__(128) k_n2f_sizes(N2fArgs a) {
     if (n2f_applies(a, c, r)) { CountSink cs{0}; if (n2f_rewrite(cs, c.heap + off, L)) out = cs.n; else { a.err[r] = N2F_HOST; out = 0; } }
     a.out_len[(size_t)blockIdx.y * a.nrows + r] = out;
 }
+#endif  // TF_KERNELS_N2F
+#ifdef TF_KERNELS_N2F
 __global__ void __launch_bounds__(128) k_n2f_write(N2fArgs a) {
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.nrows) return;
@@ -64,5 +67,6 @@ __global__ void __launch_bounds__(128) k_n2f_write(N2fArgs a) {
     if (n2f_applies(a, c, r)) { MemSink ms{o}; n2f_rewrite(ms, c.heap + off, L); }
     else for (uint32_t k = 0; k < L; k++) o[k] = c.heap[off + k];
 }
+#endif  // TF_KERNELS_N2F
 
 }  // namespace tfk

@@ -17,6 +17,7 @@ __device__ __forceinline__ uint32_t str_len(const DCol& c, const uint32_t* sel, 
 
 // encoded size (LEB128 length + payload) of every tile of TF_STR_TILE kept rows, for every String column
 #define TF_STR_GROUP 4      /* tiles per CTA: their loads are issued together, which hides the gather latency */
+#ifdef TF_KERNELS_STR
 __global__ void __launch_bounds__(TF_STR_THREADS) k_str_sizes(EncodeArgs a) {
     __shared__ uint32_t sm[33];
     const DCol c = a.cols[a.slots[blockIdx.y]];
@@ -33,6 +34,7 @@ __global__ void __launch_bounds__(TF_STR_THREADS) k_str_sizes(EncodeArgs a) {
         __syncthreads();
     }
 }
+#endif  // TF_KERNELS_STR
 
 // LEB128 length + bytes. Plain String columns (the hot case): every thread first publishes its row's piece (offset in the
 // tile, heap offset, length) in shared memory; then the tile's OUTPUT is cut into aligned 4-byte words and every thread
@@ -46,6 +48,7 @@ __device__ __forceinline__ uint32_t str_find_row(const uint32_t* ex, uint32_t x)
     for (int it = 0; it < 8; it++) { const uint32_t mid = (lo + hi) >> 1; if (ex[mid] <= x) lo = mid; else hi = mid; }
     return lo;
 }
+#ifdef TF_KERNELS_STR
 __global__ void __launch_bounds__(TF_STR_THREADS) k_encode_str_plain(EncodeArgs a) {
     __shared__ uint32_t sm[33];
     __shared__ uint32_t s_ex[TF_STR_GROUP][TF_STR_TILE + 1];
@@ -119,8 +122,10 @@ __global__ void __launch_bounds__(TF_STR_THREADS) k_encode_str_plain(EncodeArgs 
         }
     }
 }
+#endif  // TF_KERNELS_STR
 
 // LEB128 length + text of convert_to_string columns, one kept row per thread, staged in shared memory.
+#ifdef TF_KERNELS_STR
 __global__ void __launch_bounds__(TF_STR_THREADS) k_encode_str(EncodeArgs a) {
     __shared__ uint32_t sm[33];
     __shared__ __align__(16) uint8_t stage[TF_STR_STAGE + 8];
@@ -183,6 +188,7 @@ __global__ void __launch_bounds__(TF_STR_THREADS) k_encode_str(EncodeArgs a) {
         }
     }
 }
+#endif  // TF_KERNELS_STR
 
 
 }  // namespace tfk

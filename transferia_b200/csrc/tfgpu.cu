@@ -13,15 +13,7 @@
 #include "../../include/tfgpu.h"
 #include "plan.hpp"
 #include "device_types.cuh"
-#include "kernels_encode.cuh"
-#include "kernels_lz4.cuh"
-#include "kernels_str.cuh"
-#include "kernels_mask.cuh"
-#include "kernels_csv.cuh"
-#include "kernels_json_in.cuh"
-#include "kernels_dbz.cuh"
-#include "kernels_n2f.cuh"
-#include "kernels_json_out.cuh"
+#include "launch.hpp"
 
 using namespace tfk;
 
@@ -302,12 +294,12 @@ Sizes compute_sizes(const tfgpu_engine* e, const PlanDev& pd, const tf_batch* in
 // exclusive scan of the text-cell lengths of every var-width column: offsets[slot][row], col_total[slot]
 static void launch_offsets(tfgpu_engine* e, const uint32_t* d_len, uint64_t nrows, uint32_t nslots, uint32_t* d_off, uint64_t* d_tot, cudaStream_t s) {
     const uint32_t nchunks = (uint32_t)((nrows + CSV_OFF_CHUNK - 1) / CSV_OFF_CHUNK);
-    if (!nchunks || !nslots) { k_csv_offsets<<<nslots ? nslots : 1, 1024, 0, s>>>(d_len, nrows, d_off, d_tot); return; }
+    if (!nchunks || !nslots) { launch_k_csv_offsets(nslots ? nslots : 1, 1024, 0, s, d_len, nrows, d_off, d_tot); return; }
     e->off_scratch.ensure((size_t)nslots * nchunks * 8 + 256);
     uint64_t* cs = (uint64_t*)e->off_scratch.p;
-    e->prof_begin("k_offsets_sum", s); k_offsets_sum<<<dim3(nchunks, nslots), 1024, 0, s>>>(d_len, nrows, nchunks, cs); e->prof_end(s);
-    e->prof_begin("k_offsets_chunks", s); k_offsets_chunks<<<nslots, 32, 0, s>>>(cs, nchunks, d_tot); e->prof_end(s);
-    e->prof_begin("k_offsets_write", s); k_offsets_write<<<dim3(nchunks, nslots), 1024, 0, s>>>(d_len, nrows, nchunks, cs, d_tot, d_off); e->prof_end(s);
+    e->prof_begin("k_offsets_sum", s); launch_k_offsets_sum(dim3(nchunks, nslots), 1024, 0, s, d_len, nrows, nchunks, cs); e->prof_end(s);
+    e->prof_begin("k_offsets_chunks", s); launch_k_offsets_chunks(nslots, 32, 0, s, cs, nchunks, d_tot); e->prof_end(s);
+    e->prof_begin("k_offsets_write", s); launch_k_offsets_write(dim3(nchunks, nslots), 1024, 0, s, d_len, nrows, nchunks, cs, d_tot, d_off); e->prof_end(s);
 }
 
 // Launch the whole fused chain on e->stream. `cols_host` holds DEVICE pointers.
@@ -379,7 +371,7 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         CK(cudaMemcpyAsync(B + o_which, which.data(), k2 * 4, cudaMemcpyHostToDevice, s));
         if (pre_err) CK(cudaMemcpyAsync(B + o_err, pre_err, n, cudaMemcpyDeviceToDevice, s)); else CK(cudaMemsetAsync(B + o_err, 0, n, s));
         N2fArgs na{e->d_cols, (const int32_t*)(B + o_which), dev_kinds, n, (uint32_t*)(B + o_len), (const uint32_t*)(B + o_off), nullptr, (const uint64_t*)(B + o_base), B + o_err};
-        e->prof_begin("k_n2f_sizes", s); k_n2f_sizes<<<dim3((uint32_t)((n + 127) / 128), (uint32_t)k2), 128, 0, s>>>(na); e->prof_end(s);
+        e->prof_begin("k_n2f_sizes", s); launch_k_n2f_sizes(dim3((uint32_t)((n + 127) / 128), (uint32_t)k2), 128, 0, s, na); e->prof_end(s);
         launch_offsets(e, (const uint32_t*)(B + o_len), n, (uint32_t)k2, (uint32_t*)(B + o_off), (uint64_t*)(B + o_tot), s);
         std::vector<uint64_t> tot(k2), base(k2);
         CK(cudaMemcpyAsync(tot.data(), B + o_tot, k2 * 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
@@ -388,7 +380,7 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         e->n2f_heap.ensure(run + 256);
         CK(cudaMemcpyAsync(B + o_base, base.data(), k2 * 8, cudaMemcpyHostToDevice, s));
         na.heap = e->n2f_heap.p;
-        e->prof_begin("k_n2f_write", s); k_n2f_write<<<dim3((uint32_t)((n + 127) / 128), (uint32_t)k2), 128, 0, s>>>(na); e->prof_end(s);
+        e->prof_begin("k_n2f_write", s); launch_k_n2f_write(dim3((uint32_t)((n + 127) / 128), (uint32_t)k2), 128, 0, s, na); e->prof_end(s);
         for (size_t k = 0; k < k2; k++) { DCol& d = hc[pl.n2f_cols[k]]; d.offsets = (const uint32_t*)(B + o_off) + k * (n + 1); d.heap = e->n2f_heap.p + base[k]; }
         CK(cudaMemcpyAsync(e->d_cols, hc.data(), sizeof(DCol) * nc, cudaMemcpyHostToDevice, s));
         pre_err = B + o_err;                 // parser errors carried over + N2F_HOST rows
@@ -398,9 +390,9 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
     const uint32_t nb = (uint32_t)((n + 255) / 256);
     if (has_filter && n) {
         FilterArgs fa{e->d_cols, dev_kinds, n, pd.d_fsteps, pd.n_fsteps, pd.d_expr_off, pd.d_terms, pd.d_blob, e->keep, e->errcode, e->errstep, e->blockcnt, e->d_state, pre_err};
-        e->prof_begin("k_filter", s); k_filter<<<nb, 256, 0, s>>>(fa); e->prof_end(s);
-        e->prof_begin("k_scan_blockcnt", s); k_scan_blockcnt<<<1, 1024, 0, s>>>(e->blockcnt, e->blockoff, nb, e->d_state); e->prof_end(s);
-        e->prof_begin("k_compact_sel", s); k_compact_sel<<<nb, 256, 0, s>>>(e->keep, e->blockoff, n, e->sel); e->prof_end(s);
+        e->prof_begin("k_filter", s); launch_k_filter(nb, 256, 0, s, fa); e->prof_end(s);
+        e->prof_begin("k_scan_blockcnt", s); launch_k_scan_blockcnt(1, 1024, 0, s, e->blockcnt, e->blockoff, nb, e->d_state); e->prof_end(s);
+        e->prof_begin("k_compact_sel", s); launch_k_compact_sel(nb, 256, 0, s, e->keep, e->blockoff, n, e->sel); e->prof_end(s);
     }
     const uint32_t* sel = (has_filter && n) ? e->sel : nullptr;
     const uint32_t ntiles = (uint32_t)((n + TF_STR_TILE - 1) / TF_STR_TILE);
@@ -416,7 +408,7 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
     if (pl.has_sharder && n) {
         e->part_ids.ensure(n * 4 + 256);
         ShardArgs sa{e->d_cols, pd.d_shard_cols, (int)pl.shard_cols.size(), pd.d_mask_keys, sel, e->d_state, pl.shards, (uint32_t*)e->part_ids.p};
-        e->prof_begin("k_shard_ids", s); k_shard_ids<<<nb, 256, 0, s>>>(sa); e->prof_end(s);
+        e->prof_begin("k_shard_ids", s); launch_k_shard_ids(nb, 256, 0, s, sa); e->prof_end(s);
     }
     e->last_has_sharder = pl.has_sharder;
     if (json_rows) {
@@ -427,24 +419,24 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
                     dbz ? 3 : ser ? (wire_base == TF_WIRE_SER_JSON ? 1 : 2) : 0, (uint32_t)(((wire_fmt & TF_WIRE_F_CLOSING_NEWLINE) ? TF_SER_NL : 0) | ((wire_fmt & TF_WIRE_F_ANY_AS_STRING) ? TF_SER_AAS : 0)), e->errcode, e->errstep, DbzEmitArgs{}};
         if (dbz) { ja.jcols = pd.d_sjcols; e->dbz_keysz.ensure(n * 4 + 256); ja.dz = e->dbz; ja.dz.key_size = (uint32_t*)e->dbz_keysz.p; }
         if (ser && !has_filter && n) { CK(cudaMemsetAsync(e->errcode, 0, n, s)); CK(cudaMemsetAsync(e->errstep, 0, n, s)); }
-        if (jt) { e->prof_begin("k_json_sizes", s); k_json_sizes<<<jt, TF_JSON_TILE, 0, s>>>(ja); e->prof_end(s); }
+        if (jt) { e->prof_begin("k_json_sizes", s); launch_k_json_sizes(jt, TF_JSON_TILE, 0, s, ja); e->prof_end(s); }
         LayoutArgs lj{e->d_cols, 0, pd.d_out_cols, pd.d_str_slots, 1, e->tile_sum, e->tile_base, sz.ntiles_cap, pd.d_col_headers, pd.d_col_header_off,
                       e->raw.p, e->d_state, n, 1, e->frame_bytes, e->col_bytes};
-        e->prof_begin("k_layout_scan", s); k_layout_scan<<<1, 1024, 0, s>>>(lj); e->prof_end(s);
+        e->prof_begin("k_layout_scan", s); launch_k_layout_scan(1, 1024, 0, s, lj); e->prof_end(s);
         {   // row text has no useful upper bound ('f' floats reach 300+ characters): size the output from the measured total
             uint64_t total = 0; CK(cudaMemcpyAsync(&total, e->col_bytes, 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
             e->raw.ensure(total + 256); ja.raw = e->raw.p;
         }
-        e->prof_begin("k_json_write", s); k_json_write<<<jt ? jt : 1, TF_JSON_TILE, 0, s>>>(ja); e->prof_end(s);
+        e->prof_begin("k_json_write", s); launch_k_json_write(jt ? jt : 1, TF_JSON_TILE, 0, s, ja); e->prof_end(s);
         CK(cudaGetLastError());
         return;
     }
-    if (pd.n_str && ntiles) { e->prof_begin("k_str_sizes", s); k_str_sizes<<<dim3(str_gx, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
+    if (pd.n_str && ntiles) { e->prof_begin("k_str_sizes", s); launch_k_str_sizes(dim3(str_gx, pd.n_str), TF_STR_THREADS, 0, s, ea); e->prof_end(s); }
     LayoutArgs la{e->d_cols, (int)pl.out_cols.size(), pd.d_out_cols, pd.d_str_slots, pd.n_str, e->tile_sum, e->tile_base, sz.ntiles_cap, pd.d_col_headers, pd.d_col_header_off,
                   e->raw.p, e->d_state, n, 1, e->frame_bytes, e->col_bytes};
-    if (pd.n_str) { e->prof_begin("k_layout_scan", s); k_layout_scan<<<pd.n_str, 1024, 0, s>>>(la); e->prof_end(s); }
+    if (pd.n_str) { e->prof_begin("k_layout_scan", s); launch_k_layout_scan(pd.n_str, 1024, 0, s, la); e->prof_end(s); }
     if (!columnar) {
-        e->prof_begin("k_layout_finish", s); k_layout_finish<<<1, 256, 0, s>>>(la); e->prof_end(s);
+        e->prof_begin("k_layout_finish", s); launch_k_layout_finish(1, 256, 0, s, la); e->prof_end(s);
         if (n) {
             // (the fixed-width streams and the String columns write disjoint parts of the block, but running them on two streams
             // was measured slower: both are latency-bound gathers that already fill the SMs: 0.087 + 0.182 ms in sequence, 0.30 ms side by side)
@@ -452,13 +444,13 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
                 // widest stream is 8 bytes per row: words = 2n (+1 for misalignment)
                 const uint32_t gx = grid_cap(e, (uint32_t)((2 * n + 2 + TF_FIX_TILE_WORDS - 1) / TF_FIX_TILE_WORDS), (uint32_t)pd.n_fixed_slots, 6);
                 EncodeArgs fa = ea; fa.slots = pd.d_fixed_slots;
-                e->prof_begin("k_encode_fixed", s); k_encode_fixed<<<dim3(gx, pd.n_fixed_slots), 256, 0, s>>>(fa); e->prof_end(s);
+                e->prof_begin("k_encode_fixed", s); launch_k_encode_fixed(dim3(gx, pd.n_fixed_slots), 256, 0, s, fa); e->prof_end(s);
             }
-            if (pd.n_str) { e->prof_begin("k_encode_str_plain", s); k_encode_str_plain<<<dim3(str_gx, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
-            if (pd.n_str && pd.n_tostr) { e->prof_begin("k_encode_str", s); k_encode_str<<<dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
+            if (pd.n_str) { e->prof_begin("k_encode_str_plain", s); launch_k_encode_str_plain(dim3(str_gx, pd.n_str), TF_STR_THREADS, 0, s, ea); e->prof_end(s); }
+            if (pd.n_str && pd.n_tostr) { e->prof_begin("k_encode_str", s); launch_k_encode_str(dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s, ea); e->prof_end(s); }
             if (pd.n_mask_cols) {
                 MaskArgs ma{e->d_cols, pd.d_mask_slots, pd.d_mask_keys, sel, e->d_state, e->raw.p, 0};
-                e->prof_begin("k_mask_encode", s); k_mask_encode<<<dim3((uint32_t)((n + 127) / 128), pd.n_mask_cols), 128, 0, s>>>(ma); e->prof_end(s);
+                e->prof_begin("k_mask_encode", s); launch_k_mask_encode(dim3((uint32_t)((n + 127) / 128), pd.n_mask_cols), 128, 0, s, ma); e->prof_end(s);
             }
         }
     } else {
@@ -478,22 +470,22 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         }
         std::vector<int32_t> both(fixed); both.insert(both.end(), valid.begin(), valid.end());
         if (!both.empty()) CK(cudaMemcpyAsync(e->d_call_slots, both.data(), both.size() * 4, cudaMemcpyHostToDevice, s));
-        e->prof_begin("k_layout_columnar", s); k_layout_columnar<<<1, 256, 0, s>>>(la, e->d_regions); e->prof_end(s);
+        e->prof_begin("k_layout_columnar", s); launch_k_layout_columnar(1, 256, 0, s, la, e->d_regions); e->prof_end(s);
         if (n) {
             if (!fixed.empty()) {
                 const uint32_t gx = grid_cap(e, (uint32_t)((2 * n + 2 + TF_FIX_TILE_WORDS - 1) / TF_FIX_TILE_WORDS), (uint32_t)fixed.size(), 6);
                 EncodeArgs fa = ea; fa.slots = e->d_call_slots;
-                e->prof_begin("k_encode_fixed", s); k_encode_fixed<<<dim3(gx, (uint32_t)fixed.size()), 256, 0, s>>>(fa); e->prof_end(s);
+                e->prof_begin("k_encode_fixed", s); launch_k_encode_fixed(dim3(gx, (uint32_t)fixed.size()), 256, 0, s, fa); e->prof_end(s);
             }
             if (!valid.empty()) {
                 EncodeArgs va = ea; va.slots = e->d_call_slots + fixed.size();
-                e->prof_begin("k_pack_validity", s); k_pack_validity<<<dim3((uint32_t)((n / 8 + 256) / 256), (uint32_t)valid.size()), 256, 0, s>>>(va); e->prof_end(s);
+                e->prof_begin("k_pack_validity", s); launch_k_pack_validity(dim3((uint32_t)((n / 8 + 256) / 256), (uint32_t)valid.size()), 256, 0, s, va); e->prof_end(s);
             }
-            if (pd.n_str) { e->prof_begin("k_encode_str_plain", s); k_encode_str_plain<<<dim3(str_gx, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
-            if (pd.n_str && pd.n_tostr) { e->prof_begin("k_encode_str", s); k_encode_str<<<dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s>>>(ea); e->prof_end(s); }
+            if (pd.n_str) { e->prof_begin("k_encode_str_plain", s); launch_k_encode_str_plain(dim3(str_gx, pd.n_str), TF_STR_THREADS, 0, s, ea); e->prof_end(s); }
+            if (pd.n_str && pd.n_tostr) { e->prof_begin("k_encode_str", s); launch_k_encode_str(dim3(ntiles, pd.n_str), TF_STR_THREADS, 0, s, ea); e->prof_end(s); }
             if (pd.n_mask_cols) {
                 MaskArgs ma{e->d_cols, pd.d_mask_slots, pd.d_mask_keys, sel, e->d_state, e->raw.p, 1};
-                e->prof_begin("k_mask_encode", s); k_mask_encode<<<dim3((uint32_t)((n + 127) / 128), pd.n_mask_cols), 128, 0, s>>>(ma); e->prof_end(s);
+                e->prof_begin("k_mask_encode", s); launch_k_mask_encode(dim3((uint32_t)((n + 127) / 128), pd.n_mask_cols), 128, 0, s, ma); e->prof_end(s);
             }
         }
     }
@@ -503,16 +495,16 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (smem + 1024)));
         const uint32_t grid = (uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * per_sm);
         join_tail(e);            // the previous batch's checksum / gather still read the slots and sizes this kernel overwrites
-        e->prof_begin("k_lz4_frames", s); k_lz4_frames<<<grid, LZ_THREADS, smem, s>>>(za); e->prof_end(s);
+        e->prof_begin("k_lz4_frames", s); launch_k_lz4_frames(grid, LZ_THREADS, smem, s, za); e->prof_end(s);
         FrameArgs fa{e->slots.p, stride, e->comp_size, e->d_state, e->frame_bytes, e->wire_off, e->wire.p, e->d_tail};
         // frame offsets + [method][sizes] headers first; then the checksum chain (one thread per frame: latency-bound, a few warps
         // per SM) and the gather of everything behind the checksum run side by side on two streams
-        e->prof_begin("k_frame_scan", s); k_frame_scan<<<1, 1024, 0, s>>>(fa); e->prof_end(s);
+        e->prof_begin("k_frame_scan", s); launch_k_frame_scan(1, 1024, 0, s, fa); e->prof_end(s);
         cudaStream_t s2 = e->side_stream, s3 = e->side2_stream;
         CK(cudaEventRecord(e->ev_fork, s)); CK(cudaStreamWaitEvent(s2, e->ev_fork, 0)); CK(cudaStreamWaitEvent(s3, e->ev_fork, 0));
-        e->prof_begin("k_frame_seal", s3); k_frame_seal<<<(uint32_t)((sz.n_frames_max + 31) / 32), 32, SEAL_SMEM, s3>>>(fa); e->prof_end(s3);
+        e->prof_begin("k_frame_seal", s3); launch_k_frame_seal((uint32_t)((sz.n_frames_max + 31) / 32), 32, SEAL_SMEM, s3, fa); e->prof_end(s3);
         CK(cudaEventRecord(e->ev_tail2, s3));
-        e->prof_begin("k_wire_gather", s2); k_wire_gather<<<(uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * 8), 256, 0, s2>>>(fa); e->prof_end(s2);
+        e->prof_begin("k_wire_gather", s2); launch_k_wire_gather((uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * 8), 256, 0, s2, fa); e->prof_end(s2);
         CK(cudaEventRecord(e->ev_join, s2));
         e->tail_pending = true; e->tail_nrows = n; e->tail_plan = (const void*)&pd;      // joined by whoever needs the wire bytes, or by the next batch before its LZ4
     }
@@ -557,8 +549,7 @@ int tfgpu_engine_create(const char* cfg_json, const int* device_ids, int n_devic
         CK(cudaMalloc(&e->d_tail, 64)); CK(cudaMemset(e->d_tail, 0, 64));
         CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
         CK(cudaMalloc(&e->d_state, sizeof(DState)));
-        CK(cudaFuncSetAttribute(k_lz4_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024));
-        CK(cudaFuncSetAttribute(k_frame_seal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEAL_SMEM));
+        CK(lz4_kernels_init());
     } catch (const CudaError& c) { return c.e == cudaErrorMemoryAllocation ? TF_E_RETRY_OOM : TF_E_RETRY_LAUNCH; }
     catch (const std::exception&) { return TF_E_FATAL_CONFIG; }
     *out = e.release();
@@ -1024,7 +1015,7 @@ int tfgpu_measure(tfgpu_engine* e, const tf_batch* in, uint64_t* per_row, uint64
         CK(cudaMemcpyAsync(e->d_cols, hc.data(), sizeof(DCol) * nc, cudaMemcpyHostToDevice, s));
         CK(cudaMemsetAsync(d_total, 0, 8, s));
         e->prof_n = 0;
-        if (n) { MeasureArgs ma{e->d_cols, (int)nc, n, d_rows, d_total}; e->prof_begin("k_measure", s); k_measure<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(ma); e->prof_end(s); CK(cudaGetLastError()); }
+        if (n) { MeasureArgs ma{e->d_cols, (int)nc, n, d_rows, d_total}; e->prof_begin("k_measure", s); launch_k_measure((uint32_t)((n + 255) / 256), 256, 0, s, ma); e->prof_end(s); CK(cudaGetLastError()); }
         CK(cudaMemcpyAsync(total, d_total, 8, cudaMemcpyDeviceToHost, s));
         if (per_row && n) CK(cudaMemcpyAsync(per_row, d_rows, n * 8, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -1096,8 +1087,8 @@ int tfgpu_parse_csv(tfgpu_engine* e, int plan_id, const char* opts_json, const u
         if (nblk) {
             CK(cudaMemsetAsync(e->d_state, 0, sizeof(DState), s));
             e->prof_n = 0;
-            e->prof_begin("k_csv_count_nl", s); k_csv_count_nl<<<nblk, 256, 0, s>>>(d_text, len, blk_cnt, nullptr); e->prof_end(s);
-            e->prof_begin("k_scan_blockcnt", s); k_scan_blockcnt<<<1, 1024, 0, s>>>(blk_cnt, blk_off, nblk, e->d_state); e->prof_end(s);
+            e->prof_begin("k_csv_count_nl", s); launch_k_csv_count_nl(nblk, 256, 0, s, d_text, len, blk_cnt, nullptr); e->prof_end(s);
+            e->prof_begin("k_scan_blockcnt", s); launch_k_scan_blockcnt(1, 1024, 0, s, blk_cnt, blk_off, nblk, e->d_state); e->prof_end(s);
             DState st; CK(cudaMemcpyAsync(&st, e->d_state, sizeof st, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
             nlines = st.n_kept;
         }
@@ -1140,18 +1131,18 @@ int tfgpu_parse_csv(tfgpu_engine* e, int plan_id, const char* opts_json, const u
         CK(cudaMemcpyAsync(B + o_ns, next_same.data(), nc * 2, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(B + o_blob, ho.blob.data(), ho.blob.size(), cudaMemcpyHostToDevice, s));
         std::vector<uint64_t> col_total(nslots ? nslots : 1, 0), col_base(nslots ? nslots : 1, 0);
-        if (nlines) { e->prof_begin("k_csv_line_index", s); k_csv_line_index<<<nblk, 256, 0, s>>>(d_text, len, blk_off, (uint32_t*)(B + o_line), nullptr); e->prof_end(s); }
+        if (nlines) { e->prof_begin("k_csv_line_index", s); launch_k_csv_line_index(nblk, 256, 0, s, d_text, len, blk_off, (uint32_t*)(B + o_line), nullptr); e->prof_end(s); }
         if (nrows) {
             CsvArgs ca{d_text, len, (const uint32_t*)(B + o_line), nlines, skip, ho.cfg, B + o_blob, (const CsvColDev*)(B + o_cols), (int)nc,
                        (const int16_t*)(B + o_fc), nfields, (const int16_t*)(B + o_ns), (uint32_t*)(B + o_ss), (uint32_t*)(B + o_sl), B + o_err};
-            e->prof_begin("k_csv_pass1", s); k_csv_pass1<<<(uint32_t)((nrows + 127) / 128), 128, 0, s>>>(ca); e->prof_end(s);
+            e->prof_begin("k_csv_pass1", s); launch_k_csv_pass1((uint32_t)((nrows + 127) / 128), 128, 0, s, ca); e->prof_end(s);
             if (nslots) {
                 launch_offsets(e, (const uint32_t*)(B + o_sl), nrows, (uint32_t)nslots, (uint32_t*)(B + o_off), (uint64_t*)(B + o_tot), s);
                 CK(cudaMemcpyAsync(col_total.data(), B + o_tot, (size_t)nslots * 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
                 uint64_t run = 0; for (int k = 0; k < nslots; k++) { col_base[k] = run; run += col_total[k]; }
                 CK(cudaMemcpyAsync(B + o_base, col_base.data(), (size_t)nslots * 8, cudaMemcpyHostToDevice, s));
                 CsvCopyArgs cp{d_text, (const uint32_t*)(B + o_ss), (const uint32_t*)(B + o_sl), (const uint32_t*)(B + o_off), B + o_heap, (const uint64_t*)(B + o_base), nrows};
-                e->prof_begin("k_csv_pass2", s); k_csv_pass2<<<dim3((uint32_t)((nrows + 255) / 256), nslots), 256, 0, s>>>(cp); e->prof_end(s);
+                e->prof_begin("k_csv_pass2", s); launch_k_csv_pass2(dim3((uint32_t)((nrows + 255) / 256), nslots), 256, 0, s, cp); e->prof_end(s);
             }
         }
         // the staged batch, device resident
@@ -1250,9 +1241,9 @@ int tfgpu_parse_json(tfgpu_engine* e, int plan_id, const char* opts_json, const 
                 CK(cudaMemsetAsync(endbits, 0, bits_words * 4, s));
                 CK(cudaMemcpyAsync(W + w_end, h_end.data(), (size_t)n_msgs * 8, cudaMemcpyHostToDevice, s)); CK(cudaMemcpyAsync(W + w_moff, h_off.data(), (size_t)n_msgs * 8, cudaMemcpyHostToDevice, s));
                 CK(cudaMemcpyAsync(W + w_ws, h_ws.data(), (size_t)n_msgs * 8, cudaMemcpyHostToDevice, s)); CK(cudaMemcpyAsync(W + w_wn, h_wn.data(), (size_t)n_msgs * 4, cudaMemcpyHostToDevice, s));
-                e->prof_begin("k_json_mark_msgs", s); k_json_mark_msgs<<<(n_msgs + 255) / 256, 256, 0, s>>>((const uint64_t*)(W + w_end), n_msgs, endbits); e->prof_end(s);
-                e->prof_begin("k_csv_count_nl", s); k_csv_count_nl<<<nblk, 256, 0, s>>>(d_text, len, blk_cnt, endbits); e->prof_end(s);
-                e->prof_begin("k_scan_blockcnt", s); k_scan_blockcnt<<<1, 1024, 0, s>>>(blk_cnt, blk_off, nblk, e->d_state); e->prof_end(s);
+                e->prof_begin("k_json_mark_msgs", s); launch_k_json_mark_msgs((n_msgs + 255) / 256, 256, 0, s, (const uint64_t*)(W + w_end), n_msgs, endbits); e->prof_end(s);
+                e->prof_begin("k_csv_count_nl", s); launch_k_csv_count_nl(nblk, 256, 0, s, d_text, len, blk_cnt, endbits); e->prof_end(s);
+                e->prof_begin("k_scan_blockcnt", s); launch_k_scan_blockcnt(1, 1024, 0, s, blk_cnt, blk_off, nblk, e->d_state); e->prof_end(s);
                 DState st; CK(cudaMemcpyAsync(&st, e->d_state, sizeof st, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
                 nlines = st.n_kept;
             }
@@ -1287,11 +1278,11 @@ int tfgpu_parse_json(tfgpu_engine* e, int plan_id, const char* opts_json, const 
                 CK(cudaMemcpyAsync(B + o_cols, hc.data(), nc * sizeof(JsnColDev), cudaMemcpyHostToDevice, s));
                 CK(cudaMemcpyAsync(B + o_names, names.data(), names.size(), cudaMemcpyHostToDevice, s));
                 CK(cudaMemsetAsync(B + o_sl, 0, (size_t)nf * nrows * 4, s));
-                e->prof_begin("k_csv_line_index", s); k_csv_line_index<<<nblk, 256, 0, s>>>(d_text, len, blk_off, (uint32_t*)(B + o_line), endbits); e->prof_end(s);
-                e->prof_begin("k_json_count_nonempty", s); k_json_count_nonempty<<<nlb, 128, 0, s>>>(d_text, (const uint32_t*)(B + o_line), nlines, (uint32_t*)(B + o_lcnt)); e->prof_end(s);
-                e->prof_begin("k_scan_blockcnt", s); k_scan_blockcnt<<<1, 1024, 0, s>>>((const uint32_t*)(B + o_lcnt), (uint32_t*)(B + o_loff), nlb, e->d_state); e->prof_end(s);
-                e->prof_begin("k_json_rank", s); k_json_rank<<<nlb, 128, 0, s>>>(d_text, (const uint32_t*)(B + o_line), nlines, (const uint32_t*)(B + o_loff), (uint32_t*)(B + o_rank)); e->prof_end(s);
-                e->prof_begin("k_json_msg_first", s); k_json_msg_first<<<(n_msgs + 255) / 256, 256, 0, s>>>((const uint64_t*)(W + w_end), n_msgs, (const uint32_t*)(B + o_line), nlines, (const uint32_t*)(B + o_rank), (uint32_t*)(W + w_r0)); e->prof_end(s);
+                e->prof_begin("k_csv_line_index", s); launch_k_csv_line_index(nblk, 256, 0, s, d_text, len, blk_off, (uint32_t*)(B + o_line), endbits); e->prof_end(s);
+                e->prof_begin("k_json_count_nonempty", s); launch_k_json_count_nonempty(nlb, 128, 0, s, d_text, (const uint32_t*)(B + o_line), nlines, (uint32_t*)(B + o_lcnt)); e->prof_end(s);
+                e->prof_begin("k_scan_blockcnt", s); launch_k_scan_blockcnt(1, 1024, 0, s, (const uint32_t*)(B + o_lcnt), (uint32_t*)(B + o_loff), nlb, e->d_state); e->prof_end(s);
+                e->prof_begin("k_json_rank", s); launch_k_json_rank(nlb, 128, 0, s, d_text, (const uint32_t*)(B + o_line), nlines, (const uint32_t*)(B + o_loff), (uint32_t*)(B + o_rank)); e->prof_end(s);
+                e->prof_begin("k_json_msg_first", s); launch_k_json_msg_first((n_msgs + 255) / 256, 256, 0, s, (const uint64_t*)(W + w_end), n_msgs, (const uint32_t*)(B + o_line), nlines, (const uint32_t*)(B + o_rank), (uint32_t*)(W + w_r0)); e->prof_end(s);
                 JsnArgs ja; std::memset(&ja, 0, sizeof ja);
                 ja.text = d_text; ja.len = len; ja.line_end = (const uint32_t*)(B + o_line); ja.nlines = nlines;
                 ja.msg_end = (const uint64_t*)(W + w_end); ja.msg_offset = (const uint64_t*)(W + w_moff); ja.msg_wsec = (const int64_t*)(W + w_ws); ja.msg_wnsec = (const uint32_t*)(W + w_wn); ja.nmsgs = n_msgs;
@@ -1301,7 +1292,7 @@ int tfgpu_parse_json(tfgpu_engine* e, int plan_id, const char* opts_json, const 
                 ja.part_off = part_off; ja.part_len = (uint32_t)partition.size();
                 ja.span_start = (uint32_t*)(B + o_ss); ja.span_len = (uint32_t*)(B + o_sl); ja.out_len = (uint32_t*)(B + o_len);
                 ja.err = B + o_err; ja.errcol = B + o_ecol;
-                e->prof_begin("k_json_pass1", s); k_json_pass1<<<nlb, 128, JSN_STAGE, s>>>(ja); e->prof_end(s);
+                e->prof_begin("k_json_pass1", s); launch_k_json_pass1(nlb, 128, JSN_STAGE, s, ja); e->prof_end(s);
                 CK(cudaMemcpyAsync(&n_nonempty, (uint32_t*)(B + o_rank) + nlines, 4, cudaMemcpyDeviceToHost, s));
                 if (nslots) {
                     launch_offsets(e, (const uint32_t*)(B + o_len), nrows, (uint32_t)nslots, (uint32_t*)(B + o_off), (uint64_t*)(B + o_tot), s);
@@ -1312,7 +1303,7 @@ int tfgpu_parse_json(tfgpu_engine* e, int plan_id, const char* opts_json, const 
                     heap = e->in_arena.p;
                     CK(cudaMemcpyAsync(B + o_base, col_base.data(), (size_t)nslots * 8, cudaMemcpyHostToDevice, s));
                     JsnWriteArgs wa{ja, (const uint32_t*)(B + o_off), e->in_arena.p, (const uint64_t*)(B + o_base)};
-                    e->prof_begin("k_json_pass2", s); k_json_pass2<<<nlb, 128, JSN_STAGE, s>>>(wa); e->prof_end(s);
+                    e->prof_begin("k_json_pass2", s); launch_k_json_pass2(nlb, 128, JSN_STAGE, s, wa); e->prof_end(s);
                 } else CK(cudaStreamSynchronize(s));
             }
             // ---- the staged batch, device resident
@@ -1463,7 +1454,7 @@ int tfgpu_parse_debezium(tfgpu_engine* e, int plan_id, const char* opts_json, co
             da.span_start = (uint32_t*)(B + o_ss); da.span_len = (uint32_t*)(B + o_sl); da.out_len = (uint32_t*)(B + o_len);
             da.kinds = B + o_kind; da.tx_id = (uint32_t*)(B + o_tx); da.lsn = (uint64_t*)(B + o_lsn); da.commit_time = (uint64_t*)(B + o_ct); da.err = B + o_err; da.errcol = B + o_ecol;
             const uint32_t nb = (uint32_t)((n + 127) / 128);
-            e->prof_begin("k_dbz_pass1", s); k_dbz_pass1<<<nb, 128, 0, s>>>(da); e->prof_end(s);
+            e->prof_begin("k_dbz_pass1", s); launch_k_dbz_pass1(nb, 128, 0, s, da); e->prof_end(s);
             if (nslots) {
                 launch_offsets(e, (const uint32_t*)(B + o_len), n, (uint32_t)nslots, (uint32_t*)(B + o_off), (uint64_t*)(B + o_tot), s);
                 CK(cudaMemcpyAsync(col_total.data(), B + o_tot, (size_t)nslots * 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
@@ -1472,7 +1463,7 @@ int tfgpu_parse_debezium(tfgpu_engine* e, int plan_id, const char* opts_json, co
                 e->in_arena.ensure(run + 256); heap = e->in_arena.p;
                 CK(cudaMemcpyAsync(B + o_base, col_base.data(), (size_t)nslots * 8, cudaMemcpyHostToDevice, s));
                 DbzWriteArgs wa{da, (const uint32_t*)(B + o_off), e->in_arena.p, (const uint64_t*)(B + o_base)};
-                e->prof_begin("k_dbz_pass2", s); k_dbz_pass2<<<nb, 128, 0, s>>>(wa); e->prof_end(s);
+                e->prof_begin("k_dbz_pass2", s); launch_k_dbz_pass2(nb, 128, 0, s, wa); e->prof_end(s);
             }
             CK(cudaGetLastError());
         }
