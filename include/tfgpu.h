@@ -172,7 +172,8 @@ typedef struct tf_rowerr {
 typedef struct tfgpu_engine tfgpu_engine;
 typedef struct tfgpu_result tfgpu_result;
 
-/* cfg_json: {"frame_bytes":32768,"max_rows":N,...} or NULL for defaults.
+/* cfg_json: {"frame_bytes":30720,...} or NULL for defaults; frame_bytes = uncompressed bytes per ClickHouse
+ * compressed frame: a multiple of 16 in [1024, 30720] (one CTA compresses one frame in shared memory).
  * One engine drives one device (device_ids[0]); n_devices must be 1 — multi-GPU
  * is one engine per GPU with batches dealt round-robin by the host. */
 int tfgpu_engine_create(const char* cfg_json, const int* device_ids, int n_devices,

@@ -4,6 +4,9 @@ AND the oracle's decoder to exactly that block and carry valid CityHash128 check
 unpinned in the reference)."""
 import ctypes as C
 import struct
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import cityhash_independent
 
 import numpy as np
 import pytest
@@ -24,6 +27,8 @@ def decode_with_liblz4(wire: bytes, po):
         cs, rs = struct.unpack_from("<II", wire, pos + 17)
         lo, hi = po.cityhash128(wire[pos + 16: pos + 16 + cs])
         assert struct.unpack_from("<QQ", wire, pos) == (lo, hi), f"bad checksum in frame {nf}"
+        if nf < 6:      # the device checksum also against the second, independent CityHash128 (tests/cityhash_independent.py)
+            assert cityhash_independent.cityhash128(wire[pos + 16: pos + 16 + cs]) == (lo, hi), f"oracle and independent CityHash128 disagree on frame {nf}"
         dst = C.create_string_buffer(max(1, rs))
         n = lz.LZ4_decompress_safe(wire[pos + 25: pos + 16 + cs], dst, cs - 9, rs)
         assert n == rs, f"liblz4 rejected frame {nf}: {n}"

@@ -114,7 +114,7 @@ __device__ __forceinline__ bool d_in_list(const uint8_t* blob, uint32_t list, co
     return false;
 }
 // strconv.ParseInt(trimZeroDecimal(s), 0, 0): rc 0 ok, 1 error, 2 unsupported (underscores)
-__device__ inline int d_parse_int(const uint8_t* s, uint32_t n, int64_t& out) {
+static __device__ int d_parse_int(const uint8_t* s, uint32_t n, int64_t& out) {
     { bool zero = false; uint32_t i = n; for (; i > 0; i--) { const uint8_t c = s[i - 1]; if (c == '.') { if (zero) n = i - 1; break; } else if (c == '0') zero = true; else break; } }
     if (!n) return 1;
     uint32_t i = 0; bool neg = false;
@@ -137,14 +137,14 @@ __device__ inline int d_parse_int(const uint8_t* s, uint32_t n, int64_t& out) {
     out = neg ? (int64_t)(0 - v) : (int64_t)v; return 0;
 }
 __device__ __forceinline__ bool d_eq(const uint8_t* s, uint32_t n, const char* lit) { uint32_t i = 0; for (; lit[i]; i++) if (i >= n || s[i] != (uint8_t)lit[i]) return false; return i == n; }
-__device__ inline int d_parse_bool(const uint8_t* s, uint32_t n, bool& out) {   // strconv.ParseBool
+static __device__ int d_parse_bool(const uint8_t* s, uint32_t n, bool& out) {   // strconv.ParseBool
     if (d_eq(s, n, "1") || d_eq(s, n, "t") || d_eq(s, n, "T") || d_eq(s, n, "TRUE") || d_eq(s, n, "true") || d_eq(s, n, "True")) { out = true; return 0; }
     if (d_eq(s, n, "0") || d_eq(s, n, "f") || d_eq(s, n, "F") || d_eq(s, n, "FALSE") || d_eq(s, n, "false") || d_eq(s, n, "False")) { out = false; return 0; }
     return 1;
 }
 __constant__ double d_p10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
 // decimal text -> double, exact when <= 15 significant digits and |exp10| <= 22 (one correctly rounded IEEE op); rc 2 otherwise
-__device__ inline int d_parse_float(const uint8_t* s, uint32_t n, double& out) {
+static __device__ int d_parse_float(const uint8_t* s, uint32_t n, double& out) {
     uint32_t i = 0; bool neg = false;
     if (!n) return 1;
     if (s[0] == '+' || s[0] == '-') { neg = s[0] == '-'; i = 1; }
@@ -178,7 +178,7 @@ __device__ __forceinline__ int64_t d_days_from_civil(int64_t y, unsigned m, unsi
     const unsigned doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
     return era * 146097 + (int64_t)doe - 719468;
 }
-__device__ inline int d_parse_time(const uint8_t* s, uint32_t n, int64_t& sec, uint32_t& nsec) {
+static __device__ int d_parse_time(const uint8_t* s, uint32_t n, int64_t& sec, uint32_t& nsec) {
     auto dig = [&](uint32_t p, int k, int& v) { v = 0; for (int i = 0; i < k; i++) { if (p + i >= n || s[p + i] < '0' || s[p + i] > '9') return false; v = v * 10 + (s[p + i] - '0'); } return true; };
     int y, mo, d, hh = 0, mi = 0, ss = 0; nsec = 0; int64_t off = 0;
     if (!(dig(0, 4, y) && n >= 10 && s[4] == '-' && dig(5, 2, mo) && s[7] == '-' && dig(8, 2, d))) return 2;
@@ -219,7 +219,7 @@ __device__ __forceinline__ void csv_store_fixed(const CsvColDev& c, uint64_t row
 }
 
 // getCorrespondingValue + strictifyValue for one cell [p, p+n) (already sanitised); text cells return their span
-__device__ inline int csv_cell(const CsvArgs& a, const CsvColDev& c, uint64_t row, uint64_t nrows, const uint8_t* p, uint32_t n, bool has_dq) {
+static __device__ int csv_cell(const CsvArgs& a, const CsvColDev& c, uint64_t row, uint64_t nrows, const uint8_t* p, uint32_t n, bool has_dq) {
     const CsvCfg& o = a.cfg;
     if (has_dq && c.w) return CSV_UNSUPPORTED;       // a `""` inside a numeric cell: the collapsed text would have to be materialised first
     switch (c.tf) {

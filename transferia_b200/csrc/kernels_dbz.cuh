@@ -38,7 +38,7 @@ struct DbzArgs {
 // ------------------------------------------------------------------ encoding/json grammar (checkValid)
 // validates ONE value starting at s[p] (after optional whitespace); returns 0 ok / 1 syntax error / 2 too deep; p ends after the
 // value. odd_key is set when an object key holds a backslash or a non-ASCII byte (case folding / unescaping left to the host).
-__device__ inline int dbz_validate(const uint8_t* s, uint32_t n, uint32_t& p, bool& odd_key) {
+static __device__ int dbz_validate(const uint8_t* s, uint32_t n, uint32_t& p, bool& odd_key) {
     while (p < n && jsn_ws(s[p])) p++;
     uint32_t stk[DBZ_MAX_DEPTH / 32]; int depth = 0; int st = 0;      // st 0 value, 1 key, 2 after value
     for (;;) {

@@ -90,7 +90,7 @@ __device__ __forceinline__ bool contains_bytes(const uint8_t* h, uint32_t hn, co
 }
 
 // returns 0 and sets matched, or a TF_ROWERR_* code
-__device__ inline int eval_term(const RowVal& v, const DTerm& t, const uint8_t* blob, bool& matched) {
+static __device__ int eval_term(const RowVal& v, const DTerm& t, const uint8_t* blob, bool& matched) {
     const int op = t.op; const bool is_set = (op == 6 || op == 7);
     const int base = t.vtype & 15; const bool is_list = (t.vtype & 16) != 0;
     if (v.cls == 8) return TF_ROWERR_FILTER_OVERFLOW;                       // filter_rows.go:193-197

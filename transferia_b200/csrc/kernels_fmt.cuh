@@ -31,6 +31,22 @@ struct WordSink {
 };
 
 // ------------------------------------------------------------------ Ryu core
+// decimal digits without a local array (digits are packed into registers, least significant first, and read back from the top):
+// a dynamically indexed local buffer here was placed outside the thread's stack by ptxas 12.9 in the mask translation unit
+struct DigitRegs { uint64_t a, b, c; int n; };
+__device__ __forceinline__ DigitRegs digits_of(uint64_t u) {
+    DigitRegs d{0, 0, 0, 0};
+    do {
+        const uint64_t q = u / 10; const uint64_t dg = u - q * 10; u = q;
+        if (d.n < 8) d.a |= dg << (8 * d.n); else if (d.n < 16) d.b |= dg << (8 * (d.n - 8)); else d.c |= dg << (8 * (d.n - 16));
+        d.n++;
+    } while (u);
+    return d;
+}
+__device__ __forceinline__ uint8_t digit_at(const DigitRegs& d, int i) {
+    const uint64_t w = i < 8 ? d.a >> (8 * i) : (i < 16 ? d.b >> (8 * (i - 8)) : d.c >> (8 * (i - 16)));
+    return (uint8_t)('0' + (uint32_t)(w & 0xff));
+}
 struct DecF { uint64_t digits; int32_t exp10; };   // value = digits * 10^exp10
 
 __device__ __forceinline__ uint32_t ryu_pow5bits(int32_t e) { return (uint32_t)(((uint32_t)e * 1217359u) >> 19) + 1; }
@@ -45,7 +61,7 @@ __device__ __forceinline__ uint64_t ryu_mulshift(uint64_t m, const uint64_t* mul
 }
 __device__ __forceinline__ uint32_t ryu_pow5factor(uint64_t v) { uint32_t c = 0; while (v && v % 5 == 0) { v /= 5; c++; } return c; }
 
-__device__ inline DecF ryu_d2d(uint64_t mant, uint32_t expo, int mbits, int bias) {
+static __device__ DecF ryu_d2d(uint64_t mant, uint32_t expo, int mbits, int bias) {
     int32_t e2; uint64_t m2;
     if (expo == 0) { e2 = 1 - bias - mbits - 2; m2 = mant; } else { e2 = (int32_t)expo - bias - mbits - 2; m2 = (1ull << mbits) | mant; }
     const bool accept = (m2 & 1) == 0;
@@ -104,13 +120,13 @@ template <typename Sink> __device__ void fmt_float_bits(Sink& s, uint64_t bits, 
         while (*t) s.put((uint8_t)*t++);
         return;
     }
-    char d[20]; int nd = 0, dp = 0;
+    DigitRegs dr{0, 0, 0, 0}; int nd = 0, dp = 0;      // digit i (most significant first) = digit_at(dr, nd - 1 - i)
     if (expo || mant) {
         DecF r = ryu_d2d(mant, expo, mbits, bias);
-        char tmp[20]; int n = 0; uint64_t v = r.digits; while (v) { tmp[n++] = (char)('0' + v % 10); v /= 10; }
-        for (int i = 0; i < n; i++) d[i] = tmp[n - 1 - i];
-        nd = n; dp = n + r.exp10;
+        dr = digits_of(r.digits);
+        nd = dr.n; dp = nd + r.exp10;
     }
+#define TF_D(i) digit_at(dr, nd - 1 - (i))
     bool use_e = false;
     if (mode == FM_V) { const int ex = dp - 1; use_e = (ex < -4 || ex >= 6); }      // zero: nd = dp = 0 -> ex = -1 -> 'f' -> "0"
     else if (mode == FM_JSON && nd) {        // |f| < 1e-6 || |f| >= 1e21  <=> decimal exponent < -6 or >= 21
@@ -118,8 +134,8 @@ template <typename Sink> __device__ void fmt_float_bits(Sink& s, uint64_t bits, 
     }
     if (neg) s.put('-');
     if (use_e) {       // d.ddde±XX  (at least two exponent digits; encoding/json strips a leading zero: e-09 -> e-9)
-        s.put(nd ? (uint8_t)d[0] : '0');
-        if (nd > 1) { s.put('.'); for (int i = 1; i < nd; i++) s.put((uint8_t)d[i]); }
+        s.put(nd ? TF_D(0) : (uint8_t)'0');
+        if (nd > 1) { s.put('.'); for (int i = 1; i < nd; i++) s.put(TF_D(i)); }
         s.put('e');
         int ex = nd ? dp - 1 : 0;
         if (ex < 0) { s.put('-'); ex = -ex; } else s.put('+');
@@ -127,27 +143,27 @@ template <typename Sink> __device__ void fmt_float_bits(Sink& s, uint64_t bits, 
         else if (ex < 100) { s.put((uint8_t)('0' + ex / 10)); s.put((uint8_t)('0' + ex % 10)); }
         else { s.put((uint8_t)('0' + ex / 100)); s.put((uint8_t)('0' + (ex / 10) % 10)); s.put((uint8_t)('0' + ex % 10)); }
     } else {           // %f with the shortest precision
-        if (dp > 0) { int m = nd < dp ? nd : dp; for (int i = 0; i < m; i++) s.put((uint8_t)d[i]); for (; m < dp; m++) s.put('0'); }
+        if (dp > 0) { int m = nd < dp ? nd : dp; for (int i = 0; i < m; i++) s.put(TF_D(i)); for (; m < dp; m++) s.put('0'); }
         else s.put('0');
         const int prec = nd - dp > 0 ? nd - dp : 0;
-        if (prec > 0) { s.put('.'); for (int i = 0; i < prec; i++) { const int j = dp + i; s.put((j >= 0 && j < nd) ? (uint8_t)d[j] : (uint8_t)'0'); } }
+        if (prec > 0) { s.put('.'); for (int i = 0; i < prec; i++) { const int j = dp + i; s.put((j >= 0 && j < nd) ? TF_D(j) : (uint8_t)'0'); } }
     }
+#undef TF_D
 }
 
 // ------------------------------------------------------------------ integers, time, duration
 template <typename Sink> __device__ __forceinline__ void fmt_u64(Sink& s, uint64_t u) {
-    char buf[20]; int n = 0;
-    do { buf[n++] = (char)('0' + u % 10); u /= 10; } while (u);
-    while (n) s.put((uint8_t)buf[--n]);
+    const DigitRegs d = digits_of(u);
+    for (int i = d.n; i-- > 0;) s.put(digit_at(d, i));
 }
 template <typename Sink> __device__ __forceinline__ void fmt_i64(Sink& s, int64_t v) { if (v < 0) { s.put('-'); fmt_u64(s, (uint64_t)0 - (uint64_t)v); } else fmt_u64(s, (uint64_t)v); }
 template <typename Sink> __device__ __forceinline__ void fmt_pad(Sink& s, int64_t v, int wdt) {   // Go appendInt(b, v, width)
     if (v < 0) { s.put('-'); v = -v; }
-    char buf[20]; int n = 0; uint64_t u = (uint64_t)v;
-    do { buf[n++] = (char)('0' + u % 10); u /= 10; } while (u);
-    for (int i = n; i < wdt; i++) s.put('0');
-    while (n) s.put((uint8_t)buf[--n]);
+    const DigitRegs d = digits_of((uint64_t)v);
+    for (int i = d.n; i < wdt; i++) s.put('0');
+    for (int i = d.n; i-- > 0;) s.put(digit_at(d, i));
 }
+
 template <typename Sink> __device__ __forceinline__ void fmt_lit(Sink& s, const char* t) { while (*t) s.put((uint8_t)*t++); }
 
 __device__ inline void civil_from_days_d(int64_t z, int64_t& y, unsigned& m, unsigned& d) {
@@ -170,38 +186,32 @@ template <typename Sink> __device__ void fmt_time(Sink& s, int64_t sec, uint32_t
     if (date_only) return;
     s.put('T'); fmt_pad(s, sod / 3600, 2); s.put(':'); fmt_pad(s, (sod / 60) % 60, 2); s.put(':'); fmt_pad(s, sod % 60, 2);
     if (nsec) {
-        char b[9]; uint32_t v = nsec; for (int i = 8; i >= 0; i--) { b[i] = (char)('0' + v % 10); v /= 10; }
-        int n = 9; while (n > 0 && b[n - 1] == '0') n--;
-        s.put('.'); for (int i = 0; i < n; i++) s.put((uint8_t)b[i]);
+        uint32_t v = nsec; int n = 9; while (v % 10 == 0) { v /= 10; n--; }        // n significant fraction digits, v = those digits
+        s.put('.'); fmt_pad(s, v, n);
     }
     s.put('Z');
 }
 // time.Duration.String(): "72h3m0.5s", "1.5µs", "0s" (Go time/time.go Duration.String, fmtFrac, fmtInt)
 template <typename Sink> __device__ void fmt_duration(Sink& s, int64_t d) {
-    char buf[32]; int w = 32;
     uint64_t u = (uint64_t)d; const bool neg = d < 0; if (neg) u = (uint64_t)0 - u;
     if (u == 0) { s.put('0'); s.put('s'); return; }
-    auto frac = [&](uint64_t v, int prec) -> uint64_t {
-        bool print = false;
-        for (int i = 0; i < prec; i++) { const int digit = (int)(v % 10); print = print || digit != 0; if (print) buf[--w] = (char)('0' + digit); v /= 10; }
-        if (print) buf[--w] = '.';
-        return v;
+    if (neg) s.put('-');
+    // fmtFrac: v / 10^prec as "int[.frac]" with the fraction's trailing zeros dropped
+    auto int_frac = [&](uint64_t ip, uint64_t fr, int prec) {
+        fmt_u64(s, ip);
+        if (fr) { while (fr % 10 == 0) { fr /= 10; prec--; } s.put('.'); fmt_pad(s, (int64_t)fr, prec); }
     };
-    auto integer = [&](uint64_t v) { if (v == 0) buf[--w] = '0'; else while (v > 0) { buf[--w] = (char)('0' + v % 10); v /= 10; } };
-    buf[--w] = 's';
     if (u < 1000000000ull) {
-        int prec;
-        if (u < 1000ull) { prec = 0; buf[--w] = 'n'; }
-        else if (u < 1000000ull) { prec = 3; buf[--w] = (char)0xB5; buf[--w] = (char)0xC2; }     // "µ"
-        else { prec = 6; buf[--w] = 'm'; }
-        integer(frac(u, prec));
+        if (u < 1000ull) { fmt_u64(s, u); s.put('n'); }
+        else if (u < 1000000ull) { int_frac(u / 1000, u % 1000, 3); s.put(0xC2); s.put(0xB5); }     // "µ"
+        else { int_frac(u / 1000000, u % 1000000, 6); s.put('m'); }
+        s.put('s');
     } else {
-        uint64_t v = frac(u, 9);
-        integer(v % 60); v /= 60;
-        if (v > 0) { buf[--w] = 'm'; integer(v % 60); v /= 60; if (v > 0) { buf[--w] = 'h'; integer(v); } }
+        const uint64_t fr = u % 1000000000ull; uint64_t v = u / 1000000000ull;
+        const uint64_t sec = v % 60; v /= 60;
+        if (v > 0) { const uint64_t mn = v % 60; v /= 60; if (v > 0) { fmt_u64(s, v); s.put('h'); } fmt_u64(s, mn); s.put('m'); }
+        int_frac(sec, fr, 9); s.put('s');
     }
-    if (neg) buf[--w] = '-';
-    for (int i = w; i < 32; i++) s.put((uint8_t)buf[i]);
 }
 
 // encoding/json string encoder, escapeHTML = true (json.Marshal of a Go string inside an `any` column)
@@ -239,7 +249,7 @@ template <typename Sink> __device__ void fmt_json_string(Sink& s, const uint8_t*
 }
 
 // to_string.SerializeToString (pkg/transformer/registry/to_string/to_string.go:145-171) for a typed column value
-template <typename Sink> __device__ void fmt_value(Sink& s, const DCol& c, uint64_t r) {
+template <typename Sink> __device__ __noinline__ void fmt_value(Sink& s, const DCol& c, uint64_t r) {
     if (!row_valid(c, r)) { if (c.type == TF_ANY) fmt_lit(s, "null"); else fmt_lit(s, "<nil>"); return; }   // json.Marshal(nil) / %v of nil
     switch (c.type) {
     case TF_INT8: fmt_i64(s, ((const int8_t*)c.values)[r]); break;

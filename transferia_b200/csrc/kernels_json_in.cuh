@@ -158,7 +158,7 @@ struct Src {
 
 // ------------------------------------------------------------------ strconv on the device (mirrors oracle/json_oracle.hpp)
 #define D_GO_NAN __longlong_as_double(0x7FF8000000000001ll)      /* math.NaN() */
-__device__ inline bool d_underscore_ok(const uint8_t* s, uint32_t n) {
+static __device__ bool d_underscore_ok(const uint8_t* s, uint32_t n) {
     char i = '^'; uint32_t p = 0;
     if (n && (s[0] == '-' || s[0] == '+')) p = 1;
     bool hex = false;
@@ -173,7 +173,7 @@ __device__ inline bool d_underscore_ok(const uint8_t* s, uint32_t n) {
     return i != '_';
 }
 // strconv.ParseUint(s, base, bits); base 0 = by prefix with underscores. rc 0 ok, 1 syntax, 2 range
-__device__ inline int d_go_parse_uint(const uint8_t* s0, uint32_t n0, int base, int bits, uint64_t& out) {
+static __device__ int d_go_parse_uint(const uint8_t* s0, uint32_t n0, int base, int bits, uint64_t& out) {
     if (!n0) return 1;
     const uint8_t* s = s0; uint32_t n = n0; const bool base0 = base == 0;
     if (base == 0) {
@@ -198,7 +198,7 @@ __device__ inline int d_go_parse_uint(const uint8_t* s0, uint32_t n0, int base, 
     if (range) { out = maxv; return 2; }
     out = v; return 0;
 }
-__device__ inline int d_go_parse_int(const uint8_t* s, uint32_t n, int base, int bits, int64_t& out) {
+static __device__ int d_go_parse_int(const uint8_t* s, uint32_t n, int base, int bits, int64_t& out) {
     if (!n) return 1;
     const uint8_t* s0 = s; const uint32_t n0 = n; bool neg = false;
     if (s[0] == '+') { s++; n--; } else if (s[0] == '-') { neg = true; s++; n--; }
@@ -214,7 +214,7 @@ __device__ inline int d_go_parse_int(const uint8_t* s, uint32_t n, int base, int
 
 // Eisel-Lemire (the algorithm strconv.ParseFloat uses after its exact path; scripts/el_proto.py checks this port against
 // CPython's correctly rounded float()). false = not decided here.
-__device__ inline bool d_eisel_lemire(uint64_t man, int exp10, bool neg, uint64_t& bits) {
+static __device__ bool d_eisel_lemire(uint64_t man, int exp10, bool neg, uint64_t& bits) {
     if (man == 0) { bits = neg ? 0x8000000000000000ull : 0; return true; }
     if (exp10 < EL_QMIN || exp10 > EL_QMAX) return false;
     const int clz = __clzll((long long)man);
@@ -241,7 +241,7 @@ __device__ inline bool d_eisel_lemire(uint64_t man, int exp10, bool neg, uint64_
     return true;
 }
 // strconv.ParseFloat(s, 64). rc 0 ok, 1 syntax, 2 range (out = +-Inf), 3 needs the host (hex, underscores, undecided rounding)
-__device__ inline int d_go_parse_float(const uint8_t* s, uint32_t n, double& out) {
+static __device__ int d_go_parse_float(const uint8_t* s, uint32_t n, double& out) {
     if (!n) return 1;
     {   // special()
         const uint8_t* t = s; uint32_t m = n; bool neg = false, sign = false;
@@ -309,14 +309,14 @@ __device__ inline int d_go_parse_float(const uint8_t* s, uint32_t n, double& out
 }
 
 // ------------------------------------------------------------------ fastjson/fastfloat number getters
-__device__ inline uint64_t d_ff_uint64(const uint8_t* s, uint32_t n) {
+static __device__ uint64_t d_ff_uint64(const uint8_t* s, uint32_t n) {
     if (!n) return 0;
     uint32_t i = 0; uint64_t d = 0;
     while (i < n && s[i] >= '0' && s[i] <= '9') { d = d * 10 + (uint64_t)(s[i] - '0'); i++; if (i > 18) { uint64_t dd; return d_go_parse_uint(s, n, 10, 64, dd) == 0 ? dd : 0; } }
     if (i == 0 || i < n) return 0;
     return d;
 }
-__device__ inline int64_t d_ff_int64(const uint8_t* s, uint32_t n) {
+static __device__ int64_t d_ff_int64(const uint8_t* s, uint32_t n) {
     if (!n) return 0;
     uint32_t i = 0; const bool minus = s[0] == '-';
     if (minus) { i++; if (i >= n) return 0; }
@@ -334,7 +334,7 @@ __device__ __forceinline__ double d_go_pow10(int n) {     // math.Pow10
     return n > 0 ? CUDART_INF : 0.0;
 }
 // fastfloat.ParseBestEffort. rc 0 ok, JSN_HOST when the strconv fall-back cannot be decided on the device
-__device__ inline int d_ff_best(const uint8_t* s, uint32_t n, double& out) {
+static __device__ int d_ff_best(const uint8_t* s, uint32_t n, double& out) {
     out = 0;
     auto slow = [&]() -> int { double f; const int rc = d_go_parse_float(s, n, f); if (rc == 3) return JSN_HOST; out = rc == 1 ? 0.0 : f; return 0; };
     if (!n) return 0;
@@ -373,7 +373,7 @@ __device__ inline int d_ff_best(const uint8_t* s, uint32_t n, double& out) {
     return 0;
 }
 __device__ __forceinline__ int64_t d_f64_to_i64(double f) { if (!(f >= -9223372036854775808.0 && f < 9223372036854775808.0)) return (int64_t)0x8000000000000000ull; return __double2ll_rz(f); }   // amd64 CVTTSD2SQ
-__device__ inline bool d_valid_json_number(const uint8_t* s, uint32_t n) {      // encoding/json isValidNumber
+static __device__ bool d_valid_json_number(const uint8_t* s, uint32_t n) {      // encoding/json isValidNumber
     uint32_t i = 0; if (!n) return false;
     if (s[i] == '-') { i++; if (i == n) return false; }
     if (s[i] == '0') i++; else if (s[i] >= '1' && s[i] <= '9') { while (i < n && s[i] >= '0' && s[i] <= '9') i++; } else return false;
@@ -384,7 +384,7 @@ __device__ inline bool d_valid_json_number(const uint8_t* s, uint32_t n) {      
 
 // ------------------------------------------------------------------ fastjson grammar scan
 // skips one already validated value starting at p, returns the position after it
-__device__ inline uint32_t jsn_skip_value(const uint8_t* s, uint32_t p, uint32_t n, uint32_t& t) {
+static __device__ uint32_t jsn_skip_value(const uint8_t* s, uint32_t p, uint32_t n, uint32_t& t) {
     const uint8_t c = s[p];
     if (c == '"') { p++; while (p < n) { if (s[p] == '\\') { p += 2; continue; } if (s[p] == '"') break; p++; } t = JT_STRING; return p + 1; }
     if (c == '{' || c == '[') {
@@ -470,17 +470,17 @@ template <typename F> __device__ int jsn_scan(const uint8_t* s, uint32_t n, bool
 }
 
 // ------------------------------------------------------------------ keys
-__device__ inline bool jsn_key_is(const uint8_t* k, uint32_t klen, const uint8_t* name, uint32_t nlen) {
+static __device__ bool jsn_key_is(const uint8_t* k, uint32_t klen, const uint8_t* name, uint32_t nlen) {
     bool esc = false; for (uint32_t i = 0; i < klen; i++) if (k[i] == '\\') { esc = true; break; }
     if (!esc) { if (klen != nlen) return false; for (uint32_t i = 0; i < klen; i++) if (k[i] != name[i]) return false; return true; }
     Dec d(k, klen); uint32_t i = 0;
     for (;;) { const int c = d.next(); if (c < 0) return i == nlen; if (i >= nlen || name[i] != (uint8_t)c) return false; i++; }
 }
-__device__ inline int jsn_key_cmp(const uint8_t* a, uint32_t an, const uint8_t* b, uint32_t bn) {      // strings.Compare of the unescaped keys
+static __device__ int jsn_key_cmp(const uint8_t* a, uint32_t an, const uint8_t* b, uint32_t bn) {      // strings.Compare of the unescaped keys
     Dec da(a, an), db(b, bn);
     for (;;) { const int x = da.next(), y = db.next(); if (x < 0 && y < 0) return 0; if (x != y) return x < y ? -1 : 1; }
 }
-__device__ inline int jsn_find_col(const JsnArgs& a, const uint8_t* k, uint32_t klen) {
+static __device__ int jsn_find_col(const JsnArgs& a, const uint8_t* k, uint32_t klen) {
     int hit = -1;
     for (int c = 0; c < a.ncols; c++) if (jsn_key_is(k, klen, a.names + a.cols[c].name_off, a.cols[c].name_len)) hit = c;
     return hit;
@@ -656,7 +656,7 @@ __device__ __forceinline__ bool jsn_is_int(int tf) { return tf == TF_INT8 || tf 
 __device__ __forceinline__ bool jsn_is_uint(int tf) { return tf == TF_UINT8 || tf == TF_UINT16 || tf == TF_UINT32 || tf == TF_UINT64; }
 
 // Unmarshal's typed extraction + ParseVal for a fixed-width field. rc 0 (null set when the cell is nil) / JSN_PARSEVAL / JSN_HOST
-__device__ inline int jsn_fixed_cell(const JsnArgs& a, const JsnColDev& cd, const uint8_t* s, uint32_t off, uint32_t len, uint32_t t, uint64_t& v, bool& null) {
+static __device__ int jsn_fixed_cell(const JsnArgs& a, const JsnColDev& cd, const uint8_t* s, uint32_t off, uint32_t len, uint32_t t, uint64_t& v, bool& null) {
     v = 0; null = false;
     const int tf = cd.tf;
     if (t == JT_ABSENT || t == JT_NULL) { null = true; return 0; }

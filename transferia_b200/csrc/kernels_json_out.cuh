@@ -222,7 +222,7 @@ template <typename Sink> __device__ int ser_json_row(Sink& s, const DCol* cols, 
 }
 
 // does the encoding/csv field need quotes? (fieldNeedsQuotes: empty no; `\.` yes; , " \r \n yes; leading unicode space yes)
-__device__ inline bool ser_csv_needs_quotes(const uint8_t* p, uint32_t n) {
+static __device__ bool ser_csv_needs_quotes(const uint8_t* p, uint32_t n) {
     if (!n) return false;
     if (n == 2 && p[0] == '\\' && p[1] == '.') return true;
     for (uint32_t i = 0; i < n; i++) { const uint8_t c = p[i]; if (c == '\n' || c == '\r' || c == '"' || c == ',') return true; }

@@ -1,22 +1,29 @@
-// LZ4 block compression of the native block, cut into ClickHouse compressed frames, plus the
-// CityHash128 (v1.0.2) frame checksum and the final gather into one contiguous wire buffer.
+// LZ4 block compression of the native block, cut into ClickHouse compressed frames and written straight to their
+// final place in the wire buffer, plus the CityHash128 (v1.0.2) frame checksum.
 //
-// GPU-native LZ4 (not a port of any CPU compressor): one CTA per frame, the frame lives in shared
-// memory, and every phase is data-parallel:
+// GPU-native LZ4 (not a port of any CPU compressor): one CTA per frame, the frame lives in shared memory and
+// every phase is data-parallel:
 //   P1  stage the frame in shared memory (16-byte coalesced loads)
-//   P2  match finding: 2048 positions per round (4 consecutive per thread: two shared-memory words give
-//       the four 4-byte sequences) probe a 4096-entry u16 hash table in shared memory, ONE barrier,
-//       then insert; a probe therefore only ever sees earlier rounds (or, harmlessly, racing inserts of
-//       this round, filtered by `cand < pos`); candidates are verified against the data immediately;
-//       result = 1 valid bit + u16 candidate per position
-//   P3  greedy parse, one thread per 64-byte segment (matches are cut at the segment end), sequence
-//       descriptors overwrite the segment's own candidate slots in place
-//   P4  segmented scan carries pending literals across segments; block scan gives every segment its
-//       output offset; a suffix-min tells each segment which later sequence owns its trailing literals
-//   P5  all threads emit tokens/lengths/offsets and copy their own segment's literals
-// The emitted stream is a standard LZ4 block (last 5 bytes literals, last match starts >= 12 bytes
-// before the end) and decodes with stock liblz4; the bytes are NOT those of pierrec/lz4 (parity for
-// compressed bytes is unpinned in the reference).
+//   P2  match finding in rounds of 2048 positions (4 consecutive per thread: two shared-memory words give the four
+//       4-byte sequences). Every position is inserted into a 4096-entry hash table (tag16 | position); every EVEN
+//       position gets a candidate: the same sequence 4 or 8 bytes back (runs of fixed-width values: the nearest
+//       candidate gives the longest match), else the table entry of an earlier round, else (after this round's
+//       inserts) an entry of this round. Result: one u16 candidate per even position + a bitmap.
+//   P3  greedy parse, one thread per 60-byte segment (15 words: an odd stride keeps the segment walkers on
+//       different banks). A match found at an even position is extended backwards; matches are cut at the
+//       segment end. Descriptors (offset | length | start) overwrite the segment's candidate slots.
+//   P3b continuation: a match that was cut at a segment end is carried on by the next segments: each tests how
+//       far the cut match's offset still holds from its first byte (the offset travels over fully matched
+//       segments by a segmented scan); what holds is merged into the running match, so a long match costs one
+//       sequence however many segments it crosses.
+//   P4  segmented scan carries pending literals across segments; a block scan gives every segment its output
+//       offset; the frame's size is published for the frames behind it (decoupled look-back)
+//   P5  every thread emits its segment's tokens / lengths / offsets / literals into a shared-memory image of the
+//       compressed frame, which is then copied to the wire buffer with aligned 16-byte stores at the frame's
+//       final offset (prefix of the earlier frames' sizes, looked back through global memory)
+// The emitted stream is a standard LZ4 block (last 5 bytes literals, last match starts >= 12 bytes before the
+// end) and decodes with stock liblz4; the bytes are NOT those of pierrec/lz4 (parity for compressed bytes is
+// unpinned in the reference). scripts/lz4_model.cpp is the CPU model these rules were chosen with.
 #pragma once
 #include "device_types.cuh"
 #include "kernels_encode.cuh"
@@ -24,62 +31,90 @@
 namespace tfk {
 
 #define LZ_THREADS 512
-#define LZ_SEG 64
-#define LZ_HASH_BITS 11      /* 2048 entries of u32: tag16 << 16 | position */
-#define LZ_MAX_FRAME 32768
-#define LZ_HDR 25          // 16 checksum + 1 method + 4 compressed size + 4 raw size
+#define LZ_SEG 60
+#define LZ_HASH_BITS 12      /* 4096 entries of u32: tag16 << 16 | position */
+#define LZ_MAX_FRAME (LZ_THREADS * LZ_SEG)   /* 30720 */
+#define LZ_HDR 25            /* 16 checksum + 1 method + 4 compressed size + 4 raw size */
+#define LZ_NONE 0xffffffffu
+#define LZ_FLAG_AGG (1ull << 62)
+#define LZ_FLAG_INCL (2ull << 62)
+#define LZ_VAL_MASK ((1ull << 62) - 1)
 
 __host__ __device__ inline uint32_t lz4_bound(uint32_t n) { return n + n / 255 + 16; }
-__host__ __device__ inline uint32_t lz_slot_stride(uint32_t frame_bytes) { return (LZ_HDR + 7 + lz4_bound(frame_bytes) + 15) & ~15u; }
-// slot layout: [7 pad][16 checksum][0x82][u32][u32][lz4 block]; the checksum field starts at +7 so that
-// the hashed region (+23) ... keep it simple: the slot starts 16-byte aligned and the LZ4 block at +25.
+
+// shared-memory carve-up (byte offsets)
+struct LzSmem { uint32_t data, cand, bitmap, table, stg, total; };
+__host__ __device__ inline LzSmem lz_smem(uint32_t F) {
+    LzSmem s; uint32_t o = 0;
+    const uint32_t F16 = (F + 15) & ~15u;
+    s.data = o + 16; o += 16 + F16 + 16;                          // guard words in front of and behind the frame
+    s.cand = o; o += F16;                                         // u16 per even position
+    s.bitmap = o; o += ((F + 2047) / 2048) * 128 + 16;            // 1 bit per even position, whole rounds (+ spare words)
+    s.table = o; o += 4u << LZ_HASH_BITS;                         // later: the per-segment arrays
+    s.stg = o + 16; o += 16 + ((9 + lz4_bound(F) + 15) & ~15u) + 32;   // image of [method][sizes][LZ4 block]
+    s.total = o; return s;
+}
 
 struct Lz4Args {
-    const uint8_t* raw; DState* st; uint8_t* slots; uint32_t slot_stride; uint32_t* comp_size; uint32_t frame_bytes;
-    unsigned long long* phases;     // optional [8]: cycles thread 0 of every CTA spent in P1..P5 (tfgpu_debug_lz4_phases), NULL = off
+    const uint8_t* raw; DState* st; uint8_t* wire; uint32_t* comp_size; uint64_t* wire_off;
+    unsigned long long* pfx;        // [n_frames] decoupled look-back cells, zeroed before the launch
+    uint64_t* tail;                 // tail[0] = frame count for the checksum kernel (it may still run when the next batch resets DState)
+    uint32_t frame_bytes;
+    unsigned long long* phases;     // optional [8]: cycles thread 0 of every CTA spent per phase (tfgpu_debug_lz4_phases), NULL = off
 };
 #define LZ_PHASE(k) do { if (a.phases && tid == 0) { const long long t_ = clock64(); atomicAdd(&a.phases[k], (unsigned long long)(t_ - t_ph)); t_ph = t_; } } while (0)
 
-// The frame is kept in shared memory with one padding word after every 16 words (64 bytes): the parser and the emitter give
-// every thread its own 64-byte segment, so without the padding the 32 lanes of a warp would hit only two banks.
-#define LZ_PW(i) ((i) + ((i) >> 4))                 /* padded word index of data word i */
-#define LZ_PB(p) ((p) + (((p) >> 6) << 2))          /* padded byte address of data byte p */
-__host__ __device__ inline uint32_t lz_data_bytes(uint32_t frame_bytes) { return (frame_bytes + frame_bytes / 16 + 32 + 15) & ~15u; }
-__device__ __forceinline__ uint32_t ld32u(const uint32_t* w, uint32_t p) {   // 4 bytes at byte offset p of the (padded) frame in shared memory
+__device__ __forceinline__ uint32_t ld32u(const uint32_t* w, uint32_t p) {   // 4 bytes at byte offset p of the frame in shared memory
     const uint32_t i = p >> 2, s = (p & 3) * 8;
-    return __funnelshift_r(w[LZ_PW(i)], w[LZ_PW(i + 1)], s);
+    return __funnelshift_r(w[i], w[i + 1], s);
 }
 __device__ __forceinline__ uint32_t ext_bytes(uint32_t x) { return x < 15 ? 0u : 1u + (x - 15u) / 255u; }
 __device__ __forceinline__ uint8_t* put_ext(uint8_t* o, uint32_t x) {   // x >= 15
     x -= 15; while (x >= 255) { *o++ = 255; x -= 255; } *o++ = (uint8_t)x; return o;
 }
-// literal copy shared -> global: bytes up to a 4-byte boundary of the destination, then aligned words
-// (source re-aligned with a funnel shift), then the tail
-__device__ __forceinline__ void copy_s2g(uint8_t* dst, const uint32_t* data_w, uint32_t src, uint32_t n) {
-    const uint8_t* data = (const uint8_t*)data_w;
-    while (n && ((uintptr_t)dst & 3)) { *dst++ = data[LZ_PB(src)]; src++; n--; }
-    for (; n >= 4; n -= 4, dst += 4, src += 4) *(uint32_t*)dst = ld32u(data_w, src);
-    while (n) { *dst++ = data[LZ_PB(src)]; src++; n--; }
+// literal copy inside shared memory: frame bytes [src, src + n) -> image bytes at dst (aligned words once dst is aligned)
+__device__ __forceinline__ void copy_lit(uint8_t* dst, const uint32_t* dw, uint32_t src, uint32_t n) {
+    const uint8_t* data = (const uint8_t*)dw;
+    while (n && ((uint32_t)(uintptr_t)dst & 3)) { *dst++ = data[src]; src++; n--; }
+    for (; n >= 4; n -= 4, dst += 4, src += 4) *(uint32_t*)dst = ld32u(dw, src);
+    while (n) { *dst++ = data[src]; src++; n--; }
+}
+// common prefix of frame bytes at c and p, at most maxl (> 0)
+__device__ __forceinline__ uint32_t lz_match_len(const uint32_t* dw, uint32_t c, uint32_t p, uint32_t maxl) {
+    uint32_t ic = c >> 2, ip = p >> 2; const uint32_t sc = (c & 3) * 8, sp = (p & 3) * 8;
+    uint32_t wc0 = dw[ic], wp0 = dw[ip], ml = 0;
+    for (;;) {
+        const uint32_t wc1 = dw[++ic], wp1 = dw[++ip];
+        const uint32_t x = __funnelshift_r(wc0, wc1, sc) ^ __funnelshift_r(wp0, wp1, sp);
+        if (x) { ml += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+        ml += 4; if (ml >= maxl) break;
+        wc0 = wc1; wp0 = wp1;
+    }
+    return ml < maxl ? ml : maxl;
 }
 
 #ifdef TF_KERNELS_LZ4
 __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t F = a.frame_bytes;
-    const uint32_t DB = lz_data_bytes(F);
-    uint32_t* data_w = (uint32_t*)smem;                                  // the frame, padded (LZ_PW / LZ_PB)
-    uint8_t* data = smem;
-    uint16_t* cand = (uint16_t*)(smem + DB);                             // 2F bytes; later: sequence descriptors
-    uint32_t* table = (uint32_t*)(smem + DB + 2 * F);                   // 8 KB; later: per-segment arrays
-    uint8_t* vbits = smem + DB + 2 * F + (4u << LZ_HASH_BITS);          // F/8 bytes: 1 candidate bit per position
-    uint32_t* scratch = (uint32_t*)(vbits + F / 8);                      // 64 words
+    const LzSmem L = lz_smem(F);
+    uint32_t* dw = (uint32_t*)(smem + L.data);                   // the frame; dw[-2], dw[-1] and 4 words behind it are zero guards
+    const uint8_t* data = smem + L.data;
+    uint16_t* cand = (uint16_t*)(smem + L.cand);                // candidate of even position p at cand[p >> 1]; later: sequence descriptors
+    uint32_t* cand_w = (uint32_t*)(smem + L.cand);
+    uint32_t* bm = (uint32_t*)(smem + L.bitmap);                // bit i: position 2 i has a candidate
+    uint32_t* table = (uint32_t*)(smem + L.table);
+    uint8_t* stg = smem + L.stg;                                // [0x82][u32 size + 9][u32 raw size][LZ4 block]
     __shared__ uint32_t s_frame;
-    // per-segment arrays aliased onto the hash table after P2 (nseg <= 512)
-    uint32_t* seg_off = (uint32_t*)table;            // [513]
-    int32_t* delta0 = (int32_t*)(seg_off + 516);     // [512]
-    uint16_t* carry_incl = (uint16_t*)(delta0 + 512);   // [512]
-    uint16_t* next_has = carry_incl + 512;           // [512]
-    uint8_t* nseq_s = (uint8_t*)(next_has + 512);    // [512]
+    __shared__ uint32_t scratch[80];
+    __shared__ unsigned long long s_woff;
+    // per-segment arrays, aliased onto the hash table once match finding is over
+    int32_t* delta0 = (int32_t*)table;                           // [512]
+    uint32_t* scanv = (uint32_t*)(delta0 + LZ_THREADS);          // [512]
+    uint16_t* carry_incl = (uint16_t*)(scanv + LZ_THREADS);      // [512]
+    uint16_t* ext16 = carry_incl + LZ_THREADS;                   // [514]
+    uint8_t* clt8 = (uint8_t*)(ext16 + LZ_THREADS + 4);          // [512]
+    uint8_t* flg8 = clt8 + LZ_THREADS;                           // [512]
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t raw_total = a.st->raw_total, n_frames = a.st->n_frames;
 
@@ -92,107 +127,181 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
         long long t_ph = a.phases ? clock64() : 0;
         const uint64_t pos0 = (uint64_t)f * F;
         const uint32_t len = (uint32_t)((raw_total - pos0 < F) ? raw_total - pos0 : F);
-        uint8_t* out = a.slots + (size_t)f * a.slot_stride + LZ_HDR;
 
         // ---- P1: stage
         {
             const int4* g = (const int4*)(a.raw + pos0);
             const uint32_t nv = (len + 15) >> 4;
-            for (uint32_t i = tid; i < (F + 16) / 16; i += LZ_THREADS) {
-                int4 v = make_int4(0, 0, 0, 0);
-                if (i < nv) v = __ldg(g + i);
-                uint32_t* d = data_w + LZ_PW(4 * i);                      // the 4 words of a chunk share one 16-word group
-                d[0] = (uint32_t)v.x; d[1] = (uint32_t)v.y; d[2] = (uint32_t)v.z; d[3] = (uint32_t)v.w;
-            }
-            for (uint32_t i = tid; i < (1u << LZ_HASH_BITS); i += LZ_THREADS) table[i] = 0;
-        }
-        __syncthreads();
-        if (len & 15) {   // zero the bytes past len inside the last 16-byte chunk (they belong to the next frame)
-            if (tid < 16 && (len & ~15u) + tid >= len) data[LZ_PB((len & ~15u) + tid)] = 0;
+            int4* d4 = (int4*)(smem + L.data);
+            for (uint32_t i = tid; i < nv + 1; i += LZ_THREADS) d4[i] = i < nv ? __ldg(g + i) : make_int4(0, 0, 0, 0);
+            int4* t4 = (int4*)table;
+            for (uint32_t i = tid; i < (1u << LZ_HASH_BITS) / 4; i += LZ_THREADS) t4[i] = make_int4(0, 0, 0, 0);
+            if (tid < 4) ((uint32_t*)smem)[tid] = 0;
         }
         __syncthreads();
 
         LZ_PHASE(0);
         // ---- P2: match finding
-        const uint32_t nrounds = (len + 2047) / 2048;
+        const uint32_t nrounds = (len + 2047) >> 11;
         for (uint32_t rd = 0; rd < nrounds; rd++) {
-            const uint32_t p0 = rd * 2048 + tid * 4;
-            const bool active = p0 < F;                         // F is a multiple of 64, so p0 + 3 < F too
-            uint32_t idx[4], tag[4], c[4];
+            const uint32_t wi = rd * LZ_THREADS + tid, p0 = wi * 4;
+            const bool active = p0 < len;
+            uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0, e0 = 0, e1 = 0, e2 = 0, e3 = 0, c0 = LZ_NONE, c2 = LZ_NONE, t0 = 0, t2 = 0;
             if (active) {
-                const uint32_t w0 = data_w[LZ_PW(p0 >> 2)], w1 = data_w[LZ_PW((p0 >> 2) + 1)];
-                uint32_t seq[4];
-                seq[0] = w0; seq[1] = __funnelshift_r(w0, w1, 8); seq[2] = __funnelshift_r(w0, w1, 16); seq[3] = __funnelshift_r(w0, w1, 24);
-#pragma unroll
-                for (int k = 0; k < 4; k++) { const uint32_t h = seq[k] * 2654435761u; idx[k] = h >> (32 - LZ_HASH_BITS); tag[k] = (h << LZ_HASH_BITS) & 0xffff0000u; c[k] = table[idx[k]]; }
-            }
-            __syncthreads();
-            uint32_t vm = 0;      // candidate bits: the 27 known hash bits agree; the bytes are compared by the parser (P3)
-            if (active) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t p = p0 + k;
-                    if (p < len) table[idx[k]] = tag[k] | p;
-                    if ((p + 12 <= len) && (c[k] & 0xffff0000u) == tag[k] && (c[k] & 0xffffu) < p) vm |= 1u << k;   // MFLIMIT
+                const uint32_t wm2 = dw[(int)wi - 2], wm1 = dw[(int)wi - 1], w0 = dw[wi], w1 = dw[wi + 1];
+                const uint32_t s1 = __funnelshift_r(w0, w1, 8), s2 = __funnelshift_r(w0, w1, 16), s3 = __funnelshift_r(w0, w1, 24);
+                const uint32_t h0 = w0 * 2654435761u, h1 = s1 * 2654435761u, h2 = s2 * 2654435761u, h3 = s3 * 2654435761u;
+                i0 = h0 >> (32 - LZ_HASH_BITS); i1 = h1 >> (32 - LZ_HASH_BITS); i2 = h2 >> (32 - LZ_HASH_BITS); i3 = h3 >> (32 - LZ_HASH_BITS);
+                e0 = ((h0 << LZ_HASH_BITS) & 0xffff0000u) | p0; e1 = ((h1 << LZ_HASH_BITS) & 0xffff0000u) | (p0 + 1);
+                e2 = ((h2 << LZ_HASH_BITS) & 0xffff0000u) | (p0 + 2); e3 = ((h3 << LZ_HASH_BITS) & 0xffff0000u) | (p0 + 3);
+                if (p0 >= 8) {      // the same 4 bytes 4 or 8 back: a run of a fixed-width value
+                    const uint32_t a2 = __funnelshift_r(wm1, w0, 16), b2 = __funnelshift_r(wm2, wm1, 16);
+                    c0 = w0 == wm1 ? p0 - 4 : (w0 == wm2 ? p0 - 8 : LZ_NONE);
+                    c2 = s2 == a2 ? p0 - 2 : (s2 == b2 ? p0 - 6 : LZ_NONE);
                 }
+                t0 = table[i0]; t2 = table[i2];
             }
             __syncthreads();
+            if (active) {
+                table[i3] = e3; table[i2] = e2; table[i1] = e1; table[i0] = e0;
+                if (c0 == LZ_NONE && ((t0 ^ e0) >> 16) == 0) c0 = t0 & 0xffffu;      // an entry of an earlier round: position < p0
+                if (c2 == LZ_NONE && ((t2 ^ e2) >> 16) == 0) c2 = t2 & 0xffffu;
+            }
+            __syncthreads();
+            uint32_t v = 0;
             if (active) {   // second probe: sees this round's inserts, recovers repeats whose first occurrence is in this round
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t p = p0 + k;
-                    if (!((vm >> k) & 1) && p + 12 <= len) {
-                        const uint32_t c2 = table[idx[k]];
-                        if ((c2 & 0xffff0000u) == tag[k] && (c2 & 0xffffu) < p) { vm |= 1u << k; c[k] = c2; }
-                    }
-                }
-                *(uint2*)(cand + p0) = make_uint2((c[0] & 0xffffu) | (c[1] << 16), (c[2] & 0xffffu) | (c[3] << 16));
+                if (c0 == LZ_NONE) { const uint32_t t = table[i0]; if (((t ^ e0) >> 16) == 0 && (t & 0xffffu) < p0) c0 = t & 0xffffu; }
+                if (c2 == LZ_NONE) { const uint32_t t = table[i2]; if (((t ^ e2) >> 16) == 0 && (t & 0xffffu) < p0 + 2) c2 = t & 0xffffu; }
+                cand_w[wi] = (c0 & 0xffffu) | (c2 << 16);
+                v = (c0 != LZ_NONE ? 1u : 0u) | (c2 != LZ_NONE ? 2u : 0u);
             }
-            // two lanes share one byte of the bit map
-            const uint32_t other = __shfl_down_sync(0xffffffffu, vm, 1);
-            if (active && !(lane & 1)) vbits[p0 >> 3] = (uint8_t)(vm | (other << 4));
+            // 2 bits per lane -> the warp's 64 bitmap bits
+            const uint32_t x = v << (2 * (lane & 15));
+            const uint32_t lo = __reduce_or_sync(0xffffffffu, lane < 16 ? x : 0u), hi = __reduce_or_sync(0xffffffffu, lane < 16 ? 0u : x);
+            if (lane == 0) { bm[wi >> 4] = lo; bm[(wi >> 4) + 1] = hi; }
         }
+        if (tid == 0) { bm[((nrounds * LZ_THREADS) >> 4)] = 0; bm[((nrounds * LZ_THREADS) >> 4) + 1] = 0; }
         __syncthreads();
+        if (tid == 0) bm[0] &= ~1u;        // position 0 has nothing before it
 
         LZ_PHASE(1);
-        // ---- P3: greedy parse, one thread per 64-byte segment
+        // ---- P3: greedy parse, one thread per 60-byte segment
         const uint32_t nseg = (len + LZ_SEG - 1) / LZ_SEG;
-        uint32_t my_nseq = 0, my_trail = 0, seg_start = tid * LZ_SEG, seg_end = 0;
-        uint2* desc = (uint2*)(cand + seg_start);
+        const uint32_t lim5 = len >= 5 ? len - 5 : 0;
+        const int32_t pmax = (int32_t)len - 12;                               // MFLIMIT: no match starts behind it
+        const uint32_t sa = tid * LZ_SEG;
+        uint32_t sb = 0, slimit = 0, nseq = 0, d_last = 0;
+        bool reach = false, pure = false;
+        uint32_t* desc = cand_w + tid * (LZ_SEG / 4);
         if (tid < nseg) {
-            seg_end = seg_start + LZ_SEG < len ? seg_start + LZ_SEG : len;
-            const uint32_t lim5 = len >= 5 ? len - 5 : 0;
-            const uint32_t limit = seg_end < lim5 ? seg_end : lim5;       // matches end before the last 5 bytes and inside the segment
-            const uint64_t m64 = *(const uint64_t*)(vbits + 8 * tid);      // bit i = position seg_start + i has a candidate
-            uint32_t cur = 0, last_end = seg_start;
-            while (cur < LZ_SEG) {
-                const uint64_t mm = m64 >> cur;
+            sb = sa + LZ_SEG < len ? sa + LZ_SEG : len;
+            slimit = sb < lim5 ? sb : lim5;
+            const uint32_t bi = tid * (LZ_SEG / 2);
+            const uint32_t m = __funnelshift_r(bm[bi >> 5], bm[(bi >> 5) + 1], bi & 31) & 0x3fffffffu;
+            uint32_t cur = 0, anchor = sa;
+            for (;;) {
+                const uint32_t cb = (cur + 1) >> 1;
+                if (cb >= LZ_SEG / 2) break;
+                const uint32_t mm = m >> cb;
                 if (!mm) break;
-                const uint32_t r = cur + (uint32_t)__ffsll((long long)mm) - 1;
-                const uint32_t p = seg_start + r;
-                if (p + 4 > limit) break;
-                const uint32_t c = cand[p];
-                const uint32_t maxl = limit - p;
-                uint32_t ml = 0;
-                while (ml < maxl) {
-                    const uint32_t x = ld32u(data_w, c + ml) ^ ld32u(data_w, p + ml);
-                    if (x) { ml += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
-                    ml += 4;
-                }
-                if (ml > maxl) ml = maxl;
-                if (ml < 4) { cur = r + 1; continue; }            // the tag agreed but the bytes do not: not a match
-                desc[my_nseq] = make_uint2(p | (ml << 16), p - c);
-                my_nseq++; cur = r + ml; last_end = p + ml;
+                const uint32_t r = cb + (uint32_t)__ffs((int)mm) - 1;
+                uint32_t p = sa + 2 * r;
+                if (p + 4 > slimit || (int32_t)p > pmax) break;
+                uint32_t c = cand[p >> 1];
+                uint32_t ml = lz_match_len(dw, c, p, slimit - p);
+                if (ml < 4) { cur = 2 * r + 1; continue; }              // the tag agreed but the bytes do not: not a match
+                while (p > anchor && c > 0 && data[p - 1] == data[c - 1]) { p--; c--; ml++; }
+                desc[nseq++] = ((p - c) << 16) | (ml << 8) | (p - sa);
+                d_last = p - c;
+                anchor = p + ml; cur = anchor - sa;
             }
-            my_trail = seg_end - last_end;
+            reach = nseq && anchor == sa + LZ_SEG;
+            pure = nseq == 1 && reach && (desc[0] & 0xffu) == 0;
         }
-        __syncthreads();   // everyone is done reading the hash table region? (P2 finished before P3) -> reuse it now
+        __syncthreads();     // the hash table is dead from here on: its memory holds the per-segment arrays
+
+        // ---- P3b: continuation of matches that were cut at a segment end
+        // scan value: 0 = fully matched segment (the running offset passes through), 1 = no running match behind it, else (offset << 2) | 2
+        uint32_t k0 = 0, cl = 0, D = 0; bool merged = false, head = false;
+        {
+            uint32_t sv = tid < nseg ? (pure ? 0u : (reach ? (d_last << 2) | 2u : 1u)) : 1u;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, sv, d); if (lane >= (uint32_t)d && sv == 0) sv = o; }
+            if (lane == 31) scratch[warp] = sv;
+            __syncthreads();
+            if (sv == 0) { for (int w = (int)warp - 1; w >= 0; w--) { const uint32_t o = scratch[w]; if (o) { sv = o; break; } } if (sv == 0) sv = 1; }
+            scanv[tid] = sv;
+            __syncthreads();
+            const uint32_t prev = tid ? scanv[tid - 1] : 1u;
+            const bool dvalid = tid < nseg && prev >= 2;
+            D = prev >> 2;
+            uint32_t n = 0;
+            if (dvalid && slimit > sa) {        // how far does the running match's offset still hold from the first byte of this segment
+                const uint32_t maxn = slimit - sa;
+                const uint32_t q = sa - D; uint32_t iq = q >> 2; const uint32_t sq = (q & 3) * 8;
+                uint32_t wq0 = dw[iq]; const uint32_t* pw = dw + tid * (LZ_SEG / 4);
+                for (;;) {
+                    const uint32_t wq1 = dw[++iq];
+                    const uint32_t x = __funnelshift_r(wq0, wq1, sq) ^ pw[n >> 2];
+                    if (x) { n += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+                    n += 4; if (n >= maxn) break;
+                    wq0 = wq1;
+                }
+                if (n > maxn) n = maxn;
+            }
+            clt8[tid] = (uint8_t)n; flg8[tid] = (uint8_t)((pure ? 1 : 0) | (reach ? 2 : 0) | (dvalid ? 4 : 0));
+            __syncthreads();
+            if (dvalid) {
+                const uint32_t pf = flg8[tid - 1];
+                const bool alive = (pf & 1) ? (clt8[tid - 1] == LZ_SEG && (pf & 4)) : (pf & 2) != 0;
+                if (pure) {
+                    if (!(alive && n > 0) && n != LZ_SEG) n = 0;
+                    if (n && n < LZ_SEG && LZ_SEG - n < 4) n = LZ_SEG - 4;
+                } else {
+                    if (!alive) n = 0;
+                    if (reach && n > LZ_SEG - 4) n = LZ_SEG - 4;
+                }
+                if (n && !alive && (int32_t)sa > pmax) n = 0;         // a head piece starts a match
+                cl = n;
+                if (n) {
+                    merged = alive; head = !alive;
+                    while (k0 < nseq) {      // own sequences against the piece [sa, sa + n)
+                        const uint32_t dsc = desc[k0], pr = dsc & 0xffu, ml = (dsc >> 8) & 0xffu;
+                        if (pr + ml <= n) { k0++; continue; }
+                        if (pr >= n) break;
+                        const uint32_t nml = pr + ml - n;      // what is left of it behind the piece is still a match with the same offset ...
+                        if (nml >= 4 && (int32_t)(sa + n) <= pmax) desc[k0] = (dsc & 0xffff0000u) | (nml << 8) | n; else k0++;      // ... unless it would start in the last 12 bytes
+                        break;
+                    }
+                }
+            }
+            // ext(t) = bytes the running match gains from segment t on: reverse segmented sum over merged pieces
+            uint32_t es = merged ? cl : 0u, ec = (merged && cl == LZ_SEG) ? 1u : 0u;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t os = __shfl_down_sync(0xffffffffu, es, d), oc = __shfl_down_sync(0xffffffffu, ec, d);
+                if (lane + d < 32 && ec) { es += os; ec = oc; }
+            }
+            if (lane == 0) { scratch[32 + warp] = es; scratch[48 + warp] = ec; }
+            __syncthreads();
+            if (ec) for (uint32_t w = warp + 1; w < LZ_THREADS / 32; w++) { es += scratch[32 + w]; if (!scratch[48 + w]) break; }
+            ext16[tid] = (uint16_t)es;
+            if (tid == 0) ext16[LZ_THREADS] = 0;
+        }
+        __syncthreads();
+        const uint32_t ext_next = ext16[tid + 1];
 
         LZ_PHASE(2);
         // ---- P4a: segmented scan of pending literals: combine(a, b) = b.has ? b : (a.has, a.tr + b.tr)
+        const bool emits = tid < nseg && (head || k0 < nseq);
+        uint32_t my_trail = 0;
+        if (tid < nseg) {
+            uint32_t last_end = sa + cl;
+            if (k0 < nseq) { const uint32_t dsc = desc[nseq - 1]; last_end = sa + (dsc & 0xffu) + ((dsc >> 8) & 0xffu); }
+            my_trail = sb - last_end;
+        }
         {
-            uint32_t has = my_nseq > 0, tr = my_trail;
-            if (tid >= nseg) { has = 0; tr = 0; }
+            uint32_t has = emits ? 1u : 0u, tr = my_trail;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t h2 = __shfl_up_sync(0xffffffffu, has, d), t2 = __shfl_up_sync(0xffffffffu, tr, d);
@@ -207,40 +316,41 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
                     const uint32_t h2 = __shfl_up_sync(0xffffffffu, wh, d), t2 = __shfl_up_sync(0xffffffffu, wt, d);
                     if (lane >= (uint32_t)d && !wh) { wt += t2; wh = h2; }
                 }
-                // exclusive prefix for warp w = inclusive of w-1
                 const uint32_t eh = __shfl_up_sync(0xffffffffu, wh, 1), et = __shfl_up_sync(0xffffffffu, wt, 1);
                 if (lane < LZ_THREADS / 32) { scratch[lane] = lane ? eh : 0; scratch[16 + lane] = lane ? et : 0; }
             }
             __syncthreads();
             if (!has) { tr += scratch[16 + warp]; }
-            if (tid < nseg) { carry_incl[tid] = (uint16_t)tr; nseq_s[tid] = (uint8_t)my_nseq; }
+            carry_incl[tid] = (uint16_t)tr;
         }
         __syncthreads();
         const uint32_t carry_in = (tid > 0 && tid < nseg) ? carry_incl[tid - 1] : 0;
 
         // ---- P4b: encoded bytes per segment, block scan -> output offsets
-        uint32_t my_bytes = 0;
-        if (tid < nseg) {
-            uint32_t prev_end = seg_start;
-            for (uint32_t k = 0; k < my_nseq; k++) {
-                const uint2 d = desc[k];
-                const uint32_t p = d.x & 0xffff, ml = d.x >> 16;
-                const uint32_t ll = (k == 0 ? carry_in : 0) + (p - prev_end);
-                my_bytes += 1 + ext_bytes(ll) + ll + 2 + ext_bytes(ml - 4);
+        uint32_t my_bytes = 0, p_first = 0, ll_first = 0;
+        if (emits) {
+            uint32_t prev_end = sa + (merged ? cl : 0u); bool first = true;
+            if (head) {
+                const uint32_t ml = LZ_SEG + ext_next;
+                my_bytes += 1 + ext_bytes(carry_in) + carry_in + 2 + ext_bytes(ml - 4);
+                p_first = sa; ll_first = carry_in; prev_end = sa + LZ_SEG; first = false;
+            }
+            for (uint32_t k = k0; k < nseq; k++) {
+                const uint32_t dsc = desc[k], pr = dsc & 0xffu; uint32_t ml = (dsc >> 8) & 0xffu;
+                const uint32_t p = sa + pr, ll = (first ? carry_in : 0u) + (p - prev_end);
                 prev_end = p + ml;
+                if (k + 1 == nseq && pr + ml == LZ_SEG) ml += ext_next;
+                my_bytes += 1 + ext_bytes(ll) + ll + 2 + ext_bytes(ml - 4);
+                if (first) { p_first = p; ll_first = ll; first = false; }
             }
         }
         uint32_t total_seq_bytes;
         const uint32_t my_off = block_excl_scan(my_bytes, &total_seq_bytes, scratch);
-        if (tid < nseg && my_nseq) {
-            const uint32_t p0 = desc[0].x & 0xffff;
-            const uint32_t ll0 = carry_in + (p0 - seg_start);
-            delta0[tid] = (int32_t)(my_off + 1 + ext_bytes(ll0)) - (int32_t)(p0 - ll0);
-        }
-        // first later segment that has a sequence (it owns this segment's trailing literals): warp ballots + one barrier
+        if (emits) delta0[tid] = (int32_t)(my_off + 1 + ext_bytes(ll_first)) - (int32_t)(p_first - ll_first);
+        // first later segment that emits a sequence (it owns this segment's trailing literals): warp ballots + one barrier
         uint32_t my_next_has = 0xffff;
         {
-            const uint32_t hm = __ballot_sync(0xffffffffu, tid < nseg && my_nseq > 0);
+            const uint32_t hm = __ballot_sync(0xffffffffu, emits);
             if (lane == 0) scratch[40 + warp] = hm;
             __syncthreads();
             const uint32_t above = lane == 31 ? 0u : (hm >> (lane + 1));
@@ -249,39 +359,108 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
         }
         const uint32_t ll_final = nseg ? carry_incl[nseg - 1] : 0;
         const int32_t delta_final = (int32_t)(total_seq_bytes + 1 + ext_bytes(ll_final)) - (int32_t)(len - ll_final);
+        const uint32_t cs = total_seq_bytes + 1 + ext_bytes(ll_final) + ll_final;
+        if (tid == 0) { *(volatile unsigned long long*)&a.pfx[f] = LZ_FLAG_AGG | (unsigned long long)(cs + LZ_HDR); }   // the frames behind can start summing
 
         LZ_PHASE(3);
-        // ---- P5: emit
+        // ---- P5: emit into the shared-memory image
+        uint8_t* out = stg + 9;
         if (tid < nseg) {
-            uint8_t* o = out + my_off; uint32_t prev_end = seg_start;
-            for (uint32_t k = 0; k < my_nseq; k++) {
-                const uint2 d = desc[k];
-                const uint32_t p = d.x & 0xffff, ml = d.x >> 16, off = d.y;
-                const uint32_t cin = (k == 0 ? carry_in : 0);
-                const uint32_t ll = cin + (p - prev_end);
-                const uint32_t mt = ml - 4;
-                *o++ = (uint8_t)(((ll < 15 ? ll : 15) << 4) | (mt < 15 ? mt : 15));
-                if (ll >= 15) o = put_ext(o, ll);
-                copy_s2g(o + cin, data_w, prev_end, p - prev_end);
-                o += ll;
-                *o++ = (uint8_t)off; *o++ = (uint8_t)(off >> 8);
-                if (mt >= 15) o = put_ext(o, mt);
-                prev_end = p + ml;
+            uint32_t prev_end = sa + (merged ? cl : 0u);
+            if (emits) {
+                uint8_t* o = out + my_off; bool first = true;
+                if (head) {
+                    const uint32_t mt = LZ_SEG + ext_next - 4, ll = carry_in;
+                    *o++ = (uint8_t)(((ll < 15 ? ll : 15) << 4) | 15);
+                    if (ll >= 15) o = put_ext(o, ll);
+                    o += ll;
+                    *o++ = (uint8_t)D; *o++ = (uint8_t)(D >> 8);
+                    o = put_ext(o, mt);
+                    prev_end = sa + LZ_SEG; first = false;
+                }
+                for (uint32_t k = k0; k < nseq; k++) {
+                    const uint32_t dsc = desc[k], pr = dsc & 0xffu, off = dsc >> 16; uint32_t ml = (dsc >> 8) & 0xffu;
+                    const uint32_t p = sa + pr, cin = first ? carry_in : 0u, ll = cin + (p - prev_end);
+                    const uint32_t lit0 = prev_end, nlit = p - prev_end;
+                    prev_end = p + ml;
+                    if (k + 1 == nseq && pr + ml == LZ_SEG) ml += ext_next;
+                    const uint32_t mt = ml - 4;
+                    *o++ = (uint8_t)(((ll < 15 ? ll : 15) << 4) | (mt < 15 ? mt : 15));
+                    if (ll >= 15) o = put_ext(o, ll);
+                    copy_lit(o + cin, dw, lit0, nlit);
+                    o += ll;
+                    *o++ = (uint8_t)off; *o++ = (uint8_t)(off >> 8);
+                    if (mt >= 15) o = put_ext(o, mt);
+                    first = false;
+                }
             }
-            if (seg_end > prev_end) {   // trailing literals belong to the next sequence downstream
+            if (sb > prev_end) {   // trailing literals belong to the next sequence downstream
                 const uint32_t nh = my_next_has;
                 const int32_t dl = (nh != 0xffff && nh < nseg) ? delta0[nh] : delta_final;
-                copy_s2g(out + ((int32_t)prev_end + dl), data_w, prev_end, seg_end - prev_end);
+                copy_lit(out + ((int32_t)prev_end + dl), dw, prev_end, sb - prev_end);
             }
         }
         if (tid == 0) {
             uint8_t* o = out + total_seq_bytes;
             *o++ = (uint8_t)((ll_final < 15 ? ll_final : 15) << 4);
             if (ll_final >= 15) o = put_ext(o, ll_final);
-            a.comp_size[f] = total_seq_bytes + 1 + ext_bytes(ll_final) + ll_final;
+            const uint32_t c9 = cs + 9;
+            stg[0] = 0x82; stg[1] = (uint8_t)c9; stg[2] = (uint8_t)(c9 >> 8); stg[3] = (uint8_t)(c9 >> 16); stg[4] = (uint8_t)(c9 >> 24);
+            stg[5] = (uint8_t)len; stg[6] = (uint8_t)(len >> 8); stg[7] = (uint8_t)(len >> 16); stg[8] = (uint8_t)(len >> 24);
+        }
+        // ---- the frame's place in the wire buffer: sizes of the earlier frames (decoupled look-back, warp 0)
+        if (warp == 0) {
+            unsigned long long excl = 0;
+            if (f) {
+                int64_t base = (int64_t)f;           // cells [0, base) are still to be summed
+                for (uint32_t spins = 0;;) {
+                    const int64_t j = base - 1 - (int64_t)lane;
+                    unsigned long long v = j >= 0 ? *(volatile unsigned long long*)&a.pfx[j] : LZ_FLAG_INCL;
+                    const uint32_t fl = (uint32_t)(v >> 62);
+                    const uint32_t incl = __ballot_sync(0xffffffffu, fl == 2), none = __ballot_sync(0xffffffffu, fl == 0);
+                    const uint32_t upto = incl ? (uint32_t)__ffs((int)incl) - 1 : 31u;       // lanes 0..upto are needed
+                    const uint32_t need = upto == 31 ? 0xffffffffu : ((2u << upto) - 1);
+                    if (none & need) {      // an earlier frame has not got that far yet (its CTA holds a lower ticket and is running)
+                        if (++spins > (1u << 22)) { if (lane == 0) a.st->pad = 1; break; }      // never seen; a bounded wait keeps a bug from hanging the device
+                        __nanosleep(64); continue;
+                    }
+                    unsigned long long part = lane <= upto ? (v & LZ_VAL_MASK) : 0ull;
+#pragma unroll
+                    for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+                    excl += part;
+                    if (incl) break;
+                    base -= 32;
+                }
+            }
+            if (lane == 0) {
+                __threadfence();
+                *(volatile unsigned long long*)&a.pfx[f] = LZ_FLAG_INCL | (excl + cs + LZ_HDR);
+                s_woff = excl;
+                a.comp_size[f] = cs; a.wire_off[f] = excl;
+                if (f + 1 == n_frames) { a.st->wire_total = excl + cs + LZ_HDR; a.tail[0] = n_frames; }
+            }
         }
         __syncthreads();
         LZ_PHASE(4);
+        // ---- flush: the image goes to wire + offset + 16 (behind the checksum field) in aligned 16-byte stores; the bytes a
+        // first / last store carries beyond the image land in checksum fields, which k_frame_seal writes afterwards
+        {
+            uint8_t* G = a.wire + s_woff + 16;
+            const uint32_t m = (uint32_t)((uintptr_t)G & 15), total = 9 + cs;
+            const uint32_t nchunks = (m + total + 15) >> 4;
+            int4* g4 = (int4*)(G - m);
+            const uint32_t* sw = (const uint32_t*)(stg - 16);                 // image byte x is at sw byte x + 16
+            const uint32_t o0 = 16 - m, sh = (o0 & 3) * 8;
+            for (uint32_t j = tid; j < nchunks; j += LZ_THREADS) {
+                const uint32_t wi0 = (o0 + 16 * j) >> 2;
+                const uint32_t q0 = sw[wi0], q1 = sw[wi0 + 1], q2 = sw[wi0 + 2], q3 = sw[wi0 + 3], q4 = sw[wi0 + 4];
+                int4 v;
+                v.x = (int)__funnelshift_r(q0, q1, sh); v.y = (int)__funnelshift_r(q1, q2, sh);
+                v.z = (int)__funnelshift_r(q2, q3, sh); v.w = (int)__funnelshift_r(q3, q4, sh);
+                g4[j] = v;
+            }
+        }
+        LZ_PHASE(5);
     }
 }
 #endif  // TF_KERNELS_LZ4
@@ -305,7 +484,7 @@ __device__ __forceinline__ uint64_t hl16(uint64_t u, uint64_t v) {
     uint64_t a = (u ^ v) * kMul; a ^= (a >> 47);
     uint64_t b = (v ^ a) * kMul; b ^= (b >> 47); b *= kMul; return b;
 }
-__device__ inline uint64_t hl0to16(const uint8_t* s, size_t len) {
+static __device__ uint64_t hl0to16(const uint8_t* s, size_t len) {
     if (len > 8) { uint64_t a = f64(s), b = f64(s + len - 8); return hl16(a, rot(b + len, (int)len)) ^ b; }
     if (len >= 4) { uint64_t a = f32(s); return hl16(len + (a << 3), f32(s + len - 4)); }
     if (len > 0) { uint8_t a = s[0], b = s[len >> 1], c = s[len - 1]; uint32_t y = (uint32_t)a + ((uint32_t)b << 8); uint32_t z = (uint32_t)len + ((uint32_t)c << 2); return smix(y * CK2 ^ z * CK3) * CK2; }
@@ -316,7 +495,7 @@ __device__ __forceinline__ P weak32(uint64_t w, uint64_t x, uint64_t y, uint64_t
     a += w; b = rot(b + a + z, 21); const uint64_t c = a; a += x; a += y; b += rot(a, 44); P r; r.first = a + z; r.second = b + c; return r;
 }
 __device__ __forceinline__ P weak32p(const uint8_t* s, uint64_t a, uint64_t b) { return weak32(f64(s), f64(s + 8), f64(s + 16), f64(s + 24), a, b); }
-__device__ inline P murmur(const uint8_t* s, size_t len, P seed) {
+static __device__ P murmur(const uint8_t* s, size_t len, P seed) {
     uint64_t a = seed.first, b = seed.second, c = 0, d = 0; long l = (long)len - 16;
     if (l <= 0) { a = smix(a * CK1) * CK1; c = b * CK1 + hl0to16(s, len); d = smix(a + (len >= 8 ? f64(s) : c)); }
     else {
@@ -326,7 +505,7 @@ __device__ inline P murmur(const uint8_t* s, size_t len, P seed) {
     a = hl16(a, c); b = hl16(d, b);
     P r; r.first = a ^ b; r.second = hl16(b, a); return r;
 }
-__device__ inline P hash128_seed(const uint8_t* s, size_t len, P seed) {
+static __device__ P hash128_seed(const uint8_t* s, size_t len, P seed) {
     if (len < 128) return murmur(s, len, seed);
     P v, w; uint64_t x = seed.first, y = seed.second, z = len * CK1;
     v.first = rot(y ^ CK1, 49) * CK1 + f64(s);
@@ -358,7 +537,7 @@ __device__ inline P hash128_seed(const uint8_t* s, size_t len, P seed) {
     x = hl16(x, v.first); y = hl16(y, w.first);
     P r; r.first = hl16(x + v.second, w.second) + y; r.second = hl16(x + w.second, y + v.second); return r;
 }
-__device__ inline P hash128(const uint8_t* s, size_t len) {
+static __device__ P hash128(const uint8_t* s, size_t len) {
     P seed;
     if (len >= 16) { seed.first = f64(s) ^ CK3; seed.second = f64(s + 8); return hash128_seed(s + 16, len - 16, seed); }
     if (len >= 8) { seed.first = f64(s) ^ (len * CK0); seed.second = f64(s + len - 8) ^ CK1; return hash128_seed(nullptr, 0, seed); }
@@ -366,18 +545,24 @@ __device__ inline P hash128(const uint8_t* s, size_t len) {
 }
 }  // namespace cityd
 
-struct FrameArgs { uint8_t* slots; uint32_t slot_stride; const uint32_t* comp_size; DState* st; uint32_t frame_bytes; uint64_t* wire_off; uint8_t* wire;
-                   uint64_t* tail; };   // tail[0] = frame count, written by k_frame_scan: the checksum / gather kernels of this batch may still run when the next batch resets DState
+struct FrameArgs { const uint32_t* comp_size; const uint64_t* wire_off; uint8_t* wire; const uint64_t* tail; };   // tail[0] = frame count, written by k_lz4_frames
 
 // CityHash128 is a serial chain per frame, so the parallelism is ACROSS frames: one thread per frame. What a
 // thread-per-frame loop would ruin is the memory access (every lane striding through its own frame), so each
 // warp stages the next 512 bytes of all its 32 frames with coalesced 16-byte cp.async copies into shared
-// memory (double buffered) while the lanes hash the previous 512 bytes out of it.
+// memory (double buffered) while the lanes hash the previous 512 bytes out of it. The frames sit at byte
+// offsets in the wire buffer, so the copies start at the 16-byte boundary below the frame and every lane
+// reads its 8-byte words at its own shift.
 #define SEAL_STEP 512
-#define SEAL_STRIDE 528
+#define SEAL_STRIDE 544
+#define SEAL_TAIL 320
 #define SEAL_STAGES 2      /* deeper pipelines do not help: the per-frame hash is a serial dependency chain (~43 k instructions) */
-#define SEAL_SMEM ((size_t)SEAL_STAGES * 32 * SEAL_STRIDE + 32 * 304)
-__device__ __forceinline__ uint64_t sm64(const uint8_t* base, uint32_t off) { return *(const uint64_t*)(base + off); }
+#define SEAL_SMEM ((size_t)SEAL_STAGES * 32 * SEAL_STRIDE + 32 * SEAL_TAIL)
+__device__ __forceinline__ uint64_t sm64u(const uint8_t* base, uint32_t off) {      // 8 bytes at any byte offset of a shared-memory row
+    const uint32_t al = off & ~7u, s = (off & 7u) * 8;
+    const uint64_t lo = *(const uint64_t*)(base + al), hi = *(const uint64_t*)(base + al + 8);
+    return (lo >> s) | ((hi << 1) << (63 - s));
+}
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
@@ -387,49 +572,49 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 #ifdef TF_KERNELS_LZ4
 __global__ void __launch_bounds__(32) k_frame_seal(FrameArgs a) {
-    // SEAL_STAGES steps of 512 bytes per frame in flight: with one warp per SM nothing else hides the load latency
     extern __shared__ __align__(16) uint8_t seal_smem[];
     uint8_t (*s_buf)[32][SEAL_STRIDE] = (uint8_t (*)[32][SEAL_STRIDE])seal_smem;                                  // [SEAL_STAGES][32][SEAL_STRIDE]
-    uint8_t (*s_tail)[304] = (uint8_t (*)[304])(seal_smem + (size_t)SEAL_STAGES * 32 * SEAL_STRIDE);              // [32][304]
+    uint8_t (*s_tail)[SEAL_TAIL] = (uint8_t (*)[SEAL_TAIL])(seal_smem + (size_t)SEAL_STAGES * 32 * SEAL_STRIDE);  // [32][SEAL_TAIL]
     const uint32_t lane = threadIdx.x;
     const uint64_t nf = a.tail[0];
     const uint64_t f = (uint64_t)blockIdx.x * 32 + lane;
     const bool have = f < nf;
-    uint8_t* s = a.slots + (have ? f : 0) * a.slot_stride;
-    // the 9 header bytes [0x82][cs][rs] at slot + 16 were written by k_frame_scan; the checksum goes straight into the wire
-    // buffer (k_wire_gather copies everything after it, concurrently, on the side stream)
+    // the frame: [16 checksum][0x82][u32 compressed size + 9][u32 raw size][LZ4 block]; the hash covers everything behind the checksum
+    const uint8_t* H = a.wire + (have ? a.wire_off[f] : 0) + 16;
     const uint32_t cs = have ? a.comp_size[f] + 9 : 0;
-    uint8_t* wck = a.wire + (have ? a.wire_off[f] : 0);
+    uint8_t* wck = (uint8_t*)H - 16;
     auto put_checksum = [&](uint64_t lo, uint64_t hi) {
 #pragma unroll
         for (int b = 0; b < 8; b++) { wck[b] = (uint8_t)(lo >> (8 * b)); wck[8 + b] = (uint8_t)(hi >> (8 * b)); }
     };
-    const uint8_t* H = s + 16;
     const bool big = have && cs >= 16 + 128 + 16;
     if (have && !big) { const cityd::P h = cityd::hash128(H, cs); put_checksum(h.first, h.second); }
     const uint8_t* body = H + 16; const uint32_t len = big ? cs - 16 : 0;
+    const uint32_t bsh = (uint32_t)((uintptr_t)body & 15);
+    const uint8_t* body_al = body - bsh;
     const uint32_t nblk = len / 128, used = nblk * 128;
     const uint32_t nsteps = (used + SEAL_STEP - 1) / SEAL_STEP;
     uint32_t max_steps = nsteps;
 #pragma unroll
     for (int d = 16; d; d >>= 1) { const uint32_t o = __shfl_xor_sync(0xffffffffu, max_steps, d); max_steps = o > max_steps ? o : max_steps; }
     if (max_steps == 0) return;
-    const uint32_t tail_base = (len > 272 ? (len - 272) : 0) & ~15u;
-    // cooperative staging helpers: lane l copies bytes [16 l, 16 l + 16) of every frame's current 512-byte step
+    const uint32_t tail_rel = (bsh + (len > 272 ? (len - 272) : 0)) & ~15u;      // relative to body_al
+    // cooperative staging: lane l copies bytes [16 l, 16 l + 16) of every frame's current step (+ 2 more chunks for the shifted reads)
     auto stage_step = [&](uint32_t st, uint32_t bi) {
 #pragma unroll 4
         for (int j = 0; j < 32; j++) {
-            const uint8_t* bj = (const uint8_t*)__shfl_sync(0xffffffffu, (unsigned long long)body, j);
-            const uint32_t uj = __shfl_sync(0xffffffffu, used, j);
+            const uint8_t* bj = (const uint8_t*)__shfl_sync(0xffffffffu, (unsigned long long)body_al, j);
+            const uint32_t uj = __shfl_sync(0xffffffffu, used ? used + 32 : 0, j);
             const uint32_t off = st * SEAL_STEP + lane * 16;
             if (off < uj) cp_async16(&s_buf[bi][j][lane * 16], bj + off);
+            if (lane < 2 && off + 512 < uj) cp_async16(&s_buf[bi][j][512 + lane * 16], bj + off + 512);
         }
         cp_async_commit();
     };
-    for (int j = 0; j < 32; j++) {      // tail windows (<= 288 bytes each)
-        const uint8_t* bj = (const uint8_t*)__shfl_sync(0xffffffffu, (unsigned long long)body, j);
-        const uint32_t lj = __shfl_sync(0xffffffffu, len, j), tj = __shfl_sync(0xffffffffu, tail_base, j);
-        if (lane < 18 && lj && tj + 16 * lane < lj + 16) cp_async16(&s_tail[j][16 * lane], bj + tj + 16 * lane);
+    for (int j = 0; j < 32; j++) {      // tail windows
+        const uint8_t* bj = (const uint8_t*)__shfl_sync(0xffffffffu, (unsigned long long)body_al, j);
+        const uint32_t lj = __shfl_sync(0xffffffffu, len, j), tj = __shfl_sync(0xffffffffu, tail_rel, j);
+        if (lane < SEAL_TAIL / 16 && lj) cp_async16(&s_tail[j][16 * lane], bj + tj + 16 * lane);
     }
 #pragma unroll
     for (int k = 0; k < SEAL_STAGES - 1; k++) { if ((uint32_t)k < max_steps) stage_step(k, k); else cp_async_commit(); }      // the tail windows ride in the first group
@@ -449,12 +634,14 @@ __global__ void __launch_bounds__(32) k_frame_seal(FrameArgs a) {
             const uint8_t* b = s_buf[st % SEAL_STAGES][lane];
             const uint32_t nb = (nblk - st * 4 < 4) ? nblk - st * 4 : 4;
             for (uint32_t i = 0; i < 2 * nb; i++) {
-                const uint32_t o = i * 64;
-                x = cityd::rot(x + y + v.first + sm64(b, o + 16), 37) * CK1;
-                y = cityd::rot(y + v.second + sm64(b, o + 48), 42) * CK1;
+                const uint32_t o = i * 64 + bsh;
+                const uint64_t q0 = sm64u(b, o), q1 = sm64u(b, o + 8), q2 = sm64u(b, o + 16), q3 = sm64u(b, o + 24);
+                const uint64_t q4 = sm64u(b, o + 32), q5 = sm64u(b, o + 40), q6 = sm64u(b, o + 48), q7 = sm64u(b, o + 56);
+                x = cityd::rot(x + y + v.first + q2, 37) * CK1;
+                y = cityd::rot(y + v.second + q6, 42) * CK1;
                 x ^= w.second; y ^= v.first; z = cityd::rot(z ^ w.first, 33);
-                v = cityd::weak32(sm64(b, o), sm64(b, o + 8), sm64(b, o + 16), sm64(b, o + 24), v.second * CK1, x + w.first);
-                w = cityd::weak32(sm64(b, o + 32), sm64(b, o + 40), sm64(b, o + 48), sm64(b, o + 56), z + w.second, y);
+                v = cityd::weak32(q0, q1, q2, q3, v.second * CK1, x + w.first);
+                w = cityd::weak32(q4, q5, q6, q7, z + w.second, y);
                 const uint64_t t = z; z = x; x = t;
             }
         }
@@ -463,12 +650,7 @@ __global__ void __launch_bounds__(32) k_frame_seal(FrameArgs a) {
     if (big) {
         const uint32_t rem = len - used;                 // 0..127 bytes; the tail reads reach back into hashed data
         const uint8_t* tb = s_tail[lane];
-        auto t64 = [&](uint32_t off) -> uint64_t {      // unaligned 8 bytes at body + off (off >= tail_base)
-            const uint32_t o = off - tail_base; const uint32_t al = o & ~7u, sh = (o & 7) * 8;
-            const uint64_t lo = *(const uint64_t*)(tb + al);
-            if (!sh) return lo;
-            return (lo >> sh) | (*(const uint64_t*)(tb + al + 8) << (64 - sh));
-        };
+        auto t64 = [&](uint32_t off) -> uint64_t { return sm64u(tb, off + bsh - tail_rel); };      // 8 bytes at body + off
         y += cityd::rot(w.first, 37) * CK0 + z;
         x += cityd::rot(v.first + z, 49) * CK0;
         for (uint32_t td = 0; td < rem;) {
@@ -482,61 +664,6 @@ __global__ void __launch_bounds__(32) k_frame_seal(FrameArgs a) {
         }
         x = cityd::hl16(x, v.first); y = cityd::hl16(y, w.first);
         put_checksum(cityd::hl16(x + v.second, w.second) + y, cityd::hl16(x + w.second, y + v.second));
-    }
-}
-#endif  // TF_KERNELS_LZ4
-
-// exclusive scan of frame sizes (single block) -> position of every frame in the wire buffer; also stamps the 9-byte
-// [method][sizes] header of every frame, which both the checksum (k_frame_seal) and the gather read
-#ifdef TF_KERNELS_LZ4
-__global__ void __launch_bounds__(1024) k_frame_scan(FrameArgs a) {
-    __shared__ uint32_t sm[33];
-    const uint64_t nf = a.st->n_frames;
-    uint64_t carry = 0;
-    for (uint64_t base = 0; base < nf; base += blockDim.x) {
-        const uint64_t i = base + threadIdx.x;
-        const uint32_t v = i < nf ? a.comp_size[i] + LZ_HDR : 0;
-        uint32_t tot; const uint32_t ex = block_excl_scan(v, &tot, sm);
-        if (i < nf) {
-            a.wire_off[i] = carry + ex;
-            // bytes 16..31 of the slot as two aligned words: [0x82][compressed size + 9][raw size] + the first 7 bytes of the LZ4 block (kept)
-            const uint32_t cs = v - LZ_HDR + 9;
-            const uint64_t pos0 = i * a.frame_bytes;
-            const uint32_t rs = (uint32_t)((a.st->raw_total - pos0 < a.frame_bytes) ? a.st->raw_total - pos0 : a.frame_bytes);
-            uint64_t* q = (uint64_t*)(a.slots + i * a.slot_stride + 16);
-            q[0] = 0x82ull | ((uint64_t)cs << 8) | ((uint64_t)(rs & 0xffffff) << 40);
-            q[1] = (q[1] & ~0xffull) | (uint64_t)(rs >> 24);
-        }
-        carry += tot;
-    }
-    if (threadIdx.x == 0) { a.st->wire_total = carry; a.tail[0] = nf; }
-}
-#endif  // TF_KERNELS_LZ4
-
-// gather the sealed frames into one contiguous stream; source slots are 16-byte aligned, the destination
-// is re-aligned with the same shuffle + funnel-shift trick as k_encode_fixed so stores are aligned words
-#ifdef TF_KERNELS_LZ4
-__global__ void __launch_bounds__(256) k_wire_gather(FrameArgs a) {
-    const uint64_t nf = a.tail[0];
-    for (uint64_t f = blockIdx.x; f < nf; f += gridDim.x) {
-        const uint32_t* src = (const uint32_t*)(a.slots + f * a.slot_stride);
-        const uint32_t total = a.comp_size[f] + LZ_HDR;
-        const uint64_t base = a.wire_off[f];
-        const uint32_t m = (uint32_t)(base & 3);
-        const uint32_t T = (m + total + 3) >> 2;
-        uint8_t* dst0 = a.wire + (base - m);
-        for (uint32_t t = 4 + threadIdx.x; t < T; t += blockDim.x) {       // words 0..3 hold only checksum bytes (m <= 3: word 3 ends at stream byte <= 15)
-            const uint32_t wcur = src[t];                       // slot has >= 8 bytes of slack past the block
-            const uint32_t wprev = t ? src[t - 1] : 0;
-            const uint32_t val = m ? __funnelshift_r(wprev, wcur, 8 * (4 - m)) : wcur;
-            const int32_t sb = (int32_t)(4 * t) - (int32_t)m;
-            uint8_t* dst = dst0 + 4 * (uint64_t)t;
-            if (sb >= 16 && (uint32_t)sb + 4 <= total) *(uint32_t*)dst = val;          // bytes [0, 16) are the checksum: k_frame_seal writes them
-            else {
-#pragma unroll
-                for (int b = 0; b < 4; b++) { const int32_t x = sb + b; if (x >= 16 && (uint32_t)x < total) dst[b] = (uint8_t)(val >> (8 * b)); }
-            }
-        }
     }
 }
 #endif  // TF_KERNELS_LZ4

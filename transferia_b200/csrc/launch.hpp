@@ -28,8 +28,6 @@ void launch_k_mask_encode(dim3 grid, dim3 block, size_t smem, cudaStream_t s, Ma
 void launch_k_shard_ids(dim3 grid, dim3 block, size_t smem, cudaStream_t s, ShardArgs a);
 void launch_k_lz4_frames(dim3 grid, dim3 block, size_t smem, cudaStream_t s, Lz4Args a);
 void launch_k_frame_seal(dim3 grid, dim3 block, size_t smem, cudaStream_t s, FrameArgs a);
-void launch_k_frame_scan(dim3 grid, dim3 block, size_t smem, cudaStream_t s, FrameArgs a);
-void launch_k_wire_gather(dim3 grid, dim3 block, size_t smem, cudaStream_t s, FrameArgs a);
 void launch_k_csv_count_nl(dim3 grid, dim3 block, size_t smem, cudaStream_t s, const uint8_t* text, uint64_t len, uint32_t* blk_cnt, const uint32_t* endbits);
 void launch_k_csv_line_index(dim3 grid, dim3 block, size_t smem, cudaStream_t s, const uint8_t* text, uint64_t len, const uint32_t* blk_off, uint32_t* line_end, const uint32_t* endbits);
 void launch_k_csv_pass1(dim3 grid, dim3 block, size_t smem, cudaStream_t s, CsvArgs a);

@@ -66,7 +66,7 @@ struct tfgpu_engine {
     uint64_t* d_tail = nullptr;
     std::string last_error;
     uint64_t launches = 0;
-    uint32_t frame_bytes = 32768;
+    uint32_t frame_bytes = LZ_MAX_FRAME;
     int sm_count = 148;
     std::vector<std::unique_ptr<PlanDev>> plans;
     // arenas
@@ -75,7 +75,7 @@ struct tfgpu_engine {
     int32_t* d_call_slots = nullptr; ColRegions* d_regions = nullptr; size_t d_call_cap = 0;   // columnar mode, per call
     // pointers into `work` for the last call
     uint8_t *keep = nullptr, *errcode = nullptr, *errstep = nullptr; uint32_t *blockcnt = nullptr, *blockoff = nullptr, *sel = nullptr;
-    uint32_t* tile_sum = nullptr; uint64_t* tile_base = nullptr; uint64_t* col_bytes = nullptr; uint32_t* comp_size = nullptr; uint64_t* wire_off = nullptr;
+    uint32_t* tile_sum = nullptr; uint64_t* tile_base = nullptr; uint64_t* col_bytes = nullptr; uint32_t* comp_size = nullptr; uint64_t* wire_off = nullptr; unsigned long long* frame_pfx = nullptr;
     uint64_t last_nrows = 0; bool last_has_filter = false, last_has_sharder = false; int last_wire_fmt = 0;
     uint8_t* pinned = nullptr; size_t pinned_cap = 0;
     DevBuf json_sizes, dbz_keysz, dbz_meta, part_ids;
@@ -112,7 +112,7 @@ namespace {
 
 void join_tail(tfgpu_engine* e) {
     if (!e->tail_pending) return;
-    CK(cudaStreamWaitEvent(e->stream, e->ev_join, 0)); CK(cudaStreamWaitEvent(e->stream, e->ev_tail2, 0));
+    CK(cudaStreamWaitEvent(e->stream, e->ev_tail2, 0));
     e->tail_pending = false;
 }
 int fail(tfgpu_engine* e, int code, const std::string& msg) { if (e) e->last_error = msg; return code; }
@@ -284,7 +284,7 @@ Sizes compute_sizes(const tfgpu_engine* e, const PlanDev& pd, const tf_batch* in
     Sizes s;
     s.raw_bound = raw + 256;
     s.n_frames_max = (raw + e->frame_bytes - 1) / e->frame_bytes + 1;
-    s.wire_bound = s.n_frames_max * (uint64_t)(LZ_HDR + lz4_bound(e->frame_bytes)) + 256;
+    s.wire_bound = s.n_frames_max * (uint64_t)(LZ_HDR + lz4_bound(e->frame_bytes)) + 1024;
     s.ntiles_cap = (uint32_t)((n + TF_STR_TILE - 1) / TF_STR_TILE + 1);
     s.nblocks = (uint32_t)((n + 255) / 256 + 1);
     return s;
@@ -331,17 +331,16 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
     need(n); need(n); need(n); need(sz.nblocks * 4); need(sz.nblocks * 4); need(n * 4);
     const size_t nslot_alloc = (size_t)(pd.n_str > 0 ? pd.n_str : 1);
     need(nslot_alloc * sz.ntiles_cap * 4); need(nslot_alloc * sz.ntiles_cap * 8);
-    need(sz.n_frames_max * 4); need(sz.n_frames_max * 8); need(256 * 8);
+    need(sz.n_frames_max * 4); need(sz.n_frames_max * 8); need(sz.n_frames_max * 8); need(256 * 8);
     e->work.ensure(wbytes);
     uint8_t* p = e->work.p;
     e->keep = carve<uint8_t>(p, n); e->errcode = carve<uint8_t>(p, n); e->errstep = carve<uint8_t>(p, n);
     e->blockcnt = carve<uint32_t>(p, sz.nblocks); e->blockoff = carve<uint32_t>(p, sz.nblocks); e->sel = carve<uint32_t>(p, n);
     e->tile_sum = carve<uint32_t>(p, nslot_alloc * sz.ntiles_cap); e->tile_base = carve<uint64_t>(p, nslot_alloc * sz.ntiles_cap);
-    e->comp_size = carve<uint32_t>(p, sz.n_frames_max); e->wire_off = carve<uint64_t>(p, sz.n_frames_max); e->col_bytes = carve<uint64_t>(p, 256);
+    e->comp_size = carve<uint32_t>(p, sz.n_frames_max); e->wire_off = carve<uint64_t>(p, sz.n_frames_max); e->frame_pfx = carve<unsigned long long>(p, sz.n_frames_max); e->col_bytes = carve<uint64_t>(p, 256);
     e->raw.ensure(sz.raw_bound);
     const bool lz = wire_fmt == TF_WIRE_CH_NATIVE_LZ4;
-    const uint32_t stride = lz_slot_stride(e->frame_bytes);
-    if (lz) { e->slots.ensure(sz.n_frames_max * (uint64_t)stride + 4096); e->wire.ensure(sz.wire_bound); }
+    if (lz) e->wire.ensure(sz.wire_bound);
     if (e->d_cols_cap < nc) { if (e->d_cols) CK(cudaFree(e->d_cols)); CK(cudaMalloc(&e->d_cols, sizeof(DCol) * nc)); e->d_cols_cap = nc; }
     // column descriptors
     std::vector<DCol> hc(nc);
@@ -490,22 +489,20 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         }
     }
     if (lz) {
-        Lz4Args za{e->raw.p, e->d_state, e->slots.p, stride, e->comp_size, e->frame_bytes, e->lz_phases};
-        const size_t smem = lz_data_bytes(e->frame_bytes) + 2 * (size_t)e->frame_bytes + (4u << LZ_HASH_BITS) + e->frame_bytes / 8 + 64 * 4;
-        const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (smem + 1024)));
+        Lz4Args za{e->raw.p, e->d_state, e->wire.p, e->comp_size, e->wire_off, e->frame_pfx, e->d_tail, e->frame_bytes, e->lz_phases};
+        const size_t smem = lz_smem(e->frame_bytes).total;
+        const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / (smem + 1024)));
         const uint32_t grid = (uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * per_sm);
-        join_tail(e);            // the previous batch's checksum / gather still read the slots and sizes this kernel overwrites
+        join_tail(e);            // the previous batch's checksum kernel still reads the wire bytes and sizes this kernel overwrites
+        CK(cudaMemsetAsync(e->frame_pfx, 0, sz.n_frames_max * 8, s));
+        // frames are compressed and written at their final wire offset by one kernel (sizes of the earlier frames by decoupled look-back)
         e->prof_begin("k_lz4_frames", s); launch_k_lz4_frames(grid, LZ_THREADS, smem, s, za); e->prof_end(s);
-        FrameArgs fa{e->slots.p, stride, e->comp_size, e->d_state, e->frame_bytes, e->wire_off, e->wire.p, e->d_tail};
-        // frame offsets + [method][sizes] headers first; then the checksum chain (one thread per frame: latency-bound, a few warps
-        // per SM) and the gather of everything behind the checksum run side by side on two streams
-        e->prof_begin("k_frame_scan", s); launch_k_frame_scan(1, 1024, 0, s, fa); e->prof_end(s);
-        cudaStream_t s2 = e->side_stream, s3 = e->side2_stream;
-        CK(cudaEventRecord(e->ev_fork, s)); CK(cudaStreamWaitEvent(s2, e->ev_fork, 0)); CK(cudaStreamWaitEvent(s3, e->ev_fork, 0));
+        // the checksum chain (one thread per frame: latency-bound, a few warps per SM) runs on a side stream, under the next batch
+        FrameArgs fa{e->comp_size, e->wire_off, e->wire.p, e->d_tail};
+        cudaStream_t s3 = e->side2_stream;
+        CK(cudaEventRecord(e->ev_fork, s)); CK(cudaStreamWaitEvent(s3, e->ev_fork, 0));
         e->prof_begin("k_frame_seal", s3); launch_k_frame_seal((uint32_t)((sz.n_frames_max + 31) / 32), 32, SEAL_SMEM, s3, fa); e->prof_end(s3);
         CK(cudaEventRecord(e->ev_tail2, s3));
-        e->prof_begin("k_wire_gather", s2); launch_k_wire_gather((uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * 8), 256, 0, s2, fa); e->prof_end(s2);
-        CK(cudaEventRecord(e->ev_join, s2));
         e->tail_pending = true; e->tail_nrows = n; e->tail_plan = (const void*)&pd;      // joined by whoever needs the wire bytes, or by the next batch before its LZ4
     }
     CK(cudaGetLastError());
@@ -534,8 +531,8 @@ int tfgpu_engine_create(const char* cfg_json, const int* device_ids, int n_devic
     try {
         if (cfg_json && *cfg_json) {
             auto cfg = tfj::parse(cfg_json);
-            double fb = cfg->get_num("frame_bytes", 32768);
-            if (fb < 1024 || fb > LZ_MAX_FRAME || ((uint32_t)fb & 63)) return TF_E_FATAL_CONFIG;
+            double fb = cfg->get_num("frame_bytes", LZ_MAX_FRAME);
+            if (fb < 1024 || fb > LZ_MAX_FRAME || ((uint32_t)fb & 15)) return TF_E_FATAL_CONFIG;
             e->frame_bytes = (uint32_t)fb;
         }
         CK(cudaSetDevice(e->device));

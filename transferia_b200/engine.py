@@ -207,7 +207,7 @@ class PushResult:
 
 
 class Engine:
-    def __init__(self, device: int = 0, frame_bytes: int = 32768):
+    def __init__(self, device: int = 0, frame_bytes: int = 30720):
         self._L = load_library()
         self._h = C.c_void_p()
         dev = (C.c_int * 1)(device)
