@@ -16,7 +16,7 @@ struct Cfg {
     uint32_t F = 30720, SEG = 60, ROUND = 2048, HASH_BITS = 12;
     int stride = 2;          // probe every stride-th position (inserts happen at every position)
     bool second_probe = true, period8 = true, merge = true, backext = true;
-    int winner = 2; bool near_first = false;         // 0 lowest position wins an insert race, 1 highest, 2 random
+    int winner = 2; bool near_first = false; int ins_stride = 1; bool twoslot = false;         // 0 lowest position wins an insert race, 1 highest, 2 random
 };
 
 struct Seq { uint32_t p, ml, off; };
@@ -53,13 +53,53 @@ static std::vector<uint8_t> compress_frame(const uint8_t* d, uint32_t len, const
         for (uint32_t i = 0; i < order.size(); i++) order[i] = r0 + i;
         if (c.winner == 0) std::reverse(order.begin(), order.end());
         else if (c.winner == 2) std::shuffle(order.begin(), order.end(), rng);
-        for (uint32_t p : order) if (p + 4 <= len) table[idx[p - r0]] = tag[p - r0] | p;
+        for (uint32_t p : order) if (p + 4 <= len && p % c.ins_stride == 0) table[idx[p - r0]] = tag[p - r0] | p;
         if (c.second_probe)
             for (uint32_t p = r0; p < r1; p++) {
                 if (p % c.stride || p + 12 > len || cand[p] != 0xffffffffu) continue;
                 const uint32_t e = table[idx[p - r0]];
                 if ((e & 0xffff0000u) == tag[p - r0] && (e & 0xffffu) < p) cand[p] = e & 0xffffu;
             }
+    }
+    if (c.twoslot) {
+        // one barrier per round: bucket = [slot of even rounds, slot of odd rounds]; round r probes both slots BEFORE inserting into
+        // slot r % 2 (other threads' inserts of the same round may already be there), and positions of round r that found nothing
+        // look at slot r % 2 again one round later, when it holds the round's final winner
+        std::fill(cand.begin(), cand.end(), 0xffffffffu);
+        const uint32_t NB = 1u << (c.HASH_BITS - 1);
+        std::vector<uint32_t> t2(2 * NB, 0xffffffffu);
+        auto hidx = [&](uint32_t p) { const uint32_t h = rd32(d, p) * 2654435761u; return h >> (32 - (c.HASH_BITS - 1)); };
+        auto htag = [&](uint32_t p) { const uint32_t h = rd32(d, p) * 2654435761u; return (h << (c.HASH_BITS - 1)) & 0xffff0000u; };
+        uint32_t rnd = 0;
+        for (uint32_t r0 = 0; r0 < len + c.ROUND; r0 += c.ROUND, rnd++) {
+            // late probe of the previous round
+            if (r0 >= c.ROUND)
+                for (uint32_t p = r0 - c.ROUND; p < std::min(len, r0); p += c.stride) {
+                    if (p + 12 > len || cand[p] != 0xffffffffu) continue;
+                    const uint32_t e = t2[2 * hidx(p) + ((rnd - 1) & 1)];
+                    if (e != 0xffffffffu && (e & 0xffff0000u) == htag(p) && (e & 0xffffu) < p) cand[p] = e & 0xffffu;
+                }
+            if (r0 >= len) break;
+            const uint32_t r1 = std::min(len, r0 + c.ROUND);
+            std::vector<uint32_t> thr((r1 - r0 + 3) / 4);
+            for (uint32_t i = 0; i < thr.size(); i++) thr[i] = i;
+            std::shuffle(thr.begin(), thr.end(), rng);
+            for (uint32_t ti : thr) {
+                const uint32_t p0 = r0 + 4 * ti;
+                for (uint32_t p = p0; p < std::min(r1, p0 + 4); p++) {
+                    if (p % c.stride || p + 12 > len) continue;
+                    if (p >= 4 && rd32(d, p) == rd32(d, p - 4)) { cand[p] = p - 4; continue; }
+                    if (p >= 8 && rd32(d, p) == rd32(d, p - 8)) { cand[p] = p - 8; continue; }
+                    uint32_t best = 0xffffffffu;
+                    for (int sl = 0; sl < 2; sl++) {
+                        const uint32_t e = t2[2 * hidx(p) + sl];
+                        if (e != 0xffffffffu && (e & 0xffff0000u) == htag(p) && (e & 0xffffu) < p && (best == 0xffffffffu || (e & 0xffffu) > best)) best = e & 0xffffu;
+                    }
+                    cand[p] = best;
+                }
+                for (uint32_t p = p0; p < std::min(r1, p0 + 4); p++) if (p + 4 <= len && p % c.ins_stride == 0) t2[2 * hidx(p) + (rnd & 1)] = htag(p) | p;
+            }
+        }
     }
     // ---- P3: per segment greedy parse, matches cut at the segment end
     const uint32_t nseg = (len + c.SEG - 1) / c.SEG;
@@ -187,7 +227,7 @@ int main(int argc, char** argv) {
         std::string kv = argv[i]; const size_t e = kv.find('='); const std::string k = kv.substr(0, e); const int v = atoi(kv.c_str() + e + 1);
         if (k == "F") c.F = v; else if (k == "SEG") c.SEG = v; else if (k == "ROUND") c.ROUND = v; else if (k == "HB") c.HASH_BITS = v;
         else if (k == "stride") c.stride = v; else if (k == "probe2") c.second_probe = v; else if (k == "p8") c.period8 = v;
-        else if (k == "merge") c.merge = v; else if (k == "back") c.backext = v; else if (k == "winner") c.winner = v; else if (k == "step") step = v; else if (k == "near") c.near_first = v;
+        else if (k == "merge") c.merge = v; else if (k == "back") c.backext = v; else if (k == "winner") c.winner = v; else if (k == "step") step = v; else if (k == "near") c.near_first = v; else if (k == "ins") c.ins_stride = v; else if (k == "two") c.twoslot = v;
     }
     typedef int (*comp_t)(const char*, char*, int, int);
     comp_t stock = nullptr;

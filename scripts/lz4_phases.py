@@ -22,4 +22,4 @@ for _ in range(5):
     for kk in eng.profile_read(): acc[kk["name"]] = acc.get(kk["name"], 0) + kk["ms"] / 5
 ph = eng.lz4_phases(True); tot = sum(ph) or 1
 print("kernels_ms", {n: round(v, 4) for n, v in sorted(acc.items(), key=lambda kv: -kv[1])}, "step", round(sum(acc.values()), 4))
-print("lz4 phases (stage, match, parse, scan, emit) share:", [round(x / tot, 3) for x in ph], "stats", eng.resident_stats())
+print("lz4 phases (stage, match, parse+continuation, scan, emit, resolve + flush of the previous frame, -, -) share:", [round(x / tot, 3) for x in ph], "stats", eng.resident_stats())

@@ -249,7 +249,7 @@ template <typename Sink> __device__ void fmt_json_string(Sink& s, const uint8_t*
 }
 
 // to_string.SerializeToString (pkg/transformer/registry/to_string/to_string.go:145-171) for a typed column value
-template <typename Sink> __device__ __noinline__ void fmt_value(Sink& s, const DCol& c, uint64_t r) {
+template <typename Sink> __device__ void fmt_value(Sink& s, const DCol& c, uint64_t r) {
     if (!row_valid(c, r)) { if (c.type == TF_ANY) fmt_lit(s, "null"); else fmt_lit(s, "<nil>"); return; }   // json.Marshal(nil) / %v of nil
     switch (c.type) {
     case TF_INT8: fmt_i64(s, ((const int8_t*)c.values)[r]); break;

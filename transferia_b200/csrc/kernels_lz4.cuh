@@ -93,6 +93,37 @@ __device__ __forceinline__ uint32_t lz_match_len(const uint32_t* dw, uint32_t c,
     return ml < maxl ? ml : maxl;
 }
 
+// Decoupled look-back (warp 0 only): the exclusive prefix of the sizes of frames [0, f). Cells hold AGG | own size or INCL | inclusive prefix.
+__device__ __forceinline__ unsigned long long lz_lookback(const Lz4Args& a, uint32_t f, uint32_t lane) {
+    unsigned long long excl = 0;
+    if (!f) return 0;
+    int64_t base = (int64_t)f;           // cells [0, base) are still to be summed
+    for (uint32_t spins = 0;;) {
+        // four windows of 32 cells per round trip
+        unsigned long long v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int64_t j = base - 1 - 32 * k - (int64_t)lane; v[k] = j >= 0 ? *(volatile unsigned long long*)&a.pfx[j] : LZ_FLAG_INCL; }
+        bool done = false, stale = false;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (done || stale) continue;
+            const uint32_t fl = (uint32_t)(v[k] >> 62);
+            const uint32_t incl = __ballot_sync(0xffffffffu, fl == 2), none = __ballot_sync(0xffffffffu, fl == 0);
+            const uint32_t upto = incl ? (uint32_t)__ffs((int)incl) - 1 : 31u;       // lanes 0..upto are needed
+            const uint32_t need = upto == 31 ? 0xffffffffu : ((2u << upto) - 1);
+            if (none & need) { stale = true; continue; }      // an earlier frame has not got that far yet (its CTA holds a lower ticket and is running)
+            unsigned long long part = lane <= upto ? (v[k] & LZ_VAL_MASK) : 0ull;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+            excl += part; base -= 32;
+            if (incl) done = true;
+        }
+        if (done) break;
+        if (stale) { if (++spins > (1u << 20)) { if (lane == 0) a.st->pad = 1; break; } __nanosleep(100); }      // a bounded wait keeps a bug from hanging the device
+    }
+    return excl;
+}
+
 #ifdef TF_KERNELS_LZ4
 __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -118,6 +149,39 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t raw_total = a.st->raw_total, n_frames = a.st->n_frames;
 
+    // The image of a finished frame stays in shared memory while the NEXT frame is staged, matched and parsed (none of that touches the
+    // image): its place in the wire buffer is looked up only then, when the frames before it have long published their sizes, so a slow
+    // predecessor costs nothing.
+    uint32_t pend_f = 0xffffffffu, pend_cs = 0;
+    auto resolve_flush = [&](uint32_t pf, uint32_t pcs) {
+        if (warp == 0) {
+            const unsigned long long excl = lz_lookback(a, pf, lane);
+            if (lane == 0) {
+                *(volatile unsigned long long*)&a.pfx[pf] = LZ_FLAG_INCL | (excl + pcs + LZ_HDR);
+                s_woff = excl;
+                a.comp_size[pf] = pcs; a.wire_off[pf] = excl;
+                if (pf + 1 == n_frames) { a.st->wire_total = excl + pcs + LZ_HDR; a.tail[0] = n_frames; }
+            }
+        }
+        __syncthreads();
+        // the image goes to wire + offset + 16 (behind the checksum field) in aligned 16-byte stores; the bytes a first / last store
+        // carries beyond the image land in checksum fields, which k_frame_seal writes afterwards
+        uint8_t* G = a.wire + s_woff + 16;
+        const uint32_t m = (uint32_t)((uintptr_t)G & 15), total = 9 + pcs;
+        const uint32_t nchunks = (m + total + 15) >> 4;
+        int4* g4 = (int4*)(G - m);
+        const uint32_t* sw = (const uint32_t*)(stg - 16);                 // image byte x is at sw byte x + 16
+        const uint32_t o0 = 16 - m, sh = (o0 & 3) * 8;
+        for (uint32_t j = tid; j < nchunks; j += LZ_THREADS) {
+            const uint32_t wi0 = (o0 + 16 * j) >> 2;
+            const uint32_t q0 = sw[wi0], q1 = sw[wi0 + 1], q2 = sw[wi0 + 2], q3 = sw[wi0 + 3], q4 = sw[wi0 + 4];
+            int4 v;
+            v.x = (int)__funnelshift_r(q0, q1, sh); v.y = (int)__funnelshift_r(q1, q2, sh);
+            v.z = (int)__funnelshift_r(q2, q3, sh); v.w = (int)__funnelshift_r(q3, q4, sh);
+            g4[j] = v;
+        }
+        __syncthreads();
+    };
     for (;;) {
         __syncthreads();
         if (tid == 0) s_frame = atomicAdd(&a.st->frame_ticket, 1u);
@@ -361,8 +425,9 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
         const int32_t delta_final = (int32_t)(total_seq_bytes + 1 + ext_bytes(ll_final)) - (int32_t)(len - ll_final);
         const uint32_t cs = total_seq_bytes + 1 + ext_bytes(ll_final) + ll_final;
         if (tid == 0) { *(volatile unsigned long long*)&a.pfx[f] = LZ_FLAG_AGG | (unsigned long long)(cs + LZ_HDR); }   // the frames behind can start summing
-
         LZ_PHASE(3);
+        if (pend_f != 0xffffffffu) resolve_flush(pend_f, pend_cs);      // the previous frame leaves the image
+        LZ_PHASE(5);
         // ---- P5: emit into the shared-memory image
         uint8_t* out = stg + 9;
         if (tid < nseg) {
@@ -408,60 +473,10 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
             stg[0] = 0x82; stg[1] = (uint8_t)c9; stg[2] = (uint8_t)(c9 >> 8); stg[3] = (uint8_t)(c9 >> 16); stg[4] = (uint8_t)(c9 >> 24);
             stg[5] = (uint8_t)len; stg[6] = (uint8_t)(len >> 8); stg[7] = (uint8_t)(len >> 16); stg[8] = (uint8_t)(len >> 24);
         }
-        // ---- the frame's place in the wire buffer: sizes of the earlier frames (decoupled look-back, warp 0)
-        if (warp == 0) {
-            unsigned long long excl = 0;
-            if (f) {
-                int64_t base = (int64_t)f;           // cells [0, base) are still to be summed
-                for (uint32_t spins = 0;;) {
-                    const int64_t j = base - 1 - (int64_t)lane;
-                    unsigned long long v = j >= 0 ? *(volatile unsigned long long*)&a.pfx[j] : LZ_FLAG_INCL;
-                    const uint32_t fl = (uint32_t)(v >> 62);
-                    const uint32_t incl = __ballot_sync(0xffffffffu, fl == 2), none = __ballot_sync(0xffffffffu, fl == 0);
-                    const uint32_t upto = incl ? (uint32_t)__ffs((int)incl) - 1 : 31u;       // lanes 0..upto are needed
-                    const uint32_t need = upto == 31 ? 0xffffffffu : ((2u << upto) - 1);
-                    if (none & need) {      // an earlier frame has not got that far yet (its CTA holds a lower ticket and is running)
-                        if (++spins > (1u << 22)) { if (lane == 0) a.st->pad = 1; break; }      // never seen; a bounded wait keeps a bug from hanging the device
-                        __nanosleep(64); continue;
-                    }
-                    unsigned long long part = lane <= upto ? (v & LZ_VAL_MASK) : 0ull;
-#pragma unroll
-                    for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-                    excl += part;
-                    if (incl) break;
-                    base -= 32;
-                }
-            }
-            if (lane == 0) {
-                __threadfence();
-                *(volatile unsigned long long*)&a.pfx[f] = LZ_FLAG_INCL | (excl + cs + LZ_HDR);
-                s_woff = excl;
-                a.comp_size[f] = cs; a.wire_off[f] = excl;
-                if (f + 1 == n_frames) { a.st->wire_total = excl + cs + LZ_HDR; a.tail[0] = n_frames; }
-            }
-        }
-        __syncthreads();
         LZ_PHASE(4);
-        // ---- flush: the image goes to wire + offset + 16 (behind the checksum field) in aligned 16-byte stores; the bytes a
-        // first / last store carries beyond the image land in checksum fields, which k_frame_seal writes afterwards
-        {
-            uint8_t* G = a.wire + s_woff + 16;
-            const uint32_t m = (uint32_t)((uintptr_t)G & 15), total = 9 + cs;
-            const uint32_t nchunks = (m + total + 15) >> 4;
-            int4* g4 = (int4*)(G - m);
-            const uint32_t* sw = (const uint32_t*)(stg - 16);                 // image byte x is at sw byte x + 16
-            const uint32_t o0 = 16 - m, sh = (o0 & 3) * 8;
-            for (uint32_t j = tid; j < nchunks; j += LZ_THREADS) {
-                const uint32_t wi0 = (o0 + 16 * j) >> 2;
-                const uint32_t q0 = sw[wi0], q1 = sw[wi0 + 1], q2 = sw[wi0 + 2], q3 = sw[wi0 + 3], q4 = sw[wi0 + 4];
-                int4 v;
-                v.x = (int)__funnelshift_r(q0, q1, sh); v.y = (int)__funnelshift_r(q1, q2, sh);
-                v.z = (int)__funnelshift_r(q2, q3, sh); v.w = (int)__funnelshift_r(q3, q4, sh);
-                g4[j] = v;
-            }
-        }
-        LZ_PHASE(5);
+        pend_f = f; pend_cs = cs;      // written to the wire buffer while the next frame is being parsed (resolve_flush above), or after the loop
     }
+    if (pend_f != 0xffffffffu) { __syncthreads(); resolve_flush(pend_f, pend_cs); }
 }
 #endif  // TF_KERNELS_LZ4
 

@@ -366,7 +366,7 @@ class Engine:
         """Cycles spent per k_lz4_frames phase (stage, match, parse, scan, emit) since the last read (profiling aid)."""
         out = (C.c_uint64 * 8)()
         self._check(self._L.tfgpu_debug_lz4_phases(self._h, 1 if enable else 0, out))
-        return [int(x) for x in out[:5]]
+        return [int(x) for x in out]
 
     def emit_debezium(self, plan_id: int, batch: abi.Batch, opts: dict, meta: Optional[dict] = None, copy_bytes: bool = True) -> PushResult:
         """Queue Debezium serializer (Emitter.EmitKV) over the INSERT rows that survive the plan's chain: PushResult whose
