@@ -33,7 +33,13 @@ METRIC = "ChangeItems/sec on ClickBench-shaped 99-col batches (filter_rows + cas
 FALLBACK_HBM_GBS = 6650.0
 
 
-TRAFFIC_PROFILE = "profiles/r1e_traffic.json"   # written by scripts/ncu_summary.py from the capture under profiles/
+TRAFFIC_PROFILE = "profiles/r2c_traffic.json"   # written by scripts/ncu_summary.py from the capture under profiles/
+
+
+def bench_config(args, ncols: int) -> dict:
+    """The `config` object both arms print, key for key (the driver compares them)."""
+    return {"workload": "clickbench_hits_99col filter_rows+cast+ch_native+lz4 (BASELINE configs[2])", "rows_per_step_per_gpu": min(args.rows, 1_000_000) if args.impl == "reference" else args.rows,
+            "columns": ncols, "frame_bytes": args.frame_bytes, "batch_seed": "workload.SEED + rank"}
 
 
 def load_peaks():
@@ -220,6 +226,70 @@ def extra_paths(eng, args):
             res["debezium_emit_pg_hits"]["cpu_port_error"] = str(ex)
     except Exception as ex:
         res["debezium_emit_error"] = str(ex)
+    # BASELINE configs[3]: Debezium CDC envelopes (12-field payload, schema-registry framed) -> parse -> filter_rows -> cast -> native block + LZ4
+    try:
+        dcache = f"/tmp/tf_dbz_{args.dbz_msgs}.bin"
+        if os.path.exists(dcache + ".npy"):
+            ddata = open(dcache, "rb").read(); dends = np.load(dcache + ".npy"); dschema_text, dtable = workload.debezium_schema_text(), ("public", "events")
+        else:
+            ddata, dends, dschema_text, dtable = workload.make_debezium_messages(args.dbz_msgs)
+            open(dcache, "wb").write(ddata); np.save(dcache + ".npy", dends)
+        dschema = engine.debezium_table_schema(dschema_text); dtrs = workload.debezium_transformers()
+        dpid = eng.plan(dtable[0], dtable[1], dschema, dtrs, {"type": "clickhouse"})
+        kw = dict(schema_registry=True, schema_id=7, wire_fmt=abi.TF_WIRE_CH_NATIVE_LZ4)
+        for _ in range(2):
+            r, _m = eng.parse_debezium(dpid, ddata, dends, dschema_text, **kw)
+        torch.cuda.synchronize(); t0 = time.perf_counter(); k = 5
+        for _ in range(k):
+            r, _m = eng.parse_debezium(dpid, ddata, dends, dschema_text, **kw)
+        torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / k
+        eng.profile_enable(True); eng.parse_debezium(dpid, ddata, dends, dschema_text, **kw); prof = {kk["name"]: round(kk["ms"], 4) for kk in eng.profile_read()}; eng.profile_enable(False)
+        kern_ms = sum(prof.values())
+        res["debezium_parse_filter_cast"] = {"rows_per_s": len(dends) / dt, "messages": int(len(dends)), "input_MB": len(ddata) / 1e6, "ms": dt * 1e3, "rows_out": r.rows_out, "row_errors": len(r.errors),
+                                             "out_bytes": len(r.wire), "kernels_ms": prof, "kernels_GBps_of_input": {n: round(len(ddata) / 1e6 / v, 1) for n, v in prof.items() if v > 0.02},
+                                             "kernel_only_rows_per_s": len(dends) / (kern_ms / 1e3) if kern_ms else None,
+                                             "note": "wall clock around tfgpu_parse_debezium with the message bytes in host memory (pageable: the ctypes binding copies them): H2D, the fused chain and D2H of the frames included"}
+        try:
+            from oracle import pyoracle as po
+            ns = 4000; sd = ddata[: int(dends[ns - 1])]
+            t0 = time.perf_counter(); b, kinds, *_ = po.debezium_parse(sd, dends[:ns].tolist(), dschema_text, use_sr=True, schema_id=7)
+            po.push_encode(abi.Batch(b.nrows, b.columns, np.asarray(kinds, dtype=np.uint8)), po.build_plan(dtable[0], dtable[1], dschema, dtrs), abi.TF_WIRE_CH_NATIVE_LZ4, args.frame_bytes); dtc = time.perf_counter() - t0
+            res["debezium_parse_filter_cast"]["cpu_port_rows_per_s_1core"] = ns / dtc
+        except Exception as ex:
+            res["debezium_parse_filter_cast"]["cpu_port_error"] = str(ex)
+    except Exception as ex:
+        res["debezium_parse_error"] = str(ex)
+    # BASELINE configs[4]: hits-shaped CSV -> parse -> cast -> ClickHouse native block (+ LZ4)
+    try:
+        ccache = f"/tmp/tf_csv_{args.csv_rows}.bin"
+        cb, cschema = make_batch(args.csv_rows, workload.SEED)
+        cschema = [dict(c, path=str(i)) for i, c in enumerate(cschema)]
+        if os.path.exists(ccache):
+            ctext = open(ccache, "rb").read()
+        else:
+            ctext = workload.render_hits_csv(cb, cschema); open(ccache, "wb").write(ctext)
+        cpid = eng.plan("public", "hits", cschema, [], {"type": "clickhouse"})
+        for _ in range(2):
+            r, _c = eng.parse_csv(cpid, ctext, wire_fmt=abi.TF_WIRE_CH_NATIVE_LZ4)
+        torch.cuda.synchronize(); t0 = time.perf_counter(); k = 5
+        for _ in range(k):
+            r, _c = eng.parse_csv(cpid, ctext, wire_fmt=abi.TF_WIRE_CH_NATIVE_LZ4)
+        torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / k
+        eng.profile_enable(True); eng.parse_csv(cpid, ctext, wire_fmt=abi.TF_WIRE_CH_NATIVE_LZ4); prof = {kk["name"]: round(kk["ms"], 4) for kk in eng.profile_read()}; eng.profile_enable(False)
+        kern_ms = sum(prof.values())
+        res["csv_parse_cast_native"] = {"rows_per_s": args.csv_rows / dt, "rows": args.csv_rows, "input_MB": len(ctext) / 1e6, "ms": dt * 1e3, "rows_out": r.rows_out, "out_bytes": len(r.wire), "kernels_ms": prof,
+                                        "kernels_GBps_of_input": {n: round(len(ctext) / 1e6 / v, 1) for n, v in prof.items() if v > 0.02},
+                                        "kernel_only_rows_per_s": args.csv_rows / (kern_ms / 1e3) if kern_ms else None,
+                                        "note": "wall clock around tfgpu_parse_csv with the text in host memory: H2D, tokenise + cast + native block + LZ4 frames, D2H included"}
+        try:
+            from oracle import pyoracle as po
+            cut = ctext.rfind(b"\n", 0, len(ctext) // 25) + 1; sample = ctext[:cut]
+            t0 = time.perf_counter(); b, _e, _l, _c = po.csv_parse(sample, cschema); po.push_encode(b, po.build_plan("public", "hits", cschema, []), abi.TF_WIRE_CH_NATIVE_LZ4, args.frame_bytes); dtc = time.perf_counter() - t0
+            res["csv_parse_cast_native"]["cpu_port_rows_per_s_1core"] = sample.count(b"\n") / dtc
+        except Exception as ex:
+            res["csv_parse_cast_native"]["cpu_port_error"] = str(ex)
+    except Exception as ex:
+        res["csv_parse_error"] = str(ex)
     try:
         from oracle import pyoracle as po
         sample = text[: text.rfind(b"\n", 0, len(text) // 20) + 1]
@@ -254,8 +324,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "clickbench_hits_99col filter_rows+cast+ch_native+lz4 (BASELINE configs[2])", "rows_per_step": rows,
-                   "note": "CPU restatement (C++ oracle port), not Go: no Go toolchain / module cache in this image"},
+        "config": bench_config(args, len(schema)),
+        "note": "CPU restatement (C++ oracle port), not Go: no Go toolchain / module cache in this image",
         "cpu_baseline": {"value": v, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -273,6 +343,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary paths (JSON-lines parse, serializers)")
     ap.add_argument("--json-lines", type=int, default=400_000)
+    ap.add_argument("--dbz-msgs", type=int, default=200_000, help="messages of the Debezium leg (BASELINE configs[3])")
+    ap.add_argument("--csv-rows", type=int, default=100_000, help="rows of the CSV leg (BASELINE configs[4])")
     ap.add_argument("--e2e-pipelines", type=int, default=2, help="host threads (one engine handle each) pushing batches concurrently in the end-to-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -295,9 +367,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = f"cuda:{local}"
 
-    # weak scaling: every rank pushes its own copy of the SAME seeded batch (identical work per GPU: the generator's palettes
-    # and dictionaries depend on the seed, and with them selectivity and compressibility); no data-path collective
-    batch, schema = make_batch(args.rows, workload.SEED)
+    # weak scaling: every rank pushes its OWN seeded batch (seed + rank: other values, dictionaries and therefore a slightly different
+    # selectivity / compressibility per GPU, as independent table parts have); no data-path collective
+    batch, schema = make_batch(args.rows, workload.SEED + rank)
     k = workload.counterid_threshold(batch, schema)
     trs = workload.headline_transformers(k)
     eng = engine.Engine(local, args.frame_bytes)
@@ -416,12 +488,12 @@ def main():
             "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "clickbench_hits_99col filter_rows+cast+ch_native+lz4 (BASELINE configs[2])",
-                       "rows_per_step_per_gpu": args.rows, "columns": len(schema), "frame_bytes": args.frame_bytes,
-                       "selectivity": st["rows_out"] / args.rows, "lz4_ratio": st["raw_bytes"] / max(1, st["wire_bytes"]),
-                       "input_bytes_per_row": in_bytes / args.rows, "block_bytes_per_kept_row": st["raw_bytes"] / max(1, st["rows_out"]),
-                       "l2": "inputs larger than L2 (%.0f MB per step > 126 MB)" % (in_bytes / 1e6),
-                       "parallelism": f"dp{world} (one batch stream per GPU, same seeded batch on every rank, no collective)"},
+            "config": bench_config(args, len(schema)),
+            "workload_stats": {"selectivity": st["rows_out"] / args.rows, "lz4_ratio": st["raw_bytes"] / max(1, st["wire_bytes"]),
+                               "lz4_ratio_blocks_only": st["raw_bytes"] / max(1, st["wire_bytes"] - 25 * ((st["raw_bytes"] + args.frame_bytes - 1) // args.frame_bytes)),
+                               "input_bytes_per_row": in_bytes / args.rows, "block_bytes_per_kept_row": st["raw_bytes"] / max(1, st["rows_out"]),
+                               "l2": "inputs larger than L2 (%.0f MB per step > 126 MB)" % (in_bytes / 1e6),
+                               "parallelism": f"dp{world} (one batch stream per GPU, its own seeded batch on every rank, no collective)", "rank": 0},
             "clocks": sampler.result(),
             "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "pipelines": P, "timing": "host wall clock over synchronous calls"},
@@ -430,7 +502,7 @@ def main():
                          "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(lz_bytes), "kernel_ms": lz_ms,
                          "kernel_share_of_step": lz_ms / step_ms if step_ms else None,
-                         "kernel_share_basis": "sum of the per-kernel CUDA-event times (as in the serialised ncu launch list); k_frame_seal and k_wire_gather overlap the next step on side streams, so that sum exceeds ms_per_step",
+                         "kernel_share_basis": "sum of the per-kernel CUDA-event times (as in the serialised ncu launch list); k_frame_seal overlaps the next step on a side stream, so that sum exceeds ms_per_step",
                          "all_kernels_ms": {n: round(v, 4) for n, v in sorted(kernel_avg.items())}},
         }
         if world == 1 and not args.no_extra:

@@ -145,6 +145,10 @@ typedef struct tf_batch {
 /* number_to_float: a number literal inside an `any` value whose float64 rounding the device cannot decide (hex / underscored /
  * > 19 digit literals with an open Eisel-Lemire result); the shim applies the Go transformer to that row */
 #define TF_ROWERR_N2F_HOST 52
+#define TF_ROWERR_STRICT_CAST  57 /* strictify.go:46-157: the value cannot be cast to the column type (a negative into an unsigned column); term = column */
+#define TF_ROWERR_STRICT_RANGE 58 /* strictify.go:159-181 StrictifyRangeError; term = column */
+#define TF_ROWERR_SINK_KIND_HOST 54 /* tfgpu_push_encode*: an UPDATE / DELETE row reached a sink or serializer wire format; the device encodes INSERT rows only
+                                     (sink_table.go:296-305, marshal.go:92-95, json_serializer.go:17-20) — the shim routes the row through the Go sink */
 #define TF_ROWERR_DBZ_EMIT_HOST 53 /* tfgpu_emit_debezium: update / delete rows need ChangeItem.OldKeys — the shim emits them with the Go emitter */
 
 /* serializers: a value encoding/json refuses (NaN / Inf float, time.Time with a year outside [0,9999]); the reference

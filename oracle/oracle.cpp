@@ -9,6 +9,7 @@
 #include "csv_oracle.hpp"
 #include "json_oracle.hpp"
 #include "debezium_oracle.hpp"
+#include "cast_oracle.hpp"
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -575,6 +576,16 @@ uint32_t crc32_ieee(const uint8_t* p, size_t n) {            // hash/crc32 IEEE:
 }
 thread_local uint32_t g_part_id = 0; thread_local bool g_has_part = false;     // PartID the last sharder step gave the current row
 // Applies the transformer steps to row r (boxed in `row`); returns false when the row is dropped or errored.
+// Sink and serializer wire formats take INSERT rows only on the device path (sink_table.go:296-305 refuses the others on non-updatable
+// tables, marshal.go:92-95 and the queue / batch serializers need OldKeys for them): an update / delete row that survives the chain is a
+// row error (TF_ROWERR_SINK_KIND_HOST, term 0xff: not raised by a transformer) that the shim routes through the Go sink.
+static bool sink_refuses_kind(const tf_batch* in, uint64_t r, tf_rowerr* errs, uint64_t& ne) {
+    const int kind = in->kinds ? in->kinds[r] : TF_KIND_INSERT;
+    if (kind != TF_KIND_UPDATE && kind != TF_KIND_DELETE) return false;
+    errs[ne++] = tf_rowerr{(uint32_t)r, TF_ROWERR_SINK_KIND_HOST, 0xff};
+    return true;
+}
+
 bool apply_steps(const tf_batch* in, uint64_t r, const orc_step* steps, int nsteps, std::vector<Boxed>& row, std::vector<int32_t>& cur_type,
                  tf_rowerr* errs, uint64_t& ne) {
     const uint32_t nc = in->ncols;
@@ -682,6 +693,7 @@ extern "C" int orc_push_encode(const tf_batch* in, const orc_colschema* schema, 
         for (uint32_t k = 0; k < no; k++) base[k] = ch_base_type(out_type[out_cols[k]]);
         for (uint64_t r = 0; r < in->nrows; r++) {
             if (!apply_steps(in, r, steps, nsteps, row, cur_type, errs, ne)) continue;
+            if (sink_refuses_kind(in, r, errs, ne)) continue;
             text += '{'; bool has = false;
             for (uint32_t k = 0; k < no; k++) {
                 const orc_val& v = row[out_cols[k]].v;
@@ -707,6 +719,7 @@ extern "C" int orc_push_encode(const tf_batch* in, const orc_colschema* schema, 
         std::string text;
         for (uint64_t r = 0; r < in->nrows; r++) {
             if (!apply_steps(in, r, steps, nsteps, row, cur_type, errs, ne)) continue;
+            if (sink_refuses_kind(in, r, errs, ne)) continue;
             if (csv) {
                 for (uint32_t k = 0; k < no; k++) { if (k) text += ','; csv_write_field(text, ser_csv_cell(row[out_cols[k]].v, out_type[out_cols[k]])); }
                 text += '\n';
@@ -732,6 +745,7 @@ extern "C" int orc_push_encode(const tf_batch* in, const orc_colschema* schema, 
     }
     for (uint64_t r = 0; r < in->nrows; r++) {
         if (!apply_steps(in, r, steps, nsteps, row, cur_type, errs, ne)) continue;
+        if (sink_refuses_kind(in, r, errs, ne)) continue;
         // sink: restoreVals sink_table.go:698-704 + driver append
         for (uint32_t k = 0; k < no; k++) if (!append_value(cbs[k], row[out_cols[k]].v)) return TF_E_FATAL_UNSUPPORTED;
         kept++;
@@ -1147,3 +1161,71 @@ int orc_ch_decode_frames(const uint8_t* wire, uint64_t n, orc_buf* raw, uint64_t
 }
 
 }  // extern "C"
+
+
+// ---------------------------------------------------------------- typesystem casts over boxed Go values (cast_oracle.hpp), text interface for the tests
+namespace {
+bool goval_from_text(const char* go, const char* v, uint64_t vlen, gocast::GoVal& out) {
+    using namespace gocast;
+    const std::string t = go, s(v, vlen);
+    out = GoVal();
+    if (t == "nil") return true;
+    if (t == "bool") { out.k = BOOL; out.i = s == "true"; return true; }
+    if (t.rfind("int", 0) == 0) { out.k = INT; out.bits = t.size() > 3 ? std::atoi(t.c_str() + 3) : 0; out.i = (int64_t)std::strtoll(s.c_str(), nullptr, 10); return true; }
+    if (t.rfind("uint", 0) == 0) { out.k = UINT; out.bits = t.size() > 4 ? std::atoi(t.c_str() + 4) : 0; out.u = (uint64_t)std::strtoull(s.c_str(), nullptr, 10); return true; }
+    if (t == "float32") { out.k = F32; out.f = (double)(float)std::strtod(s.c_str(), nullptr); return true; }
+    if (t == "float64") { out.k = F64; out.f = std::strtod(s.c_str(), nullptr); return true; }
+    if (t == "string") { out.k = STRING; out.s = s; return true; }
+    if (t == "[]byte") { out.k = BYTES; out.s = s; return true; }
+    if (t == "json.Number") { out.k = JSONNUM; out.s = s; return true; }
+    if (t == "map") { out.k = MAP; out.s = s; return true; }
+    if (t == "time.Duration") { out.k = DURATION; out.i = (int64_t)std::strtoll(s.c_str(), nullptr, 10); return true; }
+    if (t == "time.Time") { const size_t d = s.find('.'); out.k = TIME; out.i = (int64_t)std::strtoll(s.substr(0, d).c_str(), nullptr, 10); out.nsec = d == std::string::npos ? 0 : (uint32_t)std::strtoul(s.c_str() + d + 1, nullptr, 10); return true; }
+    return false;
+}
+void goval_to_text(const gocast::GoVal& v, std::string& go, std::string& txt) {
+    using namespace gocast;
+    char b[64];
+    switch (v.k) {
+    case NIL: go = "nil"; txt = ""; break;
+    case BOOL: go = "bool"; txt = v.i ? "true" : "false"; break;
+    case INT: go = "int" + (v.bits ? std::to_string(v.bits) : std::string()); txt = std::to_string(v.i); break;
+    case UINT: go = "uint" + (v.bits ? std::to_string(v.bits) : std::string()); txt = std::to_string(v.u); break;
+    case F32: go = "float32"; std::snprintf(b, sizeof b, "%.9g", v.f); txt = b; break;
+    case F64: go = "float64"; std::snprintf(b, sizeof b, "%.17g", v.f); txt = b; break;
+    case STRING: go = "string"; txt = v.s; break;
+    case BYTES: go = "[]byte"; txt = v.s; break;
+    case JSONNUM: go = "json.Number"; txt = v.s; break;
+    case MAP: go = "map"; txt = v.s; break;
+    case DURATION: go = "time.Duration"; txt = std::to_string(v.i); break;
+    case TIME: go = "time.Time"; std::snprintf(b, sizeof b, "%lld.%09u", (long long)v.i, v.nsec); txt = b; break;
+    }
+}
+int put_out(const std::string& go, const std::string& txt, char* out_go, int go_cap, char* out_v, uint64_t v_cap, uint64_t* out_vlen) {
+    if ((int)go.size() + 1 > go_cap || txt.size() > v_cap) return -1;
+    std::memcpy(out_go, go.c_str(), go.size() + 1); std::memcpy(out_v, txt.data(), txt.size()); *out_vlen = txt.size(); return 0;
+}
+}  // namespace
+
+extern "C" int orc_strictify_value(const char* go, const char* v, uint64_t vlen, int32_t tf, char* out_go, int go_cap, char* out_v, uint64_t v_cap, uint64_t* out_vlen) {
+    gocast::GoVal in, out; if (!goval_from_text(go, v, vlen, in)) return -1;
+    const int rc = gocast::strictify_value(in, tf, out);
+    std::string g, t; goval_to_text(out, g, t);
+    if (put_out(g, t, out_go, go_cap, out_v, v_cap, out_vlen)) return -1;
+    return rc;
+}
+extern "C" int orc_restore_value(const char* go, const char* v, uint64_t vlen, const char* data_type, char* out_go, int go_cap, char* out_v, uint64_t v_cap, uint64_t* out_vlen) {
+    gocast::GoVal in, out; if (!goval_from_text(go, v, vlen, in)) return -1;
+    const int rc = gocast::restore_value(in, data_type, out);
+    std::string g, t; goval_to_text(out, g, t);
+    if (put_out(g, t, out_go, go_cap, out_v, v_cap, out_vlen)) return -1;
+    return rc;
+}
+/* csv.Splitter: row_ends[k] = end offset of the k-th complete row; returns the row count (what follows the last end is the io.EOF remainder) */
+extern "C" uint64_t orc_csv_split_rows(const uint8_t* p, uint64_t n, uint64_t* row_ends, uint64_t cap) {
+    std::vector<std::string> rows; std::string rest;
+    gocast::csv_split_rows(std::string((const char*)p, n), rows, rest);
+    uint64_t pos = 0;
+    for (size_t k = 0; k < rows.size() && k < cap; k++) { pos += rows[k].size(); row_ends[k] = pos; }
+    return rows.size();
+}

@@ -91,6 +91,12 @@ int64_t  orc_lz4_decompress(const uint8_t* src, uint64_t n, uint8_t* dst, uint64
 /* matchValue: returns 0 ok (*matched set), else TF_ROWERR_* */
 int  orc_match_value(const orc_val* v, const orc_term* t, int* matched);
 
+/* typesystem casts over one boxed Go value, values as (Go type name, text) pairs — see tests/golden/cast_goldens.json.
+ * rc: 0 ok, 1 cast error, 2 StrictifyRangeError, 3 the reference panics, 4 outside this restatement (dateparse / StringToDate tail), -1 bad call */
+int  orc_strictify_value(const char* go, const char* v, uint64_t vlen, int32_t tf, char* out_go, int go_cap, char* out_v, uint64_t v_cap, uint64_t* out_vlen);   /* strictify.go:46-157 */
+int  orc_restore_value(const char* go, const char* v, uint64_t vlen, const char* data_type, char* out_go, int go_cap, char* out_v, uint64_t v_cap, uint64_t* out_vlen);   /* restore.go:20-223 */
+uint64_t orc_csv_split_rows(const uint8_t* p, uint64_t n, uint64_t* row_ends, uint64_t cap);   /* splitter.go:38-85 */
+
 /* ---- batch entry points ---- */
 /* ClickHouse column type the sink DDL gives this column: sink_table.go:196-208 + columntypes/types.go:210-248 */
 int  orc_ch_type(const orc_colschema* c, char* dst, int cap);

@@ -1069,3 +1069,37 @@ def debezium_split(data: bytes, key_sizes, row_sizes):
     for k, r in zip(key_sizes, row_sizes):
         out.append((data[at:at + int(k)], data[at + int(k):at + int(r)])); at += int(r)
     return out
+
+
+# ---------------------------------------------------------------- typesystem casts over boxed Go values (cast_oracle.hpp)
+def _goval_call(fn, go: str, v, third):
+    L = lib()
+    raw = bytes.fromhex(v) if go == "[]byte" else (v.encode("utf-8") if isinstance(v, str) else bytes(v))
+    og = C.create_string_buffer(32); ov = C.create_string_buffer(max(4096, 4 * len(raw) + 64)); on = C.c_uint64()
+    f = getattr(L, fn); f.restype = C.c_int
+    f.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, (C.c_int32 if fn == "orc_strictify_value" else C.c_char_p), C.c_char_p, C.c_int, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    rc = f(go.encode(), raw, len(raw), third, og, 32, ov, len(ov), C.byref(on))
+    g = og.value.decode(); val = ov.raw[:on.value]
+    return rc, {"go": g, "v": val.hex() if g == "[]byte" else val.decode("utf-8")}
+
+
+def strictify_value(go: str, v, tf: int):
+    """strictify.strictifyValue over one boxed Go value: (rc, {"go", "v"}); rc 0 ok, 1 cast error, 2 range error."""
+    return _goval_call("orc_strictify_value", go, v, tf)
+
+
+def restore_value(go: str, v, data_type: str):
+    """abstract.Restore over one boxed Go value."""
+    return _goval_call("orc_restore_value", go, v, data_type.encode())
+
+
+def csv_split_rows(data: bytes):
+    """csv.Splitter.ConsumeRow until io.EOF: (rows, remainder written by the call that returned io.EOF)."""
+    L = lib(); L.orc_csv_split_rows.restype = C.c_uint64
+    L.orc_csv_split_rows.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint64]
+    ends = (C.c_uint64 * (len(data) + 1))()
+    n = L.orc_csv_split_rows(data, len(data), ends, len(data) + 1)
+    rows, pos = [], 0
+    for k in range(n):
+        rows.append(data[pos:ends[k]]); pos = ends[k]
+    return rows, data[pos:]

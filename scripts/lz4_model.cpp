@@ -16,7 +16,7 @@ struct Cfg {
     uint32_t F = 30720, SEG = 60, ROUND = 2048, HASH_BITS = 12;
     int stride = 2;          // probe every stride-th position (inserts happen at every position)
     bool second_probe = true, period8 = true, merge = true, backext = true;
-    int winner = 2; bool near_first = false; int ins_stride = 1; bool twoslot = false;         // 0 lowest position wins an insert race, 1 highest, 2 random
+    int winner = 2; bool near_first = false; int ins_stride = 1; bool twoslot = false; bool recent_first = false;         // 0 lowest position wins an insert race, 1 highest, 2 random
 };
 
 struct Seq { uint32_t p, ml, off; };
@@ -56,7 +56,8 @@ static std::vector<uint8_t> compress_frame(const uint8_t* d, uint32_t len, const
         for (uint32_t p : order) if (p + 4 <= len && p % c.ins_stride == 0) table[idx[p - r0]] = tag[p - r0] | p;
         if (c.second_probe)
             for (uint32_t p = r0; p < r1; p++) {
-                if (p % c.stride || p + 12 > len || cand[p] != 0xffffffffu) continue;
+                if (p % c.stride || p + 12 > len) continue;
+                if (cand[p] != 0xffffffffu && !(c.recent_first && cand[p] + 8 < p)) continue;     // recent_first: a near candidate (4 / 8 back) stays
                 const uint32_t e = table[idx[p - r0]];
                 if ((e & 0xffff0000u) == tag[p - r0] && (e & 0xffffu) < p) cand[p] = e & 0xffffu;
             }
@@ -227,7 +228,7 @@ int main(int argc, char** argv) {
         std::string kv = argv[i]; const size_t e = kv.find('='); const std::string k = kv.substr(0, e); const int v = atoi(kv.c_str() + e + 1);
         if (k == "F") c.F = v; else if (k == "SEG") c.SEG = v; else if (k == "ROUND") c.ROUND = v; else if (k == "HB") c.HASH_BITS = v;
         else if (k == "stride") c.stride = v; else if (k == "probe2") c.second_probe = v; else if (k == "p8") c.period8 = v;
-        else if (k == "merge") c.merge = v; else if (k == "back") c.backext = v; else if (k == "winner") c.winner = v; else if (k == "step") step = v; else if (k == "near") c.near_first = v; else if (k == "ins") c.ins_stride = v; else if (k == "two") c.twoslot = v;
+        else if (k == "merge") c.merge = v; else if (k == "back") c.backext = v; else if (k == "winner") c.winner = v; else if (k == "step") step = v; else if (k == "near") c.near_first = v; else if (k == "ins") c.ins_stride = v; else if (k == "two") c.twoslot = v; else if (k == "recent") c.recent_first = v;
     }
     typedef int (*comp_t)(const char*, char*, int, int);
     comp_t stock = nullptr;
@@ -240,7 +241,7 @@ int main(int argc, char** argv) {
         const std::vector<uint8_t> o = compress_frame(blk.data() + pos, len, c, rng, &nseq);
         if (!decode(o, dec, len) || memcmp(dec.data(), blk.data() + pos, len)) { fprintf(stderr, "frame at %zu does not round-trip\n", pos); return 1; }
         in_b += len; out_b += o.size() + 25; frames++; if (getenv("PERFRAME")) printf("FR %zu %zu\n", pos, o.size());
-        if (stock) stock_b += stock((const char*)blk.data() + pos, tmp.data(), (int)len, (int)tmp.size()) + 25;
+        if (stock) { const int sb = stock((const char*)blk.data() + pos, tmp.data(), (int)len, (int)tmp.size()); stock_b += sb + 25; if (getenv("PERFRAME")) printf("ST %zu %d\n", pos, sb); }
     }
     printf("frames %llu in %llu out %llu ratio %.4f  stock %.4f  seq/frame %.1f\n", (unsigned long long)frames, (unsigned long long)in_b,
            (unsigned long long)out_b, (double)in_b / out_b, stock_b ? (double)in_b / stock_b : 0.0, (double)nseq / frames);

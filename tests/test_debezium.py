@@ -228,3 +228,29 @@ def test_device_debezium_fuzz(eng, po):
     for seed in (1, 2):
         schema_text, msgs = _dbz_fuzz_msgs(8000, seed)
         _dbz_cmp(eng, po, schema_text, msgs, _allow_host=40)
+
+
+@pytest.mark.gpu
+def test_device_debezium_filter_cast_native_fused(eng, po):
+    """BASELINE configs[3] (Debezium CDC -> SQL-predicate filter -> typesystem cast), fused on the device and taken to the ClickHouse
+    native block (+ LZ4 frames): schema-registry framed envelopes with a 12-field payload -> tfgpu_parse_debezium with a plan
+    (parser.go:34-137 -> filter_rows.go:99-130 -> restore.go / columntypes) vs oracle(parse) -> oracle(push_encode)."""
+    from transferia_b200 import engine, workload
+    data, ends, schema_text, table = workload.make_debezium_messages(30_000)
+    schema = engine.debezium_table_schema(schema_text)
+    assert len(schema) == 12
+    trs = workload.debezium_transformers()
+    pid = eng.plan(table[0], table[1], schema, trs, {"type": "clickhouse"})
+    kw = dict(schema_registry=True, schema_id=7)
+    ref, kinds, tx, lsn, ct, rm, rerr, _ = po.debezium_parse(data, ends.tolist(), schema_text, use_sr=True, schema_id=7)
+    assert rerr == [] and ref.nrows == len(ends) and 0 < int((kinds != 0).sum()) < 0.05 * len(ends)
+    refk = abi.Batch(ref.nrows, ref.columns, np.asarray(kinds, dtype=np.uint8))
+    want = po.push_encode(refk, po.build_plan(table[0], table[1], schema, trs), abi.TF_WIRE_CH_NATIVE)
+    assert 0 < want.rows_out < ref.nrows and len(want.errors) == int((kinds != 0).sum())          # update / delete: "Found non-supported kind"
+    res, meta = eng.parse_debezium(pid, data, ends, schema_text, wire_fmt=abi.TF_WIRE_CH_NATIVE, **kw)
+    assert res.rows_in == len(ends) and res.rows_out == want.rows_out and res.errors == want.errors
+    assert res.wire == want.raw
+    assert list(meta["kinds"]) == list(kinds) and list(meta["lsn"]) == list(lsn)
+    res_lz, _ = eng.parse_debezium(pid, data, ends, schema_text, wire_fmt=abi.TF_WIRE_CH_NATIVE_LZ4, **kw)
+    raw, nf = po.ch_decode_frames(res_lz.wire)
+    assert raw == want.raw and nf == res_lz.n_frames

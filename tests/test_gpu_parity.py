@@ -164,6 +164,26 @@ def test_filter_rows_semantics_matrix(eng, po):
     assert got.rows_out == 0 and len(got.errors) == batch.nrows and got.errors[0][1] == abi.TF_ROWERR_FILTER_TYPEPAIR
 
 
+def test_update_delete_rows_refused_by_sink_formats(eng, po):
+    """A sink / serializer wire format takes INSERT rows only on the device: update / delete rows that survive the chain come back as
+    row errors (TF_ROWERR_SINK_KIND_HOST) instead of being encoded as live rows (sink_table.go:296-305, marshal.go:92-95)."""
+    batch, schema = all_types_batch(700, seed=31)
+    kinds = np.zeros(batch.nrows, dtype=np.uint8); kinds[::9] = abi.TF_KIND_UPDATE; kinds[4::13] = abi.TF_KIND_DELETE
+    b2 = abi.Batch(batch.nrows, batch.columns, kinds)
+    n_bad = int((kinds != 0).sum())
+    got, ref = check(eng, po, b2, schema, [])                                  # native + LZ4, no transformer at all
+    assert got.rows_out == batch.nrows - n_bad and len(got.errors) == n_bad and {c for _, c, _ in got.errors} == {abi.TF_ROWERR_SINK_KIND_HOST}
+    # skip_events drops them first: no error
+    got, ref = check(eng, po, b2, schema, [{"skip_events": {"events": ["update", "delete"]}}], lz=False)
+    assert got.errors == [] and got.rows_out == batch.nrows - n_bad
+    # JSONEachRow and the batch serializer
+    pid = eng.plan("db", "t", schema, [], {"type": "clickhouse"})
+    plan = po.build_plan("db", "t", schema, [])
+    for fmt in (abi.TF_WIRE_CH_JSONEACHROW, abi.TF_WIRE_SER_JSON):
+        g = eng.push_encode(pid, b2, fmt); r = po.push_encode(b2, plan, fmt)
+        assert g.wire == r.wire and g.errors == r.errors and sum(1 for _, c, _ in g.errors if c == abi.TF_ROWERR_SINK_KIND_HOST) == n_bad
+
+
 def test_skip_events_filter_columns_rename_chain(eng, po):
     """skip_events.go:52-62, filter_columns_transformer.go:228-236, rename.go:46-67 chained with filter_rows / mask_field."""
     batch, schema = all_types_batch(2500, seed=13)
@@ -494,3 +514,101 @@ def test_number_to_float(eng, po):
     a = ref.columns[1]; cell = lambda r: bytes(a.heap[a.offsets[r]:a.offsets[r + 1]])
     assert cell(0) == b'{"a":1,"b":[1.5,2000,-0,1e+21,1e-7,0.000001,1.2345678901234568e+29],"s":"12 \\" 3e4","n":null}'
     assert cell(1) == b"17" and cell(2) == b"1e400" and cell(3) == b"-100" and cell(4) == b'"just a string 5"' and cell(9) == b"3.141592653589793"
+
+
+def test_device_strictify_loose_value_types(eng, po):
+    """Strictify (strictify.go:18-181) as a pre-pass of the chain: values that arrive in another fixed-width type than the column's
+    schema type are cast like spf13/cast does and range-checked; a row that fails is a row error on its FIRST failing column
+    (TF_ROWERR_STRICT_RANGE / _CAST), the rest comes out in the schema's types. Oracle: the restatement pinned by strictify_test.go."""
+    rng = np.random.default_rng(77); n = 600
+    def pick(lo, hi, extra): return np.concatenate([rng.integers(lo, hi, n - len(extra)), np.array(extra, dtype=np.int64)]).astype(np.int64)
+    spec = [   # (column, schema type, physical type the values arrive in, values)
+        ("i8", "int8", abi.TF_INT64, pick(-128, 128, [127, 128, -128, -129, 1 << 40])),
+        ("u8", "uint8", abi.TF_INT64, pick(0, 256, [255, 256, -1, 0])),
+        ("i16", "int16", abi.TF_DOUBLE, np.concatenate([rng.uniform(-32768, 32767, n - 6), [32767.9, 32768.0, -32768.5, -32769.0, 1e300, float("nan")]])),
+        ("u16", "uint16", abi.TF_UINT64, np.concatenate([rng.integers(0, 65536, n - 3), [65535, 65536, 1 << 63]]).astype(np.uint64)),
+        ("i32", "int32", abi.TF_INT64, pick(-(1 << 31), 1 << 31, [(1 << 31) - 1, 1 << 31, -(1 << 31) - 1])),
+        ("u32", "uint32", abi.TF_FLOAT, np.concatenate([rng.uniform(0, 4e9, n - 4), [4294967040.0, 4294967296.0, -0.5, -1.0]]).astype(np.float32)),
+        ("i64", "int64", abi.TF_UINT64, np.concatenate([rng.integers(0, 1 << 62, n - 2), [(1 << 64) - 1, 1 << 63]]).astype(np.uint64)),
+        ("u64", "uint64", abi.TF_INT64, pick(0, 1 << 62, [-1, -(1 << 63), (1 << 63) - 1])),
+        ("f32", "float", abi.TF_INT64, pick(-(1 << 62), 1 << 62, [16777217, (1 << 53) + 1, -16777219])),
+        ("f64", "double", abi.TF_INT64, pick(-(1 << 62), 1 << 62, [(1 << 53) + 1, -(1 << 60) - 1])),
+        ("b", "boolean", abi.TF_INT32, rng.integers(-1, 2, n).astype(np.int64)),
+        ("ts", "timestamp", abi.TF_INT64, pick(0, 1 << 31, [0, -5])),
+        ("same", "int32", abi.TF_INT32, rng.integers(-1000, 1000, n)),
+    ]
+    go = {abi.TF_INT64: "int64", abi.TF_UINT64: "uint64", abi.TF_DOUBLE: "float64", abi.TF_FLOAT: "float32", abi.TF_INT32: "int32"}
+    schema = [{"name": c, "type": t} for c, t, _, _ in spec]
+    nulls = rng.random(n) < 0.1
+    cols = [abi.fixed_to_column(ptf, vals, nulls if c == "i8" else None) for c, t, ptf, vals in spec]
+    batch = abi.Batch(n, cols)
+    pid = eng.plan("db", "t", schema, [])
+    got, gerr = eng.push_columns(pid, batch)
+    # the oracle, cell by cell
+    want_err, keep, outv = [], [], [[] for _ in spec]
+    for r in range(n):
+        row, bad = [], None
+        for k, (c, t, ptf, vals) in enumerate(spec):
+            if c == "i8" and nulls[r]: row.append(0); continue
+            v = cols[k].values[r]
+            txt = repr(float(v)) if ptf in (abi.TF_DOUBLE, abi.TF_FLOAT) else str(int(v))
+            rc, out = po.strictify_value(go[ptf], txt, abi.YT_NAME_TO_TF[t])
+            assert rc in (0, 1, 2), (c, txt, rc)
+            if rc and bad is None: bad = (r, 57 if rc == 1 else 58, k)
+            if out["go"] == "time.Time": row.append(int(out["v"].split(".")[0]))
+            elif out["go"] == "json.Number": row.append(float(out["v"]))
+            elif out["go"] == "bool": row.append(1 if out["v"] == "true" else 0)
+            elif out["go"] in ("float32",): row.append(float(out["v"]))
+            else: row.append(int(out["v"]) if rc == 0 else 0)
+        if bad: want_err.append(bad)
+        else:
+            keep.append(r)
+            for k in range(len(spec)): outv[k].append(row[k])
+    assert gerr == want_err and 20 < len(want_err) < n // 4
+    assert got.nrows == len(keep)
+    for k, (c, t, _, _) in enumerate(spec):
+        tf = abi.YT_NAME_TO_TF[t]
+        assert got.columns[k].type == tf, c
+        want = np.asarray(outv[k], dtype=abi.FIXED_DTYPE[tf])
+        have = np.asarray(got.columns[k].values)[:len(keep)]
+        if c == "i8":      # nil rows keep an unspecified slot
+            m = ~nulls[keep]; assert np.array_equal(have[m], want[m]), c
+        else:
+            assert np.array_equal(have.view(np.uint8), want.view(np.uint8)), c
+    # a pair the device does not strictify is refused up front, not converted approximately
+    bad_schema = [{"name": "x", "type": "double"}]
+    with pytest.raises(engine.EngineError):
+        eng.push_columns(eng.plan("db", "t2", bad_schema, []), abi.Batch(2, [abi.fixed_to_column(abi.TF_FLOAT, [0.1, 0.2])]))
+
+
+def test_round_robin_dispatcher_over_real_engines(po):
+    """one host process, one engine per GPU (two engines on the same GPU when the box has one), whole batches dealt
+    round-robin by `dispatch.RoundRobinDispatcher`; results come back in submission order and every one decodes to the oracle's block."""
+    import torch
+    from transferia_b200 import dispatch
+    ndev = torch.cuda.device_count()
+    devs = list(range(ndev)) if ndev > 1 else [0, 0]
+    engs = [engine.Engine(d) for d in devs]
+    try:
+        batches = []
+        for i in range(7):
+            b, schema = workload.make_hits_batch(3000 + 500 * i, seed=100 + i)
+            batches.append(b)
+        trs = workload.headline_transformers(workload.counterid_threshold(batches[0], schema))
+        pids = [e.plan("public", "hits", schema, trs, {"type": "clickhouse"}) for e in engs]
+        plan = po.build_plan("public", "hits", schema, trs)
+        workers = [(lambda b, e=e, p=p: e.push_encode(p, b, LZ)) for e, p in zip(engs, pids)]
+        d = dispatch.RoundRobinDispatcher(workers)
+        try:
+            results = list(d.run(iter(batches)))
+        finally:
+            d.close()
+        assert len(results) == len(batches)
+        for b, r in zip(batches, results):                      # submission order is preserved
+            want = po.push_encode(b, plan, RAW, engs[0].frame_bytes)
+            assert r.rows_in == b.nrows and r.rows_out == want.rows_out
+            raw, nf = decode_with_liblz4(r.wire, po)
+            assert raw == want.raw
+    finally:
+        for e in engs:
+            e.close()

@@ -80,8 +80,10 @@ def make_row_meta(id=None, lsn=None, commit_time=None, txid_offsets=None, txid_h
     return m, (id, lsn, commit_time, txid_offsets, txid_heap)
 
 
+TF_WIRE_SER_JSON, TF_WIRE_SER_CSV = 4, 5
 TF_WIRE_DEBEZIUM = 6
 TF_ROWERR_DBZ_EMIT_HOST = 53
+TF_ROWERR_SINK_KIND_HOST = 54
 TF_ROWERR_DBZ_UNPARSED, TF_ROWERR_DBZ_HOST, TF_ROWERR_DBZ_OTHER_SCHEMA, TF_ROWERR_DBZ_OTHER_TABLE = 48, 49, 50, 51
 TF_ROWERR_JSON_PARSE, TF_ROWERR_JSON_SKIP, TF_ROWERR_JSON_NIL_REQUIRED, TF_ROWERR_JSON_PARSEVAL, TF_ROWERR_JSON_HOST = 32, 33, 34, 35, 36
 

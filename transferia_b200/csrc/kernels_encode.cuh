@@ -32,6 +32,65 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total,
     return res;
 }
 
+// ------------------------------------------------------------------ Strictify over typed columns
+// strictify.Strictify / strictifyValue / toSignedInt / toUnsignedInt (pkg/abstract/changeitem/strictify/strictify.go:18-181) for values
+// that arrive in another fixed-width type than the column's schema type (a Go int64 in an int32 column, a float64 in an int8 column ...):
+// the spf13/cast conversion (Go conversion semantics, negatives refused by the unsigned targets), then the range check on
+// cast.ToInt64 / cast.ToUint64 of the value. One thread per row walks the loose columns in schema order, so the row's error is the first
+// failing column's, like Strictify's.
+struct StrictCol { const uint8_t* src; uint8_t* dst; const uint8_t* validity; int32_t src_tf, dst_tf, col, pad; };
+struct StrictArgs { const StrictCol* cols; int ncols; uint64_t nrows; uint8_t* err; uint8_t* term; };
+__device__ __forceinline__ int64_t go_f2i64(double f) { return (f >= -9223372036854775808.0 && f < 9223372036854775808.0) ? (int64_t)f : INT64_MIN; }   // CVTTSD2SQ
+__device__ __forceinline__ uint64_t go_f2u64(double f) { return f < 9223372036854775808.0 ? (uint64_t)go_f2i64(f) : ((uint64_t)go_f2i64(f - 9223372036854775808.0) ^ 0x8000000000000000ull); }
+#ifdef TF_KERNELS_ENCODE
+__global__ void __launch_bounds__(256) k_strictify(StrictArgs a) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.nrows) return;
+    int err = 0, term = 0xff;
+    for (int k = 0; k < a.ncols; k++) {
+        const StrictCol c = a.cols[k];
+        if (c.validity && !((c.validity[r >> 3] >> (r & 7)) & 1)) continue;            // nil stays nil (:55-57); the slot keeps whatever it held
+        // the value as the three views spf13/cast takes of it
+        int cls; int64_t si = 0; uint64_t ui = 0; double f = 0;                          // cls: 0 signed, 1 unsigned, 2 float, 3 bool
+        switch (c.src_tf) {
+        case TF_INT8: cls = 0; si = ((const int8_t*)c.src)[r]; break;
+        case TF_INT16: cls = 0; si = ((const int16_t*)c.src)[r]; break;
+        case TF_INT32: cls = 0; si = ((const int32_t*)c.src)[r]; break;
+        case TF_INT64: cls = 0; si = ((const int64_t*)c.src)[r]; break;
+        case TF_UINT8: cls = 1; ui = c.src[r]; break;
+        case TF_UINT16: cls = 1; ui = ((const uint16_t*)c.src)[r]; break;
+        case TF_UINT32: cls = 1; ui = ((const uint32_t*)c.src)[r]; break;
+        case TF_UINT64: cls = 1; ui = ((const uint64_t*)c.src)[r]; break;
+        case TF_FLOAT: cls = 2; f = ((const float*)c.src)[r]; break;
+        case TF_DOUBLE: cls = 2; f = ((const double*)c.src)[r]; break;
+        default: cls = 3; si = c.src[r] ? 1 : 0; break;                                   // TF_BOOLEAN
+        }
+        int e = 0;
+        const int64_t as_i = cls == 0 || cls == 3 ? si : (cls == 1 ? (int64_t)ui : go_f2i64(f));                 // ToInt64E
+        const bool neg = cls == 0 ? si < 0 : (cls == 2 ? f < 0 : false);
+        const uint64_t as_u = cls == 0 || cls == 3 ? (uint64_t)si : (cls == 1 ? ui : go_f2u64(f));               // ToUint64E (negatives refused below)
+        auto sint = [&](int64_t lo, int64_t hi) { if (as_i < lo || as_i > hi) e = TF_ROWERR_STRICT_RANGE; };
+        auto uint_ = [&](uint64_t hi) { if (neg) e = TF_ROWERR_STRICT_CAST; else if (as_u > hi) e = TF_ROWERR_STRICT_RANGE; };
+        switch (c.dst_tf) {
+        case TF_INT8: sint(INT8_MIN, INT8_MAX); ((int8_t*)c.dst)[r] = (int8_t)as_i; break;
+        case TF_INT16: sint(INT16_MIN, INT16_MAX); ((int16_t*)c.dst)[r] = (int16_t)as_i; break;
+        case TF_INT32: sint(INT32_MIN, INT32_MAX); ((int32_t*)c.dst)[r] = (int32_t)as_i; break;
+        case TF_INT64: case TF_INTERVAL: case TF_DATE: case TF_DATETIME: case TF_TIMESTAMP:       // int64 targets: ToInt64E / Duration(v) / time.Unix(v, 0)
+            ((int64_t*)c.dst)[r] = as_i; break;
+        case TF_UINT8: uint_(UINT8_MAX); c.dst[r] = (uint8_t)as_u; break;
+        case TF_UINT16: uint_(UINT16_MAX); ((uint16_t*)c.dst)[r] = (uint16_t)as_u; break;
+        case TF_UINT32: uint_(UINT32_MAX); ((uint32_t*)c.dst)[r] = (uint32_t)as_u; break;
+        case TF_UINT64: uint_(UINT64_MAX); ((uint64_t*)c.dst)[r] = as_u; break;
+        case TF_FLOAT: ((float*)c.dst)[r] = cls == 0 || cls == 3 ? (float)si : (cls == 1 ? (float)ui : (float)f); break;     // ToFloat32E: one Go conversion
+        case TF_DOUBLE: ((double*)c.dst)[r] = cls == 0 ? (double)si : (cls == 1 ? (double)ui : f); break;                    // json.Number of the decimal text: the nearest float64
+        default: c.dst[r] = cls == 2 ? (f != 0) : (cls == 1 ? ui != 0 : si != 0); break;                                     // TF_BOOLEAN: ToBoolE
+        }
+        if (e && !err) { err = e; term = c.col < 0xff ? c.col : 0xfe; }
+    }
+    if (err && !a.err[r]) { a.err[r] = (uint8_t)err; a.term[r] = (uint8_t)term; }
+}
+#endif  // TF_KERNELS_ENCODE
+
 // ------------------------------------------------------------------ filter_rows
 // matchValue (pkg/transformer/registry/filter_rows/filter_rows.go:180-365) for typed columns.
 struct RowVal {
@@ -164,6 +223,8 @@ struct FilterArgs {
     const DTerm* terms; const uint8_t* blob;
     uint8_t* keep; uint8_t* errcode; uint8_t* errstep; uint32_t* blockcnt; DState* st;
     const uint8_t* pre_err;        // optional per-row error already raised upstream (parser): the row is dropped and reported
+    const uint8_t* pre_term;       // optional: the column an upstream error belongs to (Strictify), else the term is 0xff
+    int sink_guard;                // the rows go to a sink / serializer wire format that only takes INSERT rows here: update / delete rows that survive the chain are reported
 };
 
 // FilterRowsTransformer.Apply (filter_rows.go:99-130): one thread per row.
@@ -177,7 +238,7 @@ __global__ void __launch_bounds__(256) k_filter(FilterArgs a) {
     if (r < a.nrows) {
         keep = true; int err = 0, estep = 0;
         const int kind = a.kinds ? a.kinds[r] : TF_KIND_INSERT;
-        if (a.pre_err && a.pre_err[r]) { err = a.pre_err[r]; estep = 0xff; keep = false; }
+        if (a.pre_err && a.pre_err[r]) { err = a.pre_err[r]; estep = a.pre_term ? a.pre_term[r] : 0xff; keep = false; }
         for (int s = 0; s < a.nsteps && keep; s++) {
             const DFilterStep st = a.steps[s];
             if (st.flags & 1) { if ((st.expr_begin >> kind) & 1) keep = false; continue; }            // skip_events.go:52-62
@@ -199,6 +260,7 @@ __global__ void __launch_bounds__(256) k_filter(FilterArgs a) {
             if (err) { estep = st.step_index; keep = false; break; }
             if (!any) keep = false;
         }
+        if (keep && a.sink_guard && (kind == TF_KIND_UPDATE || kind == TF_KIND_DELETE)) { err = TF_ROWERR_SINK_KIND_HOST; estep = 0xff; keep = false; }
         a.keep[r] = keep ? 1 : 0;
         a.errcode[r] = (uint8_t)err; a.errstep[r] = (uint8_t)estep; is_err = err != 0;
     }

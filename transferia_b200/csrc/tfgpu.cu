@@ -70,7 +70,7 @@ struct tfgpu_engine {
     int sm_count = 148;
     std::vector<std::unique_ptr<PlanDev>> plans;
     // arenas
-    DevBuf in_arena, work, raw, slots, wire, csv_text, csv_stage, json_msgs, n2f_stage, n2f_heap, off_scratch;
+    DevBuf in_arena, work, raw, slots, wire, strict_stage, csv_text, csv_stage, json_msgs, n2f_stage, n2f_heap, off_scratch;
     DState* d_state = nullptr; DCol* d_cols = nullptr; size_t d_cols_cap = 0;
     int32_t* d_call_slots = nullptr; ColRegions* d_regions = nullptr; size_t d_call_cap = 0;   // columnar mode, per call
     // pointers into `work` for the last call
@@ -343,11 +343,18 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
     if (lz) e->wire.ensure(sz.wire_bound);
     if (e->d_cols_cap < nc) { if (e->d_cols) CK(cudaFree(e->d_cols)); CK(cudaMalloc(&e->d_cols, sizeof(DCol) * nc)); e->d_cols_cap = nc; }
     // column descriptors
-    std::vector<DCol> hc(nc);
+    std::vector<DCol> hc(nc); std::vector<StrictCol> strict;
     for (size_t c = 0; c < nc; c++) {
         const tf_col& ic = dev_cols[c]; DCol& d = hc[c]; std::memset(&d, 0, sizeof d);
-        if (ic.type != pl.in_schema[c].tf) throw tfplan::FatalError(TF_E_FATAL_ARG, "column " + std::to_string(c) + " type does not match the plan schema");
-        d.type = ic.type; d.out_kind = pd.col_out_kind[c]; d.in_w = in_width(ic.type); d.out_w = pd.col_out_w[c];
+        int ctype = ic.type;
+        if (ic.type != pl.in_schema[c].tf) {        // a loose value type: Strictify it to the column's type first (strictify.go:46-157)
+            const int st = ic.type, dt = pl.in_schema[c].tf;
+            const bool s_num = in_width(st) && st != TF_INTERVAL && st != TF_DATE && st != TF_DATETIME && st != TF_TIMESTAMP;
+            if ((st == TF_UTF8 && dt == TF_BYTES) || (st == TF_BYTES && dt == TF_UTF8)) ctype = dt;      // castx.ToByteSliceE(string) / ToStringE([]byte): the same bytes
+            else if (s_num && in_width(dt) && !(st == TF_FLOAT && dt == TF_DOUBLE) && !(st == TF_BOOLEAN && dt == TF_DOUBLE)) { strict.push_back(StrictCol{(const uint8_t*)ic.values, nullptr, ic.validity, st, dt, (int32_t)c, 0}); ctype = dt; }
+            else throw tfplan::FatalError(TF_E_FATAL_ARG, "column " + std::to_string(c) + ": a " + std::to_string(st) + " value cannot be strictified to the plan's column type on the device");
+        }
+        d.type = ctype; d.out_kind = pd.col_out_kind[c]; d.in_w = in_width(ctype); d.out_w = pd.col_out_w[c];
         if (columnar && d.out_kind == OK_TODT) d.out_w = 8;          // Transformed value is a time.Time: int64 seconds
         else if (columnar && d.out_kind != OK_STR && d.out_kind != OK_MASK && d.out_kind != OK_TOSTR) { d.out_kind = OK_COPY; d.out_w = d.in_w; }   // Transformed values keep their type
         d.nullable = pd.col_nullable[c]; d.str_slot = pd.col_str_slot[c]; d.mask_slot = pd.col_mask_slot[c];
@@ -357,9 +364,25 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
             if (!d.in_w && !d.offsets) throw tfplan::FatalError(TF_E_FATAL_ARG, "column " + std::to_string(c) + ": offsets pointer is NULL");
         }
     }
+    if (!pre_err) e->prof_n = 0;
+    const uint8_t* pre_term = nullptr;
+    if (!strict.empty() && n) {        // Strictify pre-pass: loose fixed-width values -> the schema's type, range / cast failures as row errors
+        size_t sb = 0; auto need3 = [&](size_t b) { size_t at = sb; sb += align_up(b ? b : 1, 256); return at; };
+        const size_t o_desc = need3(strict.size() * sizeof(StrictCol)), o_err = need3(n), o_term = need3(n);
+        std::vector<size_t> o_val(strict.size());
+        for (size_t k = 0; k < strict.size(); k++) o_val[k] = need3((size_t)in_width(strict[k].dst_tf) * n + 16);
+        e->strict_stage.ensure(sb + 256);
+        uint8_t* B = e->strict_stage.p;
+        for (size_t k = 0; k < strict.size(); k++) { strict[k].dst = B + o_val[k]; hc[strict[k].col].values = B + o_val[k]; }
+        CK(cudaMemcpyAsync(B + o_desc, strict.data(), strict.size() * sizeof(StrictCol), cudaMemcpyHostToDevice, s));
+        if (pre_err) CK(cudaMemcpyAsync(B + o_err, pre_err, n, cudaMemcpyDeviceToDevice, s)); else CK(cudaMemsetAsync(B + o_err, 0, n, s));
+        CK(cudaMemsetAsync(B + o_term, 0xff, n, s));
+        StrictArgs sa{(const StrictCol*)(B + o_desc), (int)strict.size(), n, B + o_err, B + o_term};
+        e->prof_begin("k_strictify", s); launch_k_strictify((uint32_t)((n + 255) / 256), 256, 0, s, sa); e->prof_end(s);
+        pre_err = B + o_err; pre_term = B + o_term;
+    }
     CK(cudaMemcpyAsync(e->d_cols, hc.data(), sizeof(DCol) * nc, cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(e->d_state, 0, sizeof(DState), s));
-    if (!pre_err) e->prof_n = 0;
     if (!pl.n2f_cols.empty() && n) {        // number_to_float: rewrite the JSON text of the `any` columns before anything reads them
         const size_t k2 = pl.n2f_cols.size();
         size_t sb = 0; auto need2 = [&](size_t b) { size_t at = sb; sb += align_up(b ? b : 1, 256); return at; };
@@ -384,11 +407,14 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         CK(cudaMemcpyAsync(e->d_cols, hc.data(), sizeof(DCol) * nc, cudaMemcpyHostToDevice, s));
         pre_err = B + o_err;                 // parser errors carried over + N2F_HOST rows
     }
-    const bool has_filter = pd.n_fsteps > 0 || pre_err;
+    // sink / serializer wire formats take INSERT rows only on the device (sink_table.go:296-305 refuses the others on non-updatable
+    // tables, marshal.go:92-95 and the queue serializers need OldKeys): update / delete rows that survive the chain come back as row errors
+    const bool sink_guard = dev_kinds && wire_fmt != TF_WIRE_COLUMNAR_INTERNAL && wire_base != TF_WIRE_DEBEZIUM;
+    const bool has_filter = pd.n_fsteps > 0 || pre_err || sink_guard;
     e->last_nrows = n; e->last_has_filter = has_filter; e->last_wire_fmt = wire_fmt;
     const uint32_t nb = (uint32_t)((n + 255) / 256);
     if (has_filter && n) {
-        FilterArgs fa{e->d_cols, dev_kinds, n, pd.d_fsteps, pd.n_fsteps, pd.d_expr_off, pd.d_terms, pd.d_blob, e->keep, e->errcode, e->errstep, e->blockcnt, e->d_state, pre_err};
+        FilterArgs fa{e->d_cols, dev_kinds, n, pd.d_fsteps, pd.n_fsteps, pd.d_expr_off, pd.d_terms, pd.d_blob, e->keep, e->errcode, e->errstep, e->blockcnt, e->d_state, pre_err, pre_term, sink_guard ? 1 : 0};
         e->prof_begin("k_filter", s); launch_k_filter(nb, 256, 0, s, fa); e->prof_end(s);
         e->prof_begin("k_scan_blockcnt", s); launch_k_scan_blockcnt(1, 1024, 0, s, e->blockcnt, e->blockoff, nb, e->d_state); e->prof_end(s);
         e->prof_begin("k_compact_sel", s); launch_k_compact_sel(nb, 256, 0, s, e->keep, e->blockoff, n, e->sel); e->prof_end(s);
@@ -558,7 +584,7 @@ int tfgpu_engine_destroy(tfgpu_engine* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (auto& p : e->plans) p->consts.release();
-    e->in_arena.release(); e->work.release(); e->raw.release(); e->slots.release(); e->wire.release(); e->csv_text.release(); e->csv_stage.release(); e->json_msgs.release(); e->n2f_stage.release(); e->n2f_heap.release(); e->off_scratch.release(); e->json_sizes.release();
+    e->strict_stage.release(); e->in_arena.release(); e->work.release(); e->raw.release(); e->slots.release(); e->wire.release(); e->csv_text.release(); e->csv_stage.release(); e->json_msgs.release(); e->n2f_stage.release(); e->n2f_heap.release(); e->off_scratch.release(); e->json_sizes.release();
     if (e->d_state) cudaFree(e->d_state);
     if (e->d_cols) cudaFree(e->d_cols);
     if (e->d_call_slots) { cudaFree(e->d_call_slots); cudaFree(e->d_regions); }

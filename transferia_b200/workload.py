@@ -211,3 +211,73 @@ def make_json_lines(nlines: int, seed: int = SEED + 1) -> Tuple[bytes, List[dict
         out.append('{"id":%d,"ts":%d,"user":"%s","url":"https://%s/p/%d?ref=%d","score":%r,"ok":%s,"cnt":%d,"tags":%s%s}'
                    % (ids[i], ts[i], u, hosts[hsel[i]], paths[i], cnt[i], float(score[i]), "true" if okv[i] else "false", cnt[i], t, extra))
     return ("\n".join(out) + "\n").encode("utf-8"), [dict(f) for f in JSON_FIELDS]
+
+
+# ----------------------------------------------------------------------------------------------------------- BASELINE configs[3]
+DBZ_FIELDS = [("id", "int64", False), ("counter", "int32", True), ("region", "int32", True), ("flags", "int16", True), ("dur", "int64", True),
+              ("price", "double", True), ("ok", "boolean", True), ("url", "string", True), ("title", "string", True), ("referer", "string", True),
+              ("ts", "int64", True), ("small", "int8", True)]
+
+
+def debezium_schema_text() -> str:
+    """Kafka Connect schema of the 12-field CDC table (the `schema` member of a Debezium message / what the schema registry holds)."""
+    fl = ",".join('{"type":"%s","optional":%s,"field":"%s"}' % (t, "true" if opt else "false", n) for n, t, opt in DBZ_FIELDS)
+    return ('{"type":"struct","fields":[{"type":"struct","fields":[%s],"optional":true,"field":"before"},'
+            '{"type":"struct","fields":[%s],"optional":true,"field":"after"}]}' % (fl, fl))
+
+
+def make_debezium_messages(nmsgs: int, seed: int = SEED + 3, schema_id: int = 7, dml_frac: float = 0.02):
+    """Debezium CDC envelopes with a 12-field payload, schema-registry framed (0x00 | u32be schema id | payload JSON,
+    pkg/parsers/registry/debezium/engine/parser.go:42-50) so that the schema text travels once, not per message. Mostly inserts / snapshot
+    reads (op c / r) plus a few updates and deletes, which filter_rows rejects per row (filter_rows.go:103-107).
+    Returns (bytes, message end offsets, schema_text, (namespace, table))."""
+    rng = np.random.default_rng(seed)
+    ids = rng.integers(1, 1 << 60, nmsgs); counter = rng.integers(0, 100_000, nmsgs); region = rng.integers(0, 300, nmsgs)
+    flags = rng.integers(-3, 3, nmsgs); dur = rng.integers(0, 1 << 40, nmsgs); price = np.round(rng.random(nmsgs) * 10_000, 2)
+    ok = rng.random(nmsgs) < 0.5; ts = rng.integers(1_372_636_800_000, 1_375_315_200_000, nmsgs); small = rng.integers(-128, 128, nmsgs)
+    hosts = ["example.com", "shop.example.net", "news.site.org", "yandex.ru"]
+    hsel = rng.integers(0, len(hosts), nmsgs); path = rng.integers(0, 1 << 30, nmsgs)
+    opr = rng.random(nmsgs); lsn = 1_000_000 + np.arange(nmsgs) * 8
+    frame = b"\x00" + int(schema_id).to_bytes(4, "big")
+    out = []; ends = np.zeros(nmsgs, dtype=np.uint64); pos = 0
+    for i in range(nmsgs):
+        title = "Title %d" % path[i] if i % 17 else "T\\\"quoted\\\" \\u00e9 %d" % path[i]
+        ref = "null" if i % 5 == 0 else '"https://%s/"' % hosts[(hsel[i] + 1) % len(hosts)]
+        row = ('{"id":%d,"counter":%d,"region":%d,"flags":%d,"dur":%d,"price":%r,"ok":%s,"url":"https://%s/p/%d","title":"%s","referer":%s,"ts":%d,"small":%d}'
+               % (ids[i], counter[i], region[i], flags[i], dur[i], float(price[i]), "true" if ok[i] else "false", hosts[hsel[i]], path[i], title, ref, ts[i], small[i]))
+        if opr[i] < dml_frac / 2: op, before, after = "d", row, "null"
+        elif opr[i] < dml_frac: op, before, after = "u", row, row
+        else: op, before, after = ("r" if i % 3 == 0 else "c"), "null", row
+        m = frame + ('{"before":%s,"after":%s,"source":{"version":"1.9","connector":"postgresql","name":"pg","ts_ms":%d,"snapshot":"false","db":"db","schema":"public",'
+                     '"table":"events","txId":%d,"lsn":%d},"op":"%s","ts_ms":%d}' % (before, after, ts[i], 500 + i // 10, lsn[i], op, ts[i] + 3)).encode()
+        out.append(m); pos += len(m); ends[i] = pos
+    return b"".join(out), ends, debezium_schema_text(), ("public", "events")
+
+
+def debezium_transformers(region_min: int = 150) -> List[dict]:
+    """config #4's chain: SQL-predicate filter (one int term AND one substring term); the typesystem cast is the sink's."""
+    return [{"filter_rows": {"filter": "region > %d AND url ~ 'example'" % region_min}}]
+
+
+def render_hits_csv(batch: abi.Batch, schema: List[dict], seed: int = SEED + 5) -> bytes:
+    """config #5's input: a hits-shaped batch as the CSV text a producer would write (`,` delimiter, `"` quotes doubled inside quoted cells,
+    timestamps as "YYYY-MM-DD hh:mm:ss"), one row per line."""
+    import datetime as dt
+    rng = np.random.default_rng(seed)
+    cols = []
+    for c in batch.columns:
+        if c.type in abi.VAR_TYPES:
+            quote = rng.random(batch.nrows) < 0.1; vals = []
+            for r in range(batch.nrows):
+                s = bytes(c.heap[c.offsets[r]:c.offsets[r + 1]])
+                if quote[r] or b"," in s or b'"' in s:
+                    s = b'"' + s.replace(b'"', b'""') + b'"'
+                vals.append(s)
+            cols.append(vals)
+        elif c.type == abi.TF_TIMESTAMP:
+            cols.append([dt.datetime.fromtimestamp(int(v), dt.timezone.utc).strftime("%Y-%m-%d %H:%M:%S").encode() for v in c.values])
+        elif c.type == abi.TF_DATE:
+            cols.append([dt.datetime.fromtimestamp(int(v), dt.timezone.utc).strftime("%Y-%m-%d").encode() for v in c.values])
+        else:
+            cols.append([str(int(v)).encode() for v in c.values])
+    return b"\n".join(b",".join(col[r] for col in cols) for r in range(batch.nrows)) + b"\n"
