@@ -149,7 +149,7 @@ typedef struct tf_batch {
 #define TF_ROWERR_STRICT_RANGE 58 /* strictify.go:159-181 StrictifyRangeError; term = column */
 #define TF_ROWERR_SINK_KIND_HOST 54 /* tfgpu_push_encode*: an UPDATE / DELETE row reached a sink or serializer wire format; the device encodes INSERT rows only
                                      (sink_table.go:296-305, marshal.go:92-95, json_serializer.go:17-20) — the shim routes the row through the Go sink */
-#define TF_ROWERR_DBZ_EMIT_HOST 53 /* tfgpu_emit_debezium: update / delete rows need ChangeItem.OldKeys — the shim emits them with the Go emitter */
+#define TF_ROWERR_DBZ_EMIT_HOST 53 /* (round 1; no longer raised: tfgpu_emit_debezium_crud emits update / delete events) */
 
 /* serializers: a value encoding/json refuses (NaN / Inf float, time.Time with a year outside [0,9999]); the reference
  * fails the whole Serialize call on it, so a result carrying this code must not be written; term = output column */
@@ -254,6 +254,26 @@ typedef struct tf_row_meta {
 } tf_row_meta;
 int tfgpu_emit_debezium(tfgpu_engine* e, int plan_id, const char* opts_json, const tf_batch* in, const tf_row_meta* meta,
                         tfgpu_result** out);
+/* ChangeItem.OldKeys (pkg/abstract/changeitem/old_keys.go:3-7) for a batch: KeyValues as typed cells in a second tf_batch with the
+ * plan's input schema and the batch's row count (only the listed columns are read), present_cols[c] != 0 = column c is listed in
+ * OldKeys.KeyNames, row_has[r] != 0 = row r carries OldKeys at all (NULL: every update / delete row does). */
+typedef struct tf_old_keys {
+    const tf_batch* values;
+    const uint8_t*  present_cols;   /* ncols flags (host memory) */
+    const uint8_t*  row_has;        /* nrows flags in the memory space of the batch, or NULL */
+} tf_old_keys;
+/* Emitter.emitKV for every row kind (pkg/debezium/emitter_value_converter.go:626-674): in->kinds says insert / update / delete;
+ *   insert, update that keeps its primary key  -> one message (op c|r / u; `before` = OldKeys when they list more than the keys,
+ *                                                  hasPreviousValues :277-285, else null; key from OldKeys, else from the row)
+ *   delete                                      -> the delete event (op d, after null, before = every column null + OldKeys) and its
+ *                                                  tombstone (key only) unless opts "tombstones_on_delete":false
+ *   update that changes its primary key (ChangeItem.KeysChanged) -> delete event, tombstone, insert event (op c, key from the row)
+ * The messages of a row are contiguous in the result bytes; tfgpu_result_dbz_msg_sizes gives, per output row, the message count and
+ * (key bytes, value bytes | 0xFFFFFFFF for a tombstone) per message. `old` may be NULL (no row carries OldKeys: keys come from the row
+ * and every update counts as key-changing, as in the reference). Plans whose transformers rewrite values are refused here. */
+int tfgpu_emit_debezium_crud(tfgpu_engine* e, int plan_id, const char* opts_json, const tf_batch* in, const tf_old_keys* old,
+                             const tf_row_meta* meta, tfgpu_result** out);
+const uint32_t* tfgpu_result_dbz_msg_sizes(const tfgpu_result* r);   /* 7 * rows_out entries */
 /* Host-only (no GPU): the set-up tfgpu_emit_debezium derives from a table and opts_json — the value branch of every result column
  * (0 addCommon, else the AddPg branch), the key columns in message order and the message template (text pieces + the per-row field
  * that follows each) — or the error the call would return. Same arguments as tfgpu_plan_validate plus opts_json. */

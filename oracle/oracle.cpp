@@ -867,8 +867,18 @@ std::string dbz_pack(const std::string& payload, const char* schema, int64_t sch
 
 // Emitter.EmitKV for the rows of one batch (pkg/debezium/emitter_value_converter.go:626-690; valPayload :453-512,
 // buildSource :329-372, makeKey / buildKV :259-327). INSERT rows only: update / delete events read ChangeItem.OldKeys.
+extern "C" int orc_debezium_emit_crud(const tf_batch* in, const tf_old_keys* old, int tombstones, const orc_colschema* schema, const uint8_t* is_key, const uint8_t* forms, const orc_step* steps, int nsteps,
+                                 const tf_row_meta* meta, const orc_dbz_emit_opts* o, orc_buf* out, uint32_t* key_sizes, uint32_t* row_sizes, uint32_t* msg_sizes,
+                                 uint64_t* rows_out, tf_rowerr* errs, uint64_t* nerrs);
 extern "C" int orc_debezium_emit(const tf_batch* in, const orc_colschema* schema, const uint8_t* is_key, const uint8_t* forms, const orc_step* steps, int nsteps,
                                  const tf_row_meta* meta, const orc_dbz_emit_opts* o, orc_buf* out, uint32_t* key_sizes, uint32_t* row_sizes,
+                                 uint64_t* rows_out, tf_rowerr* errs, uint64_t* nerrs) {
+    return orc_debezium_emit_crud(in, nullptr, 1, schema, is_key, forms, steps, nsteps, meta, o, out, key_sizes, row_sizes, nullptr, rows_out, errs, nerrs);
+}
+// Emitter.emitKV for every row kind (:626-674): 1 message for insert / plain update, delete event + tombstone for delete,
+// delete event + tombstone + insert event for an update whose primary key changed (ChangeItem.KeysChanged change_item.go:235-284).
+extern "C" int orc_debezium_emit_crud(const tf_batch* in, const tf_old_keys* old, int tombstones, const orc_colschema* schema, const uint8_t* is_key, const uint8_t* forms, const orc_step* steps, int nsteps,
+                                 const tf_row_meta* meta, const orc_dbz_emit_opts* o, orc_buf* out, uint32_t* key_sizes, uint32_t* row_sizes, uint32_t* msg_sizes,
                                  uint64_t* rows_out, tf_rowerr* errs, uint64_t* nerrs) {
     const uint32_t nc = in->ncols;
     std::vector<int32_t> out_type; std::vector<uint32_t> out_cols;
@@ -884,24 +894,61 @@ extern "C" int orc_debezium_emit(const tf_batch* in, const orc_colschema* schema
     std::string text;
     for (uint64_t r = 0; r < in->nrows; r++) {
         const int kind = in->kinds ? in->kinds[r] : TF_KIND_INSERT;
-        if (kind != TF_KIND_INSERT) { errs[ne++] = tf_rowerr{(uint32_t)r, TF_ROWERR_DBZ_EMIT_HOST, 0xff}; continue; }      // term 0xff: not raised by a transformer
         if (!apply_steps(in, r, steps, nsteps, row, cur_type, errs, ne)) continue;
         bool row_err = false;
-        auto obj = [&](bool keys_only) {
+        const bool old_row = old && old->values && kind != TF_KIND_INSERT && (old->row_has ? old->row_has[r] != 0 : true);      // len(OldKeys.KeyNames) > 0
+        auto present = [&](uint32_t c) { return old_row && old->present_cols && old->present_cols[c]; };
+        uint32_t n_present = 0, n_pkeys = 0;
+        for (uint32_t c = 0; c < nc; c++) { if (old && old->present_cols && old->present_cols[c]) n_present++; }
+        for (uint32_t k = 0; k < no; k++) if (is_key[out_cols[k]]) n_pkeys++;
+        auto emit = [&](std::string& t, const orc_val& v, uint32_t k) {
+            if (!dbz_emit_value(t, v, out_type[out_cols[k]], forms ? forms[out_cols[k]] : 0)) { t += "null"; if (!row_err) errs[ne++] = tf_rowerr{(uint32_t)r, TF_ROWERR_SER_VALUE, (uint16_t)k}; row_err = true; }
+        };
+        auto obj = [&](bool keys_only) {                          // buildKV over ColumnNames / ColumnValues
             std::string t = "{"; bool first = true;
             for (uint32_t j = 0; j < no; j++) {
                 const uint32_t k = order[j];
                 if (keys_only && !is_key[out_cols[k]]) continue;
                 if (!first) t += ','; first = false;
                 t += go_json_quote_nohtml((const uint8_t*)names[k].data(), names[k].size()); t += ':';
-                if (!dbz_emit_value(t, row[out_cols[k]].v, out_type[out_cols[k]], forms ? forms[out_cols[k]] : 0)) { t += "null"; if (!row_err) errs[ne++] = tf_rowerr{(uint32_t)r, TF_ROWERR_SER_VALUE, (uint16_t)k}; row_err = true; }
+                emit(t, row[out_cols[k]].v, k);
             }
             return t + "}";
         };
+        // mode 0: makeValues over OldKeys.KeyNames (keys_only: the primary keys among them); mode 1: every column null, OldKeys on top (op "d")
+        auto obj_old = [&](bool keys_only, int mode) {
+            std::string t = "{"; bool first = true;
+            for (uint32_t j = 0; j < no; j++) {
+                const uint32_t k = order[j]; const uint32_t c = out_cols[k];
+                if (keys_only && !is_key[c]) continue;
+                const bool pr = present(c);
+                if (mode == 0 && !pr) continue;
+                if (!first) t += ','; first = false;
+                t += go_json_quote_nohtml((const uint8_t*)names[k].data(), names[k].size()); t += ':';
+                if (pr) { orc_val ov; box(old->values->cols[c], r, ov); emit(t, ov, k); }
+                else if (o->source_type == 2) emit(t, row[c].v, k);            // mysql: `before` starts from ColumnValues (:469-477)
+                else t += "null";
+            }
+            return t + "}";
+        };
+        bool changed = false;
+        if (kind == TF_KIND_UPDATE)
+            for (uint32_t k = 0; k < no && !changed; k++) {
+                const uint32_t c = out_cols[k]; if (!is_key[c]) continue;
+                const orc_val& nv = row[c].v;
+                if (present(c)) {
+                    orc_val ov; box(old->values->cols[c], r, ov);
+                    if (ov.kind != nv.kind) changed = true;
+                    else if (ov.kind == OG_NIL) changed = false;
+                    else if (ov.kind == OG_STRING || ov.kind == OG_BYTES || ov.kind == OG_JSON) changed = ov.slen != nv.slen || std::memcmp(ov.s, nv.s, ov.slen) != 0;
+                    else if (ov.kind == OG_FLOAT32 || ov.kind == OG_FLOAT64) changed = std::memcmp(&ov.f, &nv.f, sizeof ov.f) != 0;
+                    else if (ov.kind == OG_TIME) changed = ov.i != nv.i || ov.nsec != nv.nsec;
+                    else if (ov.kind >= OG_UINT8 && ov.kind <= OG_UINT64) changed = ov.u != nv.u;
+                    else changed = ov.i != nv.i;
+                } else changed = nv.kind != OG_NIL;
+            }
         const uint64_t lsn = meta && meta->lsn ? meta->lsn[r] : 0, ct = meta && meta->commit_time ? meta->commit_time[r] : 0;
         const uint32_t id = meta && meta->id ? meta->id[r] : 0;
-        std::string key_msg;
-        if (!o->drop_keys) key_msg = dbz_pack(obj(true), o->key_schema, o->key_schema_id);
         const std::string snap = o->snapshot ? "\"true\"" : "\"false\"";
         std::string src = "{";
         if (o->source_type == 1) {            // pg: connector db lsn name schema snapshot table ts_ms txId version xmin
@@ -918,12 +965,32 @@ extern "C" int orc_debezium_emit(const tf_batch* in, const orc_colschema* schema
             src += "\"db\":" + q(o->database) + ",\"name\":" + q(o->name) + ",\"snapshot\":" + snap + ",\"table\":" + q(o->table) + ",\"ts_ms\":" + fmt_u64(ct / 1000000) + ",\"version\":" + q(o->version);
         }
         src += "}";
-        // payloadTSMS = time.Unix(CommitTime/1e9, CommitTime%1e9) (GetPayloadTSMS :697-699); UnixNano()/1e6 in int64
-        const std::string payload = "{\"after\":" + obj(false) + ",\"before\":null,\"op\":" + (o->snapshot ? "\"r\"" : "\"c\"") + ",\"source\":" + src +
-                                    ",\"transaction\":null,\"ts_ms\":" + fmt_i64((int64_t)ct / 1000000) + "}";
-        const std::string val_msg = dbz_pack(payload, o->val_schema, o->val_schema_id);
-        key_sizes[kept] = (uint32_t)key_msg.size(); row_sizes[kept] = (uint32_t)(key_msg.size() + val_msg.size());
-        text += key_msg; text += val_msg; kept++;
+        int plan[3], np = 0;                                       // 0 regular, 1 delete event, 2 tombstone, 3 insert event
+        if (changed) { plan[np++] = 1; if (tombstones) plan[np++] = 2; plan[np++] = 3; }
+        else if (kind == TF_KIND_DELETE) { plan[np++] = 1; if (tombstones) plan[np++] = 2; }
+        else plan[np++] = 0;
+        const bool has_prev = old_row && n_present > n_pkeys;      // hasPreviousValues :277-285
+        uint32_t total = 0;
+        if (msg_sizes) msg_sizes[7 * kept] = (uint32_t)np;
+        for (int m = 0; m < np; m++) {
+            const int mt = plan[m];
+            const bool key_from_after = mt == 3 || !old_row;      // makeKey :259-274
+            const char op = mt == 1 ? 'd' : (mt == 3 ? 'c' : (kind == TF_KIND_UPDATE ? 'u' : (kind == TF_KIND_DELETE ? 'd' : (o->snapshot ? 'r' : 'c'))));
+            std::string key_msg;
+            if (!o->drop_keys) key_msg = dbz_pack(key_from_after ? obj(true) : obj_old(true, 0), o->key_schema, o->key_schema_id);
+            if (m == 0) key_sizes[kept] = (uint32_t)key_msg.size();
+            text += key_msg; total += (uint32_t)key_msg.size();
+            if (mt == 2) { if (msg_sizes) { msg_sizes[7 * kept + 1 + 2 * m] = (uint32_t)key_msg.size(); msg_sizes[7 * kept + 2 + 2 * m] = 0xffffffffu; } continue; }
+            const std::string after = op == 'd' ? "null" : obj(false);
+            const std::string before = op == 'd' ? obj_old(false, 1) : ((op == 'u' && has_prev) ? obj_old(false, 0) : "null");
+            // payloadTSMS = time.Unix(CommitTime/1e9, CommitTime%1e9) (GetPayloadTSMS :697-699); UnixNano()/1e6 in int64
+            const std::string payload = "{\"after\":" + after + ",\"before\":" + before + ",\"op\":\"" + std::string(1, op) + "\",\"source\":" + src +
+                                        ",\"transaction\":null,\"ts_ms\":" + fmt_i64((int64_t)ct / 1000000) + "}";
+            const std::string val_msg = dbz_pack(payload, o->val_schema, o->val_schema_id);
+            text += val_msg; total += (uint32_t)val_msg.size();
+            if (msg_sizes) { msg_sizes[7 * kept + 1 + 2 * m] = (uint32_t)key_msg.size(); msg_sizes[7 * kept + 2 + 2 * m] = (uint32_t)val_msg.size(); }
+        }
+        row_sizes[kept] = total; kept++;
     }
     if (rows_out) *rows_out = kept;
     if (nerrs) *nerrs = ne;

@@ -126,6 +126,10 @@ typedef struct orc_dbz_emit_opts {
 int orc_debezium_emit(const tf_batch* in, const orc_colschema* schema, const uint8_t* is_key, const uint8_t* forms, const orc_step* steps, int nsteps,
                       const tf_row_meta* meta, const orc_dbz_emit_opts* opts, orc_buf* out, uint32_t* key_sizes, uint32_t* row_sizes,
                       uint64_t* rows_out, tf_rowerr* errs, uint64_t* nerrs);
+/* every row kind: ChangeItem.OldKeys as a second batch (tf_old_keys of include/tfgpu.h); msg_sizes: 7 per output row */
+int  orc_debezium_emit_crud(const tf_batch* in, const tf_old_keys* old, int tombstones, const orc_colschema* schema, const uint8_t* is_key, const uint8_t* forms, const orc_step* steps, int nsteps,
+                            const tf_row_meta* meta, const orc_dbz_emit_opts* o, orc_buf* out, uint32_t* key_sizes, uint32_t* row_sizes, uint32_t* msg_sizes,
+                            uint64_t* rows_out, tf_rowerr* errs, uint64_t* nerrs);
 
 /* sharder transformer (pkg/transformer/registry/sharder/sharder.go:130-145): ChangeItem.PartID of every row the chain keeps =
  * decimal(CRC32-IEEE(join(".", SerializeToString(value) of the matched columns)) % uint32(ShardsNum)). part_ids: nrows entries. */

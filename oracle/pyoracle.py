@@ -1022,9 +1022,9 @@ def debezium_pg_form(col: dict) -> int:
     return -1
 
 
-def debezium_emit(batch: abi.Batch, plan: Plan, opts: dict, meta: Optional[dict] = None):
-    """Emitter.EmitKV over the INSERT rows of `batch` after the plan's chain (emitter_value_converter.go:626-690).
-    Returns (messages bytes, key_sizes, row_sizes, errors); key then value per row."""
+def debezium_emit(batch: abi.Batch, plan: Plan, opts: dict, meta: Optional[dict] = None, old: Optional[abi.Batch] = None, old_present=None, old_row_has=None, want_msg_sizes: bool = False):
+    """Emitter.EmitKV over the rows of `batch` after the plan's chain (emitter_value_converter.go:626-690), every row kind; OldKeys as a
+    second batch. Returns (messages bytes, key_sizes, row_sizes, errors[, msg_sizes (rows x 7)])."""
     L = lib()
     keep, cschema, csteps = _marshal(plan)
     tb = batch.as_struct()
@@ -1051,16 +1051,35 @@ def debezium_emit(batch: abi.Batch, plan: Plan, opts: dict, meta: Optional[dict]
     ks = np.zeros(max(1, n), dtype=np.uint32); rs = np.zeros(max(1, n), dtype=np.uint32)
     out = OrcBuf(); rows = C.c_uint64(); nerr = C.c_uint64()
     errs = (abi.TfRowErr * max(1, 2 * n))()
-    L.orc_debezium_emit.argtypes = [C.POINTER(abi.TfBatch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(abi.TfRowMeta), C.POINTER(OrcDbzEmitOpts),
-                                    C.POINTER(OrcBuf), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_uint64)]
-    rc = L.orc_debezium_emit(C.byref(tb), C.cast(cschema, C.c_void_p), is_key.ctypes.data, forms.ctypes.data, C.cast(csteps, C.c_void_p), len(plan.steps), C.byref(m), C.byref(o),
-                             C.byref(out), ks.ctypes.data, rs.ctypes.data, C.byref(rows), C.cast(errs, C.c_void_p), C.byref(nerr))
+    ms = np.zeros((max(1, n), 7), dtype=np.uint32)
+    ok, okeep = (abi.make_old_keys(old, old_present or [], old_row_has) if old is not None else (None, None))
+    tomb = 0 if opts.get("tombstones_on_delete") is False else 1
+    L.orc_debezium_emit_crud.argtypes = [C.POINTER(abi.TfBatch), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(abi.TfRowMeta), C.POINTER(OrcDbzEmitOpts),
+                                         C.POINTER(OrcBuf), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_uint64)]
+    rc = L.orc_debezium_emit_crud(C.byref(tb), C.cast(C.pointer(ok), C.c_void_p) if ok is not None else None, tomb, C.cast(cschema, C.c_void_p), is_key.ctypes.data, forms.ctypes.data,
+                                  C.cast(csteps, C.c_void_p), len(plan.steps), C.byref(m), C.byref(o),
+                                  C.byref(out), ks.ctypes.data, rs.ctypes.data, ms.ctypes.data, C.byref(rows), C.cast(errs, C.c_void_p), C.byref(nerr))
     if rc != 0:
         raise RuntimeError(f"oracle debezium_emit rc={rc}")
     data = C.string_at(out.data, out.len) if out.len else b""
     L.orc_free(C.byref(out))
     k = rows.value
-    return data, ks[:k].copy(), rs[:k].copy(), [(errs[i].row, errs[i].code, errs[i].term) for i in range(nerr.value)]
+    res = (data, ks[:k].copy(), rs[:k].copy(), [(errs[i].row, errs[i].code, errs[i].term) for i in range(nerr.value)])
+    return res + (ms[:k].copy(),) if want_msg_sizes else res
+
+
+def debezium_messages(data: bytes, msg_sizes):
+    """[[(key bytes, value bytes | None), ...] per row] of a CRUD emission."""
+    out = []; at = 0
+    for row in msg_sizes:
+        msgs = []
+        for m in range(int(row[0])):
+            k, v = int(row[1 + 2 * m]), int(row[2 + 2 * m])
+            key = data[at:at + k]; at += k
+            if v == 0xffffffff: msgs.append((key, None))
+            else: msgs.append((key, data[at:at + v])); at += v
+        out.append(msgs)
+    return out
 
 
 def debezium_split(data: bytes, key_sizes, row_sizes):

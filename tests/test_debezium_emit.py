@@ -211,14 +211,14 @@ def test_oracle_value_forms(po):
 
 
 def test_oracle_kinds_and_chain(po):
-    """UPDATE / DELETE rows are handed back (OldKeys), the chain runs first, key columns follow the result schema."""
+    """The chain runs first: filter_rows rejects UPDATE / DELETE rows itself (filter_rows.go:103-107); key columns follow the result schema."""
     schema = [{"name": "id", "type": "int32", "key": True}, {"name": "name", "type": "utf8"}, {"name": "x", "type": "int64"}]
     b = abi.Batch(5, [abi.fixed_to_column(abi.TF_INT32, [1, 2, 3, 4, 5]), abi.strings_to_column(abi.TF_UTF8, [b"a", b"b", b"c", b"d", b"e"]),
                       abi.fixed_to_column(abi.TF_INT64, [10, 20, 30, 40, 50])], kinds=np.array([0, 1, 0, 2, 0], np.uint8))
     trs = [{"filter_rows": {"filter": "x > 10"}}, {"mask_field": {"columns": ["name"], "maskFunctionHash": {"userDefinedSalt": "s"}}}]
     plan = po.build_plan("db", "t", schema, trs)
     data, ks, rs, errs = po.debezium_emit(b, plan, OPTS)
-    assert errs == [(1, abi.TF_ROWERR_DBZ_EMIT_HOST, 255), (3, abi.TF_ROWERR_DBZ_EMIT_HOST, 255)]
+    assert errs == [(1, abi.TF_ROWERR_FILTER_KIND, 0), (3, abi.TF_ROWERR_FILTER_KIND, 0)]
     kv = po.debezium_split(data, ks, rs)
     assert [k for k, _ in kv] == [b'{"id":3}', b'{"id":5}']
     after = json.loads(kv[0][1])["after"]
@@ -295,6 +295,10 @@ def test_product_host_template_matches_oracle(po):
                     assert g == field[code], (st, extra, code)
                 elif code == 10:          # end of the key message
                     assert g == ""
+                elif code == 11:          # `before`: an insert has none
+                    assert g == "null"
+                elif code == 12:          # op (kindToOp)
+                    assert g == ("r" if extra.get("snapshot") else "c")
                 else:                     # the key / after object
                     obj = json.loads(g)
                     assert list(obj) == sorted(obj) and (code == 1) == ("zz" in obj)
@@ -400,3 +404,154 @@ def test_device_emitter_refusals(eng):
     pid = eng.plan("s", "t", [{"name": "i", "type": "int32", "key": True, "original_type": "pg:integer"}], [{"convert_to_string": {}}])
     with pytest.raises(EngineError):        # a transformer rewrote a pg-typed column: AddPg would reject the value
         eng.emit_debezium(pid, b, OPTS)
+
+
+# ----------------------------------------------------------------------------------------------------------- update / delete events
+GC = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "debezium_crud_goldens.json"), encoding="utf-8"))
+KIND = {"insert": abi.TF_KIND_INSERT, "update": abi.TF_KIND_UPDATE, "delete": abi.TF_KIND_DELETE}
+
+
+def _cell_column(tf, kind, cell):
+    import base64
+    if cell is None:
+        return abi.strings_to_column(tf, [None]) if tf in abi.VAR_TYPES else abi.fixed_to_column(tf, [0], [True])
+    if kind == "time":
+        return abi.fixed_to_column(tf, [cell[0]], None, [cell[1]])
+    if kind == "str":
+        return abi.strings_to_column(tf, [cell.encode()], tags=[1]) if tf == abi.TF_ANY else abi.strings_to_column(tf, [cell.encode()])
+    if kind == "json":
+        return abi.strings_to_column(tf, [cell.encode()], tags=[0])
+    if kind == "b64":
+        return abi.strings_to_column(tf, [base64.b64decode(cell)])
+    return abi.fixed_to_column(tf, [cell])
+
+
+def _crud_item(it):
+    """(batch with kinds, old batch, present column indexes, schema, meta) of one canon ChangeItem of the CRUD fixtures."""
+    schema, cols, ocols, present = [], [], [], []
+    old = {o["name"]: o for o in it["old"]}
+    for k, c in enumerate(it["columns"]):
+        tf = abi.YT_NAME_TO_TF[c["type"]]
+        schema.append({"name": c["name"], "type": c["type"], "key": c["key"], "required": c["required"], "original_type": c["original_type"]})
+        cols.append(_cell_column(tf, c["kind"], c["cell"] if c["present"] else None))
+        if c["name"] in old:
+            present.append(k); ocols.append(_cell_column(tf, old[c["name"]]["kind"], old[c["name"]]["cell"]))
+        else:
+            ocols.append(_cell_column(tf, c["kind"], None))
+    meta = {"id": np.array([it["id"]], np.uint32), "lsn": np.array([it["lsn"]], np.uint64), "commit_time": np.array([it["commit_time"]], np.uint64)}
+    return abi.Batch(1, cols, np.array([KIND[it["kind"]]], np.uint8)), abi.Batch(1, ocols), present, schema, meta
+
+
+def _same_value(got, want, col):
+    if col["kind"] == "json" and got is not None and want is not None:
+        return json.loads(got) == json.loads(want)
+    if col["kind"] == "f64" and got is not None and want is not None:
+        return got == pytest.approx(want, rel=1e-7)
+    return got == want and type(got) is type(want)
+
+
+def test_oracle_update_delete_against_real_debezium_messages(po):
+    """emitter_crud_test.go:15-165 and emitter_replica_identity_test.go:17-97: the message count per ChangeItem (1 for a plain update,
+    delete event + tombstone for a delete, delete + tombstone + insert for an update that changes its key), the key payloads the Go test
+    spells out, and op / before / after of what a real Debezium wrote, over the columns the device emitter takes."""
+    opts = {k: v for k, v in OPTS.items() if k != "ignore_unknown_sources"}
+    for it in GC["items"]:
+        batch, old, present, schema, meta = _crud_item(it)
+        plan = po.build_plan(it["table"][0], it["table"][1], schema, [])
+        data, ks, rs, errs, ms = po.debezium_emit(batch, plan, opts, meta, old=old, old_present=present, want_msg_sizes=True)
+        assert errs == [], it["item"]
+        (msgs,) = po.debezium_messages(data, ms)
+        want = it["events"]
+        if it.get("first_event_only"):
+            msgs = msgs[:1]          # that test checks the first event (the delete's tombstone is not in its fixture)
+        assert len(msgs) == len(want), (it["item"], len(msgs))
+        by_name = {c["name"]: c for c in it["columns"]}
+        for (key, val), ev in zip(msgs, want):
+            assert json.loads(key) == ev["key"], it["item"]
+            if ev["value"] is None:
+                assert val is None; continue
+            v = json.loads(val)
+            assert v["op"] == ev["value"]["op"] and v["transaction"] is None
+            for side in ("before", "after"):
+                w, g = ev["value"][side], v[side]
+                assert (w is None) == (g is None), (it["item"], side)
+                if w is not None:
+                    assert sorted(g) == sorted(w), (it["item"], side)
+                    for n in w:
+                        assert _same_value(g[n], w[n], by_name[n]), (it["item"], side, n, g[n], w[n])
+            for k in ("connector", "name", "db", "schema", "table", "snapshot"):
+                assert v["source"][k] == ev["value"]["source"][k], (it["item"], k)
+            assert v["source"]["txId"] == it["id"] and v["source"]["lsn"] == it["lsn"]      # the canon items were captured in another session than the messages
+
+
+def test_oracle_crud_rules(po):
+    """emitKV's branches on a small table: tombstones.on.delete=false, an update without OldKeys (every key compares against nil:
+    KeysChanged), hasPreviousValues, a delete's `before` (all columns null + OldKeys), mysql's `before` filled from the row."""
+    schema = [{"name": "id", "type": "int32", "key": True}, {"name": "name", "type": "utf8"}, {"name": "x", "type": "int64"}]
+    b = abi.Batch(4, [abi.fixed_to_column(abi.TF_INT32, [1, 2, 3, 4]), abi.strings_to_column(abi.TF_UTF8, [b"a", b"b", b"c", b"d"]), abi.fixed_to_column(abi.TF_INT64, [10, 20, 30, 40])],
+                  kinds=np.array([0, 1, 1, 2], np.uint8))
+    old = abi.Batch(4, [abi.fixed_to_column(abi.TF_INT32, [0, 2, 30, 4]), abi.strings_to_column(abi.TF_UTF8, [None, b"B", b"C", b"D"]), abi.fixed_to_column(abi.TF_INT64, [0, 0, 0, 0], [True] * 4)])
+    plan = po.build_plan("db", "t", schema, [])
+    def run(opts, **kw):
+        data, ks, rs, errs, ms = po.debezium_emit(b, plan, dict(OPTS, source_type="", **opts), None, want_msg_sizes=True, **kw)
+        assert errs == []
+        return [[(k, None if v is None else json.loads(v)) for k, v in row] for row in po.debezium_messages(data, ms)]
+    rows = run({}, old=old, old_present=[0, 1])                      # OldKeys = {id, name}: more than the keys -> before on updates
+    assert [len(r) for r in rows] == [1, 1, 3, 2]
+    assert rows[1][0][0] == b'{"id":2}' and rows[1][0][1]["op"] == "u" and rows[1][0][1]["before"] == {"id": 2, "name": "B"} and rows[1][0][1]["after"] == {"id": 2, "name": "b", "x": 20}
+    d, t, i = rows[2]
+    assert d[0] == b'{"id":30}' and d[1]["op"] == "d" and d[1]["after"] is None and d[1]["before"] == {"id": 30, "name": "C", "x": None}
+    assert t == (b'{"id":30}', None) and i[0] == b'{"id":3}' and i[1]["op"] == "c" and i[1]["before"] is None and i[1]["after"]["name"] == "c"
+    assert rows[3][0][1]["op"] == "d" and rows[3][1] == (b'{"id":4}', None)
+    assert [len(r) for r in run({"tombstones_on_delete": False}, old=old, old_present=[0, 1])] == [1, 1, 2, 1]
+    rows = run({}, old=old, old_present=[0])                         # OldKeys = the key only: no `before` on a plain update
+    assert rows[1][0][1]["before"] is None and rows[3][0][1]["before"] == {"id": 4, "name": None, "x": None}
+    rows = run({})                                                   # no OldKeys at all: keys from the row, every update counts as key-changing
+    assert [len(r) for r in rows] == [1, 3, 3, 2] and rows[1][0][0] == b'{"id":2}' and rows[3][0][1]["before"] == {"id": None, "name": None, "x": None}
+    data, ks, rs, errs, ms = po.debezium_emit(b, plan, dict(OPTS, source_type="mysql"), None, old=old, old_present=[0], want_msg_sizes=True)
+    assert json.loads(po.debezium_messages(data, ms)[3][0][1])["before"] == {"id": 4, "name": "d", "x": 40}      # mysql: ColumnValues first, OldKeys on top
+
+
+@pytest.mark.gpu
+def test_device_emitter_update_delete_equals_oracle(eng, po):
+    """tfgpu_emit_debezium_crud against the oracle, byte for byte: the reference's CRUD fixtures, then a mixed batch over every option."""
+    opts = {k: v for k, v in OPTS.items() if k != "ignore_unknown_sources"}
+    for it in GC["items"]:
+        batch, old, present, schema, meta = _crud_item(it)
+        pid = eng.plan(it["table"][0], it["table"][1], schema, []); plan = po.build_plan(it["table"][0], it["table"][1], schema, [])
+        want = po.debezium_emit(batch, plan, opts, meta, old=old, old_present=present, want_msg_sizes=True)
+        got = eng.emit_debezium(pid, batch, opts, meta, old=old, old_present=present)
+        nm = int(want[4][0][0])
+        assert got.wire == want[0] and got.errors == want[3] and np.array_equal(got.msg_sizes[:, :1 + 2 * nm], want[4][:, :1 + 2 * nm]), it["item"]
+    rng = np.random.default_rng(4); n = 3000
+    schema = [{"name": "id", "type": "int64", "key": True}, {"name": "k2", "type": "utf8", "key": True}, {"name": "name", "type": "utf8"}, {"name": "x", "type": "double"},
+              {"name": "ts", "type": "timestamp"}, {"name": "j", "type": "any"}]
+    ids = rng.integers(0, 50, n); k2 = [b"k%d" % v for v in rng.integers(0, 5, n)]
+    def mk(ids_, k2_, salt):
+        return abi.Batch(n, [abi.fixed_to_column(abi.TF_INT64, ids_), abi.strings_to_column(abi.TF_UTF8, k2_),
+                             abi.strings_to_column(abi.TF_UTF8, [None if (i + salt) % 7 == 0 else b"n<%d>" % (i * salt) for i in range(n)]),
+                             abi.fixed_to_column(abi.TF_DOUBLE, rng.random(n) * 1e3, [(i + salt) % 11 == 0 for i in range(n)]),
+                             abi.fixed_to_column(abi.TF_TIMESTAMP, rng.integers(0, 2**31, n), None, rng.integers(0, 10**9, n).astype(np.uint32)),
+                             abi.strings_to_column(abi.TF_ANY, [b'{"a":%d}' % i for i in range(n)], tags=[0] * n)])
+    kinds = rng.integers(0, 3, n).astype(np.uint8)
+    b = mk(ids, k2, 1); b.kinds = kinds
+    same = rng.random(n) < 0.6
+    old = mk(np.where(same, ids, ids + 1), [a if s_ else a + b"x" for a, s_ in zip(k2, rng.random(n) < 0.8)], 3)
+    has = (rng.random(n) < 0.9).astype(np.uint8)
+    meta = {"id": rng.integers(0, 2**32, n, dtype=np.uint32), "lsn": rng.integers(0, 2**62, n, dtype=np.uint64), "commit_time": rng.integers(0, 2**62, n, dtype=np.uint64)}
+    pid = eng.plan("public", "t", schema, []); plan = po.build_plan("public", "t", schema, [])
+    for o, present, row_has in (({}, [0, 1], None), ({}, [0, 1, 2, 3, 4, 5], has), ({"tombstones_on_delete": False, "snapshot": True}, [0], has), ({"source_type": "mysql"}, [0, 1, 2], None),
+                                ({"key_schema": '{"t":1}', "val_schema": '{"t":2}'}, [1, 2], has), ({"drop_keys": True}, [0, 1], None)):
+        oo = dict(OPTS, **o)
+        want = po.debezium_emit(b, plan, oo, meta, old=old, old_present=present, old_row_has=row_has, want_msg_sizes=True)
+        got = eng.emit_debezium(pid, b, oo, meta, old=old, old_present=present, old_row_has=row_has)
+        assert got.errors == want[3] and list(got.row_sizes) == list(want[2]), o
+        assert got.wire == want[0], o
+        cnt = want[4][:, 0]
+        for m in range(3):
+            sel = cnt > m
+            assert np.array_equal(got.msg_sizes[sel, 1 + 2 * m: 3 + 2 * m], want[4][sel, 1 + 2 * m: 3 + 2 * m]), (o, m)
+        assert np.array_equal(got.msg_sizes[:, 0], cnt) and set(cnt.tolist()) >= {1, 2}
+    # without OldKeys
+    want = po.debezium_emit(b, plan, OPTS, meta, want_msg_sizes=True); got = eng.emit_debezium(pid, b, OPTS, meta)
+    assert got.wire == want[0] and np.array_equal(got.msg_sizes[:, 0], want[4][:, 0])

@@ -74,6 +74,19 @@ class TfRowMeta(C.Structure):
     _fields_ = [("id", C.c_void_p), ("lsn", C.c_void_p), ("commit_time", C.c_void_p), ("txid_offsets", C.c_void_p), ("txid_heap", C.c_void_p)]
 
 
+class TfOldKeys(C.Structure):
+    """tf_old_keys: ChangeItem.OldKeys of a batch as a second set of typed columns (old_keys.go:3-7)."""
+    _fields_ = [("values", C.c_void_p), ("present_cols", C.c_void_p), ("row_has", C.c_void_p)]
+
+
+def make_old_keys(old_batch, present_cols, row_has=None):
+    """(struct, keepalive): `old_batch` an abi.Batch with the plan's input schema, present_cols the column indexes listed in OldKeys.KeyNames."""
+    tb = old_batch.as_struct()
+    pres = np.zeros(len(old_batch.columns), dtype=np.uint8); pres[list(present_cols)] = 1
+    ok = TfOldKeys(C.cast(C.pointer(tb), C.c_void_p), pres.ctypes.data, _ptr(row_has))
+    return ok, (tb, pres, row_has, old_batch)
+
+
 def make_row_meta(id=None, lsn=None, commit_time=None, txid_offsets=None, txid_heap=None):
     """(struct, keepalive) from numpy arrays / torch tensors; None stays NULL."""
     m = TfRowMeta(_ptr(id), _ptr(lsn), _ptr(commit_time), _ptr(txid_offsets), _ptr(txid_heap))

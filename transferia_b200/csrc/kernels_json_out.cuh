@@ -276,11 +276,18 @@ template <typename Sink> __device__ void ser_csv_row(Sink& s, const DCol* cols, 
 __device__ __forceinline__ uint32_t sink_count(const CountSink& s) { return s.n; }
 __device__ __forceinline__ uint32_t sink_count(const MemSink&) { return 0; }
 __device__ __forceinline__ uint32_t sink_count(const WordSink&) { return 0; }
-enum DbzCode : int32_t { DZ_NONE = 0, DZ_AFTER = 1, DZ_KEY = 2, DZ_LSN = 3, DZ_SRC_TS = 4, DZ_ID = 5, DZ_FILE = 6, DZ_POS = 7, DZ_GTID = 8, DZ_TS = 9, DZ_KEY_END = 10 };
+enum DbzCode : int32_t { DZ_NONE = 0, DZ_AFTER = 1, DZ_KEY = 2, DZ_LSN = 3, DZ_SRC_TS = 4, DZ_ID = 5, DZ_FILE = 6, DZ_POS = 7, DZ_GTID = 8, DZ_TS = 9, DZ_KEY_END = 10, DZ_BEFORE = 11, DZ_OP = 12 };
 struct DbzSeg { int32_t text_off, text_len, code, pad; };
 struct DbzEmitArgs {
     const DbzSeg* segs; int nseg; const uint8_t* text; const JsonCol* kcols; int nkc; const JsonCol* acols;     // acols: the sorted columns with their AddPg branch in pad1
     const uint32_t* id; const uint64_t* lsn; const uint64_t* ct; const uint32_t* gt_off; const uint8_t* gt_heap; uint32_t* key_size;
+    // update / delete events (emitter_value_converter.go:626-674): ChangeItem.Kind per row and ChangeItem.OldKeys as a second set of columns
+    const uint8_t* kinds;          // NULL = all insert
+    const DCol* old_cols;          // OldKeys.KeyValues as typed cells, one DCol per input column (NULL: no row carries OldKeys)
+    const uint8_t* old_present;    // per input column: the column is listed in OldKeys.KeyNames
+    const uint8_t* old_has;        // per row: OldKeys.KeyNames is not empty (NULL: true for every update / delete row)
+    int32_t n_old_present, n_pkeys, tombstones, mysql_src, snapshot;
+    uint32_t* msg_size;            // [7 per output row]: message count, then (key bytes, value bytes | 0xFFFFFFFF for a tombstone) per message
 };
 template <typename Inner> struct JStrSink {      // the inside of a JSON string over text that is already valid JSON (ASCII escapes, UTF-8 intact)
     Inner* in;
@@ -371,30 +378,107 @@ template <typename Sink> __device__ int dbz_object(Sink& s, const DCol* cols, co
     s.put('}');
     return bad;
 }
+// before / key objects from OldKeys: mode 0 = only the listed columns (makeValues over OldKeys.KeyNames), mode 1 = every column, the
+// listed ones from OldKeys and the others null (valPayload op "d": :461-483; a mysql source fills them from ColumnValues first)
+template <typename Sink> __device__ int dbz_object_old(Sink& s, const DCol* cols, const DCol* old_cols, const uint8_t* present, const JsonCol* jcols, int njc,
+                                                      const uint8_t* names, const MaskKey* keys, uint64_t r, bool sizing, int mode, bool mysql) {
+    int bad = -1; bool first = true;
+    s.put('{');
+    for (int k = 0; k < njc; k++) {
+        const JsonCol jc = jcols[k]; const bool pr = present && present[jc.col];
+        if (mode == 0 && !pr) continue;
+        if (!first) s.put(','); first = false;
+        for (int i = 0; i < jc.name_len; i++) s.put(names[jc.name_off + i]);
+        if (pr) { if (!dbz_json_value(s, old_cols[jc.col], r, jc, keys, sizing) && bad < 0) bad = jc.pad0; }
+        else if (mysql) { if (!dbz_json_value(s, cols[jc.col], r, jc, keys, sizing) && bad < 0) bad = jc.pad0; }
+        else fmt_lit(s, "null");
+    }
+    s.put('}');
+    return bad;
+}
+// reflect.DeepEqual of a typed cell in two columns of the same type
+__device__ __forceinline__ bool dbz_cell_equal(const DCol& a, const DCol& b, uint64_t r) {
+    const bool va = row_valid(a, r), vb = row_valid(b, r);
+    if (va != vb) return false;
+    if (!va) return true;
+    if (a.in_w) {
+        const uint8_t* x = a.values + (size_t)a.in_w * r; const uint8_t* y = b.values + (size_t)b.in_w * r;
+        for (int i = 0; i < a.in_w; i++) if (x[i] != y[i]) return false;
+        if (a.aux && b.aux && (a.type == TF_TIMESTAMP || a.type == TF_DATETIME || a.type == TF_DATE) && ((const uint32_t*)a.aux)[r] != ((const uint32_t*)b.aux)[r]) return false;
+        return true;
+    }
+    const uint32_t la = a.offsets[r + 1] - a.offsets[r], lb = b.offsets[r + 1] - b.offsets[r];
+    if (la != lb) return false;
+    const uint8_t* x = a.heap + a.offsets[r]; const uint8_t* y = b.heap + b.offsets[r];
+    for (uint32_t i = 0; i < la; i++) if (x[i] != y[i]) return false;
+    return true;
+}
+// One ChangeItem -> 1..3 Debezium messages (Emitter.emitKV :626-674): insert and plain update = one message; delete = the delete event and
+// its tombstone (key, no value); an update that changes the primary key = delete event, tombstone, insert event.
 template <typename Sink> __device__ int dbz_row(Sink& s, const DCol* cols, const JsonCol* jcols, int njc, const uint8_t* names, const MaskKey* keys,
                                                const DbzEmitArgs& z, uint64_t r, uint64_t j, bool sizing) {
     int bad = -1;
     const uint64_t lsn = z.lsn ? z.lsn[r] : 0, ct = z.ct ? z.ct[r] : 0;
-    for (int g = 0; g < z.nseg; g++) {
-        const DbzSeg sg = z.segs[g];
-        for (int i = 0; i < sg.text_len; i++) s.put(z.text[sg.text_off + i]);
-        switch (sg.code) {
-        case DZ_AFTER: { const int b = dbz_object(s, cols, z.acols, njc, names, keys, r, sizing); if (bad < 0) bad = b; break; }
-        case DZ_KEY: { const int b = dbz_object(s, cols, z.kcols, z.nkc, names, keys, r, sizing); if (bad < 0) bad = b; break; }
-        case DZ_LSN: fmt_u64(s, lsn); break;
-        case DZ_SRC_TS: fmt_u64(s, ct / 1000000ull); break;
-        case DZ_ID: fmt_u64(s, z.id ? z.id[r] : 0); break;
-        case DZ_FILE: { const uint64_t f = lsn / 1000000000000ull; fmt_pad(s, (int64_t)f, 6); break; }      // "mysql-log.%06d"
-        case DZ_POS: fmt_u64(s, lsn % 1000000000000ull); break;
-        case DZ_GTID: {
-            const uint32_t a = z.gt_off ? z.gt_off[r] : 0, b = z.gt_off ? z.gt_off[r + 1] : 0;
-            if (z.gt_heap && b > a) fmt_json_string(s, z.gt_heap + a, b - a, false); else fmt_lit(s, "null");
-            break;
+    const int kind = z.kinds ? z.kinds[r] : TF_KIND_INSERT;
+    const bool old_row = z.old_cols && kind != TF_KIND_INSERT && (z.old_has ? z.old_has[r] != 0 : true);      // len(OldKeys.KeyNames) > 0
+    bool changed = false;
+    if (kind == TF_KIND_UPDATE)                                                    // ChangeItem.KeysChanged change_item.go:235-284
+        for (int k = 0; k < z.nkc && !changed; k++) {
+            const int c = z.kcols[k].col;
+            if (old_row && z.old_present[c]) changed = !dbz_cell_equal(z.old_cols[c], cols[c], r);
+            else changed = row_valid(cols[c], r);                                  // a key OldKeys does not list compares as nil
         }
-        case DZ_TS: fmt_i64(s, (int64_t)ct / 1000000); break;
-        case DZ_KEY_END: if (sizing) z.key_size[j] = sink_count(s); break;
-        default: break;
+    // message plan: 0 regular, 1 delete event, 2 tombstone, 3 insert event
+    int plan[3], np = 0;
+    if (changed) { plan[np++] = 1; if (z.tombstones) plan[np++] = 2; plan[np++] = 3; }
+    else if (kind == TF_KIND_DELETE) { plan[np++] = 1; if (z.tombstones) plan[np++] = 2; }
+    else plan[np++] = 0;
+    if (sizing && z.msg_size) z.msg_size[7 * j] = (uint32_t)np;
+    const bool has_prev = old_row && z.n_old_present > z.n_pkeys;                  // hasPreviousValues :277-285
+    for (int m = 0; m < np; m++) {
+        const int mt = plan[m];
+        const bool key_from_after = mt == 3 || !old_row;                            // makeKey :259-274
+        const char op = mt == 1 ? 'd' : (mt == 3 ? 'c' : (kind == TF_KIND_UPDATE ? 'u' : (kind == TF_KIND_DELETE ? 'd' : (z.snapshot ? 'r' : 'c'))));      // kindToOp kind.go:8-31
+        const uint32_t at0 = sink_count(s);
+        uint32_t key_len = 0;
+        for (int g = 0; g < z.nseg; g++) {
+            const DbzSeg sg = z.segs[g];
+            for (int i = 0; i < sg.text_len; i++) s.put(z.text[sg.text_off + i]);
+            switch (sg.code) {
+            case DZ_AFTER:
+                if (op == 'd') fmt_lit(s, "null");
+                else { const int b = dbz_object(s, cols, z.acols, njc, names, keys, r, sizing); if (bad < 0) bad = b; }
+                break;
+            case DZ_BEFORE:
+                if (op == 'd') { const int b = dbz_object_old(s, cols, z.old_cols, old_row ? z.old_present : nullptr, z.acols, njc, names, keys, r, sizing, 1, z.mysql_src != 0); if (bad < 0) bad = b; }
+                else if (op == 'u' && has_prev) { const int b = dbz_object_old(s, cols, z.old_cols, z.old_present, z.acols, njc, names, keys, r, sizing, 0, false); if (bad < 0) bad = b; }
+                else fmt_lit(s, "null");
+                break;
+            case DZ_OP: s.put((uint8_t)op); break;
+            case DZ_KEY:
+                if (key_from_after) { const int b = dbz_object(s, cols, z.kcols, z.nkc, names, keys, r, sizing); if (bad < 0) bad = b; }
+                else { const int b = dbz_object_old(s, cols, z.old_cols, z.old_present, z.kcols, z.nkc, names, keys, r, sizing, 0, false); if (bad < 0) bad = b; }
+                break;
+            case DZ_LSN: fmt_u64(s, lsn); break;
+            case DZ_SRC_TS: fmt_u64(s, ct / 1000000ull); break;
+            case DZ_ID: fmt_u64(s, z.id ? z.id[r] : 0); break;
+            case DZ_FILE: { const uint64_t f = lsn / 1000000000000ull; fmt_pad(s, (int64_t)f, 6); break; }      // "mysql-log.%06d"
+            case DZ_POS: fmt_u64(s, lsn % 1000000000000ull); break;
+            case DZ_GTID: {
+                const uint32_t a = z.gt_off ? z.gt_off[r] : 0, b = z.gt_off ? z.gt_off[r + 1] : 0;
+                if (z.gt_heap && b > a) fmt_json_string(s, z.gt_heap + a, b - a, false); else fmt_lit(s, "null");
+                break;
+            }
+            case DZ_TS: fmt_i64(s, (int64_t)ct / 1000000); break;
+            case DZ_KEY_END:
+                key_len = sink_count(s) - at0;
+                if (sizing && m == 0) z.key_size[j] = key_len;
+                break;
+            default: break;
+            }
+            if (sg.code == DZ_KEY_END && mt == 2) break;                            // a tombstone is its key only
         }
+        if (sizing && z.msg_size) { z.msg_size[7 * j + 1 + 2 * m] = key_len; z.msg_size[7 * j + 2 + 2 * m] = mt == 2 ? 0xffffffffu : sink_count(s) - at0 - key_len; }
     }
     return bad;
 }

@@ -78,7 +78,7 @@ struct tfgpu_engine {
     uint32_t* tile_sum = nullptr; uint64_t* tile_base = nullptr; uint64_t* col_bytes = nullptr; uint32_t* comp_size = nullptr; uint64_t* wire_off = nullptr; unsigned long long* frame_pfx = nullptr;
     uint64_t last_nrows = 0; bool last_has_filter = false, last_has_sharder = false; int last_wire_fmt = 0;
     uint8_t* pinned = nullptr; size_t pinned_cap = 0;
-    DevBuf json_sizes, dbz_keysz, dbz_meta, part_ids;
+    DevBuf json_sizes, dbz_keysz, dbz_meta, dbz_old, dbz_msgsz, old_arena, part_ids;
     DbzEmitArgs dbz{};                                 // set by tfgpu_emit_debezium for the TF_WIRE_DEBEZIUM branch of run_chain
     unsigned long long* lz_phases = nullptr;      // debug: per-phase cycle counters of k_lz4_frames
     void* work_json_sizes(uint64_t n) { json_sizes.ensure(n * 4 + 256); return json_sizes.p; }
@@ -103,6 +103,7 @@ struct tfgpu_result {
     std::vector<uint8_t> meta_kinds; std::vector<uint32_t> meta_tx; std::vector<uint64_t> meta_lsn, meta_ct;   // debezium: per message
     std::vector<uint32_t> row_sizes;       // row-text formats: bytes of every output row (incl. its separator / newline)
     std::vector<uint32_t> key_sizes;       // Debezium emitter: key message bytes of every output row
+    std::vector<uint32_t> msg_sizes;       // Debezium emitter: 7 per output row — message count, then (key bytes, value bytes | 0xFFFFFFFF) per message
     std::vector<uint32_t> part_ids;        // sharder_transformer: ChangeItem.PartID (as an integer) of every output row
     // push_columns output
     tf_batch batch{}; std::vector<tf_col> cols; std::vector<uint8_t*> owned;
@@ -442,7 +443,7 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         JsonArgs ja{e->d_cols, ser ? (wire_base == TF_WIRE_SER_CSV ? pd.d_scsvcols : pd.d_sjcols) : pd.d_jcols, (int)pl.out_cols.size(), ser ? pd.d_snames : pd.d_jnames, pd.d_mask_keys, sel, e->d_state, e->raw.p,
                     (uint32_t*)e->work_json_sizes(n), e->tile_sum, e->tile_base, e->col_bytes,
                     dbz ? 3 : ser ? (wire_base == TF_WIRE_SER_JSON ? 1 : 2) : 0, (uint32_t)(((wire_fmt & TF_WIRE_F_CLOSING_NEWLINE) ? TF_SER_NL : 0) | ((wire_fmt & TF_WIRE_F_ANY_AS_STRING) ? TF_SER_AAS : 0)), e->errcode, e->errstep, DbzEmitArgs{}};
-        if (dbz) { ja.jcols = pd.d_sjcols; e->dbz_keysz.ensure(n * 4 + 256); ja.dz = e->dbz; ja.dz.key_size = (uint32_t*)e->dbz_keysz.p; }
+        if (dbz) { ja.jcols = pd.d_sjcols; e->dbz_keysz.ensure(n * 4 + 256); e->dbz_msgsz.ensure(n * 28 + 256); ja.dz = e->dbz; ja.dz.key_size = (uint32_t*)e->dbz_keysz.p; ja.dz.msg_size = (uint32_t*)e->dbz_msgsz.p; }
         if (ser && !has_filter && n) { CK(cudaMemsetAsync(e->errcode, 0, n, s)); CK(cudaMemsetAsync(e->errstep, 0, n, s)); }
         if (jt) { e->prof_begin("k_json_sizes", s); launch_k_json_sizes(jt, TF_JSON_TILE, 0, s, ja); e->prof_end(s); }
         LayoutArgs lj{e->d_cols, 0, pd.d_out_cols, pd.d_str_slots, 1, e->tile_sum, e->tile_base, sz.ntiles_cap, pd.d_col_headers, pd.d_col_header_off,
@@ -595,7 +596,7 @@ int tfgpu_engine_destroy(tfgpu_engine* e) {
     if (e->ev_tail2) cudaEventDestroy(e->ev_tail2);
     if (e->side2_stream) cudaStreamDestroy(e->side2_stream);
     if (e->d_tail) cudaFree(e->d_tail);
-    e->dbz_keysz.release(); e->dbz_meta.release(); e->part_ids.release();
+    e->dbz_keysz.release(); e->dbz_meta.release(); e->dbz_old.release(); e->dbz_msgsz.release(); e->old_arena.release(); e->part_ids.release();
     if (e->side_stream) cudaStreamDestroy(e->side_stream);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
@@ -708,7 +709,7 @@ int tfgpu_resident_fetch(tfgpu_engine* e, int what, uint8_t* dst, uint64_t cap) 
     } catch (const CudaError& c) { return cuda_fail(e, c); }
 }
 
-static const uint8_t* stage_input(tfgpu_engine* e, const tf_batch* in, std::vector<tf_col>& dev);
+static const uint8_t* stage_input(tfgpu_engine* e, const tf_batch* in, std::vector<tf_col>& dev, DevBuf* arena_opt = nullptr);
 static void fetch_errors(tfgpu_engine* e, uint64_t n, tfgpu_result* r);
 static void finish_wire(tfgpu_engine* e, uint64_t n, int wire_fmt, tfgpu_result* r);
 
@@ -736,7 +737,8 @@ int tfgpu_push_encode(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch
 }
 
 // shared by push_encode / push_columns: stage host columns into HBM (or pass device pointers through)
-static const uint8_t* stage_input(tfgpu_engine* e, const tf_batch* in, std::vector<tf_col>& dev) {
+static const uint8_t* stage_input(tfgpu_engine* e, const tf_batch* in, std::vector<tf_col>& dev, DevBuf* arena_opt) {
+    DevBuf& arena = arena_opt ? *arena_opt : e->in_arena;
     const uint64_t n = in->nrows; const uint32_t nc = in->ncols;
     cudaStream_t s = e->stream;
     dev.resize(nc);
@@ -754,8 +756,8 @@ static const uint8_t* stage_input(tfgpu_engine* e, const tf_batch* in, std::vect
     };
     for (uint32_t c = 0; c < nc; c++) for (int k = 0; k < 5; k++) tot += align_up(sz_of(in->cols[c], k) + 16, 256);
     tot += align_up(n + 16, 256);
-    e->in_arena.ensure(tot);
-    uint8_t* p = e->in_arena.p;
+    arena.ensure(tot);
+    uint8_t* p = arena.p;
     auto up = [&](const void* src, size_t bytes) -> uint8_t* {
         if (!src || !bytes) { return nullptr; }
         uint8_t* d = p; CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, s)); p += align_up(bytes + 16, 256); return d;
@@ -765,7 +767,7 @@ static const uint8_t* stage_input(tfgpu_engine* e, const tf_batch* in, std::vect
         d.values = up(ic.values, sz_of(ic, 0)); d.validity = up(ic.validity, sz_of(ic, 1));
         d.offsets = (const uint32_t*)up(ic.offsets, sz_of(ic, 2));
         d.heap = up(ic.heap, sz_of(ic, 3));
-        if (!in_width(ic.type) && !d.heap) d.heap = e->in_arena.p;   // empty heap: any valid pointer
+        if (!in_width(ic.type) && !d.heap) d.heap = arena.p;   // empty heap: any valid pointer
         d.aux = up(ic.aux, sz_of(ic, 4));
     }
     return in->kinds ? up(in->kinds, n) : nullptr;
@@ -821,7 +823,8 @@ static void finish_wire(tfgpu_engine* e, uint64_t n, int wire_fmt, tfgpu_result*
     CK(cudaMemcpyAsync(r->bytes, lz ? e->wire.p : e->raw.p, r->bytes_len, cudaMemcpyDeviceToHost, s));
     { const int b = wire_fmt & 0xff;
       if ((b == TF_WIRE_SER_JSON || b == TF_WIRE_SER_CSV || b == TF_WIRE_CH_JSONEACHROW || b == TF_WIRE_DEBEZIUM) && st.n_kept) { r->row_sizes.resize(st.n_kept); CK(cudaMemcpyAsync(r->row_sizes.data(), e->json_sizes.p, st.n_kept * 4, cudaMemcpyDeviceToHost, s)); }
-      if (b == TF_WIRE_DEBEZIUM && st.n_kept) { r->key_sizes.resize(st.n_kept); CK(cudaMemcpyAsync(r->key_sizes.data(), e->dbz_keysz.p, st.n_kept * 4, cudaMemcpyDeviceToHost, s)); } }
+      if (b == TF_WIRE_DEBEZIUM && st.n_kept) { r->key_sizes.resize(st.n_kept); CK(cudaMemcpyAsync(r->key_sizes.data(), e->dbz_keysz.p, st.n_kept * 4, cudaMemcpyDeviceToHost, s));
+                                                r->msg_sizes.resize(st.n_kept * 7); CK(cudaMemcpyAsync(r->msg_sizes.data(), e->dbz_msgsz.p, st.n_kept * 28, cudaMemcpyDeviceToHost, s)); } }
     if (e->last_has_sharder && st.n_kept) { r->part_ids.resize(st.n_kept); CK(cudaMemcpyAsync(r->part_ids.data(), e->part_ids.p, st.n_kept * 4, cudaMemcpyDeviceToHost, s)); }
     if (st.n_errors) fetch_errors(e, n, r);
     CK(cudaStreamSynchronize(s));
@@ -908,9 +911,11 @@ DbzHostTpl dbz_host_template(const tfplan::Plan& pl, const std::string& opts_jso
     else { std::string pre, suf; wrap("key_schema", "key_schema_id", pre, suf); seg(pre, DZ_KEY); seg(suf, DZ_KEY_END); }
     std::string pre, suf; wrap("val_schema", "val_schema_id", pre, suf);
     seg(pre + "{\"after\":", DZ_AFTER);
+    seg(",\"before\":", DZ_BEFORE);                                                  // null, or OldKeys for update (replica identity full) / delete events
+    seg(",\"op\":\"", DZ_OP);                                                        // kindToOp kind.go:8-31
     const std::string name = q(ov->get_str("topic_prefix")), db = q(ov->get_str("database")), ver = q(ov->get_str("version"));
     const std::string snap = snapshot ? "\"true\"" : "\"false\"", tbl = q(pl.out_name), sch = q(pl.out_ns);
-    const std::string head = std::string(",\"before\":null,\"op\":") + (snapshot ? "\"r\"" : "\"c\"") + ",\"source\":{";        // kindToOp kind.go:8-14
+    const std::string head = "\",\"source\":{";
     if (st == "pg") {                 // buildSource :329-372, keys in encoding/json's sorted order
         seg(head + "\"connector\":\"postgresql\",\"db\":" + db + ",\"lsn\":", DZ_LSN);
         seg(",\"name\":" + name + ",\"schema\":" + sch + ",\"snapshot\":" + snap + ",\"table\":" + tbl + ",\"ts_ms\":", DZ_SRC_TS);
@@ -980,6 +985,10 @@ int tfgpu_emit_debezium_validate(const char* ns, const char* name, const char* s
 }
 
 int tfgpu_emit_debezium(tfgpu_engine* e, int plan_id, const char* opts_json, const tf_batch* in, const tf_row_meta* meta, tfgpu_result** out) {
+    return tfgpu_emit_debezium_crud(e, plan_id, opts_json, in, nullptr, meta, out);
+}
+
+int tfgpu_emit_debezium_crud(tfgpu_engine* e, int plan_id, const char* opts_json, const tf_batch* in, const tf_old_keys* old, const tf_row_meta* meta, tfgpu_result** out) {
     if (!e || !in || !out || !opts_json || plan_id < 0 || plan_id >= (int)e->plans.size()) return TF_E_FATAL_ARG;
     *out = nullptr;
     PlanDev& pd = *e->plans[plan_id];
@@ -1009,9 +1018,40 @@ int tfgpu_emit_debezium(tfgpu_engine* e, int plan_id, const char* opts_json, con
                 }
             } else { e->dbz.id = meta->id; e->dbz.lsn = meta->lsn; e->dbz.ct = meta->commit_time; e->dbz.gt_off = meta->txid_offsets; e->dbz.gt_heap = meta->txid_heap; }
         }
-        const uint8_t* pre = nullptr;
-        if (dev_kinds && n) { e->launches++; k_dbz_kinds<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(dev_kinds, n, M + o_pre); pre = M + o_pre; }
-        run_chain(e, pd, in, dev.data(), dev_kinds, TF_WIRE_DEBEZIUM, pre);
+        // update / delete events: kinds + OldKeys (as a second set of typed columns) reach the row writer
+        {
+            auto ov = tfj::parse(opts_json);
+            const tfplan::Plan& pl = pd.plan; const size_t nc = pl.in_schema.size();
+            e->dbz.kinds = dev_kinds; e->dbz.snapshot = ov->get_bool("snapshot") ? 1 : 0; e->dbz.mysql_src = ov->get_str("source_type") == "mysql" ? 1 : 0;
+            const tfj::Value* tv = ov->get("tombstones_on_delete"); e->dbz.tombstones = (tv && tv->kind == tfj::Value::Bool && !tv->b) ? 0 : 1;      // tombstones.on.delete, default true
+            int npk = 0; for (const auto& c : pl.out_schema) if (c.key) npk++;
+            e->dbz.n_pkeys = npk; e->dbz.old_cols = nullptr; e->dbz.old_present = nullptr; e->dbz.old_has = nullptr; e->dbz.n_old_present = 0;
+            if (old && old->values) {
+                if (old->values->ncols != nc || old->values->nrows != n || old->values->mem != in->mem) return fail(e, TF_E_FATAL_ARG, "old keys: same shape and memory space as the batch expected");
+                if (!pl.masks.empty() || !pl.todt_cols.empty() || !pl.tostr_cols.empty() || !pl.n2f_cols.empty()) return fail(e, TF_E_FATAL_UNSUPPORTED, "update / delete events after a transformer that rewrites values are emitted by the Go emitter");
+                std::vector<tf_col> odev; stage_input(e, old->values, odev, &e->old_arena);
+                std::vector<DCol> oc(nc); std::vector<uint8_t> present(nc, 0); int np = 0;
+                for (size_t c = 0; c < nc; c++) {
+                    const tf_col& ic = odev[c]; DCol& d = oc[c]; std::memset(&d, 0, sizeof d);
+                    if (ic.type != pl.in_schema[c].tf) return fail(e, TF_E_FATAL_ARG, "old keys: column " + std::to_string(c) + " type does not match the plan schema");
+                    d.type = ic.type; d.out_kind = OK_COPY; d.in_w = in_width(ic.type); d.out_w = d.in_w; d.str_slot = -1; d.mask_slot = -1;
+                    d.values = (const uint8_t*)ic.values; d.validity = ic.validity; d.offsets = ic.offsets; d.heap = ic.heap; d.aux = (const uint8_t*)ic.aux;
+                    present[c] = (old->present_cols && old->present_cols[c]) ? 1 : 0; np += present[c];
+                    if (present[c] && n) { if (d.in_w && !d.values) return fail(e, TF_E_FATAL_ARG, "old keys: values pointer is NULL"); if (!d.in_w && !d.offsets) return fail(e, TF_E_FATAL_ARG, "old keys: offsets pointer is NULL"); }
+                }
+                const size_t o_oc = 0, o_pr = align_up(nc * sizeof(DCol) + 16, 256), o_has = o_pr + align_up(nc + 16, 256);
+                e->dbz_old.ensure(o_has + n + 256);
+                CK(cudaMemcpyAsync(e->dbz_old.p + o_oc, oc.data(), nc * sizeof(DCol), cudaMemcpyHostToDevice, s));
+                CK(cudaMemcpyAsync(e->dbz_old.p + o_pr, present.data(), nc, cudaMemcpyHostToDevice, s));
+                e->dbz.old_cols = (const DCol*)(e->dbz_old.p + o_oc); e->dbz.old_present = e->dbz_old.p + o_pr; e->dbz.n_old_present = np;
+                if (old->row_has && n) {
+                    if (in->mem == TF_MEM_HOST) { CK(cudaMemcpyAsync(e->dbz_old.p + o_has, old->row_has, n, cudaMemcpyHostToDevice, s)); e->dbz.old_has = e->dbz_old.p + o_has; }
+                    else e->dbz.old_has = old->row_has;
+                }
+                CK(cudaStreamSynchronize(s));      // oc / present are stack vectors
+            }
+        }
+        run_chain(e, pd, in, dev.data(), dev_kinds, TF_WIRE_DEBEZIUM, nullptr);
         auto r = std::make_unique<tfgpu_result>();
         finish_wire(e, n, TF_WIRE_DEBEZIUM, r.get());
         *out = r.release();
@@ -1529,6 +1569,7 @@ int tfgpu_debug_lz4_phases(tfgpu_engine* e, int enable, uint64_t out[8]) {
     } catch (const CudaError& c) { return cuda_fail(e, c); }
 }
 
+const uint32_t* tfgpu_result_dbz_msg_sizes(const tfgpu_result* r) { return (r && !r->msg_sizes.empty()) ? r->msg_sizes.data() : nullptr; }
 const uint32_t* tfgpu_result_selection(const tfgpu_result* r) { return (r && !r->selection.empty()) ? r->selection.data() : nullptr; }
 const uint8_t* tfgpu_result_meta_kinds(const tfgpu_result* r) { return (r && !r->meta_kinds.empty()) ? r->meta_kinds.data() : nullptr; }
 const uint32_t* tfgpu_result_meta_tx_id(const tfgpu_result* r) { return (r && !r->meta_tx.empty()) ? r->meta_tx.data() : nullptr; }

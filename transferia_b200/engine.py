@@ -88,7 +88,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "tfgpu_version", "tfgpu_engine_create", "tfgpu_engine_destroy", "tfgpu_last_error", "tfgpu_engine_set_stream",
-    "tfgpu_plan", "tfgpu_plan_validate", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_parse_csv", "tfgpu_parse_json", "tfgpu_measure", "tfgpu_emit_debezium", "tfgpu_emit_debezium_validate", "tfgpu_result_key_sizes", "tfgpu_result_part_ids", "tfgpu_result_row_sizes", "tfgpu_queue_json_batches", "tfgpu_queue_debezium_batches", "tfgpu_parse_debezium", "tfgpu_debezium_schema_validate", "tfgpu_debug_lz4_phases", "tfgpu_result_selection", "tfgpu_result_meta_kinds", "tfgpu_result_meta_tx_id", "tfgpu_result_meta_lsn", "tfgpu_result_meta_commit_time", "tfgpu_result_consumed", "tfgpu_push_encode_resident",
+    "tfgpu_plan", "tfgpu_plan_validate", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_parse_csv", "tfgpu_parse_json", "tfgpu_measure", "tfgpu_emit_debezium", "tfgpu_emit_debezium_crud", "tfgpu_result_dbz_msg_sizes", "tfgpu_emit_debezium_validate", "tfgpu_result_key_sizes", "tfgpu_result_part_ids", "tfgpu_result_row_sizes", "tfgpu_queue_json_batches", "tfgpu_queue_debezium_batches", "tfgpu_parse_debezium", "tfgpu_debezium_schema_validate", "tfgpu_debug_lz4_phases", "tfgpu_result_selection", "tfgpu_result_meta_kinds", "tfgpu_result_meta_tx_id", "tfgpu_result_meta_lsn", "tfgpu_result_meta_commit_time", "tfgpu_result_consumed", "tfgpu_push_encode_resident",
     "tfgpu_resident_stats", "tfgpu_resident_fetch", "tfgpu_result_rows_in", "tfgpu_result_rows_out",
     "tfgpu_result_n_errors", "tfgpu_result_errors", "tfgpu_result_batch", "tfgpu_result_bytes",
     "tfgpu_result_bytes_len", "tfgpu_result_raw_len", "tfgpu_result_n_frames", "tfgpu_result_release",
@@ -368,16 +368,22 @@ class Engine:
         self._check(self._L.tfgpu_debug_lz4_phases(self._h, 1 if enable else 0, out))
         return [int(x) for x in out]
 
-    def emit_debezium(self, plan_id: int, batch: abi.Batch, opts: dict, meta: Optional[dict] = None, copy_bytes: bool = True) -> PushResult:
-        """Queue Debezium serializer (Emitter.EmitKV) over the INSERT rows that survive the plan's chain: PushResult whose
-        `wire` holds key message + value message per row, `key_sizes` / `row_sizes` split them. meta: {"id", "lsn",
-        "commit_time", "txid_offsets", "txid_heap"} arrays in the same memory space as the batch."""
+    def emit_debezium(self, plan_id: int, batch: abi.Batch, opts: dict, meta: Optional[dict] = None, copy_bytes: bool = True, old: Optional[abi.Batch] = None,
+                      old_present=None, old_row_has=None) -> PushResult:
+        """Queue Debezium serializer (Emitter.EmitKV) over the rows that survive the plan's chain: PushResult whose `wire` holds the
+        messages of every row (key, value; a delete adds its tombstone key; a key-changing update is delete + tombstone + insert);
+        `key_sizes` / `row_sizes` give the first key and the total per row, `msg_sizes` (rows_out x 7) the message count and
+        (key bytes, value bytes | 0xFFFFFFFF) per message. meta: {"id", "lsn", "commit_time", "txid_offsets", "txid_heap"} arrays in the
+        memory space of the batch. old / old_present / old_row_has: ChangeItem.OldKeys (tf_old_keys)."""
         import numpy as np
         tb = batch.as_struct()
         meta = meta or {}
         m, keep = abi.make_row_meta(meta.get("id"), meta.get("lsn"), meta.get("commit_time"), meta.get("txid_offsets"), meta.get("txid_heap"))
         res = C.c_void_p()
-        self._check(self._L.tfgpu_emit_debezium(self._h, plan_id, json.dumps(opts).encode(), C.byref(tb), C.byref(m), C.byref(res)))
+        ok, okeep = (abi.make_old_keys(old, old_present or [], old_row_has) if old is not None else (None, None))
+        self._L.tfgpu_emit_debezium_crud.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        self._check(self._L.tfgpu_emit_debezium_crud(self._h, plan_id, json.dumps(opts).encode(), C.cast(C.pointer(tb), C.c_void_p),
+                                                     C.cast(C.pointer(ok), C.c_void_p) if ok is not None else None, C.cast(C.pointer(m), C.c_void_p), C.cast(C.pointer(res), C.c_void_p)))
         try:
             L = self._L
             n = L.tfgpu_result_bytes_len(res)
@@ -390,6 +396,9 @@ class Engine:
             rs = L.tfgpu_result_row_sizes(res); ks = L.tfgpu_result_key_sizes(res)
             out.row_sizes = np.ctypeslib.as_array(rs, shape=(k,)).copy() if (rs and k) else np.zeros(0, np.uint32)
             out.key_sizes = np.ctypeslib.as_array(ks, shape=(k,)).copy() if (ks and k) else np.zeros(0, np.uint32)
+            L.tfgpu_result_dbz_msg_sizes.restype = C.POINTER(C.c_uint32); L.tfgpu_result_dbz_msg_sizes.argtypes = [C.c_void_p]
+            ms = L.tfgpu_result_dbz_msg_sizes(res)
+            out.msg_sizes = np.ctypeslib.as_array(ms, shape=(k, 7)).copy() if (ms and k) else np.zeros((0, 7), np.uint32)
             return out
         finally:
             self._L.tfgpu_result_release(res)
