@@ -126,12 +126,13 @@ static __device__ int d_parse_int(const uint8_t* s, uint32_t n, int64_t& out) {
         if (i >= n) return 1;
     }
     uint64_t v = 0; const uint64_t lim = neg ? (1ull << 63) : ((1ull << 63) - 1);
+    const bool safe = n - i <= 15;             // 15 digits of any base up to 16 stay below 2^63: no overflow check (a 64-bit division) per digit
     for (; i < n; i++) {
         const uint8_t c = s[i]; uint32_t d;
         if (c == '_') return 2;
         if (c >= '0' && c <= '9') d = c - '0'; else if ((c | 0x20) >= 'a' && (c | 0x20) <= 'z') d = (c | 0x20) - 'a' + 10; else return 1;
         if (d >= base) return 1;
-        if (v > (lim - d) / base) return 1;      // v * base + d > lim
+        if (!safe && v > (lim - d) / base) return 1;      // v * base + d > lim
         v = v * base + d;
     }
     out = neg ? (int64_t)(0 - v) : (int64_t)v; return 0;
@@ -290,11 +291,9 @@ __device__ __forceinline__ void csv_default(const CsvArgs& a, const CsvColDev& c
     if (c.tf == TF_ANY) { ss[row] = 0xffffffffu; sl[row] = 2; c.aux8[row] = 0; } else { ss[row] = 0; sl[row] = 0; }
 }
 
-#ifdef TF_KERNELS_CSV
-__global__ void __launch_bounds__(128) k_csv_pass1(CsvArgs a) {
-    const uint64_t nrows = a.nlines - a.skip;
-    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= nrows) return;
+// One row, start to end, by one thread: the reference's split loop as written (pkg/csv/reader.go:229-261). The warp-parallel kernel below
+// falls back to it for lines with more delimiters than its table holds.
+static __device__ void csv_row_sequential(const CsvArgs& a, uint64_t row, uint64_t nrows) {
     const uint64_t ln = row + a.skip;
     const uint32_t ls = ln ? a.line_end[ln - 1] : 0, le = a.line_end[ln];
     const uint8_t* line = a.text + ls; const uint32_t n = le - ls;
@@ -340,6 +339,235 @@ __global__ void __launch_bounds__(128) k_csv_pass1(CsvArgs a) {
         for (int c = 0; c < a.ncols; c++) { const CsvColDev& cd = a.cols[c]; if (!cd.w) { a.span_start[(size_t)cd.slot * nrows + row] = 0; a.span_len[(size_t)cd.slot * nrows + row] = 0; if (cd.aux8) cd.aux8[row] = 0; } else csv_store_fixed(cd, row, 0, 0); }
     }
     a.err[row] = (uint8_t)err;
+}
+
+// Warp-parallel tokeniser: one warp per line. The line is read 32 bytes at a time (coalesced); ballots give the quote / delimiter bitmaps of
+// the slab; the in-quote state of every byte comes from bit counts over the quote bitmap — a quote that follows the escape character
+// leaves the state "inside" whatever it was (reader.go:236-243: inside quotes it is skipped, outside it opens a quote), every other quote
+// toggles it — so no lane walks the line; delimiters outside quotes get their ordinal from a popc prefix and land in a shared-memory
+// table. Then the lanes take the line's elements 32 at a time: trim, unquote, typed parse (csv_cell) — the field-level work of a
+// 99-column row runs 32 wide instead of serially.
+#define CSV_WARPS 8
+#define CSV_MAXF 512
+// rows [row0, row1), one warp per line; s_dpos [CSV_WARPS][CSV_MAXF], s_fq [CSV_WARPS][CSV_MAXF / 32 + 1] (bit f: element f contains a quote character)
+static __device__ void csv_rows_by_warp(const CsvArgs& a, uint64_t row0, uint64_t row1, uint32_t (*s_dpos)[CSV_MAXF], uint32_t (*s_fq)[CSV_MAXF / 32 + 1]) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, below = (1u << lane) - 1;
+    const uint64_t nrows = a.nlines - a.skip;
+    const CsvCfg& o = a.cfg;
+    for (uint64_t row = row0 + warp; row < row1; row += CSV_WARPS) {
+        const uint64_t ln = row + a.skip;
+        const uint32_t ls = ln ? a.line_end[ln - 1] : 0, le = a.line_end[ln];
+        const uint8_t* line = a.text + ls; const uint32_t n = le - ls;
+        // ---- tokenise
+        uint32_t nd = 0;
+        if (lane <= CSV_MAXF / 32) s_fq[warp][lane] = 0;
+        __syncwarp();
+        if (n > 1) {
+            uint32_t inq_carry = 0; uint32_t prevc = 0;
+            for (uint32_t base = 0; base < n; base += 32) {
+                const uint32_t i = base + lane; const bool in = i < n;
+                const uint32_t c = in ? line[i] : 0u;
+                const uint32_t up = __shfl_up_sync(0xffffffffu, c, 1); const uint32_t prev = lane ? up : prevc;
+                const bool isq = in && o.quote && c == o.quote;
+                const uint32_t qm = __ballot_sync(0xffffffffu, isq);
+                const uint32_t eqm = __ballot_sync(0xffffffffu, isq && o.escape && prev == o.escape);
+                const uint32_t nm = qm & ~eqm;
+                uint32_t inq;
+                const uint32_t eqb = eqm & below;
+                if (eqb) { const uint32_t h = 31 - __clz(eqb); inq = 1u ^ (__popc(nm & below & ~((2u << h) - 1)) & 1u); }
+                else inq = inq_carry ^ (__popc(nm & below) & 1u);
+                const bool isd = in && c == o.delimiter && !isq && !inq;
+                const uint32_t dm = __ballot_sync(0xffffffffu, isd);
+                if (isd) { const uint32_t k = nd + __popc(dm & below); if (k < CSV_MAXF) s_dpos[warp][k] = i; }
+                if (isq) { const uint32_t fo = nd + __popc(dm & below); if (fo <= CSV_MAXF) atomicOr(&s_fq[warp][fo >> 5], 1u << (fo & 31)); }
+                nd += __popc(dm);
+                if (eqm) { const uint32_t h = 31 - __clz(eqm); inq_carry = 1u ^ (__popc(nm & ~((2u << h) - 1)) & 1u); }
+                else inq_carry ^= __popc(nm) & 1u;
+                prevc = __shfl_sync(0xffffffffu, c, 31);
+            }
+        }
+        __syncwarp();
+        if (nd > CSV_MAXF) { if (lane == 0) csv_row_sequential(a, row, nrows); __syncwarp(); continue; }      // more delimiters than the table holds
+        const uint32_t nf = n > 1 ? nd + 1 : 0;
+        // ---- elements, 32 at a time
+        uint32_t err_key = 0xffffffffu, conv_key = 0xffffffffu;      // (field << 8) | code of the first split-level error; (column << 8) | code of the first conversion error
+        for (uint32_t f = lane; f < nf; f += 32) {
+            const uint32_t ea = f ? s_dpos[warp][f - 1] + 1 : (nd ? 0u : 1u);      // without any delimiter the element is line[1:] (lastDelimPosition stays 0, reader.go:255-259)
+            const uint32_t eb = f < nd ? s_dpos[warp][f] : n;
+            const uint8_t* p = line + (ea <= n ? ea : n); uint32_t m = eb - (ea <= n ? ea : n);
+            if (m && !(p[0] > 0x20 && p[0] < 0x80 && p[m - 1] > 0x20 && p[m - 1] < 0x80)) d_trim(p, m);      // (every space TrimSpace knows starts <= 0x20 or >= 0x80)
+            bool has_dq = false; int e = 0;
+            if (o.quote && ((s_fq[warp][f >> 5] >> (f & 31)) & 1)) {
+                if (m == 1 && p[0] == o.quote) e = CSV_SINGLE_QUOTE;
+                else {
+                    if (m >= 2 && p[0] == o.quote && p[m - 1] == o.quote) { p++; m -= 2; }
+                    for (uint32_t k = 0; k + 1 < m; k++) if (p[k] == '"' && p[k + 1] == '"') { has_dq = true; break; }
+                    if (has_dq && !o.double_quote) e = CSV_DOUBLE_QUOTE_DISABLED;
+                }
+            }
+            if (e) { const uint32_t key = (f << 8) | (uint32_t)e; if (key < err_key) err_key = key; continue; }
+            if ((int)f < a.nfields) for (int c = a.field_col[f]; c >= 0; c = a.next_same[c]) {
+                const int rc = csv_cell(a, a.cols[c], row, nrows, p, m, has_dq);
+                if (rc) { const uint32_t key = ((uint32_t)c << 8) | (uint32_t)rc; if (key < conv_key) conv_key = key; }
+            }
+        }
+        err_key = __reduce_min_sync(0xffffffffu, err_key); conv_key = __reduce_min_sync(0xffffffffu, conv_key);
+        int err = err_key == 0xffffffffu ? 0 : (int)(err_key & 0xff);
+        // columns whose field is missing, or that take the default value (reader_csv.go:291-313). constructCI runs over
+        // every column before Strictify does, so a missing cell outranks any conversion error.
+        bool missing = false;
+        if (!err) for (int c = (int)lane; c < a.ncols; c += 32) {
+            const CsvColDev& cd = a.cols[c];
+            if (cd.path < 0) csv_default(a, cd, row, nrows);
+            else if ((uint32_t)cd.path >= nf) { if (o.include_missing) csv_default(a, cd, row, nrows); else missing = true; }
+        }
+        if (!err && __any_sync(0xffffffffu, missing)) err = CSV_MISSING_CELL;
+        if (!err && conv_key != 0xffffffffu) err = (int)(conv_key & 0xff);
+        if (err) {   // an error row is dropped later; give its cells harmless contents
+            __syncwarp();
+            for (int c = (int)lane; c < a.ncols; c += 32) { const CsvColDev& cd = a.cols[c]; if (!cd.w) { a.span_start[(size_t)cd.slot * nrows + row] = 0; a.span_len[(size_t)cd.slot * nrows + row] = 0; if (cd.aux8) cd.aux8[row] = 0; } else csv_store_fixed(cd, row, 0, 0); }
+        }
+        if (lane == 0) a.err[row] = (uint8_t)err;
+        __syncwarp();
+    }
+}
+
+// The main kernel: a CTA takes 32 consecutive lines. Their bytes are one contiguous stretch of the text, staged in shared memory with
+// coalesced loads; the warps tokenise them (4 lines each, the ballot scheme above) into a table of element boundaries; then LANE = LINE
+// and the warps stride over the ELEMENTS: all 32 lanes parse the same column of 32 different rows — the same cell type, so no divergence
+// over types, and 32 consecutive rows of one column are stored together (coalesced). Tiles longer than the staging buffer and tables
+// with more than CSV_TF fields take the warp-per-line path.
+#define CSV_TILE_ROWS 32
+#define CSV_TILE_BYTES 28672
+#define CSV_TF 250            /* element boundaries kept per line */
+#ifdef TF_KERNELS_CSV
+__global__ void __launch_bounds__(32 * CSV_WARPS, 4) k_csv_pass1(CsvArgs a) {
+    __shared__ __align__(16) uint8_t s_tile[CSV_TILE_BYTES + 16];      // (the warp-per-line tables alias it)
+    __shared__ uint16_t s_end[CSV_TILE_ROWS][CSV_TF + 2];              // position (relative to the line) of the first CSV_TF delimiters
+    __shared__ uint32_t s_fqt[CSV_TILE_ROWS][(CSV_TF + 32) / 32];      // bit f: element f of the line contains a quote character
+    __shared__ uint32_t s_nd[CSV_TILE_ROWS], s_errk[CSV_TILE_ROWS], s_convk[CSV_TILE_ROWS], s_miss[CSV_TILE_ROWS], s_ls[CSV_TILE_ROWS + 1];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, below = (1u << lane) - 1;
+    const uint64_t nrows = a.nlines - a.skip;
+    const CsvCfg& o = a.cfg;
+    for (uint64_t row0 = (uint64_t)blockIdx.x * CSV_TILE_ROWS; row0 < nrows; row0 += (uint64_t)gridDim.x * CSV_TILE_ROWS) {
+        const uint32_t nr = (uint32_t)(nrows - row0 < CSV_TILE_ROWS ? nrows - row0 : CSV_TILE_ROWS);
+        const uint64_t ln0 = row0 + a.skip;
+        const uint32_t g0 = ln0 ? a.line_end[ln0 - 1] : 0, g1 = a.line_end[ln0 + nr - 1];
+        __syncthreads();
+        if (g1 - g0 > CSV_TILE_BYTES || a.nfields > CSV_TF) {      // long lines / wide tables: one warp per line, straight from global memory
+            csv_rows_by_warp(a, row0, row0 + nr, (uint32_t (*)[CSV_MAXF])s_tile, (uint32_t (*)[CSV_MAXF / 32 + 1])(s_tile + sizeof(uint32_t) * CSV_WARPS * CSV_MAXF));
+            continue;
+        }
+        // ---- stage the tile
+        {
+            const uint32_t mis = (uint32_t)((uintptr_t)(a.text + g0) & 15);       // 16-byte chunks of the text, aligned in global memory
+            const uint8_t* gb = a.text + g0 - mis; const uint32_t nchunk = (mis + (g1 - g0) + 15) >> 4;
+            for (uint32_t c = threadIdx.x; c < nchunk; c += blockDim.x) {
+                const uint32_t off = c * 16;
+                // the tile is kept at the same misalignment: s_tile[mis + k] = text[g0 + k]
+                if ((uint64_t)(g0 - mis) + off + 16 <= a.len) *(int4*)(s_tile + off) = __ldg((const int4*)(gb + off));
+                else for (uint32_t b = 0; b < 16; b++) s_tile[off + b] = ((uint64_t)(g0 - mis) + off + b < a.len) ? gb[off + b] : 0;      // the end of the text
+            }
+            if (threadIdx.x <= nr) s_ls[threadIdx.x] = (threadIdx.x ? a.line_end[ln0 + threadIdx.x - 1] : g0) - g0 + mis;
+            if (threadIdx.x < CSV_TILE_ROWS) { s_errk[threadIdx.x] = 0xffffffffu; s_convk[threadIdx.x] = 0xffffffffu; s_miss[threadIdx.x] = 0; s_nd[threadIdx.x] = 0; }
+            for (uint32_t k = threadIdx.x; k < CSV_TILE_ROWS * ((CSV_TF + 32) / 32); k += blockDim.x) (&s_fqt[0][0])[k] = 0;
+        }
+        __syncthreads();
+        // ---- tokenise: warp w takes lines w, w + 8, ...
+        for (uint32_t r = warp; r < nr; r += CSV_WARPS) {
+            const uint8_t* line = s_tile + s_ls[r]; const uint32_t n = s_ls[r + 1] - s_ls[r];
+            uint32_t nd = 0;
+            if (n > 1) {
+                uint32_t inq_carry = 0, prevc = 0;
+                for (uint32_t base = 0; base < n; base += 32) {
+                    const uint32_t i = base + lane; const bool in = i < n;
+                    const uint32_t c = in ? line[i] : 0u;
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, c, 1); const uint32_t prev = lane ? up : prevc;
+                    const bool isq = in && o.quote && c == o.quote;
+                    const uint32_t qm = __ballot_sync(0xffffffffu, isq);
+                    const uint32_t eqm = __ballot_sync(0xffffffffu, isq && o.escape && prev == o.escape);
+                    const uint32_t nm = qm & ~eqm;
+                    uint32_t inq;
+                    const uint32_t eqb = eqm & below;
+                    if (eqb) { const uint32_t h = 31 - __clz(eqb); inq = 1u ^ (__popc(nm & below & ~((2u << h) - 1)) & 1u); }
+                    else inq = inq_carry ^ (__popc(nm & below) & 1u);
+                    const bool isd = in && c == o.delimiter && !isq && !inq;
+                    const uint32_t dm = __ballot_sync(0xffffffffu, isd);
+                    if (isd) { const uint32_t k = nd + __popc(dm & below); if (k < CSV_TF) s_end[r][k] = (uint16_t)i; }
+                    if (isq) { const uint32_t fo = nd + __popc(dm & below); if (fo <= CSV_TF) atomicOr(&s_fqt[r][fo >> 5], 1u << (fo & 31)); }
+                    nd += __popc(dm);
+                    if (eqm) { const uint32_t h = 31 - __clz(eqm); inq_carry = 1u ^ (__popc(nm & ~((2u << h) - 1)) & 1u); }
+                    else inq_carry ^= __popc(nm) & 1u;
+                    prevc = __shfl_sync(0xffffffffu, c, 31);
+                }
+            }
+            if (lane == 0) s_nd[r] = nd | (n > 1 ? 0x80000000u : 0u);
+        }
+        __syncthreads();
+        // ---- elements: lane = line, the warps stride over the element index
+        {
+            const uint32_t r = lane; const bool live = r < nr;
+            const uint32_t ndw = live ? s_nd[r] : 0; const uint32_t nd = ndw & 0x7fffffffu; const uint32_t nf = (ndw >> 31) ? nd + 1 : 0;
+            const uint32_t n = live ? s_ls[r + 1] - s_ls[r] : 0;
+            const uint8_t* line = s_tile + (live ? s_ls[r] : 0);
+            const uint64_t row = row0 + r;
+            // csv_cell records text cells as offsets from a.text: give it a base that makes a tile pointer come out as the text offset
+            CsvArgs at = a; at.text = line - ((uint64_t)g0 + (live ? s_ls[r] : 0) - (uint32_t)((uintptr_t)(a.text + g0) & 15));
+            uint32_t nf_max = nf;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) { const uint32_t v = __shfl_xor_sync(0xffffffffu, nf_max, d); nf_max = v > nf_max ? v : nf_max; }
+            uint32_t err_key = 0xffffffffu, conv_key = 0xffffffffu;
+            for (uint32_t f = warp; f < nf_max; f += CSV_WARPS) {
+                if (f >= nf) continue;
+                if (nd > CSV_TF && f >= CSV_TF) continue;                 // boundaries beyond the table: only lines of a wider table than the schema reads (checked below)
+                const uint32_t ea0 = f ? (uint32_t)s_end[r][f - 1] + 1 : (nd ? 0u : 1u);      // without any delimiter the element is line[1:] (reader.go:255-259)
+                const uint32_t ea = ea0 <= n ? ea0 : n, eb = f < nd ? s_end[r][f] : n;
+                const uint8_t* p = line + ea; uint32_t m = eb - ea;
+                if (m && !(p[0] > 0x20 && p[0] < 0x80 && p[m - 1] > 0x20 && p[m - 1] < 0x80)) d_trim(p, m);      // (every space TrimSpace knows starts <= 0x20 or >= 0x80)
+                bool has_dq = false; int e = 0;
+                if (o.quote && ((s_fqt[r][f >> 5] >> (f & 31)) & 1)) {
+                    if (m == 1 && p[0] == o.quote) e = CSV_SINGLE_QUOTE;
+                    else {
+                        if (m >= 2 && p[0] == o.quote && p[m - 1] == o.quote) { p++; m -= 2; }
+                        for (uint32_t k = 0; k + 1 < m; k++) if (p[k] == '"' && p[k + 1] == '"') { has_dq = true; break; }
+                        if (has_dq && !o.double_quote) e = CSV_DOUBLE_QUOTE_DISABLED;
+                    }
+                }
+                if (e) { const uint32_t key = (f << 8) | (uint32_t)e; if (key < err_key) err_key = key; continue; }
+                if ((int)f < a.nfields) for (int c = a.field_col[f]; c >= 0; c = a.next_same[c]) {
+                    const int rc = csv_cell(at, a.cols[c], row, nrows, p, m, has_dq);
+                    if (rc) { const uint32_t key = ((uint32_t)c << 8) | (uint32_t)rc; if (key < conv_key) conv_key = key; }
+                }
+            }
+            if (live) { if (err_key != 0xffffffffu) atomicMin(&s_errk[r], err_key); if (conv_key != 0xffffffffu) atomicMin(&s_convk[r], conv_key); }
+            // columns whose field is missing, or that take the default value (reader_csv.go:291-313)
+            if (live) for (int c = (int)warp; c < a.ncols; c += CSV_WARPS) {
+                const CsvColDev& cd = a.cols[c];
+                if (cd.path < 0) csv_default(a, cd, row, nrows);
+                else if ((uint32_t)cd.path >= nf) { if (o.include_missing) csv_default(a, cd, row, nrows); else s_miss[r] = 1; }
+            }
+        }
+        __syncthreads();
+        // ---- the row's verdict: a split-level error of the first element that has one, else a missing cell (constructCI runs over every
+        // column before Strictify does), else the conversion error of the first schema column that fails
+        {
+            const uint32_t r = lane; const bool live = r < nr;
+            int err = 0;
+            if (live) {
+                const uint32_t ndw = s_nd[r];
+                if ((ndw & 0x7fffffffu) > CSV_TF) err = -1;                // more delimiters than the table holds: redo this line sequentially
+                else if (s_errk[r] != 0xffffffffu) err = (int)(s_errk[r] & 0xff);
+                else if (s_miss[r]) err = CSV_MISSING_CELL;
+                else if (s_convk[r] != 0xffffffffu) err = (int)(s_convk[r] & 0xff);
+            }
+            if (warp == 0 && live && err == -1) { csv_row_sequential(a, row0 + r, nrows); }
+            if (err > 0) for (int c = (int)warp; c < a.ncols; c += CSV_WARPS) {      // an error row is dropped later; give its cells harmless contents
+                const CsvColDev& cd = a.cols[c]; const uint64_t row = row0 + r;
+                if (!cd.w) { a.span_start[(size_t)cd.slot * nrows + row] = 0; a.span_len[(size_t)cd.slot * nrows + row] = 0; if (cd.aux8) cd.aux8[row] = 0; } else csv_store_fixed(cd, row, 0, 0);
+            }
+            if (warp == 0 && live && err >= 0) a.err[row0 + r] = (uint8_t)err;
+        }
+    }
 }
 #endif  // TF_KERNELS_CSV
 
