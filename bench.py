@@ -236,19 +236,20 @@ def extra_paths(eng, args):
             open(dcache, "wb").write(ddata); np.save(dcache + ".npy", dends)
         dschema = engine.debezium_table_schema(dschema_text); dtrs = workload.debezium_transformers()
         dpid = eng.plan(dtable[0], dtable[1], dschema, dtrs, {"type": "clickhouse"})
-        kw = dict(schema_registry=True, schema_id=7, wire_fmt=abi.TF_WIRE_CH_NATIVE_LZ4)
+        kw = dict(schema_registry=True, schema_id=7, wire_fmt=abi.TF_WIRE_CH_NATIVE_LZ4, copy_bytes=False)
+        dpin = torch.frombuffer(bytearray(ddata), dtype=torch.uint8).pin_memory()        # the message bytes as a consumer would hold them: pinned
         for _ in range(2):
-            r, _m = eng.parse_debezium(dpid, ddata, dends, dschema_text, **kw)
+            r, _m = eng.parse_debezium(dpid, dpin, dends, dschema_text, **kw)
         torch.cuda.synchronize(); t0 = time.perf_counter(); k = 5
         for _ in range(k):
-            r, _m = eng.parse_debezium(dpid, ddata, dends, dschema_text, **kw)
+            r, _m = eng.parse_debezium(dpid, dpin, dends, dschema_text, **kw)
         torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / k
         eng.profile_enable(True); eng.parse_debezium(dpid, ddata, dends, dschema_text, **kw); prof = {kk["name"]: round(kk["ms"], 4) for kk in eng.profile_read()}; eng.profile_enable(False)
         kern_ms = sum(prof.values())
         res["debezium_parse_filter_cast"] = {"rows_per_s": len(dends) / dt, "messages": int(len(dends)), "input_MB": len(ddata) / 1e6, "ms": dt * 1e3, "rows_out": r.rows_out, "row_errors": len(r.errors),
-                                             "out_bytes": len(r.wire), "kernels_ms": prof, "kernels_GBps_of_input": {n: round(len(ddata) / 1e6 / v, 1) for n, v in prof.items() if v > 0.02},
+                                             "out_bytes": int(r.wire_len), "kernels_ms": prof, "kernels_GBps_of_input": {n: round(len(ddata) / 1e6 / v, 1) for n, v in prof.items() if v > 0.02},
                                              "kernel_only_rows_per_s": len(dends) / (kern_ms / 1e3) if kern_ms else None,
-                                             "note": "wall clock around tfgpu_parse_debezium with the message bytes in host memory (pageable: the ctypes binding copies them): H2D, the fused chain and D2H of the frames included"}
+                                             "note": "wall clock around tfgpu_parse_debezium with the message bytes in a pinned host buffer: H2D, the fused chain and D2H of the frames into the pinned landing buffer included"}
         try:
             from oracle import pyoracle as po
             ns = 4000; sd = ddata[: int(dends[ns - 1])]
@@ -269,18 +270,19 @@ def extra_paths(eng, args):
         else:
             ctext = workload.render_hits_csv(cb, cschema); open(ccache, "wb").write(ctext)
         cpid = eng.plan("public", "hits", cschema, [], {"type": "clickhouse"})
+        cpin = torch.frombuffer(bytearray(ctext), dtype=torch.uint8).pin_memory()
         for _ in range(2):
-            r, _c = eng.parse_csv(cpid, ctext, wire_fmt=abi.TF_WIRE_CH_NATIVE_LZ4)
+            r, _c = eng.parse_csv(cpid, cpin, wire_fmt=abi.TF_WIRE_CH_NATIVE_LZ4, copy_bytes=False)
         torch.cuda.synchronize(); t0 = time.perf_counter(); k = 5
         for _ in range(k):
-            r, _c = eng.parse_csv(cpid, ctext, wire_fmt=abi.TF_WIRE_CH_NATIVE_LZ4)
+            r, _c = eng.parse_csv(cpid, cpin, wire_fmt=abi.TF_WIRE_CH_NATIVE_LZ4, copy_bytes=False)
         torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / k
         eng.profile_enable(True); eng.parse_csv(cpid, ctext, wire_fmt=abi.TF_WIRE_CH_NATIVE_LZ4); prof = {kk["name"]: round(kk["ms"], 4) for kk in eng.profile_read()}; eng.profile_enable(False)
         kern_ms = sum(prof.values())
-        res["csv_parse_cast_native"] = {"rows_per_s": args.csv_rows / dt, "rows": args.csv_rows, "input_MB": len(ctext) / 1e6, "ms": dt * 1e3, "rows_out": r.rows_out, "out_bytes": len(r.wire), "kernels_ms": prof,
+        res["csv_parse_cast_native"] = {"rows_per_s": args.csv_rows / dt, "rows": args.csv_rows, "input_MB": len(ctext) / 1e6, "ms": dt * 1e3, "rows_out": r.rows_out, "out_bytes": int(r.wire_len), "kernels_ms": prof,
                                         "kernels_GBps_of_input": {n: round(len(ctext) / 1e6 / v, 1) for n, v in prof.items() if v > 0.02},
                                         "kernel_only_rows_per_s": args.csv_rows / (kern_ms / 1e3) if kern_ms else None,
-                                        "note": "wall clock around tfgpu_parse_csv with the text in host memory: H2D, tokenise + cast + native block + LZ4 frames, D2H included"}
+                                        "note": "wall clock around tfgpu_parse_csv with the text in a pinned host buffer: H2D, tokenise + cast + native block + LZ4 frames, D2H into the pinned landing buffer included"}
         try:
             from oracle import pyoracle as po
             cut = ctext.rfind(b"\n", 0, len(ctext) // 25) + 1; sample = ctext[:cut]

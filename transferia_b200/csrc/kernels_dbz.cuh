@@ -253,15 +253,35 @@ __device__ __forceinline__ bool dbz_lit_uint(const uint8_t* s, uint32_t off, uin
     out = v; set = true; return true;
 }
 
+// The messages of one CTA are a contiguous span of the input; one thread per message walks its own message byte by byte, so the CTA
+// first copies the span into shared memory with coalesced 16-byte loads (when it fits) and the per-message code reads that copy
+// through the same offsets (cf. jsn_stage_span).
+#define DBZ_STAGE 73728
+__device__ __forceinline__ const uint8_t* dbz_stage_span(const DbzArgs& a, uint8_t* stage) {
+    const uint64_t M0 = (uint64_t)blockIdx.x * blockDim.x;
+    if (M0 >= a.nmsgs) return a.text;
+    const uint64_t Me = (M0 + blockDim.x < a.nmsgs) ? M0 + blockDim.x : a.nmsgs;
+    const uint64_t lo = M0 ? a.msg_end[M0 - 1] : 0, hi = a.msg_end[Me - 1];
+    const uint64_t lo16 = lo & ~15ull;
+    if (hi - lo16 > DBZ_STAGE || ((uintptr_t)a.text & 15)) return a.text;           // uniform over the CTA
+    const uint32_t full = (uint32_t)((hi - lo16) & ~15ull);                         // whole 16-byte chunks inside the span
+    for (uint32_t i = threadIdx.x * 16; i < full; i += blockDim.x * 16) *(int4*)(stage + i) = __ldg((const int4*)(a.text + lo16 + i));
+    for (uint64_t i = full + threadIdx.x; lo16 + i < hi; i += blockDim.x) stage[i] = a.text[lo16 + i];
+    __syncthreads();
+    return stage - lo16;
+}
+
 #ifdef TF_KERNELS_DBZ
 __global__ void __launch_bounds__(128) k_dbz_pass1(DbzArgs a) {
+    extern __shared__ __align__(16) uint8_t dbz_stage[];
+    const uint8_t* const text = dbz_stage_span(a, dbz_stage);      // the CTA's messages, copied to shared memory with coalesced loads when they fit
     const uint64_t M = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = M < a.nmsgs;
     uint32_t vb[JSN_MAX_COLS / 32]; for (int i = 0; i < JSN_MAX_COLS / 32; i++) vb[i] = 0;
     int err = 0, ecol = 0;
     if (active) {
         const uint64_t ms = M ? a.msg_end[M - 1] : 0; const uint32_t n = (uint32_t)(a.msg_end[M] - ms);
-        const uint8_t* s = a.text + ms;
+        const uint8_t* s = text + ms;
         uint32_t pay_off = 0, pay_end = 0, pay_t = JT_ABSENT;
         uint32_t sch_off = 0, sch_end = 0; bool have_schema = false;
         if (!n) err = DBZ_UNPARSED;                                              // "debezium parser received empty message"
@@ -363,9 +383,9 @@ __global__ void __launch_bounds__(128) k_dbz_pass1(DbzArgs a) {
                 if (t == JT_ABSENT) { err = DBZ_UNPARSED; ecol = c; break; }            // "unable to get field %s"
                 if (len >= (1u << 28) - 1) { err = DBZ_HOST; ecol = c; break; }
                 bool null = t == JT_NULL; int rc = 0;
-                if (!null && t == JT_STRING && dbz_is_unavailable(a.text, off, len)) rc = DBZ_HOST;
+                if (!null && t == JT_STRING && dbz_is_unavailable(text, off, len)) rc = DBZ_HOST;
                 else if (!null) {
-                    const uint8_t* v = a.text + off;
+                    const uint8_t* v = text + off;
                     switch (cd.recv) {
                     case DR_INT8: case DR_INT16: case DR_INT32: case DR_INT64: {
                         int64_t x; if (t != JT_NUMBER || d_go_parse_int(v, len, 10, 64, x)) rc = DBZ_UNPARSED;
@@ -380,19 +400,19 @@ __global__ void __launch_bounds__(128) k_dbz_pass1(DbzArgs a) {
                     case DR_VSD: {
                         if (t != JT_OBJECT) { rc = DBZ_HOST; break; }
                         uint32_t vo2 = 0, ve2 = 0, vt2 = JT_ABSENT, so2 = 0, se2 = 0, st2 = JT_ABSENT;
-                        dbz_members(a.text, off, off + len, [&](uint32_t k0, uint32_t kl, uint32_t x0, uint32_t x1, uint32_t xt) {
-                            if (dbz_key_eq(a.text + k0, kl, "value")) { vo2 = x0; ve2 = x1; vt2 = xt; } else if (dbz_key_eq(a.text + k0, kl, "scale")) { so2 = x0; se2 = x1; st2 = xt; } });
+                        dbz_members(text, off, off + len, [&](uint32_t k0, uint32_t kl, uint32_t x0, uint32_t x1, uint32_t xt) {
+                            if (dbz_key_eq(text + k0, kl, "value")) { vo2 = x0; ve2 = x1; vt2 = xt; } else if (dbz_key_eq(text + k0, kl, "scale")) { so2 = x0; se2 = x1; st2 = xt; } });
                         if (vt2 == JT_ABSENT) { rc = DBZ_UNPARSED; break; }
                         if (vt2 != JT_STRING) { rc = DBZ_HOST; break; }
                         int64_t scale = 0;
-                        if (st2 != JT_ABSENT) { if (st2 != JT_NUMBER) { rc = DBZ_HOST; break; } if (d_go_parse_int(a.text + so2, se2 - so2, 10, 64, scale)) { rc = DBZ_UNPARSED; break; } }
-                        uint8_t nb[JSN_NUMBUF + 160]; BufSink bs{nb, 0, sizeof nb, false}; DbzStr src(a.text + vo2, ve2 - vo2, JT_STRING);
+                        if (st2 != JT_ABSENT) { if (st2 != JT_NUMBER) { rc = DBZ_HOST; break; } if (d_go_parse_int(text + so2, se2 - so2, 10, 64, scale)) { rc = DBZ_UNPARSED; break; } }
+                        uint8_t nb[JSN_NUMBUF + 160]; BufSink bs{nb, 0, sizeof nb, false}; DbzStr src(text + vo2, ve2 - vo2, JT_STRING);
                         const int br = (scale < 0 || scale > 200) ? 2 : dbz_b64_numeric(bs, src, (int)scale);
                         if (br == 2 || bs.over) { rc = DBZ_HOST; break; } if (br) { rc = DBZ_UNPARSED; break; }
                         double f; const int pr = d_go_parse_float(nb, bs.n, f); if (pr) { rc = DBZ_HOST; break; }
                         ((uint64_t*)cd.values)[M] = (uint64_t)__double_as_longlong(f); break;
                     }
-                    default: { CountSink cs{0}; rc = dbz_emit_text(cs, cd, a.text, off, len, t); if (!rc) a.out_len[(size_t)cd.slot * a.nmsgs + M] = cs.n; }
+                    default: { CountSink cs{0}; rc = dbz_emit_text(cs, cd, text, off, len, t); if (!rc) a.out_len[(size_t)cd.slot * a.nmsgs + M] = cs.n; }
                     }
                 }
                 if (rc) { err = rc; ecol = c; break; }

@@ -573,7 +573,7 @@ int tfgpu_engine_create(const char* cfg_json, const int* device_ids, int n_devic
         CK(cudaMalloc(&e->d_tail, 64)); CK(cudaMemset(e->d_tail, 0, 64));
         CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
         CK(cudaMalloc(&e->d_state, sizeof(DState)));
-        CK(lz4_kernels_init());
+        CK(lz4_kernels_init()); CK(dbz_kernels_init());
     } catch (const CudaError& c) { return c.e == cudaErrorMemoryAllocation ? TF_E_RETRY_OOM : TF_E_RETRY_LAUNCH; }
     catch (const std::exception&) { return TF_E_FATAL_CONFIG; }
     *out = e.release();
@@ -1517,7 +1517,7 @@ int tfgpu_parse_debezium(tfgpu_engine* e, int plan_id, const char* opts_json, co
             da.span_start = (uint32_t*)(B + o_ss); da.span_len = (uint32_t*)(B + o_sl); da.out_len = (uint32_t*)(B + o_len);
             da.kinds = B + o_kind; da.tx_id = (uint32_t*)(B + o_tx); da.lsn = (uint64_t*)(B + o_lsn); da.commit_time = (uint64_t*)(B + o_ct); da.err = B + o_err; da.errcol = B + o_ecol;
             const uint32_t nb = (uint32_t)((n + 127) / 128);
-            e->prof_begin("k_dbz_pass1", s); launch_k_dbz_pass1(nb, 128, 0, s, da); e->prof_end(s);
+            e->prof_begin("k_dbz_pass1", s); launch_k_dbz_pass1(nb, 128, DBZ_STAGE, s, da); e->prof_end(s);
             if (nslots) {
                 launch_offsets(e, (const uint32_t*)(B + o_len), n, (uint32_t)nslots, (uint32_t*)(B + o_off), (uint64_t*)(B + o_tot), s);
                 CK(cudaMemcpyAsync(col_total.data(), B + o_tot, (size_t)nslots * 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));

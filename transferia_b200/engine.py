@@ -314,12 +314,22 @@ class Engine:
         finally:
             self._L.tfgpu_result_release(res)
 
-    def parse_csv(self, plan_id: int, data: bytes, opts: Optional[dict] = None, wire_fmt: int = 0):
-        """CSV bytes -> typed columns -> the plan's transformer chain, all on the device.
-        wire_fmt 0: (Batch, row errors, consumed bytes); otherwise (PushResult, consumed bytes)."""
-        buf = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data or b"\0")
+    @staticmethod
+    def _host_bytes(data):
+        """(pointer, length, keepalive) of a bytes object or a (pinned) torch uint8 tensor, without copying."""
+        if hasattr(data, "data_ptr"):
+            return C.c_void_p(data.data_ptr()), int(data.numel()), data
+        buf = C.c_char_p(data if data else b"\0")              # the bytes object's own storage
+        return C.cast(buf, C.c_void_p), len(data), buf
+
+    def parse_csv(self, plan_id: int, data, opts: Optional[dict] = None, wire_fmt: int = 0, copy_bytes: bool = True):
+        """CSV bytes (a bytes object or a pinned torch uint8 tensor, used in place) -> typed columns -> the plan's transformer chain, all on
+        the device. wire_fmt 0: (Batch, row errors, consumed bytes); otherwise (PushResult, consumed bytes); copy_bytes=False leaves the
+        wire bytes in the engine's pinned landing buffer and only reports their length."""
+        ptr, total, keep = self._host_bytes(data)
         res = C.c_void_p()
-        self._check(self._L.tfgpu_parse_csv(self._h, plan_id, json.dumps(opts or {}).encode(), buf, len(data), abi.TF_MEM_HOST, wire_fmt, C.byref(res)))
+        self._L.tfgpu_parse_csv.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
+        self._check(self._L.tfgpu_parse_csv(self._h, plan_id, json.dumps(opts or {}).encode(), ptr, total, abi.TF_MEM_HOST, wire_fmt, C.cast(C.pointer(res), C.c_void_p)))
         try:
             L = self._L
             consumed = int(L.tfgpu_result_consumed(res))
@@ -329,22 +339,24 @@ class Engine:
             n = L.tfgpu_result_bytes_len(res)
             ne = L.tfgpu_result_n_errors(res); ep = L.tfgpu_result_errors(res)
             out = PushResult(L.tfgpu_result_rows_in(res), L.tfgpu_result_rows_out(res), L.tfgpu_result_raw_len(res), L.tfgpu_result_n_frames(res),
-                             C.string_at(L.tfgpu_result_bytes(res), n) if n else b"", [(ep[k].row, ep[k].code, ep[k].term) for k in range(ne)])
+                             C.string_at(L.tfgpu_result_bytes(res), n) if (n and copy_bytes) else b"", [(ep[k].row, ep[k].code, ep[k].term) for k in range(ne)])
+            out.wire_len = n
             return out, consumed
         finally:
             self._L.tfgpu_result_release(res)
 
-    def parse_debezium(self, plan_id: int, data: bytes, msg_ends, schema_text: str, schema_registry: bool = False, schema_id: int = 0,
-                       check_table: bool = False, wire_fmt: int = 0):
+    def parse_debezium(self, plan_id: int, data, msg_ends, schema_text: str, schema_registry: bool = False, schema_id: int = 0,
+                       check_table: bool = False, wire_fmt: int = 0, copy_bytes: bool = True):
         """Debezium messages -> typed columns (default receivers) -> the plan's chain, on the device; one row per message.
         wire_fmt 0: (Batch, row errors, meta) with meta = {"selection", "kinds", "tx_id", "lsn", "commit_time"} (numpy; the last four
         per MESSAGE, selection per output row); otherwise (PushResult, meta)."""
         import numpy as np
         ends = np.asarray(msg_ends, dtype=np.uint64)
         opts = {"schema_text": schema_text, "schema_registry": schema_registry, "schema_id": schema_id, "check_table": check_table}
-        buf = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data or b"\0")
+        ptr, total, keep = self._host_bytes(data)
         res = C.c_void_p()
-        self._check(self._L.tfgpu_parse_debezium(self._h, plan_id, json.dumps(opts).encode(), buf, len(data), abi.TF_MEM_HOST, ends.ctypes.data, len(ends), wire_fmt, C.byref(res)))
+        self._L.tfgpu_parse_debezium.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+        self._check(self._L.tfgpu_parse_debezium(self._h, plan_id, json.dumps(opts).encode(), ptr, total, abi.TF_MEM_HOST, ends.ctypes.data, len(ends), wire_fmt, C.cast(C.pointer(res), C.c_void_p)))
         try:
             L = self._L
             nin, nout = int(L.tfgpu_result_rows_in(res)), int(L.tfgpu_result_rows_out(res))
@@ -357,8 +369,10 @@ class Engine:
                 b, errs = self._result_batch(res)
                 return b, errs, meta
             nb = L.tfgpu_result_bytes_len(res); ne = L.tfgpu_result_n_errors(res); ep = L.tfgpu_result_errors(res)
-            return PushResult(nin, nout, L.tfgpu_result_raw_len(res), L.tfgpu_result_n_frames(res), C.string_at(L.tfgpu_result_bytes(res), nb) if nb else b"",
-                              [(ep[k].row, ep[k].code, ep[k].term) for k in range(ne)]), meta
+            out = PushResult(nin, nout, L.tfgpu_result_raw_len(res), L.tfgpu_result_n_frames(res), C.string_at(L.tfgpu_result_bytes(res), nb) if (nb and copy_bytes) else b"",
+                             [(ep[k].row, ep[k].code, ep[k].term) for k in range(ne)])
+            out.wire_len = nb
+            return out, meta
         finally:
             self._L.tfgpu_result_release(res)
 
