@@ -39,7 +39,7 @@ TRAFFIC_PROFILE = "profiles/r2c_traffic.json"   # written by scripts/ncu_summary
 def bench_config(args, ncols: int) -> dict:
     """The `config` object both arms print, key for key (the driver compares them)."""
     return {"workload": "clickbench_hits_99col filter_rows+cast+ch_native+lz4 (BASELINE configs[2])", "rows_per_step_per_gpu": min(args.rows, 1_000_000) if args.impl == "reference" else args.rows,
-            "columns": ncols, "frame_bytes": args.frame_bytes, "batch_seed": "workload.SEED + rank"}
+            "columns": ncols, "frame_bytes": args.frame_bytes, "batch_seed": "workload.SEED + rank", "filter": "watchid > K AND url ~ '://' with K set for 28 % kept rows on every rank's batch"}
 
 
 def load_peaks():
@@ -311,8 +311,8 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     rows = min(args.rows, 1_000_000)
     batch, schema = make_batch(rows, workload.SEED)
-    k = workload.counterid_threshold(batch, schema)
-    trs = workload.headline_transformers(k)
+    k = workload.headline_threshold(batch, schema)
+    trs = workload.headline_transformers_watchid(k)
     per_step_budget = 2.0
     for _ in range(args.warmup):
         cpu_port_rate(batch, schema, trs, args.frame_bytes, 0.5, cores)
@@ -347,6 +347,7 @@ def main():
     ap.add_argument("--json-lines", type=int, default=400_000)
     ap.add_argument("--dbz-msgs", type=int, default=200_000, help="messages of the Debezium leg (BASELINE configs[3])")
     ap.add_argument("--csv-rows", type=int, default=100_000, help="rows of the CSV leg (BASELINE configs[4])")
+    ap.add_argument("--host-layout", default="narrow", choices=["narrow", "offsets"], help="end-to-end leg: var-width columns as uint8 / uint16 lengths (narrow) or uint32 offsets")
     ap.add_argument("--e2e-pipelines", type=int, default=2, help="host threads (one engine handle each) pushing batches concurrently in the end-to-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -372,16 +373,17 @@ def main():
     # weak scaling: every rank pushes its OWN seeded batch (seed + rank: other values, dictionaries and therefore a slightly different
     # selectivity / compressibility per GPU, as independent table parts have); no data-path collective
     batch, schema = make_batch(args.rows, workload.SEED + rank)
-    k = workload.counterid_threshold(batch, schema)
-    trs = workload.headline_transformers(k)
+    k = workload.headline_threshold(batch, schema)              # the same selectivity (0.28) on every rank's own batch
+    trs = workload.headline_transformers_watchid(k)
     eng = engine.Engine(local, args.frame_bytes)
     stream = torch.cuda.Stream()          # a real (non-default) stream: events below and every kernel share it
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     pid = eng.plan("public", "hits", schema, trs, {"type": "clickhouse"})
     dbatch = batch.to_device(dev)
-    hbatch = batch.pin()
+    hbatch = (batch.narrow() if args.host_layout == "narrow" else batch).pin()      # narrow: uint8 / uint16 lengths instead of uint32 offsets (TF_COL_LENS8 / 16)
     in_bytes = batch.input_bytes()
+    h2d_bytes = hbatch.input_bytes()
     torch.cuda.synchronize()
 
     def barrier():
@@ -497,7 +499,7 @@ def main():
                                "l2": "inputs larger than L2 (%.0f MB per step > 126 MB)" % (in_bytes / 1e6),
                                "parallelism": f"dp{world} (one batch stream per GPU, its own seeded batch on every rank, no collective)", "rank": 0},
             "clocks": sampler.result(),
-            "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": d2h,
+            "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h, "host_layout": args.host_layout,
                     "steps": e2e_steps, "pipelines": P, "timing": "host wall clock over synchronous calls"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_lz4_frames", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -96,7 +96,7 @@ typedef enum tf_type {
  */
 typedef struct tf_col {
     int32_t         type;       /* tf_type */
-    int32_t         flags;      /* reserved, 0 */
+    int32_t         flags;      /* 0, or TF_COL_LENS8 / TF_COL_LENS16 (var-width columns) */
     const void*     values;
     const uint8_t*  validity;
     const uint32_t* offsets;
@@ -104,6 +104,12 @@ typedef struct tf_col {
     const void*     aux;
     uint64_t        heap_len;
 } tf_col;
+
+/* A var-width column may carry per-row LENGTHS instead of offsets: `offsets` then points at nrows uint8 (TF_COL_LENS8) or uint16
+ * (TF_COL_LENS16) values and the engine builds the uint32 offsets on the device — a quarter / half of the offset bytes over PCIe for
+ * columns whose cells are shorter than 256 / 65536 bytes. heap_len must still be the heap's byte count. */
+#define TF_COL_LENS8  1
+#define TF_COL_LENS16 2
 
 #define TF_MEM_HOST   0   /* pointers are host memory (pinned preferred): copies are inside the call */
 #define TF_MEM_DEVICE 1   /* pointers are device memory on the engine's GPU: batch is HBM-resident   */

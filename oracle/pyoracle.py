@@ -512,8 +512,13 @@ def build_plan(ns: str, name: str, schema: List[dict], transformers: List[dict])
                     hit = (nw.get("nameSpace", ""), nw.get("name", ""))
             if hit is None:
                 continue
-            if (cur_ns, cur_name) == (ns, name):
-                cur_ns, cur_name = hit
+            nxt = None                                        # Apply: AltNames[current id] (rename.go:50-54), the last entry for an id wins
+            for r in cfg.get("renameTables") or []:
+                o, nw = r.get("originalName") or {}, r.get("newName") or {}
+                if (o.get("nameSpace", ""), o.get("name", "")) == (cur_ns, cur_name):
+                    nxt = (nw.get("nameSpace", ""), nw.get("name", ""))
+            if nxt is not None:
+                cur_ns, cur_name = nxt
             steps.append({"kind": "rename_tables", "index": idx}); idx += 1
         elif ttype == "mask_field":
             if not _tables_match(cfg.get("tables"), ns, name):

@@ -615,3 +615,26 @@ def test_round_robin_dispatcher_over_real_engines(po):
     finally:
         for e in engs:
             e.close()
+
+
+def test_narrow_length_arrays_equal_offsets(eng, po):
+    """tf_col.flags TF_COL_LENS8 / 16: uint8 / uint16 per-row lengths instead of uint32 offsets (a host layout that saves PCIe bytes);
+    the offsets are rebuilt on the device and every result equals the one of the plain layout — from host memory and from HBM."""
+    batch, schema = workload.make_hits_batch(20_000, seed=9)
+    trs = workload.headline_transformers(workload.counterid_threshold(batch, schema))
+    nb = batch.narrow()
+    widths = [getattr(c, "lens_width", 0) for c in nb.columns]
+    assert widths.count(1) + widths.count(2) == sum(1 for c in batch.columns if c.type in abi.VAR_TYPES) and nb.input_bytes() < batch.input_bytes() - 3 * 20_000 * 20
+    pid = eng.plan("public", "hits", schema, trs, {"type": "clickhouse"})
+    a = eng.push_encode(pid, batch, RAW); b = eng.push_encode(pid, nb, RAW)
+    assert a.wire == b.wire and a.rows_out == b.rows_out and a.errors == b.errors
+    assert a.wire == po.push_encode(batch, po.build_plan("public", "hits", schema, trs), RAW).raw
+    eng.push_encode_resident(pid, nb.to_device("cuda:0"), RAW)
+    st = eng.resident_stats()
+    assert eng.resident_fetch(0, st["raw_bytes"]) == a.wire
+    # a column with a cell of 300 bytes falls back to uint16 lengths; an all-types batch with nulls
+    b2, s2 = all_types_batch(3000, seed=5)
+    n2 = b2.narrow()
+    assert 2 in [getattr(c, "lens_width", 0) for c in n2.columns] or 1 in [getattr(c, "lens_width", 0) for c in n2.columns]
+    p2 = eng.plan("db", "t", s2, [], {"type": "clickhouse"})
+    assert eng.push_encode(p2, b2, RAW).wire == eng.push_encode(p2, n2, RAW).wire

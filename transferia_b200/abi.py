@@ -93,6 +93,7 @@ def make_row_meta(id=None, lsn=None, commit_time=None, txid_offsets=None, txid_h
     return m, (id, lsn, commit_time, txid_offsets, txid_heap)
 
 
+TF_COL_LENS8, TF_COL_LENS16 = 1, 2
 TF_WIRE_SER_JSON, TF_WIRE_SER_CSV = 4, 5
 TF_WIRE_DEBEZIUM = 6
 TF_ROWERR_DBZ_EMIT_HOST = 53
@@ -120,6 +121,7 @@ class Column:
     offsets: Any = None     # uint32[nrows+1]
     heap: Any = None        # uint8[]
     aux: Any = None         # time: uint32 nanos; any: uint8 tags
+    lens_width: int = 0     # 0: `offsets` holds uint32 offsets; 1 / 2: it holds uint8 / uint16 per-row LENGTHS (TF_COL_LENS8 / 16)
 
     def heap_len(self) -> int:
         if self.heap is None:
@@ -140,7 +142,7 @@ class Batch:
         arr = (TfCol * len(self.columns))()
         for i, c in enumerate(self.columns):
             arr[i].type = c.type
-            arr[i].flags = 0
+            arr[i].flags = {0: 0, 1: TF_COL_LENS8, 2: TF_COL_LENS16}[getattr(c, "lens_width", 0)]
             arr[i].values = _ptr(c.values)
             arr[i].validity = _ptr(c.validity)
             arr[i].offsets = _ptr(c.offsets)
@@ -155,6 +157,23 @@ class Batch:
         b.kinds = _ptr(self.kinds)
         self._keep = [arr]
         return b
+
+    def narrow(self) -> "Batch":
+        """The same host batch with per-row LENGTHS (uint8 where every cell of the column is shorter than 256 bytes, else uint16) in place
+        of the uint32 offsets of its var-width columns: what a shim sends to save PCIe bytes (tf_col.flags TF_COL_LENS8 / 16)."""
+        cols = []
+        for c in self.columns:
+            if c.offsets is None or c.type not in VAR_TYPES or getattr(c, "lens_width", 0):
+                cols.append(c); continue
+            off = np.asarray(c.offsets).view(np.uint32) if isinstance(c.offsets, np.ndarray) else None
+            if off is None:
+                cols.append(c); continue
+            ln = np.diff(off.astype(np.int64))
+            mx = int(ln.max()) if len(ln) else 0
+            if mx < 256: cols.append(Column(c.type, c.values, c.validity, ln.astype(np.uint8), c.heap, c.aux, 1))
+            elif mx < 65536: cols.append(Column(c.type, c.values, c.validity, ln.astype(np.uint16), c.heap, c.aux, 2))
+            else: cols.append(c)
+        return Batch(self.nrows, cols, self.kinds, self.mem)
 
     def input_bytes(self) -> int:
         """Columnar input bytes (SURVEY §8d `I`): values + offsets + heap (+validity/aux when present)."""
@@ -196,7 +215,7 @@ class Batch:
             if a is None:
                 return None
             return torch.from_numpy(np.ascontiguousarray(a).reshape(-1).view(np.uint8)).pin_memory()
-        cols = [Column(c.type, pn(c.values), pn(c.validity), pn(c.offsets), pn(c.heap), pn(c.aux)) for c in self.columns]
+        cols = [Column(c.type, pn(c.values), pn(c.validity), pn(c.offsets), pn(c.heap), pn(c.aux), getattr(c, "lens_width", 0)) for c in self.columns]
         return Batch(self.nrows, cols, pn(self.kinds), TF_MEM_HOST)
 
     def to_device(self, device="cuda:0", pinned_first: bool = False) -> "Batch":
@@ -209,7 +228,7 @@ class Batch:
             if pinned_first:
                 t = t.pin_memory()
             return t.to(device, non_blocking=pinned_first)
-        cols = [Column(c.type, mv(c.values), mv(c.validity), mv(c.offsets), mv(c.heap), mv(c.aux)) for c in self.columns]
+        cols = [Column(c.type, mv(c.values), mv(c.validity), mv(c.offsets), mv(c.heap), mv(c.aux), getattr(c, "lens_width", 0)) for c in self.columns]
         return Batch(self.nrows, cols, mv(self.kinds), TF_MEM_DEVICE)
 
 

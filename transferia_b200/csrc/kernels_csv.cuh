@@ -77,6 +77,18 @@ __global__ void __launch_bounds__(256) k_csv_line_index(const uint8_t* text, uin
 }
 #endif  // TF_KERNELS_CSV
 
+// Var-width columns may arrive with uint8 / uint16 LENGTHS instead of uint32 offsets (tf_col.flags TF_COL_LENS8 / 16: a quarter / half
+// of the offset bytes over PCIe); widened here, then scanned into offsets by the three kernels above.
+struct LensSrc { const uint8_t* p; int32_t width, pad; };
+#ifdef TF_KERNELS_CSV
+__global__ void __launch_bounds__(256) k_widen_lens(const LensSrc* src, uint64_t nrows, uint32_t* out /* [nslots][nrows] */) {
+    const LensSrc ls = src[blockIdx.y];
+    uint32_t* o = out + (size_t)blockIdx.y * nrows;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (uint64_t)gridDim.x * blockDim.x)
+        o[r] = ls.width == 1 ? (uint32_t)ls.p[r] : (uint32_t)((const uint16_t*)ls.p)[r];
+}
+#endif  // TF_KERNELS_CSV
+
 // ---- text -> value helpers (must agree with oracle/csv_oracle.hpp, which restates the Go functions)
 __device__ __forceinline__ bool d_space(const uint8_t* p, uint32_t n, uint32_t& w) {   // unicode.IsSpace
     if (!n) return false;

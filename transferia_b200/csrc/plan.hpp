@@ -451,6 +451,8 @@ inline Plan build_plan(const std::string& ns, const std::string& name, const std
                     bool col_is_str = ctf == TF_UTF8 || ctf == TF_ANY;
                     if ((base == LV_INT || base == LV_FLOAT) && (col_is_str))
                         throw FatalError(TF_E_FATAL_UNSUPPORTED, "filter_rows: numeric literal against text column '" + t.attribute + "' (strconv.ParseFloat path) is not implemented on the device");
+                    if (base == LV_TIME && (t.vtype & LV_LIST) && (col_is_str || ctf == TF_BYTES))
+                        throw FatalError(TF_E_FATAL_UNSUPPORTED, "filter_rows: list of times against text column '" + t.attribute + "' (stringToTime path, filter_rows.go:340-352) is not implemented on the device");
                     if (k) d += ",";
                     d += "{\"col\":" + std::to_string(x.col) + ",\"op\":" + std::to_string(x.op) + ",\"vtype\":" + std::to_string(x.vtype) + ",\"value\":";
                     if (!(t.vtype & LV_LIST)) {
@@ -511,8 +513,17 @@ inline Plan build_plan(const std::string& ns, const std::string& name, const std
                 if (o->get_str("nameSpace") == ns && o->get_str("name") == name) { hit = true; nns = nw->get_str("nameSpace"); nname = nw->get_str("name"); }
             }
             if (!hit) continue;                                      // Suitable: exact TableID in AltNames (ORIGINAL id)
-            // Apply looks the item's CURRENT id up again (rename.go:50-54); a chain of renames composes only if it matches
-            if (cur_ns == ns && cur_name == name) { cur_ns = nns; cur_name = nname; }
+            // Apply looks the item's CURRENT id up in AltNames (rename.go:50-54): after an earlier rename to B, a transformer that lists
+            // both A -> B and B -> C takes the item on to C; the last entry for an id wins, like the map built from the list
+            {
+                bool found = false; std::string tns, tname;
+                for (auto& r : lst->arr) {
+                    const tfj::Value* o = r->get("originalName"); const tfj::Value* nw = r->get("newName");
+                    if (!o || !nw) continue;
+                    if (o->get_str("nameSpace") == cur_ns && o->get_str("name") == cur_name) { found = true; tns = nw->get_str("nameSpace"); tname = nw->get_str("name"); }
+                }
+                if (found) { cur_ns = tns; cur_name = tname; }
+            }
             add_desc("{\"type\":\"rename_tables\",\"to\":" + tfj::quote(cur_ns.empty() ? cur_name : cur_ns + "." + cur_name) + "}"); step_no++;
         } else if (ttype == "mask_field") {
             if (!match_table(tables_filter(cfg->get("tables")), ns, name)) continue;

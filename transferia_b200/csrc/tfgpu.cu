@@ -62,7 +62,7 @@ struct tfgpu_engine {
     // The checksum chain and the wire gather of an LZ4 batch run on two side streams and are NOT joined at the end of the call: the
     // next batch's filter / encode kernels overlap them (they only wait before they reuse the frame slots). join_tail() orders the
     // main stream after them; every path that reads results, changes layout or leaves the LZ4 format calls it.
-    cudaStream_t side2_stream = nullptr; cudaEvent_t ev_tail2 = nullptr; bool tail_pending = false; uint64_t tail_nrows = 0; const void* tail_plan = nullptr;
+    cudaStream_t side2_stream = nullptr; cudaEvent_t ev_tail2 = nullptr; bool tail_pending = false; uint64_t tail_nrows = 0, tail_nframes_max = 0; const void* tail_plan = nullptr;
     uint64_t* d_tail = nullptr;
     std::string last_error;
     uint64_t launches = 0;
@@ -70,7 +70,7 @@ struct tfgpu_engine {
     int sm_count = 148;
     std::vector<std::unique_ptr<PlanDev>> plans;
     // arenas
-    DevBuf in_arena, work, raw, slots, wire, strict_stage, csv_text, csv_stage, json_msgs, n2f_stage, n2f_heap, off_scratch;
+    DevBuf in_arena, work, raw, slots, wire, strict_stage, lens_arena, lens_arena2, csv_text, csv_stage, json_msgs, n2f_stage, n2f_heap, off_scratch;
     DState* d_state = nullptr; DCol* d_cols = nullptr; size_t d_cols_cap = 0;
     int32_t* d_call_slots = nullptr; ColRegions* d_regions = nullptr; size_t d_call_cap = 0;   // columnar mode, per call
     // pointers into `work` for the last call
@@ -325,7 +325,7 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
     const Sizes sz = compute_sizes(e, pd, in, columnar, json_rows);
     cudaStream_t s = e->stream;
     // a pending checksum / gather tail may only stay in flight across a call that lays the work arena out identically
-    if (e->tail_pending && !(wire_fmt == TF_WIRE_CH_NATIVE_LZ4 && n == e->tail_nrows && (const void*)&pd == e->tail_plan)) join_tail(e);
+    if (e->tail_pending && !(wire_fmt == TF_WIRE_CH_NATIVE_LZ4 && n == e->tail_nrows && (const void*)&pd == e->tail_plan && sz.n_frames_max == e->tail_nframes_max)) join_tail(e);
     // work arena
     size_t wbytes = 0;
     auto need = [&](size_t b) { wbytes += align_up(b ? b : 1, 256); };
@@ -530,7 +530,7 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
         CK(cudaEventRecord(e->ev_fork, s)); CK(cudaStreamWaitEvent(s3, e->ev_fork, 0));
         e->prof_begin("k_frame_seal", s3); launch_k_frame_seal((uint32_t)((sz.n_frames_max + 31) / 32), 32, SEAL_SMEM, s3, fa); e->prof_end(s3);
         CK(cudaEventRecord(e->ev_tail2, s3));
-        e->tail_pending = true; e->tail_nrows = n; e->tail_plan = (const void*)&pd;      // joined by whoever needs the wire bytes, or by the next batch before its LZ4
+        e->tail_pending = true; e->tail_nrows = n; e->tail_plan = (const void*)&pd; e->tail_nframes_max = sz.n_frames_max;      // joined by whoever needs the wire bytes, or by the next batch before its LZ4
     }
     CK(cudaGetLastError());
 }
@@ -585,7 +585,7 @@ int tfgpu_engine_destroy(tfgpu_engine* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (auto& p : e->plans) p->consts.release();
-    e->strict_stage.release(); e->in_arena.release(); e->work.release(); e->raw.release(); e->slots.release(); e->wire.release(); e->csv_text.release(); e->csv_stage.release(); e->json_msgs.release(); e->n2f_stage.release(); e->n2f_heap.release(); e->off_scratch.release(); e->json_sizes.release();
+    e->strict_stage.release(); e->lens_arena.release(); e->lens_arena2.release(); e->in_arena.release(); e->work.release(); e->raw.release(); e->slots.release(); e->wire.release(); e->csv_text.release(); e->csv_stage.release(); e->json_msgs.release(); e->n2f_stage.release(); e->n2f_heap.release(); e->off_scratch.release(); e->json_sizes.release();
     if (e->d_state) cudaFree(e->d_state);
     if (e->d_cols) cudaFree(e->d_cols);
     if (e->d_call_slots) { cudaFree(e->d_call_slots); cudaFree(e->d_regions); }
@@ -739,17 +739,32 @@ int tfgpu_push_encode(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch
 // shared by push_encode / push_columns: stage host columns into HBM (or pass device pointers through)
 static const uint8_t* stage_input(tfgpu_engine* e, const tf_batch* in, std::vector<tf_col>& dev, DevBuf* arena_opt) {
     DevBuf& arena = arena_opt ? *arena_opt : e->in_arena;
+    DevBuf& larena = arena_opt ? e->lens_arena2 : e->lens_arena;
+    // var-width columns that carry lengths instead of offsets (TF_COL_LENS8 / 16): offsets are built on the device
+    auto expand_lens = [&](std::vector<tf_col>& dv) {
+        const uint64_t nr = in->nrows; std::vector<LensSrc> src; std::vector<uint32_t> which;
+        for (uint32_t c = 0; c < in->ncols; c++) if (!in_width(dv[c].type) && (dv[c].flags & (TF_COL_LENS8 | TF_COL_LENS16)) && dv[c].offsets) { src.push_back(LensSrc{(const uint8_t*)dv[c].offsets, (dv[c].flags & TF_COL_LENS8) ? 1 : 2, 0}); which.push_back(c); }
+        if (src.empty()) return;
+        const size_t K = src.size(), o_src = 0, o_len = align_up(K * sizeof(LensSrc) + 16, 256), o_off = o_len + align_up(K * nr * 4 + 16, 256), o_tot = o_off + align_up(K * (nr + 1) * 4 + 16, 256);
+        larena.ensure(o_tot + K * 8 + 256);
+        uint8_t* B = larena.p; cudaStream_t st = e->stream;
+        CK(cudaMemcpyAsync(B + o_src, src.data(), K * sizeof(LensSrc), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));          // `src` is a stack vector (the copy above is from pageable memory: already staged, but keep it simple and safe)
+        if (nr) { e->launches++; launch_k_widen_lens(dim3((uint32_t)std::min<uint64_t>((nr + 255) / 256, 2048), (uint32_t)K), 256, 0, st, (const LensSrc*)(B + o_src), nr, (uint32_t*)(B + o_len)); }
+        launch_offsets(e, (const uint32_t*)(B + o_len), nr, (uint32_t)K, (uint32_t*)(B + o_off), (uint64_t*)(B + o_tot), st);
+        for (size_t k = 0; k < K; k++) { dv[which[k]].offsets = (const uint32_t*)(B + o_off) + k * (nr + 1); dv[which[k]].flags &= ~(TF_COL_LENS8 | TF_COL_LENS16); }
+    };
     const uint64_t n = in->nrows; const uint32_t nc = in->ncols;
     cudaStream_t s = e->stream;
     dev.resize(nc);
-    if (in->mem != TF_MEM_HOST) { for (uint32_t c = 0; c < nc; c++) dev[c] = in->cols[c]; return in->kinds; }
+    if (in->mem != TF_MEM_HOST) { for (uint32_t c = 0; c < nc; c++) dev[c] = in->cols[c]; expand_lens(dev); return in->kinds; }
     size_t tot = 0;
     auto sz_of = [&](const tf_col& c, int which) -> size_t {
         const int w = in_width(c.type);
         switch (which) {
         case 0: return w ? (size_t)w * n : 0;
         case 1: return c.validity ? (n + 7) / 8 : 0;
-        case 2: return (!w && c.offsets) ? (n + 1) * 4 : 0;
+        case 2: return (!w && c.offsets) ? ((c.flags & TF_COL_LENS8) ? n : (c.flags & TF_COL_LENS16) ? 2 * n : (n + 1) * 4) : 0;
         case 3: return (!w) ? c.heap_len : 0;
         default: if (!c.aux) return 0; return (c.type == TF_ANY) ? n : (size_t)4 * n;
         }
@@ -770,7 +785,9 @@ static const uint8_t* stage_input(tfgpu_engine* e, const tf_batch* in, std::vect
         if (!in_width(ic.type) && !d.heap) d.heap = arena.p;   // empty heap: any valid pointer
         d.aux = up(ic.aux, sz_of(ic, 4));
     }
-    return in->kinds ? up(in->kinds, n) : nullptr;
+    const uint8_t* dk = in->kinds ? up(in->kinds, n) : nullptr;
+    expand_lens(dev);
+    return dk;
 }
 
 static void fetch_errors(tfgpu_engine* e, uint64_t n, tfgpu_result* r) {

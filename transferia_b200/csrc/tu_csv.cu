@@ -11,4 +11,5 @@ void launch_k_offsets_sum(dim3 grid, dim3 block, size_t smem, cudaStream_t s, co
 void launch_k_offsets_chunks(dim3 grid, dim3 block, size_t smem, cudaStream_t s, uint64_t* chunk_sum, uint32_t nchunks, uint64_t* col_total) { k_offsets_chunks<<<grid, block, smem, s>>>(chunk_sum, nchunks, col_total); }
 void launch_k_offsets_write(dim3 grid, dim3 block, size_t smem, cudaStream_t s, const uint32_t* span_len, uint64_t nrows, uint32_t nchunks, const uint64_t* chunk_base, const uint64_t* col_total, uint32_t* offsets) { k_offsets_write<<<grid, block, smem, s>>>(span_len, nrows, nchunks, chunk_base, col_total, offsets); }
 void launch_k_csv_pass2(dim3 grid, dim3 block, size_t smem, cudaStream_t s, CsvCopyArgs a) { k_csv_pass2<<<grid, block, smem, s>>>(a); }
+void launch_k_widen_lens(dim3 grid, dim3 block, size_t smem, cudaStream_t s, const LensSrc* src, uint64_t nrows, uint32_t* out) { k_widen_lens<<<grid, block, smem, s>>>(src, nrows, out); }
 }  // namespace tfk

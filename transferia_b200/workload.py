@@ -179,6 +179,26 @@ def counterid_threshold(batch: abi.Batch, schema: List[dict], keep_frac: float =
     return int(np.quantile(batch.columns[i].values, 1.0 - keep_frac))
 
 
+def headline_threshold(batch: abi.Batch, schema: List[dict], target: float = 0.28) -> int:
+    """The watchid threshold K for which `watchid > K AND url ~ '://'` keeps `target` of the rows of THIS batch. Every rank of a
+    weak-scaling run pushes its own seeded batch, and the work per GPU is only the same if the selectivity is: watchid is spread over
+    the whole int64 range, so the quantile hits the target on any batch (counterid has 64 distinct values, one of them on 23 % of the rows)."""
+    names = [c["name"] for c in schema]
+    wid = np.asarray(batch.columns[names.index("watchid")].values)
+    u = batch.columns[names.index("url")]
+    url_ok = np.diff(np.asarray(u.offsets).astype(np.int64)) > 0          # every non-empty generated URL starts with "http://"
+    if url_ok.sum() == 0:
+        return int(wid.max())
+    frac = min(1.0, target / max(url_ok.mean(), 1e-9))
+    return int(np.quantile(wid[url_ok], 1.0 - frac, method="lower"))
+
+
+def headline_transformers_watchid(k: int) -> List[dict]:
+    """BASELINE.json configs[2]: cast + filter_rows (1 int term AND 1 string `~` term), the int term on watchid (see headline_threshold)."""
+    return [{"filter_rows": {"tables": {"includeTables": ["^public\\.hits$"]},
+                             "filter": f"watchid > {k} AND url ~ '://'"}}]
+
+
 def headline_transformers(k: int) -> List[dict]:
     """BASELINE.json configs[2]: cast + filter_rows (1 int term AND 1 string `~` term)."""
     return [{"filter_rows": {"tables": {"includeTables": ["^public\\.hits$"]},
