@@ -1,0 +1,116 @@
+"""Host side of the boundary (include/tfgpu_sink.h) bound over ctypes: the ClickHouse native client writer that ships the device's
+frames (the reference's streamer, pkg/providers/clickhouse/async/streamer.go:64-265), mirrored with the reference's method names.
+
+    ClickHouseWriter.prepare_batch()  ~ conn.PrepareBatch          streamer.go:246, sink_table.go:655 (tx.PrepareContext)
+    ClickHouseWriter.append_frames()  ~ batch.Append ... Flush     streamer.go:64-118,196
+    ClickHouseWriter.send()           ~ batch.Send                 streamer.go:143,212
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from typing import List, Optional, Tuple
+
+from . import engine
+
+SINK_SYMBOLS = [
+    "tfgpu_ch_open", "tfgpu_ch_close", "tfgpu_ch_last_error", "tfgpu_ch_server_info", "tfgpu_ch_exception_code",
+    "tfgpu_ch_insert_begin", "tfgpu_ch_insert_columns", "tfgpu_ch_insert_data", "tfgpu_ch_insert_end", "tfgpu_ch_stats",
+    "tfgpu_ch_insert_query", "tfgpu_host_cityhash128",
+]
+
+_bound = False
+
+
+def lib():
+    global _bound
+    L = engine.load_library()
+    if _bound:
+        return L
+    vp, cp, i, u64 = C.c_void_p, C.c_char_p, C.c_int, C.c_uint64
+    L.tfgpu_ch_open.argtypes = [i, cp, C.POINTER(vp)]
+    L.tfgpu_ch_close.argtypes = [vp]
+    L.tfgpu_ch_last_error.argtypes = [vp]; L.tfgpu_ch_last_error.restype = cp
+    L.tfgpu_ch_server_info.argtypes = [vp]; L.tfgpu_ch_server_info.restype = cp
+    L.tfgpu_ch_exception_code.argtypes = [vp]
+    L.tfgpu_ch_insert_begin.argtypes = [vp, cp, cp, cp]
+    L.tfgpu_ch_insert_columns.argtypes = [vp]; L.tfgpu_ch_insert_columns.restype = cp
+    L.tfgpu_ch_insert_data.argtypes = [vp, vp, u64]
+    L.tfgpu_ch_insert_end.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    L.tfgpu_ch_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    L.tfgpu_ch_insert_query.argtypes = [cp, cp, cp, i, C.c_char_p, u64]; L.tfgpu_ch_insert_query.restype = C.c_int64
+    L.tfgpu_host_cityhash128.argtypes = [vp, u64, C.POINTER(u64)]; L.tfgpu_host_cityhash128.restype = None
+    _bound = True
+    return L
+
+
+def host_cityhash128(data: bytes) -> Tuple[int, int]:
+    out = (C.c_uint64 * 2)()
+    buf = C.create_string_buffer(data, len(data)) if data else None
+    lib().tfgpu_host_cityhash128(C.cast(buf, C.c_void_p) if buf else None, len(data), out)
+    return int(out[0]), int(out[1])
+
+
+def insert_query(database: str, table: str, columns: List[str], updateable: bool = False) -> str:
+    """doOperation's statement (sink_table.go:633-660) as clickhouse-go sends it (cut at VALUES)."""
+    out = C.create_string_buffer(1 << 16)
+    n = lib().tfgpu_ch_insert_query(database.encode(), table.encode(), json.dumps(columns).encode(), int(updateable), out, len(out))
+    if n < 0:
+        raise engine.EngineError(int(n), "tfgpu_ch_insert_query")
+    return out.raw[:n].decode()
+
+
+class ClickHouseWriter:
+    """One native-protocol connection over a connected socket (the caller dials and keeps the socket object alive)."""
+
+    def __init__(self, sock, database="default", user="default", password="", compression=True, read_timeout_ms=300000, client_name=None):
+        self._L = lib()
+        self._sock = sock
+        self._h = C.c_void_p()
+        opts = {"database": database, "user": user, "password": password, "compression": compression, "read_timeout_ms": read_timeout_ms}
+        if client_name:
+            opts["client_name"] = client_name
+        rc = self._L.tfgpu_ch_open(sock.fileno(), json.dumps(opts).encode(), C.byref(self._h))
+        if rc != 0:
+            msg = self._L.tfgpu_ch_last_error(self._h).decode(errors="replace") if self._h else "open failed"
+            code = self._L.tfgpu_ch_exception_code(self._h) if self._h else 0
+            if self._h:
+                self._L.tfgpu_ch_close(self._h); self._h = None
+            err = engine.EngineError(rc, msg); err.exception_code = code
+            raise err
+
+    def _check(self, rc):
+        if rc != 0:
+            err = engine.EngineError(rc, self._L.tfgpu_ch_last_error(self._h).decode(errors="replace"))
+            err.exception_code = self._L.tfgpu_ch_exception_code(self._h)
+            raise err
+
+    @property
+    def server_info(self) -> dict:
+        return json.loads(self._L.tfgpu_ch_server_info(self._h).decode())
+
+    def prepare_batch(self, query: str, query_id: str = "", settings: Optional[dict] = None) -> List[dict]:
+        self._check(self._L.tfgpu_ch_insert_begin(self._h, query.encode(), query_id.encode(), json.dumps(settings).encode() if settings else None))
+        return json.loads(self._L.tfgpu_ch_insert_columns(self._h).decode())
+
+    def append_frames(self, wire) -> None:
+        """One Data packet around the bytes tfgpu_result_bytes returned (TF_WIRE_CH_NATIVE_LZ4 frames, or the raw block without compression)."""
+        if isinstance(wire, (bytes, bytearray)):
+            buf = (C.c_uint8 * len(wire)).from_buffer_copy(wire) if len(wire) else None
+            self._check(self._L.tfgpu_ch_insert_data(self._h, C.cast(buf, C.c_void_p) if buf is not None else None, len(wire)))
+        else:                                                   # (address, length): the engine's pinned landing buffer, no copy
+            self._check(self._L.tfgpu_ch_insert_data(self._h, C.c_void_p(wire[0]), wire[1]))
+
+    def send(self) -> Tuple[int, int]:
+        wr, wb = C.c_uint64(), C.c_uint64()
+        self._check(self._L.tfgpu_ch_insert_end(self._h, C.byref(wr), C.byref(wb)))
+        return int(wr.value), int(wb.value)
+
+    def stats(self) -> dict:
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._L.tfgpu_ch_stats(self._h, C.byref(a), C.byref(b), C.byref(c))
+        return {"bytes_out": int(a.value), "bytes_in": int(b.value), "data_packets": int(c.value)}
+
+    def close(self):
+        if self._h:
+            self._L.tfgpu_ch_close(self._h); self._h = None
