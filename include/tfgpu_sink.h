@@ -67,6 +67,99 @@ int tfgpu_ch_stats(const tfgpu_ch_conn* c, uint64_t* bytes_out, uint64_t* bytes_
  * column names as a JSON array of strings. Returns the byte count written (without NUL) or a negative code when cap is too small. */
 int64_t tfgpu_ch_insert_query(const char* database, const char* table, const char* columns_json, int updateable, char* out, uint64_t cap);
 
+/* ------------------------------------------------------------------ []ChangeItem in row form (host transpose) */
+/* abstract.Kind (pkg/abstract/changeitem/kind.go:5-43). Row kinds keep tf_batch's TF_KIND_INSERT / UPDATE / DELETE. */
+#define TF_KIND_INIT_SHARDED_TABLE_LOAD 16
+#define TF_KIND_INIT_TABLE_LOAD         17
+#define TF_KIND_DONE_TABLE_LOAD         18
+#define TF_KIND_DONE_SHARDED_TABLE_LOAD 19
+#define TF_KIND_DROP_TABLE              20
+#define TF_KIND_TRUNCATE                21
+#define TF_KIND_DDL                     22
+#define TF_KIND_PG_DDL                  23
+#define TF_KIND_SYNCHRONIZE             24   /* Kind("") */
+#define TF_KIND_OTHER                   31   /* mongo:* / ch:* / es:* — opaque to this path, passed through */
+#define TF_KIND_IS_ROW(k) ((k) <= TF_KIND_DELETE)   /* RowEventKinds: ChangeItem.IsRowEvent (change_item.go:286-288) */
+
+/* One ColumnValues entry in the row image: a tag byte naming the Go dynamic type, then the payload (little-endian).
+ * The shim writes these with plain appends while it walks []interface{} — one type switch per value, no cgo call. */
+#define TF_V_NIL       0
+#define TF_V_BOOL      1   /* 1 byte */
+#define TF_V_INT8      2   /* natural width; Go `int` travels as TF_V_INT64 */
+#define TF_V_INT16     3
+#define TF_V_INT32     4
+#define TF_V_INT64     5
+#define TF_V_UINT8     6
+#define TF_V_UINT16    7
+#define TF_V_UINT32    8
+#define TF_V_UINT64    9
+#define TF_V_FLOAT32   10
+#define TF_V_FLOAT64   11
+#define TF_V_STRING    12  /* u32 length + bytes */
+#define TF_V_BYTES     13  /* u32 length + bytes */
+#define TF_V_TIME      14  /* time.Time: i64 Unix seconds + u32 nanoseconds (the UTC instant) */
+#define TF_V_DURATION  15  /* i64 nanoseconds */
+#define TF_V_JSONNUM   16  /* json.Number: u32 length + text */
+#define TF_V_JSON      17  /* anything else (map, slice, ...): u32 length + its json.Marshal text */
+
+/* What the items of one table share and never rewrite (change_item.go:44-52: ColumnNames / TableSchema are write-once). */
+typedef struct tf_table {
+    const char* schema;        /* ChangeItem.Schema (namespace) */
+    const char* table;         /* ChangeItem.Table */
+    const char* schema_json;   /* TableSchema.Columns() with the ColSchema JSON tags (col_schema.go:14-29) */
+} tf_table;
+
+/* ChangeItem (change_item.go:27-78) without its values. */
+#define TF_ITEM_SPARSE 1       /* ColumnNames is a subset of the schema (toasted update): every value is preceded by its u16 column index */
+typedef struct tf_item {
+    uint64_t lsn;              /* ChangeItem.LSN */
+    uint64_t commit_time;      /* ChangeItem.CommitTime, ns */
+    uint64_t size_read;        /* ChangeItem.Size.Read */
+    uint64_t values_off;       /* row kinds: offset of the ColumnValues image in tf_rows.values */
+    uint64_t old_keys_off;     /* offset of the OldKeys image (u16 count, then {u16 column, value}*), or UINT64_MAX */
+    uint32_t id;               /* ChangeItem.ID */
+    uint32_t table;            /* index into tf_rows.tables */
+    uint32_t n_values;         /* len(ColumnValues) */
+    uint32_t txid_off, txid_len;   /* ChangeItem.TxID in tf_rows.strings */
+    uint32_t part_off, part_len;   /* ChangeItem.PartID */
+    int32_t  counter;          /* ChangeItem.Counter */
+    uint8_t  kind;             /* TF_KIND_* */
+    uint8_t  flags;            /* TF_ITEM_* */
+    uint8_t  pad[2];
+} tf_item;
+
+typedef struct tf_rows {
+    uint64_t        n_items;
+    const tf_item*  items;
+    uint32_t        n_tables;
+    uint32_t        pad;
+    const tf_table* tables;
+    const uint8_t*  values;   uint64_t values_len;
+    const uint8_t*  strings;  uint64_t strings_len;
+} tf_rows;
+
+/* Pooled columnar buffers (grow-only, pinned when a CUDA device is present so that tfgpu_push_* copies straight from them). */
+typedef struct tfgpu_columnar tfgpu_columnar;
+int tfgpu_columnar_create(tfgpu_columnar** out);
+int tfgpu_columnar_destroy(tfgpu_columnar* p);
+const char* tfgpu_columnar_last_error(const tfgpu_columnar* p);
+
+/* The transpose: the row items `item_idx[0..n)` of `rows` (all of one table, row kinds, in this order; item_idx NULL = every row item of
+ * table `table`) become one tf_batch in the pool's buffers, valid until the next call on this pool:
+ *   - a column whose values all carry the column's canonical Go type (typesystem/values/type_checkers.go:39-84) gets the schema's type;
+ *     ints / floats of another width give a LOOSE column (tf_col.type = what arrived) that the device strictifies (strictify.go:46-157);
+ *     var-width cells shorter than 256 / 65536 bytes travel as TF_COL_LENS8 / TF_COL_LENS16 lengths;
+ *   - kinds -> tf_batch.kinds; ID / LSN / CommitTime / TxID -> *meta; OldKeys -> *old (NULL when no item carries any).
+ * Values a column cannot hold (a string in an int column, mixed signed / unsigned / float classes in one column) fail the call with
+ * TF_E_FATAL_UNSUPPORTED: that batch stays on the Go path. threads <= 0: one per core (capped at 16). */
+int tfgpu_rows_to_batch(tfgpu_columnar* pool, const tf_rows* rows, uint32_t table, const uint64_t* item_idx, uint64_t n, int threads,
+                        const tf_batch** batch, const tf_row_meta** meta, const tf_old_keys** old);
+/* The inverse, for tfgpu_push_columns results going back into []ChangeItem: every row of `b` as a ColumnValues image (the canonical Go
+ * type of each column: int8..uint64, float32, float64, bool, string for utf8, []byte for string, time.Time, time.Duration, and for `any`
+ * a Go string when the cell's tag says so, else its JSON text). row_off receives nrows + 1 offsets into out. Returns TF_E_FATAL_ARG with
+ * *need set when cap is too small. */
+int tfgpu_batch_to_rows(const tf_batch* b, uint8_t* out, uint64_t cap, uint64_t* row_off, uint64_t* need);
+
 /* Host CityHash128 (v1.0.2) as the frames' checksum uses it — exported for the tests' cross-checks against the device and the oracle. */
 void tfgpu_host_cityhash128(const uint8_t* p, uint64_t n, uint64_t out[2]);
 

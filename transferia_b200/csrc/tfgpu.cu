@@ -666,6 +666,7 @@ const char* tfgpu_plan_describe(tfgpu_engine* e, int plan_id) {
     return e->plans[plan_id]->plan.describe.c_str();
 }
 
+static const uint8_t* stage_input(tfgpu_engine* e, const tf_batch* in, std::vector<tf_col>& dev, DevBuf* arena_opt = nullptr);
 int tfgpu_push_encode_resident(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch* in) {
     if (!e || !in || plan_id < 0 || plan_id >= (int)e->plans.size()) return TF_E_FATAL_ARG;
     PlanDev& pd = *e->plans[plan_id];
@@ -676,7 +677,8 @@ int tfgpu_push_encode_resident(tfgpu_engine* e, int plan_id, int wire_fmt, const
     if (in->nrows >= (1ull << 31)) return fail(e, TF_E_FATAL_ARG, "batch too large (>= 2^31 rows)");
     try {
         CK(cudaSetDevice(e->device));
-        run_chain(e, pd, in, in->cols, in->kinds, wire_fmt);
+        std::vector<tf_col> dev; const uint8_t* dev_kinds = stage_input(e, in, dev);    // device pointers pass through; TF_COL_LENS8 / 16 lengths become offsets
+        run_chain(e, pd, in, dev.data(), dev_kinds, wire_fmt);
         return TF_OK;
     } catch (const tfplan::FatalError& f) { return fail(e, f.code, f.what()); }
     catch (const CudaError& c) { return cuda_fail(e, c); }
@@ -709,7 +711,6 @@ int tfgpu_resident_fetch(tfgpu_engine* e, int what, uint8_t* dst, uint64_t cap) 
     } catch (const CudaError& c) { return cuda_fail(e, c); }
 }
 
-static const uint8_t* stage_input(tfgpu_engine* e, const tf_batch* in, std::vector<tf_col>& dev, DevBuf* arena_opt = nullptr);
 static void fetch_errors(tfgpu_engine* e, uint64_t n, tfgpu_result* r);
 static void finish_wire(tfgpu_engine* e, uint64_t n, int wire_fmt, tfgpu_result* r);
 
@@ -749,7 +750,7 @@ static const uint8_t* stage_input(tfgpu_engine* e, const tf_batch* in, std::vect
         larena.ensure(o_tot + K * 8 + 256);
         uint8_t* B = larena.p; cudaStream_t st = e->stream;
         CK(cudaMemcpyAsync(B + o_src, src.data(), K * sizeof(LensSrc), cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));          // `src` is a stack vector (the copy above is from pageable memory: already staged, but keep it simple and safe)
+        // `src` is pageable: cudaMemcpyAsync has staged it before it returns, so the vector may go out of scope and nothing waits here
         if (nr) { e->launches++; launch_k_widen_lens(dim3((uint32_t)std::min<uint64_t>((nr + 255) / 256, 2048), (uint32_t)K), 256, 0, st, (const LensSrc*)(B + o_src), nr, (uint32_t*)(B + o_len)); }
         launch_offsets(e, (const uint32_t*)(B + o_len), nr, (uint32_t)K, (uint32_t*)(B + o_off), (uint64_t*)(B + o_tot), st);
         for (size_t k = 0; k < K; k++) { dv[which[k]].offsets = (const uint32_t*)(B + o_off) + k * (nr + 1); dv[which[k]].flags &= ~(TF_COL_LENS8 | TF_COL_LENS16); }
