@@ -1,0 +1,163 @@
+"""Host transpose: []ChangeItem in row form -> columnar tf_batch and back (tfgpu_rows_to_batch / tfgpu_batch_to_rows).
+The expectations are stated independently in numpy on the columnar side: a batch made by the workload generator is turned into ChangeItems
+carrying the canonical Go types, flattened like the shim would, transposed by the product, and must come back as the same columns."""
+import numpy as np
+import pytest
+
+from transferia_b200 import abi, engine, rows, workload
+from transferia_b200.rows import ChangeItem, go
+from test_gpu_parity import all_types_batch
+
+
+def _lens(col, n):
+    o = np.asarray(col.offsets)
+    return o.astype(np.int64) if col.lens_width else np.diff(o.astype(np.int64))
+
+
+def _valid(col, n):
+    return np.ones(n, bool) if col.validity is None else np.unpackbits(np.asarray(col.validity), bitorder="little")[:n].astype(bool)
+
+
+def assert_same_batch(got: abi.Batch, want: abi.Batch):
+    assert got.nrows == want.nrows and len(got.columns) == len(want.columns)
+    n = want.nrows
+    for k, (g, w) in enumerate(zip(got.columns, want.columns)):
+        assert g.type == w.type, (k, g.type, w.type)
+        vg, vw = _valid(g, n), _valid(w, n)
+        assert (vg == vw).all(), k
+        if w.type in abi.VAR_TYPES:
+            lw = np.where(vw, _lens(w, n), 0)
+            assert (_lens(g, n) == lw).all(), k
+            off = np.asarray(w.offsets).astype(np.int64) if not w.lens_width else np.concatenate([[0], np.cumsum(_lens(w, n))])
+            heap_w = np.asarray(w.heap).tobytes() if w.heap is not None else b""
+            want_heap = b"".join(heap_w[off[r]:off[r + 1]] for r in range(n) if vw[r])
+            assert (np.asarray(g.heap).tobytes() if g.heap is not None else b"") == want_heap, k
+            if w.type == abi.TF_ANY and w.aux is not None:
+                ga = np.zeros(n, np.uint8) if g.aux is None else np.asarray(g.aux)
+                assert (ga[vw] == np.asarray(w.aux)[vw]).all(), k
+        else:
+            a, b = np.asarray(g.values)[vw], np.asarray(w.values)[vw]
+            assert a.tobytes() == b.tobytes(), k               # bit-exact (NaN payloads, -0.0)
+            if w.type in abi.TIME_TYPES:
+                na = np.zeros(n, np.uint32) if g.aux is None else np.asarray(g.aux)
+                nb = np.zeros(n, np.uint32) if w.aux is None else np.asarray(w.aux)
+                assert (na[vw] == nb[vw]).all(), k
+
+
+def test_hits_rows_transpose_equals_generator_columns():
+    batch, schema = workload.make_hits_batch(3000, seed=4)
+    img = rows.RowsImage(rows.items_from_batch(batch), [("public", "hits", schema)])
+    pool = rows.Columnar()
+    for threads in (1, 4):
+        t = pool.rows_to_batch(img, threads=threads)
+        assert_same_batch(t.batch, batch)
+        # short cells travel as uint8 lengths (TF_COL_LENS8), exactly what Batch.narrow() builds on the Python side
+        nb = batch.narrow()
+        assert [c.lens_width for c in t.batch.columns] == [c.lens_width for c in nb.columns]
+        assert t.batch.kinds is None and t.old is None
+    pool.close()
+
+
+def test_all_types_with_nulls_round_trip_through_the_inverse():
+    batch, schema = all_types_batch(3000, seed=11)
+    image, off = rows.batch_to_rows(batch)                                # columnar -> ColumnValues images (the inverse)
+    items = rows.items_from_batch(batch)
+    want = bytearray()
+    for it in items[:50]:
+        for v in it.values: rows.encode_value(want, v)
+    assert image[:int(off[50])] == bytes(want)                            # same image the Python stand-in of the shim writes
+    # feed the product's own images back: items whose values are already encoded
+    class Raw(rows.RowsImage):
+        pass
+    img = rows.RowsImage(items, [("db", "t", schema)])
+    assert img._vals[:img.values_len].tobytes() == image
+    pool = rows.Columnar()
+    t = pool.rows_to_batch(img, threads=3)
+    assert_same_batch(t.batch, batch)
+    assert 2 in [c.lens_width for c in t.batch.columns] and 1 in [c.lens_width for c in t.batch.columns]   # 20000-byte cells -> uint16 lengths
+    pool.close()
+
+
+def test_loose_value_types_become_loose_columns():
+    schema = [{"name": "a", "type": "int32"}, {"name": "b", "type": "uint8"}, {"name": "c", "type": "double"}, {"name": "d", "type": "double"},
+              {"name": "e", "type": "int64"}, {"name": "f", "type": "any"}, {"name": "g", "type": "datetime"}, {"name": "h", "type": "float"}]
+    items = [ChangeItem(values=[go.int64(7), go.int64(200), go.float32(1.5), go.number("0.1"), go.int8(-3), go.int64(12), go.int64(1700000000), go.float32(2.5)]),
+             ChangeItem(values=[go.int64(-2 ** 40), go.int64(-1), go.float32(-0.0), go.number("1e400"), go.int64(2 ** 62), go.bool(True), go.int64(5), go.nil]),
+             ChangeItem(values=[go.nil, go.int64(3), go.float64(2.25), go.nil, go.bool(False), go.json('{"a":[1,2]}'), go.nil, go.float32(-1)])]
+    pool = rows.Columnar()
+    t = pool.rows_to_batch(rows.RowsImage(items, [("", "t", schema)]))
+    c = t.batch.columns
+    assert [x.type for x in c] == [abi.TF_INT64, abi.TF_INT64, abi.TF_DOUBLE, abi.TF_DOUBLE, abi.TF_INT64, abi.TF_ANY, abi.TF_INT64, abi.TF_FLOAT]
+    assert list(np.asarray(c[0].values)[:2]) == [7, -2 ** 40] and list(_valid(c[0], 3)) == [True, True, False]
+    assert list(np.asarray(c[1].values)) == [200, -1, 3]                  # the device's Strictify raises the range / cast errors (strictify.go:159-181)
+    assert np.asarray(c[2].values).tobytes() == np.array([1.5, -0.0, 2.25]).tobytes()          # float32 widened exactly
+    assert list(np.asarray(c[3].values)[:2]) == [0.1, np.inf]            # json.Number text -> ParseFloat
+    assert list(np.asarray(c[4].values)) == [-3, 2 ** 62, 0]              # int8 / int64 / bool mixed: one signed class, widened
+    assert np.asarray(c[5].heap).tobytes() == b'12true{"a":[1,2]}' and list(np.asarray(c[5].offsets)) == [2, 4, 11]
+    assert list(np.asarray(c[6].values)[:2]) == [1700000000, 5]
+    # refusals: the batch stays on the Go path
+    for bad in ([go.string("12")] + [go.nil] * 7, [go.int64(1), go.uint64(2)] + [go.nil] * 6):
+        its = [ChangeItem(values=bad), ChangeItem(values=[go.int64(1), go.int64(2)] + [go.nil] * 6)]
+        with pytest.raises(engine.EngineError) as ei:
+            pool.rows_to_batch(rows.RowsImage(its, [("", "t", schema)]))
+        assert ei.value.rc == -2
+    with pytest.raises(engine.EngineError) as ei:                         # a row with too few values and no TF_ITEM_SPARSE
+        pool.rows_to_batch(rows.RowsImage([ChangeItem(values=[go.int64(1)])], [("", "t", schema)]))
+    assert ei.value.rc == -3
+    pool.close()
+
+
+def test_kinds_meta_sparse_rows_and_old_keys():
+    schema = [{"name": "id", "type": "int32", "key": True}, {"name": "name", "type": "utf8"}, {"name": "ts", "type": "timestamp"}]
+    other = [{"name": "x", "type": "int8"}]
+    items = [
+        ChangeItem(rows.KIND_INIT_TABLE_LOAD, 0),
+        ChangeItem(rows.KIND_INSERT, 0, [go.int32(1), go.string("a"), go.time(10, 5)], id=7, lsn=100, commit_time=123456789, txid=b"tx-1"),
+        ChangeItem(rows.KIND_INSERT, 1, [go.int8(9)]),
+        ChangeItem(rows.KIND_UPDATE, 0, {0: go.int32(2), 1: go.string("bb")}, {0: go.int32(1)}, id=8, lsn=101, commit_time=2, txid=b"tx-22"),
+        ChangeItem(rows.KIND_DELETE, 0, {}, {0: go.int32(2), 1: go.string("bb")}, id=9, lsn=102, commit_time=3),
+        ChangeItem(rows.KIND_DONE_TABLE_LOAD, 0),
+    ]
+    img = rows.RowsImage(items, [("public", "users", schema), ("public", "other", other)])
+    pool = rows.Columnar()
+    t = pool.rows_to_batch(img, table=0)                                  # the row events of table 0, in order: items 1, 3, 4
+    b = t.batch
+    assert b.nrows == 3 and list(np.asarray(b.kinds)) == [0, 1, 2]
+    assert list(t.ids) == [7, 8, 9] and list(t.lsn) == [100, 101, 102] and list(t.commit_time) == [123456789, 2, 3]
+    m = t.meta.contents
+    assert rows._view(m.txid_heap, 9).tobytes() == b"tx-1tx-22" and list(rows._view(m.txid_offsets, 16, np.uint32)) == [0, 4, 9, 9]
+    assert list(np.asarray(b.columns[0].values)) == [1, 2, 0] and list(_valid(b.columns[0], 3)) == [True, True, False]
+    assert np.asarray(b.columns[1].heap).tobytes() == b"abb" and list(_valid(b.columns[2], 3)) == [True, False, False]
+    assert list(np.asarray(b.columns[2].aux)) == [5, 0, 0]
+    assert list(t.old_present) == [1, 1, 0] and list(t.old_row_has) == [0, 1, 1]
+    ob = t.old_batch
+    assert list(np.asarray(ob.columns[0].values)) == [0, 1, 2] and list(_valid(ob.columns[0], 3)) == [False, True, True]
+    assert np.asarray(ob.columns[1].heap).tobytes() == b"bb" and list(_valid(ob.columns[1], 3)) == [False, False, True]
+    assert ob.columns[2].values is None and ob.columns[2].offsets is None
+    t1 = pool.rows_to_batch(img, table=1)
+    assert t1.batch.nrows == 1 and list(np.asarray(t1.batch.columns[0].values)) == [9] and t1.old is None
+    # an explicit item list must name row events of that table
+    with pytest.raises(engine.EngineError):
+        pool.rows_to_batch(img, table=0, item_idx=[0])
+    assert pool.rows_to_batch(img, table=0, item_idx=[4, 1]).batch.nrows == 2
+    pool.close()
+
+
+@pytest.mark.gpu
+def test_transposed_rows_through_the_device_equal_the_oracle(eng, po):
+    """Rows -> transpose (loose int64 values in the narrow integer columns, as a JSON-decoding source hands them) -> device Strictify +
+    filter + cast + native block == the oracle on the strict columnar batch."""
+    batch, schema = workload.make_hits_batch(4000, seed=6)
+    items = rows.items_from_batch(batch)
+    loose = {k for k, c in enumerate(batch.columns) if c.type in (abi.TF_INT16, abi.TF_INT32)}
+    for it in items:
+        it.values = [go.int64(v[1]) if k in loose and v[0] != rows.V_NIL else v for k, v in enumerate(it.values)]
+    pool = rows.Columnar()
+    t = pool.rows_to_batch(rows.RowsImage(items, [("public", "hits", schema)]))
+    assert all(t.batch.columns[k].type == abi.TF_INT64 for k in loose)
+    trs = workload.headline_transformers(workload.counterid_threshold(batch, schema))
+    pid = eng.plan("public", "hits", schema, trs, {"type": "clickhouse"})
+    got = eng.push_encode(pid, t.batch, abi.TF_WIRE_CH_NATIVE)
+    want = po.push_encode(batch, po.build_plan("public", "hits", schema, trs), abi.TF_WIRE_CH_NATIVE)
+    assert got.rows_out == want.rows_out and got.wire == want.raw and not got.errors
+    pool.close()

@@ -1,0 +1,426 @@
+// Host transpose: []abstract.ChangeItem in row form (tf_rows, include/tfgpu_sink.h) <-> the columnar tf_batch the device
+// consumes. The reference keeps a batch as an array of structs whose values are boxed interfaces (pkg/abstract/changeitem/change_item.go:27-78);
+// the shim flattens that into one byte image with plain appends and this file turns the image into column buffers in two parallel passes
+// (sizes, then fill), into pooled pinned memory so that tfgpu_push_* can start its H2D copies without another staging copy.
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "../../include/tfgpu_sink.h"
+#include "plan.hpp"
+
+namespace {
+
+struct Fail { int rc; std::string msg; };
+
+struct Buf {
+    uint8_t* p = nullptr; size_t cap = 0; bool pinned = false;
+    void release() { if (!p) return; if (pinned) cudaFreeHost(p); else std::free(p); p = nullptr; cap = 0; }
+    uint8_t* ensure(size_t n, bool want_pinned) {
+        if (n <= cap && p) return p;
+        release();
+        const size_t want = std::max<size_t>(4096, n + n / 4 + 256) & ~(size_t)255;
+        if (want_pinned && cudaHostAlloc((void**)&p, want, cudaHostAllocDefault) == cudaSuccess) pinned = true;
+        else { (void)cudaGetLastError(); pinned = false; p = (uint8_t*)std::aligned_alloc(256, want); if (!p) throw Fail{TF_E_RETRY_OOM, "host allocation failed"}; }
+        cap = want; return p;
+    }
+};
+
+inline int fixed_width(int tf) {
+    switch (tf) {
+    case TF_INT8: case TF_UINT8: case TF_BOOLEAN: return 1;
+    case TF_INT16: case TF_UINT16: return 2;
+    case TF_INT32: case TF_UINT32: case TF_FLOAT: return 4;
+    case TF_INT64: case TF_UINT64: case TF_DOUBLE: case TF_INTERVAL: case TF_DATE: case TF_DATETIME: case TF_TIMESTAMP: return 8;
+    default: return 0;
+    }
+}
+inline bool is_time(int tf) { return tf == TF_DATE || tf == TF_DATETIME || tf == TF_TIMESTAMP; }
+
+// the canonical Go type of a YT type in a strict ChangeItem (typesystem/values/type_checkers.go:39-84) as a value tag
+inline int canonical_tag(int tf) {
+    switch (tf) {
+    case TF_INT8: return TF_V_INT8; case TF_INT16: return TF_V_INT16; case TF_INT32: return TF_V_INT32; case TF_INT64: return TF_V_INT64;
+    case TF_UINT8: return TF_V_UINT8; case TF_UINT16: return TF_V_UINT16; case TF_UINT32: return TF_V_UINT32; case TF_UINT64: return TF_V_UINT64;
+    case TF_FLOAT: return TF_V_FLOAT32; case TF_DOUBLE: return TF_V_FLOAT64; case TF_BOOLEAN: return TF_V_BOOL;
+    case TF_BYTES: return TF_V_BYTES; case TF_UTF8: return TF_V_STRING; case TF_ANY: return TF_V_JSON;
+    case TF_INTERVAL: return TF_V_DURATION; default: return TF_V_TIME;
+    }
+}
+// the fixed-width column type a numeric tag travels as (a loose column when it differs from the schema's)
+inline int tag_tf(int tag) {
+    switch (tag) {
+    case TF_V_BOOL: return TF_BOOLEAN;
+    case TF_V_INT8: return TF_INT8; case TF_V_INT16: return TF_INT16; case TF_V_INT32: return TF_INT32; case TF_V_INT64: return TF_INT64;
+    case TF_V_UINT8: return TF_UINT8; case TF_V_UINT16: return TF_UINT16; case TF_V_UINT32: return TF_UINT32; case TF_V_UINT64: return TF_UINT64;
+    case TF_V_FLOAT32: return TF_FLOAT; case TF_V_FLOAT64: case TF_V_JSONNUM: return TF_DOUBLE; case TF_V_DURATION: return TF_INTERVAL;
+    default: return 0;
+    }
+}
+inline uint32_t payload_fixed(int tag) {
+    switch (tag) {
+    case TF_V_NIL: return 0; case TF_V_BOOL: case TF_V_INT8: case TF_V_UINT8: return 1; case TF_V_INT16: case TF_V_UINT16: return 2;
+    case TF_V_INT32: case TF_V_UINT32: case TF_V_FLOAT32: return 4; case TF_V_INT64: case TF_V_UINT64: case TF_V_FLOAT64: case TF_V_DURATION: return 8;
+    case TF_V_TIME: return 12; default: return 0xffffffffu;     // length-prefixed
+    }
+}
+
+// one value of the image: tag, payload pointer, payload length (text length for the length-prefixed tags)
+struct Val { int tag; const uint8_t* p; uint32_t n; };
+inline bool read_val(const uint8_t*& at, const uint8_t* end, Val& v) {
+    if (at >= end) return false;
+    v.tag = *at++;
+    if (v.tag > TF_V_JSON) return false;
+    uint32_t w = payload_fixed(v.tag);
+    if (w == 0xffffffffu) { if (end - at < 4) return false; std::memcpy(&w, at, 4); at += 4; }
+    if ((size_t)(end - at) < w) return false;
+    v.p = at; v.n = w; at += w; return true;
+}
+inline int64_t val_i64(const Val& v) {
+    switch (v.tag) {
+    case TF_V_BOOL: return v.p[0] ? 1 : 0;
+    case TF_V_INT8: return (int8_t)v.p[0]; case TF_V_UINT8: return v.p[0];
+    case TF_V_INT16: { int16_t x; std::memcpy(&x, v.p, 2); return x; } case TF_V_UINT16: { uint16_t x; std::memcpy(&x, v.p, 2); return x; }
+    case TF_V_INT32: { int32_t x; std::memcpy(&x, v.p, 4); return x; } case TF_V_UINT32: { uint32_t x; std::memcpy(&x, v.p, 4); return x; }
+    default: { int64_t x; std::memcpy(&x, v.p, 8); return x; }
+    }
+}
+// text an `any` cell holds for a scalar value: what json.Marshal writes for Go ints / bools
+inline uint32_t any_scalar_text(const Val& v, char* out) {
+    if (v.tag == TF_V_BOOL) { const char* t = v.p[0] ? "true" : "false"; const uint32_t n = v.p[0] ? 4 : 5; std::memcpy(out, t, n); return n; }
+    if (v.tag == TF_V_UINT64) { uint64_t x; std::memcpy(&x, v.p, 8); return (uint32_t)std::snprintf(out, 24, "%llu", (unsigned long long)x); }
+    return (uint32_t)std::snprintf(out, 24, "%lld", (long long)val_i64(v));
+}
+
+struct ColPlan {
+    int schema_tf = 0, phys_tf = 0, width = 0, lens_width = 0;
+    bool has_nil = false, has_nsec = false, has_anytag = false;
+    uint32_t tagmask = 0; uint64_t heap_total = 0; uint32_t max_len = 0;
+    uint8_t *values = nullptr, *validity = nullptr, *lens = nullptr, *heap = nullptr, *aux = nullptr;
+};
+struct ChunkStat { uint32_t tagmask = 0; uint64_t heap = 0; uint32_t max_len = 0; bool nil = false, nsec = false; };
+
+constexpr uint32_t M_SIGNED = (1u << TF_V_INT8) | (1u << TF_V_INT16) | (1u << TF_V_INT32) | (1u << TF_V_INT64) | (1u << TF_V_BOOL);
+constexpr uint32_t M_UNSIGNED = (1u << TF_V_UINT8) | (1u << TF_V_UINT16) | (1u << TF_V_UINT32) | (1u << TF_V_UINT64);
+constexpr uint32_t M_FLOAT = (1u << TF_V_FLOAT32) | (1u << TF_V_FLOAT64) | (1u << TF_V_JSONNUM);   // json.Number: the strict form of `double` (type_checkers.go:63-65)
+constexpr uint32_t M_TEXT = (1u << TF_V_STRING) | (1u << TF_V_BYTES);
+
+}  // namespace
+
+struct tfgpu_columnar {
+    std::string err;
+    bool want_pinned = true;
+    std::map<std::string, std::vector<int>> schemas;      // schema_json -> tf types
+    std::vector<Buf> bufs; size_t next_buf = 0;
+    Buf* take() { if (next_buf == bufs.size()) bufs.emplace_back(); return &bufs[next_buf++]; }
+    // results of the last call
+    std::vector<tf_col> cols, old_cols; tf_batch batch{}, old_batch{}; tf_row_meta meta{}; tf_old_keys old{};
+    std::vector<uint8_t> present;
+    ~tfgpu_columnar() { for (auto& b : bufs) b.release(); }
+};
+
+namespace {
+
+template <class F> void parallel_chunks(uint64_t n, uint64_t chunk, int threads, F&& f) {
+    const uint64_t nchunks = (n + chunk - 1) / chunk;
+    if (nchunks <= 1 || threads <= 1) { for (uint64_t k = 0; k < nchunks; k++) f(k); return; }
+    std::atomic<uint64_t> next{0}; std::atomic<bool> failed{false}; Fail first{0, ""}; std::atomic_flag lock = ATOMIC_FLAG_INIT;
+    auto work = [&] {
+        for (;;) {
+            const uint64_t k = next.fetch_add(1); if (k >= nchunks || failed.load()) return;
+            try { f(k); } catch (const Fail& e) { if (!lock.test_and_set()) { first = e; failed = true; } return; }
+        }
+    };
+    std::vector<std::thread> ts; const int nt = (int)std::min<uint64_t>((uint64_t)threads, nchunks);
+    for (int t = 1; t < nt; t++) ts.emplace_back(work);
+    work();
+    for (auto& t : ts) t.join();
+    if (failed) throw first;
+}
+
+// Columnar image of `n` value lists. get(j, at, end, sparse, nvals): where row j's values start / end.
+// which = nullptr: every schema column; else only the listed columns are laid out (OldKeys), the others stay empty.
+struct Transposer {
+    tfgpu_columnar* pool; const std::vector<int>& tfs; uint64_t n; int threads;
+    std::vector<ColPlan> cp; uint64_t chunk = 4096, nchunks = 0;
+    std::vector<ChunkStat> stats;      // [chunk][col]
+    std::vector<uint64_t> heap_base;   // [chunk][col]
+
+    template <class Get, class On> void walk_row(Get& get, uint64_t j, bool keyed, On&& on) {
+        const uint8_t *at, *end; bool sparse; uint32_t nvals;
+        get(j, at, end, sparse, nvals);
+        const uint32_t nc = (uint32_t)tfs.size();
+        if (!sparse && !keyed && nvals != nc) throw Fail{TF_E_FATAL_ARG, "an item's value count differs from its table schema (set TF_ITEM_SPARSE for a column subset)"};
+        for (uint32_t k = 0; k < nvals; k++) {
+            uint32_t c = k;
+            if (sparse || keyed) { if (end - at < 2) throw Fail{TF_E_FATAL_ARG, "truncated value image"}; uint16_t ci; std::memcpy(&ci, at, 2); at += 2; c = ci; }
+            if (c >= nc) throw Fail{TF_E_FATAL_ARG, "column index outside the table schema"};
+            Val v; if (!read_val(at, end, v)) throw Fail{TF_E_FATAL_ARG, "malformed value image"};
+            on(c, v);
+        }
+    }
+
+    template <class Get> void run(Get get, bool keyed, std::vector<tf_col>& out_cols, const uint8_t* only /* ncols flags or nullptr */) {
+        const uint32_t nc = (uint32_t)tfs.size();
+        cp.assign(nc, ColPlan()); for (uint32_t c = 0; c < nc; c++) cp[c].schema_tf = tfs[c];
+        nchunks = (n + chunk - 1) / chunk;
+        stats.assign((size_t)nchunks * nc, ChunkStat());
+        // ---- pass 1: tags, heap bytes, longest cell per (chunk, column)
+        parallel_chunks(n, chunk, threads, [&](uint64_t k) {
+            ChunkStat* st = &stats[(size_t)k * nc];
+            std::vector<uint8_t> seen(nc);
+            for (uint64_t j = k * chunk; j < std::min(n, (k + 1) * chunk); j++) {
+                std::fill(seen.begin(), seen.end(), 0);
+                walk_row(get, j, keyed, [&](uint32_t c, const Val& v) {
+                    seen[c] = 1; ChunkStat& s = st[c];
+                    if (v.tag == TF_V_NIL) { s.nil = true; return; }
+                    s.tagmask |= 1u << v.tag;
+                    if (!fixed_width(tfs[c])) {
+                        uint32_t len = v.n;
+                        if (tfs[c] == TF_ANY && payload_fixed(v.tag) != 0xffffffffu) { char tmp[32]; len = any_scalar_text(v, tmp); }
+                        s.heap += len; s.max_len = std::max(s.max_len, len);
+                    } else if (v.tag == TF_V_TIME) { uint32_t ns; std::memcpy(&ns, v.p + 8, 4); if (ns) s.nsec = true; }
+                });
+                for (uint32_t c = 0; c < nc; c++) if (!seen[c] && (!only || only[c])) st[c].nil = true;     // absent = nil in the columnar view
+            }
+        });
+        // ---- layout decisions per column
+        heap_base.assign((size_t)nchunks * nc, 0);
+        for (uint32_t c = 0; c < nc; c++) {
+            ColPlan& p = cp[c];
+            if (only && !only[c]) continue;
+            for (uint64_t k = 0; k < nchunks; k++) {
+                const ChunkStat& s = stats[(size_t)k * nc + c];
+                heap_base[(size_t)k * nc + c] = p.heap_total;
+                p.tagmask |= s.tagmask; p.heap_total += s.heap; p.max_len = std::max(p.max_len, s.max_len); p.has_nil |= s.nil; p.has_nsec |= s.nsec;
+            }
+            const int tf = p.schema_tf; const uint32_t m = p.tagmask;
+            auto refuse = [&](const char* why) { throw Fail{TF_E_FATAL_UNSUPPORTED, "column " + std::to_string(c) + " (" + tfplan::tf_to_yt(tf) + "): " + why}; };
+            if (fixed_width(tf)) {
+                if (m == 0 || m == (1u << canonical_tag(tf)) || (tf == TF_DOUBLE && m == (1u << TF_V_JSONNUM))) p.phys_tf = tf;
+                else if (is_time(tf) && (m & (1u << TF_V_TIME))) refuse("time.Time mixed with other value types");
+                else if (m & ~(M_SIGNED | M_UNSIGNED | M_FLOAT | (1u << TF_V_DURATION))) refuse("a text / JSON value in a fixed-width column stays on the Go path (strictify casts of strings)");
+                else if ((m & (m - 1)) == 0) { int t = 0; while (!(m >> t & 1)) t++; p.phys_tf = t == TF_V_DURATION ? TF_INT64 : tag_tf(t); }   // one foreign type: a loose column of that type
+                else if (!(m & ~M_SIGNED) || !(m & ~(M_SIGNED | (1u << TF_V_DURATION)))) p.phys_tf = TF_INT64;
+                else if (!(m & ~M_UNSIGNED)) p.phys_tf = TF_UINT64;
+                else if (!(m & ~M_FLOAT)) p.phys_tf = TF_DOUBLE;
+                else refuse("signed, unsigned and float values mixed in one column");
+                p.width = fixed_width(p.phys_tf);
+            } else {
+                if (tf != TF_ANY && (m & ~M_TEXT)) refuse("a non-text value in a string column");
+                if (tf == TF_ANY && (m & (M_FLOAT | (1u << TF_V_TIME) | (1u << TF_V_DURATION) | (1u << TF_V_BYTES)))) refuse("float / time / []byte inside `any` needs encoding/json's formatter");
+                if (p.heap_total >= (1ull << 32)) refuse("heap over 4 GiB");
+                p.phys_tf = tf; p.lens_width = p.max_len < 256 ? 1 : p.max_len < 65536 ? 2 : 4;
+                p.has_anytag = tf == TF_ANY && (m & (1u << TF_V_STRING));
+            }
+        }
+        // ---- buffers
+        out_cols.assign(nc, tf_col{});
+        for (uint32_t c = 0; c < nc; c++) {
+            ColPlan& p = cp[c]; tf_col& o = out_cols[c];
+            o.type = p.phys_tf ? p.phys_tf : p.schema_tf;
+            if (only && !only[c]) continue;
+            if (p.width) { p.values = pool->take()->ensure((size_t)p.width * n + 16, pool->want_pinned); o.values = p.values; }
+            else {
+                p.lens = pool->take()->ensure((size_t)p.lens_width * (n + 1) + 16, pool->want_pinned);
+                p.heap = pool->take()->ensure((size_t)p.heap_total + 16, pool->want_pinned);
+                o.offsets = (const uint32_t*)p.lens; o.heap = p.heap; o.heap_len = p.heap_total;
+                o.flags = p.lens_width == 1 ? TF_COL_LENS8 : p.lens_width == 2 ? TF_COL_LENS16 : 0;
+            }
+            if (p.has_nil) { p.validity = pool->take()->ensure((n + 7) / 8 + 16, pool->want_pinned); o.validity = p.validity; }
+            if (p.has_nsec) { p.aux = pool->take()->ensure(4 * n + 16, pool->want_pinned); o.aux = p.aux; }
+            if (p.has_anytag) { p.aux = pool->take()->ensure(n + 16, pool->want_pinned); o.aux = p.aux; }
+        }
+        std::vector<uint32_t> wide; for (uint32_t c = 0; c < nc; c++) if (cp[c].lens && cp[c].lens_width == 4) wide.push_back(c);
+        // ---- pass 2: fill (chunks are multiples of 8 rows, so validity bytes never straddle two workers)
+        parallel_chunks(n, chunk, threads, [&](uint64_t k) {
+            const uint64_t r0 = k * chunk, r1 = std::min(n, (k + 1) * chunk);
+            std::vector<uint64_t> hp(nc); for (uint32_t c = 0; c < nc; c++) hp[c] = heap_base[(size_t)k * nc + c];
+            for (uint32_t c = 0; c < nc; c++) {                  // defaults: nil rows keep zero values / zero lengths
+                ColPlan& p = cp[c]; if (only && !only[c]) continue;
+                if (p.values) std::memset(p.values + (size_t)p.width * r0, 0, (size_t)p.width * (r1 - r0));
+                if (p.validity) std::memset(p.validity + r0 / 8, 0, (r1 - r0 + 7) / 8);
+                if (p.aux) std::memset(p.aux + (p.has_nsec ? 4 : 1) * r0, 0, (p.has_nsec ? 4 : 1) * (r1 - r0));
+                if (p.lens && p.lens_width != 4) std::memset(p.lens + (size_t)p.lens_width * r0, 0, (size_t)p.lens_width * (r1 - r0));
+            }
+            for (uint64_t j = r0; j < r1; j++) {
+                for (uint32_t c : wide) { const uint32_t o = (uint32_t)hp[c]; std::memcpy(cp[c].lens + 4 * j, &o, 4); }   // u32 offsets: a row without a value repeats the running offset
+                walk_row(get, j, keyed, [&](uint32_t c, const Val& v) {
+                    ColPlan& p = cp[c];
+                    if (v.tag == TF_V_NIL) return;
+                    if (p.validity) p.validity[j >> 3] |= (uint8_t)(1u << (j & 7));
+                    if (p.width) {
+                        uint8_t* d = p.values + (size_t)p.width * j;
+                        if (v.tag == TF_V_TIME) { std::memcpy(d, v.p, 8); if (p.aux) std::memcpy(p.aux + 4 * j, v.p + 8, 4); }
+                        else if (v.tag == TF_V_JSONNUM) { const std::string t((const char*)v.p, v.n); const double x = std::strtod(t.c_str(), nullptr); std::memcpy(d, &x, 8); }
+                        else if (tag_tf(v.tag) == p.phys_tf || (v.tag == TF_V_DURATION && p.width == 8)) std::memcpy(d, v.p, p.width);
+                        else if (p.phys_tf == TF_DOUBLE) { float f; std::memcpy(&f, v.p, 4); const double x = f; std::memcpy(d, &x, 8); }
+                        else { const int64_t x = val_i64(v); std::memcpy(d, &x, 8); }                     // widened into INT64 / UINT64
+                    } else {
+                        uint32_t len = v.n; const uint8_t* src = v.p; char tmp[32];
+                        if (p.schema_tf == TF_ANY && payload_fixed(v.tag) != 0xffffffffu) { len = any_scalar_text(v, tmp); src = (const uint8_t*)tmp; }
+                        std::memcpy(p.heap + hp[c], src, len);
+                        if (p.lens_width == 1) p.lens[j] = (uint8_t)len;
+                        else if (p.lens_width == 2) { const uint16_t l = (uint16_t)len; std::memcpy(p.lens + 2 * j, &l, 2); }
+                        hp[c] += len;
+                        if (p.has_anytag && v.tag == TF_V_STRING) p.aux[j] = 1;
+                    }
+                });
+            }
+            if (r1 == n) for (uint32_t c : wide) { const uint32_t tot = (uint32_t)cp[c].heap_total; std::memcpy(cp[c].lens + 4 * n, &tot, 4); }
+        });
+    }
+};
+
+const std::vector<int>& schema_types(tfgpu_columnar* p, const char* schema_json) {
+    auto it = p->schemas.find(schema_json);
+    if (it != p->schemas.end()) return it->second;
+    std::vector<int> tfs;
+    try { for (auto& c : tfplan::parse_schema(schema_json)) tfs.push_back(c.tf); }
+    catch (const tfplan::FatalError& f) { throw Fail{f.code, f.what()}; }
+    catch (const std::exception& e) { throw Fail{TF_E_FATAL_CONFIG, e.what()}; }
+    return p->schemas.emplace(schema_json, std::move(tfs)).first->second;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tfgpu_columnar_create(tfgpu_columnar** out) {
+    if (!out) return TF_E_FATAL_ARG;
+    auto* p = new tfgpu_columnar();
+    int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { (void)cudaGetLastError(); p->want_pinned = false; }   // pageable memory without a device: the layout is the same
+    *out = p; return TF_OK;
+}
+int tfgpu_columnar_destroy(tfgpu_columnar* p) { if (!p) return TF_E_FATAL_ARG; delete p; return TF_OK; }
+const char* tfgpu_columnar_last_error(const tfgpu_columnar* p) { return p ? p->err.c_str() : "null pool"; }
+
+int tfgpu_rows_to_batch(tfgpu_columnar* pool, const tf_rows* rows, uint32_t table, const uint64_t* item_idx, uint64_t n, int threads,
+                        const tf_batch** batch, const tf_row_meta** meta, const tf_old_keys** old) {
+    if (!pool || !rows || !batch) return TF_E_FATAL_ARG;
+    try {
+        if (table >= rows->n_tables) throw Fail{TF_E_FATAL_ARG, "table index out of range"};
+        const std::vector<int>& tfs = schema_types(pool, rows->tables[table].schema_json);
+        std::vector<uint64_t> all;
+        if (!item_idx) {
+            for (uint64_t i = 0; i < rows->n_items; i++) if (rows->items[i].table == table && TF_KIND_IS_ROW(rows->items[i].kind)) all.push_back(i);
+            item_idx = all.data(); n = all.size();
+        }
+        for (uint64_t j = 0; j < n; j++) {
+            if (item_idx[j] >= rows->n_items) throw Fail{TF_E_FATAL_ARG, "item index out of range"};
+            const tf_item& it = rows->items[item_idx[j]];
+            if (it.table != table || !TF_KIND_IS_ROW(it.kind)) throw Fail{TF_E_FATAL_ARG, "tfgpu_rows_to_batch takes the row events of ONE table"};
+            if (it.values_off > rows->values_len) throw Fail{TF_E_FATAL_ARG, "values offset outside the image"};
+        }
+        if (threads <= 0) threads = (int)std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency()));
+        pool->next_buf = 0;
+        const uint8_t* vend = rows->values + rows->values_len;
+        Transposer tr{pool, tfs, n, threads};
+        tr.run([&](uint64_t j, const uint8_t*& at, const uint8_t*& end, bool& sparse, uint32_t& nvals) {
+            const tf_item& it = rows->items[item_idx[j]];
+            at = rows->values + it.values_off; end = vend; sparse = it.flags & TF_ITEM_SPARSE; nvals = it.n_values;
+        }, false, pool->cols, nullptr);
+        // kinds + meta
+        uint8_t* kinds = pool->take()->ensure(n + 16, pool->want_pinned);
+        uint32_t* ids = (uint32_t*)pool->take()->ensure(4 * n + 16, pool->want_pinned);
+        uint64_t* lsn = (uint64_t*)pool->take()->ensure(8 * n + 16, pool->want_pinned);
+        uint64_t* ct = (uint64_t*)pool->take()->ensure(8 * n + 16, pool->want_pinned);
+        uint32_t* tx_off = (uint32_t*)pool->take()->ensure(4 * (n + 1) + 16, pool->want_pinned);
+        uint64_t tx_total = 0; bool any_noninsert = false, any_old = false;
+        for (uint64_t j = 0; j < n; j++) {
+            const tf_item& it = rows->items[item_idx[j]];
+            kinds[j] = it.kind; ids[j] = it.id; lsn[j] = it.lsn; ct[j] = it.commit_time; tx_off[j] = (uint32_t)tx_total;
+            if ((uint64_t)it.txid_off + it.txid_len > rows->strings_len) throw Fail{TF_E_FATAL_ARG, "TxID outside the strings heap"};
+            tx_total += it.txid_len; any_noninsert |= it.kind != TF_KIND_INSERT; any_old |= it.old_keys_off != UINT64_MAX;
+        }
+        if (tx_total >= (1ull << 32)) throw Fail{TF_E_FATAL_UNSUPPORTED, "TxID heap over 4 GiB"};
+        tx_off[n] = (uint32_t)tx_total;
+        uint8_t* tx_heap = pool->take()->ensure(tx_total + 16, pool->want_pinned);
+        for (uint64_t j = 0; j < n; j++) { const tf_item& it = rows->items[item_idx[j]]; std::memcpy(tx_heap + tx_off[j], rows->strings + it.txid_off, it.txid_len); }
+        pool->batch = tf_batch{n, (uint32_t)tfs.size(), TF_MEM_HOST, pool->cols.data(), any_noninsert ? kinds : nullptr};
+        pool->meta = tf_row_meta{ids, lsn, ct, tx_total ? tx_off : nullptr, tx_total ? tx_heap : nullptr};
+        *batch = &pool->batch; if (meta) *meta = &pool->meta;
+        // OldKeys (old_keys.go:3-7): KeyNames / KeyValues of the update and delete rows as a second batch over the same rows
+        if (old) {
+            *old = nullptr;
+            if (any_old) {
+                pool->present.assign(tfs.size(), 0);
+                uint8_t* row_has = pool->take()->ensure(n + 16, pool->want_pinned);
+                for (uint64_t j = 0; j < n; j++) {
+                    const tf_item& it = rows->items[item_idx[j]]; row_has[j] = it.old_keys_off != UINT64_MAX;
+                    if (!row_has[j]) continue;
+                    if (it.old_keys_off + 2 > rows->values_len) throw Fail{TF_E_FATAL_ARG, "OldKeys offset outside the image"};
+                    const uint8_t* at = rows->values + it.old_keys_off; uint16_t cnt; std::memcpy(&cnt, at, 2); at += 2;
+                    for (uint16_t k = 0; k < cnt; k++) {
+                        if (vend - at < 2) throw Fail{TF_E_FATAL_ARG, "truncated OldKeys image"};
+                        uint16_t c; std::memcpy(&c, at, 2); at += 2; Val v;
+                        if (c >= tfs.size() || !read_val(at, vend, v)) throw Fail{TF_E_FATAL_ARG, "malformed OldKeys image"};
+                        pool->present[c] = 1;
+                    }
+                }
+                Transposer to{pool, tfs, n, threads};
+                static const uint8_t none[2] = {0, 0};
+                to.run([&](uint64_t j, const uint8_t*& at, const uint8_t*& end, bool& sparse, uint32_t& nvals) {
+                    const tf_item& it = rows->items[item_idx[j]]; sparse = true; end = vend;
+                    const uint8_t* p = it.old_keys_off != UINT64_MAX ? rows->values + it.old_keys_off : none;
+                    uint16_t cnt; std::memcpy(&cnt, p, 2); nvals = cnt; at = p + 2;
+                }, true, pool->old_cols, pool->present.data());
+                pool->old_batch = tf_batch{n, (uint32_t)tfs.size(), TF_MEM_HOST, pool->old_cols.data(), nullptr};
+                pool->old = tf_old_keys{&pool->old_batch, pool->present.data(), row_has};
+                *old = &pool->old;
+            }
+        }
+        return TF_OK;
+    } catch (const Fail& f) { pool->err = f.msg; return f.rc; }
+    catch (const std::bad_alloc&) { pool->err = "host allocation failed"; return TF_E_RETRY_OOM; }
+}
+
+int tfgpu_batch_to_rows(const tf_batch* b, uint8_t* out, uint64_t cap, uint64_t* row_off, uint64_t* need) {
+    if (!b || !row_off || (b->mem != TF_MEM_HOST)) return TF_E_FATAL_ARG;
+    const uint64_t n = b->nrows; const uint32_t nc = b->ncols;
+    auto cell_len = [&](const tf_col& c, uint64_t r) -> uint32_t {
+        if (c.flags & TF_COL_LENS8) return ((const uint8_t*)c.offsets)[r];
+        if (c.flags & TF_COL_LENS16) return ((const uint16_t*)c.offsets)[r];
+        return c.offsets[r + 1] - c.offsets[r];
+    };
+    // var-width columns with narrow lengths need running offsets: one cursor per column while rows are walked in order
+    std::vector<uint64_t> cursor(nc, 0);
+    uint64_t at = 0; bool fits = out != nullptr;
+    auto put = [&](const void* p, size_t k) { if (fits && at + k <= cap) std::memcpy(out + at, p, k); else fits = false; at += k; };
+    auto put8 = [&](uint8_t v) { put(&v, 1); };
+    for (uint64_t r = 0; r < n; r++) {
+        row_off[r] = at;
+        for (uint32_t ci = 0; ci < nc; ci++) {
+            const tf_col& c = b->cols[ci];
+            const bool valid = !c.validity || (c.validity[r >> 3] >> (r & 7) & 1);
+            const int w = fixed_width(c.type);
+            uint32_t len = 0; const uint8_t* src = nullptr;
+            if (!w) {
+                len = cell_len(c, r);
+                src = c.heap + ((c.flags & (TF_COL_LENS8 | TF_COL_LENS16)) ? cursor[ci] : c.offsets[r]);
+                cursor[ci] += len;
+            }
+            if (!valid) { put8(TF_V_NIL); continue; }
+            if (w) {
+                if (is_time(c.type)) { put8(TF_V_TIME); put((const uint8_t*)c.values + 8 * r, 8); const uint32_t ns = c.aux ? ((const uint32_t*)c.aux)[r] : 0; put(&ns, 4); }
+                else { put8((uint8_t)canonical_tag(c.type)); put((const uint8_t*)c.values + (size_t)w * r, w); }
+            } else {
+                const bool go_string = c.type == TF_UTF8 || (c.type == TF_ANY && c.aux && ((const uint8_t*)c.aux)[r] == 1);
+                put8(go_string ? TF_V_STRING : c.type == TF_BYTES ? TF_V_BYTES : TF_V_JSON); put(&len, 4); put(src, len);
+            }
+        }
+    }
+    row_off[n] = at;
+    if (need) *need = at;
+    return fits ? TF_OK : TF_E_FATAL_ARG;
+}
+
+}  // extern "C"
