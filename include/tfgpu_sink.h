@@ -160,6 +160,65 @@ int tfgpu_rows_to_batch(tfgpu_columnar* pool, const tf_rows* rows, uint32_t tabl
  * *need set when cap is too small. */
 int tfgpu_batch_to_rows(const tf_batch* b, uint8_t* out, uint64_t cap, uint64_t* row_off, uint64_t* need);
 
+/* ------------------------------------------------------------------ Sinker.Push as one call */
+/* What stands below the user's transformers in every transfer's sink pipeline (pkg/sink_factory/sink_factory.go:79-108), in the
+ * reference's order, over items in row form:
+ *   transformation.Push   pkg/transformer/transformation.go:122-158: items split by table (SplitByTableID), one plan per (table, schema)
+ *                         cached like transformation.go:93-121, the plan's chain over the table's ROW events on the device; items of other
+ *                         kinds go through untouched except for skip_events (drops the listed kinds) and rename_tables (renames them);
+ *                         TransformerResult.Errors are pushed downstream first ("sink") or dropped ("devnull"), transformation.go:173-205
+ *   NonRowSeparator       pkg/middlewares/nonrow_separator.go:29-55: runs of row events stay together, every other item travels alone
+ *   Filter                pkg/middlewares/filter.go:60-77 with ExcludeSystemTables: items of registered system tables are dropped
+ *   Statistician          pkg/middlewares/statistician.go:55-68 -> stats/sink_wrapper.go:63-78, sink_wrapper_util.go:10-50: counters per
+ *                         downstream Push that succeeded
+ *   destination           the row runs encoded by the device (cfg "wire_fmt") go to the ClickHouse writer (tfgpu_sink_set_clickhouse: one
+ *                         INSERT per run, the statement of sink_table.go:633-660) or to the callback; everything else goes to the callback.
+ * Tables are visited in order of first appearance (the reference ranges over a Go map: any order is legal there).
+ * cfg_json: {"transformers":[..], "errors_output":"sink"|"devnull", "exclude_system_tables":true, "system_tables":["__consumer_keeper",..],
+ *            "sink":{"type":"clickhouse"}, "database":"db", "updateable":false, "wire_fmt":2}
+ * wire_fmt 0: row runs are handed on as columnar batches (ev.batch; with transformers the result of tfgpu_push_columns). `e` may be NULL
+ * only when there are no transformers and wire_fmt is 0 (nothing to compute: the always-on middleware alone). */
+typedef struct tfgpu_sink tfgpu_sink;
+#define TF_SINK_EV_ROWS   1   /* one downstream Push of row events of one table */
+#define TF_SINK_EV_ITEM   2   /* one downstream Push of a single non-row item */
+#define TF_SINK_EV_ERRORS 3   /* errorChangeItems (transformation.go:206-234): the failing input rows, to be pushed with `__transform_error` */
+typedef struct tf_sink_event {
+    int32_t          type;        /* TF_SINK_EV_* */
+    uint32_t         table;       /* index into tf_rows.tables of the push */
+    const char*      out_schema;  /* table id after rename_tables */
+    const char*      out_table;
+    uint64_t         n_items;     /* len(items) of this downstream Push (EV_ROWS: rows that survived the transformers) */
+    const uint64_t*  item_idx;    /* the input items behind it: EV_ITEM one entry, EV_ROWS / EV_ERRORS n_items entries */
+    const tf_rowerr* errors;      /* EV_ERRORS: n_items entries (row = position in item_idx) */
+    const tf_batch*  batch;       /* EV_ROWS with wire_fmt 0 */
+    const uint8_t*   wire;        /* EV_ROWS with a wire format: valid until the callback returns */
+    uint64_t         wire_len, raw_len, n_frames;
+    int32_t          plan_id;     /* engine plan that produced it, -1 without one */
+    int32_t          pad;
+} tf_sink_event;
+typedef int (*tf_sink_fn)(void* ctx, const tf_sink_event* ev);   /* nonzero return = the downstream Push failed: tfgpu_sink_push returns it */
+typedef struct tf_sink_stats {
+    uint64_t pushes;                 /* tfgpu_sink_push calls */
+    uint64_t downstream_pushes;      /* Push calls that reached the destination */
+    uint64_t change_items_pushed;    /* WrapperStats.ChangeItemsPushed */
+    uint64_t row_events_pushed;      /* WrapperStats.RowEventsPushed */
+    uint64_t inflight_bytes;         /* sum of Size.Read over the counted items (the shim fills Size.Values from tfgpu_measure) */
+    uint64_t filter_dropped;         /* MiddlewareFilterStats.Dropped */
+    uint64_t transform_dropped;      /* transformation stats Dropped: incoming - transformed */
+    uint64_t transform_errors;       /* transformation stats Errors */
+    uint64_t max_commit_time;        /* batchStats' `oldestTime` (sic: the reference keeps the LATEST commit time under that name) of the last push */
+    uint64_t min_commit_time;        /* its `freshestTime`; both over row + synchronize items with CommitTime != 0 */
+    uint64_t without_commit_time;    /* items whose CommitTime is 0 (the reference substitutes time.Now()) */
+    uint64_t wire_bytes;             /* bytes handed to the destination */
+} tf_sink_stats;
+int tfgpu_sink_create(tfgpu_engine* e, const char* cfg_json, tfgpu_sink** out);
+int tfgpu_sink_destroy(tfgpu_sink* s);
+const char* tfgpu_sink_last_error(const tfgpu_sink* s);
+int tfgpu_sink_set_callback(tfgpu_sink* s, tf_sink_fn fn, void* ctx);
+int tfgpu_sink_set_clickhouse(tfgpu_sink* s, tfgpu_ch_conn* conn);
+int tfgpu_sink_push(tfgpu_sink* s, const tf_rows* items);
+int tfgpu_sink_stats(const tfgpu_sink* s, tf_sink_stats* out);
+
 /* Host CityHash128 (v1.0.2) as the frames' checksum uses it — exported for the tests' cross-checks against the device and the oracle. */
 void tfgpu_host_cityhash128(const uint8_t* p, uint64_t n, uint64_t out[2]);
 

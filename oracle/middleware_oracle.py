@@ -1,0 +1,118 @@
+"""CPU restatement (TEST INFRASTRUCTURE — never imported by the product) of the reference's sink pipeline below the user transformers,
+item by item over Python lists, used to check tfgpu_sink_push's sequencing and counters:
+
+    transformation.Push      pkg/transformer/transformation.go:122-158 (SplitByTableID pkg/abstract/changeitem/utils.go:130-136; per-table do()
+                             :236-282; errors first :152-157; errorChangeItems :206-234)
+    NonRowSeparator.Push     pkg/middlewares/nonrow_separator.go:29-55
+    filter.Push              pkg/middlewares/filter.go:60-77 with ExcludeSystemTables (ChangeItem.IsSystemTable: Table in the registered set,
+                             pkg/abstract/changeitem/system_table.go:26-30)
+    statistician.Push        pkg/middlewares/statistician.go:55-68 -> WrapperStats.Log pkg/stats/sink_wrapper.go:63-78, batchStats
+                             pkg/stats/sink_wrapper_util.go:10-50
+
+Parity pinned by: nothing the reference holds as bytes for these middlewares (they have no golden files); the restatement follows the
+cited lines one to one and the reference's own unit expectations for NonRowSeparator (pkg/middlewares/nonrow_separator_test.go) are
+re-stated in tests/test_sink_push.py.
+
+`apply_row_transformers(table_index, items) -> (kept_items, error_items)` is supplied by the test (the oracle's plan over the table's row
+events); non-row items pass through every transformer except skip_events (drops the listed kinds) and rename_tables."""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Sequence, Tuple
+
+ROW_KINDS = (0, 1, 2)
+KIND_SYNCHRONIZE = 24
+KIND_NAME = {0: "insert", 1: "update", 2: "delete", 16: "init_sharded_table_load", 17: "init_load_table", 18: "done_load_table",
+             19: "done_sharded_table_load", 20: "drop_table", 21: "truncate", 22: "DDL", 23: "pg:DDL", 24: ""}
+
+
+def non_row_separator(items: List[dict]) -> List[List[dict]]:
+    """nonrow_separator.go:29-55: the downstream Push calls for one incoming batch."""
+    pushes, start, end = [], 0, 0
+    for i, it in enumerate(items):
+        if it["kind"] in ROW_KINDS:
+            end += 1; continue
+        if end > start:
+            pushes.append(items[start:end])
+        pushes.append(items[i:i + 1])
+        start = end = i + 1
+    if end > start:
+        pushes.append(items[start:end])
+    return pushes
+
+
+def filter_push(items: List[dict], system_tables: Sequence[str], stats: dict) -> List[dict]:
+    """filter.go:60-77: drop items of system tables; an empty batch is not forwarded (the caller checks)."""
+    out = []
+    for it in items:
+        if it["out_table"] in system_tables:
+            stats["filter_dropped"] += 1; continue
+        out.append(it)
+    return out
+
+
+def statistician(items: List[dict], stats: dict) -> None:
+    """sink_wrapper.go:63-78 after a successful downstream Push + batchStats sink_wrapper_util.go:10-50 (the variable the reference calls
+    `oldestTime` ends up holding the LATEST commit time: `if oldestTime.Before(eventTime) { oldestTime = eventTime }`)."""
+    stats["downstream_pushes"] += 1
+    stats["change_items_pushed"] += len(items)
+    for it in items:
+        if not (it["kind"] in ROW_KINDS or it["kind"] == KIND_SYNCHRONIZE):
+            continue
+        if it["kind"] in ROW_KINDS:
+            stats["row_events_pushed"] += 1
+        stats["inflight_bytes"] += it.get("size", 0)
+        ct = it.get("commit_time", 0)
+        if not ct:
+            stats["without_commit_time"] += 1; continue
+        stats["max_commit_time"] = max(stats["max_commit_time"], ct)
+        stats["min_commit_time"] = ct if not stats["min_commit_time"] else min(stats["min_commit_time"], ct)
+
+
+def sink_push(items: List[dict], tables: List[Tuple[str, str]], skip_events: Sequence[Tuple[Callable[[str, str], bool], Sequence[str]]],
+              renames: Dict[Tuple[str, str], Tuple[str, str]], system_tables: Sequence[str],
+              apply_row_transformers: Callable[[int, List[dict]], Tuple[List[dict], List[dict]]], errors_to_sink: bool, stats: dict) -> List[dict]:
+    """One Sinker.Push through the pipeline. items: dicts with kind, table (index), index, commit_time, size. Returns the downstream pushes as
+    {"type": "rows" | "item" | "errors", "table": k, "items": [input indexes]}. Tables are visited in order of first appearance and a push
+    never spans two tables / schemas (the product's granularity; the reference may glue the last row run of one table to the first of the
+    next — totals are the same)."""
+    stats["pushes"] += 1; stats["max_commit_time"] = stats["min_commit_time"] = 0
+    groups: Dict[Tuple[str, str], List[dict]] = {}
+    for it in items:                                                       # SplitByTableID
+        groups.setdefault(tables[it["table"]], []).append(it)
+    out: List[dict] = []
+
+    def deliver(kind: str, table: int, its: List[dict]):
+        out.append({"type": kind, "table": table, "items": [x["index"] for x in its]})
+        statistician(its, stats)
+
+    for tid, its in groups.items():
+        # transformation.do over the table's items: row events through the plan, the others through skip_events / rename only
+        seq: List = []                                                     # ("run", table, [items]) | ("item", item)
+        for it in its:
+            if it["kind"] in ROW_KINDS:
+                if seq and seq[-1][0] == "run" and seq[-1][1] == it["table"]:
+                    seq[-1][2].append(it)
+                else:
+                    seq.append(("run", it["table"], [it]))
+                continue
+            if any(suit(*tid) and KIND_NAME.get(it["kind"], "\x01other") in evs for suit, evs in skip_events):
+                stats["transform_dropped"] += 1; continue                  # gone before NonRowSeparator: the neighbouring row runs join
+            it = dict(it); it["out_table"] = renames.get(tid, tid)[1]
+            seq.append(("item", it))
+        for ent in seq:
+            if ent[0] == "item":
+                kept = filter_push([ent[1]], system_tables, stats)
+                if kept:
+                    deliver("item", ent[1]["table"], kept)
+                continue
+            _, table, run = ent
+            out_table = renames.get(tid, tid)[1]
+            if out_table in system_tables:
+                stats["filter_dropped"] += len(run); continue
+            kept, errs = apply_row_transformers(table, run)
+            stats["transform_dropped"] += len(run) - len(kept); stats["transform_errors"] += len(errs)
+            if errs and errors_to_sink:
+                deliver("errors", table, errs)
+            if kept:
+                deliver("rows", table, kept)
+    return out

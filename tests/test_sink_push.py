@@ -1,0 +1,177 @@
+"""tfgpu_sink_push — Sinker.Push through the always-on middleware: sequencing and counters against
+oracle/middleware_oracle.py (a line-by-line restatement of transformation.Push / NonRowSeparator / Filter / Statistician) on CPU, and the
+whole path (rows -> transpose -> device chain -> frames -> ClickHouse native writer -> server peer) on the GPU."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import ch_peer
+from oracle import middleware_oracle as mo
+from transferia_b200 import abi, engine, rows, sink, workload
+from transferia_b200.rows import ChangeItem, go
+
+K = rows
+SCHEMA_A = [{"name": "id", "type": "int32", "key": True}, {"name": "v", "type": "utf8"}]
+SCHEMA_B = [{"name": "x", "type": "int64"}]
+TABLES = [("public", "a", SCHEMA_A), ("public", "b", SCHEMA_B), ("public", "__consumer_keeper", SCHEMA_B), ("public", "a", SCHEMA_A + [{"name": "w", "type": "int8"}])]
+
+
+def _items(spec):
+    """spec: [(kind, table)] -> ChangeItems with values fitting the table's schema."""
+    out = []
+    for i, (kind, t) in enumerate(spec):
+        vals = None
+        if kind <= 2:
+            vals = {0: [go.int32(i), go.string(f"v{i}")], 1: [go.int64(i)], 2: [go.int64(i)], 3: [go.int32(i), go.string("z"), go.int8(1)]}[t]
+        out.append(ChangeItem(kind, t, vals, id=i, lsn=1000 + i, commit_time=0 if i % 7 == 3 else 5_000 + 13 * ((i * 7) % 11), size_read=10 + i))
+    return out
+
+
+def _oracle_items(items):
+    return [{"kind": it.kind, "table": it.table, "index": i, "commit_time": it.commit_time, "size": it.size_read} for i, it in enumerate(items)]
+
+
+def _zero_stats():
+    return {k: 0 for k in ("pushes", "downstream_pushes", "change_items_pushed", "row_events_pushed", "inflight_bytes", "filter_dropped", "transform_dropped",
+                           "transform_errors", "max_commit_time", "min_commit_time", "without_commit_time", "wire_bytes")}
+
+
+def _events(s):
+    names = {sink.EV_ROWS: "rows", sink.EV_ITEM: "item", sink.EV_ERRORS: "errors"}
+    return [{"type": names[e["type"]], "table": e["table"], "items": e["items"]} for e in s.events]
+
+
+def test_nonrow_separator_reference_cases():
+    """pkg/middlewares/nonrow_separator_test.go: every item reaches the sink; runs of rows stay together, every other item travels alone."""
+    s = sink.Sink()
+    cases = [
+        ([K.KIND_INSERT] * 3 + [K.KIND_UPDATE, K.KIND_DELETE, K.KIND_INSERT], [6]),                                        # SingleBatchOnlyRows
+        ([K.KIND_INSERT, K.KIND_INSERT, K.KIND_UPDATE, K.KIND_DROP_TABLE, K.KIND_DELETE, K.KIND_INSERT], [3, 1, 2]),         # SingleBatchWithNonRows
+        ([K.KIND_DROP_TABLE], [1]), ([K.KIND_INSERT, K.KIND_DROP_TABLE], [1, 1]), ([], []),                                # TwoBatchesWith / WithoutRows
+        ([K.KIND_DDL] * 4, [1, 1, 1, 1]),                                                                                  # MultipleNonRows
+    ]
+    for kinds, want in cases:
+        s.events.clear()
+        its = _items([(k, 0) for k in kinds])
+        s.push(rows.RowsImage(its, TABLES))
+        assert [e["n_items"] for e in s.events] == want, kinds
+        assert sum(e["n_items"] for e in s.events) == len(kinds)
+        assert [x for e in s.events for x in e["items"]] == list(range(len(kinds)))
+    s.close()
+
+
+def test_push_sequence_and_counters_equal_the_oracle():
+    rng = np.random.default_rng(5)
+    kinds = [K.KIND_INSERT] * 6 + [K.KIND_UPDATE, K.KIND_DELETE, K.KIND_INIT_TABLE_LOAD, K.KIND_DONE_TABLE_LOAD, K.KIND_TRUNCATE, K.KIND_DDL, K.KIND_SYNCHRONIZE, K.KIND_OTHER]
+    s = sink.Sink(system_tables=["__consumer_keeper", "__tm_keeper"])
+    want_stats = _zero_stats()
+    for rnd in range(30):
+        spec = [(int(rng.choice(kinds)), int(rng.choice([0, 0, 0, 1, 2, 3]))) for _ in range(int(rng.integers(0, 60)))]
+        its = _items(spec)
+        s.events.clear()
+        s.push(rows.RowsImage(its, TABLES))
+        want = mo.sink_push(_oracle_items(its), [(t[0], t[1]) for t in TABLES], [], {}, ["__consumer_keeper", "__tm_keeper"],
+                            lambda table, run: (run, []), True, want_stats)
+        assert _events(s) == want, (rnd, spec)
+        got = s.stats(); got.pop("wire_bytes"); w = dict(want_stats); w.pop("wire_bytes")
+        assert got == w, rnd
+        # row runs arrive columnar, in item order
+        for e in s.events:
+            if e["type"] == sink.EV_ROWS:
+                assert list(e["columns"][0]) == e["items"] and e["out"][1] in ("a", "b")
+    assert s.stats()["filter_dropped"] > 0 and s.stats()["without_commit_time"] > 0
+    s.close()
+
+
+def test_filter_can_be_switched_off_and_downstream_errors_propagate():
+    its = _items([(K.KIND_INSERT, 2), (K.KIND_INSERT, 0), (K.KIND_DDL, 2)])
+    s = sink.Sink(system_tables=["__consumer_keeper"], exclude_system_tables=False)      # destinations that rely on system tables (sink_factory.go:87-89)
+    s.push(rows.RowsImage(its, TABLES))
+    assert [e["n_items"] for e in s.events] == [1, 1, 1] and s.stats()["filter_dropped"] == 0
+    s.close()
+    calls = []
+    s = sink.Sink(downstream=lambda ev: (calls.append(ev["type"]), 7 if len(calls) == 2 else 0)[1])
+    with pytest.raises(engine.EngineError) as ei:
+        s.push(rows.RowsImage(_items([(K.KIND_INSERT, 0), (K.KIND_DDL, 0), (K.KIND_INSERT, 0)]), TABLES))
+    assert ei.value.rc == 7 and len(calls) == 2
+    st = s.stats()
+    assert st["downstream_pushes"] == 1 and st["change_items_pushed"] == 1                # the failed Push is not counted (statistician.go:60)
+    s.close()
+
+
+def test_transformers_need_the_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(engine.EngineError) as ei:
+        sink.Sink(transformers=[{"filter_rows": {"filter": "id > 1"}}])
+    assert ei.value.rc == engine.TF_E_FATAL_NODEVICE
+    with pytest.raises(engine.EngineError):
+        sink.Sink(wire_fmt=abi.TF_WIRE_CH_NATIVE_LZ4)
+
+
+@pytest.mark.gpu
+def test_push_with_transformers_on_the_device_equals_the_oracle(eng, po):
+    """skip_events / rename_tables / filter_rows over mixed kinds and two tables; the row runs come back as columnar batches (wire_fmt 0)
+    that equal the oracle's push_columns over the same rows; sequencing and counters equal the middleware oracle."""
+    trs = [{"skip_events": {"tables": {"includeTables": ["^public.a$"]}, "events": ["truncate", "delete"]}},
+           {"rename_tables": {"renameTables": [{"originalName": {"nameSpace": "public", "name": "a"}, "newName": {"nameSpace": "dst", "name": "a2"}}]}},
+           {"filter_rows": {"tables": {"includeTables": ["^public.a$"]}, "filter": "id > 10"}}]
+    spec = [(K.KIND_INIT_TABLE_LOAD, 0)] + [(K.KIND_INSERT, 0)] * 9 + [(K.KIND_TRUNCATE, 0)] + [(K.KIND_INSERT, 0)] * 12 + [(K.KIND_INSERT, 1)] * 5 + \
+           [(K.KIND_DELETE, 0), (K.KIND_DDL, 0), (K.KIND_INSERT, 0), (K.KIND_DONE_TABLE_LOAD, 0), (K.KIND_INSERT, 2)]
+    its = _items(spec)
+    s = sink.Sink(eng, transformers=trs, system_tables=["__consumer_keeper"])
+    s.push(rows.RowsImage(its, TABLES))
+
+    def apply(table, run):
+        if table != 0:
+            return run, []
+        kept = [x for x in run if x["kind"] != K.KIND_DELETE and x["index"] > 10]      # skip_events drops deletes, id == item index
+        return kept, []
+    want_stats = _zero_stats()
+    suit_a = lambda ns, name: (ns, name) == ("public", "a")
+    want = mo.sink_push(_oracle_items(its), [(t[0], t[1]) for t in TABLES], [(suit_a, ["truncate", "delete"])], {("public", "a"): ("dst", "a2")},
+                        ["__consumer_keeper"], apply, True, want_stats)
+    got = _events(s)
+    for g, w in zip(got, want):                                                             # rows dropped by the device: the event carries the count, not the indexes
+        assert g["type"] == w["type"] and g["table"] == w["table"]
+        assert g["items"] == w["items"] or (g["items"] is None and s.events[got.index(g)]["n_items"] == len(w["items"]))
+    assert len(got) == len(want)
+    st = s.stats(); st.pop("wire_bytes"); want_stats.pop("wire_bytes")
+    for k in ("inflight_bytes", "max_commit_time", "min_commit_time", "without_commit_time"):   # per-item figures need the indexes the device does not return
+        st.pop(k); want_stats.pop(k)
+    assert st == want_stats
+    ev_rows = [e for e in s.events if e["type"] == sink.EV_ROWS and e["table"] == 0]
+    assert all(e["out"] == ("dst", "a2") for e in ev_rows) and [e["out"] for e in s.events if e["type"] == sink.EV_ITEM][0] == ("dst", "a2")
+    assert sorted(int(v) for e in ev_rows for v in e["columns"][0]) == [i for i, (k, t) in enumerate(spec) if t == 0 and k == K.KIND_INSERT and i > 10]
+    s.close()
+
+
+@pytest.mark.gpu
+def test_push_rows_to_clickhouse_end_to_end(eng, po):
+    """Sinker.Push of ClickBench-shaped rows: transpose -> filter_rows + cast + native block + LZ4 frames on the device -> INSERT over the
+    native protocol; the server peer's copy decodes to the oracle's block and the statement is the one doOperation builds."""
+    batch, schema = workload.make_hits_batch(5000, seed=12)
+    trs = workload.headline_transformers(workload.counterid_threshold(batch, schema))
+    items = [ChangeItem(K.KIND_INIT_TABLE_LOAD, 0)] + rows.items_from_batch(batch) + [ChangeItem(K.KIND_DONE_TABLE_LOAD, 0)]
+    ref = po.push_encode(batch, po.build_plan("public", "hits", schema, trs), abi.TF_WIRE_CH_NATIVE, eng.frame_bytes)
+    names = [c["name"] for c in schema]
+    cli, srv = socket.socketpair(socket.AF_UNIX, socket.SOCK_STREAM)
+    peer = ch_peer.Peer(srv, [(n, "String") for n in names], expect_raw_len=[len(ref.raw)]); peer.start()
+    w = sink.ClickHouseWriter(cli, database="analytics", read_timeout_ms=60000)
+    s = sink.Sink(eng, transformers=trs, wire_fmt=abi.TF_WIRE_CH_NATIVE_LZ4, database="analytics", clickhouse=w)
+    s.push(rows.RowsImage(items, [("public", "hits", schema)]))
+    peer.join(60)
+    assert peer.error is None, peer.error
+    assert peer.queries[0]["body"] == sink.insert_query("analytics", "hits", names)
+    raw, _ = po.ch_decode_frames(peer.blocks[0][0])
+    assert raw == ref.raw
+    assert [e["type"] for e in s.events] == [sink.EV_ITEM, sink.EV_ITEM]                    # the control items went to the callback, the rows to the socket
+    st = s.stats()
+    assert st["row_events_pushed"] == ref.rows_out and st["change_items_pushed"] == ref.rows_out + 2 and st["transform_dropped"] == 5000 - ref.rows_out
+    assert st["wire_bytes"] == len(peer.blocks[0][0])
+    s.close(); w.close(); cli.close()

@@ -11,6 +11,8 @@ import ctypes as C
 import json
 from typing import List, Optional, Tuple
 
+import numpy as np
+
 from . import engine
 
 SINK_SYMBOLS = [
@@ -115,3 +117,86 @@ class ClickHouseWriter:
     def close(self):
         if self._h:
             self._L.tfgpu_ch_close(self._h); self._h = None
+
+
+# ------------------------------------------------------------------ Sinker.Push as one call (tfgpu_sink_*)
+SINK_SYMBOLS += ["tfgpu_sink_create", "tfgpu_sink_destroy", "tfgpu_sink_last_error", "tfgpu_sink_set_callback", "tfgpu_sink_set_clickhouse",
+                 "tfgpu_sink_push", "tfgpu_sink_stats"]
+EV_ROWS, EV_ITEM, EV_ERRORS = 1, 2, 3
+
+
+class TfSinkEvent(C.Structure):
+    _fields_ = [("type", C.c_int32), ("table", C.c_uint32), ("out_schema", C.c_char_p), ("out_table", C.c_char_p), ("n_items", C.c_uint64),
+                ("item_idx", C.POINTER(C.c_uint64)), ("errors", C.c_void_p), ("batch", C.c_void_p), ("wire", C.c_void_p),
+                ("wire_len", C.c_uint64), ("raw_len", C.c_uint64), ("n_frames", C.c_uint64), ("plan_id", C.c_int32), ("pad", C.c_int32)]
+
+
+class TfSinkStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("pushes", "downstream_pushes", "change_items_pushed", "row_events_pushed", "inflight_bytes", "filter_dropped",
+                                          "transform_dropped", "transform_errors", "max_commit_time", "min_commit_time", "without_commit_time", "wire_bytes")]
+
+
+_SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(TfSinkEvent))
+
+
+class Sink:
+    """The reference's sink pipeline below the user transformers as one object (middlewares.PlugTransformer position, Appendix A of SURVEY):
+    Sink.push(rows) ~ Sinker.Push([]ChangeItem). `downstream(event dict) -> int` plays the destination Sinker for what the ClickHouse writer
+    does not take."""
+
+    def __init__(self, eng=None, transformers=None, wire_fmt=0, system_tables=(), exclude_system_tables=True, errors_output="sink",
+                 database="default", downstream=None, clickhouse: Optional[ClickHouseWriter] = None):
+        from . import abi, rows as _rows
+        self._L = lib()
+        vp = C.c_void_p
+        self._L.tfgpu_sink_create.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+        self._L.tfgpu_sink_destroy.argtypes = [vp]
+        self._L.tfgpu_sink_last_error.argtypes = [vp]; self._L.tfgpu_sink_last_error.restype = C.c_char_p
+        self._L.tfgpu_sink_set_callback.argtypes = [vp, _SINK_FN, vp]
+        self._L.tfgpu_sink_set_clickhouse.argtypes = [vp, vp]
+        self._L.tfgpu_sink_push.argtypes = [vp, vp]
+        self._L.tfgpu_sink_stats.argtypes = [vp, C.POINTER(TfSinkStats)]
+        cfg = {"transformers": transformers or [], "wire_fmt": wire_fmt, "system_tables": list(system_tables), "exclude_system_tables": exclude_system_tables,
+               "errors_output": errors_output, "database": database}
+        self._h = vp()
+        rc = self._L.tfgpu_sink_create(eng._h if eng is not None else None, json.dumps(cfg).encode(), C.byref(self._h))
+        if rc:
+            raise engine.EngineError(rc, "tfgpu_sink_create")
+        self.events: List[dict] = []
+        self._downstream = downstream
+
+        def _cb(_ctx, evp):
+            ev = evp.contents
+            d = {"type": ev.type, "table": ev.table, "out": ((ev.out_schema or b"").decode(), (ev.out_table or b"").decode()), "n_items": int(ev.n_items),
+                 "items": [int(ev.item_idx[k]) for k in range(ev.n_items)] if ev.item_idx else None, "plan_id": ev.plan_id,
+                 "raw_len": int(ev.raw_len), "n_frames": int(ev.n_frames)}
+            if ev.wire:
+                d["wire"] = C.string_at(ev.wire, ev.wire_len)
+            if ev.batch:
+                b = _rows.batch_from_struct(C.cast(ev.batch, C.POINTER(abi.TfBatch)).contents)
+                d["batch"] = b
+                d["columns"] = [None if c.values is None else np.asarray(c.values).copy() for c in b.columns]
+            if ev.errors:
+                errs = C.cast(ev.errors, C.POINTER(abi.TfRowErr))
+                d["errors"] = [(errs[k].row, errs[k].code, errs[k].term) for k in range(ev.n_items)]
+            self.events.append(d)
+            return int(self._downstream(d)) if self._downstream else 0
+        self._cb = _SINK_FN(_cb)
+        self._L.tfgpu_sink_set_callback(self._h, self._cb, None)
+        if clickhouse is not None:
+            rc = self._L.tfgpu_sink_set_clickhouse(self._h, clickhouse._h)
+            if rc:
+                raise engine.EngineError(rc, self._L.tfgpu_sink_last_error(self._h).decode())
+
+    def push(self, rows_image) -> None:
+        rc = self._L.tfgpu_sink_push(self._h, C.byref(rows_image.struct))
+        if rc:
+            raise engine.EngineError(rc, self._L.tfgpu_sink_last_error(self._h).decode(errors="replace"))
+
+    def stats(self) -> dict:
+        st = TfSinkStats(); self._L.tfgpu_sink_stats(self._h, C.byref(st))
+        return {n: int(getattr(st, n)) for n, _ in TfSinkStats._fields_}
+
+    def close(self):
+        if self._h:
+            self._L.tfgpu_sink_destroy(self._h); self._h = None
