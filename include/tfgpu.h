@@ -222,6 +222,15 @@ int tfgpu_push_columns(tfgpu_engine* e, int plan_id, const tf_batch* in, tfgpu_r
 int tfgpu_push_encode(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch* in,
                       tfgpu_result** out);
 
+/* tfgpu_push_encode in two phases, for host batches whose plan filters rows (the headline workload keeps 28 %): only the columns the
+ * predicates read cross PCIe first and the device answers with one keep flag per row; host threads gather the kept rows (`threads` <= 0:
+ * up to 32) and only those go through the chain and the encoder. The result is the one tfgpu_push_encode gives (all transformers are
+ * row-local, filter_rows keeps what it kept; rows dropped with an error in phase one are reported with their input index). Plans without
+ * filter steps, device batches, loosely typed predicate columns and batches under 8192 rows take the one-phase path. */
+int tfgpu_push_encode_selective(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch* in, int threads, tfgpu_result** out);
+/* Bytes the engine has copied host -> device for batch columns since it was created (bench accounting of the e2e legs). */
+uint64_t tfgpu_engine_h2d_bytes(const tfgpu_engine* e);
+
 /* Queue Debezium serializer (pkg/serializer/queue/debezium_serializer.go:25-92 -> debezium.Emitter.EmitKV
  * pkg/debezium/emitter_value_converter.go:566-690). Runs the plan's chain on the device and writes, for every surviving INSERT row,
  * the Kafka key message immediately followed by the value message:

@@ -638,3 +638,31 @@ def test_narrow_length_arrays_equal_offsets(eng, po):
     assert 2 in [getattr(c, "lens_width", 0) for c in n2.columns] or 1 in [getattr(c, "lens_width", 0) for c in n2.columns]
     p2 = eng.plan("db", "t", s2, [], {"type": "clickhouse"})
     assert eng.push_encode(p2, b2, RAW).wire == eng.push_encode(p2, n2, RAW).wire
+
+
+@pytest.mark.gpu
+def test_two_phase_push_equals_one_phase(eng, po):
+    """tfgpu_push_encode_selective: predicate columns first, host gather of the kept rows, the chain over those — the block, the row count and
+    the row errors are those of the one-phase call (and of the oracle), from offsets and from narrow lengths, with per-row filter errors."""
+    batch, schema = workload.make_hits_batch(60_000, seed=21)
+    trs = workload.headline_transformers(workload.counterid_threshold(batch, schema))
+    pid = eng.plan("public", "hits", schema, trs, {"type": "clickhouse"})
+    want = po.push_encode(batch, po.build_plan("public", "hits", schema, trs), RAW)
+    for b in (batch, batch.narrow(), batch.narrow().pin()):
+        h0 = eng.h2d_bytes()
+        one = eng.push_encode(pid, b, RAW); h1 = eng.h2d_bytes()
+        two = eng.push_encode(pid, b, RAW, selective=4); h2 = eng.h2d_bytes()
+        assert two.wire == one.wire == want.raw and two.rows_out == one.rows_out and two.rows_in == 60_000 and two.errors == one.errors
+        assert (h2 - h1) < 0.6 * (h1 - h0)                     # the point of it: fewer bytes over PCIe
+    lz = eng.push_encode(pid, batch.narrow(), abi.TF_WIRE_CH_NATIVE_LZ4, selective=0)
+    raw, _ = po.ch_decode_frames(lz.wire)
+    assert raw == want.raw
+    # update / delete kinds make filter_rows fail per row (filter_rows.go:103-107): reported from phase one with the input row index
+    kb = abi.Batch(batch.nrows, batch.columns, (np.arange(batch.nrows) % 50 == 7).astype(np.uint8))
+    one = eng.push_encode(pid, kb, RAW); two = eng.push_encode(pid, kb, RAW, selective=3)
+    assert one.errors and two.errors == one.errors and two.wire == one.wire and two.rows_out == one.rows_out
+    # all-types batch: nulls, long strings, a predicate on a nullable column
+    b2, s2 = all_types_batch(30_000, seed=13)
+    t2 = [{"filter_rows": {"filter": "c_int32 > 0 AND n_int16 != NULL"}}]
+    p2 = eng.plan("db", "t", s2, t2, {"type": "clickhouse"})
+    assert eng.push_encode(p2, b2, RAW, selective=2).wire == eng.push_encode(p2, b2, RAW).wire == po.push_encode(b2, po.build_plan("db", "t", s2, t2), RAW).raw

@@ -23,6 +23,8 @@ def assert_same_batch(got: abi.Batch, want: abi.Batch):
     n = want.nrows
     for k, (g, w) in enumerate(zip(got.columns, want.columns)):
         assert g.type == w.type, (k, g.type, w.type)
+        if n == 0:
+            continue
         vg, vw = _valid(g, n), _valid(w, n)
         assert (vg == vw).all(), k
         if w.type in abi.VAR_TYPES:
@@ -160,4 +162,38 @@ def test_transposed_rows_through_the_device_equal_the_oracle(eng, po):
     got = eng.push_encode(pid, t.batch, abi.TF_WIRE_CH_NATIVE)
     want = po.push_encode(batch, po.build_plan("public", "hits", schema, trs), abi.TF_WIRE_CH_NATIVE)
     assert got.rows_out == want.rows_out and got.wire == want.raw and not got.errors
+    pool.close()
+
+
+def _numpy_select(batch: abi.Batch, keep: np.ndarray) -> abi.Batch:
+    """The expectation for tfgpu_batch_gather, stated with numpy fancy indexing over plain uint32 offsets."""
+    idx = np.nonzero(keep)[0]; n = batch.nrows; cols = []
+    for c in batch.columns:
+        val = None if c.validity is None else abi.pack_validity(np.unpackbits(np.asarray(c.validity), bitorder="little")[:n].astype(bool)[idx])
+        aux = None if c.aux is None else np.asarray(c.aux)[idx]
+        if c.type in abi.VAR_TYPES:
+            ln = _lens(c, n); off = np.concatenate([[0], np.cumsum(ln)]); heap = np.asarray(c.heap).tobytes()
+            cells = [heap[off[r]:off[r + 1]] for r in idx]
+            o = np.zeros(len(idx) + 1, np.uint32); np.cumsum([len(x) for x in cells], out=o[1:])
+            cols.append(abi.Column(c.type, None, val, o, np.frombuffer(b"".join(cells), np.uint8), aux))
+        else:
+            cols.append(abi.Column(c.type, np.asarray(c.values)[idx], val, None, None, aux))
+    return abi.Batch(len(idx), cols, None if batch.kinds is None else np.asarray(batch.kinds)[idx])
+
+
+def test_host_gather_equals_numpy_selection():
+    pool = rows.Columnar()
+    rng = np.random.default_rng(3)
+    for make, n in ((lambda: all_types_batch(70_000, seed=2)[0], 70_000), (lambda: workload.make_hits_batch(40_000, seed=8)[0].narrow(), 40_000)):
+        batch = make()
+        batch.kinds = rng.integers(0, 3, n).astype(np.uint8)
+        for p in (0.28, 0.0, 1.0):
+            keep = (rng.random(n) < p).astype(np.uint8)
+            for threads in (1, 5):
+                got, sel = pool.gather(batch, keep, threads)
+                want = _numpy_select(batch, keep)
+                assert (sel == np.nonzero(keep)[0]).all()
+                assert_same_batch(got, want)
+                assert (np.asarray(got.kinds) == np.asarray(want.kinds)).all() if want.nrows else True
+                assert [c.lens_width for c in got.columns] == [c.lens_width for c in batch.columns]     # the layout of the input is kept
     pool.close()

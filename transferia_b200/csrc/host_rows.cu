@@ -383,6 +383,107 @@ int tfgpu_rows_to_batch(tfgpu_columnar* pool, const tf_rows* rows, uint32_t tabl
     catch (const std::bad_alloc&) { pool->err = "host allocation failed"; return TF_E_RETRY_OOM; }
 }
 
+// Rows keep[r] != 0 of a host batch, in order, in the pool's buffers: the host half of a two-phase push (tfgpu_push_encode_selective) —
+// when filter_rows keeps a fraction of the rows only that fraction has to cross PCIe. Var-width columns are walked per chunk of input rows
+// (narrow length arrays have no random access), everything else is gathered through the selection vector per chunk of output rows.
+int tfgpu_batch_gather(tfgpu_columnar* pool, const tf_batch* in, const uint8_t* keep, int threads, const tf_batch** out, const uint32_t** sel_out) {
+    if (!pool || !in || !keep || !out || in->mem != TF_MEM_HOST) return TF_E_FATAL_ARG;
+    try {
+        const uint64_t n = in->nrows; const uint32_t nc = in->ncols;
+        if (threads <= 0) threads = (int)std::min<unsigned>(32, std::max(1u, std::thread::hardware_concurrency()));
+        pool->next_buf = 0;
+        const uint64_t CH = 32768, nch = (n + CH - 1) / CH;
+        std::vector<uint64_t> kept(nch + 1, 0);
+        parallel_chunks(n, CH, threads, [&](uint64_t k) { uint64_t c = 0; for (uint64_t r = k * CH; r < std::min(n, (k + 1) * CH); r++) c += keep[r] != 0; kept[k + 1] = c; });
+        for (uint64_t k = 0; k < nch; k++) kept[k + 1] += kept[k];
+        const uint64_t m = kept[nch];
+        uint32_t* sel = (uint32_t*)pool->take()->ensure(4 * m + 16, pool->want_pinned);
+        parallel_chunks(n, CH, threads, [&](uint64_t k) { uint64_t j = kept[k]; for (uint64_t r = k * CH; r < std::min(n, (k + 1) * CH); r++) if (keep[r]) sel[j++] = (uint32_t)r; });
+        pool->cols.assign(nc, tf_col{});
+        struct Var { uint32_t c; int lw; uint8_t* lens; uint8_t* heap; std::vector<uint64_t> in_base, out_base; };
+        std::vector<Var> vars;
+        for (uint32_t c = 0; c < nc; c++) {
+            const tf_col& ic = in->cols[c]; tf_col& oc = pool->cols[c]; oc.type = ic.type; oc.flags = ic.flags;
+            const int w = fixed_width(ic.type);
+            if (w) { if (ic.values) oc.values = pool->take()->ensure((size_t)w * m + 16, pool->want_pinned); }
+            else if (ic.offsets) {
+                Var v; v.c = c; v.lw = (ic.flags & TF_COL_LENS8) ? 1 : (ic.flags & TF_COL_LENS16) ? 2 : 4;
+                v.lens = pool->take()->ensure((size_t)v.lw * (m + 1) + 16, pool->want_pinned); v.heap = nullptr;
+                v.in_base.assign(nch + 1, 0); v.out_base.assign(nch + 1, 0);
+                oc.offsets = (const uint32_t*)v.lens; vars.push_back(std::move(v));
+            }
+            if (ic.validity) oc.validity = pool->take()->ensure((m + 7) / 8 + 16, pool->want_pinned);
+            if (ic.aux) oc.aux = pool->take()->ensure((size_t)(is_time(ic.type) ? 4 : 1) * m + 16, pool->want_pinned);
+        }
+        auto in_len = [&](const tf_col& ic, int lw, uint64_t r) -> uint32_t {
+            return lw == 1 ? ((const uint8_t*)ic.offsets)[r] : lw == 2 ? ((const uint16_t*)ic.offsets)[r] : ic.offsets[r + 1] - ic.offsets[r];
+        };
+        // pass A: bytes per (var column, input chunk), all rows and kept rows
+        const uint64_t nv = vars.size();
+        parallel_chunks(nv * nch, 1, threads, [&](uint64_t t) {
+            Var& v = vars[t / nch]; const uint64_t k = t % nch; const tf_col& ic = in->cols[v.c];
+            uint64_t all = 0, kb = 0; const uint64_t r0 = k * CH, r1 = std::min(n, (k + 1) * CH);
+            if (v.lw == 4) { all = ic.offsets[r1] - ic.offsets[r0]; for (uint64_t r = r0; r < r1; r++) if (keep[r]) kb += ic.offsets[r + 1] - ic.offsets[r]; }
+            else for (uint64_t r = r0; r < r1; r++) { const uint32_t l = in_len(ic, v.lw, r); all += l; if (keep[r]) kb += l; }
+            v.in_base[k + 1] = all; v.out_base[k + 1] = kb;
+        });
+        for (Var& v : vars) {
+            for (uint64_t k = 0; k < nch; k++) { v.in_base[k + 1] += v.in_base[k]; v.out_base[k + 1] += v.out_base[k]; }
+            if (v.lw == 4) v.in_base.assign(nch + 1, 0);                     // offsets give the position directly
+            v.heap = pool->take()->ensure(v.out_base[nch] + 16, pool->want_pinned);
+            tf_col& oc = pool->cols[v.c]; oc.heap = v.heap; oc.heap_len = v.out_base[nch];
+        }
+        // pass B: var-width cells per input chunk; fixed values, validity bits and aux per chunk of OUTPUT rows (whole bytes of validity)
+        const uint64_t OC = 16384, noc = (m + OC - 1) / OC;
+        parallel_chunks(nv * nch + (uint64_t)nc * noc, 1, threads, [&](uint64_t t) {
+            if (t < nv * nch) {
+                Var& v = vars[t / nch]; const uint64_t k = t % nch; const tf_col& ic = in->cols[v.c];
+                const uint64_t r0 = k * CH, r1 = std::min(n, (k + 1) * CH);
+                uint64_t ip = v.lw == 4 ? ic.offsets[r0] : v.in_base[k], op = v.out_base[k], j = kept[k];
+                for (uint64_t r = r0; r < r1; r++) {
+                    const uint32_t l = in_len(ic, v.lw, r);
+                    if (keep[r]) {
+                        std::memcpy(v.heap + op, ic.heap + ip, l);
+                        if (v.lw == 1) v.lens[j] = (uint8_t)l; else if (v.lw == 2) { const uint16_t x = (uint16_t)l; std::memcpy(v.lens + 2 * j, &x, 2); }
+                        else { const uint32_t x = (uint32_t)op; std::memcpy(v.lens + 4 * j, &x, 4); }
+                        op += l; j++;
+                    }
+                    ip += l;
+                }
+                if (v.lw == 4 && r1 == n) { const uint32_t x = (uint32_t)v.out_base[nch]; std::memcpy(v.lens + 4 * m, &x, 4); }
+                return;
+            }
+            const uint64_t u = t - nv * nch; const uint32_t c = (uint32_t)(u / noc); const uint64_t j0 = (u % noc) * OC, j1 = std::min(m, j0 + OC);
+            const tf_col& ic = in->cols[c]; tf_col& oc = pool->cols[c];
+            const int w = fixed_width(ic.type);
+            if (w && ic.values) {
+                uint8_t* o = (uint8_t*)oc.values; const uint8_t* s = (const uint8_t*)ic.values;
+                switch (w) {
+                case 1: for (uint64_t j = j0; j < j1; j++) o[j] = s[sel[j]]; break;
+                case 2: for (uint64_t j = j0; j < j1; j++) ((uint16_t*)o)[j] = ((const uint16_t*)s)[sel[j]]; break;
+                case 4: for (uint64_t j = j0; j < j1; j++) ((uint32_t*)o)[j] = ((const uint32_t*)s)[sel[j]]; break;
+                default: for (uint64_t j = j0; j < j1; j++) ((uint64_t*)o)[j] = ((const uint64_t*)s)[sel[j]]; break;
+                }
+            }
+            if (ic.validity) {
+                uint8_t* o = (uint8_t*)oc.validity;
+                for (uint64_t j = j0; j < j1; j += 8) { uint8_t b = 0; for (uint64_t q = j; q < std::min(j1, j + 8); q++) { const uint32_t r = sel[q]; b |= (uint8_t)(((ic.validity[r >> 3] >> (r & 7)) & 1) << (q - j)); } o[j >> 3] = b; }
+            }
+            if (ic.aux) {
+                if (is_time(ic.type)) for (uint64_t j = j0; j < j1; j++) ((uint32_t*)oc.aux)[j] = ((const uint32_t*)ic.aux)[sel[j]];
+                else for (uint64_t j = j0; j < j1; j++) ((uint8_t*)oc.aux)[j] = ((const uint8_t*)ic.aux)[sel[j]];
+            }
+        });
+        uint8_t* kinds = nullptr;
+        if (in->kinds) { kinds = pool->take()->ensure(m + 16, pool->want_pinned); for (uint64_t j = 0; j < m; j++) kinds[j] = in->kinds[sel[j]]; }
+        for (uint32_t c = 0; c < nc; c++) if (!fixed_width(in->cols[c].type) && in->cols[c].offsets && !pool->cols[c].heap) pool->cols[c].heap = (const uint8_t*)sel;   // empty heap: any valid pointer
+        pool->batch = tf_batch{m, nc, TF_MEM_HOST, pool->cols.data(), kinds};
+        *out = &pool->batch; if (sel_out) *sel_out = sel;
+        return TF_OK;
+    } catch (const Fail& f) { pool->err = f.msg; return f.rc; }
+    catch (const std::bad_alloc&) { pool->err = "host allocation failed"; return TF_E_RETRY_OOM; }
+}
+
 int tfgpu_batch_to_rows(const tf_batch* b, uint8_t* out, uint64_t cap, uint64_t* row_off, uint64_t* need) {
     if (!b || !row_off || (b->mem != TF_MEM_HOST)) return TF_E_FATAL_ARG;
     const uint64_t n = b->nrows; const uint32_t nc = b->ncols;

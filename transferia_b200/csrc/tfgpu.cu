@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/tfgpu.h"
+#include "../../include/tfgpu_sink.h"
 #include "plan.hpp"
 #include "device_types.cuh"
 #include "launch.hpp"
@@ -78,6 +79,9 @@ struct tfgpu_engine {
     uint32_t* tile_sum = nullptr; uint64_t* tile_base = nullptr; uint64_t* col_bytes = nullptr; uint32_t* comp_size = nullptr; uint64_t* wire_off = nullptr; unsigned long long* frame_pfx = nullptr;
     uint64_t last_nrows = 0; bool last_has_filter = false, last_has_sharder = false; int last_wire_fmt = 0;
     uint8_t* pinned = nullptr; size_t pinned_cap = 0;
+    // two-phase push (tfgpu_push_encode_selective): device flags of phase one, their pinned host copy, the host gather's buffers
+    DevBuf sel_stage; uint8_t* sel_host = nullptr; size_t sel_host_cap = 0; tfgpu_columnar* gather_pool = nullptr;
+    uint64_t h2d_bytes = 0;                            // bytes stage_input has copied to the device since creation
     DevBuf json_sizes, dbz_keysz, dbz_meta, dbz_old, dbz_msgsz, old_arena, part_ids;
     DbzEmitArgs dbz{};                                 // set by tfgpu_emit_debezium for the TF_WIRE_DEBEZIUM branch of run_chain
     unsigned long long* lz_phases = nullptr;      // debug: per-phase cycle counters of k_lz4_frames
@@ -737,6 +741,75 @@ int tfgpu_push_encode(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch
     catch (const std::bad_alloc&) { return fail(e, TF_E_RETRY_OOM, "host allocation failed"); }
 }
 
+// Two-phase push: only the predicate columns cross PCIe first; k_filter answers with the keep flags; the host gathers the kept rows
+// (tfgpu_batch_gather, multi-threaded) and only those go through the whole chain. Same result as tfgpu_push_encode: every transformer is
+// row-local, filters keep the rows they kept before, and the rows phase one dropped with an error are reported from phase one.
+int tfgpu_push_encode_selective(tfgpu_engine* e, int plan_id, int wire_fmt, const tf_batch* in, int threads, tfgpu_result** out) {
+    if (!e || !in || !out || plan_id < 0 || plan_id >= (int)e->plans.size()) return TF_E_FATAL_ARG;
+    PlanDev& pd = *e->plans[plan_id];
+    const tfplan::Plan& pl = pd.plan;
+    const uint64_t n = in->nrows; const size_t nc = pl.in_schema.size();
+    if (in->mem != TF_MEM_HOST || in->ncols != nc || pd.n_fsteps == 0 || n < 8192 || !wire_known(wire_fmt)) return tfgpu_push_encode(e, plan_id, wire_fmt, in, out);
+    std::vector<uint8_t> pred(nc, 0);
+    for (const auto& fs : pl.filters) for (const auto& ex : fs.exprs) for (const auto& t : ex) if (t.col >= 0 && (size_t)t.col < nc) pred[t.col] = 1;
+    for (size_t c = 0; c < nc; c++) if (pred[c] && in->cols[c].type != pl.in_schema[c].tf) return tfgpu_push_encode(e, plan_id, wire_fmt, in, out);   // loose predicate column: Strictify first, one phase
+    *out = nullptr;
+    try {
+        CK(cudaSetDevice(e->device));
+        join_tail(e);
+        cudaStream_t s = e->stream;
+        // ---- phase one
+        std::vector<tf_col> pc(in->cols, in->cols + nc);
+        for (size_t c = 0; c < nc; c++) if (!pred[c]) { pc[c].values = nullptr; pc[c].validity = nullptr; pc[c].offsets = nullptr; pc[c].heap = nullptr; pc[c].aux = nullptr; pc[c].heap_len = 0; pc[c].flags = 0; }
+        const tf_batch b1{n, (uint32_t)nc, TF_MEM_HOST, pc.data(), in->kinds};
+        std::vector<tf_col> dev; const uint8_t* dev_kinds = stage_input(e, &b1, dev);
+        std::vector<DCol> hc(nc);
+        for (size_t c = 0; c < nc; c++) {
+            DCol& d = hc[c]; std::memset(&d, 0, sizeof d);
+            d.type = pl.in_schema[c].tf; d.in_w = in_width(d.type); d.str_slot = -1; d.mask_slot = -1;
+            d.values = (const uint8_t*)dev[c].values; d.validity = dev[c].validity; d.offsets = dev[c].offsets; d.heap = dev[c].heap; d.aux = (const uint8_t*)dev[c].aux;
+        }
+        if (e->d_cols_cap < nc) { if (e->d_cols) CK(cudaFree(e->d_cols)); CK(cudaMalloc(&e->d_cols, sizeof(DCol) * nc)); e->d_cols_cap = nc; }
+        CK(cudaMemcpyAsync(e->d_cols, hc.data(), sizeof(DCol) * nc, cudaMemcpyHostToDevice, s));
+        CK(cudaMemsetAsync(e->d_state, 0, sizeof(DState), s));
+        const uint32_t nb = (uint32_t)((n + 255) / 256);
+        const size_t flags_bytes = align_up(3 * n, 256);
+        e->sel_stage.ensure(flags_bytes + (size_t)nb * 4 + 256);
+        uint8_t* B = e->sel_stage.p;
+        FilterArgs fa{e->d_cols, dev_kinds, n, pd.d_fsteps, pd.n_fsteps, pd.d_expr_off, pd.d_terms, pd.d_blob, B, B + n, B + 2 * n, (uint32_t*)(B + flags_bytes), e->d_state, nullptr, nullptr, 0};
+        e->prof_n = 0;
+        e->prof_begin("k_filter", s); launch_k_filter(nb, 256, 0, s, fa); e->prof_end(s);
+        if (e->sel_host_cap < 3 * n) { if (e->sel_host) CK(cudaFreeHost(e->sel_host)); e->sel_host = nullptr; e->sel_host_cap = 0; const size_t want = align_up(3 * n + 3 * n / 4 + 4096, 1 << 16); CK(cudaMallocHost(&e->sel_host, want)); e->sel_host_cap = want; }
+        CK(cudaMemcpyAsync(e->sel_host, B, 3 * n, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        const uint8_t* keep = e->sel_host; const uint8_t* ecode = keep + n; const uint8_t* estep = keep + 2 * n;
+        // ---- host gather of the kept rows
+        if (!e->gather_pool) { const int rc = tfgpu_columnar_create(&e->gather_pool); if (rc) return fail(e, rc, "cannot create the gather pool"); }
+        const tf_batch* kept = nullptr; const uint32_t* sel = nullptr;
+        int rc = tfgpu_batch_gather(e->gather_pool, in, keep, threads, &kept, &sel);
+        if (rc) return fail(e, rc, std::string("gather: ") + tfgpu_columnar_last_error(e->gather_pool));
+        // ---- phase two: the whole chain over the kept rows
+        std::vector<tf_col> dev2; const uint8_t* dev_kinds2 = stage_input(e, kept, dev2);
+        run_chain(e, pd, kept, dev2.data(), dev_kinds2, wire_fmt);
+        auto r = std::make_unique<tfgpu_result>();
+        finish_wire(e, kept->nrows, wire_fmt, r.get());
+        r->rows_in = n;
+        for (auto& er : r->errs) er.row = sel[er.row];
+        std::vector<tf_rowerr> first;
+        for (uint64_t i = 0; i < n; i++) if (ecode[i]) first.push_back(tf_rowerr{(uint32_t)i, ecode[i], estep[i]});
+        if (!first.empty()) {
+            first.insert(first.end(), r->errs.begin(), r->errs.end());
+            std::sort(first.begin(), first.end(), [](const tf_rowerr& a, const tf_rowerr& b) { return a.row < b.row; });
+            r->errs.swap(first);
+        }
+        *out = r.release();
+        return TF_OK;
+    } catch (const tfplan::FatalError& f) { return fail(e, f.code, f.what()); }
+    catch (const CudaError& c) { return cuda_fail(e, c); }
+    catch (const std::bad_alloc&) { return fail(e, TF_E_RETRY_OOM, "host allocation failed"); }
+}
+uint64_t tfgpu_engine_h2d_bytes(const tfgpu_engine* e) { return e ? e->h2d_bytes : 0; }
+
 // shared by push_encode / push_columns: stage host columns into HBM (or pass device pointers through)
 static const uint8_t* stage_input(tfgpu_engine* e, const tf_batch* in, std::vector<tf_col>& dev, DevBuf* arena_opt) {
     DevBuf& arena = arena_opt ? *arena_opt : e->in_arena;
@@ -776,7 +849,7 @@ static const uint8_t* stage_input(tfgpu_engine* e, const tf_batch* in, std::vect
     uint8_t* p = arena.p;
     auto up = [&](const void* src, size_t bytes) -> uint8_t* {
         if (!src || !bytes) { return nullptr; }
-        uint8_t* d = p; CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, s)); p += align_up(bytes + 16, 256); return d;
+        uint8_t* d = p; CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, s)); p += align_up(bytes + 16, 256); e->h2d_bytes += bytes; return d;
     };
     for (uint32_t c = 0; c < nc; c++) {
         const tf_col& ic = in->cols[c]; tf_col& d = dev[c]; d = ic;

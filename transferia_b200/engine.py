@@ -57,6 +57,8 @@ def load_library():
     L.tfgpu_plan_validate.argtypes = [cp, cp, cp, cp, cp, cp, u64, cp, u64]
     L.tfgpu_push_columns.argtypes = [vp, i, C.POINTER(abi.TfBatch), C.POINTER(vp)]
     L.tfgpu_push_encode.argtypes = [vp, i, i, C.POINTER(abi.TfBatch), C.POINTER(vp)]
+    L.tfgpu_push_encode_selective.argtypes = [vp, i, i, C.POINTER(abi.TfBatch), i, C.POINTER(vp)]
+    L.tfgpu_engine_h2d_bytes.argtypes = [vp]; L.tfgpu_engine_h2d_bytes.restype = u64
     L.tfgpu_parse_csv.argtypes = [vp, i, cp, vp, u64, i, i, C.POINTER(vp)]
     L.tfgpu_result_row_sizes.argtypes = [vp]; L.tfgpu_result_row_sizes.restype = C.POINTER(C.c_uint32)
     L.tfgpu_result_key_sizes.argtypes = [vp]; L.tfgpu_result_key_sizes.restype = C.POINTER(C.c_uint32)
@@ -88,7 +90,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "tfgpu_version", "tfgpu_engine_create", "tfgpu_engine_destroy", "tfgpu_last_error", "tfgpu_engine_set_stream",
-    "tfgpu_plan", "tfgpu_plan_validate", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_parse_csv", "tfgpu_parse_json", "tfgpu_measure", "tfgpu_emit_debezium", "tfgpu_emit_debezium_crud", "tfgpu_result_dbz_msg_sizes", "tfgpu_emit_debezium_validate", "tfgpu_result_key_sizes", "tfgpu_result_part_ids", "tfgpu_result_row_sizes", "tfgpu_queue_json_batches", "tfgpu_queue_debezium_batches", "tfgpu_parse_debezium", "tfgpu_debezium_schema_validate", "tfgpu_debug_lz4_phases", "tfgpu_result_selection", "tfgpu_result_meta_kinds", "tfgpu_result_meta_tx_id", "tfgpu_result_meta_lsn", "tfgpu_result_meta_commit_time", "tfgpu_result_consumed", "tfgpu_push_encode_resident",
+    "tfgpu_push_encode_selective", "tfgpu_engine_h2d_bytes", "tfgpu_plan", "tfgpu_plan_validate", "tfgpu_plan_describe", "tfgpu_push_columns", "tfgpu_push_encode", "tfgpu_parse_csv", "tfgpu_parse_json", "tfgpu_measure", "tfgpu_emit_debezium", "tfgpu_emit_debezium_crud", "tfgpu_result_dbz_msg_sizes", "tfgpu_emit_debezium_validate", "tfgpu_result_key_sizes", "tfgpu_result_part_ids", "tfgpu_result_row_sizes", "tfgpu_queue_json_batches", "tfgpu_queue_debezium_batches", "tfgpu_parse_debezium", "tfgpu_debezium_schema_validate", "tfgpu_debug_lz4_phases", "tfgpu_result_selection", "tfgpu_result_meta_kinds", "tfgpu_result_meta_tx_id", "tfgpu_result_meta_lsn", "tfgpu_result_meta_commit_time", "tfgpu_result_consumed", "tfgpu_push_encode_resident",
     "tfgpu_resident_stats", "tfgpu_resident_fetch", "tfgpu_result_rows_in", "tfgpu_result_rows_out",
     "tfgpu_result_n_errors", "tfgpu_result_errors", "tfgpu_result_batch", "tfgpu_result_bytes",
     "tfgpu_result_bytes_len", "tfgpu_result_raw_len", "tfgpu_result_n_frames", "tfgpu_result_release",
@@ -249,10 +251,15 @@ class Engine:
         s = self._L.tfgpu_plan_describe(self._h, plan_id)
         return json.loads(s.decode()) if s else {}
 
-    def push_encode(self, plan_id: int, batch: abi.Batch, wire_fmt: int = abi.TF_WIRE_CH_NATIVE_LZ4, copy_bytes: bool = True) -> PushResult:
+    def push_encode(self, plan_id: int, batch: abi.Batch, wire_fmt: int = abi.TF_WIRE_CH_NATIVE_LZ4, copy_bytes: bool = True, selective: Optional[int] = None) -> PushResult:
+        """selective=N: tfgpu_push_encode_selective with N host threads for the gather (0 = default) — two phases, fewer PCIe bytes when
+        the plan's filter_rows keeps a fraction of the rows; same result."""
         tb = batch.as_struct()
         res = C.c_void_p()
-        self._check(self._L.tfgpu_push_encode(self._h, plan_id, wire_fmt, C.byref(tb), C.byref(res)))
+        if selective is None:
+            self._check(self._L.tfgpu_push_encode(self._h, plan_id, wire_fmt, C.byref(tb), C.byref(res)))
+        else:
+            self._check(self._L.tfgpu_push_encode_selective(self._h, plan_id, wire_fmt, C.byref(tb), int(selective), C.byref(res)))
         try:
             L = self._L
             n = L.tfgpu_result_bytes_len(res)
@@ -269,6 +276,9 @@ class Engine:
             return out
         finally:
             self._L.tfgpu_result_release(res)
+
+    def h2d_bytes(self) -> int:
+        return int(self._L.tfgpu_engine_h2d_bytes(self._h))
 
     def _part_ids(self, res, rows_out):
         """sharder_transformer: ChangeItem.PartID of every output row as an integer (numpy uint32), None without a sharder."""

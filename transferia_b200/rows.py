@@ -195,6 +195,7 @@ def _lib():
         L.tfgpu_rows_to_batch.argtypes = [vp, C.POINTER(TfRows), C.c_uint32, vp, u64, C.c_int, C.POINTER(C.POINTER(abi.TfBatch)),
                                           C.POINTER(C.POINTER(abi.TfRowMeta)), C.POINTER(C.POINTER(abi.TfOldKeys))]
         L.tfgpu_batch_to_rows.argtypes = [C.POINTER(abi.TfBatch), vp, u64, vp, C.POINTER(u64)]
+        L.tfgpu_batch_gather.argtypes = [vp, C.POINTER(abi.TfBatch), vp, C.c_int, C.POINTER(C.POINTER(abi.TfBatch)), C.POINTER(C.POINTER(C.c_uint32))]
         _bound = True
     return L
 
@@ -233,6 +234,15 @@ class Columnar:
             t.old_batch = batch_from_struct(C.cast(o.values, C.POINTER(abi.TfBatch)).contents)
             t.old_present = _view(o.present_cols, len(b.columns)); t.old_row_has = _view(o.row_has, n)
         return t
+
+    def gather(self, batch: abi.Batch, keep: np.ndarray, threads: int = 0) -> Tuple[abi.Batch, np.ndarray]:
+        """tfgpu_batch_gather: (rows with keep != 0 as a batch in the pool's buffers, the input row of every output row)."""
+        tb = batch.as_struct(); keep = np.ascontiguousarray(keep, dtype=np.uint8)
+        pb, ps = C.POINTER(abi.TfBatch)(), C.POINTER(C.c_uint32)()
+        rc = self._L.tfgpu_batch_gather(self._h, C.byref(tb), keep.ctypes.data, threads, C.byref(pb), C.byref(ps))
+        if rc: raise engine.EngineError(rc, self._L.tfgpu_columnar_last_error(self._h).decode())
+        out = batch_from_struct(pb.contents)
+        return out, (np.ctypeslib.as_array(ps, shape=(out.nrows,)).copy() if out.nrows else np.zeros(0, np.uint32))
 
     def close(self):
         if self._h: self._L.tfgpu_columnar_destroy(self._h); self._h = None
