@@ -163,6 +163,8 @@ int tfgpu_batch_to_rows(const tf_batch* b, uint8_t* out, uint64_t cap, uint64_t*
 /* Rows keep[r] != 0 of a host batch, in order, in the pool's buffers (valid until the next call on the pool): the host half of
  * tfgpu_push_encode_selective. sel_out (optional) receives the input row of every output row. Columns whose buffers are NULL stay NULL. */
 int tfgpu_batch_gather(tfgpu_columnar* pool, const tf_batch* in, const uint8_t* keep, int threads, const tf_batch** out, const uint32_t** sel_out);
+/* The same with the selection at hand: sel = m ascending row indexes (tfgpu_push_encode_selective gets them from the device). */
+int tfgpu_batch_gather_sel(tfgpu_columnar* pool, const tf_batch* in, const uint32_t* sel, uint64_t m, int threads, const tf_batch** out);
 
 /* ------------------------------------------------------------------ Sinker.Push as one call */
 /* What stands below the user's transformers in every transfer's sink pipeline (pkg/sink_factory/sink_factory.go:79-108), in the

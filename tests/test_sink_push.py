@@ -118,9 +118,10 @@ def test_transformers_need_the_device():
 def test_push_with_transformers_on_the_device_equals_the_oracle(eng, po):
     """skip_events / rename_tables / filter_rows over mixed kinds and two tables; the row runs come back as columnar batches (wire_fmt 0)
     that equal the oracle's push_columns over the same rows; sequencing and counters equal the middleware oracle."""
+    # filter_rows before rename_tables: its Apply re-checks the table filter on the item's CURRENT id (a renamed item would pass unfiltered)
     trs = [{"skip_events": {"tables": {"includeTables": ["^public.a$"]}, "events": ["truncate", "delete"]}},
-           {"rename_tables": {"renameTables": [{"originalName": {"nameSpace": "public", "name": "a"}, "newName": {"nameSpace": "dst", "name": "a2"}}]}},
-           {"filter_rows": {"tables": {"includeTables": ["^public.a$"]}, "filter": "id > 10"}}]
+           {"filter_rows": {"tables": {"includeTables": ["^public.a$"]}, "filter": "id > 10"}},
+           {"rename_tables": {"renameTables": [{"originalName": {"nameSpace": "public", "name": "a"}, "newName": {"nameSpace": "dst", "name": "a2"}}]}}]
     spec = [(K.KIND_INIT_TABLE_LOAD, 0)] + [(K.KIND_INSERT, 0)] * 9 + [(K.KIND_TRUNCATE, 0)] + [(K.KIND_INSERT, 0)] * 12 + [(K.KIND_INSERT, 1)] * 5 + \
            [(K.KIND_DELETE, 0), (K.KIND_DDL, 0), (K.KIND_INSERT, 0), (K.KIND_DONE_TABLE_LOAD, 0), (K.KIND_INSERT, 2)]
     its = _items(spec)

@@ -6,9 +6,11 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
 #include <functional>
 #include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -124,27 +126,68 @@ struct tfgpu_columnar {
     // results of the last call
     std::vector<tf_col> cols, old_cols; tf_batch batch{}, old_batch{}; tf_row_meta meta{}; tf_old_keys old{};
     std::vector<uint8_t> present;
-    ~tfgpu_columnar() { for (auto& b : bufs) b.release(); }
+    void* workers = nullptr;              // Workers, created on first use
+    ~tfgpu_columnar();
 };
 
 namespace {
 
-template <class F> void parallel_chunks(uint64_t n, uint64_t chunk, int threads, F&& f) {
-    const uint64_t nchunks = (n + chunk - 1) / chunk;
-    if (nchunks <= 1 || threads <= 1) { for (uint64_t k = 0; k < nchunks; k++) f(k); return; }
-    std::atomic<uint64_t> next{0}; std::atomic<bool> failed{false}; Fail first{0, ""}; std::atomic_flag lock = ATOMIC_FLAG_INIT;
-    auto work = [&] {
-        for (;;) {
-            const uint64_t k = next.fetch_add(1); if (k >= nchunks || failed.load()) return;
-            try { f(k); } catch (const Fail& e) { if (!lock.test_and_set()) { first = e; failed = true; } return; }
+// Persistent host workers (spawning 32 threads per pass costs more than the pass itself on a 1 M-row gather): run(count, width, fn)
+// hands task indexes [0, count) to `width` workers (the caller is one of them) and returns when all are done.
+class Workers {
+public:
+    ~Workers() { { std::lock_guard<std::mutex> g(m_); stop_ = true; } cv_.notify_all(); for (auto& t : ts_) t.join(); }
+    void run(uint64_t count, int width, const std::function<void(uint64_t)>& fn) {
+        if (count == 0) return;
+        width = (int)std::min<uint64_t>((uint64_t)std::max(1, width), count);
+        if (width <= 1) { for (uint64_t k = 0; k < count; k++) fn(k); return; }
+        while ((int)ts_.size() < width - 1) ts_.emplace_back([this] { loop(); });
+        {
+            std::lock_guard<std::mutex> g(m_);
+            fn_ = &fn; count_ = count; next_.store(0); failed_.store(false); active_ = width - 1; wanted_ = width - 1; gen_++;
         }
-    };
-    std::vector<std::thread> ts; const int nt = (int)std::min<uint64_t>((uint64_t)threads, nchunks);
-    for (int t = 1; t < nt; t++) ts.emplace_back(work);
-    work();
-    for (auto& t : ts) t.join();
-    if (failed) throw first;
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(m_);
+        done_cv_.wait(lk, [this] { return active_ == 0; });
+        fn_ = nullptr;
+        if (failed_.load()) throw first_;
+    }
+private:
+    void work() {
+        for (;;) {
+            const uint64_t k = next_.fetch_add(1); if (k >= count_ || failed_.load()) return;
+            try { (*fn_)(k); } catch (const Fail& e) { std::lock_guard<std::mutex> g(m_); if (!failed_.exchange(true)) first_ = e; return; }
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || (gen_ != seen && wanted_ > 0); });
+                if (stop_) return;
+                seen = gen_; wanted_--;
+            }
+            work();
+            { std::lock_guard<std::mutex> g(m_); if (--active_ == 0) done_cv_.notify_one(); }
+        }
+    }
+    std::vector<std::thread> ts_; std::mutex m_; std::condition_variable cv_, done_cv_;
+    const std::function<void(uint64_t)>* fn_ = nullptr; uint64_t count_ = 0, gen_ = 0; int active_ = 0, wanted_ = 0; bool stop_ = false;
+    std::atomic<uint64_t> next_{0}; std::atomic<bool> failed_{false}; Fail first_{0, ""};
+};
+
+struct PoolWorkers { Workers w; };
+Workers& workers_of(tfgpu_columnar* pool);
+
+template <class F> void parallel_chunks(tfgpu_columnar* pool, uint64_t n, uint64_t chunk, int threads, F&& f) {
+    const uint64_t nchunks = (n + chunk - 1) / chunk;
+    const std::function<void(uint64_t)> fn = std::forward<F>(f);
+    workers_of(pool).run(nchunks, threads, fn);
 }
+
+Workers& workers_of(tfgpu_columnar* pool) { if (!pool->workers) pool->workers = new Workers(); return *(Workers*)pool->workers; }
 
 // Columnar image of `n` value lists. get(j, at, end, sparse, nvals): where row j's values start / end.
 // which = nullptr: every schema column; else only the listed columns are laid out (OldKeys), the others stay empty.
@@ -174,7 +217,7 @@ struct Transposer {
         nchunks = (n + chunk - 1) / chunk;
         stats.assign((size_t)nchunks * nc, ChunkStat());
         // ---- pass 1: tags, heap bytes, longest cell per (chunk, column)
-        parallel_chunks(n, chunk, threads, [&](uint64_t k) {
+        parallel_chunks(pool, n, chunk, threads, [&](uint64_t k) {
             ChunkStat* st = &stats[(size_t)k * nc];
             std::vector<uint8_t> seen(nc);
             for (uint64_t j = k * chunk; j < std::min(n, (k + 1) * chunk); j++) {
@@ -241,7 +284,7 @@ struct Transposer {
         }
         std::vector<uint32_t> wide; for (uint32_t c = 0; c < nc; c++) if (cp[c].lens && cp[c].lens_width == 4) wide.push_back(c);
         // ---- pass 2: fill (chunks are multiples of 8 rows, so validity bytes never straddle two workers)
-        parallel_chunks(n, chunk, threads, [&](uint64_t k) {
+        parallel_chunks(pool, n, chunk, threads, [&](uint64_t k) {
             const uint64_t r0 = k * chunk, r1 = std::min(n, (k + 1) * chunk);
             std::vector<uint64_t> hp(nc); for (uint32_t c = 0; c < nc; c++) hp[c] = heap_base[(size_t)k * nc + c];
             for (uint32_t c = 0; c < nc; c++) {                  // defaults: nil rows keep zero values / zero lengths
@@ -291,6 +334,8 @@ const std::vector<int>& schema_types(tfgpu_columnar* p, const char* schema_json)
 }
 
 }  // namespace
+
+tfgpu_columnar::~tfgpu_columnar() { for (auto& b : bufs) b.release(); delete (Workers*)workers; }
 
 extern "C" {
 
@@ -383,103 +428,139 @@ int tfgpu_rows_to_batch(tfgpu_columnar* pool, const tf_rows* rows, uint32_t tabl
     catch (const std::bad_alloc&) { pool->err = "host allocation failed"; return TF_E_RETRY_OOM; }
 }
 
-// Rows keep[r] != 0 of a host batch, in order, in the pool's buffers: the host half of a two-phase push (tfgpu_push_encode_selective) —
-// when filter_rows keeps a fraction of the rows only that fraction has to cross PCIe. Var-width columns are walked per chunk of input rows
-// (narrow length arrays have no random access), everything else is gathered through the selection vector per chunk of output rows.
+// The rows sel[0..m) of a host batch (ascending row indexes), in order, in the pool's buffers: the host half of a two-phase push
+// (tfgpu_push_encode_selective) — when filter_rows keeps a fraction of the rows only that fraction has to cross PCIe. Fixed-width values,
+// validity bits and aux go through the selection vector per chunk of OUTPUT rows; var-width columns per chunk of INPUT rows: narrow length
+// arrays have no random access, so a task first turns its chunk's lengths into a local prefix (a tight loop) and then copies only the kept cells.
+static int gather_core(tfgpu_columnar* pool, const tf_batch* in, const uint32_t* sel, uint64_t m, int threads, const tf_batch** out) {
+    const uint64_t n = in->nrows; const uint32_t nc = in->ncols;
+    const uint64_t CH = 32768, nch = (n + CH - 1) / CH;
+    std::vector<uint64_t> kept(nch + 1, 0);                       // kept[k] = first output row of input chunk k
+    for (uint64_t k = 1; k <= nch; k++) kept[k] = (uint64_t)(std::lower_bound(sel, sel + m, (uint32_t)std::min<uint64_t>(k * CH, 0xffffffffull)) - sel);
+    kept[nch] = m;
+    pool->cols.assign(nc, tf_col{});
+    struct Var { uint32_t c; int lw; uint8_t* lens; uint8_t* heap; std::vector<uint64_t> in_base, out_base; };
+    std::vector<Var> vars;
+    for (uint32_t c = 0; c < nc; c++) {
+        const tf_col& ic = in->cols[c]; tf_col& oc = pool->cols[c]; oc.type = ic.type; oc.flags = ic.flags;
+        const int w = fixed_width(ic.type);
+        if (w) { if (ic.values) oc.values = pool->take()->ensure((size_t)w * m + 16, pool->want_pinned); }
+        else if (ic.offsets) {
+            Var v; v.c = c; v.lw = (ic.flags & TF_COL_LENS8) ? 1 : (ic.flags & TF_COL_LENS16) ? 2 : 4;
+            v.lens = pool->take()->ensure((size_t)v.lw * (m + 1) + 16, pool->want_pinned); v.heap = nullptr;
+            v.in_base.assign(nch + 1, 0); v.out_base.assign(nch + 1, 0);
+            oc.offsets = (const uint32_t*)v.lens; vars.push_back(std::move(v));
+        }
+        if (ic.validity) oc.validity = pool->take()->ensure((m + 7) / 8 + 16, pool->want_pinned);
+        if (ic.aux) oc.aux = pool->take()->ensure((size_t)(is_time(ic.type) ? 4 : 1) * m + 16, pool->want_pinned);
+    }
+    // pass A: bytes per (var column, input chunk): all rows (where the chunk's cells start in the heap) and kept rows (where they go)
+    const uint64_t nv = vars.size();
+    parallel_chunks(pool, nv * nch, 1, threads, [&](uint64_t t) {
+        Var& v = vars[t / nch]; const uint64_t k = t % nch; const tf_col& ic = in->cols[v.c];
+        const uint64_t r0 = k * CH, r1 = std::min(n, (k + 1) * CH); uint64_t all = 0, kb = 0;
+        if (v.lw == 1) { const uint8_t* l = (const uint8_t*)ic.offsets; uint32_t a = 0; for (uint64_t r = r0; r < r1; r++) a += l[r]; all = a; for (uint64_t j = kept[k]; j < kept[k + 1]; j++) kb += l[sel[j]]; }
+        else if (v.lw == 2) { const uint16_t* l = (const uint16_t*)ic.offsets; for (uint64_t r = r0; r < r1; r++) all += l[r]; for (uint64_t j = kept[k]; j < kept[k + 1]; j++) kb += l[sel[j]]; }
+        else { all = ic.offsets[r1] - ic.offsets[r0]; for (uint64_t j = kept[k]; j < kept[k + 1]; j++) kb += ic.offsets[sel[j] + 1] - ic.offsets[sel[j]]; }
+        v.in_base[k + 1] = all; v.out_base[k + 1] = kb;
+    });
+    for (Var& v : vars) {
+        for (uint64_t k = 0; k < nch; k++) { v.in_base[k + 1] += v.in_base[k]; v.out_base[k + 1] += v.out_base[k]; }
+        v.heap = pool->take()->ensure(v.out_base[nch] + 32, pool->want_pinned);
+        tf_col& oc = pool->cols[v.c]; oc.heap = v.heap; oc.heap_len = v.out_base[nch];
+    }
+    // pass B
+    const uint64_t OC = 16384, noc = (m + OC - 1) / OC;
+    parallel_chunks(pool, nv * nch + (uint64_t)nc * noc, 1, threads, [&](uint64_t t) {
+        if (t < nv * nch) {
+            Var& v = vars[t / nch]; const uint64_t k = t % nch; const tf_col& ic = in->cols[v.c];
+            const uint64_t r0 = k * CH, r1 = std::min(n, (k + 1) * CH), j0 = kept[k], j1 = kept[k + 1];
+            if (v.lw == 4 && r1 == n) { const uint32_t x = (uint32_t)v.out_base[nch]; std::memcpy(v.lens + 4 * m, &x, 4); }
+            if (j0 == j1) return;
+            uint64_t op = v.out_base[k]; const uint64_t op_end = v.out_base[k + 1];
+            // a cell of up to 16 bytes is copied as one 16-byte move while that stays inside this task's share of the output heap
+            auto put = [&](const uint8_t* src, uint32_t l) {
+                if (l <= 16 && op + 16 <= op_end) std::memcpy(v.heap + op, src, 16); else std::memcpy(v.heap + op, src, l);
+                op += l;
+            };
+            if (v.lw == 4) {
+                for (uint64_t j = j0; j < j1; j++) {
+                    const uint32_t r = sel[j], o = ic.offsets[r], l = ic.offsets[r + 1] - o; const uint32_t x = (uint32_t)op;
+                    std::memcpy(v.lens + 4 * j, &x, 4);
+                    if ((uint64_t)o + 16 <= ic.heap_len) put(ic.heap + o, l); else { std::memcpy(v.heap + op, ic.heap + o, l); op += l; }
+                }
+                return;
+            }
+            thread_local std::vector<uint32_t> pre; pre.resize(CH + 1);
+            const uint64_t base = v.in_base[k]; uint32_t acc = 0;
+            if (v.lw == 1) { const uint8_t* l = (const uint8_t*)ic.offsets + r0; for (uint64_t i = 0; i < r1 - r0; i++) { pre[i] = acc; acc += l[i]; } }
+            else { const uint16_t* l = (const uint16_t*)ic.offsets + r0; for (uint64_t i = 0; i < r1 - r0; i++) { pre[i] = acc; acc += l[i]; } }
+            // the heap of a narrow column may hold trailing bytes past the last cell read 16 at a time: heap_len bounds the fast path
+            const uint64_t in_end = ic.heap_len;
+            for (uint64_t j = j0; j < j1; j++) {
+                const uint32_t r = sel[j]; const uint64_t ip = base + pre[r - r0];
+                const uint32_t l = v.lw == 1 ? ((const uint8_t*)ic.offsets)[r] : ((const uint16_t*)ic.offsets)[r];
+                if (v.lw == 1) v.lens[j] = (uint8_t)l; else { const uint16_t x = (uint16_t)l; std::memcpy(v.lens + 2 * j, &x, 2); }
+                if (ip + 16 <= in_end) put(ic.heap + ip, l); else { std::memcpy(v.heap + op, ic.heap + ip, l); op += l; }
+            }
+            return;
+        }
+        const uint64_t u = t - nv * nch; const uint32_t c = (uint32_t)(u / noc); const uint64_t j0 = (u % noc) * OC, j1 = std::min(m, j0 + OC);
+        const tf_col& ic = in->cols[c]; tf_col& oc = pool->cols[c];
+        const int w = fixed_width(ic.type);
+        if (w && ic.values) {
+            uint8_t* o = (uint8_t*)oc.values; const uint8_t* s = (const uint8_t*)ic.values;
+            switch (w) {
+            case 1: for (uint64_t j = j0; j < j1; j++) o[j] = s[sel[j]]; break;
+            case 2: for (uint64_t j = j0; j < j1; j++) ((uint16_t*)o)[j] = ((const uint16_t*)s)[sel[j]]; break;
+            case 4: for (uint64_t j = j0; j < j1; j++) ((uint32_t*)o)[j] = ((const uint32_t*)s)[sel[j]]; break;
+            default: for (uint64_t j = j0; j < j1; j++) ((uint64_t*)o)[j] = ((const uint64_t*)s)[sel[j]]; break;
+            }
+        }
+        if (ic.validity) {
+            uint8_t* o = (uint8_t*)oc.validity;
+            for (uint64_t j = j0; j < j1; j += 8) { uint8_t b = 0; for (uint64_t q = j; q < std::min(j1, j + 8); q++) { const uint32_t r = sel[q]; b |= (uint8_t)(((ic.validity[r >> 3] >> (r & 7)) & 1) << (q - j)); } o[j >> 3] = b; }
+        }
+        if (ic.aux) {
+            if (is_time(ic.type)) for (uint64_t j = j0; j < j1; j++) ((uint32_t*)oc.aux)[j] = ((const uint32_t*)ic.aux)[sel[j]];
+            else for (uint64_t j = j0; j < j1; j++) ((uint8_t*)oc.aux)[j] = ((const uint8_t*)ic.aux)[sel[j]];
+        }
+    });
+    uint8_t* kinds = nullptr;
+    if (in->kinds) { kinds = pool->take()->ensure(m + 16, pool->want_pinned); for (uint64_t j = 0; j < m; j++) kinds[j] = in->kinds[sel[j]]; }
+    for (uint32_t c = 0; c < nc; c++) if (!fixed_width(in->cols[c].type) && in->cols[c].offsets && !pool->cols[c].heap) pool->cols[c].heap = (const uint8_t*)sel;   // empty heap: any valid pointer
+    pool->batch = tf_batch{m, nc, TF_MEM_HOST, pool->cols.data(), kinds};
+    *out = &pool->batch;
+    return TF_OK;
+}
+
 int tfgpu_batch_gather(tfgpu_columnar* pool, const tf_batch* in, const uint8_t* keep, int threads, const tf_batch** out, const uint32_t** sel_out) {
     if (!pool || !in || !keep || !out || in->mem != TF_MEM_HOST) return TF_E_FATAL_ARG;
     try {
-        const uint64_t n = in->nrows; const uint32_t nc = in->ncols;
+        const uint64_t n = in->nrows;
         if (threads <= 0) threads = (int)std::min<unsigned>(32, std::max(1u, std::thread::hardware_concurrency()));
         pool->next_buf = 0;
         const uint64_t CH = 32768, nch = (n + CH - 1) / CH;
         std::vector<uint64_t> kept(nch + 1, 0);
-        parallel_chunks(n, CH, threads, [&](uint64_t k) { uint64_t c = 0; for (uint64_t r = k * CH; r < std::min(n, (k + 1) * CH); r++) c += keep[r] != 0; kept[k + 1] = c; });
+        parallel_chunks(pool, n, CH, threads, [&](uint64_t k) { uint64_t c = 0; for (uint64_t r = k * CH; r < std::min(n, (k + 1) * CH); r++) c += keep[r] != 0; kept[k + 1] = c; });
         for (uint64_t k = 0; k < nch; k++) kept[k + 1] += kept[k];
         const uint64_t m = kept[nch];
         uint32_t* sel = (uint32_t*)pool->take()->ensure(4 * m + 16, pool->want_pinned);
-        parallel_chunks(n, CH, threads, [&](uint64_t k) { uint64_t j = kept[k]; for (uint64_t r = k * CH; r < std::min(n, (k + 1) * CH); r++) if (keep[r]) sel[j++] = (uint32_t)r; });
-        pool->cols.assign(nc, tf_col{});
-        struct Var { uint32_t c; int lw; uint8_t* lens; uint8_t* heap; std::vector<uint64_t> in_base, out_base; };
-        std::vector<Var> vars;
-        for (uint32_t c = 0; c < nc; c++) {
-            const tf_col& ic = in->cols[c]; tf_col& oc = pool->cols[c]; oc.type = ic.type; oc.flags = ic.flags;
-            const int w = fixed_width(ic.type);
-            if (w) { if (ic.values) oc.values = pool->take()->ensure((size_t)w * m + 16, pool->want_pinned); }
-            else if (ic.offsets) {
-                Var v; v.c = c; v.lw = (ic.flags & TF_COL_LENS8) ? 1 : (ic.flags & TF_COL_LENS16) ? 2 : 4;
-                v.lens = pool->take()->ensure((size_t)v.lw * (m + 1) + 16, pool->want_pinned); v.heap = nullptr;
-                v.in_base.assign(nch + 1, 0); v.out_base.assign(nch + 1, 0);
-                oc.offsets = (const uint32_t*)v.lens; vars.push_back(std::move(v));
-            }
-            if (ic.validity) oc.validity = pool->take()->ensure((m + 7) / 8 + 16, pool->want_pinned);
-            if (ic.aux) oc.aux = pool->take()->ensure((size_t)(is_time(ic.type) ? 4 : 1) * m + 16, pool->want_pinned);
-        }
-        auto in_len = [&](const tf_col& ic, int lw, uint64_t r) -> uint32_t {
-            return lw == 1 ? ((const uint8_t*)ic.offsets)[r] : lw == 2 ? ((const uint16_t*)ic.offsets)[r] : ic.offsets[r + 1] - ic.offsets[r];
-        };
-        // pass A: bytes per (var column, input chunk), all rows and kept rows
-        const uint64_t nv = vars.size();
-        parallel_chunks(nv * nch, 1, threads, [&](uint64_t t) {
-            Var& v = vars[t / nch]; const uint64_t k = t % nch; const tf_col& ic = in->cols[v.c];
-            uint64_t all = 0, kb = 0; const uint64_t r0 = k * CH, r1 = std::min(n, (k + 1) * CH);
-            if (v.lw == 4) { all = ic.offsets[r1] - ic.offsets[r0]; for (uint64_t r = r0; r < r1; r++) if (keep[r]) kb += ic.offsets[r + 1] - ic.offsets[r]; }
-            else for (uint64_t r = r0; r < r1; r++) { const uint32_t l = in_len(ic, v.lw, r); all += l; if (keep[r]) kb += l; }
-            v.in_base[k + 1] = all; v.out_base[k + 1] = kb;
-        });
-        for (Var& v : vars) {
-            for (uint64_t k = 0; k < nch; k++) { v.in_base[k + 1] += v.in_base[k]; v.out_base[k + 1] += v.out_base[k]; }
-            if (v.lw == 4) v.in_base.assign(nch + 1, 0);                     // offsets give the position directly
-            v.heap = pool->take()->ensure(v.out_base[nch] + 16, pool->want_pinned);
-            tf_col& oc = pool->cols[v.c]; oc.heap = v.heap; oc.heap_len = v.out_base[nch];
-        }
-        // pass B: var-width cells per input chunk; fixed values, validity bits and aux per chunk of OUTPUT rows (whole bytes of validity)
-        const uint64_t OC = 16384, noc = (m + OC - 1) / OC;
-        parallel_chunks(nv * nch + (uint64_t)nc * noc, 1, threads, [&](uint64_t t) {
-            if (t < nv * nch) {
-                Var& v = vars[t / nch]; const uint64_t k = t % nch; const tf_col& ic = in->cols[v.c];
-                const uint64_t r0 = k * CH, r1 = std::min(n, (k + 1) * CH);
-                uint64_t ip = v.lw == 4 ? ic.offsets[r0] : v.in_base[k], op = v.out_base[k], j = kept[k];
-                for (uint64_t r = r0; r < r1; r++) {
-                    const uint32_t l = in_len(ic, v.lw, r);
-                    if (keep[r]) {
-                        std::memcpy(v.heap + op, ic.heap + ip, l);
-                        if (v.lw == 1) v.lens[j] = (uint8_t)l; else if (v.lw == 2) { const uint16_t x = (uint16_t)l; std::memcpy(v.lens + 2 * j, &x, 2); }
-                        else { const uint32_t x = (uint32_t)op; std::memcpy(v.lens + 4 * j, &x, 4); }
-                        op += l; j++;
-                    }
-                    ip += l;
-                }
-                if (v.lw == 4 && r1 == n) { const uint32_t x = (uint32_t)v.out_base[nch]; std::memcpy(v.lens + 4 * m, &x, 4); }
-                return;
-            }
-            const uint64_t u = t - nv * nch; const uint32_t c = (uint32_t)(u / noc); const uint64_t j0 = (u % noc) * OC, j1 = std::min(m, j0 + OC);
-            const tf_col& ic = in->cols[c]; tf_col& oc = pool->cols[c];
-            const int w = fixed_width(ic.type);
-            if (w && ic.values) {
-                uint8_t* o = (uint8_t*)oc.values; const uint8_t* s = (const uint8_t*)ic.values;
-                switch (w) {
-                case 1: for (uint64_t j = j0; j < j1; j++) o[j] = s[sel[j]]; break;
-                case 2: for (uint64_t j = j0; j < j1; j++) ((uint16_t*)o)[j] = ((const uint16_t*)s)[sel[j]]; break;
-                case 4: for (uint64_t j = j0; j < j1; j++) ((uint32_t*)o)[j] = ((const uint32_t*)s)[sel[j]]; break;
-                default: for (uint64_t j = j0; j < j1; j++) ((uint64_t*)o)[j] = ((const uint64_t*)s)[sel[j]]; break;
-                }
-            }
-            if (ic.validity) {
-                uint8_t* o = (uint8_t*)oc.validity;
-                for (uint64_t j = j0; j < j1; j += 8) { uint8_t b = 0; for (uint64_t q = j; q < std::min(j1, j + 8); q++) { const uint32_t r = sel[q]; b |= (uint8_t)(((ic.validity[r >> 3] >> (r & 7)) & 1) << (q - j)); } o[j >> 3] = b; }
-            }
-            if (ic.aux) {
-                if (is_time(ic.type)) for (uint64_t j = j0; j < j1; j++) ((uint32_t*)oc.aux)[j] = ((const uint32_t*)ic.aux)[sel[j]];
-                else for (uint64_t j = j0; j < j1; j++) ((uint8_t*)oc.aux)[j] = ((const uint8_t*)ic.aux)[sel[j]];
-            }
-        });
-        uint8_t* kinds = nullptr;
-        if (in->kinds) { kinds = pool->take()->ensure(m + 16, pool->want_pinned); for (uint64_t j = 0; j < m; j++) kinds[j] = in->kinds[sel[j]]; }
-        for (uint32_t c = 0; c < nc; c++) if (!fixed_width(in->cols[c].type) && in->cols[c].offsets && !pool->cols[c].heap) pool->cols[c].heap = (const uint8_t*)sel;   // empty heap: any valid pointer
-        pool->batch = tf_batch{m, nc, TF_MEM_HOST, pool->cols.data(), kinds};
-        *out = &pool->batch; if (sel_out) *sel_out = sel;
-        return TF_OK;
+        parallel_chunks(pool, n, CH, threads, [&](uint64_t k) { uint64_t j = kept[k]; for (uint64_t r = k * CH; r < std::min(n, (k + 1) * CH); r++) if (keep[r]) sel[j++] = (uint32_t)r; });
+        if (sel_out) *sel_out = sel;
+        return gather_core(pool, in, sel, m, threads, out);
+    } catch (const Fail& f) { pool->err = f.msg; return f.rc; }
+    catch (const std::bad_alloc&) { pool->err = "host allocation failed"; return TF_E_RETRY_OOM; }
+}
+
+// Same with the selection vector already at hand (the device compacts the keep flags of phase one itself): sel = m ascending row indexes.
+int tfgpu_batch_gather_sel(tfgpu_columnar* pool, const tf_batch* in, const uint32_t* sel, uint64_t m, int threads, const tf_batch** out) {
+    if (!pool || !in || (!sel && m) || !out || in->mem != TF_MEM_HOST) return TF_E_FATAL_ARG;
+    try {
+        if (threads <= 0) threads = (int)std::min<unsigned>(32, std::max(1u, std::thread::hardware_concurrency()));
+        pool->next_buf = 0;
+        if (m && sel[m - 1] >= in->nrows) throw Fail{TF_E_FATAL_ARG, "selection names a row outside the batch"};
+        return gather_core(pool, in, sel, m, threads, out);
     } catch (const Fail& f) { pool->err = f.msg; return f.rc; }
     catch (const std::bad_alloc&) { pool->err = "host allocation failed"; return TF_E_RETRY_OOM; }
 }

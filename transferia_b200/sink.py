@@ -19,7 +19,7 @@ SINK_SYMBOLS = [
     "tfgpu_ch_open", "tfgpu_ch_close", "tfgpu_ch_last_error", "tfgpu_ch_server_info", "tfgpu_ch_exception_code",
     "tfgpu_ch_insert_begin", "tfgpu_ch_insert_columns", "tfgpu_ch_insert_data", "tfgpu_ch_insert_end", "tfgpu_ch_stats",
     "tfgpu_ch_insert_query", "tfgpu_host_cityhash128",
-    "tfgpu_columnar_create", "tfgpu_columnar_destroy", "tfgpu_columnar_last_error", "tfgpu_rows_to_batch", "tfgpu_batch_to_rows", "tfgpu_batch_gather",
+    "tfgpu_columnar_create", "tfgpu_columnar_destroy", "tfgpu_columnar_last_error", "tfgpu_rows_to_batch", "tfgpu_batch_to_rows", "tfgpu_batch_gather", "tfgpu_batch_gather_sel",
 ]
 
 _bound = False
