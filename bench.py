@@ -348,9 +348,10 @@ def main():
     ap.add_argument("--dbz-msgs", type=int, default=200_000, help="messages of the Debezium leg (BASELINE configs[3])")
     ap.add_argument("--csv-rows", type=int, default=100_000, help="rows of the CSV leg (BASELINE configs[4])")
     ap.add_argument("--host-layout", default="narrow", choices=["narrow", "offsets"], help="end-to-end leg: var-width columns as uint8 / uint16 lengths (narrow) or uint32 offsets")
+    ap.add_argument("--host-buffers", default="arena", choices=["arena", "separate"], help="end-to-end leg: the pinned host batch as one arena (one DMA) or one pinned buffer per column array")
     ap.add_argument("--e2e-mode", default="auto", choices=["auto", "one-phase", "two-phase"], help="end-to-end leg: tfgpu_push_encode (one-phase), tfgpu_push_encode_selective (two-phase), or both and report the faster (auto)")
     ap.add_argument("--gather-threads", type=int, default=0, help="host threads of the two-phase gather per pipeline (0: min(32, cores / pipelines / ranks))")
-    ap.add_argument("--e2e-pipelines", type=int, default=3, help="host threads (one engine handle each) pushing batches concurrently in the end-to-end leg")
+    ap.add_argument("--e2e-pipelines", type=int, default=4, help="host threads (one engine handle each) pushing batches concurrently in the end-to-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -383,7 +384,9 @@ def main():
     eng.set_stream(stream.cuda_stream)
     pid = eng.plan("public", "hits", schema, trs, {"type": "clickhouse"})
     dbatch = batch.to_device(dev)
-    hbatch = (batch.narrow() if args.host_layout == "narrow" else batch).pin()      # narrow: uint8 / uint16 lengths instead of uint32 offsets (TF_COL_LENS8 / 16)
+    # narrow: uint8 / uint16 lengths instead of uint32 offsets (TF_COL_LENS8 / 16); one pinned arena laid out like the device staging (a single DMA per batch)
+    hb0 = batch.narrow() if args.host_layout == "narrow" else batch
+    hbatch = hb0.pin() if args.host_buffers == "separate" else hb0.pin_arena()
     in_bytes = batch.input_bytes()
     h2d_bytes = hbatch.input_bytes()
     torch.cuda.synchronize()
@@ -456,7 +459,7 @@ def main():
     pids = [pid] + [e2.plan("public", "hits", schema, trs, {"type": "clickhouse"}) for e2 in engs[1:]]
     last = [None] * P
     cores = os.cpu_count() or 1
-    gather_threads = args.gather_threads if args.gather_threads > 0 else max(1, min(32, cores // (P * world)))
+    gather_threads = args.gather_threads if args.gather_threads > 0 else max(2, min(32, cores // (2 * P * world)))     # physical cores (2 hardware threads each) shared by the pipelines of every rank
 
     def run_e2e(selective):
         """K public calls per pipeline over the pinned host batch: one phase (every column crosses PCIe) or two phases
@@ -511,7 +514,7 @@ def main():
                                "l2": "inputs larger than L2 (%.0f MB per step > 126 MB)" % (in_bytes / 1e6),
                                "parallelism": f"dp{world} (one batch stream per GPU, its own seeded batch on every rank, no collective)", "rank": 0},
             "clocks": sampler.result(),
-            "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h, "host_layout": args.host_layout,
+            "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h, "host_layout": args.host_layout, "host_buffers": args.host_buffers,
                     "mode": best, "gather_threads": gather_threads if best == "two-phase" else 0,
                     "all_modes": {k_: {"value": v_[0], "h2d_bytes_per_step": v_[1]} for k_, v_ in legs.items()},
                     "steps": e2e_steps, "pipelines": P, "timing": "host wall clock over synchronous calls (tfgpu_push_encode / tfgpu_push_encode_selective over pinned host columns; H2D counted by the engine)"},

@@ -628,6 +628,10 @@ def test_narrow_length_arrays_equal_offsets(eng, po):
     pid = eng.plan("public", "hits", schema, trs, {"type": "clickhouse"})
     a = eng.push_encode(pid, batch, RAW); b = eng.push_encode(pid, nb, RAW)
     assert a.wire == b.wire and a.rows_out == b.rows_out and a.errors == b.errors
+    # the whole batch in one pinned arena laid out like the device staging: a single DMA, the same result (one and two phases)
+    h0 = eng.h2d_bytes(); c = eng.push_encode(pid, nb.pin_arena(), RAW); h1 = eng.h2d_bytes()
+    assert c.wire == a.wire and nb.input_bytes() <= h1 - h0 <= nb.input_bytes() + 272 * 5 * len(nb.columns)
+    assert eng.push_encode(pid, nb.pin_arena(), RAW, selective=2).wire == a.wire and eng.push_encode(pid, batch.pin_arena(), RAW).wire == a.wire
     assert a.wire == po.push_encode(batch, po.build_plan("public", "hits", schema, trs), RAW).raw
     eng.push_encode_resident(pid, nb.to_device("cuda:0"), RAW)
     st = eng.resident_stats()

@@ -208,6 +208,32 @@ class Batch:
         kinds = None if self.kinds is None else np.ascontiguousarray(self.kinds[lo:hi])
         return Batch(hi - lo, cols, kinds)
 
+    def pin_arena(self) -> "Batch":
+        """Same batch in ONE page-locked arena laid out like the engine's device staging (each non-empty buffer at the next multiple of 256
+        past the previous one's end + 16; values / validity / offsets / heap / aux per column, then kinds): tfgpu_push_* then needs a single
+        DMA for the whole batch (the pooled buffers of a shim's transposer are laid out this way)."""
+        import torch
+        bufs = []
+        for c in self.columns:
+            for a in (c.values, c.validity, c.offsets, c.heap, c.aux):
+                bufs.append(None if a is None else np.ascontiguousarray(a).reshape(-1).view(np.uint8))
+        bufs.append(None if self.kinds is None else np.ascontiguousarray(self.kinds).reshape(-1).view(np.uint8))
+        stride = lambda nb: (nb + 16 + 255) // 256 * 256
+        total = sum(stride(b.size) for b in bufs if b is not None and b.size) + 256
+        arena = torch.empty(total, dtype=torch.uint8).pin_memory()
+        base = (-arena.data_ptr()) % 256                       # the device staging is 256-byte aligned: keep the same phase
+        views, at = [], base
+        for b in bufs:
+            if b is None or not b.size:
+                views.append(None if b is None else arena[at:at]); continue
+            v = arena[at:at + b.size]; v.copy_(torch.from_numpy(b)); views.append(v); at += stride(b.size)
+        cols = []
+        for i, c in enumerate(self.columns):
+            v = views[5 * i:5 * i + 5]
+            cols.append(Column(c.type, v[0], v[1], v[2], v[3], v[4], getattr(c, "lens_width", 0)))
+        out = Batch(self.nrows, cols, views[-1], TF_MEM_HOST); out._keep = [arena]
+        return out
+
     def pin(self) -> "Batch":
         """Same batch with every buffer in page-locked host memory (what the cgo shim hands over)."""
         import torch

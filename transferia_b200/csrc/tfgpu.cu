@@ -3,6 +3,7 @@
 // a CUDA device tfgpu_engine_create fails with TF_E_FATAL_NODEVICE.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -758,6 +759,8 @@ int tfgpu_push_encode_selective(tfgpu_engine* e, int plan_id, int wire_fmt, cons
         CK(cudaSetDevice(e->device));
         join_tail(e);
         cudaStream_t s = e->stream;
+        static const bool trace = std::getenv("TFGPU_SELECTIVE_TRACE") != nullptr;
+        const auto t_0 = std::chrono::steady_clock::now();
         // ---- phase one
         std::vector<tf_col> pc(in->cols, in->cols + nc);
         for (size_t c = 0; c < nc; c++) if (!pred[c]) { pc[c].values = nullptr; pc[c].validity = nullptr; pc[c].offsets = nullptr; pc[c].heap = nullptr; pc[c].aux = nullptr; pc[c].heap_len = 0; pc[c].flags = 0; }
@@ -783,17 +786,24 @@ int tfgpu_push_encode_selective(tfgpu_engine* e, int plan_id, int wire_fmt, cons
         CK(cudaMemcpyAsync(e->sel_host, B, 3 * n, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         const uint8_t* keep = e->sel_host; const uint8_t* ecode = keep + n; const uint8_t* estep = keep + 2 * n;
+        const auto t_1 = std::chrono::steady_clock::now();
         // ---- host gather of the kept rows
         if (!e->gather_pool) { const int rc = tfgpu_columnar_create(&e->gather_pool); if (rc) return fail(e, rc, "cannot create the gather pool"); }
         const tf_batch* kept = nullptr; const uint32_t* sel = nullptr;
         int rc = tfgpu_batch_gather(e->gather_pool, in, keep, threads, &kept, &sel);
         if (rc) return fail(e, rc, std::string("gather: ") + tfgpu_columnar_last_error(e->gather_pool));
+        const auto t_2 = std::chrono::steady_clock::now();
         // ---- phase two: the whole chain over the kept rows
         std::vector<tf_col> dev2; const uint8_t* dev_kinds2 = stage_input(e, kept, dev2);
         run_chain(e, pd, kept, dev2.data(), dev_kinds2, wire_fmt);
         auto r = std::make_unique<tfgpu_result>();
         finish_wire(e, kept->nrows, wire_fmt, r.get());
         r->rows_in = n;
+        if (trace) {
+            const auto t_3 = std::chrono::steady_clock::now();
+            auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+            std::fprintf(stderr, "[tfgpu selective] phase one %.2f ms, gather %.2f ms, phase two %.2f ms (kept %llu of %llu rows)\n", ms(t_0, t_1), ms(t_1, t_2), ms(t_2, t_3), (unsigned long long)kept->nrows, (unsigned long long)n);
+        }
         for (auto& er : r->errs) er.row = sel[er.row];
         std::vector<tf_rowerr> first;
         for (uint64_t i = 0; i < n; i++) if (ecode[i]) first.push_back(tf_rowerr{(uint32_t)i, ecode[i], estep[i]});
@@ -847,6 +857,33 @@ static const uint8_t* stage_input(tfgpu_engine* e, const tf_batch* in, std::vect
     tot += align_up(n + 16, 256);
     arena.ensure(tot);
     uint8_t* p = arena.p;
+    // A shim that keeps the whole batch in ONE pinned arena laid out like the device staging (every non-empty buffer at the next multiple of
+    // 256 past the previous buffer's end + 16, in the order values / validity / offsets / heap / aux per column, then kinds) gets a single
+    // DMA instead of one per buffer: a few hundred descriptors per batch cost several per cent of the PCIe time.
+    {
+        const uint8_t* first = nullptr; size_t first_off = 0, off = 0, end_off = 0; bool contiguous = true;
+        auto chk = [&](const void* src, size_t bytes) {
+            if (!src || !bytes) return;
+            if (!first) { first = (const uint8_t*)src; first_off = off; }
+            else if ((const uint8_t*)src != first + (off - first_off)) contiguous = false;
+            end_off = off + bytes; off += align_up(bytes + 16, 256);
+        };
+        for (uint32_t c = 0; c < nc && contiguous; c++) { const tf_col& ic = in->cols[c]; chk(ic.values, sz_of(ic, 0)); chk(ic.validity, sz_of(ic, 1)); chk(ic.offsets, sz_of(ic, 2)); chk(ic.heap, sz_of(ic, 3)); chk(ic.aux, sz_of(ic, 4)); }
+        if (contiguous && in->kinds) chk(in->kinds, n);
+        if (contiguous && first && end_off - first_off >= (1u << 20)) {
+            CK(cudaMemcpyAsync(p + first_off, first, end_off - first_off, cudaMemcpyHostToDevice, s)); e->h2d_bytes += end_off - first_off;
+            auto at = [&](const void* src, size_t bytes) -> uint8_t* { if (!src || !bytes) return nullptr; uint8_t* d = p; p += align_up(bytes + 16, 256); return d; };
+            for (uint32_t c = 0; c < nc; c++) {
+                const tf_col& ic = in->cols[c]; tf_col& d = dev[c]; d = ic;
+                d.values = at(ic.values, sz_of(ic, 0)); d.validity = at(ic.validity, sz_of(ic, 1)); d.offsets = (const uint32_t*)at(ic.offsets, sz_of(ic, 2));
+                d.heap = at(ic.heap, sz_of(ic, 3)); if (!in_width(ic.type) && !d.heap) d.heap = arena.p;
+                d.aux = at(ic.aux, sz_of(ic, 4));
+            }
+            const uint8_t* dk1 = in->kinds ? at(in->kinds, n) : nullptr;
+            expand_lens(dev);
+            return dk1;
+        }
+    }
     auto up = [&](const void* src, size_t bytes) -> uint8_t* {
         if (!src || !bytes) { return nullptr; }
         uint8_t* d = p; CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, s)); p += align_up(bytes + 16, 256); e->h2d_bytes += bytes; return d;
