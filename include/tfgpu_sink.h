@@ -216,6 +216,8 @@ typedef struct tf_sink_stats {
     uint64_t min_commit_time;        /* its `freshestTime`; both over row + synchronize items with CommitTime != 0 */
     uint64_t without_commit_time;    /* items whose CommitTime is 0 (the reference substitutes time.Now()) */
     uint64_t wire_bytes;             /* bytes handed to the destination */
+    uint64_t metering_input_rows;    /* InputDataMetering (pkg/middlewares/metering.go:42-48): items of the tfgpu_sink_push calls that succeeded */
+    uint64_t metering_output_rows;   /* OutputDataMetering (metering.go:63-69): items of the downstream pushes that succeeded */
 } tf_sink_stats;
 int tfgpu_sink_create(tfgpu_engine* e, const char* cfg_json, tfgpu_sink** out);
 int tfgpu_sink_destroy(tfgpu_sink* s);

@@ -78,6 +78,7 @@ def test_push_sequence_and_counters_equal_the_oracle():
                             lambda table, run: (run, []), True, want_stats)
         assert _events(s) == want, (rnd, spec)
         got = s.stats(); got.pop("wire_bytes"); w = dict(want_stats); w.pop("wire_bytes")
+        assert got.pop("metering_output_rows") == w["change_items_pushed"] and got.pop("metering_input_rows") >= w["change_items_pushed"]   # metering.go:42-48,63-69
         assert got == w, rnd
         # row runs arrive columnar, in item order
         for e in s.events:
@@ -142,7 +143,7 @@ def test_push_with_transformers_on_the_device_equals_the_oracle(eng, po):
         assert g["type"] == w["type"] and g["table"] == w["table"]
         assert g["items"] == w["items"] or (g["items"] is None and s.events[got.index(g)]["n_items"] == len(w["items"]))
     assert len(got) == len(want)
-    st = s.stats(); st.pop("wire_bytes"); want_stats.pop("wire_bytes")
+    st = s.stats(); st.pop("wire_bytes"); want_stats.pop("wire_bytes"); st.pop("metering_input_rows"); st.pop("metering_output_rows")
     for k in ("inflight_bytes", "max_commit_time", "min_commit_time", "without_commit_time"):   # per-item figures need the indexes the device does not return
         st.pop(k); want_stats.pop(k)
     assert st == want_stats

@@ -107,7 +107,7 @@ struct tfgpu_sink {
             if (rc) throw SinkFail{rc, "the downstream Push failed"};
         }
         // Statistician: counted after the downstream Push succeeded (statistician.go:60-66)
-        st.downstream_pushes++; st.change_items_pushed += ev.n_items; st.wire_bytes += ev.wire_len;
+        st.downstream_pushes++; st.change_items_pushed += ev.n_items; st.wire_bytes += ev.wire_len; st.metering_output_rows += ev.n_items;
         if (ev.type != TF_SINK_EV_ITEM) st.row_events_pushed += ev.n_items;
         if (ev.item_idx) for (uint64_t k = 0; k < ev.n_items; k++) {
             const tf_item& it = rows->items[ev.item_idx[k]];
@@ -260,7 +260,7 @@ int tfgpu_sink_set_clickhouse(tfgpu_sink* s, tfgpu_ch_conn* conn) {
 
 int tfgpu_sink_push(tfgpu_sink* s, const tf_rows* items) {
     if (!s || !items) return TF_E_FATAL_ARG;
-    try { s->push(items); return TF_OK; }
+    try { s->push(items); s->st.metering_input_rows += items->n_items; return TF_OK; }
     catch (const SinkFail& f) { s->err = f.msg; return f.rc; }
     catch (const std::bad_alloc&) { s->err = "host allocation failed"; return TF_E_RETRY_OOM; }
     catch (const std::exception& x) { s->err = x.what(); return TF_E_FATAL_CONFIG; }
