@@ -504,6 +504,21 @@ def build_plan(ns: str, name: str, schema: List[dict], transformers: List[dict])
                 continue
             cur = [c for c in cur if _filter_match(inc, exc, c["name"])]
             steps.append({"kind": "filter_columns", "index": idx, "keep": [c["_in"] for c in cur]}); idx += 1
+        elif ttype == "replace_primary_key":                       # replace_primary_key.go:84-117 (Suitable :84-86, ResultSchema :88-117)
+            keys = list(cfg.get("keys") or [])
+            if len(set(keys)) != len(keys):
+                raise ValueError("replace_primary_key: Can't use same keys column names twice")      # :133-137
+            if not _tables_match(cfg.get("tables"), ns, name):
+                continue
+            if sum(1 for n_ in names if n_ in keys) != len(keys):
+                continue
+            if len(keys) == 1:
+                cur = [dict(c, key=(c["name"] == keys[0])) for c in cur]
+                steps.append({"kind": "replace_primary_key", "index": idx, "keep": None}); idx += 1
+            else:
+                by = {c["name"]: c for c in cur}
+                cur = [dict(by[k], key=True) for k in keys] + [dict(c, key=False) for c in cur if c["name"] not in keys]
+                steps.append({"kind": "replace_primary_key", "index": idx, "keep": [c["_in"] for c in cur]}); idx += 1
         elif ttype == "rename_tables":
             hit = None
             for r in cfg.get("renameTables") or []:
@@ -675,6 +690,12 @@ def _marshal(plan: Plan):
         elif st["kind"] == "filter_columns":
             cols = keep.add(np.asarray(st["keep"], dtype=np.int32))
             s.kind = STEP_SELECT_COLS; s.cols = cols.ctypes.data; s.ncols = len(st["keep"])
+        elif st["kind"] == "replace_primary_key":
+            if st["keep"] is None:
+                s.kind = 0
+            else:                                                        # the reordered schema: the same column selection step filter_columns uses
+                cols = keep.add(np.asarray(st["keep"], dtype=np.int32))
+                s.kind = STEP_SELECT_COLS; s.cols = cols.ctypes.data; s.ncols = len(st["keep"])
         elif st["kind"] == "rename_tables":
             s.kind = 0
         elif st["kind"] == "mask_field":

@@ -670,3 +670,19 @@ def test_two_phase_push_equals_one_phase(eng, po):
     t2 = [{"filter_rows": {"filter": "c_int32 > 0 AND n_int16 != NULL"}}]
     p2 = eng.plan("db", "t", s2, t2, {"type": "clickhouse"})
     assert eng.push_encode(p2, b2, RAW, selective=2).wire == eng.push_encode(p2, b2, RAW).wire == po.push_encode(b2, po.build_plan("db", "t", s2, t2), RAW).raw
+
+
+@pytest.mark.gpu
+def test_replace_primary_key_reorders_the_block(eng, po):
+    """A composite replace_primary_key puts the key columns first in the result schema: the native block, JSONEachRow and the INSERT column
+    list follow that order (the items' values are looked up by name, replace_primary_key.go:70-82)."""
+    batch, schema = workload.make_hits_batch(3000, seed=17)
+    names = [c["name"] for c in schema]
+    keys = [names[40], names[3], names[12]]
+    trs = [{"replace_primary_key": {"keys": keys}}, {"filter_rows": {"filter": f"{names[0]} > 0"}}]
+    check(eng, po, batch, schema, trs)
+    pid = eng.plan("public", "hits", schema, trs, {"type": "clickhouse"})
+    d = eng.describe(pid)
+    assert [c["name"] for c in d["result_schema"]][:3] == keys and [c["key"] for c in d["result_schema"]] == [True] * 3 + [False] * (len(names) - 3)
+    want = po.push_encode(batch, po.build_plan("public", "hits", schema, trs), abi.TF_WIRE_CH_JSONEACHROW)
+    assert eng.push_encode(pid, batch, abi.TF_WIRE_CH_JSONEACHROW).wire == want.raw

@@ -387,3 +387,33 @@ def test_filter_grammar_fuzz_product_vs_oracle(po):
         assert _terms_from_describe(d) == _oracle_terms(plan, po), flt
         same += 1
     assert same > 1800 and errs > 50, (same, errs)
+
+
+def test_replace_primary_key_plan_reference_cases(po):
+    """registry/replace_primary_key/replace_primary_key_test.go:37-84: Suitable needs every new key in the schema; ResultSchema puts a
+    composite key's columns first, in the order given, as the only primary keys; a single key only flips the flags."""
+    def sch(cols):
+        return [{"name": n, "type": "string", "key": k} for n, k in cols]
+    tr = [{"replace_primary_key": {"keys": ["col1", "col2"]}}]
+    cases = [([("col1", False), ("col2", False), ("col3", False)], True), ([("col2", True), ("col1", False), ("col3", True)], True),
+             ([("col1", False), ("col3", False)], False), ([("col3", False), ("col1", True)], False)]
+    for cols, suitable in cases:
+        d = engine.plan_validate("", "t", sch(cols), tr)
+        o = po.build_plan("", "t", sch(cols), tr)
+        got = [(c["name"], c["key"]) for c in d["result_schema"]]
+        assert got == [(c["name"], c["key"]) for c in o.result_schema]
+        assert d["out_cols"] == o.out_cols
+        if suitable:
+            assert got[:2] == [("col1", True), ("col2", True)] and all(not k for _, k in got[2:]) and len(d["steps"]) == 1
+        else:
+            assert got == cols and d["steps"] == []
+    one = engine.plan_validate("", "t", sch(cases[1][0]), [{"replace_primary_key": {"keys": ["col3"]}}])
+    assert [(c["name"], c["key"]) for c in one["result_schema"]] == [("col2", False), ("col1", False), ("col3", True)] and one["out_cols"] == [0, 1, 2]
+    with pytest.raises(engine.EngineError) as ei:                      # NewReplacePrimaryKeyTransformer: the same key twice
+        engine.plan_validate("", "t", sch(cases[0][0]), [{"replace_primary_key": {"keys": ["key1", "key1"]}}])
+    assert ei.value.rc == -1
+    with pytest.raises(ValueError):
+        po.build_plan("", "t", sch(cases[0][0]), [{"replace_primary_key": {"keys": ["key1", "key1"]}}])
+    # a table filter that does not match leaves the schema alone
+    d = engine.plan_validate("public", "t", sch(cases[0][0]), [{"replace_primary_key": {"keys": ["col2"], "tables": {"includeTables": ["^public.other$"]}}}])
+    assert d["steps"] == [] and not any(c["key"] for c in d["result_schema"])

@@ -504,6 +504,24 @@ inline Plan build_plan(const std::string& ns, const std::string& name, const std
             for (auto& c : cur) if (cf.match(c.name)) { if (!nxt.empty()) d += ","; d += std::to_string(c.in_index); nxt.push_back(c); }
             if (nxt.empty()) throw FatalError(TF_E_FATAL_UNSUPPORTED, "filter_columns leaves no columns");
             cur = nxt; add_desc(d + "]}"); step_no++;
+        } else if (ttype == "replace_primary_key") {                 // registry/replace_primary_key/replace_primary_key.go:84-117
+            const std::vector<std::string> keys = cfg->get_str_list("keys");
+            for (size_t a = 0; a < keys.size(); a++) for (size_t b = a + 1; b < keys.size(); b++) if (keys[a] == keys[b])
+                throw FatalError(TF_E_FATAL_CONFIG, "replace_primary_key: Can't use same keys column names twice");      // NewReplacePrimaryKeyTransformer :133-137
+            if (!match_table(tables_filter(cfg->get("tables")), ns, name)) continue;
+            size_t have = 0; for (auto& c : cur) for (auto& k : keys) if (c.name == k) { have++; break; }
+            if (have != keys.size()) continue;                       // Suitable: containsAllKeys :37-45
+            auto is_key = [&](const std::string& n) { for (auto& k : keys) if (k == n) return true; return false; };
+            if (keys.size() == 1) { for (auto& c : cur) c.key = is_key(c.name); }
+            else {                                                   // composite key: the key columns lead the schema in the order given (:100-113)
+                std::vector<ColSchema> nxt;
+                for (auto& k : keys) for (auto& c : cur) if (c.name == k) { ColSchema x = c; x.key = true; nxt.push_back(x); break; }
+                for (auto& c : cur) if (!is_key(c.name)) { ColSchema x = c; x.key = false; nxt.push_back(x); }
+                cur = nxt;
+            }
+            std::string d = "{\"type\":\"replace_primary_key\",\"keys\":[";
+            for (size_t i = 0; i < keys.size(); i++) d += (i ? "," : "") + tfj::quote(keys[i]);
+            add_desc(d + "]}"); step_no++;
         } else if (ttype == "rename_tables") {                       // registry/rename/rename.go:46-67
             const tfj::Value* lst = cfg->get("renameTables");
             bool hit = false; std::string nns, nname;
