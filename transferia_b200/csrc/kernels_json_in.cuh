@@ -480,9 +480,20 @@ static __device__ int jsn_key_cmp(const uint8_t* a, uint32_t an, const uint8_t* 
     Dec da(a, an), db(b, bn);
     for (;;) { const int x = da.next(), y = db.next(); if (x < 0 && y < 0) return 0; if (x != y) return x < y ? -1 : 1; }
 }
+// The column a root member's key names: the LAST column of that name wins (the map Unmarshal fills is read by column name). The key is
+// scanned for escapes once; the common case then costs one length test per column and a byte compare only where the length fits.
 static __device__ int jsn_find_col(const JsnArgs& a, const uint8_t* k, uint32_t klen) {
+    bool esc = false; for (uint32_t i = 0; i < klen; i++) if (k[i] == '\\') { esc = true; break; }
     int hit = -1;
-    for (int c = 0; c < a.ncols; c++) if (jsn_key_is(k, klen, a.names + a.cols[c].name_off, a.cols[c].name_len)) hit = c;
+    if (esc) { for (int c = 0; c < a.ncols; c++) if (jsn_key_is(k, klen, a.names + a.cols[c].name_off, a.cols[c].name_len)) hit = c; return hit; }
+    const uint8_t k0 = klen ? k[0] : 0;
+    for (int c = 0; c < a.ncols; c++) {
+        if (a.cols[c].name_len != klen) continue;
+        const uint8_t* nm = a.names + a.cols[c].name_off;
+        if (klen && nm[0] != k0) continue;
+        bool eq = true; for (uint32_t i = 1; i < klen; i++) if (k[i] != nm[i]) { eq = false; break; }
+        if (eq) hit = c;
+    }
     return hit;
 }
 
