@@ -480,17 +480,29 @@ static __device__ int jsn_key_cmp(const uint8_t* a, uint32_t an, const uint8_t* 
     Dec da(a, an), db(b, bn);
     for (;;) { const int x = da.next(), y = db.next(); if (x < 0 && y < 0) return 0; if (x != y) return x < y ? -1 : 1; }
 }
+// Column name lengths and first bytes in shared memory (filled by jsn_stage_names at kernel start): the per-key column loop reads these
+// instead of the descriptors in global memory.
+__device__ __forceinline__ uint16_t* jsn_name_keys() { __shared__ uint16_t keys[JSN_MAX_COLS]; return keys; }   // name_len (capped at 255) | first byte << 8
+__device__ __forceinline__ void jsn_stage_names(const JsnArgs& a) {
+    uint16_t* nk = jsn_name_keys();
+    for (int c = threadIdx.x; c < a.ncols && c < JSN_MAX_COLS; c += blockDim.x) {
+        const uint32_t nl = a.cols[c].name_len;
+        nk[c] = (uint16_t)((nl < 255 ? nl : 255) | ((nl ? a.names[a.cols[c].name_off] : 0) << 8));
+    }
+    __syncthreads();
+}
 // The column a root member's key names: the LAST column of that name wins (the map Unmarshal fills is read by column name). The key is
 // scanned for escapes once; the common case then costs one length test per column and a byte compare only where the length fits.
 static __device__ int jsn_find_col(const JsnArgs& a, const uint8_t* k, uint32_t klen) {
     bool esc = false; for (uint32_t i = 0; i < klen; i++) if (k[i] == '\\') { esc = true; break; }
     int hit = -1;
     if (esc) { for (int c = 0; c < a.ncols; c++) if (jsn_key_is(k, klen, a.names + a.cols[c].name_off, a.cols[c].name_len)) hit = c; return hit; }
-    const uint8_t k0 = klen ? k[0] : 0;
+    const uint16_t* nk = jsn_name_keys();
+    const uint16_t want = (uint16_t)((klen < 255 ? klen : 255) | ((klen ? k[0] : 0) << 8));
     for (int c = 0; c < a.ncols; c++) {
-        if (a.cols[c].name_len != klen) continue;
+        if (nk[c] != want) continue;                              // length and first byte in one shared-memory compare
+        if (a.cols[c].name_len != klen) continue;                 // (names of 255 bytes and more share a length class)
         const uint8_t* nm = a.names + a.cols[c].name_off;
-        if (klen && nm[0] != k0) continue;
         bool eq = true; for (uint32_t i = 1; i < klen; i++) if (k[i] != nm[i]) { eq = false; break; }
         if (eq) hit = c;
     }
@@ -715,6 +727,7 @@ __device__ __forceinline__ const uint8_t* jsn_stage_span(const JsnArgs& a, uint8
 #ifdef TF_KERNELS_JSON_IN
 __global__ void __launch_bounds__(128) k_json_pass1(JsnArgs a) {
     extern __shared__ __align__(16) uint8_t jsn_stage[];
+    jsn_stage_names(a);
     const uint8_t* const text = jsn_stage_span(a, jsn_stage);
     const uint64_t L = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = L < a.nlines;
@@ -800,6 +813,7 @@ struct JsnWriteArgs { JsnArgs a; const uint32_t* offsets; uint8_t* heap; const u
 __global__ void __launch_bounds__(128) k_json_pass2(JsnWriteArgs w) {
     extern __shared__ __align__(16) uint8_t jsn_stage[];
     const JsnArgs& a = w.a;
+    jsn_stage_names(a);
     const uint8_t* const text = jsn_stage_span(a, jsn_stage);
     const uint64_t L = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (L >= a.nlines || a.err[L]) return;
