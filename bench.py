@@ -334,6 +334,28 @@ def run_reference(args):
     }))
 
 
+def bind_to_gpu_numa_node(local):
+    """One process per GPU, bound to the CPUs of the NUMA node the GPU hangs off (its pinned host buffers are then allocated there and the
+    DMA does not cross the socket interconnect). Returns the node, or None when the topology cannot be read."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]                                   # sysfs uses a 4-digit PCI domain
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-"); cpus += list(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -348,6 +370,7 @@ def main():
     ap.add_argument("--dbz-msgs", type=int, default=200_000, help="messages of the Debezium leg (BASELINE configs[3])")
     ap.add_argument("--csv-rows", type=int, default=100_000, help="rows of the CSV leg (BASELINE configs[4])")
     ap.add_argument("--host-layout", default="narrow", choices=["narrow", "offsets"], help="end-to-end leg: var-width columns as uint8 / uint16 lengths (narrow) or uint32 offsets")
+    ap.add_argument("--numa-bind", type=int, default=1, help="bind the process to the CPUs of its GPU's NUMA node before allocating pinned memory (0: leave the affinity alone)")
     ap.add_argument("--host-buffers", default="arena", choices=["arena", "separate"], help="end-to-end leg: the pinned host batch as one arena (one DMA) or one pinned buffer per column array")
     ap.add_argument("--e2e-mode", default="auto", choices=["auto", "one-phase", "two-phase"], help="end-to-end leg: tfgpu_push_encode (one-phase), tfgpu_push_encode_selective (two-phase), or both and report the faster (auto)")
     ap.add_argument("--gather-threads", type=int, default=0, help="host threads of the two-phase gather per pipeline (0: min(32, cores / pipelines / ranks))")
@@ -369,6 +392,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback (use --impl reference for the CPU port)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if args.numa_bind else None      # before any pinned allocation: first touch places the pages
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = f"cuda:{local}"
@@ -514,7 +538,7 @@ def main():
                                "l2": "inputs larger than L2 (%.0f MB per step > 126 MB)" % (in_bytes / 1e6),
                                "parallelism": f"dp{world} (one batch stream per GPU, its own seeded batch on every rank, no collective)", "rank": 0},
             "clocks": sampler.result(),
-            "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h, "host_layout": args.host_layout, "host_buffers": args.host_buffers,
+            "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h, "host_layout": args.host_layout, "host_buffers": args.host_buffers, "numa_node": numa,
                     "mode": best, "gather_threads": gather_threads if best == "two-phase" else 0,
                     "all_modes": {k_: {"value": v_[0], "h2d_bytes_per_step": v_[1]} for k_, v_ in legs.items()},
                     "steps": e2e_steps, "pipelines": P, "timing": "host wall clock over synchronous calls (tfgpu_push_encode / tfgpu_push_encode_selective over pinned host columns; H2D counted by the engine)"},
@@ -530,6 +554,10 @@ def main():
             out["other_paths"] = extra_paths(eng, args)
         if world == 1:
             cores = os.cpu_count() or 1
+            try:
+                os.sched_setaffinity(0, range(cores))      # the CPU baseline uses every host core, not just the GPU's NUMA node
+            except OSError:
+                pass
             v, rows_done, el = cpu_port_rate(batch, schema, trs, args.frame_bytes, args.cpu_budget, cores)
             out["cpu_baseline"] = {"value": v, "unit": "rows/s", "cores": cores, "kind": "port",
                                    "sample": f"{cores} pipelines, each over its own {min(args.rows // cores, 100000)}-row slice of the same batch, for {el:.1f}s ({rows_done} rows); C++ oracle port of the Go row loop, not Go"}
