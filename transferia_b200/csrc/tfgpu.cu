@@ -916,6 +916,10 @@ static void finish_columnar(tfgpu_engine* e, PlanDev& pd, uint64_t n, tfgpu_resu
     const size_t no = pd.plan.out_cols.size();
     std::vector<ColRegions> reg(no);
     CK(cudaMemcpyAsync(reg.data(), e->d_regions, sizeof(ColRegions) * no, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    // the returned offsets are uint32: a column of mask digests (64 bytes per row) or of convert_to_string text that passes 4 GiB would wrap
+    for (size_t k = 0; k < no; k++) if (reg[k].heap_len >= (1ull << 32))
+        throw tfplan::FatalError(TF_E_FATAL_ARG, "push_columns: output column " + std::to_string(k) + " exceeds 4 GiB of text (uint32 offsets); push fewer rows per call");
     uint8_t* buf = (uint8_t*)malloc(st.raw_total ? st.raw_total : 1);
     if (!buf) throw std::bad_alloc();
     r->owned.push_back(buf);
