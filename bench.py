@@ -465,6 +465,24 @@ def main():
     ms_max = float(t.item())
     value = world * args.rows * args.steps / (ms_max / 1e3)
 
+    # what stock liblz4 (LZ4_compress_default, the class of compressor the reference's driver uses) makes of the same block cut into the
+    # same frames: the yardstick for `lz4_ratio` (a CPU call on a sample of the frames, outside every timed region)
+    stock_ratio = None
+    if rank == 0:
+        try:
+            import ctypes as C
+            lz = C.CDLL("liblz4.so.1")
+            eng.push_encode_resident(pid, dbatch, abi.TF_WIRE_CH_NATIVE_LZ4); st2 = eng.resident_stats()
+            raw = eng.resident_fetch(0, st2["raw_bytes"])
+            F = args.frame_bytes; nfr = (len(raw) + F - 1) // F; pick = range(0, nfr, max(1, nfr // 400))
+            dst = C.create_string_buffer(F + F // 255 + 64); tot_in = tot_out = 0
+            for f in pick:
+                chunk = raw[f * F:(f + 1) * F]
+                tot_out += lz.LZ4_compress_default(chunk, dst, len(chunk), len(dst)) + 25; tot_in += len(chunk)
+            stock_ratio = tot_in / tot_out
+        except Exception:
+            stock_ratio = None
+
     # ---- end to end through the public call, host buffers ----
     # Each call is synchronous: H2D of every column, the chain, D2H of the wire bytes. The reference keeps several sink
     # pipelines busy at once (one flush in flight while the next batch collects, bufferer.go:225-242; N parallel sinkers per
@@ -534,6 +552,7 @@ def main():
             "config": bench_config(args, len(schema)),
             "workload_stats": {"selectivity": st["rows_out"] / args.rows, "lz4_ratio": st["raw_bytes"] / max(1, st["wire_bytes"]),
                                "lz4_ratio_blocks_only": st["raw_bytes"] / max(1, st["wire_bytes"] - 25 * ((st["raw_bytes"] + args.frame_bytes - 1) // args.frame_bytes)),
+                               "lz4_ratio_stock_liblz4_same_frames": stock_ratio,
                                "input_bytes_per_row": in_bytes / args.rows, "block_bytes_per_kept_row": st["raw_bytes"] / max(1, st["rows_out"]),
                                "l2": "inputs larger than L2 (%.0f MB per step > 126 MB)" % (in_bytes / 1e6),
                                "parallelism": f"dp{world} (one batch stream per GPU, its own seeded batch on every rank, no collective)", "rank": 0},

@@ -274,8 +274,10 @@ def test_plan_fuzz_product_vs_oracle(po):
 
         chain = []
         for _ in range(rnd.randint(1, 4)):
-            k = rnd.choice(["filter_rows", "skip_events", "filter_columns", "rename_tables", "mask_field", "convert_to_string", "convert_to_datetime", "number_to_float_transformer", "sharder_transformer"])
-            if k == "filter_rows":
+            k = rnd.choice(["filter_rows", "skip_events", "filter_columns", "rename_tables", "mask_field", "convert_to_string", "convert_to_datetime", "number_to_float_transformer", "sharder_transformer", "replace_primary_key"])
+            if k == "replace_primary_key":
+                chain.append({k: {"tables": tables_cfg(), "keys": rnd.sample([c["name"] for c in schema] + ["nope"], rnd.randint(1, 3))}})
+            elif k == "filter_rows":
                 if not ints:
                     continue
                 chain.append({k: {"tables": tables_cfg(), "filter": f"{rnd.choice(ints)} > {rnd.randint(-5, 5)}"}})
@@ -319,6 +321,7 @@ def test_plan_fuzz_product_vs_oracle(po):
         assert [s["type"] for s in dsteps] == [{"number_to_float": "number_to_float_transformer", "sharder": "sharder_transformer"}.get(s["kind"], s["kind"]) for s in psteps], (schema, chain)
         assert [c["name"] for c in d["result_schema"]] == [c["name"] for c in plan.result_schema], (schema, chain)
         assert [c["type"] for c in d["result_schema"]] == [c["type"] for c in plan.result_schema], (schema, chain)
+        assert [bool(c["key"]) for c in d["result_schema"]] == [bool(c.get("key")) for c in plan.result_schema], (schema, chain)
         assert d["out_cols"] == plan.out_cols, (schema, chain)
         assert d["result_table"] == ".".join(x for x in plan.result_table if x), (schema, chain)
         for ds, ps in zip(dsteps, psteps):

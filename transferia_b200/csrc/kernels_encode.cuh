@@ -272,6 +272,19 @@ __global__ void __launch_bounds__(256) k_filter(FilterArgs a) {
 }
 #endif  // TF_KERNELS_ENCODE
 
+// The rows that raised an error as (row, code, term) triples: appended through a counter (the host sorts the few it gets by row), so a
+// batch with a handful of failing rows does not ship its whole error-code arrays back.
+struct DevRowErr { uint32_t row; uint16_t code, term; };
+#ifdef TF_KERNELS_ENCODE
+__global__ void __launch_bounds__(256) k_collect_errors(const uint8_t* errcode, const uint8_t* errstep, uint64_t nrows, DevRowErr* out, unsigned long long* counter, unsigned long long cap) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint8_t c = r < nrows ? errcode[r] : 0;
+    if (!c) return;
+    const unsigned long long at = atomicAdd(counter, 1ull);
+    if (at < cap) out[at] = DevRowErr{(uint32_t)r, c, errstep[r]};
+}
+#endif  // TF_KERNELS_ENCODE
+
 // exclusive scan of per-block kept counts (single block), total -> state.n_kept
 #ifdef TF_KERNELS_ENCODE
 __global__ void __launch_bounds__(1024) k_scan_blockcnt(const uint32_t* blockcnt, uint32_t* blockoff, uint32_t nblocks, DState* st) {

@@ -81,6 +81,7 @@ struct tfgpu_engine {
     uint64_t last_nrows = 0; bool last_has_filter = false, last_has_sharder = false; int last_wire_fmt = 0;
     uint8_t* pinned = nullptr; size_t pinned_cap = 0;
     // two-phase push (tfgpu_push_encode_selective): device flags of phase one, their pinned host copy, the host gather's buffers
+    DevBuf err_list;                                   // fetch_errors: counter + (row, code, term) triples
     DevBuf sel_stage; uint8_t* sel_host = nullptr; size_t sel_host_cap = 0; tfgpu_columnar* gather_pool = nullptr;
     uint64_t h2d_bytes = 0;                            // bytes stage_input has copied to the device since creation
     DevBuf json_sizes, dbz_keysz, dbz_meta, dbz_old, dbz_msgsz, old_arena, part_ids;
@@ -902,11 +903,25 @@ static const uint8_t* stage_input(tfgpu_engine* e, const tf_batch* in, std::vect
 }
 
 static void fetch_errors(tfgpu_engine* e, uint64_t n, tfgpu_result* r) {
+    // only the failing rows come back: (row, code, term) triples collected on the device, sorted by row here
     cudaStream_t s = e->stream;
-    std::vector<uint8_t> ec(n), es(n);
-    CK(cudaMemcpyAsync(ec.data(), e->errcode, n, cudaMemcpyDeviceToHost, s)); CK(cudaMemcpyAsync(es.data(), e->errstep, n, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    for (uint64_t i = 0; i < n; i++) if (ec[i]) r->errs.push_back(tf_rowerr{(uint32_t)i, ec[i], es[i]});
+    DState st; CK(cudaMemcpyAsync(&st, e->d_state, sizeof st, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+    uint64_t cap = std::min<uint64_t>(st.n_errors, n);
+    if (!cap) return;
+    std::vector<DevRowErr> got;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        e->err_list.ensure(cap * sizeof(DevRowErr) + 64);
+        unsigned long long* counter = (unsigned long long*)e->err_list.p; DevRowErr* list = (DevRowErr*)(e->err_list.p + 16);
+        CK(cudaMemsetAsync(counter, 0, 8, s));
+        e->launches++; launch_k_collect_errors((uint32_t)((n + 255) / 256), 256, 0, s, e->errcode, e->errstep, n, list, counter, cap);
+        got.resize(cap); unsigned long long found = 0;
+        CK(cudaMemcpyAsync(got.data(), list, cap * sizeof(DevRowErr), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(&found, counter, 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+        if (found <= cap) { got.resize((size_t)found); break; }
+        cap = std::min<uint64_t>(found, n);                  // a writer of errcode that did not count its rows: collect again with room for all
+    }
+    std::sort(got.begin(), got.end(), [](const DevRowErr& a, const DevRowErr& b) { return a.row < b.row; });
+    for (const DevRowErr& g : got) r->errs.push_back(tf_rowerr{g.row, g.code, g.term});
 }
 
 static void finish_columnar(tfgpu_engine* e, PlanDev& pd, uint64_t n, tfgpu_result* r) {
