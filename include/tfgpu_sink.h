@@ -181,7 +181,10 @@ int tfgpu_batch_gather_sel(tfgpu_columnar* pool, const tf_batch* in, const uint3
  *                         INSERT per run, the statement of sink_table.go:633-660) or to the callback; everything else goes to the callback.
  * Tables are visited in order of first appearance (the reference ranges over a Go map: any order is legal there).
  * cfg_json: {"transformers":[..], "errors_output":"sink"|"devnull", "exclude_system_tables":true, "system_tables":["__consumer_keeper",..],
- *            "sink":{"type":"clickhouse"}, "database":"db", "updateable":false, "wire_fmt":2}
+ *            "sink":{"type":"clickhouse"}, "database":"db", "updateable":false, "wire_fmt":2,
+ *            "debezium":{<opts_json of tfgpu_emit_debezium>}}   (wire_fmt TF_WIRE_DEBEZIUM: the queue Debezium serializer
+ *            pkg/serializer/queue/debezium_serializer.go:25-92 — key / value / tombstone messages of every row kind through
+ *            tfgpu_emit_debezium_crud, with OldKeys and the `source` block's ID / LSN / CommitTime / TxID from the row form)
  * wire_fmt 0: row runs are handed on as columnar batches (ev.batch; with transformers the result of tfgpu_push_columns). `e` may be NULL
  * only when there are no transformers and wire_fmt is 0 (nothing to compute: the always-on middleware alone). */
 typedef struct tfgpu_sink tfgpu_sink;
@@ -199,6 +202,7 @@ typedef struct tf_sink_event {
     const tf_batch*  batch;       /* EV_ROWS with wire_fmt 0 */
     const uint8_t*   wire;        /* EV_ROWS with a wire format: valid until the callback returns */
     uint64_t         wire_len, raw_len, n_frames;
+    const uint32_t*  msg_sizes;   /* wire_fmt TF_WIRE_DEBEZIUM: 7 per row — message count, then (key bytes, value bytes | 0xFFFFFFFF tombstone) x 3 */
     int32_t          plan_id;     /* engine plan that produced it, -1 without one */
     int32_t          pad;
 } tf_sink_event;

@@ -177,3 +177,42 @@ def test_push_rows_to_clickhouse_end_to_end(eng, po):
     assert st["row_events_pushed"] == ref.rows_out and st["change_items_pushed"] == ref.rows_out + 2 and st["transform_dropped"] == 5000 - ref.rows_out
     assert st["wire_bytes"] == len(peer.blocks[0][0])
     s.close(); w.close(); cli.close()
+
+
+@pytest.mark.gpu
+def test_push_cdc_rows_to_debezium_messages(eng, po):
+    """Sinker.Push with the queue Debezium serializer as destination (wire_fmt TF_WIRE_DEBEZIUM): insert / update / delete items with OldKeys,
+    ID / LSN / CommitTime in the row form -> transpose -> tfgpu_emit_debezium_crud; the messages equal the oracle's Emitter.emitKV byte for byte."""
+    from test_debezium_emit import OPTS
+    rng = np.random.default_rng(9); n = 2000
+    schema = [{"name": "id", "type": "int64", "key": True}, {"name": "k2", "type": "utf8", "key": True}, {"name": "name", "type": "utf8"}, {"name": "x", "type": "double"},
+              {"name": "ts", "type": "timestamp"}]
+    ids = rng.integers(0, 50, n); k2 = [b"k%d" % v for v in rng.integers(0, 5, n)]
+    def mk(ids_, k2_, salt):
+        return abi.Batch(n, [abi.fixed_to_column(abi.TF_INT64, ids_), abi.strings_to_column(abi.TF_UTF8, k2_),
+                             abi.strings_to_column(abi.TF_UTF8, [None if (i + salt) % 7 == 0 else b"n<%d>" % (i * salt) for i in range(n)]),
+                             abi.fixed_to_column(abi.TF_DOUBLE, rng.random(n) * 1e3, [(i + salt) % 11 == 0 for i in range(n)]),
+                             abi.fixed_to_column(abi.TF_TIMESTAMP, rng.integers(0, 2**31, n), None, rng.integers(0, 10**9, n).astype(np.uint32))])
+    kinds = rng.integers(0, 3, n).astype(np.uint8)
+    b = mk(ids, k2, 1); b.kinds = kinds
+    same = rng.random(n) < 0.6
+    old = mk(np.where(same, ids, ids + 1), [a if s_ else a + b"x" for a, s_ in zip(k2, rng.random(n) < 0.8)], 3)
+    has = ((rng.random(n) < 0.9) & (kinds != 0)).astype(np.uint8)           # inserts carry no OldKeys
+    present = [0, 1, 2]
+    meta = {"id": rng.integers(0, 2**32, n, dtype=np.uint32), "lsn": rng.integers(0, 2**62, n, dtype=np.uint64), "commit_time": rng.integers(1, 2**62, n, dtype=np.uint64)}
+    items = rows.items_from_batch(b); olds = rows.items_from_batch(old)
+    for r, it in enumerate(items):
+        it.id, it.lsn, it.commit_time = int(meta["id"][r]), int(meta["lsn"][r]), int(meta["commit_time"][r])
+        if has[r]:
+            it.old_keys = {c: olds[r].values[c] for c in present}
+    opts = {k: v for k, v in OPTS.items()}
+    plan = po.build_plan("public", "t", schema, [])
+    want = po.debezium_emit(b, plan, opts, meta, old=old, old_present=present, old_row_has=has, want_msg_sizes=True)
+    s = sink.Sink(eng, wire_fmt=abi.TF_WIRE_DEBEZIUM, debezium=opts)
+    s.push(rows.RowsImage(items, [("public", "t", schema)]))
+    ev = [e for e in s.events if e["type"] == sink.EV_ROWS]
+    assert len(ev) == 1 and ev[0]["n_items"] == n and ev[0]["wire"] == want[0]
+    assert np.array_equal(ev[0]["msg_sizes"][:, 0], want[4][:, 0]) and set(want[4][:, 0].tolist()) >= {1, 2, 3}
+    st = s.stats()
+    assert st["row_events_pushed"] == n and st["wire_bytes"] == len(want[0])
+    s.close()

@@ -43,7 +43,7 @@ struct TablePlan {
 
 struct tfgpu_sink {
     tfgpu_engine* e = nullptr;
-    std::string err, transformers_json, sink_json, database;
+    std::string err, transformers_json, sink_json, database, debezium_opts;
     bool has_transformers = false, errors_to_sink = true, exclude_sys = true, updateable = false;
     int wire_fmt = 0;
     std::set<std::string> system_tables;
@@ -134,7 +134,10 @@ struct tfgpu_sink {
             deliver(ev, rows, &tp); return;
         }
         tfgpu_result* res = nullptr;
-        rc = wire_fmt ? tfgpu_push_encode(e, tp.plan_id, wire_fmt, batch, &res) : tfgpu_push_columns(e, tp.plan_id, batch, &res);
+        if (wire_fmt == TF_WIRE_DEBEZIUM)       // queue Debezium serializer: every row kind, OldKeys and the source block's fields from the transposer
+            rc = tfgpu_emit_debezium_crud(e, tp.plan_id, debezium_opts.c_str(), batch, old, meta, &res);
+        else
+            rc = wire_fmt ? tfgpu_push_encode(e, tp.plan_id, wire_fmt, batch, &res) : tfgpu_push_columns(e, tp.plan_id, batch, &res);
         if (rc) throw SinkFail{rc, std::string("device: ") + tfgpu_last_error(e)};
         struct Release { tfgpu_result* r; ~Release() { tfgpu_result_release(r); } } guard{res};
         const uint64_t n_out = tfgpu_result_rows_out(res), n_err = tfgpu_result_n_errors(res);
@@ -154,7 +157,7 @@ struct tfgpu_sink {
         }
         if (!n_out) return;                                                                              // filter.go:73-75 / an empty Push is not forwarded
         ev.type = TF_SINK_EV_ROWS; ev.n_items = n_out; ev.item_idx = n_out == n ? idx.data() : nullptr;
-        if (wire_fmt) { ev.wire = tfgpu_result_bytes(res); ev.wire_len = tfgpu_result_bytes_len(res); ev.raw_len = tfgpu_result_raw_len(res); ev.n_frames = tfgpu_result_n_frames(res); }
+        if (wire_fmt) { ev.wire = tfgpu_result_bytes(res); ev.wire_len = tfgpu_result_bytes_len(res); ev.raw_len = tfgpu_result_raw_len(res); ev.n_frames = tfgpu_result_n_frames(res); ev.msg_sizes = wire_fmt == TF_WIRE_DEBEZIUM ? tfgpu_result_dbz_msg_sizes(res) : nullptr; }
         else ev.batch = tfgpu_result_batch(res);
         deliver(ev, rows, &tp);
     }
@@ -238,6 +241,18 @@ int tfgpu_sink_create(tfgpu_engine* e, const char* cfg_json, tfgpu_sink** out) {
             }
         } else tj = "[]";
         s->transformers_json = tj;
+        if (s->wire_fmt == TF_WIRE_DEBEZIUM) {               // the emitter's options are passed on verbatim (tfgpu_emit_debezium's opts_json)
+            const std::string src = cfg_json ? cfg_json : ""; const size_t k = src.find("\"debezium\"");
+            if (k == std::string::npos) return TF_E_FATAL_CONFIG;
+            size_t a = src.find('{', k), depth = 0, b = a; bool in_str = false;
+            for (; a != std::string::npos && b < src.size(); b++) {
+                const char c = src[b];
+                if (in_str) { if (c == '\\') b++; else if (c == '"') in_str = false; continue; }
+                if (c == '"') in_str = true; else if (c == '{') depth++; else if (c == '}' && --depth == 0) break;
+            }
+            if (a == std::string::npos || b >= src.size()) return TF_E_FATAL_CONFIG;
+            s->debezium_opts = src.substr(a, b - a + 1);
+        }
         s->sink_json = "{\"type\":\"clickhouse\"}";
         s->database = cfg->get_str("database", "default"); s->updateable = cfg->get_bool("updateable", false);
         s->errors_to_sink = cfg->get_str("errors_output", "sink") != "devnull";

@@ -128,7 +128,7 @@ EV_ROWS, EV_ITEM, EV_ERRORS = 1, 2, 3
 class TfSinkEvent(C.Structure):
     _fields_ = [("type", C.c_int32), ("table", C.c_uint32), ("out_schema", C.c_char_p), ("out_table", C.c_char_p), ("n_items", C.c_uint64),
                 ("item_idx", C.POINTER(C.c_uint64)), ("errors", C.c_void_p), ("batch", C.c_void_p), ("wire", C.c_void_p),
-                ("wire_len", C.c_uint64), ("raw_len", C.c_uint64), ("n_frames", C.c_uint64), ("plan_id", C.c_int32), ("pad", C.c_int32)]
+                ("wire_len", C.c_uint64), ("raw_len", C.c_uint64), ("n_frames", C.c_uint64), ("msg_sizes", C.POINTER(C.c_uint32)), ("plan_id", C.c_int32), ("pad", C.c_int32)]
 
 
 class TfSinkStats(C.Structure):
@@ -146,7 +146,7 @@ class Sink:
     does not take."""
 
     def __init__(self, eng=None, transformers=None, wire_fmt=0, system_tables=(), exclude_system_tables=True, errors_output="sink",
-                 database="default", downstream=None, clickhouse: Optional[ClickHouseWriter] = None):
+                 database="default", downstream=None, clickhouse: Optional[ClickHouseWriter] = None, debezium: Optional[dict] = None):
         from . import abi, rows as _rows
         self._L = lib()
         vp = C.c_void_p
@@ -159,6 +159,8 @@ class Sink:
         self._L.tfgpu_sink_stats.argtypes = [vp, C.POINTER(TfSinkStats)]
         cfg = {"transformers": transformers or [], "wire_fmt": wire_fmt, "system_tables": list(system_tables), "exclude_system_tables": exclude_system_tables,
                "errors_output": errors_output, "database": database}
+        if debezium is not None:
+            cfg["debezium"] = debezium
         self._h = vp()
         rc = self._L.tfgpu_sink_create(eng._h if eng is not None else None, json.dumps(cfg).encode(), C.byref(self._h))
         if rc:
@@ -173,6 +175,8 @@ class Sink:
                  "raw_len": int(ev.raw_len), "n_frames": int(ev.n_frames)}
             if ev.wire:
                 d["wire"] = C.string_at(ev.wire, ev.wire_len)
+            if ev.msg_sizes:
+                d["msg_sizes"] = np.ctypeslib.as_array(ev.msg_sizes, shape=(int(ev.n_items), 7)).copy()
             if ev.batch:
                 b = _rows.batch_from_struct(C.cast(ev.batch, C.POINTER(abi.TfBatch)).contents)
                 d["batch"] = b
