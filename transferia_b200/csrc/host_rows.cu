@@ -58,7 +58,8 @@ inline int canonical_tag(int tf) {
     }
 }
 // the fixed-width column type a numeric tag travels as (a loose column when it differs from the schema's)
-inline int tag_tf(int tag) {
+static const uint8_t TAG_TF[18] = {0, TF_BOOLEAN, TF_INT8, TF_INT16, TF_INT32, TF_INT64, TF_UINT8, TF_UINT16, TF_UINT32, TF_UINT64, TF_FLOAT, TF_DOUBLE, 0, 0, 0, TF_INTERVAL, TF_DOUBLE, 0};
+inline int tag_tf_slow(int tag) {
     switch (tag) {
     case TF_V_BOOL: return TF_BOOLEAN;
     case TF_V_INT8: return TF_INT8; case TF_V_INT16: return TF_INT16; case TF_V_INT32: return TF_INT32; case TF_V_INT64: return TF_INT64;
@@ -67,13 +68,17 @@ inline int tag_tf(int tag) {
     default: return 0;
     }
 }
-inline uint32_t payload_fixed(int tag) {
+inline int tag_tf(int tag) { return TAG_TF[tag]; }
+// (table forms of the two switches below: they sit on the per-value path of both transposer passes)
+static const uint8_t PAYLOAD_W[18] = {0, 1, 1, 2, 4, 8, 1, 2, 4, 8, 4, 8, 0xff, 0xff, 12, 8, 0xff, 0xff};   // 0xff: length-prefixed
+inline uint32_t payload_fixed_slow(int tag) {
     switch (tag) {
     case TF_V_NIL: return 0; case TF_V_BOOL: case TF_V_INT8: case TF_V_UINT8: return 1; case TF_V_INT16: case TF_V_UINT16: return 2;
     case TF_V_INT32: case TF_V_UINT32: case TF_V_FLOAT32: return 4; case TF_V_INT64: case TF_V_UINT64: case TF_V_FLOAT64: case TF_V_DURATION: return 8;
     case TF_V_TIME: return 12; default: return 0xffffffffu;     // length-prefixed
     }
 }
+inline uint32_t payload_fixed(int tag) { const uint8_t w = PAYLOAD_W[tag]; return w == 0xff ? 0xffffffffu : w; }
 
 // one value of the image: tag, payload pointer, payload length (text length for the length-prefixed tags)
 struct Val { int tag; const uint8_t* p; uint32_t n; };
@@ -217,22 +222,26 @@ struct Transposer {
         nchunks = (n + chunk - 1) / chunk;
         stats.assign((size_t)nchunks * nc, ChunkStat());
         // ---- pass 1: tags, heap bytes, longest cell per (chunk, column)
+        std::vector<uint8_t> fw(nc); for (uint32_t c = 0; c < nc; c++) fw[c] = (uint8_t)fixed_width(tfs[c]);
         parallel_chunks(pool, n, chunk, threads, [&](uint64_t k) {
             ChunkStat* st = &stats[(size_t)k * nc];
             std::vector<uint8_t> seen(nc);
             for (uint64_t j = k * chunk; j < std::min(n, (k + 1) * chunk); j++) {
-                std::fill(seen.begin(), seen.end(), 0);
+                const uint8_t *at0, *end0; bool sparse0; uint32_t nv0; get(j, at0, end0, sparse0, nv0);
+                const bool track = sparse0 || keyed;                  // a dense row lists every column: nothing can be absent
+                if (track) std::fill(seen.begin(), seen.end(), 0);
                 walk_row(get, j, keyed, [&](uint32_t c, const Val& v) {
-                    seen[c] = 1; ChunkStat& s = st[c];
+                    if (track) seen[c] = 1;
+                    ChunkStat& s = st[c];
                     if (v.tag == TF_V_NIL) { s.nil = true; return; }
                     s.tagmask |= 1u << v.tag;
-                    if (!fixed_width(tfs[c])) {
+                    if (!fw[c]) {
                         uint32_t len = v.n;
                         if (tfs[c] == TF_ANY && payload_fixed(v.tag) != 0xffffffffu) { char tmp[32]; len = any_scalar_text(v, tmp); }
-                        s.heap += len; s.max_len = std::max(s.max_len, len);
+                        s.heap += len; if (len > s.max_len) s.max_len = len;
                     } else if (v.tag == TF_V_TIME) { uint32_t ns; std::memcpy(&ns, v.p + 8, 4); if (ns) s.nsec = true; }
                 });
-                for (uint32_t c = 0; c < nc; c++) if (!seen[c] && (!only || only[c])) st[c].nil = true;     // absent = nil in the columnar view
+                if (track) for (uint32_t c = 0; c < nc; c++) if (!seen[c] && (!only || only[c])) st[c].nil = true;     // absent = nil in the columnar view
             }
         });
         // ---- layout decisions per column
@@ -286,7 +295,8 @@ struct Transposer {
         // ---- pass 2: fill (chunks are multiples of 8 rows, so validity bytes never straddle two workers)
         parallel_chunks(pool, n, chunk, threads, [&](uint64_t k) {
             const uint64_t r0 = k * chunk, r1 = std::min(n, (k + 1) * chunk);
-            std::vector<uint64_t> hp(nc); for (uint32_t c = 0; c < nc; c++) hp[c] = heap_base[(size_t)k * nc + c];
+            std::vector<uint64_t> hp(nc), hend(nc);
+            for (uint32_t c = 0; c < nc; c++) { hp[c] = heap_base[(size_t)k * nc + c]; hend[c] = k + 1 < nchunks ? heap_base[(size_t)(k + 1) * nc + c] : cp[c].heap_total; }
             for (uint32_t c = 0; c < nc; c++) {                  // defaults: nil rows keep zero values / zero lengths
                 ColPlan& p = cp[c]; if (only && !only[c]) continue;
                 if (p.values) std::memset(p.values + (size_t)p.width * r0, 0, (size_t)p.width * (r1 - r0));
@@ -296,6 +306,7 @@ struct Transposer {
             }
             for (uint64_t j = r0; j < r1; j++) {
                 for (uint32_t c : wide) { const uint32_t o = (uint32_t)hp[c]; std::memcpy(cp[c].lens + 4 * j, &o, 4); }   // u32 offsets: a row without a value repeats the running offset
+                const uint8_t *at0, *vend_all; bool sparse0; uint32_t nv0; get(j, at0, vend_all, sparse0, nv0);
                 walk_row(get, j, keyed, [&](uint32_t c, const Val& v) {
                     ColPlan& p = cp[c];
                     if (v.tag == TF_V_NIL) return;
@@ -304,13 +315,16 @@ struct Transposer {
                         uint8_t* d = p.values + (size_t)p.width * j;
                         if (v.tag == TF_V_TIME) { std::memcpy(d, v.p, 8); if (p.aux) std::memcpy(p.aux + 4 * j, v.p + 8, 4); }
                         else if (v.tag == TF_V_JSONNUM) { const std::string t((const char*)v.p, v.n); const double x = std::strtod(t.c_str(), nullptr); std::memcpy(d, &x, 8); }
-                        else if (tag_tf(v.tag) == p.phys_tf || (v.tag == TF_V_DURATION && p.width == 8)) std::memcpy(d, v.p, p.width);
+                        else if (tag_tf(v.tag) == p.phys_tf || (v.tag == TF_V_DURATION && p.width == 8)) {
+                            switch (p.width) { case 1: d[0] = v.p[0]; break; case 2: std::memcpy(d, v.p, 2); break; case 4: std::memcpy(d, v.p, 4); break; default: std::memcpy(d, v.p, 8); }
+                        }
                         else if (p.phys_tf == TF_DOUBLE) { float f; std::memcpy(&f, v.p, 4); const double x = f; std::memcpy(d, &x, 8); }
                         else { const int64_t x = val_i64(v); std::memcpy(d, &x, 8); }                     // widened into INT64 / UINT64
                     } else {
                         uint32_t len = v.n; const uint8_t* src = v.p; char tmp[32];
                         if (p.schema_tf == TF_ANY && payload_fixed(v.tag) != 0xffffffffu) { len = any_scalar_text(v, tmp); src = (const uint8_t*)tmp; }
-                        std::memcpy(p.heap + hp[c], src, len);
+                        if (len <= 16 && hp[c] + 16 <= hend[c] && (src == (const uint8_t*)tmp || src + 16 <= vend_all)) std::memcpy(p.heap + hp[c], src, 16);   // one 16-byte move inside this chunk's share of the heap; the cells behind it overwrite the excess
+                        else std::memcpy(p.heap + hp[c], src, len);
                         if (p.lens_width == 1) p.lens[j] = (uint8_t)len;
                         else if (p.lens_width == 2) { const uint16_t l = (uint16_t)len; std::memcpy(p.lens + 2 * j, &l, 2); }
                         hp[c] += len;
