@@ -665,6 +665,13 @@ def test_two_phase_push_equals_one_phase(eng, po):
     kb = abi.Batch(batch.nrows, batch.columns, (np.arange(batch.nrows) % 50 == 7).astype(np.uint8))
     one = eng.push_encode(pid, kb, RAW); two = eng.push_encode(pid, kb, RAW, selective=3)
     assert one.errors and two.errors == one.errors and two.wire == one.wire and two.rows_out == one.rows_out
+    # a filter that keeps nothing / everything: phase two sees an empty batch, or the whole one
+    for flt in ("c_int64 < -9223372036854775807 AND c_int8 > 100", "c_int8 >= -128"):
+        b3, s3 = all_types_batch(20_000, seed=3)
+        t3 = [{"filter_rows": {"filter": flt}}]
+        p3 = eng.plan("db", "t3", s3, t3, {"type": "clickhouse"})
+        a3, c3 = eng.push_encode(p3, b3, RAW), eng.push_encode(p3, b3, RAW, selective=2)
+        assert c3.wire == a3.wire and c3.rows_out == a3.rows_out and c3.errors == a3.errors and a3.rows_out in (0, 20_000)
     # all-types batch: nulls, long strings, a predicate on a nullable column
     b2, s2 = all_types_batch(30_000, seed=13)
     t2 = [{"filter_rows": {"filter": "c_int32 > 0 AND n_int16 != NULL"}}]
