@@ -198,7 +198,7 @@ Workers& workers_of(tfgpu_columnar* pool) { if (!pool->workers) pool->workers = 
 // which = nullptr: every schema column; else only the listed columns are laid out (OldKeys), the others stay empty.
 struct Transposer {
     tfgpu_columnar* pool; const std::vector<int>& tfs; uint64_t n; int threads;
-    std::vector<ColPlan> cp; uint64_t chunk = 4096, nchunks = 0;
+    std::vector<ColPlan> cp; uint64_t chunk = 2048, nchunks = 0;      // rows per task: a multiple of 8 (validity bytes), small enough to keep 64 workers busy on 100 k-row batches
     std::vector<ChunkStat> stats;      // [chunk][col]
     std::vector<uint64_t> heap_base;   // [chunk][col]
 
