@@ -391,7 +391,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--rows", type=int, default=1_000_000)
-    ap.add_argument("--frame-bytes", type=int, default=30720)
+    ap.add_argument("--frame-bytes", type=int, default=15360)
     ap.add_argument("--impl", default="tfgpu")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary paths (JSON-lines parse, serializers)")

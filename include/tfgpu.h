@@ -182,8 +182,8 @@ typedef struct tf_rowerr {
 typedef struct tfgpu_engine tfgpu_engine;
 typedef struct tfgpu_result tfgpu_result;
 
-/* cfg_json: {"frame_bytes":30720,...} or NULL for defaults; frame_bytes = uncompressed bytes per ClickHouse
- * compressed frame: a multiple of 16 in [1024, 30720] (one CTA compresses one frame in shared memory).
+/* cfg_json: {"frame_bytes":15360,...} or NULL for defaults; frame_bytes = uncompressed bytes per ClickHouse
+ * compressed frame: a multiple of 16 in [1024, 15360] (one CTA of 256 threads compresses one frame in shared memory, four CTAs per SM).
  * One engine drives one device (device_ids[0]); n_devices must be 1 — multi-GPU
  * is one engine per GPU with batches dealt round-robin by the host. */
 int tfgpu_engine_create(const char* cfg_json, const int* device_ids, int n_devices,

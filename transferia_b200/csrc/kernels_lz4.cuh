@@ -4,8 +4,8 @@
 // GPU-native LZ4 (not a port of any CPU compressor): one CTA per frame, the frame lives in shared memory and
 // every phase is data-parallel:
 //   P1  stage the frame in shared memory (16-byte coalesced loads)
-//   P2  match finding in rounds of 2048 positions (4 consecutive per thread: two shared-memory words give the four
-//       4-byte sequences). Every position is inserted into a 4096-entry hash table (tag16 | position); every EVEN
+//   P2  match finding in rounds of 4 x LZ_THREADS positions (4 consecutive per thread: two shared-memory words give the four
+//       4-byte sequences). Every position is inserted into a 2^LZ_HASH_BITS-entry hash table (tag16 | position); every EVEN
 //       position gets a candidate: the same sequence 4 or 8 bytes back (runs of fixed-width values: the nearest
 //       candidate gives the longest match), else the table entry of an earlier round, else (after this round's
 //       inserts) an entry of this round. Result: one u16 candidate per even position + a bitmap.
@@ -30,10 +30,16 @@
 
 namespace tfk {
 
-#define LZ_THREADS 512
+#ifndef LZ_THREADS
+#define LZ_THREADS 256     /* measured: 4 CTAs x 256 threads on 15 KiB frames 0.387 ms, 2 x 512 on 30 KiB frames 0.420 ms per 123 MB block (ratio 1.694 / 1.751) */
+#endif
+#define LZ_CTAS_PER_SM (LZ_THREADS <= 256 ? 4 : 2)   /* register file: 64 registers x LZ_THREADS x CTAs = 64 K */
+#define LZ_ROUND (4 * LZ_THREADS)                   /* positions per match-finding round */
 #define LZ_SEG 60
-#define LZ_HASH_BITS 12      /* 4096 entries of u32: tag16 << 16 | position */
-#define LZ_MAX_FRAME (LZ_THREADS * LZ_SEG)   /* 30720 */
+#ifndef LZ_HASH_BITS
+#define LZ_HASH_BITS 11      /* 2048 entries of u32: tag16 << 16 | position (8 KiB: with a 15 KiB frame four CTAs fit the 227 KiB of an SM) */
+#endif
+#define LZ_MAX_FRAME (LZ_THREADS * LZ_SEG)   /* 15360 */
 #define LZ_HDR 25            /* 16 checksum + 1 method + 4 compressed size + 4 raw size */
 #define LZ_NONE 0xffffffffu
 #define LZ_FLAG_AGG (1ull << 62)
@@ -49,7 +55,7 @@ __host__ __device__ inline LzSmem lz_smem(uint32_t F) {
     const uint32_t F16 = (F + 15) & ~15u;
     s.data = o + 16; o += 16 + F16 + 16;                          // guard words in front of and behind the frame
     s.cand = o; o += F16;                                         // u16 per even position
-    s.bitmap = o; o += ((F + 2047) / 2048) * 128 + 16;            // 1 bit per even position, whole rounds (+ spare words)
+    s.bitmap = o; o += ((F + LZ_ROUND - 1) / LZ_ROUND) * (LZ_THREADS / 4) + 16;            // 1 bit per even position, whole rounds (+ spare words)
     s.table = o; o += 4u << LZ_HASH_BITS;                         // later: the per-segment arrays
     s.stg = o + 16; o += 16 + ((9 + lz4_bound(F) + 15) & ~15u) + 32;   // image of [method][sizes][LZ4 block]
     s.total = o; return s;
@@ -125,7 +131,7 @@ __device__ __forceinline__ unsigned long long lz_lookback(const Lz4Args& a, uint
 }
 
 #ifdef TF_KERNELS_LZ4
-__global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
+__global__ void __launch_bounds__(LZ_THREADS, LZ_CTAS_PER_SM) k_lz4_frames(Lz4Args a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t F = a.frame_bytes;
     const LzSmem L = lz_smem(F);
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz4_frames(Lz4Args a) {
 
         LZ_PHASE(0);
         // ---- P2: match finding
-        const uint32_t nrounds = (len + 2047) >> 11;
+        const uint32_t nrounds = (len + LZ_ROUND - 1) / LZ_ROUND;
         for (uint32_t rd = 0; rd < nrounds; rd++) {
             const uint32_t wi = rd * LZ_THREADS + tid, p0 = wi * 4;
             const bool active = p0 < len;

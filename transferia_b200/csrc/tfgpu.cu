@@ -524,7 +524,7 @@ void run_chain(tfgpu_engine* e, PlanDev& pd, const tf_batch* in, const tf_col* d
     if (lz) {
         Lz4Args za{e->raw.p, e->d_state, e->wire.p, e->comp_size, e->wire_off, e->frame_pfx, e->d_tail, e->frame_bytes, e->lz_phases};
         const size_t smem = lz_smem(e->frame_bytes).total;
-        const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / (smem + 1024)));
+        const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(LZ_CTAS_PER_SM, (227 * 1024) / (smem + 1024)));
         const uint32_t grid = (uint32_t)std::min<uint64_t>(sz.n_frames_max, (uint64_t)e->sm_count * per_sm);
         join_tail(e);            // the previous batch's checksum kernel still reads the wire bytes and sizes this kernel overwrites
         CK(cudaMemsetAsync(e->frame_pfx, 0, sz.n_frames_max * 8, s));

@@ -20,7 +20,7 @@ from typing import List, Optional, Tuple
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtfgpu.so")
+LIB_PATH = os.environ.get("TFGPU_LIB_PATH") or os.path.join(_HERE, "libtfgpu.so")      # TFGPU_LIB_PATH: a build variant under test
 
 TF_E_FATAL_NODEVICE = -4
 
@@ -209,7 +209,7 @@ class PushResult:
 
 
 class Engine:
-    def __init__(self, device: int = 0, frame_bytes: int = 30720):
+    def __init__(self, device: int = 0, frame_bytes: int = 15360):
         self._L = load_library()
         self._h = C.c_void_p()
         dev = (C.c_int * 1)(device)
