@@ -33,7 +33,7 @@ METRIC = "ChangeItems/sec on ClickBench-shaped 99-col batches (filter_rows + cas
 FALLBACK_HBM_GBS = 6650.0
 
 
-TRAFFIC_PROFILE = "profiles/r2f_traffic.json"   # written by scripts/ncu_summary.py from the capture under profiles/
+TRAFFIC_PROFILE = "profiles/r2h_traffic.json"   # written by scripts/ncu_summary.py from the capture under profiles/
 
 
 def bench_config(args, ncols: int) -> dict:

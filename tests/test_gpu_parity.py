@@ -280,7 +280,7 @@ def test_resident_batches_back_to_back(eng, po):
     assert raw == po.push_encode(small, plan, RAW).raw
 
 
-@pytest.mark.parametrize("frame_bytes", [1024, 4096, 16384])
+@pytest.mark.parametrize("frame_bytes", [1024, 4096, 12288, 15360])
 def test_other_frame_sizes(po, frame_bytes):
     e = engine.Engine(0, frame_bytes)
     try:
@@ -288,6 +288,14 @@ def test_other_frame_sizes(po, frame_bytes):
         check(e, po, batch, schema, workload.headline_transformers(workload.counterid_threshold(batch, schema)), "public", "hits")
     finally:
         e.close()
+
+
+def test_frame_size_limits():
+    """frame_bytes: a multiple of 16 in [1024, 15360] (one CTA of 256 threads holds one frame in shared memory); anything else is a config error."""
+    for bad in (1008, 15376, 16384, 30720, 4100):
+        with pytest.raises(engine.EngineError) as ei:
+            engine.Engine(0, bad)
+        assert ei.value.rc == -1 and not ei.value.retriable
 
 
 def test_compressible_and_incompressible_frames(eng, po):
