@@ -116,3 +116,52 @@ def sink_push(items: List[dict], tables: List[Tuple[str, str]], skip_events: Seq
             if kept:
                 deliver("rows", table, kept)
     return out
+
+
+# ------------------------------------------------------------------ table_splitter (registry/table_splitter/table_splitter.go:36-58)
+def _go_v_float(x: float, is32: bool) -> str:
+    """fmt %v of a float: strconv 'g' with the shortest digits, exponent form when exp < -4 || exp >= 6 (strconv/ftoa.go, eprec = 6)."""
+    import math
+    import numpy as np
+    if math.isnan(x): return "NaN"
+    if math.isinf(x): return "+Inf" if x > 0 else "-Inf"
+    r = np.format_float_scientific(np.float32(x) if is32 else np.float64(x), unique=True, trim="-")      # shortest digits, d.ddde+XX
+    mant, _, ex = r.partition("e"); exp = int(ex)
+    neg = mant.startswith("-"); mant = mant.lstrip("-"); digits = mant.replace(".", "")
+    if exp < -4 or exp >= 6:
+        out = digits[0] + ("." + digits[1:] if len(digits) > 1 else "") + "e%s%02d" % ("-" if exp < 0 else "+", abs(exp))
+    elif exp < 0:
+        out = "0." + "0" * (-exp - 1) + digits
+    else:
+        out = digits + "0" * (exp + 1 - len(digits)) if len(digits) <= exp + 1 else digits[:exp + 1] + "." + digits[exp + 1:]
+    return ("-" if neg else "") + out
+
+
+def serialize_to_string(value, yt_type: str) -> str:
+    """to_string.SerializeToString (registry/to_string/to_string.go:145-172) over the Go-typed (tag, value) pairs of transferia_b200.rows
+    (tags: 0 nil, 1 bool, 2-5 int8..64, 6-9 uint8..64, 10 float32, 11 float64, 12 string, 13 []byte, 14 time.Time (sec, nsec), 16 json.Number)."""
+    import datetime as dt
+    tag, v = value
+    if tag == 0: return "<nil>"
+    if tag == 1: return "true" if v else "false"
+    if 2 <= tag <= 9: return str(int(v))
+    if tag == 10: return _go_v_float(v, True)
+    if tag == 11: return _go_v_float(v, False)
+    if tag in (12, 16): return v.decode("utf-8", "surrogateescape")
+    if tag == 13 and yt_type == "string": return v.decode("utf-8", "surrogateescape")
+    if tag == 14 and yt_type in ("date", "datetime", "timestamp"):
+        t = dt.datetime(1970, 1, 1) + dt.timedelta(seconds=v[0])
+        if yt_type == "date": return t.strftime("%Y-%m-%d")
+        frac = ("." + ("%09d" % v[1]).rstrip("0")) if v[1] else ""
+        return t.strftime("%Y-%m-%dT%H:%M:%S") + frac + "Z"
+    raise NotImplementedError((tag, yt_type))
+
+
+def generate_table_name(original: str, columns, splitter: str, values_by_name: dict, types_by_name: dict) -> str:
+    """GenerateTableName table_splitter.go:36-58: the current table name (when not empty), then the text of every listed column the schema
+    knows (a column the item does not carry reads nil)."""
+    parts = [original] if original else []
+    for col in columns:
+        if col in types_by_name:
+            parts.append(serialize_to_string(values_by_name.get(col, (0, None)), types_by_name[col]))
+    return (splitter or "/").join(parts)

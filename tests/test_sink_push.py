@@ -216,3 +216,96 @@ def test_push_cdc_rows_to_debezium_messages(eng, po):
     st = s.stats()
     assert st["row_events_pushed"] == n and st["wire_bytes"] == len(want[0])
     s.close()
+
+
+def _split_sink(columns, splitter, tables=None, **kw):
+    cfg = {"columns": columns, "splitter": splitter}
+    if tables:
+        cfg["tables"] = tables
+    return sink.Sink(transformers=[{"table_splitter": cfg}], **kw)
+
+
+def test_table_splitter_reference_cases():
+    """registry/table_splitter/table_splitter_test.go:68-118: the generated table names, through Sinker.Push (host-level transformers need no
+    device: skip_events / rename_tables / table_splitter act on kinds and table names only)."""
+    s1 = [{"name": "column1", "type": "string", "key": True}, {"name": "column2", "type": "int64"}, {"name": "column3", "type": "int32"}, {"name": "column4", "type": "boolean"}]
+    s2 = [{"name": "column1", "type": "string"}, {"name": "column2", "type": "date"}, {"name": "column3", "type": "double"}, {"name": "column4", "type": "float"}]
+    f1 = lambda a, b, c, d: [go.string(a), go.int64(b), go.int32(c), go.bool(d)]
+    cases = [([], "_", "table1", s1, f1("hello", 123, 321, False), "table1"),
+             (["column1"], "_", "table2", s1, f1("hello", 456, 654, False), "table2_hello"),
+             (["column1"], "/", "table3", s1, f1("hello", 789, 987, False), "table3/hello"),
+             (["column1", "column2"], "$", "table4", s1, f1("hello", 345, 543, False), "table4$hello$345"),
+             (["column2", "column1"], "+", "table5", s1, f1("hello", 678, 876, False), "table5+678+hello"),
+             (["column1", "column2"], "", "table6", s1, f1("helloworld", 234, 432, False), "table6/helloworld/234"),
+             # 2023-08-31T16:59:07+03:00 -> the UTC date; float32 2.71828 prints with its own shortest digits
+             (["column4", "column2"], "__", "table7", s2, [go.string("helloworld"), go.time(1693490347), go.float64(3.14), go.float32(2.71828)], "table7__2.71828__2023-08-31")]
+    for cols, sp, tname, schema, vals, want in cases:
+        s = _split_sink(cols, sp)
+        s.push(rows.RowsImage([ChangeItem(K.KIND_INSERT, 0, vals)], [("db", tname, schema)]))
+        assert [e["out"][1] for e in s.events] == [want], (cols, sp)
+        assert mo.generate_table_name(tname, cols, sp, dict(zip([c["name"] for c in schema], vals)), {c["name"]: c["type"] for c in schema}) == want
+        s.close()
+    # Suitable: the table filter (table_splitter_test.go:121-169) — a table outside it keeps its name
+    s = _split_sink(["column1"], "_", tables={"includeTables": ["^db\\.table3$"]})
+    s.push(rows.RowsImage([ChangeItem(K.KIND_INSERT, 0, f1("x", 1, 2, True)), ChangeItem(K.KIND_INSERT, 1, f1("y", 1, 2, True))], [("db", "table1", s1), ("db", "table3", s1)]))
+    assert [e["out"][1] for e in s.events] == ["table1", "table3_y"]
+    s.close()
+
+
+def test_table_splitter_groups_rows_and_renames_control_items():
+    rng = np.random.default_rng(11)
+    schema = [{"name": "id", "type": "int32", "key": True}, {"name": "region", "type": "utf8"}, {"name": "day", "type": "date"}, {"name": "w", "type": "double"}]
+    regions = [b"eu", b"us", b"apac"]; days = [19000 * 86400, 19001 * 86400 + 3600]
+    items = [ChangeItem(K.KIND_INIT_TABLE_LOAD, 0)]
+    for i in range(400):
+        v = [go.int32(i), go.nil if i % 37 == 0 else go.string(regions[int(rng.integers(0, 3))]), go.time(days[int(rng.integers(0, 2))], 5), go.float64(float(rng.integers(0, 3)) * 0.25 + 1e6 * (i % 2))]
+        items.append(ChangeItem(K.KIND_UPDATE if i % 5 == 0 else K.KIND_INSERT, 0, v))
+    items.append(ChangeItem(K.KIND_DONE_TABLE_LOAD, 0))
+    trs = [{"skip_events": {"events": ["update"]}},
+           {"rename_tables": {"renameTables": [{"originalName": {"nameSpace": "public", "name": "t"}, "newName": {"nameSpace": "dst", "name": "t2"}}]}},
+           {"table_splitter": {"columns": ["region", "day", "w", "nope"], "splitter": "-"}}]
+    s = sink.Sink(transformers=trs)
+    s.push(rows.RowsImage(items, [("public", "t", schema)]))
+    types = {c["name"]: c["type"] for c in schema}; names = [c["name"] for c in schema]
+    want_groups = {}
+    for k, it in enumerate(items):
+        if it.kind == K.KIND_INSERT:
+            want_groups.setdefault(mo.generate_table_name("t2", ["region", "day", "w", "nope"], "-", dict(zip(names, it.values)), types), []).append(k)
+    ev_rows = [e for e in s.events if e["type"] == sink.EV_ROWS]
+    assert {e["out"][1]: e["items"] for e in ev_rows} == want_groups and len(want_groups) >= 12           # order of first appearance, rows in item order
+    assert [e["out"][1] for e in ev_rows] == list(want_groups)
+    assert any("<nil>" in n for n in want_groups) and any("e+06" in n for n in want_groups)
+    ctl = [e for e in s.events if e["type"] == sink.EV_ITEM]
+    assert [e["out"] for e in ctl] == [("dst", "t2-<nil>-<nil>-<nil>")] * 2 and [e["items"] for e in ctl] == [[0], [len(items) - 1]]
+    st = s.stats()
+    assert st["transform_dropped"] == 80 and st["row_events_pushed"] == 320 and st["change_items_pushed"] == 322
+    for e in ev_rows:                                                                                       # the run arrives columnar: ids of that group
+        assert list(e["columns"][0]) == [items[k].values[0][1] for k in e["items"]]
+    s.close()
+    # plain tfgpu_plan callers are refused: one block cannot hold several tables
+    with pytest.raises(engine.EngineError) as ei:
+        engine.plan_validate("public", "t", schema, [{"table_splitter": {"columns": ["region"]}}])
+    assert ei.value.rc == -2 and "tfgpu_sink_push" in str(ei.value)
+
+
+@pytest.mark.gpu
+def test_table_splitter_with_device_chain(eng, po):
+    """filter_rows on the device + table_splitter on the host: every generated table gets its own native block, equal to the oracle's block over
+    that table's rows; the plan the sink builds marks the splitter step so that the device ignores it."""
+    batch, schema = workload.make_hits_batch(3000, seed=23)
+    names = [c["name"] for c in schema]
+    ci = next(k for k, c in enumerate(batch.columns) if c.type == abi.TF_INT16 and 2 <= len(np.unique(np.asarray(c.values))) <= 6)
+    flt = {"filter_rows": {"filter": f"{names[0]} > 0"}}
+    s = sink.Sink(eng, transformers=[flt, {"table_splitter": {"columns": [names[ci]], "splitter": "_"}}], wire_fmt=abi.TF_WIRE_CH_NATIVE)
+    s.push(rows.RowsImage(rows.items_from_batch(batch), [("public", "hits", schema)]))
+    ev = [e for e in s.events if e["type"] == sink.EV_ROWS]
+    vals = np.asarray(batch.columns[ci].values)
+    assert [e["out"][1] for e in ev] == [f"hits_{v}" for v in dict.fromkeys(vals.tolist())]
+    plan = po.build_plan("public", "hits", schema, [flt]); pool = rows.Columnar()
+    for e in ev:
+        v = int(e["out"][1].split("_")[1])
+        part, _ = pool.gather(batch, (vals == v).astype(np.uint8))
+        want = po.push_encode(part, plan, abi.TF_WIRE_CH_NATIVE)
+        assert e["wire"] == want.raw and e["n_items"] == want.rows_out
+    assert s.stats()["row_events_pushed"] == po.push_encode(batch, plan, abi.TF_WIRE_CH_NATIVE).rows_out
+    s.close(); pool.close()

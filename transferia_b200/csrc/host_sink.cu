@@ -11,6 +11,8 @@
 
 #include "../../include/tfgpu_sink.h"
 #include "plan.hpp"
+#include "row_image.hpp"
+#include <charconv>
 
 namespace {
 
@@ -29,7 +31,8 @@ const char* kind_name(uint8_t k) {            // abstract.Kind strings (kind.go:
 // what a transformer does to an item that is not a row event: skip_events may drop it, rename_tables renames it, the rest pass it through
 // (filter_rows.go:110, number_to_float.go:59, mask / to_string / to_datetime touch ColumnValues of row events only)
 struct HostStep {
-    int type = 0;                              // 1 skip_events, 2 rename_tables
+    int type = 0;                              // 1 skip_events, 2 rename_tables, 3 table_splitter
+    std::vector<std::string> split_cols; std::string splitter;
     tfplan::NameFilter tables; std::set<std::string> events;
     std::vector<std::pair<std::pair<std::string, std::string>, std::pair<std::string, std::string>>> renames;
 };
@@ -37,14 +40,75 @@ struct HostStep {
 struct TablePlan {
     int plan_id = -1;
     std::string out_ns, out_name, insert_query;
+    std::vector<std::string> col_names; std::vector<int> col_tf;      // the table's input schema (table_splitter reads values by column name)
+    std::map<std::string, std::string> insert_by_table;               // INSERT statement per generated table name
 };
+
+// fmt "%v" of a float = strconv 'g' with the shortest digits: exponent form when exp < -4 || exp >= 6 (ftoa.go: eprec = 6 for the shortest form)
+std::string go_v_float(double v, bool is32) {
+    if (v != v) return "NaN";
+    if (v == 1.0 / 0.0) return "+Inf";
+    if (v == -1.0 / 0.0) return "-Inf";
+    char buf[64];
+    auto r = is32 ? std::to_chars(buf, buf + sizeof buf, (float)v, std::chars_format::scientific) : std::to_chars(buf, buf + sizeof buf, v, std::chars_format::scientific);
+    std::string sci(buf, r.ptr);                                     // d[.ddd]e[+-]XX, shortest digits that round-trip
+    const size_t epos = sci.find('e');
+    std::string mant = sci.substr(0, epos); const int exp = std::atoi(sci.c_str() + epos + 1);
+    bool neg = false; if (!mant.empty() && mant[0] == '-') { neg = true; mant.erase(0, 1); }
+    std::string digits; for (char c : mant) if (c != '.') digits += c;
+    std::string out;
+    if (exp < -4 || exp >= 6) {                                      // %e form: d.ddde+XX (at least two exponent digits)
+        out = digits.substr(0, 1); if (digits.size() > 1) out += "." + digits.substr(1);
+        char e[16]; std::snprintf(e, sizeof e, "e%c%02d", exp < 0 ? '-' : '+', exp < 0 ? -exp : exp); out += e;
+    } else if (exp < 0) { out = "0." + std::string((size_t)(-exp - 1), '0') + digits; }
+    else {
+        if ((int)digits.size() <= exp + 1) out = digits + std::string((size_t)(exp + 1 - (int)digits.size()), '0');
+        else out = digits.substr(0, (size_t)exp + 1) + "." + digits.substr((size_t)exp + 1);
+    }
+    return (neg ? "-" : "") + out;
+}
+// time.Time.UTC().Format(time.DateOnly / time.RFC3339Nano)
+std::string go_time_text(int64_t sec, uint32_t nsec, bool date_only) {
+    int64_t days = sec / 86400, rem = sec % 86400; if (rem < 0) { rem += 86400; days--; }
+    int64_t z = days + 719468; const int64_t era = (z >= 0 ? z : z - 146096) / 146097; const unsigned doe = (unsigned)(z - era * 146097);
+    const unsigned yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365; int64_t y = (int64_t)yoe + era * 400;
+    const unsigned doy = doe - (365 * yoe + yoe / 4 - yoe / 100), mp = (5 * doy + 2) / 153, d = doy - (153 * mp + 2) / 5 + 1, m = mp < 10 ? mp + 3 : mp - 9;
+    if (m <= 2) y++;
+    char b[64];
+    if (date_only) { std::snprintf(b, sizeof b, "%04lld-%02u-%02u", (long long)y, m, d); return b; }
+    std::snprintf(b, sizeof b, "%04lld-%02u-%02uT%02d:%02d:%02d", (long long)y, m, d, (int)(rem / 3600), (int)(rem / 60 % 60), (int)(rem % 60));
+    std::string out = b;
+    if (nsec) { char f[16]; std::snprintf(f, sizeof f, ".%09u", nsec); std::string fs = f; while (fs.back() == '0') fs.pop_back(); out += fs; }
+    return out + "Z";
+}
+// to_string.SerializeToString (registry/to_string/to_string.go:145-172) of one boxed value for a column of YT type tf; false = a form the
+// host side does not print (maps, a time.Time outside a time column, ...): the batch stays on the Go path
+bool serialize_to_string(int tf, const Val& v, std::string& out) {
+    switch (v.tag) {
+    case TF_V_NIL: out = "<nil>"; return true;
+    case TF_V_BOOL: out = v.p[0] ? "true" : "false"; return true;
+    case TF_V_UINT64: { uint64_t x; std::memcpy(&x, v.p, 8); out = std::to_string(x); return true; }
+    case TF_V_INT8: case TF_V_INT16: case TF_V_INT32: case TF_V_INT64: case TF_V_UINT8: case TF_V_UINT16: case TF_V_UINT32: out = std::to_string(val_i64(v)); return true;
+    case TF_V_FLOAT32: { float f; std::memcpy(&f, v.p, 4); out = go_v_float(f, true); return true; }
+    case TF_V_FLOAT64: { double f; std::memcpy(&f, v.p, 8); out = go_v_float(f, false); return true; }
+    case TF_V_STRING: case TF_V_JSONNUM: out.assign((const char*)v.p, v.n); return true;
+    case TF_V_BYTES: if (tf == TF_BYTES) { out.assign((const char*)v.p, v.n); return true; } return false;          // %v of a []byte elsewhere prints the byte list
+    case TF_V_TIME: {
+        int64_t sec; uint32_t ns; std::memcpy(&sec, v.p, 8); std::memcpy(&ns, v.p + 8, 4);
+        if (tf == TF_DATE) { out = go_time_text(sec, ns, true); return true; }
+        if (tf == TF_DATETIME || tf == TF_TIMESTAMP) { out = go_time_text(sec, ns, false); return true; }
+        return false;
+    }
+    default: return false;
+    }
+}
 
 }  // namespace
 
 struct tfgpu_sink {
     tfgpu_engine* e = nullptr;
     std::string err, transformers_json, sink_json, database, debezium_opts;
-    bool has_transformers = false, errors_to_sink = true, exclude_sys = true, updateable = false;
+    bool has_transformers = false, needs_device = false, errors_to_sink = true, exclude_sys = true, updateable = false;
     int wire_fmt = 0;
     std::set<std::string> system_tables;
     std::vector<HostStep> host_steps;
@@ -65,27 +129,42 @@ struct tfgpu_sink {
         catch (const tfplan::FatalError& f) { throw SinkFail{f.code, std::string("unable to add table plan: ") + f.what()}; }
         catch (const std::exception& x) { throw SinkFail{TF_E_FATAL_CONFIG, std::string("unable to add table plan: ") + x.what()}; }
         tp.out_ns = pl.out_ns.empty() && pl.out_name.empty() ? ns : pl.out_ns; tp.out_name = pl.out_name.empty() ? name : pl.out_name;
-        if (e && (has_transformers || wire_fmt)) {
+        for (auto& c : pl.in_schema) { tp.col_names.push_back(c.name); tp.col_tf.push_back(c.tf); }
+        if (e && (needs_device || wire_fmt)) {
             const int rc = tfgpu_plan(e, ns.c_str(), name.c_str(), t.schema_json, transformers_json.c_str(), want_sink ? sink_json.c_str() : nullptr, &tp.plan_id);
             if (rc) throw SinkFail{rc, std::string("unable to add table plan: ") + tfgpu_last_error(e)};
         }
-        if (ch) {
+        {
             std::string cols = "[";
             for (size_t i = 0; i < pl.out_schema.size(); i++) cols += (i ? "," : "") + tfj::quote(pl.out_schema[i].name);
-            cols += "]";
-            std::vector<char> q(cols.size() + tp.out_name.size() + database.size() + 256);
-            const int64_t n = tfgpu_ch_insert_query(database.c_str(), tp.out_name.c_str(), cols.c_str(), updateable, q.data(), q.size());
-            if (n < 0) throw SinkFail{(int)n, "cannot build the INSERT statement"};
-            tp.insert_query.assign(q.data(), (size_t)n);
+            tp.insert_query = cols + "]";                      // the column list; the statement is built per destination table name (insert_for)
         }
         return plans.emplace(std::move(key), std::move(tp)).first->second;
     }
 
+    const std::string& insert_for(TablePlan& tp, const std::string& table_name) {
+        auto it = tp.insert_by_table.find(table_name);
+        if (it != tp.insert_by_table.end()) return it->second;
+        std::vector<char> q(tp.insert_query.size() + table_name.size() + database.size() + 256);
+        const int64_t n = tfgpu_ch_insert_query(database.c_str(), table_name.c_str(), tp.insert_query.c_str(), updateable, q.data(), q.size());
+        if (n < 0) throw SinkFail{(int)n, "cannot build the INSERT statement"};
+        return tp.insert_by_table.emplace(table_name, std::string(q.data(), (size_t)n)).first->second;
+    }
+
     // a non-row item through the transformer list: false = dropped by skip_events; the table id it leaves with in (ns, name)
-    bool host_chain(const std::string& orig_ns, const std::string& orig_name, uint8_t kind, std::string& ns, std::string& name) const {
+    bool host_chain(const std::string& orig_ns, const std::string& orig_name, uint8_t kind, std::string& ns, std::string& name, const TablePlan* tp) const {
         ns = orig_ns; name = orig_name;
         for (const HostStep& h : host_steps) {
             if (h.type == 1) { if (tfplan::match_table(h.tables, orig_ns, orig_name) && h.events.count(kind_name(kind))) return false; }
+            else if (h.type == 3) {
+                // GenerateTableName over an item without values (table_splitter.go:36-58): AsMap() is empty, every listed column the schema knows
+                // contributes SerializeToString(nil) = "<nil>"
+                if (!tfplan::match_table(h.tables, orig_ns, orig_name) || !tp) continue;
+                std::vector<std::string> parts; if (!name.empty()) parts.push_back(name);
+                for (auto& cn : h.split_cols) for (auto& have : tp->col_names) if (have == cn) { parts.push_back("<nil>"); break; }
+                std::string j; for (size_t i = 0; i < parts.size(); i++) j += (i ? h.splitter : "") + parts[i];
+                name = j;
+            }
             else {
                 bool suitable = false; for (auto& r : h.renames) if (r.first.first == orig_ns && r.first.second == orig_name) suitable = true;   // Suitable on the original id
                 if (!suitable) continue;
@@ -98,7 +177,7 @@ struct tfgpu_sink {
     int deliver(const tf_sink_event& ev, const tf_rows* rows, TablePlan* tp) {
         int rc = 0;
         if (ev.type == TF_SINK_EV_ROWS && ch && ev.wire) {
-            rc = tfgpu_ch_insert_begin(ch, tp->insert_query.c_str(), "", nullptr);
+            rc = tfgpu_ch_insert_begin(ch, insert_for(*tp, ev.out_table).c_str(), "", nullptr);
             if (!rc) rc = tfgpu_ch_insert_data(ch, ev.wire, ev.wire_len);
             if (!rc) rc = tfgpu_ch_insert_end(ch, nullptr, nullptr);
             if (rc) throw SinkFail{rc, std::string("clickhouse: ") + tfgpu_ch_last_error(ch)};
@@ -120,12 +199,62 @@ struct tfgpu_sink {
         return 0;
     }
 
-    // one maximal run of row events of one (table, schema): transformers + encode on the device, then downstream
-    void push_run(const tf_rows* rows, uint32_t table, const std::vector<uint64_t>& idx, TablePlan& tp) {
+    // one maximal run of row events of one (table, schema): what the host-level steps do to it (skip_events without a device plan,
+    // table_splitter's per-row table names), then every group of rows that shares a destination table goes down on its own
+    void push_run(const tf_rows* rows, uint32_t table, const std::vector<uint64_t>& idx_in, TablePlan& tp) {
+        if (idx_in.empty()) return;
+        const tf_table& t = rows->tables[table];
+        const std::string ons = t.schema ? t.schema : "", oname = t.table ? t.table : "";
+        std::vector<uint64_t> kept; const std::vector<uint64_t>* idx = &idx_in;
+        if (tp.plan_id < 0) {                                   // no device plan: skip_events drops row kinds here (skip_events.go:52-62)
+            for (const HostStep& h : host_steps) if (h.type == 1 && tfplan::match_table(h.tables, ons, oname)) {
+                std::vector<uint64_t> nxt;
+                for (uint64_t i : *idx) { if (h.events.count(kind_name(rows->items[i].kind))) st.transform_dropped++; else nxt.push_back(i); }
+                kept.swap(nxt); idx = &kept;
+            }
+            if (idx->empty()) return;
+        }
+        const HostStep* sp = nullptr;
+        for (const HostStep& h : host_steps) if (h.type == 3 && tfplan::match_table(h.tables, ons, oname)) sp = &h;       // the plan keeps table_splitter last: at most one applies
+        if (!sp) { push_rows(rows, table, *idx, tp, tp.out_name); return; }
+        // GenerateTableName (table_splitter.go:36-58): current table name, then SerializeToString of every listed column the schema knows
+        std::vector<int> cols;                                  // schema index of every split column (in the configured order)
+        for (auto& cn : sp->split_cols) for (size_t c = 0; c < tp.col_names.size(); c++) if (tp.col_names[c] == cn) { cols.push_back((int)c); break; }
+        int max_col = -1; for (int c : cols) max_col = std::max(max_col, c);
+        std::vector<std::pair<std::string, std::vector<uint64_t>>> groups; std::map<std::string, size_t> where;
+        const uint8_t* vend = rows->values + rows->values_len;
+        std::vector<Val> vals(tp.col_names.size()); std::vector<uint8_t> have(tp.col_names.size());
+        for (uint64_t i : *idx) {
+            const tf_item& it = rows->items[i];
+            std::fill(have.begin(), have.end(), 0);
+            const uint8_t* at = rows->values + it.values_off; const bool sparse = it.flags & TF_ITEM_SPARSE;
+            for (uint32_t k = 0; k < it.n_values && max_col >= 0; k++) {
+                uint32_t c = k;
+                if (sparse) { if (vend - at < 2) throw SinkFail{TF_E_FATAL_ARG, "truncated value image"}; uint16_t ci; std::memcpy(&ci, at, 2); at += 2; c = ci; }
+                Val v; if (!read_val(at, vend, v)) throw SinkFail{TF_E_FATAL_ARG, "malformed value image"};
+                if (c < vals.size()) { vals[c] = v; have[c] = 1; }
+                if (!sparse && (int)c >= max_col) break;
+            }
+            std::string name = tp.out_name.empty() ? "" : tp.out_name; bool first = tp.out_name.empty();
+            for (int c : cols) {
+                std::string text; Val nil{TF_V_NIL, nullptr, 0};
+                if (!serialize_to_string(tp.col_tf[c], have[c] ? vals[c] : nil, text))
+                    throw SinkFail{TF_E_FATAL_UNSUPPORTED, "table_splitter: a value of column '" + tp.col_names[c] + "' has a form the host side does not print"};
+                if (!first) name += sp->splitter; name += text; first = false;
+            }
+            auto w = where.find(name);
+            if (w == where.end()) { w = where.emplace(name, groups.size()).first; groups.emplace_back(name, std::vector<uint64_t>()); }
+            groups[w->second].second.push_back(i);
+        }
+        for (auto& g : groups) push_rows(rows, table, g.second, tp, g.first);
+    }
+
+    // rows of one destination table: transformers + encode on the device, then downstream
+    void push_rows(const tf_rows* rows, uint32_t table, const std::vector<uint64_t>& idx, TablePlan& tp, const std::string& out_name) {
         const uint64_t n = idx.size();
         if (!n) return;
-        tf_sink_event ev{}; ev.table = table; ev.out_schema = tp.out_ns.c_str(); ev.out_table = tp.out_name.c_str(); ev.plan_id = tp.plan_id;
-        if (exclude_sys && system_tables.count(tp.out_name)) { st.filter_dropped += n; return; }           // ChangeItem.IsSystemTable looks at Table only
+        tf_sink_event ev{}; ev.table = table; ev.out_schema = tp.out_ns.c_str(); ev.out_table = out_name.c_str(); ev.plan_id = tp.plan_id;
+        if (exclude_sys && system_tables.count(out_name)) { st.filter_dropped += n; return; }           // ChangeItem.IsSystemTable looks at Table only
         const tf_batch* batch = nullptr; const tf_row_meta* meta = nullptr; const tf_old_keys* old = nullptr;
         int rc = tfgpu_rows_to_batch(pool, rows, table, idx.data(), n, 0, &batch, &meta, &old);
         if (rc) throw SinkFail{rc, std::string("transpose: ") + tfgpu_columnar_last_error(pool)};
@@ -188,7 +317,7 @@ struct tfgpu_sink {
                     run.push_back(i); continue;
                 }
                 std::string ns, name;
-                if (!host_chain(t.schema ? t.schema : "", t.table ? t.table : "", it.kind, ns, name)) { st.transform_dropped++; continue; }   // the run is NOT cut: the item is gone before NonRowSeparator sees it
+                if (!host_chain(t.schema ? t.schema : "", t.table ? t.table : "", it.kind, ns, name, &plan_for(t))) { st.transform_dropped++; continue; }   // the run is NOT cut: the item is gone before NonRowSeparator sees it
                 flush();                                                                                  // nonrow_separator.go:38-47
                 if (exclude_sys && system_tables.count(name)) { st.filter_dropped++; continue; }
                 tf_sink_event ev{}; ev.type = TF_SINK_EV_ITEM; ev.table = it.table; ev.out_schema = ns.c_str(); ev.out_table = name.c_str();
@@ -211,7 +340,11 @@ int tfgpu_sink_create(tfgpu_engine* e, const char* cfg_json, tfgpu_sink** out) {
         s->e = e; s->wire_fmt = (int)cfg->get_num("wire_fmt", 0);
         const tfj::Value* trs = cfg->get("transformers");
         s->has_transformers = trs && trs->kind == tfj::Value::Arr && !trs->arr.empty();
-        if ((s->has_transformers || s->wire_fmt) && !e) return TF_E_FATAL_NODEVICE;                      // nothing here computes on the CPU
+        if (s->has_transformers) for (auto& tr : trs->arr) if (tr->kind == tfj::Value::Obj) for (auto& kv : tr->obj)
+            if (kv.first != "transformerId" && kv.first != "skip_events" && kv.first != "rename_tables" && kv.first != "table_splitter") s->needs_device = true;
+        // skip_events / rename_tables / table_splitter act on kinds and table names only: with wire_fmt 0 they run on the host alone; every
+        // other transformer and every wire format computes on the device — nothing here computes on the CPU in its place
+        if ((s->needs_device || s->wire_fmt) && !e) return TF_E_FATAL_NODEVICE;
         // the transformer list, re-serialised for tfgpu_plan, and its effect on non-row items
         std::string tj = "[";
         if (s->has_transformers) {
@@ -229,6 +362,12 @@ int tfgpu_sink_create(tfgpu_engine* e, const char* cfg_json, tfgpu_sink** out) {
                 for (auto& kv : tr->obj) {
                     const tfj::Value* c = kv.second.get();
                     if (kv.first == "skip_events") { HostStep h; h.type = 1; h.tables = tfplan::tables_filter(c->get("tables")); for (auto& ev : c->get_str_list("events")) h.events.insert(ev); s->host_steps.push_back(std::move(h)); }
+                    else if (kv.first == "table_splitter") {
+                        HostStep h; h.type = 3; h.tables = tfplan::tables_filter(c->get("tables")); h.split_cols = c->get_str_list("columns");
+                        h.splitter = c->get_str("splitter", ""); if (h.splitter.empty()) h.splitter = "/";      // defaultSplitter table_splitter.go:17,48-50
+                        if (c->get_bool("useLegacyLf")) return TF_E_FATAL_UNSUPPORTED;
+                        s->host_steps.push_back(std::move(h));
+                    }
                     else if (kv.first == "rename_tables") {
                         HostStep h; h.type = 2; const tfj::Value* lst = c->get("renameTables");
                         if (lst && lst->kind == tfj::Value::Arr) for (auto& r : lst->arr) {
@@ -240,6 +379,7 @@ int tfgpu_sink_create(tfgpu_engine* e, const char* cfg_json, tfgpu_sink** out) {
                 }
             }
         } else tj = "[]";
+        for (size_t at = 0; (at = tj.find("\"table_splitter\"", at)) != std::string::npos; at += 22) tj.replace(at, 16, "\"table_splitter@sink\"");   // see plan.hpp: the unmarked form is refused
         s->transformers_json = tj;
         if (s->wire_fmt == TF_WIRE_DEBEZIUM) {               // the emitter's options are passed on verbatim (tfgpu_emit_debezium's opts_json)
             const std::string src = cfg_json ? cfg_json : ""; const size_t k = src.find("\"debezium\"");

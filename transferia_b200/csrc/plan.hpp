@@ -349,6 +349,7 @@ struct Plan {
     // input value (also after convert_to_string: the text of a text is itself), 1 = the mask digest, 3 = the converted datetime
     bool has_sharder = false; uint32_t shards = 0; std::vector<int> shard_cols, shard_form; int shard_step_index = -1;
     std::vector<int> mask_step_index;
+    bool has_splitter = false; int splitter_step = -1;   // table_splitter@sink: the last step of the chain (checked at the end of build_plan)
     std::vector<uint8_t> blob;         // literal pool referenced by DTerm
     std::string describe;
     // sink
@@ -522,6 +523,18 @@ inline Plan build_plan(const std::string& ns, const std::string& name, const std
             std::string d = "{\"type\":\"replace_primary_key\",\"keys\":[";
             for (size_t i = 0; i < keys.size(); i++) d += (i ? "," : "") + tfj::quote(keys[i]);
             add_desc(d + "]}"); step_no++;
+        } else if (ttype == "table_splitter@sink" || ttype == "table_splitter") {   // registry/table_splitter/table_splitter.go:36-101
+            // The transformer changes ChangeItem.Table per ROW (original name + splitter + the text of the listed columns): nothing for the device to
+            // compute on the values, but the rows of one batch then belong to several tables. tfgpu_sink_push groups the rows by the generated
+            // name on the host and pushes every group on its own; it marks the step "@sink" when it forwards the list. Plain tfgpu_push_* callers
+            // would get ONE block for all rows, so the unmarked form is refused.
+            if (ttype == "table_splitter") throw FatalError(TF_E_FATAL_UNSUPPORTED, "table_splitter is applied by tfgpu_sink_push (rows are grouped by the generated table name on the host)");
+            if (cfg->get_bool("useLegacyLf")) throw FatalError(TF_E_FATAL_UNSUPPORTED, "table_splitter: useLegacyLf is not implemented");
+            if (!match_table(tables_filter(cfg->get("tables")), ns, name)) continue;
+            for (auto& cn : cfg->get_str_list("columns")) for (auto& c : cur) if (c.name == cn && (c.tf == TF_ANY || c.tf == TF_INTERVAL))
+                throw FatalError(TF_E_FATAL_UNSUPPORTED, "table_splitter over an `any` / interval column is not implemented");
+            pl.has_splitter = true; pl.splitter_step = step_no;
+            add_desc("{\"type\":\"table_splitter\"}"); step_no++;
         } else if (ttype == "rename_tables") {                       // registry/rename/rename.go:46-67
             const tfj::Value* lst = cfg->get("renameTables");
             bool hit = false; std::string nns, nname;
@@ -669,6 +682,8 @@ inline Plan build_plan(const std::string& ns, const std::string& name, const std
                 throw FatalError(TF_E_FATAL_UNSUPPORTED, "sharder_transformer over an `any` column that number_to_float rewrites is not supported");
         }
     }
+    if (pl.has_splitter && pl.splitter_step != step_no - 1)
+        throw FatalError(TF_E_FATAL_UNSUPPORTED, "a transformer behind table_splitter would see per-row table names: not implemented (put table_splitter last)");
     pl.out_schema = cur; pl.out_ns = cur_ns; pl.out_name = cur_name;
     for (auto& c : cur) pl.out_cols.push_back(c.in_index);
     std::string sink_desc = "null";
