@@ -186,7 +186,13 @@ int tfgpu_batch_gather_sel(tfgpu_columnar* pool, const tf_batch* in, const uint3
  *            pkg/serializer/queue/debezium_serializer.go:25-92 — key / value / tombstone messages of every row kind through
  *            tfgpu_emit_debezium_crud, with OldKeys and the `source` block's ID / LSN / CommitTime / TxID from the row form)
  * wire_fmt 0: row runs are handed on as columnar batches (ev.batch; with transformers the result of tfgpu_push_columns). `e` may be NULL
- * only when there are no transformers and wire_fmt is 0 (nothing to compute: the always-on middleware alone). */
+ * only when wire_fmt is 0 and the transformer list holds nothing but skip_events / rename_tables / table_splitter: those act on kinds and
+ * table names, which the host decides (nothing to compute: the always-on middleware alone); everything else needs the device.
+ * table_splitter (pkg/transformer/registry/table_splitter/table_splitter.go:36-101) is applied HERE, not by tfgpu_plan: the generated name
+ * (current table name + splitter + to_string.SerializeToString of the listed columns, "<nil>" for nil / absent values and for items without
+ * values) is computed per row from the row image, the rows of a run are grouped by it in order of first appearance and every group goes
+ * down on its own (ev.out_table, its own INSERT). It must be the last transformer of the list; `any` / interval columns, []byte outside
+ * `string` columns and useLegacyLf are refused. */
 typedef struct tfgpu_sink tfgpu_sink;
 #define TF_SINK_EV_ROWS   1   /* one downstream Push of row events of one table */
 #define TF_SINK_EV_ITEM   2   /* one downstream Push of a single non-row item */
