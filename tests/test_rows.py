@@ -197,3 +197,136 @@ def test_host_gather_equals_numpy_selection():
                 assert (np.asarray(got.kinds) == np.asarray(want.kinds)).all() if want.nrows else True
                 assert [c.lens_width for c in got.columns] == [c.lens_width for c in batch.columns]     # the layout of the input is kept
     pool.close()
+
+
+def _py_transpose(items, schema):
+    """The documented transposer rules (include/tfgpu_sink.h, tfgpu_rows_to_batch) restated over Python lists: per column the physical type
+    (schema type when every value carries the canonical tag; the single foreign numeric type; else INT64 / UINT64 / DOUBLE by class), values,
+    validity, text cells. Returns [(phys_tf, values list with None for nil)] or raises ValueError where the product refuses."""
+    R = rows
+    canon = {abi.TF_INT8: R.V_INT8, abi.TF_INT16: R.V_INT16, abi.TF_INT32: R.V_INT32, abi.TF_INT64: R.V_INT64, abi.TF_UINT8: R.V_UINT8, abi.TF_UINT16: R.V_UINT16,
+             abi.TF_UINT32: R.V_UINT32, abi.TF_UINT64: R.V_UINT64, abi.TF_FLOAT: R.V_FLOAT32, abi.TF_DOUBLE: R.V_FLOAT64, abi.TF_BOOLEAN: R.V_BOOL,
+             abi.TF_INTERVAL: R.V_DURATION, abi.TF_DATE: R.V_TIME, abi.TF_DATETIME: R.V_TIME, abi.TF_TIMESTAMP: R.V_TIME}
+    tag_tf = {R.V_BOOL: abi.TF_BOOLEAN, R.V_INT8: abi.TF_INT8, R.V_INT16: abi.TF_INT16, R.V_INT32: abi.TF_INT32, R.V_INT64: abi.TF_INT64, R.V_UINT8: abi.TF_UINT8,
+              R.V_UINT16: abi.TF_UINT16, R.V_UINT32: abi.TF_UINT32, R.V_UINT64: abi.TF_UINT64, R.V_FLOAT32: abi.TF_FLOAT, R.V_FLOAT64: abi.TF_DOUBLE, R.V_JSONNUM: abi.TF_DOUBLE}
+    signed, unsigned, floats = {R.V_BOOL, R.V_INT8, R.V_INT16, R.V_INT32, R.V_INT64}, {R.V_UINT8, R.V_UINT16, R.V_UINT32, R.V_UINT64}, {R.V_FLOAT32, R.V_FLOAT64, R.V_JSONNUM}
+    out = []
+    for c, col in enumerate(schema):
+        tf = abi.YT_NAME_TO_TF[col["type"]]
+        cells = []
+        for it in items:
+            v = it.values.get(c, go.nil) if isinstance(it.values, dict) else it.values[c]
+            cells.append(v)
+        tags = {v[0] for v in cells if v[0] != R.V_NIL}
+        if tf in abi.VAR_TYPES:
+            if tf != abi.TF_ANY and tags - {R.V_STRING, R.V_BYTES}: raise ValueError("non-text in a string column")
+            if tf == abi.TF_ANY and tags & (floats - {R.V_JSONNUM} | {R.V_TIME, R.V_DURATION, R.V_BYTES}): raise ValueError("float / time inside any")
+            def text(v):
+                if v[0] == R.V_NIL: return None
+                if v[0] in (R.V_STRING, R.V_BYTES, R.V_JSON, R.V_JSONNUM): return bytes(v[1])
+                if v[0] == R.V_BOOL: return b"true" if v[1] else b"false"
+                return str(int(v[1])).encode()
+            out.append((tf, [text(v) for v in cells])); continue
+        if not tags or tags == {canon[tf]} or (tf == abi.TF_DOUBLE and tags == {R.V_JSONNUM}): phys = tf
+        elif R.V_TIME in tags and tf in abi.TIME_TYPES: raise ValueError("time mixed")
+        elif tags - (signed | unsigned | floats | {R.V_DURATION}): raise ValueError("text in a fixed column")
+        elif len(tags) == 1: t = next(iter(tags)); phys = abi.TF_INT64 if t == R.V_DURATION else tag_tf[t]
+        elif not (tags - signed) or not (tags - (signed | {R.V_DURATION})): phys = abi.TF_INT64
+        elif not (tags - unsigned): phys = abi.TF_UINT64
+        elif not (tags - floats): phys = abi.TF_DOUBLE
+        else: raise ValueError("mixed classes")
+        def num(v):
+            if v[0] == R.V_NIL: return None
+            if v[0] == R.V_TIME: return v[1]
+            if v[0] == R.V_JSONNUM: return float(v[1])
+            if v[0] == R.V_FLOAT32: return float(np.float32(v[1]))
+            return v[1]
+        out.append((phys, [num(v) for v in cells]))
+    return out
+
+
+def test_transposer_fuzz_against_the_documented_rules():
+    rng = np.random.default_rng(77)
+    types = ["int8", "int32", "int64", "uint16", "uint64", "float", "double", "boolean", "utf8", "string", "any", "date", "timestamp", "interval"]
+    pool = rows.Columnar()
+    agreed = refused = 0
+    for rnd in range(120):
+        ncol = int(rng.integers(1, 9)); n = int(rng.integers(1, 400))
+        schema = [{"name": f"c{k}", "type": str(rng.choice(types))} for k in range(ncol)]
+        def value(tf, mode):
+            if rng.random() < 0.12: return go.nil
+            if tf in (abi.TF_UTF8, abi.TF_BYTES):
+                b = bytes(rng.integers(0, 256, int(rng.integers(0, 300 if mode else 20)), dtype=np.uint8))
+                return go.string(b) if rng.random() < 0.7 else go.bytes(b)
+            if tf == abi.TF_ANY:
+                k = rng.integers(0, 4); return [go.json(b'{"a":1}'), go.string("s"), go.int64(int(rng.integers(-5, 5))), go.bool(rng.random() < 0.5)][int(k)]
+            if tf in abi.TIME_TYPES: return go.time(int(rng.integers(-10**9, 10**10)), int(rng.integers(0, 10**9)) if mode else 0)
+            if tf == abi.TF_INTERVAL: return go.duration(int(rng.integers(-10**12, 10**12)))
+            if tf == abi.TF_BOOLEAN and not mode: return go.bool(rng.random() < 0.5)
+            if tf in (abi.TF_FLOAT, abi.TF_DOUBLE):
+                if mode == 0: return go.float32(float(rng.standard_normal())) if tf == abi.TF_FLOAT else go.float64(float(rng.standard_normal()))
+                return [go.float32(1.5), go.float64(2.25), go.number("0.125")][int(rng.integers(0, 3))]
+            canon = {abi.TF_INT8: go.int8, abi.TF_INT32: go.int32, abi.TF_INT64: go.int64, abi.TF_UINT16: go.uint16, abi.TF_UINT64: go.uint64, abi.TF_BOOLEAN: go.bool}[tf]
+            if mode == 0: return canon(int(rng.integers(0, 100)))
+            if mode == 1: return go.int64(int(rng.integers(-1000, 1000)))                      # one foreign type
+            return [go.int8, go.int16, go.int64, go.bool][int(rng.integers(0, 4))](int(rng.integers(0, 2)))   # mixed signed widths
+        modes = [int(rng.integers(0, 3)) for _ in range(ncol)]
+        if rng.random() < 0.1: modes[0] = 9                                                       # provoke a refusal
+        items = []
+        for r in range(n):
+            vals = [value(abi.YT_NAME_TO_TF[c["type"]], m) if m != 9 else (go.string("x") if abi.YT_NAME_TO_TF[c["type"]] not in abi.VAR_TYPES else go.int64(1)) for c, m in zip(schema, modes)]
+            if rng.random() < 0.15:
+                keep = [k for k in range(ncol) if rng.random() < 0.7]
+                items.append(ChangeItem(rows.KIND_UPDATE, 0, {k: vals[k] for k in keep}))
+            else:
+                items.append(ChangeItem(rows.KIND_INSERT, 0, vals))
+        try:
+            want = _py_transpose(items, schema)
+        except ValueError:
+            want = None
+        try:
+            got = pool.rows_to_batch(rows.RowsImage(items, [("d", "t", schema)]), threads=int(rng.integers(1, 5)))
+        except engine.EngineError as ex:
+            assert want is None and ex.rc == -2, (rnd, schema, modes)
+            refused += 1; continue
+        assert want is not None, (rnd, schema, modes)
+        agreed += 1
+        b = got.batch
+        for c, (phys, cells) in enumerate(want):
+            col = b.columns[c]
+            assert col.type == phys, (rnd, c, col.type, phys)
+            valid = _valid(col, n)
+            assert list(valid) == [v is not None for v in cells], (rnd, c)
+            if phys in abi.VAR_TYPES:
+                ln = _lens(col, n); heap = np.asarray(col.heap).tobytes() if col.heap is not None else b""
+                assert heap == b"".join(v for v in cells if v is not None) and [int(x) for x in ln] == [0 if v is None else len(v) for v in cells], (rnd, c)
+            elif phys in abi.TIME_TYPES:
+                vals = np.asarray(col.values); ns = np.zeros(n, np.uint32) if col.aux is None else np.asarray(col.aux)
+                assert [(int(vals[r]), int(ns[r])) for r in range(n) if valid[r]] == [v for v in cells if v is not None], (rnd, c)
+            else:
+                vals = np.asarray(col.values)
+                wantv = np.array([0 if v is None else v for v in cells]).astype(abi.FIXED_DTYPE[phys])
+                assert vals[valid].tobytes() == wantv[valid].tobytes(), (rnd, c, phys)
+    assert agreed > 60 and refused > 3, (agreed, refused)
+    pool.close()
+
+
+def test_two_pools_in_two_threads_do_not_interfere():
+    import threading
+    batch, schema = workload.make_hits_batch(20_000, seed=31)
+    img = rows.RowsImage(rows.items_from_batch(batch.slice(0, 3000)), [("public", "hits", schema)])
+    keep = (np.arange(20_000) % 3 == 0).astype(np.uint8)
+    errs = []
+    def work(k):
+        try:
+            pool = rows.Columnar()
+            for _ in range(6):
+                assert_same_batch(pool.rows_to_batch(img, threads=3).batch, batch.slice(0, 3000))
+                g, sel = pool.gather(batch, keep, 3)
+                assert g.nrows == int(keep.sum()) and (sel == np.nonzero(keep)[0]).all()
+            pool.close()
+        except BaseException as ex:   # noqa: BLE001
+            errs.append(ex)
+    ths = [threading.Thread(target=work, args=(k,)) for k in range(3)]
+    [t.start() for t in ths]; [t.join() for t in ths]
+    assert not errs, errs
