@@ -188,3 +188,19 @@ def test_device_csv_cases_and_errors(eng, po):
         assert consumed == rcons, text
         assert [(r, c) for r, c, _ in gerr] == [(r, c) for r, c, _ in rerr], (text, gerr, rerr)
         _assert_equal(got, ref)
+
+
+def test_malformed_row_is_a_row_level_error(po):
+    """pkg/providers/s3/reader/registry/csv/data_error_matrix_test.go:113-160 (TestCSVMalformedRow_DataPolicies): `1\\nnot_int\\n` into one int64
+    column gives row-level failures (`_unparsed` items under UnparsedPolicyContinue; Fail / Retry turn the same row error into a fatal /
+    retriable error of the whole read: the provider's policy, not the parser's). The reference test only asks for > 0 unparsed rows — and in
+    fact BOTH rows fail there: without a delimiter splitString takes line[lastDelimPosition+1:] = line[1:] for the only element
+    (pkg/csv/reader.go:262), so "1" reads as "" as well. With a second column the first row parses."""
+    sch1 = [{"name": "v", "type": "int64", "path": "0"}]
+    b, errs, lines, cons = po.csv_parse(b"1\nnot_int\n", sch1)
+    assert lines == 2 and b.nrows == 0 and cons == 10 and errs == [(0, 18, 0), (1, 18, 0)]          # TF_ROWERR_CSV_BAD_INT twice
+    b, errs, lines, cons = po.csv_parse(b"1,x\nnot_int,y\n", sch1 + [{"name": "s", "type": "utf8", "path": "1"}])
+    assert b.nrows == 1 and list(b.columns[0].values) == [1] and errs == [(1, 18, 0)]
+    # TestCSVEmptySample: an empty object yields no rows at all (the `_unparsed` item there is the reader's empty-sample marker)
+    b, errs, lines, cons = po.csv_parse(b"", sch1)
+    assert b.nrows == 0 and not errs and lines == 0 and cons == 0
