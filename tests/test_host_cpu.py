@@ -420,3 +420,27 @@ def test_replace_primary_key_plan_reference_cases(po):
     # a table filter that does not match leaves the schema alone
     d = engine.plan_validate("public", "t", sch(cases[0][0]), [{"replace_primary_key": {"keys": ["col2"], "tables": {"includeTables": ["^public.other$"]}}}])
     assert d["steps"] == [] and not any(c["key"] for c in d["result_schema"])
+
+
+def test_transformation_test_multiple_transformers(po):
+    """pkg/transformer/transformation_test.go:29-111 (TestMultipleTransformers): replace_primary_key [field2, field1] followed by
+    filter_columns [field2, field1, field4] over four key columns -> TableSchema {field2 key, field1 key, field4 not key}; the control item and
+    the insert both reach the sink (2 items). The item's values stay addressed by column NAME (the reference keeps ColumnNames / ColumnValues in
+    item order, ["test", 2, "{}"]): in the columnar result every output column carries its own input column (out_cols)."""
+    schema = [{"name": "field1", "type": "utf8", "key": True}, {"name": "field2", "type": "int64", "key": True},
+              {"name": "field3", "type": "double", "key": True}, {"name": "field4", "type": "utf8", "key": True}]
+    trs = [{"replace_primary_key": {"keys": ["field2", "field1"], "tables": {"includeTables": ["test_table"]}}},
+           {"filter_columns": {"tables": {"includeTables": ["test_table"]}, "columns": {"includeColumns": ["field2", "field1", "field4"]}}}]
+    d = engine.plan_validate("", "test_table", schema, trs)
+    o = po.build_plan("", "test_table", schema, trs)
+    want = [("field2", True), ("field1", True), ("field4", False)]
+    assert [(c["name"], c["key"]) for c in d["result_schema"]] == want == [(c["name"], bool(c.get("key"))) for c in o.result_schema]
+    assert d["out_cols"] == [1, 0, 3] == o.out_cols and [s["type"] for s in d["steps"]] == ["replace_primary_key", "filter_columns"]
+    # through Sinker.Push: the init_load_table item travels alone, then the row — 2 items at the sink, as the reference asserts
+    from transferia_b200 import rows, sink
+    from transferia_b200.rows import ChangeItem, go
+    s = sink.Sink()        # (the always-on middleware alone: the chain itself is checked above and on the device in tests/test_gpu_parity.py)
+    s.push(rows.RowsImage([ChangeItem(rows.KIND_INIT_TABLE_LOAD, 0), ChangeItem(rows.KIND_INSERT, 0, [go.string("test"), go.int64(2), go.float64(1.23), go.string("{}")])],
+                          [("", "test_table", schema)]))
+    assert [e["n_items"] for e in s.events] == [1, 1] and s.stats()["change_items_pushed"] == 2
+    s.close()
