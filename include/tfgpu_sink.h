@@ -115,6 +115,7 @@ typedef struct tf_item {
     uint64_t lsn;              /* ChangeItem.LSN */
     uint64_t commit_time;      /* ChangeItem.CommitTime, ns */
     uint64_t size_read;        /* ChangeItem.Size.Read */
+    uint64_t size_values;      /* ChangeItem.Size.Values (set by the Measurer, tfgpu_measure): what batchStats sums (sink_wrapper_util.go:24) */
     uint64_t values_off;       /* row kinds: offset of the ColumnValues image in tf_rows.values */
     uint64_t old_keys_off;     /* offset of the OldKeys image (u16 count, then {u16 column, value}*), or UINT64_MAX */
     uint32_t id;               /* ChangeItem.ID */
@@ -218,7 +219,7 @@ typedef struct tf_sink_stats {
     uint64_t downstream_pushes;      /* Push calls that reached the destination */
     uint64_t change_items_pushed;    /* WrapperStats.ChangeItemsPushed */
     uint64_t row_events_pushed;      /* WrapperStats.RowEventsPushed */
-    uint64_t inflight_bytes;         /* sum of Size.Read over the counted items (the shim fills Size.Values from tfgpu_measure) */
+    uint64_t inflight_bytes;         /* batchStats' bytes: sum of Size.Values over the counted items */
     uint64_t filter_dropped;         /* MiddlewareFilterStats.Dropped */
     uint64_t transform_dropped;      /* transformation stats Dropped: incoming - transformed */
     uint64_t transform_errors;       /* transformation stats Errors */

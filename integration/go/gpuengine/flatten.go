@@ -112,7 +112,7 @@ func (f *flattener) value(v any) {
 
 func (f *flattener) add(it *abstract.ChangeItem) {
 	var ci C.tf_item
-	ci.lsn, ci.commit_time, ci.size_read = C.uint64_t(it.LSN), C.uint64_t(it.CommitTime), C.uint64_t(it.Size.Read)
+	ci.lsn, ci.commit_time, ci.size_read, ci.size_values = C.uint64_t(it.LSN), C.uint64_t(it.CommitTime), C.uint64_t(it.Size.Read), C.uint64_t(it.Size.Values)
 	ci.id, ci.counter, ci.table = C.uint32_t(it.ID), C.int32_t(it.Counter), C.uint32_t(f.table(it))
 	if k, ok := kindCode[it.Kind]; ok {
 		ci.kind = k

@@ -27,12 +27,12 @@ def _items(spec):
         vals = None
         if kind <= 2:
             vals = {0: [go.int32(i), go.string(f"v{i}")], 1: [go.int64(i)], 2: [go.int64(i)], 3: [go.int32(i), go.string("z"), go.int8(1)]}[t]
-        out.append(ChangeItem(kind, t, vals, id=i, lsn=1000 + i, commit_time=0 if i % 7 == 3 else 5_000 + 13 * ((i * 7) % 11), size_read=10 + i))
+        out.append(ChangeItem(kind, t, vals, id=i, lsn=1000 + i, commit_time=0 if i % 7 == 3 else 5_000 + 13 * ((i * 7) % 11), size_read=1, size_values=10 + i))
     return out
 
 
 def _oracle_items(items):
-    return [{"kind": it.kind, "table": it.table, "index": i, "commit_time": it.commit_time, "size": it.size_read} for i, it in enumerate(items)]
+    return [{"kind": it.kind, "table": it.table, "index": i, "commit_time": it.commit_time, "size": it.size_values} for i, it in enumerate(items)]
 
 
 def _zero_stats():
@@ -330,7 +330,7 @@ def test_host_level_transformer_fuzz_against_the_oracle():
         items = []
         for i, (kind, t) in enumerate(spec):
             vals = [go.int32(i), go.nil if i % 9 == 0 else go.string(["p", "q", "r"][int(rng.integers(0, 3))])] if kind <= 2 else None
-            items.append(ChangeItem(kind, t, vals, commit_time=100 + i, size_read=1))
+            items.append(ChangeItem(kind, t, vals, commit_time=100 + i, size_values=1))
         s.events.clear()
         s.push(rows.RowsImage(items, tables))
         # expected: tables in order of first appearance; per table the item sequence with delete / truncate of `a` gone; maximal row runs; every
@@ -363,4 +363,18 @@ def test_host_level_transformer_fuzz_against_the_oracle():
         assert got == want, (rnd, spec)
     st = s.stats()
     assert st["filter_dropped"] > 0 and st["transform_dropped"] > 0 and st["change_items_pushed"] == st["metering_output_rows"]
+    s.close()
+
+
+def test_batch_stats_reference_case():
+    """pkg/stats/sink_wrapper_util_test.go:18-28 (TestBatchStats, default case): two inserts with CommitTime 19 and 99 and Size.Values 1 and 2 ->
+    `oldestTime` 99 (sic: the latest), `freshestTime` 19, 2 row events, 3 bytes. A Synchronize item counts for the times but not as a row event."""
+    s = sink.Sink()
+    s.push(rows.RowsImage([ChangeItem(K.KIND_INSERT, 0, [go.int32(1), go.string("a")], commit_time=19, size_read=1, size_values=1),
+                           ChangeItem(K.KIND_INSERT, 0, [go.int32(2), go.string("b")], commit_time=99, size_read=1, size_values=2)], TABLES))
+    st = s.stats()
+    assert (st["max_commit_time"], st["min_commit_time"], st["row_events_pushed"], st["inflight_bytes"]) == (99, 19, 2, 3)
+    s.push(rows.RowsImage([ChangeItem(K.KIND_SYNCHRONIZE, 0, None, commit_time=0)], TABLES))
+    st = s.stats()
+    assert st["row_events_pushed"] == 2 and st["without_commit_time"] == 1 and st["change_items_pushed"] == 3 and st["inflight_bytes"] == 3
     s.close()

@@ -191,7 +191,7 @@ struct tfgpu_sink {
         if (ev.item_idx) for (uint64_t k = 0; k < ev.n_items; k++) {
             const tf_item& it = rows->items[ev.item_idx[k]];
             if (!(TF_KIND_IS_ROW(it.kind) || it.kind == TF_KIND_SYNCHRONIZE)) continue;              // batchStats :16-18
-            st.inflight_bytes += it.size_read;
+            st.inflight_bytes += it.size_values;
             if (!it.commit_time) { st.without_commit_time++; continue; }
             if (!st.max_commit_time || it.commit_time > st.max_commit_time) st.max_commit_time = it.commit_time;
             if (!st.min_commit_time || it.commit_time < st.min_commit_time) st.min_commit_time = it.commit_time;

@@ -64,7 +64,7 @@ class ChangeItem:
     table: int = 0                                   # index into the tables list (Schema, Table, TableSchema)
     values: Optional[Sequence] = None                # ColumnValues as Go-typed pairs, schema order (or {column index: value} when sparse)
     old_keys: Optional[Dict[int, Any]] = None        # OldKeys: {column index: value}
-    id: int = 0; lsn: int = 0; commit_time: int = 0; counter: int = 0; size_read: int = 0
+    id: int = 0; lsn: int = 0; commit_time: int = 0; counter: int = 0; size_read: int = 0; size_values: int = 0
     txid: bytes = b""; part_id: bytes = b""
 
 
@@ -73,7 +73,7 @@ class TfTable(C.Structure):
 
 
 class TfItem(C.Structure):
-    _fields_ = [("lsn", C.c_uint64), ("commit_time", C.c_uint64), ("size_read", C.c_uint64), ("values_off", C.c_uint64), ("old_keys_off", C.c_uint64),
+    _fields_ = [("lsn", C.c_uint64), ("commit_time", C.c_uint64), ("size_read", C.c_uint64), ("size_values", C.c_uint64), ("values_off", C.c_uint64), ("old_keys_off", C.c_uint64),
                 ("id", C.c_uint32), ("table", C.c_uint32), ("n_values", C.c_uint32), ("txid_off", C.c_uint32), ("txid_len", C.c_uint32),
                 ("part_off", C.c_uint32), ("part_len", C.c_uint32), ("counter", C.c_int32), ("kind", C.c_uint8), ("flags", C.c_uint8), ("pad", C.c_uint8 * 2)]
 
@@ -95,7 +95,7 @@ class RowsImage:
         arr = (TfItem * max(1, len(items)))()
         for i, it in enumerate(items):
             a = arr[i]
-            a.lsn, a.commit_time, a.size_read, a.id, a.table, a.counter, a.kind = it.lsn, it.commit_time, it.size_read, it.id, it.table, it.counter, it.kind
+            a.lsn, a.commit_time, a.size_read, a.size_values, a.id, a.table, a.counter, a.kind = it.lsn, it.commit_time, it.size_read, it.size_values, it.id, it.table, it.counter, it.kind
             a.txid_off, a.txid_len = len(strs), len(it.txid); strs += it.txid
             a.part_off, a.part_len = len(strs), len(it.part_id); strs += it.part_id
             a.values_off = len(vals); a.flags = 0; a.n_values = 0
