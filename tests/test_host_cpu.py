@@ -444,3 +444,18 @@ def test_transformation_test_multiple_transformers(po):
                           [("", "test_table", schema)]))
     assert [e["n_items"] for e in s.events] == [1, 1] and s.stats()["change_items_pushed"] == 2
     s.close()
+
+
+def test_headers_are_plain_c(tmp_path):
+    """The boundary is a C ABI: both headers compile as C99 (`gcc -std=c99 -pedantic`), and the struct sizes the Python binding assumes are the
+    ones the C compiler lays out."""
+    from transferia_b200 import rows, sink
+    src = tmp_path / "hdr.c"
+    src.write_text('#include <stdio.h>\n#include "tfgpu.h"\n#include "tfgpu_sink.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(tf_col), sizeof(tf_batch), sizeof(tf_item), sizeof(tf_rows), sizeof(tf_table),'
+                   ' sizeof(tf_sink_event), sizeof(tf_sink_stats)); return 0; }\n')
+    exe = tmp_path / "hdr"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [C.sizeof(abi.TfCol), C.sizeof(abi.TfBatch), C.sizeof(rows.TfItem), C.sizeof(rows.TfRows), C.sizeof(rows.TfTable), C.sizeof(sink.TfSinkEvent), C.sizeof(sink.TfSinkStats)]
+    assert got == want, (got, want)
