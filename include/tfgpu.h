@@ -254,7 +254,8 @@ uint64_t tfgpu_engine_h2d_bytes(const tfgpu_engine* e);
  *                     refused by the call (TF_E_FATAL_UNSUPPORTED): the table stays on the Go emitter.
  * A value EmitKV fails on (date / interval without a pg type, `any` arrays / scalars, NaN, years outside [0,9999], a non-string in a
  * pg string type) is reported as TF_ROWERR_SER_VALUE (term = output column) and the shim fails the batch like Serialize does.
- * UPDATE / DELETE rows need OldKeys, which tf_batch does not carry: TF_ROWERR_DBZ_EMIT_HOST, emitted by the shim in Go.
+ * UPDATE / DELETE rows need ChangeItem.OldKeys: tfgpu_emit_debezium_crud (below) takes them as a second typed batch and emits every row kind;
+ * this INSERT-only entry point is the same call with old == NULL.
  * opts_json: {"ignore_unknown_sources":bool, "snapshot":bool, "drop_keys":bool, "source_type":""|"pg"|"mysql", "version":"..",
  *   "topic_prefix":"..", "database":"..", "key_schema":"<json>"|null, "val_schema":"<json>"|null (what
  *   Emitter.ToKafkaSchemaKey/Val return for the plan's result schema; the lightning cache computes them once per table,
