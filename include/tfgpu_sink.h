@@ -37,7 +37,8 @@ typedef struct tfgpu_ch_conn tfgpu_ch_conn;
  * DBMS_TCP_PROTOCOL_VERSION) and negotiates min(54460, server revision) like the driver.
  * opts_json: {"database":"default","user":"default","password":"","client_name":"transferia-tfgpu","compression":true,
  *             "read_timeout_ms":300000}   (conn/connection.go:38-51: LZ4 compression, 5 min read timeout).
- * The fd stays owned by the caller; tfgpu_ch_close only frees the handle. */
+ * The fd stays owned by the caller; tfgpu_ch_close only frees the handle. When the call fails *out still holds a handle (tfgpu_ch_last_error /
+ * tfgpu_ch_exception_code say why): close it. */
 int tfgpu_ch_open(int fd, const char* opts_json, tfgpu_ch_conn** out);
 int tfgpu_ch_close(tfgpu_ch_conn* c);
 const char* tfgpu_ch_last_error(const tfgpu_ch_conn* c);
@@ -106,7 +107,7 @@ int64_t tfgpu_ch_insert_query(const char* database, const char* table, const cha
 typedef struct tf_table {
     const char* schema;        /* ChangeItem.Schema (namespace) */
     const char* table;         /* ChangeItem.Table */
-    const char* schema_json;   /* TableSchema.Columns() with the ColSchema JSON tags (col_schema.go:14-29) */
+    const char* schema_json;   /* TableSchema.Columns() with the ColSchema JSON tags (col_schema.go:14-29); NULL for items without a schema (DDL, drop) */
 } tf_table;
 
 /* ChangeItem (change_item.go:27-78) without its values. */

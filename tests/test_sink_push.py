@@ -378,3 +378,18 @@ def test_batch_stats_reference_case():
     st = s.stats()
     assert st["row_events_pushed"] == 2 and st["without_commit_time"] == 1 and st["change_items_pushed"] == 3 and st["inflight_bytes"] == 3
     s.close()
+
+
+def test_control_items_without_a_table_schema():
+    """DDL / drop_table items may carry no TableSchema: they travel alone like every non-row item, renamed by rename_tables; table_splitter
+    has no columns to read there and leaves the name alone."""
+    trs = [{"rename_tables": {"renameTables": [{"originalName": {"nameSpace": "public", "name": "ghost"}, "newName": {"nameSpace": "x", "name": "ghost2"}}]}},
+           {"table_splitter": {"columns": ["id"], "splitter": "_"}}]
+    for t in (None, trs):
+        s = sink.Sink(transformers=t)
+        s.push(rows.RowsImage([ChangeItem(K.KIND_DDL, 1), ChangeItem(K.KIND_INSERT, 0, [go.int32(1), go.string("a")]), ChangeItem(K.KIND_DROP_TABLE, 1)],
+                              [("public", "a", SCHEMA_A), ("public", "ghost", None)]))
+        # tables in order of first appearance: `ghost` (item 0) before `a`
+        assert [(e["type"], e["items"]) for e in s.events] == [(sink.EV_ITEM, [0]), (sink.EV_ITEM, [2]), (sink.EV_ROWS, [1])]
+        assert [e["out"] for e in s.events] == ([("public", "ghost")] * 2 + [("public", "a")] if t is None else [("x", "ghost2")] * 2 + [("public", "a_1")])
+        s.close()

@@ -317,7 +317,10 @@ struct tfgpu_sink {
                     run.push_back(i); continue;
                 }
                 std::string ns, name;
-                if (!host_chain(t.schema ? t.schema : "", t.table ? t.table : "", it.kind, ns, name, &plan_for(t))) { st.transform_dropped++; continue; }   // the run is NOT cut: the item is gone before NonRowSeparator sees it
+                // DDL / drop / truncate items may come without a TableSchema: only table_splitter looks at it (which columns it knows)
+                const TablePlan* tpp = nullptr;
+                if (t.schema_json && t.schema_json[0] && std::strcmp(t.schema_json, "[]") != 0) for (const HostStep& h : host_steps) if (h.type == 3) { tpp = &plan_for(t); break; }
+                if (!host_chain(t.schema ? t.schema : "", t.table ? t.table : "", it.kind, ns, name, tpp)) { st.transform_dropped++; continue; }   // the run is NOT cut: the item is gone before NonRowSeparator sees it
                 flush();                                                                                  // nonrow_separator.go:38-47
                 if (exclude_sys && system_tables.count(name)) { st.filter_dropped++; continue; }
                 tf_sink_event ev{}; ev.type = TF_SINK_EV_ITEM; ev.table = it.table; ev.out_schema = ns.c_str(); ev.out_table = name.c_str();

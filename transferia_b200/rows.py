@@ -119,7 +119,7 @@ class RowsImage:
         self._tabs = (TfTable * max(1, len(tables)))()
         self._keep = []
         for k, (ns, name, schema) in enumerate(tables):
-            sj = (json.dumps([{k: v for k, v in c.items() if not k.startswith("_")} for c in schema]).encode() if not isinstance(schema, (bytes, str))
+            sj = (None if schema is None else json.dumps([{k: v for k, v in c.items() if not k.startswith("_")} for c in schema]).encode() if not isinstance(schema, (bytes, str))
                   else (schema.encode() if isinstance(schema, str) else schema))
             self._keep.append((ns.encode(), name.encode(), sj))
             self._tabs[k].schema, self._tabs[k].table, self._tabs[k].schema_json = self._keep[-1]
