@@ -104,6 +104,23 @@ def test_two_inserts_on_one_connection_and_quiet_server(po):
     w.close(); cli.close()
 
 
+def test_uncompressed_connection_sends_the_raw_block(po):
+    """compression off (clickhouse_go.Options.Compression nil): the Query packet says so, the Data packet body is the native block itself
+    (TF_WIRE_CH_NATIVE) and the server's sample block comes back uncompressed too."""
+    batch, schema, trs, plan = _headline(po, 800)
+    ref = po.push_encode(batch, plan, abi.TF_WIRE_CH_NATIVE)
+    cli, srv = _pair()
+    peer = ch_peer.Peer(srv, [("a", "Int64"), ("b", "Nullable(String)")], expect_raw_len=[len(ref.raw)]); peer.start()
+    w = sink.ClickHouseWriter(cli, compression=False, read_timeout_ms=20000)
+    assert w.prepare_batch("INSERT INTO `d`.`t` (`a`,`b`) VALUES") == [{"name": "a", "type": "Int64"}, {"name": "b", "type": "Nullable(String)"}]
+    w.append_frames(ref.raw)
+    assert w.send() == (1234, 12340)
+    peer.join(20)
+    assert peer.error is None, peer.error
+    assert peer.queries[0]["compression"] == 0 and peer.blocks[0] == [ref.raw]
+    w.close(); cli.close()
+
+
 def test_server_exception_and_auth_failure():
     cli, srv = _pair()
     peer = ch_peer.Peer(srv, [("a", "String")], fail_hello=True); peer.start()
