@@ -239,6 +239,21 @@ int tfgpu_sink_set_clickhouse(tfgpu_sink* s, tfgpu_ch_conn* conn);
 int tfgpu_sink_push(tfgpu_sink* s, const tf_rows* items);
 int tfgpu_sink_stats(const tfgpu_sink* s, tf_sink_stats* out);
 
+/* ------------------------------------------------------------------ N pipelines in one process */
+/* Batches dealt round-robin over N sinks (one engine per GPU behind each, created by the caller): every sink's pushes run on a host thread of
+ * its own, so the transposes, copies and kernels of consecutive batches overlap across GPUs — there is no collective, rows are independent.
+ * What the reference guarantees is the order of a table's rows (transformation.go:131-141 keeps per-table order, not cross-table order): the
+ * DELIVERIES of batch k (callback events, ClickHouse INSERTs) start only when every delivery of batch k - 1 has finished, whichever GPU worked
+ * on it; the device work of batch k's first run is done by then. tfgpu_dispatcher_submit returns at once (at most two batches queue per sink,
+ * like the bufferer's one flush in flight + one collecting, bufferer.go:225-242); `items` and everything it points to must stay valid until
+ * tfgpu_dispatcher_wait(seq) returned. The sinks must not be pushed to directly while they belong to a dispatcher. */
+typedef struct tfgpu_dispatcher tfgpu_dispatcher;
+int tfgpu_dispatcher_create(tfgpu_sink* const* sinks, int n, tfgpu_dispatcher** out);
+int tfgpu_dispatcher_submit(tfgpu_dispatcher* d, const tf_rows* items, uint64_t* seq);
+int tfgpu_dispatcher_wait(tfgpu_dispatcher* d, uint64_t seq);       /* the return code of that batch's tfgpu_sink_push */
+int tfgpu_dispatcher_drain(tfgpu_dispatcher* d);                    /* waits for everything submitted; the first non-zero code, else 0 */
+int tfgpu_dispatcher_destroy(tfgpu_dispatcher* d);                  /* drains, stops the threads; the sinks stay the caller's */
+
 /* Host CityHash128 (v1.0.2) as the frames' checksum uses it — exported for the tests' cross-checks against the device and the oracle. */
 void tfgpu_host_cityhash128(const uint8_t* p, uint64_t n, uint64_t out[2]);
 

@@ -393,3 +393,43 @@ def test_control_items_without_a_table_schema():
         assert [(e["type"], e["items"]) for e in s.events] == [(sink.EV_ITEM, [0]), (sink.EV_ITEM, [2]), (sink.EV_ROWS, [1])]
         assert [e["out"] for e in s.events] == ([("public", "ghost")] * 2 + [("public", "a")] if t is None else [("x", "ghost2")] * 2 + [("public", "a_1")])
         s.close()
+
+
+def test_dispatcher_delivers_in_submission_order():
+    """tfgpu_dispatcher over three sinks: batches are dealt round-robin and worked on concurrently, but what reaches the destination arrives batch
+    by batch in submission order, whichever sink finished first (slow and fast destinations mixed); a failing Push surfaces on its own batch."""
+    import threading, time
+    log, lock = [], threading.Lock()
+    def downstream(k):
+        def f(ev):
+            time.sleep(0.004 * ((ev["items"][0] * 7 + k) % 3))      # uneven destinations
+            with lock:
+                log.append((k, ev["type"], tuple(ev["columns"][0]) if ev.get("columns") else None))
+            return 9 if (ev.get("columns") and 404 in list(ev["columns"][0])) else 0
+        return f
+    sinks = [sink.Sink(downstream=downstream(k)) for k in range(3)]
+    d = sink.Dispatcher(sinks)
+    images, seqs = [], []
+    for b in range(14):
+        ids = [404] if b == 9 else list(range(b * 10, b * 10 + 3 + b % 4))
+        its = [ChangeItem(K.KIND_INSERT, 0, [go.int32(i), go.string("x")]) for i in ids] + ([ChangeItem(K.KIND_DDL, 0)] if b % 5 == 2 else [])
+        img = rows.RowsImage(its, TABLES); images.append((ids, b % 5 == 2)); seqs.append(d.submit(img))
+    assert seqs == list(range(14))
+    failed = []
+    for s_ in seqs:
+        try:
+            d.wait(s_)
+        except engine.EngineError as ex:
+            failed.append((s_, ex.rc))
+    assert failed == [(9, 9)]
+    want = []
+    for b, (ids, ddl) in enumerate(images):
+        want.append((b % 3, sink.EV_ROWS, tuple(ids)))
+        if ddl: want.append((b % 3, sink.EV_ITEM, None))
+    assert log == want
+    assert d.drain() == 9 and d.drain() == 0
+    assert sum(s_.stats()["row_events_pushed"] for s_ in sinks) == sum(len(i) for i, _ in images) - 1      # the failed Push is not counted
+    d.close()
+    for s_ in sinks:
+        s_.push(rows.RowsImage([ChangeItem(K.KIND_INSERT, 0, [go.int32(1), go.string("y")])], TABLES))      # usable on their own again
+        s_.close()

@@ -13,6 +13,11 @@
 #include "plan.hpp"
 #include "row_image.hpp"
 #include <charconv>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <thread>
 
 namespace {
 
@@ -116,6 +121,8 @@ struct tfgpu_sink {
     tfgpu_columnar* pool = nullptr;
     std::map<std::string, TablePlan> plans;
     tf_sink_stats st{};
+    // delivery gate (tfgpu_dispatcher): entered before the first downstream delivery of a push, left when the push is over
+    void (*gate_enter)(void*) = nullptr; void (*gate_leave)(void*) = nullptr; void* gate_ctx = nullptr; bool in_gate = false;
 
     TablePlan& plan_for(const tf_table& t) {
         std::string key = std::string(t.schema ? t.schema : "") + '\0' + (t.table ? t.table : "") + '\0' + (t.schema_json ? t.schema_json : "");
@@ -176,6 +183,7 @@ struct tfgpu_sink {
 
     int deliver(const tf_sink_event& ev, const tf_rows* rows, TablePlan* tp) {
         int rc = 0;
+        if (gate_enter && !in_gate) { gate_enter(gate_ctx); in_gate = true; }
         if (ev.type == TF_SINK_EV_ROWS && ch && ev.wire) {
             rc = tfgpu_ch_insert_begin(ch, insert_for(*tp, ev.out_table).c_str(), "", nullptr);
             if (!rc) rc = tfgpu_ch_insert_data(ch, ev.wire, ev.wire_len);
@@ -418,6 +426,7 @@ int tfgpu_sink_set_clickhouse(tfgpu_sink* s, tfgpu_ch_conn* conn) {
 
 int tfgpu_sink_push(tfgpu_sink* s, const tf_rows* items) {
     if (!s || !items) return TF_E_FATAL_ARG;
+    struct Leave { tfgpu_sink* s; ~Leave() { if (s->gate_enter && !s->in_gate) s->gate_enter(s->gate_ctx); if (s->gate_leave) s->gate_leave(s->gate_ctx); s->in_gate = false; } } leave{s};   // a push without deliveries still takes its turn
     try { s->push(items); s->st.metering_input_rows += items->n_items; return TF_OK; }
     catch (const SinkFail& f) { s->err = f.msg; return f.rc; }
     catch (const std::bad_alloc&) { s->err = "host allocation failed"; return TF_E_RETRY_OOM; }
@@ -425,5 +434,96 @@ int tfgpu_sink_push(tfgpu_sink* s, const tf_rows* items) {
 }
 
 int tfgpu_sink_stats(const tfgpu_sink* s, tf_sink_stats* out) { if (!s || !out) return TF_E_FATAL_ARG; *out = s->st; return TF_OK; }
+
+}  // extern "C"
+
+
+// ------------------------------------------------------------------ round-robin dispatcher over N sinks
+struct tfgpu_dispatcher {
+    struct Job { uint64_t seq; const tf_rows* items; };
+    struct Lane { tfgpu_sink* sink; std::deque<Job> q; std::thread th; uint64_t cur_seq = 0; tfgpu_dispatcher* d = nullptr; };
+    std::vector<std::unique_ptr<Lane>> lanes;
+    std::mutex m; std::condition_variable cv;
+    uint64_t submitted = 0, deliver_turn = 0;               // deliver_turn: the batch whose deliveries may run
+    std::map<uint64_t, int> done;                            // seq -> rc of finished batches not yet waited for
+    bool stop = false; int first_error = 0;
+
+    static void enter(void* ctx) { Lane* l = (Lane*)ctx; std::unique_lock<std::mutex> lk(l->d->m); l->d->cv.wait(lk, [&] { return l->d->deliver_turn == l->cur_seq; }); }
+    static void leave(void* ctx) { Lane* l = (Lane*)ctx; { std::lock_guard<std::mutex> g(l->d->m); l->d->deliver_turn = l->cur_seq + 1; } l->d->cv.notify_all(); }
+
+    void loop(Lane* l) {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [&] { return stop || !l->q.empty(); });
+                if (l->q.empty()) return;
+                j = l->q.front(); l->cur_seq = j.seq;
+            }
+            const int rc = tfgpu_sink_push(l->sink, j.items);      // its deliveries wait for their turn inside (gate), and pass it on when the push is over
+            {
+                std::lock_guard<std::mutex> g(m);
+                l->q.pop_front(); done[j.seq] = rc; if (rc && !first_error) first_error = rc;
+            }
+            cv.notify_all();
+        }
+    }
+    std::set<uint64_t> waited;
+};
+
+extern "C" {
+
+int tfgpu_dispatcher_create(tfgpu_sink* const* sinks, int n, tfgpu_dispatcher** out) {
+    if (!sinks || n <= 0 || !out) return TF_E_FATAL_ARG;
+    auto d = std::make_unique<tfgpu_dispatcher>();
+    for (int i = 0; i < n; i++) {
+        if (!sinks[i] || sinks[i]->gate_enter) return TF_E_FATAL_ARG;
+        auto l = std::make_unique<tfgpu_dispatcher::Lane>(); l->sink = sinks[i]; l->d = d.get();
+        d->lanes.push_back(std::move(l));
+    }
+    for (auto& l : d->lanes) { l->sink->gate_enter = &tfgpu_dispatcher::enter; l->sink->gate_leave = &tfgpu_dispatcher::leave; l->sink->gate_ctx = l.get(); tfgpu_dispatcher* dp = d.get(); tfgpu_dispatcher::Lane* lp = l.get(); l->th = std::thread([dp, lp] { dp->loop(lp); }); }
+    *out = d.release();
+    return TF_OK;
+}
+
+int tfgpu_dispatcher_submit(tfgpu_dispatcher* d, const tf_rows* items, uint64_t* seq) {
+    if (!d || !items) return TF_E_FATAL_ARG;
+    std::unique_lock<std::mutex> lk(d->m);
+    const uint64_t s = d->submitted; tfgpu_dispatcher::Lane* l = d->lanes[s % d->lanes.size()].get();
+    d->cv.wait(lk, [&] { return l->q.size() < 2; });                  // one batch in work + one waiting per sink
+    l->q.push_back({s, items}); d->submitted++;
+    if (seq) *seq = s;
+    lk.unlock(); d->cv.notify_all();
+    return TF_OK;
+}
+
+int tfgpu_dispatcher_wait(tfgpu_dispatcher* d, uint64_t seq) {
+    if (!d) return TF_E_FATAL_ARG;
+    std::unique_lock<std::mutex> lk(d->m);
+    if (seq >= d->submitted) return TF_E_FATAL_ARG;
+    d->cv.wait(lk, [&] { return d->done.count(seq) || d->waited.count(seq); });
+    if (d->waited.count(seq)) return TF_E_FATAL_ARG;                  // waited for twice
+    const int rc = d->done[seq]; d->done.erase(seq); d->waited.insert(seq);
+    while (!d->waited.empty() && *d->waited.begin() + 1024 < seq) d->waited.erase(d->waited.begin());      // bounded memory on long runs
+    return rc;
+}
+
+int tfgpu_dispatcher_drain(tfgpu_dispatcher* d) {
+    if (!d) return TF_E_FATAL_ARG;
+    std::unique_lock<std::mutex> lk(d->m);
+    d->cv.wait(lk, [&] { for (auto& l : d->lanes) if (!l->q.empty()) return false; return true; });
+    const int rc = d->first_error; d->first_error = 0;
+    return rc;
+}
+
+int tfgpu_dispatcher_destroy(tfgpu_dispatcher* d) {
+    if (!d) return TF_E_FATAL_ARG;
+    tfgpu_dispatcher_drain(d);
+    { std::lock_guard<std::mutex> g(d->m); d->stop = true; }
+    d->cv.notify_all();
+    for (auto& l : d->lanes) { if (l->th.joinable()) l->th.join(); l->sink->gate_enter = nullptr; l->sink->gate_leave = nullptr; l->sink->gate_ctx = nullptr; }
+    delete d;
+    return TF_OK;
+}
 
 }  // extern "C"

@@ -121,7 +121,8 @@ class ClickHouseWriter:
 
 # ------------------------------------------------------------------ Sinker.Push as one call (tfgpu_sink_*)
 SINK_SYMBOLS += ["tfgpu_sink_create", "tfgpu_sink_destroy", "tfgpu_sink_last_error", "tfgpu_sink_set_callback", "tfgpu_sink_set_clickhouse",
-                 "tfgpu_sink_push", "tfgpu_sink_stats"]
+                 "tfgpu_sink_push", "tfgpu_sink_stats",
+                 "tfgpu_dispatcher_create", "tfgpu_dispatcher_submit", "tfgpu_dispatcher_wait", "tfgpu_dispatcher_drain", "tfgpu_dispatcher_destroy"]
 EV_ROWS, EV_ITEM, EV_ERRORS = 1, 2, 3
 
 
@@ -205,3 +206,44 @@ class Sink:
     def close(self):
         if self._h:
             self._L.tfgpu_sink_destroy(self._h); self._h = None
+
+
+class Dispatcher:
+    """tfgpu_dispatcher: batches dealt round-robin over N sinks (one engine per GPU behind each), every sink on a host thread of its own,
+    deliveries in submission order. submit() returns a sequence number; wait(seq) the outcome of that batch's push."""
+
+    def __init__(self, sinks):
+        self._L = lib(); vp = C.c_void_p
+        self._L.tfgpu_dispatcher_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(vp)]
+        self._L.tfgpu_dispatcher_submit.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
+        self._L.tfgpu_dispatcher_wait.argtypes = [vp, C.c_uint64]
+        self._L.tfgpu_dispatcher_drain.argtypes = [vp]
+        self._L.tfgpu_dispatcher_destroy.argtypes = [vp]
+        self.sinks = list(sinks)
+        arr = (vp * len(self.sinks))(*[s._h for s in self.sinks])
+        self._h = vp(); self._keep = {}
+        rc = self._L.tfgpu_dispatcher_create(arr, len(self.sinks), C.byref(self._h))
+        if rc:
+            raise engine.EngineError(rc, "tfgpu_dispatcher_create")
+
+    def submit(self, rows_image) -> int:
+        seq = C.c_uint64()
+        rc = self._L.tfgpu_dispatcher_submit(self._h, C.byref(rows_image.struct), C.byref(seq))
+        if rc:
+            raise engine.EngineError(rc, "tfgpu_dispatcher_submit")
+        self._keep[int(seq.value)] = rows_image                 # the image must outlive the push
+        return int(seq.value)
+
+    def wait(self, seq: int) -> None:
+        rc = self._L.tfgpu_dispatcher_wait(self._h, seq)
+        self._keep.pop(seq, None)
+        if rc:
+            s = self.sinks[seq % len(self.sinks)]
+            raise engine.EngineError(rc, s._L.tfgpu_sink_last_error(s._h).decode(errors="replace"))
+
+    def drain(self) -> int:
+        return int(self._L.tfgpu_dispatcher_drain(self._h))
+
+    def close(self):
+        if self._h:
+            self._L.tfgpu_dispatcher_destroy(self._h); self._h = None; self._keep.clear()
