@@ -433,3 +433,29 @@ def test_dispatcher_delivers_in_submission_order():
     for s_ in sinks:
         s_.push(rows.RowsImage([ChangeItem(K.KIND_INSERT, 0, [go.int32(1), go.string("y")])], TABLES))      # usable on their own again
         s_.close()
+
+
+def test_table_splitter_float_and_time_text_fuzz():
+    """The host's SerializeToString of float32 / float64 (fmt %v = strconv 'g' with the shortest digits: exponent form below 1e-4 and from
+    1e+06 on), int64 extremes, dates and timestamps with nanoseconds, against the oracle's restatement (numpy's shortest repr + Go's layout
+    rules): two implementations that share no code."""
+    rng = np.random.default_rng(33)
+    f64 = np.concatenate([rng.standard_normal(150) * 10.0 ** rng.integers(-12, 25, 150), [0.0, -0.0, 1e5, 1e6, 999999.0, 123456.7, 1e-4, 1e-5, 0.000123, 1e21, 1e22, 5e-324, 1.7976931348623157e308, 100.0, 2.5]])
+    f32 = np.concatenate([(rng.standard_normal(150) * 10.0 ** rng.integers(-8, 20, 150)).astype(np.float32), np.array([2.71828, 16777216.0, 1e6, 999999.0, 1e-5, 0.1, 3.4028235e38], np.float32)])
+    secs = np.concatenate([rng.integers(-10**9, 4 * 10**9, 60), [0, -1, 86399, 951782400, 1709164800]])
+    schema = [{"name": "d", "type": "double"}, {"name": "f", "type": "float"}, {"name": "i", "type": "int64"}, {"name": "day", "type": "date"}, {"name": "ts", "type": "timestamp"}]
+    types = {c["name"]: c["type"] for c in schema}
+    items = []
+    for k in range(max(len(f64), len(f32))):
+        items.append(ChangeItem(K.KIND_INSERT, 0, [go.float64(f64[k % len(f64)]), go.float32(f32[k % len(f32)]), go.int64([-2**63, 2**63 - 1, 0, -7][k % 4]),
+                                                   go.time(int(secs[k % len(secs)])), go.time(int(secs[(k * 7) % len(secs)]), [0, 5, 500_000_000, 123_456_789][k % 4])]))
+    for cols in (["d"], ["f"], ["i", "day"], ["ts"]):
+        s = sink.Sink(transformers=[{"table_splitter": {"columns": cols, "splitter": "|"}}])
+        s.push(rows.RowsImage(items, [("", "t", schema)]))
+        got = {}
+        for e in s.events:
+            for i in e["items"]: got[i] = e["out"][1]
+        for i, it in enumerate(items):
+            want = mo.generate_table_name("t", cols, "|", dict(zip([c["name"] for c in schema], it.values)), types)
+            assert got[i] == want, (cols, it.values, got[i], want)
+        s.close()
