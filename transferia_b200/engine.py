@@ -477,9 +477,9 @@ class Engine:
         return {"rows_out": a.value, "raw_bytes": b.value, "wire_bytes": c.value, "n_errors": d.value}
 
     def resident_fetch(self, what: int, nbytes: int) -> bytes:
-        buf = (C.c_uint8 * max(1, nbytes))()
+        buf = C.create_string_buffer(max(1, nbytes))           # (a c_uint8 array would come back as a list of ints when sliced)
         self._check(self._L.tfgpu_resident_fetch(self._h, what, buf, nbytes))
-        return bytes(buf[:nbytes])
+        return C.string_at(buf, nbytes)
 
     def profile_enable(self, on: bool = True):
         self._check(self._L.tfgpu_profile_enable(self._h, 1 if on else 0))
