@@ -596,6 +596,9 @@ int tfgpu_engine_destroy(tfgpu_engine* e) {
     if (e->d_cols) cudaFree(e->d_cols);
     if (e->d_call_slots) { cudaFree(e->d_call_slots); cudaFree(e->d_regions); }
     if (e->pinned) cudaFreeHost(e->pinned);
+    if (e->sel_host) cudaFreeHost(e->sel_host);
+    if (e->gather_pool) tfgpu_columnar_destroy(e->gather_pool);
+    e->sel_stage.release(); e->err_list.release();
     for (auto ev : e->prof_ev) cudaEventDestroy(ev);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
