@@ -367,13 +367,19 @@ def bind_to_gpu_numa_node(local):
     """One process per GPU, bound to the CPUs of the NUMA node the GPU hangs off (its pinned host buffers are then allocated there and the
     DMA does not cross the socket interconnect). Returns the node, or None when the topology cannot be read."""
     try:
-        import pynvml
-        pynvml.nvmlInit()
-        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
-        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
-        if len(bus.split(":")[0]) == 8:
-            bus = bus[4:]                                   # sysfs uses a 4-digit PCI domain
-        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        node = None
+        try:                                                    # the CUDA device of this rank (honours CUDA_VISIBLE_DEVICES, unlike an NVML index)
+            import torch
+            pr = torch.cuda.get_device_properties(local)
+            node = int(open("/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)).read())
+        except Exception:
+            import pynvml
+            pynvml.nvmlInit()
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+            bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+            if len(bus.split(":")[0]) == 8:
+                bus = bus[4:]                                   # sysfs uses a 4-digit PCI domain
+            node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
         if node < 0:
             return None
         cpus = []
