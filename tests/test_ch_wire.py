@@ -178,3 +178,55 @@ def test_device_frames_reach_the_peer_full_size(eng, po):
     raw, nframes = po.ch_decode_frames(peer.blocks[0][0])
     assert raw == ref.raw and nframes == res.n_frames
     w.close(); cli.close()
+
+
+def test_client_survives_garbage_from_the_server():
+    """Whatever bytes a broken or hostile peer sends (random data, truncated packets, absurd lengths, a frame whose checksum or LZ4 body is wrong),
+    the client answers with an error code — never a crash, never a hang past its read timeout."""
+    rng = np.random.default_rng(99)
+    hello_ok = (ch_peer.uvarint(0) + ch_peer.string("ClickHouse") + ch_peer.uvarint(24) + ch_peer.uvarint(3) + ch_peer.uvarint(54467) +
+                ch_peer.string("UTC") + ch_peer.string("x") + ch_peer.uvarint(1))
+    sample = ch_peer.block([("a", "String", b"")], 0)
+    good_frame = ch_peer.compress_frame(sample)
+    bad_sum = bytes([good_frame[0] ^ 1]) + good_frame[1:]
+    bad_lz4 = bytearray(ch_peer.compress_frame(b"A" * 4000)); bad_lz4[30] ^= 0xff
+    # recompute nothing: the body no longer matches its checksum either way; a frame with a valid checksum over a broken body:
+    import struct as st
+    body = b"\xf0" + b"\xff" * 40                                             # literal length runs past the end
+    f = b"\x82" + st.pack("<II", len(body) + 9, 100) + body; lo, hi = cityhash128(f); broken_body = st.pack("<QQ", lo, hi) + f
+    answers = [b"", b"\x00", hello_ok[:7], rng.integers(0, 256, 64, dtype=np.uint8).tobytes(), b"\xff" * 40,
+               hello_ok + rng.integers(0, 256, 200, dtype=np.uint8).tobytes(),
+               hello_ok + ch_peer.uvarint(1) + ch_peer.string("") + bad_sum,
+               hello_ok + ch_peer.uvarint(1) + ch_peer.string("") + bytes(bad_lz4),
+               hello_ok + ch_peer.uvarint(1) + ch_peer.string("") + broken_body,
+               hello_ok + ch_peer.uvarint(1) + ch_peer.uvarint(2 ** 40),                             # a string of a terabyte
+               hello_ok + ch_peer.uvarint(10) + ch_peer.string("") + ch_peer.block([("m", "Map(String, String)", b"")], 3),   # a Log block with a type the reader cannot skip
+               hello_ok + ch_peer.uvarint(99)]
+    for _ in range(40):
+        n = int(rng.integers(1, 120)); answers.append(hello_ok + rng.integers(0, 20, n, dtype=np.uint8).tobytes())
+    import threading
+    for ans in answers:
+        cli, srv = _pair()
+        def serve(s=srv, a=ans):
+            try:
+                s.recv(4096)
+                if a: s.sendall(a)
+                s.settimeout(0.3)
+                try:
+                    while s.recv(65536): pass
+                except OSError: pass
+            finally:
+                s.close()
+        th = threading.Thread(target=serve, daemon=True); th.start()
+        try:
+            w = sink.ClickHouseWriter(cli, read_timeout_ms=400)
+            try:
+                w.prepare_batch("INSERT INTO `d`.`t` (`a`) VALUES")
+                w.append_frames(good_frame); w.send()
+                raise AssertionError("garbage was accepted as a complete INSERT exchange")
+            except engine.EngineError as ex:
+                assert ex.rc in (3, 4, -2, -5), ex.rc
+            w.close()
+        except engine.EngineError as ex:
+            assert ex.rc in (3, 4, -2, -5), ex.rc
+        cli.close(); th.join(3)
