@@ -330,3 +330,35 @@ def test_two_pools_in_two_threads_do_not_interfere():
     ths = [threading.Thread(target=work, args=(k,)) for k in range(3)]
     [t.start() for t in ths]; [t.join() for t in ths]
     assert not errs, errs
+
+
+def test_transposer_rejects_malformed_images_without_crashing():
+    """Truncated / random value images, offsets past the end, column indexes outside the schema, wild value counts: an error code, never a
+    read past the image (the image ends right at the buffer's end here, so an overrun would fault under the allocator's guard more often than not)."""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    schema = [{"name": "a", "type": "int32"}, {"name": "s", "type": "utf8"}, {"name": "t", "type": "timestamp"}]
+    good = rows.RowsImage([ChangeItem(rows.KIND_INSERT, 0, [go.int32(1), go.string("abc"), go.time(5, 6)], old_keys={0: go.int32(0)}) for _ in range(50)], [("d", "t", schema)])
+    base = good._vals[:good.values_len].copy()
+    pool = rows.Columnar(); outcomes = set()
+    for trial in range(300):
+        vals = base.copy()
+        kind = trial % 6
+        if kind == 0: vals = vals[: int(rng.integers(0, len(vals)))]                                  # truncated
+        elif kind == 1: vals[rng.integers(0, len(vals), 8)] = rng.integers(0, 256, 8)                  # flipped bytes (tags, lengths, indexes)
+        elif kind == 2: vals = rng.integers(0, 256, int(rng.integers(1, 400)), dtype=np.uint8)         # noise
+        img = rows.RowsImage([], [("d", "t", schema)])
+        items = (rows.TfItem * 50)()
+        for r in range(50):
+            C.memmove(C.byref(items[r]), C.byref(good._items[r]), C.sizeof(rows.TfItem))
+            if kind == 3: items[r].values_off = int(rng.integers(0, 2 ** 40))
+            if kind == 4: items[r].n_values = int(rng.integers(0, 2 ** 31))
+            if kind == 5: items[r].old_keys_off = int(rng.integers(0, 2 ** 20))
+        buf = np.ascontiguousarray(vals)
+        img.struct.n_items = 50; img.struct.items = C.cast(items, C.POINTER(rows.TfItem)); img.struct.values = buf.ctypes.data if len(buf) else None; img.struct.values_len = len(buf)
+        try:
+            pool.rows_to_batch(img, threads=2); outcomes.add(0)
+        except engine.EngineError as ex:
+            assert ex.rc in (-2, -3), ex.rc; outcomes.add(ex.rc)
+    assert -3 in outcomes
+    pool.close()
