@@ -459,3 +459,16 @@ def test_headers_are_plain_c(tmp_path):
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [C.sizeof(abi.TfCol), C.sizeof(abi.TfBatch), C.sizeof(rows.TfItem), C.sizeof(rows.TfRows), C.sizeof(rows.TfTable), C.sizeof(sink.TfSinkEvent), C.sizeof(sink.TfSinkStats)]
     assert got == want, (got, want)
+
+
+def test_c_example_compiles_links_and_refuses_without_a_device(tmp_path):
+    """examples/push_clickhouse.c — plain C99 against the two headers, linked against libtfgpu.so: every symbol it uses resolves; without a GPU
+    the program stops at tfgpu_engine_create (no CPU fallback)."""
+    exe = tmp_path / "push_clickhouse"
+    subprocess.run(["gcc", "-std=c99", "-D_POSIX_C_SOURCE=200809L", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "push_clickhouse.c"), "-L", os.path.dirname(engine.LIB_PATH), "-ltfgpu", "-o", str(exe)], check=True)
+    import torch
+    if torch.cuda.is_available():
+        return
+    r = subprocess.run([str(exe)], capture_output=True, text=True, env=dict(os.environ, LD_LIBRARY_PATH=os.path.dirname(engine.LIB_PATH)))
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
