@@ -309,3 +309,39 @@ def test_measure_reference_cases(po):
     assert list(per) == [24 + 4 * 16 + 1 + 8 + 8 + (16 + 10)] and tot == int(per[0])
     b = abi.Batch(2, [abi.strings_to_column(abi.TF_BYTES, [b"xyz", None]), abi.fixed_to_column(abi.TF_TIMESTAMP, [0, 1]), abi.fixed_to_column(abi.TF_INT16, [1, 2], [False, True])])
     assert list(po.measure(b)[0]) == [24 + 3 * 16 + (24 + 3) + 24 + 2, 24 + 3 * 16 + 0 + 24 + 0]    # []byte = slice header + len; time.Time = 3 words; nil = the interface only
+
+
+def test_native_block_read_back_by_an_independent_reader(po):
+    """The oracle's native block of the all-types batch (nulls, clamps, long strings) parsed by tests/ch_block_reader.py — a reader written from
+    the format, not from the encoder — gives back the input values after the reference's casts (columntypes/types.go:15-115): widths, column order,
+    null maps (one byte per row in front of Nullable columns), LEB128 string framing, Date as days, DateTime as seconds, DateTime64(6) as micros."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import ch_block_reader
+    from test_gpu_parity import all_types_batch
+    from transferia_b200 import abi
+    batch, schema = all_types_batch(2000, seed=8)
+    res = po.push_encode(batch, po.build_plan("db", "t", schema, []), abi.TF_WIRE_CH_NATIVE)
+    cols, nrows, data = ch_block_reader.read_block(res.raw)
+    assert nrows == 2000 and [n for n, _ in cols] == [c["name"] for c in schema]
+    CH_MIN, CH_MAX = 0, 4291747200                       # 1970-01-01 .. 2106-01-01 (types.go:15-29)
+    for (name, typ), col, sc in zip(cols, batch.columns, schema):
+        assert typ.startswith("Nullable(") == (not sc["required"]), (name, typ)
+        valid = np.ones(2000, bool) if col.validity is None else np.unpackbits(np.asarray(col.validity), bitorder="little")[:2000].astype(bool)
+        got = data[name]
+        if col.type in abi.VAR_TYPES:
+            off = np.asarray(col.offsets).astype(np.int64); heap = np.asarray(col.heap).tobytes()
+            want = [heap[off[r]:off[r + 1]] if valid[r] else (None if typ.startswith("Nullable") else b"") for r in range(2000)]
+        else:
+            v = np.asarray(col.values)
+            if col.type == abi.TF_DATE: conv = lambda r: int(min(max(int(v[r]), CH_MIN), CH_MAX) // 86400)
+            elif col.type == abi.TF_DATETIME: conv = lambda r: int(min(max(int(v[r]), CH_MIN), CH_MAX))
+            elif col.type == abi.TF_TIMESTAMP: conv = lambda r: int(v[r]) * 1_000_000 + (int(np.asarray(col.aux)[r]) // 1000 if col.aux is not None else 0)
+            elif col.type in (abi.TF_FLOAT, abi.TF_DOUBLE): conv = lambda r: v[r]
+            else: conv = lambda r: int(v[r])
+            want = [conv(r) if valid[r] else (None if typ.startswith("Nullable") else 0) for r in range(2000)]
+        for r in range(2000):
+            g, w = got[r], want[r]
+            if w is None or g is None: assert g is None and w is None, (name, r)
+            elif isinstance(w, (float, np.floating)): assert np.array(g).tobytes() == np.array(w, dtype=np.asarray(g).dtype).tobytes(), (name, r)
+            else: assert int(g) == int(w) if not isinstance(w, bytes) else g == w, (name, r, g, w)
