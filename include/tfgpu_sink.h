@@ -190,6 +190,11 @@ int tfgpu_batch_gather_sel(tfgpu_columnar* pool, const tf_batch* in, const uint3
  * wire_fmt 0: row runs are handed on as columnar batches (ev.batch; with transformers the result of tfgpu_push_columns). `e` may be NULL
  * only when wire_fmt is 0 and the transformer list holds nothing but skip_events / rename_tables / table_splitter: those act on kinds and
  * table names, which the host decides (nothing to compute: the always-on middleware alone); everything else needs the device.
+ * "updateable": true (model.ChSinkParams.IsUpdateable): the destination table carries `__data_transfer_commit_time` / `__data_transfer_delete_time`
+ * (UInt64) behind its columns; buildChangeItemArgs / buildDeleteKindArgs (sink_table.go:397-432) run on the row image before the transpose — an
+ * insert keeps its values + (CommitTime, 0), a delete is rebuilt from OldKeys (nil for the columns OldKeys does not list: insert_null_as_default
+ * fills them on the server) + (CommitTime, CommitTime) — and the device encodes ordinary rows of the extended schema. Update items (Collapse,
+ * toast lookup: sink_table.go:618-626) and transformer chains are refused in this mode.
  * table_splitter (pkg/transformer/registry/table_splitter/table_splitter.go:36-101) is applied HERE, not by tfgpu_plan: the generated name
  * (current table name + splitter + to_string.SerializeToString of the listed columns, "<nil>" for nil / absent values and for items without
  * values) is computed per row from the row image, the rows of a run are grouped by it in order of first appearance and every group goes

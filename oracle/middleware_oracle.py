@@ -165,3 +165,16 @@ def generate_table_name(original: str, columns, splitter: str, values_by_name: d
         if col in types_by_name:
             parts.append(serialize_to_string(values_by_name.get(col, (0, None)), types_by_name[col]))
     return (splitter or "/").join(parts)
+
+
+# ------------------------------------------------------------------ updatable ClickHouse tables (pkg/providers/clickhouse/sink_table.go:397-432)
+def updatable_args(kind: int, values, old_keys: dict, commit_time: int, ncols: int):
+    """buildChangeItemArgs for one item of an updatable table, as the list of per-column values (None = nil) followed by
+    (__data_transfer_commit_time, __data_transfer_delete_time): an insert keeps its values + (CommitTime, 0); a delete is built from OldKeys
+    (buildDeleteKindArgs: the old value of every column OldKeys lists, nil for the others — fillRequiredColumn is false on current servers)
+    + (CommitTime, CommitTime)."""
+    if kind == 0:
+        return list(values) + [commit_time, 0]
+    if kind == 2:
+        return [old_keys.get(c) for c in range(ncols)] + [commit_time, commit_time]
+    raise NotImplementedError("updates go through Collapse / the toast lookup")

@@ -459,3 +459,42 @@ def test_table_splitter_float_and_time_text_fuzz():
             want = mo.generate_table_name("t", cols, "|", dict(zip([c["name"] for c in schema], it.values)), types)
             assert got[i] == want, (cols, it.values, got[i], want)
         s.close()
+
+
+def test_updatable_clickhouse_table_rows():
+    """cfg.updateable (model.ChSinkParams.IsUpdateable): inserts get (CommitTime, 0) behind their values, deletes are rebuilt from OldKeys with
+    (CommitTime, CommitTime) — buildChangeItemArgs / buildDeleteKindArgs, sink_table.go:397-432 — and go down as ordinary rows of the table
+    extended by `__data_transfer_commit_time` / `__data_transfer_delete_time`; updates and transformer chains are refused."""
+    schema = [{"name": "id", "type": "int32", "key": True}, {"name": "k2", "type": "utf8", "key": True}, {"name": "v", "type": "double"}]
+    items = []
+    for i in range(40):
+        if i % 4 == 3:
+            items.append(ChangeItem(K.KIND_DELETE, 0, {}, {0: go.int32(i), 1: go.string(f"k{i}")}, commit_time=1000 + i))
+        else:
+            items.append(ChangeItem(K.KIND_INSERT, 0, [go.int32(i), go.string(f"k{i}"), go.nil if i % 5 == 0 else go.float64(i / 4)], commit_time=1000 + i))
+    s = sink.Sink(updateable=True)
+    s.push(rows.RowsImage(items, [("public", "t", schema)]))
+    (ev,) = [e for e in s.events if e["type"] == sink.EV_ROWS]
+    b = ev["batch"]
+    assert ev["items"] == list(range(40)) and b.nrows == 40 and len(b.columns) == 5 and b.kinds is None
+    want = [mo.updatable_args(it.kind, [None if v[0] == 0 else v[1] for v in (it.values or [])], {c: v[1] for c, v in (it.old_keys or {}).items()}, it.commit_time, 3) for it in items]
+    ids, valid0 = np.asarray(b.columns[0].values), np.ones(40, bool) if b.columns[0].validity is None else np.unpackbits(np.asarray(b.columns[0].validity), bitorder="little")[:40].astype(bool)
+    assert [int(ids[r]) if valid0[r] else None for r in range(40)] == [w[0] for w in want]
+    ln = np.asarray(b.columns[1].offsets).astype(np.int64); heap = np.asarray(b.columns[1].heap).tobytes(); off = np.concatenate([[0], np.cumsum(ln)])
+    assert [heap[off[r]:off[r + 1]] for r in range(40)] == [w[1] for w in want]
+    v2 = np.unpackbits(np.asarray(b.columns[2].validity), bitorder="little")[:40].astype(bool); dv = np.asarray(b.columns[2].values)
+    assert [float(dv[r]) if v2[r] else None for r in range(40)] == [w[2] for w in want]          # nil for every delete: the column is not in OldKeys
+    assert b.columns[3].type == abi.TF_UINT64 and list(np.asarray(b.columns[3].values)) == [w[3] for w in want]
+    assert list(np.asarray(b.columns[4].values)) == [w[4] for w in want] and sum(1 for w in want if w[4]) == 10
+    s.close()
+    # the INSERT statement of such a table lists the two system columns once (sink_table.go:643-648)
+    d = engine.plan_validate("public", "t", schema + [{"name": "__data_transfer_commit_time", "type": "uint64", "required": True}, {"name": "__data_transfer_delete_time", "type": "uint64", "required": True}], [], {"type": "clickhouse"})
+    assert d["sink"]["columns"][-2:] == ["UInt64", "UInt64"]
+    # refusals: an update, a transformer chain
+    s = sink.Sink(updateable=True)
+    with pytest.raises(engine.EngineError) as ei:
+        s.push(rows.RowsImage([ChangeItem(K.KIND_UPDATE, 0, [go.int32(1), go.string("a"), go.float64(1)], {0: go.int32(1)})], [("public", "t", schema)]))
+    assert ei.value.rc == -2 and "Collapse" in str(ei.value)
+    s.close()
+    with pytest.raises(engine.EngineError):
+        sink.Sink(transformers=[{"rename_tables": {"renameTables": []}}], updateable=True)

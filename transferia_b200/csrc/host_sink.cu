@@ -47,6 +47,7 @@ struct TablePlan {
     std::string out_ns, out_name, insert_query;
     std::vector<std::string> col_names; std::vector<int> col_tf;      // the table's input schema (table_splitter reads values by column name)
     std::map<std::string, std::string> insert_by_table;               // INSERT statement per generated table name
+    std::string aug_schema;                                           // updatable ClickHouse tables: the schema with the two system columns behind it
 };
 
 // fmt "%v" of a float = strconv 'g' with the shortest digits: exponent form when exp < -4 || exp >= 6 (ftoa.go: eprec = 6 for the shortest form)
@@ -132,13 +133,23 @@ struct tfgpu_sink {
         const std::string ns = t.schema ? t.schema : "", name = t.table ? t.table : "";
         const bool want_sink = wire_fmt == TF_WIRE_CH_NATIVE || wire_fmt == TF_WIRE_CH_NATIVE_LZ4 || wire_fmt == TF_WIRE_CH_JSONEACHROW;
         tfplan::Plan pl;
-        try { pl = tfplan::build_plan(ns, name, t.schema_json ? t.schema_json : "[]", transformers_json, want_sink ? sink_json : ""); }
+        std::string schema_text = t.schema_json ? t.schema_json : "[]";
+        if (updateable) {
+            // sink_table.go:633-650: an updatable table takes `__data_transfer_commit_time` and `__data_transfer_delete_time` (UInt64) behind its columns
+            const size_t close = schema_text.rfind(']');
+            if (close == std::string::npos) throw SinkFail{TF_E_FATAL_CONFIG, "schema_json is not an array"};
+            const bool empty = schema_text.find('{') == std::string::npos;
+            schema_text = schema_text.substr(0, close) + (empty ? "" : ",") +
+                "{\"name\":\"__data_transfer_commit_time\",\"type\":\"uint64\",\"required\":true},{\"name\":\"__data_transfer_delete_time\",\"type\":\"uint64\",\"required\":true}]";
+            tp.aug_schema = schema_text;
+        }
+        try { pl = tfplan::build_plan(ns, name, schema_text, transformers_json, want_sink ? sink_json : ""); }
         catch (const tfplan::FatalError& f) { throw SinkFail{f.code, std::string("unable to add table plan: ") + f.what()}; }
         catch (const std::exception& x) { throw SinkFail{TF_E_FATAL_CONFIG, std::string("unable to add table plan: ") + x.what()}; }
         tp.out_ns = pl.out_ns.empty() && pl.out_name.empty() ? ns : pl.out_ns; tp.out_name = pl.out_name.empty() ? name : pl.out_name;
         for (auto& c : pl.in_schema) { tp.col_names.push_back(c.name); tp.col_tf.push_back(c.tf); }
         if (e && (needs_device || wire_fmt)) {
-            const int rc = tfgpu_plan(e, ns.c_str(), name.c_str(), t.schema_json, transformers_json.c_str(), want_sink ? sink_json.c_str() : nullptr, &tp.plan_id);
+            const int rc = tfgpu_plan(e, ns.c_str(), name.c_str(), schema_text.c_str(), transformers_json.c_str(), want_sink ? sink_json.c_str() : nullptr, &tp.plan_id);
             if (rc) throw SinkFail{rc, std::string("unable to add table plan: ") + tfgpu_last_error(e)};
         }
         {
@@ -153,7 +164,7 @@ struct tfgpu_sink {
         auto it = tp.insert_by_table.find(table_name);
         if (it != tp.insert_by_table.end()) return it->second;
         std::vector<char> q(tp.insert_query.size() + table_name.size() + database.size() + 256);
-        const int64_t n = tfgpu_ch_insert_query(database.c_str(), table_name.c_str(), tp.insert_query.c_str(), updateable, q.data(), q.size());
+        const int64_t n = tfgpu_ch_insert_query(database.c_str(), table_name.c_str(), tp.insert_query.c_str(), 0 /* the plan's schema already lists the system columns */, q.data(), q.size());
         if (n < 0) throw SinkFail{(int)n, "cannot build the INSERT statement"};
         return tp.insert_by_table.emplace(table_name, std::string(q.data(), (size_t)n)).first->second;
     }
@@ -264,7 +275,40 @@ struct tfgpu_sink {
         tf_sink_event ev{}; ev.table = table; ev.out_schema = tp.out_ns.c_str(); ev.out_table = out_name.c_str(); ev.plan_id = tp.plan_id;
         if (exclude_sys && system_tables.count(out_name)) { st.filter_dropped += n; return; }           // ChangeItem.IsSystemTable looks at Table only
         const tf_batch* batch = nullptr; const tf_row_meta* meta = nullptr; const tf_old_keys* old = nullptr;
-        int rc = tfgpu_rows_to_batch(pool, rows, table, idx.data(), n, 0, &batch, &meta, &old);
+        int rc;
+        if (updateable) {
+            // buildChangeItemArgs (sink_table.go:411-432) on the row image: an insert keeps its values and gets (CommitTime, 0) behind them; a delete
+            // is rebuilt from OldKeys (buildDeleteKindArgs :397-409: the key columns' old values, nil for the rest — insert_null_as_default fills them
+            // on the server) with (CommitTime, CommitTime). Updates need Collapse and the toast lookup of doOperation (:618-626): Go sink.
+            const uint32_t ncols = (uint32_t)tp.col_names.size() - 2;
+            std::vector<tf_item> aitems(n); std::vector<uint8_t> avals; avals.reserve((size_t)n * 64);
+            const uint8_t* vend = rows->values + rows->values_len;
+            auto put_u64 = [&](uint64_t v) { avals.push_back(TF_V_UINT64); const uint8_t* b = (const uint8_t*)&v; avals.insert(avals.end(), b, b + 8); };
+            auto put_idx = [&](uint16_t c) { const uint8_t* b = (const uint8_t*)&c; avals.insert(avals.end(), b, b + 2); };
+            for (uint64_t j = 0; j < n; j++) {
+                const tf_item& it = rows->items[idx[j]]; tf_item& a = aitems[j]; a = it;
+                a.table = 0; a.kind = TF_KIND_INSERT; a.old_keys_off = UINT64_MAX; a.values_off = avals.size();
+                if (it.kind == TF_KIND_INSERT) {
+                    if ((it.flags & TF_ITEM_SPARSE) || it.n_values != ncols) throw SinkFail{TF_E_FATAL_UNSUPPORTED, "updatable table: an insert with a column subset needs the Go sink"};
+                    const uint8_t* at = rows->values + it.values_off; const uint8_t* p = at;
+                    for (uint32_t k = 0; k < ncols; k++) { Val v; if (!read_val(p, vend, v)) throw SinkFail{TF_E_FATAL_ARG, "malformed value image"}; }
+                    avals.insert(avals.end(), at, p); put_u64(it.commit_time); put_u64(0);
+                    a.n_values = ncols + 2; a.flags = 0;
+                } else if (it.kind == TF_KIND_DELETE) {
+                    if (it.old_keys_off == UINT64_MAX || it.old_keys_off + 2 > rows->values_len) throw SinkFail{TF_E_FATAL_UNSUPPORTED, "updatable table: a delete without OldKeys"};
+                    const uint8_t* p = rows->values + it.old_keys_off; uint16_t cnt; std::memcpy(&cnt, p, 2); p += 2; const uint8_t* at = p;
+                    for (uint16_t k = 0; k < cnt; k++) { if (vend - p < 2) throw SinkFail{TF_E_FATAL_ARG, "truncated OldKeys image"}; uint16_t c; std::memcpy(&c, p, 2); p += 2; Val v; if (c >= ncols || !read_val(p, vend, v)) throw SinkFail{TF_E_FATAL_ARG, "malformed OldKeys image"}; }
+                    avals.insert(avals.end(), at, p);                                        // {u16 column, value}*: already the sparse row form
+                    put_idx((uint16_t)ncols); put_u64(it.commit_time); put_idx((uint16_t)(ncols + 1)); put_u64(it.commit_time);
+                    a.n_values = (uint32_t)cnt + 2; a.flags = TF_ITEM_SPARSE;
+                } else throw SinkFail{TF_E_FATAL_UNSUPPORTED, "updatable table: update items go through abstract.Collapse and the toast lookup of the Go sink (sink_table.go:618-626)"};
+            }
+            avals.push_back(0);
+            tf_table at_{rows->tables[table].schema, rows->tables[table].table, tp.aug_schema.c_str()};
+            tf_rows ar{}; ar.n_items = n; ar.items = aitems.data(); ar.n_tables = 1; ar.tables = &at_; ar.values = avals.data(); ar.values_len = avals.size() - 1;
+            ar.strings = rows->strings; ar.strings_len = rows->strings_len;
+            rc = tfgpu_rows_to_batch(pool, &ar, 0, nullptr, 0, 0, &batch, &meta, &old);
+        } else rc = tfgpu_rows_to_batch(pool, rows, table, idx.data(), n, 0, &batch, &meta, &old);
         if (rc) throw SinkFail{rc, std::string("transpose: ") + tfgpu_columnar_last_error(pool)};
         if (tp.plan_id < 0) {                                                                           // no transformers, columnar hand-over
             ev.type = TF_SINK_EV_ROWS; ev.n_items = n; ev.item_idx = idx.data(); ev.batch = batch;
@@ -406,6 +450,7 @@ int tfgpu_sink_create(tfgpu_engine* e, const char* cfg_json, tfgpu_sink** out) {
         }
         s->sink_json = "{\"type\":\"clickhouse\"}";
         s->database = cfg->get_str("database", "default"); s->updateable = cfg->get_bool("updateable", false);
+        if (s->updateable && s->has_transformers) return TF_E_FATAL_UNSUPPORTED;      // the system columns are the SINK's: a chain over the augmented schema would see them
         s->errors_to_sink = cfg->get_str("errors_output", "sink") != "devnull";
         s->exclude_sys = cfg->get_bool("exclude_system_tables", true);
         for (auto& t : cfg->get_str_list("system_tables")) s->system_tables.insert(t);

@@ -147,7 +147,7 @@ class Sink:
     does not take."""
 
     def __init__(self, eng=None, transformers=None, wire_fmt=0, system_tables=(), exclude_system_tables=True, errors_output="sink",
-                 database="default", downstream=None, clickhouse: Optional[ClickHouseWriter] = None, debezium: Optional[dict] = None):
+                 database="default", downstream=None, clickhouse: Optional[ClickHouseWriter] = None, debezium: Optional[dict] = None, updateable: bool = False):
         from . import abi, rows as _rows
         self._L = lib()
         vp = C.c_void_p
@@ -159,7 +159,7 @@ class Sink:
         self._L.tfgpu_sink_push.argtypes = [vp, vp]
         self._L.tfgpu_sink_stats.argtypes = [vp, C.POINTER(TfSinkStats)]
         cfg = {"transformers": transformers or [], "wire_fmt": wire_fmt, "system_tables": list(system_tables), "exclude_system_tables": exclude_system_tables,
-               "errors_output": errors_output, "database": database}
+               "errors_output": errors_output, "database": database, "updateable": updateable}
         if debezium is not None:
             cfg["debezium"] = debezium
         self._h = vp()
