@@ -150,10 +150,11 @@ def serialize_to_string(value, yt_type: str) -> str:
     if tag in (12, 16): return v.decode("utf-8", "surrogateescape")
     if tag == 13 and yt_type == "string": return v.decode("utf-8", "surrogateescape")
     if tag == 14 and yt_type in ("date", "datetime", "timestamp"):
-        t = dt.datetime(1970, 1, 1) + dt.timedelta(seconds=v[0])
-        if yt_type == "date": return t.strftime("%Y-%m-%d")
+        import numpy as np
+        text = str(np.datetime64(int(v[0]), "s"))                 # proleptic Gregorian, any year: "YYYY-MM-DDTHH:MM:SS" ("-1232-..", "14124-..")
+        if yt_type == "date": return text.split("T")[0]
         frac = ("." + ("%09d" % v[1]).rstrip("0")) if v[1] else ""
-        return t.strftime("%Y-%m-%dT%H:%M:%S") + frac + "Z"
+        return text + frac + "Z"
     raise NotImplementedError((tag, yt_type))
 
 

@@ -498,3 +498,25 @@ def test_updatable_clickhouse_table_rows():
     s.close()
     with pytest.raises(engine.EngineError):
         sink.Sink(transformers=[{"rename_tables": {"renameTables": []}}], updateable=True)
+
+
+def test_serialize_to_string_reference_cases():
+    """registry/to_string/to_string_test.go:130-168 (TestAllTypesToStringTransformer): the expected text of SerializeToString per type, checked on the
+    host formatter table_splitter uses (through generated table names) and on the oracle's restatement — years before 0 and beyond 9999, nanoseconds,
+    float32 / float64 shortest forms, nil as "<nil>"."""
+    def secs(text):
+        return int(np.datetime64(text, "s").astype(np.int64))
+    cases = [("int64", go.int64(981274987), "981274987"), ("int32", go.int32(-12049182), "-12049182"), ("int16", go.int16(12313), "12313"), ("int8", go.int8(-14), "-14"),
+             ("uint64", go.uint64(1142423562), "1142423562"), ("uint32", go.uint32(0), "0"), ("uint16", go.uint16(65212), "65212"), ("uint8", go.uint8(213), "213"),
+             ("float", go.float32(123.123), "123.123"), ("double", go.float64(-12344.12334341), "-12344.12334341"),
+             ("string", go.bytes(b"bytes"), "bytes"), ("utf8", go.string("string"), "string"), ("boolean", go.bool(True), "true"),
+             ("date", go.time(secs("-1232-02-23T00:00:00")), "-1232-02-23"), ("date", go.time(secs("14124-01-12T00:00:00")), "14124-01-12"),
+             ("datetime", go.time(secs("2311-12-01T01:02:04"), 5), "2311-12-01T01:02:04.000000005Z"),
+             ("timestamp", go.time(secs("1231-05-23T09:08:07"), 6), "1231-05-23T09:08:07.000000006Z"),
+             ("date", go.nil, "<nil>"), ("datetime", go.nil, "<nil>"), ("boolean", go.nil, "<nil>"), ("utf8", go.nil, "<nil>"), ("int64", go.nil, "<nil>")]
+    for typ, val, want in cases:
+        assert mo.serialize_to_string(val, typ) == want, (typ, val)
+        s = sink.Sink(transformers=[{"table_splitter": {"columns": ["c"], "splitter": "|"}}])
+        s.push(rows.RowsImage([ChangeItem(K.KIND_INSERT, 0, [val])], [("", "", [{"name": "c", "type": typ}])]))
+        assert [e["out"][1] for e in s.events] == [want], (typ, val)          # an empty original table name contributes no component
+        s.close()
