@@ -345,3 +345,25 @@ def test_native_block_read_back_by_an_independent_reader(po):
             if w is None or g is None: assert g is None and w is None, (name, r)
             elif isinstance(w, (float, np.floating)): assert np.array(g).tobytes() == np.array(w, dtype=np.asarray(g).dtype).tobytes(), (name, r)
             else: assert int(g) == int(w) if not isinstance(w, bytes) else g == w, (name, r, g, w)
+
+
+def test_to_string_all_types_reference_cases(po):
+    """registry/to_string/to_string_test.go:130-168 (TestAllTypesToStringTransformer) on the C++ oracle's SerializeToString: every case of the
+    reference's table incl. the `any` list / map texts, dates before year 0 and beyond 9999, nanoseconds, the interval's Duration.String()."""
+    s = lambda val, t: po.serialize_to_string(val, abi.YT_NAME_TO_TF[t]).decode()
+    mk = po.make_val
+    secs = lambda text: int(np.datetime64(text, "s").astype(np.int64))
+    cases = [(mk(po.OG_JSON, s=b'[1,"string",3,4.123,6,true]'), "any", '[1,"string",3,4.123,6,true]'),
+             (mk(po.OG_JSON, s=b'{"someName":"someValue","someName2":1234}'), "any", '{"someName":"someValue","someName2":1234}'),
+             (mk(po.OG_INT64, i=981274987), "int64", "981274987"), (mk(po.OG_INT32, i=-12049182), "int32", "-12049182"), (mk(po.OG_INT16, i=12313), "int16", "12313"),
+             (mk(po.OG_INT8, i=-14), "int8", "-14"), (mk(po.OG_UINT64, u=1142423562), "uint64", "1142423562"), (mk(po.OG_UINT32, u=0), "uint32", "0"),
+             (mk(po.OG_UINT16, u=65212), "uint16", "65212"), (mk(po.OG_UINT8, u=213), "uint8", "213"),
+             (mk(po.OG_FLOAT32, f=float(np.float32(123.123))), "float", "123.123"), (mk(po.OG_FLOAT64, f=-12344.12334341), "double", "-12344.12334341"),
+             (mk(po.OG_BYTES, s=b"bytes"), "string", "bytes"), (mk(po.OG_STRING, s=b"string"), "utf8", "string"), (mk(po.OG_BOOL, i=1), "boolean", "true"),
+             (mk(po.OG_TIME, i=secs("-1232-02-23T00:00:00"), nsec=0), "date", "-1232-02-23"), (mk(po.OG_TIME, i=secs("14124-01-12T00:00:00"), nsec=0), "date", "14124-01-12"),
+             (mk(po.OG_TIME, i=secs("2311-12-01T01:02:04"), nsec=5), "datetime", "2311-12-01T01:02:04.000000005Z"),
+             (mk(po.OG_TIME, i=secs("1231-05-23T09:08:07"), nsec=6), "timestamp", "1231-05-23T09:08:07.000000006Z"),
+             (mk(po.OG_DURATION, i=((12 * 3600 + 53 * 60 + 21) * 10**9 + 87_182_124)), "interval", "12h53m21.087182124s"),
+             (mk(po.OG_NIL), "date", "<nil>"), (mk(po.OG_NIL), "datetime", "<nil>"), (mk(po.OG_NIL), "boolean", "<nil>"), (mk(po.OG_NIL), "utf8", "<nil>"), (mk(po.OG_NIL), "int64", "<nil>")]
+    for val, typ, want in cases:
+        assert s(val, typ) == want, (typ, want)
