@@ -472,3 +472,48 @@ def test_c_example_compiles_links_and_refuses_without_a_device(tmp_path):
         return
     r = subprocess.run([str(exe)], capture_output=True, text=True, env=dict(os.environ, LD_LIBRARY_PATH=os.path.dirname(engine.LIB_PATH)))
     assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+def test_name_filter_reference_cases(po):
+    """registry/filter/filter_test.go:9-33 (TestFilter): empty filter, exclude only, include + exclude, exclude wins over include, a bad regexp
+    is a construction error — through convert_to_string's column filter (the same filter.Filter) in the product's plan and the oracle's."""
+    schema = [{"name": n, "type": "int32"} for n in ("include", "exclude", "other", "any_value")]
+    def converted(cols_cfg):
+        trs = [{"convert_to_string": {"columns": cols_cfg}}]
+        d = engine.plan_validate("", "t", schema, trs); o = po.build_plan("", "t", schema, trs)
+        got = [c["name"] for c in d["result_schema"] if c["type"] == "utf8"]
+        assert got == [c["name"] for c in o.result_schema if c["type"] == "utf8"]
+        return got
+    assert converted({}) == ["include", "exclude", "other", "any_value"]
+    assert converted({"excludeColumns": ["exclude"]}) == ["include", "other", "any_value"]
+    assert converted({"includeColumns": ["include"], "excludeColumns": ["exclude"]}) == ["include"]
+    assert converted({"includeColumns": ["include", "other.*"], "excludeColumns": [".*other.*"]}) == ["include"]
+    with pytest.raises(engine.EngineError) as ei:
+        engine.plan_validate("", "t", schema, [{"convert_to_string": {"columns": {"includeColumns": ["include", "*"], "excludeColumns": [".*other.*"]}}}])
+    assert ei.value.rc == -1
+
+
+def test_skip_events_and_rename_reference_cases():
+    """registry/filter/skip_events_test.go (TestSkipEvents): table1 with delete / truncate / drop_table skipped -> init_load, done_load, insert and
+    update remain, in order; table2 is not Suitable. registry/rename/rename_test.go (TestRenameTableTransformer): public.objects_0 ->
+    service.objects, public.objects untouched. Both through Sinker.Push (kinds and table names are host decisions)."""
+    from transferia_b200 import rows, sink
+    from transferia_b200.rows import ChangeItem, go
+    K = rows
+    schema = [{"name": "id", "type": "int32"}]
+    kinds = [K.KIND_DROP_TABLE, K.KIND_TRUNCATE, K.KIND_INIT_TABLE_LOAD, K.KIND_DONE_TABLE_LOAD, K.KIND_INSERT, K.KIND_UPDATE, K.KIND_DELETE]
+    items = [ChangeItem(k, t, [go.int32(i)] if k <= 2 else None) for t in (0, 1) for i, k in enumerate(kinds)]
+    s = sink.Sink(transformers=[{"skip_events": {"tables": {"includeTables": ["table1"]}, "events": ["delete", "truncate", "drop_table"]}}])
+    s.push(rows.RowsImage(items, [("", "table1", schema), ("", "table2", schema)]))
+    per_table = {0: [], 1: []}
+    for e in s.events:
+        per_table[e["table"]] += [items[i].kind for i in e["items"]]
+    assert per_table[0] == [K.KIND_INIT_TABLE_LOAD, K.KIND_DONE_TABLE_LOAD, K.KIND_INSERT, K.KIND_UPDATE] and per_table[1] == kinds
+    s.close()
+    ren = {"rename_tables": {"renameTables": [{"originalName": {"nameSpace": "public", "name": "objects_0"}, "newName": {"nameSpace": "service", "name": "objects"}},
+                                              {"originalName": {"nameSpace": "public", "name": "objects_1"}, "newName": {"nameSpace": "service", "name": "objects"}}]}}
+    s = sink.Sink(transformers=[ren])
+    s.push(rows.RowsImage([ChangeItem(K.KIND_INSERT, 0, [go.int32(1)]), ChangeItem(K.KIND_INSERT, 1, [go.int32(2)]), ChangeItem(K.KIND_DDL, 1)],
+                          [("public", "objects", schema), ("public", "objects_0", schema)]))
+    assert [e["out"] for e in s.events] == [("public", "objects"), ("service", "objects"), ("service", "objects")]
+    s.close()
