@@ -262,6 +262,13 @@ int tfgpu_dispatcher_destroy(tfgpu_dispatcher* d);                  /* drains, s
 /* Host CityHash128 (v1.0.2) as the frames' checksum uses it — exported for the tests' cross-checks against the device and the oracle. */
 void tfgpu_host_cityhash128(const uint8_t* p, uint64_t n, uint64_t out[2]);
 
+/* regexp.MustCompile(pattern).ReplaceAll(src, rule) as the regex_replace_transformer step of tfgpu_sink_push computes it
+ * (pkg/transformer/registry/regex_replace/transformer.go:127-142; Go's RE2 syntax, leftmost-first, rune-wise): host only, exported for the
+ * parity tests and for a shim that wants to validate a transfer's expression up front. Returns the result's length (the bytes are written
+ * when they fit `cap`), TF_E_FATAL_CONFIG for an expression regexp.Compile refuses too, TF_E_FATAL_UNSUPPORTED for valid syntax this
+ * library does not carry ((?i), (?U), \p{..} classes, oversized programs): such a transfer keeps the Go transformer. */
+int64_t tfgpu_regex_replace_all(const char* pattern, const char* rule, const uint8_t* src, uint64_t src_len, uint8_t* dst, uint64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,7 +39,7 @@ g++ -std=c++17 -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer -fPIC
 cd "$ROOT"
 TFGPU_LIB_PATH="$OUT/libtfhost_asan.so" LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)" \
     ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1 \
-    python -m pytest tests/test_rows.py tests/test_sink_push.py tests/test_ch_wire.py tests/test_host_cpu.py -q -m "not gpu" -p no:cacheprovider \
+    python -m pytest tests/test_rows.py tests/test_sink_push.py tests/test_ch_wire.py tests/test_host_cpu.py tests/test_regex_replace.py -q -m "not gpu" -p no:cacheprovider \
     -k "not exports and not sm100a and not no_cpu_fallback and not gloo and not bench_reference and not c_example"
 # the threaded parts (worker pool of the transposer / gather, dispatcher lanes and its delivery gate) under ThreadSanitizer
 g++ -std=c++17 -O1 -g -fsanitize=thread -fno-omit-frame-pointer -fPIC -shared -I/usr/local/cuda/include \

@@ -12,6 +12,7 @@
 #include "../../include/tfgpu_sink.h"
 #include "plan.hpp"
 #include "row_image.hpp"
+#include "host_regex.hpp"
 #include <charconv>
 #include <condition_variable>
 #include <deque>
@@ -36,8 +37,9 @@ const char* kind_name(uint8_t k) {            // abstract.Kind strings (kind.go:
 // what a transformer does to an item that is not a row event: skip_events may drop it, rename_tables renames it, the rest pass it through
 // (filter_rows.go:110, number_to_float.go:59, mask / to_string / to_datetime touch ColumnValues of row events only)
 struct HostStep {
-    int type = 0;                              // 1 skip_events, 2 rename_tables, 3 table_splitter
+    int type = 0;                              // 1 skip_events, 2 rename_tables, 3 table_splitter, 4 regex_replace_transformer
     std::vector<std::string> split_cols; std::string splitter;
+    tfplan::NameFilter columns; std::shared_ptr<tfre::Prog> prog; tfre::Template tpl; std::shared_ptr<tfre::Machine> vm;    // type 4
     tfplan::NameFilter tables; std::set<std::string> events;
     std::vector<std::pair<std::pair<std::string, std::string>, std::pair<std::string, std::string>>> renames;
 };
@@ -343,8 +345,61 @@ struct tfgpu_sink {
         deliver(ev, rows, &tp);
     }
 
+    // regex_replace_transformer (registry/regex_replace/transformer.go:87-142) over the row image, before anything else looks at the values
+    // (the plan keeps these steps at the head of the chain): every row event of a table the step's table filter takes gets its string values
+    // (schema type utf8 holding a Go string) and []byte values (schema type string) of the matched columns replaced. The type is read at the
+    // value's POSITION in the item (`item.TableSchema.Columns()[i]`, :108), the name from ColumnNames — they differ for an item that carries
+    // a column subset. The image is copied once with the rewritten value lists appended; OldKeys are not touched by Apply.
+    struct Rewritten { tf_rows rows; std::vector<tf_item> items; std::vector<uint8_t> values; };
+    bool regex_rewrite(const tf_rows* in, Rewritten& out) {
+        bool any = false; for (const HostStep& h : host_steps) if (h.type == 4) any = true;
+        if (!any) return false;
+        struct PerTable { bool looked = false; std::vector<std::vector<const HostStep*>> by_col; const TablePlan* tp = nullptr; bool hit = false; };
+        std::vector<PerTable> per(in->n_tables);
+        out.values.assign(in->values, in->values + in->values_len);
+        out.items.assign(in->items, in->items + in->n_items);
+        const uint8_t* vend = in->values + in->values_len;
+        std::string a, b;
+        for (uint64_t i = 0; i < in->n_items; i++) {
+            const tf_item& it = in->items[i];
+            if (!TF_KIND_IS_ROW(it.kind)) continue;
+            if (it.table >= in->n_tables) throw SinkFail{TF_E_FATAL_ARG, "item names a table outside tf_rows.tables"};
+            PerTable& pt = per[it.table];
+            if (!pt.looked) {
+                pt.looked = true;
+                const tf_table& t = in->tables[it.table]; const std::string name = t.table ? t.table : "";
+                pt.tp = &plan_for(t); pt.by_col.resize(pt.tp->col_names.size());
+                for (const HostStep& h : host_steps) if (h.type == 4 && h.tables.match(name))
+                    for (size_t c = 0; c < pt.tp->col_names.size(); c++) if (h.columns.match(pt.tp->col_names[c])) { pt.by_col[c].push_back(&h); pt.hit = true; }
+            }
+            if (!pt.hit || !it.n_values) continue;
+            const uint8_t* at = in->values + it.values_off; const bool sparse = it.flags & TF_ITEM_SPARSE;
+            const uint64_t new_off = out.values.size();
+            for (uint32_t k = 0; k < it.n_values; k++) {
+                uint32_t c = k;
+                if (sparse) { if (vend - at < 2) throw SinkFail{TF_E_FATAL_ARG, "truncated value image"}; uint16_t ci; std::memcpy(&ci, at, 2); out.values.insert(out.values.end(), at, at + 2); at += 2; c = ci; }
+                const uint8_t* v0 = at; Val v; if (!read_val(at, vend, v)) throw SinkFail{TF_E_FATAL_ARG, "malformed value image"};
+                const int typ = k < pt.tp->col_tf.size() ? pt.tp->col_tf[k] : -1;
+                const bool takes = c < pt.by_col.size() && !pt.by_col[c].empty() && ((typ == TF_UTF8 && v.tag == TF_V_STRING) || (typ == TF_BYTES && v.tag == TF_V_BYTES));
+                if (!takes) { out.values.insert(out.values.end(), v0, at); continue; }
+                a.assign((const char*)v.p, v.n);
+                for (const HostStep* h : pt.by_col[c]) { tfre::replace_all(*h->vm, h->tpl, (const uint8_t*)a.data(), a.size(), b); a.swap(b); }
+                if (a.size() > 0xffffffffull) throw SinkFail{TF_E_FATAL_UNSUPPORTED, "regex_replace_transformer: a value grew past 4 GiB"};
+                const uint32_t len = (uint32_t)a.size();
+                out.values.push_back((uint8_t)v.tag); out.values.insert(out.values.end(), (const uint8_t*)&len, (const uint8_t*)&len + 4);
+                out.values.insert(out.values.end(), a.begin(), a.end());
+            }
+            out.items[i].values_off = new_off;
+        }
+        out.values.push_back(0);
+        out.rows = *in; out.rows.items = out.items.data(); out.rows.values = out.values.data(); out.rows.values_len = out.values.size() - 1;
+        return true;
+    }
+
     void push(const tf_rows* rows) {
         st.pushes++; st.max_commit_time = st.min_commit_time = 0;
+        Rewritten rw;
+        if (regex_rewrite(rows, rw)) rows = &rw.rows;
         // SplitByTableID (utils.go:130-136): groups in order of first appearance, items in input order
         std::vector<std::pair<std::string, std::vector<uint64_t>>> groups; std::map<std::string, size_t> where;
         for (uint64_t i = 0; i < rows->n_items; i++) {
@@ -396,7 +451,7 @@ int tfgpu_sink_create(tfgpu_engine* e, const char* cfg_json, tfgpu_sink** out) {
         const tfj::Value* trs = cfg->get("transformers");
         s->has_transformers = trs && trs->kind == tfj::Value::Arr && !trs->arr.empty();
         if (s->has_transformers) for (auto& tr : trs->arr) if (tr->kind == tfj::Value::Obj) for (auto& kv : tr->obj)
-            if (kv.first != "transformerId" && kv.first != "skip_events" && kv.first != "rename_tables" && kv.first != "table_splitter") s->needs_device = true;
+            if (kv.first != "transformerId" && kv.first != "skip_events" && kv.first != "rename_tables" && kv.first != "table_splitter" && kv.first != "regex_replace_transformer") s->needs_device = true;
         // skip_events / rename_tables / table_splitter act on kinds and table names only: with wire_fmt 0 they run on the host alone; every
         // other transformer and every wire format computes on the device — nothing here computes on the CPU in its place
         if ((s->needs_device || s->wire_fmt) && !e) return TF_E_FATAL_NODEVICE;
@@ -423,6 +478,18 @@ int tfgpu_sink_create(tfgpu_engine* e, const char* cfg_json, tfgpu_sink** out) {
                         if (c->get_bool("useLegacyLf")) return TF_E_FATAL_UNSUPPORTED;
                         s->host_steps.push_back(std::move(h));
                     }
+                    else if (kv.first == "regex_replace_transformer") {
+                        // regexp.Compile(cfg.RegexMatch) + the two filters, transformer.go:18-41: a bad expression fails the construction
+                        HostStep h; h.type = 4; h.tables = tfplan::tables_filter(c->get("tables"));
+                        const tfj::Value* cc = c->get("columns");
+                        h.columns = tfplan::make_filter(cc ? cc->get_str_list("includeColumns") : std::vector<std::string>(), cc ? cc->get_str_list("excludeColumns") : std::vector<std::string>());
+                        try {
+                            h.prog = std::make_shared<tfre::Prog>(tfre::compile(c->get_str("regexMatch", "")));
+                            h.tpl = tfre::parse_template(c->get_str("replaceRule", ""), *h.prog);
+                        } catch (const tfre::Unsupported&) { return TF_E_FATAL_UNSUPPORTED; }
+                        h.vm = std::make_shared<tfre::Machine>(*h.prog);
+                        s->host_steps.push_back(std::move(h));
+                    }
                     else if (kv.first == "rename_tables") {
                         HostStep h; h.type = 2; const tfj::Value* lst = c->get("renameTables");
                         if (lst && lst->kind == tfj::Value::Arr) for (auto& r : lst->arr) {
@@ -435,6 +502,7 @@ int tfgpu_sink_create(tfgpu_engine* e, const char* cfg_json, tfgpu_sink** out) {
             }
         } else tj = "[]";
         for (size_t at = 0; (at = tj.find("\"table_splitter\"", at)) != std::string::npos; at += 22) tj.replace(at, 16, "\"table_splitter@sink\"");   // see plan.hpp: the unmarked form is refused
+        for (size_t at = 0; (at = tj.find("\"regex_replace_transformer\"", at)) != std::string::npos; at += 32) tj.replace(at, 27, "\"regex_replace_transformer@sink\"");
         s->transformers_json = tj;
         if (s->wire_fmt == TF_WIRE_DEBEZIUM) {               // the emitter's options are passed on verbatim (tfgpu_emit_debezium's opts_json)
             const std::string src = cfg_json ? cfg_json : ""; const size_t k = src.find("\"debezium\"");
@@ -458,6 +526,21 @@ int tfgpu_sink_create(tfgpu_engine* e, const char* cfg_json, tfgpu_sink** out) {
     } catch (const std::exception& x) { return TF_E_FATAL_CONFIG; }
     *out = s.release();
     return TF_OK;
+}
+
+int64_t tfgpu_regex_replace_all(const char* pattern, const char* rule, const uint8_t* src, uint64_t src_len, uint8_t* dst, uint64_t cap) {
+    if (!pattern || !rule || (!src && src_len) || (!dst && cap)) return TF_E_FATAL_ARG;
+    try {
+        const tfre::Prog prog = tfre::compile(pattern);
+        const tfre::Template tpl = tfre::parse_template(rule, prog);
+        tfre::Machine vm(prog); std::string out;
+        static const uint8_t none = 0;
+        tfre::replace_all(vm, tpl, src ? src : &none, src_len, out);
+        if (out.size() <= cap && !out.empty()) std::memcpy(dst, out.data(), out.size());
+        return (int64_t)out.size();
+    } catch (const tfre::Unsupported&) { return TF_E_FATAL_UNSUPPORTED; }
+    catch (const tfre::SyntaxError&) { return TF_E_FATAL_CONFIG; }
+    catch (const std::exception&) { return TF_E_FATAL_CONFIG; }
 }
 
 int tfgpu_sink_destroy(tfgpu_sink* s) { if (!s) return TF_E_FATAL_ARG; if (s->pool) tfgpu_columnar_destroy(s->pool); delete s; return TF_OK; }

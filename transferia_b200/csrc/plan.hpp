@@ -350,6 +350,7 @@ struct Plan {
     bool has_sharder = false; uint32_t shards = 0; std::vector<int> shard_cols, shard_form; int shard_step_index = -1;
     std::vector<int> mask_step_index;
     bool has_splitter = false; int splitter_step = -1;   // table_splitter@sink: the last step of the chain (checked at the end of build_plan)
+    int n_regex_steps = 0;             // regex_replace_transformer@sink: rewrites the row image before the transposer, so these steps lead the chain
     std::vector<uint8_t> blob;         // literal pool referenced by DTerm
     std::string describe;
     // sink
@@ -535,6 +536,16 @@ inline Plan build_plan(const std::string& ns, const std::string& name, const std
                 throw FatalError(TF_E_FATAL_UNSUPPORTED, "table_splitter over an `any` / interval column is not implemented");
             pl.has_splitter = true; pl.splitter_step = step_no;
             add_desc("{\"type\":\"table_splitter\"}"); step_no++;
+        } else if (ttype == "regex_replace_transformer@sink" || ttype == "regex_replace_transformer") {   // registry/regex_replace/transformer.go:64-142
+            // Go's regexp over the string / []byte values of the matched columns; the schema does not change. tfgpu_sink_push applies it to the
+            // row image before the transposer (csrc/host_regex.hpp) and marks the step "@sink": nothing on the device runs a regular expression,
+            // so a plain tfgpu_push_* caller is refused, and so is a chain that would have to see the values before the replacement.
+            if (ttype == "regex_replace_transformer") throw FatalError(TF_E_FATAL_UNSUPPORTED, "regex_replace_transformer is applied by tfgpu_sink_push (to the row image, before the device chain)");
+            if (!tables_filter(cfg->get("tables")).match(name)) continue;       // Suitable :64-66: Tables.Match(table.Name), the bare name
+            if (step_no != pl.n_regex_steps)
+                throw FatalError(TF_E_FATAL_UNSUPPORTED, "regex_replace_transformer behind another transformer: tfgpu_sink_push rewrites the values before the chain runs (put it first)");
+            pl.n_regex_steps++;
+            add_desc("{\"type\":\"regex_replace_transformer\"}"); step_no++;
         } else if (ttype == "rename_tables") {                       // registry/rename/rename.go:46-67
             const tfj::Value* lst = cfg->get("renameTables");
             bool hit = false; std::string nns, nname;

@@ -18,7 +18,7 @@ from . import engine
 SINK_SYMBOLS = [
     "tfgpu_ch_open", "tfgpu_ch_close", "tfgpu_ch_last_error", "tfgpu_ch_server_info", "tfgpu_ch_exception_code",
     "tfgpu_ch_insert_begin", "tfgpu_ch_insert_columns", "tfgpu_ch_insert_data", "tfgpu_ch_insert_end", "tfgpu_ch_stats",
-    "tfgpu_ch_insert_query", "tfgpu_host_cityhash128",
+    "tfgpu_ch_insert_query", "tfgpu_host_cityhash128", "tfgpu_regex_replace_all",
     "tfgpu_columnar_create", "tfgpu_columnar_destroy", "tfgpu_columnar_last_error", "tfgpu_rows_to_batch", "tfgpu_batch_to_rows", "tfgpu_batch_gather", "tfgpu_batch_gather_sel",
 ]
 
@@ -43,6 +43,7 @@ def lib():
     L.tfgpu_ch_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     L.tfgpu_ch_insert_query.argtypes = [cp, cp, cp, i, C.c_char_p, u64]; L.tfgpu_ch_insert_query.restype = C.c_int64
     L.tfgpu_host_cityhash128.argtypes = [vp, u64, C.POINTER(u64)]; L.tfgpu_host_cityhash128.restype = None
+    L.tfgpu_regex_replace_all.argtypes = [cp, cp, cp, u64, cp, u64]; L.tfgpu_regex_replace_all.restype = C.c_int64
     _bound = True
     return L
 
@@ -52,6 +53,23 @@ def host_cityhash128(data: bytes) -> Tuple[int, int]:
     buf = C.create_string_buffer(data, len(data)) if data else None
     lib().tfgpu_host_cityhash128(C.cast(buf, C.c_void_p) if buf else None, len(data), out)
     return int(out[0]), int(out[1])
+
+
+def regex_replace_all(pattern: str, rule: str, src: bytes) -> bytes:
+    """regexp.MustCompile(pattern).ReplaceAll(src, rule) (regex_replace/transformer.go:127-142) as tfgpu_sink_push applies it; EngineError with
+    rc TF_E_FATAL_CONFIG for an expression Go refuses too, TF_E_FATAL_UNSUPPORTED for syntax the library does not carry."""
+    pat, rl = pattern.encode("utf-8", "surrogateescape"), rule.encode("utf-8", "surrogateescape")
+    if b"\0" in pat or b"\0" in rl:
+        raise ValueError("a NUL inside the expression does not travel as a C string (write \\x00)")
+    cap = max(64, 2 * len(src) + 64)
+    while True:
+        out = C.create_string_buffer(cap)
+        n = lib().tfgpu_regex_replace_all(pat, rl, src, len(src), out, cap)
+        if n < 0:
+            raise engine.EngineError(int(n), "tfgpu_regex_replace_all")
+        if n <= cap:
+            return out.raw[:n]
+        cap = int(n)
 
 
 def insert_query(database: str, table: str, columns: List[str], updateable: bool = False) -> str:
@@ -182,6 +200,7 @@ class Sink:
                 b = _rows.batch_from_struct(C.cast(ev.batch, C.POINTER(abi.TfBatch)).contents)
                 d["batch"] = b
                 d["columns"] = [None if c.values is None else np.asarray(c.values).copy() for c in b.columns]
+                d["text"] = [None if c.values is not None else _var_cells(c, b.nrows) for c in b.columns]      # the batch's buffers are the pool's: copied here
             if ev.errors:
                 errs = C.cast(ev.errors, C.POINTER(abi.TfRowErr))
                 d["errors"] = [(errs[k].row, errs[k].code, errs[k].term) for k in range(ev.n_items)]
@@ -206,6 +225,15 @@ class Sink:
     def close(self):
         if self._h:
             self._L.tfgpu_sink_destroy(self._h); self._h = None
+
+
+def _var_cells(col, n: int) -> list:
+    """The cells of a var-width host column as bytes (None = null)."""
+    raw = np.asarray(col.offsets).astype(np.int64)
+    off = np.concatenate([[0], np.cumsum(raw)]) if col.lens_width else raw
+    heap = np.asarray(col.heap).tobytes() if col.heap is not None else b""
+    valid = np.ones(n, bool) if col.validity is None else np.unpackbits(np.asarray(col.validity), bitorder="little")[:n].astype(bool)
+    return [heap[off[r]:off[r + 1]] if valid[r] else None for r in range(n)]
 
 
 class Dispatcher:
