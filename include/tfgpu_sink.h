@@ -188,8 +188,8 @@ int tfgpu_batch_gather_sel(tfgpu_columnar* pool, const tf_batch* in, const uint3
  *            pkg/serializer/queue/debezium_serializer.go:25-92 — key / value / tombstone messages of every row kind through
  *            tfgpu_emit_debezium_crud, with OldKeys and the `source` block's ID / LSN / CommitTime / TxID from the row form)
  * wire_fmt 0: row runs are handed on as columnar batches (ev.batch; with transformers the result of tfgpu_push_columns). `e` may be NULL
- * only when wire_fmt is 0 and the transformer list holds nothing but skip_events / rename_tables / table_splitter: those act on kinds and
- * table names, which the host decides (nothing to compute: the always-on middleware alone); everything else needs the device.
+ * only when wire_fmt is 0 and the transformer list holds nothing but skip_events / rename_tables / table_splitter / regex_replace_transformer:
+ * those act on kinds, table names and (regex_replace) the row image, which the host handles; everything else needs the device.
  * "updateable": true (model.ChSinkParams.IsUpdateable): the destination table carries `__data_transfer_commit_time` / `__data_transfer_delete_time`
  * (UInt64) behind its columns; buildChangeItemArgs / buildDeleteKindArgs (sink_table.go:397-432) run on the row image before the transpose — an
  * insert keeps its values + (CommitTime, 0), a delete is rebuilt from OldKeys (nil for the columns OldKeys does not list: insert_null_as_default
@@ -199,7 +199,12 @@ int tfgpu_batch_gather_sel(tfgpu_columnar* pool, const tf_batch* in, const uint3
  * (current table name + splitter + to_string.SerializeToString of the listed columns, "<nil>" for nil / absent values and for items without
  * values) is computed per row from the row image, the rows of a run are grouped by it in order of first appearance and every group goes
  * down on its own (ev.out_table, its own INSERT). It must be the last transformer of the list; `any` / interval columns, []byte outside
- * `string` columns and useLegacyLf are refused. */
+ * `string` columns and useLegacyLf are refused.
+ * regex_replace_transformer (pkg/transformer/registry/regex_replace/transformer.go:87-142) is applied HERE as well, to the row image before
+ * the transposer: Go string values of utf8 columns and []byte values of string columns that the step's column filter names are replaced by
+ * Regexp.ReplaceAll (see tfgpu_regex_replace_all). No kernel runs regular expressions, so the step (several are fine) must stand at the head
+ * of the transformer list; an expression regexp.Compile refuses fails tfgpu_sink_create with TF_E_FATAL_CONFIG like the transformer's
+ * constructor, one this library does not carry ((?i), (?U), \p{..}) with TF_E_FATAL_UNSUPPORTED. */
 typedef struct tfgpu_sink tfgpu_sink;
 #define TF_SINK_EV_ROWS   1   /* one downstream Push of row events of one table */
 #define TF_SINK_EV_ITEM   2   /* one downstream Push of a single non-row item */

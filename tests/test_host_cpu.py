@@ -491,6 +491,17 @@ def test_name_filter_reference_cases(po):
     with pytest.raises(engine.EngineError) as ei:
         engine.plan_validate("", "t", schema, [{"convert_to_string": {"columns": {"includeColumns": ["include", "*"], "excludeColumns": [".*other.*"]}}}])
     assert ei.value.rc == -1
+    # the expressions are Go's (regexp.Compile), not ECMAScript's: \z, \A, POSIX classes, named groups; what the library's engine does not
+    # carry is an unsupported plan, not a silently different match
+    def product_only(cols_cfg):
+        d = engine.plan_validate("", "t", schema, [{"convert_to_string": {"columns": cols_cfg}}])
+        return [c["name"] for c in d["result_schema"] if c["type"] == "utf8"]
+    assert product_only({"includeColumns": [r"\Aother\z"]}) == ["other"]
+    assert product_only({"includeColumns": [r"^[[:lower:]]+_[[:alpha:]]+$"]}) == ["any_value"]
+    assert product_only({"includeColumns": [r"^(?P<stem>in|ex)clude$"]}) == ["include", "exclude"]
+    with pytest.raises(engine.EngineError) as ei:
+        product_only({"includeColumns": ["(?i)INCLUDE"]})
+    assert ei.value.rc == -2
 
 
 def test_skip_events_and_rename_reference_cases():

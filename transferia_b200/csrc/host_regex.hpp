@@ -539,6 +539,9 @@ struct Machine {
     }
 };
 
+// Regexp.MatchString: is there a match anywhere in the text
+inline bool match_string(const Prog& p, const std::string& text) { Machine m(p); return m.search((const uint8_t*)text.data(), text.size(), 0); }
+
 // ---------------------------------------------------------------- Regexp.Expand templates + ReplaceAll (regexp.go)
 struct Template {
     struct Piece { std::string text; bool ref = false; std::vector<int> groups; };   // ref: the first listed group that took part in the match (none listed: nothing)

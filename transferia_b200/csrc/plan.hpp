@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <regex>
+#include "host_regex.hpp"
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -285,23 +286,26 @@ private:
 };
 
 // ------------------------------------------------------------------ table / column name filters
+// The patterns are Go regular expressions (regexp.Compile in filter.NewFilter, filter.go:46-71): compiled by the Go-syntax engine of
+// host_regex.hpp, so `\z`, POSIX classes, ASCII `\d` / `\w` and the errors are Go's, not ECMAScript's.
 struct NameFilter {
     std::vector<std::string> inc_src, exc_src;
-    std::vector<std::regex> inc, exc;
+    std::vector<std::shared_ptr<tfre::Prog>> inc, exc;
     bool empty() const { return inc_src.empty() && exc_src.empty(); }
     bool match(const std::string& v) const {          // filter.go:27-44
-        for (auto& r : exc) if (std::regex_search(v, r)) return false;
+        for (auto& r : exc) if (tfre::match_string(*r, v)) return false;
         if (inc_src.empty()) return true;
-        for (auto& r : inc) if (std::regex_search(v, r)) return true;
+        for (auto& r : inc) if (tfre::match_string(*r, v)) return true;
         return false;
     }
 };
 inline NameFilter make_filter(const std::vector<std::string>& inc, const std::vector<std::string>& exc) {
     NameFilter f; f.inc_src = inc; f.exc_src = exc;
     try {
-        for (auto& s : inc) f.inc.emplace_back(s, std::regex::ECMAScript);
-        for (auto& s : exc) f.exc.emplace_back(s, std::regex::ECMAScript);
-    } catch (const std::regex_error& e) { throw FatalError(TF_E_FATAL_CONFIG, std::string("unable to compile regexp: ") + e.what()); }
+        for (auto& s : inc) f.inc.push_back(std::make_shared<tfre::Prog>(tfre::compile(s)));
+        for (auto& s : exc) f.exc.push_back(std::make_shared<tfre::Prog>(tfre::compile(s)));
+    } catch (const tfre::SyntaxError& e) { throw FatalError(TF_E_FATAL_CONFIG, std::string("unable to compile regexp: ") + e.what()); }
+    catch (const tfre::Unsupported& e) { throw FatalError(TF_E_FATAL_UNSUPPORTED, std::string("a table / column filter expression this library does not carry: ") + e.what()); }
     return f;
 }
 inline NameFilter tables_filter(const tfj::Value* cfg) {
