@@ -1,6 +1,7 @@
 """Host transpose: []ChangeItem in row form -> columnar tf_batch and back (tfgpu_rows_to_batch / tfgpu_batch_to_rows).
 The expectations are stated independently in numpy on the columnar side: a batch made by the workload generator is turned into ChangeItems
 carrying the canonical Go types, flattened like the shim would, transposed by the product, and must come back as the same columns."""
+import os
 import numpy as np
 import pytest
 
@@ -361,4 +362,49 @@ def test_transposer_rejects_malformed_images_without_crashing():
         except engine.EngineError as ex:
             assert ex.rc in (-2, -3), ex.rc; outcomes.add(ex.rc)
     assert -3 in outcomes
+    pool.close()
+
+
+def test_strict_single_decode_path_equals_the_general_path():
+    """Strictly typed value lists take the one-decode path of the transposer (fixed-width values written while decoding, var-width cells
+    copied from noted image offsets); TFGPU_TRANSPOSE_GENERAL forces the two-pass path that also lays out loose columns. Same columns
+    byte for byte: dense and sparse rows, nils, nanoseconds, raw strings inside `any`, empty and > 64 KiB cells, several chunk sizes."""
+    rng = np.random.default_rng(99)
+    batch, schema = all_types_batch(5000, seed=23)
+    items = rows.items_from_batch(batch)
+    for k in range(0, len(items), 7):                                     # every 7th row carries a column subset (absent = nil)
+        keep = sorted(rng.choice(len(schema), size=int(rng.integers(0, len(schema))), replace=False).tolist())
+        items[k] = ChangeItem(rows.KIND_UPDATE, 0, {c: items[k].values[c] for c in keep}, {0: items[k].values[0]})
+    any_col = [i for i, c in enumerate(schema) if c["type"] == "any"]
+    utf_col = [i for i, c in enumerate(schema) if c["type"] == "utf8"]
+    for k in range(3, len(items), 11):
+        if isinstance(items[k].values, list):
+            for c in any_col: items[k].values[c] = go.string("raw text %d" % k)
+            for c in utf_col[:1]: items[k].values[c] = go.string("x" * (70000 if k % 5 == 0 else 0))
+    img = rows.RowsImage(items, [("db", "t", schema)])
+    pool = rows.Columnar()
+
+    def snapshot(t):
+        out = []
+        for c in t.batch.columns:
+            out.append((c.type, c.lens_width, *(None if a is None else np.asarray(a).tobytes() for a in (c.values, c.validity, c.offsets, c.heap, c.aux))))
+        return out, None if t.batch.kinds is None else np.asarray(t.batch.kinds).tobytes()
+    try:
+        for threads in (1, 3, 8):
+            os.environ.pop("TFGPU_TRANSPOSE_GENERAL", None)
+            strict = snapshot(pool.rows_to_batch(img, threads=threads))
+            os.environ["TFGPU_TRANSPOSE_GENERAL"] = "1"
+            general = snapshot(pool.rows_to_batch(img, threads=threads))
+            assert len(strict[0]) == len(general[0]) and strict[1] == general[1]
+            for c, (a, b) in enumerate(zip(strict[0], general[0])):
+                assert a[:2] == b[:2], (c, a[:2], b[:2])
+                for name, x, y in zip(("values", "validity", "offsets", "heap", "aux"), a[2:], b[2:]):
+                    if name == "validity" and x is not None and y is not None:
+                        n = len(items); assert x[:n // 8] == y[:n // 8] and (n % 8 == 0 or x[n // 8] == y[n // 8]), (c, name)
+                    elif name == "heap" and x is not None and y is not None:
+                        assert x == y, (c, name)
+                    else:
+                        assert (x is None) == (y is None) and (x is None or x == y), (c, name, threads)
+    finally:
+        os.environ.pop("TFGPU_TRANSPOSE_GENERAL", None)
     pool.close()

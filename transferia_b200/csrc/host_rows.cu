@@ -7,6 +7,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <condition_variable>
+#include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -98,6 +100,8 @@ struct tfgpu_columnar {
     std::map<std::string, std::vector<int>> schemas;      // schema_json -> tf types
     std::vector<Buf> bufs; size_t next_buf = 0;
     Buf* take() { if (next_buf == bufs.size()) bufs.emplace_back(); return &bufs[next_buf++]; }
+    std::vector<Buf> tmp_bufs; size_t next_tmp = 0;       // scratch of the strict transposer path (never handed out, never pinned)
+    uint8_t* take_tmp(size_t n) { if (next_tmp == tmp_bufs.size()) tmp_bufs.emplace_back(); return tmp_bufs[next_tmp++].ensure(n, false); }
     // results of the last call
     std::vector<tf_col> cols, old_cols; tf_batch batch{}, old_batch{}; tf_row_meta meta{}; tf_old_keys old{};
     std::vector<uint8_t> present;
@@ -186,9 +190,137 @@ struct Transposer {
         }
     }
 
-    template <class Get> void run(Get get, bool keyed, std::vector<tf_col>& out_cols, const uint8_t* only /* ncols flags or nullptr */) {
+    // The strict path (every value carries the canonical Go type of its column, type_checkers.go:39-84, or is nil — what a source that honours
+    // the contract sends): ONE decode of the row image. Fixed-width values go straight to their columns; of a var-width cell the pass only
+    // notes where it lies in the image and how long it is, and a second pass copies the cells column by column (sequential writes, no
+    // decoding). A value of another type makes the call start over on the general two-pass path below, which lays out loose columns.
+    template <class Get> bool run_strict(Get get, std::vector<tf_col>& out_cols, const uint8_t* image, uint64_t image_len) {
         const uint32_t nc = (uint32_t)tfs.size();
+        if (n == 0 || image_len >= (1ull << 32) || std::getenv("TFGPU_TRANSPOSE_GENERAL")) return false;
+        const bool trace = std::getenv("TFGPU_TRANSPOSE_TRACE") != nullptr; const auto t_start = std::chrono::steady_clock::now();
+        if (threads > 1 && n / ((uint64_t)threads * 4) < chunk) chunk = std::max<uint64_t>(256, n / ((uint64_t)threads * 4) & ~7ull);
+        nchunks = (n + chunk - 1) / chunk;
+        struct SCol { uint8_t want = 0, also = 0, w = 0; bool time = false; uint8_t *values = nullptr, *validity = nullptr, *aux = nullptr; uint32_t vi = 0; };
+        std::vector<SCol> sc(nc); uint32_t nvar = 0;
+        for (uint32_t c = 0; c < nc; c++) {
+            SCol& x = sc[c]; x.want = x.also = (uint8_t)canonical_tag(tfs[c]); x.w = (uint8_t)fixed_width(tfs[c]); x.time = is_time(tfs[c]);
+            if (tfs[c] == TF_UTF8) x.also = TF_V_BYTES; else if (tfs[c] == TF_BYTES) x.also = TF_V_STRING;          // a text cell is its bytes either way (M_TEXT below)
+            else if (tfs[c] == TF_ANY) { x.also = TF_V_STRING; x.aux = pool->take()->ensure(n + 16, pool->want_pinned); }   // a raw Go string inside `any`: the cell's aux tag
+            if (x.w) { x.values = pool->take()->ensure((size_t)x.w * n + 16, pool->want_pinned); if (x.time) x.aux = pool->take()->ensure(4 * n + 16, pool->want_pinned); }
+            else x.vi = nvar++;
+            x.validity = pool->take()->ensure((n + 7) / 8 + 16, pool->want_pinned);
+        }
+        // where every var-width cell lies in the image and how long it is: (offset, length) per (row, var column), row-major — written and
+        // read back as one stream
+        uint32_t* cells = (uint32_t*)pool->take_tmp((size_t)8 * nvar * n + 16);
+        stats.assign((size_t)nchunks * nc, ChunkStat());
+        std::atomic<bool> loose{false};
+        parallel_chunks(pool, n, chunk, threads, [&](uint64_t k) {
+            if (loose.load(std::memory_order_relaxed)) return;
+            const uint64_t r0 = k * chunk, r1 = std::min(n, (k + 1) * chunk);
+            ChunkStat* st = &stats[(size_t)k * nc];
+            for (uint32_t c = 0; c < nc; c++) {                  // a row without a value for the column: zero value, zero length, validity bit cleared below
+                SCol& x = sc[c];
+                std::memset(x.validity + r0 / 8, 0xff, (r1 - r0 + 7) / 8);
+                if (x.values) std::memset(x.values + (size_t)x.w * r0, 0, (size_t)x.w * (r1 - r0));
+                if (x.aux) { const size_t aw = x.time ? 4 : 1; std::memset(x.aux + aw * r0, 0, aw * (r1 - r0)); }
+            }
+            std::memset(cells + (size_t)2 * nvar * r0, 0, (size_t)8 * nvar * (r1 - r0));
+            std::vector<uint8_t> seen(nc);
+            for (uint64_t j = r0; j < r1; j++) {
+                const uint8_t *at, *end; bool sparse; uint32_t nvals; get(j, at, end, sparse, nvals);
+                if (!sparse && nvals != nc) throw Fail{TF_E_FATAL_ARG, "an item's value count differs from its table schema (set TF_ITEM_SPARSE for a column subset)"};
+                if (sparse) std::fill(seen.begin(), seen.end(), 0);
+                const uint8_t vbit = (uint8_t)(1u << (j & 7)); const uint64_t vbyte = j >> 3;
+                for (uint32_t v = 0; v < nvals; v++) {
+                    uint32_t c = v;
+                    if (sparse) {
+                        if (end - at < 2) throw Fail{TF_E_FATAL_ARG, "truncated value image"};
+                        uint16_t ci; std::memcpy(&ci, at, 2); at += 2; c = ci;
+                        if (c >= nc) throw Fail{TF_E_FATAL_ARG, "column index outside the table schema"};
+                        seen[c] = 1;
+                    }
+                    if (at >= end) throw Fail{TF_E_FATAL_ARG, "malformed value image"};
+                    const uint8_t tag = *at++; SCol& x = sc[c];
+                    if (tag == x.want || tag == x.also) {
+                        if (x.w) {
+                            const uint32_t pw = x.time ? 12u : x.w;
+                            if ((size_t)(end - at) < pw) throw Fail{TF_E_FATAL_ARG, "malformed value image"};
+                            uint8_t* d = x.values + (size_t)x.w * j;
+                            switch (x.w) { case 1: d[0] = at[0]; break; case 2: std::memcpy(d, at, 2); break; case 4: std::memcpy(d, at, 4); break; default: std::memcpy(d, at, 8); }
+                            if (x.time) { uint32_t ns; std::memcpy(&ns, at + 8, 4); if (ns) { std::memcpy(x.aux + 4 * j, &ns, 4); st[c].nsec = true; } }
+                            at += pw;
+                        } else {
+                            if (end - at < 4) throw Fail{TF_E_FATAL_ARG, "malformed value image"};
+                            uint32_t len; std::memcpy(&len, at, 4); at += 4;
+                            if ((size_t)(end - at) < len) throw Fail{TF_E_FATAL_ARG, "malformed value image"};
+                            uint32_t* rec = cells + ((size_t)j * nvar + x.vi) * 2; rec[0] = (uint32_t)(at - image); rec[1] = len; st[c].heap += len; if (len > st[c].max_len) st[c].max_len = len;
+                            at += len;
+                            if (x.aux && tag == TF_V_STRING) { x.aux[j] = 1; st[c].nsec = true; }
+                        }
+                    } else if (tag == TF_V_NIL) { x.validity[vbyte] &= (uint8_t)~vbit; st[c].nil = true; }
+                    else { if (trace && !loose.exchange(true)) fprintf(stderr, "[transpose strict] column %u (type %d) holds a value of tag %d: general path\n", c, tfs[c], (int)tag); loose.store(true, std::memory_order_relaxed); return; }
+                }
+                if (sparse) for (uint32_t c = 0; c < nc; c++) if (!seen[c]) { sc[c].validity[vbyte] &= (uint8_t)~vbit; st[c].nil = true; }   // absent = nil in the columnar view
+            }
+            if (r1 == n && (n & 7)) for (uint32_t c = 0; c < nc; c++) sc[c].validity[n >> 3] &= (uint8_t)((1u << (n & 7)) - 1);   // no stray bits behind the last row
+        });
+        if (loose.load()) return false;
+        const auto t_p1 = std::chrono::steady_clock::now();
+        // ---- layout
+        cp.assign(nc, ColPlan()); heap_base.assign((size_t)nchunks * nc, 0); out_cols.assign(nc, tf_col{});
+        for (uint32_t c = 0; c < nc; c++) {
+            ColPlan& p = cp[c]; SCol& x = sc[c]; tf_col& o = out_cols[c];
+            p.schema_tf = p.phys_tf = tfs[c]; p.width = x.w; o.type = tfs[c];
+            for (uint64_t k = 0; k < nchunks; k++) {
+                const ChunkStat& s = stats[(size_t)k * nc + c];
+                heap_base[(size_t)k * nc + c] = p.heap_total;
+                p.heap_total += s.heap; p.max_len = std::max(p.max_len, s.max_len); p.has_nil |= s.nil; p.has_nsec |= s.nsec;
+            }
+            if (p.has_nil) o.validity = x.validity;
+            if (x.w) { o.values = x.values; if (p.has_nsec) o.aux = x.aux; continue; }
+            if (x.aux && p.has_nsec) { p.has_anytag = true; p.has_nsec = false; o.aux = x.aux; }
+            if (p.heap_total >= (1ull << 32)) throw Fail{TF_E_FATAL_UNSUPPORTED, "column " + std::to_string(c) + " (" + tfplan::tf_to_yt(tfs[c]) + "): heap over 4 GiB"};
+            p.lens_width = p.max_len < 256 ? 1 : p.max_len < 65536 ? 2 : 4;
+            p.lens = pool->take()->ensure((size_t)p.lens_width * (n + 1) + 16, pool->want_pinned);
+            p.heap = pool->take()->ensure((size_t)p.heap_total + 16, pool->want_pinned);
+            o.offsets = (const uint32_t*)p.lens; o.heap = p.heap; o.heap_len = p.heap_total;
+            o.flags = p.lens_width == 1 ? TF_COL_LENS8 : p.lens_width == 2 ? TF_COL_LENS16 : 0;
+        }
+        // ---- pass 2: the var-width cells, row by row (a row's cells lie together in the image), one running heap offset per column
+        std::vector<uint32_t> var_cols; for (uint32_t c = 0; c < nc; c++) if (!cp[c].width) var_cols.push_back(c);
+        parallel_chunks(pool, n, chunk, threads, [&](uint64_t k) {
+            const uint64_t r0 = k * chunk, r1 = std::min(n, (k + 1) * chunk); const size_t nv = var_cols.size();
+            std::vector<uint64_t> off(nv), hend(nv);
+            for (size_t i = 0; i < nv; i++) { const uint32_t c = var_cols[i]; off[i] = heap_base[(size_t)k * nc + c]; hend[i] = k + 1 < nchunks ? heap_base[(size_t)(k + 1) * nc + c] : cp[c].heap_total; }
+            for (uint64_t j = r0; j < r1; j++) {
+                const uint32_t* rec = cells + (size_t)j * nv * 2;
+                for (size_t i = 0; i < nv; i++) {
+                    const ColPlan& p = cp[var_cols[i]];
+                    const uint32_t at = rec[2 * i], len = rec[2 * i + 1]; const uint8_t* src = image + at; const uint64_t o = off[i];
+                    if (p.lens_width == 1) p.lens[j] = (uint8_t)len;
+                    else if (p.lens_width == 2) { const uint16_t l = (uint16_t)len; std::memcpy(p.lens + 2 * j, &l, 2); }
+                    else { const uint32_t o32 = (uint32_t)o; std::memcpy(p.lens + 4 * j, &o32, 4); }
+                    if (len <= 16 && o + 16 <= hend[i] && (uint64_t)at + 16 <= image_len) std::memcpy(p.heap + o, src, 16);   // one 16-byte move inside this chunk's share; the next cell overwrites the excess
+                    else std::memcpy(p.heap + o, src, len);
+                    off[i] = o + len;
+                }
+            }
+            if (r1 == n) for (uint32_t c : var_cols) if (cp[c].lens_width == 4) { const uint32_t tot = (uint32_t)cp[c].heap_total; std::memcpy(cp[c].lens + 4 * n, &tot, 4); }
+        });
+        if (trace) {
+            const auto t_end = std::chrono::steady_clock::now(); auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+            fprintf(stderr, "[transpose strict] n=%llu decode %.2f ms, cells %.2f ms\n", (unsigned long long)n, ms(t_start, t_p1), ms(t_p1, t_end));
+        }
+        return true;
+    }
+
+    template <class Get> void run(Get get, bool keyed, std::vector<tf_col>& out_cols, const uint8_t* only /* ncols flags or nullptr */) {
+        const uint32_t nc = (uint32_t)tfs.size(); const auto t_start = std::chrono::steady_clock::now();
         cp.assign(nc, ColPlan()); for (uint32_t c = 0; c < nc; c++) cp[c].schema_tf = tfs[c];
+        // four tasks per worker at least (98 tasks of 2048 rows leave a third of 64 workers idle in the second round of a 200 k-row batch), never
+        // below 256 rows (the per-task setup is per column), a multiple of 8 (validity bytes)
+        if (threads > 1 && n / ((uint64_t)threads * 4) < chunk) chunk = std::max<uint64_t>(256, n / ((uint64_t)threads * 4) & ~7ull);
         nchunks = (n + chunk - 1) / chunk;
         stats.assign((size_t)nchunks * nc, ChunkStat());
         // ---- pass 1: tags, heap bytes, longest cell per (chunk, column)
@@ -214,6 +346,7 @@ struct Transposer {
                 if (track) for (uint32_t c = 0; c < nc; c++) if (!seen[c] && (!only || only[c])) st[c].nil = true;     // absent = nil in the columnar view
             }
         });
+        const bool trace = std::getenv("TFGPU_TRANSPOSE_TRACE") != nullptr; const auto t_p1 = std::chrono::steady_clock::now();
         // ---- layout decisions per column
         heap_base.assign((size_t)nchunks * nc, 0);
         for (uint32_t c = 0; c < nc; c++) {
@@ -262,6 +395,7 @@ struct Transposer {
             if (p.has_anytag) { p.aux = pool->take()->ensure(n + 16, pool->want_pinned); o.aux = p.aux; }
         }
         std::vector<uint32_t> wide; for (uint32_t c = 0; c < nc; c++) if (cp[c].lens && cp[c].lens_width == 4) wide.push_back(c);
+        const auto t_buf = std::chrono::steady_clock::now();
         // ---- pass 2: fill (chunks are multiples of 8 rows, so validity bytes never straddle two workers)
         parallel_chunks(pool, n, chunk, threads, [&](uint64_t k) {
             const uint64_t r0 = k * chunk, r1 = std::min(n, (k + 1) * chunk);
@@ -304,6 +438,10 @@ struct Transposer {
             }
             if (r1 == n) for (uint32_t c : wide) { const uint32_t tot = (uint32_t)cp[c].heap_total; std::memcpy(cp[c].lens + 4 * n, &tot, 4); }
         });
+        if (trace) {
+            const auto t_end = std::chrono::steady_clock::now(); auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+            fprintf(stderr, "[transpose] n=%llu pass1 %.2f ms, layout+buffers %.2f ms, pass2 %.2f ms\n", (unsigned long long)n, ms(t_start, t_p1), ms(t_p1, t_buf), ms(t_buf, t_end));
+        }
     }
 };
 
@@ -319,7 +457,7 @@ const std::vector<int>& schema_types(tfgpu_columnar* p, const char* schema_json)
 
 }  // namespace
 
-tfgpu_columnar::~tfgpu_columnar() { for (auto& b : bufs) b.release(); delete (Workers*)workers; }
+tfgpu_columnar::~tfgpu_columnar() { for (auto& b : bufs) b.release(); for (auto& b : tmp_bufs) b.release(); delete (Workers*)workers; }
 
 extern "C" {
 
@@ -352,11 +490,14 @@ int tfgpu_rows_to_batch(tfgpu_columnar* pool, const tf_rows* rows, uint32_t tabl
         if (threads <= 0) threads = (int)std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency()));
         pool->next_buf = 0;
         const uint8_t* vend = rows->values + rows->values_len;
-        Transposer tr{pool, tfs, n, threads};
-        tr.run([&](uint64_t j, const uint8_t*& at, const uint8_t*& end, bool& sparse, uint32_t& nvals) {
+        auto value_list = [&](uint64_t j, const uint8_t*& at, const uint8_t*& end, bool& sparse, uint32_t& nvals) {
             const tf_item& it = rows->items[item_idx[j]];
             at = rows->values + it.values_off; end = vend; sparse = it.flags & TF_ITEM_SPARSE; nvals = it.n_values;
-        }, false, pool->cols, nullptr);
+        };
+        pool->next_tmp = 0;
+        bool strict;
+        { Transposer ts{pool, tfs, n, threads}; strict = ts.run_strict(value_list, pool->cols, rows->values, rows->values_len); }
+        if (!strict) { pool->next_buf = 0; Transposer tr{pool, tfs, n, threads}; tr.run(value_list, false, pool->cols, nullptr); }
         // kinds + meta
         uint8_t* kinds = pool->take()->ensure(n + 16, pool->want_pinned);
         uint32_t* ids = (uint32_t*)pool->take()->ensure(4 * n + 16, pool->want_pinned);
