@@ -13,7 +13,9 @@ leftmost-first rules on the syntax both share) and re-states around it what diff
     advances by one rune;
   * Regexp.Expand's template ($1, ${1}, $name, $$; the longest run of letters / digits / _ is the name; `$1x` is the NAME "1x"; a
     malformed $ is text).
-Not translated (NotImplementedError; the product refuses the same with TF_E_FATAL_UNSUPPORTED): (?i), (?U), \\p{..}; and flag groups that
+  * (?i) folds ASCII letters by unicode.SimpleFold's orbits (k, K also U+212A; s, S also U+017F), perl / POSIX classes folded before they are
+    negated — done here on the translated sets, Python's IGNORECASE is not used (it adds U+0130 / U+0131, which Go does not);
+Not translated (NotImplementedError; the product refuses the same with TF_E_FATAL_UNSUPPORTED): (?U), \\p{..}, (?i) over non-ASCII runes; and flag groups that
 are not at the start of the expression or scoped `(?s:...)` (Python cannot state them; the product takes them).
 
 Parity pinned by: every case of the reference's transformer_test.go (TestTransformer_Apply, TestReplace, TestReplaceMultipleMatches,
@@ -45,6 +47,19 @@ def _negate(rs):
     return out
 
 
+def _fold(rs):
+    """unicode.SimpleFold orbits, ASCII only (what the product carries): the other case of a letter, U+212A for k / K, U+017F for s / S."""
+    out = list(rs)
+    for lo, hi in rs:
+        if hi >= 128: raise NotImplementedError("(?i) over runes outside ASCII")
+        for c in range(lo, hi + 1):
+            ch = chr(c)
+            if ch.isalpha(): out.append((ord(ch.swapcase()),) * 2)
+            if ch in "kK": out.append((0x212A, 0x212A))
+            if ch in "sS": out.append((0x017F, 0x017F))
+    return out
+
+
 def _u(cp: int) -> str:
     return "\\U%08x" % cp
 
@@ -53,6 +68,12 @@ def _cls(rs, neg=False) -> str:
     if neg: rs = _negate(rs)
     if not rs: return "[^\\U00000000-\\U0010ffff]"
     return "[" + "".join(_u(lo) if lo == hi else _u(lo) + "-" + _u(hi) for lo, hi in rs) + "]"
+
+
+def _lit(cp: int, fold: bool) -> str:
+    if not fold: return _u(cp)
+    rs = sorted(set(_fold([(cp, cp)])))
+    return _u(cp) if len(rs) == 1 else _cls(rs)
 
 
 def _escape(p: str, i: int) -> Tuple[int, int]:
@@ -86,6 +107,7 @@ def translate(p: str) -> Tuple[str, int]:
     """Go expression -> (Python expression, flags)."""
     out: List[str] = []; i = 0; flags = re.ASCII
     multi = [False]                                     # (?m) state per open group
+    fold = [False]                                      # (?i) state per open group: folded here, Python's IGNORECASE is not used
     last_repeat = False; can_repeat = False
     while i < len(p):
         c = p[i]; rep = False
@@ -94,31 +116,35 @@ def translate(p: str) -> Tuple[str, int]:
                 j = p.find(">", i)
                 name = p[i + (4 if p[i + 2] == "P" else 3):j] if j >= 0 else ""
                 if not name or not re.fullmatch(r"[A-Za-z0-9_]+", name): raise GoSyntaxError("capture name")
-                out.append("(?P<%s>" % name); i = j + 1; multi.append(multi[-1]); can_repeat = False
+                out.append("(?P<%s>" % name); i = j + 1; multi.append(multi[-1]); fold.append(fold[-1]); can_repeat = False
             elif p.startswith("(?", i):
                 j = i + 2; fl = ""
                 while j < len(p) and p[j] not in ":)": fl += p[j]; j += 1
                 if j >= len(p): raise GoSyntaxError("missing )")
-                if any(ch in fl for ch in "iU"): raise NotImplementedError("(?i) / (?U)")
-                if not all(ch in "ms-" for ch in fl) or fl.count("-") > 1 or fl.endswith("-"): raise GoSyntaxError("flags")
+                if "U" in fl: raise NotImplementedError("(?U)")
+                if not all(ch in "ims-" for ch in fl) or fl.count("-") > 1 or fl.endswith("-"): raise GoSyntaxError("flags")
                 on, _, off = fl.partition("-")
-                m = multi[-1]
+                m, f = multi[-1], fold[-1]
                 if "m" in on: m = True
                 if "m" in off: m = False
+                if "i" in on: f = True
+                if "i" in off: f = False
+                pyfl = on.replace("i", "") + ("-" + off.replace("i", "") if off.replace("i", "") else "")
                 if p[j] == ":":
-                    out.append("(?" + fl + ":" if fl else "(?:"); multi.append(m); can_repeat = False
+                    out.append("(?" + pyfl + ":" if pyfl else "(?:"); multi.append(m); fold.append(f); can_repeat = False
                 else:
-                    if i != 0 or "-" in fl or not fl: raise NotImplementedError("flag group inside the expression")
+                    if not fl: raise GoSyntaxError("flags")
+                    if pyfl and (i != 0 or "-" in fl): raise NotImplementedError("flag group inside the expression")      # (?i) alone is folded here: fine anywhere
                     if "m" in on: flags |= re.MULTILINE
                     if "s" in on: flags |= re.DOTALL
-                    multi[-1] = m; can_repeat = False
+                    multi[-1] = m; fold[-1] = f; can_repeat = False
                 i = j + 1
             else:
-                out.append("("); i += 1; multi.append(multi[-1]); can_repeat = False
+                out.append("("); i += 1; multi.append(multi[-1]); fold.append(fold[-1]); can_repeat = False
             last_repeat = False; continue
         if c == ")":
             if len(multi) == 1: raise GoSyntaxError("unexpected )")
-            multi.pop(); out.append(")"); i += 1; can_repeat = True; last_repeat = False; continue
+            multi.pop(); fold.pop(); out.append(")"); i += 1; can_repeat = True; last_repeat = False; continue
         if c == "|":
             out.append("|"); i += 1; can_repeat = False; last_repeat = False; continue
         if c in "*+?" or c == "{":
@@ -148,10 +174,13 @@ def translate(p: str) -> Tuple[str, int]:
                 if p.startswith("[:", i) and p.find(":]", i) >= 0:
                     j = p.find(":]", i); name = p[i + 2:j]; pn = name.startswith("^"); name = name.lstrip("^") if pn else name
                     if name not in _POSIX: raise GoSyntaxError("class")
-                    rs += _negate(_POSIX[name]) if pn else _POSIX[name]; i = j + 2; continue
+                    base = _fold(_POSIX[name]) if fold[-1] else _POSIX[name]
+                    rs += _negate(base) if pn else base; i = j + 2; continue
                 if p[i] == "\\" and i + 1 < len(p) and p[i + 1] in "pP": raise NotImplementedError("\\p")
                 if p[i] == "\\" and i + 1 < len(p) and p[i + 1] in "dDsSwW":
-                    base = _PERL[p[i + 1].lower()]; rs += _negate(base) if p[i + 1].isupper() else base; i += 2; continue
+                    base = _PERL[p[i + 1].lower()]
+                    if fold[-1]: base = _fold(base)
+                    rs += _negate(base) if p[i + 1].isupper() else base; i += 2; continue
                 if p[i] == "\\": lo, i = _escape(p, i + 1)
                 else: lo = ord(p[i]); i += 1
                 hi = lo
@@ -161,7 +190,7 @@ def translate(p: str) -> Tuple[str, int]:
                     if p[i] == "\\": hi, i = _escape(p, i + 1)
                     else: hi = ord(p[i]); i += 1
                     if hi < lo: raise GoSyntaxError("class range")
-                rs.append((lo, hi))
+                rs += _fold([(lo, hi)]) if fold[-1] else [(lo, hi)]
             out.append(_cls(rs, neg)); i += 1; can_repeat = True; last_repeat = False; continue
         elif c == "\\":
             if i + 1 >= len(p): raise GoSyntaxError("trailing backslash")
@@ -170,15 +199,15 @@ def translate(p: str) -> Tuple[str, int]:
             if e == "C": raise GoSyntaxError("\\C")
             if e == "Q":
                 j = p.find("\\E", i + 2); lit = p[i + 2:] if j < 0 else p[i + 2:j]
-                out.append("".join(_u(ord(ch)) for ch in lit)); i = len(p) if j < 0 else j + 2
+                out.append("".join(_lit(ord(ch), fold[-1]) for ch in lit)); i = len(p) if j < 0 else j + 2
                 can_repeat = bool(lit) or can_repeat; last_repeat = False; continue
-            if e in "dDsSwW": out.append(_cls(_PERL[e.lower()], e.isupper())); i += 2; can_repeat = True; last_repeat = False; continue
+            if e in "dDsSwW": out.append(_cls(_fold(_PERL[e.lower()]) if fold[-1] else _PERL[e.lower()], e.isupper())); i += 2; can_repeat = True; last_repeat = False; continue
             if e == "A": out.append("\\A"); i += 2; can_repeat = True; last_repeat = False; continue
             if e == "z": out.append("\\Z"); i += 2; can_repeat = True; last_repeat = False; continue
             if e in "bB": out.append("\\" + e); i += 2; can_repeat = True; last_repeat = False; continue
-            r, i = _escape(p, i + 1); out.append(_u(r)); can_repeat = True; last_repeat = False; continue
+            r, i = _escape(p, i + 1); out.append(_lit(r, fold[-1])); can_repeat = True; last_repeat = False; continue
         else:
-            out.append(_u(ord(c)))
+            out.append(_lit(ord(c), fold[-1]))
         i += 1; can_repeat = True; last_repeat = rep
     if len(multi) != 1: raise GoSyntaxError("missing )")
     return "".join(out), flags

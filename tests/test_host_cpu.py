@@ -499,8 +499,9 @@ def test_name_filter_reference_cases(po):
     assert product_only({"includeColumns": [r"\Aother\z"]}) == ["other"]
     assert product_only({"includeColumns": [r"^[[:lower:]]+_[[:alpha:]]+$"]}) == ["any_value"]
     assert product_only({"includeColumns": [r"^(?P<stem>in|ex)clude$"]}) == ["include", "exclude"]
+    assert product_only({"includeColumns": ["(?i)^INCLUDE$"]}) == ["include"]
     with pytest.raises(engine.EngineError) as ei:
-        product_only({"includeColumns": ["(?i)INCLUDE"]})
+        product_only({"includeColumns": ["(?U)incl.*"]})
     assert ei.value.rc == -2
 
 

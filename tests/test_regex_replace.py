@@ -109,6 +109,25 @@ def test_go_specifics():
     assert R(r"(|a)*", "<$1>", b"aa") == b"<>a<>a<>" and R(r"(|a)+", "<$1>", b"aa") == b"<>a<>a<>"
 
 
+def test_case_folding():
+    """(?i): unicode.SimpleFold orbits for ASCII (Go folds literals, ranges, perl and POSIX classes — the classes before they are negated);
+    K (U+212A) folds into k and ſ (U+017F) into s, so both match under (?i) — and so does \\w. Python's own IGNORECASE is not involved
+    in the oracle (it would add U+0130 / U+0131)."""
+    assert both("(?i)hello", "X", b"Hello hELLO hallo") == b"X X hallo"
+    assert both("(?i)k+", "X", "kK\u212a k".encode()) == b"X X" and both("(?i)[r-t]+", "X", "sS\u017f!".encode()) == b"X!"
+    assert both(r"(?i)\w+", "X", "s\u017fS\u212a!".encode()) == b"X!" and both(r"(?i)\W", "X", "s\u017f-".encode()) == "s\u017fX".encode()
+    assert both(r"\w+", "X", "s\u017f".encode()) == "X\u017f".encode()                               # not without (?i)
+    assert both("(?i)[^s]", "X", "s\u017fSt".encode()) == "s\u017fSX".encode()
+    assert both("(?i)[[:upper:]]+", "X", b"abC-") == b"X-" and both("(?i)[[:^upper:]]", "X", b"abC-") == b"abCX"
+    assert both("(?i:a)b", "X", b"Ab AB ab") == b"X AB X" and both("a(?i)b(?-i)c", "X", b"abc aBc aBC Abc") == b"X X aBC Abc"
+    assert both("(?i)i", "X", "iI\u0130\u0131".encode()) == "XX\u0130\u0131".encode()                 # the dotted / dotless i are not in i's orbit
+    assert both(r"(?i)\Qk.\E", "X", "K.k.k".encode()) == b"XXk" and both(r"(?i)\x4b", "X", b"k") == b"X"
+    assert both("(?i)(?P<w>straSSe)", "<$w>", "STRASSE stra\u017fse".encode()) == "<STRASSE> <stra\u017fse>".encode()
+    schema = [{"name": n, "type": "int32"} for n in ("Include", "exclude")]
+    d = engine.plan_validate("", "T", schema, [{"convert_to_string": {"tables": {"includeTables": ["(?i)^t$"]}, "columns": {"includeColumns": ["(?i)^INCLUDE$"]}}}])
+    assert [c["type"] for c in d["result_schema"]] == ["utf8", "int32"]
+
+
 @pytest.mark.parametrize("pattern", ["(", ")", "a)", "(?P<n>a", "(?P<>a)", "(?P<a b>c)", "[a", "[z-a]", "a**", "a*+", "a??*", "*a", "|*", "(*)", "a{2}{3}",
                                      r"\1", r"\8", "a\\", r"\C", r"\xZ", r"\x{110000}", r"\y", "a{1001}", "a{2,1}", "(a{500}){3}", "[[:bogus:]]",
                                      "(?z)", "(?-)", "(?s-:a)", "(?<=a)", "(?=a)", "(?!a)", "x{99999999999}", "\udcff"])
@@ -126,7 +145,7 @@ def test_expressions_go_refuses(pattern):
     assert ei.value.rc == -1
 
 
-@pytest.mark.parametrize("pattern", ["(?i)a", "(?U)a+", r"\pL", r"[\p{Greek}]", r"\PN", "(?i:a)b", "(a{30}){30}" * 12])
+@pytest.mark.parametrize("pattern", ["(?U)a+", r"\pL", r"[\p{Greek}]", r"\PN", "(?i)é", "(?i:[а-я])b", r"(?i)[\x00-\x{ffff}]", "(a{30}){30}" * 12])
 def test_valid_go_the_library_does_not_carry(pattern):
     with pytest.raises(engine.EngineError) as ei:
         R(pattern, "", b"x")
@@ -141,11 +160,12 @@ def _gen(rng, depth=0):
     on everything else; Go's own rule for the empty case is pinned by the issue-46123 lines above)."""
     def atom():
         k = rng.random()
-        if k < 0.30: return rng.choice(["a", "b", "c", "ab", "日", "\\.", "-", "\\n", "\\x61"]), False
+        if k < 0.30: return rng.choice(["a", "b", "c", "ab", "日", "\\.", "-", "\\n", "\\x61", "K", "s", "(?i:k)", "(?i:aS)", "(?i:[r-t])", "(?i:\\w)", "(?i:[^ab])"]), False
         if k < 0.45: return rng.choice(["[ab]", "[^a]", "[a-c]", "[^\\n]", "\\d", "\\w", "\\W", "\\s", "\\S", ".", "[\\d_]", "[[:alpha:]]", "[^[:^digit:]x]", "[\\Db]"]), False
         if k < 0.55: return rng.choice(["^", "$", "\\b", "\\B", "\\A", "\\z"]), True
         if k < 0.85 and depth < 3:
             inner, nullable = _gen(rng, depth + 1)
+            if "日" not in inner and rng.random() < 0.15: return "(?i:%s)" % inner, nullable
             return rng.choice(["(%s)", "(?:%s)", "(?P<g%d>%%s)" % rng.randrange(1000, 9999), "(?s:%s)", "(?m:%s)"]) % inner, nullable
         return "", True
     alts = []
@@ -165,7 +185,7 @@ def _gen(rng, depth=0):
 
 def test_random_expressions_against_the_oracle():
     rng = random.Random(20260923)
-    alphabet = ["a", "b", "c", "ab", "1", "_", " ", "\n", ".", "-", "日", "é", b"\xff", b"\xe6\x97", "x"]
+    alphabet = ["a", "b", "c", "ab", "1", "_", " ", "\n", ".", "-", "日", "é", b"\xff", b"\xe6\x97", "x", "A", "B", "k", "K", "S", "s", "\u212a", "\u017f"]
     rules = ["", "X", "<$0>", "[$1|$2]", "${1}x$1x", "$$1", "$", "${g}", "$g1234", "a$0b$9"]
     n_checked = n_changed = 0
     for _ in range(4000):

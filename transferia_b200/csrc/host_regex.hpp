@@ -6,8 +6,9 @@
 // sparse set per step, the first match cuts the lower-priority threads), the ReplaceAll loop of regexp.go (an empty match right behind a
 // match is not replaced; always advance one rune) and Regexp.Expand's template rules ($1, ${1}, $name, $$, the longest name wins, a
 // malformed $ stays as text).
-// Not taken (compile() throws Unsupported and the step stays with the Go transformer): case folding (?i), (?U), \pL / \PL Unicode class
-// tables, programs above MAX_INST instructions, a non-ASCII rune inside a $name of the replace rule.
+// Not taken (compile() throws Unsupported and the step stays with the Go transformer): (?U), \pL / \PL Unicode class tables, case folding
+// (?i) over runes outside ASCII (ASCII letters fold, with the two runes that fold into them: K U+212A and s U+017F), programs above
+// MAX_INST instructions, a non-ASCII rune inside a $name of the replace rule.
 #pragma once
 #include <algorithm>
 #include <cstdint>
@@ -70,7 +71,7 @@ inline NodeP mk(Op op) { NodeP n(new Node); n->op = op; return n; }
 
 struct Parser {
     const uint8_t* s; size_t n, at = 0; int ncap = 0; std::vector<std::string> names{""};
-    bool dot_nl = false, one_line = true; int depth = 0;
+    bool dot_nl = false, one_line = true, fold = false; int depth = 0;
     explicit Parser(const std::string& p) : s((const uint8_t*)p.data()), n(p.size()) {}
 
     bool more() const { return at < n; }
@@ -82,6 +83,26 @@ struct Parser {
     bool eat(char c) { if (at < n && s[at] == (uint8_t)c) { at++; return true; } return false; }
     bool looking(const char* lit) const { const size_t l = std::strlen(lit); return n - at >= l && !std::memcmp(s + at, lit, l); }
 
+    // Case folding (?i): unicode.SimpleFold orbits. Carried for ASCII only — a letter and its other case, and the two runes outside ASCII that
+    // fold INTO it: U+212A KELVIN SIGN (k, K) and U+017F LATIN SMALL LETTER LONG S (s, S). A rune >= 0x80 under (?i) would need the tables.
+    static void add_folds(Ranges& r) {
+        Ranges extra;
+        for (auto& x : r) {
+            if (x.second >= 0x80) throw Unsupported("case folding (?i) over runes outside ASCII (the Unicode folding tables are not carried)");
+            for (int32_t c = x.first; c <= x.second; c++) {
+                if (c >= 'a' && c <= 'z') extra.push_back({c - 32, c - 32});
+                else if (c >= 'A' && c <= 'Z') extra.push_back({c + 32, c + 32});
+                if (c == 'k' || c == 'K') extra.push_back({0x212A, 0x212A});
+                if (c == 's' || c == 'S') extra.push_back({0x017F, 0x017F});
+            }
+        }
+        r.insert(r.end(), extra.begin(), extra.end());
+    }
+    Ranges perl(char c) const {                               // \d \w \s and their negations under the current flags: fold first, negate after (appendGroup)
+        Ranges r = perl_class((char)(c | 0x20));
+        if (fold) { add_folds(r); normalise(r); }
+        return (c >= 'A' && c <= 'Z') ? negate(r) : r;
+    }
     static Ranges perl_class(char c) {
         Ranges r;
         switch (c | 0x20) {
@@ -164,15 +185,17 @@ struct Parser {
                     std::string name = rest.substr(2, close - 2); bool pneg = false;
                     if (!name.empty() && name[0] == '^') { pneg = true; name.erase(0, 1); }
                     Ranges pr; if (!posix_class(name, pr)) throw SyntaxError("invalid character class range");
+                    if (fold) add_folds(pr);
                     if (pneg) pr = negate(pr);
                     r.insert(r.end(), pr.begin(), pr.end()); at += close + 2; continue;
                 }
             }
             if (n - at >= 2 && s[at] == '\\' && (s[at + 1] == 'p' || s[at + 1] == 'P')) throw Unsupported("Unicode class tables (\\p) are not carried");
-            if (n - at >= 2 && s[at] == '\\' && std::strchr("dDsSwW", s[at + 1])) { const Ranges pr = perl_class((char)s[at + 1]); r.insert(r.end(), pr.begin(), pr.end()); at += 2; continue; }
+            if (n - at >= 2 && s[at] == '\\' && std::strchr("dDsSwW", s[at + 1])) { const Ranges pr = perl((char)s[at + 1]); r.insert(r.end(), pr.begin(), pr.end()); at += 2; continue; }
             const int32_t lo = class_char(); int32_t hi = lo;
             if (n - at >= 2 && s[at] == '-' && s[at + 1] != ']') { at++; hi = class_char(); if (hi < lo) throw SyntaxError("invalid character class range"); }
-            r.push_back({lo, hi});
+            if (fold) { Ranges one{{lo, hi}}; add_folds(one); r.insert(r.end(), one.begin(), one.end()); }      // appendFoldedRange
+            else r.push_back({lo, hi});
         }
         at++;                                                 // ']'
         normalise(r);
@@ -225,12 +248,18 @@ struct Parser {
 
     NodeP parse_cat() {
         std::vector<NodeP> items; bool last_repeat = false;
-        auto lit = [&](int32_t c) { NodeP l = mk(LIT); l->rune = c; items.push_back(l); };
+        auto lit = [&](int32_t c) {
+            if (fold) {                                       // OpLiteral with FoldCase: the rune's SimpleFold orbit
+                Ranges one{{c, c}}; add_folds(one); normalise(one);
+                if (one.size() > 1 || one[0].first != one[0].second) { NodeP k = mk(CLASS); k->cls = one; items.push_back(k); return; }
+            }
+            NodeP l = mk(LIT); l->rune = c; items.push_back(l);
+        };
         while (more() && s[at] != '|' && s[at] != ')') {
             bool is_repeat = false;
             const uint8_t c = s[at];
             if (c == '(') {
-                const bool sv_dot = dot_nl, sv_one = one_line;
+                const bool sv_dot = dot_nl, sv_one = one_line, sv_fold = fold;
                 if (n - at >= 2 && s[at + 1] == '?') {
                     if (looking("(?P<") || (looking("(?<") && !looking("(?<=") && !looking("(?<!"))) {
                         at += looking("(?P<") ? 4 : 3;
@@ -244,14 +273,14 @@ struct Parser {
                         NodeP cp = mk(CAPTURE); cp->cap = ++ncap; names.push_back(name);
                         cp->sub.push_back(parse_alt());
                         if (!eat(')')) throw SyntaxError("missing closing )");
-                        dot_nl = sv_dot; one_line = sv_one; items.push_back(cp);
+                        dot_nl = sv_dot; one_line = sv_one; fold = sv_fold; items.push_back(cp);
                     } else {
                         at += 2;                              // parsePerlFlags
-                        bool neg = false, saw = false, group = false, done = false; bool f_dot = dot_nl, f_one = one_line;
+                        bool neg = false, saw = false, group = false, done = false; bool f_dot = dot_nl, f_one = one_line, f_fold = fold;
                         while (more() && !done) {
                             const int32_t f = next();
                             switch (f) {
-                            case 'i': throw Unsupported("case folding (?i) is not carried");
+                            case 'i': f_fold = !neg; saw = true; break;
                             case 'U': throw Unsupported("(?U) is not carried");
                             case 'm': f_one = neg; saw = true; break;
                             case 's': f_dot = !neg; saw = true; break;
@@ -263,11 +292,11 @@ struct Parser {
                             }
                         }
                         if (!done) throw SyntaxError("missing closing )");
-                        dot_nl = f_dot; one_line = f_one;
+                        dot_nl = f_dot; one_line = f_one; fold = f_fold;
                         if (group) {
                             NodeP g = parse_alt();
                             if (!eat(')')) throw SyntaxError("missing closing )");
-                            dot_nl = sv_dot; one_line = sv_one; items.push_back(g);
+                            dot_nl = sv_dot; one_line = sv_one; fold = sv_fold; items.push_back(g);
                         } else { last_repeat = false; continue; }      // flags stay until the enclosing group closes; not an operand
                     }
                 } else {
@@ -275,7 +304,7 @@ struct Parser {
                     NodeP cp = mk(CAPTURE); cp->cap = ++ncap; names.push_back("");
                     cp->sub.push_back(parse_alt());
                     if (!eat(')')) throw SyntaxError("missing closing )");
-                    dot_nl = sv_dot; one_line = sv_one; items.push_back(cp);
+                    dot_nl = sv_dot; one_line = sv_one; fold = sv_fold; items.push_back(cp);
                 }
             }
             else if (c == '^') { at++; items.push_back(mk(one_line ? BEGIN_TEXT : BEGIN_LINE)); }
@@ -312,7 +341,7 @@ struct Parser {
                         last_repeat = false; continue;
                     }
                     if (e == 'p' || e == 'P') throw Unsupported("Unicode class tables (\\p) are not carried");
-                    if (std::strchr("dDsSwW", e)) { at += 2; NodeP k = mk(CLASS); k->cls = perl_class((char)e); normalise(k->cls); items.push_back(k); last_repeat = false; continue; }
+                    if (std::strchr("dDsSwW", e)) { at += 2; NodeP k = mk(CLASS); k->cls = perl((char)e); normalise(k->cls); items.push_back(k); last_repeat = false; continue; }
                 }
                 at++; lit(escape_rune());
             }
