@@ -208,7 +208,7 @@ def test_random_expressions_against_the_oracle():
 
 
 def _text_col(ev, c):
-    return ev["text"][c]
+    return sink.var_cells(ev, c)
 
 
 def _push(transformers, items, tables):

@@ -200,7 +200,9 @@ class Sink:
                 b = _rows.batch_from_struct(C.cast(ev.batch, C.POINTER(abi.TfBatch)).contents)
                 d["batch"] = b
                 d["columns"] = [None if c.values is None else np.asarray(c.values).copy() for c in b.columns]
-                d["text"] = [None if c.values is not None else _var_cells(c, b.nrows) for c in b.columns]      # the batch's buffers are the pool's: copied here
+                # the batch's buffers are the pool's (the next push overwrites them): var-width columns are copied here, read with var_cells()
+                d["var"] = [None if c.values is not None else tuple(None if a is None else np.asarray(a).copy() for a in (c.offsets, c.heap, c.validity)) + (c.lens_width, b.nrows)
+                            for c in b.columns]
             if ev.errors:
                 errs = C.cast(ev.errors, C.POINTER(abi.TfRowErr))
                 d["errors"] = [(errs[k].row, errs[k].code, errs[k].term) for k in range(ev.n_items)]
@@ -227,13 +229,14 @@ class Sink:
             self._L.tfgpu_sink_destroy(self._h); self._h = None
 
 
-def _var_cells(col, n: int) -> list:
-    """The cells of a var-width host column as bytes (None = null)."""
-    raw = np.asarray(col.offsets).astype(np.int64)
-    off = np.concatenate([[0], np.cumsum(raw)]) if col.lens_width else raw
-    heap = np.asarray(col.heap).tobytes() if col.heap is not None else b""
-    valid = np.ones(n, bool) if col.validity is None else np.unpackbits(np.asarray(col.validity), bitorder="little")[:n].astype(bool)
-    return [heap[off[r]:off[r + 1]] if valid[r] else None for r in range(n)]
+def var_cells(event: dict, c: int) -> list:
+    """The cells of var-width column `c` of a rows event as bytes (None = null), from the copies the callback took."""
+    offsets, heap, validity, lens_width, n = event["var"][c]
+    raw = offsets.astype(np.int64)
+    off = np.concatenate([[0], np.cumsum(raw)]) if lens_width else raw
+    text = heap.tobytes() if heap is not None else b""
+    valid = np.ones(n, bool) if validity is None else np.unpackbits(validity, bitorder="little")[:n].astype(bool)
+    return [text[off[r]:off[r + 1]] if valid[r] else None for r in range(n)]
 
 
 class Dispatcher:
