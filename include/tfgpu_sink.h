@@ -204,7 +204,7 @@ int tfgpu_batch_gather_sel(tfgpu_columnar* pool, const tf_batch* in, const uint3
  * the transposer: Go string values of utf8 columns and []byte values of string columns that the step's column filter names are replaced by
  * Regexp.ReplaceAll (see tfgpu_regex_replace_all). No kernel runs regular expressions, so the step (several are fine) must stand at the head
  * of the transformer list; an expression regexp.Compile refuses fails tfgpu_sink_create with TF_E_FATAL_CONFIG like the transformer's
- * constructor, one this library does not carry ((?U), \p{..}, (?i) over runes outside ASCII) with TF_E_FATAL_UNSUPPORTED. */
+ * constructor, one this library does not carry (\p{..}, (?i) over runes outside ASCII) with TF_E_FATAL_UNSUPPORTED. */
 typedef struct tfgpu_sink tfgpu_sink;
 #define TF_SINK_EV_ROWS   1   /* one downstream Push of row events of one table */
 #define TF_SINK_EV_ITEM   2   /* one downstream Push of a single non-row item */
@@ -271,7 +271,7 @@ void tfgpu_host_cityhash128(const uint8_t* p, uint64_t n, uint64_t out[2]);
  * (pkg/transformer/registry/regex_replace/transformer.go:127-142; Go's RE2 syntax, leftmost-first, rune-wise): host only, exported for the
  * parity tests and for a shim that wants to validate a transfer's expression up front. Returns the result's length (the bytes are written
  * when they fit `cap`), TF_E_FATAL_CONFIG for an expression regexp.Compile refuses too, TF_E_FATAL_UNSUPPORTED for valid syntax this
- * library does not carry ((?U), \p{..} classes, (?i) over runes outside ASCII, oversized programs): such a transfer keeps the Go transformer. */
+ * library does not carry (\p{..} classes, (?i) over runes outside ASCII, oversized programs): such a transfer keeps the Go transformer. */
 int64_t tfgpu_regex_replace_all(const char* pattern, const char* rule, const uint8_t* src, uint64_t src_len, uint8_t* dst, uint64_t cap);
 
 #ifdef __cplusplus

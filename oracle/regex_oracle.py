@@ -15,7 +15,7 @@ leftmost-first rules on the syntax both share) and re-states around it what diff
     malformed $ is text).
   * (?i) folds ASCII letters by unicode.SimpleFold's orbits (k, K also U+212A; s, S also U+017F), perl / POSIX classes folded before they are
     negated — done here on the translated sets, Python's IGNORECASE is not used (it adds U+0130 / U+0131, which Go does not);
-Not translated (NotImplementedError; the product refuses the same with TF_E_FATAL_UNSUPPORTED): (?U), \\p{..}, (?i) over non-ASCII runes; and flag groups that
+Not translated (NotImplementedError; the product refuses the same with TF_E_FATAL_UNSUPPORTED): \\p{..}, (?i) over non-ASCII runes; and flag groups that
 are not at the start of the expression or scoped `(?s:...)` (Python cannot state them; the product takes them).
 
 Parity pinned by: every case of the reference's transformer_test.go (TestTransformer_Apply, TestReplace, TestReplaceMultipleMatches,
@@ -108,6 +108,7 @@ def translate(p: str) -> Tuple[str, int]:
     out: List[str] = []; i = 0; flags = re.ASCII
     multi = [False]                                     # (?m) state per open group
     fold = [False]                                      # (?i) state per open group: folded here, Python's IGNORECASE is not used
+    ungreedy = [False]                                  # (?U) state per open group: the trailing ? of a repeat is flipped here
     last_repeat = False; can_repeat = False
     while i < len(p):
         c = p[i]; rep = False
@@ -116,35 +117,37 @@ def translate(p: str) -> Tuple[str, int]:
                 j = p.find(">", i)
                 name = p[i + (4 if p[i + 2] == "P" else 3):j] if j >= 0 else ""
                 if not name or not re.fullmatch(r"[A-Za-z0-9_]+", name): raise GoSyntaxError("capture name")
-                out.append("(?P<%s>" % name); i = j + 1; multi.append(multi[-1]); fold.append(fold[-1]); can_repeat = False
+                out.append("(?P<%s>" % name); i = j + 1; multi.append(multi[-1]); fold.append(fold[-1]); ungreedy.append(ungreedy[-1]); can_repeat = False
             elif p.startswith("(?", i):
                 j = i + 2; fl = ""
                 while j < len(p) and p[j] not in ":)": fl += p[j]; j += 1
                 if j >= len(p): raise GoSyntaxError("missing )")
-                if "U" in fl: raise NotImplementedError("(?U)")
-                if not all(ch in "ims-" for ch in fl) or fl.count("-") > 1 or fl.endswith("-"): raise GoSyntaxError("flags")
+                if not all(ch in "imsU-" for ch in fl) or fl.count("-") > 1 or fl.endswith("-"): raise GoSyntaxError("flags")
                 on, _, off = fl.partition("-")
-                m, f = multi[-1], fold[-1]
+                m, f, u = multi[-1], fold[-1], ungreedy[-1]
+                if "U" in on: u = True
+                if "U" in off: u = False
                 if "m" in on: m = True
                 if "m" in off: m = False
                 if "i" in on: f = True
                 if "i" in off: f = False
-                pyfl = on.replace("i", "") + ("-" + off.replace("i", "") if off.replace("i", "") else "")
+                strip = lambda t: t.replace("i", "").replace("U", "")
+                pyfl = strip(on) + ("-" + strip(off) if strip(off) else "")
                 if p[j] == ":":
-                    out.append("(?" + pyfl + ":" if pyfl else "(?:"); multi.append(m); fold.append(f); can_repeat = False
+                    out.append("(?" + pyfl + ":" if pyfl else "(?:"); multi.append(m); fold.append(f); ungreedy.append(u); can_repeat = False
                 else:
                     if not fl: raise GoSyntaxError("flags")
                     if pyfl and (i != 0 or "-" in fl): raise NotImplementedError("flag group inside the expression")      # (?i) alone is folded here: fine anywhere
                     if "m" in on: flags |= re.MULTILINE
                     if "s" in on: flags |= re.DOTALL
-                    multi[-1] = m; fold[-1] = f; can_repeat = False
+                    multi[-1] = m; fold[-1] = f; ungreedy[-1] = u; can_repeat = False
                 i = j + 1
             else:
-                out.append("("); i += 1; multi.append(multi[-1]); fold.append(fold[-1]); can_repeat = False
+                out.append("("); i += 1; multi.append(multi[-1]); fold.append(fold[-1]); ungreedy.append(ungreedy[-1]); can_repeat = False
             last_repeat = False; continue
         if c == ")":
             if len(multi) == 1: raise GoSyntaxError("unexpected )")
-            multi.pop(); fold.pop(); out.append(")"); i += 1; can_repeat = True; last_repeat = False; continue
+            multi.pop(); fold.pop(); ungreedy.pop(); out.append(")"); i += 1; can_repeat = True; last_repeat = False; continue
         if c == "|":
             out.append("|"); i += 1; can_repeat = False; last_repeat = False; continue
         if c in "*+?" or c == "{":
@@ -158,7 +161,9 @@ def translate(p: str) -> Tuple[str, int]:
                 tok = m.group(0); i += len(tok)
             else:
                 tok = c; i += 1
-            if i < len(p) and p[i] == "?": tok += "?"; i += 1
+            lazy = False
+            if i < len(p) and p[i] == "?": lazy = True; i += 1
+            if lazy != ungreedy[-1]: tok += "?"
             if last_repeat: raise GoSyntaxError("nested repetition")
             if not can_repeat: raise GoSyntaxError("missing argument to repetition")
             out.append(tok); last_repeat = True; continue

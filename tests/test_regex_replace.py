@@ -122,6 +122,9 @@ def test_case_folding():
     assert both("(?i:a)b", "X", b"Ab AB ab") == b"X AB X" and both("a(?i)b(?-i)c", "X", b"abc aBc aBC Abc") == b"X X aBC Abc"
     assert both("(?i)i", "X", "iI\u0130\u0131".encode()) == "XX\u0130\u0131".encode()                 # the dotted / dotless i are not in i's orbit
     assert both(r"(?i)\Qk.\E", "X", "K.k.k".encode()) == b"XXk" and both(r"(?i)\x4b", "X", b"k") == b"X"
+    # (?U) swaps greedy and lazy
+    assert both("(?U)a+", "X", b"aaa") == b"XXX" and both("(?U)a+?", "X", b"aaa") == b"X" and both("(?U:a*)b", "X", b"aab") == b"X"
+    assert both("(?U)(a{1,3})(a*)", "[$1|$2]", b"aaaa") == b"[a|][a|][a|][a|]" and both("(?iU)A+?b", "X", b"aab") == b"X"
     assert both("(?i)(?P<w>straSSe)", "<$w>", "STRASSE stra\u017fse".encode()) == "<STRASSE> <stra\u017fse>".encode()
     schema = [{"name": n, "type": "int32"} for n in ("Include", "exclude")]
     d = engine.plan_validate("", "T", schema, [{"convert_to_string": {"tables": {"includeTables": ["(?i)^t$"]}, "columns": {"includeColumns": ["(?i)^INCLUDE$"]}}}])
@@ -145,7 +148,7 @@ def test_expressions_go_refuses(pattern):
     assert ei.value.rc == -1
 
 
-@pytest.mark.parametrize("pattern", ["(?U)a+", r"\pL", r"[\p{Greek}]", r"\PN", "(?i)é", "(?i:[а-я])b", r"(?i)[\x00-\x{ffff}]", "(a{30}){30}" * 12])
+@pytest.mark.parametrize("pattern", [r"\pL", r"[\p{Greek}]", r"\PN", "(?i)é", "(?i:[а-я])b", r"(?i)[\x00-\x{ffff}]", "(a{30}){30}" * 12])
 def test_valid_go_the_library_does_not_carry(pattern):
     with pytest.raises(engine.EngineError) as ei:
         R(pattern, "", b"x")
@@ -166,6 +169,7 @@ def _gen(rng, depth=0):
         if k < 0.85 and depth < 3:
             inner, nullable = _gen(rng, depth + 1)
             if "日" not in inner and rng.random() < 0.15: return "(?i:%s)" % inner, nullable
+            if rng.random() < 0.08: return "(?U:%s)" % inner, nullable
             return rng.choice(["(%s)", "(?:%s)", "(?P<g%d>%%s)" % rng.randrange(1000, 9999), "(?s:%s)", "(?m:%s)"]) % inner, nullable
         return "", True
     alts = []

@@ -6,7 +6,7 @@
 // sparse set per step, the first match cuts the lower-priority threads), the ReplaceAll loop of regexp.go (an empty match right behind a
 // match is not replaced; always advance one rune) and Regexp.Expand's template rules ($1, ${1}, $name, $$, the longest name wins, a
 // malformed $ stays as text).
-// Not taken (compile() throws Unsupported and the step stays with the Go transformer): (?U), \pL / \PL Unicode class tables, case folding
+// Not taken (compile() throws Unsupported and the step stays with the Go transformer): \pL / \PL Unicode class tables, case folding
 // (?i) over runes outside ASCII (ASCII letters fold, with the two runes that fold into them: K U+212A and s U+017F), programs above
 // MAX_INST instructions, a non-ASCII rune inside a $name of the replace rule.
 #pragma once
@@ -71,7 +71,7 @@ inline NodeP mk(Op op) { NodeP n(new Node); n->op = op; return n; }
 
 struct Parser {
     const uint8_t* s; size_t n, at = 0; int ncap = 0; std::vector<std::string> names{""};
-    bool dot_nl = false, one_line = true, fold = false; int depth = 0;
+    bool dot_nl = false, one_line = true, fold = false, ungreedy = false; int depth = 0;
     explicit Parser(const std::string& p) : s((const uint8_t*)p.data()), n(p.size()) {}
 
     bool more() const { return at < n; }
@@ -259,7 +259,7 @@ struct Parser {
             bool is_repeat = false;
             const uint8_t c = s[at];
             if (c == '(') {
-                const bool sv_dot = dot_nl, sv_one = one_line, sv_fold = fold;
+                const bool sv_dot = dot_nl, sv_one = one_line, sv_fold = fold, sv_ung = ungreedy;
                 if (n - at >= 2 && s[at + 1] == '?') {
                     if (looking("(?P<") || (looking("(?<") && !looking("(?<=") && !looking("(?<!"))) {
                         at += looking("(?P<") ? 4 : 3;
@@ -273,15 +273,15 @@ struct Parser {
                         NodeP cp = mk(CAPTURE); cp->cap = ++ncap; names.push_back(name);
                         cp->sub.push_back(parse_alt());
                         if (!eat(')')) throw SyntaxError("missing closing )");
-                        dot_nl = sv_dot; one_line = sv_one; fold = sv_fold; items.push_back(cp);
+                        dot_nl = sv_dot; one_line = sv_one; fold = sv_fold; ungreedy = sv_ung; items.push_back(cp);
                     } else {
                         at += 2;                              // parsePerlFlags
-                        bool neg = false, saw = false, group = false, done = false; bool f_dot = dot_nl, f_one = one_line, f_fold = fold;
+                        bool neg = false, saw = false, group = false, done = false; bool f_dot = dot_nl, f_one = one_line, f_fold = fold, f_ung = ungreedy;
                         while (more() && !done) {
                             const int32_t f = next();
                             switch (f) {
                             case 'i': f_fold = !neg; saw = true; break;
-                            case 'U': throw Unsupported("(?U) is not carried");
+                            case 'U': f_ung = !neg; saw = true; break;
                             case 'm': f_one = neg; saw = true; break;
                             case 's': f_dot = !neg; saw = true; break;
                             case '-': if (neg) throw SyntaxError("missing closing )"); neg = true; saw = false; break;
@@ -292,11 +292,11 @@ struct Parser {
                             }
                         }
                         if (!done) throw SyntaxError("missing closing )");
-                        dot_nl = f_dot; one_line = f_one; fold = f_fold;
+                        dot_nl = f_dot; one_line = f_one; fold = f_fold; ungreedy = f_ung;
                         if (group) {
                             NodeP g = parse_alt();
                             if (!eat(')')) throw SyntaxError("missing closing )");
-                            dot_nl = sv_dot; one_line = sv_one; fold = sv_fold; items.push_back(g);
+                            dot_nl = sv_dot; one_line = sv_one; fold = sv_fold; ungreedy = sv_ung; items.push_back(g);
                         } else { last_repeat = false; continue; }      // flags stay until the enclosing group closes; not an operand
                     }
                 } else {
@@ -304,7 +304,7 @@ struct Parser {
                     NodeP cp = mk(CAPTURE); cp->cap = ++ncap; names.push_back("");
                     cp->sub.push_back(parse_alt());
                     if (!eat(')')) throw SyntaxError("missing closing )");
-                    dot_nl = sv_dot; one_line = sv_one; fold = sv_fold; items.push_back(cp);
+                    dot_nl = sv_dot; one_line = sv_one; fold = sv_fold; ungreedy = sv_ung; items.push_back(cp);
                 }
             }
             else if (c == '^') { at++; items.push_back(mk(one_line ? BEGIN_TEXT : BEGIN_LINE)); }
@@ -317,7 +317,7 @@ struct Parser {
                     if (!parse_repeat(mn, mx)) { at++; lit('{'); last_repeat = false; continue; }
                     if (mn < 0 || mn > 1000 || mx > 1000 || (mx >= 0 && mn > mx)) throw SyntaxError("invalid repeat count");
                 } else at++;
-                const bool lazy = eat('?');
+                const bool lazy = eat('?') != ungreedy;                  // (?U) swaps the meaning of x* and x*? (flags ^= NonGreedy)
                 if (last_repeat) throw SyntaxError("invalid nested repetition operator");
                 if (items.empty()) throw SyntaxError("missing argument to repetition operator");
                 NodeP r = mk(op); r->lazy = lazy; r->min = mn; r->max = mx; r->sub.push_back(items.back());
