@@ -158,6 +158,9 @@ def test_valid_go_the_library_does_not_carry(pattern):
     assert ei.value.rc == -2
 
 
+_names = iter(range(1000, 10 ** 9))          # a name used twice is legal in Go but not in Python: the generator never repeats one
+
+
 def _gen(rng, depth=0):
     """A random expression of the shared syntax; repeats are only put on operands that cannot match the empty text (Python and Go agree
     on everything else; Go's own rule for the empty case is pinned by the issue-46123 lines above)."""
@@ -170,7 +173,7 @@ def _gen(rng, depth=0):
             inner, nullable = _gen(rng, depth + 1)
             if "日" not in inner and rng.random() < 0.15: return "(?i:%s)" % inner, nullable
             if rng.random() < 0.08: return "(?U:%s)" % inner, nullable
-            return rng.choice(["(%s)", "(?:%s)", "(?P<g%d>%%s)" % rng.randrange(1000, 9999), "(?s:%s)", "(?m:%s)"]) % inner, nullable
+            return rng.choice(["(%s)", "(?:%s)", "(?P<g%d>%%s)" % next(_names), "(?s:%s)", "(?m:%s)"]) % inner, nullable
         return "", True
     alts = []
     any_nullable = False
