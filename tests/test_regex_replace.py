@@ -308,3 +308,36 @@ def test_type_is_read_at_the_value_position_for_column_subsets():
     items = [ChangeItem(K.KIND_UPDATE, 0, {0: go.int32(1), 2: go.string("xx")}, {0: go.int32(1)}), ChangeItem(K.KIND_UPDATE, 0, {2: go.string("xx")}, {0: go.int32(1)})]
     ((_, _, b),) = _push(tr, items, [("public", "t", schema)])
     assert _text_col(b, 2) == [b"yy", b"xx"]
+
+
+def test_malformed_row_images_are_refused_by_the_replace_step():
+    """The replace step reads the row image before the transposer does: truncated / noisy images, offsets past the end and wild value counts
+    come back as error codes (run under the sanitizers by scripts/host_asan.sh)."""
+    import ctypes as C
+    rng = np.random.default_rng(6)
+    schema = [{"name": "a", "type": "int32"}, {"name": "s", "type": "utf8"}, {"name": "b", "type": "string"}]
+    good = rows.RowsImage([ChangeItem(K.KIND_INSERT, 0, [go.int32(1), go.string("a_b"), go.bytes(b"c_d")]) for _ in range(40)] +
+                          [ChangeItem(K.KIND_UPDATE, 0, {1: go.string("x_y")}, {0: go.int32(0)}) for _ in range(10)], [("d", "t", schema)])
+    base = good._vals[:good.values_len].copy()
+    s = sink.Sink(transformers=[{"regex_replace_transformer": {"regexMatch": "_", "replaceRule": "--"}}])
+    outcomes = set()
+    for trial in range(250):
+        vals = base.copy(); kind = trial % 5
+        if kind == 0: vals = vals[: int(rng.integers(0, len(vals)))]
+        elif kind == 1: vals[rng.integers(0, len(vals), 6)] = rng.integers(0, 256, 6)
+        elif kind == 2: vals = rng.integers(0, 256, int(rng.integers(1, 300)), dtype=np.uint8)
+        img = rows.RowsImage([], [("d", "t", schema)])
+        items = (rows.TfItem * 50)()
+        for r in range(50):
+            C.memmove(C.byref(items[r]), C.byref(good._items[r]), C.sizeof(rows.TfItem))
+            if kind == 3: items[r].values_off = int(rng.integers(0, 2 ** 40))
+            if kind == 4: items[r].n_values = int(rng.integers(0, 2 ** 31))
+        buf = np.ascontiguousarray(vals)
+        img.struct.n_items = 50; img.struct.items = C.cast(items, C.POINTER(rows.TfItem)); img.struct.values = buf.ctypes.data if len(buf) else None; img.struct.values_len = len(buf)
+        s.events.clear()
+        try:
+            s.push(img); outcomes.add(0)
+        except engine.EngineError as ex:
+            assert ex.rc in (-2, -3), ex.rc; outcomes.add(ex.rc)
+    assert -3 in outcomes
+    s.close()

@@ -373,6 +373,7 @@ struct tfgpu_sink {
                     for (size_t c = 0; c < pt.tp->col_names.size(); c++) if (h.columns.match(pt.tp->col_names[c])) { pt.by_col[c].push_back(&h); pt.hit = true; }
             }
             if (!pt.hit || !it.n_values) continue;
+            if (it.values_off > in->values_len) throw SinkFail{TF_E_FATAL_ARG, "values offset outside the image"};
             const uint8_t* at = in->values + it.values_off; const bool sparse = it.flags & TF_ITEM_SPARSE;
             const uint64_t new_off = out.values.size();
             for (uint32_t k = 0; k < it.n_values; k++) {
