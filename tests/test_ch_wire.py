@@ -45,6 +45,11 @@ def test_insert_query_text():
     assert sink.insert_query("db", "hits", ["a", "b c"]) == "INSERT INTO `db`.`hits` (`a`,`b c`) VALUES"
     assert sink.insert_query("db", "t", ["x"], updateable=True) == \
         "INSERT INTO `db`.`t` (`x`,`__data_transfer_commit_time`,`__data_transfer_delete_time`) VALUES"
+    # the statement sqlmock expects in sink_table_test.go:126-127 (TestTable_doOperation_updatable_delete), up to VALUES where the driver cuts it
+    cols = ["id", "old_status", "new_status", "claim_id", "event_time", "comment", "ticket", "old_current_point", "new_current_point"]
+    assert sink.insert_query("db", "test_table", cols, updateable=True) == \
+        "INSERT INTO `db`.`test_table` (`id`,`old_status`,`new_status`,`claim_id`,`event_time`,`comment`,`ticket`,`old_current_point`,`new_current_point`," \
+        "`__data_transfer_commit_time`,`__data_transfer_delete_time`) VALUES"
 
 
 def test_insert_exchange_with_oracle_frames(po):
