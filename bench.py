@@ -170,6 +170,57 @@ def cpu_port_rate(batch, schema, transformers, frame_bytes, budget_s: float, thr
     return sum(done) / el, sum(done), el
 
 
+def host_paths(res: dict) -> None:
+    """The host-only legs (no device involved): the transposer in front of every push of boxed items, and the regex_replace host step."""
+    # SURVEY §8f-1: the host transpose ([]ChangeItem in row form -> columns) that sits in front of every push in a real transfer. The row
+    # image of 200 k hits rows is made by the inverse (tfgpu_batch_to_rows) and timed through tfgpu_rows_to_batch: host-only C++ threads.
+    try:
+        import ctypes as C
+        from transferia_b200 import rows as rws, workload
+        nb_rows = 200_000
+        hb, hschema = make_batch(nb_rows, workload.SEED)
+        image, off = rws.batch_to_rows(hb)
+        items = (rws.TfItem * nb_rows)(); offs = off.astype(np.uint64)
+        for r_ in range(nb_rows):
+            it = items[r_]; it.values_off = int(offs[r_]); it.n_values = len(hschema); it.old_keys_off = rws.NO_OLD_KEYS
+        img = rws.RowsImage([], [("public", "hits", hschema)])
+        vals = np.frombuffer(image, dtype=np.uint8).copy()
+        img.struct.n_items = nb_rows; img.struct.items = C.cast(items, C.POINTER(rws.TfItem)); img.struct.values = vals.ctypes.data; img.struct.values_len = len(image)
+        pool = rws.Columnar(); rates = {}
+        for th in (1, 8, 16, 64):
+            if th > (os.cpu_count() or 1):
+                continue
+            pool.rows_to_batch(img, threads=th)
+            t0 = time.perf_counter(); k = 3
+            for _ in range(k):
+                pool.rows_to_batch(img, threads=th)
+            rates[str(th)] = nb_rows * k / (time.perf_counter() - t0)
+        pool.close()
+        best = max(rates.values())
+        res["host_transpose_rows_to_columns"] = {"rows_per_s": best, "ms": nb_rows / best * 1e3, "rows": nb_rows, "image_bytes_per_row": len(image) / nb_rows, "rows_per_s_by_threads": rates,
+                                                 "note": "tfgpu_rows_to_batch over the row image of ClickBench-shaped items (99 boxed values per row): what a shim pays per batch before any push; CPU only"}
+    except Exception as ex:
+        res["host_transpose_error"] = str(ex)
+    # SURVEY §8f-4: regex_replace_transformer runs on the host inside tfgpu_sink_push (Go's regexp as a Pike machine over the row image,
+    # then the transpose): 200 k hits rows, the two URL-like columns rewritten.
+    try:
+        from transferia_b200 import sink as snk
+        if "host_transpose_error" in res:
+            raise RuntimeError("no row image")
+        tr = [{"regex_replace_transformer": {"regexMatch": r"^(https?)://([^/]+)", "replaceRule": "$2 via $1", "columns": {"includeColumns": ["^url$", "^referer$"]}}}]
+        s_ = snk.Sink(transformers=tr, record="counts")
+        s_.push(img); s_.events.clear()
+        t0 = time.perf_counter(); k = 3
+        for _ in range(k):
+            s_.push(img); s_.events.clear()
+        dt = (time.perf_counter() - t0) / k
+        s_.close()
+        res["host_regex_replace_then_transpose"] = {"rows_per_s": nb_rows / dt, "ms": dt * 1e3, "rows": nb_rows,
+                                                    "note": "tfgpu_sink_push without a device plan: the transposer, then two string columns through Regexp.ReplaceAll on the host workers (up to 16 threads); CPU only"}
+    except Exception as ex:
+        res["host_regex_error"] = str(ex)
+
+
 def extra_paths(eng, args):
     """Secondary §8 paths, measured end to end through the public call with HOST bytes (not the headline metric):
     BASELINE configs[1] JSON lines -> parse -> mask_field -> ClickHouse JSONEachRow / native+LZ4, and the batch serializers."""
@@ -292,35 +343,7 @@ def extra_paths(eng, args):
             res["csv_parse_cast_native"]["cpu_port_error"] = str(ex)
     except Exception as ex:
         res["csv_parse_error"] = str(ex)
-    # the host transpose ([]ChangeItem in row form -> columns) that sits in front of every push in a real transfer. The row
-    # image of 200 k hits rows is made by the inverse (tfgpu_batch_to_rows) and timed through tfgpu_rows_to_batch: host-only C++ threads.
-    try:
-        import ctypes as C
-        from transferia_b200 import rows as rws
-        nb_rows = 200_000
-        hb, hschema = make_batch(nb_rows, workload.SEED)
-        image, off = rws.batch_to_rows(hb)
-        items = (rws.TfItem * nb_rows)(); offs = off.astype(np.uint64)
-        for r_ in range(nb_rows):
-            it = items[r_]; it.values_off = int(offs[r_]); it.n_values = len(hschema); it.old_keys_off = rws.NO_OLD_KEYS
-        img = rws.RowsImage([], [("public", "hits", hschema)])
-        vals = np.frombuffer(image, dtype=np.uint8).copy()
-        img.struct.n_items = nb_rows; img.struct.items = C.cast(items, C.POINTER(rws.TfItem)); img.struct.values = vals.ctypes.data; img.struct.values_len = len(image)
-        pool = rws.Columnar(); rates = {}
-        for th in (1, 16, 64):
-            if th > (os.cpu_count() or 1):
-                continue
-            pool.rows_to_batch(img, threads=th)
-            t0 = time.perf_counter(); k = 3
-            for _ in range(k):
-                pool.rows_to_batch(img, threads=th)
-            rates[str(th)] = nb_rows * k / (time.perf_counter() - t0)
-        pool.close()
-        best = max(rates.values())
-        res["host_transpose_rows_to_columns"] = {"rows_per_s": best, "ms": nb_rows / best * 1e3, "rows": nb_rows, "image_bytes_per_row": len(image) / nb_rows, "rows_per_s_by_threads": rates,
-                                                 "note": "tfgpu_rows_to_batch over the row image of ClickBench-shaped items (99 boxed values per row): what a shim pays per batch before any push; CPU only"}
-    except Exception as ex:
-        res["host_transpose_error"] = str(ex)
+    host_paths(res)
     try:
         from oracle import pyoracle as po
         sample = text[: text.rfind(b"\n", 0, len(text) // 20) + 1]

@@ -200,8 +200,8 @@ int tfgpu_batch_gather_sel(tfgpu_columnar* pool, const tf_batch* in, const uint3
  * values) is computed per row from the row image, the rows of a run are grouped by it in order of first appearance and every group goes
  * down on its own (ev.out_table, its own INSERT). It must be the last transformer of the list; `any` / interval columns, []byte outside
  * `string` columns and useLegacyLf are refused.
- * regex_replace_transformer (pkg/transformer/registry/regex_replace/transformer.go:87-142) is applied HERE as well, to the row image before
- * the transposer: Go string values of utf8 columns and []byte values of string columns that the step's column filter names are replaced by
+ * regex_replace_transformer (pkg/transformer/registry/regex_replace/transformer.go:87-142) is applied HERE as well (to the transposed text
+ * columns on the host workers, or to the row image before the transposer when items carry column subsets or mixed text types): Go string values of utf8 columns and []byte values of string columns that the step's column filter names are replaced by
  * Regexp.ReplaceAll (see tfgpu_regex_replace_all). No kernel runs regular expressions, so the step (several are fine) must stand at the head
  * of the transformer list; an expression regexp.Compile refuses fails tfgpu_sink_create with TF_E_FATAL_CONFIG like the transformer's
  * constructor, one this library does not carry (\p{..}, (?i) over runes outside ASCII) with TF_E_FATAL_UNSUPPORTED. */

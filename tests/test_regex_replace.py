@@ -245,9 +245,13 @@ def test_reference_apply_cases():
     assert _text_col(b, 0) == [b"value-1"] and _text_col(b, 3) == [b"value@2"]
 
 
-def test_replace_steps_over_mixed_batches_equal_the_oracle():
-    """Two chained steps with table and column filters over inserts / updates / deletes of two tables, nil values, control items in between,
+@pytest.mark.parametrize("on_rows", [False, True])
+def test_replace_steps_over_mixed_batches_equal_the_oracle(on_rows, monkeypatch):
+    """(tfgpu_sink_push runs the steps on the transposed text columns when every row event lists all its columns — on_rows forces the
+    row-image form, which it takes for column subsets, mixed text types and in front of table_splitter; same result.)
+    Two chained steps with table and column filters over inserts / updates / deletes of two tables, nil values, control items in between,
     OldKeys untouched (Apply rewrites ColumnValues only, transformer.go:98-118)."""
+    if on_rows: monkeypatch.setenv("TFGPU_REGEX_ON_ROWS", "1")
     rng = random.Random(7)
     schema_a = [{"name": "id", "type": "int32", "key": True}, {"name": "name", "type": "utf8"}, {"name": "raw", "type": "string"}, {"name": "note_private", "type": "utf8"}, {"name": "doc", "type": "any"}]
     schema_b = [{"name": "k", "type": "utf8", "key": True}, {"name": "v", "type": "double"}]
@@ -341,3 +345,18 @@ def test_malformed_row_images_are_refused_by_the_replace_step():
             assert ex.rc in (-2, -3), ex.rc; outcomes.add(ex.rc)
     assert -3 in outcomes
     s.close()
+
+
+def test_mixed_text_types_keep_the_type_assertion():
+    """replace() takes a Go string only in a utf8 column and a []byte only in a `string` column (transformer.go:129-139): a []byte that sits in
+    a utf8 column stays as it is — the columnar form of the step notices the mix and hands the run to the row-image form."""
+    schema = [{"name": "id", "type": "int32", "key": True}, {"name": "u", "type": "utf8"}, {"name": "b", "type": "string"}]
+    items = [ChangeItem(K.KIND_INSERT, 0, [go.int32(1), go.string("a_1"), go.bytes(b"b_1")]),
+             ChangeItem(K.KIND_INSERT, 0, [go.int32(2), go.bytes(b"a_2"), go.string("b_2")]),
+             ChangeItem(K.KIND_INSERT, 0, [go.int32(3), go.nil, go.bytes(b"")])]
+    ((_, _, e),) = _push([{"regex_replace_transformer": {"regexMatch": "_", "replaceRule": "-"}}, {"regex_replace_transformer": {"regexMatch": "^", "replaceRule": ">"}}], items, [("d", "t", schema)])
+    assert _text_col(e, 1) == [b">a-1", b"a_2", None] and _text_col(e, 2) == [b">b-1", b"b_2", b">"]
+    for it in items: it.values[1] = go.string("x_y") if it.values[1][0] else it.values[1]            # all strings: the columnar form
+    items[1].values[2] = go.bytes(b"b_2")
+    ((_, _, e),) = _push([{"regex_replace_transformer": {"regexMatch": "_", "replaceRule": "-" * 300}}], items, [("d", "t", schema)])
+    assert _text_col(e, 1) == [b"x" + b"-" * 300 + b"y"] * 2 + [None] and _text_col(e, 2) == [b"b" + b"-" * 300 + b"1", b"b" + b"-" * 300 + b"2", b""]

@@ -11,6 +11,7 @@
 // MAX_INST instructions, a non-ASCII rune inside a $name of the replace rule.
 #pragma once
 #include <algorithm>
+#include <array>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -408,6 +409,12 @@ struct Inst { InstOp op = I_FAIL; uint32_t out = 0, arg = 0; int32_t rune = 0; u
 
 struct Prog {
     std::vector<Inst> inst; std::vector<Ranges> classes; uint32_t start = 0; int ncap = 0; std::vector<std::string> names;
+    bool anchored = false;            // Prog.StartCond() has EmptyBeginText: a match can only begin at offset 0 (exec.go stops looking elsewhere)
+    int32_t first_rune = -1;          // Prog.Prefix(), its first rune: every match begins with this literal (the search jumps to its next occurrence)
+    uint8_t first_byte = 0;
+    std::vector<std::array<uint64_t, 2>> ascii;   // per class: membership of the runes below 0x80
+    bool has_empty = false;           // some assertion instruction: only then the context conditions are worth computing
+    bool first_any = true; bool first[256] = {};   // the bytes a match can begin with (a superset; first_any: no restriction, e.g. the empty match)
 };
 
 struct Compiler {
@@ -483,6 +490,49 @@ inline Prog compile(const std::string& pattern) {
     Compiler::Frag f = c.compile(*tree);
     Compiler::Frag m = c.inst(I_MATCH);
     if (f.i) { c.patch(f.out, m.i); c.p.start = f.i; } else c.p.start = 0;
+    uint8_t cond = 0; uint32_t pc = c.p.start;
+    while (pc) {
+        const Inst& in = c.p.inst[pc];
+        if (in.op == I_EMPTY) cond |= (uint8_t)in.arg; else if (in.op != I_CAP && in.op != I_NOP) break;
+        pc = in.out;
+    }
+    c.p.anchored = cond & E_BEGIN_TEXT;
+    pc = c.p.start;
+    while (pc && (c.p.inst[pc].op == I_CAP || c.p.inst[pc].op == I_NOP)) pc = c.p.inst[pc].out;
+    if (pc && c.p.inst[pc].op == I_RUNE1) {
+        const int32_t r = c.p.inst[pc].rune; c.p.first_rune = r;
+        c.p.first_byte = r < 0x80 ? (uint8_t)r : r < 0x800 ? (uint8_t)(0xC0 | (r >> 6)) : r < 0x10000 ? (uint8_t)(0xE0 | (r >> 12)) : (uint8_t)(0xF0 | (r >> 18));
+        if (r >= 0xD800 && r <= 0xDFFF) c.p.first_rune = -1;                  // no text holds it as a rune
+    }
+    for (auto& cl : c.p.classes) {
+        std::array<uint64_t, 2> bits{0, 0};
+        for (auto& r : cl) for (int32_t x = r.first; x <= std::min(r.second, 0x7F); x++) bits[x >> 6] |= 1ull << (x & 63);
+        c.p.ascii.push_back(bits);
+    }
+    for (auto& in : c.p.inst) if (in.op == I_EMPTY) c.p.has_empty = true;
+    {   // first-byte set: everything reachable from the start without consuming a rune (assertions taken as passable)
+        std::vector<uint8_t> seen(c.p.inst.size(), 0); std::vector<uint32_t> todo{c.p.start}; bool any = c.p.start == 0;
+        while (!todo.empty() && !any) {
+            const uint32_t at = todo.back(); todo.pop_back();
+            if (!at || seen[at]) continue;
+            seen[at] = 1; const Inst& in = c.p.inst[at];
+            switch (in.op) {
+            case I_ALT: todo.push_back(in.out); todo.push_back(in.arg); break;
+            case I_CAP: case I_NOP: case I_EMPTY: todo.push_back(in.out); break;
+            case I_MATCH: any = true; break;
+            case I_RUNE1: case I_CLASS: {
+                auto mark = [&](int32_t lo, int32_t hi) {
+                    for (int32_t b = lo; b <= std::min(hi, 0x7F); b++) c.p.first[b] = true;
+                    if (hi >= 0x80) for (int b = 0x80; b < 0x100; b++) c.p.first[b] = true;      // some multi-byte rune, or U+FFFD standing for an invalid byte
+                };
+                if (in.op == I_RUNE1) mark(in.rune, in.rune); else for (auto& r : c.p.classes[in.cls]) mark(r.first, r.second);
+                break;
+            }
+            default: break;
+            }
+        }
+        c.p.first_any = any;
+    }
     return std::move(c.p);
 }
 
@@ -491,14 +541,14 @@ struct Machine {
     const Prog& p; const int nslot;
     struct Queue {
         std::vector<uint32_t> sparse, dense_pc; std::vector<int32_t> slot;    // slot: index into caps (in units of nslot), -1 for a bookkeeping entry
-        std::vector<int64_t> caps; uint32_t n = 0;
+        std::vector<int64_t> caps; uint32_t n = 0, nthreads = 0;              // caps: one row of nslot per thread, sized once for every instruction
         bool has(uint32_t pc) const { const uint32_t j = sparse[pc]; return j < n && dense_pc[j] == pc; }
-        void clear() { n = 0; caps.clear(); }
+        void clear() { n = 0; nthreads = 0; }
     } q[2];
     std::vector<int64_t> cur, matchcap; bool matched = false;
 
     explicit Machine(const Prog& prog) : p(prog), nslot(2 * (prog.ncap + 1)) {
-        for (auto& x : q) { x.sparse.assign(p.inst.size(), 0); x.dense_pc.assign(p.inst.size(), 0); x.slot.assign(p.inst.size(), -1); }
+        for (auto& x : q) { x.sparse.assign(p.inst.size(), 0); x.dense_pc.assign(p.inst.size(), 0); x.slot.assign(p.inst.size(), -1); x.caps.assign(p.inst.size() * (size_t)nslot, -1); }
         cur.assign(nslot, -1); matchcap.assign(nslot, -1);
     }
     static bool word(int32_t r) { return (r >= '0' && r <= '9') || (r >= 'A' && r <= 'Z') || (r >= 'a' && r <= 'z') || r == '_'; }
@@ -521,11 +571,12 @@ struct Machine {
             case I_NOP: pc = in.out; continue;
             case I_CAP: { const int64_t old = cur[in.arg]; cur[in.arg] = pos; add(qq, in.out, pos, cond); cur[in.arg] = old; return; }
             default:                                           // MATCH, RUNE1, CLASS: a thread
-                qq.slot[j] = (int32_t)(qq.caps.size() / nslot); qq.caps.insert(qq.caps.end(), cur.begin(), cur.end()); return;
+                qq.slot[j] = (int32_t)qq.nthreads; std::copy(cur.begin(), cur.end(), qq.caps.begin() + (size_t)qq.nthreads * nslot); qq.nthreads++; return;
             }
         }
     }
     bool in_class(uint32_t k, int32_t r) const {
+        if (r < 0x80) return p.ascii[k][r >> 6] >> (r & 63) & 1;
         const Ranges& rg = p.classes[k];
         size_t lo = 0, hi = rg.size();
         while (lo < hi) { const size_t mid = (lo + hi) / 2; if (r > rg[mid].second) lo = mid + 1; else if (r < rg[mid].first) hi = mid; else return true; }
@@ -539,12 +590,31 @@ struct Machine {
         int32_t r0 = pos == 0 ? END_OF_TEXT : (s[pos - 1] < 0x80 ? (int32_t)s[pos - 1] : RUNE_ERROR);   // only '\n' and ASCII word-ness are ever asked of it
         int w; int32_t r = decode_rune(s + pos, n - pos, w);
         while (true) {
-            if (runq->n == 0 && matched) break;
-            const uint8_t cond = cond_of(r0, r);
-            if (!matched) { std::fill(cur.begin(), cur.end(), -1); cur[0] = (int64_t)pos; add(*runq, p.start, (int64_t)pos, cond); }
+            if (runq->n == 0) {
+                if (matched || (p.anchored && pos != 0)) break;
+                if (p.first_rune >= 0) {                      // no thread alive: the next match starts at the next occurrence of the leading literal
+                    size_t at = pos; bool found = false;
+                    while (at < n) {
+                        const uint8_t* f = (const uint8_t*)std::memchr(s + at, p.first_byte, n - at);
+                        if (!f) break;
+                        at = (size_t)(f - s); int fw;
+                        if (decode_rune(s + at, n - at, fw) == p.first_rune) { found = true; break; }
+                        at++;
+                    }
+                    if (!found) break;
+                    if (at != pos) { pos = at; r0 = s[pos - 1] < 0x80 ? (int32_t)s[pos - 1] : RUNE_ERROR; r = decode_rune(s + pos, n - pos, w); }
+                } else if (!p.first_any) {                    // ... or at the next byte some match can begin with
+                    size_t at = pos;
+                    while (at < n && !p.first[s[at]]) at++;
+                    if (at == n) break;
+                    if (at != pos) { pos = at; r0 = s[pos - 1] < 0x80 ? (int32_t)s[pos - 1] : RUNE_ERROR; r = decode_rune(s + pos, n - pos, w); }
+                }
+            }
+            const uint8_t cond = p.has_empty ? cond_of(r0, r) : 0;
+            if (!matched && (!p.anchored || pos == 0)) { std::fill(cur.begin(), cur.end(), -1); cur[0] = (int64_t)pos; add(*runq, p.start, (int64_t)pos, cond); }
             // step: every thread of runq over the rune r; the followers are added with the context at pos + w
             const size_t npos = pos + w; int w1 = 0; const int32_t r1 = w ? decode_rune(s + npos, n - npos, w1) : END_OF_TEXT;
-            const uint8_t ncond = cond_of(r, r1);
+            const uint8_t ncond = p.has_empty ? cond_of(r, r1) : 0;
             for (uint32_t j = 0; j < runq->n; j++) {
                 const int32_t sl = runq->slot[j];
                 if (sl < 0) continue;

@@ -21,6 +21,7 @@
 #include "../../include/tfgpu_sink.h"
 #include "plan.hpp"
 #include "row_image.hpp"
+#include "host_internal.hpp"
 
 namespace {
 
@@ -105,6 +106,7 @@ struct tfgpu_columnar {
     // results of the last call
     std::vector<tf_col> cols, old_cols; tf_batch batch{}, old_batch{}; tf_row_meta meta{}; tf_old_keys old{};
     std::vector<uint8_t> present;
+    std::vector<uint8_t> text_mixed;      // [col] of the last tfgpu_rows_to_batch: a text cell carried Go's other text type (see host_internal.hpp)
     void* workers = nullptr;              // Workers, created on first use
     ~tfgpu_columnar();
 };
@@ -257,6 +259,7 @@ struct Transposer {
                             uint32_t* rec = cells + ((size_t)j * nvar + x.vi) * 2; rec[0] = (uint32_t)(at - image); rec[1] = len; st[c].heap += len; if (len > st[c].max_len) st[c].max_len = len;
                             at += len;
                             if (x.aux && tag == TF_V_STRING) { x.aux[j] = 1; st[c].nsec = true; }
+                            else if (tag != x.want) st[c].tagmask = 1;                                     // the column's other text type was seen
                         }
                     } else if (tag == TF_V_NIL) { x.validity[vbyte] &= (uint8_t)~vbit; st[c].nil = true; }
                     else { if (trace && !loose.exchange(true)) fprintf(stderr, "[transpose strict] column %u (type %d) holds a value of tag %d: general path\n", c, tfs[c], (int)tag); loose.store(true, std::memory_order_relaxed); return; }
@@ -268,15 +271,16 @@ struct Transposer {
         if (loose.load()) return false;
         const auto t_p1 = std::chrono::steady_clock::now();
         // ---- layout
-        cp.assign(nc, ColPlan()); heap_base.assign((size_t)nchunks * nc, 0); out_cols.assign(nc, tf_col{});
+        cp.assign(nc, ColPlan()); heap_base.assign((size_t)nchunks * nc, 0); out_cols.assign(nc, tf_col{}); pool->text_mixed.assign(nc, 0);
         for (uint32_t c = 0; c < nc; c++) {
             ColPlan& p = cp[c]; SCol& x = sc[c]; tf_col& o = out_cols[c];
             p.schema_tf = p.phys_tf = tfs[c]; p.width = x.w; o.type = tfs[c];
             for (uint64_t k = 0; k < nchunks; k++) {
                 const ChunkStat& s = stats[(size_t)k * nc + c];
                 heap_base[(size_t)k * nc + c] = p.heap_total;
-                p.heap_total += s.heap; p.max_len = std::max(p.max_len, s.max_len); p.has_nil |= s.nil; p.has_nsec |= s.nsec;
+                p.heap_total += s.heap; p.max_len = std::max(p.max_len, s.max_len); p.has_nil |= s.nil; p.has_nsec |= s.nsec; p.tagmask |= s.tagmask;
             }
+            pool->text_mixed[c] = p.tagmask != 0;
             if (p.has_nil) o.validity = x.validity;
             if (x.w) { o.values = x.values; if (p.has_nsec) o.aux = x.aux; continue; }
             if (x.aux && p.has_nsec) { p.has_anytag = true; p.has_nsec = false; o.aux = x.aux; }
@@ -323,6 +327,7 @@ struct Transposer {
         if (threads > 1 && n / ((uint64_t)threads * 4) < chunk) chunk = std::max<uint64_t>(256, n / ((uint64_t)threads * 4) & ~7ull);
         nchunks = (n + chunk - 1) / chunk;
         stats.assign((size_t)nchunks * nc, ChunkStat());
+        if (!keyed && !only) pool->text_mixed.assign(nc, 0);
         // ---- pass 1: tags, heap bytes, longest cell per (chunk, column)
         std::vector<uint8_t> fw(nc); for (uint32_t c = 0; c < nc; c++) fw[c] = (uint8_t)fixed_width(tfs[c]);
         parallel_chunks(pool, n, chunk, threads, [&](uint64_t k) {
@@ -374,6 +379,7 @@ struct Transposer {
                 if (tf == TF_ANY && (m & (M_FLOAT | (1u << TF_V_TIME) | (1u << TF_V_DURATION) | (1u << TF_V_BYTES)))) refuse("float / time / []byte inside `any` needs encoding/json's formatter");
                 if (p.heap_total >= (1ull << 32)) refuse("heap over 4 GiB");
                 p.phys_tf = tf; p.lens_width = p.max_len < 256 ? 1 : p.max_len < 65536 ? 2 : 4;
+                if (!keyed && !only) pool->text_mixed[c] = tf != TF_ANY && (m & (1u << (tf == TF_UTF8 ? TF_V_BYTES : TF_V_STRING))) != 0;
                 p.has_anytag = tf == TF_ANY && (m & (1u << TF_V_STRING));
             }
         }
@@ -458,6 +464,60 @@ const std::vector<int>& schema_types(tfgpu_columnar* p, const char* schema_json)
 }  // namespace
 
 tfgpu_columnar::~tfgpu_columnar() { for (auto& b : bufs) b.release(); for (auto& b : tmp_bufs) b.release(); delete (Workers*)workers; }
+
+bool tfgpu_columnar_text_was_mixed(const tfgpu_columnar* pool, uint32_t col) { return pool && col < pool->text_mixed.size() && pool->text_mixed[col]; }
+
+int tfgpu_columnar_rewrite_text(tfgpu_columnar* pool, uint32_t col, const std::function<tf_text_fn()>& make, int threads) {
+    if (!pool || col >= pool->cols.size()) return TF_E_FATAL_ARG;
+    try {
+        tf_col& o = pool->cols[col]; const uint64_t n = pool->batch.nrows;
+        if (o.values || (!o.offsets && n)) throw Fail{TF_E_FATAL_ARG, "not a var-width column"};
+        if (!n) return TF_OK;
+        if (threads <= 0) threads = (int)std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency()));
+        const int lw = o.flags & TF_COL_LENS8 ? 1 : o.flags & TF_COL_LENS16 ? 2 : 4;
+        const uint8_t* lens = (const uint8_t*)o.offsets;
+        auto cell_len = [&](uint64_t j) -> uint32_t { if (lw == 1) return lens[j]; if (lw == 2) { uint16_t l; std::memcpy(&l, lens + 2 * j, 2); return l; } uint32_t a, b; std::memcpy(&a, lens + 4 * j, 4); std::memcpy(&b, lens + 4 * j + 4, 4); return b - a; };
+        const uint64_t chunk = std::max<uint64_t>(512, std::min<uint64_t>(8192, n / ((uint64_t)threads * 4) & ~7ull));
+        const uint64_t nchunks = (n + chunk - 1) / chunk;
+        std::vector<uint64_t> in_base(nchunks + 1, 0);                       // where every task's cells start in the old heap
+        for (uint64_t k = 0; k < nchunks; k++) { uint64_t sum = 0; for (uint64_t j = k * chunk; j < std::min(n, (k + 1) * chunk); j++) sum += cell_len(j); in_base[k + 1] = in_base[k] + sum; }
+        struct Out { std::string heap; std::vector<uint32_t> len; uint32_t max_len = 0; };
+        std::vector<Out> outs(nchunks);
+        parallel_chunks(pool, n, chunk, threads, [&](uint64_t k) {
+            const tf_text_fn fn = make(); Out& w = outs[k]; std::string cell;
+            const uint64_t r0 = k * chunk, r1 = std::min(n, (k + 1) * chunk); uint64_t at = in_base[k];
+            w.len.resize(r1 - r0); w.heap.reserve((size_t)(in_base[k + 1] - in_base[k]) + 64);
+            for (uint64_t j = r0; j < r1; j++) {
+                const uint32_t len = cell_len(j);
+                if (o.validity && !(o.validity[j >> 3] >> (j & 7) & 1)) { w.len[j - r0] = 0; at += len; continue; }      // nil stays nil
+                fn(o.heap + at, len, cell); at += len;
+                if (cell.size() >= (1ull << 32)) throw Fail{TF_E_FATAL_UNSUPPORTED, "a replaced cell over 4 GiB"};
+                w.len[j - r0] = (uint32_t)cell.size(); w.max_len = std::max(w.max_len, (uint32_t)cell.size()); w.heap += cell;
+            }
+        });
+        uint64_t total = 0; uint32_t max_len = 0; std::vector<uint64_t> out_base(nchunks);
+        for (uint64_t k = 0; k < nchunks; k++) { out_base[k] = total; total += outs[k].heap.size(); max_len = std::max(max_len, outs[k].max_len); }
+        if (total >= (1ull << 32)) throw Fail{TF_E_FATAL_UNSUPPORTED, "column " + std::to_string(col) + ": heap over 4 GiB"};
+        const int nlw = max_len < 256 ? 1 : max_len < 65536 ? 2 : 4;
+        uint8_t* nl = pool->take()->ensure((size_t)nlw * (n + 1) + 16, pool->want_pinned);
+        uint8_t* nh = pool->take()->ensure((size_t)total + 16, pool->want_pinned);
+        parallel_chunks(pool, n, chunk, threads, [&](uint64_t k) {
+            const Out& w = outs[k]; const uint64_t r0 = k * chunk; uint64_t off = out_base[k];
+            std::memcpy(nh + off, w.heap.data(), w.heap.size());
+            for (size_t i = 0; i < w.len.size(); i++) {
+                const uint64_t j = r0 + i;
+                if (nlw == 1) nl[j] = (uint8_t)w.len[i];
+                else if (nlw == 2) { const uint16_t l = (uint16_t)w.len[i]; std::memcpy(nl + 2 * j, &l, 2); }
+                else { const uint32_t o32 = (uint32_t)off; std::memcpy(nl + 4 * j, &o32, 4); }
+                off += w.len[i];
+            }
+        });
+        if (nlw == 4) { const uint32_t t32 = (uint32_t)total; std::memcpy(nl + 4 * n, &t32, 4); }
+        o.offsets = (const uint32_t*)nl; o.heap = nh; o.heap_len = total; o.flags = nlw == 1 ? TF_COL_LENS8 : nlw == 2 ? TF_COL_LENS16 : 0;
+        return TF_OK;
+    } catch (const Fail& f) { pool->err = f.msg; return f.rc; }
+    catch (const std::bad_alloc&) { pool->err = "host allocation failed"; return TF_E_RETRY_OOM; }
+}
 
 extern "C" {
 

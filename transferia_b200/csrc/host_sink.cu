@@ -13,7 +13,10 @@
 #include "plan.hpp"
 #include "row_image.hpp"
 #include "host_regex.hpp"
+#include "host_internal.hpp"
 #include <charconv>
+#include <chrono>
+#include <cstdio>
 #include <condition_variable>
 #include <deque>
 #include <memory>
@@ -120,6 +123,7 @@ struct tfgpu_sink {
     int wire_fmt = 0;
     std::set<std::string> system_tables;
     std::vector<HostStep> host_steps;
+    bool regex_on_columns = false;             // this push: the replace steps run on the transposed text columns (push_rows) instead of the row image
     tf_sink_fn fn = nullptr; void* ctx = nullptr; tfgpu_ch_conn* ch = nullptr;
     tfgpu_columnar* pool = nullptr;
     std::map<std::string, TablePlan> plans;
@@ -312,6 +316,37 @@ struct tfgpu_sink {
             rc = tfgpu_rows_to_batch(pool, &ar, 0, nullptr, 0, 0, &batch, &meta, &old);
         } else rc = tfgpu_rows_to_batch(pool, rows, table, idx.data(), n, 0, &batch, &meta, &old);
         if (rc) throw SinkFail{rc, std::string("transpose: ") + tfgpu_columnar_last_error(pool)};
+        Rewritten rw_run;
+        if (regex_on_columns) {
+            const std::string name = rows->tables[table].table ? rows->tables[table].table : "";
+            std::vector<std::vector<const HostStep*>> by_col(tp.col_names.size()); bool mixed = false;
+            for (const HostStep& h : host_steps) if (h.type == 4 && h.tables.match(name))
+                for (size_t c = 0; c < tp.col_names.size(); c++) if ((tp.col_tf[c] == TF_UTF8 || tp.col_tf[c] == TF_BYTES) && h.columns.match(tp.col_names[c])) {
+                    by_col[c].push_back(&h); mixed |= tfgpu_columnar_text_was_mixed(pool, (uint32_t)c);
+                }
+            if (mixed) {
+                // a []byte inside a utf8 column (or a string inside a `string` column) fails the transformer's type assertion and stays as it is:
+                // only the row image knows which cells those are
+                if (regex_rewrite(rows, rw_run)) rc = tfgpu_rows_to_batch(pool, &rw_run.rows, table, idx.data(), n, 0, &batch, &meta, &old);
+                if (rc) throw SinkFail{rc, std::string("transpose: ") + tfgpu_columnar_last_error(pool)};
+            } else for (size_t c = 0; c < by_col.size(); c++) {
+                if (by_col[c].empty()) continue;
+                const std::vector<const HostStep*>& steps = by_col[c];
+                rc = tfgpu_columnar_rewrite_text(pool, (uint32_t)c, [&steps]() -> tf_text_fn {
+                    auto vms = std::make_shared<std::vector<tfre::Machine>>(); for (const HostStep* h : steps) vms->emplace_back(*h->prog);
+                    auto tmp = std::make_shared<std::string>();
+                    return [vms, tmp, &steps](const uint8_t* p, uint32_t len, std::string& out) {
+                        const uint8_t* src = p; size_t n = len;
+                        for (size_t k = 0; k < steps.size(); k++) {
+                            std::string& dst = (k & 1) ? *tmp : out;
+                            tfre::replace_all((*vms)[k], steps[k]->tpl, src, n, dst); src = (const uint8_t*)dst.data(); n = dst.size();
+                        }
+                        if (!(steps.size() & 1)) out.swap(*tmp);                  // an even number of steps left the result in tmp
+                    };
+                }, 0);
+                if (rc) throw SinkFail{rc, std::string("regex_replace: ") + tfgpu_columnar_last_error(pool)};
+            }
+        }
         if (tp.plan_id < 0) {                                                                           // no transformers, columnar hand-over
             ev.type = TF_SINK_EV_ROWS; ev.n_items = n; ev.item_idx = idx.data(); ev.batch = batch;
             deliver(ev, rows, &tp); return;
@@ -356,10 +391,11 @@ struct tfgpu_sink {
         if (!any) return false;
         struct PerTable { bool looked = false; std::vector<std::vector<const HostStep*>> by_col; const TablePlan* tp = nullptr; bool hit = false; };
         std::vector<PerTable> per(in->n_tables);
+        out.values.reserve((size_t)in->values_len * 2 + 4096);
         out.values.assign(in->values, in->values + in->values_len);
         out.items.assign(in->items, in->items + in->n_items);
         const uint8_t* vend = in->values + in->values_len;
-        std::string a, b;
+        std::string a, b; const auto t_begin = std::chrono::steady_clock::now(); double rx_ns = 0; const bool trace = std::getenv("TFGPU_SINK_TRACE") != nullptr;
         for (uint64_t i = 0; i < in->n_items; i++) {
             const tf_item& it = in->items[i];
             if (!TF_KIND_IS_ROW(it.kind)) continue;
@@ -376,22 +412,28 @@ struct tfgpu_sink {
             if (it.values_off > in->values_len) throw SinkFail{TF_E_FATAL_ARG, "values offset outside the image"};
             const uint8_t* at = in->values + it.values_off; const bool sparse = it.flags & TF_ITEM_SPARSE;
             const uint64_t new_off = out.values.size();
+            const uint8_t* run = at;                             // bytes of the list not yet copied: untouched values go over in one piece
             for (uint32_t k = 0; k < it.n_values; k++) {
                 uint32_t c = k;
-                if (sparse) { if (vend - at < 2) throw SinkFail{TF_E_FATAL_ARG, "truncated value image"}; uint16_t ci; std::memcpy(&ci, at, 2); out.values.insert(out.values.end(), at, at + 2); at += 2; c = ci; }
+                if (sparse) { if (vend - at < 2) throw SinkFail{TF_E_FATAL_ARG, "truncated value image"}; uint16_t ci; std::memcpy(&ci, at, 2); at += 2; c = ci; }
                 const uint8_t* v0 = at; Val v; if (!read_val(at, vend, v)) throw SinkFail{TF_E_FATAL_ARG, "malformed value image"};
                 const int typ = k < pt.tp->col_tf.size() ? pt.tp->col_tf[k] : -1;
                 const bool takes = c < pt.by_col.size() && !pt.by_col[c].empty() && ((typ == TF_UTF8 && v.tag == TF_V_STRING) || (typ == TF_BYTES && v.tag == TF_V_BYTES));
-                if (!takes) { out.values.insert(out.values.end(), v0, at); continue; }
+                if (!takes) continue;
+                out.values.insert(out.values.end(), run, v0); run = at;        // (the column index of a sparse value lies before v0: copied with the run)
                 a.assign((const char*)v.p, v.n);
+                const auto t0 = trace ? std::chrono::steady_clock::now() : std::chrono::steady_clock::time_point();
                 for (const HostStep* h : pt.by_col[c]) { tfre::replace_all(*h->vm, h->tpl, (const uint8_t*)a.data(), a.size(), b); a.swap(b); }
+                if (trace) rx_ns += std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count();
                 if (a.size() > 0xffffffffull) throw SinkFail{TF_E_FATAL_UNSUPPORTED, "regex_replace_transformer: a value grew past 4 GiB"};
                 const uint32_t len = (uint32_t)a.size();
                 out.values.push_back((uint8_t)v.tag); out.values.insert(out.values.end(), (const uint8_t*)&len, (const uint8_t*)&len + 4);
                 out.values.insert(out.values.end(), a.begin(), a.end());
             }
+            out.values.insert(out.values.end(), run, at);
             out.items[i].values_off = new_off;
         }
+        if (std::getenv("TFGPU_SINK_TRACE")) fprintf(stderr, "[sink] regex step: %.2f ms over %llu items (%.2f ms inside ReplaceAll)\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(), (unsigned long long)in->n_items, rx_ns / 1e6);
         out.values.push_back(0);
         out.rows = *in; out.rows.items = out.items.data(); out.rows.values = out.values.data(); out.rows.values_len = out.values.size() - 1;
         return true;
@@ -399,8 +441,18 @@ struct tfgpu_sink {
 
     void push(const tf_rows* rows) {
         st.pushes++; st.max_commit_time = st.min_commit_time = 0;
-        Rewritten rw;
-        if (regex_rewrite(rows, rw)) rows = &rw.rows;
+        // regex_replace steps: on the transposed text columns when that is the same thing (every row event lists all its columns, so the
+        // type-by-position rule of transformer.go:108 is the column's type, and nothing reads the values before the transposer does);
+        // else on the row image up front
+        Rewritten rw; regex_on_columns = false;
+        bool has_regex = false, has_splitter = false;
+        for (const HostStep& h : host_steps) { has_regex |= h.type == 4; has_splitter |= h.type == 3; }
+        if (has_regex) {
+            bool dense = !has_splitter && !std::getenv("TFGPU_REGEX_ON_ROWS");
+            for (uint64_t i = 0; dense && i < rows->n_items; i++) if (TF_KIND_IS_ROW(rows->items[i].kind) && (rows->items[i].flags & TF_ITEM_SPARSE)) dense = false;
+            if (dense) regex_on_columns = true;
+            else if (regex_rewrite(rows, rw)) rows = &rw.rows;
+        }
         // SplitByTableID (utils.go:130-136): groups in order of first appearance, items in input order
         std::vector<std::pair<std::string, std::vector<uint64_t>>> groups; std::map<std::string, size_t> where;
         for (uint64_t i = 0; i < rows->n_items; i++) {

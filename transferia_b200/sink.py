@@ -165,7 +165,10 @@ class Sink:
     does not take."""
 
     def __init__(self, eng=None, transformers=None, wire_fmt=0, system_tables=(), exclude_system_tables=True, errors_output="sink",
-                 database="default", downstream=None, clickhouse: Optional[ClickHouseWriter] = None, debezium: Optional[dict] = None, updateable: bool = False):
+                 database="default", downstream=None, clickhouse: Optional[ClickHouseWriter] = None, debezium: Optional[dict] = None, updateable: bool = False,
+                 record: str = "full"):
+        """record: "full" keeps item indexes and copies of the delivered columns per event (tests); "counts" keeps type / table / n_items
+        only (timing runs: the copies would be what is measured)."""
         from . import abi, rows as _rows
         self._L = lib()
         vp = C.c_void_p
@@ -189,6 +192,10 @@ class Sink:
 
         def _cb(_ctx, evp):
             ev = evp.contents
+            if record == "counts":
+                d = {"type": ev.type, "table": ev.table, "n_items": int(ev.n_items)}
+                self.events.append(d)
+                return int(self._downstream(d)) if self._downstream else 0
             d = {"type": ev.type, "table": ev.table, "out": ((ev.out_schema or b"").decode(), (ev.out_table or b"").decode()), "n_items": int(ev.n_items),
                  "items": [int(ev.item_idx[k]) for k in range(ev.n_items)] if ev.item_idx else None, "plan_id": ev.plan_id,
                  "raw_len": int(ev.raw_len), "n_frames": int(ev.n_frames)}
