@@ -41,9 +41,9 @@ TFGPU_LIB_PATH="$OUT/libtfhost_asan.so" LD_PRELOAD="$(gcc -print-file-name=libas
     ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1 \
     python -m pytest tests/test_rows.py tests/test_sink_push.py tests/test_ch_wire.py tests/test_host_cpu.py tests/test_regex_replace.py -q -m "not gpu" -p no:cacheprovider \
     -k "not exports and not sm100a and not no_cpu_fallback and not gloo and not bench_reference and not c_example"
-# the threaded parts (worker pool of the transposer / gather, dispatcher lanes and its delivery gate) under ThreadSanitizer
+# the threaded parts (worker pool of the transposer / gather / column-wise replace, dispatcher lanes and its delivery gate) under ThreadSanitizer
 g++ -std=c++17 -O1 -g -fsanitize=thread -fno-omit-frame-pointer -fPIC -shared -I/usr/local/cuda/include \
     -x c++ "$ROOT/transferia_b200/csrc/host_rows.cu" "$ROOT/transferia_b200/csrc/host_sink.cu" "$ROOT/transferia_b200/csrc/host_chwire.cu" "$OUT/stubs.cpp" "$OUT/plan_validate.cpp" \
     -o "$OUT/libtfhost_tsan.so" -L/usr/local/cuda/lib64 -lcudart
 TFGPU_LIB_PATH="$OUT/libtfhost_tsan.so" LD_PRELOAD="$(gcc -print-file-name=libtsan.so)" TSAN_OPTIONS="halt_on_error=1 report_signal_unsafe=0" \
-    python -m pytest tests/test_rows.py tests/test_sink_push.py -q -m "not gpu" -p no:cacheprovider -k "dispatcher or two_pools or host_gather or transposer_fuzz"
+    python -m pytest tests/test_rows.py tests/test_sink_push.py tests/test_regex_replace.py -q -m "not gpu" -p no:cacheprovider -k "dispatcher or two_pools or host_gather or transposer_fuzz or strict_single or replace_steps or mixed_text"
