@@ -190,7 +190,16 @@ def _gen(rng, depth=0):
     return "|".join(alts), any_nullable
 
 
+class _OracleTooSlow(Exception):
+    pass
+
+
 def test_random_expressions_against_the_oracle():
+    import signal
+
+    def on_alarm(_sig, _frm):
+        raise _OracleTooSlow()
+    signal.signal(signal.SIGALRM, on_alarm)
     rng = random.Random(20260923)
     alphabet = ["a", "b", "c", "ab", "1", "_", " ", "\n", ".", "-", "日", "é", b"\xff", b"\xe6\x97", "x", "A", "B", "k", "K", "S", "s", "\u212a", "\u017f"]
     rules = ["", "X", "<$0>", "[$1|$2]", "${1}x$1x", "$$1", "$", "${g}", "$g1234", "a$0b$9"]
@@ -209,7 +218,14 @@ def test_random_expressions_against_the_oracle():
             if not src and "\\B" in pat:
                 continue                    # Python before 3.14 never matches \B on the empty text; Go does (EmptyOpContext(-1, -1) is a no-boundary)
             got = R(pat, rule, src)
-            assert got == ro.replace_all(pat, rule, src), (pat, rule, src)
+            signal.alarm(10)                # Python's backtracking engine can go exponential on nested repeats (the product's machine is linear): such a pair is skipped
+            try:
+                want = ro.replace_all(pat, rule, src)
+            except _OracleTooSlow:
+                continue
+            finally:
+                signal.alarm(0)
+            assert got == want, (pat, rule, src)
             n_checked += 1; n_changed += got != src
     assert n_checked > 10000 and n_changed > 3000
 
