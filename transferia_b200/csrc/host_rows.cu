@@ -138,7 +138,11 @@ private:
     void work() {
         for (;;) {
             const uint64_t k = next_.fetch_add(1); if (k >= count_ || failed_.load()) return;
-            try { (*fn_)(k); } catch (const Fail& e) { std::lock_guard<std::mutex> g(m_); if (!failed_.exchange(true)) first_ = e; return; }
+            auto fail = [&](const Fail& e) { std::lock_guard<std::mutex> g(m_); if (!failed_.exchange(true)) first_ = e; };
+            try { (*fn_)(k); }
+            catch (const Fail& e) { fail(e); return; }
+            catch (const std::bad_alloc&) { fail(Fail{TF_E_RETRY_OOM, "host allocation failed"}); return; }       // (an exception leaving a worker thread would end the process)
+            catch (const std::exception& e) { fail(Fail{TF_E_FATAL_ARG, e.what()}); return; }
         }
     }
     void loop() {
