@@ -114,6 +114,18 @@ def test_oracle_serializer_forms(po):
     assert r.errors == [(0, 40, 0)]
 
 
+def test_json_serializer_complex_as_str_reference_case(po):
+    """pkg/serializer/json_test.go:52-112 (TestJSONSerializerComplexAsStr): id 1, a JSON object, a JSON array and nil in `any` columns, with
+    AnyAsString and without — the four substrings the reference requires."""
+    schema = [{"name": "id", "type": "int16"}, {"name": "jsonObject", "type": "any"}, {"name": "jsonArray", "type": "any"}, {"name": "nil", "type": "any"}]
+    batch = abi.Batch(1, [abi.fixed_to_column(abi.TF_INT16, [1]), abi.strings_to_column(abi.TF_ANY, [b'{"key":"value"}'], tags=[0]),
+                          abi.strings_to_column(abi.TF_ANY, [b"[1,2,3]"], tags=[0]), abi.strings_to_column(abi.TF_ANY, [None], tags=[0])])
+    plan = po.build_plan("s", "t", schema, [])
+    for flags, obj, arr in ((F_AAS, '"{\\"key\\":\\"value\\"}"', '"[1,2,3]"'), (0, '{"key":"value"}', "[1,2,3]")):
+        line = po.push_encode(batch, plan, SER_JSON | flags).wire.decode()
+        assert '"id":1' in line and f'"jsonObject":{obj}' in line and f'"jsonArray":{arr}' in line and '"nil":null' in line, line
+
+
 # ----------------------------------------------------------------------------------------------------------- GPU parity
 def _ser_cases():
     from test_gpu_parity import all_types_batch
