@@ -555,3 +555,32 @@ def test_device_emitter_update_delete_equals_oracle(eng, po):
     # without OldKeys
     want = po.debezium_emit(b, plan, OPTS, meta, want_msg_sizes=True); got = eng.emit_debezium(pid, b, OPTS, meta)
     assert got.wire == want[0] and np.array_equal(got.msg_sizes[:, 0], want[4][:, 0])
+
+
+def test_oracle_against_the_serializer_test_messages(po):
+    """pkg/serializer/queue/debezium_serializer_test.go:43-145 (TestDebeziumSerializerSnapshot, ...TopicName, ...TopicPrefix): the complete key
+    and value messages of one pg item (id 601, LSN 25051056, CommitTime 1643660670333075000, columns id / val `pg:integer`) with the
+    include-schema packer, byte for byte — snapshot on (op "r") and off (op "c"), three table names, two topic prefixes. The two schema texts
+    are what the shim passes in (the reference caches them per table); the payloads, the source block and the wrapper are computed."""
+    schema = [{"name": "id", "type": "int32", "key": True, "original_type": "pg:integer"}, {"name": "val", "type": "int32", "original_type": "pg:integer"}]
+    b = abi.Batch(1, [abi.fixed_to_column(abi.TF_INT32, [1]), abi.fixed_to_column(abi.TF_INT32, [-8388605])])
+    meta = {"id": np.array([601], np.uint32), "lsn": np.array([25051056], np.uint64), "commit_time": np.array([1643660670333075000], np.uint64)}
+    for table, prefix, snap in (("snapshot", "__data_transfer_stub", True), ("table0", "__data_transfer_stub", False), ("table1", "__data_transfer_stub", False), ("basic_types15", "my_topic_prefix", False)):
+        fq = f"{prefix}.public.{table}"
+        key_schema = '{"fields":[{"field":"id","optional":false,"type":"int32"}],"name":"%s.Key","optional":false,"type":"struct"}' % fq
+        val_schema = ('{"fields":[{"field":"before","fields":[{"field":"id","optional":false,"type":"int32"},{"field":"val","optional":true,"type":"int32"}],"name":"FQ.Value","optional":true,"type":"struct"},'
+                      '{"field":"after","fields":[{"field":"id","optional":false,"type":"int32"},{"field":"val","optional":true,"type":"int32"}],"name":"FQ.Value","optional":true,"type":"struct"},'
+                      '{"field":"source","fields":[{"field":"version","optional":false,"type":"string"},{"field":"connector","optional":false,"type":"string"},{"field":"name","optional":false,"type":"string"},{"field":"ts_ms","optional":false,"type":"int64"},'
+                      '{"default":"false","field":"snapshot","name":"io.debezium.data.Enum","optional":true,"parameters":{"allowed":"true,last,false"},"type":"string","version":1},{"field":"db","optional":false,"type":"string"},'
+                      '{"field":"table","optional":false,"type":"string"},{"field":"lsn","optional":true,"type":"int64"},{"field":"schema","optional":false,"type":"string"},{"field":"txId","optional":true,"type":"int64"},{"field":"xmin","optional":true,"type":"int64"}],'
+                      '"name":"io.debezium.connector.postgresql.Source","optional":false,"type":"struct"},{"field":"op","optional":false,"type":"string"},{"field":"ts_ms","optional":true,"type":"int64"},'
+                      '{"field":"transaction","fields":[{"field":"id","optional":false,"type":"string"},{"field":"total_order","optional":false,"type":"int64"},{"field":"data_collection_order","optional":false,"type":"int64"}],"optional":true,"type":"struct"}],'
+                      '"name":"FQ.Envelope","optional":false,"type":"struct"}').replace("FQ", fq)
+        opts = {"version": "1.1.2.Final", "topic_prefix": prefix, "database": "", "source_type": "pg", "snapshot": snap, "key_schema": key_schema, "val_schema": val_schema}
+        d, ks, rs, errs = po.debezium_emit(b, po.build_plan("public", table, schema, []), opts, meta=meta)
+        (key, val), = po.debezium_split(d, ks, rs)
+        assert not errs
+        assert key.decode() == '{"payload":{"id":1},"schema":' + key_schema + '}'
+        assert val.decode() == ('{"payload":{"after":{"id":1,"val":-8388605},"before":null,"op":"%s","source":{"connector":"postgresql","db":"","lsn":25051056,"name":"%s","schema":"public",'
+                                '"snapshot":"%s","table":"%s","ts_ms":1643660670333,"txId":601,"version":"1.1.2.Final","xmin":null},"transaction":null,"ts_ms":1643660670333},"schema":'
+                                % ("r" if snap else "c", prefix, "true" if snap else "false", table)) + val_schema + '}'
