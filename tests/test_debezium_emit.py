@@ -584,3 +584,25 @@ def test_oracle_against_the_serializer_test_messages(po):
         assert val.decode() == ('{"payload":{"after":{"id":1,"val":-8388605},"before":null,"op":"%s","source":{"connector":"postgresql","db":"","lsn":25051056,"name":"%s","schema":"public",'
                                 '"snapshot":"%s","table":"%s","ts_ms":1643660670333,"txId":601,"version":"1.1.2.Final","xmin":null},"transaction":null,"ts_ms":1643660670333},"schema":'
                                 % ("r" if snap else "c", prefix, "true" if snap else "false", table)) + val_schema + '}'
+
+
+def test_oracle_pg_time_forms_against_typeutil_tests(po):
+    """pkg/debezium/typeutil/helpers_test.go: TestGetTimeDivider (:329-376 — `timestamp(p) without time zone` travels in milliseconds for
+    p 1..3, in microseconds for p 4..6 and without a precision) and TestSprintfDebeziumTime (:488-496 — timestamptz text with the trailing
+    zeros of the fraction cut) on the emitter oracle."""
+    import calendar
+    sec = calendar.timegm((2022, 8, 28, 19, 49, 47))
+
+    def emit(ot, ns):
+        schema = [{"name": "id", "type": "int32", "key": True, "original_type": "pg:integer"}, {"name": "t", "type": "timestamp", "original_type": ot}]
+        b = abi.Batch(1, [abi.fixed_to_column(abi.TF_INT32, [1]), abi.fixed_to_column(abi.TF_TIMESTAMP, [sec], None, [ns])])
+        d, ks, rs, errs = po.debezium_emit(b, po.build_plan("public", "t", schema, []), {"version": "1", "topic_prefix": "p", "database": "", "source_type": "pg"})
+        (_, v), = po.debezium_split(d, ks, rs)
+        assert not errs
+        return json.loads(v)["after"]["t"]
+    micros = sec * 1_000_000 + 749906
+    for p, divider in ((1, 1000), (3, 1000), (4, 1), (6, 1)):
+        assert emit(f"pg:timestamp({p}) without time zone", 749906000) == micros // divider
+    assert emit("pg:timestamp without time zone", 749906000) == micros
+    assert emit("pg:timestamp with time zone", 749906000) == "2022-08-28T19:49:47.749906Z"
+    assert emit("pg:timestamp with time zone", 90000000) == "2022-08-28T19:49:47.09Z"
