@@ -84,6 +84,12 @@ def test_base64_to_numeric(po):
     assert f("MDk=", 0) == "12345" and f("ME8=", 2) == "123.67" and f("AeJA", 0) == "123456" and f("EAAAAAAAAAAAAAAAAA==", 0) == "1267650600228229401496703205376"
     assert f(base64.b64encode(b"\xff").decode(), 0) == "-1" and f(base64.b64encode(b"\x80\x00").decode(), 1) == "-3276.8"
     assert f(base64.b64encode(b"\x0c").decode(), 2) == ".12" and f(base64.b64encode(b"\x01").decode(), 2) == "0.01" and f(base64.b64encode(b"\x00").decode(), 3) == "0"
+    # pkg/debezium/typeutil/helpers_test.go: TestBase64ToNumeric (:417-421) and, read backwards, the (numeric, base64, scale) triples of
+    # TestDecimalToDebezium / TestDecimalToDebeziumPrimitivesImpl (:223-254) whose text form is unambiguous
+    assert f("AQ==", 2) == "0.01"
+    for text, b64, scale in (("100.00", "JxA=", 2), ("-100.00", "2PA=", 2), ("2345678901", "AIvQODU=", 0), ("-2345678901", "/3Qvx8s=", 0),
+                             ("1267650600228229401496703205376", "EAAAAAAAAAAAAAAAAA==", 0), ("126765060022822940149670320537.6", "EAAAAAAAAAAAAAAAAA==", 1)):
+        assert f(b64, scale) == text, (b64, scale)
 
 
 def test_oracle_message_shapes(po):
@@ -254,3 +260,4 @@ def test_device_debezium_filter_cast_native_fused(eng, po):
     res_lz, _ = eng.parse_debezium(pid, data, ends, schema_text, wire_fmt=abi.TF_WIRE_CH_NATIVE_LZ4, **kw)
     raw, nf = po.ch_decode_frames(res_lz.wire)
     assert raw == want.raw and nf == res_lz.n_frames
+
