@@ -408,3 +408,28 @@ def test_strict_single_decode_path_equals_the_general_path():
     finally:
         os.environ.pop("TFGPU_TRANSPOSE_GENERAL", None)
     pool.close()
+
+
+def test_inverse_transposer_in_parallel_equals_the_sequential_walk(monkeypatch):
+    """tfgpu_batch_to_rows measures and writes its row ranges on several threads from 8192 rows on (TFGPU_INVERSE_SEQUENTIAL forces one walk
+    over all rows): same image and offsets, for uint32 offsets and for narrow length arrays, with nulls in every column."""
+    batch, _schema = all_types_batch(20000, seed=31)
+    for b in (batch, batch.narrow()):
+        monkeypatch.delenv("TFGPU_INVERSE_SEQUENTIAL", raising=False)
+        image, off = rows.batch_to_rows(b)
+        monkeypatch.setenv("TFGPU_INVERSE_SEQUENTIAL", "1")
+        image_s, off_s = rows.batch_to_rows(b)
+        assert image == image_s and (off == off_s).all() and int(off[-1]) == len(image)
+    monkeypatch.delenv("TFGPU_INVERSE_SEQUENTIAL", raising=False)
+    pool = rows.Columnar()                                                       # and back: the transposer reads what the inverse wrote
+    import ctypes as C
+    n = batch.nrows
+    image, off = rows.batch_to_rows(batch)
+    items = (rows.TfItem * n)()
+    for r in range(n):
+        items[r].values_off = int(off[r]); items[r].n_values = len(_schema); items[r].old_keys_off = rows.NO_OLD_KEYS
+    img = rows.RowsImage([], [("db", "t", _schema)])
+    vals = np.frombuffer(image, dtype=np.uint8).copy()
+    img.struct.n_items = n; img.struct.items = C.cast(items, C.POINTER(rows.TfItem)); img.struct.values = vals.ctypes.data; img.struct.values_len = len(image)
+    assert_same_batch(pool.rows_to_batch(img, threads=4).batch, batch)
+    pool.close()

@@ -762,35 +762,71 @@ int tfgpu_batch_to_rows(const tf_batch* b, uint8_t* out, uint64_t cap, uint64_t*
         if (c.flags & TF_COL_LENS16) return ((const uint16_t*)c.offsets)[r];
         return c.offsets[r + 1] - c.offsets[r];
     };
-    // var-width columns with narrow lengths need running offsets: one cursor per column while rows are walked in order
-    std::vector<uint64_t> cursor(nc, 0);
-    uint64_t at = 0; bool fits = out != nullptr;
-    auto put = [&](const void* p, size_t k) { if (fits && at + k <= cap) std::memcpy(out + at, p, k); else fits = false; at += k; };
-    auto put8 = [&](uint8_t v) { put(&v, 1); };
-    for (uint64_t r = 0; r < n; r++) {
-        row_off[r] = at;
-        for (uint32_t ci = 0; ci < nc; ci++) {
-            const tf_col& c = b->cols[ci];
-            const bool valid = !c.validity || (c.validity[r >> 3] >> (r & 7) & 1);
-            const int w = fixed_width(c.type);
-            uint32_t len = 0; const uint8_t* src = nullptr;
-            if (!w) {
-                len = cell_len(c, r);
-                src = c.heap + ((c.flags & (TF_COL_LENS8 | TF_COL_LENS16)) ? cursor[ci] : c.offsets[r]);
-                cursor[ci] += len;
-            }
-            if (!valid) { put8(TF_V_NIL); continue; }
-            if (w) {
-                if (is_time(c.type)) { put8(TF_V_TIME); put((const uint8_t*)c.values + 8 * r, 8); const uint32_t ns = c.aux ? ((const uint32_t*)c.aux)[r] : 0; put(&ns, 4); }
-                else { put8((uint8_t)canonical_tag(c.type)); put((const uint8_t*)c.values + (size_t)w * r, w); }
-            } else {
-                const bool go_string = c.type == TF_UTF8 || (c.type == TF_ANY && c.aux && ((const uint8_t*)c.aux)[r] == 1);
-                put8(go_string ? TF_V_STRING : c.type == TF_BYTES ? TF_V_BYTES : TF_V_JSON); put(&len, 4); put(src, len);
+    std::vector<int> width(nc); std::vector<uint8_t> narrow(nc);
+    for (uint32_t ci = 0; ci < nc; ci++) { width[ci] = fixed_width(b->cols[ci].type); narrow[ci] = !width[ci] && (b->cols[ci].flags & (TF_COL_LENS8 | TF_COL_LENS16)); }
+    // Rows [r0, r1) written at `at` (or only measured when dst is null); cursor[ci]: where the rows' cells start in a heap whose column
+    // carries lengths instead of offsets. Returns the end position.
+    auto walk = [&](uint64_t r0, uint64_t r1, uint64_t at, uint64_t* cursor, uint8_t* dst, bool offsets_out) -> uint64_t {
+        auto put = [&](const void* p, size_t k) { if (dst) std::memcpy(dst + at, p, k); at += k; };
+        auto put8 = [&](uint8_t v) { if (dst) dst[at] = v; at++; };
+        for (uint64_t r = r0; r < r1; r++) {
+            if (offsets_out) row_off[r] = at;
+            for (uint32_t ci = 0; ci < nc; ci++) {
+                const tf_col& c = b->cols[ci];
+                const bool valid = !c.validity || (c.validity[r >> 3] >> (r & 7) & 1);
+                const int w = width[ci];
+                uint32_t len = 0; const uint8_t* src = nullptr;
+                if (!w) {
+                    len = cell_len(c, r);
+                    src = c.heap + (narrow[ci] ? cursor[ci] : c.offsets[r]);
+                    cursor[ci] += len;
+                }
+                if (!valid) { put8(TF_V_NIL); continue; }
+                if (w) {
+                    if (is_time(c.type)) { put8(TF_V_TIME); put((const uint8_t*)c.values + 8 * r, 8); const uint32_t ns = c.aux ? ((const uint32_t*)c.aux)[r] : 0; put(&ns, 4); }
+                    else { put8((uint8_t)canonical_tag(c.type)); put((const uint8_t*)c.values + (size_t)w * r, w); }
+                } else {
+                    const bool go_string = c.type == TF_UTF8 || (c.type == TF_ANY && c.aux && ((const uint8_t*)c.aux)[r] == 1);
+                    put8(go_string ? TF_V_STRING : c.type == TF_BYTES ? TF_V_BYTES : TF_V_JSON); put(&len, 4); put(src, len);
+                }
             }
         }
+        return at;
+    };
+    int threads = (int)std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency()));
+    if (n < 8192 || threads < 2 || std::getenv("TFGPU_INVERSE_SEQUENTIAL")) {
+        std::vector<uint64_t> cursor(nc, 0);
+        const uint64_t total = walk(0, n, 0, cursor.data(), nullptr, false);                    // measure, then write when it fits
+        const bool fits = out && total <= cap;
+        std::fill(cursor.begin(), cursor.end(), 0);
+        walk(0, n, 0, cursor.data(), fits ? out : nullptr, true);
+        row_off[n] = total; if (need) *need = total;
+        return fits ? TF_OK : TF_E_FATAL_ARG;
     }
-    row_off[n] = at;
-    if (need) *need = at;
+    // in parallel: every task measures its rows, a prefix over the tasks gives each its place in the image (and in the heaps of the columns
+    // that carry lengths), then every task writes its rows
+    const uint64_t chunk = std::max<uint64_t>(1024, (n + (uint64_t)threads * 4 - 1) / ((uint64_t)threads * 4));
+    const uint64_t nchunks = (n + chunk - 1) / chunk;
+    std::vector<uint64_t> bytes(nchunks + 1, 0), cur((nchunks + 1) * (size_t)nc, 0);
+    auto run = [&](const std::function<void(uint64_t)>& task) {
+        std::atomic<uint64_t> next{0}; std::vector<std::thread> ts;
+        auto loop = [&] { for (;;) { const uint64_t k = next.fetch_add(1); if (k >= nchunks) return; task(k); } };
+        for (int t = 1; t < threads; t++) ts.emplace_back(loop);
+        loop();
+        for (auto& t : ts) t.join();
+    };
+    run([&](uint64_t k) {
+        std::vector<uint64_t> c0(nc, 0);
+        bytes[k + 1] = walk(k * chunk, std::min(n, (k + 1) * chunk), 0, c0.data(), nullptr, false);
+        for (uint32_t ci = 0; ci < nc; ci++) cur[(k + 1) * (size_t)nc + ci] = c0[ci];
+    });
+    for (uint64_t k = 0; k < nchunks; k++) { bytes[k + 1] += bytes[k]; for (uint32_t ci = 0; ci < nc; ci++) cur[(k + 1) * (size_t)nc + ci] += cur[k * (size_t)nc + ci]; }
+    const uint64_t total = bytes[nchunks]; const bool fits = out && total <= cap;
+    run([&](uint64_t k) {
+        std::vector<uint64_t> c0(cur.begin() + k * (size_t)nc, cur.begin() + (k + 1) * (size_t)nc);
+        walk(k * chunk, std::min(n, (k + 1) * chunk), bytes[k], c0.data(), fits ? out : nullptr, true);
+    });
+    row_off[n] = total; if (need) *need = total;
     return fits ? TF_OK : TF_E_FATAL_ARG;
 }
 
