@@ -46,4 +46,4 @@ g++ -std=c++17 -O1 -g -fsanitize=thread -fno-omit-frame-pointer -fPIC -shared -I
     -x c++ "$ROOT/transferia_b200/csrc/host_rows.cu" "$ROOT/transferia_b200/csrc/host_sink.cu" "$ROOT/transferia_b200/csrc/host_chwire.cu" "$OUT/stubs.cpp" "$OUT/plan_validate.cpp" \
     -o "$OUT/libtfhost_tsan.so" -L/usr/local/cuda/lib64 -lcudart
 TFGPU_LIB_PATH="$OUT/libtfhost_tsan.so" LD_PRELOAD="$(gcc -print-file-name=libtsan.so)" TSAN_OPTIONS="halt_on_error=1 report_signal_unsafe=0" \
-    python -m pytest tests/test_rows.py tests/test_sink_push.py tests/test_regex_replace.py -q -m "not gpu" -p no:cacheprovider -k "dispatcher or two_pools or host_gather or transposer_fuzz or strict_single or replace_steps or mixed_text or inverse_transposer"
+    python -m pytest tests/test_rows.py tests/test_sink_push.py tests/test_regex_replace.py -q -m "not gpu" -p no:cacheprovider -k "dispatcher or two_pools or host_gather or transposer_fuzz or strict_single or replace_steps or mixed_text or inverse_transposer or under_the_dispatcher"

@@ -376,3 +376,31 @@ def test_mixed_text_types_keep_the_type_assertion():
     items[1].values[2] = go.bytes(b"b_2")
     ((_, _, e),) = _push([{"regex_replace_transformer": {"regexMatch": "_", "replaceRule": "-" * 300}}], items, [("d", "t", schema)])
     assert _text_col(e, 1) == [b"x" + b"-" * 300 + b"y"] * 2 + [None] and _text_col(e, 2) == [b"b" + b"-" * 300 + b"1", b"b" + b"-" * 300 + b"2", b""]
+
+
+def test_replace_steps_under_the_dispatcher():
+    """Three sinks with their own replace steps behind tfgpu_dispatcher (a regexp machine belongs to one thread: the row form keeps one per
+    sink, the column form makes one per worker task): 30 batches, every delivered text equals the oracle's."""
+    import threading
+    schema = [{"name": "id", "type": "int32", "key": True}, {"name": "s", "type": "utf8"}]
+    got, lock = {}, threading.Lock()
+    def downstream(ev):
+        if ev["type"] == sink.EV_ROWS:
+            with lock:
+                for i, text in zip(ev["columns"][0], sink.var_cells(ev, 1)): got[int(i)] = text
+        return 0
+    tr = [{"regex_replace_transformer": {"regexMatch": r"(\w+)@(\w+)", "replaceRule": "$2 at $1"}}, {"regex_replace_transformer": {"regexMatch": "(?i)x+", "replaceRule": "-"}}]
+    sinks = [sink.Sink(transformers=tr, downstream=downstream) for _ in range(3)]
+    d = sink.Dispatcher(sinks)
+    want = {}
+    for b in range(30):
+        its = []
+        for i in range(b * 100, b * 100 + 40 + b):
+            text = ("user%d@hostXx%d " % (i, i % 7)) * (1 + i % 3)
+            want[i] = ro.replace_all("(?i)x+", "-", ro.replace_all(r"(\w+)@(\w+)", "$2 at $1", text.encode()))
+            its.append(ChangeItem(K.KIND_INSERT, 0, [go.int32(i), go.string(text)]) if (b % 4 or i % 5) else ChangeItem(K.KIND_UPDATE, 0, {0: go.int32(i), 1: go.string(text)}, {0: go.int32(i)}))
+        d.submit(rows.RowsImage(its, [("public", "t", schema)]))
+    assert d.drain() == 0
+    d.close()
+    for s in sinks: s.close()
+    assert got == want
